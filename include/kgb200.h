@@ -1,0 +1,125 @@
+/* kgb200.h - C ABI of the B200-native KataGo NN-evaluator backend (libkgb200.so).
+ *
+ * Drop-in boundary: the reference selects ONE translation unit defining `namespace NeuralNet`
+ * (cpp/neuralnet/nninterface.h:32-182) at link time.  A maintainer adds `neuralnet/b200backend.cpp`
+ * (integration/b200backend.cpp in this repository) whose functions forward 1:1 to the entry
+ * points below.  Plain pointers and sizes only; no exceptions, no C++ or torch types cross this boundary; every
+ * function returns KGB_OK (0) or a negative status with the message available from kgb_last_error().
+ * Buffers passed to kgb_forward are HOST memory owned by the caller (the reference's NNResultBuf / NNOutput arrays);
+ * host<->device copies happen inside the call, exactly like cudabackend.cpp:3714-3782.
+ */
+#ifndef KGB200_H_
+#define KGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KGB_API __attribute__((visibility("default")))
+#else
+#define KGB_API
+#endif
+
+#define KGB_OK 0
+#define KGB_ERR_INVALID (-1)   /* bad argument / unsupported model */
+#define KGB_ERR_IO (-2)        /* model file could not be read / sha256 mismatch */
+#define KGB_ERR_CUDA (-3)      /* CUDA runtime or driver failure, or no sm_100 device */
+
+typedef struct kgb_model kgb_model;     /* replaces LoadedModel     (nninterface.h:27, eigenbackend.cpp:94-107) */
+typedef struct kgb_context kgb_context; /* replaces ComputeContext  (nninterface.h:17) */
+typedef struct kgb_handle kgb_handle;   /* replaces ComputeHandle   (nninterface.h:21) - one per server thread, not thread-safe */
+
+/* Subset of ModelDesc (cpp/neuralnet/desc.h:508-571) that NNEvaluator reads through getModelDesc(). */
+typedef struct kgb_model_info {
+  char name[128];
+  char sha256[65];
+  int32_t model_version;
+  int32_t num_input_channels;
+  int32_t num_input_global_channels;
+  int32_t num_policy_channels;
+  int32_t num_value_channels;
+  int32_t num_score_value_channels;
+  int32_t num_ownership_channels;
+  int32_t trunk_num_channels;
+  int32_t num_blocks;
+  int32_t prefer_pass_alive_under_suicide_rules;
+  float td_score_multiplier;
+  float score_mean_multiplier;
+  float score_stdev_multiplier;
+  float lead_multiplier;
+  float variance_time_multiplier;
+  float shortterm_value_error_multiplier;
+  float shortterm_score_error_multiplier;
+  int64_t conv_macs_per_position; /* direct-convolution MACs per board point (ModelDesc::iterConvLayers, desc.cpp:2643) */
+} kgb_model_info;
+
+/* NeuralNet::globalInitialize / globalCleanup (nninterface.h:34-36). */
+KGB_API int kgb_global_init(void);
+KGB_API int kgb_global_cleanup(void);
+/* Message of the last failure on the calling thread ("" if none). */
+KGB_API const char* kgb_last_error(void);
+/* NeuralNet::printDevices (nninterface.h:39): number of CUDA devices and, per device, name/compute capability. */
+KGB_API int kgb_device_count(int* count);
+KGB_API int kgb_device_name(int device, char* buf, int buf_len, int* cc_major, int* cc_minor);
+
+/* NeuralNet::loadModelFile / freeLoadedModel / getModelDesc (nninterface.h:43-46).
+ * expected_sha256 may be NULL or "" to skip verification. */
+KGB_API int kgb_model_load_file(const char* path, const char* expected_sha256, kgb_model** out);
+KGB_API void kgb_model_free(kgb_model* model);
+KGB_API int kgb_model_get_info(const kgb_model* model, kgb_model_info* out);
+
+/* NeuralNet::createComputeContext / freeComputeContext (nninterface.h:50-65).
+ * fp16_mode: 0 = "fp32-equivalent" (3-term split-fp16 on the tensor pipe, fp32 streams), 1 = fp16 operands with fp32
+ * accumulation, -1 = auto (fp16). */
+KGB_API int kgb_context_create(const int* gpu_idxs, int num_gpu_idxs, int nn_x_len, int nn_y_len, int fp16_mode,
+                       const kgb_model* model, kgb_context** out);
+KGB_API void kgb_context_free(kgb_context* ctx);
+
+/* NeuralNet::createComputeHandle / freeComputeHandle / isUsingFP16 (nninterface.h:76-94).
+ * gpu_idx == -1 selects the context's first device (or device 0).  inputs_nhwc selects the layout of `spatial`
+ * in kgb_forward: 1 = [n][Y][X][C], 0 = [n][C][Y][X]. */
+KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_batch_size, int require_exact_nn_len,
+                      int inputs_nhwc, int gpu_idx, kgb_handle** out);
+KGB_API void kgb_handle_free(kgb_handle* handle);
+KGB_API int kgb_handle_is_fp16(const kgb_handle* handle);
+
+/* NeuralNet::getOutput (nninterface.h:117-123).  For each of the n rows:
+ *   spatial        [n][num_input_channels * X * Y]   NNResultBuf::rowSpatialBuf (fillRowV7 output, no symmetry applied)
+ *   global         [n][num_input_global_channels]    NNResultBuf::rowGlobalBuf
+ *   symmetry       [n] in 0..7                       NNResultBuf::symmetry (applied to inputs, inverted on outputs)
+ *   policy_optimism[n]                               NNResultBuf::policyOptimism
+ * Outputs (raw logits; NNEvaluator does the softmax/tanh post-processing, nneval.cpp:960-1249):
+ *   policy         [n][X*Y + 1]  NNOutput::policyProbs (pass last)
+ *   value          [n][3]        whiteWinProb, whiteLossProb, whiteNoResultProb
+ *   score_value    [n][6]        whiteScoreMean, whiteScoreMeanSq, whiteLead, varTimeLeft, shorttermWinlossError,
+ *                                shorttermScoreError (filled by model version as eigenbackend.cpp:2583-2626)
+ *   ownership      [n][X*Y] or NULL (NNOutput::whiteOwnerMap)
+ */
+KGB_API int kgb_forward(kgb_handle* handle, int n, const float* spatial, const float* global, const int32_t* symmetry,
+                const float* policy_optimism, float* policy, float* value, float* score_value, float* ownership);
+
+/* Same computation with every buffer already resident in this handle's device memory (used by the device-resident
+ * self-play loop and by bench.py's HBM-resident timing).  Pointers are device pointers; the call is asynchronous on the
+ * handle's stream - use kgb_handle_sync() before reading results from another stream. */
+KGB_API int kgb_forward_device(kgb_handle* handle, int n, const float* d_spatial, const float* d_global, const int32_t* d_symmetry,
+                       const float* d_policy_optimism, float* d_policy, float* d_value, float* d_score_value,
+                       float* d_ownership);
+KGB_API int kgb_handle_sync(kgb_handle* handle);
+/* cudaStream_t of the handle (as an integer) so a torch/CUDA caller can order its own work against it. */
+KGB_API uint64_t kgb_handle_stream(kgb_handle* handle);
+/* Number of kernel launches one kgb_forward of batch n issues (for bench.py's gpu_launches accounting). */
+KGB_API int kgb_handle_launches_per_forward(const kgb_handle* handle);
+
+/* FOR TESTING: NeuralNet::testEvaluateConv (nninterface.h:134-143).  weights in the model-file order
+ * [ky][kx][in_c][out_c]; input/output [n][Y][X][C] (NHWC) fp32.  use_fp16 selects the operand mode as in
+ * kgb_context_create.  Returns KGB_OK and fills output[n*Y*X*out_c]. */
+KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
+                  const float* input, float* output);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGB200_H_ */

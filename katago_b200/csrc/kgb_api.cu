@@ -1,0 +1,761 @@
+// C-ABI of libkgb200.so (include/kgb200.h) and the forward-pass engine behind it.
+//
+// The engine turns a ModelDesc into a flat list of launches ("ops") at handle creation:
+//   pack-input -> initial conv(+global matmul bias) -> residual / gpool / nested-bottleneck blocks -> fused head conv
+//   -> pooling, tiny matmuls, policy / ownership / value outputs.
+// Every convolution is one launch of the tcgen05 kernel with the NEXT layer's BN+activation+mask fused into its
+// epilogue (kgb_conv.cuh), so a trunk layer is exactly one kernel.  Per batch size the whole list is captured once into
+// a CUDA graph (no tracing compiler: the op list is static).  Reference structure mirrored: Model/Trunk/heads
+// eigenbackend.cpp:1909-2216, getOutput :2445-2628 (and cudabackend.cpp:3649-3888 for the host<->device traffic).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/kgb200.h"
+#include "kgb_conv.cuh"
+#include "kgb_kernels.cuh"
+#include "kgb_model.h"
+
+using namespace kgb;
+
+// ------------------------------------------------------------------------------------------------------------
+// Error plumbing
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError;
+
+struct CudaFailure : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CK(expr)                                                                                                       \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if(_e != cudaSuccess)                                                                                              \
+      throw CudaFailure(std::string("CUDA error ") + cudaGetErrorName(_e) + " (" + cudaGetErrorString(_e) + ") at " + \
+                        __FILE__ + ":" + std::to_string(__LINE__) + ": " #expr);                                       \
+  } while(0)
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return KGB_OK;
+  }
+  catch(const CudaFailure& e) { g_lastError = e.what(); return KGB_ERR_CUDA; }
+  catch(const std::invalid_argument& e) { g_lastError = e.what(); return KGB_ERR_INVALID; }
+  catch(const std::exception& e) { g_lastError = e.what(); return KGB_ERR_IO; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled getEncodeTiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if(fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if(p == nullptr || qres != cudaDriverEntryPointSuccess) throw CudaFailure("cuTensorMapEncodeTiled is not available from this driver");
+    fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major tensor [rows][cols], box {64 cols, boxRows}, 128B swizzle, zero OOB fill.
+static CUtensorMap makeTmap2D(const void* ptr, uint64_t rows, uint64_t cols, uint32_t boxRows) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(__half)};
+  cuuint32_t box[2] = {64, boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = getEncodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if(r != CUDA_SUCCESS) throw CudaFailure("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Opaque handles
+// ------------------------------------------------------------------------------------------------------------
+struct kgb_model {
+  std::unique_ptr<ModelDesc> desc;
+};
+
+struct kgb_context {
+  std::vector<int> gpuIdxs;
+  int X = 0, Y = 0;
+  int fp16 = 1;
+  const kgb_model* model = nullptr;
+};
+
+static inline int cpad(int c) { return (c + 63) / 64 * 64; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct ConvWeights {
+  __half* w = nullptr;     // packed [taps][cout_p][cin_p * (split ? 2 : 1)]
+  int ky = 0, kx = 0, cin_p = 0, cout_p = 0, n_tile = 0, num_n_tiles = 0;
+  CUtensorMap tmapB;
+};
+
+struct kgb_handle {
+  int device = 0;
+  int numSMs = 0;
+  cudaStream_t stream = nullptr;
+  const ModelDesc* model = nullptr;
+  Layout L{};
+  int maxBatch = 0;
+  int split = 0;          // fp32-equivalent mode
+  bool nhwc = true;
+  bool streamTrunkFp32 = true, streamInnerFp32 = false;
+  bool useSimt = false, useGraph = true;
+  std::vector<void*> allocs;
+  // inputs / outputs (device, fixed addresses so graphs can be replayed)
+  float *dSpatial = nullptr, *dGlobal = nullptr, *dOptimism = nullptr;
+  int* dSymmetry = nullptr;
+  float *dPolicy = nullptr, *dValue = nullptr, *dScore = nullptr, *dOwnership = nullptr;
+  // pinned staging
+  float *hSpatial = nullptr, *hGlobal = nullptr, *hOptimism = nullptr, *hPolicy = nullptr, *hValue = nullptr, *hScore = nullptr,
+        *hOwnership = nullptr;
+  int* hSymmetry = nullptr;
+  float *dMask = nullptr, *dMaskSum = nullptr;
+  std::vector<std::function<void(int, cudaStream_t)>> ops;
+  int launchesPerForward = 0;
+  std::map<int, cudaGraphExec_t> graphs;
+
+  template <class T>
+  T* dalloc(size_t count) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    CK(cudaMemset(p, 0, count * sizeof(T)));
+    allocs.push_back(p);
+    return (T*)p;
+  }
+  float* upload(const std::vector<float>& v, size_t padTo = 0) {
+    size_t n = std::max(v.size(), padTo);
+    float* d = dalloc<float>(n);
+    if(!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Graph builder
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ConvSource {
+  const ConvDesc* conv;
+};
+
+struct Builder {
+  kgb_handle& h;
+  const ModelDesc& m;
+  size_t Mmax;
+  int actMul;  // 2 in split mode ([hi | lo])
+  Builder(kgb_handle& hh) : h(hh), m(*hh.model), Mmax((size_t)hh.maxBatch * hh.L.P), actMul(hh.split ? 2 : 1) {}
+
+  struct Level {
+    int C = 0, cp = 0;
+    bool fp32 = false;
+    void* S = nullptr;       // raw stream [M][cp]
+    __half* A = nullptr;     // act(preBN(S)) for the next consumer
+    __half* T = nullptr;     // mid activations inside residual units
+    float* G = nullptr;      // fp32 raw output of the gpool unit's first conv
+    int gcp = 0;
+  };
+
+  // Levels with the same channel count share their buffers (all nested blocks of a net reuse one set): a line that is
+  // overwritten while still in L2 never costs an HBM write-back, and the footprint stays ~0.5 GB at batch 256.
+  std::map<int, Level> levelCache;
+
+  Level makeLevel(int C, bool fp32, const std::vector<BlockDesc>& blocks) {
+    Level& lv = levelCache[C * 2 + (fp32 ? 1 : 0)];
+    if(lv.S == nullptr) {
+      lv.C = C; lv.cp = cpad(C); lv.fp32 = fp32;
+      lv.S = fp32 ? (void*)h.dalloc<float>(Mmax * lv.cp) : (void*)h.dalloc<__half>(Mmax * lv.cp);
+      lv.A = h.dalloc<__half>(Mmax * lv.cp * actMul);
+    }
+    bool needT = false;
+    int gcp = 0;
+    for(const auto& b : blocks) {
+      if(b.kind != BLOCK_NESTED) needT = true;
+      if(b.kind == BLOCK_GPOOL) gcp = std::max(gcp, cpad(b.conv1.cout + b.gpoolConv.cout));
+    }
+    if(needT && lv.T == nullptr) lv.T = h.dalloc<__half>(Mmax * lv.cp * actMul);
+    if(gcp > lv.gcp) { lv.G = h.dalloc<float>(Mmax * gcp); lv.gcp = gcp; }
+    return lv;
+  }
+
+  // Pack one or more convs (concatenated along cout) as fp16 [tap][cout_p][cin_p (* 2)]
+  ConvWeights packConv(const std::vector<const ConvDesc*>& convs) {
+    const ConvDesc& c0 = *convs[0];
+    ConvWeights cw;
+    cw.ky = c0.ky; cw.kx = c0.kx;
+    cw.cin_p = cpad(c0.cin);
+    int cout = 0;
+    for(auto c : convs) {
+      if(c->ky != c0.ky || c->kx != c0.kx || c->cin != c0.cin) throw std::invalid_argument("cannot fuse convolutions of different shapes");
+      cout += c->cout;
+    }
+    cw.cout_p = cpad(cout);
+    int nt = (cw.cout_p + 255) / 256;
+    while(cw.cout_p % nt != 0 || (cw.cout_p / nt) % 32 != 0) nt++;
+    cw.num_n_tiles = nt;
+    cw.n_tile = cw.cout_p / nt;
+    int taps = cw.ky * cw.kx;
+    int ldw = cw.cin_p * actMul;
+    std::vector<__half> host((size_t)taps * cw.cout_p * ldw, __float2half(0.0f));
+    int coBase = 0;
+    for(auto c : convs) {
+      for(int t = 0; t < taps; t++)
+        for(int ci = 0; ci < c->cin; ci++)
+          for(int co = 0; co < c->cout; co++) {
+            float w = c->w[((size_t)t * c->cin + ci) * c->cout + co];
+            __half hi = __float2half_rn(w);
+            size_t o = ((size_t)t * cw.cout_p + coBase + co) * ldw + ci;
+            host[o] = hi;
+            if(h.split) host[o + cw.cin_p] = __float2half_rn(w - __half2float(hi));
+          }
+      coBase += c->cout;
+    }
+    cw.w = h.dalloc<__half>(host.size());
+    CK(cudaMemcpy(cw.w, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    cw.tmapB = makeTmap2D(cw.w, (uint64_t)taps * cw.cout_p, (uint64_t)ldw, (uint32_t)cw.n_tile);
+    return cw;
+  }
+
+  struct BNDev {
+    const float* scale = nullptr;
+    const float* bias = nullptr;
+    int act = ACT_IDENTITY;
+  };
+  BNDev uploadBN(const BNDesc& bn, int act, int cp) {
+    BNDev d;
+    d.scale = h.upload(bn.scale, cp);
+    d.bias = h.upload(bn.bias, cp);
+    d.act = act;
+    return d;
+  }
+
+  // Emit one convolution op.  residual/rawOut may alias (in-place residual update).
+  void emitConv(const ConvWeights& cw, const __half* A, const void* residual, bool residualFp32, const float* ncbias, void* rawOut,
+                bool rawFp32, __half* actOut, BNDev bn) {
+    kgb_handle* hp = &h;
+    const int actMulL = actMul;
+    h.ops.push_back([=](int n, cudaStream_t s) {
+      ConvParams p;
+      memset(&p, 0, sizeof(p));
+      p.M = n * hp->L.P;
+      p.P = hp->L.P;
+      p.Wp = hp->L.Wp;
+      p.ky = cw.ky; p.kx = cw.kx;
+      p.cin_p = cw.cin_p; p.cout_p = cw.cout_p;
+      p.n_tile = cw.n_tile;
+      p.num_m_tiles = (p.M + 127) / 128;
+      p.num_n_tiles = cw.num_n_tiles;
+      p.split = hp->split;
+      p.residual = residual; p.residual_fp32 = residualFp32 ? 1 : 0;
+      p.ncbias = ncbias;
+      p.raw_out = rawOut; p.raw_fp32 = rawFp32 ? 1 : 0;
+      p.act_out = actOut;
+      p.bn_scale = bn.scale; p.bn_bias = bn.bias; p.act = bn.act;
+      p.mask = hp->dMask;
+      if(hp->useSimt) {
+        CK(launchConvSimt(A, cw.cin_p * actMulL, cw.w, p, s));
+      }
+      else {
+        CUtensorMap tmA = makeTmap2D(A, (uint64_t)p.M, (uint64_t)cw.cin_p * actMulL, 128);
+        CK(launchConvTC(tmA, cw.tmapB, p, hp->numSMs, s));
+      }
+    });
+    h.launchesPerForward++;
+  }
+
+  // blocks operate on stream lv.S, with lv.A = act(preBN_0(S)) on entry and = act(finalBN(S_out)) on exit.
+  void emitBlocks(const std::vector<BlockDesc>& blocks, Level& lv, const BNDesc& finalBN, int finalAct, bool keepFinalRaw) {
+    for(size_t i = 0; i < blocks.size(); i++) {
+      const BlockDesc& b = blocks[i];
+      bool last = i + 1 == blocks.size();
+      const BNDesc& nextBNd = last ? finalBN : blocks[i + 1].preBN;
+      int nextAct = last ? finalAct : blocks[i + 1].preAct;
+      BNDev nextBN = uploadBN(nextBNd, nextAct, lv.cp);
+      void* rawOut = (last && !keepFinalRaw) ? nullptr : lv.S;
+      if(b.kind == BLOCK_ORDINARY) {
+        ConvWeights w1 = packConv({&b.conv1});
+        ConvWeights w2 = packConv({&b.conv2});
+        BNDev mid = uploadBN(b.midBN, b.midAct, w1.cout_p);
+        emitConv(w1, lv.A, nullptr, false, nullptr, nullptr, false, lv.T, mid);
+        emitConv(w2, lv.T, lv.S, lv.fp32, nullptr, rawOut, lv.fp32, lv.A, nextBN);
+      }
+      else if(b.kind == BLOCK_GPOOL) {
+        ConvWeights w1 = packConv({&b.conv1, &b.gpoolConv});
+        ConvWeights w2 = packConv({&b.conv2});
+        const int regC = b.conv1.cout, gC = b.gpoolConv.cout;
+        BNDev none;
+        emitConv(w1, lv.A, nullptr, false, nullptr, lv.G, true, nullptr, none);
+        BNDev gbn = uploadBN(b.gpoolBN, b.gpoolAct, gC);
+        float* pooled = h.dalloc<float>((size_t)h.maxBatch * 3 * gC);
+        float* bias = h.dalloc<float>((size_t)h.maxBatch * regC);
+        const float* Wg = h.upload(b.gpoolToBias.w);
+        BNDev mid = uploadBN(b.midBN, b.midAct, regC);
+        kgb_handle* hp = &h;
+        float* G = lv.G; __half* T = lv.T;
+        const int gld = w1.cout_p, tcp = w2.cin_p, split = h.split;
+        h.ops.push_back([=](int n, cudaStream_t s) {
+          CK(launchGPool(G, 1, gld, regC, gC, gbn.scale, gbn.bias, gbn.act, hp->dMask, hp->dMaskSum, n, hp->L, 0, pooled, s));
+          CK(launchMatMulNC(pooled, 3 * gC, Wg, nullptr, n, 3 * gC, regC, ACT_IDENTITY, bias, regC, s));
+          CK(launchBiasAct(G, 1, gld, regC, bias, regC, mid.scale, mid.bias, mid.act, hp->dMask, n * hp->L.P, hp->L.P, T, tcp, split, s));
+        });
+        h.launchesPerForward += 3;
+        emitConv(w2, lv.T, lv.S, lv.fp32, nullptr, rawOut, lv.fp32, lv.A, nextBN);
+      }
+      else {
+        ConvWeights wpre = packConv({&b.conv1});
+        ConvWeights wpost = packConv({&b.conv2});
+        Level inner = makeLevel(b.conv1.cout, h.streamInnerFp32, b.blocks);
+        BNDev innerPre = uploadBN(b.blocks[0].preBN, b.blocks[0].preAct, inner.cp);
+        emitConv(wpre, lv.A, nullptr, false, nullptr, inner.S, inner.fp32, inner.A, innerPre);
+        emitBlocks(b.blocks, inner, b.midBN, b.midAct, false);
+        emitConv(wpost, inner.A, lv.S, lv.fp32, nullptr, rawOut, lv.fp32, lv.A, nextBN);
+      }
+    }
+  }
+
+  void build() {
+    const Layout& L = h.L;
+    const int XY = L.X * L.Y;
+    const int cinP = cpad(m.numInputChannels);
+    // inputs / outputs
+    h.dSpatial = h.dalloc<float>((size_t)h.maxBatch * m.numInputChannels * XY);
+    h.dGlobal = h.dalloc<float>((size_t)h.maxBatch * m.numInputGlobalChannels);
+    h.dOptimism = h.dalloc<float>(h.maxBatch);
+    h.dSymmetry = h.dalloc<int>(h.maxBatch);
+    h.dPolicy = h.dalloc<float>((size_t)h.maxBatch * (XY + 1));
+    h.dValue = h.dalloc<float>((size_t)h.maxBatch * 3);
+    h.dScore = h.dalloc<float>((size_t)h.maxBatch * 6);
+    h.dOwnership = h.dalloc<float>((size_t)h.maxBatch * XY);
+    h.dMask = h.dalloc<float>(Mmax + 128);
+    h.dMaskSum = h.dalloc<float>(h.maxBatch);
+    __half* inAct = h.dalloc<__half>(Mmax * cinP * actMul);
+    kgb_handle* hp = &h;
+    const int C = m.numInputChannels, split = h.split;
+    h.ops.push_back([=](int n, cudaStream_t s) {
+      CK(launchPackInput(hp->dSpatial, n, C, hp->nhwc, hp->dSymmetry, hp->L, inAct, cinP, split, hp->dMask, hp->dMaskSum, s));
+    });
+    h.launchesPerForward += 4;
+    // trunk
+    Level trunk = makeLevel(m.trunkC, h.streamTrunkFp32, m.blocks);
+    float* initBias = h.dalloc<float>((size_t)h.maxBatch * trunk.cp);
+    const float* Wglob = h.upload(m.initialMatMul.w);
+    const int G = m.numInputGlobalChannels, trunkC = m.trunkC, trunkCp = trunk.cp;
+    h.ops.push_back([=](int n, cudaStream_t s) {
+      CK(launchMatMulNC(hp->dGlobal, G, Wglob, nullptr, n, G, trunkC, ACT_IDENTITY, initBias, trunkCp, s));
+    });
+    h.launchesPerForward++;
+    ConvWeights winit = packConv({&m.initialConv});
+    BNDev firstPre = uploadBN(m.blocks[0].preBN, m.blocks[0].preAct, trunk.cp);
+    emitConv(winit, inAct, nullptr, false, initBias, trunk.S, trunk.fp32, trunk.A, firstPre);
+    emitBlocks(m.blocks, trunk, m.tipBN, m.tipAct, false);
+    // heads: one fused 1x1 conv [p1 | g1 | v1] -> fp32 raw H
+    ConvWeights wheads = packConv({&m.p1Conv, &m.g1Conv, &m.v1Conv});
+    float* H = h.dalloc<float>(Mmax * wheads.cout_p);
+    BNDev none;
+    emitConv(wheads, trunk.A, nullptr, false, nullptr, H, true, nullptr, none);
+    const int p1C = m.p1Conv.cout, g1C = m.g1Conv.cout, v1C = m.v1Conv.cout, hld = wheads.cout_p;
+    BNDev g1bn = uploadBN(m.g1BN, m.g1Act, g1C);
+    BNDev p1bn = uploadBN(m.p1BN, m.p1Act, p1C);
+    BNDev v1bn = uploadBN(m.v1BN, m.v1Act, v1C);
+    float* g1pool = h.dalloc<float>((size_t)h.maxBatch * 3 * g1C);
+    float* g1bias = h.dalloc<float>((size_t)h.maxBatch * p1C);
+    const float* Wg2b = h.upload(m.gpoolToBias.w);
+    const float* Wp2 = h.upload(m.p2Conv.w);
+    const int cp2 = m.policyOutChannels;
+    const float* Wpass = h.upload(m.gpoolToPass.w);
+    const int passMid = m.gpoolToPass.cout;
+    const float* passBias = m.version >= 15 ? h.upload(m.gpoolToPassBias.w) : nullptr;
+    const float* Wpass2 = m.version >= 15 ? h.upload(m.gpoolToPass2.w) : nullptr;
+    const int passAct = m.passAct, version = m.version;
+    float* passH = h.dalloc<float>((size_t)h.maxBatch * std::max(passMid, 4));
+    float* passLogits = h.dalloc<float>((size_t)h.maxBatch * 4);
+    float* v1pool = h.dalloc<float>((size_t)h.maxBatch * 3 * v1C);
+    const int v2C = m.v2Mul.cout;
+    float* v2 = h.dalloc<float>((size_t)h.maxBatch * v2C);
+    const float* Wv2 = h.upload(m.v2Mul.w); const float* bv2 = h.upload(m.v2Bias.w); const int v2Act = m.v2Act;
+    const float* Wv3 = h.upload(m.v3Mul.w); const float* bv3 = h.upload(m.v3Bias.w);
+    const float* Wsv3 = h.upload(m.sv3Mul.w); const float* bsv3 = h.upload(m.sv3Bias.w);
+    const int numSV = m.sv3Mul.cout;
+    float* value = h.dalloc<float>((size_t)h.maxBatch * 3);
+    float* sv = h.dalloc<float>((size_t)h.maxBatch * 8);
+    const float* Wown = h.upload(m.ownershipConv.w);
+    h.ops.push_back([=](int n, cudaStream_t s) {
+      // policy head
+      CK(launchGPool(H, 1, hld, p1C, g1C, g1bn.scale, g1bn.bias, g1bn.act, hp->dMask, hp->dMaskSum, n, hp->L, 0, g1pool, s));
+      CK(launchMatMulNC(g1pool, 3 * g1C, Wg2b, nullptr, n, 3 * g1C, p1C, ACT_IDENTITY, g1bias, p1C, s));
+      CK(launchPolicyOut(H, hld, 0, p1C, g1bias, p1C, p1bn.scale, p1bn.bias, p1bn.act, Wp2, cp2, hp->dMask, hp->dSymmetry,
+                         hp->dOptimism, n, hp->L, hp->dPolicy, s));
+      if(version >= 15) {
+        CK(launchMatMulNC(g1pool, 3 * g1C, Wpass, passBias, n, 3 * g1C, passMid, passAct, passH, passMid, s));
+        CK(launchMatMulNC(passH, passMid, Wpass2, nullptr, n, passMid, cp2, ACT_IDENTITY, passLogits, 4, s));
+      }
+      else {
+        CK(launchMatMulNC(g1pool, 3 * g1C, Wpass, nullptr, n, 3 * g1C, cp2, ACT_IDENTITY, passLogits, 4, s));
+      }
+      // value head
+      CK(launchGPool(H, 1, hld, p1C + g1C, v1C, v1bn.scale, v1bn.bias, v1bn.act, hp->dMask, hp->dMaskSum, n, hp->L, 1, v1pool, s));
+      CK(launchMatMulNC(v1pool, 3 * v1C, Wv2, bv2, n, 3 * v1C, v2C, v2Act, v2, v2C, s));
+      CK(launchMatMulNC(v2, v2C, Wv3, bv3, n, v2C, 3, ACT_IDENTITY, value, 3, s));
+      CK(launchMatMulNC(v2, v2C, Wsv3, bsv3, n, v2C, numSV, ACT_IDENTITY, sv, numSV, s));
+      CK(launchOwnershipOut(H, hld, p1C + g1C, v1C, v1bn.scale, v1bn.bias, v1bn.act, Wown, hp->dMask, hp->dSymmetry, n, hp->L,
+                            hp->dOwnership, s));
+      CK(launchFinalize(passLogits, 4, cp2, hp->dOptimism, value, sv, numSV, version, n, hp->L.X * hp->L.Y + 1, hp->dPolicy,
+                        hp->dValue, hp->dScore, s));
+    });
+    h.launchesPerForward += (version >= 15 ? 11 : 10);
+  }
+};
+
+void runOps(kgb_handle* h, int n) {
+  if(!h->useGraph) {
+    for(auto& op : h->ops) op(n, h->stream);
+    return;
+  }
+  auto it = h->graphs.find(n);
+  if(it == h->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      for(auto& op : h->ops) op(n, h->stream);
+    }
+    catch(...) {
+      cudaStreamEndCapture(h->stream, &graph);
+      if(graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CK(cudaStreamEndCapture(h->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    it = h->graphs.emplace(n, exec).first;
+  }
+  CK(cudaGraphLaunch(it->second, h->stream));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+KGB_API int kgb_global_init(void) { return KGB_OK; }
+KGB_API int kgb_global_cleanup(void) { return KGB_OK; }
+KGB_API const char* kgb_last_error(void) { return g_lastError.c_str(); }
+
+KGB_API int kgb_device_count(int* count) {
+  return guarded([&] {
+    if(!count) throw std::invalid_argument("kgb_device_count: count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if(e != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *count = c;
+  });
+}
+
+KGB_API int kgb_device_name(int device, char* buf, int buf_len, int* cc_major, int* cc_minor) {
+  return guarded([&] {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if(buf && buf_len > 0) { strncpy(buf, prop.name, buf_len - 1); buf[buf_len - 1] = 0; }
+    if(cc_major) *cc_major = prop.major;
+    if(cc_minor) *cc_minor = prop.minor;
+  });
+}
+
+KGB_API int kgb_model_load_file(const char* path, const char* expected_sha256, kgb_model** out) {
+  return guarded([&] {
+    if(!path || !out) throw std::invalid_argument("kgb_model_load_file: NULL argument");
+    std::unique_ptr<kgb_model> m(new kgb_model());
+    m->desc = loadModelFile(path, expected_sha256 ? expected_sha256 : "");
+    *out = m.release();
+  });
+}
+
+KGB_API void kgb_model_free(kgb_model* model) { delete model; }
+
+KGB_API int kgb_model_get_info(const kgb_model* model, kgb_model_info* out) {
+  return guarded([&] {
+    if(!model || !out) throw std::invalid_argument("kgb_model_get_info: NULL argument");
+    const ModelDesc& d = *model->desc;
+    memset(out, 0, sizeof(*out));
+    strncpy(out->name, d.name.c_str(), sizeof(out->name) - 1);
+    strncpy(out->sha256, d.sha256.c_str(), sizeof(out->sha256) - 1);
+    out->model_version = d.version;
+    out->num_input_channels = d.numInputChannels;
+    out->num_input_global_channels = d.numInputGlobalChannels;
+    out->num_policy_channels = d.policyOutChannels;
+    out->num_value_channels = d.v3Mul.cout;
+    out->num_score_value_channels = d.sv3Mul.cout;
+    out->num_ownership_channels = d.ownershipConv.cout;
+    out->trunk_num_channels = d.trunkC;
+    out->num_blocks = (int)d.blocks.size();
+    out->prefer_pass_alive_under_suicide_rules = d.preferPassAliveUnderSuicideRules;
+    out->td_score_multiplier = d.tdScoreMultiplier;
+    out->score_mean_multiplier = d.scoreMeanMultiplier;
+    out->score_stdev_multiplier = d.scoreStdevMultiplier;
+    out->lead_multiplier = d.leadMultiplier;
+    out->variance_time_multiplier = d.varianceTimeMultiplier;
+    out->shortterm_value_error_multiplier = d.shorttermValueErrorMultiplier;
+    out->shortterm_score_error_multiplier = d.shorttermScoreErrorMultiplier;
+    out->conv_macs_per_position = d.convMacsPerPosition();
+  });
+}
+
+KGB_API int kgb_context_create(const int* gpu_idxs, int num_gpu_idxs, int nn_x_len, int nn_y_len, int fp16_mode, const kgb_model* model,
+                       kgb_context** out) {
+  return guarded([&] {
+    if(!model || !out) throw std::invalid_argument("kgb_context_create: NULL argument");
+    if(nn_x_len < 2 || nn_y_len < 2 || nn_x_len > 37 || nn_y_len > 37) throw std::invalid_argument("kgb_context_create: nnXLen/nnYLen out of range");
+    std::unique_ptr<kgb_context> c(new kgb_context());
+    for(int i = 0; i < num_gpu_idxs; i++) c->gpuIdxs.push_back(gpu_idxs[i]);
+    c->X = nn_x_len; c->Y = nn_y_len;
+    c->fp16 = (fp16_mode == 0) ? 0 : 1;
+    c->model = model;
+    *out = c.release();
+  });
+}
+
+KGB_API void kgb_context_free(kgb_context* ctx) { delete ctx; }
+
+static void destroyHandle(kgb_handle* h) {
+  if(!h) return;
+  cudaSetDevice(h->device);
+  for(auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+  for(void* p : h->allocs) cudaFree(p);
+  for(void* p : {(void*)h->hSpatial, (void*)h->hGlobal, (void*)h->hOptimism, (void*)h->hPolicy, (void*)h->hValue, (void*)h->hScore,
+                 (void*)h->hOwnership, (void*)h->hSymmetry})
+    if(p) cudaFreeHost(p);
+  if(h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_batch_size, int require_exact_nn_len, int inputs_nhwc,
+                      int gpu_idx, kgb_handle** out) {
+  (void)require_exact_nn_len;  // masking is always on: it is what zeroes our pad rows
+  kgb_handle* raw = nullptr;
+  int rc = guarded([&] {
+    if(!ctx || !model || !out) throw std::invalid_argument("kgb_handle_create: NULL argument");
+    if(max_batch_size < 1 || max_batch_size > 65536) throw std::invalid_argument("kgb_handle_create: maxBatchSize out of range");
+    int dev = gpu_idx;
+    if(dev < 0) dev = (!ctx->gpuIdxs.empty() && ctx->gpuIdxs[0] >= 0) ? ctx->gpuIdxs[0] : 0;
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      throw CudaFailure("libkgb200: no CUDA device is visible; the B200 backend has no CPU fallback");
+    if(dev >= count) throw std::invalid_argument("kgb_handle_create: gpu index " + std::to_string(dev) + " >= device count");
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if(prop.major != 10)
+      throw CudaFailure(std::string("libkgb200 is built for sm_100a (B200) only; device ") + prop.name + " is sm_" +
+                        std::to_string(prop.major) + std::to_string(prop.minor));
+    raw = new kgb_handle();
+    kgb_handle& h = *raw;
+    h.device = dev;
+    h.numSMs = prop.multiProcessorCount;
+    h.model = model->desc.get();
+    h.maxBatch = max_batch_size;
+    h.split = ctx->fp16 ? 0 : 1;
+    h.nhwc = inputs_nhwc != 0;
+    int pad = h.model->maxConvRadius();
+    h.L.X = ctx->X; h.L.Y = ctx->Y; h.L.pad = pad; h.L.Wp = ctx->X + pad; h.L.P = (ctx->Y + pad) * (ctx->X + pad);
+    const char* env = getenv("KGB_STREAM_FP32");  // "all" | "trunk" | "none"
+    std::string streams = env ? env : (h.split ? "all" : "trunk");
+    h.streamTrunkFp32 = streams != "none";
+    h.streamInnerFp32 = streams == "all";
+    env = getenv("KGB_CONV_IMPL");
+    h.useSimt = env && std::string(env) == "simt";
+    env = getenv("KGB_NO_GRAPH");
+    h.useGraph = !(env && std::string(env) == "1");
+    CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    CK(convTCInit());
+    Builder b(h);
+    b.build();
+    const int XY = h.L.X * h.L.Y;
+    const ModelDesc& m = *h.model;
+    CK(cudaMallocHost((void**)&h.hSpatial, (size_t)h.maxBatch * m.numInputChannels * XY * sizeof(float)));
+    CK(cudaMallocHost((void**)&h.hGlobal, (size_t)h.maxBatch * m.numInputGlobalChannels * sizeof(float)));
+    CK(cudaMallocHost((void**)&h.hOptimism, (size_t)h.maxBatch * sizeof(float)));
+    CK(cudaMallocHost((void**)&h.hSymmetry, (size_t)h.maxBatch * sizeof(int)));
+    CK(cudaMallocHost((void**)&h.hPolicy, (size_t)h.maxBatch * (XY + 1) * sizeof(float)));
+    CK(cudaMallocHost((void**)&h.hValue, (size_t)h.maxBatch * 3 * sizeof(float)));
+    CK(cudaMallocHost((void**)&h.hScore, (size_t)h.maxBatch * 6 * sizeof(float)));
+    CK(cudaMallocHost((void**)&h.hOwnership, (size_t)h.maxBatch * XY * sizeof(float)));
+    CK(cudaDeviceSynchronize());
+    *out = raw;
+    raw = nullptr;
+  });
+  if(raw) destroyHandle(raw);
+  return rc;
+}
+
+KGB_API void kgb_handle_free(kgb_handle* handle) { destroyHandle(handle); }
+
+KGB_API int kgb_handle_is_fp16(const kgb_handle* handle) { return handle && !handle->split ? 1 : 0; }
+KGB_API uint64_t kgb_handle_stream(kgb_handle* handle) { return handle ? (uint64_t)(uintptr_t)handle->stream : 0; }
+KGB_API int kgb_handle_launches_per_forward(const kgb_handle* handle) { return handle ? handle->launchesPerForward : 0; }
+
+KGB_API int kgb_handle_sync(kgb_handle* handle) {
+  return guarded([&] {
+    if(!handle) throw std::invalid_argument("kgb_handle_sync: NULL handle");
+    CK(cudaSetDevice(handle->device));
+    CK(cudaStreamSynchronize(handle->stream));
+  });
+}
+
+static void checkForwardArgs(kgb_handle* h, int n, const void* a, const void* b, const void* c, const void* d, const void* e) {
+  if(!h) throw std::invalid_argument("kgb_forward: NULL handle");
+  if(n < 1 || n > h->maxBatch) throw std::invalid_argument("kgb_forward: batch size " + std::to_string(n) + " not in [1, maxBatchSize]");
+  if(!a || !b || !c || !d || !e) throw std::invalid_argument("kgb_forward: NULL buffer");
+}
+
+KGB_API int kgb_forward(kgb_handle* h, int n, const float* spatial, const float* global, const int32_t* symmetry, const float* policy_optimism,
+                float* policy, float* value, float* score_value, float* ownership) {
+  return guarded([&] {
+    checkForwardArgs(h, n, spatial, global, policy, value, score_value);
+    CK(cudaSetDevice(h->device));
+    const ModelDesc& m = *h->model;
+    const int XY = h->L.X * h->L.Y;
+    const size_t spB = (size_t)n * m.numInputChannels * XY * sizeof(float);
+    const size_t glB = (size_t)n * m.numInputGlobalChannels * sizeof(float);
+    memcpy(h->hSpatial, spatial, spB);
+    memcpy(h->hGlobal, global, glB);
+    for(int i = 0; i < n; i++) {
+      h->hSymmetry[i] = symmetry ? symmetry[i] : 0;
+      h->hOptimism[i] = policy_optimism ? policy_optimism[i] : 0.0f;
+      if(h->hSymmetry[i] < 0 || h->hSymmetry[i] > 7) throw std::invalid_argument("kgb_forward: symmetry must be in 0..7");
+    }
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->dSpatial, h->hSpatial, spB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->dGlobal, h->hGlobal, glB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->dSymmetry, h->hSymmetry, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->dOptimism, h->hOptimism, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    runOps(h, n);
+    CK(cudaMemcpyAsync(h->hPolicy, h->dPolicy, (size_t)n * (XY + 1) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hValue, h->dValue, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hScore, h->dScore, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if(ownership) CK(cudaMemcpyAsync(h->hOwnership, h->dOwnership, (size_t)n * XY * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(policy, h->hPolicy, (size_t)n * (XY + 1) * sizeof(float));
+    memcpy(value, h->hValue, (size_t)n * 3 * sizeof(float));
+    memcpy(score_value, h->hScore, (size_t)n * 6 * sizeof(float));
+    if(ownership) memcpy(ownership, h->hOwnership, (size_t)n * XY * sizeof(float));
+  });
+}
+
+KGB_API int kgb_forward_device(kgb_handle* h, int n, const float* d_spatial, const float* d_global, const int32_t* d_symmetry,
+                       const float* d_policy_optimism, float* d_policy, float* d_value, float* d_score_value, float* d_ownership) {
+  return guarded([&] {
+    checkForwardArgs(h, n, d_spatial, d_global, d_policy, d_value, d_score_value);
+    CK(cudaSetDevice(h->device));
+    const ModelDesc& m = *h->model;
+    const int XY = h->L.X * h->L.Y;
+    cudaStream_t s = h->stream;
+    if(d_spatial != h->dSpatial)
+      CK(cudaMemcpyAsync(h->dSpatial, d_spatial, (size_t)n * m.numInputChannels * XY * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if(d_global != h->dGlobal)
+      CK(cudaMemcpyAsync(h->dGlobal, d_global, (size_t)n * m.numInputGlobalChannels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if(d_symmetry) CK(cudaMemcpyAsync(h->dSymmetry, d_symmetry, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    else CK(cudaMemsetAsync(h->dSymmetry, 0, n * sizeof(int), s));
+    if(d_policy_optimism) CK(cudaMemcpyAsync(h->dOptimism, d_policy_optimism, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    else CK(cudaMemsetAsync(h->dOptimism, 0, n * sizeof(float), s));
+    runOps(h, n);
+    CK(cudaMemcpyAsync(d_policy, h->dPolicy, (size_t)n * (XY + 1) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(d_value, h->dValue, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(d_score_value, h->dScore, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if(d_ownership) CK(cudaMemcpyAsync(d_ownership, h->dOwnership, (size_t)n * XY * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  });
+}
+
+KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
+                  const float* input, float* output) {
+  return guarded([&] {
+    if(!weights || !input || !output || n < 1) throw std::invalid_argument("kgb_test_conv: bad argument");
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaFailure("libkgb200: no CUDA device is visible");
+    // Stand-alone: build a one-conv "handle" by hand.
+    kgb_handle h;
+    struct Cleanup {
+      kgb_handle& h;
+      ~Cleanup() { for(void* p : h.allocs) cudaFree(p); if(h.stream) cudaStreamDestroy(h.stream); }
+    } cleanup{h};
+    CK(cudaGetDevice(&h.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h.device));
+    h.numSMs = prop.multiProcessorCount;
+    ModelDesc dummy;
+    h.model = &dummy;
+    h.maxBatch = n;
+    h.split = use_fp16 ? 0 : 1;
+    int pad = std::max(ky / 2, kx / 2);
+    if(pad < 1) pad = 1;
+    h.L.X = nn_x_len; h.L.Y = nn_y_len; h.L.pad = pad; h.L.Wp = nn_x_len + pad; h.L.P = (nn_y_len + pad) * (nn_x_len + pad);
+    const char* env = getenv("KGB_CONV_IMPL");
+    h.useSimt = env && std::string(env) == "simt";
+    CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    CK(convTCInit());
+    Builder b(h);
+    ConvDesc cd;
+    cd.ky = ky; cd.kx = kx; cd.cin = in_c; cd.cout = out_c;
+    cd.w.assign(weights, weights + (size_t)ky * kx * in_c * out_c);
+    ConvWeights cw = b.packConv({&cd});
+    const int XY = nn_x_len * nn_y_len;
+    const size_t M = (size_t)n * h.L.P;
+    float* dIn = h.dalloc<float>((size_t)n * XY * in_c);
+    CK(cudaMemcpy(dIn, input, (size_t)n * XY * in_c * sizeof(float), cudaMemcpyHostToDevice));
+    __half* A = h.dalloc<__half>(M * cw.cin_p * b.actMul);
+    h.dMask = h.dalloc<float>(M + 128);
+    h.dMaskSum = h.dalloc<float>(n);
+    float* raw = h.dalloc<float>(M * cw.cout_p);
+    // pack (mask := input channel 0 is NOT wanted here: use an all-ones board mask instead)
+    CK(launchPackInput(dIn, n, in_c, true, nullptr, h.L, A, cw.cin_p, h.split, h.dMask, h.dMaskSum, h.stream));
+    {
+      std::vector<float> hm(M, 0.0f);
+      for(int i = 0; i < n; i++)
+        for(int y = 0; y < nn_y_len; y++)
+          for(int x = 0; x < nn_x_len; x++) hm[(size_t)i * h.L.P + (size_t)(y + pad) * h.L.Wp + x] = 1.0f;
+      CK(cudaStreamSynchronize(h.stream));
+      CK(cudaMemcpy(h.dMask, hm.data(), M * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    Builder::BNDev none;
+    b.emitConv(cw, A, nullptr, false, nullptr, raw, true, nullptr, none);
+    h.ops.back()(n, h.stream);
+    CK(cudaStreamSynchronize(h.stream));
+    std::vector<float> hr(M * cw.cout_p);
+    CK(cudaMemcpy(hr.data(), raw, hr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for(int i = 0; i < n; i++)
+      for(int y = 0; y < nn_y_len; y++)
+        for(int x = 0; x < nn_x_len; x++) {
+          size_t row = (size_t)i * h.L.P + (size_t)(y + pad) * h.L.Wp + x;
+          for(int c = 0; c < out_c; c++) output[(((size_t)i * nn_y_len + y) * nn_x_len + x) * out_c + c] = hr[row * cw.cout_p + c];
+        }
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a: the trunk hot op of the NN evaluator
+// (reference call sites: ConvLayer::apply eigenbackend.cpp:448-701,
+// cudnnConvolutionForward / cublasHgemm cudabackend.cpp:788-841, BN+act+mask cudahelpers.cu:1370-2101).
+//
+// GEMM view:  D[M = batch*P rows, N = cout]  =  sum over taps t, k-blocks kb of  A_t[M, 64] * W_t[64, N]
+//   A_t = the activation matrix shifted by the tap's row offset (see kgb_conv.cuh "padded rows"), loaded by ONE 2-D TMA
+//         box {64 channels, 128 rows} per (tap, k-block) with 128B swizzle; out-of-range rows are zero-filled by TMA.
+//   W   = packed [tap][cout_p][cin_p] fp16 (K-major), box {64, n_tile}.
+//   D   = fp32 accumulator in TMEM, 2 stages x n_tile columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Persistent, warp-specialised CTA (1 per SM, 384 threads):
+//   warp 0     TMA producer            (one elected lane)
+//   warp 1     tcgen05.mma issuer      (one elected lane), UMMA 128 x n_tile x 16, kind::f16, fp32 accumulate
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue: tcgen05.ld -> (+ncbias, +residual) -> raw store, BN+act+mask -> fp16 store (next layer's A)
+// Pipelines: smem full/empty mbarriers per stage (TMA <-> MMA), tmem full/empty mbarriers per accumulator stage.
+//
+// "split" mode computes a*w ~= ah*wh + al*wh + ah*wl with a = ah + al, w = wh + wl in fp16 (fp32 accumulate):
+// fp32-grade accuracy on the fp16 tensor pipe at 3x the MMA count (the backend's useFP16=false mode).
+#include "kgb_conv.cuh"
+
+namespace kgb {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;    // fp16 elements = one 128B swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 384;
+static constexpr int EPI_WARP0 = 4;
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+static constexpr int MAX_STAGES = 8;
+static constexpr int SMEM_LIMIT = 227 * 1024;
+
+int convTCSmemBytes(int n_tile, int* stagesOut) {
+  int stageBytes = A_STAGE_BYTES + n_tile * BLOCK_K * 2;
+  int stages = (SMEM_LIMIT - 2048) / stageBytes;
+  if(stages > MAX_STAGES) stages = MAX_STAGES;
+  if(stagesOut) *stagesOut = stages;
+  return stages * stageBytes + 2048;  // 1024 alignment slack + barrier block
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while(!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+    ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+    ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+    : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=1024B: 8 rows x 128B)
+//   | [46,48) version=1 | [61,64) layout_type=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format F32 (bit 4), a/b F16 (0), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct __align__(8) BarrierBlock {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                   const __grid_constant__ ConvParams p, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_stage_bytes = p.n_tile * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  BarrierBlock* bars = reinterpret_cast<BarrierBlock*>(smem_aligned + (size_t)stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int taps = p.ky * p.kx;
+  const int kblocks = p.cin_p / BLOCK_K;
+  const int parts = p.split ? 3 : 1;
+  const int iters = taps * kblocks * parts;
+
+  if(warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+  }
+  if(warp == 1 && lane == 0) {
+    for(int s = 0; s < stages; s++) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for(int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&bars->tmem_full[s]), 1);
+      mbar_init(smem_u32(&bars->tmem_empty[s]), NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if(warp == 0) {
+    // ===================== TMA producer =====================
+    if(lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int ry = p.ky / 2, rx = p.kx / 2;
+      for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * p.n_tile;
+        for(int tap = 0; tap < taps; tap++) {
+          const int dy = tap / p.kx - ry, dx = tap % p.kx - rx;
+          const int rowA = m0 + dy * p.Wp + dx;
+          const int rowB = tap * p.cout_p + n0;
+          for(int kb = 0; kb < kblocks; kb++) {
+            for(int part = 0; part < parts; part++) {
+              mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+              const uint32_t full = smem_u32(&bars->full[stage]);
+              mbar_arrive_expect_tx(full, (uint32_t)stage_bytes);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              const int colA = kb * BLOCK_K + (part == 1 ? p.cin_p : 0);
+              const int colB = kb * BLOCK_K + (part == 2 ? p.cin_p : 0);
+              tma_load_2d(sa, &tmapA, full, colA, rowA);
+              tma_load_2d(sa + A_STAGE_BYTES, &tmapB, full, colB, rowB);
+              if(++stage == stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  }
+  else if(warp == 1) {
+    // ===================== MMA issuer =====================
+    if(lane == 0) {
+      const uint32_t idesc = make_idesc(p.n_tile);
+      int stage = 0; uint32_t phase = 0;
+      int acc_stage = 0; uint32_t acc_phase = 0;
+      for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&bars->tmem_empty[acc_stage]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc_stage * p.n_tile;
+        for(int it = 0; it < iters; it++) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+          for(int k = 0; k < BLOCK_K / UMMA_K; k++) {
+            // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte descriptor units
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(smem_u32(&bars->empty[stage]));
+          if(++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(smem_u32(&bars->tmem_full[acc_stage]));
+        if(++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  else if(warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int half = (warp - EPI_WARP0) >> 2;     // which half of the tile's columns
+    const int cols_per_half = p.n_tile >> 1;
+    int acc_stage = 0; uint32_t acc_phase = 0;
+    for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * p.n_tile;
+      const int row = m0 + quad * 32 + lane;
+      const bool valid = row < p.M;
+      const float maskv = valid ? __ldg(p.mask + row) : 0.0f;
+      const int img = valid ? row / p.P : 0;
+      mbar_wait(smem_u32(&bars->tmem_full[acc_stage]), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * p.n_tile + half * cols_per_half;
+      for(int c = 0; c < cols_per_half; c += 16) {
+        uint32_t acc[16];
+        tmem_ld16(taddr + c, acc);
+        tmem_ld_wait();
+        if(valid) epilogue_chunk(p, acc, row, n0 + half * cols_per_half + c, maskv, img);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if(lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc_stage]));
+      if(++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if(warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+cudaError_t convTCInit() {
+  return cudaFuncSetAttribute(kgb_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+}
+
+cudaError_t launchConvTC(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const ConvParams& p, int numSMs, cudaStream_t stream) {
+  int stages = 0;
+  int smem = convTCSmemBytes(p.n_tile, &stages);
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < numSMs ? tiles : numSMs;
+  kgb_conv_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmapA, tmapB, p, stages);
+  return cudaGetLastError();
+}
+
+}  // namespace kgb

@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's backend interface `namespace NeuralNet` (cpp/neuralnet/nninterface.h:32-182)
+over the C ABI of libkgb200.so (include/kgb200.h).  Same names, argument meaning and error behaviour as the
+reference: failures raise (StringError there, KGBError here); there is NO CPU fallback - a missing library or a
+missing sm_100 device is an error.
+
+    model  = NeuralNet.loadModelFile(path, expectedSha256)          # nninterface.h:43
+    ctx    = NeuralNet.createComputeContext([0], nnXLen, nnYLen, useFP16Mode, model)   # :50
+    handle = NeuralNet.createComputeHandle(ctx, model, maxBatchSize, requireExactNNLen, inputsUseNHWC, gpuIdx)  # :76
+    out    = NeuralNet.getOutput(handle, spatial, global_, symmetry, policyOptimism)   # :117
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+
+class KGBError(RuntimeError):
+    pass
+
+
+class _ModelInfo(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 128), ("sha256", C.c_char * 65),
+        ("model_version", C.c_int32), ("num_input_channels", C.c_int32), ("num_input_global_channels", C.c_int32),
+        ("num_policy_channels", C.c_int32), ("num_value_channels", C.c_int32), ("num_score_value_channels", C.c_int32),
+        ("num_ownership_channels", C.c_int32), ("trunk_num_channels", C.c_int32), ("num_blocks", C.c_int32),
+        ("prefer_pass_alive_under_suicide_rules", C.c_int32),
+        ("td_score_multiplier", C.c_float), ("score_mean_multiplier", C.c_float), ("score_stdev_multiplier", C.c_float),
+        ("lead_multiplier", C.c_float), ("variance_time_multiplier", C.c_float),
+        ("shortterm_value_error_multiplier", C.c_float), ("shortterm_score_error_multiplier", C.c_float),
+        ("conv_macs_per_position", C.c_int64),
+    ]
+
+
+# Every symbol include/kgb200.h declares (tests/test_abi.py checks the library exports all of them).
+ABI_SYMBOLS = [
+    "kgb_global_init", "kgb_global_cleanup", "kgb_last_error", "kgb_device_count", "kgb_device_name",
+    "kgb_model_load_file", "kgb_model_free", "kgb_model_get_info", "kgb_context_create", "kgb_context_free",
+    "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
+    "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv",
+]
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkgb200.so")
+
+
+def load_library():
+    """dlopen the in-tree libkgb200.so; raises KGBError (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise KGBError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(katago_b200/csrc/build.sh). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    P, I, F = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+    lib.kgb_last_error.restype = C.c_char_p
+    lib.kgb_device_count.argtypes = [C.POINTER(I)]
+    lib.kgb_device_name.argtypes = [I, C.c_char_p, I, C.POINTER(I), C.POINTER(I)]
+    lib.kgb_model_load_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(P)]
+    lib.kgb_model_free.argtypes = [P]
+    lib.kgb_model_free.restype = None
+    lib.kgb_model_get_info.argtypes = [P, C.POINTER(_ModelInfo)]
+    lib.kgb_context_create.argtypes = [C.POINTER(I), I, I, I, I, P, C.POINTER(P)]
+    lib.kgb_context_free.argtypes = [P]
+    lib.kgb_context_free.restype = None
+    lib.kgb_handle_create.argtypes = [P, P, I, I, I, I, C.POINTER(P)]
+    lib.kgb_handle_free.argtypes = [P]
+    lib.kgb_handle_free.restype = None
+    lib.kgb_handle_is_fp16.argtypes = [P]
+    lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
+    lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
+    lib.kgb_handle_sync.argtypes = [P]
+    lib.kgb_handle_stream.argtypes = [P]
+    lib.kgb_handle_stream.restype = C.c_uint64
+    lib.kgb_handle_launches_per_forward.argtypes = [P]
+    lib.kgb_test_conv.argtypes = [I, I, I, I, P, I, I, I, I, P, P]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise KGBError(load_library().kgb_last_error().decode("utf-8", "replace"))
+
+
+class LoadedModel:
+    """LoadedModel (nninterface.h:27).  `.desc` mirrors the ModelDesc fields NNEvaluator reads."""
+
+    def __init__(self, file: str, expectedSha256: str = ""):
+        lib = load_library()
+        self._p = C.c_void_p()
+        _check(lib.kgb_model_load_file(file.encode(), (expectedSha256 or "").encode(), C.byref(self._p)))
+        info = _ModelInfo()
+        _check(lib.kgb_model_get_info(self._p, C.byref(info)))
+        self.desc = {k: (getattr(info, k).decode() if isinstance(getattr(info, k), bytes) else getattr(info, k))
+                     for k, _ in _ModelInfo._fields_}
+
+    def free(self):
+        if self._p:
+            load_library().kgb_model_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ComputeContext:
+    def __init__(self, gpuIdxs: Sequence[int], nnXLen: int, nnYLen: int, useFP16Mode, loadedModel: LoadedModel):
+        lib = load_library()
+        arr = (C.c_int * max(1, len(gpuIdxs)))(*gpuIdxs)
+        fp16 = {True: 1, False: 0, None: -1, "auto": -1, "true": 1, "false": 0}.get(useFP16Mode, useFP16Mode)
+        self._p = C.c_void_p()
+        self.nnXLen, self.nnYLen, self.model = nnXLen, nnYLen, loadedModel
+        _check(lib.kgb_context_create(arr, len(gpuIdxs), nnXLen, nnYLen, int(fp16), loadedModel._p, C.byref(self._p)))
+
+    def free(self):
+        if self._p:
+            load_library().kgb_context_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ComputeHandle:
+    def __init__(self, context: ComputeContext, loadedModel: LoadedModel, maxBatchSize: int, requireExactNNLen: bool,
+                 inputsUseNHWC: bool, gpuIdxForThisThread: int = -1):
+        lib = load_library()
+        self._p = C.c_void_p()
+        self.context, self.model = context, loadedModel
+        self.maxBatchSize, self.inputsUseNHWC = maxBatchSize, inputsUseNHWC
+        _check(lib.kgb_handle_create(context._p, loadedModel._p, maxBatchSize, int(requireExactNNLen), int(inputsUseNHWC),
+                                     gpuIdxForThisThread, C.byref(self._p)))
+
+    @property
+    def launches_per_forward(self) -> int:
+        return load_library().kgb_handle_launches_per_forward(self._p)
+
+    @property
+    def stream(self) -> int:
+        return load_library().kgb_handle_stream(self._p)
+
+    def sync(self):
+        _check(load_library().kgb_handle_sync(self._p))
+
+    def free(self):
+        if self._p:
+            load_library().kgb_handle_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class NeuralNet:
+    """Static functions named as in `namespace NeuralNet`."""
+
+    @staticmethod
+    def globalInitialize():
+        _check(load_library().kgb_global_init())
+
+    @staticmethod
+    def globalCleanup():
+        _check(load_library().kgb_global_cleanup())
+
+    @staticmethod
+    def printDevices():
+        lib = load_library()
+        n = C.c_int(0)
+        _check(lib.kgb_device_count(C.byref(n)))
+        out = []
+        for i in range(n.value):
+            buf = C.create_string_buffer(256)
+            ma, mi = C.c_int(0), C.c_int(0)
+            _check(lib.kgb_device_name(i, buf, 256, C.byref(ma), C.byref(mi)))
+            out.append((i, buf.value.decode(), ma.value, mi.value))
+            print(f"Found CUDA device {i}: {buf.value.decode()} (sm_{ma.value}{mi.value})")
+        return out
+
+    @staticmethod
+    def loadModelFile(file: str, expectedSha256: str = "") -> LoadedModel:
+        return LoadedModel(file, expectedSha256)
+
+    @staticmethod
+    def freeLoadedModel(m: LoadedModel):
+        m.free()
+
+    @staticmethod
+    def getModelDesc(m: LoadedModel) -> dict:
+        return m.desc
+
+    @staticmethod
+    def createComputeContext(gpuIdxs, nnXLen, nnYLen, useFP16Mode, loadedModel) -> ComputeContext:
+        return ComputeContext(gpuIdxs, nnXLen, nnYLen, useFP16Mode, loadedModel)
+
+    @staticmethod
+    def freeComputeContext(c: ComputeContext):
+        c.free()
+
+    @staticmethod
+    def createComputeHandle(context, loadedModel, maxBatchSize, requireExactNNLen, inputsUseNHWC, gpuIdxForThisThread=-1,
+                            serverThreadIdx=0) -> ComputeHandle:
+        return ComputeHandle(context, loadedModel, maxBatchSize, requireExactNNLen, inputsUseNHWC, gpuIdxForThisThread)
+
+    @staticmethod
+    def freeComputeHandle(h: ComputeHandle):
+        h.free()
+
+    @staticmethod
+    def isUsingFP16(h: ComputeHandle) -> bool:
+        return bool(load_library().kgb_handle_is_fp16(h._p))
+
+    @staticmethod
+    def getOutput(handle: ComputeHandle, spatial, global_, symmetry=None, policyOptimism=None, includeOwnerMap=True) -> dict:
+        """spatial [n, C*X*Y] (layout per inputsUseNHWC), global_ [n, G] -> dict(policy [n,X*Y+1], value [n,3],
+        score_value [n,6], ownership [n,X*Y] or None); raw logits as NeuralNet::getOutput writes into NNOutput."""
+        lib = load_library()
+        sp, gl = _f32(spatial), _f32(global_)
+        n = sp.shape[0]
+        xy = handle.context.nnXLen * handle.context.nnYLen
+        d = handle.model.desc
+        if sp.size != n * d["num_input_channels"] * xy or gl.size != n * d["num_input_global_channels"]:
+            raise KGBError("getOutput: input buffer sizes do not match the model / nnXLen*nnYLen")
+        sym = np.zeros(n, np.int32) if symmetry is None else np.ascontiguousarray(symmetry, dtype=np.int32)
+        opt = np.zeros(n, np.float32) if policyOptimism is None else _f32(policyOptimism)
+        policy = np.empty((n, xy + 1), np.float32)
+        value = np.empty((n, 3), np.float32)
+        score = np.empty((n, 6), np.float32)
+        own = np.empty((n, xy), np.float32) if includeOwnerMap else None
+        _check(lib.kgb_forward(handle._p, n, sp.ctypes.data, gl.ctypes.data, sym.ctypes.data, opt.ctypes.data,
+                               policy.ctypes.data, value.ctypes.data, score.ctypes.data,
+                               own.ctypes.data if own is not None else None))
+        return dict(policy=policy, value=value, score_value=score, ownership=own)
+
+    @staticmethod
+    def testEvaluateConv(convYSize, convXSize, inChannels, outChannels, weights, batchSize, nnXLen, nnYLen, useFP16, inputBuffer):
+        """NeuralNet::testEvaluateConv (nninterface.h:134-143), NHWC; weights in model-file order [ky][kx][ic][oc]."""
+        lib = load_library()
+        w, x = _f32(weights), _f32(inputBuffer)
+        out = np.empty((batchSize, nnYLen, nnXLen, outChannels), np.float32)
+        _check(lib.kgb_test_conv(convYSize, convXSize, inChannels, outChannels, w.ctypes.data, batchSize, nnXLen, nnYLen,
+                                 int(bool(useFP16)), x.ctypes.data, out.ctypes.data))
+        return out
