@@ -47,21 +47,24 @@ struct ConvParams {
 // fp32 activation functions shared by every epilogue (reference: eigenbackend.cpp:780-809, cudahelpers.cu mish/silu).
 // mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)   (exact identity; x clamped at 20 like the
 // reference so that e^2x cannot overflow).
+__device__ __forceinline__ float kgb_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float kgb_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float kgb_activate(float x, int act) {
   if(act == 1) return fmaxf(x, 0.0f);
   if(act == 2) {
-    float e = __expf(fminf(x, 20.0f));
-    float n = e * (e + 2.0f);
-    return x * __fdividef(n, n + 2.0f);
+    float e = kgb_ex2(fminf(x, 20.0f) * 1.4426950408889634f);
+    float n = fmaf(e, e, e + e);
+    return x * (n * kgb_rcp(n + 2.0f));
   }
-  if(act == 3) return __fdividef(x, 1.0f + __expf(-x));
+  if(act == 3) return x * kgb_rcp(1.0f + kgb_ex2(x * -1.4426950408889634f));
   return x;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Epilogue for one 16-column chunk of one accumulator row
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&acc)[16], int row, int col, float maskv, int img) {
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&acc)[16], int row, int col, float maskv, int img,
+                                               const float* sc, const float* bi) {
   float v[16];
 #pragma unroll
   for(int j = 0; j < 16; j++) v[j] = __uint_as_float(acc[j]);
@@ -117,11 +120,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
   }
   if(p.act_out != nullptr) {
     float a[16];
-    const float4* s4 = reinterpret_cast<const float4*>(p.bn_scale + col);
-    const float4* b4 = reinterpret_cast<const float4*>(p.bn_bias + col);
+    const float4* s4 = reinterpret_cast<const float4*>(sc);
+    const float4* b4 = reinterpret_cast<const float4*>(bi);
 #pragma unroll
     for(int q = 0; q < 4; q++) {
-      float4 s = __ldg(s4 + q), b = __ldg(b4 + q);
+      float4 s = s4[q], b = b4[q];
       a[4 * q] = kgb_activate(fmaf(v[4 * q], s.x, b.x), p.act) * maskv;
       a[4 * q + 1] = kgb_activate(fmaf(v[4 * q + 1], s.y, b.y), p.act) * maskv;
       a[4 * q + 2] = kgb_activate(fmaf(v[4 * q + 2], s.z, b.z), p.act) * maskv;
@@ -157,7 +160,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 // Launchers (defined in kgb_conv_tc.cu / kgb_kernels.cu)
 cudaError_t launchConvTC(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const ConvParams& p, int numSMs, cudaStream_t stream);
 cudaError_t launchConvSimt(const __half* A, int lda, const __half* W, const ConvParams& p, cudaStream_t stream);
-int convTCSmemBytes(int n_tile, int* stagesOut);
+int convTCSmemBytes(int n_tile, int cout_p, int* stagesOut);
 cudaError_t convTCInit();  // per device, before the first launch
 
 }  // namespace kgb

@@ -24,19 +24,20 @@ namespace kgb {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;    // fp16 elements = one 128B swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 384;
-static constexpr int EPI_WARP0 = 4;
-static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int EPI_WARP0 = 4;            // warps 0-3: TMA, MMA, TMEM alloc, spare; epilogue warps follow
+static constexpr int MAX_THREADS = 128 + 512;   // up to 16 epilogue warps (4 per TMEM lane quadrant)
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 static constexpr int MAX_STAGES = 8;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 
-int convTCSmemBytes(int n_tile, int* stagesOut) {
+// dynamic smem: [<=1023 B alignment slack][stages x (A tile | B tile)][BarrierBlock, 512 B][bn scale | bn bias: 2 x cout_p fp32]
+int convTCSmemBytes(int n_tile, int cout_p, int* stagesOut) {
   int stageBytes = A_STAGE_BYTES + n_tile * BLOCK_K * 2;
-  int stages = (SMEM_LIMIT - 2048) / stageBytes;
+  int extra = 1024 + 512 + 8 * cout_p;
+  int stages = (SMEM_LIMIT - extra) / stageBytes;
   if(stages > MAX_STAGES) stages = MAX_STAGES;
   if(stagesOut) *stagesOut = stages;
-  return stages * stageBytes + 2048;  // 1024 alignment slack + barrier block
+  return stages * stageBytes + extra;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -85,9 +86,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-    : "r"(taddr) : "memory");
+    : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait names the destination registers as in/out operands so no consumer can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+    : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+    :: "memory");
+}
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=1024B: 8 rows x 128B)
@@ -118,15 +125,17 @@ struct __align__(8) BarrierBlock {
 // ------------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                   const __grid_constant__ ConvParams p, int stages) {
+                   const __grid_constant__ ConvParams p, int stages, int epi_per_quad) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = p.n_tile * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
   BarrierBlock* bars = reinterpret_cast<BarrierBlock*>(smem_aligned + (size_t)stages * stage_bytes);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  float* s_bias = s_scale + p.cout_p;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,13 +156,16 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     }
     for(int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&bars->tmem_full[s]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[s]), NUM_EPI_WARPS);
+      mbar_init(smem_u32(&bars->tmem_empty[s]), 4 * epi_per_quad);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if(warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if(p.act_out != nullptr) {
+    for(int c = threadIdx.x; c < p.cout_p; c += blockDim.x) { s_scale[c] = p.bn_scale[c]; s_bias[c] = p.bn_bias[c]; }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -220,25 +232,33 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   }
   else if(warp >= EPI_WARP0) {
     // ===================== epilogue =====================
-    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int half = (warp - EPI_WARP0) >> 2;     // which half of the tile's columns
-    const int cols_per_half = p.n_tile >> 1;
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int part = (warp - EPI_WARP0) >> 2;           // which slice of the tile's columns
+    const int cols_per_part = p.n_tile / epi_per_quad;  // multiple of 16
+    const int nchunks = cols_per_part >> 4;
     int acc_stage = 0; uint32_t acc_phase = 0;
     for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-      const int n0 = (tile % p.num_n_tiles) * p.n_tile;
+      const int n0 = (tile % p.num_n_tiles) * p.n_tile + part * cols_per_part;
       const int row = m0 + quad * 32 + lane;
       const bool valid = row < p.M;
       const float maskv = valid ? __ldg(p.mask + row) : 0.0f;
       const int img = valid ? row / p.P : 0;
       mbar_wait(smem_u32(&bars->tmem_full[acc_stage]), acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * p.n_tile + half * cols_per_half;
-      for(int c = 0; c < cols_per_half; c += 16) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + c, acc);
-        tmem_ld_wait();
-        if(valid) epilogue_chunk(p, acc, row, n0 + half * cols_per_half + c, maskv, img);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * p.n_tile + part * cols_per_part;
+      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue math
+      uint32_t accA[16], accB[16];
+      tmem_ld16(taddr, accA);
+      for(int c = 0; c < nchunks; c += 2) {
+        if(c + 1 < nchunks) tmem_ld16(taddr + (c + 1) * 16, accB);
+        tmem_ld_wait(accA);
+        if(valid) epilogue_chunk(p, accA, row, n0 + c * 16, maskv, img, s_scale + n0 + c * 16, s_bias + n0 + c * 16);
+        if(c + 1 < nchunks) {
+          if(c + 2 < nchunks) tmem_ld16(taddr + (c + 2) * 16, accA);
+          tmem_ld_wait(accB);
+          if(valid) epilogue_chunk(p, accB, row, n0 + (c + 1) * 16, maskv, img, s_scale + n0 + (c + 1) * 16, s_bias + n0 + (c + 1) * 16);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -261,10 +281,13 @@ cudaError_t convTCInit() {
 
 cudaError_t launchConvTC(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const ConvParams& p, int numSMs, cudaStream_t stream) {
   int stages = 0;
-  int smem = convTCSmemBytes(p.n_tile, &stages);
+  int smem = convTCSmemBytes(p.n_tile, p.cout_p, &stages);
+  // 4 epilogue warps per TMEM lane quadrant when the tile's columns split evenly into 16-column chunks, else 2
+  int epi_per_quad = (p.n_tile % 64 == 0) ? 4 : 2;
+  int threads = 128 + 128 * epi_per_quad;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < numSMs ? tiles : numSMs;
-  kgb_conv_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmapA, tmapB, p, stages);
+  kgb_conv_tc_kernel<<<grid, threads, smem, stream>>>(tmapA, tmapB, p, stages, epi_per_quad);
   return cudaGetLastError();
 }
 

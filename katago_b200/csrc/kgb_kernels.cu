@@ -307,7 +307,8 @@ __global__ void convSimtKernel(const __half* __restrict__ A, int lda, const __ha
   uint32_t accu[16];
 #pragma unroll
   for(int j = 0; j < 16; j++) accu[j] = __float_as_uint(acc[j]);
-  epilogue_chunk(p, accu, row, col, p.mask[row], row / p.P);
+  epilogue_chunk(p, accu, row, col, p.mask[row], row / p.P, p.bn_scale ? p.bn_scale + col : nullptr,
+                 p.bn_bias ? p.bn_bias + col : nullptr);
 }
 
 cudaError_t launchConvSimt(const __half* A, int lda, const __half* W, const ConvParams& p, cudaStream_t stream) {
