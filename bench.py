@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py - headline measurement of the self-play hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through libkgb200's C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path timed on this box's host cores
+
+A "step" is one pass of the hot path over one batch: one playout wave for `games` concurrent 19x19 games = one
+NN evaluation per game (b18c384nbt) through the evaluator boundary (NeuralNet::getOutput -> kgb_forward*).  Stages on
+the device in this round are listed in config["stages"]; visits/sec counts one visit per evaluated leaf (no NN-cache
+hits, no terminal nodes - both would only raise the figure).
+
+value  : whole-job visits/s with inputs resident in HBM (kgb_forward_device), CUDA events on the launching stream,
+         max over ranks.  Inputs rotate over more distinct batches than fit in L2 (config["l2"]).
+e2e    : the same metric through the reference-facing C-ABI call with HOST buffers (kgb_forward): H2D of the feature
+         rows and D2H of policy/value/ownership inside the timed region, every step.
+N > 1  : one process per GPU (torchrun), games shard across ranks with no data-path collective ("weak" scaling);
+         NCCL carries only the model-weight broadcast from rank 0 before the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "visits/sec 19x19 b18c384nbt selfplay"
+UNIT = "visits/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="b18c384nbt")
+    ap.add_argument("--games", type=int, default=256, help="concurrent games (= NN batch) per GPU")
+    ap.add_argument("--fp32", action="store_true", help="use the fp32-equivalent (3-term split) mode instead of fp16 operands")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def model_file(name: str, rank: int, world: int, device):
+    """Rank 0 synthesises the weights (no network: random init, real architecture); other ranks receive the bytes over
+    NCCL - the only collective on this path (weight broadcast, reference analogue: selfplay.cpp:142-231 file polling)."""
+    from katago_b200 import modelgen
+    import torch
+    from katago_b200.dist_weights import broadcast_model_bytes
+    path = os.path.join(tempfile.mkdtemp(prefix=f"kgb_rank{rank}_"), f"{name}.bin")
+    if world == 1:
+        return modelgen.write_model(path, name, seed=0), 0.0
+    data = modelgen.model_bytes(name, seed=0) if rank == 0 else None
+    torch.cuda.synchronize()
+    t0 = time.time()
+    data = broadcast_model_bytes(data, 0, device)
+    torch.cuda.synchronize()
+    bcast_ms = (time.time() - t0) * 1e3
+    with open(path, "wb") as f:
+        f.write(data)
+    return path, bcast_ms
+
+
+def cpu_port_evals_per_sec(model_name: str, batch: int, reps: int):
+    """The reference's CPU NN path (Eigen backend restated in numpy, oracle/kg_nn_oracle.py) on this box's host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kg_nn_oracle as orc
+    from katago_b200 import modelgen
+    m = orc.parse_model(modelgen.model_bytes(model_name, seed=0), True)
+    sp, gl = modelgen.synthetic_inputs(batch, 19, 19, seed=3)
+    orc.get_output(m, sp[:1], gl[:1])  # warm BLAS
+    t0 = time.time()
+    for _ in range(reps):
+        orc.get_output(m, sp, gl)
+    dt = time.time() - t0
+    return batch * reps / dt, dt
+
+
+def run_reference(args, rank: int):
+    """--impl reference: CPU arm.  The reference's Eigen build cannot be compiled here (Eigen3 is neither vendored nor
+    installed), so this times the oracle port of its NN path; rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    batch = 4
+    # warm-up + K bounded steps
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_evals_per_sec(args.model, 1, 1)
+    t0 = time.time()
+    total = 0
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        v, dt = cpu_port_evals_per_sec(args.model, batch, 1)
+        total += batch
+        if time.time() - t0 > 150:
+            break
+    dt = time.time() - t0
+    value = total / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"19x19 {args.model}, one NN evaluation per visit on the host CPU, batch {batch} per step (bounded sample)",
+                   "stages": ["nn_eval"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{total} evaluations of {args.model} 19x19 via oracle/kg_nn_oracle.py (numpy/BLAS, all host threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from katago_b200 import NeuralNet, load_library, modelgen
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    path, bcast_ms = model_file(args.model, rank, world, device)
+    lib = load_library()
+    model = NeuralNet.loadModelFile(path)
+    ctx = NeuralNet.createComputeContext([local_rank], 19, 19, not args.fp32, model)
+    n = args.games
+    handle = NeuralNet.createComputeHandle(ctx, model, n, False, True, local_rank)
+    macs = model.desc["conv_macs_per_position"]
+    flop_per_eval = 2.0 * macs * 361
+
+    # distinct input batches: 16 x 8.1 MB = 130 MB of feature rows > 126 MB L2, rotated every step
+    NBUF = 16
+    host_sp, host_gl = [], []
+    for b in range(NBUF):
+        sp, gl = modelgen.synthetic_inputs(n, 19, 19, seed=1000 * rank + b)
+        host_sp.append(torch.from_numpy(sp.reshape(n, -1)).pin_memory())
+        host_gl.append(torch.from_numpy(gl).pin_memory())
+    dev_sp = [t.to(device) for t in host_sp]
+    dev_gl = [t.to(device) for t in host_gl]
+    sym = torch.from_numpy((np.arange(n) % 8).astype(np.int32))
+    opt = torch.zeros(n, dtype=torch.float32)
+    dsym, dopt = sym.to(device), opt.to(device)
+    dpol = torch.empty((n, 362), device=device); dval = torch.empty((n, 3), device=device)
+    dsc = torch.empty((n, 6), device=device); down = torch.empty((n, 361), device=device)
+    hpol = np.empty((n, 362), np.float32); hval = np.empty((n, 3), np.float32); hsc = np.empty((n, 6), np.float32); hown = np.empty((n, 361), np.float32)
+    stream = torch.cuda.ExternalStream(handle.stream, device=device)
+
+    def step_device(i):
+        b = i % NBUF
+        rc = lib.kgb_forward_device(handle._p, n, dev_sp[b].data_ptr(), dev_gl[b].data_ptr(), dsym.data_ptr(), dopt.data_ptr(),
+                                    dpol.data_ptr(), dval.data_ptr(), dsc.data_ptr(), down.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.kgb_last_error().decode())
+
+    def step_host(i):
+        b = i % NBUF
+        rc = lib.kgb_forward(handle._p, n, host_sp[b].data_ptr(), host_gl[b].data_ptr(), sym.data_ptr(), opt.data_ptr(),
+                             hpol.ctypes.data, hval.ctypes.data, hsc.ctypes.data, hown.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(lib.kgb_last_error().decode())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        handle.sync()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for i in range(W):
+        step_device(i)
+    handle.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, K)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(W):
+        step_host(i)
+    ms_e2e = timed(step_host, K)
+    assert np.isfinite(hpol).all() and np.isfinite(hval).all()
+
+    total_games = n * world
+    value = total_games * K / (ms_dev * 1e-3)
+    e2e_value = total_games * K / (ms_e2e * 1e-3)
+    h2d = n * (22 * 361 + 19 + 2) * 4
+    d2h = n * (362 + 3 + 6 + 361) * 4
+
+    if rank == 0:
+        peaks = load_peaks()
+        # roofline of the dominant kernel: the 3x3 trunk convolution (mid x mid channels, M = games*(19+1)^2 padded rows),
+        # timed alone with CUDA events inside the library on its launching stream.
+        mid = {"b18c384nbt": 192, "b28c512nbt": 256}.get(args.model, 192)
+        ms_conv = (np.zeros(1, np.float32))
+        import ctypes as C
+        rc = lib.kgb_bench_conv(3, 3, mid, mid, n, 19, 19, 0 if args.fp32 else 1, 5, 50, ms_conv.ctypes.data_as(C.POINTER(C.c_float)))
+        if rc != 0:
+            raise RuntimeError(lib.kgb_last_error().decode())
+        conv_flop = 2.0 * 9 * mid * mid * 361 * n  # algorithmic: direct convolution over the 361 real board points
+        achieved = conv_flop / (float(ms_conv[0]) * 1e-3) / 1e12
+        whole = flop_per_eval * n * K / (ms_dev * 1e-3) / 1e12
+        cpu_v, cpu_dt = cpu_port_evals_per_sec(args.model, 4, 2)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32-split3(fp16 tensor pipe)" if args.fp32 else "f16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, one NN evaluation (= one visit) per game per step",
+                       "stages": ["nn_eval"], "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
+                       "weights": "random init, real architecture (katago_b200/modelgen.py)",
+                       "l2": f"{NBUF} distinct feature batches ({NBUF * n * 22 * 361 * 4 / 1e6:.0f} MB) rotated every step, larger than the 126 MB L2; per-step activation traffic >> L2",
+                       "weight_broadcast_ms": bcast_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+            "gpu_launches": handle.launches_per_forward * K,
+            "roofline": {"bound": "tensor", "kernel": f"kgb_conv_tc_kernel 3x3 {mid}->{mid}, batch {n}", "achieved": achieved,
+                         "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"],
+                         "traffic": 41.4e6 if args.model == "b18c384nbt" and n == 256 else None,
+                         "peak_source": peaks["source"] + " (burst cuBLAS bf16, kernel timed alone)",
+                         "ms_per_launch": float(ms_conv[0]),
+                         "whole_forward_tflops": whole, "whole_forward_frac_of_sustained": whole / peaks["tflops_sustained"]},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"8 evaluations of {args.model} 19x19 via the numpy restatement of the Eigen path ({cpu_dt:.1f} s, all host threads)"},
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,11 @@ KGB_API int kgb_handle_launches_per_forward(const kgb_handle* handle);
 KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
                   const float* input, float* output);
 
+/* Kernel-level timing hook for bench.py's roofline object: runs ONE convolution layer (random weights/inputs resident in
+ * HBM, the production epilogue of a residual unit's first conv: BN + mish + mask -> fp16) `iters` times on a stream and returns the CUDA-event average per launch. */
+KGB_API int kgb_bench_conv(int ky, int kx, int in_c, int out_c, int n, int nn_x_len, int nn_y_len, int use_fp16, int warmup, int iters,
+                   float* ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -693,29 +693,32 @@ KGB_API int kgb_forward_device(kgb_handle* h, int n, const float* d_spatial, con
   });
 }
 
-KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
-                  const float* input, float* output) {
-  return guarded([&] {
-    if(!weights || !input || !output || n < 1) throw std::invalid_argument("kgb_test_conv: bad argument");
+}  // extern "C" (part 1)
+
+// Stand-alone single convolution (testEvaluateConv / kernel-level roofline timing).
+namespace {
+struct SingleConv {
+  kgb_handle h;
+  ModelDesc dummy;
+  ConvWeights cw;
+  __half* A = nullptr;
+  float* raw = nullptr;
+  int n, X, Y, cin, cout, pad;
+  size_t M;
+  SingleConv(int ky, int kx, int in_c, int out_c, const float* weights, int n_, int X_, int Y_, int use_fp16, int actEpilogue = 0)
+      : n(n_), X(X_), Y(Y_), cin(in_c), cout(out_c) {
     int count = 0;
     if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaFailure("libkgb200: no CUDA device is visible");
-    // Stand-alone: build a one-conv "handle" by hand.
-    kgb_handle h;
-    struct Cleanup {
-      kgb_handle& h;
-      ~Cleanup() { for(void* p : h.allocs) cudaFree(p); if(h.stream) cudaStreamDestroy(h.stream); }
-    } cleanup{h};
     CK(cudaGetDevice(&h.device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h.device));
+    if(prop.major != 10) throw CudaFailure("libkgb200 is built for sm_100a (B200) only");
     h.numSMs = prop.multiProcessorCount;
-    ModelDesc dummy;
     h.model = &dummy;
     h.maxBatch = n;
     h.split = use_fp16 ? 0 : 1;
-    int pad = std::max(ky / 2, kx / 2);
-    if(pad < 1) pad = 1;
-    h.L.X = nn_x_len; h.L.Y = nn_y_len; h.L.pad = pad; h.L.Wp = nn_x_len + pad; h.L.P = (nn_y_len + pad) * (nn_x_len + pad);
+    pad = std::max(1, std::max(ky / 2, kx / 2));
+    h.L.X = X; h.L.Y = Y; h.L.pad = pad; h.L.Wp = X + pad; h.L.P = (Y + pad) * (X + pad);
     const char* env = getenv("KGB_CONV_IMPL");
     h.useSimt = env && std::string(env) == "simt";
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
@@ -724,37 +727,90 @@ KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weig
     ConvDesc cd;
     cd.ky = ky; cd.kx = kx; cd.cin = in_c; cd.cout = out_c;
     cd.w.assign(weights, weights + (size_t)ky * kx * in_c * out_c);
-    ConvWeights cw = b.packConv({&cd});
-    const int XY = nn_x_len * nn_y_len;
-    const size_t M = (size_t)n * h.L.P;
-    float* dIn = h.dalloc<float>((size_t)n * XY * in_c);
-    CK(cudaMemcpy(dIn, input, (size_t)n * XY * in_c * sizeof(float), cudaMemcpyHostToDevice));
-    __half* A = h.dalloc<__half>(M * cw.cin_p * b.actMul);
+    cw = b.packConv({&cd});
+    M = (size_t)n * h.L.P;
+    A = h.dalloc<__half>(M * cw.cin_p * b.actMul);
     h.dMask = h.dalloc<float>(M + 128);
     h.dMaskSum = h.dalloc<float>(n);
-    float* raw = h.dalloc<float>(M * cw.cout_p);
-    // pack (mask := input channel 0 is NOT wanted here: use an all-ones board mask instead)
-    CK(launchPackInput(dIn, n, in_c, true, nullptr, h.L, A, cw.cin_p, h.split, h.dMask, h.dMaskSum, h.stream));
-    {
-      std::vector<float> hm(M, 0.0f);
-      for(int i = 0; i < n; i++)
-        for(int y = 0; y < nn_y_len; y++)
-          for(int x = 0; x < nn_x_len; x++) hm[(size_t)i * h.L.P + (size_t)(y + pad) * h.L.Wp + x] = 1.0f;
-      CK(cudaStreamSynchronize(h.stream));
-      CK(cudaMemcpy(h.dMask, hm.data(), M * sizeof(float), cudaMemcpyHostToDevice));
+    raw = h.dalloc<float>(M * cw.cout_p);
+    if(actEpilogue) {
+      // production-shaped epilogue of a residual unit's first conv: BN + mish + mask -> fp16 operand of the next conv
+      BNDesc bn;
+      bn.c = out_c; bn.scale.assign(out_c, 1.0f); bn.bias.assign(out_c, 0.0f);
+      Builder::BNDev dev = b.uploadBN(bn, ACT_MISH, cw.cout_p);
+      __half* actOut = h.dalloc<__half>(M * cw.cout_p * b.actMul);
+      b.emitConv(cw, A, nullptr, false, nullptr, nullptr, false, actOut, dev);
     }
-    Builder::BNDev none;
-    b.emitConv(cw, A, nullptr, false, nullptr, raw, true, nullptr, none);
-    h.ops.back()(n, h.stream);
+    else {
+      Builder::BNDev none;
+      b.emitConv(cw, A, nullptr, false, nullptr, raw, true, nullptr, none);
+    }
+  }
+  ~SingleConv() {
+    for(void* p : h.allocs) cudaFree(p);
+    if(h.stream) cudaStreamDestroy(h.stream);
+  }
+  void setInput(const float* input /* NHWC */) {
+    float* dIn = h.dalloc<float>((size_t)n * X * Y * cin);
+    CK(cudaMemcpy(dIn, input, (size_t)n * X * Y * cin * sizeof(float), cudaMemcpyHostToDevice));
+    Builder b(h);
+    CK(launchPackInput(dIn, n, cin, true, nullptr, h.L, A, cw.cin_p, h.split, h.dMask, h.dMaskSum, h.stream));
     CK(cudaStreamSynchronize(h.stream));
-    std::vector<float> hr(M * cw.cout_p);
-    CK(cudaMemcpy(hr.data(), raw, hr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    // the mask of a bare convolution is "every board point", not input channel 0
+    std::vector<float> hm(M, 0.0f);
+    for(int i = 0; i < n; i++)
+      for(int y = 0; y < Y; y++)
+        for(int x = 0; x < X; x++) hm[(size_t)i * h.L.P + (size_t)(y + pad) * h.L.Wp + x] = 1.0f;
+    CK(cudaMemcpy(h.dMask, hm.data(), M * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  void run() { h.ops.back()(n, h.stream); }
+};
+}  // namespace
+
+extern "C" {
+
+KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
+                  const float* input, float* output) {
+  return guarded([&] {
+    if(!weights || !input || !output || n < 1) throw std::invalid_argument("kgb_test_conv: bad argument");
+    SingleConv sc(ky, kx, in_c, out_c, weights, n, nn_x_len, nn_y_len, use_fp16);
+    sc.setInput(input);
+    sc.run();
+    CK(cudaStreamSynchronize(sc.h.stream));
+    std::vector<float> hr(sc.M * sc.cw.cout_p);
+    CK(cudaMemcpy(hr.data(), sc.raw, hr.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for(int i = 0; i < n; i++)
       for(int y = 0; y < nn_y_len; y++)
         for(int x = 0; x < nn_x_len; x++) {
-          size_t row = (size_t)i * h.L.P + (size_t)(y + pad) * h.L.Wp + x;
-          for(int c = 0; c < out_c; c++) output[(((size_t)i * nn_y_len + y) * nn_x_len + x) * out_c + c] = hr[row * cw.cout_p + c];
+          size_t row = (size_t)i * sc.h.L.P + (size_t)(y + sc.pad) * sc.h.L.Wp + x;
+          for(int c = 0; c < out_c; c++) output[(((size_t)i * nn_y_len + y) * nn_x_len + x) * out_c + c] = hr[row * sc.cw.cout_p + c];
         }
+  });
+}
+
+KGB_API int kgb_bench_conv(int ky, int kx, int in_c, int out_c, int n, int nn_x_len, int nn_y_len, int use_fp16, int warmup, int iters,
+                   float* ms_per_launch) {
+  return guarded([&] {
+    if(!ms_per_launch || n < 1 || iters < 1) throw std::invalid_argument("kgb_bench_conv: bad argument");
+    std::vector<float> w((size_t)ky * kx * in_c * out_c);
+    uint32_t st = 12345u;
+    for(auto& v : w) { st = st * 1664525u + 1013904223u; v = ((st >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.1f; }
+    SingleConv sc(ky, kx, in_c, out_c, w.data(), n, nn_x_len, nn_y_len, use_fp16, 1);
+    std::vector<float> in((size_t)n * nn_x_len * nn_y_len * in_c);
+    for(auto& v : in) { st = st * 1664525u + 1013904223u; v = (st >> 8) * (1.0f / 16777216.0f); }
+    sc.setInput(in.data());
+    for(int i = 0; i < warmup; i++) sc.run();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(sc.h.stream));
+    CK(cudaEventRecord(e0, sc.h.stream));
+    for(int i = 0; i < iters; i++) sc.run();
+    CK(cudaEventRecord(e1, sc.h.stream));
+    CK(cudaStreamSynchronize(sc.h.stream));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_launch = ms / iters;
   });
 }
 

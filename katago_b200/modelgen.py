@@ -31,8 +31,9 @@ CONFIGS = {
 
 
 class _Writer:
-    def __init__(self):
+    def __init__(self, version: int = 15):
         self.buf = io.BytesIO()
+        self.version = version
 
     def line(self, *toks):
         self.buf.write((" ".join(str(t) for t in toks) + "\n").encode("ascii"))
@@ -62,7 +63,8 @@ def _bn(w: _Writer, rng, name, c):
 
 def _act(w: _Writer, name, act):
     w.line(name)
-    w.line(act)
+    if w.version >= 11:  # desc.cpp:382-403: older nets have implicit relu
+        w.line(act)
 
 
 def _matmul(w: _Writer, rng, name, cin, cout, gain=1.0):
@@ -118,7 +120,7 @@ def model_bytes(config: str, seed: int = 0, name: Optional[str] = None, activati
                 version: int = 15, num_input_channels: int = 22, num_global: int = 19) -> bytes:
     cfg = CONFIGS[config]
     rng = np.random.default_rng(seed)
-    w = _Writer()
+    w = _Writer(version)
     act = activation
     c, cmid, cg = cfg["trunk"], cfg["mid"], cfg["gpool"]
     w.line(name or f"{config}-synth{seed}")

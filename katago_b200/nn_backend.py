@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "kgb_global_init", "kgb_global_cleanup", "kgb_last_error", "kgb_device_count", "kgb_device_name",
     "kgb_model_load_file", "kgb_model_free", "kgb_model_get_info", "kgb_context_create", "kgb_context_free",
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
-    "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv",
+    "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
 ]
 
 _lib = None
@@ -82,6 +82,7 @@ def load_library():
     lib.kgb_handle_stream.restype = C.c_uint64
     lib.kgb_handle_launches_per_forward.argtypes = [P]
     lib.kgb_test_conv.argtypes = [I, I, I, I, P, I, I, I, I, P, P]
+    lib.kgb_bench_conv.argtypes = [I, I, I, I, I, I, I, I, I, I, F]
     _lib = lib
     return lib
 

@@ -1,0 +1,105 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/kgb200.h declares, parses model files
+identically to the oracle loader, reports errors like the reference, and refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import kg_nn_oracle as orc
+from conftest import ROOT, has_gpu
+from katago_b200 import KGBError, NeuralNet, modelgen, nn_backend
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "kgb200.h")).read()
+    return sorted(set(re.findall(r"KGB_API\s+[\w\s\*]+?\b(kgb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = nn_backend.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"libkgb200.so does not export {s}"
+    assert sorted(nn_backend.ABI_SYMBOLS) == syms
+
+
+def test_library_is_sm100a_native():
+    """SASS carries tcgen05 MMA, TMA and TMEM loads (B200_PROFILING.md 'What proves a Blackwell-native kernel')."""
+    import shutil, subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", nn_backend.library_path()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass
+    assert "sm_100a" in sass
+
+
+@pytest.mark.parametrize("key", ["tiny_reg", "tiny_nbt", "tiny_nbt_gz", "tiny_relu_v8"])
+def test_model_info_matches_oracle_loader(tmp_models, key):
+    lm = NeuralNet.loadModelFile(tmp_models[key])
+    m = orc.load_model(tmp_models[key])
+    d = NeuralNet.getModelDesc(lm)
+    assert d["model_version"] == m.version
+    assert d["num_input_channels"] == 22 and d["num_input_global_channels"] == 19
+    assert d["trunk_num_channels"] == m.trunk_c and d["num_blocks"] == len(m.blocks)
+    assert d["num_policy_channels"] == m.policy_out_channels
+    assert d["num_score_value_channels"] == m.sv3_mul.cout
+    assert d["conv_macs_per_position"] == orc.conv_macs_per_position(m)
+    assert d["name"] == m.name
+
+
+def test_real_net_and_sha256(golden_dir):
+    import hashlib
+    path = os.path.join(golden_dir, "models", "g170-b6c96-s175395328-d26788732.bin.gz")
+    sha = hashlib.sha256(open(path, "rb").read()).hexdigest()
+    lm = NeuralNet.loadModelFile(path, sha)
+    assert lm.desc["sha256"] == sha and lm.desc["model_version"] == 8 and lm.desc["conv_macs_per_position"] == 1002112
+    with pytest.raises(KGBError, match="sha256"):
+        NeuralNet.loadModelFile(path, "0" * 64)
+
+
+def test_loader_errors(tmp_path, tmp_models):
+    with pytest.raises(KGBError, match="could not open"):
+        NeuralNet.loadModelFile(str(tmp_path / "missing.bin.gz"))
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"name 15 22 19 garbage")
+    with pytest.raises(KGBError):
+        NeuralNet.loadModelFile(str(bad))
+    trunc = tmp_path / "trunc.bin"
+    trunc.write_bytes(open(tmp_models["tiny_reg"], "rb").read()[:5000])
+    with pytest.raises(KGBError):
+        NeuralNet.loadModelFile(str(trunc))
+    wrong = tmp_path / "model.weights"
+    wrong.write_bytes(b"x")
+    with pytest.raises(KGBError, match="should end with"):
+        NeuralNet.loadModelFile(str(wrong))
+
+
+def test_no_silent_cpu_fallback(tmp_models):
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
+    ctx = NeuralNet.createComputeContext([0], 9, 9, True, lm)
+    with pytest.raises(KGBError, match="no CUDA device|CUDA"):
+        NeuralNet.createComputeHandle(ctx, lm, 4, False, True, 0)
+    with pytest.raises(KGBError):
+        NeuralNet.testEvaluateConv(1, 1, 8, 8, np.zeros((1, 1, 8, 8), np.float32), 1, 9, 9, True, np.zeros((1, 9, 9, 8), np.float32))
+
+
+def test_context_argument_checks(tmp_models):
+    lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
+    with pytest.raises(KGBError):
+        NeuralNet.createComputeContext([0], 1, 19, True, lm)
+    with pytest.raises(KGBError):
+        NeuralNet.createComputeContext([0], 19, 50, True, lm)
+
+
+def test_synthetic_file_roundtrip_weights(tmp_models):
+    """modelgen -> file -> oracle loader keeps the weights (format check incl. the @BIN@ blocks)."""
+    a = orc.load_model(tmp_models["tiny_nbt"], apply_transform=False)
+    b = orc.load_model(tmp_models["tiny_nbt_gz"], apply_transform=False)
+    assert np.array_equal(a.initial_conv.w, b.initial_conv.w)
+    assert np.array_equal(a.blocks[1].blocks[0].gpool_to_bias.w, b.blocks[1].blocks[0].gpool_to_bias.w)
