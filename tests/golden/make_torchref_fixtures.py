@@ -19,9 +19,10 @@ from katago.train.model_pytorch import Model  # noqa: E402
 from katago_b200 import modelgen  # noqa: E402
 
 
-def make(cfg_name: str, n: int, seed: int, sizes=None):
+def make(cfg_name: str, n: int, seed: int, sizes=None, base=None, override=None):
     torch.manual_seed(seed)
-    cfg = dict(modelconfigs.config_of_name[cfg_name])
+    cfg = dict(modelconfigs.config_of_name[base or cfg_name])
+    cfg.update(override or {})
     model = Model(cfg, 19)
     model.initialize()
     with torch.no_grad():
@@ -52,5 +53,10 @@ def make(cfg_name: str, n: int, seed: int, sizes=None):
 
 if __name__ == "__main__":
     make("b2c16", 4, 1, sizes=[(19, 19), (9, 9), (19, 19), (13, 7)])
-    make("b1c6nbt", 4, 2, sizes=[(19, 19), (19, 19), (11, 11), (19, 19)])
+    # the stock b1c6nbt config has regularC = mid - gpool = 0, which the reference's own C++ loader rejects
+    # (desc.cpp:1700-1704); use the same nested-bottleneck family with a gpool inner block instead
+    make("b2c32nbt", 4, 2, sizes=[(19, 19), (19, 19), (11, 11), (19, 19)], base="b1c6nbt",
+         override=dict(trunk_num_channels=32, mid_num_channels=16, gpool_num_channels=8,
+                       block_kind=[["rconv1", "bottlenest2"], ["rconv2", "bottlenest2gpool"]],
+                       p1_num_channels=8, g1_num_channels=8, v1_num_channels=12, v2_size=16))
     make("b4c32", 3, 3)

@@ -59,7 +59,7 @@ def test_conv_layer(ky, cin, cout, n, X, Y, fp16):
 
 
 @pytest.mark.parametrize("fp16", [False, True])
-@pytest.mark.parametrize("cfg", ["b2c16", "b1c6nbt", "b4c32"])
+@pytest.mark.parametrize("cfg", ["b2c16", "b2c32nbt", "b4c32"])
 def test_golden_reference_pytorch_outputs(golden_dir, cfg, fp16):
     d = np.load(os.path.join(golden_dir, f"torchref_{cfg}.npz"))
     sp, gl = d["spatial_nhwc"].astype(np.float32), d["global_"]

@@ -9,7 +9,7 @@ import kg_nn_oracle as orc
 from katago_b200 import modelgen
 
 
-@pytest.mark.parametrize("cfg", ["b2c16", "b1c6nbt", "b4c32"])
+@pytest.mark.parametrize("cfg", ["b2c16", "b2c32nbt", "b4c32"])
 def test_oracle_matches_reference_pytorch_model(golden_dir, cfg):
     d = np.load(os.path.join(golden_dir, f"torchref_{cfg}.npz"))
     m = orc.load_model(os.path.join(golden_dir, "models", f"torchref_{cfg}.bin.gz"))
