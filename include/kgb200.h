@@ -119,6 +119,61 @@ KGB_API int kgb_handle_launches_per_forward(const kgb_handle* handle);
 KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
                   const float* input, float* output);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Boundary 2: device-resident self-play slots.  Boards, MCTS node pools and NN rows stay in HBM; one
+ * kgb_selfplay_run(steps) call performs `steps` playout waves (select+featurize -> NN forward -> backup, one visit per
+ * game per wave) without returning to the host.  Replaces, for the supported rule/parameter subset,
+ * Search::runWholeSearch/playoutDescend (search.cpp:473,1189), selectBestChildToDescend (searchexplorehelpers.cpp:324),
+ * NNEvaluator::evaluate's featurize/post-process halves (nneval.cpp:861-1262) and the per-move core of Play::runGame
+ * (play.cpp:1757-1936).  Parameters are the reference's SearchParams names (search/searchparams.h). */
+typedef struct kgb_selfplay kgb_selfplay;
+
+typedef struct kgb_selfplay_config {
+  int32_t num_games;                 /* concurrent games (= NN batch per wave); <= the handle's max_batch_size */
+  int32_t max_visits;                /* maxVisits: visits per move on a cleared tree */
+  int32_t max_moves;                 /* game length cap (0 = 2*X*Y) */
+  int32_t multi_stone_suicide_legal; /* Rules::multiStoneSuicideLegal */
+  int32_t early_temperature_moves;   /* moves chosen proportionally to visits (chosenMoveTemperatureEarly = 1), then argmax */
+  float komi;
+  double cpuct_exploration;          /* cpuctExploration       (default 1.0) */
+  double cpuct_exploration_log;      /* cpuctExplorationLog    (0.45 in selfplay cfgs) */
+  double cpuct_exploration_base;     /* cpuctExplorationBase   (500) */
+  double fpu_reduction_max;          /* fpuReductionMax        (0.2) */
+  double root_fpu_reduction_max;     /* rootFpuReductionMax    (0.1 in selfplay cfgs) */
+  double win_loss_utility_factor;    /* winLossUtilityFactor   (1.0) */
+  double no_result_utility_for_white;
+  uint64_t seed;
+} kgb_selfplay_config;
+
+typedef struct kgb_selfplay_stats {
+  uint64_t total_visits;     /* playouts completed (sum over games of root visits) */
+  uint64_t total_moves;      /* root moves played */
+  uint64_t games_finished;
+  uint64_t black_wins;
+  uint64_t nodes_allocated;
+  uint64_t sum_leaf_depth;   /* sum over playouts of the leaf depth */
+} kgb_selfplay_stats;
+
+KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out);
+KGB_API void kgb_selfplay_free(kgb_selfplay* sp);
+/* Enqueue `steps` playout waves on the handle's stream (asynchronous; kgb_handle_sync() to wait). */
+KGB_API int kgb_selfplay_run(kgb_selfplay* sp, int steps);
+KGB_API int kgb_selfplay_get_stats(kgb_selfplay* sp, kgb_selfplay_stats* out);
+/* Root position of game g: colors[Y*X] (0 empty, 1 black, 2 white); info[6] = move number, black-to-move, ko point
+ * (y*32+x or -1), black stones captured, white stones captured, root visits. */
+KGB_API int kgb_selfplay_get_game(kgb_selfplay* sp, int game, uint8_t* colors, int32_t* info);
+/* Root children of game g, indexed by move position 0..X*Y (pass last): visit counts, NN policy (-1 illegal), utility sums. */
+KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* util_sum);
+/* Kernel launches per playout wave (evaluator launches + 2). */
+KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp);
+
+/* FOR TESTING (rows a1/a2): replay move streams on the device board.  moves[b][m] = {x, y (or -1,-1 = pass), pla (1 black,
+ * 2 white)}; after every move returns stones, simple-ko point {x,y or -1,-1}, capture counters {black stones captured,
+ * white stones captured}, liberty class of every stone (1,2,3, 0 = more / empty) and Board::isLegal of every point for
+ * the NEXT player. */
+KGB_API int kgb_test_board_replay(int x_size, int y_size, int num_boards, int num_moves, int multi_stone_suicide_legal, const int8_t* moves,
+                          uint8_t* colors, int8_t* ko, int16_t* caps, uint8_t* lib_class, uint8_t* legal_next);
+
 /* Kernel-level timing hook for bench.py's roofline object: runs ONE convolution layer (random weights/inputs resident in
  * HBM, the production epilogue of a residual unit's first conv: BN + mish + mask -> fp16) `iters` times on a stream and returns the CUDA-event average per launch. */
 KGB_API int kgb_bench_conv(int ky, int kx, int in_c, int out_c, int n, int nn_x_len, int nn_y_len, int use_fp16, int warmup, int iters,

@@ -25,6 +25,7 @@
 #include "kgb_conv.cuh"
 #include "kgb_kernels.cuh"
 #include "kgb_model.h"
+#include "kgb_selfplay.h"
 
 using namespace kgb;
 
@@ -811,6 +812,106 @@ KGB_API int kgb_bench_conv(int ky, int kx, int in_c, int out_c, int n, int nn_x_
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms_per_launch = ms / iters;
+  });
+}
+
+// ---- Boundary 2: device-resident self-play ------------------------------------------------------------------
+struct kgb_selfplay {
+  kgb_handle* h = nullptr;
+  SelfplayImpl* impl = nullptr;
+  int n = 0;
+  cudaGraphExec_t stepGraph = nullptr;
+};
+
+static void selfplayStepLaunches(kgb_selfplay* sp, cudaStream_t s) {
+  selfplayLaunchSelect(sp->impl, s);
+  for(auto& op : sp->h->ops) op(sp->n, s);
+  selfplayLaunchBackup(sp->impl, s);
+}
+
+KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out) {
+  return guarded([&] {
+    if(!handle || !config || !out) throw std::invalid_argument("kgb_selfplay_create: NULL argument");
+    if(config->num_games > handle->maxBatch) throw std::invalid_argument("kgb_selfplay_create: num_games exceeds the handle's max_batch_size");
+    if(!handle->nhwc) throw std::invalid_argument("kgb_selfplay_create: the handle must be created with inputs_nhwc = 1");
+    if(handle->model->numInputChannels != 22 || handle->model->numInputGlobalChannels != 19)
+      throw std::invalid_argument("kgb_selfplay_create: the device loop writes V7 features (22 spatial, 19 global)");
+    CK(cudaSetDevice(handle->device));
+    std::unique_ptr<kgb_selfplay> sp(new kgb_selfplay());
+    sp->h = handle;
+    sp->n = config->num_games;
+    SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue};
+    sp->impl = selfplayCreate(*config, handle->L.X, handle->L.Y, nn, handle->stream);
+    *out = sp.release();
+  });
+}
+
+KGB_API void kgb_selfplay_free(kgb_selfplay* sp) {
+  if(!sp) return;
+  if(sp->stepGraph) cudaGraphExecDestroy(sp->stepGraph);
+  selfplayDestroy(sp->impl);
+  delete sp;
+}
+
+KGB_API int kgb_selfplay_run(kgb_selfplay* sp, int steps) {
+  return guarded([&] {
+    if(!sp || steps < 0) throw std::invalid_argument("kgb_selfplay_run: bad argument");
+    kgb_handle* h = sp->h;
+    CK(cudaSetDevice(h->device));
+    if(!h->useGraph) {
+      for(int i = 0; i < steps; i++) selfplayStepLaunches(sp, h->stream);
+      return;
+    }
+    if(!sp->stepGraph) {
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      try { selfplayStepLaunches(sp, h->stream); }
+      catch(...) { cudaStreamEndCapture(h->stream, &graph); if(graph) cudaGraphDestroy(graph); throw; }
+      CK(cudaStreamEndCapture(h->stream, &graph));
+      CK(cudaGraphInstantiate(&sp->stepGraph, graph, 0));
+      CK(cudaGraphDestroy(graph));
+    }
+    for(int i = 0; i < steps; i++) CK(cudaGraphLaunch(sp->stepGraph, h->stream));
+  });
+}
+
+KGB_API int kgb_selfplay_get_stats(kgb_selfplay* sp, kgb_selfplay_stats* out) {
+  return guarded([&] {
+    if(!sp || !out) throw std::invalid_argument("kgb_selfplay_get_stats: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadStats(sp->impl, out);
+  });
+}
+
+KGB_API int kgb_selfplay_get_game(kgb_selfplay* sp, int game, uint8_t* colors, int32_t* info) {
+  return guarded([&] {
+    if(!sp || !colors || !info) throw std::invalid_argument("kgb_selfplay_get_game: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadGame(sp->impl, game, colors, info);
+  });
+}
+
+KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* util_sum) {
+  return guarded([&] {
+    if(!sp || !visits || !policy || !util_sum) throw std::invalid_argument("kgb_selfplay_get_root_children: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadRootChildren(sp->impl, game, visits, policy, util_sum);
+  });
+}
+
+KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp) { return sp ? sp->h->launchesPerForward + 2 : 0; }
+
+KGB_API int kgb_test_board_replay(int x_size, int y_size, int num_boards, int num_moves, int multi_stone_suicide_legal, const int8_t* moves,
+                          uint8_t* colors, int8_t* ko, int16_t* caps, uint8_t* lib_class, uint8_t* legal_next) {
+  return guarded([&] {
+    if(!moves || !colors || !ko || !caps || !lib_class || !legal_next || num_boards < 1 || num_moves < 1)
+      throw std::invalid_argument("kgb_test_board_replay: bad argument");
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaFailure("libkgb200: no CUDA device is visible");
+    boardReplay(x_size, y_size, num_boards, num_moves, multi_stone_suicide_legal, moves, colors, ko, caps, lib_class, legal_next);
   });
 }
 

@@ -1,0 +1,582 @@
+// Device-resident self-play playout loop (round-1 scope: see DESIGN.md §8 "device loop" for what is and is not
+// reference-equivalent yet).  One warp per game; a "step" = one playout for every game:
+//
+//   spSelectKernel   (a) root move + tree reset when the visit budget is reached        play.cpp:1757-1936 (core only)
+//                    (b) PUCT descent from the root on a register-resident bitboard      search.cpp:1189-1463,
+//                        Board::playMoveAssumeLegal per edge (kgb_board.cuh)             searchexplorehelpers.cpp:22-54,265-643
+//                    (c) leaf: liberty classes, legality, NN input row                   nninputs.cpp:2288-2731 (planes listed below)
+//   NN forward       the CUDA-graph op list of the evaluator (kgb_api.cu), batch = number of games
+//   spBackupKernel   (d) policy: legality mask + softmax; value: softmax -> white utility nneval.cpp:960-1051,1112-1215
+//                    (e) backup along the path                                           searchupdatehelpers.cpp:11-81,139-360
+//
+// Tree layout (per game, per node, SoA, indexed by move position 0..X*Y (pass last)):
+//   policy[pos] fp32 (-1 = illegal), childNode[pos] i32 (-1 = not expanded), childVisits[pos] i32, childUtilSum[pos] f64
+// so selection reads four coalesced arrays and never chases child pointers (the reference keeps stats in the child
+// nodes: searchnode.h:17-41,105-138).  With unit weights the reference's recomputed weighted average
+// (searchupdatehelpers.cpp:167-360) equals this running mean.
+//
+// NN input planes written this round: 0 on-board, 1/2 own/opp stones, 3/4/5 liberties 1/2/3, 6 simple-ko ban,
+// 9-13 previous five move locations; globals 0-4 pass history, 5 selfKomi/20, 8 multi-stone suicide, 14 pass would end
+// the phase, 18 komi parity wave.  NOT yet written (stay 0): ladder planes 14-17, pass-alive area planes 18-19,
+// superko bans in plane 6, encore planes (territory rules) - rows a4/a5 of SURVEY.md §8.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/kgb200.h"
+#include "kgb_board.cuh"
+#include "kgb_selfplay.h"
+
+namespace kgb {
+
+struct SPDev {
+  // configuration
+  int X, Y, XY, policySize, numGames, maxVisits, maxNodes, maxDepth, maxMoves, multiSuicide, earlyMoves;
+  float komi;
+  double cpuctExploration, cpuctExplorationLog, cpuctExplorationBase, fpuReductionMax, rootFpuReductionMax;
+  double winLossUtilityFactor, noResultUtilityForWhite;
+  uint64_t seed;
+  // root state [game]
+  uint32_t *rootB, *rootW;          // [game][32]
+  int *rootKo, *rootBlackToMove, *rootCapB, *rootCapW, *moveNum, *consecPasses;
+  int* hist;                        // [game][5] last moves, most recent first: -1 none, -2 pass, else y*32+x
+  uint64_t* gameCounter;            // games started per slot (RNG stream)
+  // tree [game][node]...
+  int* nodeCount;                   // [game]
+  int* nodeVisits;                  // [game][maxNodes]
+  double* nodeUtilSum;              // [game][maxNodes]   (white's perspective)
+  int8_t* nodeTerminal;             // [game][maxNodes]   0 no, 1 yes
+  float* policy;                    // [game][maxNodes][policySize]
+  int* childNode;                   // same shape
+  int* childVisits;
+  double* childUtilSum;
+  // per-playout scratch
+  int *pathLen, *pathNode, *pathMove;   // [game], [game][maxDepth] x2
+  int *leafNode, *leafTerminal, *leafBlackToMove;
+  double* leafTerminalUtil;
+  uint32_t* leafLegal;              // [game][32] row masks of legal points for the player to move at the leaf
+  // statistics
+  unsigned long long *totalVisits, *totalMoves, *gamesFinished, *blackWins, *nodesAllocated, *sumDepth;
+  // evaluator buffers (owned by the kgb_handle)
+  float *nnSpatial, *nnGlobal, *nnOptimism;
+  int* nnSymmetry;
+  const float *nnPolicy, *nnValue;
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ int posOf(int p, int X) { return (p >> 5) * X + (p & 31); }   // y*32+x -> y*X+x
+__device__ __forceinline__ int pointOfPos(int pos, int X) { return ((pos / X) << 5) | (pos % X); }
+
+__device__ __forceinline__ double warpSumD(double v) {
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(KGB_FULL, v, o);
+  return v;
+}
+
+// Reset a node's per-move arrays (coalesced).
+__device__ __forceinline__ void nodeInit(const SPDev& d, size_t nodeBase, int lane) {
+  for(int i = lane; i < d.policySize; i += 32) {
+    d.childNode[nodeBase + i] = -1;
+    d.childVisits[nodeBase + i] = 0;
+    d.childUtilSum[nodeBase + i] = 0.0;
+    d.policy[nodeBase + i] = -1.0f;
+  }
+}
+
+// Choose and play the root move once the visit budget is spent; restart the game when it is over.
+__device__ void rootAdvance(const SPDev& d, int g, int lane) {
+  const size_t gb = (size_t)g * d.maxNodes;
+  const size_t rootBase = gb * d.policySize;
+  // visit counts of the root's children
+  int best = -1, bestV = -1;
+  long long total = 0;
+  const bool early = d.moveNum[g] < d.earlyMoves;
+  uint64_t r = splitmix64(d.seed ^ splitmix64(((uint64_t)g << 32) ^ (d.gameCounter[g] * 1315423911ULL) ^ (uint64_t)d.moveNum[g]));
+  // pass 1: totals / argmax
+  int myBest = -1, myBestV = -1;
+  long long mySum = 0;
+  for(int i = lane; i < d.policySize; i += 32) {
+    int v = d.childVisits[rootBase + i];
+    mySum += v;
+    if(v > myBestV) { myBestV = v; myBest = i; }
+  }
+  for(int o = 16; o > 0; o >>= 1) {
+    int ov = __shfl_xor_sync(KGB_FULL, myBestV, o), oi = __shfl_xor_sync(KGB_FULL, myBest, o);
+    if(ov > myBestV || (ov == myBestV && oi < myBest)) { myBestV = ov; myBest = oi; }
+    mySum += __shfl_xor_sync(KGB_FULL, mySum, o);
+  }
+  best = myBest; bestV = myBestV; total = mySum;
+  if(early && total > 0) {
+    // sample proportionally to visits (temperature 1): walk the cumulative distribution in position order
+    long long target = (long long)(r % (uint64_t)total);
+    long long run = 0;
+    int chosen = best;
+    bool found = false;
+    for(int base = 0; base < d.policySize && !found; base += 32) {
+      int i = base + lane;
+      long long v = i < d.policySize ? d.childVisits[rootBase + i] : 0;
+      long long incl = v;
+      for(int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(KGB_FULL, incl, o);
+        if(lane >= o) incl += t;
+      }
+      unsigned hit = __ballot_sync(KGB_FULL, v > 0 && run + incl > target);
+      if(hit) { chosen = base + __ffs(hit) - 1; found = true; }
+      run += __shfl_sync(KGB_FULL, incl, 31);
+    }
+    best = chosen;
+  }
+  if(bestV <= 0) best = d.policySize - 1;  // nothing searched (cannot happen with maxVisits >= 2): pass
+  // play it on the root board
+  WarpBoard bd;
+  boardInit(bd, d.X, d.Y);
+  bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
+  bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
+  const bool black = d.rootBlackToMove[g] != 0;
+  const bool isPass = best == d.policySize - 1;
+  const int p = isPass ? -1 : pointOfPos(best, d.X);
+  boardPlay(bd, p, black);
+  int passes = isPass ? d.consecPasses[g] + 1 : 0;
+  int mv = d.moveNum[g] + 1;
+  bool over = passes >= 2 || mv >= d.maxMoves;
+  if(over) {
+    int diff = boardAreaScoreBlackMinusWhite(bd);
+    float whiteScore = d.komi - (float)diff;
+    if(lane == 0) {
+      atomicAdd(d.gamesFinished, 1ULL);
+      if(whiteScore < 0) atomicAdd(d.blackWins, 1ULL);
+      d.gameCounter[g] += 1;
+    }
+    boardInit(bd, d.X, d.Y);
+    passes = 0; mv = 0;
+    if(lane < 5) d.hist[g * 5 + lane] = -1;
+    if(lane == 0) d.rootBlackToMove[g] = 1;
+  }
+  else {
+    int h = lane < 5 ? d.hist[g * 5 + lane] : -1;
+    int shifted = __shfl_up_sync(KGB_FULL, h, 1);
+    if(lane < 5) d.hist[g * 5 + lane] = lane == 0 ? (isPass ? -2 : p) : shifted;
+    if(lane == 0) d.rootBlackToMove[g] = black ? 0 : 1;
+  }
+  d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
+  if(lane == 0) {
+    d.rootKo[g] = bd.ko; d.rootCapB[g] = bd.capB; d.rootCapW[g] = bd.capW;
+    d.moveNum[g] = mv; d.consecPasses[g] = passes;
+    atomicAdd(d.totalMoves, 1ULL);
+    // reset the tree: node 0 = unevaluated root
+    d.nodeCount[g] = 1;
+    d.nodeVisits[gb] = 0; d.nodeUtilSum[gb] = 0.0; d.nodeTerminal[gb] = 0;
+  }
+  nodeInit(d, rootBase, lane);
+  __syncwarp();
+}
+
+__global__ void spSelectKernel(const SPDev d) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  const size_t gb = (size_t)g * d.maxNodes;
+  if(d.nodeVisits[gb] >= d.maxVisits) rootAdvance(d, g, lane);
+
+  WarpBoard bd;
+  boardInit(bd, d.X, d.Y);
+  bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
+  bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
+  bool black = d.rootBlackToMove[g] != 0;
+  int passes = d.consecPasses[g];
+  int h0 = d.hist[g * 5 + 0], h1 = d.hist[g * 5 + 1], h2 = d.hist[g * 5 + 2], h3 = d.hist[g * 5 + 3], h4 = d.hist[g * 5 + 4];
+  int node = 0, depth = 0;
+  bool terminal = false;
+  while(true) {
+    const int visits = d.nodeVisits[gb + node];
+    terminal = d.nodeTerminal[gb + node] != 0;
+    if(visits == 0 || terminal || depth >= d.maxDepth - 1) break;
+    const size_t nb = (gb + node) * d.policySize;
+    // ---- pass 1: visited policy mass, total child weight; keep this lane's entries in registers
+    float P[12]; int CV[12]; double CU[12];
+    double massVisited = 0.0, totalW = 0.0;
+#pragma unroll
+    for(int k = 0; k < 12; k++) {
+      int i = k * 32 + lane;
+      bool in = i < d.policySize;
+      P[k] = in ? d.policy[nb + i] : -1.0f;
+      CV[k] = in ? d.childVisits[nb + i] : 0;
+      CU[k] = in ? d.childUtilSum[nb + i] : 0.0;
+      if(CV[k] > 0 && P[k] >= 0.0f) { massVisited += (double)P[k]; totalW += (double)CV[k]; }
+    }
+    massVisited = warpSumD(massVisited);
+    totalW = warpSumD(totalW);
+    // ---- FPU and exploration scaling (searchexplorehelpers.cpp:22-29, 265-321)
+    const double parentUtility = d.nodeUtilSum[gb + node] / (double)visits;
+    const double fpuRed = (node == 0 ? d.rootFpuReductionMax : d.fpuReductionMax) * sqrt(massVisited);
+    const double fpuValue = black ? parentUtility + fpuRed : parentUtility - fpuRed;   // white's perspective
+    const double cpuct = d.cpuctExploration + d.cpuctExplorationLog * log((totalW + d.cpuctExplorationBase) / d.cpuctExplorationBase);
+    const double exploreScaling = cpuct * sqrt(totalW + 0.01);
+    // ---- pass 2: best existing child and best new move
+    double bestVal = -1e50; int bestIdx = -1;
+    float bestNewP = -1.0f; int bestNewIdx = -1;
+#pragma unroll
+    for(int k = 0; k < 12; k++) {
+      int i = k * 32 + lane;
+      if(P[k] < 0.0f) continue;
+      if(CV[k] > 0) {
+        double u = CU[k] / (double)CV[k];
+        double val = exploreScaling * (double)P[k] / (1.0 + (double)CV[k]) + (black ? -u : u);
+        if(val > bestVal) { bestVal = val; bestIdx = i; }
+      }
+      else if(P[k] > bestNewP) { bestNewP = P[k]; bestNewIdx = i; }
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(KGB_FULL, bestVal, o); int oi = __shfl_xor_sync(KGB_FULL, bestIdx, o);
+      if(oi >= 0 && (bestIdx < 0 || ov > bestVal || (ov == bestVal && oi < bestIdx))) { bestVal = ov; bestIdx = oi; }
+      float op = __shfl_xor_sync(KGB_FULL, bestNewP, o); int on = __shfl_xor_sync(KGB_FULL, bestNewIdx, o);
+      if(on >= 0 && (bestNewIdx < 0 || op > bestNewP || (op == bestNewP && on < bestNewIdx))) { bestNewP = op; bestNewIdx = on; }
+    }
+    int move = bestIdx;
+    if(bestNewIdx >= 0) {
+      double newVal = exploreScaling * (double)bestNewP + (black ? -fpuValue : fpuValue);
+      if(bestIdx < 0 || newVal > bestVal) move = bestNewIdx;
+    }
+    if(move < 0) break;  // no legal move at all (cannot happen: pass is always legal)
+    // ---- descend
+    const bool isPass = move == d.policySize - 1;
+    const int p = isPass ? -1 : pointOfPos(move, d.X);
+    boardPlay(bd, p, black);
+    passes = isPass ? passes + 1 : 0;
+    h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
+    black = !black;
+    int child = d.childNode[nb + move];
+    if(child < 0) {
+      child = d.nodeCount[g];
+      if(child >= d.maxNodes) break;  // pool exhausted (sized maxVisits+2: cannot happen)
+      __syncwarp();
+      if(lane == 0) {
+        d.nodeCount[g] = child + 1;
+        d.childNode[nb + move] = child;
+        d.nodeVisits[gb + child] = 0;
+        d.nodeUtilSum[gb + child] = 0.0;
+        d.nodeTerminal[gb + child] = (passes >= 2) ? 1 : 0;
+        atomicAdd(d.nodesAllocated, 1ULL);
+      }
+      nodeInit(d, (gb + child) * d.policySize, lane);
+      __syncwarp();
+    }
+    if(lane == 0) { d.pathNode[(size_t)g * d.maxDepth + depth] = node; d.pathMove[(size_t)g * d.maxDepth + depth] = move; }
+    depth++;
+    node = child;
+  }
+  terminal = d.nodeTerminal[gb + node] != 0;
+
+  // ---- leaf: liberties, legality, features
+  uint32_t lib1, lib2, lib3;
+  boardLibertyClasses(bd, lib1, lib2, lib3);
+  const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, lib1);
+  d.leafLegal[g * 32 + lane] = legal;
+  if(lane == 0) {
+    d.pathLen[g] = depth; d.leafNode[g] = node; d.leafTerminal[g] = terminal ? 1 : 0; d.leafBlackToMove[g] = black ? 1 : 0;
+    atomicAdd(d.sumDepth, (unsigned long long)depth);
+  }
+  if(terminal) {
+    int diff = boardAreaScoreBlackMinusWhite(bd);
+    float whiteScore = d.komi - (float)diff;
+    double u = whiteScore > 0 ? d.winLossUtilityFactor : whiteScore < 0 ? -d.winLossUtilityFactor : 0.0;
+    if(lane == 0) d.leafTerminalUtil[g] = u;
+  }
+  // NN input row (NHWC [pos][22]) - zero fill, then the ones
+  float* row = d.nnSpatial + (size_t)g * d.XY * 22;
+  for(int i = lane; i < d.XY * 22; i += 32) row[i] = 0.0f;
+  float* gl = d.nnGlobal + (size_t)g * 19;
+  if(lane < 19) gl[lane] = 0.0f;
+  __syncwarp();
+  const uint32_t own = black ? bd.b : bd.w, opp = black ? bd.w : bd.b;
+  if(lane < d.Y) {
+    for(int x = 0; x < d.X; x++) {
+      float* f = row + (size_t)(lane * d.X + x) * 22;
+      const uint32_t bit = 1u << x;
+      f[0] = 1.0f;
+      if(own & bit) f[1] = 1.0f; else if(opp & bit) f[2] = 1.0f;
+      if(lib1 & bit) f[3] = 1.0f; else if(lib2 & bit) f[4] = 1.0f; else if(lib3 & bit) f[5] = 1.0f;
+    }
+  }
+  __syncwarp();
+  if(lane == 0) {
+    if(bd.ko >= 0) row[(size_t)posOf(bd.ko, d.X) * 22 + 6] = 1.0f;
+    // history planes 9..13: the move k plies ago must have been made by the right colour, which alternation guarantees
+    int hs[5] = {h0, h1, h2, h3, h4};
+    for(int k = 0; k < 5; k++) {
+      if(hs[k] == -1) break;                       // no more history (game start)
+      if(hs[k] == -2) gl[k] = 1.0f;
+      else row[(size_t)posOf(hs[k], d.X) * 22 + 9 + k] = 1.0f;
+    }
+    float selfKomi = black ? -d.komi : d.komi;
+    float bArea = (float)d.XY;
+    selfKomi = fminf(fmaxf(selfKomi, -bArea - 20.0f), bArea + 20.0f);
+    gl[5] = selfKomi / 20.0f;
+    if(d.multiSuicide) gl[8] = 1.0f;
+    gl[14] = passes >= 1 ? 1.0f : 0.0f;          // BoardHistory::passWouldEndPhase under area scoring, simple ko
+    // komi parity wave (nninputs.cpp:2696-2729)
+    bool drawableKomisAreEven = (d.XY % 2) == 0;
+    float komiFloor = drawableKomisAreEven ? floorf(selfKomi / 2.0f) * 2.0f : floorf((selfKomi - 1.0f) / 2.0f) * 2.0f + 1.0f;
+    float delta = fminf(fmaxf(selfKomi - komiFloor, 0.0f), 2.0f);
+    gl[18] = delta < 0.5f ? delta : (delta < 1.5f ? 1.0f - delta : delta - 2.0f);
+    d.nnSymmetry[g] = (int)(splitmix64(d.seed ^ ((uint64_t)g << 40) ^ (d.gameCounter[g] << 28) ^ ((uint64_t)d.moveNum[g] << 14) ^
+                                       (uint64_t)d.nodeVisits[gb]) & 7);   // nneval.cpp:698-707: random symmetry per row
+    d.nnOptimism[g] = 0.0f;
+  }
+}
+
+__global__ void spBackupKernel(const SPDev d) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  const size_t gb = (size_t)g * d.maxNodes;
+  const int node = d.leafNode[g];
+  const bool terminal = d.leafTerminal[g] != 0;
+  double u;
+  if(terminal) u = d.leafTerminalUtil[g];
+  else {
+    // ---- policy: legality mask + softmax (nneval.cpp:960-1051)
+    const float* logits = d.nnPolicy + (size_t)g * d.policySize;
+    const uint32_t legalRow = d.leafLegal[g * 32 + lane];
+    float v[12]; bool ok[12];
+    float mx = -1e25f;
+#pragma unroll
+    for(int k = 0; k < 12; k++) {
+      int i = k * 32 + lane;
+      ok[k] = false; v[k] = -1e30f;
+      const int ic = i < d.XY ? i : d.XY - 1;                       // every lane takes part in the shuffle
+      const uint32_t rowBits = __shfl_sync(KGB_FULL, legalRow, ic / d.X);
+      if(i < d.policySize) {
+        const bool legal = (i == d.policySize - 1) ? true : (((rowBits >> (ic % d.X)) & 1u) != 0);
+        ok[k] = legal;
+        if(legal) v[k] = logits[i];
+        mx = fmaxf(mx, v[k]);
+      }
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(KGB_FULL, mx, o));
+    float sum = 0.0f;
+#pragma unroll
+    for(int k = 0; k < 12; k++) { v[k] = ok[k] ? expf(v[k] - mx) : 0.0f; sum += v[k]; }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(KGB_FULL, sum, o);
+    const size_t nb = (gb + node) * d.policySize;
+#pragma unroll
+    for(int k = 0; k < 12; k++) {
+      int i = k * 32 + lane;
+      if(i < d.policySize) d.policy[nb + i] = ok[k] ? v[k] / sum : -1.0f;
+    }
+    // ---- value: softmax(win, loss, noResult) from the mover's perspective -> white utility (nneval.cpp:1112-1215)
+    const float* val = d.nnValue + (size_t)g * 3;
+    double wl = val[0], ll = val[1], nl = val[2];
+    double m = fmax(fmax(wl, ll), nl);
+    double w = exp(wl - m), l = exp(ll - m), n = exp(nl - m);
+    double s = w + l + n;
+    w /= s; l /= s; n /= s;
+    const bool black = d.leafBlackToMove[g] != 0;
+    double whiteWin = black ? l : w, whiteLoss = black ? w : l;
+    u = d.winLossUtilityFactor * (whiteWin - whiteLoss) + d.noResultUtilityForWhite * n;
+  }
+  __syncwarp();
+  // ---- backup (one lane: a handful of scattered read-modify-writes along the path)
+  if(lane == 0) {
+    d.nodeVisits[gb + node] += 1;
+    d.nodeUtilSum[gb + node] += u;
+    const int len = d.pathLen[g];
+    for(int k = len - 1; k >= 0; k--) {
+      int pn = d.pathNode[(size_t)g * d.maxDepth + k], mv = d.pathMove[(size_t)g * d.maxDepth + k];
+      size_t nb = (gb + pn) * d.policySize;
+      d.childVisits[nb + mv] += 1;
+      d.childUtilSum[nb + mv] += u;
+      d.nodeVisits[gb + pn] += 1;
+      d.nodeUtilSum[gb + pn] += u;
+    }
+    atomicAdd(d.totalVisits, 1ULL);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Board test kernel: replays move streams (parity tests against the reference Board fixtures)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void boardReplayKernel(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves /*[b][m][3]: x,y,pla(1=black,2=white)*/,
+                                  uint8_t* colors /*[b][m][Y*X]*/, int8_t* ko /*[b][m][2]*/, int16_t* caps /*[b][m][2]*/,
+                                  uint8_t* libClass /*[b][m][Y*X] 0..3 (0 = >3 or empty)*/, uint8_t* legalNext /*[b][m][Y*X]*/) {
+  const int bidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(bidx >= numBoards) return;
+  WarpBoard bd;
+  boardInit(bd, X, Y);
+  for(int m = 0; m < numMoves; m++) {
+    const int8_t* mv = moves + ((size_t)bidx * numMoves + m) * 3;
+    const bool black = mv[2] == 1;
+    const int p = mv[0] < 0 ? -1 : (mv[1] * 32 + mv[0]);
+    boardPlay(bd, p, black);
+    uint32_t l1, l2, l3;
+    boardLibertyClasses(bd, l1, l2, l3);
+    uint32_t legal = boardLegalMask(bd, !black, multiSuicide != 0, l1);
+    const size_t o = ((size_t)bidx * numMoves + m) * X * Y;
+    if(lane < Y)
+      for(int x = 0; x < X; x++) {
+        uint32_t bit = 1u << x;
+        colors[o + lane * X + x] = (bd.b & bit) ? 1 : (bd.w & bit) ? 2 : 0;
+        libClass[o + lane * X + x] = (l1 & bit) ? 1 : (l2 & bit) ? 2 : (l3 & bit) ? 3 : 0;
+        legalNext[o + lane * X + x] = (legal & bit) ? 1 : 0;
+      }
+    if(lane == 0) {
+      size_t q = (size_t)bidx * numMoves + m;
+      ko[q * 2] = bd.ko < 0 ? -1 : (int8_t)(bd.ko & 31);
+      ko[q * 2 + 1] = bd.ko < 0 ? -1 : (int8_t)(bd.ko >> 5);
+      caps[q * 2] = (int16_t)bd.capB; caps[q * 2 + 1] = (int16_t)bd.capW;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------------
+#define SPCK(expr)                                                                                               \
+  do {                                                                                                           \
+    cudaError_t _e = (expr);                                                                                     \
+    if(_e != cudaSuccess) throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(_e) + " at " #expr); \
+  } while(0)
+
+struct SelfplayImpl {
+  SPDev d;
+  std::vector<void*> allocs;
+  cudaStream_t stream;
+  template <class T> T* alloc(size_t n) {
+    void* p = nullptr;
+    SPCK(cudaMalloc(&p, n * sizeof(T)));
+    SPCK(cudaMemset(p, 0, n * sizeof(T)));
+    allocs.push_back(p);
+    return (T*)p;
+  }
+  ~SelfplayImpl() { for(void* p : allocs) cudaFree(p); }
+};
+
+SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const SelfplayNNBuffers& nn, cudaStream_t stream) {
+  if(X > 19 || Y > 19 || X < 2 || Y < 2) throw std::invalid_argument("selfplay: board sizes 2..19 only");
+  if(c.num_games < 1 || c.max_visits < 2) throw std::invalid_argument("selfplay: num_games >= 1 and max_visits >= 2 required");
+  std::unique_ptr<SelfplayImpl> sp(new SelfplayImpl());
+  sp->stream = stream;
+  SPDev& d = sp->d;
+  memset(&d, 0, sizeof(d));
+  d.X = X; d.Y = Y; d.XY = X * Y; d.policySize = X * Y + 1;
+  if(d.policySize > 12 * 32) throw std::invalid_argument("selfplay: policy size too large");
+  d.numGames = c.num_games; d.maxVisits = c.max_visits; d.maxNodes = c.max_visits + 2;
+  d.maxDepth = std::min(c.max_visits + 2, 512);
+  d.maxMoves = c.max_moves > 0 ? c.max_moves : 2 * X * Y;
+  d.multiSuicide = c.multi_stone_suicide_legal; d.earlyMoves = c.early_temperature_moves;
+  d.komi = c.komi;
+  d.cpuctExploration = c.cpuct_exploration; d.cpuctExplorationLog = c.cpuct_exploration_log; d.cpuctExplorationBase = c.cpuct_exploration_base;
+  d.fpuReductionMax = c.fpu_reduction_max; d.rootFpuReductionMax = c.root_fpu_reduction_max;
+  d.winLossUtilityFactor = c.win_loss_utility_factor; d.noResultUtilityForWhite = c.no_result_utility_for_white;
+  d.seed = c.seed;
+  const size_t G = d.numGames, N = d.maxNodes, PS = d.policySize;
+  d.rootB = sp->alloc<uint32_t>(G * 32); d.rootW = sp->alloc<uint32_t>(G * 32);
+  d.rootKo = sp->alloc<int>(G); d.rootBlackToMove = sp->alloc<int>(G); d.rootCapB = sp->alloc<int>(G); d.rootCapW = sp->alloc<int>(G);
+  d.moveNum = sp->alloc<int>(G); d.consecPasses = sp->alloc<int>(G); d.hist = sp->alloc<int>(G * 5);
+  d.gameCounter = sp->alloc<uint64_t>(G);
+  d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); d.nodeUtilSum = sp->alloc<double>(G * N);
+  d.nodeTerminal = sp->alloc<int8_t>(G * N);
+  d.policy = sp->alloc<float>(G * N * PS); d.childNode = sp->alloc<int>(G * N * PS); d.childVisits = sp->alloc<int>(G * N * PS);
+  d.childUtilSum = sp->alloc<double>(G * N * PS);
+  d.pathLen = sp->alloc<int>(G); d.pathNode = sp->alloc<int>(G * d.maxDepth); d.pathMove = sp->alloc<int>(G * d.maxDepth);
+  d.leafNode = sp->alloc<int>(G); d.leafTerminal = sp->alloc<int>(G); d.leafBlackToMove = sp->alloc<int>(G);
+  d.leafTerminalUtil = sp->alloc<double>(G); d.leafLegal = sp->alloc<uint32_t>(G * 32);
+  unsigned long long* stats = sp->alloc<unsigned long long>(8);
+  d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
+  d.sumDepth = stats + 5;
+  d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
+  d.nnPolicy = nn.policy; d.nnValue = nn.value;
+  // initial state: empty boards, black to move, history empty, one unevaluated root node per game
+  std::vector<int> ones(G, 1), minus(G * 5, -1), kos(G, -1);
+  SPCK(cudaMemcpy(d.rootBlackToMove, ones.data(), G * sizeof(int), cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(d.nodeCount, ones.data(), G * sizeof(int), cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(d.hist, minus.data(), G * 5 * sizeof(int), cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(d.rootKo, kos.data(), G * sizeof(int), cudaMemcpyHostToDevice));
+  SPCK(cudaMemset(d.childNode, 0xff, G * N * PS * sizeof(int)));
+  return sp.release();
+}
+
+void selfplayDestroy(SelfplayImpl* sp) { delete sp; }
+
+void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s) {
+  int threads = 128, warpsPerBlock = threads / 32;
+  spSelectKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d);
+  SPCK(cudaGetLastError());
+}
+void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s) {
+  int threads = 128, warpsPerBlock = threads / 32;
+  spBackupKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d);
+  SPCK(cudaGetLastError());
+}
+
+void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {
+  unsigned long long h[8];
+  SPCK(cudaMemcpy(h, sp->d.totalVisits, sizeof(h), cudaMemcpyDeviceToHost));
+  out->total_visits = h[0]; out->total_moves = h[1]; out->games_finished = h[2]; out->black_wins = h[3];
+  out->nodes_allocated = h[4]; out->sum_leaf_depth = h[5];
+}
+
+void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  uint32_t b[32], w[32];
+  SPCK(cudaMemcpy(b, d.rootB + (size_t)g * 32, sizeof(b), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(w, d.rootW + (size_t)g * 32, sizeof(w), cudaMemcpyDeviceToHost));
+  for(int y = 0; y < d.Y; y++)
+    for(int x = 0; x < d.X; x++) colors[y * d.X + x] = (b[y] >> x) & 1 ? 1 : (w[y] >> x) & 1 ? 2 : 0;
+  int h[6];
+  SPCK(cudaMemcpy(&h[0], d.moveNum + g, sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(&h[1], d.rootBlackToMove + g, sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(&h[2], d.rootKo + g, sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(&h[3], d.rootCapB + g, sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(&h[4], d.rootCapW + g, sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(&h[5], d.nodeVisits + (size_t)g * d.maxNodes, sizeof(int), cudaMemcpyDeviceToHost));
+  for(int i = 0; i < 6; i++) info[i] = h[i];
+}
+
+void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  size_t nb = (size_t)g * d.maxNodes * d.policySize;
+  SPCK(cudaMemcpy(visits, d.childVisits + nb, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(policy, d.policy + nb, d.policySize * sizeof(float), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(utilSum, d.childUtilSum + nb, d.policySize * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,
+                 uint8_t* libClass, uint8_t* legalNext) {
+  if(X > 19 || Y > 19 || X < 2 || Y < 2) throw std::invalid_argument("board replay: board sizes 2..19 only");
+  size_t nm = (size_t)numBoards * numMoves, cells = nm * X * Y;
+  int8_t *dMoves, *dKo; uint8_t *dColors, *dLib, *dLegal; int16_t* dCaps;
+  SPCK(cudaMalloc(&dMoves, nm * 3)); SPCK(cudaMalloc(&dKo, nm * 2)); SPCK(cudaMalloc(&dCaps, nm * 2 * sizeof(int16_t)));
+  SPCK(cudaMalloc(&dColors, cells)); SPCK(cudaMalloc(&dLib, cells)); SPCK(cudaMalloc(&dLegal, cells));
+  SPCK(cudaMemcpy(dMoves, moves, nm * 3, cudaMemcpyHostToDevice));
+  int threads = 128;
+  boardReplayKernel<<<(numBoards * 32 + threads - 1) / threads, threads>>>(X, Y, numBoards, numMoves, multiSuicide, dMoves, dColors, dKo, dCaps, dLib, dLegal);
+  cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) {
+    cudaMemcpy(colors, dColors, cells, cudaMemcpyDeviceToHost); cudaMemcpy(libClass, dLib, cells, cudaMemcpyDeviceToHost);
+    cudaMemcpy(legalNext, dLegal, cells, cudaMemcpyDeviceToHost); cudaMemcpy(ko, dKo, nm * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(caps, dCaps, nm * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dMoves); cudaFree(dKo); cudaFree(dCaps); cudaFree(dColors); cudaFree(dLib); cudaFree(dLegal);
+  SPCK(e);
+}
+
+}  // namespace kgb

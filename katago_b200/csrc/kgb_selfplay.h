@@ -1,0 +1,29 @@
+// Internal interface between the C-ABI layer (kgb_api.cu) and the device self-play loop (kgb_selfplay.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+
+#include "../../include/kgb200.h"
+
+namespace kgb {
+
+struct SelfplayImpl;
+
+struct SelfplayNNBuffers {  // device buffers of the evaluator handle the loop writes to / reads from
+  float* spatial; float* global; float* optimism; int* symmetry;
+  const float* policy; const float* value;
+};
+
+SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const SelfplayNNBuffers& nn, cudaStream_t stream);
+void selfplayDestroy(SelfplayImpl* sp);
+void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
+void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
+void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
+void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
+void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum);
+void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,
+                 uint8_t* libClass, uint8_t* legalNext);
+
+}  // namespace kgb

@@ -35,12 +35,30 @@ class _ModelInfo(C.Structure):
     ]
 
 
+class SelfplayConfig(C.Structure):
+    """kgb_selfplay_config: the reference's SearchParams / rules names (search/searchparams.h, game/rules.h)."""
+    _fields_ = [
+        ("num_games", C.c_int32), ("max_visits", C.c_int32), ("max_moves", C.c_int32), ("multi_stone_suicide_legal", C.c_int32),
+        ("early_temperature_moves", C.c_int32), ("komi", C.c_float),
+        ("cpuct_exploration", C.c_double), ("cpuct_exploration_log", C.c_double), ("cpuct_exploration_base", C.c_double),
+        ("fpu_reduction_max", C.c_double), ("root_fpu_reduction_max", C.c_double), ("win_loss_utility_factor", C.c_double),
+        ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class SelfplayStats(C.Structure):
+    _fields_ = [("total_visits", C.c_uint64), ("total_moves", C.c_uint64), ("games_finished", C.c_uint64), ("black_wins", C.c_uint64),
+                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64)]
+
+
 # Every symbol include/kgb200.h declares (tests/test_abi.py checks the library exports all of them).
 ABI_SYMBOLS = [
     "kgb_global_init", "kgb_global_cleanup", "kgb_last_error", "kgb_device_count", "kgb_device_name",
     "kgb_model_load_file", "kgb_model_free", "kgb_model_get_info", "kgb_context_create", "kgb_context_free",
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
+    "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_test_board_replay",
 ]
 
 _lib = None
@@ -83,6 +101,15 @@ def load_library():
     lib.kgb_handle_launches_per_forward.argtypes = [P]
     lib.kgb_test_conv.argtypes = [I, I, I, I, P, I, I, I, I, P, P]
     lib.kgb_bench_conv.argtypes = [I, I, I, I, I, I, I, I, I, I, F]
+    lib.kgb_selfplay_create.argtypes = [P, C.POINTER(SelfplayConfig), C.POINTER(P)]
+    lib.kgb_selfplay_free.argtypes = [P]
+    lib.kgb_selfplay_free.restype = None
+    lib.kgb_selfplay_run.argtypes = [P, I]
+    lib.kgb_selfplay_get_stats.argtypes = [P, C.POINTER(SelfplayStats)]
+    lib.kgb_selfplay_get_game.argtypes = [P, I, P, P]
+    lib.kgb_selfplay_get_root_children.argtypes = [P, I, P, P, P]
+    lib.kgb_selfplay_launches_per_step.argtypes = [P]
+    lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P]
     _lib = lib
     return lib
 
@@ -263,3 +290,71 @@ class NeuralNet:
         _check(lib.kgb_test_conv(convYSize, convXSize, inChannels, outChannels, w.ctypes.data, batchSize, nnXLen, nnYLen,
                                  int(bool(useFP16)), x.ctypes.data, out.ctypes.data))
         return out
+
+
+def board_replay(x_size: int, y_size: int, moves, multi_stone_suicide_legal: bool):
+    """kgb_test_board_replay: moves int8 [boards, m, 3] = (x, y, pla) with (-1,-1) = pass, pla 1 black / 2 white.
+    Returns dict(colors [b,m,Y,X], ko [b,m,2], caps [b,m,2], lib_class [b,m,Y,X], legal_next [b,m,Y,X])."""
+    lib = load_library()
+    mv = np.ascontiguousarray(moves, dtype=np.int8)
+    nb, nm = mv.shape[0], mv.shape[1]
+    colors = np.zeros((nb, nm, y_size, x_size), np.uint8)
+    libc = np.zeros_like(colors); legal = np.zeros_like(colors)
+    ko = np.zeros((nb, nm, 2), np.int8); caps = np.zeros((nb, nm, 2), np.int16)
+    _check(lib.kgb_test_board_replay(x_size, y_size, nb, nm, int(bool(multi_stone_suicide_legal)), mv.ctypes.data, colors.ctypes.data,
+                                     ko.ctypes.data, caps.ctypes.data, libc.ctypes.data, legal.ctypes.data))
+    return dict(colors=colors, ko=ko, caps=caps, lib_class=libc, legal_next=legal)
+
+
+class SelfPlay:
+    """Device-resident self-play slots on one ComputeHandle (include/kgb200.h "Boundary 2")."""
+
+    def __init__(self, handle: ComputeHandle, num_games: int, max_visits: int, komi: float = 7.5, max_moves: int = 0,
+                 multi_stone_suicide_legal: bool = True, early_temperature_moves: int = 30, cpuct_exploration: float = 1.0,
+                 cpuct_exploration_log: float = 0.45, cpuct_exploration_base: float = 500.0, fpu_reduction_max: float = 0.2,
+                 root_fpu_reduction_max: float = 0.1, win_loss_utility_factor: float = 1.0, no_result_utility_for_white: float = 0.0,
+                 seed: int = 0):
+        lib = load_library()
+        self.handle = handle
+        self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
+                                  cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
+                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed)
+        self._p = C.c_void_p()
+        _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
+        self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
+
+    def run(self, steps: int):
+        _check(load_library().kgb_selfplay_run(self._p, steps))
+
+    def stats(self) -> dict:
+        s = SelfplayStats()
+        _check(load_library().kgb_selfplay_get_stats(self._p, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in SelfplayStats._fields_}
+
+    def game(self, g: int):
+        colors = np.zeros((self.y, self.x), np.uint8)
+        info = np.zeros(6, np.int32)
+        _check(load_library().kgb_selfplay_get_game(self._p, g, colors.ctypes.data, info.ctypes.data))
+        return colors, dict(move_num=int(info[0]), black_to_move=bool(info[1]), ko=int(info[2]), cap_b=int(info[3]), cap_w=int(info[4]),
+                            root_visits=int(info[5]))
+
+    def root_children(self, g: int):
+        n = self.x * self.y + 1
+        visits = np.zeros(n, np.int32); policy = np.zeros(n, np.float32); util = np.zeros(n, np.float64)
+        _check(load_library().kgb_selfplay_get_root_children(self._p, g, visits.ctypes.data, policy.ctypes.data, util.ctypes.data))
+        return visits, policy, util
+
+    @property
+    def launches_per_step(self) -> int:
+        return load_library().kgb_selfplay_launches_per_step(self._p)
+
+    def free(self):
+        if self._p:
+            load_library().kgb_selfplay_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
