@@ -4,15 +4,16 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through libkgb200's C ABI)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path timed on this box's host cores
 
-A "step" is one pass of the hot path over one batch: one playout wave for `games` concurrent 19x19 games = one
-NN evaluation per game (b18c384nbt) through the evaluator boundary (NeuralNet::getOutput -> kgb_forward*).  Stages on
-the device in this round are listed in config["stages"]; visits/sec counts one visit per evaluated leaf (no NN-cache
-hits, no terminal nodes - both would only raise the figure).
+A "step" is one pass of the hot path over one batch: one playout wave for `games` concurrent 19x19 games - for every
+game one PUCT descent on its device-resident tree and bitboard, leaf featurisation, one b18c384nbt evaluation, policy /
+value post-processing and backup (kgb_selfplay_run; stages in config["stages"]).  One visit per game per step; games
+that reach maxVisits play their move and clear the tree inside the same kernels, so the loop never returns to the host.
 
-value  : whole-job visits/s with inputs resident in HBM (kgb_forward_device), CUDA events on the launching stream,
-         max over ranks.  Inputs rotate over more distinct batches than fit in L2 (config["l2"]).
-e2e    : the same metric through the reference-facing C-ABI call with HOST buffers (kgb_forward): H2D of the feature
-         rows and D2H of policy/value/ownership inside the timed region, every step.
+value  : whole-job visits/s of that device-resident loop (boards, trees and NN rows live in HBM), CUDA events on the
+         launching stream, max over ranks.  Per-step working set (tree arrays ~1 GB, activations ~0.5 GB) >> L2.
+e2e    : visits/s through the reference-facing evaluator boundary (NeuralNet::getOutput -> kgb_forward) with HOST
+         buffers: one evaluation = one visit, H2D of the feature rows and D2H of policy/value/ownership inside the timed
+         region, every step, rotating over more distinct input batches than fit in L2.
 N > 1  : one process per GPU (torchrun), games shard across ranks with no data-path collective ("weak" scaling);
          NCCL carries only the model-weight broadcast from rank 0 before the timed region.
 """
@@ -43,6 +44,7 @@ def parse_args():
     ap.add_argument("--model", default="b18c384nbt")
     ap.add_argument("--games", type=int, default=256, help="concurrent games (= NN batch) per GPU")
     ap.add_argument("--fp32", action="store_true", help="use the fp32-equivalent (3-term split) mode instead of fp16 operands")
+    ap.add_argument("--visits", type=int, default=600, help="maxVisits per move (BASELINE.json configs[1]: 600)")
     return ap.parse_args()
 
 
@@ -180,7 +182,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from katago_b200 import NeuralNet, load_library, modelgen
+    from katago_b200 import NeuralNet, SelfPlay, load_library, modelgen
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -251,14 +253,22 @@ def main():
         return float(ms.item())
 
     W, K = max(3, args.warmup), max(1, args.steps)
-    for i in range(W):
-        step_device(i)
+    # device-resident self-play loop: selfplay8mainb18.cfg search parameters that the loop implements
+    sp = SelfPlay(handle, n, args.visits, komi=7.5, multi_stone_suicide_legal=True, early_temperature_moves=30,
+                  cpuct_exploration=1.0, cpuct_exploration_log=0.45, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
+                  root_fpu_reduction_max=0.1, seed=1234 + rank)
+    # bring the games into mid-search (trees a few hundred nodes deep) before timing
+    sp.run(W + 64)
     handle.sync()
+    before = sp.stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, K)
+    ms_dev = timed(lambda i: sp.run(1), K)
     clocks = sampler.stop() if rank == 0 else None
+    after = sp.stats()
+    assert after["total_visits"] - before["total_visits"] == n * K, "every wave must add one visit per game"
+    ms_nn = timed(step_device, K)
     for i in range(W):
         step_host(i)
     ms_e2e = timed(step_host, K)
@@ -282,19 +292,25 @@ def main():
             raise RuntimeError(lib.kgb_last_error().decode())
         conv_flop = 2.0 * 9 * mid * mid * 361 * n  # algorithmic: direct convolution over the 361 real board points
         achieved = conv_flop / (float(ms_conv[0]) * 1e-3) / 1e12
-        whole = flop_per_eval * n * K / (ms_dev * 1e-3) / 1e12
+        whole = flop_per_eval * n * K / (ms_nn * 1e-3) / 1e12
         cpu_v, cpu_dt = cpu_port_evals_per_sec(args.model, 4, 2)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32-split3(fp16 tensor pipe)" if args.fp32 else "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, one NN evaluation (= one visit) per game per step",
-                       "stages": ["nn_eval"], "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
+            "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, maxVisits {args.visits}, one playout (visit) per game per step, device-resident loop",
+                       "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(V7 planes 0-6,9-13 + globals; ladder/area planes pending)",
+                                  "nn_eval", "policy/value postprocess", "backup"],
+                       "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
+                       "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
                        "weights": "random init, real architecture (katago_b200/modelgen.py)",
-                       "l2": f"{NBUF} distinct feature batches ({NBUF * n * 22 * 361 * 4 / 1e6:.0f} MB) rotated every step, larger than the 126 MB L2; per-step activation traffic >> L2",
+                       "l2": "per-step working set (tree arrays ~1 GB + activations ~0.5 GB) far larger than the 126 MB L2; "
+                             f"e2e rotates {NBUF} distinct feature batches ({NBUF * n * 22 * 361 * 4 / 1e6:.0f} MB)",
+                       "avg_leaf_depth": (after["sum_leaf_depth"] - before["sum_leaf_depth"]) / max(1, after["total_visits"] - before["total_visits"]),
+                       "nn_only_ms_per_step": ms_nn / K,
                        "weight_broadcast_ms": bcast_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
-            "gpu_launches": handle.launches_per_forward * K,
+            "gpu_launches": sp.launches_per_step * K,
             "roofline": {"bound": "tensor", "kernel": f"kgb_conv_tc_kernel 3x3 {mid}->{mid}, batch {n}", "achieved": achieved,
                          "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"],
                          "traffic": 41.4e6 if args.model == "b18c384nbt" and n == 256 else None,

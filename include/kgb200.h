@@ -143,6 +143,8 @@ typedef struct kgb_selfplay_config {
   double win_loss_utility_factor;    /* winLossUtilityFactor   (1.0) */
   double no_result_utility_for_white;
   uint64_t seed;
+  int32_t debug_fake_nn;             /* TEST ONLY: replace the evaluator by the deterministic hash net of oracle/ref_driver.cpp */
+  int32_t reserved;
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -164,6 +166,8 @@ KGB_API int kgb_selfplay_get_stats(kgb_selfplay* sp, kgb_selfplay_stats* out);
 KGB_API int kgb_selfplay_get_game(kgb_selfplay* sp, int game, uint8_t* colors, int32_t* info);
 /* Root children of game g, indexed by move position 0..X*Y (pass last): visit counts, NN policy (-1 illegal), utility sums. */
 KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* util_sum);
+/* Play a fixed move list on EVERY game's root (x,y pairs, -1,-1 = pass; colours alternate) and clear the trees. */
+KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves);
 /* Kernel launches per playout wave (evaluator launches + 2). */
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp);
 

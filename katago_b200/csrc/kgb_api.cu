@@ -820,12 +820,14 @@ struct kgb_selfplay {
   kgb_handle* h = nullptr;
   SelfplayImpl* impl = nullptr;
   int n = 0;
+  bool fakeNN = false;
   cudaGraphExec_t stepGraph = nullptr;
 };
 
 static void selfplayStepLaunches(kgb_selfplay* sp, cudaStream_t s) {
   selfplayLaunchSelect(sp->impl, s);
-  for(auto& op : sp->h->ops) op(sp->n, s);
+  if(sp->fakeNN) selfplayLaunchFakeNN(sp->impl, sp->h->dPolicy, sp->h->dValue, s);
+  else for(auto& op : sp->h->ops) op(sp->n, s);
   selfplayLaunchBackup(sp->impl, s);
 }
 
@@ -840,6 +842,7 @@ KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* c
     std::unique_ptr<kgb_selfplay> sp(new kgb_selfplay());
     sp->h = handle;
     sp->n = config->num_games;
+    sp->fakeNN = config->debug_fake_nn != 0;
     SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue};
     sp->impl = selfplayCreate(*config, handle->L.X, handle->L.Y, nn, handle->stream);
     *out = sp.release();
@@ -899,6 +902,14 @@ KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* 
     CK(cudaSetDevice(sp->h->device));
     CK(cudaStreamSynchronize(sp->h->stream));
     selfplayReadRootChildren(sp->impl, game, visits, policy, util_sum);
+  });
+}
+
+KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves) {
+  return guarded([&] {
+    if(!sp || (!moves_xy && num_moves > 0) || num_moves < 0) throw std::invalid_argument("kgb_selfplay_play_moves: bad argument");
+    CK(cudaSetDevice(sp->h->device));
+    selfplayPlayMoves(sp->impl, moves_xy, num_moves, sp->h->stream);
   });
 }
 

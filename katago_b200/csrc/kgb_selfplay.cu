@@ -409,6 +409,70 @@ __global__ void spBackupKernel(const SPDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// TEST SUPPORT: deterministic fake net (identical to the one oracle/ref_driver.cpp gives the reference Search, so tree
+// parity can be checked against the reference without any real net) and root-position setup.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  const float* row = d.nnSpatial + (size_t)g * d.XY * 22;
+  uint64_t h = 0;
+  for(int pos = lane; pos < d.XY; pos += 32) {
+    int s = row[pos * 22 + 1] != 0.0f ? 1 : row[pos * 22 + 2] != 0.0f ? 2 : 0;
+    if(s) h += splitmix64((uint64_t)pos * 4 + s);
+  }
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(KGB_FULL, h, o);
+  if(d.nnGlobal[(size_t)g * 19 + 5] < 0.0f) h ^= 0xABCDEFULL;
+  for(int i = lane; i < d.policySize; i += 32) {
+    uint32_t u = (uint32_t)(splitmix64(h + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL) >> 48);
+    float logit = (float)u * (1.0f / 8192.0f) - 4.0f;
+    if(i == d.policySize - 1) logit -= 3.0f;
+    policyOut[(size_t)g * d.policySize + i] = logit;
+  }
+  if(lane == 0) {
+    valueOut[g * 3 + 0] = (float)(uint32_t)(splitmix64(h ^ 0x1111ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
+    valueOut[g * 3 + 1] = (float)(uint32_t)(splitmix64(h ^ 0x2222ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
+    valueOut[g * 3 + 2] = -30.0f;
+  }
+}
+
+// Apply a move list (x, y, or -1,-1 = pass; colours alternate from the current player) to every game's root.
+__global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMoves) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  WarpBoard bd;
+  boardInit(bd, d.X, d.Y);
+  bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
+  bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
+  bool black = d.rootBlackToMove[g] != 0;
+  int passes = d.consecPasses[g], mv = d.moveNum[g];
+  int h[5];
+  for(int k = 0; k < 5; k++) h[k] = d.hist[g * 5 + k];
+  for(int m = 0; m < numMoves; m++) {
+    const bool isPass = moves[m * 2] < 0;
+    const int p = isPass ? -1 : (moves[m * 2 + 1] * 32 + moves[m * 2]);
+    boardPlay(bd, p, black);
+    passes = isPass ? passes + 1 : 0;
+    for(int k = 4; k > 0; k--) h[k] = h[k - 1];
+    h[0] = isPass ? -2 : p;
+    black = !black;
+    mv++;
+  }
+  d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
+  const size_t gb = (size_t)g * d.maxNodes;
+  if(lane == 0) {
+    d.rootKo[g] = bd.ko; d.rootCapB[g] = bd.capB; d.rootCapW[g] = bd.capW;
+    d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = passes; d.moveNum[g] = mv;
+    for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
+    d.nodeCount[g] = 1; d.nodeVisits[gb] = 0; d.nodeUtilSum[gb] = 0.0; d.nodeTerminal[gb] = 0;
+  }
+  nodeInit(d, gb * d.policySize, lane);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Board test kernel: replays move streams (parity tests against the reference Board fixtures)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void boardReplayKernel(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves /*[b][m][3]: x,y,pla(1=black,2=white)*/,
@@ -523,6 +587,23 @@ void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s) {
   int threads = 128, warpsPerBlock = threads / 32;
   spBackupKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d);
   SPCK(cudaGetLastError());
+}
+
+void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, cudaStream_t s) {
+  int threads = 128, warpsPerBlock = threads / 32;
+  spFakeNNKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, policyOut, valueOut);
+  SPCK(cudaGetLastError());
+}
+
+void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s) {
+  int8_t* dm = nullptr;
+  SPCK(cudaMalloc(&dm, (size_t)numMoves * 2));
+  SPCK(cudaMemcpyAsync(dm, movesXY, (size_t)numMoves * 2, cudaMemcpyHostToDevice, s));
+  int threads = 128, warpsPerBlock = threads / 32;
+  spPlayMovesKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, dm, numMoves);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(dm);
+  SPCK(e);
 }
 
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {

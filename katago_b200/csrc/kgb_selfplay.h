@@ -20,6 +20,8 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
 void selfplayDestroy(SelfplayImpl* sp);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
+void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, cudaStream_t s);
+void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
 void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum);

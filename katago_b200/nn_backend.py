@@ -42,7 +42,7 @@ class SelfplayConfig(C.Structure):
         ("early_temperature_moves", C.c_int32), ("komi", C.c_float),
         ("cpuct_exploration", C.c_double), ("cpuct_exploration_log", C.c_double), ("cpuct_exploration_base", C.c_double),
         ("fpu_reduction_max", C.c_double), ("root_fpu_reduction_max", C.c_double), ("win_loss_utility_factor", C.c_double),
-        ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64),
+        ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64), ("debug_fake_nn", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_test_board_replay",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_test_board_replay",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def load_library():
     lib.kgb_selfplay_get_game.argtypes = [P, I, P, P]
     lib.kgb_selfplay_get_root_children.argtypes = [P, I, P, P, P]
     lib.kgb_selfplay_launches_per_step.argtypes = [P]
+    lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P]
     _lib = lib
     return lib
@@ -313,18 +314,23 @@ class SelfPlay:
                  multi_stone_suicide_legal: bool = True, early_temperature_moves: int = 30, cpuct_exploration: float = 1.0,
                  cpuct_exploration_log: float = 0.45, cpuct_exploration_base: float = 500.0, fpu_reduction_max: float = 0.2,
                  root_fpu_reduction_max: float = 0.1, win_loss_utility_factor: float = 1.0, no_result_utility_for_white: float = 0.0,
-                 seed: int = 0):
+                 seed: int = 0, debug_fake_nn: bool = False):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
                                   cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
-                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed)
+                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), 0)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
 
     def run(self, steps: int):
         _check(load_library().kgb_selfplay_run(self._p, steps))
+
+    def play_moves(self, moves_xy):
+        """moves_xy: iterable of (x, y) or None for pass; applied to every game's root, trees cleared."""
+        arr = np.array([(-1, -1) if m is None else (m[0], m[1]) for m in moves_xy], dtype=np.int8).reshape(-1, 2)
+        _check(load_library().kgb_selfplay_play_moves(self._p, arr.ctypes.data if len(arr) else None, len(arr)))
 
     def stats(self) -> dict:
         s = SelfplayStats()

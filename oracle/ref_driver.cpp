@@ -2,6 +2,10 @@
 // dumps golden fixtures / answers parity queries straight from the reference's own classes.  Never shipped or timed as
 // product.  Built by oracle/Makefile.drivers into oracle/_ref/kgref_driver.
 //
+//   kgref_driver searchfake MODELFILE X Y MAXVISITS "x,y x,y pass ..."
+//       reference Search (search/search.cpp) with the deterministic hash-based fake net defined below as its NeuralNet
+//       backend (this file IS the backend TU of the driver); prints the root children's visit counts.  The device loop
+//       has the same fake net (kgb_selfplay_config.debug_fake_nn) so tree parity is tested without any real net.
 //   kgref_driver boardstream X Y NMOVES SEED MULTISUICIDE OUT.bin
 //       random legal move stream on a reference Board (game/board.h): after every move records the board, ko, capture
 //       counters, pos_hash, per-stone liberty counts and the legality mask of the player to move next.
@@ -9,12 +13,18 @@
 #include "game/boardhistory.h"
 #include "game/rules.h"
 #include "neuralnet/nninputs.h"
+#include "neuralnet/nninterface.h"
+#include "neuralnet/nneval.h"
+#include "search/search.h"
+#include "search/searchnode.h"
+#include "core/logger.h"
 
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <sstream>
 #include <vector>
 
 using namespace std;
@@ -87,10 +97,143 @@ static int cmdBoardStream(int argc, char** argv) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fake NeuralNet backend of this driver: logits are exact dyadic rationals derived from an order-independent integer hash of
+// the stone planes (features 1,2) and the sign of selfKomi, so the CUDA side reproduces them bit-for-bit.
+// ------------------------------------------------------------------------------------------------------------
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+struct LoadedModel { ModelDesc modelDesc; };
+struct ComputeContext { int nnXLen, nnYLen; };
+struct ComputeHandle { int nnXLen, nnYLen; };
+struct InputBuffers { int dummy; };
+void NeuralNet::globalInitialize() {}
+void NeuralNet::globalCleanup() {}
+void NeuralNet::printDevices() {}
+LoadedModel* NeuralNet::loadModelFile(const string& file, const string& expectedSha256) {
+  LoadedModel* m = new LoadedModel();
+  ModelDesc::loadFromFileMaybeGZipped(file, m->modelDesc, expectedSha256);
+  return m;
+}
+void NeuralNet::freeLoadedModel(LoadedModel* m) { delete m; }
+const ModelDesc& NeuralNet::getModelDesc(const LoadedModel* m) { return m->modelDesc; }
+ComputeContext* NeuralNet::createComputeContext(const std::vector<int>&, Logger*, int nnXLen, int nnYLen, const string&, enabled_t, const LoadedModel*, ConfigParser&) {
+  ComputeContext* c = new ComputeContext(); c->nnXLen = nnXLen; c->nnYLen = nnYLen; return c;
+}
+void NeuralNet::freeComputeContext(ComputeContext* c) { delete c; }
+ComputeHandle* NeuralNet::createComputeHandle(ComputeContext* c, const LoadedModel*, Logger*, int, bool, bool inputsUseNHWC, int, int) {
+  if(!inputsUseNHWC) throw StringError("fake backend wants NHWC");
+  ComputeHandle* h = new ComputeHandle(); h->nnXLen = c->nnXLen; h->nnYLen = c->nnYLen; return h;
+}
+void NeuralNet::freeComputeHandle(ComputeHandle* h) { delete h; }
+bool NeuralNet::isUsingFP16(const ComputeHandle*) { return false; }
+bool NeuralNet::setIsWarmup(const ComputeHandle*, bool) { return false; }
+InputBuffers* NeuralNet::createInputBuffers(const LoadedModel*, int, int, int) { return new InputBuffers(); }
+void NeuralNet::freeInputBuffers(InputBuffers* b) { delete b; }
+void NeuralNet::getOutput(ComputeHandle* h, InputBuffers*, int n, NNResultBuf** inputBufs, vector<NNOutput*>& outputs) {
+  const int xy = h->nnXLen * h->nnYLen;
+  for(int r = 0; r < n; r++) {
+    const float* sp = inputBufs[r]->rowSpatialBuf.data();
+    const float* gl = inputBufs[r]->rowGlobalBuf.data();
+    if(inputBufs[r]->symmetry != 0) throw StringError("fake backend expects symmetry 0");
+    uint64_t hsh = 0;
+    for(int pos = 0; pos < xy; pos++) {
+      int s = sp[pos * 22 + 1] != 0.0f ? 1 : sp[pos * 22 + 2] != 0.0f ? 2 : 0;
+      if(s) hsh += splitmix64((uint64_t)pos * 4 + s);
+    }
+    if(gl[5] < 0.0f) hsh ^= 0xABCDEFULL;
+    NNOutput* o = outputs[r];
+    for(int i = 0; i <= xy; i++) {
+      uint32_t u = (uint32_t)(splitmix64(hsh + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL) >> 48);
+      float logit = (float)u * (1.0f / 8192.0f) - 4.0f;
+      if(i == xy) logit -= 3.0f;
+      o->policyProbs[i] = logit;
+    }
+    o->whiteWinProb = (float)(uint32_t)(splitmix64(hsh ^ 0x1111ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
+    o->whiteLossProb = (float)(uint32_t)(splitmix64(hsh ^ 0x2222ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
+    o->whiteNoResultProb = -30.0f;
+    o->whiteScoreMean = 0; o->whiteScoreMeanSq = 0; o->whiteLead = 0; o->varTimeLeft = 0; o->shorttermWinlossError = 0; o->shorttermScoreError = 0;
+    if(o->whiteOwnerMap != NULL) std::fill(o->whiteOwnerMap, o->whiteOwnerMap + xy, 0.0f);
+  }
+}
+bool NeuralNet::testEvaluateConv(const ConvLayerDesc*, int, int, int, bool, bool, const std::vector<float>&, std::vector<float>&) { return false; }
+bool NeuralNet::testEvaluateBatchNorm(const BatchNormLayerDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
+bool NeuralNet::testEvaluateResidualBlock(const ResidualBlockDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
+bool NeuralNet::testEvaluateGlobalPoolingResidualBlock(const GlobalPoolingResidualBlockDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
+
+static int cmdSearchFake(int argc, char** argv) {
+  if(argc != 7) { cerr << "usage: searchfake MODELFILE X Y MAXVISITS MOVES" << endl; return 1; }
+  string modelFile = argv[2];
+  int X = atoi(argv[3]), Y = atoi(argv[4]), maxVisits = atoi(argv[5]);
+  Board::initHash();
+  ScoreValue::initTables();
+  Logger logger(nullptr, false, false, false);
+  ConfigParser cfg;
+  NNEvaluator* nnEval = new NNEvaluator("fake", modelFile, "", &logger, 4, X, Y, true, true, 10, 8, false, "", enabled_t::False, 1,
+                                        vector<int>{0}, "seed", false, 0, true, cfg);
+  nnEval->spawnServerThreads();
+  // Reference SearchParams restricted to what the device loop implements: everything else at its default.
+  SearchParams params;
+  params.maxVisits = maxVisits;
+  params.numThreads = 1;
+  params.cpuctExploration = 1.0; params.cpuctExplorationLog = 0.45; params.cpuctExplorationBase = 500;
+  params.fpuReductionMax = 0.2; params.rootFpuReductionMax = 0.1;
+  params.staticScoreUtilityFactor = 0.0; params.dynamicScoreUtilityFactor = 0.0;
+  params.valueWeightExponent = 0.0;
+  params.rootNoiseEnabled = false;
+  Rules rules;  // defaults, then the rule subset of the loop
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.friendlyPassOk = false; rules.komi = 7.5f;
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  {
+    std::istringstream in(argv[6]);
+    string tok;
+    while(in >> tok) {
+      Loc loc;
+      if(tok == "pass") loc = Board::PASS_LOC;
+      else { int x, y; if(sscanf(tok.c_str(), "%d,%d", &x, &y) != 2) { cerr << "bad move " << tok << endl; return 1; } loc = Location::getLoc(x, y, X); }
+      if(!hist.isLegal(board, loc, pla)) { cerr << "illegal move " << tok << endl; return 1; }
+      hist.makeBoardMoveAssumeLegal(board, loc, pla, NULL);
+      pla = getOpp(pla);
+    }
+  }
+  Search* search = new Search(params, nnEval, &logger, "searchfake");
+  search->setPosition(pla, board, hist);
+  search->runWholeSearch(pla);
+  const SearchNode* root = search->rootNode;
+  SearchNodeState st = (SearchNodeState)root->state.load();
+  ConstSearchNodeChildrenReference children = root->getChildren(st);
+  cout << "rootvisits " << root->stats.visits.load() << " utilityAvg " << Global::strprintf("%.17g", root->stats.utilityAvg.load()) << endl;
+  for(int i = 0; i < children.getCapacity(); i++) {
+    const SearchChildPointer& cp = children[i];
+    const SearchNode* child = cp.getIfAllocated();
+    if(child == NULL) break;
+    Loc loc = cp.getMoveLoc();
+    int x = loc == Board::PASS_LOC ? -1 : Location::getX(loc, X), y = loc == Board::PASS_LOC ? -1 : Location::getY(loc, X);
+    cout << "child " << x << " " << y << " " << cp.getEdgeVisits() << " " << Global::strprintf("%.17g", child->stats.utilityAvg.load()) << endl;
+  }
+  const NNOutput* nn = root->getNNOutput();
+  cout << "policy";
+  for(int i = 0; i <= X * Y; i++) cout << " " << Global::strprintf("%.9g", nn->policyProbs[i]);
+  cout << endl;
+  delete search;
+  delete nnEval;
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if(argc < 2) { cerr << "usage: kgref_driver <boardstream|...> ..." << endl; return 1; }
   string cmd = argv[1];
   if(cmd == "boardstream") return cmdBoardStream(argc, argv);
+  if(cmd == "searchfake") return cmdSearchFake(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;
 }

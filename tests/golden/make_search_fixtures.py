@@ -1,0 +1,65 @@
+"""Generates tests/golden/searchfake.npz from the REFERENCE Search (oracle/_ref/kgref_driver searchfake ...).
+
+The reference's MCTS (search/search.cpp, searchexplorehelpers.cpp, searchupdatehelpers.cpp) runs single-threaded with a
+deterministic hash-based fake net as its NeuralNet backend (oracle/ref_driver.cpp), restricted to the SearchParams subset
+the device loop implements.  Stored per case: the move prefix, maxVisits, and for the root: each child's
+visit count, the post-processed NN policy and the utility average.  The device loop is given the same fake net
+(debug_fake_nn) and must reproduce the visit counts."""
+import os, subprocess, sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DRIVER = os.path.join(HERE, "..", "..", "oracle", "_ref", "kgref_driver")
+MODEL = os.path.join(HERE, "models", "torchref_b2c16.bin.gz")   # only supplies a ModelDesc (version 15) to NNEvaluator
+
+
+def prefix_from_stream(name, n):
+    d = np.load(os.path.join(HERE, name))
+    mv = d["moves"][:n]
+    out = []
+    for x, y, _ in mv:
+        out.append(None if x < 0 else (int(x), int(y)))
+    for i, (a, b) in enumerate(zip(out, out[1:])):
+        if a is None and b is None:      # two passes in a row would end the game: stop the prefix before the second one
+            return out[:i + 1]
+    return out
+
+
+def run(X, Y, visits, moves):
+    s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
+    out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s], capture_output=True, text=True, check=True).stdout
+    v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None
+    for ln in out.splitlines():
+        f = ln.split()
+        if f[0] == "rootvisits":
+            root = (int(f[1]), float(f[3]))
+        elif f[0] == "child":
+            x, y = int(f[1]), int(f[2])
+            i = X * Y if x < 0 else y * X + x
+            v[i] = int(f[3]); u[i] = float(f[4])
+        elif f[0] == "policy":
+            pol = np.array([float(t) for t in f[1:]], np.float32)
+    return root, v, u, pol
+
+
+if __name__ == "__main__":
+    cases = [
+        (9, 9, 100, prefix_from_stream("boardstream_9x9_multisuicide.npz", 0)),
+        (9, 9, 400, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12)),
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31)),
+        (19, 19, 200, prefix_from_stream("boardstream_19x19_multisuicide.npz", 0)),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40)),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 131)),
+        (13, 7, 300, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20)),
+        (5, 5, 500, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9)),
+    ]
+    store = {"num_cases": len(cases)}
+    for i, (X, Y, visits, moves) in enumerate(cases):
+        root, v, u, pol = run(X, Y, visits, moves)
+        assert root[0] == visits and v.sum() == visits - 1
+        store[f"c{i}_shape"] = np.array([X, Y, visits], np.int32)
+        store[f"c{i}_moves"] = np.array([(-1, -1) if m is None else m for m in moves], np.int8).reshape(-1, 2)
+        store[f"c{i}_visits"] = v; store[f"c{i}_util"] = u; store[f"c{i}_policy"] = pol
+        store[f"c{i}_root_util"] = np.float64(root[1])
+        print(i, X, Y, visits, len(moves), "children", int((v > 0).sum()), "max visits", int(v.max()), "root util", root[1])
+    np.savez_compressed(os.path.join(HERE, "searchfake.npz"), **store)
