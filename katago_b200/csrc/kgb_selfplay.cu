@@ -387,8 +387,11 @@ __global__ void spBackupKernel(const SPDev d) {
     double s = w + l + n;
     w /= s; l /= s; n /= s;
     const bool black = d.leafBlackToMove[g] != 0;
-    double whiteWin = black ? l : w, whiteLoss = black ? w : l;
-    u = d.winLossUtilityFactor * (whiteWin - whiteLoss) + d.noResultUtilityForWhite * n;
+    // NNOutput stores the probabilities as float (nneval.cpp:1200-1215); the search widens them again
+    // (searchupdatehelpers.cpp:87-88) - mirror that rounding so utilities agree to the last bit.
+    const float wf = (float)w, lf = (float)l, nf = (float)n;
+    const double whiteWin = black ? (double)lf : (double)wf, whiteLoss = black ? (double)wf : (double)lf;
+    u = (whiteWin - whiteLoss) * d.winLossUtilityFactor + (double)nf * d.noResultUtilityForWhite;
   }
   __syncwarp();
   // ---- backup (one lane: a handful of scattered read-modify-writes along the path)
