@@ -283,7 +283,7 @@ struct Builder {
         CK(launchConvSimt(A, cw.cin_p * actMulL, cw.w, p, s));
       }
       else {
-        CUtensorMap tmA = makeTmap2D(A, (uint64_t)p.M, (uint64_t)cw.cin_p * actMulL, 128);
+        CUtensorMap tmA = makeTmap2D(A, (uint64_t)p.M, (uint64_t)cw.cin_p * actMulL, (uint32_t)convTCABoxRows(cw.ky, cw.kx, p.Wp));
         CK(launchConvTC(tmA, cw.tmapB, p, hp->numSMs, s));
       }
     });

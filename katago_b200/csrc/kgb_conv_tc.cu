@@ -3,9 +3,11 @@
 // cudnnConvolutionForward / cublasHgemm cudabackend.cpp:788-841, BN+act+mask cudahelpers.cu:1370-2101).
 //
 // GEMM view:  D[M = batch*P rows, N = cout]  =  sum over taps t, k-blocks kb of  A_t[M, 64] * W_t[64, N]
-//   A_t = the activation matrix shifted by the tap's row offset (see kgb_conv.cuh "padded rows"), loaded by ONE 2-D TMA
-//         box {64 channels, 128 rows} per (tap, k-block) with 128B swizzle; out-of-range rows are zero-filled by TMA.
-//   W   = packed [tap][cout_p][cin_p] fp16 (K-major), box {64, n_tile}.
+//   A_t = the activation matrix shifted by the tap's row offset (see kgb_conv.cuh "padded rows").  All taps of one k-block
+//         read the SAME rows of A, only shifted: the producer loads ONE halo tile {64 channels, 128 + 2*halo rows}
+//         (halo = ry*(X+pad)+rx, 128B swizzle, out-of-range rows zero-filled by TMA) and the MMA issuer addresses tap t
+//         by starting its shared-memory descriptor `halo + dy*(X+pad)+dx` rows (128 B each) into that tile.  A is fetched from L2 once instead of 9 times.
+//   W   = packed [tap][cout_p][cin_p] fp16 (K-major), box {64, n_tile}, one TMA box per (k-block, tap).
 //   D   = fp32 accumulator in TMEM, 2 stages x n_tile columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Persistent, warp-specialised CTA (1 per SM, 384 threads):
@@ -19,6 +21,8 @@
 // fp32-grade accuracy on the fp16 tensor pipe at 3x the MMA count (the backend's useFP16=false mode).
 #include "kgb_conv.cuh"
 
+#include <cstdlib>
+
 namespace kgb {
 
 static constexpr int BLOCK_M = 128;
@@ -26,18 +30,18 @@ static constexpr int BLOCK_K = 64;    // fp16 elements = one 128B swizzle row
 static constexpr int UMMA_K = 16;
 static constexpr int EPI_WARP0 = 4;            // warps 0-3: TMA, MMA, TMEM alloc, spare; epilogue warps follow
 static constexpr int MAX_THREADS = 128 + 512;   // up to 16 epilogue warps (4 per TMEM lane quadrant)
-static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 static constexpr int MAX_STAGES = 8;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 
-// dynamic smem: [<=1023 B alignment slack][stages x (A tile | B tile)][BarrierBlock, 512 B][bn scale | bn bias: 2 x cout_p fp32]
-int convTCSmemBytes(int n_tile, int cout_p, int* stagesOut) {
-  int stageBytes = A_STAGE_BYTES + n_tile * BLOCK_K * 2;
-  int extra = 1024 + 512 + 8 * cout_p;
-  int stages = (SMEM_LIMIT - extra) / stageBytes;
+// dynamic smem: [<=1023 B slack][2 x A halo tile][stages x B tile][BarrierBlock, 512 B][bn scale | bn bias: 2 x cout_p fp32]
+static inline int aBufBytes(int a_box_rows) { return (a_box_rows * BLOCK_K * 2 + 1023) / 1024 * 1024; }
+int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int* stagesOut) {
+  int bStage = n_tile * BLOCK_K * 2;
+  int fixed = 1024 + 2 * aBufBytes(a_box_rows) + 512 + 8 * cout_p;
+  int stages = (SMEM_LIMIT - fixed) / bStage;
   if(stages > MAX_STAGES) stages = MAX_STAGES;
   if(stagesOut) *stagesOut = stages;
-  return stages * stageBytes + extra;
+  return stages * bStage + fixed;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -99,6 +103,10 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=1024B: 8 rows x 128B)
 //   | [46,48) version=1 | [61,64) layout_type=2 (SWIZZLE_128B)
+// The start address may sit on ANY 128-byte row of a 1024B-aligned swizzled tile (the per-tap views of the A halo tile):
+// measured on B200, the tensor core applies the 128B XOR swizzle to absolute shared-memory address bits [4,7)^[7,10) -
+// exactly how TMA wrote the tile - so base_offset [49,52) must stay 0 (setting it to (start>>7)&7 gives wrong results;
+// profiles/r01_descriptor_shift_experiment.md).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -114,8 +122,10 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 struct __align__(8) BarrierBlock {
-  uint64_t full[MAX_STAGES];
-  uint64_t empty[MAX_STAGES];
+  uint64_t full[MAX_STAGES];    // B tile landed
+  uint64_t empty[MAX_STAGES];   // B tile consumed
+  uint64_t a_full[2];           // A halo tile landed
+  uint64_t a_empty[2];          // A halo tile consumed by all of its taps
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -131,9 +141,13 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = p.n_tile * BLOCK_K * 2;
-  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);          // rows of A above / below the tile that the taps reach
+  const int a_box_rows = BLOCK_M + 2 * halo;
+  const int a_tx_bytes = a_box_rows * BLOCK_K * 2;
+  const int a_buf_bytes = (a_tx_bytes + 1023) / 1024 * 1024;
+  const uint32_t smem_b = smem_base + 2 * a_buf_bytes;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  BarrierBlock* bars = reinterpret_cast<BarrierBlock*>(smem_aligned + (size_t)stages * stage_bytes);
+  BarrierBlock* bars = reinterpret_cast<BarrierBlock*>(smem_aligned + 2 * (size_t)a_buf_bytes + (size_t)stages * b_stage_bytes);
   float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
   float* s_bias = s_scale + p.cout_p;
 
@@ -143,7 +157,7 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   const int taps = p.ky * p.kx;
   const int kblocks = p.cin_p / BLOCK_K;
   const int parts = p.split ? 3 : 1;
-  const int iters = taps * kblocks * parts;
+  const int phases = kblocks * parts;                         // one A halo tile per (k-block, split part)
 
   if(warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
@@ -155,6 +169,8 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
       mbar_init(smem_u32(&bars->empty[s]), 1);
     }
     for(int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&bars->a_full[s]), 1);
+      mbar_init(smem_u32(&bars->a_empty[s]), 1);
       mbar_init(smem_u32(&bars->tmem_full[s]), 1);
       mbar_init(smem_u32(&bars->tmem_empty[s]), 4 * epi_per_quad);
     }
@@ -176,26 +192,25 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     // ===================== TMA producer =====================
     if(lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const int ry = p.ky / 2, rx = p.kx / 2;
+      int abuf = 0; uint32_t aphase = 0;
       for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
         const int n0 = (tile % p.num_n_tiles) * p.n_tile;
-        for(int tap = 0; tap < taps; tap++) {
-          const int dy = tap / p.kx - ry, dx = tap % p.kx - rx;
-          const int rowA = m0 + dy * p.Wp + dx;
-          const int rowB = tap * p.cout_p + n0;
-          for(int kb = 0; kb < kblocks; kb++) {
-            for(int part = 0; part < parts; part++) {
-              mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
-              const uint32_t full = smem_u32(&bars->full[stage]);
-              mbar_arrive_expect_tx(full, (uint32_t)stage_bytes);
-              const uint32_t sa = smem_base + stage * stage_bytes;
-              const int colA = kb * BLOCK_K + (part == 1 ? p.cin_p : 0);
-              const int colB = kb * BLOCK_K + (part == 2 ? p.cin_p : 0);
-              tma_load_2d(sa, &tmapA, full, colA, rowA);
-              tma_load_2d(sa + A_STAGE_BYTES, &tmapB, full, colB, rowB);
-              if(++stage == stages) { stage = 0; phase ^= 1; }
-            }
+        for(int ph = 0; ph < phases; ph++) {
+          const int kb = ph / parts, part = ph - kb * parts;
+          const int colA = kb * BLOCK_K + (part == 1 ? p.cin_p : 0);
+          const int colB = kb * BLOCK_K + (part == 2 ? p.cin_p : 0);
+          mbar_wait(smem_u32(&bars->a_empty[abuf]), aphase ^ 1);
+          const uint32_t afull = smem_u32(&bars->a_full[abuf]);
+          mbar_arrive_expect_tx(afull, (uint32_t)a_tx_bytes);
+          tma_load_2d(smem_base + abuf * a_buf_bytes, &tmapA, afull, colA, m0 - halo);
+          if(++abuf == 2) { abuf = 0; aphase ^= 1; }
+          for(int tap = 0; tap < taps; tap++) {
+            mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+            const uint32_t full = smem_u32(&bars->full[stage]);
+            mbar_arrive_expect_tx(full, (uint32_t)b_stage_bytes);
+            tma_load_2d(smem_b + stage * b_stage_bytes, &tmapB, full, colB, tap * p.cout_p + n0);
+            if(++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -205,25 +220,34 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     // ===================== MMA issuer =====================
     if(lane == 0) {
       const uint32_t idesc = make_idesc(p.n_tile);
+      const int ry = p.ky / 2, rx = p.kx / 2;
       int stage = 0; uint32_t phase = 0;
+      int abuf = 0; uint32_t aphase = 0;
       int acc_stage = 0; uint32_t acc_phase = 0;
       for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bars->tmem_empty[acc_stage]), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc_stage * p.n_tile;
-        for(int it = 0; it < iters; it++) {
-          mbar_wait(smem_u32(&bars->full[stage]), phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t da = make_smem_desc(sa);
-          const uint64_t db = make_smem_desc(sa + A_STAGE_BYTES);
+        for(int ph = 0; ph < phases; ph++) {
+          mbar_wait(smem_u32(&bars->a_full[abuf]), aphase);
+          const uint32_t a_base = smem_base + abuf * a_buf_bytes;
+          for(int tap = 0; tap < taps; tap++) {
+            mbar_wait(smem_u32(&bars->full[stage]), phase);
+            tcgen05_fence_after();
+            const int dy = tap / p.kx - ry, dx = tap - (tap / p.kx) * p.kx - rx;
+            // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
+            const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
+            const uint64_t db = make_smem_desc(smem_b + stage * b_stage_bytes);
 #pragma unroll
-          for(int k = 0; k < BLOCK_K / UMMA_K; k++) {
-            // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte descriptor units
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for(int k = 0; k < BLOCK_K / UMMA_K; k++) {
+              // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte descriptor units
+              umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (ph > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            tcgen05_commit(smem_u32(&bars->empty[stage]));
+            if(++stage == stages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(smem_u32(&bars->empty[stage]));
-          if(++stage == stages) { stage = 0; phase ^= 1; }
+          tcgen05_commit(smem_u32(&bars->a_empty[abuf]));
+          if(++abuf == 2) { abuf = 0; aphase ^= 1; }
         }
         tcgen05_commit(smem_u32(&bars->tmem_full[acc_stage]));
         if(++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
@@ -281,7 +305,9 @@ cudaError_t convTCInit() {
 
 cudaError_t launchConvTC(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const ConvParams& p, int numSMs, cudaStream_t stream) {
   int stages = 0;
-  int smem = convTCSmemBytes(p.n_tile, p.cout_p, &stages);
+  int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
+  int smem = convTCSmemBytes(p.n_tile, p.cout_p, BLOCK_M + 2 * halo, &stages);
+  if(BLOCK_M + 2 * halo > 256 || stages < 2) return cudaErrorInvalidValue;  // TMA box limit / pipeline depth
   // 4 epilogue warps per TMEM lane quadrant when the tile's columns split evenly into 16-column chunks, else 2
   int epi_per_quad = (p.n_tile % 64 == 0) ? 4 : 2;
   int threads = 128 + 128 * epi_per_quad;
