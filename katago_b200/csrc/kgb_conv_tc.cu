@@ -34,10 +34,11 @@ static constexpr int MAX_STAGES = 8;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 
 // dynamic smem: [<=1023 B slack][2 x A halo tile][stages x B tile][BarrierBlock, 512 B][bn scale | bn bias: 2 x cout_p fp32]
+//               [16 x 4 KB epilogue staging tiles]
 static inline int aBufBytes(int a_box_rows) { return (a_box_rows * BLOCK_K * 2 + 1023) / 1024 * 1024; }
 int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int* stagesOut) {
   int bStage = n_tile * BLOCK_K * 2;
-  int fixed = 1024 + 2 * aBufBytes(a_box_rows) + 512 + 8 * cout_p;
+  int fixed = 1024 + 2 * aBufBytes(a_box_rows) + 512 + 8 * cout_p + 16 * 4096;
   int stages = (SMEM_LIMIT - fixed) / bStage;
   if(stages > MAX_STAGES) stages = MAX_STAGES;
   if(stagesOut) *stagesOut = stages;
@@ -133,6 +134,157 @@ struct __align__(8) BarrierBlock {
 };
 
 // ------------------------------------------------------------------------------------------------------------
+// Staged epilogue for one 16-column chunk of a warp's 32 accumulator rows.
+// The accumulator arrives row-per-thread (tcgen05.ld 32x32b); writing global memory in that shape touches 32 different
+// 128-byte lines with 16 bytes each per instruction.  Instead every tensor goes through a small per-warp shared-memory
+// tile and is moved to / from global memory with lanes laid out along the rows: 64 B (fp32) or 32 B (fp16) contiguous per
+// row per instruction, i.e. full sectors and 4x / 2x fewer LSU wavefronts.
+//   S: fp32 tile [32 rows][16 cols], row stride 20 words;  T: fp16 tile [32 rows][16 cols], row stride 12 words.
+// (strides chosen so that both the row-wise 16-byte accesses and the piece-wise ones are bank-conflict free per quarter warp)
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int EPI_S_WORDS = 32 * 20;
+static constexpr int EPI_T_WORDS = 32 * 12;
+static constexpr int EPI_SMEM_PER_WARP = (EPI_S_WORDS + EPI_T_WORDS) * 4;   // 4 KB
+
+__device__ __forceinline__ void tile_ld_f32(float* S, const float* g, int pitch, int rowsValid, int lane) {
+#pragma unroll
+  for(int k = 0; k < 4; k++) {
+    int piece = k * 32 + lane, r = piece >> 2, part = piece & 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(r < rowsValid) v = *reinterpret_cast<const float4*>(g + (size_t)r * pitch + part * 4);
+    *reinterpret_cast<float4*>(S + r * 20 + part * 4) = v;
+  }
+}
+__device__ __forceinline__ void tile_st_f32(const float* S, float* g, int pitch, int rowsValid, int lane) {
+#pragma unroll
+  for(int k = 0; k < 4; k++) {
+    int piece = k * 32 + lane, r = piece >> 2, part = piece & 3;
+    if(r < rowsValid) *reinterpret_cast<float4*>(g + (size_t)r * pitch + part * 4) = *reinterpret_cast<const float4*>(S + r * 20 + part * 4);
+  }
+}
+__device__ __forceinline__ void tile_ld_f16(uint32_t* T, const __half* g, int pitch, int rowsValid, int lane) {
+#pragma unroll
+  for(int k = 0; k < 2; k++) {
+    int piece = k * 32 + lane, r = piece >> 1, part = piece & 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if(r < rowsValid) v = *reinterpret_cast<const uint4*>(g + (size_t)r * pitch + part * 8);
+    *reinterpret_cast<uint4*>(T + r * 12 + part * 4) = v;
+  }
+}
+__device__ __forceinline__ void tile_st_f16(const uint32_t* T, __half* g, int pitch, int rowsValid, int lane) {
+#pragma unroll
+  for(int k = 0; k < 2; k++) {
+    int piece = k * 32 + lane, r = piece >> 1, part = piece & 1;
+    if(r < rowsValid) *reinterpret_cast<uint4*>(g + (size_t)r * pitch + part * 8) = *reinterpret_cast<const uint4*>(T + r * 12 + part * 4);
+  }
+}
+
+// rowBase = first of the warp's 32 rows, rowsValid = how many of them are < M; col = first of the 16 columns.
+__device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&acc)[16], int rowBase, int rowsValid, int lane, int col,
+                                                      float maskv, int img, const float* sc, const float* bi, float* S, uint32_t* T) {
+  float v[16];
+#pragma unroll
+  for(int j = 0; j < 16; j++) v[j] = __uint_as_float(acc[j]);
+  const bool valid = lane < rowsValid;
+  if(p.ncbias != nullptr && valid) {
+    const float4* b = reinterpret_cast<const float4*>(p.ncbias + (size_t)img * p.cout_p + col);
+#pragma unroll
+    for(int q = 0; q < 4; q++) {
+      float4 t = __ldg(b + q);
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+  const size_t off = (size_t)rowBase * p.cout_p + col;
+  if(p.residual != nullptr) {
+    if(p.residual_fp32) {
+      tile_ld_f32(S, reinterpret_cast<const float*>(p.residual) + off, p.cout_p, rowsValid, lane);
+      __syncwarp();
+#pragma unroll
+      for(int q = 0; q < 4; q++) {
+        float4 t = *reinterpret_cast<const float4*>(S + lane * 20 + q * 4);
+        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+      }
+    }
+    else {
+      tile_ld_f16(T, reinterpret_cast<const __half*>(p.residual) + off, p.cout_p, rowsValid, lane);
+      __syncwarp();
+#pragma unroll
+      for(int q = 0; q < 2; q++) {
+        uint4 t = *reinterpret_cast<const uint4*>(T + lane * 12 + q * 4);
+        const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+        for(int e = 0; e < 4; e++) {
+          float2 f = __half22float2(h[e]);
+          v[8 * q + 2 * e] += f.x; v[8 * q + 2 * e + 1] += f.y;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if(p.raw_out != nullptr) {
+    if(p.raw_fp32) {
+#pragma unroll
+      for(int q = 0; q < 4; q++)
+        *reinterpret_cast<float4*>(S + lane * 20 + q * 4) = make_float4(v[4 * q] * maskv, v[4 * q + 1] * maskv, v[4 * q + 2] * maskv, v[4 * q + 3] * maskv);
+      __syncwarp();
+      tile_st_f32(S, reinterpret_cast<float*>(p.raw_out) + off, p.cout_p, rowsValid, lane);
+    }
+    else {
+#pragma unroll
+      for(int q = 0; q < 2; q++) {
+        uint4 t;
+        __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+        for(int e = 0; e < 4; e++) h[e] = __floats2half2_rn(v[8 * q + 2 * e] * maskv, v[8 * q + 2 * e + 1] * maskv);
+        *reinterpret_cast<uint4*>(T + lane * 12 + q * 4) = t;
+      }
+      __syncwarp();
+      tile_st_f16(T, reinterpret_cast<__half*>(p.raw_out) + off, p.cout_p, rowsValid, lane);
+    }
+    __syncwarp();
+  }
+  if(p.act_out != nullptr) {
+    float a[16];
+#pragma unroll
+    for(int q = 0; q < 4; q++) {
+      float4 s = *reinterpret_cast<const float4*>(sc + q * 4), b = *reinterpret_cast<const float4*>(bi + q * 4);
+      a[4 * q] = kgb_activate(fmaf(v[4 * q], s.x, b.x), p.act) * maskv;
+      a[4 * q + 1] = kgb_activate(fmaf(v[4 * q + 1], s.y, b.y), p.act) * maskv;
+      a[4 * q + 2] = kgb_activate(fmaf(v[4 * q + 2], s.z, b.z), p.act) * maskv;
+      a[4 * q + 3] = kgb_activate(fmaf(v[4 * q + 3], s.w, b.w), p.act) * maskv;
+    }
+    if(maskv == 0.0f) {
+#pragma unroll
+      for(int j = 0; j < 16; j++) a[j] = 0.0f;  // guards NaN/inf garbage at pad rows
+    }
+    const int ldo = p.split ? 2 * p.cout_p : p.cout_p;
+    __half* dst = p.act_out + (size_t)rowBase * ldo + col;
+    uint4 hi[2], lo[2];
+    __half2* hh = reinterpret_cast<__half2*>(hi);
+    __half2* hl = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+    for(int e = 0; e < 8; e++) {
+      __half2 h = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
+      hh[e] = h;
+      float2 hf = __half22float2(h);
+      hl[e] = __floats2half2_rn(a[2 * e] - hf.x, a[2 * e + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(T + lane * 12) = hi[0];
+    *reinterpret_cast<uint4*>(T + lane * 12 + 4) = hi[1];
+    __syncwarp();
+    tile_st_f16(T, dst, ldo, rowsValid, lane);
+    __syncwarp();
+    if(p.split) {
+      *reinterpret_cast<uint4*>(T + lane * 12) = lo[0];
+      *reinterpret_cast<uint4*>(T + lane * 12 + 4) = lo[1];
+      __syncwarp();
+      tile_st_f16(T, dst + p.cout_p, ldo, rowsValid, lane);
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MAX_THREADS, 1)
@@ -150,6 +302,7 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   BarrierBlock* bars = reinterpret_cast<BarrierBlock*>(smem_aligned + 2 * (size_t)a_buf_bytes + (size_t)stages * b_stage_bytes);
   float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
   float* s_bias = s_scale + p.cout_p;
+  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_bias + p.cout_p);   // 16-byte aligned: cout_p is a multiple of 64
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,24 +417,31 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     for(int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * p.n_tile + part * cols_per_part;
-      const int row = m0 + quad * 32 + lane;
+      const int rowBase = m0 + quad * 32;
+      const int row = rowBase + lane;
+      const int rowsValid = min(32, p.M - rowBase);          // may be <= 0 in the last tile
       const bool valid = row < p.M;
       const float maskv = valid ? __ldg(p.mask + row) : 0.0f;
       const int img = valid ? row / p.P : 0;
+      float* S = reinterpret_cast<float*>(s_epi + (size_t)(warp - EPI_WARP0) * EPI_SMEM_PER_WARP);
+      uint32_t* T = reinterpret_cast<uint32_t*>(S + EPI_S_WORDS);
       mbar_wait(smem_u32(&bars->tmem_full[acc_stage]), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * p.n_tile + part * cols_per_part;
-      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue math
+      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue
       uint32_t accA[16], accB[16];
       tmem_ld16(taddr, accA);
       for(int c = 0; c < nchunks; c += 2) {
         if(c + 1 < nchunks) tmem_ld16(taddr + (c + 1) * 16, accB);
         tmem_ld_wait(accA);
-        if(valid) epilogue_chunk(p, accA, row, n0 + c * 16, maskv, img, s_scale + n0 + c * 16, s_bias + n0 + c * 16);
+        if(rowsValid > 0)
+          epilogue_chunk_staged(p, accA, rowBase, rowsValid, lane, n0 + c * 16, maskv, img, s_scale + n0 + c * 16, s_bias + n0 + c * 16, S, T);
         if(c + 1 < nchunks) {
           if(c + 2 < nchunks) tmem_ld16(taddr + (c + 2) * 16, accA);
           tmem_ld_wait(accB);
-          if(valid) epilogue_chunk(p, accB, row, n0 + (c + 1) * 16, maskv, img, s_scale + n0 + (c + 1) * 16, s_bias + n0 + (c + 1) * 16);
+          if(rowsValid > 0)
+            epilogue_chunk_staged(p, accB, rowBase, rowsValid, lane, n0 + (c + 1) * 16, maskv, img, s_scale + n0 + (c + 1) * 16,
+                                  s_bias + n0 + (c + 1) * 16, S, T);
         }
       }
       tcgen05_fence_before();
