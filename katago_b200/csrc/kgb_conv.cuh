@@ -160,7 +160,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 // Launchers (defined in kgb_conv_tc.cu / kgb_kernels.cu)
 cudaError_t launchConvTC(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const ConvParams& p, int numSMs, cudaStream_t stream);
 cudaError_t launchConvSimt(const __half* A, int lda, const __half* W, const ConvParams& p, cudaStream_t stream);
-int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int* stagesOut);
+int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int tps, int epi_warps, int* stagesOut);
 inline int convTCABoxRows(int ky, int kx, int Wp) { return 128 + 2 * ((ky / 2) * Wp + (kx / 2)); }  // TMA box rows of the A halo tile
 cudaError_t convTCInit();  // per device, before the first launch
 

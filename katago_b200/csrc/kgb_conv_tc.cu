@@ -34,11 +34,13 @@ static constexpr int MAX_STAGES = 8;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 
 // dynamic smem: [<=1023 B slack][2 x A halo tile][stages x B tile][BarrierBlock, 512 B][bn scale | bn bias: 2 x cout_p fp32]
-//               [16 x 4 KB epilogue staging tiles]
+//               [epilogue warps x 4 KB staging tiles]
 static inline int aBufBytes(int a_box_rows) { return (a_box_rows * BLOCK_K * 2 + 1023) / 1024 * 1024; }
-int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int* stagesOut) {
-  int bStage = n_tile * BLOCK_K * 2;
-  int fixed = 1024 + 2 * aBufBytes(a_box_rows) + 512 + 8 * cout_p + 16 * 4096;
+// One pipeline stage carries the weight tiles of `tps` consecutive taps (same k-block): fewer, fatter barrier round trips
+// per MMA (measured: ~400 cycles of producer<->issuer handshake per stage, as long as the 4 MMAs of one tap).
+int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int tps, int epi_warps, int* stagesOut) {
+  int bStage = tps * n_tile * BLOCK_K * 2;
+  int fixed = 1024 + 2 * aBufBytes(a_box_rows) + 512 + 8 * cout_p + epi_warps * 4096;
   int stages = (SMEM_LIMIT - fixed) / bStage;
   if(stages > MAX_STAGES) stages = MAX_STAGES;
   if(stagesOut) *stagesOut = stages;
@@ -289,10 +291,11 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                   const __grid_constant__ ConvParams p, int stages, int epi_per_quad) {
+                   const __grid_constant__ ConvParams p, int stages, int epi_per_quad, int tps, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_stage_bytes = p.n_tile * BLOCK_K * 2;
+  const int b_tile_bytes = p.n_tile * BLOCK_K * 2;             // one tap's weight tile
+  const int b_stage_bytes = tps * b_tile_bytes;                // a stage = `tps` taps of one k-block
   const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);          // rows of A above / below the tile that the taps reach
   const int a_box_rows = BLOCK_M + 2 * halo;
   const int a_tx_bytes = a_box_rows * BLOCK_K * 2;
@@ -311,6 +314,7 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   const int kblocks = p.cin_p / BLOCK_K;
   const int parts = p.split ? 3 : 1;
   const int phases = kblocks * parts;                         // one A halo tile per (k-block, split part)
+  const int tap_groups = (taps + tps - 1) / tps;
 
   if(warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
@@ -355,14 +359,22 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
           const int colB = kb * BLOCK_K + (part == 2 ? p.cin_p : 0);
           mbar_wait(smem_u32(&bars->a_empty[abuf]), aphase ^ 1);
           const uint32_t afull = smem_u32(&bars->a_full[abuf]);
-          mbar_arrive_expect_tx(afull, (uint32_t)a_tx_bytes);
-          tma_load_2d(smem_base + abuf * a_buf_bytes, &tmapA, afull, colA, m0 - halo);
+          if(dbg & 1) mbar_arrive(afull);
+          else {
+            mbar_arrive_expect_tx(afull, (uint32_t)a_tx_bytes);
+            tma_load_2d(smem_base + abuf * a_buf_bytes, &tmapA, afull, colA, m0 - halo);
+          }
           if(++abuf == 2) { abuf = 0; aphase ^= 1; }
-          for(int tap = 0; tap < taps; tap++) {
+          for(int tg = 0; tg < tap_groups; tg++) {
+            const int nb = min(tps, taps - tg * tps);
             mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
             const uint32_t full = smem_u32(&bars->full[stage]);
-            mbar_arrive_expect_tx(full, (uint32_t)b_stage_bytes);
-            tma_load_2d(smem_b + stage * b_stage_bytes, &tmapB, full, colB, tap * p.cout_p + n0);
+            if(dbg & 1) mbar_arrive(full);
+            else {
+              mbar_arrive_expect_tx(full, (uint32_t)(nb * b_tile_bytes));
+              for(int j = 0; j < nb; j++)
+                tma_load_2d(smem_b + stage * b_stage_bytes + j * b_tile_bytes, &tmapB, full, colB, (tg * tps + j) * p.cout_p + n0);
+            }
             if(++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -384,17 +396,21 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
         for(int ph = 0; ph < phases; ph++) {
           mbar_wait(smem_u32(&bars->a_full[abuf]), aphase);
           const uint32_t a_base = smem_base + abuf * a_buf_bytes;
-          for(int tap = 0; tap < taps; tap++) {
+          for(int tg = 0; tg < tap_groups; tg++) {
+            const int nb = min(tps, taps - tg * tps);
             mbar_wait(smem_u32(&bars->full[stage]), phase);
             tcgen05_fence_after();
-            const int dy = tap / p.kx - ry, dx = tap - (tap / p.kx) * p.kx - rx;
-            // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
-            const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
-            const uint64_t db = make_smem_desc(smem_b + stage * b_stage_bytes);
+            for(int j = 0; j < nb; j++) {
+              const int tap = tg * tps + j;
+              const int dy = tap / p.kx - ry, dx = tap - (tap / p.kx) * p.kx - rx;
+              // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
+              const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
+              const uint64_t db = make_smem_desc(smem_b + stage * b_stage_bytes + j * b_tile_bytes);
 #pragma unroll
-            for(int k = 0; k < BLOCK_K / UMMA_K; k++) {
-              // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte descriptor units
-              umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (ph > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for(int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte descriptor units
+                if(!(dbg & 2)) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (ph > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
             }
             tcgen05_commit(smem_u32(&bars->empty[stage]));
             if(++stage == stages) { stage = 0; phase ^= 1; }
@@ -430,16 +446,16 @@ kgb_conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * p.n_tile + part * cols_per_part;
       // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue
       uint32_t accA[16], accB[16];
-      tmem_ld16(taddr, accA);
-      for(int c = 0; c < nchunks; c += 2) {
+      if(!(dbg & 4)) tmem_ld16(taddr, accA);
+      for(int c = 0; c < ((dbg & 4) ? 0 : nchunks); c += 2) {
         if(c + 1 < nchunks) tmem_ld16(taddr + (c + 1) * 16, accB);
         tmem_ld_wait(accA);
-        if(rowsValid > 0)
+        if(rowsValid > 0 && !(dbg & 8))
           epilogue_chunk_staged(p, accA, rowBase, rowsValid, lane, n0 + c * 16, maskv, img, s_scale + n0 + c * 16, s_bias + n0 + c * 16, S, T);
         if(c + 1 < nchunks) {
           if(c + 2 < nchunks) tmem_ld16(taddr + (c + 2) * 16, accA);
           tmem_ld_wait(accB);
-          if(rowsValid > 0)
+          if(rowsValid > 0 && !(dbg & 8))
             epilogue_chunk_staged(p, accB, rowBase, rowsValid, lane, n0 + (c + 1) * 16, maskv, img, s_scale + n0 + (c + 1) * 16,
                                   s_bias + n0 + (c + 1) * 16, S, T);
         }
@@ -464,16 +480,33 @@ cudaError_t convTCInit() {
 }
 
 cudaError_t launchConvTC(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const ConvParams& p, int numSMs, cudaStream_t stream) {
-  int stages = 0;
-  int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
-  int smem = convTCSmemBytes(p.n_tile, p.cout_p, BLOCK_M + 2 * halo, &stages);
-  if(BLOCK_M + 2 * halo > 256 || stages < 2) return cudaErrorInvalidValue;  // TMA box limit / pipeline depth
+  static int dbg = -1, maxStages = 0, envTps = 0, envEpi = 0;
+  if(dbg < 0) {  // bring-up knobs (timing experiments only): KGB_CONV_DBG bit0 = no TMA traffic, bit1 = no MMA, bit2 = no epilogue,
+                 // bit3 = no epilogue stores; KGB_CONV_STAGES caps the ring; KGB_CONV_TPS / KGB_CONV_EPI override the tiling choice
+    const char* e = getenv("KGB_CONV_DBG"); dbg = e ? atoi(e) : 0;
+    e = getenv("KGB_CONV_STAGES"); maxStages = e ? atoi(e) : 0;
+    e = getenv("KGB_CONV_TPS"); envTps = e ? atoi(e) : 0;
+    e = getenv("KGB_CONV_EPI"); envEpi = e ? atoi(e) : 0;
+  }
+  const int taps = p.ky * p.kx;
+  const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
+  if(BLOCK_M + 2 * halo > 256) return cudaErrorInvalidValue;  // TMA box limit
   // 4 epilogue warps per TMEM lane quadrant when the tile's columns split evenly into 16-column chunks, else 2
   int epi_per_quad = (p.n_tile % 64 == 0) ? 4 : 2;
+  if(envEpi == 2 || envEpi == 4) epi_per_quad = (p.n_tile % (16 * envEpi) == 0) ? envEpi : epi_per_quad;
+  // taps per stage: as many as still leave a 2-deep ring (3x3: 2 taps per stage with 16 epilogue warps at n_tile 192)
+  int tps = 1, stages = 0, smem = 0;
+  for(int t = (envTps > 0 ? envTps : 3); t >= 1; t--) {
+    if(t > taps) continue;
+    smem = convTCSmemBytes(p.n_tile, p.cout_p, BLOCK_M + 2 * halo, t, 4 * epi_per_quad, &stages);
+    if(stages >= 2) { tps = t; break; }
+  }
+  if(stages < 2) return cudaErrorInvalidValue;
   int threads = 128 + 128 * epi_per_quad;
+  if(maxStages > 0 && stages > maxStages) stages = maxStages;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < numSMs ? tiles : numSMs;
-  kgb_conv_tc_kernel<<<grid, threads, smem, stream>>>(tmapA, tmapB, p, stages, epi_per_quad);
+  kgb_conv_tc_kernel<<<grid, threads, smem, stream>>>(tmapA, tmapB, p, stages, epi_per_quad, tps, dbg);
   return cudaGetLastError();
 }
 
