@@ -113,7 +113,8 @@ struct DevBuf {
 struct ConvWeights {
   __half* w = nullptr;     // packed [taps][cout_p][cin_p * (split ? 2 : 1)]
   int ky = 0, kx = 0, cin_p = 0, cout_p = 0, n_tile = 0, num_n_tiles = 0;
-  CUtensorMap tmapB;
+  CUtensorMap tmapB;       // box {64, n_tile}
+  CUtensorMap tmapBhalf;   // box {64, n_tile/2}: each CTA of a pair loads half of the weight tile
 };
 
 struct kgb_handle {
@@ -126,7 +127,7 @@ struct kgb_handle {
   int split = 0;          // fp32-equivalent mode
   bool nhwc = true;
   bool streamTrunkFp32 = true, streamInnerFp32 = false;
-  bool useSimt = false, useGraph = true;
+  bool useSimt = false, useGraph = true, usePair = false;
   std::vector<void*> allocs;
   // inputs / outputs (device, fixed addresses so graphs can be replayed)
   float *dSpatial = nullptr, *dGlobal = nullptr, *dOptimism = nullptr;
@@ -240,6 +241,7 @@ struct Builder {
     cw.w = h.dalloc<__half>(host.size());
     CK(cudaMemcpy(cw.w, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice));
     cw.tmapB = makeTmap2D(cw.w, (uint64_t)taps * cw.cout_p, (uint64_t)ldw, (uint32_t)cw.n_tile);
+    cw.tmapBhalf = makeTmap2D(cw.w, (uint64_t)taps * cw.cout_p, (uint64_t)ldw, (uint32_t)(cw.n_tile / 2));
     return cw;
   }
 
@@ -284,7 +286,9 @@ struct Builder {
       }
       else {
         CUtensorMap tmA = makeTmap2D(A, (uint64_t)p.M, (uint64_t)cw.cin_p * actMulL, (uint32_t)convTCABoxRows(cw.ky, cw.kx, p.Wp));
-        CK(launchConvTC(tmA, cw.tmapB, p, hp->numSMs, s));
+        cudaError_t e = hp->usePair ? launchConvTC2(tmA, cw.tmapBhalf, p, hp->numSMs, s) : cudaErrorNotSupported;
+        if(e == cudaErrorNotSupported) e = launchConvTC(tmA, cw.tmapB, p, hp->numSMs, s);
+        CK(e);
       }
     });
     h.launchesPerForward++;
@@ -592,10 +596,12 @@ KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_
     h.streamInnerFp32 = streams == "all";
     env = getenv("KGB_CONV_IMPL");
     h.useSimt = env && std::string(env) == "simt";
+    h.usePair = env && std::string(env) == "tc2";        // "tc2" = CTA-pair kernel (correct, not faster yet: profiles/r01_conv_pipeline_experiments.md)
     env = getenv("KGB_NO_GRAPH");
     h.useGraph = !(env && std::string(env) == "1");
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
     CK(convTCInit());
+    CK(convTC2Init());
     Builder b(h);
     b.build();
     const int XY = h.L.X * h.L.Y;
@@ -722,8 +728,10 @@ struct SingleConv {
     h.L.X = X; h.L.Y = Y; h.L.pad = pad; h.L.Wp = X + pad; h.L.P = (Y + pad) * (X + pad);
     const char* env = getenv("KGB_CONV_IMPL");
     h.useSimt = env && std::string(env) == "simt";
+    h.usePair = env && std::string(env) == "tc2";
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
     CK(convTCInit());
+    CK(convTC2Init());
     Builder b(h);
     ConvDesc cd;
     cd.ky = ky; cd.kx = kx; cd.cin = in_c; cd.cout = out_c;

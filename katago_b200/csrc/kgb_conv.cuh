@@ -163,5 +163,8 @@ cudaError_t launchConvSimt(const __half* A, int lda, const __half* W, const Conv
 int convTCSmemBytes(int n_tile, int cout_p, int a_box_rows, int tps, int epi_warps, int* stagesOut);
 inline int convTCABoxRows(int ky, int kx, int Wp) { return 128 + 2 * ((ky / 2) * Wp + (kx / 2)); }  // TMA box rows of the A halo tile
 cudaError_t convTCInit();  // per device, before the first launch
+// CTA-pair kernel (kgb_conv_tc2.cu); tmapBhalf has box rows n_tile/2.  cudaErrorNotSupported = shape not handled, use launchConvTC.
+cudaError_t convTC2Init();
+cudaError_t launchConvTC2(const CUtensorMap& tmapA, const CUtensorMap& tmapBhalf, const ConvParams& p, int numSMs, cudaStream_t stream);
 
 }  // namespace kgb
