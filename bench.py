@@ -269,6 +269,10 @@ def main():
     after = sp.stats()
     assert after["total_visits"] - before["total_visits"] == n * K, "every wave must add one visit per game"
     ms_nn = timed(step_device, K)
+    s0 = sp.stats()
+    ms_select, ms_backup = sp.time_tree_kernels(20)
+    s1 = sp.stats()
+    tree_depth = (s1["sum_leaf_depth"] - s0["sum_leaf_depth"]) / max(1, s1["total_visits"] - s0["total_visits"])
     for i in range(W):
         step_host(i)
     ms_e2e = timed(step_host, K)
@@ -317,6 +321,18 @@ def main():
                          "peak_source": peaks["source"] + " (burst cuBLAS bf16, kernel timed alone)",
                          "ms_per_launch": float(ms_conv[0]),
                          "whole_forward_tflops": whole, "whole_forward_frac_of_sustained": whole / peaks["tflops_sustained"]},
+            # tree / board kernels: HBM-bound byte work.  Algorithmic bytes per playout: every node on the descent
+            # path reads its policy/childNode/childVisits/childUtilSum arrays (362 x 20 B); the leaf initialises its arrays
+            # (362 x 20 B written), writes the NN row (22*361+19 floats, zero-fill + ones) and the legality mask; the backup reads
+            # 362 logits, writes 362 policy floats and updates 2 x 12 B + 2 x 12 B per path node.
+            "roofline_tree": (lambda bytes_sel, bytes_bak: {
+                "bound": "hbm", "kernel": "spSelectKernel + spBackupKernel (one warp per game)",
+                "achieved": (bytes_sel + bytes_bak) * n / ((ms_select + ms_backup) * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": (bytes_sel + bytes_bak) * n / ((ms_select + ms_backup) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "ms_select": ms_select, "ms_backup": ms_backup, "avg_depth": tree_depth,
+                "bytes_per_playout": bytes_sel + bytes_bak, "traffic": None,
+                "note": "latency-bound at 256 warps per launch (1.7 warps per SM); see DESIGN.md §6"})(
+                    tree_depth * 362 * 20 + 362 * 20 + (22 * 361 + 19) * 4 * 2 + 128, 362 * 8 + tree_depth * 48 + 64),
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": f"8 evaluations of {args.model} 19x19 via the numpy restatement of the Eigen path ({cpu_dt:.1f} s, all host threads)"},
             "clocks": clocks,

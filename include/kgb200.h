@@ -168,6 +168,9 @@ KGB_API int kgb_selfplay_get_game(kgb_selfplay* sp, int game, uint8_t* colors, i
 KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* util_sum);
 /* Play a fixed move list on EVERY game's root (x,y pairs, -1,-1 = pass; colours alternate) and clear the trees. */
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves);
+/* Timing hook for bench.py's tree/board roofline entry: runs `iters` waves of ONLY the select(+board+featurize) and backup
+ * kernels (evaluator outputs of the last wave are reused) and returns their CUDA-event averages per launch. */
+KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* ms_select, float* ms_backup);
 /* Kernel launches per playout wave (evaluator launches + 2). */
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp);
 

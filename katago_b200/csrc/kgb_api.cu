@@ -921,6 +921,31 @@ KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, in
   });
 }
 
+KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* ms_select, float* ms_backup) {
+  return guarded([&] {
+    if(!sp || iters < 1 || !ms_select || !ms_backup) throw std::invalid_argument("kgb_selfplay_time_tree_kernels: bad argument");
+    kgb_handle* h = sp->h;
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    float accS = 0.f, accB = 0.f;
+    CK(cudaStreamSynchronize(h->stream));
+    for(int i = 0; i < iters; i++) {   // the evaluator outputs of the last wave are reused: the trees keep growing normally
+      CK(cudaEventRecord(e0, h->stream));
+      selfplayLaunchSelect(sp->impl, h->stream);
+      CK(cudaEventRecord(e1, h->stream));
+      selfplayLaunchBackup(sp->impl, h->stream);
+      CK(cudaEventRecord(e2, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      float a = 0.f, b = 0.f;
+      CK(cudaEventElapsedTime(&a, e0, e1)); CK(cudaEventElapsedTime(&b, e1, e2));
+      accS += a; accB += b;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    *ms_select = accS / iters; *ms_backup = accB / iters;
+  });
+}
+
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp) { return sp ? sp->h->launchesPerForward + 2 : 0; }
 
 KGB_API int kgb_test_board_replay(int x_size, int y_size, int num_boards, int num_moves, int multi_stone_suicide_legal, const int8_t* moves,

@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_test_board_replay",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_test_board_replay",
 ]
 
 _lib = None
@@ -110,6 +110,7 @@ def load_library():
     lib.kgb_selfplay_get_root_children.argtypes = [P, I, P, P, P]
     lib.kgb_selfplay_launches_per_step.argtypes = [P]
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
+    lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P]
     _lib = lib
     return lib
@@ -349,6 +350,12 @@ class SelfPlay:
         visits = np.zeros(n, np.int32); policy = np.zeros(n, np.float32); util = np.zeros(n, np.float64)
         _check(load_library().kgb_selfplay_get_root_children(self._p, g, visits.ctypes.data, policy.ctypes.data, util.ctypes.data))
         return visits, policy, util
+
+    def time_tree_kernels(self, iters: int = 20):
+        """(ms_select, ms_backup): CUDA-event averages of the two tree kernels alone (evaluator skipped)."""
+        a, b = C.c_float(0), C.c_float(0)
+        _check(load_library().kgb_selfplay_time_tree_kernels(self._p, iters, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def launches_per_step(self) -> int:
