@@ -174,12 +174,16 @@ KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* m
 /* Kernel launches per playout wave (evaluator launches + 2). */
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp);
 
+/* Zobrist data of the reference Board (game/board.cpp:151-216, Rand seeded "Board::initHash()"), regenerated by the backend's
+ * own Rand restatement: board_hash[y][x][colour (0 black, 1 white)][2 x u64] and the empty-board hash size_hash[2]. */
+KGB_API int kgb_zobrist_tables(int x_size, int y_size, uint64_t* board_hash, uint64_t* size_hash);
+
 /* FOR TESTING (rows a1/a2): replay move streams on the device board.  moves[b][m] = {x, y (or -1,-1 = pass), pla (1 black,
  * 2 white)}; after every move returns stones, simple-ko point {x,y or -1,-1}, capture counters {black stones captured,
- * white stones captured}, liberty class of every stone (1,2,3, 0 = more / empty) and Board::isLegal of every point for
- * the NEXT player. */
+ * white stones captured}, liberty class of every stone (1,2,3, 0 = more / empty), Board::isLegal of every point for
+ * the NEXT player, Board::pos_hash {hash0, hash1}, and Board::calculateArea (all flags on; 0 none, 1 black, 2 white). */
 KGB_API int kgb_test_board_replay(int x_size, int y_size, int num_boards, int num_moves, int multi_stone_suicide_legal, const int8_t* moves,
-                          uint8_t* colors, int8_t* ko, int16_t* caps, uint8_t* lib_class, uint8_t* legal_next);
+                          uint8_t* colors, int8_t* ko, int16_t* caps, uint8_t* lib_class, uint8_t* legal_next, uint64_t* pos_hash, uint8_t* area);
 
 /* Kernel-level timing hook for bench.py's roofline object: runs ONE convolution layer (random weights/inputs resident in
  * HBM, the production epilogue of a residual unit's first conv: BN + mish + mask -> fp16) `iters` times on a stream and returns the CUDA-event average per launch. */

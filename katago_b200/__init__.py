@@ -4,5 +4,5 @@ Only what the path needs lives here: csrc/ (CUDA kernels + the C ABI in include/
 mirror of the reference's `namespace NeuralNet`, cpp/neuralnet/nninterface.h), modelgen.py (synthetic model files).
 """
 from .nn_backend import (  # noqa: F401
-    ComputeContext, ComputeHandle, KGBError, LoadedModel, NeuralNet, SelfPlay, board_replay, library_path, load_library,
+    ComputeContext, ComputeHandle, KGBError, LoadedModel, NeuralNet, SelfPlay, board_replay, library_path, load_library, zobrist_tables,
 )

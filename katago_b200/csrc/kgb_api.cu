@@ -26,6 +26,7 @@
 #include "kgb_kernels.cuh"
 #include "kgb_model.h"
 #include "kgb_selfplay.h"
+#include "kgb_rand.h"
 
 using namespace kgb;
 
@@ -948,14 +949,29 @@ KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* m
 
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp) { return sp ? sp->h->launchesPerForward + 2 : 0; }
 
-KGB_API int kgb_test_board_replay(int x_size, int y_size, int num_boards, int num_moves, int multi_stone_suicide_legal, const int8_t* moves,
-                          uint8_t* colors, int8_t* ko, int16_t* caps, uint8_t* lib_class, uint8_t* legal_next) {
+KGB_API int kgb_zobrist_tables(int x_size, int y_size, uint64_t* board_hash, uint64_t* size_hash) {
   return guarded([&] {
-    if(!moves || !colors || !ko || !caps || !lib_class || !legal_next || num_boards < 1 || num_moves < 1)
+    if(!board_hash || !size_hash || x_size < 2 || y_size < 2 || x_size > 19 || y_size > 19) throw std::invalid_argument("kgb_zobrist_tables: bad argument");
+    ZobristTables z = makeZobristTables(x_size, y_size);
+    for(int y = 0; y < y_size; y++)
+      for(int x = 0; x < x_size; x++)
+        for(int c = 0; c < 2; c++) {
+          const Hash128& h = z.board[(y * 32 + x) * 2 + c];
+          uint64_t* o = board_hash + (((size_t)y * x_size + x) * 2 + c) * 2;
+          o[0] = h.h0; o[1] = h.h1;
+        }
+    size_hash[0] = z.sizeHash.h0; size_hash[1] = z.sizeHash.h1;
+  });
+}
+
+KGB_API int kgb_test_board_replay(int x_size, int y_size, int num_boards, int num_moves, int multi_stone_suicide_legal, const int8_t* moves,
+                          uint8_t* colors, int8_t* ko, int16_t* caps, uint8_t* lib_class, uint8_t* legal_next, uint64_t* pos_hash, uint8_t* area) {
+  return guarded([&] {
+    if(!moves || !colors || !ko || !caps || !lib_class || !legal_next || !pos_hash || !area || num_boards < 1 || num_moves < 1)
       throw std::invalid_argument("kgb_test_board_replay: bad argument");
     int count = 0;
     if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaFailure("libkgb200: no CUDA device is visible");
-    boardReplay(x_size, y_size, num_boards, num_moves, multi_stone_suicide_legal, moves, colors, ko, caps, lib_class, legal_next);
+    boardReplay(x_size, y_size, num_boards, num_moves, multi_stone_suicide_legal, moves, colors, ko, caps, lib_class, legal_next, pos_hash, area);
   });
 }
 

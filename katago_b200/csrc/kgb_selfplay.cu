@@ -32,6 +32,7 @@
 #include "../../include/kgb200.h"
 #include "kgb_board.cuh"
 #include "kgb_selfplay.h"
+#include "kgb_rand.h"
 
 namespace kgb {
 
@@ -480,20 +481,25 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
 // ------------------------------------------------------------------------------------------------------------
 __global__ void boardReplayKernel(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves /*[b][m][3]: x,y,pla(1=black,2=white)*/,
                                   uint8_t* colors /*[b][m][Y*X]*/, int8_t* ko /*[b][m][2]*/, int16_t* caps /*[b][m][2]*/,
-                                  uint8_t* libClass /*[b][m][Y*X] 0..3 (0 = >3 or empty)*/, uint8_t* legalNext /*[b][m][Y*X]*/) {
+                                  uint8_t* libClass /*[b][m][Y*X] 0..3 (0 = >3 or empty)*/, uint8_t* legalNext /*[b][m][Y*X]*/,
+                                  const ZobEntry* zob, unsigned long long sizeH0, unsigned long long sizeH1, unsigned long long* posHash /*[b][m][2]*/,
+                                  uint8_t* area /*[b][m][Y*X] Board::calculateArea, all flags on*/) {
   const int bidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(bidx >= numBoards) return;
   WarpBoard bd;
   boardInit(bd, X, Y);
+  bd.h0 = sizeH0; bd.h1 = sizeH1;
   for(int m = 0; m < numMoves; m++) {
     const int8_t* mv = moves + ((size_t)bidx * numMoves + m) * 3;
     const bool black = mv[2] == 1;
     const int p = mv[0] < 0 ? -1 : (mv[1] * 32 + mv[0]);
-    boardPlay(bd, p, black);
+    boardPlay(bd, p, black, zob);
     uint32_t l1, l2, l3;
     boardLibertyClasses(bd, l1, l2, l3);
     uint32_t legal = boardLegalMask(bd, !black, multiSuicide != 0, l1);
+    uint32_t aB, aW;
+    boardCalculateArea(bd, true, true, true, multiSuicide != 0, aB, aW);
     const size_t o = ((size_t)bidx * numMoves + m) * X * Y;
     if(lane < Y)
       for(int x = 0; x < X; x++) {
@@ -501,12 +507,14 @@ __global__ void boardReplayKernel(int X, int Y, int numBoards, int numMoves, int
         colors[o + lane * X + x] = (bd.b & bit) ? 1 : (bd.w & bit) ? 2 : 0;
         libClass[o + lane * X + x] = (l1 & bit) ? 1 : (l2 & bit) ? 2 : (l3 & bit) ? 3 : 0;
         legalNext[o + lane * X + x] = (legal & bit) ? 1 : 0;
+        area[o + lane * X + x] = (aB & bit) ? 1 : (aW & bit) ? 2 : 0;
       }
     if(lane == 0) {
       size_t q = (size_t)bidx * numMoves + m;
       ko[q * 2] = bd.ko < 0 ? -1 : (int8_t)(bd.ko & 31);
       ko[q * 2 + 1] = bd.ko < 0 ? -1 : (int8_t)(bd.ko >> 5);
       caps[q * 2] = (int16_t)bd.capB; caps[q * 2 + 1] = (int16_t)bd.capW;
+      posHash[q * 2] = bd.h0; posHash[q * 2 + 1] = bd.h1;
     }
   }
 }
@@ -644,16 +652,25 @@ void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* polic
 }
 
 void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,
-                 uint8_t* libClass, uint8_t* legalNext) {
+                 uint8_t* libClass, uint8_t* legalNext, uint64_t* posHash, uint8_t* area) {
   if(X > 19 || Y > 19 || X < 2 || Y < 2) throw std::invalid_argument("board replay: board sizes 2..19 only");
   size_t nm = (size_t)numBoards * numMoves, cells = nm * X * Y;
   int8_t *dMoves, *dKo; uint8_t *dColors, *dLib, *dLegal; int16_t* dCaps;
   SPCK(cudaMalloc(&dMoves, nm * 3)); SPCK(cudaMalloc(&dKo, nm * 2)); SPCK(cudaMalloc(&dCaps, nm * 2 * sizeof(int16_t)));
   SPCK(cudaMalloc(&dColors, cells)); SPCK(cudaMalloc(&dLib, cells)); SPCK(cudaMalloc(&dLegal, cells));
   SPCK(cudaMemcpy(dMoves, moves, nm * 3, cudaMemcpyHostToDevice));
+  ZobristTables zt = makeZobristTables(X, Y);
+  ZobEntry* dZob; unsigned long long* dHash; uint8_t* dArea;
+  SPCK(cudaMalloc(&dZob, zt.board.size() * sizeof(ZobEntry))); SPCK(cudaMalloc(&dHash, nm * 2 * sizeof(unsigned long long)));
+  SPCK(cudaMalloc(&dArea, cells));
+  static_assert(sizeof(ZobEntry) == sizeof(Hash128), "layout");
+  SPCK(cudaMemcpy(dZob, zt.board.data(), zt.board.size() * sizeof(ZobEntry), cudaMemcpyHostToDevice));
   int threads = 128;
-  boardReplayKernel<<<(numBoards * 32 + threads - 1) / threads, threads>>>(X, Y, numBoards, numMoves, multiSuicide, dMoves, dColors, dKo, dCaps, dLib, dLegal);
+  boardReplayKernel<<<(numBoards * 32 + threads - 1) / threads, threads>>>(X, Y, numBoards, numMoves, multiSuicide, dMoves, dColors, dKo, dCaps, dLib, dLegal,
+                                                                           dZob, zt.sizeHash.h0, zt.sizeHash.h1, dHash, dArea);
   cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) { cudaMemcpy(posHash, dHash, nm * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost); cudaMemcpy(area, dArea, cells, cudaMemcpyDeviceToHost); }
+  cudaFree(dZob); cudaFree(dHash); cudaFree(dArea);
   if(e == cudaSuccess) {
     cudaMemcpy(colors, dColors, cells, cudaMemcpyDeviceToHost); cudaMemcpy(libClass, dLib, cells, cudaMemcpyDeviceToHost);
     cudaMemcpy(legalNext, dLegal, cells, cudaMemcpyDeviceToHost); cudaMemcpy(ko, dKo, nm * 2, cudaMemcpyDeviceToHost);

@@ -26,6 +26,6 @@ void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
 void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum);
 void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,
-                 uint8_t* libClass, uint8_t* legalNext);
+                 uint8_t* libClass, uint8_t* legalNext, uint64_t* posHash, uint8_t* area);
 
 }  // namespace kgb

@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_test_board_replay",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_test_board_replay",
 ]
 
 _lib = None
@@ -111,7 +111,8 @@ def load_library():
     lib.kgb_selfplay_launches_per_step.argtypes = [P]
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
-    lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P]
+    lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
+    lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
     _lib = lib
     return lib
 
@@ -294,6 +295,15 @@ class NeuralNet:
         return out
 
 
+def zobrist_tables(x_size: int, y_size: int):
+    """(board_hash uint64 [Y, X, 2 colours, 2], size_hash uint64 [2]) - the reference's Zobrist data (Board::initHash)."""
+    lib = load_library()
+    bh = np.zeros((y_size, x_size, 2, 2), np.uint64)
+    sh = np.zeros(2, np.uint64)
+    _check(lib.kgb_zobrist_tables(x_size, y_size, bh.ctypes.data, sh.ctypes.data))
+    return bh, sh
+
+
 def board_replay(x_size: int, y_size: int, moves, multi_stone_suicide_legal: bool):
     """kgb_test_board_replay: moves int8 [boards, m, 3] = (x, y, pla) with (-1,-1) = pass, pla 1 black / 2 white.
     Returns dict(colors [b,m,Y,X], ko [b,m,2], caps [b,m,2], lib_class [b,m,Y,X], legal_next [b,m,Y,X])."""
@@ -303,9 +313,12 @@ def board_replay(x_size: int, y_size: int, moves, multi_stone_suicide_legal: boo
     colors = np.zeros((nb, nm, y_size, x_size), np.uint8)
     libc = np.zeros_like(colors); legal = np.zeros_like(colors)
     ko = np.zeros((nb, nm, 2), np.int8); caps = np.zeros((nb, nm, 2), np.int16)
+    pos_hash = np.zeros((nb, nm, 2), np.uint64)
+    area = np.zeros_like(colors)
     _check(lib.kgb_test_board_replay(x_size, y_size, nb, nm, int(bool(multi_stone_suicide_legal)), mv.ctypes.data, colors.ctypes.data,
-                                     ko.ctypes.data, caps.ctypes.data, libc.ctypes.data, legal.ctypes.data))
-    return dict(colors=colors, ko=ko, caps=caps, lib_class=libc, legal_next=legal)
+                                     ko.ctypes.data, caps.ctypes.data, libc.ctypes.data, legal.ctypes.data, pos_hash.ctypes.data,
+                                     area.ctypes.data))
+    return dict(colors=colors, ko=ko, caps=caps, lib_class=libc, legal_next=legal, pos_hash=pos_hash, area=area)
 
 
 class SelfPlay:

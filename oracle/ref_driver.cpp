@@ -8,7 +8,8 @@
 //       has the same fake net (kgb_selfplay_config.debug_fake_nn) so tree parity is tested without any real net.
 //   kgref_driver boardstream X Y NMOVES SEED MULTISUICIDE OUT.bin
 //       random legal move stream on a reference Board (game/board.h): after every move records the board, ko, capture
-//       counters, pos_hash, per-stone liberty counts and the legality mask of the player to move next.
+//       counters, pos_hash, per-stone liberty counts, the legality mask of the player to move next and the Benson pass-alive /
+//       territory area (Board::calculateArea, all flags on).
 #include "game/board.h"
 #include "game/boardhistory.h"
 #include "game/rules.h"
@@ -92,6 +93,11 @@ static int cmdBoardStream(int argc, char** argv) {
         Loc loc = Location::getLoc(x, y, X);
         put<uint8_t>(out, board.isLegal(loc, next, multi) ? 1 : 0);
       }
+    // Board::calculateArea as fillRowV7 calls it for area scoring / no tax (nninputs.cpp:2375-2382): all three flags on
+    Color area[Board::MAX_ARR_SIZE];
+    board.calculateArea(area, true, true, true, multi);
+    for(int y = 0; y < Y; y++)
+      for(int x = 0; x < X; x++) put<uint8_t>(out, (uint8_t)area[Location::getLoc(x, y, X)]);
     pla = next;
   }
   return 0;

@@ -103,3 +103,18 @@ def test_synthetic_file_roundtrip_weights(tmp_models):
     b = orc.load_model(tmp_models["tiny_nbt_gz"], apply_transform=False)
     assert np.array_equal(a.initial_conv.w, b.initial_conv.w)
     assert np.array_equal(a.blocks[1].blocks[0].gpool_to_bias.w, b.blocks[1].blocks[0].gpool_to_bias.w)
+
+
+def test_zobrist_tables_reproduce_reference_pos_hash(golden_dir):
+    """Row a25: the backend's restatement of Rand (MD5 + SHA-256 seeding, XorShift1024* + PCG32) and of Board::initHash's draw
+    order regenerates the reference's Zobrist tables: XOR over the stones of fixture positions == the reference's pos_hash."""
+    from katago_b200 import zobrist_tables
+    for name in ("boardstream_19x19_multisuicide", "boardstream_9x9_multisuicide", "boardstream_13x7_nosuicide", "boardstream_5x5_multisuicide"):
+        d = np.load(os.path.join(golden_dir, name + ".npz"))
+        bh, sh = zobrist_tables(int(d["X"]), int(d["Y"]))
+        for m in range(0, len(d["moves"]), 11):
+            col = d["colors"][m]
+            h = sh.copy()
+            for yy, xx in zip(*np.nonzero(col)):
+                h ^= bh[yy, xx, col[yy, xx] - 1]
+            assert np.array_equal(h, d["pos_hash"][m]), (name, m)
