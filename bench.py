@@ -303,7 +303,7 @@ def main():
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32-split3(fp16 tensor pipe)" if args.fp32 else "f16 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, maxVisits {args.visits}, one playout (visit) per game per step, device-resident loop",
-                       "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(V7 planes 0-6,9-13 + globals; ladder/area planes pending)",
+                       "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(V7 planes 0-6,9-13,18-19 + globals; ladder planes 14-17 pending)",
                                   "nn_eval", "policy/value postprocess", "backup"],
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",

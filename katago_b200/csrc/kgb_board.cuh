@@ -237,14 +237,12 @@ __device__ __forceinline__ void boardCalculateArea(const WarpBoard& bd, bool non
   }
 }
 
-// Tromp-Taylor area score, black minus white, komi not included (Board::calculateArea with all flags on reduces to this
-// for finished games; used only for terminal values inside the search this round).
-__device__ __forceinline__ int boardAreaScoreBlackMinusWhite(const WarpBoard& bd) {
-  const uint32_t rm = bd.rowMask;
-  const uint32_t empty = ~(bd.b | bd.w) & rm;
-  uint32_t reachB = flood(nbrs(bd.b, rm) & empty, empty, rm);
-  uint32_t reachW = flood(nbrs(bd.w, rm) & empty, empty, rm);
-  return warpCount(bd.b | (reachB & ~reachW)) - warpCount(bd.w | (reachW & ~reachB));
+// Area score black minus white (komi not included) as BoardHistory::endAndScoreGameNow counts it under area scoring:
+// Board::calculateArea with nonPassAliveStones, safeBigTerritories, unsafeBigTerritories all on (boardhistory.cpp, countAreaScoreWhiteMinusBlack).
+__device__ __forceinline__ int boardAreaScoreBlackMinusWhite(const WarpBoard& bd, bool multiStoneSuicideLegal) {
+  uint32_t aB, aW;
+  boardCalculateArea(bd, true, true, true, multiStoneSuicideLegal, aB, aW);
+  return warpCount(aB) - warpCount(aW);
 }
 
 }  // namespace kgb

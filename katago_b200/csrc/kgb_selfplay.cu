@@ -16,9 +16,9 @@
 // (searchupdatehelpers.cpp:167-360) equals this running mean.
 //
 // NN input planes written this round: 0 on-board, 1/2 own/opp stones, 3/4/5 liberties 1/2/3, 6 simple-ko ban,
-// 9-13 previous five move locations; globals 0-4 pass history, 5 selfKomi/20, 8 multi-stone suicide, 14 pass would end
-// the phase, 18 komi parity wave.  NOT yet written (stay 0): ladder planes 14-17, pass-alive area planes 18-19,
-// superko bans in plane 6, encore planes (territory rules) - rows a4/a5 of SURVEY.md §8.
+// 9-13 previous five move locations, 18/19 pass-alive + territory area (Benson, kgb_board.cuh); globals 0-4 pass history,
+// 5 selfKomi/20, 8 multi-stone suicide, 14 pass would end the phase, 18 komi parity wave.  NOT yet written (stay 0): ladder
+// planes 14-17 (row a5), superko bans in plane 6, encore planes (territory rules).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -153,7 +153,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   int mv = d.moveNum[g] + 1;
   bool over = passes >= 2 || mv >= d.maxMoves;
   if(over) {
-    int diff = boardAreaScoreBlackMinusWhite(bd);
+    int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
     float whiteScore = d.komi - (float)diff;
     if(lane == 0) {
       atomicAdd(d.gamesFinished, 1ULL);
@@ -291,7 +291,7 @@ __global__ void spSelectKernel(const SPDev d) {
     atomicAdd(d.sumDepth, (unsigned long long)depth);
   }
   if(terminal) {
-    int diff = boardAreaScoreBlackMinusWhite(bd);
+    int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
     float whiteScore = d.komi - (float)diff;
     double u = whiteScore > 0 ? d.winLossUtilityFactor : whiteScore < 0 ? -d.winLossUtilityFactor : 0.0;
     if(lane == 0) d.leafTerminalUtil[g] = u;
@@ -303,6 +303,10 @@ __global__ void spSelectKernel(const SPDev d) {
   if(lane < 19) gl[lane] = 0.0f;
   __syncwarp();
   const uint32_t own = black ? bd.b : bd.w, opp = black ? bd.w : bd.b;
+  // planes 18/19: pass-alive + territory area for area scoring without tax (nninputs.cpp:2375-2382, 2425-2436)
+  uint32_t areaB, areaW;
+  boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);
+  const uint32_t areaOwn = black ? areaB : areaW, areaOpp = black ? areaW : areaB;
   if(lane < d.Y) {
     for(int x = 0; x < d.X; x++) {
       float* f = row + (size_t)(lane * d.X + x) * 22;
@@ -310,6 +314,7 @@ __global__ void spSelectKernel(const SPDev d) {
       f[0] = 1.0f;
       if(own & bit) f[1] = 1.0f; else if(opp & bit) f[2] = 1.0f;
       if(lib1 & bit) f[3] = 1.0f; else if(lib2 & bit) f[4] = 1.0f; else if(lib3 & bit) f[5] = 1.0f;
+      if(areaOwn & bit) f[18] = 1.0f; else if(areaOpp & bit) f[19] = 1.0f;
     }
   }
   __syncwarp();
