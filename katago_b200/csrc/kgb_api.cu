@@ -914,6 +914,18 @@ KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* 
   });
 }
 
+KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global) {
+  return guarded([&] {
+    if(!sp || !spatial || !global || game < 0 || game >= sp->n) throw std::invalid_argument("kgb_selfplay_get_nn_row: bad argument");
+    kgb_handle* h = sp->h;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t XY = (size_t)h->L.X * h->L.Y;
+    CK(cudaMemcpy(spatial, h->dSpatial + (size_t)game * XY * 22, XY * 22 * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(global, h->dGlobal + (size_t)game * 19, 19 * sizeof(float), cudaMemcpyDeviceToHost));
+  });
+}
+
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves) {
   return guarded([&] {
     if(!sp || (!moves_xy && num_moves > 0) || num_moves < 0) throw std::invalid_argument("kgb_selfplay_play_moves: bad argument");

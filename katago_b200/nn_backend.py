@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_test_board_replay",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def load_library():
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
+    lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
     _lib = lib
     return lib
@@ -345,6 +346,12 @@ class SelfPlay:
         """moves_xy: iterable of (x, y) or None for pass; applied to every game's root, trees cleared."""
         arr = np.array([(-1, -1) if m is None else (m[0], m[1]) for m in moves_xy], dtype=np.int8).reshape(-1, 2)
         _check(load_library().kgb_selfplay_play_moves(self._p, arr.ctypes.data if len(arr) else None, len(arr)))
+
+    def nn_row(self, g: int):
+        """(spatial [X*Y, 22], global [19]) written by the last wave for game g."""
+        sp = np.zeros((self.x * self.y, 22), np.float32); gl = np.zeros(19, np.float32)
+        _check(load_library().kgb_selfplay_get_nn_row(self._p, g, sp.ctypes.data, gl.ctypes.data))
+        return sp, gl
 
     def stats(self) -> dict:
         s = SelfplayStats()

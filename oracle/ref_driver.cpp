@@ -6,6 +6,9 @@
 //       reference Search (search/search.cpp) with the deterministic hash-based fake net defined below as its NeuralNet
 //       backend (this file IS the backend TU of the driver); prints the root children's visit counts.  The device loop
 //       has the same fake net (kgb_selfplay_config.debug_fake_nn) so tree parity is tested without any real net.
+//   kgref_driver featstream X Y MULTISUICIDE KOMI "x,y x,y pass ..." EVERY OUT.bin
+//       NNInputs::fillRowV7 (neuralnet/nninputs.cpp:2288-2731) rows along a game played through BoardHistory with the rule
+//       subset of the device loop (area scoring, simple ko, no tax): after every EVERY-th move writes the NHWC row + globals.
 //   kgref_driver boardstream X Y NMOVES SEED MULTISUICIDE OUT.bin
 //       random legal move stream on a reference Board (game/board.h): after every move records the board, ko, capture
 //       counters, pos_hash, per-stone liberty counts, the legality mask of the player to move next and the Benson pass-alive /
@@ -235,11 +238,80 @@ static int cmdSearchFake(int argc, char** argv) {
   return 0;
 }
 
+static int cmdFeatStream(int argc, char** argv) {
+  if(argc != 9) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT" << endl; return 1; }
+  int X = atoi(argv[2]), Y = atoi(argv[3]);
+  bool multi = atoi(argv[4]) != 0;
+  float komi = (float)atof(argv[5]);
+  int every = atoi(argv[7]);
+  Board::initHash();
+  ScoreValue::initTables();
+  Rules rules;
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = multi; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.friendlyPassOk = false; rules.komi = komi;
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  ofstream out(argv[8], ios::binary);
+  // MOVES may be "random:SEED:N": N random legal moves (BoardHistory::isLegal), 1/40 passes but never two in a row;
+  // the generated list is written to OUT.moves so the other side can replay it.
+  string movesArg = argv[6];
+  if(movesArg.rfind("random:", 0) == 0) {
+    uint64_t seed = 0; int count = 0;
+    sscanf(movesArg.c_str(), "random:%lu:%d", &seed, &count);
+    Lcg rng(seed);
+    Board b2(X, Y); Player p2 = P_BLACK; BoardHistory h2(b2, p2, rules, 0, false);
+    string gen; bool prevPass = false;
+    for(int i = 0; i < count; i++) {
+      vector<Loc> legal;
+      for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(h2.isLegal(b2, l, p2)) legal.push_back(l); }
+      Loc mv;
+      if(legal.empty() || (!prevPass && rng.next() % 40 == 0)) { if(prevPass) break; mv = Board::PASS_LOC; }
+      else mv = legal[rng.next() % legal.size()];
+      prevPass = mv == Board::PASS_LOC;
+      gen += prevPass ? "pass " : (Global::intToString(Location::getX(mv, X)) + "," + Global::intToString(Location::getY(mv, X)) + " ");
+      h2.makeBoardMoveAssumeLegal(b2, mv, p2, NULL);
+      p2 = getOpp(p2);
+    }
+    movesArg = gen;
+    ofstream mo(string(argv[8]) + ".moves");
+    mo << gen << endl;
+  }
+  std::istringstream in(movesArg);
+  string tok;
+  int n = 0, written = 0;
+  vector<float> rowBin(NNInputs::NUM_FEATURES_SPATIAL_V7 * X * Y), rowGlobal(NNInputs::NUM_FEATURES_GLOBAL_V7);
+  auto dump = [&]() {
+    MiscNNInputParams params;
+    NNInputs::fillRowV7(board, hist, pla, params, X, Y, true, rowBin.data(), rowGlobal.data());
+    put<int32_t>(out, n);
+    out.write((const char*)rowBin.data(), rowBin.size() * sizeof(float));
+    out.write((const char*)rowGlobal.data(), rowGlobal.size() * sizeof(float));
+    written++;
+  };
+  dump();
+  while(in >> tok) {
+    Loc loc;
+    if(tok == "pass") loc = Board::PASS_LOC;
+    else { int x, y; if(sscanf(tok.c_str(), "%d,%d", &x, &y) != 2) { cerr << "bad move " << tok << endl; return 1; } loc = Location::getLoc(x, y, X); }
+    if(!hist.isLegal(board, loc, pla)) { cerr << "illegal move " << tok << " at " << n << endl; return 1; }
+    hist.makeBoardMoveAssumeLegal(board, loc, pla, NULL);
+    pla = getOpp(pla);
+    n++;
+    if(hist.isGameFinished) break;
+    if(n % every == 0) dump();
+  }
+  cerr << "wrote " << written << " rows" << endl;
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if(argc < 2) { cerr << "usage: kgref_driver <boardstream|...> ..." << endl; return 1; }
   string cmd = argv[1];
   if(cmd == "boardstream") return cmdBoardStream(argc, argv);
   if(cmd == "searchfake") return cmdSearchFake(argc, argv);
+  if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;
 }
