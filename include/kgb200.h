@@ -144,7 +144,7 @@ typedef struct kgb_selfplay_config {
   double no_result_utility_for_white;
   uint64_t seed;
   int32_t debug_fake_nn;             /* TEST ONLY: replace the evaluator by the deterministic hash net of oracle/ref_driver.cpp */
-  int32_t reserved;
+  int32_t disable_ladder_features;   /* 1 = leave NN input planes 14-17 zero (timing experiments only) */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {

@@ -17,8 +17,8 @@
 //
 // NN input planes written this round: 0 on-board, 1/2 own/opp stones, 3/4/5 liberties 1/2/3, 6 simple-ko ban,
 // 9-13 previous five move locations, 18/19 pass-alive + territory area (Benson, kgb_board.cuh); globals 0-4 pass history,
-// 5 selfKomi/20, 8 multi-stone suicide, 14 pass would end the phase, 18 komi parity wave.  NOT yet written (stay 0): ladder
-// planes 14-17 (row a5), superko bans in plane 6, encore planes (territory rules).
+// 5 selfKomi/20, 8 multi-stone suicide, 14 pass would end the phase, 18 komi parity wave; ladder planes 14-17 (kgb_ladder.cuh).
+// NOT written (stay 0, not reachable under the supported rule subset): superko bans in plane 6, encore planes 7/8/20/21.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -31,6 +31,7 @@
 
 #include "../../include/kgb200.h"
 #include "kgb_board.cuh"
+#include "kgb_ladder.cuh"
 #include "kgb_selfplay.h"
 #include "kgb_rand.h"
 
@@ -46,6 +47,10 @@ struct SPDev {
   // root state [game]
   uint32_t *rootB, *rootW;          // [game][32]
   int *rootKo, *rootBlackToMove, *rootCapB, *rootCapW, *moveNum, *consecPasses;
+  uint32_t *prevB, *prevW;          // [2][game][32]: boards 1 and 2 moves ago (BoardHistory::getRecentBoard), for ladder planes 15/16
+  int* prevKo;                      // [2][game]
+  uint32_t* ladderScratch;          // [game][ladderScratchWordsPerWarp()]
+  int enableLadders;
   int* hist;                        // [game][5] last moves, most recent first: -1 none, -2 pass, else y*32+x
   uint64_t* gameCounter;            // games started per slot (RNG stream)
   // tree [game][node]...
@@ -148,6 +153,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   const bool black = d.rootBlackToMove[g] != 0;
   const bool isPass = best == d.policySize - 1;
   const int p = isPass ? -1 : pointOfPos(best, d.X);
+  const uint32_t beforeB = bd.b, beforeW = bd.w; const int beforeKo = bd.ko;
   boardPlay(bd, p, black);
   int passes = isPass ? d.consecPasses[g] + 1 : 0;
   int mv = d.moveNum[g] + 1;
@@ -170,6 +176,10 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     int shifted = __shfl_up_sync(KGB_FULL, h, 1);
     if(lane < 5) d.hist[g * 5 + lane] = lane == 0 ? (isPass ? -2 : p) : shifted;
     if(lane == 0) d.rootBlackToMove[g] = black ? 0 : 1;
+    const size_t G32 = (size_t)d.numGames * 32;
+    d.prevB[G32 + g * 32 + lane] = d.prevB[g * 32 + lane]; d.prevW[G32 + g * 32 + lane] = d.prevW[g * 32 + lane];
+    d.prevB[g * 32 + lane] = beforeB; d.prevW[g * 32 + lane] = beforeW;
+    if(lane == 0) { d.prevKo[d.numGames + g] = d.prevKo[g]; d.prevKo[g] = beforeKo; }
   }
   d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
   if(lane == 0) {
@@ -198,6 +208,10 @@ __global__ void spSelectKernel(const SPDev d) {
   bool black = d.rootBlackToMove[g] != 0;
   int passes = d.consecPasses[g];
   int h0 = d.hist[g * 5 + 0], h1 = d.hist[g * 5 + 1], h2 = d.hist[g * 5 + 2], h3 = d.hist[g * 5 + 3], h4 = d.hist[g * 5 + 4];
+  // boards one and two moves ago (ladder planes 15/16): the root's recent boards, shifted as the descent plays moves
+  const size_t G32 = (size_t)d.numGames * 32;
+  uint32_t p1B = d.prevB[g * 32 + lane], p1W = d.prevW[g * 32 + lane], p2B = d.prevB[G32 + g * 32 + lane], p2W = d.prevW[G32 + g * 32 + lane];
+  int p1Ko = d.prevKo[g], p2Ko = d.prevKo[d.numGames + g];
   int node = 0, depth = 0;
   bool terminal = false;
   while(true) {
@@ -255,6 +269,7 @@ __global__ void spSelectKernel(const SPDev d) {
     // ---- descend
     const bool isPass = move == d.policySize - 1;
     const int p = isPass ? -1 : pointOfPos(move, d.X);
+    p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
     boardPlay(bd, p, black);
     passes = isPass ? passes + 1 : 0;
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
@@ -307,6 +322,23 @@ __global__ void spSelectKernel(const SPDev d) {
   uint32_t areaB, areaW;
   boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);
   const uint32_t areaOwn = black ? areaB : areaW, areaOpp = black ? areaW : areaB;
+  // planes 14-17: ladders on the current board and on the boards 1 and 2 moves ago (nninputs.cpp:2547-2583)
+  uint32_t lad0 = 0, lad1 = 0, lad2 = 0, work17 = 0;
+  if(d.enableLadders) {
+    const LadderScratch sc = ladderScratchAt(d.ladderScratch + (size_t)g * ladderScratchWordsPerWarp());
+    uint32_t wB, wW;
+    boardLadders(bd, sc, d.X, d.Y, lad0, wB, wW);
+    work17 = black ? wW : wB;   // working moves against the OPPONENT's 2-liberty chains
+    const int numHist = (h0 == -1) ? 0 : (h1 == -1) ? 1 : 2;   // min(2, moves of history included)
+    WarpBoard pb = bd;
+    if(numHist >= 1) { pb.b = p1B; pb.w = p1W; pb.ko = p1Ko; }
+    const bool same1 = !__any_sync(KGB_FULL, pb.b != bd.b || pb.w != bd.w) && pb.ko == bd.ko;
+    if(same1) lad1 = lad0; else boardLadders(pb, sc, d.X, d.Y, lad1, wB, wW);
+    WarpBoard qb = pb;
+    if(numHist >= 2) { qb.b = p2B; qb.w = p2W; qb.ko = p2Ko; }
+    const bool same2 = !__any_sync(KGB_FULL, qb.b != pb.b || qb.w != pb.w) && qb.ko == pb.ko;
+    if(same2) lad2 = lad1; else boardLadders(qb, sc, d.X, d.Y, lad2, wB, wW);
+  }
   if(lane < d.Y) {
     for(int x = 0; x < d.X; x++) {
       float* f = row + (size_t)(lane * d.X + x) * 22;
@@ -315,6 +347,10 @@ __global__ void spSelectKernel(const SPDev d) {
       if(own & bit) f[1] = 1.0f; else if(opp & bit) f[2] = 1.0f;
       if(lib1 & bit) f[3] = 1.0f; else if(lib2 & bit) f[4] = 1.0f; else if(lib3 & bit) f[5] = 1.0f;
       if(areaOwn & bit) f[18] = 1.0f; else if(areaOpp & bit) f[19] = 1.0f;
+      if(lad0 & bit) f[14] = 1.0f;
+      if(lad1 & bit) f[15] = 1.0f;
+      if(lad2 & bit) f[16] = 1.0f;
+      if(work17 & bit) f[17] = 1.0f;
     }
   }
   __syncwarp();
@@ -460,9 +496,13 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
   int passes = d.consecPasses[g], mv = d.moveNum[g];
   int h[5];
   for(int k = 0; k < 5; k++) h[k] = d.hist[g * 5 + k];
+  const size_t G32 = (size_t)d.numGames * 32;
+  uint32_t p1B = d.prevB[g * 32 + lane], p1W = d.prevW[g * 32 + lane], p2B = d.prevB[G32 + g * 32 + lane], p2W = d.prevW[G32 + g * 32 + lane];
+  int p1Ko = d.prevKo[g], p2Ko = d.prevKo[d.numGames + g];
   for(int m = 0; m < numMoves; m++) {
     const bool isPass = moves[m * 2] < 0;
     const int p = isPass ? -1 : (moves[m * 2 + 1] * 32 + moves[m * 2]);
+    p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
     boardPlay(bd, p, black);
     passes = isPass ? passes + 1 : 0;
     for(int k = 4; k > 0; k--) h[k] = h[k - 1];
@@ -471,8 +511,10 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     mv++;
   }
   d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
+  d.prevB[g * 32 + lane] = p1B; d.prevW[g * 32 + lane] = p1W; d.prevB[G32 + g * 32 + lane] = p2B; d.prevW[G32 + g * 32 + lane] = p2W;
   const size_t gb = (size_t)g * d.maxNodes;
   if(lane == 0) {
+    d.prevKo[g] = p1Ko; d.prevKo[d.numGames + g] = p2Ko;
     d.rootKo[g] = bd.ko; d.rootCapB[g] = bd.capB; d.rootCapW[g] = bd.capW;
     d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = passes; d.moveNum[g] = mv;
     for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
@@ -570,6 +612,10 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.rootKo = sp->alloc<int>(G); d.rootBlackToMove = sp->alloc<int>(G); d.rootCapB = sp->alloc<int>(G); d.rootCapW = sp->alloc<int>(G);
   d.moveNum = sp->alloc<int>(G); d.consecPasses = sp->alloc<int>(G); d.hist = sp->alloc<int>(G * 5);
   d.gameCounter = sp->alloc<uint64_t>(G);
+  d.prevB = sp->alloc<uint32_t>(2 * G * 32); d.prevW = sp->alloc<uint32_t>(2 * G * 32); d.prevKo = sp->alloc<int>(2 * G);
+  d.enableLadders = c.disable_ladder_features ? 0 : 1;
+  d.ladderScratch = sp->alloc<uint32_t>(G * ladderScratchWordsPerWarp());
+  { std::vector<int> kos2(2 * G, -1); SPCK(cudaMemcpy(d.prevKo, kos2.data(), 2 * G * sizeof(int), cudaMemcpyHostToDevice)); }
   d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); d.nodeUtilSum = sp->alloc<double>(G * N);
   d.nodeTerminal = sp->alloc<int8_t>(G * N);
   d.policy = sp->alloc<float>(G * N * PS); d.childNode = sp->alloc<int>(G * N * PS); d.childVisits = sp->alloc<int>(G * N * PS);

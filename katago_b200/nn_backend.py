@@ -42,7 +42,7 @@ class SelfplayConfig(C.Structure):
         ("early_temperature_moves", C.c_int32), ("komi", C.c_float),
         ("cpuct_exploration", C.c_double), ("cpuct_exploration_log", C.c_double), ("cpuct_exploration_base", C.c_double),
         ("fpu_reduction_max", C.c_double), ("root_fpu_reduction_max", C.c_double), ("win_loss_utility_factor", C.c_double),
-        ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64), ("debug_fake_nn", C.c_int32), ("reserved", C.c_int32),
+        ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64), ("debug_fake_nn", C.c_int32), ("disable_ladder_features", C.c_int32),
     ]
 
 
@@ -329,12 +329,12 @@ class SelfPlay:
                  multi_stone_suicide_legal: bool = True, early_temperature_moves: int = 30, cpuct_exploration: float = 1.0,
                  cpuct_exploration_log: float = 0.45, cpuct_exploration_base: float = 500.0, fpu_reduction_max: float = 0.2,
                  root_fpu_reduction_max: float = 0.1, win_loss_utility_factor: float = 1.0, no_result_utility_for_white: float = 0.0,
-                 seed: int = 0, debug_fake_nn: bool = False):
+                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
                                   cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
-                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), 0)
+                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features))
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
