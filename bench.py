@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--model", default="b18c384nbt")
     ap.add_argument("--games", type=int, default=256, help="concurrent games (= NN batch) per GPU")
     ap.add_argument("--fp32", action="store_true", help="use the fp32-equivalent (3-term split) mode instead of fp16 operands")
+    ap.add_argument("--ladder-nodes-per-wave", type=int, default=256,
+                    help="ladder-reader moves per warp per wave before a game's unfinished searches are carried into the next wave "
+                         "(0 = finish inside the wave); results are identical, only the schedule changes")
     ap.add_argument("--visits", type=int, default=600, help="maxVisits per move (BASELINE.json configs[1]: 600)")
     return ap.parse_args()
 
@@ -256,7 +259,7 @@ def main():
     # device-resident self-play loop: selfplay8mainb18.cfg search parameters that the loop implements
     sp = SelfPlay(handle, n, args.visits, komi=7.5, multi_stone_suicide_legal=True, early_temperature_moves=30,
                   cpuct_exploration=1.0, cpuct_exploration_log=0.45, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
-                  root_fpu_reduction_max=0.1, seed=1234 + rank)
+                  root_fpu_reduction_max=0.1, seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave)
     # bring the games into mid-search (trees a few hundred nodes deep) before timing
     sp.run(W + 64)
     handle.sync()
@@ -267,7 +270,13 @@ def main():
     ms_dev = timed(lambda i: sp.run(1), K)
     clocks = sampler.stop() if rank == 0 else None
     after = sp.stats()
-    assert after["total_visits"] - before["total_visits"] == n * K, "every wave must add one visit per game"
+    # a wave adds one visit per game, except for games whose ladder searches are still running (stalled_waves)
+    done = after["total_visits"] - before["total_visits"]
+    assert done + (after["stalled_waves"] - before["stalled_waves"]) == n * K, (before, after)
+    visits_done = torch.tensor([float(done)], device=device)
+    if world > 1:
+        dist.all_reduce(visits_done, op=dist.ReduceOp.SUM)
+    visits_done = float(visits_done.item())
     ms_nn = timed(step_device, K)
     s0 = sp.stats()
     ms_select, ms_backup = sp.time_tree_kernels(20)
@@ -279,7 +288,7 @@ def main():
     assert np.isfinite(hpol).all() and np.isfinite(hval).all()
 
     total_games = n * world
-    value = total_games * K / (ms_dev * 1e-3)
+    value = visits_done / (ms_dev * 1e-3)      # playouts actually completed by all ranks / max-over-ranks device time
     e2e_value = total_games * K / (ms_e2e * 1e-3)
     h2d = n * (22 * 361 + 19 + 2) * 4
     d2h = n * (362 + 3 + 6 + 361) * 4
@@ -303,7 +312,7 @@ def main():
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32-split3(fp16 tensor pipe)" if args.fp32 else "f16 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, maxVisits {args.visits}, one playout (visit) per game per step, device-resident loop",
-                       "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(V7 planes 0-6,9-13,18-19 + globals; ladder planes 14-17 pending)",
+                       "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(all 22 V7 planes incl. ladders 14-17 and pass-alive area 18-19, 19 globals)",
                                   "nn_eval", "policy/value postprocess", "backup"],
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
@@ -312,6 +321,11 @@ def main():
                              f"e2e rotates {NBUF} distinct feature batches ({NBUF * n * 22 * 361 * 4 / 1e6:.0f} MB)",
                        "avg_leaf_depth": (after["sum_leaf_depth"] - before["sum_leaf_depth"]) / max(1, after["total_visits"] - before["total_visits"]),
                        "nn_only_ms_per_step": ms_nn / K,
+                       "ladder": {"nodes_per_warp_per_wave": args.ladder_nodes_per_wave,
+                                  "searches": after["ladder_searches"] - before["ladder_searches"],
+                                  "search_moves": after["ladder_nodes"] - before["ladder_nodes"],
+                                  "game_waves_without_leaf": after["stalled_waves"] - before["stalled_waves"],
+                                  "game_waves": n * K},
                        "weight_broadcast_ms": bcast_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
             "gpu_launches": sp.launches_per_step * K,
@@ -326,7 +340,7 @@ def main():
             # (362 x 20 B written), writes the NN row (22*361+19 floats, zero-fill + ones) and the legality mask; the backup reads
             # 362 logits, writes 362 policy floats and updates 2 x 12 B + 2 x 12 B per path node.
             "roofline_tree": (lambda bytes_sel, bytes_bak: {
-                "bound": "hbm", "kernel": "spSelectKernel + spBackupKernel (one warp per game)",
+                "bound": "hbm", "kernel": "spSelectKernel (one 8-warp block per game) + spBackupKernel (one warp per game)",
                 "achieved": (bytes_sel + bytes_bak) * n / ((ms_select + ms_backup) * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (bytes_sel + bytes_bak) * n / ((ms_select + ms_backup) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "ms_select": ms_select, "ms_backup": ms_backup, "avg_depth": tree_depth,

@@ -145,6 +145,10 @@ typedef struct kgb_selfplay_config {
   uint64_t seed;
   int32_t debug_fake_nn;             /* TEST ONLY: replace the evaluator by the deterministic hash net of oracle/ref_driver.cpp */
   int32_t disable_ladder_features;   /* 1 = leave NN input planes 14-17 zero (timing experiments only) */
+  int32_t ladder_nodes_per_wave;     /* > 0: each of a game's 8 ladder-reader warps plays at most this many search moves per wave;
+                                        a game whose searches are unfinished skips the wave (no visit) and resumes in the next.
+                                        0 = run every search to the end inside the wave.  Features are identical either way. */
+  int32_t reserved0;
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -154,6 +158,9 @@ typedef struct kgb_selfplay_stats {
   uint64_t black_wins;
   uint64_t nodes_allocated;
   uint64_t sum_leaf_depth;   /* sum over playouts of the leaf depth */
+  uint64_t ladder_searches;  /* ladder searches run for feature planes 14-17 */
+  uint64_t ladder_nodes;     /* moves played inside those searches */
+  uint64_t stalled_waves;    /* game-waves without a leaf because ladder searches were still running (ladder_nodes_per_wave) */
 } kgb_selfplay_stats;
 
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out);
@@ -169,6 +176,9 @@ KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* 
 /* The NN input row (NHWC [X*Y][22] + 19 globals) the last wave wrote for game g - what NNInputs::fillRowV7 would produce
  * for that leaf (planes listed in DESIGN.md §8; used by the feature parity tests). */
 KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global);
+/* The moves from the root to the leaf the last wave selected for game g (x,y pairs, -1,-1 = pass; at most max_len pairs are
+ * written, *len_out is the full length) and whether that wave delivered a finished leaf (see ladder_nodes_per_wave). */
+KGB_API int kgb_selfplay_get_leaf_path(kgb_selfplay* sp, int game, int32_t* moves_xy, int32_t max_len, int32_t* len_out, int32_t* valid_out);
 /* Play a fixed move list on EVERY game's root (x,y pairs, -1,-1 = pass; colours alternate) and clear the trees. */
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves);
 /* Timing hook for bench.py's tree/board roofline entry: runs `iters` waves of ONLY the select(+board+featurize) and backup

@@ -926,6 +926,15 @@ KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, 
   });
 }
 
+KGB_API int kgb_selfplay_get_leaf_path(kgb_selfplay* sp, int game, int32_t* moves_xy, int32_t max_len, int32_t* len_out, int32_t* valid_out) {
+  return guarded([&] {
+    if(!sp || !moves_xy || !len_out || !valid_out || max_len < 0) throw std::invalid_argument("kgb_selfplay_get_leaf_path: bad argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    *len_out = selfplayReadLeafPath(sp->impl, game, moves_xy, max_len, valid_out);
+  });
+}
+
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves) {
   return guarded([&] {
     if(!sp || (!moves_xy && num_moves > 0) || num_moves < 0) throw std::invalid_argument("kgb_selfplay_play_moves: bad argument");

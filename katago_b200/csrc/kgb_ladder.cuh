@@ -21,25 +21,34 @@
 namespace kgb {
 
 static constexpr int LADDER_MAX_LEVELS = 19 * 19 * 3 / 2 + 3;
-static constexpr int LADDER_MOVEBUF = 4096;
 static constexpr int LADDER_NODE_BUDGET = 25000;
 
-struct LadderScratch {   // per-warp global scratch
-  uint32_t* sB;          // [LADDER_MAX_LEVELS][32]
-  uint32_t* sW;
+// Per-warp global scratch.  The search stack holds, per level, the position before that level's move, the hunted chain and
+// the moves not tried yet - all as lane-distributed masks (one coalesced 128-byte line each), written when the search goes
+// down and read back in one round trip when it comes back up.
+struct LadderScratch {
+  uint32_t *sB, *sW;     // [LADDER_MAX_LEVELS][32]
+  uint32_t* sC;          // [LADDER_MAX_LEVELS][32] the hunted chain at that level
+  uint32_t* sR;          // [LADDER_MAX_LEVELS][32] moves of that level still to try (tried in bitboard order)
   int* sKo;              // [LADDER_MAX_LEVELS]
-  int* listStart;        // [LADDER_MAX_LEVELS]
-  int* listLen;
-  int* listCur;
-  int* moves;            // [LADDER_MOVEBUF]
+  // suspended-work state (a position's searches can be spread over several kernel launches, see boardLaddersResumable)
+  int* st;               // [LADDER_ST_INTS]
+  uint32_t *stB, *stW;   // [32] board of the suspended search
+  uint32_t *accLad, *accWB, *accWW;   // [32] results of this part's finished searches
+  unsigned long long* counters;   // [2] searches, nodes (statistics; may be null)
 };
-__host__ __device__ inline size_t ladderScratchWordsPerWarp() { return (size_t)LADDER_MAX_LEVELS * (64 + 4) + LADDER_MOVEBUF; }
+static constexpr int LADDER_ST_INTS = 16;
+enum { LST_NEXT_ITEM = 0, LST_ACTIVE, LST_LEVEL, LST_NODES, LST_RET, LST_FRESH, LST_KO, LST_PLA_BLACK };
+__host__ __device__ inline size_t ladderScratchWordsPerWarp() { return (size_t)LADDER_MAX_LEVELS * (128 + 1) + LADDER_ST_INTS + 5 * 32; }
 __device__ __forceinline__ LadderScratch ladderScratchAt(uint32_t* base) {
   LadderScratch s;
-  s.sB = base; s.sW = base + (size_t)LADDER_MAX_LEVELS * 32;
-  int* ib = reinterpret_cast<int*>(base + (size_t)LADDER_MAX_LEVELS * 64);
-  s.sKo = ib; s.listStart = ib + LADDER_MAX_LEVELS; s.listLen = ib + 2 * LADDER_MAX_LEVELS; s.listCur = ib + 3 * LADDER_MAX_LEVELS;
-  s.moves = ib + 4 * LADDER_MAX_LEVELS;
+  const size_t L32 = (size_t)LADDER_MAX_LEVELS * 32;
+  s.sB = base; s.sW = base + L32; s.sC = base + 2 * L32; s.sR = base + 3 * L32;
+  s.sKo = reinterpret_cast<int*>(base + 4 * L32);
+  s.st = s.sKo + LADDER_MAX_LEVELS;
+  uint32_t* ub = reinterpret_cast<uint32_t*>(s.st + LADDER_ST_INTS);
+  s.stB = ub; s.stW = ub + 32; s.accLad = ub + 64; s.accWB = ub + 96; s.accWW = ub + 128;
+  s.counters = nullptr;
   return s;
 }
 
@@ -119,44 +128,105 @@ __device__ __forceinline__ int pointLibsAfterPlay(const WarpBoard& bd, int p, bo
   return n < maxv ? n : maxv;
 }
 
+// boardPlay for the search: no capture counters, no hash; `known` is a complete chain of colour knownBlack on bd (the hunted
+// chain, which the search tracks anyway) so that the two flood fills that would walk its whole length start from all of it.
+__device__ __forceinline__ void ladderPlay(WarpBoard& bd, int p, bool black, uint32_t known, bool knownBlack) {
+  const uint32_t rm = bd.rowMask;
+  const uint32_t stone = pointMask(p);
+  uint32_t own = (black ? bd.b : bd.w) | stone;
+  uint32_t opp = black ? bd.w : bd.b;
+  uint32_t adjOpp = nbrs(stone, rm) & opp;
+  int captured = 0, possibleKo = -1;
+  while(true) {
+    const int q = firstPoint(adjOpp);
+    if(q < 0) break;
+    const bool isKnown = knownBlack != black && __any_sync(KGB_FULL, (pointMask(q) & known) != 0);
+    const uint32_t chain = isKnown ? known : flood(pointMask(q), opp, rm);
+    const uint32_t empty = ~(own | opp) & rm;
+    if(!__any_sync(KGB_FULL, (nbrs(chain, rm) & empty) != 0)) {
+      captured += warpCount(chain);
+      opp &= ~chain;
+      possibleKo = q;
+    }
+    adjOpp &= ~chain;
+  }
+  uint32_t seed = stone;
+  if(knownBlack == black && __any_sync(KGB_FULL, (nbrs(stone, rm) & known) != 0)) seed |= known;
+  const uint32_t mine = flood(seed, own, rm);
+  const uint32_t empty = ~(own | opp) & rm;
+  const int myLibs = warpCount(nbrs(mine, rm) & empty);
+  bd.ko = -1;
+  if(captured == 1 && myLibs == 1 && warpCount(mine) == 1) bd.ko = possibleKo;
+  if(myLibs == 0) own &= ~mine;   // suicide
+  if(black) { bd.b = own; bd.w = opp; } else { bd.w = own; bd.b = opp; }
+}
+
 // Board::searchIsLadderCaptured(loc, defenderFirst, buf).  `bd` is a private copy (passed by value).
-__device__ bool ladderSearch(WarpBoard bd, int loc, bool defenderFirst, const LadderScratch& sc, int X, int Y) {
+// Returns 0 / 1, or 2 = suspended: `budget` (moves this call may still play) ran out; the whole search state (board, level,
+// counters; the stack is in `sc` anyway) is saved in `sc` and the same call with resume = true carries on where it stopped.
+__device__ int ladderSearchImpl(WarpBoard bd, int loc, bool defenderFirst, const LadderScratch& sc, int X, int Y, int& nodes, int& budget,
+                                bool resume) {
   const int lane = kgbLane();
   const uint32_t rm = bd.rowMask;
-  const bool plaBlack = __any_sync(KGB_FULL, (pointMask(loc) & bd.b) != 0);
-  {
-    uint32_t chain0 = flood(pointMask(loc), plaBlack ? bd.b : bd.w, rm);
-    int libs0 = chainLibCount(bd, chain0);
-    if(libs0 > 2 || (defenderFirst && libs0 > 1)) return false;
+  nodes = 0;
+  bool plaBlack;
+  int level = 0;
+  bool ret = false;
+  bool fresh = true;        // this level was just entered (its move list is not built yet); false = came back up from level + 1
+  uint32_t chain = 0;       // the hunted chain at the current level (also kept per level in sc.sC)
+  bool chainHint = false;   // `chain` is the parent level's chain and the move from there was just played
+  if(resume) {
+    bd.b = sc.stB[lane]; bd.w = sc.stW[lane]; bd.ko = sc.st[LST_KO];
+    level = sc.st[LST_LEVEL]; nodes = sc.st[LST_NODES]; ret = sc.st[LST_RET] != 0; fresh = sc.st[LST_FRESH] != 0;
+    plaBlack = sc.st[LST_PLA_BLACK] != 0;
   }
-  if(defenderFirst) bd.ko = -1;
+  else {
+    plaBlack = __any_sync(KGB_FULL, (pointMask(loc) & bd.b) != 0);
+    chain = flood(pointMask(loc), plaBlack ? bd.b : bd.w, rm);
+    const int libs0 = chainLibCount(bd, chain);
+    if(libs0 > 2 || (defenderFirst && libs0 > 1)) return 0;
+    if(defenderFirst) bd.ko = -1;
+    chainHint = true;
+  }
   const int stackSize = X * Y * 3 / 2 + 1;
-  int level = 0, nodes = 0;
-  bool ret = false, fromDeeper = false;
-  if(lane == 0) { sc.listCur[0] = -1; sc.listStart[0] = 0; sc.listLen[0] = 0; }
-  __syncwarp();
   while(true) {
-    if(level < 0) return ret;
-    if(level >= stackSize - 1) { ret = true; fromDeeper = true; level--; continue; }
-    if(nodes >= LADDER_NODE_BUDGET) return false;
+    if(level < 0) return ret ? 1 : 0;
+    if(level >= stackSize - 1) { ret = true; fresh = false; level--; continue; }
+    if(nodes >= LADDER_NODE_BUDGET) return 0;
+    if(budget <= 0) {
+      sc.stB[lane] = bd.b; sc.stW[lane] = bd.w;
+      if(lane == 0) {
+        sc.st[LST_KO] = bd.ko; sc.st[LST_LEVEL] = level; sc.st[LST_NODES] = nodes; sc.st[LST_RET] = ret ? 1 : 0;
+        sc.st[LST_FRESH] = fresh ? 1 : 0; sc.st[LST_PLA_BLACK] = plaBlack ? 1 : 0;
+      }
+      __syncwarp();
+      return 2;
+    }
     const bool isDef = (defenderFirst && (level % 2) == 0) || (!defenderFirst && (level % 2) == 1);
-    int cur = sc.listCur[level];
-    if(cur == -1) {
+    uint32_t rem;   // moves of this level not tried yet
+    if(fresh) {
       const uint32_t own = plaBlack ? bd.b : bd.w, opp = plaBlack ? bd.w : bd.b;
-      const uint32_t chain = flood(pointMask(loc), own, rm);
+      // the chain only ever grows along a line of play: start the fill from the parent's chain
+      chain = flood(chainHint ? (chain | pointMask(loc)) : pointMask(loc), own, rm);
+      chainHint = false;
       const uint32_t empty = ~(bd.b | bd.w) & rm;
       const uint32_t L = nbrs(chain, rm) & empty;
       const int libs = warpCount(L);
-      if(!isDef && libs <= 1) { ret = true; fromDeeper = true; level--; continue; }
-      if(!isDef && libs >= 3) { ret = false; fromDeeper = true; level--; continue; }
-      if(isDef && libs >= 2) { ret = false; fromDeeper = true; level--; continue; }
-      if(isDef && bd.ko >= 0) { ret = false; fromDeeper = true; level--; continue; }
-      const int start = sc.listStart[level];
-      int len = 0;
+      if((!isDef && libs <= 1) || (!isDef && libs >= 3) || (isDef && libs >= 2) || (isDef && bd.ko >= 0)) {
+        // attacker to move: 1 liberty = captured, 3 = escaped; defender to move: 2 liberties or a ko left by the attacker = escaped
+        ret = !isDef && libs <= 1;
+        fresh = false; level--; continue;
+      }
       if(isDef) {
-        // capture moves: the liberty of every adjacent opponent chain in atari, then the chain's own liberty
+        // capture moves: the liberty of every adjacent opponent chain in atari, then the chain's own liberty.
+        // Opponent chains holding a stone with two empty neighbours are ruled out for the whole board in one multi-seed fill.
         uint32_t M = 0;
         uint32_t adj = nbrs(chain, rm) & opp;
+        {
+          const uint32_t ea = empty << 1, eb = empty >> 1, ec = rowAbove(empty), ed = rowBelow(empty);
+          const uint32_t atLeast2 = (ea & eb) | (ec & ed) | ((ea | eb) & (ec | ed));
+          if(__any_sync(KGB_FULL, adj != 0)) adj &= ~flood(opp & atLeast2, opp, rm);
+        }
         while(true) {
           int q = firstPoint(adj);
           if(q < 0) break;
@@ -165,14 +235,7 @@ __device__ bool ladderSearch(WarpBoard bd, int loc, bool defenderFirst, const La
           if(warpCount(cl) == 1) M |= cl;
           adj &= ~c;
         }
-        uint32_t all = M | L;
-        while(true) {
-          int q = firstPoint(all);
-          if(q < 0) break;
-          if(lane == 0 && start + len < LADDER_MOVEBUF) sc.moves[start + len] = q;
-          len++;
-          all &= ~pointMask(q);
-        }
+        rem = M | L;
       }
       else {
         const int l0 = firstPoint(L);
@@ -190,58 +253,78 @@ __device__ bool ladderSearch(WarpBoard bd, int loc, bool defenderFirst, const La
               if(chainLibCount(bd, c) == 1) gaining = true;
               adj &= ~c;
             }
-            if(!gaining) { ret = true; fromDeeper = true; level--; continue; }
+            if(!gaining) { ret = true; fresh = false; level--; continue; }
           }
         }
-        int m0 = l0, m1 = l1;
-        len = 2;
+        rem = L;
         const bool adjacent = __any_sync(KGB_FULL, (nbrs(pointMask(l0), rm) & pointMask(l1)) != 0);
         if(!adjacent) {
-          if(imm0 >= 3 && imm1 >= 3) { ret = false; fromDeeper = true; level--; continue; }
-          else if(imm0 >= 3) len = 1;
-          else if(imm1 >= 3) { m0 = l1; len = 1; }
+          if(imm0 >= 3 && imm1 >= 3) { ret = false; fresh = false; level--; continue; }
+          else if(imm0 >= 3) rem = pointMask(l0);
+          else if(imm1 >= 3) rem = pointMask(l1);
         }
-        if(lane == 0 && start + 1 < LADDER_MOVEBUF) { sc.moves[start] = m0; sc.moves[start + 1] = m1; }
       }
-      if(start + len >= LADDER_MOVEBUF) return false;   // scratch exhausted: same as the node budget
-      if(lane == 0) { sc.listLen[level] = len; sc.listCur[level] = 0; }
-      __syncwarp();
-      cur = 0;
     }
     else {
-      if(fromDeeper) {   // undo: restore the position saved before this level's move
-        bd.b = sc.sB[level * 32 + lane]; bd.w = sc.sW[level * 32 + lane]; bd.ko = sc.sKo[level];
-      }
-      if(isDef && !ret) { fromDeeper = true; level--; continue; }
-      if(!isDef && ret) { fromDeeper = true; level--; continue; }
-      cur += 1;
-      if(lane == 0) sc.listCur[level] = cur;
-      __syncwarp();
+      // back from level + 1 with its verdict in `ret`: a refutation found ends this level
+      if((isDef && !ret) || (!isDef && ret)) { level--; continue; }
+      bd.b = sc.sB[level * 32 + lane]; bd.w = sc.sW[level * 32 + lane]; bd.ko = sc.sKo[level];
+      chain = sc.sC[level * 32 + lane]; rem = sc.sR[level * 32 + lane];
     }
-    const int len = sc.listLen[level];
-    if(cur >= len) { ret = isDef; fromDeeper = true; level--; continue; }
-    const int move = sc.moves[sc.listStart[level] + cur];
+    // next legal move of this level (illegal ones - ko, suicide - are skipped)
     const bool moverBlack = isDef ? plaBlack : !plaBlack;
-    if(!pointIsLegalNoSuicide(bd, move, moverBlack)) { ret = isDef; fromDeeper = false; continue; }
-    sc.sB[level * 32 + lane] = bd.b; sc.sW[level * 32 + lane] = bd.w;
+    int move = -1;
+    while(true) {
+      const int q = firstPoint(rem);
+      if(q < 0) break;
+      rem &= ~pointMask(q);
+      if(pointIsLegalNoSuicide(bd, q, moverBlack)) { move = q; break; }
+    }
+    if(move < 0) { ret = isDef; fresh = false; level--; continue; }   // out of moves: the side to move here has failed
+    sc.sB[level * 32 + lane] = bd.b; sc.sW[level * 32 + lane] = bd.w; sc.sC[level * 32 + lane] = chain; sc.sR[level * 32 + lane] = rem;
     if(lane == 0) sc.sKo[level] = bd.ko;
-    boardPlay(bd, move, moverBlack);
+    __syncwarp();   // sKo is written by lane 0 and read by every lane
+    ladderPlay(bd, move, moverBlack, chain, plaBlack);
+    chainHint = true;
     nodes++;
+    budget--;
     level++;
-    if(lane == 0) { sc.listCur[level] = -1; sc.listStart[level] = sc.listStart[level - 1] + sc.listLen[level - 1]; sc.listLen[level] = 0; }
-    __syncwarp();
+    fresh = true;
   }
 }
 
+__device__ __forceinline__ int ladderSearch(const WarpBoard& bd, int loc, bool defenderFirst, const LadderScratch& sc, int X, int Y, int& budget,
+                                            bool resume) {
+  int nodes;
+  const int r = ladderSearchImpl(bd, loc, defenderFirst, sc, X, Y, nodes, budget, resume);
+  if(r != 2 && sc.counters != nullptr && kgbLane() == 0) { atomicAdd(sc.counters, 1ULL); atomicAdd(sc.counters + 1, (unsigned long long)nodes); }
+  return r;
+}
+
 // iterLadders (nninputs.cpp:815-866): laddered = stones of chains with 1 or 2 liberties that are ladder-capturable;
-// working = for 2-liberty chains the attacker's first moves that work (only filled when wantWorking).
-__device__ void boardLadders(const WarpBoard& bd, const LadderScratch& sc, int X, int Y, uint32_t& laddered, uint32_t& workingOfBlackChains,
-                             uint32_t& workingOfWhiteChains) {
+// working = for 2-liberty chains the attacker's first moves that work.
+//   * `candidates` = the stones of chains with exactly 1 or 2 liberties (boardLibertyClasses' lib1 | lib2): only those chains
+//     are walked.
+//   * The searches of one position are independent: `part` of `nparts` takes every nparts-th search (in enumeration order);
+//     the caller ORs the parts' results (sc.accLad / accWB / accWW) together.
+//   * `budget` bounds the moves played in this call.  When it runs out the work is suspended in `sc` and false is returned;
+//     calling again with fresh = false (same board, same part) continues.  The results do not depend on how the work was cut.
+__device__ bool boardLaddersResumable(const WarpBoard& bd, uint32_t candidates, const LadderScratch& sc, int X, int Y, int part, int nparts,
+                                      int& budget, bool fresh) {
+  const int lane = kgbLane();
   const uint32_t rm = bd.rowMask;
   const uint32_t empty = ~(bd.b | bd.w) & rm;
-  laddered = 0; workingOfBlackChains = 0; workingOfWhiteChains = 0;
-  uint32_t todoB = bd.b, todoW = bd.w;
-  while(true) {
+  int nextItem = 0;
+  bool active = false;
+  uint32_t laddered = 0, workB = 0, workW = 0;
+  if(!fresh) {
+    nextItem = sc.st[LST_NEXT_ITEM]; active = sc.st[LST_ACTIVE] != 0;
+    laddered = sc.accLad[lane]; workB = sc.accWB[lane]; workW = sc.accWW[lane];
+  }
+  int item = 0;
+  bool suspended = false;
+  uint32_t todoB = bd.b & candidates, todoW = bd.w & candidates;
+  while(!suspended) {
     int q = firstPoint(todoB);
     const bool isB = q >= 0;
     if(!isB) q = firstPoint(todoW);
@@ -251,26 +334,50 @@ __device__ void boardLadders(const WarpBoard& bd, const LadderScratch& sc, int X
     const uint32_t L = nbrs(chain, rm) & empty;
     const int libs = warpCount(L);
     if(libs == 1) {
-      if(ladderSearch(bd, q, true, sc, X, Y)) laddered |= chain;
+      const int idx = item++;
+      if((idx % nparts) != part || idx < nextItem) continue;
+      const int r = ladderSearch(bd, q, true, sc, X, Y, budget, active && idx == nextItem);
+      active = false;
+      if(r == 2) { nextItem = idx; active = true; suspended = true; }
+      else if(r == 1) laddered |= chain;
     }
     else if(libs == 2) {
       // searchIsLadderCapturedAttackerFirst2Libs (game/board.cpp:1581-1626)
       const int m0 = firstPoint(L), m1 = firstPoint(L & ~pointMask(m0));
-      bool any = false;
-      for(int k = 0; k < 2; k++) {
+      for(int k = 0; k < 2 && !suspended; k++) {
         const int m = k == 0 ? m0 : m1;
-        if(pointIsLegalNoSuicide(bd, m, !isB)) {
+        const int idx = item++;
+        if((idx % nparts) != part || idx < nextItem) continue;
+        const bool resume = active && idx == nextItem;
+        active = false;
+        if(resume || pointIsLegalNoSuicide(bd, m, !isB)) {
           WarpBoard c = bd;
-          boardPlay(c, m, !isB);
-          if(ladderSearch(c, q, true, sc, X, Y)) {
-            any = true;
-            if(isB) workingOfBlackChains |= pointMask(m); else workingOfWhiteChains |= pointMask(m);
+          if(!resume) boardPlay(c, m, !isB);
+          const int r = ladderSearch(c, q, true, sc, X, Y, budget, resume);
+          if(r == 2) { nextItem = idx; active = true; suspended = true; }
+          else if(r == 1) {
+            laddered |= chain;
+            if(isB) workB |= pointMask(m); else workW |= pointMask(m);
           }
         }
       }
-      if(any) laddered |= chain;
     }
   }
+  sc.accLad[lane] = laddered; sc.accWB[lane] = workB; sc.accWW[lane] = workW;
+  if(lane == 0) { sc.st[LST_NEXT_ITEM] = suspended ? nextItem : 0x7fffffff; sc.st[LST_ACTIVE] = (suspended && active) ? 1 : 0; }
+  __syncwarp();
+  return !suspended;
+}
+
+// One-shot form (no budget, no partition).
+__device__ void boardLadders(const WarpBoard& bd, const LadderScratch& sc, int X, int Y, uint32_t& laddered, uint32_t& workingOfBlackChains,
+                             uint32_t& workingOfWhiteChains) {
+  uint32_t l1, l2, l3;
+  boardLibertyClasses(bd, l1, l2, l3);
+  int budget = 0x7fffffff;
+  boardLaddersResumable(bd, l1 | l2, sc, X, Y, 0, 1, budget, true);
+  const int lane = kgbLane();
+  laddered = sc.accLad[lane]; workingOfBlackChains = sc.accWB[lane]; workingOfWhiteChains = sc.accWW[lane];
 }
 
 }  // namespace kgb

@@ -37,6 +37,8 @@
 
 namespace kgb {
 
+static constexpr int SP_LADDER_WARPS = 8;   // warps per game in the select kernel (ladder searches are dealt out to all of them)
+
 struct SPDev {
   // configuration
   int X, Y, XY, policySize, numGames, maxVisits, maxNodes, maxDepth, maxMoves, multiSuicide, earlyMoves;
@@ -49,7 +51,17 @@ struct SPDev {
   int *rootKo, *rootBlackToMove, *rootCapB, *rootCapW, *moveNum, *consecPasses;
   uint32_t *prevB, *prevW;          // [2][game][32]: boards 1 and 2 moves ago (BoardHistory::getRecentBoard), for ladder planes 15/16
   int* prevKo;                      // [2][game]
-  uint32_t* ladderScratch;          // [game][ladderScratchWordsPerWarp()]
+  int* leafNumHist;                 // [game] min(2, moves of history) at the current leaf
+  uint32_t *leafB, *leafW, *leafCand;   // [game][32] leaf board and its 1-2 liberty stones, kept while its ladder searches run
+  int* leafKo;                      // [game]
+  int* ladPending;                  // [game] 1 = the leaf's ladder searches were cut off by ladderNodesPerWave; resume next wave
+  int* leafValid;                   // [game] 1 = this wave produced a finished leaf (features complete) for the evaluator / backup
+  int ladderNodesPerWave;           // per warp; 0 = unlimited
+  unsigned long long* stalledWaves; // game-waves that did not produce a leaf
+  uint32_t* ladderScratch;          // [game][SP_LADDER_WARPS][ladderScratchWordsPerWarp()]
+  uint32_t* prevLad;                // [2][game][32]: laddered stones (plane 14) of those two boards = planes 15/16 at the root
+  uint32_t* nodeLad;                // [game][maxNodes][32]: laddered stones of the node's own board, kept for its descendants
+  unsigned long long* ladderCounters;   // [2] searches, search nodes
   int enableLadders;
   int* hist;                        // [game][5] last moves, most recent first: -1 none, -2 pass, else y*32+x
   uint64_t* gameCounter;            // games started per slot (RNG stream)
@@ -180,6 +192,8 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     d.prevB[G32 + g * 32 + lane] = d.prevB[g * 32 + lane]; d.prevW[G32 + g * 32 + lane] = d.prevW[g * 32 + lane];
     d.prevB[g * 32 + lane] = beforeB; d.prevW[g * 32 + lane] = beforeW;
     if(lane == 0) { d.prevKo[d.numGames + g] = d.prevKo[g]; d.prevKo[g] = beforeKo; }
+    d.prevLad[G32 + g * 32 + lane] = d.prevLad[g * 32 + lane];
+    d.prevLad[g * 32 + lane] = d.nodeLad[gb * 32 + lane];   // the old root was evaluated, so its ladders are known
   }
   d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
   if(lane == 0) {
@@ -194,10 +208,8 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   __syncwarp();
 }
 
-__global__ void spSelectKernel(const SPDev d) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if(g >= d.numGames) return;
+// Warp 0 of a game's block: PUCT descent, leaf board, legality and every feature except the leaf's own ladder searches.
+__device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, uint32_t* shW, uint32_t* shCand, int& shKo, int& shDoLadders) {
   const size_t gb = (size_t)g * d.maxNodes;
   if(d.nodeVisits[gb] >= d.maxVisits) rootAdvance(d, g, lane);
 
@@ -210,8 +222,9 @@ __global__ void spSelectKernel(const SPDev d) {
   int h0 = d.hist[g * 5 + 0], h1 = d.hist[g * 5 + 1], h2 = d.hist[g * 5 + 2], h3 = d.hist[g * 5 + 3], h4 = d.hist[g * 5 + 4];
   // boards one and two moves ago (ladder planes 15/16): the root's recent boards, shifted as the descent plays moves
   const size_t G32 = (size_t)d.numGames * 32;
-  uint32_t p1B = d.prevB[g * 32 + lane], p1W = d.prevW[g * 32 + lane], p2B = d.prevB[G32 + g * 32 + lane], p2W = d.prevW[G32 + g * 32 + lane];
-  int p1Ko = d.prevKo[g], p2Ko = d.prevKo[d.numGames + g];
+  // Their laddered stones were computed when those positions were leaves themselves (a node's board is its child's
+  // previous board), so only the leaf's own board ever needs a ladder search.
+  uint32_t lad1 = d.prevLad[g * 32 + lane], lad2 = d.prevLad[G32 + g * 32 + lane];
   int node = 0, depth = 0;
   bool terminal = false;
   while(true) {
@@ -269,7 +282,7 @@ __global__ void spSelectKernel(const SPDev d) {
     // ---- descend
     const bool isPass = move == d.policySize - 1;
     const int p = isPass ? -1 : pointOfPos(move, d.X);
-    p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
+    lad2 = lad1; lad1 = d.nodeLad[(gb + node) * 32 + lane];
     boardPlay(bd, p, black);
     passes = isPass ? passes + 1 : 0;
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
@@ -322,23 +335,15 @@ __global__ void spSelectKernel(const SPDev d) {
   uint32_t areaB, areaW;
   boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);
   const uint32_t areaOwn = black ? areaB : areaW, areaOpp = black ? areaW : areaB;
-  // planes 14-17: ladders on the current board and on the boards 1 and 2 moves ago (nninputs.cpp:2547-2583)
-  uint32_t lad0 = 0, lad1 = 0, lad2 = 0, work17 = 0;
-  if(d.enableLadders) {
-    const LadderScratch sc = ladderScratchAt(d.ladderScratch + (size_t)g * ladderScratchWordsPerWarp());
-    uint32_t wB, wW;
-    boardLadders(bd, sc, d.X, d.Y, lad0, wB, wW);
-    work17 = black ? wW : wB;   // working moves against the OPPONENT's 2-liberty chains
-    const int numHist = (h0 == -1) ? 0 : (h1 == -1) ? 1 : 2;   // min(2, moves of history included)
-    WarpBoard pb = bd;
-    if(numHist >= 1) { pb.b = p1B; pb.w = p1W; pb.ko = p1Ko; }
-    const bool same1 = !__any_sync(KGB_FULL, pb.b != bd.b || pb.w != bd.w) && pb.ko == bd.ko;
-    if(same1) lad1 = lad0; else boardLadders(pb, sc, d.X, d.Y, lad1, wB, wW);
-    WarpBoard qb = pb;
-    if(numHist >= 2) { qb.b = p2B; qb.w = p2W; qb.ko = p2Ko; }
-    const bool same2 = !__any_sync(KGB_FULL, qb.b != pb.b || qb.w != pb.w) && qb.ko == pb.ko;
-    if(same2) lad2 = lad1; else boardLadders(qb, sc, d.X, d.Y, lad2, wB, wW);
-  }
+  // planes 14-17: ladders on the current board and on the boards 1 and 2 moves ago (nninputs.cpp:2547-2583).  15/16 come
+  // from the ancestors' cached results; 14/17 are searched by the whole block after this function returns.
+  const int numHist = (h0 == -1) ? 0 : (h1 == -1) ? 1 : 2;   // min(2, moves of history included)
+  const bool doLadders = d.enableLadders && !terminal;
+  if(!doLadders || numHist < 1) { lad1 = 0; lad2 = 0; }       // numHist 0: copies of plane 14, written with it
+  else if(numHist < 2) lad2 = lad1;
+  shB[lane] = bd.b; shW[lane] = bd.w; shCand[lane] = lib1 | lib2;
+  d.leafB[g * 32 + lane] = bd.b; d.leafW[g * 32 + lane] = bd.w; d.leafCand[g * 32 + lane] = lib1 | lib2;
+  if(lane == 0) { shKo = bd.ko; d.leafKo[g] = bd.ko; shDoLadders = doLadders ? 1 : 0; d.leafNumHist[g] = numHist; d.leafValid[g] = 1; }
   if(lane < d.Y) {
     for(int x = 0; x < d.X; x++) {
       float* f = row + (size_t)(lane * d.X + x) * 22;
@@ -347,10 +352,8 @@ __global__ void spSelectKernel(const SPDev d) {
       if(own & bit) f[1] = 1.0f; else if(opp & bit) f[2] = 1.0f;
       if(lib1 & bit) f[3] = 1.0f; else if(lib2 & bit) f[4] = 1.0f; else if(lib3 & bit) f[5] = 1.0f;
       if(areaOwn & bit) f[18] = 1.0f; else if(areaOpp & bit) f[19] = 1.0f;
-      if(lad0 & bit) f[14] = 1.0f;
       if(lad1 & bit) f[15] = 1.0f;
       if(lad2 & bit) f[16] = 1.0f;
-      if(work17 & bit) f[17] = 1.0f;
     }
   }
   __syncwarp();
@@ -380,10 +383,80 @@ __global__ void spSelectKernel(const SPDev d) {
   }
 }
 
+
+// One block per game.  Warp 0 walks the tree, plays the moves and writes the features; the ladder searches of the leaf
+// position (independent of each other, and by far the most expensive feature) are dealt out to all SP_LADDER_WARPS warps.
+// With ladderNodesPerWave > 0 every warp stops after that many search moves: a game whose searches are unfinished delivers no
+// leaf this wave (leafValid = 0: the evaluator's row for it is ignored, nothing is backed up) and carries on in the next one,
+// so one deep ladder costs its own game a few waves instead of making all games wait.  Features are identical either way.
+__global__ void __launch_bounds__(SP_LADDER_WARPS * 32) spSelectKernel(const SPDev d) {
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  __shared__ uint32_t shB[32], shW[32], shCand[32];
+  __shared__ int shKo, shDoLadders, shFresh, shUnfinished;
+  if(warp == 0) {
+    if(d.ladPending[g]) {
+      shB[lane] = d.leafB[g * 32 + lane]; shW[lane] = d.leafW[g * 32 + lane]; shCand[lane] = d.leafCand[g * 32 + lane];
+      if(lane == 0) { shKo = d.leafKo[g]; shDoLadders = 1; shFresh = 0; }
+    }
+    else {
+      spSelectWarp0(d, g, lane, shB, shW, shCand, shKo, shDoLadders);
+      if(lane == 0) shFresh = 1;
+    }
+    if(lane == 0) shUnfinished = 0;
+  }
+  __syncthreads();
+  if(!shDoLadders) return;
+  const LadderScratch sc0 = ladderScratchAt(d.ladderScratch + (size_t)g * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
+  {
+    WarpBoard bd;
+    boardInit(bd, d.X, d.Y);
+    bd.b = shB[lane]; bd.w = shW[lane]; bd.ko = shKo;
+    LadderScratch sc = ladderScratchAt(d.ladderScratch + ((size_t)g * SP_LADDER_WARPS + warp) * ladderScratchWordsPerWarp());
+    sc.counters = d.ladderCounters;
+    int budget = d.ladderNodesPerWave > 0 ? d.ladderNodesPerWave : 0x7fffffff;
+    const bool fresh = shFresh != 0;
+    bool done = true;
+    if(fresh || sc.st[LST_NEXT_ITEM] != 0x7fffffff) done = boardLaddersResumable(bd, shCand[lane], sc, d.X, d.Y, warp, SP_LADDER_WARPS, budget, fresh);
+    if(!done && lane == 0) atomicAdd(&shUnfinished, 1);
+  }
+  __syncthreads();
+  if(warp == 0) {
+    if(shUnfinished != 0) {
+      if(lane == 0) { d.ladPending[g] = 1; d.leafValid[g] = 0; atomicAdd(d.stalledWaves, 1ULL); }
+      return;
+    }
+    uint32_t lad0 = 0, wB = 0, wW = 0;
+    for(int w = 0; w < SP_LADDER_WARPS; w++) {
+      const uint32_t* acc = sc0.accLad + (size_t)w * ladderScratchWordsPerWarp();   // accLad, accWB, accWW are consecutive
+      lad0 |= acc[lane]; wB |= acc[32 + lane]; wW |= acc[64 + lane];
+    }
+    const uint32_t work17 = d.leafBlackToMove[g] ? wW : wB;   // working moves against the OPPONENT's 2-liberty chains
+    const int node = d.leafNode[g];
+    d.nodeLad[((size_t)g * d.maxNodes + node) * 32 + lane] = lad0;
+    if(lane == 0) { d.ladPending[g] = 0; d.leafValid[g] = 1; }
+    float* row = d.nnSpatial + (size_t)g * d.XY * 22;
+    const int numHist = d.leafNumHist[g];
+    if(lane < d.Y) {
+      for(int x = 0; x < d.X; x++) {
+        float* f = row + (size_t)(lane * d.X + x) * 22;
+        const uint32_t bit = 1u << x;
+        if(lad0 & bit) {
+          f[14] = 1.0f;
+          if(numHist < 1) { f[15] = 1.0f; f[16] = 1.0f; }   // no earlier board: the reference reuses the current one
+        }
+        if(work17 & bit) f[17] = 1.0f;
+      }
+    }
+  }
+}
+
 __global__ void spBackupKernel(const SPDev d) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
+  if(!d.leafValid[g]) return;   // ladder searches of this game's leaf still running (ladderNodesPerWave)
   const size_t gb = (size_t)g * d.maxNodes;
   const int node = d.leafNode[g];
   const bool terminal = d.leafTerminal[g] != 0;
@@ -512,6 +585,16 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
   }
   d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
   d.prevB[g * 32 + lane] = p1B; d.prevW[g * 32 + lane] = p1W; d.prevB[G32 + g * 32 + lane] = p2B; d.prevW[G32 + g * 32 + lane] = p2W;
+  if(d.enableLadders) {
+    const LadderScratch sc = ladderScratchAt(d.ladderScratch + (size_t)g * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
+    WarpBoard pb = bd;
+    uint32_t l1, l2, wB, wW;
+    pb.b = p1B; pb.w = p1W; pb.ko = p1Ko;
+    boardLadders(pb, sc, d.X, d.Y, l1, wB, wW);
+    pb.b = p2B; pb.w = p2W; pb.ko = p2Ko;
+    boardLadders(pb, sc, d.X, d.Y, l2, wB, wW);
+    d.prevLad[g * 32 + lane] = l1; d.prevLad[G32 + g * 32 + lane] = l2;
+  }
   const size_t gb = (size_t)g * d.maxNodes;
   if(lane == 0) {
     d.prevKo[g] = p1Ko; d.prevKo[d.numGames + g] = p2Ko;
@@ -519,6 +602,7 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = passes; d.moveNum[g] = mv;
     for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
     d.nodeCount[g] = 1; d.nodeVisits[gb] = 0; d.nodeUtilSum[gb] = 0.0; d.nodeTerminal[gb] = 0;
+    d.ladPending[g] = 0; d.leafValid[g] = 0;
   }
   nodeInit(d, gb * d.policySize, lane);
 }
@@ -614,7 +698,12 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.gameCounter = sp->alloc<uint64_t>(G);
   d.prevB = sp->alloc<uint32_t>(2 * G * 32); d.prevW = sp->alloc<uint32_t>(2 * G * 32); d.prevKo = sp->alloc<int>(2 * G);
   d.enableLadders = c.disable_ladder_features ? 0 : 1;
-  d.ladderScratch = sp->alloc<uint32_t>(G * ladderScratchWordsPerWarp());
+  d.ladderScratch = sp->alloc<uint32_t>(G * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
+  d.prevLad = sp->alloc<uint32_t>(2 * G * 32); d.nodeLad = sp->alloc<uint32_t>(G * (size_t)(c.max_visits + 2) * 32);
+  d.leafNumHist = sp->alloc<int>(G);
+  d.leafB = sp->alloc<uint32_t>(G * 32); d.leafW = sp->alloc<uint32_t>(G * 32); d.leafCand = sp->alloc<uint32_t>(G * 32);
+  d.leafKo = sp->alloc<int>(G); d.ladPending = sp->alloc<int>(G); d.leafValid = sp->alloc<int>(G);
+  d.ladderNodesPerWave = c.ladder_nodes_per_wave > 0 ? c.ladder_nodes_per_wave : 0;
   { std::vector<int> kos2(2 * G, -1); SPCK(cudaMemcpy(d.prevKo, kos2.data(), 2 * G * sizeof(int), cudaMemcpyHostToDevice)); }
   d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); d.nodeUtilSum = sp->alloc<double>(G * N);
   d.nodeTerminal = sp->alloc<int8_t>(G * N);
@@ -623,9 +712,9 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.pathLen = sp->alloc<int>(G); d.pathNode = sp->alloc<int>(G * d.maxDepth); d.pathMove = sp->alloc<int>(G * d.maxDepth);
   d.leafNode = sp->alloc<int>(G); d.leafTerminal = sp->alloc<int>(G); d.leafBlackToMove = sp->alloc<int>(G);
   d.leafTerminalUtil = sp->alloc<double>(G); d.leafLegal = sp->alloc<uint32_t>(G * 32);
-  unsigned long long* stats = sp->alloc<unsigned long long>(8);
+  unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
-  d.sumDepth = stats + 5;
+  d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8;
   d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
   d.nnPolicy = nn.policy; d.nnValue = nn.value;
   // initial state: empty boards, black to move, history empty, one unevaluated root node per game
@@ -641,8 +730,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
 void selfplayDestroy(SelfplayImpl* sp) { delete sp; }
 
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s) {
-  int threads = 128, warpsPerBlock = threads / 32;
-  spSelectKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d);
+  spSelectKernel<<<sp->d.numGames, SP_LADDER_WARPS * 32, 0, s>>>(sp->d);
   SPCK(cudaGetLastError());
 }
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s) {
@@ -669,10 +757,26 @@ void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cu
 }
 
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {
-  unsigned long long h[8];
+  unsigned long long h[16];
   SPCK(cudaMemcpy(h, sp->d.totalVisits, sizeof(h), cudaMemcpyDeviceToHost));
   out->total_visits = h[0]; out->total_moves = h[1]; out->games_finished = h[2]; out->black_wins = h[3];
-  out->nodes_allocated = h[4]; out->sum_leaf_depth = h[5];
+  out->nodes_allocated = h[4]; out->sum_leaf_depth = h[5]; out->ladder_searches = h[6]; out->ladder_nodes = h[7];
+  out->stalled_waves = h[8];
+}
+
+int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  int len = 0;
+  SPCK(cudaMemcpy(&len, d.pathLen + g, sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(valid, d.leafValid + g, sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> mv(len > 0 ? len : 1);
+  if(len > 0) SPCK(cudaMemcpy(mv.data(), d.pathMove + (size_t)g * d.maxDepth, len * sizeof(int), cudaMemcpyDeviceToHost));
+  for(int i = 0; i < len && i < maxLen; i++) {
+    const bool pass = mv[i] == d.policySize - 1;
+    movesXY[2 * i] = pass ? -1 : mv[i] % d.X; movesXY[2 * i + 1] = pass ? -1 : mv[i] / d.X;
+  }
+  return len;
 }
 
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info) {

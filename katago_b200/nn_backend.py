@@ -43,12 +43,13 @@ class SelfplayConfig(C.Structure):
         ("cpuct_exploration", C.c_double), ("cpuct_exploration_log", C.c_double), ("cpuct_exploration_base", C.c_double),
         ("fpu_reduction_max", C.c_double), ("root_fpu_reduction_max", C.c_double), ("win_loss_utility_factor", C.c_double),
         ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64), ("debug_fake_nn", C.c_int32), ("disable_ladder_features", C.c_int32),
+        ("ladder_nodes_per_wave", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
 class SelfplayStats(C.Structure):
     _fields_ = [("total_visits", C.c_uint64), ("total_moves", C.c_uint64), ("games_finished", C.c_uint64), ("black_wins", C.c_uint64),
-                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64)]
+                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64), ("ladder_searches", C.c_uint64), ("ladder_nodes", C.c_uint64), ("stalled_waves", C.c_uint64)]
 
 
 # Every symbol include/kgb200.h declares (tests/test_abi.py checks the library exports all of them).
@@ -58,7 +59,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path",
 ]
 
 _lib = None
@@ -113,6 +114,7 @@ def load_library():
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
+    lib.kgb_selfplay_get_leaf_path.argtypes = [P, I, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
     _lib = lib
     return lib
@@ -329,12 +331,13 @@ class SelfPlay:
                  multi_stone_suicide_legal: bool = True, early_temperature_moves: int = 30, cpuct_exploration: float = 1.0,
                  cpuct_exploration_log: float = 0.45, cpuct_exploration_base: float = 500.0, fpu_reduction_max: float = 0.2,
                  root_fpu_reduction_max: float = 0.1, win_loss_utility_factor: float = 1.0, no_result_utility_for_white: float = 0.0,
-                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False):
+                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False, ladder_nodes_per_wave: int = 0):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
                                   cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
-                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features))
+                                  root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features),
+                                  int(ladder_nodes_per_wave), 0)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
@@ -352,6 +355,12 @@ class SelfPlay:
         sp = np.zeros((self.x * self.y, 22), np.float32); gl = np.zeros(19, np.float32)
         _check(load_library().kgb_selfplay_get_nn_row(self._p, g, sp.ctypes.data, gl.ctypes.data))
         return sp, gl
+
+    def leaf_path(self, g: int, max_len: int = 512):
+        """(moves, valid): the (x, y) / None moves from the root to game g's leaf of the last wave; valid = that wave delivered it."""
+        mv = np.zeros((max_len, 2), np.int32); n = C.c_int32(0); v = C.c_int32(0)
+        _check(load_library().kgb_selfplay_get_leaf_path(self._p, g, mv.ctypes.data, max_len, C.byref(n), C.byref(v)))
+        return [None if m[0] < 0 else (int(m[0]), int(m[1])) for m in mv[:min(n.value, max_len)]], bool(v.value)
 
     def stats(self) -> dict:
         s = SelfplayStats()
