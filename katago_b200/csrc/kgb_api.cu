@@ -763,6 +763,7 @@ struct SingleConv {
   void setInput(const float* input /* NHWC */) {
     float* dIn = h.dalloc<float>((size_t)n * X * Y * cin);
     CK(cudaMemcpy(dIn, input, (size_t)n * X * Y * cin * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());   // see below: the pack kernel runs on a non-blocking stream
     Builder b(h);
     CK(launchPackInput(dIn, n, cin, true, nullptr, h.L, A, cw.cin_p, h.split, h.dMask, h.dMaskSum, h.stream));
     CK(cudaStreamSynchronize(h.stream));
@@ -772,6 +773,9 @@ struct SingleConv {
       for(int y = 0; y < Y; y++)
         for(int x = 0; x < X; x++) hm[(size_t)i * h.L.P + (size_t)(y + pad) * h.L.Wp + x] = 1.0f;
     CK(cudaMemcpy(h.dMask, hm.data(), M * sizeof(float), cudaMemcpyHostToDevice));
+    // cudaMemcpy from pageable memory may return before the DMA has landed, and h.stream is non-blocking:
+    // nothing else orders these uploads before the kernels launched on it.
+    CK(cudaDeviceSynchronize());
   }
   void run() { h.ops.back()(n, h.stream); }
 };

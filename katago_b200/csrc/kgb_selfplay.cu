@@ -724,6 +724,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   SPCK(cudaMemcpy(d.hist, minus.data(), G * 5 * sizeof(int), cudaMemcpyHostToDevice));
   SPCK(cudaMemcpy(d.rootKo, kos.data(), G * sizeof(int), cudaMemcpyHostToDevice));
   SPCK(cudaMemset(d.childNode, 0xff, G * N * PS * sizeof(int)));
+  SPCK(cudaDeviceSynchronize());   // the uploads above are not ordered against the (non-blocking) stream the loop runs on
   return sp.release();
 }
 
