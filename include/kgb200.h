@@ -149,6 +149,13 @@ typedef struct kgb_selfplay_config {
                                         a game whose searches are unfinished skips the wave (no visit) and resumes in the next.
                                         0 = run every search to the end inside the wave.  Features are identical either way. */
   int32_t reserved0;
+  /* Score utility (Search::getScoreUtility, searchhelpers.cpp:272-279; selfplay8mainb18.cfg: 0.05, 0.30, 0.25, 0.50).
+   * Both factors 0 = win/loss utility only. */
+  double static_score_utility_factor;
+  double dynamic_score_utility_factor;
+  double dynamic_score_center_zero_weight;
+  double dynamic_score_center_scale;
+  double draw_equivalent_wins_for_white;   /* 0.5 in every stock config; used for integer komi results */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -163,6 +170,10 @@ typedef struct kgb_selfplay_stats {
   uint64_t stalled_waves;    /* game-waves without a leaf because ladder searches were still running (ladder_nodes_per_wave) */
 } kgb_selfplay_stats;
 
+/* ScoreValue::expectedWhiteScoreValue (neuralnet/nninputs.cpp:160-192) on the host, with the table the device loop uploads:
+ * n independent lookups.  Test hook for the score-utility table. */
+KGB_API int kgb_expected_white_score_value(int n, const double* mean, const double* stdev, const double* center, const double* scale,
+                                           const double* sqrt_board_area, double* out);
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out);
 KGB_API void kgb_selfplay_free(kgb_selfplay* sp);
 /* Enqueue `steps` playout waves on the handle's stream (asynchronous; kgb_handle_sync() to wait). */

@@ -8,16 +8,16 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 mkdir -p ../_build
 for f in kgb_conv_tc.cu kgb_conv_tc2.cu kgb_kernels.cu kgb_api.cu kgb_selfplay.cu; do
   o=../_build/${f%.cu}.o
-  if [ ! -f $o ] || [ $f -nt $o ] || [ kgb_conv.cuh -nt $o ] || [ kgb_conv_tc_common.cuh -nt $o ] || [ kgb_kernels.cuh -nt $o ] || [ kgb_model.h -nt $o ] || [ kgb_board.cuh -nt $o ] || [ kgb_selfplay.h -nt $o ] || [ kgb_rand.h -nt $o ] || [ ../../include/kgb200.h -nt $o ]; then
+  if [ ! -f $o ] || [ $f -nt $o ] || [ kgb_conv.cuh -nt $o ] || [ kgb_conv_tc_common.cuh -nt $o ] || [ kgb_kernels.cuh -nt $o ] || [ kgb_model.h -nt $o ] || [ kgb_board.cuh -nt $o ] || [ kgb_ladder.cuh -nt $o ] || [ kgb_scorevalue.h -nt $o ] || [ kgb_selfplay.h -nt $o ] || [ kgb_rand.h -nt $o ] || [ ../../include/kgb200.h -nt $o ]; then
     $NVCC $FLAGS ${EXTRA_NVCC_FLAGS} -c $f -o $o &
   fi
 done
-for f in kgb_model.cpp kgb_rand.cpp; do
+for f in kgb_model.cpp kgb_rand.cpp kgb_scorevalue.cpp; do
   o=../_build/${f%.cpp}.o
-  if [ ! -f $o ] || [ $f -nt $o ] || [ kgb_model.h -nt $o ] || [ kgb_rand.h -nt $o ]; then
+  if [ ! -f $o ] || [ $f -nt $o ] || [ kgb_model.h -nt $o ] || [ kgb_rand.h -nt $o ] || [ kgb_scorevalue.h -nt $o ]; then
     g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -c $f -o $o &
   fi
 done
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o -lz -cudart shared
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o ../_build/kgb_scorevalue.o -lz -cudart shared
 echo "built $(readlink -f $OUT)"

@@ -26,6 +26,7 @@
 #include "kgb_kernels.cuh"
 #include "kgb_model.h"
 #include "kgb_selfplay.h"
+#include "kgb_scorevalue.h"
 #include "kgb_rand.h"
 
 using namespace kgb;
@@ -839,9 +840,18 @@ struct kgb_selfplay {
 
 static void selfplayStepLaunches(kgb_selfplay* sp, cudaStream_t s) {
   selfplayLaunchSelect(sp->impl, s);
-  if(sp->fakeNN) selfplayLaunchFakeNN(sp->impl, sp->h->dPolicy, sp->h->dValue, s);
+  if(sp->fakeNN) selfplayLaunchFakeNN(sp->impl, sp->h->dPolicy, sp->h->dValue, sp->h->dScore, s);
   else for(auto& op : sp->h->ops) op(sp->n, s);
   selfplayLaunchBackup(sp->impl, s);
+}
+
+KGB_API int kgb_expected_white_score_value(int n, const double* mean, const double* stdev, const double* center, const double* scale,
+                                           const double* sqrt_board_area, double* out) {
+  return guarded([&] {
+    if(n < 0 || !mean || !stdev || !center || !scale || !sqrt_board_area || !out) throw std::invalid_argument("kgb_expected_white_score_value: bad argument");
+    static const std::vector<double> table = makeExpectedSVTable();
+    for(int i = 0; i < n; i++) out[i] = svExpectedWhiteScoreValue(table.data(), mean[i], stdev[i], center[i], scale[i], sqrt_board_area[i]);
+  });
 }
 
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out) {
@@ -856,7 +866,8 @@ KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* c
     sp->h = handle;
     sp->n = config->num_games;
     sp->fakeNN = config->debug_fake_nn != 0;
-    SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue};
+    SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue, handle->dScore,
+                         (double)handle->model->scoreMeanMultiplier, (double)handle->model->scoreStdevMultiplier};
     sp->impl = selfplayCreate(*config, handle->L.X, handle->L.Y, nn, handle->stream);
     *out = sp.release();
   });

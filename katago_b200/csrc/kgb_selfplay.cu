@@ -32,6 +32,7 @@
 #include "../../include/kgb200.h"
 #include "kgb_board.cuh"
 #include "kgb_ladder.cuh"
+#include "kgb_scorevalue.h"
 #include "kgb_selfplay.h"
 #include "kgb_rand.h"
 
@@ -45,6 +46,13 @@ struct SPDev {
   float komi;
   double cpuctExploration, cpuctExplorationLog, cpuctExplorationBase, fpuReductionMax, rootFpuReductionMax;
   double winLossUtilityFactor, noResultUtilityForWhite;
+  // score utility (searchhelpers.cpp:272-279): static * SV(mean, stdev; 0, 2) + dynamic * SV(mean, stdev; recentScoreCenter, scale)
+  double staticScoreUtilityFactor, dynamicScoreUtilityFactor, dynamicScoreCenterZeroWeight, dynamicScoreCenterScale, drawEquivalentWinsForWhite;
+  double scoreMeanMultiplier, scoreStdevMultiplier;   // ModelPostProcessParams of the net
+  const double* svTable;            // ScoreValue's expectedSVTable [842][421]
+  double* recentScoreCenter;        // [game] Search::recentScoreCenter of the current root
+  float* leafTerminalScore;         // [game] finalWhiteMinusBlackScore of a terminal leaf
+  const float* nnScore;             // [game][6] raw score head (whiteScoreMean, stdev pre-softplus, lead, ...)
   uint64_t seed;
   // root state [game]
   uint32_t *rootB, *rootW;          // [game][32]
@@ -321,8 +329,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   if(terminal) {
     int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
     float whiteScore = d.komi - (float)diff;
-    double u = whiteScore > 0 ? d.winLossUtilityFactor : whiteScore < 0 ? -d.winLossUtilityFactor : 0.0;
-    if(lane == 0) d.leafTerminalUtil[g] = u;
+    if(lane == 0) d.leafTerminalScore[g] = whiteScore;
   }
   // NN input row (NHWC [pos][22]) - zero fill, then the ones
   float* row = d.nnSpatial + (size_t)g * d.XY * 22;
@@ -460,8 +467,32 @@ __global__ void spBackupKernel(const SPDev d) {
   const size_t gb = (size_t)g * d.maxNodes;
   const int node = d.leafNode[g];
   const bool terminal = d.leafTerminal[g] != 0;
+  const double sqrtBoardArea = sqrt((double)d.XY);
+  // Search::getScoreUtility (searchhelpers.cpp:272-279)
+  auto scoreUtility = [&](double scoreMean, double scoreMeanSq, double center) -> double {
+    const double stdev = svScoreStdev(scoreMean, scoreMeanSq);
+    double r = 0.0;
+    if(d.staticScoreUtilityFactor != 0.0) r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, 0.0, 2.0, sqrtBoardArea) * d.staticScoreUtilityFactor;
+    if(d.dynamicScoreUtilityFactor != 0.0)
+      r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, center, d.dynamicScoreCenterScale, sqrtBoardArea) * d.dynamicScoreUtilityFactor;
+    return r;
+  };
   double u;
-  if(terminal) u = d.leafTerminalUtil[g];
+  if(terminal) {
+    // search.cpp:1213-1222: the game result as a leaf value (area scoring: no "no result")
+    const double score = (double)d.leafTerminalScore[g];
+    const double whiteWins = score > 0 ? 1.0 : score < 0 ? 0.0 : d.drawEquivalentWinsForWhite;       // ScoreValue::whiteWinsOfWinner
+    const double winLoss = 2.0 * whiteWins - 1.0;
+    const bool integral = score == floor(score);
+    // BoardHistory::whiteKomiAdjustmentForDraws folds the draw value into integer results; whiteScoreMeanSqOfScoreGridded
+    const double scoreMean = score + (integral ? (double)(float)(d.drawEquivalentWinsForWhite - 0.5) : 0.0);
+    double scoreMeanSq = score * score;
+    if(integral) {
+      const double lo = (score - 0.5) * (score - 0.5), hi = (score + 0.5) * (score + 0.5);
+      scoreMeanSq = lo + (hi - lo) * d.drawEquivalentWinsForWhite;
+    }
+    u = winLoss * d.winLossUtilityFactor + scoreUtility(scoreMean, scoreMeanSq, d.recentScoreCenter[g]);
+  }
   else {
     // ---- policy: legality mask + softmax (nneval.cpp:960-1051)
     const float* logits = d.nnPolicy + (size_t)g * d.policySize;
@@ -507,6 +538,29 @@ __global__ void spBackupKernel(const SPDev d) {
     const float wf = (float)w, lf = (float)l, nf = (float)n;
     const double whiteWin = black ? (double)lf : (double)wf, whiteLoss = black ? (double)wf : (double)lf;
     u = (whiteWin - whiteLoss) * d.winLossUtilityFactor + (double)nf * d.noResultUtilityForWhite;
+    if(d.staticScoreUtilityFactor != 0.0 || d.dynamicScoreUtilityFactor != 0.0) {
+      // score head (nneval.cpp:1150-1160, 1200-1215): mean * 20, softplus(stdev) * 20, both scaled by P(result), stored as float
+      const float* sc = d.nnScore + (size_t)g * 6;
+      double scoreMean = (double)sc[0] * d.scoreMeanMultiplier;
+      const double pre = (double)sc[1];
+      const double stdev = (pre > 40.0 ? pre : log(1.0 + exp(pre))) * d.scoreStdevMultiplier;
+      double scoreMeanSq = scoreMean * scoreMean + stdev * stdev;
+      scoreMean = scoreMean * (1.0 - n);
+      scoreMeanSq = scoreMeanSq * (1.0 - n);
+      const double whiteScoreMean = black ? (double)(-(float)scoreMean) : (double)(float)scoreMean;
+      const double whiteScoreMeanSq = (double)(float)scoreMeanSq;
+      if(node == 0 && d.nodeVisits[gb] == 0) {
+        // fresh root: Search::beginSearch centres the dynamic score utility on the root's expected score (search.cpp:1125-1154)
+        double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
+        const double cap = sqrtBoardArea * d.dynamicScoreCenterScale;
+        if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
+        if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
+        __syncwarp();
+        if(lane == 0) d.recentScoreCenter[g] = c;
+        __syncwarp();
+      }
+      u += scoreUtility(whiteScoreMean, whiteScoreMeanSq, d.recentScoreCenter[g]);
+    }
   }
   __syncwarp();
   // ---- backup (one lane: a handful of scattered read-modify-writes along the path)
@@ -530,7 +584,7 @@ __global__ void spBackupKernel(const SPDev d) {
 // TEST SUPPORT: deterministic fake net (identical to the one oracle/ref_driver.cpp gives the reference Search, so tree
 // parity can be checked against the reference without any real net) and root-position setup.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut) {
+__global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut, float* scoreOut) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
@@ -553,6 +607,10 @@ __global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut)
     valueOut[g * 3 + 0] = (float)(uint32_t)(splitmix64(h ^ 0x1111ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
     valueOut[g * 3 + 1] = (float)(uint32_t)(splitmix64(h ^ 0x2222ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
     valueOut[g * 3 + 2] = -30.0f;
+    scoreOut[g * 6 + 0] = (float)(uint32_t)(splitmix64(h ^ 0x3333ULL) >> 48) * (1.0f / 32768.0f) - 1.0f;
+    scoreOut[g * 6 + 1] = (float)(uint32_t)(splitmix64(h ^ 0x4444ULL) >> 48) * (1.0f / 16384.0f) - 2.0f;
+    scoreOut[g * 6 + 2] = (float)(uint32_t)(splitmix64(h ^ 0x5555ULL) >> 48) * (1.0f / 32768.0f) - 1.0f;
+    scoreOut[g * 6 + 3] = 0.0f; scoreOut[g * 6 + 4] = 0.0f; scoreOut[g * 6 + 5] = 0.0f;
   }
 }
 
@@ -690,6 +748,11 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.cpuctExploration = c.cpuct_exploration; d.cpuctExplorationLog = c.cpuct_exploration_log; d.cpuctExplorationBase = c.cpuct_exploration_base;
   d.fpuReductionMax = c.fpu_reduction_max; d.rootFpuReductionMax = c.root_fpu_reduction_max;
   d.winLossUtilityFactor = c.win_loss_utility_factor; d.noResultUtilityForWhite = c.no_result_utility_for_white;
+  d.staticScoreUtilityFactor = c.static_score_utility_factor; d.dynamicScoreUtilityFactor = c.dynamic_score_utility_factor;
+  d.dynamicScoreCenterZeroWeight = c.dynamic_score_center_zero_weight; d.dynamicScoreCenterScale = c.dynamic_score_center_scale;
+  d.drawEquivalentWinsForWhite = c.draw_equivalent_wins_for_white;
+  if(d.dynamicScoreUtilityFactor != 0.0 && !(d.dynamicScoreCenterScale > 0.0)) throw std::invalid_argument("selfplay: dynamic_score_center_scale must be > 0");
+  d.scoreMeanMultiplier = nn.scoreMeanMultiplier; d.scoreStdevMultiplier = nn.scoreStdevMultiplier;
   d.seed = c.seed;
   const size_t G = d.numGames, N = d.maxNodes, PS = d.policySize;
   d.rootB = sp->alloc<uint32_t>(G * 32); d.rootW = sp->alloc<uint32_t>(G * 32);
@@ -716,7 +779,14 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
   d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8;
   d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
-  d.nnPolicy = nn.policy; d.nnValue = nn.value;
+  d.nnPolicy = nn.policy; d.nnValue = nn.value; d.nnScore = nn.score;
+  {
+    const std::vector<double> table = makeExpectedSVTable();
+    double* dt = sp->alloc<double>(table.size());
+    SPCK(cudaMemcpy(dt, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.svTable = dt;
+  }
+  d.recentScoreCenter = sp->alloc<double>(G); d.leafTerminalScore = sp->alloc<float>(G);
   // initial state: empty boards, black to move, history empty, one unevaluated root node per game
   std::vector<int> ones(G, 1), minus(G * 5, -1), kos(G, -1);
   SPCK(cudaMemcpy(d.rootBlackToMove, ones.data(), G * sizeof(int), cudaMemcpyHostToDevice));
@@ -740,9 +810,9 @@ void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s) {
   SPCK(cudaGetLastError());
 }
 
-void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, cudaStream_t s) {
+void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, cudaStream_t s) {
   int threads = 128, warpsPerBlock = threads / 32;
-  spFakeNNKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, policyOut, valueOut);
+  spFakeNNKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, policyOut, valueOut, scoreOut);
   SPCK(cudaGetLastError());
 }
 

@@ -13,14 +13,15 @@ struct SelfplayImpl;
 
 struct SelfplayNNBuffers {  // device buffers of the evaluator handle the loop writes to / reads from
   float* spatial; float* global; float* optimism; int* symmetry;
-  const float* policy; const float* value;
+  const float* policy; const float* value; const float* score;
+  double scoreMeanMultiplier, scoreStdevMultiplier;   // ModelPostProcessParams (desc.h) of the loaded net
 };
 
 SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const SelfplayNNBuffers& nn, cudaStream_t stream);
 void selfplayDestroy(SelfplayImpl* sp);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
-void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, cudaStream_t s);
+void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, cudaStream_t s);
 void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);

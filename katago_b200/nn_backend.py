@@ -44,6 +44,9 @@ class SelfplayConfig(C.Structure):
         ("fpu_reduction_max", C.c_double), ("root_fpu_reduction_max", C.c_double), ("win_loss_utility_factor", C.c_double),
         ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64), ("debug_fake_nn", C.c_int32), ("disable_ladder_features", C.c_int32),
         ("ladder_nodes_per_wave", C.c_int32), ("reserved0", C.c_int32),
+        ("static_score_utility_factor", C.c_double), ("dynamic_score_utility_factor", C.c_double),
+        ("dynamic_score_center_zero_weight", C.c_double), ("dynamic_score_center_scale", C.c_double),
+        ("draw_equivalent_wins_for_white", C.c_double),
     ]
 
 
@@ -59,7 +62,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value",
 ]
 
 _lib = None
@@ -114,6 +117,7 @@ def load_library():
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
+    lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
     lib.kgb_selfplay_get_leaf_path.argtypes = [P, I, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
     _lib = lib
@@ -307,6 +311,14 @@ def zobrist_tables(x_size: int, y_size: int):
     return bh, sh
 
 
+def expected_white_score_value(mean, stdev, center, scale, sqrt_board_area):
+    """ScoreValue::expectedWhiteScoreValue for arrays of arguments (host-side lookup in the table the device loop uses)."""
+    a = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, np.float64), np.shape(mean))) for v in (mean, stdev, center, scale, sqrt_board_area)]
+    out = np.zeros(a[0].shape, np.float64)
+    _check(load_library().kgb_expected_white_score_value(out.size, *[v.ctypes.data for v in a], out.ctypes.data))
+    return out
+
+
 def board_replay(x_size: int, y_size: int, moves, multi_stone_suicide_legal: bool):
     """kgb_test_board_replay: moves int8 [boards, m, 3] = (x, y, pla) with (-1,-1) = pass, pla 1 black / 2 white.
     Returns dict(colors [b,m,Y,X], ko [b,m,2], caps [b,m,2], lib_class [b,m,Y,X], legal_next [b,m,Y,X])."""
@@ -331,13 +343,17 @@ class SelfPlay:
                  multi_stone_suicide_legal: bool = True, early_temperature_moves: int = 30, cpuct_exploration: float = 1.0,
                  cpuct_exploration_log: float = 0.45, cpuct_exploration_base: float = 500.0, fpu_reduction_max: float = 0.2,
                  root_fpu_reduction_max: float = 0.1, win_loss_utility_factor: float = 1.0, no_result_utility_for_white: float = 0.0,
-                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False, ladder_nodes_per_wave: int = 0):
+                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False, ladder_nodes_per_wave: int = 0,
+                 static_score_utility_factor: float = 0.0, dynamic_score_utility_factor: float = 0.0,
+                 dynamic_score_center_zero_weight: float = 0.0, dynamic_score_center_scale: float = 1.0,
+                 draw_equivalent_wins_for_white: float = 0.5):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
                                   cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
                                   root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features),
-                                  int(ladder_nodes_per_wave), 0)
+                                  int(ladder_nodes_per_wave), 0, static_score_utility_factor, dynamic_score_utility_factor,
+                                  dynamic_score_center_zero_weight, dynamic_score_center_scale, draw_equivalent_wins_for_white)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen

@@ -2,7 +2,7 @@
 // dumps golden fixtures / answers parity queries straight from the reference's own classes.  Never shipped or timed as
 // product.  Built by oracle/Makefile.drivers into oracle/_ref/kgref_driver.
 //
-//   kgref_driver searchfake MODELFILE X Y MAXVISITS "x,y x,y pass ..."
+//   kgref_driver searchfake MODELFILE X Y MAXVISITS "x,y x,y pass ..." [STATIC DYNAMIC ZEROWEIGHT SCALE]
 //       reference Search (search/search.cpp) with the deterministic hash-based fake net defined below as its NeuralNet
 //       backend (this file IS the backend TU of the driver); prints the root children's visit counts.  The device loop
 //       has the same fake net (kgb_selfplay_config.debug_fake_nn) so tree parity is tested without any real net.
@@ -166,7 +166,11 @@ void NeuralNet::getOutput(ComputeHandle* h, InputBuffers*, int n, NNResultBuf** 
     o->whiteWinProb = (float)(uint32_t)(splitmix64(hsh ^ 0x1111ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
     o->whiteLossProb = (float)(uint32_t)(splitmix64(hsh ^ 0x2222ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
     o->whiteNoResultProb = -30.0f;
-    o->whiteScoreMean = 0; o->whiteScoreMeanSq = 0; o->whiteLead = 0; o->varTimeLeft = 0; o->shorttermWinlossError = 0; o->shorttermScoreError = 0;
+    // raw score head: mean in [-1,1) (x scoreMeanMultiplier 20 = +-20 points), stdev pre-softplus in [-2,2), lead like mean
+    o->whiteScoreMean = (float)(uint32_t)(splitmix64(hsh ^ 0x3333ULL) >> 48) * (1.0f / 32768.0f) - 1.0f;
+    o->whiteScoreMeanSq = (float)(uint32_t)(splitmix64(hsh ^ 0x4444ULL) >> 48) * (1.0f / 16384.0f) - 2.0f;
+    o->whiteLead = (float)(uint32_t)(splitmix64(hsh ^ 0x5555ULL) >> 48) * (1.0f / 32768.0f) - 1.0f;
+    o->varTimeLeft = 0; o->shorttermWinlossError = 0; o->shorttermScoreError = 0;
     if(o->whiteOwnerMap != NULL) std::fill(o->whiteOwnerMap, o->whiteOwnerMap + xy, 0.0f);
   }
 }
@@ -176,7 +180,7 @@ bool NeuralNet::testEvaluateResidualBlock(const ResidualBlockDesc*, int, int, in
 bool NeuralNet::testEvaluateGlobalPoolingResidualBlock(const GlobalPoolingResidualBlockDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
 
 static int cmdSearchFake(int argc, char** argv) {
-  if(argc != 7) { cerr << "usage: searchfake MODELFILE X Y MAXVISITS MOVES" << endl; return 1; }
+  if(argc != 7 && argc != 11) { cerr << "usage: searchfake MODELFILE X Y MAXVISITS MOVES [STATICSCOREUTIL DYNAMICSCOREUTIL CENTERZEROWEIGHT CENTERSCALE]" << endl; return 1; }
   string modelFile = argv[2];
   int X = atoi(argv[3]), Y = atoi(argv[4]), maxVisits = atoi(argv[5]);
   Board::initHash();
@@ -193,6 +197,10 @@ static int cmdSearchFake(int argc, char** argv) {
   params.cpuctExploration = 1.0; params.cpuctExplorationLog = 0.45; params.cpuctExplorationBase = 500;
   params.fpuReductionMax = 0.2; params.rootFpuReductionMax = 0.1;
   params.staticScoreUtilityFactor = 0.0; params.dynamicScoreUtilityFactor = 0.0;
+  if(argc == 11) {   // score utility (searchhelpers.cpp:272-279), e.g. selfplay8mainb18.cfg: 0.05 0.30 0.25 0.50
+    params.staticScoreUtilityFactor = atof(argv[7]); params.dynamicScoreUtilityFactor = atof(argv[8]);
+    params.dynamicScoreCenterZeroWeight = atof(argv[9]); params.dynamicScoreCenterScale = atof(argv[10]);
+  }
   params.valueWeightExponent = 0.0;
   params.rootNoiseEnabled = false;
   Rules rules;  // defaults, then the rule subset of the loop
@@ -221,6 +229,7 @@ static int cmdSearchFake(int argc, char** argv) {
   SearchNodeState st = (SearchNodeState)root->state.load();
   ConstSearchNodeChildrenReference children = root->getChildren(st);
   cout << "rootvisits " << root->stats.visits.load() << " utilityAvg " << Global::strprintf("%.17g", root->stats.utilityAvg.load()) << endl;
+  cout << "recentScoreCenter " << Global::strprintf("%.17g", search->recentScoreCenter) << endl;
   for(int i = 0; i < children.getCapacity(); i++) {
     const SearchChildPointer& cp = children[i];
     const SearchNode* child = cp.getIfAllocated();
@@ -235,6 +244,27 @@ static int cmdSearchFake(int argc, char** argv) {
   cout << endl;
   delete search;
   delete nnEval;
+  return 0;
+}
+
+// svsamples N SEED: N pseudo-random argument tuples and ScoreValue::expectedWhiteScoreValue of each (text, %.17g)
+static int cmdSVSamples(int argc, char** argv) {
+  if(argc != 4) { cerr << "usage: svsamples N SEED" << endl; return 1; }
+  int n = atoi(argv[2]);
+  Lcg rng(strtoull(argv[3], NULL, 10));
+  ScoreValue::initTables();
+  auto unit = [&]() { return (double)rng.next() / 2147483648.0; };
+  for(int i = 0; i < n; i++) {
+    static const double areas[4] = {19.0, 9.0, 13.0, 9.539392014169456};
+    double sqrtArea = areas[rng.next() % 4];
+    double mean = (unit() - 0.5) * (i % 7 == 0 ? 1200.0 : 80.0);
+    double stdev = unit() * (i % 5 == 0 ? 600.0 : 30.0);
+    if(i % 11 == 0) stdev = 0.0;
+    double center = (i % 3 == 0) ? 0.0 : (unit() - 0.5) * 40.0;
+    double scale = (i % 3 == 0) ? 2.0 : 0.25 + unit();
+    double v = ScoreValue::expectedWhiteScoreValue(mean, stdev, center, scale, sqrtArea);
+    cout << Global::strprintf("%.17g %.17g %.17g %.17g %.17g %.17g", mean, stdev, center, scale, sqrtArea, v) << endl;
+  }
   return 0;
 }
 
@@ -311,6 +341,7 @@ int main(int argc, char** argv) {
   string cmd = argv[1];
   if(cmd == "boardstream") return cmdBoardStream(argc, argv);
   if(cmd == "searchfake") return cmdSearchFake(argc, argv);
+  if(cmd == "svsamples") return cmdSVSamples(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

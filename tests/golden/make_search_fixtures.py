@@ -25,21 +25,24 @@ def prefix_from_stream(name, n):
     return out
 
 
-def run(X, Y, visits, moves):
+def run(X, Y, visits, moves, score=None):
     s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
-    out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s], capture_output=True, text=True, check=True).stdout
-    v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None
+    extra = [] if score is None else [repr(float(t)) for t in score]
+    out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
+    v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     for ln in out.splitlines():
         f = ln.split()
         if f[0] == "rootvisits":
             root = (int(f[1]), float(f[3]))
+        elif f[0] == "recentScoreCenter":
+            center = float(f[1])
         elif f[0] == "child":
             x, y = int(f[1]), int(f[2])
             i = X * Y if x < 0 else y * X + x
             v[i] = int(f[3]); u[i] = float(f[4])
         elif f[0] == "policy":
             pol = np.array([float(t) for t in f[1:]], np.float32)
-    return root, v, u, pol
+    return root, v, u, pol, center
 
 
 if __name__ == "__main__":
@@ -52,10 +55,20 @@ if __name__ == "__main__":
         (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 131)),
         (13, 7, 300, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20)),
         (5, 5, 500, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9)),
+        # score utility on (a21): static, dynamic, dynamicScoreCenterZeroWeight, dynamicScoreCenterScale
+        (9, 9, 500, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), (0.05, 0.30, 0.25, 0.50)),    # selfplay8mainb18.cfg
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), (0.05, 0.30, 0.25, 0.50)),
+        (19, 19, 400, prefix_from_stream("boardstream_19x19_multisuicide.npz", 131), (0.3, 0.0, 0.0, 1.0)),   # SearchParams defaults
+        (13, 7, 300, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), (0.1, 0.3, 0.25, 0.5)),
+        (5, 5, 600, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), (0.05, 0.30, 0.25, 0.50)),      # reaches terminal nodes
     ]
     store = {"num_cases": len(cases)}
-    for i, (X, Y, visits, moves) in enumerate(cases):
-        root, v, u, pol = run(X, Y, visits, moves)
+    for i, case in enumerate(cases):
+        X, Y, visits, moves = case[:4]
+        score = case[4] if len(case) > 4 else None
+        root, v, u, pol, center = run(X, Y, visits, moves, score)
+        store[f"c{i}_score_params"] = np.array(score if score is not None else (0.0, 0.0, 0.0, 1.0), np.float64)
+        store[f"c{i}_recent_score_center"] = np.float64(center)
         assert root[0] == visits and v.sum() == visits - 1
         store[f"c{i}_shape"] = np.array([X, Y, visits], np.int32)
         store[f"c{i}_moves"] = np.array([(-1, -1) if m is None else m for m in moves], np.int8).reshape(-1, 2)

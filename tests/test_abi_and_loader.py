@@ -118,3 +118,14 @@ def test_zobrist_tables_reproduce_reference_pos_hash(golden_dir):
             for yy, xx in zip(*np.nonzero(col)):
                 h ^= bh[yy, xx, col[yy, xx] - 1]
             assert np.array_equal(h, d["pos_hash"][m]), (name, m)
+
+
+def test_score_value_table_is_bit_exact_vs_reference(golden_dir):
+    """Row a21: ScoreValue::expectedWhiteScoreValue (table built by the reference's quadrature, bilinear lookup) on 3000 argument
+    tuples incl. clamped means, zero and huge stdevs, static (0, 2) and dynamic centres/scales, four board areas.
+    Fixture: tests/golden/make_scorevalue_fixture.py (the reference's own function)."""
+    from katago_b200.nn_backend import expected_white_score_value
+    d = np.load(os.path.join(golden_dir, "scorevalue_samples.npz"))
+    a = d["args"]
+    got = expected_white_score_value(a[:, 0], a[:, 1], a[:, 2], a[:, 3], a[:, 4])
+    assert np.array_equal(got, d["value"])
