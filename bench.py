@@ -258,8 +258,10 @@ def main():
     W, K = max(3, args.warmup), max(1, args.steps)
     # device-resident self-play loop: selfplay8mainb18.cfg search parameters that the loop implements
     sp = SelfPlay(handle, n, args.visits, komi=7.5, multi_stone_suicide_legal=True, early_temperature_moves=30,
-                  cpuct_exploration=1.0, cpuct_exploration_log=0.45, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
-                  root_fpu_reduction_max=0.1, seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
+                  cpuct_exploration=1.05, cpuct_exploration_log=0.28, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
+                  root_fpu_reduction_max=0.0, value_weight_exponent=0.5, fpu_parent_weight_by_visited_policy=True,
+                  fpu_parent_weight_by_visited_policy_pow=2.0, root_desired_per_child_visits_coeff=2.0,
+                  seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
     # bring the games into mid-search (trees a few hundred nodes deep) before timing
@@ -315,7 +317,11 @@ def main():
             "dtype": "f32-split3(fp16 tensor pipe)" if args.fp32 else "f16 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, maxVisits {args.visits}, one playout (visit) per game per step, device-resident loop",
                        "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(all 22 V7 planes incl. ladders 14-17 and pass-alive area 18-19, 19 globals)",
-                                  "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)", "backup"],
+                                  "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)",
+                                  "backup = recomputeNodeStats per path node (value weighting, exponent 0.5)"],
+                       "search_params": "selfplay8mainb18.cfg: cpuct 1.05/0.28/500, fpu 0.2 (root 0), fpuParentWeightByVisitedPolicy^2, valueWeightExponent 0.5, "
+                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2; not yet: graph search, subtree value bias, "
+                                        "root noise/temperature, multi-symmetry root, LCB move selection",
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
                        "weights": "random init, real architecture (katago_b200/modelgen.py)",

@@ -156,6 +156,19 @@ typedef struct kgb_selfplay_config {
   double dynamic_score_center_zero_weight;
   double dynamic_score_center_scale;
   double draw_equivalent_wins_for_white;   /* 0.5 in every stock config; used for integer komi results */
+  /* More SearchParams of the selection / backup formulas (search/searchparams.h), by their cfg names.  All 0 = the plain
+   * PUCT + visit-weighted average of the first fixtures. */
+  double value_weight_exponent;                   /* valueWeightExponent (0.5): t-CDF value weighting in the backup */
+  int32_t fpu_parent_weight_by_visited_policy;    /* fpuParentWeightByVisitedPolicy */
+  int32_t reserved1;
+  double fpu_parent_weight_by_visited_policy_pow; /* fpuParentWeightByVisitedPolicyPow */
+  double fpu_parent_weight;                       /* fpuParentWeight */
+  double fpu_loss_prop;                           /* fpuLossProp */
+  double root_fpu_loss_prop;                      /* rootFpuLossProp */
+  double cpuct_utility_stdev_prior;               /* cpuctUtilityStdevPrior (0.25) */
+  double cpuct_utility_stdev_prior_weight;        /* cpuctUtilityStdevPriorWeight (1.0) */
+  double cpuct_utility_stdev_scale;               /* cpuctUtilityStdevScale (0 = off) */
+  double root_desired_per_child_visits_coeff;     /* rootDesiredPerChildVisitsCoeff */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -182,8 +195,9 @@ KGB_API int kgb_selfplay_get_stats(kgb_selfplay* sp, kgb_selfplay_stats* out);
 /* Root position of game g: colors[Y*X] (0 empty, 1 black, 2 white); info[6] = move number, black-to-move, ko point
  * (y*32+x or -1), black stones captured, white stones captured, root visits. */
 KGB_API int kgb_selfplay_get_game(kgb_selfplay* sp, int game, uint8_t* colors, int32_t* info);
-/* Root children of game g, indexed by move position 0..X*Y (pass last): visit counts, NN policy (-1 illegal), utility sums. */
-KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* util_sum);
+/* Root children of game g, indexed by move position 0..X*Y (pass last): edge visit counts, NN policy (-1 illegal), and each
+ * child's utilityAvg (white's perspective; 0 where there is no child). */
+KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* utility_avg);
 /* The NN input row (NHWC [X*Y][22] + 19 globals) the last wave wrote for game g - what NNInputs::fillRowV7 would produce
  * for that leaf (planes listed in DESIGN.md §8; used by the feature parity tests). */
 KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global);

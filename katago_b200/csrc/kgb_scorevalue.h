@@ -15,6 +15,11 @@ static constexpr int SV_STDEV_LEN = SV_ASSUMED_BSIZE * SV_ASSUMED_BSIZE + SV_EXT
 // by the same 101-point quadrature, in the same order of operations, as ScoreValue::initTables.
 std::vector<double> makeExpectedSVTable();
 
+// Value-weighting t-distribution CDF table (search.cpp:131-137; search/distributiontable.h) - row a20.
+static constexpr int VW_TABLE_SIZE = 2000;
+static constexpr double VW_MIN_Z = -50.0, VW_MAX_Z = 50.0;
+std::vector<double> makeValueWeightCdfTable();
+
 #ifdef __CUDACC__
 #define KGB_HD __host__ __device__
 #else
@@ -51,6 +56,16 @@ KGB_HD inline double svExpectedWhiteScoreValue(const double* table, double white
   const double b0 = KGB_SV_ADD(a00, KGB_SV_MUL(lambdaStdev, KGB_SV_SUB(a01, a00)));
   const double b1 = KGB_SV_ADD(a10, KGB_SV_MUL(lambdaStdev, KGB_SV_SUB(a11, a10)));
   return KGB_SV_ADD(b0, KGB_SV_MUL(lambdaMean, KGB_SV_SUB(b1, b0)));
+}
+// DistributionTable::getCdf (search/distributiontable.h:58-70)
+KGB_HD inline double vwCdf(const double* table, double z) {
+  const double d = KGB_SV_MUL((double)(VW_TABLE_SIZE - 1), KGB_SV_SUB(z, VW_MIN_Z)) / (VW_MAX_Z - VW_MIN_Z);
+  if(d <= 0) return 0.0;
+  const int idx = (int)d;
+  if(idx >= VW_TABLE_SIZE - 1) return 1.0;
+  const double lambda = KGB_SV_SUB(d, (double)idx);
+  const double y0 = table[idx], y1 = table[idx + 1];
+  return KGB_SV_ADD(y0, KGB_SV_MUL(lambda, KGB_SV_SUB(y1, y0)));
 }
 // ScoreValue::getScoreStdev
 KGB_HD inline double svScoreStdev(double scoreMean, double scoreMeanSq) {

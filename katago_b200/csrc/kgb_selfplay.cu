@@ -9,11 +9,15 @@
 //   spBackupKernel   (d) policy: legality mask + softmax; value: softmax -> white utility nneval.cpp:960-1051,1112-1215
 //                    (e) backup along the path                                           searchupdatehelpers.cpp:11-81,139-360
 //
-// Tree layout (per game, per node, SoA, indexed by move position 0..X*Y (pass last)):
-//   policy[pos] fp32 (-1 = illegal), childNode[pos] i32 (-1 = not expanded), childVisits[pos] i32, childUtilSum[pos] f64
-// so selection reads four coalesced arrays and never chases child pointers (the reference keeps stats in the child
-// nodes: searchnode.h:17-41,105-138).  With unit weights the reference's recomputed weighted average
-// (searchupdatehelpers.cpp:167-360) equals this running mean.
+// Tree layout (per game, per node, SoA):
+//   by move position 0..X*Y (pass last): policy[pos] fp32 (-1 = illegal), childNode[pos] i32 (-1 = not expanded),
+//                                        childVisits[pos] i32 (edge visits);
+//   childOrder[k] = move position of the k-th child in CREATION order (the reference walks its children array in that order and
+//                   breaks ties by it; sums over children are done sequentially in that order so doubles match);
+//   node statistics as in NodeStats (searchnode.h:17-41): visits, weightSum, weightSqSum, utilityAvg, utilitySqAvg, plus the
+//                   node's own evaluation utility (the reference keeps the NNOutput).
+// Backup = the reference's recompute (searchupdatehelpers.cpp:139-360): every node on the path re-derives its statistics from
+// its children (value weighting by the t-CDF of each child's z-score, :402-491) and its own evaluation.
 //
 // NN input planes written this round: 0 on-board, 1/2 own/opp stones, 3/4/5 liberties 1/2/3, 6 simple-ko ban,
 // 9-13 previous five move locations, 18/19 pass-alive + territory area (Benson, kgb_board.cuh); globals 0-4 pass history,
@@ -45,6 +49,10 @@ struct SPDev {
   int X, Y, XY, policySize, numGames, maxVisits, maxNodes, maxDepth, maxMoves, multiSuicide, earlyMoves;
   float komi;
   double cpuctExploration, cpuctExplorationLog, cpuctExplorationBase, fpuReductionMax, rootFpuReductionMax;
+  double cpuctUtilityStdevPrior, cpuctUtilityStdevPriorWeight, cpuctUtilityStdevScale;
+  double fpuLossProp, rootFpuLossProp, fpuParentWeight, fpuParentWeightByVisitedPolicyPow, valueWeightExponent, rootDesiredPerChildVisitsCoeff;
+  int fpuParentWeightByVisitedPolicy;
+  const double* vwCdfTable;         // value-weighting t-CDF table [2000]
   double winLossUtilityFactor, noResultUtilityForWhite;
   // score utility (searchhelpers.cpp:272-279): static * SV(mean, stdev; 0, 2) + dynamic * SV(mean, stdev; recentScoreCenter, scale)
   double staticScoreUtilityFactor, dynamicScoreUtilityFactor, dynamicScoreCenterZeroWeight, dynamicScoreCenterScale, drawEquivalentWinsForWhite;
@@ -76,16 +84,17 @@ struct SPDev {
   // tree [game][node]...
   int* nodeCount;                   // [game]
   int* nodeVisits;                  // [game][maxNodes]
-  double* nodeUtilSum;              // [game][maxNodes]   (white's perspective)
+  double *nodeWeightSum, *nodeWeightSqSum, *nodeUtilAvg, *nodeUtilSqAvg;   // [game][maxNodes] NodeStats (white's perspective)
+  double* nodeNNUtil;               // [game][maxNodes] utility of the node's own evaluation (Search::getUtilityFromNN)
+  int* nodeNumChildren;             // [game][maxNodes]
+  uint16_t* childOrder;             // [game][maxNodes][policySize] move position of the k-th created child
   int8_t* nodeTerminal;             // [game][maxNodes]   0 no, 1 yes
   float* policy;                    // [game][maxNodes][policySize]
   int* childNode;                   // same shape
-  int* childVisits;
-  double* childUtilSum;
+  int* childVisits;                 // edge visits
   // per-playout scratch
   int *pathLen, *pathNode, *pathMove;   // [game], [game][maxDepth] x2
   int *leafNode, *leafTerminal, *leafBlackToMove;
-  double* leafTerminalUtil;
   uint32_t* leafLegal;              // [game][32] row masks of legal points for the player to move at the leaf
   // statistics
   unsigned long long *totalVisits, *totalMoves, *gamesFinished, *blackWins, *nodesAllocated, *sumDepth;
@@ -116,9 +125,21 @@ __device__ __forceinline__ void nodeInit(const SPDev& d, size_t nodeBase, int la
   for(int i = lane; i < d.policySize; i += 32) {
     d.childNode[nodeBase + i] = -1;
     d.childVisits[nodeBase + i] = 0;
-    d.childUtilSum[nodeBase + i] = 0.0;
     d.policy[nodeBase + i] = -1.0f;
   }
+}
+// Fresh node: no visits, no children (one lane).
+__device__ __forceinline__ void nodeStatsReset(const SPDev& d, size_t gn, bool terminal) {
+  d.nodeVisits[gn] = 0; d.nodeWeightSum[gn] = 0.0; d.nodeWeightSqSum[gn] = 0.0; d.nodeUtilAvg[gn] = 0.0; d.nodeUtilSqAvg[gn] = 0.0;
+  d.nodeNNUtil[gn] = 0.0; d.nodeNumChildren[gn] = 0; d.nodeTerminal[gn] = terminal ? 1 : 0;
+}
+// acc += v[0] + v[1] + ... + v[n-1] added one after the other in lane order (the order the reference adds its children in),
+// for two quantities at once; every lane returns the same sums.  sh: 64 doubles of this warp's shared memory.
+__device__ __forceinline__ void orderedAdd2(double a, double b, int n, double& accA, double& accB, double* sh, int lane) {
+  sh[lane] = a; sh[32 + lane] = b;
+  __syncwarp();
+  for(int j = 0; j < n; j++) { accA += sh[j]; accB += sh[32 + j]; }
+  __syncwarp();
 }
 
 // Choose and play the root move once the visit budget is spent; restart the game when it is over.
@@ -210,14 +231,15 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     atomicAdd(d.totalMoves, 1ULL);
     // reset the tree: node 0 = unevaluated root
     d.nodeCount[g] = 1;
-    d.nodeVisits[gb] = 0; d.nodeUtilSum[gb] = 0.0; d.nodeTerminal[gb] = 0;
+    nodeStatsReset(d, gb, false);
   }
   nodeInit(d, rootBase, lane);
   __syncwarp();
 }
 
 // Warp 0 of a game's block: PUCT descent, leaf board, legality and every feature except the leaf's own ladder searches.
-__device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, uint32_t* shW, uint32_t* shCand, int& shKo, int& shDoLadders) {
+__device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, uint32_t* shW, uint32_t* shCand, int& shKo, int& shDoLadders,
+                              double* shSum) {
   const size_t gb = (size_t)g * d.maxNodes;
   if(d.nodeVisits[gb] >= d.maxVisits) rootAdvance(d, g, lane);
 
@@ -240,51 +262,104 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     terminal = d.nodeTerminal[gb + node] != 0;
     if(visits == 0 || terminal || depth >= d.maxDepth - 1) break;
     const size_t nb = (gb + node) * d.policySize;
-    // ---- pass 1: visited policy mass, total child weight; keep this lane's entries in registers
-    float P[12]; int CV[12]; double CU[12];
+    const int nc = d.nodeNumChildren[gb + node];
+    // ---- pass 1 over the children in creation order (searchexplorehelpers.cpp:338-364): visited policy mass, total child weight
+    float P[12]; double CW[12], CU[12]; int CVis[12];
     double massVisited = 0.0, totalW = 0.0;
 #pragma unroll
-    for(int k = 0; k < 12; k++) {
-      int i = k * 32 + lane;
-      bool in = i < d.policySize;
-      P[k] = in ? d.policy[nb + i] : -1.0f;
-      CV[k] = in ? d.childVisits[nb + i] : 0;
-      CU[k] = in ? d.childUtilSum[nb + i] : 0.0;
-      if(CV[k] > 0 && P[k] >= 0.0f) { massVisited += (double)P[k]; totalW += (double)CV[k]; }
-    }
-    massVisited = warpSumD(massVisited);
-    totalW = warpSumD(totalW);
-    // ---- FPU and exploration scaling (searchexplorehelpers.cpp:22-29, 265-321)
-    const double parentUtility = d.nodeUtilSum[gb + node] / (double)visits;
-    const double fpuRed = (node == 0 ? d.rootFpuReductionMax : d.fpuReductionMax) * sqrt(massVisited);
-    const double fpuValue = black ? parentUtility + fpuRed : parentUtility - fpuRed;   // white's perspective
-    const double cpuct = d.cpuctExploration + d.cpuctExplorationLog * log((totalW + d.cpuctExplorationBase) / d.cpuctExplorationBase);
-    const double exploreScaling = cpuct * sqrt(totalW + 0.01);
-    // ---- pass 2: best existing child and best new move
-    double bestVal = -1e50; int bestIdx = -1;
-    float bestNewP = -1.0f; int bestNewIdx = -1;
-#pragma unroll
-    for(int k = 0; k < 12; k++) {
-      int i = k * 32 + lane;
-      if(P[k] < 0.0f) continue;
-      if(CV[k] > 0) {
-        double u = CU[k] / (double)CV[k];
-        double val = exploreScaling * (double)P[k] / (1.0 + (double)CV[k]) + (black ? -u : u);
-        if(val > bestVal) { bestVal = val; bestIdx = i; }
+    for(int ch = 0; ch < 12; ch++) {
+      P[ch] = -1.0f; CW[ch] = 0.0; CU[ch] = 0.0; CVis[ch] = 0;
+      if(ch * 32 < nc) {
+        const int k = ch * 32 + lane;
+        const bool in = k < nc;
+        const int mv = in ? (int)d.childOrder[nb + k] : 0;
+        const int c = in ? d.childNode[nb + mv] : 0;
+        const int ev = in ? d.childVisits[nb + mv] : 0;
+        const int cv = in ? d.nodeVisits[gb + c] : 0;
+        const double cw = in ? d.nodeWeightSum[gb + c] : 0.0;
+        const float p = in ? d.policy[nb + mv] : -1.0f;
+        const double w = cw * ((double)ev / (double)(cv > 1 ? cv : 1));     // NodeStats::childWeight (searchnode.h:64-66)
+        P[ch] = p; CW[ch] = w; CU[ch] = in ? d.nodeUtilAvg[gb + c] : 0.0; CVis[ch] = cv;
+        const bool counts = in && p >= 0.0f;
+        const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
+        orderedAdd2(counts ? (double)p : 0.0, counts ? w : 0.0, n, massVisited, totalW, shSum, lane);
       }
-      else if(P[k] > bestNewP) { bestNewP = P[k]; bestNewIdx = i; }
+    }
+    // ---- FPU and exploration scaling (searchexplorehelpers.cpp:22-29, 265-321)
+    const double parentUtility = d.nodeUtilAvg[gb + node];
+    const bool isRoot = node == 0;
+    double stdevFactor = 1.0;
+    if(d.cpuctUtilityStdevScale != 0.0) {
+      const double weightSum = d.nodeWeightSum[gb + node];
+      double utilitySqAvg = d.nodeUtilSqAvg[gb + node];
+      const double variancePrior = d.cpuctUtilityStdevPrior * d.cpuctUtilityStdevPrior;
+      double stdev;
+      if(visits <= 0 || weightSum <= 1) stdev = d.cpuctUtilityStdevPrior;
+      else {
+        const double utilitySq = parentUtility * parentUtility;
+        if(utilitySqAvg < utilitySq) utilitySqAvg = utilitySq;
+        stdev = sqrt(fmax(0.0, ((utilitySq + variancePrior) * d.cpuctUtilityStdevPriorWeight + utilitySqAvg * weightSum) /
+                                     (d.cpuctUtilityStdevPriorWeight + weightSum - 1.0) - utilitySq));
+      }
+      stdevFactor = 1.0 + d.cpuctUtilityStdevScale * (stdev / d.cpuctUtilityStdevPrior - 1.0);
+    }
+    double parentUtilityForFPU = parentUtility;
+    if(d.fpuParentWeightByVisitedPolicy) {
+      const double pw = d.fpuParentWeightByVisitedPolicyPow;
+      const double raised = pw == 1.0 ? massVisited : pw == 2.0 ? massVisited * massVisited : pow(massVisited, pw);
+      const double avgWeight = fmin(1.0, raised);
+      parentUtilityForFPU = avgWeight * parentUtility + (1.0 - avgWeight) * d.nodeNNUtil[gb + node];
+    }
+    else if(d.fpuParentWeight > 0.0) parentUtilityForFPU = d.fpuParentWeight * d.nodeNNUtil[gb + node] + (1.0 - d.fpuParentWeight) * parentUtility;
+    double fpuValue;
+    {
+      const double reduction = (isRoot ? d.rootFpuReductionMax : d.fpuReductionMax) * sqrt(massVisited);
+      const double lossProp = isRoot ? d.rootFpuLossProp : d.fpuLossProp;
+      const double utilityRadius = d.winLossUtilityFactor + d.staticScoreUtilityFactor + d.dynamicScoreUtilityFactor;
+      fpuValue = black ? parentUtilityForFPU + reduction : parentUtilityForFPU - reduction;   // utilities are white's
+      const double lossValue = black ? utilityRadius : -utilityRadius;
+      fpuValue = fpuValue + (lossValue - fpuValue) * lossProp;
+    }
+    const double cpuct = d.cpuctExploration + d.cpuctExplorationLog * log((totalW + d.cpuctExplorationBase) / d.cpuctExplorationBase);
+    const double exploreScaling = cpuct * sqrt(totalW + 0.01) * stdevFactor;
+    // ---- pass 2: best existing child (first in creation order among equals, :452-486) ...
+    double bestVal = -1e50; int bestK = -1;
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) {
+      const int k = ch * 32 + lane;
+      if(k >= nc) continue;
+      double val = -1e50;                                           // POLICY_ILLEGAL_SELECTION_VALUE
+      if(P[ch] >= 0.0f) {
+        const double cu = (CVis[ch] <= 0 || CW[ch] <= 0.0) ? fpuValue : CU[ch];
+        val = exploreScaling * (double)P[ch] / (1.0 + CW[ch]) + (black ? -cu : cu);
+        if(isRoot && d.rootDesiredPerChildVisitsCoeff > 0.0 && P[ch] > 0.0f &&
+           CW[ch] < sqrt((double)P[ch] * totalW * d.rootDesiredPerChildVisitsCoeff)) val = 1e20;
+      }
+      if(val > bestVal) { bestVal = val; bestK = k; }
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(KGB_FULL, bestVal, o); int oi = __shfl_xor_sync(KGB_FULL, bestIdx, o);
-      if(oi >= 0 && (bestIdx < 0 || ov > bestVal || (ov == bestVal && oi < bestIdx))) { bestVal = ov; bestIdx = oi; }
+      double ov = __shfl_xor_sync(KGB_FULL, bestVal, o); int ok = __shfl_xor_sync(KGB_FULL, bestK, o);
+      if(ok >= 0 && (bestK < 0 || ov > bestVal || (ov == bestVal && ok < bestK))) { bestVal = ov; bestK = ok; }
+    }
+    // ... and the unexpanded move with the largest prior (first in position order among equals, :548-590)
+    float bestNewP = -1.0f; int bestNewIdx = -1;
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) {
+      const int i = ch * 32 + lane;
+      if(i >= d.policySize) continue;
+      const float p = d.policy[nb + i];
+      if(p >= 0.0f && d.childNode[nb + i] < 0 && p > bestNewP) { bestNewP = p; bestNewIdx = i; }
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
       float op = __shfl_xor_sync(KGB_FULL, bestNewP, o); int on = __shfl_xor_sync(KGB_FULL, bestNewIdx, o);
       if(on >= 0 && (bestNewIdx < 0 || op > bestNewP || (op == bestNewP && on < bestNewIdx))) { bestNewP = op; bestNewIdx = on; }
     }
-    int move = bestIdx;
+    int move = bestK >= 0 ? (int)d.childOrder[nb + bestK] : -1;
     if(bestNewIdx >= 0) {
-      double newVal = exploreScaling * (double)bestNewP + (black ? -fpuValue : fpuValue);
-      if(bestIdx < 0 || newVal > bestVal) move = bestNewIdx;
+      const double newVal = exploreScaling * (double)bestNewP / (1.0 + 0.0) + (black ? -fpuValue : fpuValue);
+      if(bestK < 0 || newVal > bestVal) move = bestNewIdx;
     }
     if(move < 0) break;  // no legal move at all (cannot happen: pass is always legal)
     // ---- descend
@@ -303,9 +378,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(lane == 0) {
         d.nodeCount[g] = child + 1;
         d.childNode[nb + move] = child;
-        d.nodeVisits[gb + child] = 0;
-        d.nodeUtilSum[gb + child] = 0.0;
-        d.nodeTerminal[gb + child] = (passes >= 2) ? 1 : 0;
+        d.childOrder[nb + nc] = (uint16_t)move;
+        d.nodeNumChildren[gb + node] = nc + 1;
+        nodeStatsReset(d, gb + child, passes >= 2);
         atomicAdd(d.nodesAllocated, 1ULL);
       }
       nodeInit(d, (gb + child) * d.policySize, lane);
@@ -402,13 +477,14 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32) spSelectKernel(const SPD
   const int warp = threadIdx.x >> 5;
   __shared__ uint32_t shB[32], shW[32], shCand[32];
   __shared__ int shKo, shDoLadders, shFresh, shUnfinished;
+  __shared__ double shSum[64];
   if(warp == 0) {
     if(d.ladPending[g]) {
       shB[lane] = d.leafB[g * 32 + lane]; shW[lane] = d.leafW[g * 32 + lane]; shCand[lane] = d.leafCand[g * 32 + lane];
       if(lane == 0) { shKo = d.leafKo[g]; shDoLadders = 1; shFresh = 0; }
     }
     else {
-      spSelectWarp0(d, g, lane, shB, shW, shCand, shKo, shDoLadders);
+      spSelectWarp0(d, g, lane, shB, shW, shCand, shKo, shDoLadders, shSum);
       if(lane == 0) shFresh = 1;
     }
     if(lane == 0) shUnfinished = 0;
@@ -459,7 +535,89 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32) spSelectKernel(const SPD
   }
 }
 
+// Search::recomputeNodeStats (searchupdatehelpers.cpp:167-360) for the parameter subset of the loop (no noise pruning, no root
+// noise subtraction, no subtree value bias, no uncertainty weights: the node's own evaluation has weight 1), one warp per node.
+// Children are visited in creation order and every sum is accumulated in that order (orderedAdd2), like the reference's loops.
+__device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePlaWhite, double* sh, int lane) {
+  const size_t gb = (size_t)g * d.maxNodes, gn = gb + node, nb = gn * d.policySize;
+  const int nc = d.nodeNumChildren[gn];
+  double WA[12], CU[12], CUSQ[12], CWS[12], CWSQ[12];   // weightAdjusted, child utilityAvg / utilitySqAvg / weightSum / weightSqSum
+  double origTotal = 0.0, simpleValueSum = 0.0;
+#pragma unroll
+  for(int ch = 0; ch < 12; ch++) {
+    WA[ch] = 0.0; CU[ch] = 0.0; CUSQ[ch] = 0.0; CWS[ch] = 1.0; CWSQ[ch] = 0.0;
+    if(ch * 32 < nc) {
+      const int k = ch * 32 + lane;
+      const bool in = k < nc;
+      const int mv = in ? (int)d.childOrder[nb + k] : 0;
+      const int c = in ? d.childNode[nb + mv] : 0;
+      const int ev = in ? d.childVisits[nb + mv] : 0;
+      const int cv = in ? d.nodeVisits[gb + c] : 0;
+      const double cw = in ? d.nodeWeightSum[gb + c] : 0.0;
+      const bool good = in && cv > 0 && cw > 0.0 && ev > 0;
+      if(good) {
+        WA[ch] = cw * ((double)ev / (double)(cv > 1 ? cv : 1));
+        CU[ch] = d.nodeUtilAvg[gb + c]; CUSQ[ch] = d.nodeUtilSqAvg[gb + c]; CWS[ch] = cw; CWSQ[ch] = d.nodeWeightSqSum[gb + c];
+      }
+      const double selfU = nodePlaWhite ? CU[ch] : -CU[ch];
+      const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
+      orderedAdd2(WA[ch], good ? selfU * WA[ch] : 0.0, n, origTotal, simpleValueSum, sh, lane);
+    }
+  }
+  // downweightBadChildrenAndNormalizeWeight (:402-491) with nothing to subtract or prune
+  if(d.valueWeightExponent != 0.0 && origTotal > 0.0) {
+    const double simpleValue = simpleValueSum / origTotal;
+    double totalNew = 0.0, unused = 0.0;
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) {
+      if(ch * 32 < nc) {
+        if(WA[ch] > 0.0) {
+          const double selfU = nodePlaWhite ? CU[ch] : -CU[ch];
+          const double precision = 1.5 * sqrt(WA[ch]);
+          const double stdev = sqrt(0.00000001 + 1.0 / precision);
+          const double z = (selfU - simpleValue) / stdev;
+          const double p = vwCdf(d.vwCdfTable, z) + 0.0001;
+          WA[ch] *= d.valueWeightExponent == 0.5 ? sqrt(p) : pow(p, d.valueWeightExponent);
+        }
+        const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
+        orderedAdd2(WA[ch], 0.0, n, totalNew, unused, sh, lane);
+      }
+    }
+    const double factor = origTotal / totalNew;
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) WA[ch] *= factor;
+  }
+  double utilitySum = 0.0, utilitySqSum = 0.0, weightSqSum = 0.0, unused = 0.0;
+#pragma unroll
+  for(int ch = 0; ch < 12; ch++) {
+    if(ch * 32 < nc) {
+      const double scaling = WA[ch] / CWS[ch];
+      const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
+      orderedAdd2(WA[ch] * CU[ch], WA[ch] * CUSQ[ch], n, utilitySum, utilitySqSum, sh, lane);
+      orderedAdd2(scaling * scaling * CWSQ[ch], 0.0, n, weightSqSum, unused, sh, lane);
+    }
+  }
+  double weightSum = origTotal;
+  // the node's own evaluation, weight 1
+  const double utility = d.nodeNNUtil[gn];
+  utilitySum += utility * 1.0;
+  utilitySqSum += utility * utility * 1.0;
+  weightSqSum += 1.0 * 1.0;
+  weightSum += 1.0;
+  __syncwarp();
+  if(lane == 0) {
+    d.nodeUtilAvg[gn] = utilitySum / weightSum;
+    d.nodeUtilSqAvg[gn] = utilitySqSum / weightSum;
+    d.nodeWeightSqSum[gn] = weightSqSum;
+    d.nodeWeightSum[gn] = weightSum;
+    d.nodeVisits[gn] = d.nodeVisits[gn] + 1;
+  }
+  __syncwarp();
+}
+
 __global__ void spBackupKernel(const SPDev d) {
+  __shared__ double shSumAll[4][64];
+  double* shSum = shSumAll[(threadIdx.x >> 5) & 3];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
@@ -467,6 +625,7 @@ __global__ void spBackupKernel(const SPDev d) {
   const size_t gb = (size_t)g * d.maxNodes;
   const int node = d.leafNode[g];
   const bool terminal = d.leafTerminal[g] != 0;
+  const bool leafBlack = d.leafBlackToMove[g] != 0;
   const double sqrtBoardArea = sqrt((double)d.XY);
   // Search::getScoreUtility (searchhelpers.cpp:272-279)
   auto scoreUtility = [&](double scoreMean, double scoreMeanSq, double center) -> double {
@@ -532,7 +691,7 @@ __global__ void spBackupKernel(const SPDev d) {
     double w = exp(wl - m), l = exp(ll - m), n = exp(nl - m);
     double s = w + l + n;
     w /= s; l /= s; n /= s;
-    const bool black = d.leafBlackToMove[g] != 0;
+    const bool black = leafBlack;
     // NNOutput stores the probabilities as float (nneval.cpp:1200-1215); the search widens them again
     // (searchupdatehelpers.cpp:87-88) - mirror that rounding so utilities agree to the last bit.
     const float wf = (float)w, lf = (float)l, nf = (float)n;
@@ -563,21 +722,40 @@ __global__ void spBackupKernel(const SPDev d) {
     }
   }
   __syncwarp();
-  // ---- backup (one lane: a handful of scattered read-modify-writes along the path)
-  if(lane == 0) {
-    d.nodeVisits[gb + node] += 1;
-    d.nodeUtilSum[gb + node] += u;
-    const int len = d.pathLen[g];
-    for(int k = len - 1; k >= 0; k--) {
-      int pn = d.pathNode[(size_t)g * d.maxDepth + k], mv = d.pathMove[(size_t)g * d.maxDepth + k];
-      size_t nb = (gb + pn) * d.policySize;
-      d.childVisits[nb + mv] += 1;
-      d.childUtilSum[nb + mv] += u;
-      d.nodeVisits[gb + pn] += 1;
-      d.nodeUtilSum[gb + pn] += u;
+  // ---- the leaf's own statistics (Search::addLeafValue, searchupdatehelpers.cpp:11-81; evaluation weight 1)
+  const size_t gl = gb + node;
+  const int leafVisits = d.nodeVisits[gl];
+  __syncwarp();
+  if(terminal) {
+    if(lane == 0) {
+      const double oldW = d.nodeWeightSum[gl], newW = oldW + 1.0;
+      d.nodeUtilAvg[gl] = (d.nodeUtilAvg[gl] * oldW + u * 1.0) / newW;
+      d.nodeUtilSqAvg[gl] = (d.nodeUtilSqAvg[gl] * oldW + (u * u) * 1.0) / newW;
+      d.nodeWeightSqSum[gl] = d.nodeWeightSqSum[gl] + 1.0;
+      d.nodeWeightSum[gl] = newW;
+      d.nodeVisits[gl] = leafVisits + 1;
     }
-    atomicAdd(d.totalVisits, 1ULL);
   }
+  else if(leafVisits == 0) {
+    if(lane == 0) {
+      d.nodeNNUtil[gl] = u;
+      d.nodeUtilAvg[gl] = u; d.nodeUtilSqAvg[gl] = u * u; d.nodeWeightSqSum[gl] = 1.0; d.nodeWeightSum[gl] = 1.0;
+      d.nodeVisits[gl] = 1;
+    }
+  }
+  else recomputeNodeStats(d, g, node, !leafBlack, shSum, lane);   // depth cap reached on an expanded node: one more visit, same evaluation
+  __syncwarp();
+  // ---- backup: edge visit, then the parent re-derives its statistics from its children (updateStatsAfterPlayout)
+  const int len = d.pathLen[g];
+  for(int k = len - 1; k >= 0; k--) {
+    const int pn = d.pathNode[(size_t)g * d.maxDepth + k], mv = d.pathMove[(size_t)g * d.maxDepth + k];
+    if(lane == 0) d.childVisits[(gb + pn) * d.policySize + mv] += 1;
+    __syncwarp();
+    const bool pnBlack = ((len - k) & 1) ? !leafBlack : leafBlack;   // players alternate along the path
+    recomputeNodeStats(d, g, pn, !pnBlack, shSum, lane);
+    __syncwarp();
+  }
+  if(lane == 0) atomicAdd(d.totalVisits, 1ULL);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -659,7 +837,7 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     d.rootKo[g] = bd.ko; d.rootCapB[g] = bd.capB; d.rootCapW[g] = bd.capW;
     d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = passes; d.moveNum[g] = mv;
     for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
-    d.nodeCount[g] = 1; d.nodeVisits[gb] = 0; d.nodeUtilSum[gb] = 0.0; d.nodeTerminal[gb] = 0;
+    d.nodeCount[g] = 1; nodeStatsReset(d, gb, false);
     d.ladPending[g] = 0; d.leafValid[g] = 0;
   }
   nodeInit(d, gb * d.policySize, lane);
@@ -747,6 +925,14 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.komi = c.komi;
   d.cpuctExploration = c.cpuct_exploration; d.cpuctExplorationLog = c.cpuct_exploration_log; d.cpuctExplorationBase = c.cpuct_exploration_base;
   d.fpuReductionMax = c.fpu_reduction_max; d.rootFpuReductionMax = c.root_fpu_reduction_max;
+  d.cpuctUtilityStdevPrior = c.cpuct_utility_stdev_prior; d.cpuctUtilityStdevPriorWeight = c.cpuct_utility_stdev_prior_weight;
+  d.cpuctUtilityStdevScale = c.cpuct_utility_stdev_scale;
+  if(d.cpuctUtilityStdevScale != 0.0 && !(d.cpuctUtilityStdevPrior > 0.0)) throw std::invalid_argument("selfplay: cpuct_utility_stdev_prior must be > 0");
+  d.fpuLossProp = c.fpu_loss_prop; d.rootFpuLossProp = c.root_fpu_loss_prop; d.fpuParentWeight = c.fpu_parent_weight;
+  d.fpuParentWeightByVisitedPolicy = c.fpu_parent_weight_by_visited_policy;
+  d.fpuParentWeightByVisitedPolicyPow = c.fpu_parent_weight_by_visited_policy_pow;
+  d.valueWeightExponent = c.value_weight_exponent; d.rootDesiredPerChildVisitsCoeff = c.root_desired_per_child_visits_coeff;
+  if(c.max_visits + 2 > 65535) throw std::invalid_argument("selfplay: max_visits above 65533 not supported");
   d.winLossUtilityFactor = c.win_loss_utility_factor; d.noResultUtilityForWhite = c.no_result_utility_for_white;
   d.staticScoreUtilityFactor = c.static_score_utility_factor; d.dynamicScoreUtilityFactor = c.dynamic_score_utility_factor;
   d.dynamicScoreCenterZeroWeight = c.dynamic_score_center_zero_weight; d.dynamicScoreCenterScale = c.dynamic_score_center_scale;
@@ -768,13 +954,15 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafKo = sp->alloc<int>(G); d.ladPending = sp->alloc<int>(G); d.leafValid = sp->alloc<int>(G);
   d.ladderNodesPerWave = c.ladder_nodes_per_wave > 0 ? c.ladder_nodes_per_wave : 0;
   { std::vector<int> kos2(2 * G, -1); SPCK(cudaMemcpy(d.prevKo, kos2.data(), 2 * G * sizeof(int), cudaMemcpyHostToDevice)); }
-  d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); d.nodeUtilSum = sp->alloc<double>(G * N);
+  d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); 
+  d.nodeWeightSum = sp->alloc<double>(G * N); d.nodeWeightSqSum = sp->alloc<double>(G * N); d.nodeUtilAvg = sp->alloc<double>(G * N);
+  d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
+  d.childOrder = sp->alloc<uint16_t>(G * N * PS);
   d.nodeTerminal = sp->alloc<int8_t>(G * N);
   d.policy = sp->alloc<float>(G * N * PS); d.childNode = sp->alloc<int>(G * N * PS); d.childVisits = sp->alloc<int>(G * N * PS);
-  d.childUtilSum = sp->alloc<double>(G * N * PS);
   d.pathLen = sp->alloc<int>(G); d.pathNode = sp->alloc<int>(G * d.maxDepth); d.pathMove = sp->alloc<int>(G * d.maxDepth);
   d.leafNode = sp->alloc<int>(G); d.leafTerminal = sp->alloc<int>(G); d.leafBlackToMove = sp->alloc<int>(G);
-  d.leafTerminalUtil = sp->alloc<double>(G); d.leafLegal = sp->alloc<uint32_t>(G * 32);
+  d.leafLegal = sp->alloc<uint32_t>(G * 32);
   unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
   d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8;
@@ -785,6 +973,10 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     double* dt = sp->alloc<double>(table.size());
     SPCK(cudaMemcpy(dt, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
     d.svTable = dt;
+    const std::vector<double> cdf = makeValueWeightCdfTable();
+    double* dc = sp->alloc<double>(cdf.size());
+    SPCK(cudaMemcpy(dc, cdf.data(), cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.vwCdfTable = dc;
   }
   d.recentScoreCenter = sp->alloc<double>(G); d.leafTerminalScore = sp->alloc<float>(G);
   // initial state: empty boards, black to move, history empty, one unevaluated root node per game
@@ -874,7 +1066,11 @@ void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* polic
   size_t nb = (size_t)g * d.maxNodes * d.policySize;
   SPCK(cudaMemcpy(visits, d.childVisits + nb, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
   SPCK(cudaMemcpy(policy, d.policy + nb, d.policySize * sizeof(float), cudaMemcpyDeviceToHost));
-  SPCK(cudaMemcpy(utilSum, d.childUtilSum + nb, d.policySize * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<int> child(d.policySize);
+  std::vector<double> avg(d.maxNodes);
+  SPCK(cudaMemcpy(child.data(), d.childNode + nb, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(avg.data(), d.nodeUtilAvg + (size_t)g * d.maxNodes, d.maxNodes * sizeof(double), cudaMemcpyDeviceToHost));
+  for(int i = 0; i < d.policySize; i++) utilSum[i] = child[i] >= 0 ? avg[child[i]] : 0.0;
 }
 
 void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,

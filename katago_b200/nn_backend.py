@@ -47,6 +47,10 @@ class SelfplayConfig(C.Structure):
         ("static_score_utility_factor", C.c_double), ("dynamic_score_utility_factor", C.c_double),
         ("dynamic_score_center_zero_weight", C.c_double), ("dynamic_score_center_scale", C.c_double),
         ("draw_equivalent_wins_for_white", C.c_double),
+        ("value_weight_exponent", C.c_double), ("fpu_parent_weight_by_visited_policy", C.c_int32), ("reserved1", C.c_int32),
+        ("fpu_parent_weight_by_visited_policy_pow", C.c_double), ("fpu_parent_weight", C.c_double), ("fpu_loss_prop", C.c_double),
+        ("root_fpu_loss_prop", C.c_double), ("cpuct_utility_stdev_prior", C.c_double), ("cpuct_utility_stdev_prior_weight", C.c_double),
+        ("cpuct_utility_stdev_scale", C.c_double), ("root_desired_per_child_visits_coeff", C.c_double),
     ]
 
 
@@ -346,14 +350,21 @@ class SelfPlay:
                  seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False, ladder_nodes_per_wave: int = 0,
                  static_score_utility_factor: float = 0.0, dynamic_score_utility_factor: float = 0.0,
                  dynamic_score_center_zero_weight: float = 0.0, dynamic_score_center_scale: float = 1.0,
-                 draw_equivalent_wins_for_white: float = 0.5):
+                 draw_equivalent_wins_for_white: float = 0.5, value_weight_exponent: float = 0.0,
+                 fpu_parent_weight_by_visited_policy: bool = False, fpu_parent_weight_by_visited_policy_pow: float = 1.0,
+                 fpu_parent_weight: float = 0.0, fpu_loss_prop: float = 0.0, root_fpu_loss_prop: float = 0.0,
+                 cpuct_utility_stdev_prior: float = 0.25, cpuct_utility_stdev_prior_weight: float = 1.0,
+                 cpuct_utility_stdev_scale: float = 0.0, root_desired_per_child_visits_coeff: float = 0.0):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
                                   cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
                                   root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features),
                                   int(ladder_nodes_per_wave), 0, static_score_utility_factor, dynamic_score_utility_factor,
-                                  dynamic_score_center_zero_weight, dynamic_score_center_scale, draw_equivalent_wins_for_white)
+                                  dynamic_score_center_zero_weight, dynamic_score_center_scale, draw_equivalent_wins_for_white,
+                                  value_weight_exponent, int(fpu_parent_weight_by_visited_policy), 0, fpu_parent_weight_by_visited_policy_pow,
+                                  fpu_parent_weight, fpu_loss_prop, root_fpu_loss_prop, cpuct_utility_stdev_prior,
+                                  cpuct_utility_stdev_prior_weight, cpuct_utility_stdev_scale, root_desired_per_child_visits_coeff)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen

@@ -21,6 +21,8 @@
 #include "neuralnet/nneval.h"
 #include "search/search.h"
 #include "search/searchnode.h"
+#include "search/distributiontable.h"
+#include "core/fancymath.h"
 #include "core/logger.h"
 
 #include <cstdint>
@@ -180,7 +182,7 @@ bool NeuralNet::testEvaluateResidualBlock(const ResidualBlockDesc*, int, int, in
 bool NeuralNet::testEvaluateGlobalPoolingResidualBlock(const GlobalPoolingResidualBlockDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
 
 static int cmdSearchFake(int argc, char** argv) {
-  if(argc != 7 && argc != 11) { cerr << "usage: searchfake MODELFILE X Y MAXVISITS MOVES [STATICSCOREUTIL DYNAMICSCOREUTIL CENTERZEROWEIGHT CENTERSCALE]" << endl; return 1; }
+  if(argc < 7) { cerr << "usage: searchfake MODELFILE X Y MAXVISITS MOVES [key=value ...]" << endl; return 1; }
   string modelFile = argv[2];
   int X = atoi(argv[3]), Y = atoi(argv[4]), maxVisits = atoi(argv[5]);
   Board::initHash();
@@ -197,12 +199,33 @@ static int cmdSearchFake(int argc, char** argv) {
   params.cpuctExploration = 1.0; params.cpuctExplorationLog = 0.45; params.cpuctExplorationBase = 500;
   params.fpuReductionMax = 0.2; params.rootFpuReductionMax = 0.1;
   params.staticScoreUtilityFactor = 0.0; params.dynamicScoreUtilityFactor = 0.0;
-  if(argc == 11) {   // score utility (searchhelpers.cpp:272-279), e.g. selfplay8mainb18.cfg: 0.05 0.30 0.25 0.50
-    params.staticScoreUtilityFactor = atof(argv[7]); params.dynamicScoreUtilityFactor = atof(argv[8]);
-    params.dynamicScoreCenterZeroWeight = atof(argv[9]); params.dynamicScoreCenterScale = atof(argv[10]);
-  }
   params.valueWeightExponent = 0.0;
   params.rootNoiseEnabled = false;
+  for(int i = 7; i < argc; i++) {   // SearchParams overrides, by their cfg names
+    string kv = argv[i];
+    size_t eq = kv.find('=');
+    if(eq == string::npos) { cerr << "bad override " << kv << endl; return 1; }
+    string k = kv.substr(0, eq); double v = atof(kv.substr(eq + 1).c_str());
+    if(k == "staticScoreUtilityFactor") params.staticScoreUtilityFactor = v;
+    else if(k == "dynamicScoreUtilityFactor") params.dynamicScoreUtilityFactor = v;
+    else if(k == "dynamicScoreCenterZeroWeight") params.dynamicScoreCenterZeroWeight = v;
+    else if(k == "dynamicScoreCenterScale") params.dynamicScoreCenterScale = v;
+    else if(k == "valueWeightExponent") params.valueWeightExponent = v;
+    else if(k == "fpuParentWeightByVisitedPolicy") params.fpuParentWeightByVisitedPolicy = v != 0;
+    else if(k == "fpuParentWeightByVisitedPolicyPow") params.fpuParentWeightByVisitedPolicyPow = v;
+    else if(k == "fpuParentWeight") params.fpuParentWeight = v;
+    else if(k == "fpuLossProp") params.fpuLossProp = v;
+    else if(k == "rootFpuLossProp") params.rootFpuLossProp = v;
+    else if(k == "fpuReductionMax") params.fpuReductionMax = v;
+    else if(k == "rootFpuReductionMax") params.rootFpuReductionMax = v;
+    else if(k == "cpuctExploration") params.cpuctExploration = v;
+    else if(k == "cpuctExplorationLog") params.cpuctExplorationLog = v;
+    else if(k == "cpuctUtilityStdevScale") params.cpuctUtilityStdevScale = v;
+    else if(k == "cpuctUtilityStdevPrior") params.cpuctUtilityStdevPrior = v;
+    else if(k == "cpuctUtilityStdevPriorWeight") params.cpuctUtilityStdevPriorWeight = v;
+    else if(k == "rootDesiredPerChildVisitsCoeff") params.rootDesiredPerChildVisitsCoeff = v;
+    else { cerr << "unknown override " << k << endl; return 1; }
+  }
   Rules rules;  // defaults, then the rule subset of the loop
   rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
   rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
@@ -265,6 +288,17 @@ static int cmdSVSamples(int argc, char** argv) {
     double v = ScoreValue::expectedWhiteScoreValue(mean, stdev, center, scale, sqrtArea);
     cout << Global::strprintf("%.17g %.17g %.17g %.17g %.17g %.17g", mean, stdev, center, scale, sqrtArea, v) << endl;
   }
+  return 0;
+}
+
+// vwtable: the value-weighting CDF table built the way Search's constructor builds it (search.cpp:131-137: the reference's
+// DistributionTable over the reference's FancyMath::tdistcdf, 3 degrees of freedom), 2000 lines of %.17g
+static int cmdVWTable(int, char**) {
+  DistributionTable table(
+    [](double z) { return FancyMath::tdistpdf(z, 3.0); },
+    [](double z) { return FancyMath::tdistcdf(z, 3.0); },
+    -50.0, 50.0, 2000);
+  for(int i = 0; i < table.size; i++) cout << Global::strprintf("%.17g", table.cdfTable[i]) << endl;
   return 0;
 }
 
@@ -342,6 +376,7 @@ int main(int argc, char** argv) {
   if(cmd == "boardstream") return cmdBoardStream(argc, argv);
   if(cmd == "searchfake") return cmdSearchFake(argc, argv);
   if(cmd == "svsamples") return cmdSVSamples(argc, argv);
+  if(cmd == "vwtable") return cmdVWTable(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

@@ -5,7 +5,7 @@ deterministic hash-based fake net as its NeuralNet backend (oracle/ref_driver.cp
 the device loop implements.  Stored per case: the move prefix, maxVisits, and for the root: each child's
 visit count, the post-processed NN policy and the utility average.  The device loop is given the same fake net
 (debug_fake_nn) and must reproduce the visit counts."""
-import os, subprocess, sys
+import json, os, subprocess, sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -25,9 +25,21 @@ def prefix_from_stream(name, n):
     return out
 
 
+SCORE_KEYS = ("staticScoreUtilityFactor", "dynamicScoreUtilityFactor", "dynamicScoreCenterZeroWeight", "dynamicScoreCenterScale")
+# the search part of cpp/configs/training/selfplay8mainb18.cfg that the device loop implements
+SELFPLAY8B18 = {"staticScoreUtilityFactor": 0.05, "dynamicScoreUtilityFactor": 0.30, "dynamicScoreCenterZeroWeight": 0.25,
+                "dynamicScoreCenterScale": 0.50, "cpuctExploration": 1.05, "cpuctExplorationLog": 0.28, "fpuReductionMax": 0.2,
+                "rootFpuReductionMax": 0.0, "valueWeightExponent": 0.5, "fpuParentWeightByVisitedPolicy": 1,
+                "fpuParentWeightByVisitedPolicyPow": 2.0, "rootDesiredPerChildVisitsCoeff": 2}
+
+
 def run(X, Y, visits, moves, score=None):
     s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
-    extra = [] if score is None else [repr(float(t)) for t in score]
+    if score is None:
+        score = {}
+    elif not isinstance(score, dict):
+        score = dict(zip(SCORE_KEYS, score))
+    extra = [f"{k}={float(v)!r}" for k, v in score.items()]
     out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     for ln in out.splitlines():
@@ -61,13 +73,26 @@ if __name__ == "__main__":
         (19, 19, 400, prefix_from_stream("boardstream_19x19_multisuicide.npz", 131), (0.3, 0.0, 0.0, 1.0)),   # SearchParams defaults
         (13, 7, 300, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), (0.1, 0.3, 0.25, 0.5)),
         (5, 5, 600, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), (0.05, 0.30, 0.25, 0.50)),      # reaches terminal nodes
+        # value weighting, FPU blending, utility-stdev exploration scaling, root per-child visit floor (a19/a20 widened)
+        (9, 9, 400, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), {"valueWeightExponent": 0.5}),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), {"valueWeightExponent": 0.5}),
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), SELFPLAY8B18),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), SELFPLAY8B18),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 0), SELFPLAY8B18),
+        (13, 7, 500, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), SELFPLAY8B18),
+        (5, 5, 600, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), SELFPLAY8B18),
+        (9, 9, 500, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12),
+         {"valueWeightExponent": 0.25, "cpuctUtilityStdevScale": 0.85, "cpuctUtilityStdevPrior": 0.4, "cpuctUtilityStdevPriorWeight": 2.0,
+          "fpuParentWeight": 0.3, "fpuLossProp": 0.1, "rootFpuLossProp": 0.05, "staticScoreUtilityFactor": 0.1}),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
         X, Y, visits, moves = case[:4]
         score = case[4] if len(case) > 4 else None
         root, v, u, pol, center = run(X, Y, visits, moves, score)
-        store[f"c{i}_score_params"] = np.array(score if score is not None else (0.0, 0.0, 0.0, 1.0), np.float64)
+        if score is not None and not isinstance(score, dict):
+            score = dict(zip(SCORE_KEYS, score))
+        store[f"c{i}_params"] = np.array(json.dumps(score or {}))
         store[f"c{i}_recent_score_center"] = np.float64(center)
         assert root[0] == visits and v.sum() == visits - 1
         store[f"c{i}_shape"] = np.array([X, Y, visits], np.int32)
