@@ -187,6 +187,9 @@ typedef struct kgb_selfplay_stats {
  * n independent lookups.  Test hook for the score-utility table. */
 KGB_API int kgb_expected_white_score_value(int n, const double* mean, const double* stdev, const double* center, const double* scale,
                                            const double* sqrt_board_area, double* out);
+/* The value-weighting CDF table the device loop uploads (Search's DistributionTable over tdistcdf(z, 3), search.cpp:131-137):
+ * n must be 2000.  Test hook (row a20). */
+KGB_API int kgb_value_weight_cdf_table(double* out, int n);
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out);
 KGB_API void kgb_selfplay_free(kgb_selfplay* sp);
 /* Enqueue `steps` playout waves on the handle's stream (asynchronous; kgb_handle_sync() to wait). */

@@ -854,6 +854,14 @@ KGB_API int kgb_expected_white_score_value(int n, const double* mean, const doub
   });
 }
 
+KGB_API int kgb_value_weight_cdf_table(double* out, int n) {
+  return guarded([&] {
+    if(!out || n != VW_TABLE_SIZE) throw std::invalid_argument("kgb_value_weight_cdf_table: out must hold 2000 doubles");
+    const std::vector<double> t = makeValueWeightCdfTable();
+    std::copy(t.begin(), t.end(), out);
+  });
+}
+
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out) {
   return guarded([&] {
     if(!handle || !config || !out) throw std::invalid_argument("kgb_selfplay_create: NULL argument");

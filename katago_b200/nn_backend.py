@@ -66,7 +66,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load_library():
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
     lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
+    lib.kgb_value_weight_cdf_table.argtypes = [P, I]
     lib.kgb_selfplay_get_leaf_path.argtypes = [P, I, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
     _lib = lib
@@ -313,6 +314,12 @@ def zobrist_tables(x_size: int, y_size: int):
     sh = np.zeros(2, np.uint64)
     _check(lib.kgb_zobrist_tables(x_size, y_size, bh.ctypes.data, sh.ctypes.data))
     return bh, sh
+
+
+def value_weight_cdf_table():
+    out = np.zeros(2000, np.float64)
+    _check(load_library().kgb_value_weight_cdf_table(out.ctypes.data, 2000))
+    return out
 
 
 def expected_white_score_value(mean, stdev, center, scale, sqrt_board_area):

@@ -129,3 +129,10 @@ def test_score_value_table_is_bit_exact_vs_reference(golden_dir):
     a = d["args"]
     got = expected_white_score_value(a[:, 0], a[:, 1], a[:, 2], a[:, 3], a[:, 4])
     assert np.array_equal(got, d["value"])
+
+
+def test_value_weight_cdf_table_is_bit_exact_vs_reference(golden_dir):
+    """Row a20: the t-distribution (3 dof) CDF table of the value weighting, as Search's constructor builds it from
+    FancyMath::tdistcdf (fixture: the reference's own DistributionTable, tests/golden/make_scorevalue_fixture.py)."""
+    from katago_b200.nn_backend import value_weight_cdf_table
+    assert np.array_equal(value_weight_cdf_table(), np.load(os.path.join(golden_dir, "value_weight_cdf_table.npy")))
