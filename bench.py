@@ -261,6 +261,7 @@ def main():
                   cpuct_exploration=1.05, cpuct_exploration_log=0.28, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
                   root_fpu_reduction_max=0.0, value_weight_exponent=0.5, fpu_parent_weight_by_visited_policy=True,
                   fpu_parent_weight_by_visited_policy_pow=2.0, root_desired_per_child_visits_coeff=2.0,
+                  subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8,
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
@@ -320,7 +321,7 @@ def main():
                                   "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)",
                                   "backup = recomputeNodeStats per path node (value weighting, exponent 0.5)"],
                        "search_params": "selfplay8mainb18.cfg: cpuct 1.05/0.28/500, fpu 0.2 (root 0), fpuParentWeightByVisitedPolicy^2, valueWeightExponent 0.5, "
-                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2; not yet: graph search, subtree value bias, "
+                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8; not yet: graph search, "
                                         "root noise/temperature, multi-symmetry root, LCB move selection",
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",

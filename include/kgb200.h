@@ -169,6 +169,8 @@ typedef struct kgb_selfplay_config {
   double cpuct_utility_stdev_prior_weight;        /* cpuctUtilityStdevPriorWeight (1.0) */
   double cpuct_utility_stdev_scale;               /* cpuctUtilityStdevScale (0 = off) */
   double root_desired_per_child_visits_coeff;     /* rootDesiredPerChildVisitsCoeff */
+  double subtree_value_bias_factor;               /* subtreeValueBiasFactor (0.30 in selfplay8mainb18.cfg; 0 = off) */
+  double subtree_value_bias_weight_exponent;      /* subtreeValueBiasWeightExponent (0.8) */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {

@@ -52,6 +52,13 @@ struct SPDev {
   double cpuctUtilityStdevPrior, cpuctUtilityStdevPriorWeight, cpuctUtilityStdevScale;
   double fpuLossProp, rootFpuLossProp, fpuParentWeight, fpuParentWeightByVisitedPolicyPow, valueWeightExponent, rootDesiredPerChildVisitsCoeff;
   int fpuParentWeightByVisitedPolicy;
+  // subtree value bias (search.cpp:913-922, searchupdatehelpers.cpp:26-36, 273-310; subtreevaluebiastable.cpp): per game, per move
+  double subtreeValueBiasFactor, subtreeValueBiasWeightExponent;
+  int biasTableSize;                // slots per game (power of two)
+  unsigned long long* biasKey;      // [game][biasTableSize] 0 = empty
+  double *biasDeltaSum, *biasWeightSum;   // [game][biasTableSize] SubtreeValueBiasEntry
+  int* nodeBiasEntry;               // [game][maxNodes] slot or -1
+  double *nodeLastBiasDelta, *nodeLastBiasWeight;   // [game][maxNodes]
   const double* vwCdfTable;         // value-weighting t-CDF table [2000]
   double winLossUtilityFactor, noResultUtilityForWhite;
   // score utility (searchhelpers.cpp:272-279): static * SV(mean, stdev; 0, 2) + dynamic * SV(mean, stdev; recentScoreCenter, scale)
@@ -132,6 +139,52 @@ __device__ __forceinline__ void nodeInit(const SPDev& d, size_t nodeBase, int la
 __device__ __forceinline__ void nodeStatsReset(const SPDev& d, size_t gn, bool terminal) {
   d.nodeVisits[gn] = 0; d.nodeWeightSum[gn] = 0.0; d.nodeWeightSqSum[gn] = 0.0; d.nodeUtilAvg[gn] = 0.0; d.nodeUtilSqAvg[gn] = 0.0;
   d.nodeNNUtil[gn] = 0.0; d.nodeNumChildren[gn] = 0; d.nodeTerminal[gn] = terminal ? 1 : 0;
+  d.nodeBiasEntry[gn] = -1; d.nodeLastBiasDelta[gn] = 0.0; d.nodeLastBiasWeight[gn] = 0.0;
+}
+// Key of a SubtreeValueBiasTable entry (subtreevaluebiastable.cpp:70-88, localpattern.cpp:52-87): who moved, the move before,
+// the move, the ko point and the 5x5 neighbourhood of the move on the board BEFORE it (colour and in-atari per on-board cell).
+// The reference XORs Zobrist codes of exactly this information; any injective-enough hash of it defines the same classes.
+__device__ unsigned long long biasEntryKey(const WarpBoard& bd, int X, int Y, bool moverBlack, int prevMove /*hist code*/, int p) {
+  uint32_t lib1, lib2, lib3;
+  boardLibertyClasses(bd, lib1, lib2, lib3);
+  const int x = p & 31, y = p >> 5;
+  unsigned long long lo = 0, hi = 0;
+#pragma unroll
+  for(int dy = -2; dy <= 2; dy++) {
+    const int yy = y + dy;
+    const int src = yy < 0 ? 0 : yy > 31 ? 31 : yy;
+    const uint32_t rb = __shfl_sync(KGB_FULL, bd.b, src), rw = __shfl_sync(KGB_FULL, bd.w, src), ra = __shfl_sync(KGB_FULL, lib1, src);
+#pragma unroll
+    for(int dx = -2; dx <= 2; dx++) {
+      const int xx = x + dx;
+      unsigned long long code = 0;
+      if(yy >= 0 && yy < Y && xx >= 0 && xx < X) {
+        const uint32_t bit = 1u << xx;
+        code = 8ull | ((rb & bit) ? 1ull : (rw & bit) ? 2ull : 0ull) | ((ra & bit) ? 4ull : 0ull);
+      }
+      const int cell = (dy + 2) * 5 + (dx + 2);
+      if(cell < 16) lo |= code << (cell * 4); else hi |= code << ((cell - 16) * 4);
+    }
+  }
+  hi |= (unsigned long long)(moverBlack ? 1 : 2) << 40;
+  hi |= (unsigned long long)(unsigned)(prevMove + 2) << 42;      // -2 pass, else y*32+x (< 1024)
+  hi |= (unsigned long long)(unsigned)p << 53;
+  unsigned long long k = splitmix64(lo ^ splitmix64(hi ^ splitmix64((unsigned long long)(bd.ko + 1) * 0x9E3779B97F4A7C15ULL)));
+  return k == 0 ? 1 : k;
+}
+__device__ int biasFindOrInsert(const SPDev& d, int g, unsigned long long key) {   // one lane
+  const size_t tb = (size_t)g * d.biasTableSize;
+  int slot = (int)(key & (unsigned long long)(d.biasTableSize - 1));
+  while(true) {
+    const unsigned long long k = d.biasKey[tb + slot];
+    if(k == key) return slot;
+    if(k == 0) { d.biasKey[tb + slot] = key; d.biasDeltaSum[tb + slot] = 0.0; d.biasWeightSum[tb + slot] = 0.0; return slot; }
+    slot = (slot + 1) & (d.biasTableSize - 1);   // table is sized 2x the node pool: never full
+  }
+}
+__device__ __forceinline__ void biasTableClear(const SPDev& d, int g, int lane) {
+  const size_t tb = (size_t)g * d.biasTableSize;
+  for(int i = lane; i < d.biasTableSize; i += 32) d.biasKey[tb + i] = 0;
 }
 // acc += v[0] + v[1] + ... + v[n-1] added one after the other in lane order (the order the reference adds its children in),
 // for two quantities at once; every lane returns the same sums.  sh: 64 doubles of this warp's shared memory.
@@ -234,6 +287,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     nodeStatsReset(d, gb, false);
   }
   nodeInit(d, rootBase, lane);
+  biasTableClear(d, g, lane);   // all nodes freed: every entry is unused and dropped (search.cpp:860-861)
   __syncwarp();
 }
 
@@ -366,6 +420,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     const bool isPass = move == d.policySize - 1;
     const int p = isPass ? -1 : pointOfPos(move, d.X);
     lad2 = lad1; lad1 = d.nodeLad[(gb + node) * 32 + lane];
+    // a new child gets its subtree-value-bias entry from the position before the move (search.cpp:913-922): needs a previous
+    // move in the history and a non-pass move
+    unsigned long long biasKeyNew = 0;
+    if(d.subtreeValueBiasFactor != 0.0 && d.childNode[nb + move] < 0 && !isPass && h0 != -1) biasKeyNew = biasEntryKey(bd, d.X, d.Y, black, h0, p);
     boardPlay(bd, p, black);
     passes = isPass ? passes + 1 : 0;
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
@@ -381,6 +439,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
         d.childOrder[nb + nc] = (uint16_t)move;
         d.nodeNumChildren[gb + node] = nc + 1;
         nodeStatsReset(d, gb + child, passes >= 2);
+        if(biasKeyNew != 0) d.nodeBiasEntry[gb + child] = biasFindOrInsert(d, g, biasKeyNew);
         atomicAdd(d.nodesAllocated, 1ULL);
       }
       nodeInit(d, (gb + child) * d.policySize, lane);
@@ -599,7 +658,25 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
   }
   double weightSum = origTotal;
   // the node's own evaluation, weight 1
-  const double utility = d.nodeNNUtil[gn];
+  double utility = d.nodeNNUtil[gn];
+  const int entry = d.subtreeValueBiasFactor != 0.0 ? d.nodeBiasEntry[gn] : -1;
+  if(entry >= 0) {
+    // searchupdatehelpers.cpp:273-310: the node reports how far its children's average is from its own evaluation to the entry
+    // shared by all nodes reached by the same local move, and shifts its own evaluation by the entry's average observation
+    const size_t te = (size_t)g * d.biasTableSize + entry;
+    double newDelta, newWeight;
+    if(origTotal > 1e-10) {
+      const double utilityChildren = utilitySum / origTotal;
+      const double biasWeight = pow(origTotal, d.subtreeValueBiasWeightExponent);
+      const double biasDelta = (utilityChildren - utility) * biasWeight;
+      newDelta = d.biasDeltaSum[te] + (biasDelta - d.nodeLastBiasDelta[gn]);
+      newWeight = d.biasWeightSum[te] + (biasWeight - d.nodeLastBiasWeight[gn]);
+      __syncwarp();
+      if(lane == 0) { d.biasDeltaSum[te] = newDelta; d.biasWeightSum[te] = newWeight; d.nodeLastBiasDelta[gn] = biasDelta; d.nodeLastBiasWeight[gn] = biasWeight; }
+    }
+    else { newDelta = d.biasDeltaSum[te]; newWeight = d.biasWeightSum[te]; }
+    if(newWeight > 0.001) utility += d.subtreeValueBiasFactor * newDelta / newWeight;
+  }
   utilitySum += utility * 1.0;
   utilitySqSum += utility * utility * 1.0;
   weightSqSum += 1.0 * 1.0;
@@ -739,6 +816,12 @@ __global__ void spBackupKernel(const SPDev d) {
   else if(leafVisits == 0) {
     if(lane == 0) {
       d.nodeNNUtil[gl] = u;
+      const int entry = d.subtreeValueBiasFactor != 0.0 ? d.nodeBiasEntry[gl] : -1;
+      if(entry >= 0) {   // searchupdatehelpers.cpp:26-36
+        const size_t te = (size_t)g * d.biasTableSize + entry;
+        const double ew = d.biasWeightSum[te];
+        if(ew > 0.001) u += d.subtreeValueBiasFactor * d.biasDeltaSum[te] / ew;
+      }
       d.nodeUtilAvg[gl] = u; d.nodeUtilSqAvg[gl] = u * u; d.nodeWeightSqSum[gl] = 1.0; d.nodeWeightSum[gl] = 1.0;
       d.nodeVisits[gl] = 1;
     }
@@ -841,6 +924,7 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     d.ladPending[g] = 0; d.leafValid[g] = 0;
   }
   nodeInit(d, gb * d.policySize, lane);
+  biasTableClear(d, g, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -931,6 +1015,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.fpuLossProp = c.fpu_loss_prop; d.rootFpuLossProp = c.root_fpu_loss_prop; d.fpuParentWeight = c.fpu_parent_weight;
   d.fpuParentWeightByVisitedPolicy = c.fpu_parent_weight_by_visited_policy;
   d.fpuParentWeightByVisitedPolicyPow = c.fpu_parent_weight_by_visited_policy_pow;
+  d.subtreeValueBiasFactor = c.subtree_value_bias_factor; d.subtreeValueBiasWeightExponent = c.subtree_value_bias_weight_exponent;
   d.valueWeightExponent = c.value_weight_exponent; d.rootDesiredPerChildVisitsCoeff = c.root_desired_per_child_visits_coeff;
   if(c.max_visits + 2 > 65535) throw std::invalid_argument("selfplay: max_visits above 65533 not supported");
   d.winLossUtilityFactor = c.win_loss_utility_factor; d.noResultUtilityForWhite = c.no_result_utility_for_white;
@@ -958,6 +1043,11 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.nodeWeightSum = sp->alloc<double>(G * N); d.nodeWeightSqSum = sp->alloc<double>(G * N); d.nodeUtilAvg = sp->alloc<double>(G * N);
   d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
+  d.biasTableSize = 64;
+  while(d.biasTableSize < 2 * (int)N) d.biasTableSize *= 2;
+  d.biasKey = sp->alloc<unsigned long long>(G * d.biasTableSize); d.biasDeltaSum = sp->alloc<double>(G * d.biasTableSize);
+  d.biasWeightSum = sp->alloc<double>(G * d.biasTableSize);
+  d.nodeBiasEntry = sp->alloc<int>(G * N); d.nodeLastBiasDelta = sp->alloc<double>(G * N); d.nodeLastBiasWeight = sp->alloc<double>(G * N);
   d.nodeTerminal = sp->alloc<int8_t>(G * N);
   d.policy = sp->alloc<float>(G * N * PS); d.childNode = sp->alloc<int>(G * N * PS); d.childVisits = sp->alloc<int>(G * N * PS);
   d.pathLen = sp->alloc<int>(G); d.pathNode = sp->alloc<int>(G * d.maxDepth); d.pathMove = sp->alloc<int>(G * d.maxDepth);

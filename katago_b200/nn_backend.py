@@ -51,6 +51,7 @@ class SelfplayConfig(C.Structure):
         ("fpu_parent_weight_by_visited_policy_pow", C.c_double), ("fpu_parent_weight", C.c_double), ("fpu_loss_prop", C.c_double),
         ("root_fpu_loss_prop", C.c_double), ("cpuct_utility_stdev_prior", C.c_double), ("cpuct_utility_stdev_prior_weight", C.c_double),
         ("cpuct_utility_stdev_scale", C.c_double), ("root_desired_per_child_visits_coeff", C.c_double),
+        ("subtree_value_bias_factor", C.c_double), ("subtree_value_bias_weight_exponent", C.c_double),
     ]
 
 
@@ -361,7 +362,8 @@ class SelfPlay:
                  fpu_parent_weight_by_visited_policy: bool = False, fpu_parent_weight_by_visited_policy_pow: float = 1.0,
                  fpu_parent_weight: float = 0.0, fpu_loss_prop: float = 0.0, root_fpu_loss_prop: float = 0.0,
                  cpuct_utility_stdev_prior: float = 0.25, cpuct_utility_stdev_prior_weight: float = 1.0,
-                 cpuct_utility_stdev_scale: float = 0.0, root_desired_per_child_visits_coeff: float = 0.0):
+                 cpuct_utility_stdev_scale: float = 0.0, root_desired_per_child_visits_coeff: float = 0.0,
+                 subtree_value_bias_factor: float = 0.0, subtree_value_bias_weight_exponent: float = 0.5):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -371,7 +373,8 @@ class SelfPlay:
                                   dynamic_score_center_zero_weight, dynamic_score_center_scale, draw_equivalent_wins_for_white,
                                   value_weight_exponent, int(fpu_parent_weight_by_visited_policy), 0, fpu_parent_weight_by_visited_policy_pow,
                                   fpu_parent_weight, fpu_loss_prop, root_fpu_loss_prop, cpuct_utility_stdev_prior,
-                                  cpuct_utility_stdev_prior_weight, cpuct_utility_stdev_scale, root_desired_per_child_visits_coeff)
+                                  cpuct_utility_stdev_prior_weight, cpuct_utility_stdev_scale, root_desired_per_child_visits_coeff,
+                                  subtree_value_bias_factor, subtree_value_bias_weight_exponent)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen

@@ -33,6 +33,9 @@ SELFPLAY8B18 = {"staticScoreUtilityFactor": 0.05, "dynamicScoreUtilityFactor": 0
                 "fpuParentWeightByVisitedPolicyPow": 2.0, "rootDesiredPerChildVisitsCoeff": 2}
 
 
+BIAS = {"subtreeValueBiasFactor": 0.30, "subtreeValueBiasWeightExponent": 0.8}
+
+
 def run(X, Y, visits, moves, score=None):
     s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
     if score is None:
@@ -84,6 +87,13 @@ if __name__ == "__main__":
         (9, 9, 500, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12),
          {"valueWeightExponent": 0.25, "cpuctUtilityStdevScale": 0.85, "cpuctUtilityStdevPrior": 0.4, "cpuctUtilityStdevPriorWeight": 2.0,
           "fpuParentWeight": 0.3, "fpuLossProp": 0.1, "rootFpuLossProp": 0.05, "staticScoreUtilityFactor": 0.1}),
+        # subtree value bias (a23, tree search): entries shared by nodes reached by the same local move
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), dict(SELFPLAY8B18, **BIAS)),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), dict(SELFPLAY8B18, **BIAS)),
+        (19, 19, 400, prefix_from_stream("boardstream_19x19_multisuicide.npz", 0), dict(SELFPLAY8B18, **BIAS)),
+        (13, 7, 500, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), dict(SELFPLAY8B18, **BIAS)),
+        (5, 5, 600, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), dict(SELFPLAY8B18, **BIAS)),
+        (9, 9, 500, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), {"subtreeValueBiasFactor": 0.45, "subtreeValueBiasWeightExponent": 0.5}),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
