@@ -261,7 +261,7 @@ def main():
                   cpuct_exploration=1.05, cpuct_exploration_log=0.28, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
                   root_fpu_reduction_max=0.0, value_weight_exponent=0.5, fpu_parent_weight_by_visited_policy=True,
                   fpu_parent_weight_by_visited_policy_pow=2.0, root_desired_per_child_visits_coeff=2.0,
-                  subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8,
+                  subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8, use_graph_search=True, graph_search_rep_bound=11,
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
@@ -275,9 +275,11 @@ def main():
     ms_dev = timed(lambda i: sp.run(1), K)
     clocks = sampler.stop() if rank == 0 else None
     after = sp.stats()
-    # a wave adds one visit per game, except for games whose ladder searches are still running (stalled_waves)
+    # a wave delivers one evaluated leaf per game, except for games whose ladder searches are still running (stalled_waves);
+    # under graph search a game can also finish extra playouts inside the wave on edges that only need to catch up
     done = after["total_visits"] - before["total_visits"]
-    assert done + (after["stalled_waves"] - before["stalled_waves"]) == n * K, (before, after)
+    instant = after["instant_playouts"] - before["instant_playouts"]
+    assert (done - instant) + (after["stalled_waves"] - before["stalled_waves"]) == n * K, (before, after)
     visits_done = torch.tensor([float(done)], device=device)
     if world > 1:
         dist.all_reduce(visits_done, op=dist.ReduceOp.SUM)
@@ -321,7 +323,7 @@ def main():
                                   "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)",
                                   "backup = recomputeNodeStats per path node (value weighting, exponent 0.5)"],
                        "search_params": "selfplay8mainb18.cfg: cpuct 1.05/0.28/500, fpu 0.2 (root 0), fpuParentWeightByVisitedPolicy^2, valueWeightExponent 0.5, "
-                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8; not yet: graph search, "
+                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8, useGraphSearch (repBound 11); not yet: "
                                         "root noise/temperature, multi-symmetry root, LCB move selection",
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
@@ -334,6 +336,7 @@ def main():
                                   "searches": after["ladder_searches"] - before["ladder_searches"],
                                   "search_moves": after["ladder_nodes"] - before["ladder_nodes"],
                                   "game_waves_without_leaf": after["stalled_waves"] - before["stalled_waves"],
+                                  "playouts_without_evaluation(graph search catch-up)": instant,
                                   "game_waves": n * K},
                        "weight_broadcast_ms": bcast_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},

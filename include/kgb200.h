@@ -171,6 +171,10 @@ typedef struct kgb_selfplay_config {
   double root_desired_per_child_visits_coeff;     /* rootDesiredPerChildVisitsCoeff */
   double subtree_value_bias_factor;               /* subtreeValueBiasFactor (0.30 in selfplay8mainb18.cfg; 0 = off) */
   double subtree_value_bias_weight_exponent;      /* subtreeValueBiasWeightExponent (0.8) */
+  int32_t use_graph_search;                       /* useGraphSearch: transpositions share a node (search.cpp:875-936) */
+  int32_t graph_search_rep_bound;                 /* graphSearchRepBound (11) */
+  int32_t debug_hold_at_max_visits;               /* TEST ONLY: a game whose root has max_visits visits idles instead of moving */
+  int32_t reserved2;
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -182,7 +186,9 @@ typedef struct kgb_selfplay_stats {
   uint64_t sum_leaf_depth;   /* sum over playouts of the leaf depth */
   uint64_t ladder_searches;  /* ladder searches run for feature planes 14-17 */
   uint64_t ladder_nodes;     /* moves played inside those searches */
-  uint64_t stalled_waves;    /* game-waves without a leaf because ladder searches were still running (ladder_nodes_per_wave) */
+  uint64_t stalled_waves;    /* game-waves without a leaf: ladder searches still running (ladder_nodes_per_wave), or every playout
+                                of the wave ended on an existing edge */
+  uint64_t instant_playouts; /* graph search: playouts that ended on an edge catch-up or a cycle and needed no evaluation */
 } kgb_selfplay_stats;
 
 /* ScoreValue::expectedWhiteScoreValue (neuralnet/nninputs.cpp:160-192) on the host, with the table the device loop uploads:

@@ -42,6 +42,7 @@
 
 namespace kgb {
 
+static constexpr int SP_MAX_PLAYOUTS_PER_WAVE = 16;   // playouts a game may finish inside one wave without needing the evaluator
 static constexpr int SP_LADDER_WARPS = 8;   // warps per game in the select kernel (ladder searches are dealt out to all of them)
 
 struct SPDev {
@@ -58,6 +59,15 @@ struct SPDev {
   unsigned long long* biasKey;      // [game][biasTableSize] 0 = empty
   double *biasDeltaSum, *biasWeightSum;   // [game][biasTableSize] SubtreeValueBiasEntry
   int* nodeBiasEntry;               // [game][maxNodes] slot or -1
+  // graph search (search.cpp:875-936, game/graphhash.cpp): transposition table per game, cleared with the tree
+  int useGraphSearch, graphSearchRepBound, holdAtMaxVisits;
+  int nodeTableSize;                // slots per game (power of two)
+  unsigned long long *nodeTableKey0, *nodeTableKey1;   // [game][nodeTableSize]
+  int* nodeTableNode;               // [game][nodeTableSize] node index or -1
+  unsigned long long *nodePosH0, *nodePosH1, *nodeGH0, *nodeGH1;   // [game][maxNodes] Zobrist position hash and graph hash
+  unsigned long long *rootPosH;     // [game][2]
+  const ZobEntry* zob;              // Board::ZOBRIST_BOARD_HASH for this board size
+  unsigned long long* instantPlayouts;   // playouts that ended on an edge catch-up or a cycle (no evaluation needed)
   double *nodeLastBiasDelta, *nodeLastBiasWeight;   // [game][maxNodes]
   const double* vwCdfTable;         // value-weighting t-CDF table [2000]
   double winLossUtilityFactor, noResultUtilityForWhite;
@@ -195,6 +205,64 @@ __device__ __forceinline__ void orderedAdd2(double a, double b, int n, double& a
   __syncwarp();
 }
 
+// GraphHash::getStateHash (game/graphhash.cpp:4-24) for the rule subset: position, player to move, ko point, whether a pass
+// ends the phase, game over, consecutive passes.  (Own mixing constants: only equality of hashes matters to the search.)
+__device__ __forceinline__ void stateHash(unsigned long long posH0, unsigned long long posH1, bool nextBlack, int ko, int passes, bool gameOver,
+                                          unsigned long long& s0, unsigned long long& s1) {
+  s0 = posH0 ^ (nextBlack ? 0x8F1BBCDCA62C1D6BULL : 0x5A827999ED9EBA1FULL);
+  s1 = posH1 ^ (nextBlack ? 0xC3A5C85C97CB3127ULL : 0xB492B66FBE98F273ULL);
+  if(ko >= 0) { const unsigned long long k = splitmix64((unsigned long long)ko + 0x51ED27ULL); s0 ^= k; s1 ^= splitmix64(k); }
+  if(passes >= 1) { s0 ^= 0x9AE16A3B2F90404FULL; s1 ^= 0xCBF29CE484222325ULL; }     // passWouldEndPhase
+  if(gameOver) { s0 ^= 0x2545F4914F6CDD1DULL; s1 ^= 0x106689D45497FDB5ULL; }
+  s0 += 2862933555777941757ULL * (unsigned long long)passes;
+  s1 += 3202034522624059733ULL * (unsigned long long)passes;
+}
+// Board::simpleRepetitionBoundGt (board.cpp:2825-2888) on the board AFTER the move at p: stones of the chain at p plus all
+// empty points of the regions its liberties belong to (or, if p is empty after a suicide, the empty region around p) > bound.
+__device__ __forceinline__ bool simpleRepetitionBoundGt(const WarpBoard& bd, int p, int bound) {
+  if(p < 0) return false;
+  const uint32_t rm = bd.rowMask, pt = pointMask(p);
+  const uint32_t empty = ~(bd.b | bd.w) & rm;
+  const bool isB = __any_sync(KGB_FULL, (pt & bd.b) != 0), isW = __any_sync(KGB_FULL, (pt & bd.w) != 0);
+  if(!isB && !isW) return warpCount(flood(pt, empty, rm)) > bound;
+  const uint32_t chain = flood(pt, isB ? bd.b : bd.w, rm);
+  const uint32_t region = flood(nbrs(chain, rm) & empty, empty, rm);
+  return warpCount(chain) + warpCount(region) > bound;
+}
+// GraphHash::getGraphHash (game/graphhash.cpp:26-41): state hash alone when the last move cannot be part of a repetition,
+// otherwise chained with the parent's graph hash (the node is then only shared by identical histories).
+__device__ __forceinline__ void graphHashOfChild(unsigned long long pg0, unsigned long long pg1, unsigned long long s0, unsigned long long s1,
+                                                 bool repetitionImpossible, unsigned long long& g0, unsigned long long& g1) {
+  if(repetitionImpossible) { g0 = s0; g1 = s1; return; }
+  g0 = splitmix64(pg0 ^ pg1);
+  g1 = splitmix64(pg1 * 0x9FB21C651E98DF25ULL + 0x632BE59BD9B4E019ULL) + g0;
+  g0 += s0; g1 += s1;
+}
+__device__ int nodeTableFind(const SPDev& d, int g, unsigned long long k0, unsigned long long k1, int& slotOut) {   // uniform
+  const size_t tb = (size_t)g * d.nodeTableSize;
+  int slot = (int)((k0 ^ (k1 >> 7)) & (unsigned long long)(d.nodeTableSize - 1));
+  while(true) {
+    const int n = d.nodeTableNode[tb + slot];
+    if(n < 0) { slotOut = slot; return -1; }
+    if(d.nodeTableKey0[tb + slot] == k0 && d.nodeTableKey1[tb + slot] == k1) { slotOut = slot; return n; }
+    slot = (slot + 1) & (d.nodeTableSize - 1);
+  }
+}
+__device__ __forceinline__ void nodeTableClear(const SPDev& d, int g, int lane) {
+  const size_t tb = (size_t)g * d.nodeTableSize;
+  for(int i = lane; i < d.nodeTableSize; i += 32) d.nodeTableNode[tb + i] = -1;
+}
+// The root node's hashes (after the root position changed): its position hash is tracked with the root board.
+__device__ __forceinline__ void rootHashesInit(const SPDev& d, int g, int lane) {
+  if(lane == 0) {
+    const size_t gb = (size_t)g * d.maxNodes;
+    const unsigned long long h0 = d.rootPosH[g * 2], h1 = d.rootPosH[g * 2 + 1];
+    unsigned long long s0, s1;
+    stateHash(h0, h1, d.rootBlackToMove[g] != 0, d.rootKo[g], d.consecPasses[g], false, s0, s1);
+    d.nodePosH0[gb] = h0; d.nodePosH1[gb] = h1; d.nodeGH0[gb] = s0; d.nodeGH1[gb] = s1;
+  }
+}
+
 // Choose and play the root move once the visit budget is spent; restart the game when it is over.
 __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   const size_t gb = (size_t)g * d.maxNodes;
@@ -248,7 +316,8 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   const bool isPass = best == d.policySize - 1;
   const int p = isPass ? -1 : pointOfPos(best, d.X);
   const uint32_t beforeB = bd.b, beforeW = bd.w; const int beforeKo = bd.ko;
-  boardPlay(bd, p, black);
+  bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];
+  boardPlay(bd, p, black, d.zob);
   int passes = isPass ? d.consecPasses[g] + 1 : 0;
   int mv = d.moveNum[g] + 1;
   bool over = passes >= 2 || mv >= d.maxMoves;
@@ -280,6 +349,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
   if(lane == 0) {
     d.rootKo[g] = bd.ko; d.rootCapB[g] = bd.capB; d.rootCapW[g] = bd.capW;
+    d.rootPosH[g * 2] = bd.h0; d.rootPosH[g * 2 + 1] = bd.h1;   // boardInit zeroes them for a new game
     d.moveNum[g] = mv; d.consecPasses[g] = passes;
     atomicAdd(d.totalMoves, 1ULL);
     // reset the tree: node 0 = unevaluated root
@@ -288,29 +358,44 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   }
   nodeInit(d, rootBase, lane);
   biasTableClear(d, g, lane);   // all nodes freed: every entry is unused and dropped (search.cpp:860-861)
+  nodeTableClear(d, g, lane);
+  __syncwarp();
+  rootHashesInit(d, g, lane);
   __syncwarp();
 }
+
+__device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePlaWhite, double* sh, int lane);
 
 // Warp 0 of a game's block: PUCT descent, leaf board, legality and every feature except the leaf's own ladder searches.
 __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, uint32_t* shW, uint32_t* shCand, int& shKo, int& shDoLadders,
                               double* shSum) {
   const size_t gb = (size_t)g * d.maxNodes;
-  if(d.nodeVisits[gb] >= d.maxVisits) rootAdvance(d, g, lane);
-
+  const size_t G32 = (size_t)d.numGames * 32;
   WarpBoard bd;
+  bool black = true, terminal = false, gotLeaf = false;
+  int passes = 0, h0 = -1, h1 = -1, h2 = -1, h3 = -1, h4 = -1, node = 0, depth = 0;
+  uint32_t lad1 = 0, lad2 = 0;
+  // Under graph search a playout can end without reaching a new leaf (edge catch-up, cycle): it is backed up at once and the
+  // next playout starts, so that the wave still delivers a leaf for the evaluator.
+  for(int attempt = 0; attempt < SP_MAX_PLAYOUTS_PER_WAVE && !gotLeaf; attempt++) {
+  if(d.nodeVisits[gb] >= d.maxVisits) {
+    if(d.holdAtMaxVisits) break;   // test mode: keep the finished tree for inspection
+    rootAdvance(d, g, lane);
+  }
   boardInit(bd, d.X, d.Y);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
   bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
-  bool black = d.rootBlackToMove[g] != 0;
-  int passes = d.consecPasses[g];
-  int h0 = d.hist[g * 5 + 0], h1 = d.hist[g * 5 + 1], h2 = d.hist[g * 5 + 2], h3 = d.hist[g * 5 + 3], h4 = d.hist[g * 5 + 4];
-  // boards one and two moves ago (ladder planes 15/16): the root's recent boards, shifted as the descent plays moves
-  const size_t G32 = (size_t)d.numGames * 32;
+  const bool rootBlack = d.rootBlackToMove[g] != 0;
+  black = rootBlack;
+  passes = d.consecPasses[g];
+  h0 = d.hist[g * 5 + 0]; h1 = d.hist[g * 5 + 1]; h2 = d.hist[g * 5 + 2]; h3 = d.hist[g * 5 + 3]; h4 = d.hist[g * 5 + 4];
+  // boards one and two moves ago (ladder planes 15/16): the root's recent boards, shifted as the descent plays moves.
   // Their laddered stones were computed when those positions were leaves themselves (a node's board is its child's
   // previous board), so only the leaf's own board ever needs a ladder search.
-  uint32_t lad1 = d.prevLad[g * 32 + lane], lad2 = d.prevLad[G32 + g * 32 + lane];
-  int node = 0, depth = 0;
-  bool terminal = false;
+  lad1 = d.prevLad[g * 32 + lane]; lad2 = d.prevLad[G32 + g * 32 + lane];
+  node = 0; depth = 0;
+  terminal = false;
+  bool instant = false;   // this playout ended on an existing edge: back it up here, no leaf
   while(true) {
     const int visits = d.nodeVisits[gb + node];
     terminal = d.nodeTerminal[gb + node] != 0;
@@ -416,6 +501,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(bestK < 0 || newVal > bestVal) move = bestNewIdx;
     }
     if(move < 0) break;  // no legal move at all (cannot happen: pass is always legal)
+    if(lane == 0) { d.pathNode[(size_t)g * d.maxDepth + depth] = node; d.pathMove[(size_t)g * d.maxDepth + depth] = move; }
+    __syncwarp();
+    // ---- graph search: an edge with fewer visits than its (shared) child catches up without descending (search.cpp:1468-1504)
+    if(d.useGraphSearch && d.childNode[nb + move] >= 0 && d.childVisits[nb + move] < d.nodeVisits[gb + d.childNode[nb + move]]) { instant = true; break; }
     // ---- descend
     const bool isPass = move == d.policySize - 1;
     const int p = isPass ? -1 : pointOfPos(move, d.X);
@@ -424,30 +513,75 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     // move in the history and a non-pass move
     unsigned long long biasKeyNew = 0;
     if(d.subtreeValueBiasFactor != 0.0 && d.childNode[nb + move] < 0 && !isPass && h0 != -1) biasKeyNew = biasEntryKey(bd, d.X, d.Y, black, h0, p);
-    boardPlay(bd, p, black);
+    int child = d.childNode[nb + move];
+    const bool newEdge = child < 0;
+    if(newEdge && d.useGraphSearch) { bd.h0 = d.nodePosH0[gb + node]; bd.h1 = d.nodePosH1[gb + node]; }
+    boardPlay(bd, p, black, (newEdge && d.useGraphSearch) ? d.zob : nullptr);
     passes = isPass ? passes + 1 : 0;
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
     black = !black;
-    int child = d.childNode[nb + move];
-    if(child < 0) {
-      child = d.nodeCount[g];
-      if(child >= d.maxNodes) break;  // pool exhausted (sized maxVisits+2: cannot happen)
+    if(newEdge) {
+      // Search::allocateOrFindNode (search.cpp:875-936): under graph search the child may already exist (transposition)
+      unsigned long long cg0 = 0, cg1 = 0;
+      int tableSlot = -1, found = -1;
+      if(d.useGraphSearch) {
+        unsigned long long s0, s1;
+        stateHash(bd.h0, bd.h1, black, bd.ko, passes, passes >= 2, s0, s1);
+        graphHashOfChild(d.nodeGH0[gb + node], d.nodeGH1[gb + node], s0, s1, simpleRepetitionBoundGt(bd, p, d.graphSearchRepBound), cg0, cg1);
+        found = nodeTableFind(d, g, cg0, cg1, tableSlot);
+      }
+      if(found >= 0) child = found;
+      else {
+        child = d.nodeCount[g];
+        if(child >= d.maxNodes) break;  // pool exhausted (sized maxVisits+2: cannot happen)
+      }
       __syncwarp();
       if(lane == 0) {
-        d.nodeCount[g] = child + 1;
         d.childNode[nb + move] = child;
         d.childOrder[nb + nc] = (uint16_t)move;
         d.nodeNumChildren[gb + node] = nc + 1;
-        nodeStatsReset(d, gb + child, passes >= 2);
-        if(biasKeyNew != 0) d.nodeBiasEntry[gb + child] = biasFindOrInsert(d, g, biasKeyNew);
-        atomicAdd(d.nodesAllocated, 1ULL);
+        if(found < 0) {
+          d.nodeCount[g] = child + 1;
+          nodeStatsReset(d, gb + child, passes >= 2);
+          if(biasKeyNew != 0) d.nodeBiasEntry[gb + child] = biasFindOrInsert(d, g, biasKeyNew);
+          if(d.useGraphSearch) {
+            const size_t ts = (size_t)g * d.nodeTableSize + tableSlot;
+            d.nodeTableKey0[ts] = cg0; d.nodeTableKey1[ts] = cg1; d.nodeTableNode[ts] = child;
+            d.nodePosH0[gb + child] = bd.h0; d.nodePosH1[gb + child] = bd.h1; d.nodeGH0[gb + child] = cg0; d.nodeGH1[gb + child] = cg1;
+          }
+          atomicAdd(d.nodesAllocated, 1ULL);
+        }
       }
-      nodeInit(d, (gb + child) * d.policySize, lane);
+      if(found < 0) nodeInit(d, (gb + child) * d.policySize, lane);
       __syncwarp();
     }
-    if(lane == 0) { d.pathNode[(size_t)g * d.maxDepth + depth] = node; d.pathMove[(size_t)g * d.maxDepth + depth] = move; }
     depth++;
+    if(d.useGraphSearch) {
+      // a child that is already on this playout's path closes a cycle: count the edge and stop (search.cpp:1425-1443)
+      bool onPath = false;
+      for(int k = lane; k < depth; k += 32) onPath |= d.pathNode[(size_t)g * d.maxDepth + k] == child;
+      if(__any_sync(KGB_FULL, onPath)) { depth--; instant = true; break; }
+    }
     node = child;
+  }
+  if(instant) {
+    // edge visit + updateStatsAfterPlayout for the node where the playout stopped and for every ancestor
+    for(int k = depth; k >= 0; k--) {
+      const int pn = d.pathNode[(size_t)g * d.maxDepth + k], mv = d.pathMove[(size_t)g * d.maxDepth + k];
+      if(lane == 0) d.childVisits[(gb + pn) * d.policySize + mv] += 1;
+      __syncwarp();
+      const bool pnBlack = (k & 1) ? !rootBlack : rootBlack;
+      recomputeNodeStats(d, g, pn, !pnBlack, shSum, lane);
+      __syncwarp();
+    }
+    if(lane == 0) { atomicAdd(d.totalVisits, 1ULL); atomicAdd(d.instantPlayouts, 1ULL); }
+    continue;
+  }
+  gotLeaf = true;
+  }   // attempts
+  if(!gotLeaf) {   // every playout of this wave ended on an existing edge: nothing for the evaluator
+    if(lane == 0) { shDoLadders = 0; d.leafValid[g] = 0; atomicAdd(d.stalledWaves, 1ULL); }
+    return;
   }
   terminal = d.nodeTerminal[gb + node] != 0;
 
@@ -891,11 +1025,12 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
   const size_t G32 = (size_t)d.numGames * 32;
   uint32_t p1B = d.prevB[g * 32 + lane], p1W = d.prevW[g * 32 + lane], p2B = d.prevB[G32 + g * 32 + lane], p2W = d.prevW[G32 + g * 32 + lane];
   int p1Ko = d.prevKo[g], p2Ko = d.prevKo[d.numGames + g];
+  bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];
   for(int m = 0; m < numMoves; m++) {
     const bool isPass = moves[m * 2] < 0;
     const int p = isPass ? -1 : (moves[m * 2 + 1] * 32 + moves[m * 2]);
     p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
-    boardPlay(bd, p, black);
+    boardPlay(bd, p, black, d.zob);
     passes = isPass ? passes + 1 : 0;
     for(int k = 4; k > 0; k--) h[k] = h[k - 1];
     h[0] = isPass ? -2 : p;
@@ -922,9 +1057,21 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
     d.nodeCount[g] = 1; nodeStatsReset(d, gb, false);
     d.ladPending[g] = 0; d.leafValid[g] = 0;
+    d.rootPosH[g * 2] = bd.h0; d.rootPosH[g * 2 + 1] = bd.h1;
   }
   nodeInit(d, gb * d.policySize, lane);
   biasTableClear(d, g, lane);
+  nodeTableClear(d, g, lane);
+  __syncwarp();
+  rootHashesInit(d, g, lane);
+}
+
+__global__ void spInitRootsKernel(const SPDev d) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  nodeTableClear(d, g, lane);
+  rootHashesInit(d, g, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1043,6 +1190,22 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.nodeWeightSum = sp->alloc<double>(G * N); d.nodeWeightSqSum = sp->alloc<double>(G * N); d.nodeUtilAvg = sp->alloc<double>(G * N);
   d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
+  d.holdAtMaxVisits = c.debug_hold_at_max_visits ? 1 : 0;
+  d.useGraphSearch = c.use_graph_search ? 1 : 0; d.graphSearchRepBound = c.graph_search_rep_bound;
+  d.nodeTableSize = 64;
+  while(d.nodeTableSize < 2 * (int)N) d.nodeTableSize *= 2;
+  d.nodeTableKey0 = sp->alloc<unsigned long long>(G * d.nodeTableSize); d.nodeTableKey1 = sp->alloc<unsigned long long>(G * d.nodeTableSize);
+  d.nodeTableNode = sp->alloc<int>(G * d.nodeTableSize);
+  d.nodePosH0 = sp->alloc<unsigned long long>(G * N); d.nodePosH1 = sp->alloc<unsigned long long>(G * N);
+  d.nodeGH0 = sp->alloc<unsigned long long>(G * N); d.nodeGH1 = sp->alloc<unsigned long long>(G * N);
+  d.rootPosH = sp->alloc<unsigned long long>(G * 2);
+  {
+    const ZobristTables zt = makeZobristTables(X, Y);
+    static_assert(sizeof(ZobEntry) == sizeof(Hash128), "layout");
+    ZobEntry* dz = sp->alloc<ZobEntry>(zt.board.size());
+    SPCK(cudaMemcpy(dz, zt.board.data(), zt.board.size() * sizeof(ZobEntry), cudaMemcpyHostToDevice));
+    d.zob = dz;
+  }
   d.biasTableSize = 64;
   while(d.biasTableSize < 2 * (int)N) d.biasTableSize *= 2;
   d.biasKey = sp->alloc<unsigned long long>(G * d.biasTableSize); d.biasDeltaSum = sp->alloc<double>(G * d.biasTableSize);
@@ -1055,7 +1218,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafLegal = sp->alloc<uint32_t>(G * 32);
   unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
-  d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8;
+  d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8; d.instantPlayouts = stats + 9;
   d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
   d.nnPolicy = nn.policy; d.nnValue = nn.value; d.nnScore = nn.score;
   {
@@ -1076,6 +1239,9 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   SPCK(cudaMemcpy(d.hist, minus.data(), G * 5 * sizeof(int), cudaMemcpyHostToDevice));
   SPCK(cudaMemcpy(d.rootKo, kos.data(), G * sizeof(int), cudaMemcpyHostToDevice));
   SPCK(cudaMemset(d.childNode, 0xff, G * N * PS * sizeof(int)));
+  SPCK(cudaDeviceSynchronize());
+  spInitRootsKernel<<<(unsigned)((G * 32 + 127) / 128), 128>>>(d);
+  SPCK(cudaGetLastError());
   SPCK(cudaDeviceSynchronize());   // the uploads above are not ordered against the (non-blocking) stream the loop runs on
   return sp.release();
 }
@@ -1114,7 +1280,7 @@ void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {
   SPCK(cudaMemcpy(h, sp->d.totalVisits, sizeof(h), cudaMemcpyDeviceToHost));
   out->total_visits = h[0]; out->total_moves = h[1]; out->games_finished = h[2]; out->black_wins = h[3];
   out->nodes_allocated = h[4]; out->sum_leaf_depth = h[5]; out->ladder_searches = h[6]; out->ladder_nodes = h[7];
-  out->stalled_waves = h[8];
+  out->stalled_waves = h[8]; out->instant_playouts = h[9];
 }
 
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid) {

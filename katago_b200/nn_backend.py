@@ -52,12 +52,14 @@ class SelfplayConfig(C.Structure):
         ("root_fpu_loss_prop", C.c_double), ("cpuct_utility_stdev_prior", C.c_double), ("cpuct_utility_stdev_prior_weight", C.c_double),
         ("cpuct_utility_stdev_scale", C.c_double), ("root_desired_per_child_visits_coeff", C.c_double),
         ("subtree_value_bias_factor", C.c_double), ("subtree_value_bias_weight_exponent", C.c_double),
+        ("use_graph_search", C.c_int32), ("graph_search_rep_bound", C.c_int32),
+        ("debug_hold_at_max_visits", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
 class SelfplayStats(C.Structure):
     _fields_ = [("total_visits", C.c_uint64), ("total_moves", C.c_uint64), ("games_finished", C.c_uint64), ("black_wins", C.c_uint64),
-                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64), ("ladder_searches", C.c_uint64), ("ladder_nodes", C.c_uint64), ("stalled_waves", C.c_uint64)]
+                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64), ("ladder_searches", C.c_uint64), ("ladder_nodes", C.c_uint64), ("stalled_waves", C.c_uint64), ("instant_playouts", C.c_uint64)]
 
 
 # Every symbol include/kgb200.h declares (tests/test_abi.py checks the library exports all of them).
@@ -363,7 +365,8 @@ class SelfPlay:
                  fpu_parent_weight: float = 0.0, fpu_loss_prop: float = 0.0, root_fpu_loss_prop: float = 0.0,
                  cpuct_utility_stdev_prior: float = 0.25, cpuct_utility_stdev_prior_weight: float = 1.0,
                  cpuct_utility_stdev_scale: float = 0.0, root_desired_per_child_visits_coeff: float = 0.0,
-                 subtree_value_bias_factor: float = 0.0, subtree_value_bias_weight_exponent: float = 0.5):
+                 subtree_value_bias_factor: float = 0.0, subtree_value_bias_weight_exponent: float = 0.5,
+                 use_graph_search: bool = False, graph_search_rep_bound: int = 11, debug_hold_at_max_visits: bool = False):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -374,7 +377,8 @@ class SelfPlay:
                                   value_weight_exponent, int(fpu_parent_weight_by_visited_policy), 0, fpu_parent_weight_by_visited_policy_pow,
                                   fpu_parent_weight, fpu_loss_prop, root_fpu_loss_prop, cpuct_utility_stdev_prior,
                                   cpuct_utility_stdev_prior_weight, cpuct_utility_stdev_scale, root_desired_per_child_visits_coeff,
-                                  subtree_value_bias_factor, subtree_value_bias_weight_exponent)
+                                  subtree_value_bias_factor, subtree_value_bias_weight_exponent, int(use_graph_search),
+                                  int(graph_search_rep_bound), int(debug_hold_at_max_visits), 0)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen

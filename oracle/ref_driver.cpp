@@ -224,6 +224,8 @@ static int cmdSearchFake(int argc, char** argv) {
     else if(k == "cpuctUtilityStdevPrior") params.cpuctUtilityStdevPrior = v;
     else if(k == "cpuctUtilityStdevPriorWeight") params.cpuctUtilityStdevPriorWeight = v;
     else if(k == "rootDesiredPerChildVisitsCoeff") params.rootDesiredPerChildVisitsCoeff = v;
+    else if(k == "useGraphSearch") params.useGraphSearch = v != 0;
+    else if(k == "graphSearchRepBound") params.graphSearchRepBound = (int)v;
     else if(k == "subtreeValueBiasFactor") params.subtreeValueBiasFactor = v;
     else if(k == "subtreeValueBiasWeightExponent") params.subtreeValueBiasWeightExponent = v;
     else { cerr << "unknown override " << k << endl; return 1; }

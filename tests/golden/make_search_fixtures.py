@@ -94,6 +94,14 @@ if __name__ == "__main__":
         (13, 7, 500, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), dict(SELFPLAY8B18, **BIAS)),
         (5, 5, 600, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), dict(SELFPLAY8B18, **BIAS)),
         (9, 9, 500, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), {"subtreeValueBiasFactor": 0.45, "subtreeValueBiasWeightExponent": 0.5}),
+        # graph search (a23): transpositions share nodes
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), {"useGraphSearch": 1}),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), {"useGraphSearch": 1}),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), {"useGraphSearch": 1}),
+        (9, 9, 800, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
+        (13, 7, 600, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
+        (5, 5, 1000, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
@@ -104,7 +112,7 @@ if __name__ == "__main__":
             score = dict(zip(SCORE_KEYS, score))
         store[f"c{i}_params"] = np.array(json.dumps(score or {}))
         store[f"c{i}_recent_score_center"] = np.float64(center)
-        assert root[0] == visits and v.sum() == visits - 1
+        assert root[0] == visits and v.sum() == visits - 1, (root, v.sum())
         store[f"c{i}_shape"] = np.array([X, Y, visits], np.int32)
         store[f"c{i}_moves"] = np.array([(-1, -1) if m is None else m for m in moves], np.int8).reshape(-1, 2)
         store[f"c{i}_visits"] = v; store[f"c{i}_util"] = u; store[f"c{i}_policy"] = pol
