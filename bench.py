@@ -262,6 +262,8 @@ def main():
                   root_fpu_reduction_max=0.0, value_weight_exponent=0.5, fpu_parent_weight_by_visited_policy=True,
                   fpu_parent_weight_by_visited_policy_pow=2.0, root_desired_per_child_visits_coeff=2.0,
                   subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8, use_graph_search=True, graph_search_rep_bound=11,
+                  root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83, root_dirichlet_noise_weight=0.25,
+                  root_policy_temperature=1.1, root_policy_temperature_early=1.5, chosen_move_temperature_halflife=19.0,
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
@@ -323,7 +325,7 @@ def main():
                                   "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)",
                                   "backup = recomputeNodeStats per path node (value weighting, exponent 0.5)"],
                        "search_params": "selfplay8mainb18.cfg: cpuct 1.05/0.28/500, fpu 0.2 (root 0), fpuParentWeightByVisitedPolicy^2, valueWeightExponent 0.5, "
-                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8, useGraphSearch (repBound 11); not yet: "
+                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8, useGraphSearch (repBound 11), root Dirichlet noise 10.83/0.25, root policy temperature 1.1 (early 1.5); not yet: rootNumSymmetriesToSample 4, "
                                         "root noise/temperature, multi-symmetry root, LCB move selection",
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",

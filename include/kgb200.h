@@ -174,7 +174,12 @@ typedef struct kgb_selfplay_config {
   int32_t use_graph_search;                       /* useGraphSearch: transpositions share a node (search.cpp:875-936) */
   int32_t graph_search_rep_bound;                 /* graphSearchRepBound (11) */
   int32_t debug_hold_at_max_visits;               /* TEST ONLY: a game whose root has max_visits visits idles instead of moving */
-  int32_t reserved2;
+  int32_t root_noise_enabled;                     /* rootNoiseEnabled: Dirichlet noise on the root policy */
+  double root_dirichlet_noise_total_concentration;/* rootDirichletNoiseTotalConcentration (10.83) */
+  double root_dirichlet_noise_weight;             /* rootDirichletNoiseWeight (0.25) */
+  double root_policy_temperature;                 /* rootPolicyTemperature (0 = unset = 1.0) */
+  double root_policy_temperature_early;           /* rootPolicyTemperatureEarly (0 = unset = 1.0) */
+  double chosen_move_temperature_halflife;        /* chosenMoveTemperatureHalflife (0 = unset = 19): also the half-life of the early root temperature */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -198,6 +203,12 @@ KGB_API int kgb_expected_white_score_value(int n, const double* mean, const doub
 /* The value-weighting CDF table the device loop uploads (Search's DistributionTable over tdistcdf(z, 3), search.cpp:131-137):
  * n must be 2000.  Test hook (row a20). */
 KGB_API int kgb_value_weight_cdf_table(double* out, int n);
+/* TEST HOOK (rows a22/a25): the device loop's root-policy temperature + Dirichlet noise on a given policy (-1 = illegal), with the
+ * device Rand initialised from seed_string like the reference's Rand(seed_string): the counterpart of
+ * Search::maybeAddPolicyNoiseAndTemp / addDirichletNoise (searchhelpers.cpp:78-215). */
+KGB_API int kgb_test_root_policy_noise(const char* seed_string, int x_len, int y_len, int policy_size, int turn_number, int noise_enabled,
+                                       double concentration, double weight, double temperature, double temperature_early, double halflife,
+                                       const float* policy_in, float* policy_out);
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out);
 KGB_API void kgb_selfplay_free(kgb_selfplay* sp);
 /* Enqueue `steps` playout waves on the handle's stream (asynchronous; kgb_handle_sync() to wait). */

@@ -862,6 +862,16 @@ KGB_API int kgb_value_weight_cdf_table(double* out, int n) {
   });
 }
 
+KGB_API int kgb_test_root_policy_noise(const char* seed_string, int x_len, int y_len, int policy_size, int turn_number, int noise_enabled,
+                                       double concentration, double weight, double temperature, double temperature_early, double halflife,
+                                       const float* policy_in, float* policy_out) {
+  return guarded([&] {
+    if(!seed_string || !policy_in || !policy_out || policy_size < 1 || policy_size > 362) throw std::invalid_argument("kgb_test_root_policy_noise: bad argument");
+    rootNoiseTest(seed_string, x_len, y_len, policy_size, turn_number, noise_enabled, concentration, weight, temperature, temperature_early, halflife,
+                  policy_in, policy_out);
+  });
+}
+
 KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* config, kgb_selfplay** out) {
   return guarded([&] {
     if(!handle || !config || !out) throw std::invalid_argument("kgb_selfplay_create: NULL argument");

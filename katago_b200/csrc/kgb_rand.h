@@ -14,6 +14,8 @@ class RefRand {
   void init(const std::string& seed);
   uint32_t nextUInt();
   uint64_t nextUInt64();
+  // the generator's state, for upload to the device twin (kgb_devrand.cuh)
+  void exportState(uint64_t a[16], uint64_t& aIdx, uint64_t& pcg) const { for(int i = 0; i < 16; i++) a[i] = a_[i]; aIdx = aIdx_; pcg = pcg_; }
 
  private:
   uint64_t a_[16];

@@ -35,6 +35,7 @@
 
 #include "../../include/kgb200.h"
 #include "kgb_board.cuh"
+#include "kgb_devrand.cuh"
 #include "kgb_ladder.cuh"
 #include "kgb_scorevalue.h"
 #include "kgb_selfplay.h"
@@ -61,6 +62,11 @@ struct SPDev {
   int* nodeBiasEntry;               // [game][maxNodes] slot or -1
   // graph search (search.cpp:875-936, game/graphhash.cpp): transposition table per game, cleared with the tree
   int useGraphSearch, graphSearchRepBound, holdAtMaxVisits;
+  // root policy temperature and Dirichlet noise (searchhelpers.cpp:78-215)
+  int rootNoiseEnabled;
+  double rootDirichletNoiseTotalConcentration, rootDirichletNoiseWeight, rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
+  DevRandState* searchRand;         // [game] the search thread's Rand
+  double* noiseScratch;             // [game][policySize]
   int nodeTableSize;                // slots per game (power of two)
   unsigned long long *nodeTableKey0, *nodeTableKey1;   // [game][nodeTableSize]
   int* nodeTableNode;               // [game][nodeTableSize] node index or -1
@@ -728,6 +734,58 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32) spSelectKernel(const SPD
   }
 }
 
+// Search::maybeAddPolicyNoiseAndTemp (searchhelpers.cpp:150-215) on the root's post-processed policy: temperature
+// (interpolateEarly :541-545), then Dirichlet noise (addDirichletNoise / computeDirichletAlphaDistribution :78-147).
+// One thread; every sum runs over the policy in position order like the reference's loops.
+__device__ void rootPolicyTemperatureAndNoise(float* pol, int policySize, int X, int Y, int turnNumber, bool noise, double concentration,
+                                              double weight, double temperature, double temperatureEarly, double halflife, DevRandState* randState,
+                                              double* r) {
+  if(temperature != 1.0 || temperatureEarly != 1.0) {
+    const double rawHalflives = (double)turnNumber / halflife;
+    const double halflives = rawHalflives * 19.0 / sqrt((double)(X * Y));
+    const double temp = temperature + (temperatureEarly - temperature) * pow(0.5, halflives);
+    double maxValue = 0.0;
+    for(int i = 0; i < policySize; i++) { const double prob = pol[i]; if(prob > maxValue) maxValue = prob; }
+    const double logMaxValue = log(maxValue), invTemp = 1.0 / temp;
+    double sum = 0.0;
+    for(int i = 0; i < policySize; i++)
+      if(pol[i] > 0) { const float p = (float)exp((log((double)pol[i]) - logMaxValue) * invTemp); pol[i] = p; sum += p; }
+    for(int i = 0; i < policySize; i++)
+      if(pol[i] >= 0) pol[i] = (float)(pol[i] / sum);
+  }
+  if(!noise) return;
+  int legalCount = 0;
+  for(int i = 0; i < policySize; i++) if(pol[i] >= 0) legalCount++;
+  // half of the alpha mass uniform, half shaped by the log policy (clipped at 0.01) above its mean
+  double logPolicySum = 0.0;
+  for(int i = 0; i < policySize; i++)
+    if(pol[i] >= 0) { r[i] = log(fmin(0.01, (double)pol[i]) + 1e-20); logPolicySum += r[i]; }
+  const double logPolicyMean = logPolicySum / legalCount;
+  double alphaPropSum = 0.0;
+  for(int i = 0; i < policySize; i++)
+    if(pol[i] >= 0) { r[i] = fmax(0.0, r[i] - logPolicyMean); alphaPropSum += r[i]; }
+  const double uniformProb = 1.0 / legalCount;
+  for(int i = 0; i < policySize; i++)
+    if(pol[i] >= 0) r[i] = alphaPropSum <= 0.0 ? uniformProb : 0.5 * (r[i] / alphaPropSum + uniformProb);
+  DevRand rand;
+  rand.s = *randState;
+  double rSum = 0.0;
+  for(int i = 0; i < policySize; i++) {
+    if(pol[i] >= 0) { r[i] = rand.nextGamma(r[i] * concentration); rSum += r[i]; }
+    else r[i] = 0.0;
+  }
+  *randState = rand.s;
+  for(int i = 0; i < policySize; i++) r[i] /= rSum;
+  for(int i = 0; i < policySize; i++)
+    if(pol[i] >= 0) pol[i] = (float)(r[i] * weight + pol[i] * (1.0 - weight));
+}
+
+__global__ void rootNoiseTestKernel(float* pol, int policySize, int X, int Y, int turnNumber, int noise, double concentration, double weight,
+                                    double temperature, double temperatureEarly, double halflife, DevRandState* randState, double* scratch) {
+  if(threadIdx.x == 0 && blockIdx.x == 0)
+    rootPolicyTemperatureAndNoise(pol, policySize, X, Y, turnNumber, noise != 0, concentration, weight, temperature, temperatureEarly, halflife, randState, scratch);
+}
+
 // Search::recomputeNodeStats (searchupdatehelpers.cpp:167-360) for the parameter subset of the loop (no noise pruning, no root
 // noise subtraction, no subtree value bias, no uncertainty weights: the node's own evaluation has weight 1), one warp per node.
 // Children are visited in creation order and every sum is accumulated in that order (orderedAdd2), like the reference's loops.
@@ -894,6 +952,15 @@ __global__ void spBackupKernel(const SPDev d) {
     for(int k = 0; k < 12; k++) {
       int i = k * 32 + lane;
       if(i < d.policySize) d.policy[nb + i] = ok[k] ? v[k] / sum : -1.0f;
+    }
+    // ---- the root's policy gets the root temperature and the Dirichlet noise when it is first evaluated (searchnnhelpers.cpp:61-173)
+    if(node == 0 && d.nodeVisits[gb] == 0 && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
+      __syncwarp();
+      if(lane == 0)
+        rootPolicyTemperatureAndNoise(d.policy + nb, d.policySize, d.X, d.Y, d.moveNum[g], d.rootNoiseEnabled != 0, d.rootDirichletNoiseTotalConcentration,
+                                      d.rootDirichletNoiseWeight, d.rootPolicyTemperature, d.rootPolicyTemperatureEarly, d.chosenMoveTemperatureHalflife,
+                                      d.searchRand + g, d.noiseScratch + (size_t)g * d.policySize);
+      __syncwarp();
     }
     // ---- value: softmax(win, loss, noResult) from the mover's perspective -> white utility (nneval.cpp:1112-1215)
     const float* val = d.nnValue + (size_t)g * 3;
@@ -1191,6 +1258,27 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
   d.holdAtMaxVisits = c.debug_hold_at_max_visits ? 1 : 0;
+  d.rootNoiseEnabled = c.root_noise_enabled ? 1 : 0;
+  d.rootDirichletNoiseTotalConcentration = c.root_dirichlet_noise_total_concentration; d.rootDirichletNoiseWeight = c.root_dirichlet_noise_weight;
+  d.rootPolicyTemperature = c.root_policy_temperature == 0.0 ? 1.0 : c.root_policy_temperature;                 // 0 = unset
+  d.rootPolicyTemperatureEarly = c.root_policy_temperature_early == 0.0 ? 1.0 : c.root_policy_temperature_early;
+  d.chosenMoveTemperatureHalflife = c.chosen_move_temperature_halflife == 0.0 ? 19.0 : c.chosen_move_temperature_halflife;
+  d.noiseScratch = sp->alloc<double>(G * PS);
+  {
+    // one generator per game, seeded like the reference's Rand from a string (the reference reseeds its search thread's
+    // generator for every search from strings the device cannot hash; here the stream simply continues from move to move)
+    std::vector<DevRandState> st(G);
+    for(size_t g2 = 0; g2 < G; g2++) {
+      RefRand rr("kgb200$seed" + std::to_string(c.seed) + "$game" + std::to_string(g2) + "$searchThread");
+      memset(&st[g2], 0, sizeof(DevRandState));
+      uint64_t a[16], idx, pcg;
+      rr.exportState(a, idx, pcg);
+      for(int i = 0; i < 16; i++) st[g2].a[i] = a[i];
+      st[g2].aIdx = idx; st[g2].pcg = pcg;
+    }
+    d.searchRand = sp->alloc<DevRandState>(G);
+    SPCK(cudaMemcpy(d.searchRand, st.data(), G * sizeof(DevRandState), cudaMemcpyHostToDevice));
+  }
   d.useGraphSearch = c.use_graph_search ? 1 : 0; d.graphSearchRepBound = c.graph_search_rep_bound;
   d.nodeTableSize = 64;
   while(d.nodeTableSize < 2 * (int)N) d.nodeTableSize *= 2;
@@ -1327,6 +1415,26 @@ void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* polic
   SPCK(cudaMemcpy(child.data(), d.childNode + nb, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
   SPCK(cudaMemcpy(avg.data(), d.nodeUtilAvg + (size_t)g * d.maxNodes, d.maxNodes * sizeof(double), cudaMemcpyDeviceToHost));
   for(int i = 0; i < d.policySize; i++) utilSum[i] = child[i] >= 0 ? avg[child[i]] : 0.0;
+}
+
+void rootNoiseTest(const char* seedString, int X, int Y, int policySize, int turnNumber, int noise, double concentration, double weight,
+                   double temperature, double temperatureEarly, double halflife, const float* policyIn, float* policyOut) {
+  RefRand rr(seedString);
+  DevRandState st;
+  memset(&st, 0, sizeof(st));
+  uint64_t a[16], idx, pcg;
+  rr.exportState(a, idx, pcg);
+  for(int i = 0; i < 16; i++) st.a[i] = a[i];
+  st.aIdx = idx; st.pcg = pcg;
+  float* dp; DevRandState* ds; double* dr;
+  SPCK(cudaMalloc(&dp, policySize * sizeof(float))); SPCK(cudaMalloc(&ds, sizeof(st))); SPCK(cudaMalloc(&dr, policySize * sizeof(double)));
+  SPCK(cudaMemcpy(dp, policyIn, policySize * sizeof(float), cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(ds, &st, sizeof(st), cudaMemcpyHostToDevice));
+  rootNoiseTestKernel<<<1, 32>>>(dp, policySize, X, Y, turnNumber, noise, concentration, weight, temperature, temperatureEarly, halflife, ds, dr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) e = cudaMemcpy(policyOut, dp, policySize * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dp); cudaFree(ds); cudaFree(dr);
+  SPCK(e);
 }
 
 void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,

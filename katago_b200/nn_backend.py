@@ -53,7 +53,10 @@ class SelfplayConfig(C.Structure):
         ("cpuct_utility_stdev_scale", C.c_double), ("root_desired_per_child_visits_coeff", C.c_double),
         ("subtree_value_bias_factor", C.c_double), ("subtree_value_bias_weight_exponent", C.c_double),
         ("use_graph_search", C.c_int32), ("graph_search_rep_bound", C.c_int32),
-        ("debug_hold_at_max_visits", C.c_int32), ("reserved2", C.c_int32),
+        ("debug_hold_at_max_visits", C.c_int32), ("root_noise_enabled", C.c_int32),
+        ("root_dirichlet_noise_total_concentration", C.c_double), ("root_dirichlet_noise_weight", C.c_double),
+        ("root_policy_temperature", C.c_double), ("root_policy_temperature_early", C.c_double),
+        ("chosen_move_temperature_halflife", C.c_double),
     ]
 
 
@@ -69,7 +72,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise",
 ]
 
 _lib = None
@@ -126,6 +129,7 @@ def load_library():
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
     lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
     lib.kgb_value_weight_cdf_table.argtypes = [P, I]
+    lib.kgb_test_root_policy_noise.argtypes = [C.c_char_p, I, I, I, I, I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, P, P]
     lib.kgb_selfplay_get_leaf_path.argtypes = [P, I, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
     _lib = lib
@@ -319,6 +323,15 @@ def zobrist_tables(x_size: int, y_size: int):
     return bh, sh
 
 
+def root_policy_noise(seed_string, x, y, policy, turn_number=0, noise=True, concentration=10.83, weight=0.25, temperature=1.0,
+                      temperature_early=1.0, halflife=19.0):
+    """The device loop's root temperature + Dirichlet noise on `policy` (-1 = illegal), Rand seeded from seed_string (GPU)."""
+    pin = np.ascontiguousarray(policy, np.float32); out = np.zeros_like(pin)
+    _check(load_library().kgb_test_root_policy_noise(seed_string.encode(), x, y, pin.size, turn_number, int(noise), concentration, weight,
+                                                     temperature, temperature_early, halflife, pin.ctypes.data, out.ctypes.data))
+    return out
+
+
 def value_weight_cdf_table():
     out = np.zeros(2000, np.float64)
     _check(load_library().kgb_value_weight_cdf_table(out.ctypes.data, 2000))
@@ -366,7 +379,10 @@ class SelfPlay:
                  cpuct_utility_stdev_prior: float = 0.25, cpuct_utility_stdev_prior_weight: float = 1.0,
                  cpuct_utility_stdev_scale: float = 0.0, root_desired_per_child_visits_coeff: float = 0.0,
                  subtree_value_bias_factor: float = 0.0, subtree_value_bias_weight_exponent: float = 0.5,
-                 use_graph_search: bool = False, graph_search_rep_bound: int = 11, debug_hold_at_max_visits: bool = False):
+                 use_graph_search: bool = False, graph_search_rep_bound: int = 11, debug_hold_at_max_visits: bool = False,
+                 root_noise_enabled: bool = False, root_dirichlet_noise_total_concentration: float = 10.83,
+                 root_dirichlet_noise_weight: float = 0.25, root_policy_temperature: float = 1.0,
+                 root_policy_temperature_early: float = 1.0, chosen_move_temperature_halflife: float = 19.0):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -378,7 +394,9 @@ class SelfPlay:
                                   fpu_parent_weight, fpu_loss_prop, root_fpu_loss_prop, cpuct_utility_stdev_prior,
                                   cpuct_utility_stdev_prior_weight, cpuct_utility_stdev_scale, root_desired_per_child_visits_coeff,
                                   subtree_value_bias_factor, subtree_value_bias_weight_exponent, int(use_graph_search),
-                                  int(graph_search_rep_bound), int(debug_hold_at_max_visits), 0)
+                                  int(graph_search_rep_bound), int(debug_hold_at_max_visits), int(root_noise_enabled),
+                                  root_dirichlet_noise_total_concentration, root_dirichlet_noise_weight, root_policy_temperature,
+                                  root_policy_temperature_early, chosen_move_temperature_halflife)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen

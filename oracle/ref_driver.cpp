@@ -224,6 +224,9 @@ static int cmdSearchFake(int argc, char** argv) {
     else if(k == "cpuctUtilityStdevPrior") params.cpuctUtilityStdevPrior = v;
     else if(k == "cpuctUtilityStdevPriorWeight") params.cpuctUtilityStdevPriorWeight = v;
     else if(k == "rootDesiredPerChildVisitsCoeff") params.rootDesiredPerChildVisitsCoeff = v;
+    else if(k == "rootPolicyTemperature") params.rootPolicyTemperature = v;
+    else if(k == "rootPolicyTemperatureEarly") params.rootPolicyTemperatureEarly = v;
+    else if(k == "chosenMoveTemperatureHalflife") params.chosenMoveTemperatureHalflife = v;
     else if(k == "useGraphSearch") params.useGraphSearch = v != 0;
     else if(k == "graphSearchRepBound") params.graphSearchRepBound = (int)v;
     else if(k == "subtreeValueBiasFactor") params.subtreeValueBiasFactor = v;
@@ -267,7 +270,7 @@ static int cmdSearchFake(int argc, char** argv) {
   }
   const NNOutput* nn = root->getNNOutput();
   cout << "policy";
-  for(int i = 0; i <= X * Y; i++) cout << " " << Global::strprintf("%.9g", nn->policyProbs[i]);
+  for(int i = 0; i <= X * Y; i++) cout << " " << Global::strprintf("%.9g", nn->getPolicyProbsMaybeNoised()[i]);
   cout << endl;
   delete search;
   delete nnEval;
@@ -303,6 +306,33 @@ static int cmdVWTable(int, char**) {
     [](double z) { return FancyMath::tdistcdf(z, 3.0); },
     -50.0, 50.0, 2000);
   for(int i = 0; i < table.size; i++) cout << Global::strprintf("%.17g", table.cdfTable[i]) << endl;
+  return 0;
+}
+
+// rootnoise SEEDSTRING POLICYSIZE POLICYSEED CONCENTRATION WEIGHT: Search::addDirichletNoise (searchhelpers.cpp:121-147) with
+// Rand(SEEDSTRING) on a pseudo-random policy (some moves illegal = -1); prints the policy before and after.
+static int cmdRootNoise(int argc, char** argv) {
+  if(argc != 7) { cerr << "usage: rootnoise SEEDSTRING POLICYSIZE POLICYSEED CONCENTRATION WEIGHT" << endl; return 1; }
+  Rand rand(argv[2]);
+  int n = atoi(argv[3]);
+  Lcg rng(strtoull(argv[4], NULL, 10));
+  SearchParams params;
+  params.rootDirichletNoiseTotalConcentration = atof(argv[5]);
+  params.rootDirichletNoiseWeight = atof(argv[6]);
+  vector<float> p(NNPos::MAX_NN_POLICY_SIZE, -1.0f);
+  double sum = 0.0;
+  for(int i = 0; i < n; i++) {
+    bool legal = i == n - 1 || rng.next() % 5 != 0;
+    if(legal) { double v = pow((double)rng.next() / 2147483648.0, 6.0) + 1e-7; p[i] = (float)v; sum += v; }
+  }
+  for(int i = 0; i < n; i++) if(p[i] >= 0) p[i] = (float)(p[i] / sum);
+  cout << "in";
+  for(int i = 0; i < n; i++) cout << " " << Global::strprintf("%.9g", p[i]);
+  cout << endl;
+  Search::addDirichletNoise(params, rand, n, p.data());
+  cout << "out";
+  for(int i = 0; i < n; i++) cout << " " << Global::strprintf("%.9g", p[i]);
+  cout << endl;
   return 0;
 }
 
@@ -381,6 +411,7 @@ int main(int argc, char** argv) {
   if(cmd == "searchfake") return cmdSearchFake(argc, argv);
   if(cmd == "svsamples") return cmdSVSamples(argc, argv);
   if(cmd == "vwtable") return cmdVWTable(argc, argv);
+  if(cmd == "rootnoise") return cmdRootNoise(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

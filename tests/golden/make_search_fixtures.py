@@ -102,6 +102,11 @@ if __name__ == "__main__":
         (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
         (13, 7, 600, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
         (5, 5, 1000, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS)),
+        # root policy temperature (a22), early-game interpolation by turn number
+        (9, 9, 400, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), {"rootPolicyTemperature": 1.1, "rootPolicyTemperatureEarly": 1.5}),
+        (19, 19, 500, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40),
+         dict(SELFPLAY8B18, useGraphSearch=1, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.5, chosenMoveTemperatureHalflife=19, **BIAS)),
+        (13, 7, 400, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), {"rootPolicyTemperature": 0.8, "chosenMoveTemperatureHalflife": 10}),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
