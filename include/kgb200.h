@@ -180,6 +180,19 @@ typedef struct kgb_selfplay_config {
   double root_policy_temperature;                 /* rootPolicyTemperature (0 = unset = 1.0) */
   double root_policy_temperature_early;           /* rootPolicyTemperatureEarly (0 = unset = 1.0) */
   double chosen_move_temperature_halflife;        /* chosenMoveTemperatureHalflife (0 = unset = 19): also the half-life of the early root temperature */
+  /* Root move choice like Search::getChosenMoveLoc (play selection values, LCB, temperature).  use_play_selection = 0 keeps the
+   * simple rule: proportional to visits for the first early_temperature_moves moves, then the most visited. */
+  int32_t use_play_selection;
+  int32_t use_lcb_for_selection;                  /* useLcbForSelection */
+  int32_t use_non_buggy_lcb;                      /* useNonBuggyLcb */
+  int32_t reserved3;
+  double lcb_stdevs;                              /* lcbStdevs (5.0) */
+  double min_visit_prop_for_lcb;                  /* minVisitPropForLCB (0.15) */
+  double chosen_move_temperature;                 /* chosenMoveTemperature (0.15) */
+  double chosen_move_temperature_early;           /* chosenMoveTemperatureEarly (0.75) */
+  double chosen_move_temperature_only_below_prob; /* chosenMoveTemperatureOnlyBelowProb (0 = unset = 1.0) */
+  double chosen_move_subtract;                    /* chosenMoveSubtract (0) */
+  double chosen_move_prune;                       /* chosenMovePrune (1) */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -203,6 +216,13 @@ KGB_API int kgb_expected_white_score_value(int n, const double* mean, const doub
 /* The value-weighting CDF table the device loop uploads (Search's DistributionTable over tdistcdf(z, 3), search.cpp:131-137):
  * n must be 2000.  Test hook (row a20). */
 KGB_API int kgb_value_weight_cdf_table(double* out, int n);
+/* Search::getPlaySelectionValues of game g's root (searchresults.cpp:66-330), indexed by move position (-1 = no child):
+ * the weights the root move is drawn from (reduced weights, LCB bonus, subtract / prune applied). */
+KGB_API int kgb_selfplay_get_play_selection_values(kgb_selfplay* sp, int game, double* values);
+/* TEST HOOK: `count` consecutive draws of Search::chooseIndexWithTemperature (searchhelpers.cpp:12-76) from the device Rand
+ * seeded with seed_string. */
+KGB_API int kgb_test_choose_index_with_temperature(const char* seed_string, const double* relative_probs, int n, double temperature,
+                                                   double only_below_prob, int count, int32_t* chosen);
 /* TEST HOOK (rows a22/a25): the device loop's root-policy temperature + Dirichlet noise on a given policy (-1 = illegal), with the
  * device Rand initialised from seed_string like the reference's Rand(seed_string): the counterpart of
  * Search::maybeAddPolicyNoiseAndTemp / addDirichletNoise (searchhelpers.cpp:78-215). */

@@ -862,6 +862,23 @@ KGB_API int kgb_value_weight_cdf_table(double* out, int n) {
   });
 }
 
+KGB_API int kgb_selfplay_get_play_selection_values(kgb_selfplay* sp, int game, double* values) {
+  return guarded([&] {
+    if(!sp || !values) throw std::invalid_argument("kgb_selfplay_get_play_selection_values: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadPlaySelection(sp->impl, game, values);
+  });
+}
+
+KGB_API int kgb_test_choose_index_with_temperature(const char* seed_string, const double* relative_probs, int n, double temperature,
+                                                   double only_below_prob, int count, int32_t* chosen) {
+  return guarded([&] {
+    if(!seed_string || !relative_probs || !chosen || n < 1 || count < 1) throw std::invalid_argument("kgb_test_choose_index_with_temperature: bad argument");
+    chooseIndexTest(seed_string, relative_probs, n, temperature, only_below_prob, count, chosen);
+  });
+}
+
 KGB_API int kgb_test_root_policy_noise(const char* seed_string, int x_len, int y_len, int policy_size, int turn_number, int noise_enabled,
                                        double concentration, double weight, double temperature, double temperature_early, double halflife,
                                        const float* policy_in, float* policy_out) {

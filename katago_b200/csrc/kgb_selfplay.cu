@@ -65,6 +65,12 @@ struct SPDev {
   // root policy temperature and Dirichlet noise (searchhelpers.cpp:78-215)
   int rootNoiseEnabled;
   double rootDirichletNoiseTotalConcentration, rootDirichletNoiseWeight, rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
+  // root move choice (searchresults.cpp:24-330 play selection values, :573-598 getChosenMoveLoc, searchhelpers.cpp:12-76)
+  int usePlaySelection, useLcbForSelection, useNonBuggyLcb;
+  double lcbStdevs, minVisitPropForLCB, chosenMoveTemperature, chosenMoveTemperatureEarly, chosenMoveTemperatureOnlyBelowProb,
+    chosenMoveSubtract, chosenMovePrune;
+  DevRandState* nonSearchRand;      // [game] Search::nonSearchRand
+  double* selScratch;               // [game][3][policySize] play selection values, lcb, radius
   DevRandState* searchRand;         // [game] the search thread's Rand
   double* noiseScratch;             // [game][policySize]
   int nodeTableSize;                // slots per game (power of two)
@@ -269,6 +275,185 @@ __device__ __forceinline__ void rootHashesInit(const SPDev& d, int g, int lane) 
   }
 }
 
+// Search::getPlaySelectionValues for the root (searchresults.cpp:66-330; no human policy, no pass suppression, no ending
+// bonus): values by child in creation order into psv[0..nc), their moves into moves[].  One thread.  Returns the child count.
+__device__ int rootPlaySelectionValues(const SPDev& d, int g, double* psv, double* lcbBuf, double* radiusBuf) {
+  const size_t gb = (size_t)g * d.maxNodes, nb = gb * d.policySize;
+  const int nc = d.nodeNumChildren[gb];
+  const bool rootWhite = d.rootBlackToMove[g] == 0;
+  auto childWeightOf = [&](int k, int& mv, int& c, int& ev, int& cv) -> double {
+    mv = (int)d.childOrder[nb + k]; c = d.childNode[nb + mv]; ev = d.childVisits[nb + mv]; cv = d.nodeVisits[gb + c];
+    return d.nodeWeightSum[gb + c] * ((double)ev / (double)(cv > 1 ? cv : 1));
+  };
+  double totalChildWeight = 0.0;
+  for(int k = 0; k < nc; k++) {
+    int mv, c, ev, cv;
+    const double w = childWeightOf(k, mv, c, ev, cv);
+    totalChildWeight += w;
+    psv[k] = d.policy[nb + mv] < 0 ? 0.0 : w;
+  }
+  // the most stably explored child: weight discounted by one visit, tiny prior term
+  int nonLCBBestIdx = 0;
+  double nonLCBBestChildWeight = -1e30, maxGoodness = -1e30;
+  for(int k = 0; k < nc; k++) {
+    const int mv = (int)d.childOrder[nb + k];
+    const double edgeVisits = (double)d.childVisits[nb + mv];
+    const double policyProb = d.policy[nb + mv];
+    const double gdn = psv[k] * fmax(0.0, edgeVisits - 1.0) / fmax(1.0, edgeVisits) + 2.0 * policyProb;
+    if(gdn > maxGoodness) { maxGoodness = gdn; nonLCBBestChildWeight = psv[k]; nonLCBBestIdx = k; }
+  }
+  if(nc > 0) {
+    // children that got more visits than the final selection values justify are cut back to the weight PUCT would have wanted
+    const int visits = d.nodeVisits[gb];
+    const double weightSum = d.nodeWeightSum[gb], parentUtility = d.nodeUtilAvg[gb];
+    double stdevFactor = 1.0;
+    if(d.cpuctUtilityStdevScale != 0.0) {
+      double utilitySqAvg = d.nodeUtilSqAvg[gb];
+      const double variancePrior = d.cpuctUtilityStdevPrior * d.cpuctUtilityStdevPrior;
+      double stdev;
+      if(visits <= 0 || weightSum <= 1) stdev = d.cpuctUtilityStdevPrior;
+      else {
+        const double utilitySq = parentUtility * parentUtility;
+        if(utilitySqAvg < utilitySq) utilitySqAvg = utilitySq;
+        stdev = sqrt(fmax(0.0, ((utilitySq + variancePrior) * d.cpuctUtilityStdevPriorWeight + utilitySqAvg * weightSum) /
+                                     (d.cpuctUtilityStdevPriorWeight + weightSum - 1.0) - utilitySq));
+      }
+      stdevFactor = 1.0 + d.cpuctUtilityStdevScale * (stdev / d.cpuctUtilityStdevPrior - 1.0);
+    }
+    const double cpuct = d.cpuctExploration + d.cpuctExplorationLog * log((totalChildWeight + d.cpuctExplorationBase) / d.cpuctExplorationBase);
+    const double exploreScaling = cpuct * sqrt(totalChildWeight + 0.01) * stdevFactor;
+    double bestValue;
+    {
+      int mv, c, ev, cv;
+      const double w = childWeightOf(nonLCBBestIdx, mv, c, ev, cv);
+      const float P = d.policy[nb + mv];
+      // getExploreSelectionValueOfChild outside the search: a child without visits or weight would take the FPU value; the
+      // most explored child always has both
+      const double cu = d.nodeUtilAvg[gb + c];
+      bestValue = P < 0 ? -1e50 : exploreScaling * (double)P / (1.0 + w) + (rootWhite ? cu : -cu);
+    }
+    for(int k = 0; k < nc; k++) {
+      if(k == nonLCBBestIdx) continue;
+      int mv, c, ev, cv;
+      const double w = childWeightOf(k, mv, c, ev, cv);
+      double reduced = 0.0;
+      if(!(cv <= 0 || w <= 0.0)) {
+        const float P = d.policy[nb + mv];
+        const double cu = d.nodeUtilAvg[gb + c];
+        double wanted = 0.0;                                               // getExploreSelectionValueInverse
+        if(!(P < 0)) {
+          const double valueComponent = rootWhite ? cu : -cu;
+          const double exploreComponent = bestValue - valueComponent;
+          if(exploreComponent <= 0) wanted = 1e100;
+          else { wanted = exploreScaling * (double)P / exploreComponent - 1; if(wanted < 0) wanted = 0; }
+        }
+        reduced = w > wanted ? wanted : w;
+      }
+      psv[k] = ceil(reduced);
+    }
+  }
+  if(d.useLcbForSelection && nc > 0) {
+    // Search::getSelfUtilityLCBAndRadius (searchhelpers.cpp:555-604)
+    const double utilityRangeRadius = d.winLossUtilityFactor + d.staticScoreUtilityFactor + d.dynamicScoreUtilityFactor;
+    double bestLcb = -1e10; int bestLcbIndex = -1;
+    for(int k = 0; k < nc; k++) {
+      int mv, c, ev, cv;
+      double weightSum = childWeightOf(k, mv, c, ev, cv);
+      double weightSqSum = d.nodeWeightSqSum[gb + c] * ((double)ev / (double)(cv > 1 ? cv : 1));
+      const double utilityAvg = d.nodeUtilAvg[gb + c];
+      double utilitySqAvg = d.nodeUtilSqAvg[gb + c];
+      radiusBuf[k] = 2.0 * utilityRangeRadius * d.lcbStdevs;
+      lcbBuf[k] = -radiusBuf[k];
+      if(!(cv <= 0 || weightSum <= 0.0 || weightSqSum <= 0.0)) {
+        double ess = weightSum * weightSum / weightSqSum;
+        const double priorWeight = weightSum / (ess * ess * ess);
+        utilitySqAvg = fmax(utilitySqAvg, utilityAvg * utilityAvg + 1e-8);
+        utilitySqAvg = (utilitySqAvg * weightSum + (utilitySqAvg + utilityRangeRadius * utilityRangeRadius) * priorWeight) / (weightSum + priorWeight);
+        weightSum += priorWeight;
+        weightSqSum += priorWeight * priorWeight;
+        ess = weightSum * weightSum / weightSqSum;
+        const double utilityWithBonus = utilityAvg + 0.0;
+        const double selfUtility = rootWhite ? utilityWithBonus : -utilityWithBonus;
+        const double utilityVariance = utilitySqAvg - utilityAvg * utilityAvg;
+        const double radius = sqrt(utilityVariance / ess) * d.lcbStdevs;
+        lcbBuf[k] = selfUtility - radius;
+        radiusBuf[k] = radius;
+      }
+      const double weight = psv[k];
+      if(weight > 0 && weight >= d.minVisitPropForLCB * nonLCBBestChildWeight && lcbBuf[k] > bestLcb) { bestLcb = lcbBuf[k]; bestLcbIndex = k; }
+    }
+    if(d.useNonBuggyLcb ? (bestLcbIndex >= 0) : (bestLcbIndex > 0)) {
+      double adjustedWeight = psv[bestLcbIndex];
+      for(int k = 0; k < nc; k++) {
+        if(k == bestLcbIndex) continue;
+        const double excessValue = bestLcb - lcbBuf[k];
+        if(excessValue < 0) continue;
+        const double radius = radiusBuf[k];
+        const double radiusFactor = (radius + excessValue) / (radius + 0.20 * excessValue);
+        const double lbound = radiusFactor * radiusFactor * psv[k];
+        if(lbound > adjustedWeight) adjustedWeight = lbound;
+      }
+      psv[bestLcbIndex] = adjustedWeight;
+    }
+  }
+  if(nc == 0) return 0;
+  double maxValue = 0.0;
+  for(int k = 0; k < nc; k++) if(psv[k] > maxValue) maxValue = psv[k];
+  if(maxValue <= 1e-50) {
+    for(int k = 0; k < nc; k++) psv[k] = fmax(0.0, (double)d.policy[nb + (int)d.childOrder[nb + k]]);
+    for(int k = 0; k < nc; k++) if(psv[k] > maxValue) maxValue = psv[k];
+    if(maxValue <= 1e-50) return 0;
+  }
+  const double amountToSubtract = fmin(d.chosenMoveSubtract, maxValue / 64.0), amountToPrune = fmin(d.chosenMovePrune, maxValue / 64.0);
+  for(int k = 0; k < nc; k++) {
+    if(psv[k] < amountToPrune) psv[k] = 0.0;
+    else { psv[k] -= amountToSubtract; if(psv[k] <= 0.0) psv[k] = 0.0; }
+  }
+  return nc;
+}
+// Search::chooseIndexWithTemperature (searchhelpers.cpp:12-76) with Rand::nextUInt(relProbs, n) (core/rand.h:222-243).  One thread.
+__device__ int chooseIndexWithTemperature(DevRand& rand, const double* relativeProbs, int n, double temperature, double onlyBelowProb, double* processed) {
+  double maxRelProb = 0.0, sumRelProb = 0.0;
+  for(int i = 0; i < n; i++) { sumRelProb += fmax(0.0, relativeProbs[i]); if(relativeProbs[i] > maxRelProb) maxRelProb = relativeProbs[i]; }
+  if(temperature <= 1.0e-4 && onlyBelowProb >= 1.0) {
+    double bestProb = relativeProbs[0]; int bestIdx = 0;
+    for(int i = 1; i < n; i++) if(relativeProbs[i] > bestProb) { bestProb = relativeProbs[i]; bestIdx = i; }
+    return bestIdx;
+  }
+  const double logMaxRelProb = log(maxRelProb), logSumRelProb = log(sumRelProb), logOnlyBelowProb = log(fmax(1e-50, onlyBelowProb));
+  double sum = 0.0;
+  for(int i = 0; i < n; i++) {
+    if(relativeProbs[i] <= 0.0) processed[i] = 0.0;
+    else {
+      const double logRelProb = log(relativeProbs[i]) - logMaxRelProb;
+      const double logRelProbThreshold = fmin(0.0, logOnlyBelowProb + logSumRelProb - logMaxRelProb);
+      const double newLogRelProb = logRelProb > logRelProbThreshold ? logRelProb : (logRelProb - logRelProbThreshold) / temperature + logRelProbThreshold;
+      processed[i] = exp(newLogRelProb);
+    }
+    sum += processed[i];
+  }
+  double total = 0;
+  for(int i = 0; i < n; i++) total += processed[i];
+  const double dd = rand.nextDouble() * total;
+  double run = 0.0;
+  for(int i = 0; i < n; i++) { run += processed[i]; if(run > dd) return i; }
+  return n - 1;
+}
+// Search::getChosenMoveLoc (searchresults.cpp:573-598): move position chosen for game g's root, or -1 if nothing can be chosen.
+__device__ int rootChooseMove(const SPDev& d, int g) {
+  double* psv = d.selScratch + (size_t)g * 3 * d.policySize;
+  double* lcb = psv + d.policySize; double* radius = lcb + d.policySize;
+  const int nc = rootPlaySelectionValues(d, g, psv, lcb, radius);
+  if(nc <= 0) return -1;
+  const double halflives = ((double)d.moveNum[g] / d.chosenMoveTemperatureHalflife) * 19.0 / sqrt((double)d.XY);
+  const double temperature = d.chosenMoveTemperature + (d.chosenMoveTemperatureEarly - d.chosenMoveTemperature) * pow(0.5, halflives);
+  DevRand rand;
+  rand.s = d.nonSearchRand[g];
+  const int k = chooseIndexWithTemperature(rand, psv, nc, temperature, d.chosenMoveTemperatureOnlyBelowProb, lcb /*reused as scratch*/);
+  d.nonSearchRand[g] = rand.s;
+  return (int)d.childOrder[(size_t)g * d.maxNodes * d.policySize + k];
+}
+
 // Choose and play the root move once the visit budget is spent; restart the game when it is over.
 __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   const size_t gb = (size_t)g * d.maxNodes;
@@ -311,6 +496,12 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
       run += __shfl_sync(KGB_FULL, incl, 31);
     }
     best = chosen;
+  }
+  if(d.usePlaySelection) {
+    int chosen = -1;
+    if(lane == 0) chosen = rootChooseMove(d, g);
+    chosen = __shfl_sync(KGB_FULL, chosen, 0);
+    if(chosen >= 0) { best = chosen; bestV = 1; }
   }
   if(bestV <= 0) best = d.policySize - 1;  // nothing searched (cannot happen with maxVisits >= 2): pass
   // play it on the root board
@@ -778,6 +969,21 @@ __device__ void rootPolicyTemperatureAndNoise(float* pol, int policySize, int X,
   for(int i = 0; i < policySize; i++) r[i] /= rSum;
   for(int i = 0; i < policySize; i++)
     if(pol[i] >= 0) pol[i] = (float)(r[i] * weight + pol[i] * (1.0 - weight));
+}
+
+__global__ void playSelectionKernel(const SPDev d, int g, double* out /*[policySize] by move position*/) {
+  if(threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* psv = d.selScratch + (size_t)g * 3 * d.policySize;
+  for(int i = 0; i < d.policySize; i++) out[i] = -1.0;
+  const int nc = rootPlaySelectionValues(d, g, psv, psv + d.policySize, psv + 2 * d.policySize);
+  for(int k = 0; k < nc; k++) out[(int)d.childOrder[(size_t)g * d.maxNodes * d.policySize + k]] = psv[k];
+}
+__global__ void chooseIndexTestKernel(DevRandState* st, const double* probs, int n, double temperature, double onlyBelowProb, int count, int* out,
+                                      double* scratch) {
+  if(threadIdx.x != 0 || blockIdx.x != 0) return;
+  DevRand rand;
+  rand.s = *st;
+  for(int i = 0; i < count; i++) out[i] = chooseIndexWithTemperature(rand, probs, n, temperature, onlyBelowProb, scratch);
 }
 
 __global__ void rootNoiseTestKernel(float* pol, int policySize, int X, int Y, int turnNumber, int noise, double concentration, double weight,
@@ -1264,6 +1470,12 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.rootPolicyTemperatureEarly = c.root_policy_temperature_early == 0.0 ? 1.0 : c.root_policy_temperature_early;
   d.chosenMoveTemperatureHalflife = c.chosen_move_temperature_halflife == 0.0 ? 19.0 : c.chosen_move_temperature_halflife;
   d.noiseScratch = sp->alloc<double>(G * PS);
+  d.selScratch = sp->alloc<double>(G * 3 * PS);
+  d.usePlaySelection = c.use_play_selection ? 1 : 0; d.useLcbForSelection = c.use_lcb_for_selection ? 1 : 0; d.useNonBuggyLcb = c.use_non_buggy_lcb ? 1 : 0;
+  d.lcbStdevs = c.lcb_stdevs; d.minVisitPropForLCB = c.min_visit_prop_for_lcb;
+  d.chosenMoveTemperature = c.chosen_move_temperature; d.chosenMoveTemperatureEarly = c.chosen_move_temperature_early;
+  d.chosenMoveTemperatureOnlyBelowProb = c.chosen_move_temperature_only_below_prob == 0.0 ? 1.0 : c.chosen_move_temperature_only_below_prob;
+  d.chosenMoveSubtract = c.chosen_move_subtract; d.chosenMovePrune = c.chosen_move_prune;
   {
     // one generator per game, seeded like the reference's Rand from a string (the reference reseeds its search thread's
     // generator for every search from strings the device cannot hash; here the stream simply continues from move to move)
@@ -1278,6 +1490,16 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     }
     d.searchRand = sp->alloc<DevRandState>(G);
     SPCK(cudaMemcpy(d.searchRand, st.data(), G * sizeof(DevRandState), cudaMemcpyHostToDevice));
+    for(size_t g2 = 0; g2 < G; g2++) {
+      RefRand rr("kgb200$seed" + std::to_string(c.seed) + "$game" + std::to_string(g2) + "$nonSearchRand");
+      memset(&st[g2], 0, sizeof(DevRandState));
+      uint64_t a[16], idx, pcg;
+      rr.exportState(a, idx, pcg);
+      for(int i = 0; i < 16; i++) st[g2].a[i] = a[i];
+      st[g2].aIdx = idx; st[g2].pcg = pcg;
+    }
+    d.nonSearchRand = sp->alloc<DevRandState>(G);
+    SPCK(cudaMemcpy(d.nonSearchRand, st.data(), G * sizeof(DevRandState), cudaMemcpyHostToDevice));
   }
   d.useGraphSearch = c.use_graph_search ? 1 : 0; d.graphSearchRepBound = c.graph_search_rep_bound;
   d.nodeTableSize = 64;
@@ -1415,6 +1637,37 @@ void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* polic
   SPCK(cudaMemcpy(child.data(), d.childNode + nb, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
   SPCK(cudaMemcpy(avg.data(), d.nodeUtilAvg + (size_t)g * d.maxNodes, d.maxNodes * sizeof(double), cudaMemcpyDeviceToHost));
   for(int i = 0; i < d.policySize; i++) utilSum[i] = child[i] >= 0 ? avg[child[i]] : 0.0;
+}
+
+void selfplayReadPlaySelection(SelfplayImpl* sp, int g, double* out) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  double* dout;
+  SPCK(cudaMalloc(&dout, d.policySize * sizeof(double)));
+  playSelectionKernel<<<1, 32>>>(d, g, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) e = cudaMemcpy(out, dout, d.policySize * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dout);
+  SPCK(e);
+}
+
+void chooseIndexTest(const char* seedString, const double* probs, int n, double temperature, double onlyBelowProb, int count, int* out) {
+  RefRand rr(seedString);
+  DevRandState st;
+  memset(&st, 0, sizeof(st));
+  uint64_t a[16], idx, pcg;
+  rr.exportState(a, idx, pcg);
+  for(int i = 0; i < 16; i++) st.a[i] = a[i];
+  st.aIdx = idx; st.pcg = pcg;
+  DevRandState* ds; double *dp, *dscr; int* dout;
+  SPCK(cudaMalloc(&ds, sizeof(st))); SPCK(cudaMalloc(&dp, n * sizeof(double))); SPCK(cudaMalloc(&dscr, n * sizeof(double))); SPCK(cudaMalloc(&dout, count * sizeof(int)));
+  SPCK(cudaMemcpy(ds, &st, sizeof(st), cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(dp, probs, n * sizeof(double), cudaMemcpyHostToDevice));
+  chooseIndexTestKernel<<<1, 32>>>(ds, dp, n, temperature, onlyBelowProb, count, dout, dscr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) e = cudaMemcpy(out, dout, count * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(ds); cudaFree(dp); cudaFree(dscr); cudaFree(dout);
+  SPCK(e);
 }
 
 void rootNoiseTest(const char* seedString, int X, int Y, int policySize, int turnNumber, int noise, double concentration, double weight,

@@ -27,6 +27,8 @@ void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid);
 void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum);
+void selfplayReadPlaySelection(SelfplayImpl* sp, int g, double* out);
+void chooseIndexTest(const char* seedString, const double* probs, int n, double temperature, double onlyBelowProb, int count, int* out);
 void rootNoiseTest(const char* seedString, int X, int Y, int policySize, int turnNumber, int noise, double concentration, double weight,
                    double temperature, double temperatureEarly, double halflife, const float* policyIn, float* policyOut);
 void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,

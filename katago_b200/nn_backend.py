@@ -57,6 +57,10 @@ class SelfplayConfig(C.Structure):
         ("root_dirichlet_noise_total_concentration", C.c_double), ("root_dirichlet_noise_weight", C.c_double),
         ("root_policy_temperature", C.c_double), ("root_policy_temperature_early", C.c_double),
         ("chosen_move_temperature_halflife", C.c_double),
+        ("use_play_selection", C.c_int32), ("use_lcb_for_selection", C.c_int32), ("use_non_buggy_lcb", C.c_int32), ("reserved3", C.c_int32),
+        ("lcb_stdevs", C.c_double), ("min_visit_prop_for_lcb", C.c_double), ("chosen_move_temperature", C.c_double),
+        ("chosen_move_temperature_early", C.c_double), ("chosen_move_temperature_only_below_prob", C.c_double),
+        ("chosen_move_subtract", C.c_double), ("chosen_move_prune", C.c_double),
     ]
 
 
@@ -72,7 +76,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_test_choose_index_with_temperature",
 ]
 
 _lib = None
@@ -129,6 +133,8 @@ def load_library():
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
     lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
     lib.kgb_value_weight_cdf_table.argtypes = [P, I]
+    lib.kgb_selfplay_get_play_selection_values.argtypes = [P, I, P]
+    lib.kgb_test_choose_index_with_temperature.argtypes = [C.c_char_p, P, I, C.c_double, C.c_double, I, P]
     lib.kgb_test_root_policy_noise.argtypes = [C.c_char_p, I, I, I, I, I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, P, P]
     lib.kgb_selfplay_get_leaf_path.argtypes = [P, I, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.kgb_test_board_replay.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P]
@@ -332,6 +338,13 @@ def root_policy_noise(seed_string, x, y, policy, turn_number=0, noise=True, conc
     return out
 
 
+def choose_index_with_temperature(seed_string, relative_probs, temperature, only_below_prob=1.0, count=1):
+    p = np.ascontiguousarray(relative_probs, np.float64); out = np.zeros(count, np.int32)
+    _check(load_library().kgb_test_choose_index_with_temperature(seed_string.encode(), p.ctypes.data, p.size, temperature, only_below_prob, count,
+                                                                 out.ctypes.data))
+    return out
+
+
 def value_weight_cdf_table():
     out = np.zeros(2000, np.float64)
     _check(load_library().kgb_value_weight_cdf_table(out.ctypes.data, 2000))
@@ -382,7 +395,11 @@ class SelfPlay:
                  use_graph_search: bool = False, graph_search_rep_bound: int = 11, debug_hold_at_max_visits: bool = False,
                  root_noise_enabled: bool = False, root_dirichlet_noise_total_concentration: float = 10.83,
                  root_dirichlet_noise_weight: float = 0.25, root_policy_temperature: float = 1.0,
-                 root_policy_temperature_early: float = 1.0, chosen_move_temperature_halflife: float = 19.0):
+                 root_policy_temperature_early: float = 1.0, chosen_move_temperature_halflife: float = 19.0,
+                 use_play_selection: bool = False, use_lcb_for_selection: bool = False, use_non_buggy_lcb: bool = False,
+                 lcb_stdevs: float = 4.0, min_visit_prop_for_lcb: float = 0.05, chosen_move_temperature: float = 0.0,
+                 chosen_move_temperature_early: float = 0.0, chosen_move_temperature_only_below_prob: float = 1.0,
+                 chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -396,7 +413,10 @@ class SelfPlay:
                                   subtree_value_bias_factor, subtree_value_bias_weight_exponent, int(use_graph_search),
                                   int(graph_search_rep_bound), int(debug_hold_at_max_visits), int(root_noise_enabled),
                                   root_dirichlet_noise_total_concentration, root_dirichlet_noise_weight, root_policy_temperature,
-                                  root_policy_temperature_early, chosen_move_temperature_halflife)
+                                  root_policy_temperature_early, chosen_move_temperature_halflife,
+                                  int(use_play_selection), int(use_lcb_for_selection), int(use_non_buggy_lcb), 0, lcb_stdevs, min_visit_prop_for_lcb,
+                                  chosen_move_temperature, chosen_move_temperature_early, chosen_move_temperature_only_below_prob,
+                                  chosen_move_subtract, chosen_move_prune)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
@@ -432,6 +452,12 @@ class SelfPlay:
         _check(load_library().kgb_selfplay_get_game(self._p, g, colors.ctypes.data, info.ctypes.data))
         return colors, dict(move_num=int(info[0]), black_to_move=bool(info[1]), ko=int(info[2]), cap_b=int(info[3]), cap_w=int(info[4]),
                             root_visits=int(info[5]))
+
+    def play_selection_values(self, g: int):
+        """Search::getPlaySelectionValues of the root by move position (-1 = no child)."""
+        out = np.zeros(self.x * self.y + 1, np.float64)
+        _check(load_library().kgb_selfplay_get_play_selection_values(self._p, g, out.ctypes.data))
+        return out
 
     def root_children(self, g: int):
         n = self.x * self.y + 1

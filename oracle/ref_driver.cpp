@@ -224,6 +224,12 @@ static int cmdSearchFake(int argc, char** argv) {
     else if(k == "cpuctUtilityStdevPrior") params.cpuctUtilityStdevPrior = v;
     else if(k == "cpuctUtilityStdevPriorWeight") params.cpuctUtilityStdevPriorWeight = v;
     else if(k == "rootDesiredPerChildVisitsCoeff") params.rootDesiredPerChildVisitsCoeff = v;
+    else if(k == "useLcbForSelection") params.useLcbForSelection = v != 0;
+    else if(k == "useNonBuggyLcb") params.useNonBuggyLcb = v != 0;
+    else if(k == "lcbStdevs") params.lcbStdevs = v;
+    else if(k == "minVisitPropForLCB") params.minVisitPropForLCB = v;
+    else if(k == "chosenMoveSubtract") params.chosenMoveSubtract = v;
+    else if(k == "chosenMovePrune") params.chosenMovePrune = v;
     else if(k == "rootPolicyTemperature") params.rootPolicyTemperature = v;
     else if(k == "rootPolicyTemperatureEarly") params.rootPolicyTemperatureEarly = v;
     else if(k == "chosenMoveTemperatureHalflife") params.chosenMoveTemperatureHalflife = v;
@@ -267,6 +273,16 @@ static int cmdSearchFake(int argc, char** argv) {
     Loc loc = cp.getMoveLoc();
     int x = loc == Board::PASS_LOC ? -1 : Location::getX(loc, X), y = loc == Board::PASS_LOC ? -1 : Location::getY(loc, X);
     cout << "child " << x << " " << y << " " << cp.getEdgeVisits() << " " << Global::strprintf("%.17g", child->stats.utilityAvg.load()) << endl;
+  }
+  {
+    vector<Loc> locs; vector<double> psv;
+    bool suc = search->getPlaySelectionValues(locs, psv, 0.0);
+    cout << "playselection " << (suc ? 1 : 0);
+    for(size_t i = 0; i < locs.size(); i++) {
+      int x = locs[i] == Board::PASS_LOC ? -1 : Location::getX(locs[i], X), y = locs[i] == Board::PASS_LOC ? -1 : Location::getY(locs[i], X);
+      cout << " " << x << " " << y << " " << Global::strprintf("%.17g", psv[i]);
+    }
+    cout << endl;
   }
   const NNOutput* nn = root->getNNOutput();
   cout << "policy";
@@ -332,6 +348,26 @@ static int cmdRootNoise(int argc, char** argv) {
   Search::addDirichletNoise(params, rand, n, p.data());
   cout << "out";
   for(int i = 0; i < n; i++) cout << " " << Global::strprintf("%.9g", p[i]);
+  cout << endl;
+  return 0;
+}
+
+// chooseidx SEEDSTRING N PROBSEED TEMPERATURE ONLYBELOWPROB COUNT: COUNT consecutive Search::chooseIndexWithTemperature draws
+// (searchhelpers.cpp:12-76) from Rand(SEEDSTRING) over N pseudo-random relative weights (some zero); prints weights and draws.
+static int cmdChooseIdx(int argc, char** argv) {
+  if(argc != 8) { cerr << "usage: chooseidx SEEDSTRING N PROBSEED TEMPERATURE ONLYBELOWPROB COUNT" << endl; return 1; }
+  Rand rand(argv[2]);
+  int n = atoi(argv[3]);
+  Lcg rng(strtoull(argv[4], NULL, 10));
+  double temperature = atof(argv[5]), onlyBelow = atof(argv[6]);
+  int count = atoi(argv[7]);
+  vector<double> w(n);
+  for(int i = 0; i < n; i++) w[i] = (rng.next() % 4 == 0) ? 0.0 : ceil(pow((double)rng.next() / 2147483648.0, 4.0) * 300.0);
+  w[rng.next() % n] = 250.0;
+  cout << "weights";
+  for(int i = 0; i < n; i++) cout << " " << Global::strprintf("%.17g", w[i]);
+  cout << endl << "draws";
+  for(int i = 0; i < count; i++) cout << " " << Search::chooseIndexWithTemperature(rand, w.data(), n, temperature, onlyBelow, NULL);
   cout << endl;
   return 0;
 }
@@ -412,6 +448,7 @@ int main(int argc, char** argv) {
   if(cmd == "svsamples") return cmdSVSamples(argc, argv);
   if(cmd == "vwtable") return cmdVWTable(argc, argv);
   if(cmd == "rootnoise") return cmdRootNoise(argc, argv);
+  if(cmd == "chooseidx") return cmdChooseIdx(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

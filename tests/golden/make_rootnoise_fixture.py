@@ -13,3 +13,14 @@ for i, (seed, n, pseed, conc, w) in enumerate(cases):
     store[f"c{i}_seed"] = np.array(seed); store[f"c{i}_params"] = np.array([conc, w]); store[f"c{i}_in"] = lines["in"]; store[f"c{i}_out"] = lines["out"]
     print(i, seed, n, float(lines["in"][lines["in"] >= 0].sum()), float(lines["out"][lines["out"] >= 0].sum()))
 np.savez_compressed(os.path.join(HERE, "rootnoise.npz"), **store)
+
+# Search::chooseIndexWithTemperature draws (oracle/_ref/kgref_driver chooseidx)
+cases = [("s", 10, 3, 0.75, 1.0, 200), ("nonSearchRand", 80, 5, 0.15, 1.0, 200), ("t1", 30, 7, 1.0, 1.0, 200), ("below", 40, 9, 0.5, 0.1, 200),
+         ("argmax", 25, 11, 0.0, 1.0, 5)]
+store = {"num": len(cases)}
+for i, (seed, n, pseed, temp, below, count) in enumerate(cases):
+    out = subprocess.run([DRIVER, "chooseidx", seed, str(n), str(pseed), repr(temp), repr(below), str(count)], capture_output=True, text=True, check=True).stdout
+    lines = {ln.split()[0]: ln.split()[1:] for ln in out.splitlines()}
+    store[f"c{i}_seed"] = np.array(seed); store[f"c{i}_params"] = np.array([temp, below])
+    store[f"c{i}_weights"] = np.array([float(t) for t in lines["weights"]], np.float64); store[f"c{i}_draws"] = np.array([int(t) for t in lines["draws"]], np.int32)
+np.savez_compressed(os.path.join(HERE, "chooseidx.npz"), **store)

@@ -33,6 +33,7 @@ SELFPLAY8B18 = {"staticScoreUtilityFactor": 0.05, "dynamicScoreUtilityFactor": 0
                 "fpuParentWeightByVisitedPolicyPow": 2.0, "rootDesiredPerChildVisitsCoeff": 2}
 
 
+LCB = {"useLcbForSelection": 1, "lcbStdevs": 5.0, "minVisitPropForLCB": 0.15, "useNonBuggyLcb": 1, "chosenMoveSubtract": 0, "chosenMovePrune": 1}
 BIAS = {"subtreeValueBiasFactor": 0.30, "subtreeValueBiasWeightExponent": 0.8}
 
 
@@ -45,10 +46,15 @@ def run(X, Y, visits, moves, score=None):
     extra = [f"{k}={float(v)!r}" for k, v in score.items()]
     out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
+    psv = np.full(X * Y + 1, -1.0, np.float64)
     for ln in out.splitlines():
         f = ln.split()
         if f[0] == "rootvisits":
             root = (int(f[1]), float(f[3]))
+        elif f[0] == "playselection":
+            for j in range(2, len(f), 3):
+                x, y = int(f[j]), int(f[j + 1])
+                psv[X * Y if x < 0 else y * X + x] = float(f[j + 2])
         elif f[0] == "recentScoreCenter":
             center = float(f[1])
         elif f[0] == "child":
@@ -57,7 +63,7 @@ def run(X, Y, visits, moves, score=None):
             v[i] = int(f[3]); u[i] = float(f[4])
         elif f[0] == "policy":
             pol = np.array([float(t) for t in f[1:]], np.float32)
-    return root, v, u, pol, center
+    return root, v, u, pol, center, psv
 
 
 if __name__ == "__main__":
@@ -107,12 +113,19 @@ if __name__ == "__main__":
         (19, 19, 500, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40),
          dict(SELFPLAY8B18, useGraphSearch=1, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.5, chosenMoveTemperatureHalflife=19, **BIAS)),
         (13, 7, 400, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), {"rootPolicyTemperature": 0.8, "chosenMoveTemperatureHalflife": 10}),
+        # play selection values with LCB (a22 / §8f move choice): selfplay8mainb18.cfg and variants
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS, **LCB)),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS, **LCB)),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS, **LCB)),
+        (13, 7, 500, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20),
+         {"useLcbForSelection": 1, "lcbStdevs": 3.0, "minVisitPropForLCB": 0.05, "chosenMoveSubtract": 2.0, "chosenMovePrune": 3.0, "valueWeightExponent": 0.5}),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
         X, Y, visits, moves = case[:4]
         score = case[4] if len(case) > 4 else None
-        root, v, u, pol, center = run(X, Y, visits, moves, score)
+        root, v, u, pol, center, psv = run(X, Y, visits, moves, score)
+        store[f"c{i}_play_selection"] = psv
         if score is not None and not isinstance(score, dict):
             score = dict(zip(SCORE_KEYS, score))
         store[f"c{i}_params"] = np.array(json.dumps(score or {}))
