@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--ladder-nodes-per-wave", type=int, default=256,
                     help="ladder-reader moves per warp per wave before a game's unfinished searches are carried into the next wave "
                          "(0 = finish inside the wave); results are identical, only the schedule changes")
+    ap.add_argument("--nn-cache-pow2", type=int, default=20, help="evaluation cache entries per GPU = 2^N (nnCacheSizePowerOfTwo; 0 = off)")
     ap.add_argument("--visits", type=int, default=600, help="maxVisits per move (BASELINE.json configs[1]: 600)")
     return ap.parse_args()
 
@@ -264,7 +265,7 @@ def main():
                   subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8, use_graph_search=True, graph_search_rep_bound=11,
                   root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83, root_dirichlet_noise_weight=0.25,
                   root_policy_temperature=1.1, root_policy_temperature_early=1.5, chosen_move_temperature_halflife=19.0,
-                  use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
+                  nn_cache_size_power_of_two=args.nn_cache_pow2, use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
                   chosen_move_temperature=0.15, chosen_move_temperature_early=0.75, chosen_move_subtract=0.0, chosen_move_prune=1.0,
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
@@ -283,7 +284,8 @@ def main():
     # under graph search a game can also finish extra playouts inside the wave on edges that only need to catch up
     done = after["total_visits"] - before["total_visits"]
     instant = after["instant_playouts"] - before["instant_playouts"]
-    assert (done - instant) + (after["stalled_waves"] - before["stalled_waves"]) == n * K, (before, after)
+    cache_hits = after["nn_cache_hits"] - before["nn_cache_hits"]
+    assert (done - instant - cache_hits) + (after["stalled_waves"] - before["stalled_waves"]) == n * K, (before, after)
     visits_done = torch.tensor([float(done)], device=device)
     if world > 1:
         dist.all_reduce(visits_done, op=dist.ReduceOp.SUM)
@@ -341,6 +343,7 @@ def main():
                                   "search_moves": after["ladder_nodes"] - before["ladder_nodes"],
                                   "game_waves_without_leaf": after["stalled_waves"] - before["stalled_waves"],
                                   "playouts_without_evaluation(graph search catch-up)": instant,
+                                  "playouts_served_by_nn_cache": cache_hits, "nn_cache_entries": (1 << args.nn_cache_pow2) if args.nn_cache_pow2 > 0 else 0,
                                   "game_waves": n * K},
                        "weight_broadcast_ms": bcast_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},

@@ -193,6 +193,8 @@ typedef struct kgb_selfplay_config {
   double chosen_move_temperature_only_below_prob; /* chosenMoveTemperatureOnlyBelowProb (0 = unset = 1.0) */
   double chosen_move_subtract;                    /* chosenMoveSubtract (0) */
   double chosen_move_prune;                       /* chosenMovePrune (1) */
+  int32_t nn_cache_size_power_of_two;             /* nnCacheSizePowerOfTwo: evaluation cache shared by the games of this GPU (0 = off) */
+  int32_t reserved4;
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -207,6 +209,8 @@ typedef struct kgb_selfplay_stats {
   uint64_t stalled_waves;    /* game-waves without a leaf: ladder searches still running (ladder_nodes_per_wave), or every playout
                                 of the wave ended on an existing edge */
   uint64_t instant_playouts; /* graph search: playouts that ended on an edge catch-up or a cycle and needed no evaluation */
+  uint64_t nn_cache_hits;    /* playouts whose leaf evaluation came from the evaluation cache */
+  uint64_t nn_cache_stores;
 } kgb_selfplay_stats;
 
 /* ScoreValue::expectedWhiteScoreValue (neuralnet/nninputs.cpp:160-192) on the host, with the table the device loop uploads:

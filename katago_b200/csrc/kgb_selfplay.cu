@@ -62,6 +62,18 @@ struct SPDev {
   int* nodeBiasEntry;               // [game][maxNodes] slot or -1
   // graph search (search.cpp:875-936, game/graphhash.cpp): transposition table per game, cleared with the tree
   int useGraphSearch, graphSearchRepBound, holdAtMaxVisits;
+  // evaluation cache (NNCacheTable, nneval.cpp:1273-1353; key = NNInputs::getHash, nninputs.cpp:869-943): direct mapped, shared by
+  // all games of the GPU.  An entry holds what NNOutput holds for the search: post-processed policy, white win/loss/noResult,
+  // white score mean / mean-square, plus the position's laddered stones (a function of the same position, needed by descendants).
+  int cacheSize;                    // entries (power of two), 0 = off
+  unsigned long long *cacheKey0, *cacheKey1;
+  int* cacheLock;
+  float* cachePolicy;               // [cacheSize][policySize]
+  float* cacheVals;                 // [cacheSize][8]
+  uint32_t* cacheLad;               // [cacheSize][32]
+  unsigned long long *leafKey;      // [game][2] cache key of the current leaf
+  unsigned long long *cacheHits, *cacheStores;
+  int trackPosHash;                 // graph search or cache: nodes carry their Zobrist position hash
   // root policy temperature and Dirichlet noise (searchhelpers.cpp:78-215)
   int rootNoiseEnabled;
   double rootDirichletNoiseTotalConcentration, rootDirichletNoiseWeight, rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
@@ -562,6 +574,11 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
 }
 
 __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePlaWhite, double* sh, int lane);
+__device__ void finishPlayout(const SPDev& d, int g, int node, double u, bool terminal, bool leafBlack, int len, double* shSum, int lane);
+__device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWin, float whiteLoss, float noResult, float whiteScoreMeanF,
+                                  float whiteScoreMeanSqF, int lane);
+__device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane);
+__device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, float vals[5], int lane);
 
 // Warp 0 of a game's block: PUCT descent, leaf board, legality and every feature except the leaf's own ladder searches.
 __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, uint32_t* shW, uint32_t* shCand, int& shKo, int& shDoLadders,
@@ -712,8 +729,8 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     if(d.subtreeValueBiasFactor != 0.0 && d.childNode[nb + move] < 0 && !isPass && h0 != -1) biasKeyNew = biasEntryKey(bd, d.X, d.Y, black, h0, p);
     int child = d.childNode[nb + move];
     const bool newEdge = child < 0;
-    if(newEdge && d.useGraphSearch) { bd.h0 = d.nodePosH0[gb + node]; bd.h1 = d.nodePosH1[gb + node]; }
-    boardPlay(bd, p, black, (newEdge && d.useGraphSearch) ? d.zob : nullptr);
+    if(newEdge && d.trackPosHash) { bd.h0 = d.nodePosH0[gb + node]; bd.h1 = d.nodePosH1[gb + node]; }
+    boardPlay(bd, p, black, (newEdge && d.trackPosHash) ? d.zob : nullptr);
     passes = isPass ? passes + 1 : 0;
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
     black = !black;
@@ -741,10 +758,11 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
           d.nodeCount[g] = child + 1;
           nodeStatsReset(d, gb + child, passes >= 2);
           if(biasKeyNew != 0) d.nodeBiasEntry[gb + child] = biasFindOrInsert(d, g, biasKeyNew);
+          if(d.trackPosHash) { d.nodePosH0[gb + child] = bd.h0; d.nodePosH1[gb + child] = bd.h1; }
           if(d.useGraphSearch) {
             const size_t ts = (size_t)g * d.nodeTableSize + tableSlot;
             d.nodeTableKey0[ts] = cg0; d.nodeTableKey1[ts] = cg1; d.nodeTableNode[ts] = child;
-            d.nodePosH0[gb + child] = bd.h0; d.nodePosH1[gb + child] = bd.h1; d.nodeGH0[gb + child] = cg0; d.nodeGH1[gb + child] = cg1;
+            d.nodeGH0[gb + child] = cg0; d.nodeGH1[gb + child] = cg1;
           }
           atomicAdd(d.nodesAllocated, 1ULL);
         }
@@ -773,6 +791,20 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
     if(lane == 0) { atomicAdd(d.totalVisits, 1ULL); atomicAdd(d.instantPlayouts, 1ULL); }
     continue;
+  }
+  if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0) {
+    // NNEvaluator::evaluate's cache lookup (nneval.cpp:861-905): the key is the situation, not the history behind it
+    unsigned long long k0, k1;
+    stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
+    if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
+    float vals[5];
+    if(cacheLookup(d, g, node, k0, k1, vals, lane)) {
+      maybeRootNoise(d, g, node, lane);
+      const double u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], lane);
+      finishPlayout(d, g, node, u, false, black, depth, shSum, lane);
+      if(lane == 0) atomicAdd(d.cacheHits, 1ULL);
+      continue;
+    }
   }
   gotLeaf = true;
   }   // attempts
@@ -1090,27 +1122,148 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
   __syncwarp();
 }
 
+// Search::getScoreUtility (searchhelpers.cpp:272-279)
+__device__ double scoreUtilityOf(const SPDev& d, double scoreMean, double scoreMeanSq, double center) {
+  const double sqrtBoardArea = sqrt((double)d.XY);
+  const double stdev = svScoreStdev(scoreMean, scoreMeanSq);
+  double r = 0.0;
+  if(d.staticScoreUtilityFactor != 0.0) r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, 0.0, 2.0, sqrtBoardArea) * d.staticScoreUtilityFactor;
+  if(d.dynamicScoreUtilityFactor != 0.0)
+    r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, center, d.dynamicScoreCenterScale, sqrtBoardArea) * d.dynamicScoreUtilityFactor;
+  return r;
+}
+// Search::getUtilityFromNN (searchhelpers.cpp:304-307) from the NNOutput fields (floats, white's perspective); a fresh root
+// first centres the dynamic score utility on its expected score (Search::beginSearch, search.cpp:1125-1154).
+__device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWin, float whiteLoss, float noResult, float whiteScoreMeanF,
+                                  float whiteScoreMeanSqF, int lane) {
+  const size_t gb = (size_t)g * d.maxNodes;
+  double u = ((double)whiteWin - (double)whiteLoss) * d.winLossUtilityFactor + (double)noResult * d.noResultUtilityForWhite;
+  if(d.staticScoreUtilityFactor != 0.0 || d.dynamicScoreUtilityFactor != 0.0) {
+    const double whiteScoreMean = (double)whiteScoreMeanF, whiteScoreMeanSq = (double)whiteScoreMeanSqF;
+    if(node == 0 && d.nodeVisits[gb] == 0) {
+      double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
+      const double cap = sqrt((double)d.XY) * d.dynamicScoreCenterScale;
+      if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
+      if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
+      __syncwarp();
+      if(lane == 0) d.recentScoreCenter[g] = c;
+      __syncwarp();
+    }
+    u += scoreUtilityOf(d, whiteScoreMean, whiteScoreMeanSq, d.recentScoreCenter[g]);
+  }
+  return u;
+}
+// Root policy temperature + Dirichlet noise on the root's first evaluation (searchnnhelpers.cpp:61-173).
+__device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane) {
+  const size_t gb = (size_t)g * d.maxNodes;
+  if(node == 0 && d.nodeVisits[gb] == 0 && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
+    __syncwarp();
+    if(lane == 0)
+      rootPolicyTemperatureAndNoise(d.policy + gb * d.policySize, d.policySize, d.X, d.Y, d.moveNum[g], d.rootNoiseEnabled != 0,
+                                    d.rootDirichletNoiseTotalConcentration, d.rootDirichletNoiseWeight, d.rootPolicyTemperature,
+                                    d.rootPolicyTemperatureEarly, d.chosenMoveTemperatureHalflife, d.searchRand + g, d.noiseScratch + (size_t)g * d.policySize);
+    __syncwarp();
+  }
+}
+// The end of a playout whose leaf value is known: the leaf's own statistics (Search::addLeafValue, searchupdatehelpers.cpp:11-81,
+// evaluation weight 1), then edge visit + recomputeNodeStats for every node on the path (updateStatsAfterPlayout).
+__device__ void finishPlayout(const SPDev& d, int g, int node, double u, bool terminal, bool leafBlack, int len, double* shSum, int lane) {
+  const size_t gb = (size_t)g * d.maxNodes, gl = gb + node;
+  const int leafVisits = d.nodeVisits[gl];
+  __syncwarp();
+  if(terminal) {
+    if(lane == 0) {
+      const double oldW = d.nodeWeightSum[gl], newW = oldW + 1.0;
+      d.nodeUtilAvg[gl] = (d.nodeUtilAvg[gl] * oldW + u * 1.0) / newW;
+      d.nodeUtilSqAvg[gl] = (d.nodeUtilSqAvg[gl] * oldW + (u * u) * 1.0) / newW;
+      d.nodeWeightSqSum[gl] = d.nodeWeightSqSum[gl] + 1.0;
+      d.nodeWeightSum[gl] = newW;
+      d.nodeVisits[gl] = leafVisits + 1;
+    }
+  }
+  else if(leafVisits == 0) {
+    if(lane == 0) {
+      d.nodeNNUtil[gl] = u;
+      const int entry = d.subtreeValueBiasFactor != 0.0 ? d.nodeBiasEntry[gl] : -1;
+      if(entry >= 0) {   // searchupdatehelpers.cpp:26-36
+        const size_t te = (size_t)g * d.biasTableSize + entry;
+        const double ew = d.biasWeightSum[te];
+        if(ew > 0.001) u += d.subtreeValueBiasFactor * d.biasDeltaSum[te] / ew;
+      }
+      d.nodeUtilAvg[gl] = u; d.nodeUtilSqAvg[gl] = u * u; d.nodeWeightSqSum[gl] = 1.0; d.nodeWeightSum[gl] = 1.0;
+      d.nodeVisits[gl] = 1;
+    }
+  }
+  else recomputeNodeStats(d, g, node, !leafBlack, shSum, lane);   // depth cap reached on an expanded node: one more visit, same evaluation
+  __syncwarp();
+  for(int k = len - 1; k >= 0; k--) {
+    const int pn = d.pathNode[(size_t)g * d.maxDepth + k], mv = d.pathMove[(size_t)g * d.maxDepth + k];
+    if(lane == 0) d.childVisits[(gb + pn) * d.policySize + mv] += 1;
+    __syncwarp();
+    const bool pnBlack = ((len - k) & 1) ? !leafBlack : leafBlack;   // players alternate along the path
+    recomputeNodeStats(d, g, pn, !pnBlack, shSum, lane);
+    __syncwarp();
+  }
+  if(lane == 0) atomicAdd(d.totalVisits, 1ULL);
+}
+
+// ---- evaluation cache -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t cacheSlotOf(const SPDev& d, unsigned long long k0, unsigned long long k1) {
+  return (size_t)((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) & (unsigned long long)(d.cacheSize - 1));
+}
+// Looks the leaf's key up; on a hit copies policy, values and laddered stones into the node (whole warp).  Writers hold the
+// entry's lock while they change it and readers check key and lock before and after copying, so a torn entry is never used.
+__device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, float vals[5], int lane) {
+  const size_t slot = cacheSlotOf(d, k0, k1);
+  bool ok = false;
+  if(lane == 0) ok = atomicAdd(&d.cacheLock[slot], 0) == 0 && __ldcg(d.cacheKey0 + slot) == k0 && __ldcg(d.cacheKey1 + slot) == k1;
+  ok = __shfl_sync(KGB_FULL, ok ? 1 : 0, 0) != 0;
+  if(!ok) return false;
+  __threadfence();
+  const size_t gb = (size_t)g * d.maxNodes, nb = (gb + node) * d.policySize;
+  for(int i = lane; i < d.policySize; i += 32) d.policy[nb + i] = __ldcg(d.cachePolicy + slot * d.policySize + i);
+  d.nodeLad[(gb + node) * 32 + lane] = __ldcg(d.cacheLad + slot * 32 + lane);
+  float v = lane < 5 ? __ldcg(d.cacheVals + slot * 8 + lane) : 0.0f;
+  __threadfence();
+  if(lane == 0) ok = atomicAdd(&d.cacheLock[slot], 0) == 0 && __ldcg(d.cacheKey0 + slot) == k0 && __ldcg(d.cacheKey1 + slot) == k1;
+  ok = __shfl_sync(KGB_FULL, ok ? 1 : 0, 0) != 0;
+#pragma unroll
+  for(int i = 0; i < 5; i++) vals[i] = __shfl_sync(KGB_FULL, v, i);
+  return ok;
+}
+__device__ void cacheStore(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, const float vals[5], int lane) {
+  const size_t slot = cacheSlotOf(d, k0, k1);
+  bool mine = false;
+  if(lane == 0) mine = atomicCAS(&d.cacheLock[slot], 0, 1) == 0;
+  mine = __shfl_sync(KGB_FULL, mine ? 1 : 0, 0) != 0;
+  if(!mine) return;   // somebody else is writing this entry: skip, it is only a cache
+  if(lane == 0) { d.cacheKey0[slot] = 0; d.cacheKey1[slot] = 0; }
+  __threadfence();
+  const size_t gb = (size_t)g * d.maxNodes, nb = (gb + node) * d.policySize;
+  for(int i = lane; i < d.policySize; i += 32) d.cachePolicy[slot * d.policySize + i] = d.policy[nb + i];
+  d.cacheLad[slot * 32 + lane] = d.nodeLad[(gb + node) * 32 + lane];
+  if(lane < 5) d.cacheVals[slot * 8 + lane] = vals[lane];
+  __threadfence();
+  __syncwarp();
+  if(lane == 0) {
+    d.cacheKey1[slot] = k1; d.cacheKey0[slot] = k0;
+    __threadfence();
+    atomicExch(&d.cacheLock[slot], 0);
+    atomicAdd(d.cacheStores, 1ULL);
+  }
+}
+
 __global__ void spBackupKernel(const SPDev d) {
   __shared__ double shSumAll[4][64];
   double* shSum = shSumAll[(threadIdx.x >> 5) & 3];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
-  if(!d.leafValid[g]) return;   // ladder searches of this game's leaf still running (ladderNodesPerWave)
+  if(!d.leafValid[g]) return;   // no leaf this wave (ladder searches still running, or every playout ended inside the select kernel)
   const size_t gb = (size_t)g * d.maxNodes;
   const int node = d.leafNode[g];
   const bool terminal = d.leafTerminal[g] != 0;
   const bool leafBlack = d.leafBlackToMove[g] != 0;
-  const double sqrtBoardArea = sqrt((double)d.XY);
-  // Search::getScoreUtility (searchhelpers.cpp:272-279)
-  auto scoreUtility = [&](double scoreMean, double scoreMeanSq, double center) -> double {
-    const double stdev = svScoreStdev(scoreMean, scoreMeanSq);
-    double r = 0.0;
-    if(d.staticScoreUtilityFactor != 0.0) r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, 0.0, 2.0, sqrtBoardArea) * d.staticScoreUtilityFactor;
-    if(d.dynamicScoreUtilityFactor != 0.0)
-      r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, center, d.dynamicScoreCenterScale, sqrtBoardArea) * d.dynamicScoreUtilityFactor;
-    return r;
-  };
   double u;
   if(terminal) {
     // search.cpp:1213-1222: the game result as a leaf value (area scoring: no "no result")
@@ -1125,7 +1278,7 @@ __global__ void spBackupKernel(const SPDev d) {
       const double lo = (score - 0.5) * (score - 0.5), hi = (score + 0.5) * (score + 0.5);
       scoreMeanSq = lo + (hi - lo) * d.drawEquivalentWinsForWhite;
     }
-    u = winLoss * d.winLossUtilityFactor + scoreUtility(scoreMean, scoreMeanSq, d.recentScoreCenter[g]);
+    u = winLoss * d.winLossUtilityFactor + scoreUtilityOf(d, scoreMean, scoreMeanSq, d.recentScoreCenter[g]);
   }
   else {
     // ---- policy: legality mask + softmax (nneval.cpp:960-1051)
@@ -1159,93 +1312,33 @@ __global__ void spBackupKernel(const SPDev d) {
       int i = k * 32 + lane;
       if(i < d.policySize) d.policy[nb + i] = ok[k] ? v[k] / sum : -1.0f;
     }
-    // ---- the root's policy gets the root temperature and the Dirichlet noise when it is first evaluated (searchnnhelpers.cpp:61-173)
-    if(node == 0 && d.nodeVisits[gb] == 0 && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
-      __syncwarp();
-      if(lane == 0)
-        rootPolicyTemperatureAndNoise(d.policy + nb, d.policySize, d.X, d.Y, d.moveNum[g], d.rootNoiseEnabled != 0, d.rootDirichletNoiseTotalConcentration,
-                                      d.rootDirichletNoiseWeight, d.rootPolicyTemperature, d.rootPolicyTemperatureEarly, d.chosenMoveTemperatureHalflife,
-                                      d.searchRand + g, d.noiseScratch + (size_t)g * d.policySize);
-      __syncwarp();
-    }
-    // ---- value: softmax(win, loss, noResult) from the mover's perspective -> white utility (nneval.cpp:1112-1215)
+    // ---- value: softmax(win, loss, noResult) from the mover's perspective -> white's (nneval.cpp:1112-1215); NNOutput stores the
+    // results as float and the search widens them again (searchupdatehelpers.cpp:87-88) - the same rounding happens here
     const float* val = d.nnValue + (size_t)g * 3;
     double wl = val[0], ll = val[1], nl = val[2];
     double m = fmax(fmax(wl, ll), nl);
     double w = exp(wl - m), l = exp(ll - m), n = exp(nl - m);
     double s = w + l + n;
     w /= s; l /= s; n /= s;
-    const bool black = leafBlack;
-    // NNOutput stores the probabilities as float (nneval.cpp:1200-1215); the search widens them again
-    // (searchupdatehelpers.cpp:87-88) - mirror that rounding so utilities agree to the last bit.
     const float wf = (float)w, lf = (float)l, nf = (float)n;
-    const double whiteWin = black ? (double)lf : (double)wf, whiteLoss = black ? (double)wf : (double)lf;
-    u = (whiteWin - whiteLoss) * d.winLossUtilityFactor + (double)nf * d.noResultUtilityForWhite;
-    if(d.staticScoreUtilityFactor != 0.0 || d.dynamicScoreUtilityFactor != 0.0) {
-      // score head (nneval.cpp:1150-1160, 1200-1215): mean * 20, softplus(stdev) * 20, both scaled by P(result), stored as float
-      const float* sc = d.nnScore + (size_t)g * 6;
-      double scoreMean = (double)sc[0] * d.scoreMeanMultiplier;
-      const double pre = (double)sc[1];
-      const double stdev = (pre > 40.0 ? pre : log(1.0 + exp(pre))) * d.scoreStdevMultiplier;
-      double scoreMeanSq = scoreMean * scoreMean + stdev * stdev;
-      scoreMean = scoreMean * (1.0 - n);
-      scoreMeanSq = scoreMeanSq * (1.0 - n);
-      const double whiteScoreMean = black ? (double)(-(float)scoreMean) : (double)(float)scoreMean;
-      const double whiteScoreMeanSq = (double)(float)scoreMeanSq;
-      if(node == 0 && d.nodeVisits[gb] == 0) {
-        // fresh root: Search::beginSearch centres the dynamic score utility on the root's expected score (search.cpp:1125-1154)
-        double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
-        const double cap = sqrtBoardArea * d.dynamicScoreCenterScale;
-        if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
-        if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
-        __syncwarp();
-        if(lane == 0) d.recentScoreCenter[g] = c;
-        __syncwarp();
-      }
-      u += scoreUtility(whiteScoreMean, whiteScoreMeanSq, d.recentScoreCenter[g]);
-    }
-  }
-  __syncwarp();
-  // ---- the leaf's own statistics (Search::addLeafValue, searchupdatehelpers.cpp:11-81; evaluation weight 1)
-  const size_t gl = gb + node;
-  const int leafVisits = d.nodeVisits[gl];
-  __syncwarp();
-  if(terminal) {
-    if(lane == 0) {
-      const double oldW = d.nodeWeightSum[gl], newW = oldW + 1.0;
-      d.nodeUtilAvg[gl] = (d.nodeUtilAvg[gl] * oldW + u * 1.0) / newW;
-      d.nodeUtilSqAvg[gl] = (d.nodeUtilSqAvg[gl] * oldW + (u * u) * 1.0) / newW;
-      d.nodeWeightSqSum[gl] = d.nodeWeightSqSum[gl] + 1.0;
-      d.nodeWeightSum[gl] = newW;
-      d.nodeVisits[gl] = leafVisits + 1;
-    }
-  }
-  else if(leafVisits == 0) {
-    if(lane == 0) {
-      d.nodeNNUtil[gl] = u;
-      const int entry = d.subtreeValueBiasFactor != 0.0 ? d.nodeBiasEntry[gl] : -1;
-      if(entry >= 0) {   // searchupdatehelpers.cpp:26-36
-        const size_t te = (size_t)g * d.biasTableSize + entry;
-        const double ew = d.biasWeightSum[te];
-        if(ew > 0.001) u += d.subtreeValueBiasFactor * d.biasDeltaSum[te] / ew;
-      }
-      d.nodeUtilAvg[gl] = u; d.nodeUtilSqAvg[gl] = u * u; d.nodeWeightSqSum[gl] = 1.0; d.nodeWeightSum[gl] = 1.0;
-      d.nodeVisits[gl] = 1;
-    }
-  }
-  else recomputeNodeStats(d, g, node, !leafBlack, shSum, lane);   // depth cap reached on an expanded node: one more visit, same evaluation
-  __syncwarp();
-  // ---- backup: edge visit, then the parent re-derives its statistics from its children (updateStatsAfterPlayout)
-  const int len = d.pathLen[g];
-  for(int k = len - 1; k >= 0; k--) {
-    const int pn = d.pathNode[(size_t)g * d.maxDepth + k], mv = d.pathMove[(size_t)g * d.maxDepth + k];
-    if(lane == 0) d.childVisits[(gb + pn) * d.policySize + mv] += 1;
+    // score head (nneval.cpp:1150-1160, 1200-1215): mean * 20, softplus(stdev) * 20, both scaled by P(result)
+    const float* sc = d.nnScore + (size_t)g * 6;
+    double scoreMean = (double)sc[0] * d.scoreMeanMultiplier;
+    const double pre = (double)sc[1];
+    const double stdev = (pre > 40.0 ? pre : log(1.0 + exp(pre))) * d.scoreStdevMultiplier;
+    double scoreMeanSq = scoreMean * scoreMean + stdev * stdev;
+    scoreMean = scoreMean * (1.0 - n);
+    scoreMeanSq = scoreMeanSq * (1.0 - n);
+    float vals[5];
+    vals[0] = leafBlack ? lf : wf; vals[1] = leafBlack ? wf : lf; vals[2] = nf;
+    vals[3] = leafBlack ? -(float)scoreMean : (float)scoreMean; vals[4] = (float)scoreMeanSq;
     __syncwarp();
-    const bool pnBlack = ((len - k) & 1) ? !leafBlack : leafBlack;   // players alternate along the path
-    recomputeNodeStats(d, g, pn, !pnBlack, shSum, lane);
-    __syncwarp();
+    if(d.cacheSize > 0) cacheStore(d, g, node, d.leafKey[g * 2], d.leafKey[g * 2 + 1], vals, lane);   // before any root noise: the raw evaluation
+    maybeRootNoise(d, g, node, lane);
+    u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], lane);
   }
-  if(lane == 0) atomicAdd(d.totalVisits, 1ULL);
+  __syncwarp();
+  finishPlayout(d, g, node, u, terminal, leafBlack, d.pathLen[g], shSum, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1501,6 +1594,16 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     d.nonSearchRand = sp->alloc<DevRandState>(G);
     SPCK(cudaMemcpy(d.nonSearchRand, st.data(), G * sizeof(DevRandState), cudaMemcpyHostToDevice));
   }
+  d.cacheSize = 0;
+  if(c.nn_cache_size_power_of_two > 0) {
+    if(c.nn_cache_size_power_of_two > 26) throw std::invalid_argument("selfplay: nn_cache_size_power_of_two above 26 not supported");
+    d.cacheSize = 1 << c.nn_cache_size_power_of_two;
+    const size_t S = (size_t)d.cacheSize;
+    d.cacheKey0 = sp->alloc<unsigned long long>(S); d.cacheKey1 = sp->alloc<unsigned long long>(S); d.cacheLock = sp->alloc<int>(S);
+    d.cachePolicy = sp->alloc<float>(S * PS); d.cacheVals = sp->alloc<float>(S * 8); d.cacheLad = sp->alloc<uint32_t>(S * 32);
+  }
+  d.leafKey = sp->alloc<unsigned long long>(G * 2);
+  d.trackPosHash = (c.use_graph_search || d.cacheSize > 0) ? 1 : 0;
   d.useGraphSearch = c.use_graph_search ? 1 : 0; d.graphSearchRepBound = c.graph_search_rep_bound;
   d.nodeTableSize = 64;
   while(d.nodeTableSize < 2 * (int)N) d.nodeTableSize *= 2;
@@ -1528,7 +1631,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafLegal = sp->alloc<uint32_t>(G * 32);
   unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
-  d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8; d.instantPlayouts = stats + 9;
+  d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8; d.instantPlayouts = stats + 9; d.cacheHits = stats + 10; d.cacheStores = stats + 11;
   d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
   d.nnPolicy = nn.policy; d.nnValue = nn.value; d.nnScore = nn.score;
   {
@@ -1590,7 +1693,7 @@ void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {
   SPCK(cudaMemcpy(h, sp->d.totalVisits, sizeof(h), cudaMemcpyDeviceToHost));
   out->total_visits = h[0]; out->total_moves = h[1]; out->games_finished = h[2]; out->black_wins = h[3];
   out->nodes_allocated = h[4]; out->sum_leaf_depth = h[5]; out->ladder_searches = h[6]; out->ladder_nodes = h[7];
-  out->stalled_waves = h[8]; out->instant_playouts = h[9];
+  out->stalled_waves = h[8]; out->instant_playouts = h[9]; out->nn_cache_hits = h[10]; out->nn_cache_stores = h[11];
 }
 
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid) {

@@ -61,12 +61,14 @@ class SelfplayConfig(C.Structure):
         ("lcb_stdevs", C.c_double), ("min_visit_prop_for_lcb", C.c_double), ("chosen_move_temperature", C.c_double),
         ("chosen_move_temperature_early", C.c_double), ("chosen_move_temperature_only_below_prob", C.c_double),
         ("chosen_move_subtract", C.c_double), ("chosen_move_prune", C.c_double),
+        ("nn_cache_size_power_of_two", C.c_int32), ("reserved4", C.c_int32),
     ]
 
 
 class SelfplayStats(C.Structure):
     _fields_ = [("total_visits", C.c_uint64), ("total_moves", C.c_uint64), ("games_finished", C.c_uint64), ("black_wins", C.c_uint64),
-                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64), ("ladder_searches", C.c_uint64), ("ladder_nodes", C.c_uint64), ("stalled_waves", C.c_uint64), ("instant_playouts", C.c_uint64)]
+                ("nodes_allocated", C.c_uint64), ("sum_leaf_depth", C.c_uint64), ("ladder_searches", C.c_uint64), ("ladder_nodes", C.c_uint64), ("stalled_waves", C.c_uint64), ("instant_playouts", C.c_uint64), ("nn_cache_hits", C.c_uint64),
+                ("nn_cache_stores", C.c_uint64)]
 
 
 # Every symbol include/kgb200.h declares (tests/test_abi.py checks the library exports all of them).
@@ -399,7 +401,7 @@ class SelfPlay:
                  use_play_selection: bool = False, use_lcb_for_selection: bool = False, use_non_buggy_lcb: bool = False,
                  lcb_stdevs: float = 4.0, min_visit_prop_for_lcb: float = 0.05, chosen_move_temperature: float = 0.0,
                  chosen_move_temperature_early: float = 0.0, chosen_move_temperature_only_below_prob: float = 1.0,
-                 chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0):
+                 chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0, nn_cache_size_power_of_two: int = 0):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -416,7 +418,7 @@ class SelfPlay:
                                   root_policy_temperature_early, chosen_move_temperature_halflife,
                                   int(use_play_selection), int(use_lcb_for_selection), int(use_non_buggy_lcb), 0, lcb_stdevs, min_visit_prop_for_lcb,
                                   chosen_move_temperature, chosen_move_temperature_early, chosen_move_temperature_only_below_prob,
-                                  chosen_move_subtract, chosen_move_prune)
+                                  chosen_move_subtract, chosen_move_prune, int(nn_cache_size_power_of_two), 0)
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
