@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--ladder-nodes-per-wave", type=int, default=256,
                     help="ladder-reader moves per warp per wave before a game's unfinished searches are carried into the next wave "
                          "(0 = finish inside the wave); results are identical, only the schedule changes")
+    ap.add_argument("--opening-max", type=int, default=150, help="games start from their own random legal play-out of 0..N moves "
+                    "(a self-play server holds games at all stages; SURVEY.md 8d), then search")
+    ap.add_argument("--settle-waves", type=int, default=700, help="untimed waves after the openings, so that every game has finished a move "
+                    "and the evaluation cache holds what a running server's cache would hold")
     ap.add_argument("--nn-cache-pow2", type=int, default=20, help="evaluation cache entries per GPU = 2^N (nnCacheSizePowerOfTwo; 0 = off)")
     ap.add_argument("--visits", type=int, default=600, help="maxVisits per move (BASELINE.json configs[1]: 600)")
     return ap.parse_args()
@@ -270,8 +274,9 @@ def main():
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
-    # bring the games into mid-search (trees a few hundred nodes deep) before timing
-    sp.run(W + 64)
+    # steady state before timing: games at different stages, trees hundreds of nodes deep, cache filled by the previous moves
+    sp.random_openings(args.opening_max)
+    sp.run(W + args.settle_waves)
     handle.sync()
     before = sp.stats()
     sampler = ClockSampler(local_rank)
@@ -334,6 +339,7 @@ def main():
                        "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
                        "weights": "random init, real architecture (katago_b200/modelgen.py)",
+                       "positions": f"every game starts from its own random legal play-out of 0..{args.opening_max} moves, then {W + args.settle_waves} untimed waves",
                        "l2": "per-step working set (tree arrays ~1 GB + activations ~0.5 GB) far larger than the 126 MB L2; "
                              f"e2e rotates {NBUF} distinct feature batches ({NBUF * n * 22 * 361 * 4 / 1e6:.0f} MB)",
                        "avg_leaf_depth": (after["sum_leaf_depth"] - before["sum_leaf_depth"]) / max(1, after["total_visits"] - before["total_visits"]),

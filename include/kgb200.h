@@ -250,6 +250,9 @@ KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, 
 /* The moves from the root to the leaf the last wave selected for game g (x,y pairs, -1,-1 = pass; at most max_len pairs are
  * written, *len_out is the full length) and whether that wave delivered a finished leaf (see ladder_nodes_per_wave). */
 KGB_API int kgb_selfplay_get_leaf_path(kgb_selfplay* sp, int game, int32_t* moves_xy, int32_t max_len, int32_t* len_out, int32_t* valid_out);
+/* Desynchronise the games (bench / test support): every game plays its own random number (0..max_moves) of uniformly random
+ * legal non-pass moves from its current root and clears its tree - positions "from random legal play-outs" (SURVEY.md §8d). */
+KGB_API int kgb_selfplay_random_openings(kgb_selfplay* sp, int max_moves);
 /* Play a fixed move list on EVERY game's root (x,y pairs, -1,-1 = pass; colours alternate) and clear the trees. */
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves);
 /* Timing hook for bench.py's tree/board roofline entry: runs `iters` waves of ONLY the select(+board+featurize) and backup

@@ -937,6 +937,14 @@ KGB_API int kgb_selfplay_run(kgb_selfplay* sp, int steps) {
   });
 }
 
+KGB_API int kgb_selfplay_random_openings(kgb_selfplay* sp, int max_moves) {
+  return guarded([&] {
+    if(!sp || max_moves < 0) throw std::invalid_argument("kgb_selfplay_random_openings: bad argument");
+    CK(cudaSetDevice(sp->h->device));
+    selfplayRandomOpenings(sp->impl, max_moves, sp->h->stream);
+  });
+}
+
 KGB_API int kgb_selfplay_get_stats(kgb_selfplay* sp, kgb_selfplay_stats* out) {
   return guarded([&] {
     if(!sp || !out) throw std::invalid_argument("kgb_selfplay_get_stats: NULL argument");

@@ -1432,6 +1432,88 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
   rootHashesInit(d, g, lane);
 }
 
+// Desynchronise the games: every game's root is advanced by its own random number (0..maxLen) of uniformly random legal
+// non-pass moves (its own generator).  Bench / test support: a steady-state self-play server holds games at all stages, and
+// SURVEY.md §8d asks for positions "from random legal play-outs" for the kernel-level measurements.
+__global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  WarpBoard bd;
+  boardInit(bd, d.X, d.Y);
+  bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
+  bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
+  bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];
+  bool black = d.rootBlackToMove[g] != 0;
+  int mv = d.moveNum[g];
+  int h[5];
+  for(int k = 0; k < 5; k++) h[k] = d.hist[g * 5 + k];
+  const size_t G32 = (size_t)d.numGames * 32;
+  uint32_t p1B = d.prevB[g * 32 + lane], p1W = d.prevW[g * 32 + lane], p2B = d.prevB[G32 + g * 32 + lane], p2W = d.prevW[G32 + g * 32 + lane];
+  int p1Ko = d.prevKo[g], p2Ko = d.prevKo[d.numGames + g];
+  DevRand rand;
+  if(lane == 0) rand.s = d.nonSearchRand[g];
+  unsigned len = 0;
+  if(lane == 0) len = maxLen > 0 ? rand.nextUInt() % (unsigned)(maxLen + 1) : 0;
+  len = __shfl_sync(KGB_FULL, len, 0);
+  for(unsigned m = 0; m < len; m++) {
+    uint32_t l1, l2, l3;
+    boardLibertyClasses(bd, l1, l2, l3);
+    const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, l1);
+    const int n = warpCount(legal);
+    if(n == 0) break;
+    unsigned r = 0;
+    if(lane == 0) r = rand.nextUInt() % (unsigned)n;
+    r = __shfl_sync(KGB_FULL, r, 0);
+    // the r-th legal point in row-major order
+    int mine = __popc(legal), incl = mine;
+    for(int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(KGB_FULL, incl, o); if(lane >= o) incl += t; }
+    const int before = incl - mine;
+    int p = -1;
+    if((int)r >= before && (int)r < incl) {
+      uint32_t bits = legal;
+      for(int k = (int)r - before; k > 0; k--) bits &= bits - 1;
+      p = lane * 32 + (__ffs(bits) - 1);
+    }
+    const unsigned who = __ballot_sync(KGB_FULL, p >= 0);
+    p = __shfl_sync(KGB_FULL, p, __ffs(who) - 1);
+    p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
+    boardPlay(bd, p, black, d.zob);
+    for(int k = 4; k > 0; k--) h[k] = h[k - 1];
+    h[0] = p;
+    black = !black;
+    mv++;
+  }
+  d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
+  d.prevB[g * 32 + lane] = p1B; d.prevW[g * 32 + lane] = p1W; d.prevB[G32 + g * 32 + lane] = p2B; d.prevW[G32 + g * 32 + lane] = p2W;
+  if(d.enableLadders) {
+    const LadderScratch sc = ladderScratchAt(d.ladderScratch + (size_t)g * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
+    WarpBoard pb = bd;
+    uint32_t la, lb, wB, wW;
+    pb.b = p1B; pb.w = p1W; pb.ko = p1Ko;
+    boardLadders(pb, sc, d.X, d.Y, la, wB, wW);
+    pb.b = p2B; pb.w = p2W; pb.ko = p2Ko;
+    boardLadders(pb, sc, d.X, d.Y, lb, wB, wW);
+    d.prevLad[g * 32 + lane] = la; d.prevLad[G32 + g * 32 + lane] = lb;
+  }
+  const size_t gb = (size_t)g * d.maxNodes;
+  if(lane == 0) {
+    d.nonSearchRand[g] = rand.s;
+    d.prevKo[g] = p1Ko; d.prevKo[d.numGames + g] = p2Ko;
+    d.rootKo[g] = bd.ko; d.rootCapB[g] = bd.capB; d.rootCapW[g] = bd.capW;
+    d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = 0; d.moveNum[g] = mv;
+    for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
+    d.nodeCount[g] = 1; nodeStatsReset(d, gb, false);
+    d.ladPending[g] = 0; d.leafValid[g] = 0;
+    d.rootPosH[g * 2] = bd.h0; d.rootPosH[g * 2 + 1] = bd.h1;
+  }
+  nodeInit(d, gb * d.policySize, lane);
+  biasTableClear(d, g, lane);
+  nodeTableClear(d, g, lane);
+  __syncwarp();
+  rootHashesInit(d, g, lane);
+}
+
 __global__ void spInitRootsKernel(const SPDev d) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -1686,6 +1768,12 @@ void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cu
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(dm);
   SPCK(e);
+}
+
+void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s) {
+  spRandomOpeningsKernel<<<(sp->d.numGames * 32 + 127) / 128, 128, 0, s>>>(sp->d, maxLen);
+  SPCK(cudaGetLastError());
+  SPCK(cudaStreamSynchronize(s));
 }
 
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {

@@ -78,7 +78,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_test_choose_index_with_temperature",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_test_choose_index_with_temperature",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def load_library():
     lib.kgb_selfplay_get_root_children.argtypes = [P, I, P, P, P]
     lib.kgb_selfplay_launches_per_step.argtypes = [P]
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
+    lib.kgb_selfplay_random_openings.argtypes = [P, I]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
@@ -425,6 +426,10 @@ class SelfPlay:
 
     def run(self, steps: int):
         _check(load_library().kgb_selfplay_run(self._p, steps))
+
+    def random_openings(self, max_moves: int):
+        """Every game plays its own random number (0..max_moves) of uniformly random legal moves; trees cleared."""
+        _check(load_library().kgb_selfplay_random_openings(self._p, max_moves))
 
     def play_moves(self, moves_xy):
         """moves_xy: iterable of (x, y) or None for pass; applied to every game's root, trees cleared."""
