@@ -1,0 +1,22 @@
+"""A few playout waves of the bench configuration for ncu: python tests/gpu_checks/wave_for_ncu.py [waves]"""
+import os, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from katago_b200 import NeuralNet, SelfPlay, modelgen
+waves = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+p = modelgen.write_model(os.path.join(tempfile.mkdtemp(), "b18.bin"), "b18c384nbt", seed=0)
+lm = NeuralNet.loadModelFile(p)
+ctx = NeuralNet.createComputeContext([0], 19, 19, True, lm)
+h = NeuralNet.createComputeHandle(ctx, lm, 256, False, True, 0)
+sp = SelfPlay(h, 256, 600, komi=7.5, seed=1234, cpuct_exploration=1.05, cpuct_exploration_log=0.28, fpu_reduction_max=0.2, root_fpu_reduction_max=0.0,
+              value_weight_exponent=0.5, fpu_parent_weight_by_visited_policy=True, fpu_parent_weight_by_visited_policy_pow=2.0,
+              root_desired_per_child_visits_coeff=2.0, subtree_value_bias_factor=0.3, subtree_value_bias_weight_exponent=0.8, use_graph_search=True,
+              root_noise_enabled=True, root_policy_temperature=1.1, root_policy_temperature_early=1.5, nn_cache_size_power_of_two=20,
+              use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
+              chosen_move_temperature=0.15, chosen_move_temperature_early=0.75, static_score_utility_factor=0.05, dynamic_score_utility_factor=0.3,
+              dynamic_score_center_zero_weight=0.25, dynamic_score_center_scale=0.5, ladder_nodes_per_wave=256)
+sp.random_openings(150)
+os.environ["KGB_NO_GRAPH"] = os.environ.get("KGB_NO_GRAPH", "0")
+sp.run(waves)
+h.sync()
+print(sp.stats())
