@@ -194,7 +194,7 @@ typedef struct kgb_selfplay_config {
   double chosen_move_subtract;                    /* chosenMoveSubtract (0) */
   double chosen_move_prune;                       /* chosenMovePrune (1) */
   int32_t nn_cache_size_power_of_two;             /* nnCacheSizePowerOfTwo: evaluation cache shared by the games of this GPU (0 = off) */
-  int32_t reserved4;
+  int32_t root_num_symmetries_to_sample;          /* rootNumSymmetriesToSample (4): the root is evaluated under that many symmetries, one per wave */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -250,6 +250,9 @@ KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, 
 /* The moves from the root to the leaf the last wave selected for game g (x,y pairs, -1,-1 = pass; at most max_len pairs are
  * written, *len_out is the full length) and whether that wave delivered a finished leaf (see ladder_nodes_per_wave). */
 KGB_API int kgb_selfplay_get_leaf_path(kgb_selfplay* sp, int game, int32_t* moves_xy, int32_t max_len, int32_t* len_out, int32_t* valid_out);
+/* Re-seed every game's search-thread generator like the reference's Rand(seed_string) (tests: reproduce a reference search whose
+ * SearchThread seed string is known). */
+KGB_API int kgb_selfplay_set_search_rand(kgb_selfplay* sp, const char* seed_string);
 /* Desynchronise the games (bench / test support): every game plays its own random number (0..max_moves) of uniformly random
  * legal non-pass moves from its current root and clears its tree - positions "from random legal play-outs" (SURVEY.md §8d). */
 KGB_API int kgb_selfplay_random_openings(kgb_selfplay* sp, int max_moves);

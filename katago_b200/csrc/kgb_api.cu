@@ -940,6 +940,15 @@ KGB_API int kgb_selfplay_run(kgb_selfplay* sp, int steps) {
   });
 }
 
+KGB_API int kgb_selfplay_set_search_rand(kgb_selfplay* sp, const char* seed_string) {
+  return guarded([&] {
+    if(!sp || !seed_string) throw std::invalid_argument("kgb_selfplay_set_search_rand: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplaySetSearchRand(sp->impl, seed_string);
+  });
+}
+
 KGB_API int kgb_selfplay_random_openings(kgb_selfplay* sp, int max_moves) {
   return guarded([&] {
     if(!sp || max_moves < 0) throw std::invalid_argument("kgb_selfplay_random_openings: bad argument");

@@ -75,6 +75,12 @@ struct SPDev {
   unsigned long long *cacheHits, *cacheStores;
   int trackPosHash;                 // graph search or cache: nodes carry their Zobrist position hash
   // root policy temperature and Dirichlet noise (searchhelpers.cpp:78-215)
+  // rootNumSymmetriesToSample (searchnnhelpers.cpp:95-101, nneval.cpp:811-838, nninputs.cpp:324-430): the root is evaluated under
+  // several distinct symmetries, one per wave, and the post-processed outputs are averaged
+  int rootNumSymmetries, fakeNN;
+  int* rootSymCount;                // [game] evaluations of the current root accumulated so far
+  int* rootSymOrder;                // [game][8] the sampled symmetry order
+  float* rootSymAcc;                // [game][8] sums of whiteWin, whiteLoss, noResult, whiteScoreMean, whiteScoreMeanSq
   int rootNoiseEnabled;
   double rootDirichletNoiseTotalConcentration, rootDirichletNoiseWeight, rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
   // root move choice (searchresults.cpp:24-330 play selection values, :573-598 getChosenMoveLoc, searchhelpers.cpp:12-76)
@@ -564,6 +570,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     // reset the tree: node 0 = unevaluated root
     d.nodeCount[g] = 1;
     nodeStatsReset(d, gb, false);
+    d.rootSymCount[g] = 0;
   }
   nodeInit(d, rootBase, lane);
   biasTableClear(d, g, lane);   // all nodes freed: every entry is unused and dropped (search.cpp:860-861)
@@ -792,7 +799,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     if(lane == 0) { atomicAdd(d.totalVisits, 1ULL); atomicAdd(d.instantPlayouts, 1ULL); }
     continue;
   }
-  if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0) {
+  if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0 && !(node == 0 && d.rootNumSymmetries > 1)) {
     // NNEvaluator::evaluate's cache lookup (nneval.cpp:861-905): the key is the situation, not the history behind it
     unsigned long long k0, k1;
     stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
@@ -881,8 +888,32 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     float komiFloor = drawableKomisAreEven ? floorf(selfKomi / 2.0f) * 2.0f : floorf((selfKomi - 1.0f) / 2.0f) * 2.0f + 1.0f;
     float delta = fminf(fmaxf(selfKomi - komiFloor, 0.0f), 2.0f);
     gl[18] = delta < 0.5f ? delta : (delta < 1.5f ? 1.0f - delta : delta - 2.0f);
-    d.nnSymmetry[g] = (int)(splitmix64(d.seed ^ ((uint64_t)g << 40) ^ (d.gameCounter[g] << 28) ^ ((uint64_t)d.moveNum[g] << 14) ^
-                                       (uint64_t)d.nodeVisits[gb]) & 7);   // nneval.cpp:698-707: random symmetry per row
+    int sym = (int)(splitmix64(d.seed ^ ((uint64_t)g << 40) ^ (d.gameCounter[g] << 28) ^ ((uint64_t)d.moveNum[g] << 14) ^
+                               (uint64_t)d.nodeVisits[gb]) & 7);   // nneval.cpp:698-707: random symmetry per row
+    if(d.fakeNN) sym = 0;                                          // the reference's evaluator without nnRandomize
+    if(node == 0 && d.rootNumSymmetries > 1 && d.nodeVisits[gb] == 0) {
+      // NNEvaluator::averageMultipleSymmetries: a partial Fisher-Yates shuffle of 0..7 drawn from the search thread's generator
+      // With a dynamic score utility Search::beginSearch first takes ONE ordinary evaluation of the root to centre it on
+      // (computeRootNNEvaluation, search.cpp:1140-1147): evaluation 0 of the root is that one, the symmetric ones follow.
+      const int lead = d.dynamicScoreUtilityFactor != 0.0 ? 1 : 0;
+      int* order = d.rootSymOrder + g * 8;
+      int cnt = d.rootSymCount[g] - lead;
+      if(cnt == 0) {
+        DevRand rand;
+        rand.s = d.searchRand[g];
+        for(int i = 0; i < 8; i++) order[i] = i;
+        for(int i = 0; i < d.rootNumSymmetries; i++) {
+          const uint32_t n = (uint32_t)(8 - i);
+          uint32_t bits, val;
+          do { bits = rand.nextUInt(); val = bits % n; } while((uint32_t)(bits - val + (n - 1)) < (uint32_t)(bits - val));   // Rand::nextUInt(n)
+          const int j = i + (int)val, t = order[i];
+          order[i] = order[j]; order[j] = t;
+        }
+        d.searchRand[g] = rand.s;
+      }
+      if(cnt >= 0) sym = order[cnt];
+    }
+    d.nnSymmetry[g] = sym;
     d.nnOptimism[g] = 0.0f;
   }
 }
@@ -1140,7 +1171,7 @@ __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWi
   double u = ((double)whiteWin - (double)whiteLoss) * d.winLossUtilityFactor + (double)noResult * d.noResultUtilityForWhite;
   if(d.staticScoreUtilityFactor != 0.0 || d.dynamicScoreUtilityFactor != 0.0) {
     const double whiteScoreMean = (double)whiteScoreMeanF, whiteScoreMeanSq = (double)whiteScoreMeanSqF;
-    if(node == 0 && d.nodeVisits[gb] == 0) {
+    if(node == 0 && d.nodeVisits[gb] == 0 && d.rootNumSymmetries <= 1) {
       double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
       const double cap = sqrt((double)d.XY) * d.dynamicScoreCenterScale;
       if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
@@ -1307,10 +1338,16 @@ __global__ void spBackupKernel(const SPDev d) {
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(KGB_FULL, sum, o);
     const size_t nb = (gb + node) * d.policySize;
+    const bool multiSymRoot = node == 0 && d.rootNumSymmetries > 1 && d.nodeVisits[gb] == 0;
+    const int symLead = d.dynamicScoreUtilityFactor != 0.0 ? 1 : 0;           // evaluation 0 only centres the dynamic score utility
+    const int symCount = multiSymRoot ? d.rootSymCount[g] - symLead : 0;
 #pragma unroll
     for(int k = 0; k < 12; k++) {
       int i = k * 32 + lane;
-      if(i < d.policySize) d.policy[nb + i] = ok[k] ? v[k] / sum : -1.0f;
+      if(i < d.policySize) {
+        const float pk = ok[k] ? v[k] / sum : -1.0f;
+        d.policy[nb + i] = symCount > 0 ? d.policy[nb + i] + pk : pk;     // NNOutput(others): float sums in evaluation order
+      }
     }
     // ---- value: softmax(win, loss, noResult) from the mover's perspective -> white's (nneval.cpp:1112-1215); NNOutput stores the
     // results as float and the search widens them again (searchupdatehelpers.cpp:87-88) - the same rounding happens here
@@ -1333,7 +1370,32 @@ __global__ void spBackupKernel(const SPDev d) {
     vals[0] = leafBlack ? lf : wf; vals[1] = leafBlack ? wf : lf; vals[2] = nf;
     vals[3] = leafBlack ? -(float)scoreMean : (float)scoreMean; vals[4] = (float)scoreMeanSq;
     __syncwarp();
-    if(d.cacheSize > 0) cacheStore(d, g, node, d.leafKey[g * 2], d.leafKey[g * 2 + 1], vals, lane);   // before any root noise: the raw evaluation
+    if(multiSymRoot) {
+      if(symCount < 0) {
+        // the centring evaluation: recentScoreCenter from its expected score (search.cpp:1148-1153), nothing else is kept
+        const double whiteScoreMean = (double)vals[3];
+        double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
+        const double cap = sqrt((double)d.XY) * d.dynamicScoreCenterScale;
+        if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
+        if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
+        if(lane == 0) { d.recentScoreCenter[g] = c; d.rootSymCount[g] = 1; }
+        return;
+      }
+      float* acc = d.rootSymAcc + g * 8;
+      if(lane < 5) acc[lane] = symCount > 0 ? acc[lane] + vals[lane] : vals[lane];
+      __syncwarp();
+      if(symCount + 1 < d.rootNumSymmetries) {
+        if(lane == 0) d.rootSymCount[g] = symCount + symLead + 1;   // the root stays unvisited: the next wave evaluates it under the next symmetry
+        return;
+      }
+      const float floatLen = (float)d.rootNumSymmetries;
+      for(int i = lane; i < d.policySize; i += 32) d.policy[nb + i] = d.policy[nb + i] / floatLen;
+#pragma unroll
+      for(int i = 0; i < 5; i++) vals[i] = acc[i] / floatLen;
+      if(lane == 0) d.rootSymCount[g] = 0;
+      __syncwarp();
+    }
+    else if(d.cacheSize > 0) cacheStore(d, g, node, d.leafKey[g * 2], d.leafKey[g * 2 + 1], vals, lane);   // before any root noise: the raw evaluation
     maybeRootNoise(d, g, node, lane);
     u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], lane);
   }
@@ -1358,6 +1420,7 @@ __global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut,
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(KGB_FULL, h, o);
   if(d.nnGlobal[(size_t)g * 19 + 5] < 0.0f) h ^= 0xABCDEFULL;
+  if(d.nnSymmetry[g] != 0) h ^= splitmix64(0x5151ULL + (uint64_t)d.nnSymmetry[g]);   // outputs differ per symmetry, in the original orientation
   for(int i = lane; i < d.policySize; i += 32) {
     uint32_t u = (uint32_t)(splitmix64(h + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL) >> 48);
     float logit = (float)u * (1.0f / 8192.0f) - 4.0f;
@@ -1422,7 +1485,7 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = passes; d.moveNum[g] = mv;
     for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
     d.nodeCount[g] = 1; nodeStatsReset(d, gb, false);
-    d.ladPending[g] = 0; d.leafValid[g] = 0;
+    d.ladPending[g] = 0; d.leafValid[g] = 0; d.rootSymCount[g] = 0;
     d.rootPosH[g * 2] = bd.h0; d.rootPosH[g * 2 + 1] = bd.h1;
   }
   nodeInit(d, gb * d.policySize, lane);
@@ -1504,7 +1567,7 @@ __global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
     d.rootBlackToMove[g] = black ? 1 : 0; d.consecPasses[g] = 0; d.moveNum[g] = mv;
     for(int k = 0; k < 5; k++) d.hist[g * 5 + k] = h[k];
     d.nodeCount[g] = 1; nodeStatsReset(d, gb, false);
-    d.ladPending[g] = 0; d.leafValid[g] = 0;
+    d.ladPending[g] = 0; d.leafValid[g] = 0; d.rootSymCount[g] = 0;
     d.rootPosH[g * 2] = bd.h0; d.rootPosH[g * 2 + 1] = bd.h1;
   }
   nodeInit(d, gb * d.policySize, lane);
@@ -1639,6 +1702,9 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
   d.holdAtMaxVisits = c.debug_hold_at_max_visits ? 1 : 0;
+  d.fakeNN = c.debug_fake_nn ? 1 : 0;
+  d.rootNumSymmetries = c.root_num_symmetries_to_sample > 1 ? (c.root_num_symmetries_to_sample > 8 ? 8 : c.root_num_symmetries_to_sample) : 1;
+  d.rootSymCount = sp->alloc<int>(G); d.rootSymOrder = sp->alloc<int>(G * 8); d.rootSymAcc = sp->alloc<float>(G * 8);
   d.rootNoiseEnabled = c.root_noise_enabled ? 1 : 0;
   d.rootDirichletNoiseTotalConcentration = c.root_dirichlet_noise_total_concentration; d.rootDirichletNoiseWeight = c.root_dirichlet_noise_weight;
   d.rootPolicyTemperature = c.root_policy_temperature == 0.0 ? 1.0 : c.root_policy_temperature;                 // 0 = unset
@@ -1768,6 +1834,19 @@ void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cu
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(dm);
   SPCK(e);
+}
+
+void selfplaySetSearchRand(SelfplayImpl* sp, const char* seedString) {
+  RefRand rr(seedString);
+  DevRandState st;
+  memset(&st, 0, sizeof(st));
+  uint64_t a[16], idx, pcg;
+  rr.exportState(a, idx, pcg);
+  for(int i = 0; i < 16; i++) st.a[i] = a[i];
+  st.aIdx = idx; st.pcg = pcg;
+  std::vector<DevRandState> all(sp->d.numGames, st);
+  SPCK(cudaMemcpy(sp->d.searchRand, all.data(), all.size() * sizeof(DevRandState), cudaMemcpyHostToDevice));
+  SPCK(cudaDeviceSynchronize());
 }
 
 void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s) {

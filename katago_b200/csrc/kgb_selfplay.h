@@ -23,6 +23,7 @@ void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, cudaStream_t s);
 void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s);
+void selfplaySetSearchRand(SelfplayImpl* sp, const char* seedString);
 void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);

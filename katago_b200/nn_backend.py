@@ -61,7 +61,7 @@ class SelfplayConfig(C.Structure):
         ("lcb_stdevs", C.c_double), ("min_visit_prop_for_lcb", C.c_double), ("chosen_move_temperature", C.c_double),
         ("chosen_move_temperature_early", C.c_double), ("chosen_move_temperature_only_below_prob", C.c_double),
         ("chosen_move_subtract", C.c_double), ("chosen_move_prune", C.c_double),
-        ("nn_cache_size_power_of_two", C.c_int32), ("reserved4", C.c_int32),
+        ("nn_cache_size_power_of_two", C.c_int32), ("root_num_symmetries_to_sample", C.c_int32),
     ]
 
 
@@ -78,7 +78,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_test_choose_index_with_temperature",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_test_choose_index_with_temperature",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def load_library():
     lib.kgb_selfplay_launches_per_step.argtypes = [P]
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
     lib.kgb_selfplay_random_openings.argtypes = [P, I]
+    lib.kgb_selfplay_set_search_rand.argtypes = [P, C.c_char_p]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
@@ -402,7 +403,7 @@ class SelfPlay:
                  use_play_selection: bool = False, use_lcb_for_selection: bool = False, use_non_buggy_lcb: bool = False,
                  lcb_stdevs: float = 4.0, min_visit_prop_for_lcb: float = 0.05, chosen_move_temperature: float = 0.0,
                  chosen_move_temperature_early: float = 0.0, chosen_move_temperature_only_below_prob: float = 1.0,
-                 chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0, nn_cache_size_power_of_two: int = 0):
+                 chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0, nn_cache_size_power_of_two: int = 0, root_num_symmetries_to_sample: int = 1):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -419,13 +420,17 @@ class SelfPlay:
                                   root_policy_temperature_early, chosen_move_temperature_halflife,
                                   int(use_play_selection), int(use_lcb_for_selection), int(use_non_buggy_lcb), 0, lcb_stdevs, min_visit_prop_for_lcb,
                                   chosen_move_temperature, chosen_move_temperature_early, chosen_move_temperature_only_below_prob,
-                                  chosen_move_subtract, chosen_move_prune, int(nn_cache_size_power_of_two), 0)
+                                  chosen_move_subtract, chosen_move_prune, int(nn_cache_size_power_of_two), int(root_num_symmetries_to_sample))
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
 
     def run(self, steps: int):
         _check(load_library().kgb_selfplay_run(self._p, steps))
+
+    def set_search_rand(self, seed_string: str):
+        """Every game's search-thread generator := Rand(seed_string) (tests)."""
+        _check(load_library().kgb_selfplay_set_search_rand(self._p, seed_string.encode()))
 
     def random_openings(self, max_moves: int):
         """Every game plays its own random number (0..max_moves) of uniformly random legal moves; trees cleared."""

@@ -151,13 +151,14 @@ void NeuralNet::getOutput(ComputeHandle* h, InputBuffers*, int n, NNResultBuf** 
   for(int r = 0; r < n; r++) {
     const float* sp = inputBufs[r]->rowSpatialBuf.data();
     const float* gl = inputBufs[r]->rowGlobalBuf.data();
-    if(inputBufs[r]->symmetry != 0) throw StringError("fake backend expects symmetry 0");
     uint64_t hsh = 0;
     for(int pos = 0; pos < xy; pos++) {
       int s = sp[pos * 22 + 1] != 0.0f ? 1 : sp[pos * 22 + 2] != 0.0f ? 2 : 0;
       if(s) hsh += splitmix64((uint64_t)pos * 4 + s);
     }
     if(gl[5] < 0.0f) hsh ^= 0xABCDEFULL;
+    // a net that answers differently per requested symmetry (always in the original orientation), for rootNumSymmetriesToSample
+    if(inputBufs[r]->symmetry != 0) hsh ^= splitmix64(0x5151ULL + (uint64_t)inputBufs[r]->symmetry);
     NNOutput* o = outputs[r];
     for(int i = 0; i <= xy; i++) {
       uint32_t u = (uint32_t)(splitmix64(hsh + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL) >> 48);
@@ -224,6 +225,7 @@ static int cmdSearchFake(int argc, char** argv) {
     else if(k == "cpuctUtilityStdevPrior") params.cpuctUtilityStdevPrior = v;
     else if(k == "cpuctUtilityStdevPriorWeight") params.cpuctUtilityStdevPriorWeight = v;
     else if(k == "rootDesiredPerChildVisitsCoeff") params.rootDesiredPerChildVisitsCoeff = v;
+    else if(k == "rootNumSymmetriesToSample") params.rootNumSymmetriesToSample = (int)v;
     else if(k == "useLcbForSelection") params.useLcbForSelection = v != 0;
     else if(k == "useNonBuggyLcb") params.useNonBuggyLcb = v != 0;
     else if(k == "lcbStdevs") params.lcbStdevs = v;
@@ -265,6 +267,11 @@ static int cmdSearchFake(int argc, char** argv) {
   SearchNodeState st = (SearchNodeState)root->state.load();
   ConstSearchNodeChildrenReference children = root->getChildren(st);
   cout << "rootvisits " << root->stats.visits.load() << " utilityAvg " << Global::strprintf("%.17g", root->stats.utilityAvg.load()) << endl;
+ {
+    std::ostringstream ss;   // makeSeed(search, 0) (search.cpp:24-36): the seed string of search thread 0's Rand
+    ss << "searchfake" << "$searchThread$" << 0 << "$" << board.pos_hash << "$" << hist.moveHistory.size() << "$" << search->numSearchesBegun;
+    cout << "threadseed " << ss.str() << endl;
+  }
   cout << "recentScoreCenter " << Global::strprintf("%.17g", search->recentScoreCenter) << endl;
   for(int i = 0; i < children.getCapacity(); i++) {
     const SearchChildPointer& cp = children[i];

@@ -46,11 +46,13 @@ def run(X, Y, visits, moves, score=None):
     extra = [f"{k}={float(v)!r}" for k, v in score.items()]
     out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
-    psv = np.full(X * Y + 1, -1.0, np.float64)
+    psv = np.full(X * Y + 1, -1.0, np.float64); threadseed = ""
     for ln in out.splitlines():
         f = ln.split()
         if f[0] == "rootvisits":
             root = (int(f[1]), float(f[3]))
+        elif f[0] == "threadseed":
+            threadseed = ln.split(" ", 1)[1]
         elif f[0] == "playselection":
             for j in range(2, len(f), 3):
                 x, y = int(f[j]), int(f[j + 1])
@@ -63,7 +65,7 @@ def run(X, Y, visits, moves, score=None):
             v[i] = int(f[3]); u[i] = float(f[4])
         elif f[0] == "policy":
             pol = np.array([float(t) for t in f[1:]], np.float32)
-    return root, v, u, pol, center, psv
+    return root, v, u, pol, center, psv, threadseed
 
 
 if __name__ == "__main__":
@@ -119,12 +121,19 @@ if __name__ == "__main__":
         (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), dict(SELFPLAY8B18, useGraphSearch=1, **BIAS, **LCB)),
         (13, 7, 500, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20),
          {"useLcbForSelection": 1, "lcbStdevs": 3.0, "minVisitPropForLCB": 0.05, "chosenMoveSubtract": 2.0, "chosenMovePrune": 3.0, "valueWeightExponent": 0.5}),
+        # rootNumSymmetriesToSample (a22): the root's evaluation is the average over symmetries drawn from the search thread's Rand
+        (9, 9, 400, prefix_from_stream("boardstream_9x9_multisuicide.npz", 12), {"rootNumSymmetriesToSample": 4}),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 40),
+         dict(SELFPLAY8B18, useGraphSearch=1, rootNumSymmetriesToSample=4, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.5, **BIAS, **LCB)),
+        (13, 7, 300, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), {"rootNumSymmetriesToSample": 8, "valueWeightExponent": 0.5}),
+        (5, 5, 500, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), {"rootNumSymmetriesToSample": 2, "staticScoreUtilityFactor": 0.1}),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
         X, Y, visits, moves = case[:4]
         score = case[4] if len(case) > 4 else None
-        root, v, u, pol, center, psv = run(X, Y, visits, moves, score)
+        root, v, u, pol, center, psv, threadseed = run(X, Y, visits, moves, score)
+        store[f"c{i}_thread_seed"] = np.array(threadseed)
         store[f"c{i}_play_selection"] = psv
         if score is not None and not isinstance(score, dict):
             score = dict(zip(SCORE_KEYS, score))
