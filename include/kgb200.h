@@ -244,6 +244,9 @@ KGB_API int kgb_selfplay_get_game(kgb_selfplay* sp, int game, uint8_t* colors, i
 /* Root children of game g, indexed by move position 0..X*Y (pass last): edge visit counts, NN policy (-1 illegal), and each
  * child's utilityAvg (white's perspective; 0 where there is no child). */
 KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* visits, float* policy, double* utility_avg);
+/* NodeStats moments (searchnode.h:17-41; white's perspective) of game g's root and of its children by move position:
+ * winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg.  child_stats[(X*Y+1)*5] (0 where no child), root_stats[5]. */
+KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double* child_stats, double* root_stats);
 /* The NN input row (NHWC [X*Y][22] + 19 globals) the last wave wrote for game g - what NNInputs::fillRowV7 would produce
  * for that leaf (planes listed in DESIGN.md §8; used by the feature parity tests). */
 KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global);

@@ -905,7 +905,7 @@ KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* c
     sp->n = config->num_games;
     sp->fakeNN = config->debug_fake_nn != 0;
     SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue, handle->dScore,
-                         (double)handle->model->scoreMeanMultiplier, (double)handle->model->scoreStdevMultiplier};
+                         (double)handle->model->scoreMeanMultiplier, (double)handle->model->scoreStdevMultiplier, (double)handle->model->leadMultiplier};
     sp->impl = selfplayCreate(*config, handle->L.X, handle->L.Y, nn, handle->stream);
     *out = sp.release();
   });
@@ -981,6 +981,15 @@ KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* 
     CK(cudaSetDevice(sp->h->device));
     CK(cudaStreamSynchronize(sp->h->stream));
     selfplayReadRootChildren(sp->impl, game, visits, policy, util_sum);
+  });
+}
+
+KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double* child_stats, double* root_stats) {
+  return guarded([&] {
+    if(!sp || !child_stats || !root_stats) throw std::invalid_argument("kgb_selfplay_get_root_value_stats: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadRootMoments(sp->impl, game, child_stats, root_stats);
   });
 }
 

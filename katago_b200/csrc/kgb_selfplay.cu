@@ -133,6 +133,12 @@ struct SPDev {
   int* nodeVisits;                  // [game][maxNodes]
   double *nodeWeightSum, *nodeWeightSqSum, *nodeUtilAvg, *nodeUtilSqAvg;   // [game][maxNodes] NodeStats (white's perspective)
   double* nodeNNUtil;               // [game][maxNodes] utility of the node's own evaluation (Search::getUtilityFromNN)
+  // the other five moments of NodeStats (searchnode.h:17-41): winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg
+  // (white's perspective) and the node's own evaluation of them; they feed targets and reports, not the selection
+  double* nodeMoments;              // [game][maxNodes][5]
+  double* nodeNNMoments;            // [game][maxNodes][5]
+  double* leafMoments;              // [game][5] the current leaf's own values, set where its utility is computed
+  double leadMultiplier;
   int* nodeNumChildren;             // [game][maxNodes]
   uint16_t* childOrder;             // [game][maxNodes][policySize] move position of the k-th created child
   int8_t* nodeTerminal;             // [game][maxNodes]   0 no, 1 yes
@@ -179,6 +185,7 @@ __device__ __forceinline__ void nodeInit(const SPDev& d, size_t nodeBase, int la
 __device__ __forceinline__ void nodeStatsReset(const SPDev& d, size_t gn, bool terminal) {
   d.nodeVisits[gn] = 0; d.nodeWeightSum[gn] = 0.0; d.nodeWeightSqSum[gn] = 0.0; d.nodeUtilAvg[gn] = 0.0; d.nodeUtilSqAvg[gn] = 0.0;
   d.nodeNNUtil[gn] = 0.0; d.nodeNumChildren[gn] = 0; d.nodeTerminal[gn] = terminal ? 1 : 0;
+  for(int i = 0; i < 5; i++) { d.nodeMoments[gn * 5 + i] = 0.0; d.nodeNNMoments[gn * 5 + i] = 0.0; }
   d.nodeBiasEntry[gn] = -1; d.nodeLastBiasDelta[gn] = 0.0; d.nodeLastBiasWeight[gn] = 0.0;
 }
 // Key of a SubtreeValueBiasTable entry (subtreevaluebiastable.cpp:70-88, localpattern.cpp:52-87): who moved, the move before,
@@ -583,9 +590,9 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
 __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePlaWhite, double* sh, int lane);
 __device__ void finishPlayout(const SPDev& d, int g, int node, double u, bool terminal, bool leafBlack, int len, double* shSum, int lane);
 __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWin, float whiteLoss, float noResult, float whiteScoreMeanF,
-                                  float whiteScoreMeanSqF, int lane);
+                                  float whiteScoreMeanSqF, float whiteLeadF, int lane);
 __device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane);
-__device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, float vals[5], int lane);
+__device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, float vals[6], int lane);
 
 // Warp 0 of a game's block: PUCT descent, leaf board, legality and every feature except the leaf's own ladder searches.
 __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, uint32_t* shW, uint32_t* shCand, int& shKo, int& shDoLadders,
@@ -804,10 +811,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     unsigned long long k0, k1;
     stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
     if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
-    float vals[5];
+    float vals[6];
     if(cacheLookup(d, g, node, k0, k1, vals, lane)) {
       maybeRootNoise(d, g, node, lane);
-      const double u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], lane);
+      const double u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], lane);
       finishPlayout(d, g, node, u, false, black, depth, shSum, lane);
       if(lane == 0) atomicAdd(d.cacheHits, 1ULL);
       continue;
@@ -1117,6 +1124,22 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
       orderedAdd2(scaling * scaling * CWSQ[ch], 0.0, n, weightSqSum, unused, sh, lane);
     }
   }
+  // the other moments: sum of weightAdjusted * child average (searchupdatehelpers.cpp:246-251), same order
+  double mom[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for(int ch = 0; ch < 12; ch++) {
+    if(ch * 32 < nc) {
+      const int k = ch * 32 + lane;
+      const bool in = k < nc;
+      const int c = in ? d.childNode[nb + (int)d.childOrder[nb + k]] : 0;
+      const double* cm = d.nodeMoments + (gb + c) * 5;
+      const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
+      const bool use = in && WA[ch] > 0.0;
+      orderedAdd2(use ? WA[ch] * cm[0] : 0.0, use ? WA[ch] * cm[1] : 0.0, n, mom[0], mom[1], sh, lane);
+      orderedAdd2(use ? WA[ch] * cm[2] : 0.0, use ? WA[ch] * cm[3] : 0.0, n, mom[2], mom[3], sh, lane);
+      orderedAdd2(use ? WA[ch] * cm[4] : 0.0, 0.0, n, mom[4], mom[5], sh, lane);
+    }
+  }
   double weightSum = origTotal;
   // the node's own evaluation, weight 1
   double utility = d.nodeNNUtil[gn];
@@ -1144,6 +1167,7 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
   weightSum += 1.0;
   __syncwarp();
   if(lane == 0) {
+    for(int i = 0; i < 5; i++) d.nodeMoments[gn * 5 + i] = (mom[i] + d.nodeNNMoments[gn * 5 + i] * 1.0) / weightSum;
     d.nodeUtilAvg[gn] = utilitySum / weightSum;
     d.nodeUtilSqAvg[gn] = utilitySqSum / weightSum;
     d.nodeWeightSqSum[gn] = weightSqSum;
@@ -1166,8 +1190,13 @@ __device__ double scoreUtilityOf(const SPDev& d, double scoreMean, double scoreM
 // Search::getUtilityFromNN (searchhelpers.cpp:304-307) from the NNOutput fields (floats, white's perspective); a fresh root
 // first centres the dynamic score utility on its expected score (Search::beginSearch, search.cpp:1125-1154).
 __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWin, float whiteLoss, float noResult, float whiteScoreMeanF,
-                                  float whiteScoreMeanSqF, int lane) {
+                                  float whiteScoreMeanSqF, float whiteLeadF, int lane) {
   const size_t gb = (size_t)g * d.maxNodes;
+  if(lane == 0) {   // the evaluation's contribution to the NodeStats moments (searchupdatehelpers.cpp:83-112)
+    d.leafMoments[g * 5 + 0] = (double)whiteWin - (double)whiteLoss; d.leafMoments[g * 5 + 1] = (double)noResult;
+    d.leafMoments[g * 5 + 2] = (double)whiteScoreMeanF; d.leafMoments[g * 5 + 3] = (double)whiteScoreMeanSqF; d.leafMoments[g * 5 + 4] = (double)whiteLeadF;
+  }
+  __syncwarp();
   double u = ((double)whiteWin - (double)whiteLoss) * d.winLossUtilityFactor + (double)noResult * d.noResultUtilityForWhite;
   if(d.staticScoreUtilityFactor != 0.0 || d.dynamicScoreUtilityFactor != 0.0) {
     const double whiteScoreMean = (double)whiteScoreMeanF, whiteScoreMeanSq = (double)whiteScoreMeanSqF;
@@ -1205,6 +1234,7 @@ __device__ void finishPlayout(const SPDev& d, int g, int node, double u, bool te
   if(terminal) {
     if(lane == 0) {
       const double oldW = d.nodeWeightSum[gl], newW = oldW + 1.0;
+      for(int i = 0; i < 5; i++) d.nodeMoments[gl * 5 + i] = (d.nodeMoments[gl * 5 + i] * oldW + d.leafMoments[g * 5 + i] * 1.0) / newW;
       d.nodeUtilAvg[gl] = (d.nodeUtilAvg[gl] * oldW + u * 1.0) / newW;
       d.nodeUtilSqAvg[gl] = (d.nodeUtilSqAvg[gl] * oldW + (u * u) * 1.0) / newW;
       d.nodeWeightSqSum[gl] = d.nodeWeightSqSum[gl] + 1.0;
@@ -1215,6 +1245,7 @@ __device__ void finishPlayout(const SPDev& d, int g, int node, double u, bool te
   else if(leafVisits == 0) {
     if(lane == 0) {
       d.nodeNNUtil[gl] = u;
+      for(int i = 0; i < 5; i++) { d.nodeNNMoments[gl * 5 + i] = d.leafMoments[g * 5 + i]; d.nodeMoments[gl * 5 + i] = d.leafMoments[g * 5 + i]; }
       const int entry = d.subtreeValueBiasFactor != 0.0 ? d.nodeBiasEntry[gl] : -1;
       if(entry >= 0) {   // searchupdatehelpers.cpp:26-36
         const size_t te = (size_t)g * d.biasTableSize + entry;
@@ -1244,7 +1275,7 @@ __device__ __forceinline__ size_t cacheSlotOf(const SPDev& d, unsigned long long
 }
 // Looks the leaf's key up; on a hit copies policy, values and laddered stones into the node (whole warp).  Writers hold the
 // entry's lock while they change it and readers check key and lock before and after copying, so a torn entry is never used.
-__device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, float vals[5], int lane) {
+__device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, float vals[6], int lane) {
   const size_t slot = cacheSlotOf(d, k0, k1);
   bool ok = false;
   if(lane == 0) ok = atomicAdd(&d.cacheLock[slot], 0) == 0 && __ldcg(d.cacheKey0 + slot) == k0 && __ldcg(d.cacheKey1 + slot) == k1;
@@ -1254,15 +1285,15 @@ __device__ bool cacheLookup(const SPDev& d, int g, int node, unsigned long long 
   const size_t gb = (size_t)g * d.maxNodes, nb = (gb + node) * d.policySize;
   for(int i = lane; i < d.policySize; i += 32) d.policy[nb + i] = __ldcg(d.cachePolicy + slot * d.policySize + i);
   d.nodeLad[(gb + node) * 32 + lane] = __ldcg(d.cacheLad + slot * 32 + lane);
-  float v = lane < 5 ? __ldcg(d.cacheVals + slot * 8 + lane) : 0.0f;
+  float v = lane < 6 ? __ldcg(d.cacheVals + slot * 8 + lane) : 0.0f;
   __threadfence();
   if(lane == 0) ok = atomicAdd(&d.cacheLock[slot], 0) == 0 && __ldcg(d.cacheKey0 + slot) == k0 && __ldcg(d.cacheKey1 + slot) == k1;
   ok = __shfl_sync(KGB_FULL, ok ? 1 : 0, 0) != 0;
 #pragma unroll
-  for(int i = 0; i < 5; i++) vals[i] = __shfl_sync(KGB_FULL, v, i);
+  for(int i = 0; i < 6; i++) vals[i] = __shfl_sync(KGB_FULL, v, i);
   return ok;
 }
-__device__ void cacheStore(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, const float vals[5], int lane) {
+__device__ void cacheStore(const SPDev& d, int g, int node, unsigned long long k0, unsigned long long k1, const float vals[6], int lane) {
   const size_t slot = cacheSlotOf(d, k0, k1);
   bool mine = false;
   if(lane == 0) mine = atomicCAS(&d.cacheLock[slot], 0, 1) == 0;
@@ -1273,7 +1304,7 @@ __device__ void cacheStore(const SPDev& d, int g, int node, unsigned long long k
   const size_t gb = (size_t)g * d.maxNodes, nb = (gb + node) * d.policySize;
   for(int i = lane; i < d.policySize; i += 32) d.cachePolicy[slot * d.policySize + i] = d.policy[nb + i];
   d.cacheLad[slot * 32 + lane] = d.nodeLad[(gb + node) * 32 + lane];
-  if(lane < 5) d.cacheVals[slot * 8 + lane] = vals[lane];
+  if(lane < 6) d.cacheVals[slot * 8 + lane] = vals[lane];
   __threadfence();
   __syncwarp();
   if(lane == 0) {
@@ -1310,6 +1341,11 @@ __global__ void spBackupKernel(const SPDev d) {
       scoreMeanSq = lo + (hi - lo) * d.drawEquivalentWinsForWhite;
     }
     u = winLoss * d.winLossUtilityFactor + scoreUtilityOf(d, scoreMean, scoreMeanSq, d.recentScoreCenter[g]);
+    if(lane == 0) {   // search.cpp:1213-1222: winLoss, no "no result", score, its square, lead = score
+      d.leafMoments[g * 5 + 0] = winLoss; d.leafMoments[g * 5 + 1] = 0.0; d.leafMoments[g * 5 + 2] = scoreMean;
+      d.leafMoments[g * 5 + 3] = scoreMeanSq; d.leafMoments[g * 5 + 4] = scoreMean;
+    }
+    __syncwarp();
   }
   else {
     // ---- policy: legality mask + softmax (nneval.cpp:960-1051)
@@ -1366,9 +1402,10 @@ __global__ void spBackupKernel(const SPDev d) {
     double scoreMeanSq = scoreMean * scoreMean + stdev * stdev;
     scoreMean = scoreMean * (1.0 - n);
     scoreMeanSq = scoreMeanSq * (1.0 - n);
-    float vals[5];
+    const double lead = (double)sc[2] * d.leadMultiplier * (1.0 - n);
+    float vals[6];
     vals[0] = leafBlack ? lf : wf; vals[1] = leafBlack ? wf : lf; vals[2] = nf;
-    vals[3] = leafBlack ? -(float)scoreMean : (float)scoreMean; vals[4] = (float)scoreMeanSq;
+    vals[3] = leafBlack ? -(float)scoreMean : (float)scoreMean; vals[4] = (float)scoreMeanSq; vals[5] = leafBlack ? -(float)lead : (float)lead;
     __syncwarp();
     if(multiSymRoot) {
       if(symCount < 0) {
@@ -1382,7 +1419,7 @@ __global__ void spBackupKernel(const SPDev d) {
         return;
       }
       float* acc = d.rootSymAcc + g * 8;
-      if(lane < 5) acc[lane] = symCount > 0 ? acc[lane] + vals[lane] : vals[lane];
+      if(lane < 6) acc[lane] = symCount > 0 ? acc[lane] + vals[lane] : vals[lane];
       __syncwarp();
       if(symCount + 1 < d.rootNumSymmetries) {
         if(lane == 0) d.rootSymCount[g] = symCount + symLead + 1;   // the root stays unvisited: the next wave evaluates it under the next symmetry
@@ -1391,13 +1428,13 @@ __global__ void spBackupKernel(const SPDev d) {
       const float floatLen = (float)d.rootNumSymmetries;
       for(int i = lane; i < d.policySize; i += 32) d.policy[nb + i] = d.policy[nb + i] / floatLen;
 #pragma unroll
-      for(int i = 0; i < 5; i++) vals[i] = acc[i] / floatLen;
+      for(int i = 0; i < 6; i++) vals[i] = acc[i] / floatLen;
       if(lane == 0) d.rootSymCount[g] = 0;
       __syncwarp();
     }
     else if(d.cacheSize > 0) cacheStore(d, g, node, d.leafKey[g * 2], d.leafKey[g * 2 + 1], vals, lane);   // before any root noise: the raw evaluation
     maybeRootNoise(d, g, node, lane);
-    u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], lane);
+    u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], lane);
   }
   __syncwarp();
   finishPlayout(d, g, node, u, terminal, leafBlack, d.pathLen[g], shSum, lane);
@@ -1681,7 +1718,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.dynamicScoreCenterZeroWeight = c.dynamic_score_center_zero_weight; d.dynamicScoreCenterScale = c.dynamic_score_center_scale;
   d.drawEquivalentWinsForWhite = c.draw_equivalent_wins_for_white;
   if(d.dynamicScoreUtilityFactor != 0.0 && !(d.dynamicScoreCenterScale > 0.0)) throw std::invalid_argument("selfplay: dynamic_score_center_scale must be > 0");
-  d.scoreMeanMultiplier = nn.scoreMeanMultiplier; d.scoreStdevMultiplier = nn.scoreStdevMultiplier;
+  d.scoreMeanMultiplier = nn.scoreMeanMultiplier; d.scoreStdevMultiplier = nn.scoreStdevMultiplier; d.leadMultiplier = nn.leadMultiplier;
   d.seed = c.seed;
   const size_t G = d.numGames, N = d.maxNodes, PS = d.policySize;
   d.rootB = sp->alloc<uint32_t>(G * 32); d.rootW = sp->alloc<uint32_t>(G * 32);
@@ -1701,6 +1738,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.nodeWeightSum = sp->alloc<double>(G * N); d.nodeWeightSqSum = sp->alloc<double>(G * N); d.nodeUtilAvg = sp->alloc<double>(G * N);
   d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
+  d.nodeMoments = sp->alloc<double>(G * N * 5); d.nodeNNMoments = sp->alloc<double>(G * N * 5); d.leafMoments = sp->alloc<double>(G * 5);
   d.holdAtMaxVisits = c.debug_hold_at_max_visits ? 1 : 0;
   d.fakeNN = c.debug_fake_nn ? 1 : 0;
   d.rootNumSymmetries = c.root_num_symmetries_to_sample > 1 ? (c.root_num_symmetries_to_sample > 8 ? 8 : c.root_num_symmetries_to_sample) : 1;
@@ -1861,6 +1899,18 @@ void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {
   out->total_visits = h[0]; out->total_moves = h[1]; out->games_finished = h[2]; out->black_wins = h[3];
   out->nodes_allocated = h[4]; out->sum_leaf_depth = h[5]; out->ladder_searches = h[6]; out->ladder_nodes = h[7];
   out->stalled_waves = h[8]; out->instant_playouts = h[9]; out->nn_cache_hits = h[10]; out->nn_cache_stores = h[11];
+}
+
+void selfplayReadRootMoments(SelfplayImpl* sp, int g, double* childMoments /*[policySize][5]*/, double* rootMoments /*[5]*/) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  std::vector<int> child(d.policySize);
+  std::vector<double> mom((size_t)d.maxNodes * 5);
+  SPCK(cudaMemcpy(child.data(), d.childNode + (size_t)g * d.maxNodes * d.policySize, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(mom.data(), d.nodeMoments + (size_t)g * d.maxNodes * 5, mom.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for(int i = 0; i < d.policySize; i++)
+    for(int k = 0; k < 5; k++) childMoments[i * 5 + k] = child[i] >= 0 ? mom[(size_t)child[i] * 5 + k] : 0.0;
+  for(int k = 0; k < 5; k++) rootMoments[k] = mom[k];
 }
 
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid) {

@@ -14,7 +14,7 @@ struct SelfplayImpl;
 struct SelfplayNNBuffers {  // device buffers of the evaluator handle the loop writes to / reads from
   float* spatial; float* global; float* optimism; int* symmetry;
   const float* policy; const float* value; const float* score;
-  double scoreMeanMultiplier, scoreStdevMultiplier;   // ModelPostProcessParams (desc.h) of the loaded net
+  double scoreMeanMultiplier, scoreStdevMultiplier, leadMultiplier;   // ModelPostProcessParams (desc.h) of the loaded net
 };
 
 SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const SelfplayNNBuffers& nn, cudaStream_t stream);
@@ -27,6 +27,7 @@ void selfplaySetSearchRand(SelfplayImpl* sp, const char* seedString);
 void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
+void selfplayReadRootMoments(SelfplayImpl* sp, int g, double* childMoments, double* rootMoments);
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid);
 void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum);
 void selfplayReadPlaySelection(SelfplayImpl* sp, int g, double* out);

@@ -78,7 +78,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_test_choose_index_with_temperature",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def load_library():
     lib.kgb_selfplay_launches_per_step.argtypes = [P]
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
     lib.kgb_selfplay_random_openings.argtypes = [P, I]
+    lib.kgb_selfplay_get_root_value_stats.argtypes = [P, I, P, P]
     lib.kgb_selfplay_set_search_rand.argtypes = [P, C.c_char_p]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
@@ -464,6 +465,12 @@ class SelfPlay:
         _check(load_library().kgb_selfplay_get_game(self._p, g, colors.ctypes.data, info.ctypes.data))
         return colors, dict(move_num=int(info[0]), black_to_move=bool(info[1]), ko=int(info[2]), cap_b=int(info[3]), cap_w=int(info[4]),
                             root_visits=int(info[5]))
+
+    def root_value_stats(self, g: int):
+        """(children [X*Y+1, 5], root [5]): winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg."""
+        ch = np.zeros((self.x * self.y + 1, 5), np.float64); rt = np.zeros(5, np.float64)
+        _check(load_library().kgb_selfplay_get_root_value_stats(self._p, g, ch.ctypes.data, rt.ctypes.data))
+        return ch, rt
 
     def play_selection_values(self, g: int):
         """Search::getPlaySelectionValues of the root by move position (-1 = no child)."""

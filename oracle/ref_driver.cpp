@@ -272,6 +272,8 @@ static int cmdSearchFake(int argc, char** argv) {
     ss << "searchfake" << "$searchThread$" << 0 << "$" << board.pos_hash << "$" << hist.moveHistory.size() << "$" << search->numSearchesBegun;
     cout << "threadseed " << ss.str() << endl;
   }
+ cout << "rootstats " << Global::strprintf("%.17g %.17g %.17g %.17g %.17g", root->stats.winLossValueAvg.load(), root->stats.noResultValueAvg.load(),
+                                            root->stats.scoreMeanAvg.load(), root->stats.scoreMeanSqAvg.load(), root->stats.leadAvg.load()) << endl;
   cout << "recentScoreCenter " << Global::strprintf("%.17g", search->recentScoreCenter) << endl;
   for(int i = 0; i < children.getCapacity(); i++) {
     const SearchChildPointer& cp = children[i];
@@ -279,7 +281,9 @@ static int cmdSearchFake(int argc, char** argv) {
     if(child == NULL) break;
     Loc loc = cp.getMoveLoc();
     int x = loc == Board::PASS_LOC ? -1 : Location::getX(loc, X), y = loc == Board::PASS_LOC ? -1 : Location::getY(loc, X);
-    cout << "child " << x << " " << y << " " << cp.getEdgeVisits() << " " << Global::strprintf("%.17g", child->stats.utilityAvg.load()) << endl;
+    cout << "child " << x << " " << y << " " << cp.getEdgeVisits() << " " << Global::strprintf("%.17g", child->stats.utilityAvg.load())
+         << " " << Global::strprintf("%.17g %.17g %.17g %.17g %.17g", child->stats.winLossValueAvg.load(), child->stats.noResultValueAvg.load(),
+                                     child->stats.scoreMeanAvg.load(), child->stats.scoreMeanSqAvg.load(), child->stats.leadAvg.load()) << endl;
   }
   {
     vector<Loc> locs; vector<double> psv;

@@ -47,6 +47,7 @@ def run(X, Y, visits, moves, score=None):
     out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     psv = np.full(X * Y + 1, -1.0, np.float64); threadseed = ""
+    cstats = np.zeros((X * Y + 1, 5), np.float64); rstats = np.zeros(5, np.float64)
     for ln in out.splitlines():
         f = ln.split()
         if f[0] == "rootvisits":
@@ -62,10 +63,12 @@ def run(X, Y, visits, moves, score=None):
         elif f[0] == "child":
             x, y = int(f[1]), int(f[2])
             i = X * Y if x < 0 else y * X + x
-            v[i] = int(f[3]); u[i] = float(f[4])
+            v[i] = int(f[3]); u[i] = float(f[4]); cstats[i] = [float(t) for t in f[5:10]]
+        elif f[0] == "rootstats":
+            rstats[:] = [float(t) for t in f[1:6]]
         elif f[0] == "policy":
             pol = np.array([float(t) for t in f[1:]], np.float32)
-    return root, v, u, pol, center, psv, threadseed
+    return root, v, u, pol, center, psv, threadseed, cstats, rstats
 
 
 if __name__ == "__main__":
@@ -132,7 +135,8 @@ if __name__ == "__main__":
     for i, case in enumerate(cases):
         X, Y, visits, moves = case[:4]
         score = case[4] if len(case) > 4 else None
-        root, v, u, pol, center, psv, threadseed = run(X, Y, visits, moves, score)
+        root, v, u, pol, center, psv, threadseed, cstats, rstats = run(X, Y, visits, moves, score)
+        store[f"c{i}_child_stats"] = cstats; store[f"c{i}_root_stats"] = rstats
         store[f"c{i}_thread_seed"] = np.array(threadseed)
         store[f"c{i}_play_selection"] = psv
         if score is not None and not isinstance(score, dict):
