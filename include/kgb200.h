@@ -227,6 +227,12 @@ KGB_API int kgb_selfplay_get_play_selection_values(kgb_selfplay* sp, int game, d
  * seeded with seed_string. */
 KGB_API int kgb_test_choose_index_with_temperature(const char* seed_string, const double* relative_probs, int n, double temperature,
                                                    double only_below_prob, int count, int32_t* chosen);
+/* TEST HOOK (row a3): replay num_games games (moves_xy [game][max_moves][2]: x,y; -1,-1 pass; -2 = end of that game; black first) through
+ * the device ko rules (ko_rule 0 simple, 1 positional, 2 situational; area scoring).  Per move: flags (1 game over, 2 no result,
+ * 4 a pass by the next player would end the phase), legality of every point for the next player (incl. ko and superko bans), and
+ * the superko-banned points - BoardHistory::makeBoardMoveAssumeLegal / isLegal / passWouldEndPhase (game/boardhistory.cpp). */
+KGB_API int kgb_test_history_replay(int x_len, int y_len, int ko_rule, int multi_stone_suicide_legal, int num_games, int max_moves, const int8_t* moves_xy,
+                                    uint8_t* flags, uint8_t* legal_next, uint8_t* super_ko_banned);
 /* TEST HOOK (rows a22/a25): the device loop's root-policy temperature + Dirichlet noise on a given policy (-1 = illegal), with the
  * device Rand initialised from seed_string like the reference's Rand(seed_string): the counterpart of
  * Search::maybeAddPolicyNoiseAndTemp / addDirichletNoise (searchhelpers.cpp:78-215). */

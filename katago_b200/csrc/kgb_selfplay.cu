@@ -36,6 +36,7 @@
 #include "../../include/kgb200.h"
 #include "kgb_board.cuh"
 #include "kgb_devrand.cuh"
+#include "kgb_history.cuh"
 #include "kgb_ladder.cuh"
 #include "kgb_scorevalue.h"
 #include "kgb_selfplay.h"
@@ -1665,6 +1666,44 @@ __global__ void boardReplayKernel(int X, int Y, int numBoards, int numMoves, int
   }
 }
 
+// Rules test kernel: replays games through histMakeMove (parity tests against the reference BoardHistory fixtures).
+__global__ void historyReplayKernel(int X, int Y, int koRule, int multiSuicide, int numGames, int maxMoves, const int8_t* moves /*[g][m][2]*/,
+                                    const ZobEntry* zob, unsigned long long* lists /*[g][3][maxMoves+2]*/, uint8_t* flags /*[g][m]*/,
+                                    uint8_t* legal /*[g][m][Y*X]*/, uint8_t* banned /*[g][m][Y*X]*/) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= numGames) return;
+  WarpBoard bd;
+  boardInit(bd, X, Y);
+  const int cap = maxMoves + 2;
+  HistLists L;
+  L.gKo = nullptr; L.gKoLen = 0; L.gKoStart = 0; L.gPassB = nullptr; L.gPassBLen = 0; L.gPassW = nullptr; L.gPassWLen = 0;
+  L.pKo = lists + (size_t)g * 3 * cap; L.pPassB = L.pKo + cap; L.pPassW = L.pKo + 2 * cap;
+  L.pKoLen = 0; L.pPassBLen = 0; L.pPassWLen = 0;
+  HistState st;
+  st.passes = 0; st.finished = false; st.noResult = false; st.everOcc = 0; st.banned = 0;
+  // BoardHistory::clear: the history starts with the initial situation
+  if(lane == 0) L.pKo[0] = koHashOf(koRule, bd.h0, true);
+  L.pKoLen = 1;
+  __syncwarp();
+  bool black = true;
+  for(int m = 0; m < maxMoves; m++) {
+    const int8_t* mv = moves + ((size_t)g * maxMoves + m) * 2;
+    if(mv[0] == -2) break;
+    const int p = mv[0] < 0 ? -1 : (mv[1] * 32 + mv[0]);
+    histMakeMove(bd, st, L, p, black, koRule, multiSuicide != 0, zob);
+    black = !black;
+    uint32_t l1, l2, l3;
+    boardLibertyClasses(bd, l1, l2, l3);
+    const uint32_t lg = boardLegalMask(bd, black, multiSuicide != 0, l1) & ~st.banned;
+    const bool pwe = histPassWouldEndPhase(bd, st, L, black, koRule);
+    const size_t o = ((size_t)g * maxMoves + m) * X * Y;
+    if(lane < Y)
+      for(int x = 0; x < X; x++) { legal[o + lane * X + x] = (lg >> x) & 1; banned[o + lane * X + x] = (st.banned >> x) & 1; }
+    if(lane == 0) flags[(size_t)g * maxMoves + m] = (st.finished ? 1 : 0) | (st.noResult ? 2 : 0) | (pwe ? 4 : 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------------
@@ -1987,6 +2026,24 @@ void chooseIndexTest(const char* seedString, const double* probs, int n, double 
   cudaError_t e = cudaDeviceSynchronize();
   if(e == cudaSuccess) e = cudaMemcpy(out, dout, count * sizeof(int), cudaMemcpyDeviceToHost);
   cudaFree(ds); cudaFree(dp); cudaFree(dscr); cudaFree(dout);
+  SPCK(e);
+}
+
+void historyReplay(int X, int Y, int koRule, int multiSuicide, int numGames, int maxMoves, const int8_t* moves, uint8_t* flags, uint8_t* legal,
+                   uint8_t* banned) {
+  if(X > 19 || Y > 19 || X < 2 || Y < 2) throw std::invalid_argument("history replay: board sizes 2..19 only");
+  const size_t nm = (size_t)numGames * maxMoves, cells = nm * X * Y;
+  int8_t* dMoves; uint8_t *dFlags, *dLegal, *dBanned; unsigned long long* dLists; ZobEntry* dZob;
+  const ZobristTables zt = makeZobristTables(X, Y);
+  SPCK(cudaMalloc(&dMoves, nm * 2)); SPCK(cudaMalloc(&dFlags, nm)); SPCK(cudaMalloc(&dLegal, cells)); SPCK(cudaMalloc(&dBanned, cells));
+  SPCK(cudaMalloc(&dLists, (size_t)numGames * 3 * (maxMoves + 2) * sizeof(unsigned long long))); SPCK(cudaMalloc(&dZob, zt.board.size() * sizeof(ZobEntry)));
+  SPCK(cudaMemcpy(dMoves, moves, nm * 2, cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(dZob, zt.board.data(), zt.board.size() * sizeof(ZobEntry), cudaMemcpyHostToDevice));
+  SPCK(cudaMemset(dFlags, 0, nm)); SPCK(cudaMemset(dLegal, 0, cells)); SPCK(cudaMemset(dBanned, 0, cells));
+  historyReplayKernel<<<(numGames * 32 + 127) / 128, 128>>>(X, Y, koRule, multiSuicide, numGames, maxMoves, dMoves, dZob, dLists, dFlags, dLegal, dBanned);
+  cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) { cudaMemcpy(flags, dFlags, nm, cudaMemcpyDeviceToHost); cudaMemcpy(legal, dLegal, cells, cudaMemcpyDeviceToHost); cudaMemcpy(banned, dBanned, cells, cudaMemcpyDeviceToHost); }
+  cudaFree(dMoves); cudaFree(dFlags); cudaFree(dLegal); cudaFree(dBanned); cudaFree(dLists); cudaFree(dZob);
   SPCK(e);
 }
 

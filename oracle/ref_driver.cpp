@@ -383,6 +383,51 @@ static int cmdChooseIdx(int argc, char** argv) {
   return 0;
 }
 
+// histstream X Y KORULE(0 simple,1 positional,2 situational) MULTISUICIDE SEED NGAMES MAXMOVES OUT
+//   random games through the reference's BoardHistory (area scoring): moves are drawn from BoardHistory::isLegal, passes with
+//   probability 1/7 (also consecutive ones), until the history says the game is over.  Per move: flags (finished, noResult,
+//   passWouldEndPhase for the next player), hist.isLegal of every point for the next player, hist.superKoBanned.
+static int cmdHistStream(int argc, char** argv) {
+  if(argc != 10) { cerr << "usage: histstream X Y KORULE MULTISUICIDE SEED NGAMES MAXMOVES OUT" << endl; return 1; }
+  int X = atoi(argv[2]), Y = atoi(argv[3]), koRule = atoi(argv[4]);
+  bool multi = atoi(argv[5]) != 0;
+  Lcg rng(strtoull(argv[6], NULL, 10));
+  int nGames = atoi(argv[7]), maxMoves = atoi(argv[8]);
+  Board::initHash();
+  ScoreValue::initTables();
+  Rules rules;
+  rules.koRule = koRule == 0 ? Rules::KO_SIMPLE : koRule == 1 ? Rules::KO_POSITIONAL : Rules::KO_SITUATIONAL;
+  rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = multi; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.friendlyPassOk = false; rules.komi = 7.5f;
+  ofstream out(argv[9], ios::binary);
+  put<int32_t>(out, X); put<int32_t>(out, Y); put<int32_t>(out, koRule); put<int32_t>(out, multi ? 1 : 0); put<int32_t>(out, nGames); put<int32_t>(out, maxMoves);
+  for(int gi = 0; gi < nGames; gi++) {
+    Board board(X, Y);
+    Player pla = P_BLACK;
+    BoardHistory hist(board, pla, rules, 0, false);
+    vector<char> rec;
+    int n = 0;
+    while(n < maxMoves && !hist.isGameFinished) {
+      vector<Loc> legal;
+      for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(hist.isLegal(board, l, pla)) legal.push_back(l); }
+      Loc mv = (legal.empty() || rng.next() % 7 == 0) ? Board::PASS_LOC : legal[rng.next() % legal.size()];
+      hist.makeBoardMoveAssumeLegal(board, mv, pla, NULL);
+      pla = getOpp(pla);
+      rec.push_back(mv == Board::PASS_LOC ? -1 : (char)Location::getX(mv, X));
+      rec.push_back(mv == Board::PASS_LOC ? -1 : (char)Location::getY(mv, X));
+      char flags = (hist.isGameFinished ? 1 : 0) | (hist.isNoResult ? 2 : 0) | (hist.passWouldEndPhase(board, pla) ? 4 : 0);
+      rec.push_back(flags);
+      for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) rec.push_back(hist.isLegal(board, Location::getLoc(x, y, X), pla) ? 1 : 0);
+      for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) rec.push_back(hist.superKoBanned[Location::getLoc(x, y, X)] ? 1 : 0);
+      n++;
+    }
+    put<int32_t>(out, n);
+    out.write(rec.data(), rec.size());
+  }
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -460,6 +505,7 @@ int main(int argc, char** argv) {
   if(cmd == "vwtable") return cmdVWTable(argc, argv);
   if(cmd == "rootnoise") return cmdRootNoise(argc, argv);
   if(cmd == "chooseidx") return cmdChooseIdx(argc, argv);
+  if(cmd == "histstream") return cmdHistStream(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;
