@@ -195,6 +195,10 @@ typedef struct kgb_selfplay_config {
   double chosen_move_prune;                       /* chosenMovePrune (1) */
   int32_t nn_cache_size_power_of_two;             /* nnCacheSizePowerOfTwo: evaluation cache shared by the games of this GPU (0 = off) */
   int32_t root_num_symmetries_to_sample;          /* rootNumSymmetriesToSample (4): the root is evaluated under that many symmetries, one per wave */
+  int32_t ko_rule;                                /* Rules::koRule: 0 simple, 1 positional superko, 2 situational superko (area scoring) */
+  int32_t full_history_rules;                     /* 1 = BoardHistory's game-end rules also under simple ko: a pass in a situation the same
+                                                     player already passed in ends the game, a third repetition since the last pass is "no
+                                                     result".  Implied by ko_rule != 0.  0 = two consecutive passes only. */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {

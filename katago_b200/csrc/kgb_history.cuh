@@ -94,7 +94,9 @@ __device__ uint32_t histSuperKoBanned(const WarpBoard& bd, const HistLists& L, u
 }
 
 // BoardHistory::makeBoardMoveAssumeLegal for the rule subset.  p = y*32+x or < 0 for a pass; bd carries the Zobrist hash.
-__device__ void histMakeMove(WarpBoard& bd, HistState& st, HistLists& L, int p, bool black, int koRule, bool multiSuicide, const ZobEntry* zob) {
+// computeBans = false leaves st.banned untouched (a search only needs the bans where it creates or evaluates a position).
+__device__ void histMakeMove(WarpBoard& bd, HistState& st, HistLists& L, int p, bool black, int koRule, bool multiSuicide, const ZobEntry* zob,
+                             bool computeBans = true) {
   const int lane = kgbLane();
   bool spight = false;
   if(p >= 0) st.passes = 0;
@@ -114,7 +116,7 @@ __device__ void histMakeMove(WarpBoard& bd, HistState& st, HistLists& L, int p, 
   L.pKoLen++;
   __syncwarp();
   if(p >= 0) st.everOcc |= pointMask(p);
-  st.banned = koRule != KGB_KO_SIMPLE ? histSuperKoBanned(bd, L, st.everOcc, !black, koRule, multiSuicide, zob) : 0u;
+  if(computeBans) st.banned = koRule != KGB_KO_SIMPLE ? histSuperKoBanned(bd, L, st.everOcc, !black, koRule, multiSuicide, zob) : 0u;
   st.finished = st.passes >= 2 || spight;
   st.noResult = false;
   if(p >= 0 && koRule == KGB_KO_SIMPLE && koCount(L, ha) >= 3) { st.noResult = true; st.finished = true; }
@@ -124,6 +126,21 @@ __device__ void histMakeMove(WarpBoard& bd, HistState& st, HistLists& L, int p, 
 __device__ __forceinline__ bool histPassWouldEndPhase(const WarpBoard& bd, const HistState& st, const HistLists& L, bool black, int koRule) {
   if(st.passes + 1 >= 2) return true;
   return koRule == KGB_KO_SIMPLE && passSeen(L, black, koHashOf(koRule, bd.h0, black));
+}
+
+// Order-independent hash of a set of points (the superko bans enter the state / cache keys, boardhistory.cpp:1238-1244).
+__device__ __forceinline__ unsigned long long pointSetHash(uint32_t rowBits) {
+  unsigned long long h = 0;
+  const int y = kgbLane();
+  while(rowBits) {
+    const int x = __ffs(rowBits) - 1;
+    rowBits &= rowBits - 1;
+    unsigned long long z = (unsigned long long)(y * 32 + x) + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; h ^= z ^ (z >> 31);
+  }
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) h ^= __shfl_xor_sync(KGB_FULL, h, o);
+  return h;
 }
 
 }  // namespace kgb

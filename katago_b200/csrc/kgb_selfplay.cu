@@ -61,6 +61,12 @@ struct SPDev {
   unsigned long long* biasKey;      // [game][biasTableSize] 0 = empty
   double *biasDeltaSum, *biasWeightSum;   // [game][biasTableSize] SubtreeValueBiasEntry
   int* nodeBiasEntry;               // [game][maxNodes] slot or -1
+  // full ko rules / game end (kgb_history.cuh): ko-hash history, pass situations, ever-occupied points, superko bans
+  int histRules, koRule, histCap, pathCap;
+  unsigned long long *gKo, *gPassB, *gPassW;   // [game][histCap]
+  int *gKoLen, *gPassBLen, *gPassWLen;         // [game]
+  uint32_t *gEverOcc, *rootBanned;             // [game][32]
+  unsigned long long *pKo, *pPassB, *pPassW;   // [game][pathCap] the path part of the lists during a playout
   // graph search (search.cpp:875-936, game/graphhash.cpp): transposition table per game, cleared with the tree
   int useGraphSearch, graphSearchRepBound, holdAtMaxVisits;
   // evaluation cache (NNCacheTable, nneval.cpp:1273-1353; key = NNInputs::getHash, nninputs.cpp:869-943): direct mapped, shared by
@@ -255,6 +261,57 @@ __device__ __forceinline__ void stateHash(unsigned long long posH0, unsigned lon
   s0 += 2862933555777941757ULL * (unsigned long long)passes;
   s1 += 3202034522624059733ULL * (unsigned long long)passes;
 }
+// The same with the full rules: a pass can also end the phase because the situation was passed in before, and the superko bans
+// are part of the situation (boardhistory.cpp:1238-1244).
+__device__ __forceinline__ void stateHashX(unsigned long long posH0, unsigned long long posH1, bool nextBlack, int ko, int passes, bool gameOver,
+                                           bool passEnds, unsigned long long bannedHash, unsigned long long& s0, unsigned long long& s1) {
+  stateHash(posH0, posH1, nextBlack, ko, passes, gameOver, s0, s1);
+  if(passEnds != (passes >= 1)) { s0 ^= 0x9AE16A3B2F90404FULL; s1 ^= 0xCBF29CE484222325ULL; }
+  s0 ^= bannedHash; s1 ^= splitmix64(bannedHash + 0x1234567ULL) * (bannedHash != 0 ? 1ULL : 0ULL);
+}
+// ---- the lists of kgb_history.cuh for a game (appendable) and for a playout (game part read-only + path part)
+__device__ __forceinline__ HistLists gameLists(const SPDev& d, int g) {
+  HistLists L;
+  L.gKo = nullptr; L.gKoLen = 0; L.gKoStart = 0; L.gPassB = nullptr; L.gPassBLen = 0; L.gPassW = nullptr; L.gPassWLen = 0;
+  L.pKo = d.gKo + (size_t)g * d.histCap; L.pKoLen = d.gKoLen[g];
+  L.pPassB = d.gPassB + (size_t)g * d.histCap; L.pPassBLen = d.gPassBLen[g];
+  L.pPassW = d.gPassW + (size_t)g * d.histCap; L.pPassWLen = d.gPassWLen[g];
+  return L;
+}
+__device__ __forceinline__ HistLists playoutLists(const SPDev& d, int g) {
+  HistLists L;
+  L.gKo = d.gKo + (size_t)g * d.histCap; L.gKoLen = d.gKoLen[g]; L.gKoStart = 0;
+  L.gPassB = d.gPassB + (size_t)g * d.histCap; L.gPassBLen = d.gPassBLen[g];
+  L.gPassW = d.gPassW + (size_t)g * d.histCap; L.gPassWLen = d.gPassWLen[g];
+  L.pKo = d.pKo + (size_t)g * d.pathCap; L.pKoLen = 0;
+  L.pPassB = d.pPassB + (size_t)g * d.pathCap; L.pPassBLen = 0;
+  L.pPassW = d.pPassW + (size_t)g * d.pathCap; L.pPassWLen = 0;
+  return L;
+}
+// A fresh game: the history starts with the initial situation (BoardHistory::clear).
+__device__ __forceinline__ void gameHistReset(const SPDev& d, int g, int lane) {
+  if(!d.histRules) return;
+  d.gEverOcc[g * 32 + lane] = 0; d.rootBanned[g * 32 + lane] = 0;
+  if(lane == 0) { d.gKo[(size_t)g * d.histCap] = koHashOf(d.koRule, 0ULL, true); d.gKoLen[g] = 1; d.gPassBLen[g] = 0; d.gPassWLen[g] = 0; }
+}
+// One move of the GAME (root): board, Zobrist hash, pass count and - with the full rules - the game's lists, bans and end flags.
+__device__ void gameMakeMove(const SPDev& d, int g, WarpBoard& bd, int p, bool black, int lane, int& passes, bool& finished, bool& noResult) {
+  if(!d.histRules) {
+    boardPlay(bd, p, black, d.zob);
+    passes = p < 0 ? passes + 1 : 0;
+    finished = passes >= 2; noResult = false;
+    return;
+  }
+  HistLists L = gameLists(d, g);
+  HistState st;
+  st.passes = passes; st.finished = false; st.noResult = false; st.everOcc = d.gEverOcc[g * 32 + lane]; st.banned = 0;
+  histMakeMove(bd, st, L, p, black, d.koRule, d.multiSuicide != 0, d.zob, true);
+  d.gEverOcc[g * 32 + lane] = st.everOcc; d.rootBanned[g * 32 + lane] = st.banned;
+  __syncwarp();
+  if(lane == 0) { d.gKoLen[g] = L.pKoLen; d.gPassBLen[g] = L.pPassBLen; d.gPassWLen[g] = L.pPassWLen; }
+  __syncwarp();
+  passes = st.passes; finished = st.finished; noResult = st.noResult;
+}
 // Board::simpleRepetitionBoundGt (board.cpp:2825-2888) on the board AFTER the move at p: stones of the chain at p plus all
 // empty points of the regions its liberties belong to (or, if p is empty after a suicide, the empty region around p) > bound.
 __device__ __forceinline__ bool simpleRepetitionBoundGt(const WarpBoard& bd, int p, int bound) {
@@ -292,13 +349,21 @@ __device__ __forceinline__ void nodeTableClear(const SPDev& d, int g, int lane) 
 }
 // The root node's hashes (after the root position changed): its position hash is tracked with the root board.
 __device__ __forceinline__ void rootHashesInit(const SPDev& d, int g, int lane) {
-  if(lane == 0) {
-    const size_t gb = (size_t)g * d.maxNodes;
-    const unsigned long long h0 = d.rootPosH[g * 2], h1 = d.rootPosH[g * 2 + 1];
-    unsigned long long s0, s1;
-    stateHash(h0, h1, d.rootBlackToMove[g] != 0, d.rootKo[g], d.consecPasses[g], false, s0, s1);
-    d.nodePosH0[gb] = h0; d.nodePosH1[gb] = h1; d.nodeGH0[gb] = s0; d.nodeGH1[gb] = s1;
+  const size_t gb = (size_t)g * d.maxNodes;
+  const unsigned long long h0 = d.rootPosH[g * 2], h1 = d.rootPosH[g * 2 + 1];
+  unsigned long long s0, s1;
+  if(!d.histRules) stateHash(h0, h1, d.rootBlackToMove[g] != 0, d.rootKo[g], d.consecPasses[g], false, s0, s1);
+  else {
+    WarpBoard bd;
+    boardInit(bd, d.X, d.Y);
+    bd.h0 = h0;
+    HistLists L = playoutLists(d, g);
+    HistState st;
+    st.passes = d.consecPasses[g]; st.finished = false; st.noResult = false; st.everOcc = 0; st.banned = d.rootBanned[g * 32 + lane];
+    const bool black = d.rootBlackToMove[g] != 0;
+    stateHashX(h0, h1, black, d.rootKo[g], st.passes, false, histPassWouldEndPhase(bd, st, L, black, d.koRule), pointSetHash(st.banned), s0, s1);
   }
+  if(lane == 0) { d.nodePosH0[gb] = h0; d.nodePosH1[gb] = h1; d.nodeGH0[gb] = s0; d.nodeGH1[gb] = s1; }
 }
 
 // Search::getPlaySelectionValues for the root (searchresults.cpp:66-330; no human policy, no pass suppression, no ending
@@ -540,19 +605,21 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   const int p = isPass ? -1 : pointOfPos(best, d.X);
   const uint32_t beforeB = bd.b, beforeW = bd.w; const int beforeKo = bd.ko;
   bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];
-  boardPlay(bd, p, black, d.zob);
-  int passes = isPass ? d.consecPasses[g] + 1 : 0;
+  int passes = d.consecPasses[g];
+  bool finished = false, noResult = false;
+  gameMakeMove(d, g, bd, p, black, lane, passes, finished, noResult);
   int mv = d.moveNum[g] + 1;
-  bool over = passes >= 2 || mv >= d.maxMoves;
+  bool over = finished || mv >= d.maxMoves;
   if(over) {
     int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
     float whiteScore = d.komi - (float)diff;
     if(lane == 0) {
       atomicAdd(d.gamesFinished, 1ULL);
-      if(whiteScore < 0) atomicAdd(d.blackWins, 1ULL);
+      if(whiteScore < 0 && !noResult) atomicAdd(d.blackWins, 1ULL);
       d.gameCounter[g] += 1;
     }
     boardInit(bd, d.X, d.Y);
+    gameHistReset(d, g, lane);
     passes = 0; mv = 0;
     if(lane < 5) d.hist[g * 5 + lane] = -1;
     if(lane == 0) d.rootBlackToMove[g] = 1;
@@ -604,6 +671,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   bool black = true, terminal = false, gotLeaf = false;
   int passes = 0, h0 = -1, h1 = -1, h2 = -1, h3 = -1, h4 = -1, node = 0, depth = 0;
   uint32_t lad1 = 0, lad2 = 0;
+  HistLists HL = playoutLists(d, g);
+  HistState hst;
+  hst.passes = 0; hst.finished = false; hst.noResult = false; hst.everOcc = 0; hst.banned = 0;
+  bool bannedValid = false;     // hst.banned belongs to the current position
   // Under graph search a playout can end without reaching a new leaf (edge catch-up, cycle): it is backed up at once and the
   // next playout starts, so that the wave still delivers a leaf for the evaluator.
   for(int attempt = 0; attempt < SP_MAX_PLAYOUTS_PER_WAVE && !gotLeaf; attempt++) {
@@ -624,6 +695,13 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   lad1 = d.prevLad[g * 32 + lane]; lad2 = d.prevLad[G32 + g * 32 + lane];
   node = 0; depth = 0;
   terminal = false;
+  if(d.histRules) {
+    HL = playoutLists(d, g);
+    hst.passes = passes; hst.finished = false; hst.noResult = false;
+    hst.everOcc = d.gEverOcc[g * 32 + lane]; hst.banned = d.rootBanned[g * 32 + lane];
+    bannedValid = true;
+    bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];   // the hash follows the whole path: ko hashes are taken from it
+  }
   bool instant = false;   // this playout ended on an existing edge: back it up here, no leaf
   while(true) {
     const int visits = d.nodeVisits[gb + node];
@@ -744,9 +822,21 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     if(d.subtreeValueBiasFactor != 0.0 && d.childNode[nb + move] < 0 && !isPass && h0 != -1) biasKeyNew = biasEntryKey(bd, d.X, d.Y, black, h0, p);
     int child = d.childNode[nb + move];
     const bool newEdge = child < 0;
+    if(d.histRules) {
+      // BoardHistory::makeBoardMoveAssumeLegal along the path: pass situations, ko-hash history, game end by repetition rules
+      histMakeMove(bd, hst, HL, p, black, d.koRule, d.multiSuicide != 0, d.zob, false);
+      bannedValid = false;
+      if(newEdge && d.koRule != KGB_KO_SIMPLE) {
+        hst.banned = histSuperKoBanned(bd, HL, hst.everOcc, !black, d.koRule, d.multiSuicide != 0, d.zob);
+        bannedValid = true;
+      }
+      passes = hst.passes;
+    }
+    else {
     if(newEdge && d.trackPosHash) { bd.h0 = d.nodePosH0[gb + node]; bd.h1 = d.nodePosH1[gb + node]; }
     boardPlay(bd, p, black, (newEdge && d.trackPosHash) ? d.zob : nullptr);
     passes = isPass ? passes + 1 : 0;
+    }
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
     black = !black;
     if(newEdge) {
@@ -755,7 +845,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       int tableSlot = -1, found = -1;
       if(d.useGraphSearch) {
         unsigned long long s0, s1;
-        stateHash(bd.h0, bd.h1, black, bd.ko, passes, passes >= 2, s0, s1);
+        if(d.histRules)
+          stateHashX(bd.h0, bd.h1, black, bd.ko, passes, hst.finished, histPassWouldEndPhase(bd, hst, HL, black, d.koRule),
+                     d.koRule != KGB_KO_SIMPLE ? pointSetHash(hst.banned) : 0ULL, s0, s1);
+        else stateHash(bd.h0, bd.h1, black, bd.ko, passes, passes >= 2, s0, s1);
         graphHashOfChild(d.nodeGH0[gb + node], d.nodeGH1[gb + node], s0, s1, simpleRepetitionBoundGt(bd, p, d.graphSearchRepBound), cg0, cg1);
         found = nodeTableFind(d, g, cg0, cg1, tableSlot);
       }
@@ -771,7 +864,8 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
         d.nodeNumChildren[gb + node] = nc + 1;
         if(found < 0) {
           d.nodeCount[g] = child + 1;
-          nodeStatsReset(d, gb + child, passes >= 2);
+          nodeStatsReset(d, gb + child, d.histRules ? hst.finished : passes >= 2);
+          if(d.histRules && hst.noResult) d.nodeTerminal[gb + child] = 2;
           if(biasKeyNew != 0) d.nodeBiasEntry[gb + child] = biasFindOrInsert(d, g, biasKeyNew);
           if(d.trackPosHash) { d.nodePosH0[gb + child] = bd.h0; d.nodePosH1[gb + child] = bd.h1; }
           if(d.useGraphSearch) {
@@ -810,7 +904,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0 && !(node == 0 && d.rootNumSymmetries > 1)) {
     // NNEvaluator::evaluate's cache lookup (nneval.cpp:861-905): the key is the situation, not the history behind it
     unsigned long long k0, k1;
-    stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
+    if(d.histRules)
+      stateHashX(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, histPassWouldEndPhase(bd, hst, HL, black, d.koRule),
+                 (d.koRule != KGB_KO_SIMPLE && bannedValid) ? pointSetHash(hst.banned) : 0ULL, k0, k1);
+    else stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
     if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
     float vals[6];
     if(cacheLookup(d, g, node, k0, k1, vals, lane)) {
@@ -832,10 +929,15 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   // ---- leaf: liberties, legality, features
   uint32_t lib1, lib2, lib3;
   boardLibertyClasses(bd, lib1, lib2, lib3);
-  const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, lib1);
+  uint32_t superKo = 0;
+  if(d.histRules && d.koRule != KGB_KO_SIMPLE) {
+    if(!bannedValid) { hst.banned = histSuperKoBanned(bd, HL, hst.everOcc, black, d.koRule, d.multiSuicide != 0, d.zob); bannedValid = true; }
+    superKo = hst.banned;
+  }
+  const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, lib1) & ~superKo;    // BoardHistory::isLegal
   d.leafLegal[g * 32 + lane] = legal;
   if(lane == 0) {
-    d.pathLen[g] = depth; d.leafNode[g] = node; d.leafTerminal[g] = terminal ? 1 : 0; d.leafBlackToMove[g] = black ? 1 : 0;
+    d.pathLen[g] = depth; d.leafNode[g] = node; d.leafTerminal[g] = (int)d.nodeTerminal[gb + node]; d.leafBlackToMove[g] = black ? 1 : 0;
     atomicAdd(d.sumDepth, (unsigned long long)depth);
   }
   if(terminal) {
@@ -868,6 +970,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       float* f = row + (size_t)(lane * d.X + x) * 22;
       const uint32_t bit = 1u << x;
       f[0] = 1.0f;
+      if(superKo & bit) f[6] = 1.0f;                 // superko bans join the simple-ko point in plane 6 (nninputs.cpp:2342-2356)
       if(own & bit) f[1] = 1.0f; else if(opp & bit) f[2] = 1.0f;
       if(lib1 & bit) f[3] = 1.0f; else if(lib2 & bit) f[4] = 1.0f; else if(lib3 & bit) f[5] = 1.0f;
       if(areaOwn & bit) f[18] = 1.0f; else if(areaOpp & bit) f[19] = 1.0f;
@@ -876,6 +979,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
   }
   __syncwarp();
+  const bool passEndsLeaf = d.histRules ? histPassWouldEndPhase(bd, hst, HL, black, d.koRule) : passes >= 1;
   if(lane == 0) {
     if(bd.ko >= 0) row[(size_t)posOf(bd.ko, d.X) * 22 + 6] = 1.0f;
     // history planes 9..13: the move k plies ago must have been made by the right colour, which alternation guarantees
@@ -890,7 +994,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     selfKomi = fminf(fmaxf(selfKomi, -bArea - 20.0f), bArea + 20.0f);
     gl[5] = selfKomi / 20.0f;
     if(d.multiSuicide) gl[8] = 1.0f;
-    gl[14] = passes >= 1 ? 1.0f : 0.0f;          // BoardHistory::passWouldEndPhase under area scoring, simple ko
+    gl[14] = passEndsLeaf ? 1.0f : 0.0f;         // BoardHistory::passWouldEndPhase
+    if(d.koRule == KGB_KO_POSITIONAL) { gl[6] = 1.0f; gl[7] = 0.5f; }            // ko rule (nninputs.cpp:2612-2621)
+    else if(d.koRule == KGB_KO_SITUATIONAL) { gl[6] = 1.0f; gl[7] = -0.5f; }
     // komi parity wave (nninputs.cpp:2696-2729)
     bool drawableKomisAreEven = (d.XY % 2) == 0;
     float komiFloor = drawableKomisAreEven ? floorf(selfKomi / 2.0f) * 2.0f : floorf((selfKomi - 1.0f) / 2.0f) * 2.0f + 1.0f;
@@ -1328,7 +1434,13 @@ __global__ void spBackupKernel(const SPDev d) {
   const bool terminal = d.leafTerminal[g] != 0;
   const bool leafBlack = d.leafBlackToMove[g] != 0;
   double u;
-  if(terminal) {
+  if(d.leafTerminal[g] == 2) {
+    // search.cpp:1204-1212: a game ended without result (long cycle under simple ko)
+    u = 1.0 * d.noResultUtilityForWhite + scoreUtilityOf(d, 0.0, 0.0, d.recentScoreCenter[g]);
+    if(lane == 0) { d.leafMoments[g * 5 + 0] = 0.0; d.leafMoments[g * 5 + 1] = 1.0; d.leafMoments[g * 5 + 2] = 0.0; d.leafMoments[g * 5 + 3] = 0.0; d.leafMoments[g * 5 + 4] = 0.0; }
+    __syncwarp();
+  }
+  else if(terminal) {
     // search.cpp:1213-1222: the game result as a leaf value (area scoring: no "no result")
     const double score = (double)d.leafTerminalScore[g];
     const double whiteWins = score > 0 ? 1.0 : score < 0 ? 0.0 : d.drawEquivalentWinsForWhite;       // ScoreValue::whiteWinsOfWinner
@@ -1391,7 +1503,9 @@ __global__ void spBackupKernel(const SPDev d) {
     const float* val = d.nnValue + (size_t)g * 3;
     double wl = val[0], ll = val[1], nl = val[2];
     double m = fmax(fmax(wl, ll), nl);
+    if(d.koRule != KGB_KO_SIMPLE) { nl -= 100000.0; m = fmax(fmax(wl, ll), nl); }   // nneval.cpp:1136-1147: no "no result" under superko
     double w = exp(wl - m), l = exp(ll - m), n = exp(nl - m);
+    if(d.koRule != KGB_KO_SIMPLE) n = 0.0;
     double s = w + l + n;
     w /= s; l /= s; n /= s;
     const float wf = (float)w, lf = (float)l, nf = (float)n;
@@ -1497,8 +1611,8 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     const bool isPass = moves[m * 2] < 0;
     const int p = isPass ? -1 : (moves[m * 2 + 1] * 32 + moves[m * 2]);
     p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
-    boardPlay(bd, p, black, d.zob);
-    passes = isPass ? passes + 1 : 0;
+    bool fin, nores;
+    gameMakeMove(d, g, bd, p, black, lane, passes, fin, nores);
     for(int k = 4; k > 0; k--) h[k] = h[k - 1];
     h[0] = isPass ? -2 : p;
     black = !black;
@@ -1560,7 +1674,7 @@ __global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
   for(unsigned m = 0; m < len; m++) {
     uint32_t l1, l2, l3;
     boardLibertyClasses(bd, l1, l2, l3);
-    const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, l1);
+    const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, l1) & ~(d.histRules ? d.rootBanned[g * 32 + lane] : 0u);
     const int n = warpCount(legal);
     if(n == 0) break;
     unsigned r = 0;
@@ -1579,7 +1693,8 @@ __global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
     const unsigned who = __ballot_sync(KGB_FULL, p >= 0);
     p = __shfl_sync(KGB_FULL, p, __ffs(who) - 1);
     p2B = p1B; p2W = p1W; p2Ko = p1Ko; p1B = bd.b; p1W = bd.w; p1Ko = bd.ko;
-    boardPlay(bd, p, black, d.zob);
+    int passesTmp = 0; bool fin, nores;
+    gameMakeMove(d, g, bd, p, black, lane, passesTmp, fin, nores);
     for(int k = 4; k > 0; k--) h[k] = h[k - 1];
     h[0] = p;
     black = !black;
@@ -1620,6 +1735,8 @@ __global__ void spInitRootsKernel(const SPDev d) {
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
   nodeTableClear(d, g, lane);
+  gameHistReset(d, g, lane);
+  __syncwarp();
   rootHashesInit(d, g, lane);
 }
 
@@ -1778,6 +1895,14 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.nodeUtilSqAvg = sp->alloc<double>(G * N); d.nodeNNUtil = sp->alloc<double>(G * N); d.nodeNumChildren = sp->alloc<int>(G * N);
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
   d.nodeMoments = sp->alloc<double>(G * N * 5); d.nodeNNMoments = sp->alloc<double>(G * N * 5); d.leafMoments = sp->alloc<double>(G * 5);
+  d.koRule = c.ko_rule;
+  if(d.koRule < 0 || d.koRule > 2) throw std::invalid_argument("selfplay: ko_rule must be 0 (simple), 1 (positional) or 2 (situational)");
+  d.histRules = (c.full_history_rules || d.koRule != 0) ? 1 : 0;
+  d.histCap = d.maxMoves + 8; d.pathCap = d.maxDepth + 8;
+  d.gKo = sp->alloc<unsigned long long>(G * d.histCap); d.gPassB = sp->alloc<unsigned long long>(G * d.histCap); d.gPassW = sp->alloc<unsigned long long>(G * d.histCap);
+  d.gKoLen = sp->alloc<int>(G); d.gPassBLen = sp->alloc<int>(G); d.gPassWLen = sp->alloc<int>(G);
+  d.gEverOcc = sp->alloc<uint32_t>(G * 32); d.rootBanned = sp->alloc<uint32_t>(G * 32);
+  d.pKo = sp->alloc<unsigned long long>(G * d.pathCap); d.pPassB = sp->alloc<unsigned long long>(G * d.pathCap); d.pPassW = sp->alloc<unsigned long long>(G * d.pathCap);
   d.holdAtMaxVisits = c.debug_hold_at_max_visits ? 1 : 0;
   d.fakeNN = c.debug_fake_nn ? 1 : 0;
   d.rootNumSymmetries = c.root_num_symmetries_to_sample > 1 ? (c.root_num_symmetries_to_sample > 8 ? 8 : c.root_num_symmetries_to_sample) : 1;

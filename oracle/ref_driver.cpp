@@ -194,6 +194,7 @@ static int cmdSearchFake(int argc, char** argv) {
                                         vector<int>{0}, "seed", false, 0, true, cfg);
   nnEval->spawnServerThreads();
   // Reference SearchParams restricted to what the device loop implements: everything else at its default.
+  int koRuleOverride = 0;
   SearchParams params;
   params.maxVisits = maxVisits;
   params.numThreads = 1;
@@ -226,6 +227,7 @@ static int cmdSearchFake(int argc, char** argv) {
     else if(k == "cpuctUtilityStdevPriorWeight") params.cpuctUtilityStdevPriorWeight = v;
     else if(k == "rootDesiredPerChildVisitsCoeff") params.rootDesiredPerChildVisitsCoeff = v;
     else if(k == "rootNumSymmetriesToSample") params.rootNumSymmetriesToSample = (int)v;
+    else if(k == "koRule") koRuleOverride = (int)v;
     else if(k == "useLcbForSelection") params.useLcbForSelection = v != 0;
     else if(k == "useNonBuggyLcb") params.useNonBuggyLcb = v != 0;
     else if(k == "lcbStdevs") params.lcbStdevs = v;
@@ -242,7 +244,8 @@ static int cmdSearchFake(int argc, char** argv) {
     else { cerr << "unknown override " << k << endl; return 1; }
   }
   Rules rules;  // defaults, then the rule subset of the loop
-  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.koRule = koRuleOverride == 1 ? Rules::KO_POSITIONAL : koRuleOverride == 2 ? Rules::KO_SITUATIONAL : Rules::KO_SIMPLE;
+  rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
   rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
   rules.friendlyPassOk = false; rules.komi = 7.5f;
   Board board(X, Y);
@@ -429,7 +432,7 @@ static int cmdHistStream(int argc, char** argv) {
 }
 
 static int cmdFeatStream(int argc, char** argv) {
-  if(argc != 9) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT" << endl; return 1; }
+  if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
   bool multi = atoi(argv[4]) != 0;
   float komi = (float)atof(argv[5]);
@@ -438,6 +441,7 @@ static int cmdFeatStream(int argc, char** argv) {
   ScoreValue::initTables();
   Rules rules;
   rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  if(argc == 10) rules.koRule = atoi(argv[9]) == 1 ? Rules::KO_POSITIONAL : atoi(argv[9]) == 2 ? Rules::KO_SITUATIONAL : Rules::KO_SIMPLE;
   rules.multiStoneSuicideLegal = multi; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
   rules.friendlyPassOk = false; rules.komi = komi;
   Board board(X, Y);

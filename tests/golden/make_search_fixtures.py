@@ -43,7 +43,7 @@ def run(X, Y, visits, moves, score=None):
         score = {}
     elif not isinstance(score, dict):
         score = dict(zip(SCORE_KEYS, score))
-    extra = [f"{k}={float(v)!r}" for k, v in score.items()]
+    extra = [f"{k}={float(v)!r}" for k, v in score.items() if k != "fullHistoryRules"]
     out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     psv = np.full(X * Y + 1, -1.0, np.float64); threadseed = ""
@@ -130,6 +130,12 @@ if __name__ == "__main__":
          dict(SELFPLAY8B18, useGraphSearch=1, rootNumSymmetriesToSample=4, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.5, **BIAS, **LCB)),
         (13, 7, 300, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), {"rootNumSymmetriesToSample": 8, "valueWeightExponent": 0.5}),
         (5, 5, 500, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), {"rootNumSymmetriesToSample": 2, "staticScoreUtilityFactor": 0.1}),
+        # ko rules inside the search (a3): superko bans and repetition endings along the playout paths
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 9), {"koRule": 1}),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), dict(SELFPLAY8B18, useGraphSearch=1, koRule=2, **BIAS)),
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), dict(SELFPLAY8B18, useGraphSearch=1, koRule=1, **BIAS, **LCB)),
+        (5, 5, 1000, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"fullHistoryRules": 1, "useGraphSearch": 1}),
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 55), dict(SELFPLAY8B18, fullHistoryRules=1)),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
