@@ -1,0 +1,98 @@
+// Search-shaped C++ facade over the device-resident game slots of libkgb200 (boundary 2).
+//
+// The reference drives one `Search` object per game from a game thread (program/play.cpp:1757-1936):
+//     bot->setPosition(pla, board, hist);  bot->runWholeSearch(pla);  Loc loc = bot->getChosenMoveLoc();  bot->makeMove(loc, pla);
+// Here all games of a GPU advance together: `runWaves` spends playouts on every slot, each slot chooses and plays its move when its
+// visit budget is used up, and restarts when its game ends.  The readers below have the names and meanings of the reference's
+// (search/search.h: getRootVisits, getPlaySelectionValues; search/searchresults.cpp) so that the game-recording code above them can
+// stay as it is.  Plain C++17, no CUDA headers: everything goes through the C ABI of include/kgb200.h.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../include/kgb200.h"
+
+namespace b200 {
+
+struct Move { int x = -1, y = -1; bool isPass() const { return x < 0; } };
+
+class GameSlots {
+ public:
+  // handle: an evaluator handle created with inputs_nhwc = 1 (NeuralNet::createComputeHandle in b200backend.cpp); cfg: SearchParams /
+  // Rules fields by their cfg names.
+  GameSlots(kgb_handle* handle, const kgb_selfplay_config& cfg, int xLen, int yLen) : x_(xLen), y_(yLen), n_(cfg.num_games) {
+    check(kgb_selfplay_create(handle, &cfg, &sp_));
+    handle_ = handle;
+  }
+  ~GameSlots() { if(sp_) kgb_selfplay_free(sp_); }
+  GameSlots(const GameSlots&) = delete;
+  GameSlots& operator=(const GameSlots&) = delete;
+
+  int numSlots() const { return n_; }
+  // Search::setPosition + makeMove for an opening common to all slots (x, y pairs; pass = -1, -1)
+  void playOpening(const std::vector<Move>& moves) {
+    std::vector<int8_t> xy;
+    for(const Move& m : moves) { xy.push_back((int8_t)m.x); xy.push_back((int8_t)m.y); }
+    check(kgb_selfplay_play_moves(sp_, xy.data(), (int)moves.size()));
+  }
+  // the playout loop: `waves` playout waves for every slot (asynchronous), then wait
+  void runWaves(int waves) { check(kgb_selfplay_run(sp_, waves)); check(kgb_handle_sync(handle_)); }
+
+  // Search::getRootVisits
+  int64_t getRootVisits(int slot) const { return gameInfo(slot)[5]; }
+  int moveNumber(int slot) const { return gameInfo(slot)[0]; }
+  bool blackToMove(int slot) const { return gameInfo(slot)[1] != 0; }
+  // root board, row-major [y][x]: 0 empty, 1 black, 2 white
+  std::vector<uint8_t> rootBoard(int slot) const {
+    std::vector<uint8_t> colors((size_t)x_ * y_);
+    int32_t info[6];
+    check(kgb_selfplay_get_game(sp_, slot, colors.data(), info));
+    return colors;
+  }
+  // Search::getPlaySelectionValues: (move, value) for every root child, in move-position order
+  std::vector<std::pair<Move, double>> getPlaySelectionValues(int slot) const {
+    std::vector<double> v((size_t)x_ * y_ + 1);
+    check(kgb_selfplay_get_play_selection_values(sp_, slot, v.data()));
+    std::vector<std::pair<Move, double>> out;
+    for(size_t i = 0; i < v.size(); i++)
+      if(v[i] >= 0.0) { Move m; if(i < (size_t)x_ * y_) { m.x = (int)(i % x_); m.y = (int)(i / x_); } out.emplace_back(m, v[i]); }
+    return out;
+  }
+  // per root child: edge visits, policy prior (the noised one at the root), utilityAvg - what ReportedSearchValues are built from
+  struct ChildStats { Move move; int visits; float prior; double utilityAvg, winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg; };
+  std::vector<ChildStats> rootChildren(int slot) const {
+    const size_t ps = (size_t)x_ * y_ + 1;
+    std::vector<int32_t> visits(ps); std::vector<float> policy(ps); std::vector<double> util(ps), mom(ps * 5), rootMom(5);
+    check(kgb_selfplay_get_root_children(sp_, slot, visits.data(), policy.data(), util.data()));
+    check(kgb_selfplay_get_root_value_stats(sp_, slot, mom.data(), rootMom.data()));
+    std::vector<ChildStats> out;
+    for(size_t i = 0; i < ps; i++) {
+      if(visits[i] <= 0) continue;
+      ChildStats c;
+      if(i < ps - 1) { c.move.x = (int)(i % x_); c.move.y = (int)(i / x_); }
+      c.visits = visits[i]; c.prior = policy[i]; c.utilityAvg = util[i];
+      c.winLossValueAvg = mom[i * 5]; c.noResultValueAvg = mom[i * 5 + 1]; c.scoreMeanAvg = mom[i * 5 + 2]; c.scoreMeanSqAvg = mom[i * 5 + 3]; c.leadAvg = mom[i * 5 + 4];
+      out.push_back(c);
+    }
+    return out;
+  }
+  kgb_selfplay_stats stats() const { kgb_selfplay_stats s; check(kgb_selfplay_get_stats(sp_, &s)); return s; }
+
+ private:
+  struct Info { int32_t v[6]; int32_t operator[](int i) const { return v[i]; } };
+  Info gameInfo(int slot) const {
+    std::vector<uint8_t> colors((size_t)x_ * y_);
+    Info info;
+    check(kgb_selfplay_get_game(sp_, slot, colors.data(), info.v));
+    return info;
+  }
+  static void check(int rc) { if(rc != 0) throw std::runtime_error(std::string("libkgb200: ") + kgb_last_error()); }
+  kgb_selfplay* sp_ = nullptr;
+  kgb_handle* handle_ = nullptr;
+  int x_, y_, n_;
+};
+
+}  // namespace b200

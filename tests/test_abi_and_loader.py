@@ -136,3 +136,16 @@ def test_value_weight_cdf_table_is_bit_exact_vs_reference(golden_dir):
     FancyMath::tdistcdf (fixture: the reference's own DistributionTable, tests/golden/make_scorevalue_fixture.py)."""
     from katago_b200.nn_backend import value_weight_cdf_table
     assert np.array_equal(value_weight_cdf_table(), np.load(os.path.join(golden_dir, "value_weight_cdf_table.npy")))
+
+
+def test_search_shaped_facade_compiles_against_the_abi(tmp_path):
+    """integration/b200selfplay.h (boundary 2: the Search-shaped C++ facade over the device game slots) is plain C++17 over
+    include/kgb200.h; it must compile and link against the library (no GPU needed for that)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "facade.cpp"
+    src.write_text('#include "integration/b200selfplay.h"\nint main(int argc, char**) { if(argc > 100) { kgb_selfplay_config c = {}; b200::GameSlots s(nullptr, c, 19, 19); s.runWaves(1); return (int)s.getRootVisits(0); } return 0; }\n')
+    exe = tmp_path / "facade"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", root, str(src), "-o", str(exe), "-L", os.path.join(root, "katago_b200"), "-lkgb200",
+                    "-Wl,-rpath," + os.path.join(root, "katago_b200")], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
