@@ -195,7 +195,7 @@ typedef struct kgb_selfplay_config {
   double chosen_move_prune;                       /* chosenMovePrune (1) */
   int32_t nn_cache_size_power_of_two;             /* nnCacheSizePowerOfTwo: evaluation cache shared by the games of this GPU (0 = off) */
   int32_t root_num_symmetries_to_sample;          /* rootNumSymmetriesToSample (4): the root is evaluated under that many symmetries, one per wave */
-  int32_t ko_rule;                                /* Rules::koRule: 0 simple, 1 positional superko, 2 situational superko (area scoring) */
+  int32_t ko_rule;                                /* Rules::koRule: 0 simple, 1 positional superko, 2 situational superko, 3 spight (area scoring) */
   int32_t full_history_rules;                     /* 1 = BoardHistory's game-end rules also under simple ko: a pass in a situation the same
                                                      player already passed in ends the game, a third repetition since the last pass is "no
                                                      result".  Implied by ko_rule != 0.  0 = two consecutive passes only. */
@@ -232,7 +232,7 @@ KGB_API int kgb_selfplay_get_play_selection_values(kgb_selfplay* sp, int game, d
 KGB_API int kgb_test_choose_index_with_temperature(const char* seed_string, const double* relative_probs, int n, double temperature,
                                                    double only_below_prob, int count, int32_t* chosen);
 /* TEST HOOK (row a3): replay num_games games (moves_xy [game][max_moves][2]: x,y; -1,-1 pass; -2 = end of that game; black first) through
- * the device ko rules (ko_rule 0 simple, 1 positional, 2 situational; area scoring).  Per move: flags (1 game over, 2 no result,
+ * the device ko rules (ko_rule 0 simple, 1 positional, 2 situational, 3 spight; area scoring).  Per move: flags (1 game over, 2 no result,
  * 4 a pass by the next player would end the phase), legality of every point for the next player (incl. ko and superko bans), and
  * the superko-banned points - BoardHistory::makeBoardMoveAssumeLegal / isLegal / passWouldEndPhase (game/boardhistory.cpp). */
 KGB_API int kgb_test_history_replay(int x_len, int y_len, int ko_rule, int multi_stone_suicide_legal, int num_games, int max_moves, const int8_t* moves_xy,

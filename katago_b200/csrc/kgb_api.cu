@@ -885,7 +885,7 @@ KGB_API int kgb_test_choose_index_with_temperature(const char* seed_string, cons
 KGB_API int kgb_test_history_replay(int x_len, int y_len, int ko_rule, int multi_stone_suicide_legal, int num_games, int max_moves, const int8_t* moves_xy,
                                     uint8_t* flags, uint8_t* legal_next, uint8_t* super_ko_banned) {
   return guarded([&] {
-    if(!moves_xy || !flags || !legal_next || !super_ko_banned || num_games < 1 || max_moves < 1 || ko_rule < 0 || ko_rule > 2)
+    if(!moves_xy || !flags || !legal_next || !super_ko_banned || num_games < 1 || max_moves < 1 || ko_rule < 0 || ko_rule > 3)
       throw std::invalid_argument("kgb_test_history_replay: bad argument");
     historyReplay(x_len, y_len, ko_rule, multi_stone_suicide_legal, num_games, max_moves, moves_xy, flags, legal_next, super_ko_banned);
   });

@@ -6,7 +6,7 @@
 //                                        are "no result" (third occurrence of a situation since the last pass)
 //   isLegal :786-812                     board legality and not superko-banned
 //   passWouldEndPhase :874-880
-// Not here: spight ko rule, territory scoring, encore phases, button, handicap bonus.
+// Ko rules: simple, positional, situational, spight.  Not here: territory scoring, encore phases, button, handicap bonus.
 //
 // Histories are lists of 64-bit ko hashes (first half of the 128-bit Zobrist position hash, XOR a player constant unless the
 // rule is positional).  A position reached inside a search extends its game's lists by a path part; HistLists carries both.
@@ -15,7 +15,9 @@
 
 namespace kgb {
 
-enum { KGB_KO_SIMPLE = 0, KGB_KO_POSITIONAL = 1, KGB_KO_SITUATIONAL = 2 };
+enum { KGB_KO_SIMPLE = 0, KGB_KO_POSITIONAL = 1, KGB_KO_SITUATIONAL = 2, KGB_KO_SPIGHT = 3 };
+// BoardHistory::phaseHasSpightlikeEndingAndPassHistoryClearing (:856-860) in the main phase
+__device__ __forceinline__ bool koRuleSpightlike(int koRule) { return koRule == KGB_KO_SIMPLE || koRule == KGB_KO_SPIGHT; }
 
 struct HistLists {
   // game part (read-only while searching)
@@ -37,7 +39,7 @@ struct HistState {           // per position, warp-uniform except the two masks
 };
 
 __device__ __forceinline__ unsigned long long koHashOf(int koRule, unsigned long long posH0, bool plaBlack) {
-  if(koRule == KGB_KO_POSITIONAL) return posH0;
+  if(koRule == KGB_KO_POSITIONAL || koRule == KGB_KO_SPIGHT) return posH0;
   return posH0 ^ (plaBlack ? 0x6A09E667F3BCC908ULL : 0xBB67AE8584CAA73BULL);
 }
 // warp-parallel membership / count over one list
@@ -101,10 +103,10 @@ __device__ void histMakeMove(WarpBoard& bd, HistState& st, HistLists& L, int p, 
   bool spight = false;
   if(p >= 0) st.passes = 0;
   else {
-    if(koRule == KGB_KO_SIMPLE) { L.gKoStart = L.gKoLen; L.pKoLen = 0; }   // passes clear the ko-hash history under simple ko
+    if(koRuleSpightlike(koRule)) { L.gKoStart = L.gKoLen; L.pKoLen = 0; }   // passes clear the ko-hash history under simple / spight ko
     const unsigned long long hb = koHashOf(koRule, bd.h0, black);
-    st.passes += 1;
-    spight = koRule == KGB_KO_SIMPLE && passSeen(L, black, hb);            // checked BEFORE this pass is recorded
+    st.passes = koRule == KGB_KO_SPIGHT ? 0 : st.passes + 1;              // newConsecutiveEndingPassesAfterPass (:831-851)
+    spight = koRuleSpightlike(koRule) && passSeen(L, black, hb);          // checked BEFORE this pass is recorded
     __syncwarp();
     if(lane == 0) { if(black) L.pPassB[L.pPassBLen] = hb; else L.pPassW[L.pPassWLen] = hb; }
     if(black) L.pPassBLen++; else L.pPassWLen++;
@@ -124,8 +126,8 @@ __device__ void histMakeMove(WarpBoard& bd, HistState& st, HistLists& L, int p, 
 
 // BoardHistory::passWouldEndPhase (:874-880) for the player to move
 __device__ __forceinline__ bool histPassWouldEndPhase(const WarpBoard& bd, const HistState& st, const HistLists& L, bool black, int koRule) {
-  if(st.passes + 1 >= 2) return true;
-  return koRule == KGB_KO_SIMPLE && passSeen(L, black, koHashOf(koRule, bd.h0, black));
+  if(koRule != KGB_KO_SPIGHT && st.passes + 1 >= 2) return true;
+  return koRuleSpightlike(koRule) && passSeen(L, black, koHashOf(koRule, bd.h0, black));
 }
 
 // Order-independent hash of a set of points (the superko bans enter the state / cache keys, boardhistory.cpp:1238-1244).

@@ -995,7 +995,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     gl[5] = selfKomi / 20.0f;
     if(d.multiSuicide) gl[8] = 1.0f;
     gl[14] = passEndsLeaf ? 1.0f : 0.0f;         // BoardHistory::passWouldEndPhase
-    if(d.koRule == KGB_KO_POSITIONAL) { gl[6] = 1.0f; gl[7] = 0.5f; }            // ko rule (nninputs.cpp:2612-2621)
+    if(d.koRule == KGB_KO_POSITIONAL || d.koRule == KGB_KO_SPIGHT) { gl[6] = 1.0f; gl[7] = 0.5f; }   // ko rule (nninputs.cpp:2612-2621)
     else if(d.koRule == KGB_KO_SITUATIONAL) { gl[6] = 1.0f; gl[7] = -0.5f; }
     // komi parity wave (nninputs.cpp:2696-2729)
     bool drawableKomisAreEven = (d.XY % 2) == 0;
@@ -1896,7 +1896,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.childOrder = sp->alloc<uint16_t>(G * N * PS);
   d.nodeMoments = sp->alloc<double>(G * N * 5); d.nodeNNMoments = sp->alloc<double>(G * N * 5); d.leafMoments = sp->alloc<double>(G * 5);
   d.koRule = c.ko_rule;
-  if(d.koRule < 0 || d.koRule > 2) throw std::invalid_argument("selfplay: ko_rule must be 0 (simple), 1 (positional) or 2 (situational)");
+  if(d.koRule < 0 || d.koRule > 3) throw std::invalid_argument("selfplay: ko_rule must be 0 (simple), 1 (positional), 2 (situational) or 3 (spight)");
   d.histRules = (c.full_history_rules || d.koRule != 0) ? 1 : 0;
   d.histCap = d.maxMoves + 8; d.pathCap = d.maxDepth + 8;
   d.gKo = sp->alloc<unsigned long long>(G * d.histCap); d.gPassB = sp->alloc<unsigned long long>(G * d.histCap); d.gPassW = sp->alloc<unsigned long long>(G * d.histCap);

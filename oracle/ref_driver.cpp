@@ -386,7 +386,7 @@ static int cmdChooseIdx(int argc, char** argv) {
   return 0;
 }
 
-// histstream X Y KORULE(0 simple,1 positional,2 situational) MULTISUICIDE SEED NGAMES MAXMOVES OUT
+// histstream X Y KORULE(0 simple,1 positional,2 situational,3 spight) MULTISUICIDE SEED NGAMES MAXMOVES OUT
 //   random games through the reference's BoardHistory (area scoring): moves are drawn from BoardHistory::isLegal, passes with
 //   probability 1/7 (also consecutive ones), until the history says the game is over.  Per move: flags (finished, noResult,
 //   passWouldEndPhase for the next player), hist.isLegal of every point for the next player, hist.superKoBanned.
@@ -399,7 +399,7 @@ static int cmdHistStream(int argc, char** argv) {
   Board::initHash();
   ScoreValue::initTables();
   Rules rules;
-  rules.koRule = koRule == 0 ? Rules::KO_SIMPLE : koRule == 1 ? Rules::KO_POSITIONAL : Rules::KO_SITUATIONAL;
+  rules.koRule = koRule == 0 ? Rules::KO_SIMPLE : koRule == 1 ? Rules::KO_POSITIONAL : koRule == 2 ? Rules::KO_SITUATIONAL : Rules::KO_SPIGHT;
   rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
   rules.multiStoneSuicideLegal = multi; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
   rules.friendlyPassOk = false; rules.komi = 7.5f;

@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DRIVER = os.path.join(HERE, "..", "..", "oracle", "_ref", "kgref_driver")
 cases = [("simple_3x3", 3, 3, 0, 1, 11, 60, 60), ("simple_4x4", 4, 4, 0, 0, 12, 60, 80), ("positional_3x3", 3, 3, 1, 1, 13, 60, 60),
          ("positional_5x4", 5, 4, 1, 0, 14, 40, 120), ("situational_3x3", 3, 3, 2, 1, 15, 60, 60), ("situational_5x5", 5, 5, 2, 1, 16, 30, 150),
-         ("positional_9x9", 9, 9, 1, 1, 17, 6, 300), ("simple_2x3", 3, 2, 0, 1, 18, 80, 50)]
+         ("positional_9x9", 9, 9, 1, 1, 17, 6, 300), ("simple_2x3", 3, 2, 0, 1, 18, 80, 50),
+         ("spight_3x3", 3, 3, 3, 1, 19, 60, 80), ("spight_4x4", 4, 4, 3, 0, 20, 40, 120)]
 for name, X, Y, ko, multi, seed, games, maxmoves in cases:
     tmp = os.path.join("/tmp", f"hist_{name}.bin")
     subprocess.run([DRIVER, "histstream", str(X), str(Y), str(ko), str(multi), str(seed), str(games), str(maxmoves), tmp], check=True)
