@@ -5,6 +5,13 @@ cd "$(dirname "$0")"
 OUT=../libkgb200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcompiler -Wall"
+# nothing to do when the library was built from exactly these sources (content hash; the object directory does not travel to
+# the GPU box and file times may not survive the copy)
+SRCHASH=$(cat *.cu *.cuh *.cpp *.h ../../include/*.h build.sh | sha256sum | cut -d' ' -f1)
+if [ -f $OUT ] && [ -f $OUT.srchash ] && [ "$(cat $OUT.srchash)" = "$SRCHASH" ] && [ -z "${KGB_FORCE_BUILD}" ]; then
+  echo "up to date $(readlink -f $OUT)"
+  exit 0
+fi
 mkdir -p ../_build
 for f in kgb_conv_tc.cu kgb_conv_tc2.cu kgb_kernels.cu kgb_api.cu kgb_selfplay.cu; do
   o=../_build/${f%.cu}.o
@@ -23,4 +30,5 @@ for f in kgb_model.cpp kgb_rand.cpp kgb_scorevalue.cpp; do
 done
 wait
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o ../_build/kgb_scorevalue.o -lz -cudart shared
+echo $SRCHASH > $OUT.srchash
 echo "built $(readlink -f $OUT)"
