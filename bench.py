@@ -269,7 +269,8 @@ def main():
                   subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8, use_graph_search=True, graph_search_rep_bound=11,
                   root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83, root_dirichlet_noise_weight=0.25,
                   root_policy_temperature=1.1, root_policy_temperature_early=1.5, chosen_move_temperature_halflife=19.0,
-                  nn_cache_size_power_of_two=args.nn_cache_pow2, root_num_symmetries_to_sample=4, use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
+                  nn_cache_size_power_of_two=args.nn_cache_pow2, root_num_symmetries_to_sample=4, ko_rule=0, full_history_rules=True,
+                  use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
                   chosen_move_temperature=0.15, chosen_move_temperature_early=0.75, chosen_move_subtract=0.0, chosen_move_prune=1.0,
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
@@ -336,7 +337,7 @@ def main():
                        "search_params": "selfplay8mainb18.cfg: cpuct 1.05/0.28/500, fpu 0.2 (root 0), fpuParentWeightByVisitedPolicy^2, valueWeightExponent 0.5, "
                                         "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8, useGraphSearch (repBound 11), root Dirichlet noise 10.83/0.25, root policy temperature 1.1 (early 1.5), move choice by play selection values with LCB 5.0/0.15 and chosenMoveTemperature 0.75->0.15; rootNumSymmetriesToSample 4; not yet: rootEndingBonusPoints, rootPruneUselessMoves, "
                                         "",
-                       "rules": "area scoring, simple ko, multi-stone suicide legal, komi 7.5 (superko / territory rules pending)",
+                       "rules": "area scoring, simple ko with BoardHistory's game-end rules (two passes, spight-like ending pass, third repetition = no result), multi-stone suicide legal, komi 7.5 (positional / situational / spight superko available via ko_rule; territory scoring and encore not built)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
                        "weights": "random init, real architecture (katago_b200/modelgen.py)",
                        "positions": f"every game starts from its own random legal play-out of 0..{args.opening_max} moves, then {W + args.settle_waves} untimed waves",

@@ -231,6 +231,9 @@ KGB_API int kgb_selfplay_get_play_selection_values(kgb_selfplay* sp, int game, d
  * seeded with seed_string. */
 KGB_API int kgb_test_choose_index_with_temperature(const char* seed_string, const double* relative_probs, int n, double temperature,
                                                    double only_below_prob, int count, int32_t* chosen);
+/* TEST HOOK (row a23): Board::simpleRepetitionBoundGt(move, bound) after every move of a stream (x, y, player 1 black / 2 white; x < 0 pass)
+ * - the predicate that decides whether a graph-search node may be shared between histories (game/board.cpp:2853-2888). */
+KGB_API int kgb_test_repetition_bound(int x_len, int y_len, int num_moves, int bound, const int8_t* moves_xyp, uint8_t* out);
 /* TEST HOOK (row a3): replay num_games games (moves_xy [game][max_moves][2]: x,y; -1,-1 pass; -2 = end of that game; black first) through
  * the device ko rules (ko_rule 0 simple, 1 positional, 2 situational, 3 spight; area scoring).  Per move: flags (1 game over, 2 no result,
  * 4 a pass by the next player would end the phase), legality of every point for the next player (incl. ko and superko bans), and

@@ -891,6 +891,13 @@ KGB_API int kgb_test_history_replay(int x_len, int y_len, int ko_rule, int multi
   });
 }
 
+KGB_API int kgb_test_repetition_bound(int x_len, int y_len, int num_moves, int bound, const int8_t* moves_xyp, uint8_t* out) {
+  return guarded([&] {
+    if(!moves_xyp || !out || num_moves < 1) throw std::invalid_argument("kgb_test_repetition_bound: bad argument");
+    repBoundTest(x_len, y_len, num_moves, bound, moves_xyp, out);
+  });
+}
+
 KGB_API int kgb_test_root_policy_noise(const char* seed_string, int x_len, int y_len, int policy_size, int turn_number, int noise_enabled,
                                        double concentration, double weight, double temperature, double temperature_early, double halflife,
                                        const float* policy_in, float* policy_out) {

@@ -878,6 +878,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       }
       if(found < 0) nodeInit(d, (gb + child) * d.policySize, lane);
       __syncwarp();
+      // a new edge onto an existing node starts with 0 visits against the node's n: it catches up right away instead of
+      // descending (search.cpp:1382-1389, the same maybeCatchUpEdgeVisits as for existing edges)
+      if(found >= 0 && d.nodeVisits[gb + found] > 0) { instant = true; break; }
     }
     depth++;
     if(d.useGraphSearch) {
@@ -1783,6 +1786,20 @@ __global__ void boardReplayKernel(int X, int Y, int numBoards, int numMoves, int
   }
 }
 
+// Test kernel for Board::simpleRepetitionBoundGt: one board, a move stream (x, y, pla 1/2), flag after every move.
+__global__ void repBoundKernel(int X, int Y, int numMoves, int bound, const int8_t* moves, uint8_t* out) {
+  const int lane = threadIdx.x & 31;
+  if(blockIdx.x != 0 || threadIdx.x >= 32) return;
+  WarpBoard bd;
+  boardInit(bd, X, Y);
+  for(int m = 0; m < numMoves; m++) {
+    const int p = moves[m * 3] < 0 ? -1 : (moves[m * 3 + 1] * 32 + moves[m * 3]);
+    boardPlay(bd, p, moves[m * 3 + 2] == 1);
+    const bool r = simpleRepetitionBoundGt(bd, p, bound);
+    if(lane == 0) out[m] = r ? 1 : 0;
+  }
+}
+
 // Rules test kernel: replays games through histMakeMove (parity tests against the reference BoardHistory fixtures).
 __global__ void historyReplayKernel(int X, int Y, int koRule, int multiSuicide, int numGames, int maxMoves, const int8_t* moves /*[g][m][2]*/,
                                     const ZobEntry* zob, unsigned long long* lists /*[g][3][maxMoves+2]*/, uint8_t* flags /*[g][m]*/,
@@ -1898,7 +1915,8 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.koRule = c.ko_rule;
   if(d.koRule < 0 || d.koRule > 3) throw std::invalid_argument("selfplay: ko_rule must be 0 (simple), 1 (positional), 2 (situational) or 3 (spight)");
   d.histRules = (c.full_history_rules || d.koRule != 0) ? 1 : 0;
-  d.histCap = d.maxMoves + 8; d.pathCap = d.maxDepth + 8;
+  d.histCap = (d.maxMoves > 1024 ? d.maxMoves : 1024) + 16;   // also holds openings given by kgb_selfplay_play_moves (up to 1024 moves)
+  d.pathCap = d.maxDepth + 8;
   d.gKo = sp->alloc<unsigned long long>(G * d.histCap); d.gPassB = sp->alloc<unsigned long long>(G * d.histCap); d.gPassW = sp->alloc<unsigned long long>(G * d.histCap);
   d.gKoLen = sp->alloc<int>(G); d.gPassBLen = sp->alloc<int>(G); d.gPassWLen = sp->alloc<int>(G);
   d.gEverOcc = sp->alloc<uint32_t>(G * 32); d.rootBanned = sp->alloc<uint32_t>(G * 32);
@@ -2169,6 +2187,17 @@ void historyReplay(int X, int Y, int koRule, int multiSuicide, int numGames, int
   cudaError_t e = cudaDeviceSynchronize();
   if(e == cudaSuccess) { cudaMemcpy(flags, dFlags, nm, cudaMemcpyDeviceToHost); cudaMemcpy(legal, dLegal, cells, cudaMemcpyDeviceToHost); cudaMemcpy(banned, dBanned, cells, cudaMemcpyDeviceToHost); }
   cudaFree(dMoves); cudaFree(dFlags); cudaFree(dLegal); cudaFree(dBanned); cudaFree(dLists); cudaFree(dZob);
+  SPCK(e);
+}
+
+void repBoundTest(int X, int Y, int numMoves, int bound, const int8_t* moves, uint8_t* out) {
+  int8_t* dm; uint8_t* dout;
+  SPCK(cudaMalloc(&dm, (size_t)numMoves * 3)); SPCK(cudaMalloc(&dout, numMoves));
+  SPCK(cudaMemcpy(dm, moves, (size_t)numMoves * 3, cudaMemcpyHostToDevice));
+  repBoundKernel<<<1, 32>>>(X, Y, numMoves, bound, dm, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if(e == cudaSuccess) e = cudaMemcpy(out, dout, numMoves, cudaMemcpyDeviceToHost);
+  cudaFree(dm); cudaFree(dout);
   SPCK(e);
 }
 

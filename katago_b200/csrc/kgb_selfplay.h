@@ -34,6 +34,7 @@ void selfplayReadPlaySelection(SelfplayImpl* sp, int g, double* out);
 void chooseIndexTest(const char* seedString, const double* probs, int n, double temperature, double onlyBelowProb, int count, int* out);
 void historyReplay(int X, int Y, int koRule, int multiSuicide, int numGames, int maxMoves, const int8_t* moves, uint8_t* flags, uint8_t* legal,
                    uint8_t* banned);
+void repBoundTest(int X, int Y, int numMoves, int bound, const int8_t* moves, uint8_t* out);
 void rootNoiseTest(const char* seedString, int X, int Y, int policySize, int turnNumber, int noise, double concentration, double weight,
                    double temperature, double temperatureEarly, double halflife, const float* policyIn, float* policyOut);
 void boardReplay(int X, int Y, int numBoards, int numMoves, int multiSuicide, const int8_t* moves, uint8_t* colors, int8_t* ko, int16_t* caps,

@@ -431,6 +431,27 @@ static int cmdHistStream(int argc, char** argv) {
   return 0;
 }
 
+// repbound X Y NMOVES SEED BOUND: random legal move stream (like boardstream); after every move prints x y pla and
+// Board::simpleRepetitionBoundGt(moveLoc, BOUND) on the board after the move (game/board.cpp:2853-2888).
+static int cmdRepBound(int argc, char** argv) {
+  if(argc != 7) { cerr << "usage: repbound X Y NMOVES SEED BOUND" << endl; return 1; }
+  int X = atoi(argv[2]), Y = atoi(argv[3]), nMoves = atoi(argv[4]), bound = atoi(argv[6]);
+  Lcg rng(strtoull(argv[5], NULL, 10));
+  Board::initHash();
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  for(int step = 0; step < nMoves; step++) {
+    vector<Loc> legal;
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(board.isLegal(l, pla, true)) legal.push_back(l); }
+    Loc mv = (legal.empty() || rng.next() % 30 == 0) ? Board::PASS_LOC : legal[rng.next() % legal.size()];
+    board.playMoveAssumeLegal(mv, pla);
+    int x = mv == Board::PASS_LOC ? -1 : Location::getX(mv, X), y = mv == Board::PASS_LOC ? -1 : Location::getY(mv, X);
+    cout << x << " " << y << " " << (int)pla << " " << (board.simpleRepetitionBoundGt(mv, bound) ? 1 : 0) << endl;
+    pla = getOpp(pla);
+  }
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -510,6 +531,7 @@ int main(int argc, char** argv) {
   if(cmd == "rootnoise") return cmdRootNoise(argc, argv);
   if(cmd == "chooseidx") return cmdChooseIdx(argc, argv);
   if(cmd == "histstream") return cmdHistStream(argc, argv);
+  if(cmd == "repbound") return cmdRepBound(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

@@ -136,6 +136,10 @@ if __name__ == "__main__":
         (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), dict(SELFPLAY8B18, useGraphSearch=1, koRule=1, **BIAS, **LCB)),
         (5, 5, 1000, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"fullHistoryRules": 1, "useGraphSearch": 1}),
         (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 55), dict(SELFPLAY8B18, fullHistoryRules=1)),
+        (5, 5, 1000, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"fullHistoryRules": 1}),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"koRule": 2}),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"useGraphSearch": 1}),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {}),
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):
