@@ -210,8 +210,8 @@ typedef struct kgb_selfplay_stats {
   uint64_t sum_leaf_depth;   /* sum over playouts of the leaf depth */
   uint64_t ladder_searches;  /* ladder searches run for feature planes 14-17 */
   uint64_t ladder_nodes;     /* moves played inside those searches */
-  uint64_t stalled_waves;    /* game-waves without a leaf: ladder searches still running (ladder_nodes_per_wave), or every playout
-                                of the wave ended on an existing edge */
+  uint64_t stalled_waves;    /* game-waves that finished no playout: ladder searches still running (ladder_nodes_per_wave), every
+                                playout of the wave ended on an existing edge, or one of the root's extra symmetric evaluations */
   uint64_t instant_playouts; /* graph search: playouts that ended on an edge catch-up or a cycle and needed no evaluation */
   uint64_t nn_cache_hits;    /* playouts whose leaf evaluation came from the evaluation cache */
   uint64_t nn_cache_stores;

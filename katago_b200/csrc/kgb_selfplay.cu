@@ -1533,14 +1533,14 @@ __global__ void spBackupKernel(const SPDev d) {
         const double cap = sqrt((double)d.XY) * d.dynamicScoreCenterScale;
         if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
         if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
-        if(lane == 0) { d.recentScoreCenter[g] = c; d.rootSymCount[g] = 1; }
+        if(lane == 0) { d.recentScoreCenter[g] = c; d.rootSymCount[g] = 1; atomicAdd(d.stalledWaves, 1ULL); }   // a wave without a playout
         return;
       }
       float* acc = d.rootSymAcc + g * 8;
       if(lane < 6) acc[lane] = symCount > 0 ? acc[lane] + vals[lane] : vals[lane];
       __syncwarp();
       if(symCount + 1 < d.rootNumSymmetries) {
-        if(lane == 0) d.rootSymCount[g] = symCount + symLead + 1;   // the root stays unvisited: the next wave evaluates it under the next symmetry
+        if(lane == 0) { d.rootSymCount[g] = symCount + symLead + 1; atomicAdd(d.stalledWaves, 1ULL); }   // the root stays unvisited: next wave, next symmetry
         return;
       }
       const float floatLen = (float)d.rootNumSymmetries;
