@@ -23,6 +23,7 @@
 #include "search/searchnode.h"
 #include "search/distributiontable.h"
 #include "core/fancymath.h"
+#include "dataio/numpywrite.h"
 #include "core/logger.h"
 
 #include <cstdint>
@@ -452,6 +453,27 @@ static int cmdRepBound(int argc, char** argv) {
   return 0;
 }
 
+// npyheader ROWS: the 256-byte NumPy headers the reference's NumpyBuffer writes (dataio/numpywrite.cpp:97-226) for the seven arrays of a
+// training .npz with ROWS rows (trainingwrite.cpp:854-886), as hex, one line per array: name hex
+static int cmdNpyHeader(int argc, char** argv) {
+  if(argc != 3) { cerr << "usage: npyheader ROWS" << endl; return 1; }
+  int64_t rows = atoll(argv[2]);
+  const int64_t maxRows = rows > 4 ? rows : 4;
+  auto dump = [&](const char* name, const char* hdr) {
+    cout << name << " ";
+    for(int i = 0; i < 256; i++) cout << Global::strprintf("%02x", (unsigned)(unsigned char)hdr[i]);
+    cout << endl;
+  };
+  { NumpyBuffer<uint8_t> b({maxRows, 22, 46}); b.prepareHeaderWithNumRows(rows); dump("binaryInputNCHWPacked", (const char*)b.dataIncludingHeader); }
+  { NumpyBuffer<float> b({maxRows, 19}); b.prepareHeaderWithNumRows(rows); dump("globalInputNC", (const char*)b.dataIncludingHeader); }
+  { NumpyBuffer<int16_t> b({maxRows, 2, 362}); b.prepareHeaderWithNumRows(rows); dump("policyTargetsNCMove", (const char*)b.dataIncludingHeader); }
+  { NumpyBuffer<float> b({maxRows, 80}); b.prepareHeaderWithNumRows(rows); dump("globalTargetsNC", (const char*)b.dataIncludingHeader); }
+  { NumpyBuffer<int8_t> b({maxRows, 842}); b.prepareHeaderWithNumRows(rows); dump("scoreDistrN", (const char*)b.dataIncludingHeader); }
+  { NumpyBuffer<int8_t> b({maxRows, 5, 19, 19}); b.prepareHeaderWithNumRows(rows); dump("valueTargetsNCHW", (const char*)b.dataIncludingHeader); }
+  { NumpyBuffer<int16_t> b({maxRows, 3, 362}); b.prepareHeaderWithNumRows(rows); dump("qValueTargetsNCMove", (const char*)b.dataIncludingHeader); }
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -532,6 +554,7 @@ int main(int argc, char** argv) {
   if(cmd == "chooseidx") return cmdChooseIdx(argc, argv);
   if(cmd == "histstream") return cmdHistStream(argc, argv);
   if(cmd == "repbound") return cmdRepBound(argc, argv);
+  if(cmd == "npyheader") return cmdNpyHeader(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;
