@@ -357,7 +357,7 @@ def main():
             "gpu_launches": sp.launches_per_step * K,
             "roofline": {"bound": "tensor", "kernel": f"kgb_conv_tc_kernel 3x3 {mid}->{mid}, batch {n}", "achieved": achieved,
                          "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"],
-                         "traffic": 41.4e6 if args.model == "b18c384nbt" and n == 256 else None,
+                         "traffic": 43.1e6 if args.model == "b18c384nbt" and n == 256 else None,   # dram read 40.46 MB + write 2.62 MB per launch (profiles/r01_conv3x3_192_ncu_raw.csv)
                          "peak_source": peaks["source"] + " (burst cuBLAS bf16, kernel timed alone)",
                          "ms_per_launch": float(ms_conv[0]),
                          "whole_forward_tflops": whole, "whole_forward_frac_of_sustained": whole / peaks["tflops_sustained"]},
