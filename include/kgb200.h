@@ -221,6 +221,9 @@ typedef struct kgb_selfplay_stats {
  * n independent lookups.  Test hook for the score-utility table. */
 KGB_API int kgb_expected_white_score_value(int n, const double* mean, const double* stdev, const double* center, const double* scale,
                                            const double* sqrt_board_area, double* out);
+/* The first n 32-bit outputs of the reference's Rand(seed_string) as the library's host generator produces them (core/rand.h:149-152,
+ * core/rand.cpp:279-320).  Test hook (row a25): the reference's own self-test vector for "abc" (core/rand.cpp:386-415) pins it. */
+KGB_API int kgb_rand_uint32_stream(const char* seed_string, int n, uint32_t* out);
 /* The value-weighting CDF table the device loop uploads (Search's DistributionTable over tdistcdf(z, 3), search.cpp:131-137):
  * n must be 2000.  Test hook (row a20). */
 KGB_API int kgb_value_weight_cdf_table(double* out, int n);

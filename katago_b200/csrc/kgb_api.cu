@@ -857,6 +857,14 @@ KGB_API int kgb_expected_white_score_value(int n, const double* mean, const doub
   });
 }
 
+KGB_API int kgb_rand_uint32_stream(const char* seed_string, int n, uint32_t* out) {
+  return guarded([&] {
+    if(!seed_string || !out || n < 0) throw std::invalid_argument("kgb_rand_uint32_stream: bad argument");
+    RefRand r(seed_string);
+    for(int i = 0; i < n; i++) out[i] = r.nextUInt();
+  });
+}
+
 KGB_API int kgb_value_weight_cdf_table(double* out, int n) {
   return guarded([&] {
     if(!out || n != VW_TABLE_SIZE) throw std::invalid_argument("kgb_value_weight_cdf_table: out must hold 2000 doubles");

@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def load_library():
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
     lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
     lib.kgb_value_weight_cdf_table.argtypes = [P, I]
+    lib.kgb_rand_uint32_stream.argtypes = [C.c_char_p, I, P]
     lib.kgb_test_repetition_bound.argtypes = [I, I, I, I, P, P]
     lib.kgb_test_history_replay.argtypes = [I, I, I, I, I, I, P, P, P, P]
     lib.kgb_selfplay_get_play_selection_values.argtypes = [P, I, P]
@@ -367,6 +368,12 @@ def history_replay(x, y, ko_rule, multi_stone_suicide_legal, moves):
     _check(load_library().kgb_test_history_replay(x, y, ko_rule, int(multi_stone_suicide_legal), g, m, mv.ctypes.data, flags.ctypes.data,
                                                   legal.ctypes.data, banned.ctypes.data))
     return flags, legal, banned
+
+
+def rand_uint32_stream(seed_string: str, n: int):
+    out = np.zeros(n, np.uint32)
+    _check(load_library().kgb_rand_uint32_stream(seed_string.encode(), n, out.ctypes.data))
+    return out
 
 
 def value_weight_cdf_table():

@@ -149,3 +149,12 @@ def test_search_shaped_facade_compiles_against_the_abi(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-Wall", "-I", root, str(src), "-o", str(exe), "-L", os.path.join(root, "katago_b200"), "-lkgb200",
                     "-Wl,-rpath," + os.path.join(root, "katago_b200")], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_rand_reproduces_the_reference_self_test_vector():
+    """Row a25: the reference's own known-answer test for its generator (core/rand.cpp:386-415: Rand("abc"), 24 outputs)."""
+    from katago_b200.nn_backend import rand_uint32_stream
+    expected = [0x1C6B83BD, 0xFB7677DB, 0x698688D5, 0xA3CD21C3, 0xD0AD5B77, 0x8F889E6E, 0x22852278, 0xD71A114D, 0x295EF301, 0xAA0CCA48, 0x0B7271BB,
+                0x4FE798FB, 0x26B4DD4B, 0x78B77C1B, 0x231C4DFB, 0x17FB87C6, 0x9CC23870, 0x1C2C2CF7, 0x62D51240, 0xF1D1A7FF, 0x44C45C0A, 0xF93ACFCE,
+                0x42B1D236, 0xC1069B75]
+    assert rand_uint32_stream("abc", 24).tolist() == expected
