@@ -9,10 +9,16 @@ and packs the binary input planes like `packBits` (trainingwrite.cpp:314-334: 8 
 What fills the arrays: `rows_from_root_observations` turns what the device loop exposes for a root position - the fillRowV7 row
 and the root's play selection values - into rows with the input planes, the global inputs and policy target 0
 (`Play::extractPolicyTarget`, program/play.cpp:810-846: the selection values scaled so that the largest is at least 10, capped at
-30000, rounded to int16; `fillPolicyTarget`, trainingwrite.cpp:346-357).  The value / ownership / score / Q targets of `TrainingWriteBuffers::addRow` (:448-852) need the
-finished game and are NOT built yet: their weights in globalTargetsNC (C27, C28, C29, C33, C34; C24 and C35 = 1) say so, which
-is the reference's own way of marking a row's missing targets.
+30000, rounded to int16; `fillPolicyTarget`, trainingwrite.cpp:346-357), every game-dependent target at weight zero.
+
+`TrainingWriteBuffers` mirrors the reference class of that name: `add_row` restates `addRow` (trainingwrite.cpp:448-852) - TD value
+targets, lead, time of arrival, weights, history masks, game hash, metadata, score distribution, ownership / future boards /
+scoring planes, Q targets - including the stochastic rounding, which draws from the reference's `Rand` in the reference's order
+(`RowRand`), so a row is equal to the reference's byte for byte given the same arguments and seed (tests/test_npz_writer.py
+against tests/golden/addrow_*.json, dumped from the reference's own addRow).  The input planes and global inputs of a row are
+what the device loop's fillRowV7 produced; this module does not recompute them.
 """
+import math
 import zipfile
 
 import numpy as np
@@ -102,3 +108,239 @@ def rows_from_root_observations(spatial_nhwc, global_in, play_selection_values, 
     if num_visits is not None:
         gt[:, 60] = np.asarray(num_visits, np.float32)
     return out
+
+
+class RowRand:
+    """The reference's `Rand` (core/rand.h) as far as addRow uses it: nextDouble (:245-257, 53 bits of nextUInt64 = two
+    nextUInt, low word first) and nextBool (:271-274).  The uint32 stream comes from the library's host Rand twin."""
+
+    def __init__(self, seed_string: str, prefetch: int = 4096):
+        self._seed, self._n, self._i = seed_string, 0, 0
+        self._buf = np.zeros(0, np.uint32)
+        self._grow(prefetch)
+
+    def _grow(self, n):
+        from .nn_backend import rand_uint32_stream
+        self._buf = rand_uint32_stream(self._seed, n)     # a longer stream of the same seed has the old one as its prefix
+        self._n = n
+
+    def next_uint(self) -> int:
+        if self._i >= self._n:
+            self._grow(self._n * 2)
+        v = int(self._buf[self._i])
+        self._i += 1
+        return v
+
+    def next_double(self) -> float:
+        lo = self.next_uint()
+        hi = self.next_uint()
+        return float((lo | (hi << 32)) & ((1 << 53) - 1)) / float(1 << 53)
+
+    def next_bool(self, prob: float) -> bool:
+        return self.next_double() < prob
+
+
+_f32 = np.float32
+
+
+def _c_round(x) -> int:
+    """C `round`: halves away from zero."""
+    x = float(x)
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def _clamp_to_radius(x, radius: int, rand: RowRand) -> int:
+    """clampToRadius120 / clampToRadius32000 (trainingwrite.cpp:358-383): x (float32) to an integer whose expectation is x."""
+    x = _f32(x)
+    low = int(math.floor(float(x)))
+    high = low + 1
+    if low < -radius:
+        return -radius
+    if high > radius:
+        return radius
+    lam = _f32(x - _f32(low))
+    if lam == 0.0:
+        return low
+    return high if rand.next_bool(float(lam)) else low
+
+
+def _value_td_targets(white_value_targets, idx, white_to_move, now_factor):
+    """fillValueTDTargets (trainingwrite.cpp:411-446): exponentially weighted average of the value targets from this turn on."""
+    win = loss = no_result = score = 0.0
+    weight_left = 1.0
+    n = len(white_value_targets)
+    for i in range(idx, n):
+        if i == n - 1:
+            weight_now, weight_left = weight_left, 0.0
+        else:
+            weight_now = weight_left * now_factor
+            weight_left *= (1.0 - now_factor)
+        t = white_value_targets[i]
+        w, l, nr, sc = float(_f32(t[0])), float(_f32(t[1])), float(_f32(t[2])), float(_f32(t[3]))
+        win += weight_now * (w if white_to_move else l)
+        loss += weight_now * (l if white_to_move else w)
+        no_result += weight_now * nr
+        score += weight_now * (sc if white_to_move else -sc)
+    cap = 19 * 19 + SCORE_DISTR_RADIUS          # NNPos::MAX_BOARD_AREA + EXTRA_SCORE_DISTR_RADIUS
+    score = min(max(score, -cap), cap)
+    return [_f32(win), _f32(loss), _f32(no_result), _f32(score)]
+
+
+P_BLACK, P_WHITE = 1, 2
+
+
+class TrainingWriteBuffers:
+    """Row buffers of one output file, like the reference's class (dataio/trainingwrite.h:245-352).  Boards are x_size * y_size
+    inside a data_len * data_len frame (pos = y * data_len + x, pass = data_len^2).  Colours: 0 empty, 1 black, 2 white."""
+
+    def __init__(self, max_rows: int, data_len: int = 19):
+        self.L, self.max_rows, self.cur_rows = data_len, max_rows, 0
+        self.arrays = {k: np.zeros((max_rows,) + tuple(rest), np.dtype(descr)) for k, (descr, rest) in schema(data_len).items()}
+
+    def _pos(self, x, y):
+        return self.L * self.L if x < 0 else y * self.L + x     # NNPos::locToPos
+
+    def add_row(self, *, x_size, y_size, next_player, packed_input, global_input, turn_idx, target_weight, unreduced_num_visits,
+                policy_target0, policy_target1, policy_surprise, policy_entropy, search_entropy, white_value_targets, white_q_value_targets,
+                white_value_targets_idx, value_target_weight, td_value_target_weight, lead_target_weight_factor, nn_raw_stats,
+                final_full_area, final_ownership, final_white_scoring, pos_hist_for_future_boards, is_side_position,
+                num_neural_nets_behind_latest, game_hash, num_changed_neural_nets, hit_turn_limit, num_extra_black, mode, rand: RowRand,
+                self_komi, area_scoring_or_encore2=True, start_hist_moves=0, initial_turn_number=0, white_bonus_now=0.0, white_bonus_end=0.0,
+                end_finished=True, end_no_result=False, always_pass_alive_under_suicide_rules=False, reanalysis=(False, 0.0, 0.0, 0)):
+            """One row.  Arguments follow addRow's (trainingwrite.cpp:448-485); what addRow reads from its three BoardHistory
+            arguments is passed as scalars (self_komi = hist.currentSelfKomi(nextPlayer, drawEquivalentWinsForWhite), ...).
+            policy targets: list of (x, y, value) with x < 0 for pass, or None.  white_value_targets: per turn
+            (win, loss, noResult, score, hasLead, lead).  white_q_value_targets: list of (x, y, winLoss, score, visits).
+            final_* planes: row-major [y_size * x_size] or None.  pos_hist_for_future_boards: one board per value target, or None."""
+            if self.cur_rows >= self.max_rows:
+                raise ValueError("TrainingWriteBuffers full")
+            L, A, r = self.L, self.L * self.L, self.cur_rows
+            P = A + 1
+            white = next_player == P_WHITE
+            opp = P_BLACK if white else P_WHITE
+            self.arrays["binaryInputNCHWPacked"][r] = packed_input
+            self.arrays["globalInputNC"][r] = global_input
+            g = self.arrays["globalTargetsNC"][r]
+            g[:] = 0
+            g[25] = target_weight
+            pol = self.arrays["policyTargetsNCMove"][r]
+            for ch, wt_col, target in ((0, 26, policy_target0), (1, 28, policy_target1)):
+                if target is None:
+                    pol[ch, :] = 1                       # uniformPolicyTarget, weight 0
+                    g[wt_col] = 0.0
+                else:
+                    pol[ch, :] = 0
+                    for (x, y, v) in target:
+                        pol[ch, self._pos(x, y)] = v
+                    g[wt_col] = 1.0
+            board_area = x_size * y_size
+            idx = white_value_targets_idx
+            for k, now_factor in enumerate((0.0, 1.0 / (1.0 + board_area * 0.176), 1.0 / (1.0 + board_area * 0.056), 1.0 / (1.0 + board_area * 0.016), 1.0)):
+                g[4 * k:4 * k + 4] = _value_td_targets(white_value_targets, idx, white, now_factor)
+            vtw, tdw = _f32(value_target_weight), _f32(td_value_target_weight)
+            no_result_end = bool(end_finished) and bool(end_no_result)
+            this = white_value_targets[idx]
+            if this[4] and not no_result_end:
+                lead = _f32(this[5]) if white else -_f32(this[5])
+                cap = _f32(19 * 19 + SCORE_DISTR_RADIUS)
+                g[21] = min(max(lead, -cap), cap)
+                g[29] = vtw * _f32(lead_target_weight_factor)
+            s = 0.0
+            for i in range(idx + 1, len(white_value_targets)):
+                prev, cur = white_value_targets[i - 1], white_value_targets[i]
+                prev_wl = float(_f32(prev[0]) - _f32(prev[1]))
+                next_wl = float(_f32(cur[0]) - _f32(cur[1]))
+                s += (i - idx) * ((next_wl - prev_wl) * (next_wl - prev_wl))
+            g[22] = s
+            g[24] = _f32(1.0) - tdw
+            g[30], g[31], g[32] = policy_surprise, policy_entropy, search_entropy
+            g[35] = _f32(1.0) - vtw
+            use = True
+            for k in range(5):                           # each earlier history step is kept with probability 0.98 (:628-637)
+                use = use and rand.next_double() < 0.98
+                g[36 + k] = 1.0 if use else 0.0
+            h0, h1 = int(game_hash[0]), int(game_hash[1])
+            g[41], g[42], g[43] = h0 & 0x3FFFFF, (h0 >> 22) & 0x3FFFFF, (h0 >> 44) & 0xFFFFF
+            g[44], g[45], g[46] = h1 & 0x3FFFFF, (h1 >> 22) & 0x3FFFFF, (h1 >> 44) & 0xFFFFF
+            g[47] = self_komi
+            g[48] = 1.0 if area_scoring_or_encore2 else 0.0
+            g[49] = 1.0 if num_changed_neural_nets > 0 else 0.0
+            g[50] = num_neural_nets_behind_latest
+            g[51] = turn_idx
+            g[52] = 1.0 if hit_turn_limit else 0.0
+            g[53] = start_hist_moves
+            g[54] = num_extra_black
+            g[55] = mode
+            g[56] = initial_turn_number
+            g[57] = nn_raw_stats[0] if white else -nn_raw_stats[0]
+            g[58] = nn_raw_stats[1] if white else -nn_raw_stats[1]
+            g[59] = nn_raw_stats[2]
+            g[60] = unreduced_num_visits
+            if not is_side_position:
+                wb = _f32(white_bonus_end) - _f32(white_bonus_now)
+                sb = wb if white else -wb
+                g[61] = sb if sb != 0 else 0.0
+            g[62] = 1.0 if (not is_side_position and end_finished and not hit_turn_limit) else 0.0
+            g[63] = 3.0
+            if reanalysis[0]:
+                g[64], g[65], g[66], g[67] = 1.0, reanalysis[1], reanalysis[2], float(reanalysis[3])
+
+            sd = self.arrays["scoreDistrN"][r]
+            own = self.arrays["valueTargetsNCHW"][r].reshape(VALUE_SPATIAL_CHANNELS, A)
+            sd[:] = 0
+            own[:] = 0
+            sd_len, sd_mid = 2 * A + 2 * SCORE_DISTR_RADIUS, A + SCORE_DISTR_RADIUS
+            frame = (np.arange(y_size)[:, None] * L + np.arange(x_size)[None, :]).reshape(-1)    # NNPos::xyToPos of the board's points
+            if final_ownership is None or no_result_end:
+                sd[sd_mid - 1] = 50
+                sd[sd_mid] = 50
+            else:
+                g[27] = vtw
+                last = white_value_targets[-1]
+                score = _f32(last[3]) if white else -_f32(last[3])
+                g[20] = score
+                fo, fa = np.asarray(final_ownership).reshape(-1), np.asarray(final_full_area).reshape(-1)
+                own[0, frame] = np.where(fo == next_player, 1, np.where(fo == opp, -1, 0))
+                own[1, frame] = np.where((fa != 0) & (fo == 0), np.where(fa == next_player, 1, -1), 0)
+                center = _c_round(score)
+                lower, upper = center + sd_mid - 1, center + sd_mid
+                if upper <= 0:
+                    sd[0] = 100
+                elif lower >= sd_len - 1:
+                    sd[sd_len - 1] = 100
+                else:
+                    lam = _f32(score - _f32(_f32(center) - _f32(0.5)))
+                    up = _c_round(_f32(lam * _f32(100.0)))
+                    sd[lower] = 100 - up
+                    sd[upper] = up
+            if pos_hist_for_future_boards is not None:
+                boards = pos_hist_for_future_boards
+                if len(boards) != len(white_value_targets):
+                    raise ValueError("pos_hist_for_future_boards must hold one board per value target")
+                g[33] = 1.0
+                end = len(boards) - 1
+                for ch, ahead in ((2, 8), (3, 32)):
+                    b = np.asarray(boards[min(idx + ahead, end)]).reshape(-1)
+                    own[ch, frame] = np.where(b == next_player, 1, np.where(b == opp, -1, 0))
+            if final_white_scoring is not None and not no_result_end:
+                g[34] = vtw
+                sc = np.asarray(final_white_scoring, np.float32).reshape(-1)
+                for j in range(board_area):               # y, x order: the order the reference draws its random numbers in
+                    v = sc[j] if white else -sc[j]
+                    own[4, frame[j]] = _clamp_to_radius(_f32(v * _f32(120.0)), 120, rand)
+            q = self.arrays["qValueTargetsNCMove"][r]
+            q[:] = 0
+            cap = _f32(19 * 19 + SCORE_DISTR_RADIUS)
+            for (x, y, wl, sc, visits) in white_q_value_targets:          # fillQValueTarget (:385-409)
+                pos = self._pos(x, y)
+                wl = _f32(wl) if white else -_f32(wl)
+                sc = _f32(sc) if white else -_f32(sc)
+                sc = min(max(sc, -cap), cap)
+                q[0, pos] = _clamp_to_radius(_f32(wl * _f32(32000.0)), 32000, rand)
+                q[1, pos] = _clamp_to_radius(_f32(sc * _f32(60.0)), 32000, rand)
+                q[2, pos] = max(0, min(int(visits), 32000))
+            self.cur_rows += 1
+
+    def write_to_zip_file(self, path: str, compress: bool = True):
+        """writeToZipFile (trainingwrite.cpp:854-886): the first cur_rows rows of every array."""
+        return write_npz(path, {k: v[:self.cur_rows] for k, v in self.arrays.items()}, self.L, compress)

@@ -24,6 +24,7 @@
 #include "search/distributiontable.h"
 #include "core/fancymath.h"
 #include "dataio/numpywrite.h"
+#include "dataio/trainingwrite.h"
 #include "core/logger.h"
 
 #include <cstdint>
@@ -474,6 +475,176 @@ static int cmdNpyHeader(int argc, char** argv) {
   return 0;
 }
 
+// addrow X Y DATALEN NTURNS SEED NORESULT BONUS OUT.json: TrainingWriteBuffers::addRow (dataio/trainingwrite.cpp:448-852) on a synthetic
+// finished game: NTURNS random legal moves, random value / Q / policy targets, Benson ownership of the final board, random scoring
+// plane; one row per turn with every optional argument toggled by the turn index.  Dumps each row's arguments and the seven
+// buffers the reference filled.  The row Rand is Rand("addrow"+SEED), shared by all rows like the writer's own.
+static int cmdAddRow(int argc, char** argv) {
+  if(argc != 10) { cerr << "usage: addrow X Y DATALEN NTURNS SEED NORESULT BONUS OUT.json" << endl; return 1; }
+  const int X = atoi(argv[2]), Y = atoi(argv[3]), D = atoi(argv[4]), nTurns = atoi(argv[5]);
+  const string seedStr = argv[6];
+  const bool endNoResult = atoi(argv[7]) != 0;
+  const float bonus = (float)atof(argv[8]);
+  Board::initHash();
+  ScoreValue::initTables();
+  Rules rules;
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.friendlyPassOk = false; rules.komi = 7.0f;
+  Lcg rng(strtoull(seedStr.c_str(), NULL, 10));
+  auto unif = [&]() { return (float)((rng.next() & 0xFFFFFF) / 16777216.0); };
+
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  const BoardHistory startHist = hist;
+  vector<Board> boards; vector<BoardHistory> hists; vector<Player> plas;
+  bool prevPass = false;
+  for(int t = 0; t < nTurns; t++) {
+    boards.push_back(board); hists.push_back(hist); plas.push_back(pla);
+    vector<Loc> legal;
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(hist.isLegal(board, l, pla)) legal.push_back(l); }
+    Loc mv = (legal.empty() || (!prevPass && rng.next() % 30 == 0)) ? Board::PASS_LOC : legal[rng.next() % legal.size()];
+    if(prevPass && mv == Board::PASS_LOC && !legal.empty()) mv = legal[0];
+    prevPass = mv == Board::PASS_LOC;
+    hist.makeBoardMoveAssumeLegal(board, mv, pla, NULL);
+    pla = getOpp(pla);
+  }
+  boards.push_back(board);   // posHistForFutureBoards has one board per value target (trainingwrite.cpp:782)
+  BoardHistory endHist = hist;
+  if(endNoResult) { endHist.isGameFinished = true; endHist.isNoResult = true; }
+  else if(nTurns % 2 == 0) endHist.isGameFinished = true;
+  endHist.whiteBonusScore += bonus;
+
+  vector<ValueTargets> vts(nTurns + 1);
+  for(auto& v : vts) {
+    float a = unif(), b = unif() * (1.0f - a);
+    v.win = a; v.loss = b; v.noResult = 1.0f - a - b;
+    v.score = (unif() - 0.5f) * (rng.next() % 5 == 0 ? 1300.0f : 60.0f);
+    v.hasLead = rng.next() % 4 != 0;
+    v.lead = (unif() - 0.5f) * (rng.next() % 5 == 0 ? 1300.0f : 50.0f);
+  }
+  if(nTurns % 3 == 0) vts.back().score = 0.5f * (float)((int)(rng.next() % 41) - 20);   // finished games have half-integer scores
+  if(strtoull(seedStr.c_str(), NULL, 10) % 10 == 9) vts.back().score = 500.5f;   // beyond either end of the score distribution (colours alternate)
+
+  Color fullArea[Board::MAX_ARR_SIZE], ownership[Board::MAX_ARR_SIZE];
+  float scoring[Board::MAX_ARR_SIZE];
+  board.calculateArea(fullArea, true, true, true, true);
+  board.calculateArea(ownership, false, false, false, true);
+  for(int i = 0; i < Board::MAX_ARR_SIZE; i++) scoring[i] = 0.0f;
+  for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) {
+    Loc l = Location::getLoc(x, y, X);
+    const uint32_t k = rng.next() % 6;
+    scoring[l] = k == 0 ? 1.0f : k == 1 ? -1.0f : k == 2 ? 0.0f : k == 3 ? (float)((int)(rng.next() % 241) - 120) / 120.0f : unif() * 2.0f - 1.0f;
+    if(scoring[l] > 1.0f) scoring[l] = 1.0f;
+    if(scoring[l] < -1.0f) scoring[l] = -1.0f;
+  }
+  Hash128 gameHash(((uint64_t)rng.next() << 32) ^ ((uint64_t)rng.next() << 11) ^ rng.next(), ((uint64_t)rng.next() << 33) ^ ((uint64_t)rng.next() << 9) ^ rng.next());
+
+  TrainingWriteBuffers buf(7, nTurns, NNInputs::NUM_FEATURES_SPATIAL_V7, NNInputs::NUM_FEATURES_GLOBAL_V7, D, D, false);
+  Rand rowRand("addrow" + seedStr);
+  const int P = D * D + 1, A = D * D, SD = A * 2 + NNPos::EXTRA_SCORE_DISTR_RADIUS * 2, packed = (A + 7) / 8;
+
+  ofstream out(argv[9]);
+  auto f9 = [](double v) { return Global::strprintf("%.9g", v); };
+  auto f17 = [](double v) { return Global::strprintf("%.17g", v); };
+  auto locJson = [&](Loc l) { return l == Board::PASS_LOC ? string("-1,-1") : Global::intToString(Location::getX(l, X)) + "," + Global::intToString(Location::getY(l, X)); };
+  out << "{\"X\":" << X << ",\"Y\":" << Y << ",\"dataLen\":" << D << ",\"seed\":\"" << seedStr << "\",\"gameHash\":[" << gameHash.hash0 << "," << gameHash.hash1 << "],\n";
+  out << "\"valueTargets\":[";
+  for(size_t i = 0; i < vts.size(); i++) out << (i ? "," : "") << "[" << f9(vts[i].win) << "," << f9(vts[i].loss) << "," << f9(vts[i].noResult) << "," << f9(vts[i].score) << "," << (vts[i].hasLead ? 1 : 0) << "," << f9(vts[i].lead) << "]";
+  out << "],\n\"boards\":[";
+  for(size_t i = 0; i < boards.size(); i++) {
+    out << (i ? "," : "") << "[";
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) out << ((y || x) ? "," : "") << (int)boards[i].colors[Location::getLoc(x, y, X)];
+    out << "]";
+  }
+  auto plane = [&](const char* name, auto fn) {
+    out << "],\n\"" << name << "\":[";
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) out << ((y || x) ? "," : "") << fn(Location::getLoc(x, y, X));
+  };
+  plane("finalOwnership", [&](Loc l) { return Global::intToString((int)ownership[l]); });
+  plane("finalFullArea", [&](Loc l) { return Global::intToString((int)fullArea[l]); });
+  plane("finalWhiteScoring", [&](Loc l) { return f9(scoring[l]); });
+  out << "],\n\"endFinished\":" << (endHist.isGameFinished ? 1 : 0) << ",\"endNoResult\":" << (endHist.isNoResult ? 1 : 0) << ",\"endWhiteBonus\":" << f9(endHist.whiteBonusScore)
+      << ",\"startHistMoves\":" << startHist.moveHistory.size() << ",\n\"rows\":[\n";
+
+  vector<QValueTargets> qts(nTurns + 1);
+  for(int t = 0; t < nTurns; t++) {
+    const Board& b = boards[t]; const BoardHistory& h = hists[t]; const Player p = plas[t];
+    vector<Loc> legal;
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(h.isLegal(b, l, p)) legal.push_back(l); }
+    legal.push_back(Board::PASS_LOC);
+    vector<PolicyTargetMove> pt0, pt1;
+    for(Loc l : legal) {
+      if(rng.next() % 3 == 0) pt0.push_back(PolicyTargetMove(l, (int16_t)(rng.next() % 600)));
+      if(rng.next() % 5 == 0) pt1.push_back(PolicyTargetMove(l, (int16_t)(rng.next() % 2)));
+      if(rng.next() % 3 == 0) {
+        const uint32_t k = rng.next() % 8;
+        float wl = k == 0 ? 1.0f : k == 1 ? -1.0f : k == 2 ? 0.0f : unif() * 2.0f - 1.0f;
+        float sc = k == 3 ? 500.0f : k == 4 ? -500.0f : k == 5 ? (float)((int)(rng.next() % 81) - 40) * 0.5f : (unif() - 0.5f) * 80.0f;
+        int64_t visits = k == 6 ? 100000 : k == 7 ? -3 : (int64_t)(rng.next() % 700);
+        qts[t].targets.push_back(QValueTargetMove(l, wl, sc, visits));
+      }
+    }
+    const bool hasP0 = t % 7 != 3, hasP1 = t % 2 == 0, hasOwn = t % 5 != 4, hasFuture = t % 3 != 2, hasScoring = t % 4 != 1;
+    const bool hitTurnLimit = (nTurns + (int)strtoull(seedStr.c_str(), NULL, 10)) % 2 == 1, isSide = false;
+    const float targetWeight = unif(), valueTargetWeight = rng.next() % 3 == 0 ? 1.0f : unif(), tdValueTargetWeight = rng.next() % 3 == 0 ? 1.0f : unif(), leadFactor = unif();
+    const int64_t unreduced = 100 + rng.next() % 2000;
+    const double policySurprise = unif() * 2.0, policyEntropy = unif() * 3.0, searchEntropy = unif() * 3.0;
+    NNRawStats raw; raw.whiteWinLoss = unif() * 2.0 - 1.0; raw.whiteScoreMean = (unif() - 0.5) * 40.0; raw.policyEntropy = unif() * 4.0;
+    const int numBehind = (int)(rng.next() % 3), numExtraBlack = (int)(rng.next() % 3), mode = (int)(rng.next() % 4);
+    const double drawEq = 0.5 + 0.1 * (int)(rng.next() % 3);
+    vector<ChangedNeuralNet*> changed;
+    ChangedNeuralNet dummy("x", 3);
+    if(t % 6 == 5) changed.push_back(&dummy);
+    ReanalysisData re;
+    if(t % 8 == 6) { re.wasReanalyzed = true; re.selectionPolicySurprise = unif(); re.selectionValueSurprise = unif(); re.originalNumVisits = 50 + rng.next() % 100; }
+    const int rowsBefore = (int)buf.curRows;
+    buf.addRow(b, h, p, startHist, endHist, t, targetWeight, unreduced, hasP0 ? &pt0 : NULL, hasP1 ? &pt1 : NULL, policySurprise, policyEntropy, searchEntropy,
+               vts, qts, t, valueTargetWeight, tdValueTargetWeight, leadFactor, raw, &board, fullArea, hasOwn ? ownership : NULL, hasScoring ? scoring : NULL,
+               hasFuture ? &boards : NULL, isSide, numBehind, drawEq, C_EMPTY, 0.0, gameHash, changed, hitTurnLimit, numExtraBlack, mode, NULL, rowRand, re);
+    const int r = rowsBefore;
+    out << (t ? ",\n" : "") << "{\"turnIdx\":" << t << ",\"nextPlayer\":" << (int)p << ",\"targetWeight\":" << f9(targetWeight) << ",\"unreducedNumVisits\":" << unreduced;
+    auto ptJson = [&](const char* name, const vector<PolicyTargetMove>* v) {
+      out << ",\"" << name << "\":";
+      if(!v) { out << "null"; return; }
+      out << "[";
+      for(size_t i = 0; i < v->size(); i++) out << (i ? "," : "") << "[" << locJson((*v)[i].loc) << "," << (*v)[i].policyTarget << "]";
+      out << "]";
+    };
+    ptJson("policyTarget0", hasP0 ? &pt0 : NULL); ptJson("policyTarget1", hasP1 ? &pt1 : NULL);
+    out << ",\"qTargets\":[";
+    for(size_t i = 0; i < qts[t].targets.size(); i++) { const QValueTargetMove& q = qts[t].targets[i]; out << (i ? "," : "") << "[" << locJson(q.loc) << "," << f9(q.winLoss) << "," << f9(q.score) << "," << q.visits << "]"; }
+    out << "],\"policySurprise\":" << f17(policySurprise) << ",\"policyEntropy\":" << f17(policyEntropy) << ",\"searchEntropy\":" << f17(searchEntropy)
+        << ",\"valueTargetWeight\":" << f9(valueTargetWeight) << ",\"tdValueTargetWeight\":" << f9(tdValueTargetWeight) << ",\"leadTargetWeightFactor\":" << f9(leadFactor)
+        << ",\"nnRawStats\":[" << f17(raw.whiteWinLoss) << "," << f17(raw.whiteScoreMean) << "," << f17(raw.policyEntropy) << "]"
+        << ",\"hasOwnership\":" << (hasOwn ? 1 : 0) << ",\"hasFutureBoards\":" << (hasFuture ? 1 : 0) << ",\"hasScoring\":" << (hasScoring ? 1 : 0)
+        << ",\"isSidePosition\":" << (isSide ? 1 : 0) << ",\"numNeuralNetsBehindLatest\":" << numBehind << ",\"drawEquivalentWinsForWhite\":" << f17(drawEq)
+        << ",\"numChangedNeuralNets\":" << changed.size() << ",\"hitTurnLimit\":" << (hitTurnLimit ? 1 : 0) << ",\"numExtraBlack\":" << numExtraBlack << ",\"mode\":" << mode
+        << ",\"reanalysis\":[" << (re.wasReanalyzed ? 1 : 0) << "," << f9(re.selectionPolicySurprise) << "," << f9(re.selectionValueSurprise) << "," << re.originalNumVisits << "]"
+        << ",\"selfKomi\":" << f9(h.currentSelfKomi(p, drawEq)) << ",\"areaScoringOrEncore2\":" << ((h.encorePhase == 2 || h.rules.scoringRule == Rules::SCORING_AREA) ? 1 : 0)
+        << ",\"initialTurnNumber\":" << h.initialTurnNumber << ",\"whiteBonusScore\":" << f9(h.whiteBonusScore)
+        << ",\"alwaysComputePassAliveUnderSuicideRules\":" << (h.alwaysComputePassAliveUnderSuicideRules ? 1 : 0);
+    out << ",\n \"out_binaryInputNCHWPacked\":\"";
+    for(int i = 0; i < NNInputs::NUM_FEATURES_SPATIAL_V7 * packed; i++) out << Global::strprintf("%02x", (unsigned)buf.binaryInputNCHWPacked.data[(size_t)r * NNInputs::NUM_FEATURES_SPATIAL_V7 * packed + i]);
+    out << "\"";
+    auto arr = [&](const char* name, auto* data, size_t n, bool isFloat) {
+      out << ",\n \"" << name << "\":[";
+      for(size_t i = 0; i < n; i++) { out << (i ? "," : ""); if(isFloat) out << f9((double)data[i]); else out << (long long)data[i]; }
+      out << "]";
+    };
+    arr("out_globalInputNC", buf.globalInputNC.data + (size_t)r * NNInputs::NUM_FEATURES_GLOBAL_V7, NNInputs::NUM_FEATURES_GLOBAL_V7, true);
+    arr("out_policyTargetsNCMove", buf.policyTargetsNCMove.data + (size_t)r * 2 * P, 2 * P, false);
+    arr("out_globalTargetsNC", buf.globalTargetsNC.data + (size_t)r * 80, 80, true);
+    arr("out_scoreDistrN", buf.scoreDistrN.data + (size_t)r * SD, SD, false);
+    arr("out_valueTargetsNCHW", buf.valueTargetsNCHW.data + (size_t)r * 5 * A, 5 * A, false);
+    arr("out_qValueTargetsNCMove", buf.qValueTargetsNCMove.data + (size_t)r * 3 * P, 3 * P, false);
+    out << "}";
+  }
+  out << "\n]}\n";
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -555,6 +726,7 @@ int main(int argc, char** argv) {
   if(cmd == "histstream") return cmdHistStream(argc, argv);
   if(cmd == "repbound") return cmdRepBound(argc, argv);
   if(cmd == "npyheader") return cmdNpyHeader(argc, argv);
+  if(cmd == "addrow") return cmdAddRow(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

@@ -75,3 +75,100 @@ def test_policy_target_follows_extract_policy_target():
     """Play::extractPolicyTarget: largest value scaled up to 10 when smaller, capped at 30000 when larger, rounded to int16."""
     t = W.policy_target_from_play_selection(np.array([[-1.0, 2.0, 0.5, -1.0], [-1.0, 60000.0, 15000.0, 1.0], [12.0, 3.4, -1.0, 7.5]]))
     assert t.tolist() == [[0, 10, 3, 0], [0, 30000, 7500, 1], [12, 3, 0, 8]]
+
+
+# ---- TrainingWriteBuffers.add_row against the reference's own addRow (tests/golden/make_addrow_fixtures.py) -------------------------
+import glob
+import gzip
+import json
+
+ADDROW_FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "addrow_*.json.gz")))
+
+
+def _replay_addrow_fixture(path):
+    from katago_b200.npz_writer import RowRand, TrainingWriteBuffers
+    d = json.loads(gzip.open(path, "rb").read())
+    X, Y, L = d["X"], d["Y"], d["dataLen"]
+    rows = d["rows"]
+    buf = TrainingWriteBuffers(len(rows), L)
+    rand = RowRand("addrow" + d["seed"])                 # one Rand for all rows of the file, like the reference's writer
+    packed = (L * L + 7) // 8
+    q_by_turn = [r["qTargets"] for r in rows]
+    for r in rows:
+        t = r["turnIdx"]
+        buf.add_row(
+            x_size=X, y_size=Y, next_player=r["nextPlayer"],
+            packed_input=np.frombuffer(bytes.fromhex(r["out_binaryInputNCHWPacked"]), np.uint8).reshape(22, packed),
+            global_input=np.asarray(r["out_globalInputNC"], np.float32),
+            turn_idx=t, target_weight=r["targetWeight"], unreduced_num_visits=r["unreducedNumVisits"],
+            policy_target0=r["policyTarget0"], policy_target1=r["policyTarget1"],
+            policy_surprise=r["policySurprise"], policy_entropy=r["policyEntropy"], search_entropy=r["searchEntropy"],
+            white_value_targets=d["valueTargets"], white_q_value_targets=q_by_turn[t], white_value_targets_idx=t,
+            value_target_weight=r["valueTargetWeight"], td_value_target_weight=r["tdValueTargetWeight"],
+            lead_target_weight_factor=r["leadTargetWeightFactor"], nn_raw_stats=r["nnRawStats"],
+            final_full_area=d["finalFullArea"], final_ownership=d["finalOwnership"] if r["hasOwnership"] else None,
+            final_white_scoring=d["finalWhiteScoring"] if r["hasScoring"] else None,
+            pos_hist_for_future_boards=d["boards"] if r["hasFutureBoards"] else None,
+            is_side_position=bool(r["isSidePosition"]), num_neural_nets_behind_latest=r["numNeuralNetsBehindLatest"],
+            game_hash=d["gameHash"], num_changed_neural_nets=r["numChangedNeuralNets"], hit_turn_limit=bool(r["hitTurnLimit"]),
+            num_extra_black=r["numExtraBlack"], mode=r["mode"], rand=rand, self_komi=r["selfKomi"],
+            area_scoring_or_encore2=bool(r["areaScoringOrEncore2"]), start_hist_moves=d["startHistMoves"],
+            initial_turn_number=r["initialTurnNumber"], white_bonus_now=r["whiteBonusScore"], white_bonus_end=d["endWhiteBonus"],
+            end_finished=bool(d["endFinished"]), end_no_result=bool(d["endNoResult"]),
+            always_pass_alive_under_suicide_rules=bool(r["alwaysComputePassAliveUnderSuicideRules"]), reanalysis=tuple(r["reanalysis"]))
+    return d, buf
+
+
+@pytest.mark.parametrize("path", ADDROW_FIXTURES, ids=[os.path.basename(p)[7:-8] for p in ADDROW_FIXTURES])
+def test_add_row_matches_reference_add_row(path):
+    """Every target array of every row equals what the reference's addRow wrote - bit for bit, including the stochastically
+    rounded scoring plane and Q targets (same Rand, same draw order) and the float32 global targets."""
+    d, buf = _replay_addrow_fixture(path)
+    L = d["dataLen"]
+    assert buf.cur_rows == len(d["rows"])
+    for i, r in enumerate(d["rows"]):
+        for name, key in (("policyTargetsNCMove", "out_policyTargetsNCMove"), ("scoreDistrN", "out_scoreDistrN"),
+                          ("valueTargetsNCHW", "out_valueTargetsNCHW"), ("qValueTargetsNCMove", "out_qValueTargetsNCMove")):
+            want = np.asarray(r[key], np.int64)
+            got = buf.arrays[name][i].reshape(-1).astype(np.int64)
+            assert np.array_equal(got, want), (i, name, np.flatnonzero(got != want)[:8])
+        want = np.asarray(r["out_globalTargetsNC"], np.float32)
+        got = buf.arrays["globalTargetsNC"][i]
+        bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+        bad = [int(c) for c in bad if not (got[c] == 0 and want[c] == 0)]      # -0.0 vs 0.0 would still be reported by value below
+        assert not bad, (i, bad, got[bad], want[bad])
+
+
+def test_add_row_fixtures_cover_the_branches():
+    """The fixtures exercise what addRow branches on: missing policy / ownership / future boards / scoring, no-result ending,
+    bonus points, reanalysed rows, capped scores and leads, both colours, boards smaller than the data frame."""
+    assert len(ADDROW_FIXTURES) >= 7
+    seen = dict(p0_null=0, p1_null=0, own_null=0, fut_null=0, sc_null=0, rean=0, white=0, black=0, nores=0, bonus=0, small=0, capped=0, distr_low=0, distr_high=0)
+    for path in ADDROW_FIXTURES:
+        d = json.loads(gzip.open(path, "rb").read())
+        seen["nores"] += d["endNoResult"]
+        seen["bonus"] += d["endWhiteBonus"] != 0
+        seen["small"] += d["X"] < d["dataLen"]
+        for r in d["rows"]:
+            seen["p0_null"] += r["policyTarget0"] is None
+            seen["p1_null"] += r["policyTarget1"] is None
+            seen["own_null"] += not r["hasOwnership"]
+            seen["fut_null"] += not r["hasFutureBoards"]
+            seen["sc_null"] += not r["hasScoring"]
+            seen["rean"] += r["reanalysis"][0]
+            seen["white"] += r["nextPlayer"] == 2
+            seen["black"] += r["nextPlayer"] == 1
+            seen["distr_low"] += r["out_scoreDistrN"][0] == 100
+            seen["distr_high"] += r["out_scoreDistrN"][-1] == 100
+            seen["capped"] += abs(r["out_globalTargetsNC"][21]) == 421.0 or abs(r["out_globalTargetsNC"][3]) == 421.0
+    assert all(v > 0 for v in seen.values()), seen
+
+
+def test_training_write_buffers_file_is_read_back(tmp_path):
+    """write_to_zip_file: the rows of a replayed fixture survive the container (np.load) unchanged."""
+    d, buf = _replay_addrow_fixture(ADDROW_FIXTURES[0])
+    path = str(tmp_path / "rows.npz")
+    assert buf.write_to_zip_file(path) == len(d["rows"])
+    with np.load(path) as z:
+        for k, v in buf.arrays.items():
+            assert np.array_equal(z[k], v[:buf.cur_rows]) and z[k].dtype == v.dtype
