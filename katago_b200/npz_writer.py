@@ -344,3 +344,163 @@ class TrainingWriteBuffers:
     def write_to_zip_file(self, path: str, compress: bool = True):
         """writeToZipFile (trainingwrite.cpp:854-886): the first cur_rows rows of every array."""
         return write_npz(path, {k: v[:self.cur_rows] for k, v in self.arrays.items()}, self.L, compress)
+
+
+# ---- a finished game and the writer that turns it into rows ---------------------------------------------------------------------------
+
+class FinishedGameData:
+    """What `Play::runGame` hands to the writer (dataio/trainingwrite.h:84-170), for the rule subset of the device loop (area
+    scoring, no tax, no button, no handicap bonus).  Per-turn lists have one entry per move of the training period; the
+    value targets have one more (the game outcome).  `packed_input_by_turn` / `global_input_by_turn` are the fillRowV7 rows
+    of the root positions as the device loop produced them when it searched them."""
+
+    def __init__(self, x_size, y_size, komi, start_pla=P_BLACK):
+        self.x_size, self.y_size, self.komi, self.start_pla = x_size, y_size, float(komi), start_pla
+        self.game_hash = (0, 0)
+        self.draw_equivalent_wins_for_white = 0.5
+        self.hit_turn_limit = False
+        self.num_extra_black = 0
+        self.mode = 0
+        self.training_weight = 1.0
+        self.start_hist_moves = 0                  # moves before the training period (startHist.moveHistory.size())
+        self.initial_turn_number = 0
+        self.always_pass_alive_under_suicide_rules = False
+        self.end_finished, self.end_no_result = True, False
+        self.boards_by_turn = []                   # nTurns + 1 boards (colours, row-major): the position before each move and the final one
+        self.next_player_by_turn = []
+        self.packed_input_by_turn, self.global_input_by_turn = [], []
+        self.target_weight_by_turn = []
+        self.policy_targets_by_turn = []           # (list of (x, y, value), unreducedNumVisits)
+        self.policy_surprise_by_turn, self.policy_entropy_by_turn, self.search_entropy_by_turn = [], [], []
+        self.white_value_targets_by_turn = []
+        self.white_q_value_targets_by_turn = []
+        self.nn_raw_stats_by_turn = []
+        self.reanalysis_by_turn = []               # empty, or per turn (wasReanalyzed, usedOutcomeTargets, polSurprise, valSurprise, origVisits, netChangesSoFar)
+        self.changed_neural_net_turns = []         # turn index at which each new net took over
+        self.final_full_area = self.final_ownership = self.final_white_scoring = None
+
+    def self_komi(self, next_player):
+        """BoardHistory::currentSelfKomi (game/boardhistory.cpp:570-589) without bonus points: komi plus the draw adjustment
+        when results are integers."""
+        komi_is_int = float(int(self.komi)) == self.komi
+        adj = _f32(self.draw_equivalent_wins_for_white - 0.5) if komi_is_int else _f32(0.0)
+        w = _f32(_f32(self.komi) + adj)
+        return w if next_player == P_WHITE else -w
+
+
+def final_value_targets(winner, final_white_minus_black_score, draw_equivalent_wins_for_white, komi, no_result=False):
+    """The outcome entry of the value targets (program/play.cpp:1977-2000): win / loss from the winner (a draw counts as
+    drawEquivalentWinsForWhite), the draw-adjusted score, lead = score."""
+    if no_result:
+        return (0.0, 0.0, 1.0, 0.0, 0, 0.0)
+    win = _f32(1.0 if winner == P_WHITE else 0.0 if winner == P_BLACK else draw_equivalent_wins_for_white)
+    komi_is_int = float(int(komi)) == float(komi)
+    adj = float(_f32(draw_equivalent_wins_for_white - 0.5)) if komi_is_int else 0.0     # whiteKomiAdjustmentForDraws returns float
+    score = _f32(float(final_white_minus_black_score) + adj)
+    return (win, _f32(1.0) - win, 0.0, score, 1, score)
+
+
+def scoring_from_area(area):
+    """NNInputs::fillScoring without group tax (neuralnet/nninputs.cpp:204-226): white area +1, black area -1."""
+    a = np.asarray(area)
+    return np.where(a == P_WHITE, 1.0, np.where(a == P_BLACK, -1.0, 0.0)).astype(np.float32)
+
+
+class TrainingDataWriter:
+    """The reference's writer (dataio/trainingwrite.cpp:987-1325): rows of finished games go into a TrainingWriteBuffers that is
+    written out as <16 hex digits>.npz whenever it is full; the first file of a writer is cut short at random so that writers
+    started together do not all flush at once.  One Rand (seeded by `rand_seed`) serves the first-file size, the fractional
+    target weights, addRow's rounding and the file names, in the reference's order."""
+
+    def __init__(self, output_dir, max_rows_per_file, first_file_min_rand_prop, data_len, rand_seed, on_flush=None):
+        if not (0.0 <= first_file_min_rand_prop <= 1.0):
+            raise ValueError("first_file_min_rand_prop not in [0,1]")
+        self.output_dir, self.L = output_dir, data_len
+        self.rand = RowRand(rand_seed)
+        self.buffers = TrainingWriteBuffers(max_rows_per_file, data_len)
+        self.is_first_file = True
+        if first_file_min_rand_prop >= 1.0:
+            self.first_file_max_rows = max_rows_per_file
+        else:
+            self.first_file_max_rows = max_rows_per_file - int(max_rows_per_file * (1.0 - first_file_min_rand_prop) * self.rand.next_double())
+        self.row_count = 0
+        self.on_flush = on_flush                   # tests: called with the buffers instead of writing a file
+
+    def is_empty(self):
+        return self.buffers.cur_rows <= 0
+
+    def flush_if_nonempty(self):
+        if self.buffers.cur_rows <= 0:
+            return None
+        self.is_first_file = False
+        if self.on_flush is not None:
+            self.on_flush(self.buffers)
+            name = ""
+        else:
+            lo = self.rand.next_uint()
+            hi = self.rand.next_uint()
+            name = "%s/%016X.npz" % (self.output_dir, lo | (hi << 32))
+            import os
+            self.buffers.write_to_zip_file(name + ".tmp")
+            os.replace(name + ".tmp", name)
+        self.buffers.cur_rows = 0
+        return name
+
+    def _write_and_clear_if_full(self):
+        b = self.buffers
+        if b.cur_rows >= b.max_rows or (self.is_first_file and b.cur_rows >= self.first_file_max_rows):
+            self.flush_if_nonempty()
+
+    def write_game(self, data: FinishedGameData):
+        """writeGame, main-line rows (:1097-1256): a turn with target weight w gives floor(w) rows plus one more with probability
+        frac(w); policy target 1 is the next turn's policy target; reanalysed turns may drop the outcome-derived targets."""
+        n = len(data.target_weight_by_turn)
+        if not (len(data.policy_targets_by_turn) == len(data.white_q_value_targets_by_turn) == len(data.nn_raw_stats_by_turn) == n
+                and len(data.white_value_targets_by_turn) == n + 1 and len(data.boards_by_turn) == n + 1
+                and len(data.reanalysis_by_turn) in (0, n)):
+            raise ValueError("FinishedGameData: per-turn lists disagree in length")
+        if not data.end_finished and not data.hit_turn_limit:
+            raise ValueError("FinishedGameData: unfinished game that did not hit the turn limit")
+        for t in range(n):
+            target_weight = float(_f32(data.target_weight_by_turn[t]))
+            turn_idx = t + data.start_hist_moves
+            policy0, unreduced = data.policy_targets_by_turn[t]
+            policy1 = data.policy_targets_by_turn[t + 1][0] if t + 1 < n else None
+            re = data.reanalysis_by_turn[t] if t < len(data.reanalysis_by_turn) else (False, True, 0.0, 0.0, 0, 0)
+            nets = data.changed_neural_net_turns
+            behind = 0
+            if re[0]:
+                behind = len(nets) - re[5]
+            else:
+                for i, net_turn in enumerate(nets):
+                    if net_turn > turn_idx:
+                        behind = len(nets) - i
+                        break
+            skip_outcome = bool(re[0]) and not bool(re[1])
+            pla = data.next_player_by_turn[t]
+            while target_weight > 0.0:
+                if target_weight >= 1.0 or self.rand.next_bool(target_weight):
+                    self.buffers.add_row(
+                        x_size=data.x_size, y_size=data.y_size, next_player=pla,
+                        packed_input=data.packed_input_by_turn[t], global_input=data.global_input_by_turn[t],
+                        turn_idx=turn_idx, target_weight=_f32(data.training_weight), unreduced_num_visits=unreduced,
+                        policy_target0=policy0, policy_target1=None if skip_outcome else policy1,
+                        policy_surprise=data.policy_surprise_by_turn[t], policy_entropy=data.policy_entropy_by_turn[t],
+                        search_entropy=data.search_entropy_by_turn[t], white_value_targets=data.white_value_targets_by_turn,
+                        white_q_value_targets=data.white_q_value_targets_by_turn[t], white_value_targets_idx=t,
+                        value_target_weight=1.0, td_value_target_weight=1.0, lead_target_weight_factor=1.0,
+                        nn_raw_stats=data.nn_raw_stats_by_turn[t],
+                        final_full_area=None if skip_outcome else data.final_full_area,
+                        final_ownership=None if skip_outcome else data.final_ownership,
+                        final_white_scoring=None if skip_outcome else data.final_white_scoring,
+                        pos_hist_for_future_boards=None if skip_outcome else data.boards_by_turn,
+                        is_side_position=False, num_neural_nets_behind_latest=behind, game_hash=data.game_hash,
+                        num_changed_neural_nets=len(nets), hit_turn_limit=data.hit_turn_limit, num_extra_black=data.num_extra_black,
+                        mode=data.mode, rand=self.rand, self_komi=data.self_komi(pla), area_scoring_or_encore2=True,
+                        start_hist_moves=data.start_hist_moves, initial_turn_number=data.initial_turn_number,
+                        end_finished=data.end_finished, end_no_result=data.end_no_result,
+                        always_pass_alive_under_suicide_rules=data.always_pass_alive_under_suicide_rules,
+                        reanalysis=(bool(re[0]), re[2], re[3], re[4]))
+                    self._write_and_clear_if_full()
+                    self.row_count += 1
+                target_weight -= 1.0

@@ -645,6 +645,179 @@ static int cmdAddRow(int argc, char** argv) {
   return 0;
 }
 
+// writegame X Y DATALEN NTURNS SEED MAXROWS FIRSTFILEPROP NORESULT OUT.json: TrainingDataWriter::writeGame (dataio/trainingwrite.cpp:1097-1325)
+// on a synthetic FinishedGameData (main-line rows; no side positions) through the writer's text sink: fractional and multiple target
+// weights, reanalysed turns that skip the outcome targets, net changes, file splits at MAXROWS / the randomised first-file size.
+// Dumps the game and the text the writer emitted (every flush = one block of the seven arrays).
+static int cmdWriteGame(int argc, char** argv) {
+  if(argc != 11) { cerr << "usage: writegame X Y DATALEN NTURNS SEED MAXROWS FIRSTFILEPROP NORESULT OUT.json" << endl; return 1; }
+  const int X = atoi(argv[2]), Y = atoi(argv[3]), D = atoi(argv[4]), nTurns = atoi(argv[5]);
+  const string seedStr = argv[6];
+  const int maxRows = atoi(argv[7]);
+  const double firstFileProp = atof(argv[8]);
+  const bool endNoResult = atoi(argv[9]) != 0;
+  Board::initHash();
+  ScoreValue::initTables();
+  Rules rules;
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  const uint64_t seedNum = strtoull(seedStr.c_str(), NULL, 10);
+  const double drawEq = 0.5 + 0.1 * (double)(seedNum % 3);
+  rules.friendlyPassOk = false; rules.komi = (seedNum % 2) ? 7.0f : 6.5f;
+  Lcg rng(seedNum);
+  auto unif = [&]() { return (float)((rng.next() & 0xFFFFFF) / 16777216.0); };
+
+  FinishedGameData data;
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  data.startBoard = board; data.startHist = hist; data.startPla = pla;
+  vector<Board> boards; vector<Player> plas; vector<vector<Loc>> legalByTurn; vector<string> moveStrs, packedHex; vector<vector<float>> globalRows;
+  bool prevPass = false;
+  for(int t = 0; t < nTurns; t++) {
+    boards.push_back(board); plas.push_back(pla);
+    {   // the input rows addRow will compute for this turn (fillRowV7, NCHW, the game's drawEquivalentWinsForWhite), packed like packBits
+      MiscNNInputParams ip; ip.drawEquivalentWinsForWhite = drawEq;
+      vector<float> rowBin((size_t)NNInputs::NUM_FEATURES_SPATIAL_V7 * D * D), rowGlobal(NNInputs::NUM_FEATURES_GLOBAL_V7);
+      NNInputs::fillRowV7(board, hist, pla, ip, D, D, false, rowBin.data(), rowGlobal.data());
+      string hex;
+      const int A = D * D, packed = (A + 7) / 8;
+      for(int c = 0; c < NNInputs::NUM_FEATURES_SPATIAL_V7; c++) for(int b = 0; b < packed; b++) {
+        unsigned v = 0;
+        for(int k = 0; k < 8; k++) { const int idx = b * 8 + k; if(idx < A && rowBin[(size_t)c * A + idx] != 0.0f) v |= 1u << (7 - k); }
+        hex += Global::strprintf("%02x", v);
+      }
+      packedHex.push_back(hex); globalRows.push_back(rowGlobal);
+    }
+    vector<Loc> legal;
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(hist.isLegal(board, l, pla)) legal.push_back(l); }
+    Loc mv = (legal.empty() || (!prevPass && rng.next() % 30 == 0)) ? Board::PASS_LOC : legal[rng.next() % legal.size()];
+    if(prevPass && mv == Board::PASS_LOC && !legal.empty()) mv = legal[0];
+    prevPass = mv == Board::PASS_LOC;
+    legal.push_back(Board::PASS_LOC);
+    legalByTurn.push_back(legal);
+    moveStrs.push_back(mv == Board::PASS_LOC ? string("-1,-1") : Global::intToString(Location::getX(mv, X)) + "," + Global::intToString(Location::getY(mv, X)));
+    hist.makeBoardMoveAssumeLegal(board, mv, pla, NULL);
+    pla = getOpp(pla);
+  }
+  boards.push_back(board);
+  data.finalFullArea = new Color[Board::MAX_ARR_SIZE];
+  data.finalOwnership = new Color[Board::MAX_ARR_SIZE];
+  data.finalSekiAreas = new bool[Board::MAX_ARR_SIZE];
+  data.finalWhiteScoring = new float[Board::MAX_ARR_SIZE];
+  std::fill(data.finalSekiAreas, data.finalSekiAreas + Board::MAX_ARR_SIZE, false);
+  ValueTargets finalTargets;
+  if(endNoResult) {
+    hist.isGameFinished = true; hist.isNoResult = true; hist.winner = C_EMPTY;
+    std::fill(data.finalFullArea, data.finalFullArea + Board::MAX_ARR_SIZE, C_EMPTY);
+    std::fill(data.finalOwnership, data.finalOwnership + Board::MAX_ARR_SIZE, C_EMPTY);
+    finalTargets.win = 0.0f; finalTargets.loss = 0.0f; finalTargets.noResult = 1.0f; finalTargets.score = 0.0f;
+  }
+  else {   // what Play::runGame does at the end of a game (program/play.cpp:1989-2000)
+    hist.endAndScoreGameNow(board, data.finalOwnership);
+    board.calculateArea(data.finalFullArea, true, true, true, hist.suicideLegalForPassAlive());
+    finalTargets.win = (float)ScoreValue::whiteWinsOfWinner(hist.winner, drawEq);
+    finalTargets.loss = 1.0f - finalTargets.win; finalTargets.noResult = 0.0f;
+    finalTargets.score = (float)ScoreValue::whiteScoreDrawAdjust(hist.finalWhiteMinusBlackScore, drawEq, hist);
+    finalTargets.hasLead = true; finalTargets.lead = finalTargets.score;
+  }
+  NNInputs::fillScoring(board, data.finalOwnership, false, data.finalWhiteScoring);
+  data.endHist = hist;
+  data.hitTurnLimit = false;
+  data.gameHash = Hash128(((uint64_t)rng.next() << 32) ^ ((uint64_t)rng.next() << 11) ^ rng.next(), ((uint64_t)rng.next() << 33) ^ ((uint64_t)rng.next() << 9) ^ rng.next());
+  data.drawEquivalentWinsForWhite = drawEq;
+  data.playoutDoublingAdvantagePla = C_EMPTY; data.playoutDoublingAdvantage = 0.0;
+  data.numExtraBlack = 0; data.mode = (int)(rng.next() % 3); data.hasFullData = true;
+  data.trainingWeight = rng.next() % 2 == 0 ? 1.0 : 0.75;
+  const int numChanges = (int)(rng.next() % 3);
+  for(int i = 0; i < numChanges; i++) data.changedNeuralNets.push_back(new ChangedNeuralNet("net" + Global::intToString(i), (int)((i + 1) * nTurns / 3)));
+  const bool withReanalysis = rng.next() % 2 == 0;
+  for(int t = 0; t < nTurns; t++) {
+    static const float weights[8] = {0.0f, 1.0f, 1.0f, 0.35f, 1.6f, 2.0f, 0.9f, 3.25f};
+    const float w = weights[rng.next() % 8];
+    data.targetWeightByTurn.push_back(w); data.targetWeightByTurnUnrounded.push_back(w);
+    vector<PolicyTargetMove>* pt = new vector<PolicyTargetMove>();
+    QValueTargets q;
+    for(Loc l : legalByTurn[t]) {
+      if(rng.next() % 3 == 0) pt->push_back(PolicyTargetMove(l, (int16_t)(1 + rng.next() % 600)));
+      if(rng.next() % 4 == 0) q.targets.push_back(QValueTargetMove(l, unif() * 2.0f - 1.0f, (unif() - 0.5f) * 80.0f, (int64_t)(rng.next() % 700)));
+    }
+    data.policyTargetsByTurn.push_back(PolicyTarget(pt, 100 + rng.next() % 2000));
+    data.whiteQValueTargetsByTurn.push_back(q);
+    data.policySurpriseByTurn.push_back(unif() * 2.0); data.policyEntropyByTurn.push_back(unif() * 3.0); data.searchEntropyByTurn.push_back(unif() * 3.0);
+    ValueTargets v;
+    float a = unif(), b = unif() * (1.0f - a);
+    v.win = a; v.loss = b; v.noResult = 1.0f - a - b; v.score = (unif() - 0.5f) * 60.0f; v.hasLead = rng.next() % 4 != 0; v.lead = (unif() - 0.5f) * 50.0f;
+    data.whiteValueTargetsByTurn.push_back(v);
+    NNRawStats raw; raw.whiteWinLoss = unif() * 2.0 - 1.0; raw.whiteScoreMean = (unif() - 0.5) * 40.0; raw.policyEntropy = unif() * 4.0;
+    data.nnRawStatsByTurn.push_back(raw);
+    if(withReanalysis) {
+      ReanalysisData re;
+      if(rng.next() % 4 == 0) {
+        re.wasReanalyzed = true; re.usedOutcomeTargets = rng.next() % 2 == 0; re.selectionPolicySurprise = unif(); re.selectionValueSurprise = unif();
+        re.originalNumVisits = 50 + rng.next() % 100; re.numNeuralNetChangesSoFar = numChanges > 0 ? (int)(rng.next() % (numChanges + 1)) : 0;
+      }
+      data.reanalysisByTurn.push_back(re);
+    }
+  }
+  data.whiteValueTargetsByTurn.push_back(finalTargets);
+
+  ostringstream sink;
+  {
+    TrainingDataWriter writer(&sink, 7, maxRows, firstFileProp, D, D, 1, "writegame" + seedStr);
+    writer.writeGame(data);
+    writer.flushIfNonempty();
+  }
+
+  ofstream out(argv[10]);
+  auto f9 = [](double v) { return Global::strprintf("%.9g", v); };
+  auto f17 = [](double v) { return Global::strprintf("%.17g", v); };
+  auto locJson = [&](Loc l) { return l == Board::PASS_LOC ? string("-1,-1") : Global::intToString(Location::getX(l, X)) + "," + Global::intToString(Location::getY(l, X)); };
+  out << "{\"X\":" << X << ",\"Y\":" << Y << ",\"dataLen\":" << D << ",\"seed\":\"" << seedStr << "\",\"maxRows\":" << maxRows << ",\"firstFileMinRandProp\":" << f17(firstFileProp)
+      << ",\"gameHash\":[" << data.gameHash.hash0 << "," << data.gameHash.hash1 << "],\"komi\":" << f9(rules.komi) << ",\"drawEquivalentWinsForWhite\":" << f17(drawEq)
+      << ",\"mode\":" << data.mode << ",\"trainingWeight\":" << f17(data.trainingWeight) << ",\"hitTurnLimit\":0,\"numExtraBlack\":0"
+      << ",\"endFinished\":" << (data.endHist.isGameFinished ? 1 : 0) << ",\"endNoResult\":" << (data.endHist.isNoResult ? 1 : 0)
+      << ",\"winner\":" << (int)data.endHist.winner << ",\"finalWhiteMinusBlackScore\":" << f9(data.endHist.finalWhiteMinusBlackScore) << ",\n";
+  out << "\"changedNeuralNetTurns\":[";
+  for(size_t i = 0; i < data.changedNeuralNets.size(); i++) out << (i ? "," : "") << data.changedNeuralNets[i]->turnIdx;
+  out << "],\n\"moves\":[";
+  for(size_t i = 0; i < moveStrs.size(); i++) out << (i ? "," : "") << "[" << moveStrs[i] << "]";
+  out << "],\n\"valueTargets\":[";
+  for(size_t i = 0; i < data.whiteValueTargetsByTurn.size(); i++) { const ValueTargets& v = data.whiteValueTargetsByTurn[i]; out << (i ? "," : "") << "[" << f9(v.win) << "," << f9(v.loss) << "," << f9(v.noResult) << "," << f9(v.score) << "," << (v.hasLead ? 1 : 0) << "," << f9(v.lead) << "]"; }
+  out << "],\n\"boards\":[";
+  for(size_t i = 0; i < boards.size(); i++) {
+    out << (i ? "," : "") << "[";
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) out << ((y || x) ? "," : "") << (int)boards[i].colors[Location::getLoc(x, y, X)];
+    out << "]";
+  }
+  auto plane = [&](const char* name, auto fn) {
+    out << "],\n\"" << name << "\":[";
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) out << ((y || x) ? "," : "") << fn(Location::getLoc(x, y, X));
+  };
+  plane("finalOwnership", [&](Loc l) { return Global::intToString((int)data.finalOwnership[l]); });
+  plane("finalFullArea", [&](Loc l) { return Global::intToString((int)data.finalFullArea[l]); });
+  plane("finalWhiteScoring", [&](Loc l) { return f9(data.finalWhiteScoring[l]); });
+  out << "],\n\"turns\":[\n";
+  for(int t = 0; t < nTurns; t++) {
+    out << (t ? ",\n" : "") << "{\"packedInput\":\"" << packedHex[t] << "\",\"globalInput\":[";
+    for(size_t i = 0; i < globalRows[t].size(); i++) out << (i ? "," : "") << f9(globalRows[t][i]);
+    out << "],\"nextPlayer\":" << (int)plas[t] << ",\"targetWeight\":" << f9(data.targetWeightByTurn[t]) << ",\"unreducedNumVisits\":" << data.policyTargetsByTurn[t].unreducedNumVisits << ",\"policyTarget\":[";
+    const vector<PolicyTargetMove>& pt = *data.policyTargetsByTurn[t].policyTargets;
+    for(size_t i = 0; i < pt.size(); i++) out << (i ? "," : "") << "[" << locJson(pt[i].loc) << "," << pt[i].policyTarget << "]";
+    out << "],\"qTargets\":[";
+    const vector<QValueTargetMove>& q = data.whiteQValueTargetsByTurn[t].targets;
+    for(size_t i = 0; i < q.size(); i++) out << (i ? "," : "") << "[" << locJson(q[i].loc) << "," << f9(q[i].winLoss) << "," << f9(q[i].score) << "," << q[i].visits << "]";
+    out << "],\"policySurprise\":" << f17(data.policySurpriseByTurn[t]) << ",\"policyEntropy\":" << f17(data.policyEntropyByTurn[t]) << ",\"searchEntropy\":" << f17(data.searchEntropyByTurn[t])
+        << ",\"nnRawStats\":[" << f17(data.nnRawStatsByTurn[t].whiteWinLoss) << "," << f17(data.nnRawStatsByTurn[t].whiteScoreMean) << "," << f17(data.nnRawStatsByTurn[t].policyEntropy) << "]";
+    if(withReanalysis) { const ReanalysisData& re = data.reanalysisByTurn[t]; out << ",\"reanalysis\":[" << (re.wasReanalyzed ? 1 : 0) << "," << (re.usedOutcomeTargets ? 1 : 0) << "," << f9(re.selectionPolicySurprise) << "," << f9(re.selectionValueSurprise) << "," << re.originalNumVisits << "," << re.numNeuralNetChangesSoFar << "]"; }
+    out << "}";
+  }
+  out << "\n],\n\"dump\":\"";
+  for(char c : sink.str()) { if(c == '\n') out << "\\n"; else if(c == '"' || c == '\\') out << '\\' << c; else out << c; }
+  out << "\"}\n";
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -727,6 +900,7 @@ int main(int argc, char** argv) {
   if(cmd == "repbound") return cmdRepBound(argc, argv);
   if(cmd == "npyheader") return cmdNpyHeader(argc, argv);
   if(cmd == "addrow") return cmdAddRow(argc, argv);
+  if(cmd == "writegame") return cmdWriteGame(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

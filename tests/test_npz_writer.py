@@ -172,3 +172,110 @@ def test_training_write_buffers_file_is_read_back(tmp_path):
     with np.load(path) as z:
         for k, v in buf.arrays.items():
             assert np.array_equal(z[k], v[:buf.cur_rows]) and z[k].dtype == v.dtype
+
+
+# ---- TrainingDataWriter.write_game against the reference's own writeGame (tests/golden/make_writegame_fixtures.py) ------------------
+
+WRITEGAME_FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "writegame_*.json.gz")))
+ARRAY_NAMES = ["binaryInputNCHWPacked", "globalInputNC", "policyTargetsNCMove", "globalTargetsNC", "scoreDistrN", "valueTargetsNCHW", "qValueTargetsNCMove"]
+
+
+def _parse_text_dump(text):
+    """The writer's text sink (TrainingWriteBuffers::writeToTextOstream, trainingwrite.cpp:888-983): per flush, per array: name,
+    header line, one line per row, blank line.  Returns a list of flushes, each {name: list of rows}."""
+    flushes, cur, lines, i = [], None, text.split("\n"), 0
+    while i < len(lines):
+        ln = lines[i]
+        if ln in ARRAY_NAMES:
+            if ln == ARRAY_NAMES[0]:
+                cur = {}
+                flushes.append(cur)
+            rows, i = [], i + 2                     # skip the header line
+            while i < len(lines) and lines[i] != "":
+                rows.append(lines[i])
+                i += 1
+            cur[ln] = rows if ln == ARRAY_NAMES[0] else [np.array(r.split(), np.float64) for r in rows]
+        i += 1
+    return flushes
+
+
+def _game_from_fixture(d):
+    from katago_b200.npz_writer import FinishedGameData
+    L = d["dataLen"]
+    packed = (L * L + 7) // 8
+    g = FinishedGameData(d["X"], d["Y"], d["komi"])
+    g.game_hash, g.mode, g.training_weight = d["gameHash"], d["mode"], d["trainingWeight"]
+    g.draw_equivalent_wins_for_white = d["drawEquivalentWinsForWhite"]
+    g.hit_turn_limit, g.num_extra_black = bool(d["hitTurnLimit"]), d["numExtraBlack"]
+    g.end_finished, g.end_no_result = bool(d["endFinished"]), bool(d["endNoResult"])
+    g.boards_by_turn = d["boards"]
+    g.white_value_targets_by_turn = d["valueTargets"]
+    g.changed_neural_net_turns = d["changedNeuralNetTurns"]
+    g.final_full_area, g.final_ownership, g.final_white_scoring = d["finalFullArea"], d["finalOwnership"], d["finalWhiteScoring"]
+    for t in d["turns"]:
+        g.next_player_by_turn.append(t["nextPlayer"])
+        g.packed_input_by_turn.append(np.frombuffer(bytes.fromhex(t["packedInput"]), np.uint8).reshape(22, packed))
+        g.global_input_by_turn.append(np.asarray(t["globalInput"], np.float32))
+        g.target_weight_by_turn.append(t["targetWeight"])
+        g.policy_targets_by_turn.append((t["policyTarget"], t["unreducedNumVisits"]))
+        g.white_q_value_targets_by_turn.append(t["qTargets"])
+        g.policy_surprise_by_turn.append(t["policySurprise"]); g.policy_entropy_by_turn.append(t["policyEntropy"]); g.search_entropy_by_turn.append(t["searchEntropy"])
+        g.nn_raw_stats_by_turn.append(t["nnRawStats"])
+        if "reanalysis" in t:
+            g.reanalysis_by_turn.append(tuple(t["reanalysis"]))
+    return g
+
+
+@pytest.mark.parametrize("path", WRITEGAME_FIXTURES, ids=[os.path.basename(p)[10:-8] for p in WRITEGAME_FIXTURES])
+def test_write_game_matches_reference_write_game(path):
+    """Same files (row counts per flush, incl. the randomised first file), same rows in the same order, same integer targets
+    (the scoring plane and Q targets depend on every earlier Rand draw, so the draw order is checked too); float arrays to the
+    6 digits the reference's text sink prints."""
+    from katago_b200.npz_writer import TrainingDataWriter
+    d = json.loads(gzip.open(path, "rb").read())
+    want = _parse_text_dump(d["dump"])
+    got = []
+    w = TrainingDataWriter(None, d["maxRows"], d["firstFileMinRandProp"], d["dataLen"], "writegame" + d["seed"],
+                           on_flush=lambda b: got.append({k: v[:b.cur_rows].copy() for k, v in b.arrays.items()}))
+    w.write_game(_game_from_fixture(d))
+    w.flush_if_nonempty()
+    assert [len(f["globalTargetsNC"]) for f in want] == [len(f["globalTargetsNC"]) for f in got]
+    assert w.row_count == sum(len(f["globalTargetsNC"]) for f in want)
+    for fw, fg in zip(want, got):
+        n = len(fw["globalTargetsNC"])
+        assert [bytes.fromhex(r) for r in fw["binaryInputNCHWPacked"]] == [fg["binaryInputNCHWPacked"][i].tobytes() for i in range(n)]
+        for name in ("policyTargetsNCMove", "scoreDistrN", "valueTargetsNCHW", "qValueTargetsNCMove"):
+            a = np.stack(fw[name]).astype(np.int64)
+            b = fg[name].reshape(n, -1).astype(np.int64)
+            assert np.array_equal(a, b), (name, np.argwhere(a != b)[:5])
+        for name in ("globalInputNC", "globalTargetsNC"):
+            a = np.stack(fw[name])
+            b = fg[name].reshape(n, -1).astype(np.float64)
+            assert np.allclose(a, b, rtol=2e-5, atol=1e-30), (name, np.argwhere(~np.isclose(a, b, rtol=2e-5))[:5])
+
+
+def test_final_value_targets_and_scoring_match_the_reference_game_end():
+    """final_value_targets / scoring_from_area against what the driver computed with the reference's game-end code
+    (endAndScoreGameNow, ScoreValue::whiteWinsOfWinner / whiteScoreDrawAdjust, NNInputs::fillScoring)."""
+    from katago_b200.npz_writer import final_value_targets, scoring_from_area
+    for path in WRITEGAME_FIXTURES:
+        d = json.loads(gzip.open(path, "rb").read())
+        want = d["valueTargets"][-1]
+        got = final_value_targets(d["winner"], d["finalWhiteMinusBlackScore"], d["drawEquivalentWinsForWhite"], d["komi"], bool(d["endNoResult"]))
+        assert [float(np.float32(v)) for v in want[:4]] == [float(v) for v in got[:4]]
+        if not d["endNoResult"]:
+            assert want[4] == 1 and np.float32(want[5]) == got[5]
+        assert np.array_equal(scoring_from_area(d["finalOwnership"]), np.asarray(d["finalWhiteScoring"], np.float32))
+
+
+def test_writer_file_names_and_split(tmp_path):
+    """Real files: <16 hex digits>.npz named by the writer's Rand, rows split at max_rows_per_file, all rows present."""
+    from katago_b200.npz_writer import TrainingDataWriter
+    d = json.loads(gzip.open(WRITEGAME_FIXTURES[0], "rb").read())
+    w = TrainingDataWriter(str(tmp_path), 10, 1.0, d["dataLen"], "files")
+    w.write_game(_game_from_fixture(d))
+    w.flush_if_nonempty()
+    files = sorted(os.listdir(tmp_path))
+    assert all(len(f) == 20 and f.endswith(".npz") and f[:16] == f[:16].upper() for f in files)
+    rows = [np.load(os.path.join(tmp_path, f))["globalTargetsNC"].shape[0] for f in files]
+    assert sum(rows) == w.row_count and max(rows) <= 10 and len(files) == -(-w.row_count // 10)
