@@ -173,7 +173,7 @@ typedef struct kgb_selfplay_config {
   double subtree_value_bias_weight_exponent;      /* subtreeValueBiasWeightExponent (0.8) */
   int32_t use_graph_search;                       /* useGraphSearch: transpositions share a node (search.cpp:875-936) */
   int32_t graph_search_rep_bound;                 /* graphSearchRepBound (11) */
-  int32_t debug_hold_at_max_visits;               /* TEST ONLY: a game whose root has max_visits visits idles instead of moving */
+  int32_t debug_hold_at_max_visits;               /* hold mode: a game whose root has max_visits visits idles until kgb_selfplay_release (tests; game recording) */
   int32_t root_noise_enabled;                     /* rootNoiseEnabled: Dirichlet noise on the root policy */
   double root_dirichlet_noise_total_concentration;/* rootDirichletNoiseTotalConcentration (10.83) */
   double root_dirichlet_noise_weight;             /* rootDirichletNoiseWeight (0.25) */
@@ -263,6 +263,21 @@ KGB_API int kgb_selfplay_get_root_children(kgb_selfplay* sp, int game, int32_t* 
 /* NodeStats moments (searchnode.h:17-41; white's perspective) of game g's root and of its children by move position:
  * winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg.  child_stats[(X*Y+1)*5] (0 where no child), root_stats[5]. */
 KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double* child_stats, double* root_stats);
+/* Game recording (replaces the bookkeeping around the search in Play::runGame, program/play.cpp:1757-1936).
+ * With kgb_selfplay_config.debug_hold_at_max_visits = 1 a game whose search reached max_visits idles until it is released; the
+ * host reads the finished search (getters above and below), releases, and the next wave lets the device choose and play the move
+ * as usual.  games_mask[num_games] (1 = release) or NULL = all.  A released game holds again at its next finished search. */
+KGB_API int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* games_mask);
+/* Root visits of every game (visits[num_games]): a game is held when its entry has reached max_visits. */
+KGB_API int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* visits);
+/* What extractQValueTargets / computeNNRawStats (play.cpp:859-914) read besides the NodeStats: visits of the root's child NODES by
+ * move position (0 = no child), and the root's own evaluation root_nn_stats[5] = winLoss, noResult, scoreMean, scoreMeanSq, lead (white). */
+KGB_API int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int game, int32_t* child_node_visits, double* root_nn_stats);
+/* The last root move of slot `game`: info[4] = move position (X*Y = pass), flags (1 = it ended the game | 2 = without result | 4 = by
+ * the move limit), the move number it was played at, the slot's game index.  If it ended the game: final_score = white minus black
+ * with komi, final_colors[Y*X] and final_area[Y*X] (0 none, 1 black, 2 white; Board::calculateArea with every flag on, which under
+ * area scoring without tax is both the ownership and the full area of FinishedGameData). */
+KGB_API int kgb_selfplay_get_last_move(kgb_selfplay* sp, int game, int32_t* info, float* final_score, uint8_t* final_colors, uint8_t* final_area);
 /* The NN input row (NHWC [X*Y][22] + 19 globals) the last wave wrote for game g - what NNInputs::fillRowV7 would produce
  * for that leaf (planes listed in DESIGN.md §8; used by the feature parity tests). */
 KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global);

@@ -1017,6 +1017,42 @@ KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double
   });
 }
 
+KGB_API int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* games_mask) {
+  return guarded([&] {
+    if(!sp) throw std::invalid_argument("kgb_selfplay_release: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayRelease(sp->impl, games_mask);
+  });
+}
+
+KGB_API int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* visits) {
+  return guarded([&] {
+    if(!sp || !visits) throw std::invalid_argument("kgb_selfplay_get_root_visits: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadRootVisitsAll(sp->impl, visits);
+  });
+}
+
+KGB_API int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int game, int32_t* child_node_visits, double* root_nn_stats) {
+  return guarded([&] {
+    if(!sp || !child_node_visits || !root_nn_stats) throw std::invalid_argument("kgb_selfplay_get_root_extra: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadRootExtra(sp->impl, game, child_node_visits, root_nn_stats);
+  });
+}
+
+KGB_API int kgb_selfplay_get_last_move(kgb_selfplay* sp, int game, int32_t* info, float* final_score, uint8_t* final_colors, uint8_t* final_area) {
+  return guarded([&] {
+    if(!sp || !info || !final_score || !final_colors || !final_area) throw std::invalid_argument("kgb_selfplay_get_last_move: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadLastMove(sp->impl, game, info, final_score, final_colors, final_area);
+  });
+}
+
 KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global) {
   return guarded([&] {
     if(!sp || !spatial || !global || game < 0 || game >= sp->n) throw std::invalid_argument("kgb_selfplay_get_nn_row: bad argument");

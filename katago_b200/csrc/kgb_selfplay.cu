@@ -134,6 +134,12 @@ struct SPDev {
   unsigned long long* ladderCounters;   // [2] searches, search nodes
   int enableLadders;
   int* hist;                        // [game][5] last moves, most recent first: -1 none, -2 pass, else y*32+x
+  // game recording (hold mode): a held game moves once the host has read its search and set its release flag; the root move and, when
+  // it ended the game, the final position with its area stay readable until the slot's next move
+  uint8_t* releaseFlag;             // [game]
+  int* lastMove;                    // [game][4]: move position (policySize-1 = pass), 1 over | 2 no result | 4 move limit, its move number, games started
+  float* lastScore;                 // [game] white minus black incl. komi of the game the last move ended
+  uint32_t* finalBoard;             // [game][4][32]: black, white, black area, white area of that game's final position
   uint64_t* gameCounter;            // games started per slot (RNG stream)
   // tree [game][node]...
   int* nodeCount;                   // [game]
@@ -610,9 +616,20 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   gameMakeMove(d, g, bd, p, black, lane, passes, finished, noResult);
   int mv = d.moveNum[g] + 1;
   bool over = finished || mv >= d.maxMoves;
+  if(lane == 0) {
+    d.lastMove[g * 4 + 0] = best;
+    d.lastMove[g * 4 + 1] = over ? (1 | (noResult ? 2 : 0) | (finished ? 0 : 4)) : 0;
+    d.lastMove[g * 4 + 2] = mv - 1;
+    d.lastMove[g * 4 + 3] = (int)d.gameCounter[g];
+  }
   if(over) {
-    int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
+    uint32_t areaB, areaW;
+    boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);    // = the area boardAreaScoreBlackMinusWhite counts
+    int diff = warpCount(areaB) - warpCount(areaW);
     float whiteScore = d.komi - (float)diff;
+    uint32_t* fb = d.finalBoard + (size_t)g * 128;
+    fb[lane] = bd.b; fb[32 + lane] = bd.w; fb[64 + lane] = areaB; fb[96 + lane] = areaW;
+    if(lane == 0) d.lastScore[g] = whiteScore;
     if(lane == 0) {
       atomicAdd(d.gamesFinished, 1ULL);
       if(whiteScore < 0 && !noResult) atomicAdd(d.blackWins, 1ULL);
@@ -679,8 +696,12 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   // next playout starts, so that the wave still delivers a leaf for the evaluator.
   for(int attempt = 0; attempt < SP_MAX_PLAYOUTS_PER_WAVE && !gotLeaf; attempt++) {
   if(d.nodeVisits[gb] >= d.maxVisits) {
-    if(d.holdAtMaxVisits) break;   // test mode: keep the finished tree for inspection
+    // hold mode (tests, game recording): keep the finished tree until the host has read it and released the game
+    const bool released = d.releaseFlag[g] != 0;
+    __syncwarp();
+    if(d.holdAtMaxVisits && !released) break;
     rootAdvance(d, g, lane);
+    if(lane == 0) d.releaseFlag[g] = 0;
   }
   boardInit(bd, d.X, d.Y);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
@@ -1898,6 +1919,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.rootKo = sp->alloc<int>(G); d.rootBlackToMove = sp->alloc<int>(G); d.rootCapB = sp->alloc<int>(G); d.rootCapW = sp->alloc<int>(G);
   d.moveNum = sp->alloc<int>(G); d.consecPasses = sp->alloc<int>(G); d.hist = sp->alloc<int>(G * 5);
   d.gameCounter = sp->alloc<uint64_t>(G);
+  d.releaseFlag = sp->alloc<uint8_t>(G); d.lastMove = sp->alloc<int>(G * 4); d.lastScore = sp->alloc<float>(G); d.finalBoard = sp->alloc<uint32_t>(G * 128);
   d.prevB = sp->alloc<uint32_t>(2 * G * 32); d.prevW = sp->alloc<uint32_t>(2 * G * 32); d.prevKo = sp->alloc<int>(2 * G);
   d.enableLadders = c.disable_ladder_features ? 0 : 1;
   d.ladderScratch = sp->alloc<uint32_t>(G * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
@@ -2093,6 +2115,48 @@ void selfplayReadRootMoments(SelfplayImpl* sp, int g, double* childMoments /*[po
   for(int i = 0; i < d.policySize; i++)
     for(int k = 0; k < 5; k++) childMoments[i * 5 + k] = child[i] >= 0 ? mom[(size_t)child[i] * 5 + k] : 0.0;
   for(int k = 0; k < 5; k++) rootMoments[k] = mom[k];
+}
+
+// ---- game recording support (hold mode) ------------------------------------------------------------------------------------------
+void selfplayRelease(SelfplayImpl* sp, const uint8_t* mask /*[numGames] or NULL = all*/) {
+  const SPDev& d = sp->d;
+  if(mask) SPCK(cudaMemcpy(d.releaseFlag, mask, d.numGames, cudaMemcpyHostToDevice));
+  else SPCK(cudaMemset(d.releaseFlag, 1, d.numGames));
+  SPCK(cudaDeviceSynchronize());   // the loop's stream does not synchronise with the default stream these ran on
+}
+
+void selfplayReadRootVisitsAll(SelfplayImpl* sp, int* out /*[numGames]*/) {
+  const SPDev& d = sp->d;
+  SPCK(cudaMemcpy2D(out, sizeof(int), d.nodeVisits, (size_t)d.maxNodes * sizeof(int), sizeof(int), d.numGames, cudaMemcpyDeviceToHost));
+}
+
+// Visits of the root's child NODES by move position (0 where there is no child; under graph search a node's visits can exceed its
+// edge's) and the root's own evaluation: winLoss, noResult, scoreMean, scoreMeanSq, lead (white's perspective).
+void selfplayReadRootExtra(SelfplayImpl* sp, int g, int* childNodeVisits, double* rootNN) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  std::vector<int> child(d.policySize), nv(d.maxNodes);
+  SPCK(cudaMemcpy(child.data(), d.childNode + (size_t)g * d.maxNodes * d.policySize, d.policySize * sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(nv.data(), d.nodeVisits + (size_t)g * d.maxNodes, d.maxNodes * sizeof(int), cudaMemcpyDeviceToHost));
+  for(int i = 0; i < d.policySize; i++) childNodeVisits[i] = child[i] >= 0 ? nv[child[i]] : 0;
+  SPCK(cudaMemcpy(rootNN, d.nodeNNMoments + (size_t)g * d.maxNodes * 5, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+// The last root move of game slot g: info[4] = move position (X*Y = pass), flags (1 it ended the game | 2 without result | 4 by the
+// move limit), the move number it was played at, the slot's game index; when it ended the game also the final score (white minus
+// black, komi included), the final position and its area (0 none, 1 black, 2 white).
+void selfplayReadLastMove(SelfplayImpl* sp, int g, int* info, float* score, uint8_t* finalColors, uint8_t* finalArea) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  SPCK(cudaMemcpy(info, d.lastMove + (size_t)g * 4, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(score, d.lastScore + g, sizeof(float), cudaMemcpyDeviceToHost));
+  uint32_t fb[128];
+  SPCK(cudaMemcpy(fb, d.finalBoard + (size_t)g * 128, sizeof(fb), cudaMemcpyDeviceToHost));
+  for(int y = 0; y < d.Y; y++)
+    for(int x = 0; x < d.X; x++) {
+      finalColors[y * d.X + x] = (fb[y] >> x) & 1 ? 1 : (fb[32 + y] >> x) & 1 ? 2 : 0;
+      finalArea[y * d.X + x] = (fb[64 + y] >> x) & 1 ? 1 : (fb[96 + y] >> x) & 1 ? 2 : 0;
+    }
 }
 
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid) {

@@ -28,6 +28,10 @@ void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
 void selfplayReadRootMoments(SelfplayImpl* sp, int g, double* childMoments, double* rootMoments);
+void selfplayRelease(SelfplayImpl* sp, const uint8_t* mask);
+void selfplayReadRootVisitsAll(SelfplayImpl* sp, int* out);
+void selfplayReadRootExtra(SelfplayImpl* sp, int g, int* childNodeVisits, double* rootNN);
+void selfplayReadLastMove(SelfplayImpl* sp, int g, int* info, float* score, uint8_t* finalColors, uint8_t* finalArea);
 int selfplayReadLeafPath(SelfplayImpl* sp, int g, int* movesXY, int maxLen, int* valid);
 void selfplayReadRootChildren(SelfplayImpl* sp, int g, int* visits, float* policy, double* utilSum);
 void selfplayReadPlaySelection(SelfplayImpl* sp, int g, double* out);

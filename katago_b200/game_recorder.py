@@ -1,0 +1,196 @@
+"""Per-turn training targets from a finished root search, and the recorder that turns the device loop's games into
+`FinishedGameData` for the training-data writer.
+
+The reference derives a turn's targets from its `Search` right after the search ends (`extractSearchTargetsThisTurn`,
+program/play.cpp:931-948).  The functions here do the same from what the device loop exposes for a root - NodeStats moments of
+the root and its children, play selection values, the (possibly noised) root policy - all by move position (y * X + x, pass
+last).  CPU parity: tests/test_game_recorder.py against tests/golden/searchtargets.npz (dumped from the reference `Search`).
+
+`GameRecorder` drives a `SelfPlay` created with `debug_hold_at_max_visits=True`: a game whose search is finished idles until the
+recorder has read its root (a handful of small device reads per game and move, against a search of max_visits waves) and releases
+it; the device then chooses and plays the move exactly as it does without a recorder.  Finished games go to a `TrainingDataWriter`.
+Not recorded (the reference's options that the device loop does not have): side positions, cheap searches / reduced visits and
+their target weights (every turn has weight 1), lead estimation (hasLead only on the outcome entry), reanalysis, net changes.
+"""
+import math
+
+import numpy as np
+
+from .npz_writer import FinishedGameData, P_BLACK, P_WHITE, final_value_targets, pack_bits, policy_target_from_play_selection, scoring_from_area
+
+_f32 = np.float32
+
+
+def reported_search_values(moments):
+    """ReportedSearchValues (search/reportedsearchvalues.cpp:10-51) from NodeStats moments (winLossValueAvg, noResultValueAvg,
+    scoreMeanAvg, scoreMeanSqAvg, leadAvg), white's perspective: (winValue, lossValue, noResultValue, winLossValue, expectedScore)."""
+    win_loss, no_result, score_mean = float(moments[0]), float(moments[1]), float(moments[2])
+    win_loss = min(max(win_loss, -1.0), 1.0)
+    no_result = min(max(no_result, 0.0), 1.0 - abs(win_loss))
+    win = min(max(0.5 * (win_loss + (1.0 - no_result)), 0.0), 1.0)
+    loss = min(max(0.5 * (-win_loss + (1.0 - no_result)), 0.0), 1.0)
+    return win, loss, no_result, win_loss, score_mean
+
+
+def value_targets_from_root(root_moments):
+    """extractValueTargets (play.cpp:848-857): (win, loss, noResult, score, hasLead, lead) as float32; lead is not estimated."""
+    win, loss, no_result, _, score = reported_search_values(root_moments)
+    return (_f32(win), _f32(loss), _f32(no_result), _f32(score), 0, _f32(0.0))
+
+
+def q_targets_from_children(child_moments, child_node_visits, x_size):
+    """extractQValueTargets (play.cpp:859-888): one (x, y, winLoss, score, visits) per child with visits, white's perspective;
+    visits are the child NODE's visits (under graph search they can exceed the edge's)."""
+    out = []
+    n = len(child_node_visits)
+    for pos in range(n):
+        v = int(child_node_visits[pos])
+        if v <= 0:
+            continue
+        _, _, _, win_loss, score = reported_search_values(child_moments[pos])
+        x, y = (-1, -1) if pos == n - 1 else (pos % x_size, pos // x_size)
+        out.append((x, y, _f32(win_loss), _f32(score), v))
+    return out
+
+
+def policy_surprise_and_entropy(play_selection_values, policy):
+    """Search::getPolicySurpriseAndEntropy (search/searchresults.cpp:631-695): KL(target || policy), entropy of the target and of
+    the policy, where target = play selection values normalised.  play_selection_values: -1 where there is no child."""
+    psv = np.asarray(play_selection_values, np.float64)
+    pol = np.asarray(policy, np.float32)
+    idx = np.flatnonzero(psv >= 0)
+    total = 0.0
+    for i in idx:
+        total += psv[i]
+    surprise = search_entropy = 0.0
+    for i in idx:
+        p = max(float(pol[i]), 1e-100)
+        target = psv[i] / total
+        if target > 1e-100:
+            lt = math.log(target)
+            surprise += target * (lt - math.log(p))
+            search_entropy += -target * lt
+    policy_entropy = 0.0
+    for p in pol:
+        p = float(p)
+        if p > 1e-100:
+            policy_entropy += -p * math.log(p)
+    return max(surprise, 0.0), max(search_entropy, 0.0), max(policy_entropy, 0.0)
+
+
+def policy_target_moves(play_selection_values, x_size):
+    """Play::extractPolicyTarget as the sparse list the writer takes: (x, y, int16 value) for every child."""
+    psv = np.asarray(play_selection_values, np.float64)
+    vals = policy_target_from_play_selection(psv)
+    n = len(psv)
+    return [((-1, -1) if pos == n - 1 else (pos % x_size, pos // x_size)) + (int(vals[pos]),) for pos in range(n) if psv[pos] >= 0]
+
+
+class _GameInProgress:
+    def __init__(self):
+        self.turns = []       # per turn: what the finished root search gave
+        self.boards = []      # position before each move
+
+
+class GameRecorder:
+    """Records every game of a `SelfPlay` in hold mode and hands finished games to `writer.write_game`.
+
+    sp: katago_b200.nn_backend.SelfPlay created with debug_hold_at_max_visits=True (and ladder_nodes_per_wave=0, so that the wave
+    that evaluates a new root always carries its complete fillRowV7 row).  `step()` = one move of every game:
+      1. waves until every game is held at max_visits;
+      2. per game: root position, the root's input row (captured from the wave that evaluated the root), root / child statistics,
+         play selection values, root policy -> this turn's targets (functions above);
+      3. release; the next wave lets the device choose and play each move (its own Rand, temperature, LCB - unchanged) and
+         evaluates the new roots; a move that ended a game leaves the final position, its area and score readable, the recorder
+         builds the FinishedGameData (game-end targets of program/play.cpp:1977-2027) and the slot has already started a new game.
+    The game hash (FinishedGameData::gameHash, two 64-bit draws of the game's Rand in the reference) comes from `game_hash_fn`."""
+
+    def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None):
+        self.sp, self.writer, self.X, self.Y, self.komi = sp, writer, sp.x, sp.y, float(komi)
+        self.draw_eq = draw_equivalent_wins_for_white
+        self.games = [_GameInProgress() for _ in range(sp.num_games)]
+        self.on_game = on_game
+        self.game_hash_fn = game_hash_fn or (lambda slot, index: (((slot + 1) * 0x9E3779B97F4A7C15 + index) & (2 ** 64 - 1),
+                                                                  ((index + 1) * 0xC2B2AE3D27D4EB4F + slot) & (2 ** 64 - 1)))
+        self.games_written = 0
+        self.moves_recorded = 0
+        sp.run(1)                                    # evaluates every root: the rows of this wave are the roots' input rows
+        self.root_rows = [sp.nn_row(g) for g in range(sp.num_games)]
+
+    def step(self, max_waves=1000000):
+        sp, n = self.sp, self.sp.num_games
+        waves = 0
+        while int(sp.root_visits().min()) < sp.max_visits:
+            sp.run(8)
+            waves += 8
+            if waves > max_waves:
+                raise RuntimeError("GameRecorder: games did not reach max_visits")
+        for g in range(n):
+            colors, info = sp.game(g)
+            spatial, glob = self.root_rows[g]
+            _, policy, _ = sp.root_children(g)
+            child_stats, root_stats = sp.root_value_stats(g)
+            psv = sp.play_selection_values(g)
+            extra = sp.root_extra(g)
+            surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
+            nn = extra["root_nn_moments"]
+            gm = self.games[g]
+            gm.boards.append(np.asarray(colors, np.uint8).reshape(-1).copy())
+            gm.turns.append(dict(
+                next_player=P_BLACK if info["black_to_move"] else P_WHITE, move_num=info["move_num"],
+                packed=pack_bits(np.transpose(np.asarray(spatial, np.float32).reshape(1, self.X * self.Y, 22), (0, 2, 1)))[0],
+                global_input=np.asarray(glob, np.float32).copy(),
+                policy_target=(policy_target_moves(psv, self.X), int(info["root_visits"])),
+                value_targets=value_targets_from_root(root_stats),
+                q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
+                surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
+                # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy as searched
+                nn_raw_stats=(float(nn[0]), float(nn[2]), policy_entropy)))
+        sp.release()
+        sp.run(1)
+        self.moves_recorded += n
+        for g in range(n):
+            self.root_rows[g] = sp.nn_row(g)
+            last = sp.last_move(g)
+            self.games[g].turns[-1]["move"] = last["xy"]
+            if last["game_over"]:
+                self._finish_game(g, last)
+        return waves + 1
+
+    def _finish_game(self, g, last):
+        gm = self.games[g]
+        X, Y = self.X, self.Y
+        data = FinishedGameData(X, Y, self.komi)
+        data.draw_equivalent_wins_for_white = self.draw_eq
+        data.game_hash = self.game_hash_fn(g, last["game_index"])
+        data.end_finished = not last["hit_move_limit"]
+        data.hit_turn_limit = bool(last["hit_move_limit"])
+        data.end_no_result = bool(last["no_result"])
+        data.moves = [t["move"] for t in gm.turns]
+        data.boards_by_turn = gm.boards + [np.asarray(last["final_colors"], np.uint8).reshape(-1).copy()]
+        for t in gm.turns:
+            data.next_player_by_turn.append(t["next_player"])
+            data.packed_input_by_turn.append(t["packed"]); data.global_input_by_turn.append(t["global_input"])
+            data.target_weight_by_turn.append(1.0)
+            data.policy_targets_by_turn.append(t["policy_target"])
+            data.policy_surprise_by_turn.append(t["surprise"]); data.policy_entropy_by_turn.append(t["policy_entropy"]); data.search_entropy_by_turn.append(t["search_entropy"])
+            data.white_value_targets_by_turn.append(t["value_targets"])
+            data.white_q_value_targets_by_turn.append(t["q_targets"])
+            data.nn_raw_stats_by_turn.append(t["nn_raw_stats"])
+        if data.end_no_result:
+            area = np.zeros(X * Y, np.uint8)          # "nobody owns anything" (play.cpp:1977-1988)
+            data.white_value_targets_by_turn.append(final_value_targets(0, 0.0, self.draw_eq, self.komi, no_result=True))
+        else:
+            # area scoring without tax: ownership = full area = calculateArea with every flag on (boardhistory.cpp:591-610)
+            area = np.asarray(last["final_area"], np.uint8).reshape(-1).copy()
+            score = float(last["final_white_minus_black_score"])
+            winner = P_WHITE if score > 0 else P_BLACK if score < 0 else 0
+            data.white_value_targets_by_turn.append(final_value_targets(winner, score, self.draw_eq, self.komi))
+        data.final_full_area, data.final_ownership = area, area
+        data.final_white_scoring = scoring_from_area(area)
+        if self.writer is not None:
+            self.writer.write_game(data)
+        self.games_written += 1
+        if self.on_game is not None:
+            self.on_game(g, data)
+        self.games[g] = _GameInProgress()

@@ -80,6 +80,7 @@ ABI_SYMBOLS = [
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
     "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
+    "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
 ]
 
 _lib = None
@@ -133,6 +134,10 @@ def load_library():
     lib.kgb_selfplay_play_moves.argtypes = [P, P, I]
     lib.kgb_selfplay_random_openings.argtypes = [P, I]
     lib.kgb_selfplay_get_root_value_stats.argtypes = [P, I, P, P]
+    lib.kgb_selfplay_release.argtypes = [P, P]
+    lib.kgb_selfplay_get_root_visits.argtypes = [P, P]
+    lib.kgb_selfplay_get_root_extra.argtypes = [P, I, P, P]
+    lib.kgb_selfplay_get_last_move.argtypes = [P, I, P, P, P, P]
     lib.kgb_selfplay_set_search_rand.argtypes = [P, C.c_char_p]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
@@ -453,6 +458,7 @@ class SelfPlay:
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen
+        self.num_games, self.max_visits = int(num_games), int(max_visits)
 
     def run(self, steps: int):
         _check(load_library().kgb_selfplay_run(self._p, steps))
@@ -499,6 +505,37 @@ class SelfPlay:
         ch = np.zeros((self.x * self.y + 1, 5), np.float64); rt = np.zeros(5, np.float64)
         _check(load_library().kgb_selfplay_get_root_value_stats(self._p, g, ch.ctypes.data, rt.ctypes.data))
         return ch, rt
+
+    # ---- game recording (hold mode, kgb200.h) ----
+    def release(self, mask=None):
+        """Let held games (all, or those with mask[g] != 0) choose and play their move in the next wave."""
+        if mask is None:
+            _check(load_library().kgb_selfplay_release(self._p, None))
+        else:
+            m = np.ascontiguousarray(mask, np.uint8)
+            if m.shape != (self.num_games,):
+                raise ValueError("release: mask must have one entry per game")
+            _check(load_library().kgb_selfplay_release(self._p, m.ctypes.data))
+
+    def root_visits(self):
+        out = np.zeros(self.num_games, np.int32)
+        _check(load_library().kgb_selfplay_get_root_visits(self._p, out.ctypes.data))
+        return out
+
+    def root_extra(self, g: int):
+        """Visits of the root's child nodes by move position and the root's own evaluation (winLoss, noResult, scoreMean, scoreMeanSq, lead)."""
+        nv = np.zeros(self.x * self.y + 1, np.int32); nn = np.zeros(5, np.float64)
+        _check(load_library().kgb_selfplay_get_root_extra(self._p, g, nv.ctypes.data, nn.ctypes.data))
+        return dict(child_node_visits=nv, root_nn_moments=nn)
+
+    def last_move(self, g: int):
+        info = np.zeros(4, np.int32); score = np.zeros(1, np.float32)
+        colors = np.zeros((self.y, self.x), np.uint8); area = np.zeros((self.y, self.x), np.uint8)
+        _check(load_library().kgb_selfplay_get_last_move(self._p, g, info.ctypes.data, score.ctypes.data, colors.ctypes.data, area.ctypes.data))
+        pos = int(info[0])
+        return dict(pos=pos, xy=(-1, -1) if pos == self.x * self.y else (pos % self.x, pos // self.x), game_over=bool(info[1] & 1),
+                    no_result=bool(info[1] & 2), hit_move_limit=bool(info[1] & 4), move_num=int(info[2]), game_index=int(info[3]),
+                    final_white_minus_black_score=float(score[0]), final_colors=colors, final_area=area)
 
     def play_selection_values(self, g: int):
         """Search::getPlaySelectionValues of the root by move position (-1 = no child)."""

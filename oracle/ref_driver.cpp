@@ -25,6 +25,7 @@
 #include "core/fancymath.h"
 #include "dataio/numpywrite.h"
 #include "dataio/trainingwrite.h"
+#include "program/play.h"
 #include "core/logger.h"
 
 #include <cstdint>
@@ -304,6 +305,32 @@ static int cmdSearchFake(int argc, char** argv) {
   cout << "policy";
   for(int i = 0; i <= X * Y; i++) cout << " " << Global::strprintf("%.9g", nn->getPolicyProbsMaybeNoised()[i]);
   cout << endl;
+  {   // what Play::runGame records for this turn (program/play.cpp:848-948): value / Q / policy targets, surprise and entropies
+    ReportedSearchValues rv;
+    if(search->getNodeValues(root, rv))
+      cout << "valuetargets " << Global::strprintf("%.9g %.9g %.9g %.9g", (float)rv.winValue, (float)rv.lossValue, (float)rv.noResultValue, (float)rv.expectedScore) << endl;
+    double surprise = 0, searchEntropy = 0, policyEntropy = 0;
+    if(search->getPolicySurpriseAndEntropy(surprise, searchEntropy, policyEntropy))
+      cout << "surprise " << Global::strprintf("%.17g %.17g %.17g", surprise, searchEntropy, policyEntropy) << endl;
+    for(int i = 0; i < children.getCapacity(); i++) {
+      const SearchChildPointer& cp = children[i];
+      const SearchNode* child = cp.getIfAllocated();
+      if(child == NULL) break;
+      ReportedSearchValues cv;
+      if(!search->getNodeValues(child, cv) || cv.visits <= 0) continue;
+      Loc loc = cp.getMoveLoc();
+      int x = loc == Board::PASS_LOC ? -1 : Location::getX(loc, X), y = loc == Board::PASS_LOC ? -1 : Location::getY(loc, X);
+      cout << "qtarget " << x << " " << y << " " << Global::strprintf("%.9g %.9g", (float)cv.winLossValue, (float)cv.expectedScore) << " " << cv.visits << endl;
+    }
+    vector<PolicyTargetMove> pt; vector<Loc> locsBuf; vector<double> psvBuf;
+    Play::extractPolicyTarget(pt, search, root, locsBuf, psvBuf);
+    cout << "policytarget";
+    for(const PolicyTargetMove& m : pt) {
+      int x = m.loc == Board::PASS_LOC ? -1 : Location::getX(m.loc, X), y = m.loc == Board::PASS_LOC ? -1 : Location::getY(m.loc, X);
+      cout << " " << x << " " << y << " " << m.policyTarget;
+    }
+    cout << endl;
+  }
   delete search;
   delete nnEval;
   return 0;

@@ -1,0 +1,151 @@
+"""Per-turn training targets and the game recorder.
+
+CPU: the target functions of katago_b200/game_recorder.py against what the reference derives from its own finished `Search`
+(tests/golden/searchtargets.npz, generator tests/golden/make_searchtargets_fixture.py).
+GPU: whole games recorded from the device loop in hold mode and written as training rows."""
+import os, sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from katago_b200 import game_recorder as R
+from katago_b200 import npz_writer as W
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _cases():
+    d = np.load(os.path.join(GOLDEN, "searchtargets.npz"))
+    return d, int(d["num_cases"])
+
+
+def test_value_targets_match_reference_get_node_values():
+    d, n = _cases()
+    for i in range(n):
+        got = R.value_targets_from_root(d[f"c{i}_root_stats"])
+        assert [np.float32(v) for v in got[:4]] == list(d[f"c{i}_value_targets"]), i
+
+
+def test_q_targets_match_reference_extract_q_value_targets():
+    d, n = _cases()
+    for i in range(n):
+        X = int(d[f"c{i}_shape"][0])
+        q, mask = d[f"c{i}_q"], d[f"c{i}_q_mask"]
+        got = R.q_targets_from_children(d[f"c{i}_child_stats"], np.where(mask, q[:, 2], 0).astype(np.int64), X)
+        assert len(got) == int(mask.sum()) > 0
+        for (x, y, wl, sc, v) in got:
+            pos = len(mask) - 1 if x < 0 else y * X + x
+            assert mask[pos] and wl == np.float32(q[pos, 0]) and sc == np.float32(q[pos, 1]) and v == int(q[pos, 2]), (i, pos)
+
+
+def test_policy_surprise_and_entropies_match_reference():
+    d, n = _cases()
+    for i in range(n):
+        got = R.policy_surprise_and_entropy(d[f"c{i}_play_selection"], d[f"c{i}_policy"])
+        # the fixture's policy is printed with 9 significant digits and the sums run in child order there, position order here
+        assert np.allclose(got, d[f"c{i}_surprise"], rtol=1e-9, atol=1e-12), (i, got, d[f"c{i}_surprise"])
+
+
+def test_policy_target_matches_reference_extract_policy_target():
+    """Including the case where one move has more than 30000 visits (everything is scaled to fit int16)."""
+    d, n = _cases()
+    saw_cap = False
+    for i in range(n):
+        X = int(d[f"c{i}_shape"][0])
+        want = d[f"c{i}_policy_target"]
+        got = R.policy_target_moves(d[f"c{i}_play_selection"], X)
+        dense = np.full(len(want), -1, np.int32)
+        for (x, y, v) in got:
+            dense[len(want) - 1 if x < 0 else y * X + x] = v
+        assert np.array_equal(dense, want), (i, np.flatnonzero(dense != want)[:5])
+        saw_cap |= int(want.max()) == 30000
+    assert saw_cap
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("ko_rule,graph", [(0, True), (1, False)])
+def test_recorder_turns_device_games_into_training_rows(tmp_path, tmp_models, ko_rule, graph):
+    """Games of the device loop (9x9, deterministic fake net, selfplay8mainb18-style search) recorded move by move in hold mode:
+    the recorded moves replay to the recorded boards (device board replay), the final area / score / outcome targets agree with
+    each other, and the written .npz rows carry the positions, policy targets and outcome of the games they came from."""
+    from katago_b200.nn_backend import NeuralNet, SelfPlay, board_replay
+    lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
+    L, G, V = 9, 6, 48
+    ctx = NeuralNet.createComputeContext([0], L, L, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, G, False, True, 0)
+    komi = 7.0 if ko_rule else 6.5
+    sp = SelfPlay(h, G, V, komi=komi, seed=11, max_moves=70, debug_fake_nn=True, debug_hold_at_max_visits=True, use_graph_search=graph,
+                  value_weight_exponent=0.5, static_score_utility_factor=0.05, dynamic_score_utility_factor=0.3,
+                  dynamic_score_center_zero_weight=0.25, dynamic_score_center_scale=0.5, use_play_selection=True, use_lcb_for_selection=True,
+                  use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15, chosen_move_temperature=0.15,
+                  chosen_move_temperature_early=0.75, root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83,
+                  root_dirichlet_noise_weight=0.25, ko_rule=ko_rule, full_history_rules=True)
+    games = []
+    writer = W.TrainingDataWriter(str(tmp_path), 4096, 1.0, L, "recorder-test")    # one file: rows stay in write order
+    rec = R.GameRecorder(sp, writer, komi, on_game=lambda g, data: games.append((g, data)))
+    steps = 0
+    while len(games) < G and steps < 80:
+        rec.step()
+        steps += 1
+    st = sp.stats()
+    assert st["total_moves"] == steps * G            # hold / release: exactly one move per game and step
+    assert len(games) >= G, (len(games), steps)
+    writer.flush_if_nonempty()
+
+    total_rows = 0
+    for g, data in games:
+        n = len(data.moves)
+        total_rows += n
+        assert n == len(data.target_weight_by_turn) and len(data.boards_by_turn) == n + 1 and len(data.white_value_targets_by_turn) == n + 1
+        # the recorded moves reproduce the recorded boards, final position included
+        mv = np.array([[(x, y, data.next_player_by_turn[t]) for t, (x, y) in enumerate(data.moves)]], np.int8)
+        rep = board_replay(L, L, mv, True)
+        for t in range(n):
+            assert np.array_equal(rep["colors"][0, t].reshape(-1), data.boards_by_turn[t + 1]), (g, t)
+        assert (data.boards_by_turn[0] == 0).all()
+        assert [p for p in data.next_player_by_turn] == [1 + (t % 2) for t in range(n)]
+        # outcome: area of the final position (every flag on) as replayed == the area the loop scored
+        if not data.end_no_result:
+            area = rep["area"][0, n - 1].reshape(-1)
+            assert np.array_equal(area, data.final_ownership)
+            score = float((area == 2).sum()) - float((area == 1).sum()) + komi
+            last = data.white_value_targets_by_turn[-1]
+            adj = (data.draw_equivalent_wins_for_white - 0.5) if float(int(komi)) == komi else 0.0
+            assert last[3] == np.float32(score + adj) and last[0] == (1.0 if score > 0 else 0.0 if score < 0 else 0.5)
+        assert data.hit_turn_limit == (n >= 70 and not data.end_finished) and (data.end_finished or data.hit_turn_limit)
+        for t in range(n):
+            win, loss, nores, score = data.white_value_targets_by_turn[t][:4]
+            assert 0 <= win <= 1 and 0 <= loss <= 1 and abs(win + loss + nores - 1) < 1e-6 and abs(score) < 200
+            moves, visits = data.policy_targets_by_turn[t]
+            assert visits >= V and max(v for _, _, v in moves) >= 10
+            # the move played is one of the searched moves
+            assert tuple(data.moves[t]) in {(x, y) for x, y, v in moves}
+            q = data.white_q_value_targets_by_turn[t]
+            assert len(q) > 0 and all(abs(wl) <= 1 and v >= 1 for _, _, wl, _, v in q)
+
+    files = sorted(os.listdir(tmp_path))
+    rows = {k: np.concatenate([np.load(os.path.join(tmp_path, f))[k] for f in files]) for k in W.schema(L)}
+    assert rows["globalTargetsNC"].shape[0] == total_rows == writer.row_count
+    # rows come game by game, turn by turn: check positions, side to move and policy targets of the first recorded game
+    g0, d0 = games[0]
+    n0 = len(d0.moves)
+    planes = np.unpackbits(rows["binaryInputNCHWPacked"][:n0], axis=2)[:, :, :L * L]
+    for t in range(n0):
+        own, opp = d0.next_player_by_turn[t], 3 - d0.next_player_by_turn[t]
+        assert np.array_equal(planes[t, 1], (d0.boards_by_turn[t] == own).astype(np.uint8))
+        assert np.array_equal(planes[t, 2], (d0.boards_by_turn[t] == opp).astype(np.uint8))
+        assert rows["globalTargetsNC"][t, 51] == t
+        dense = np.zeros(L * L + 1, np.int16)
+        for x, y, v in d0.policy_targets_by_turn[t][0]:
+            dense[L * L if x < 0 else y * L + x] = v
+        assert np.array_equal(rows["policyTargetsNCMove"][t, 0], dense)
+        if t + 1 < n0:
+            assert rows["globalTargetsNC"][t, 28] == 1.0
+    assert rows["globalTargetsNC"][n0 - 1, 28] == 0.0          # the last turn has no next-turn policy
+    if not d0.end_no_result:
+        own_area = np.where(d0.final_ownership == d0.next_player_by_turn[0], 1, np.where(d0.final_ownership == 0, 0, -1))
+        assert np.array_equal(rows["valueTargetsNCHW"][0, 0].reshape(-1), own_area)
+    sp.free(); h.free(); ctx.free()
