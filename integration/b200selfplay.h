@@ -62,24 +62,76 @@ class GameSlots {
     return out;
   }
   // per root child: edge visits, policy prior (the noised one at the root), utilityAvg - what ReportedSearchValues are built from
-  struct ChildStats { Move move; int visits; float prior; double utilityAvg, winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg; };
+  struct ChildStats { Move move; int visits; int nodeVisits; float prior; double utilityAvg, winLossValueAvg, noResultValueAvg, scoreMeanAvg, scoreMeanSqAvg, leadAvg; };
   std::vector<ChildStats> rootChildren(int slot) const {
     const size_t ps = (size_t)x_ * y_ + 1;
     std::vector<int32_t> visits(ps); std::vector<float> policy(ps); std::vector<double> util(ps), mom(ps * 5), rootMom(5);
     check(kgb_selfplay_get_root_children(sp_, slot, visits.data(), policy.data(), util.data()));
     check(kgb_selfplay_get_root_value_stats(sp_, slot, mom.data(), rootMom.data()));
+    const std::vector<int32_t> nodeVisits = childNodeVisits(slot);
     std::vector<ChildStats> out;
     for(size_t i = 0; i < ps; i++) {
       if(visits[i] <= 0) continue;
       ChildStats c;
       if(i < ps - 1) { c.move.x = (int)(i % x_); c.move.y = (int)(i / x_); }
-      c.visits = visits[i]; c.prior = policy[i]; c.utilityAvg = util[i];
+      c.visits = visits[i]; c.nodeVisits = nodeVisits[i]; c.prior = policy[i]; c.utilityAvg = util[i];
       c.winLossValueAvg = mom[i * 5]; c.noResultValueAvg = mom[i * 5 + 1]; c.scoreMeanAvg = mom[i * 5 + 2]; c.scoreMeanSqAvg = mom[i * 5 + 3]; c.leadAvg = mom[i * 5 + 4];
       out.push_back(c);
     }
     return out;
   }
   kgb_selfplay_stats stats() const { kgb_selfplay_stats s; check(kgb_selfplay_get_stats(sp_, &s)); return s; }
+
+  // ---- game recording (kgb_selfplay_config.debug_hold_at_max_visits = 1): a slot whose search is finished idles until release() ----
+  std::vector<int32_t> rootVisitsAll() const { std::vector<int32_t> v((size_t)n_); check(kgb_selfplay_get_root_visits(sp_, v.data())); return v; }
+  bool allHeld(int maxVisits) const { for(int32_t v : rootVisitsAll()) if(v < maxVisits) return false; return true; }
+  void release() { check(kgb_selfplay_release(sp_, nullptr)); }
+  void release(const std::vector<uint8_t>& mask) { if((int)mask.size() != n_) throw std::invalid_argument("release: one entry per slot"); check(kgb_selfplay_release(sp_, mask.data())); }
+  // NodeStats moments of the root (white's perspective): what Search::getNodeValues(rootNode) is built from; and of the root's own evaluation
+  struct ValueStats { double winLossValueAvg = 0, noResultValueAvg = 0, scoreMeanAvg = 0, scoreMeanSqAvg = 0, leadAvg = 0; };
+  ValueStats rootStats(int slot) const {
+    std::vector<double> mom(((size_t)x_ * y_ + 1) * 5), r(5);
+    check(kgb_selfplay_get_root_value_stats(sp_, slot, mom.data(), r.data()));
+    return ValueStats{r[0], r[1], r[2], r[3], r[4]};
+  }
+  ValueStats rootNNStats(int slot) const {
+    std::vector<int32_t> nv((size_t)x_ * y_ + 1); double r[5];
+    check(kgb_selfplay_get_root_extra(sp_, slot, nv.data(), r));
+    return ValueStats{r[0], r[1], r[2], r[3], r[4]};
+  }
+  // visits of the root's child nodes by move position (0 = no child; not the edge visits under graph search)
+  std::vector<int32_t> childNodeVisits(int slot) const {
+    std::vector<int32_t> nv((size_t)x_ * y_ + 1); double r[5];
+    check(kgb_selfplay_get_root_extra(sp_, slot, nv.data(), r));
+    return nv;
+  }
+  // root policy by move position as searched (temperature and noise applied), -1 = illegal: NNOutput::getPolicyProbsMaybeNoised
+  std::vector<float> rootPolicy(int slot) const {
+    const size_t ps = (size_t)x_ * y_ + 1;
+    std::vector<int32_t> visits(ps); std::vector<float> policy(ps); std::vector<double> util(ps);
+    check(kgb_selfplay_get_root_children(sp_, slot, visits.data(), policy.data(), util.data()));
+    return policy;
+  }
+  // the NN input row of the slot's last wave (NHWC [y*x][22] and 19 globals); right after a release + one wave it is the new root's
+  void inputRow(int slot, std::vector<float>& spatial, std::vector<float>& global) const {
+    spatial.resize((size_t)x_ * y_ * 22); global.resize(19);
+    check(kgb_selfplay_get_nn_row(sp_, slot, spatial.data(), global.data()));
+  }
+  struct LastMove {
+    Move move; bool gameOver = false, noResult = false, hitMoveLimit = false; int moveNumber = 0, gameIndex = 0;
+    float finalWhiteMinusBlackScore = 0;           // komi included
+    std::vector<uint8_t> finalColors, finalArea;   // [y][x]: 0 none, 1 black, 2 white (valid when gameOver)
+  };
+  LastMove lastMove(int slot) const {
+    LastMove m; int32_t info[4];
+    m.finalColors.resize((size_t)x_ * y_); m.finalArea.resize((size_t)x_ * y_);
+    check(kgb_selfplay_get_last_move(sp_, slot, info, &m.finalWhiteMinusBlackScore, m.finalColors.data(), m.finalArea.data()));
+    if(info[0] < x_ * y_) { m.move.x = info[0] % x_; m.move.y = info[0] / x_; }
+    m.gameOver = info[1] & 1; m.noResult = info[1] & 2; m.hitMoveLimit = info[1] & 4; m.moveNumber = info[2]; m.gameIndex = info[3];
+    return m;
+  }
+  int xLen() const { return x_; }
+  int yLen() const { return y_; }
 
  private:
   struct Info { int32_t v[6]; int32_t operator[](int i) const { return v[i]; } };

@@ -1,0 +1,192 @@
+"""`python -m katago_b200.selfplay_cli` - the reference's `katago selfplay` command (command/selfplay.cpp) on the device loop
+(first slice).
+
+    python -m katago_b200.selfplay_cli -models-dir DIR -output-dir DIR -config selfplay.cfg [-max-games-total N]
+                                       [-override-config "key=value,key=value"] [-games-per-gpu N] [-strict]
+
+Same arguments and the same output layout as the reference (`<output-dir>/<model name>/tdata/<16 hex>.npz`, selfplay.cpp:177-221),
+and it reads the reference's own .cfg files: every search / rules / data key the device loop implements is mapped to its
+`kgb_selfplay_config` field (`selfplay_kwargs_from_cfg`), every other key is reported - either as irrelevant here (logging, thread
+and device placement of the reference's CPU threads) or as NOT BUILT (options that change the data distribution: forks, cheap
+searches, komi / rules / board-size randomisation, ...).  `-strict` turns the second group into an error.
+
+The reference randomises rules and board size per game; one loop instance plays one rule set on one board size, so list-valued
+keys (`koRules`, `bSizes`, ...) must contain a value the loop supports and the first such value is used (reported).
+There is no CPU fallback: without a B200 the command fails when it creates the evaluator."""
+import argparse
+import glob
+import os
+import sys
+
+# reference key -> (SelfPlay keyword, converter)
+_B = lambda s: s.strip().lower() in ("true", "1", "yes")
+_SEARCH_KEYS = {
+    "maxVisits": ("max_visits", int),
+    "cpuctExploration": ("cpuct_exploration", float), "cpuctExplorationLog": ("cpuct_exploration_log", float),
+    "cpuctExplorationBase": ("cpuct_exploration_base", float), "fpuReductionMax": ("fpu_reduction_max", float),
+    "rootFpuReductionMax": ("root_fpu_reduction_max", float), "fpuLossProp": ("fpu_loss_prop", float), "rootFpuLossProp": ("root_fpu_loss_prop", float),
+    "fpuParentWeight": ("fpu_parent_weight", float), "fpuParentWeightByVisitedPolicy": ("fpu_parent_weight_by_visited_policy", _B),
+    "fpuParentWeightByVisitedPolicyPow": ("fpu_parent_weight_by_visited_policy_pow", float), "valueWeightExponent": ("value_weight_exponent", float),
+    "cpuctUtilityStdevPrior": ("cpuct_utility_stdev_prior", float), "cpuctUtilityStdevPriorWeight": ("cpuct_utility_stdev_prior_weight", float),
+    "cpuctUtilityStdevScale": ("cpuct_utility_stdev_scale", float), "rootDesiredPerChildVisitsCoeff": ("root_desired_per_child_visits_coeff", float),
+    "subtreeValueBiasFactor": ("subtree_value_bias_factor", float), "subtreeValueBiasWeightExponent": ("subtree_value_bias_weight_exponent", float),
+    "useGraphSearch": ("use_graph_search", _B), "graphSearchRepBound": ("graph_search_rep_bound", int),
+    "rootNoiseEnabled": ("root_noise_enabled", _B), "rootDirichletNoiseTotalConcentration": ("root_dirichlet_noise_total_concentration", float),
+    "rootDirichletNoiseWeight": ("root_dirichlet_noise_weight", float), "rootPolicyTemperature": ("root_policy_temperature", float),
+    "rootPolicyTemperatureEarly": ("root_policy_temperature_early", float), "chosenMoveTemperature": ("chosen_move_temperature", float),
+    "chosenMoveTemperatureEarly": ("chosen_move_temperature_early", float), "chosenMoveTemperatureHalflife": ("chosen_move_temperature_halflife", float),
+    "chosenMoveTemperatureOnlyBelowProb": ("chosen_move_temperature_only_below_prob", float),
+    "chosenMoveSubtract": ("chosen_move_subtract", float), "chosenMovePrune": ("chosen_move_prune", float),
+    "useLcbForSelection": ("use_lcb_for_selection", _B), "lcbStdevs": ("lcb_stdevs", float), "minVisitPropForLCB": ("min_visit_prop_for_lcb", float),
+    "useNonBuggyLcb": ("use_non_buggy_lcb", _B), "winLossUtilityFactor": ("win_loss_utility_factor", float),
+    "staticScoreUtilityFactor": ("static_score_utility_factor", float), "dynamicScoreUtilityFactor": ("dynamic_score_utility_factor", float),
+    "dynamicScoreCenterZeroWeight": ("dynamic_score_center_zero_weight", float), "dynamicScoreCenterScale": ("dynamic_score_center_scale", float),
+    "noResultUtilityForWhite": ("no_result_utility_for_white", float), "drawEquivalentWinsForWhite": ("draw_equivalent_wins_for_white", float),
+    "rootNumSymmetriesToSample": ("root_num_symmetries_to_sample", int), "nnCacheSizePowerOfTwo": ("nn_cache_size_power_of_two", int),
+    "maxMovesPerGame": ("max_moves", int),
+}
+# keys that only place or log the reference's own CPU threads / evaluator servers: nothing to do here
+_IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
+                        "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir")
+# neutral values: the option is switched off, so not having it changes nothing
+_NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0, "cheapSearchProb": 0.0,
+            "reduceVisits": False, "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0, "policySurpriseDataWeight": 0.0,
+            "valueSurpriseDataWeight": 0.0, "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
+            "handicapProb": 0.0, "komiStdev": 0.0, "komiBigStdevProb": 0.0, "komiBiggerStdevProb": 0.0, "allowRectangleProb": 0.0,
+            "rootEndingBonusPoints": 0.0, "rootPruneUselessMoves": False, "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
+_KO_RULES = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2, "SPIGHT": 3}
+
+
+def parse_cfg(path_or_text, is_text=False):
+    """KataGo .cfg: `key = value` lines, `#` comments (core/config_parser.cpp).  `@include` is not supported.  Later keys win."""
+    text = path_or_text if is_text else open(path_or_text).read()
+    out = {}
+    for n, raw in enumerate(text.splitlines(), 1):
+        line = raw.split("#", 1)[0].strip()
+        if not line:
+            continue
+        if line.startswith("@"):
+            raise ValueError(f"line {n}: '{line.split()[0]}' directives are not supported")
+        if "=" not in line:
+            raise ValueError(f"line {n}: expected 'key = value', got {raw!r}")
+        k, v = line.split("=", 1)
+        out[k.strip()] = v.strip()
+    return out
+
+
+def _first_supported(cfg, key, supported, report, default):
+    if key not in cfg:
+        return default
+    vals = [v.strip() for v in cfg[key].split(",") if v.strip()]
+    ok = [v for v in vals if v.upper() in supported or v.lower() in supported]
+    if not ok:
+        raise ValueError(f"{key} = {cfg[key]}: none of these is built (supported: {sorted(supported)})")
+    if len(set(vals)) > 1:
+        report["fixed"].append(f"{key}: the reference draws one of [{cfg[key]}] per game; this loop plays '{ok[0]}' in every game")
+    return ok[0]
+
+
+def selfplay_kwargs_from_cfg(cfg, strict=False):
+    """(kwargs for nn_backend.SelfPlay, data settings, report) from a parsed reference .cfg.
+    report: {"mapped": [...], "irrelevant": [...], "fixed": [...], "not_built": [...]}."""
+    report = {"mapped": [], "irrelevant": [], "fixed": [], "not_built": []}
+    kw = {}
+    used = set()
+    for key, (name, conv) in _SEARCH_KEYS.items():
+        if key in cfg:
+            kw[name] = conv(cfg[key])
+            used.add(key); report["mapped"].append(key)
+    kw["use_play_selection"] = True                       # Search::getChosenMoveLoc always goes through the play selection values
+    # rules: one value per list
+    ko = _first_supported(cfg, "koRules", set(_KO_RULES), report, "SIMPLE").upper()
+    kw["ko_rule"] = _KO_RULES[ko]
+    kw["full_history_rules"] = True
+    _first_supported(cfg, "scoringRules", {"AREA"}, report, "AREA")
+    _first_supported(cfg, "taxRules", {"NONE"}, report, "NONE")
+    _first_supported(cfg, "hasButtons", {"false"}, report, "false")
+    kw["multi_stone_suicide_legal"] = _B(_first_supported(cfg, "multiStoneSuicideLegals", {"false", "true"}, report, "true"))
+    size = int(_first_supported(cfg, "bSizes", {str(s) for s in range(2, 20)}, report, "19"))
+    used.update(("koRules", "scoringRules", "taxRules", "hasButtons", "multiStoneSuicideLegals", "bSizes", "bSizeRelProbs"))
+    komi = float(cfg["komiMean"]) if "komiMean" in cfg else 7.5      # komiAuto under area scoring
+    used.update(("komiMean", "komiAuto"))
+    data = {"board_size": size, "komi": komi,
+            "data_board_len": int(cfg.get("dataBoardLen", size)), "max_rows_per_train_file": int(cfg.get("maxRowsPerTrainFile", 20000)),
+            "first_file_rand_min_prop": float(cfg.get("firstFileRandMinProp", 1.0)), "num_game_threads": int(cfg.get("numGameThreads", 256))}
+    used.update(("dataBoardLen", "maxRowsPerTrainFile", "firstFileRandMinProp", "numGameThreads"))
+    if data["data_board_len"] != size:
+        raise ValueError(f"dataBoardLen = {data['data_board_len']} but the board is {size}x{size}: rows smaller than the data frame are not built")
+    for key, val in cfg.items():
+        if key in used:
+            continue
+        if key.startswith(_IRRELEVANT_PREFIXES):
+            report["irrelevant"].append(key)
+            continue
+        neutral = _NEUTRAL.get(key, None)
+        if neutral is not None:
+            cur = _B(val) if isinstance(neutral, bool) else float(val)
+            if cur == neutral:
+                continue
+        report["not_built"].append(f"{key} = {val}")
+    if strict and report["not_built"]:
+        raise ValueError("options that are not built: " + "; ".join(report["not_built"]))
+    return kw, data, report
+
+
+def newest_model(models_dir):
+    """The reference polls the models dir for the newest net (command/selfplay.cpp:150-176); this takes the newest once."""
+    files = [f for ext in ("*.bin.gz", "*.bin", "*.txt.gz", "*.txt") for f in glob.glob(os.path.join(models_dir, ext))]
+    files += [f for f in glob.glob(os.path.join(models_dir, "*", "model.bin.gz"))]
+    if not files:
+        raise FileNotFoundError(f"no model file in {models_dir}")
+    return max(files, key=os.path.getmtime)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="katago_b200.selfplay_cli", description="Self-play data generation on the B200 device loop", prefix_chars="-")
+    ap.add_argument("-models-dir", required=True)
+    ap.add_argument("-output-dir", required=True)
+    ap.add_argument("-config", required=True)
+    ap.add_argument("-max-games-total", type=int, default=0, help="stop after this many finished games (0 = run until interrupted)")
+    ap.add_argument("-override-config", default="", help="key=value,key=value")
+    ap.add_argument("-games-per-gpu", type=int, default=256, help="concurrent games (the evaluator batch); numGameThreads is capped by it")
+    ap.add_argument("-strict", action="store_true", help="fail if the config asks for an option that is not built")
+    ap.add_argument("-seed", type=int, default=0)
+    a = ap.parse_args(argv)
+    cfg = parse_cfg(a.config)
+    for kv in [s for s in a.override_config.split(",") if s.strip()]:
+        k, v = kv.split("=", 1)
+        cfg[k.strip()] = v.strip()
+    kw, data, report = selfplay_kwargs_from_cfg(cfg, strict=a.strict)
+    for line in report["fixed"]:
+        print("[config] " + line, file=sys.stderr)
+    if report["not_built"]:
+        print("[config] NOT BUILT, ignored: " + "; ".join(report["not_built"]), file=sys.stderr)
+
+    from .nn_backend import NeuralNet, SelfPlay          # loads libkgb200; fails loudly without a B200
+    from .npz_writer import TrainingDataWriter
+    from .game_recorder import GameRecorder
+    model_path = newest_model(a.models_dir)
+    model_name = os.path.basename(os.path.dirname(model_path)) if os.path.basename(model_path) == "model.bin.gz" else os.path.basename(model_path).split(".")[0]
+    tdata = os.path.join(a.output_dir, model_name, "tdata")
+    os.makedirs(tdata, exist_ok=True)
+    L = data["board_size"]
+    games = min(a.games_per_gpu, data["num_game_threads"])
+    lm = NeuralNet.loadModelFile(model_path)
+    ctx = NeuralNet.createComputeContext([0], L, L, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, 0)
+    sp = SelfPlay(h, games, kw.pop("max_visits", 600), komi=data["komi"], seed=a.seed, debug_hold_at_max_visits=True, **kw)
+    writer = TrainingDataWriter(tdata, data["max_rows_per_train_file"], data["first_file_rand_min_prop"], L, f"selfplay{a.seed}")
+    rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5))
+    try:
+        while a.max_games_total <= 0 or rec.games_written < a.max_games_total:
+            rec.step()
+    except KeyboardInterrupt:
+        pass
+    writer.flush_if_nonempty()
+    print(f"{rec.games_written} games, {writer.row_count} rows -> {tdata}")
+    sp.free(); h.free(); ctx.free()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

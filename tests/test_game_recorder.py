@@ -149,3 +149,73 @@ def test_recorder_turns_device_games_into_training_rows(tmp_path, tmp_models, ko
         own_area = np.where(d0.final_ownership == d0.next_player_by_turn[0], 1, np.where(d0.final_ownership == 0, 0, -1))
         assert np.array_equal(rows["valueTargetsNCHW"][0, 0].reshape(-1), own_area)
     sp.free(); h.free(); ctx.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ko_rule", [0, 1])
+def test_recorded_games_through_the_reference_writer(tmp_path, tmp_models, ko_rule):
+    """The integrated configuration: oracle/_ref/kgref_record plays games on the device loop, fills the REFERENCE's
+    FinishedGameData (integration/b200record.h) and lets the reference's own TrainingDataWriter write them - every input plane
+    recomputed by the reference's fillRowV7 on its own Board / BoardHistory, every move re-checked by its isLegal, game end and
+    final score by its BoardHistory.  The same configuration recorded by katago_b200/game_recorder.py + npz_writer.py must give the
+    same rows: input planes bit for bit (the device's featurization of whole games vs the reference's), integer targets exactly,
+    float columns to the 6 digits of the reference's text sink."""
+    import ctypes, subprocess
+    from katago_b200.nn_backend import NeuralNet, SelfPlay
+    from test_npz_writer import _parse_text_dump
+    exe = os.path.join(ROOT, "oracle", "_ref", "kgref_record")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/kgref_record not built (needs the reference sources at build time)")
+    L, G, V, NUM = 9, 6, 40, 6
+    komi = 7.0 if ko_rule else 6.5
+    lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
+    ctx = NeuralNet.createComputeContext([0], L, L, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, G, False, True, 0)
+    sp = SelfPlay(h, G, V, komi=komi, seed=23, max_moves=60, debug_fake_nn=True, debug_hold_at_max_visits=True, use_graph_search=(ko_rule == 0),
+                  value_weight_exponent=0.5, static_score_utility_factor=0.05, dynamic_score_utility_factor=0.3,
+                  dynamic_score_center_zero_weight=0.25, dynamic_score_center_scale=0.5, use_play_selection=True, use_lcb_for_selection=True,
+                  use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15, chosen_move_temperature=0.15,
+                  chosen_move_temperature_early=0.75, root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83,
+                  root_dirichlet_noise_weight=0.25, ko_rule=ko_rule, full_history_rules=True)
+    cfg_path = tmp_path / "config.bin"
+    cfg_path.write_bytes(ctypes.string_at(ctypes.addressof(sp.cfg), ctypes.sizeof(sp.cfg)))
+    out_path = tmp_path / "reference_rows.txt"
+    r = subprocess.run([exe, tmp_models["tiny_reg"], str(L), str(cfg_path), str(NUM), str(out_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = _parse_text_dump(out_path.read_text())
+    assert len(want) == 1
+
+    got = []
+    writer = W.TrainingDataWriter(None, 4096, 1.0, L, "recorder-test", on_flush=lambda b: got.append({k: v[:b.cur_rows].copy() for k, v in b.arrays.items()}))
+    games = []
+
+    class FirstGames:                      # the driver writes the first NUM finished games, in the order they finish
+        def write_game(self, data):
+            if len(games) < NUM:
+                writer.write_game(data)
+            games.append(data)
+    rec = R.GameRecorder(sp, FirstGames(), komi)
+    steps = 0
+    while len(games) < NUM and steps < 2000:
+        rec.step()
+        steps += 1
+    writer.flush_if_nonempty()
+    assert len(got) == 1
+    fw, fg = want[0], got[0]
+    n = len(fw["globalTargetsNC"])
+    assert n == fg["globalTargetsNC"].shape[0] == sum(len(d.moves) for d in games[:NUM]) > 0
+    ref_planes = [bytes.fromhex(r) for r in fw["binaryInputNCHWPacked"]]
+    for i in range(n):
+        if ref_planes[i] != fg["binaryInputNCHWPacked"][i].tobytes():
+            a = np.unpackbits(np.frombuffer(ref_planes[i], np.uint8).reshape(22, -1), axis=1)[:, :L * L]
+            b = np.unpackbits(fg["binaryInputNCHWPacked"][i], axis=1)[:, :L * L]
+            raise AssertionError(("input planes differ", i, sorted(set(np.argwhere(a != b)[:, 0].tolist()))))
+    for name in ("policyTargetsNCMove", "scoreDistrN", "valueTargetsNCHW", "qValueTargetsNCMove"):
+        a = np.stack(fw[name]).astype(np.int64)
+        b = fg[name].reshape(n, -1).astype(np.int64)
+        assert np.array_equal(a, b), (name, np.argwhere(a != b)[:5])
+    for name in ("globalInputNC", "globalTargetsNC"):
+        a = np.stack(fw[name])
+        b = fg[name].reshape(n, -1).astype(np.float64)
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-30), (name, np.argwhere(~np.isclose(a, b, rtol=2e-5, atol=1e-30))[:5])
+    sp.free(); h.free(); ctx.free()

@@ -1,0 +1,83 @@
+"""CPU tests of the `selfplay` command's configuration layer: the reference's .cfg syntax and key names."""
+import inspect, os, sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from katago_b200 import selfplay_cli as C
+
+CFG = os.path.join(ROOT, "tests", "golden", "selfplay_like_b18.cfg")
+
+
+def test_stock_training_config_maps_onto_the_loop():
+    cfg = C.parse_cfg(CFG)
+    kw, data, report = C.selfplay_kwargs_from_cfg(cfg)
+    # the search block of the stock configuration arrives under the loop's parameter names
+    assert kw["max_visits"] == 2000 and kw["cpuct_exploration"] == 1.05 and kw["cpuct_exploration_log"] == 0.28
+    assert kw["root_fpu_reduction_max"] == 0.0 and kw["value_weight_exponent"] == 0.5 and kw["use_graph_search"] is True
+    assert kw["subtree_value_bias_factor"] == 0.30 and kw["root_num_symmetries_to_sample"] == 4 and kw["use_lcb_for_selection"] is True
+    assert kw["root_policy_temperature_early"] == 1.5 and kw["chosen_move_temperature_halflife"] == 19.0 and kw["nn_cache_size_power_of_two"] == 24
+    assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
+    assert data == {"board_size": 19, "komi": 7.5, "data_board_len": 19, "max_rows_per_train_file": 20000, "first_file_rand_min_prop": 0.15, "num_game_threads": 800}
+    # every keyword exists on the loop
+    from katago_b200.nn_backend import SelfPlay
+    params = set(inspect.signature(SelfPlay.__init__).parameters)
+    assert set(kw) <= params, set(kw) - params
+    # per-game randomisation the loop does not have is reported, as are the data-distribution options that are not built
+    assert any(s.startswith("koRules") for s in report["fixed"]) and any(s.startswith("bSizes") for s in report["fixed"])
+    nb = " ".join(report["not_built"])
+    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "rootEndingBonusPoints", "rootPruneUselessMoves", "handicapProb", "komiStdev"):
+        assert key in nb, key
+    assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
+    assert not any(k in nb for k in ("maxVisits", "cpuctExploration", "koRules", "dataBoardLen"))
+    with pytest.raises(ValueError, match="not built"):
+        C.selfplay_kwargs_from_cfg(cfg, strict=True)
+
+
+def test_neutral_values_and_unsupported_rules():
+    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\ncheapSearchProb = 0\nreduceVisits = false\nkoRules = POSITIONAL\nbSizes = 9\nkomiMean = 7\n", is_text=True), strict=True)
+    assert kw["ko_rule"] == 1 and data["board_size"] == 9 and data["komi"] == 7.0 and report["not_built"] == [] and report["fixed"] == []
+    with pytest.raises(ValueError, match="none of these is built"):
+        C.selfplay_kwargs_from_cfg(C.parse_cfg("scoringRules = TERRITORY\n", is_text=True))
+    with pytest.raises(ValueError, match="dataBoardLen"):
+        C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9\ndataBoardLen = 19\n", is_text=True))
+    with pytest.raises(ValueError, match="expected 'key = value'"):
+        C.parse_cfg("maxVisits 100\n", is_text=True)
+    assert C.parse_cfg("a = 1 # comment\n\n# only a comment\nb=x=y\n", is_text=True) == {"a": "1", "b": "x=y"}
+
+
+def test_command_fails_loudly_without_a_gpu(tmp_path):
+    """No CPU fallback: on a machine without a B200 the command stops at the evaluator with the library's error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from katago_b200 import modelgen
+    models = tmp_path / "models"; models.mkdir()
+    modelgen.write_model(str(models / "tiny.bin"), "tiny_reg", seed=3)
+    with pytest.raises(Exception, match="no CUDA device|CUDA"):
+        C.main(["-models-dir", str(models), "-output-dir", str(tmp_path / "out"), "-config", CFG, "-max-games-total", "1", "-override-config", "bSizes=9,dataBoardLen=9"])
+
+
+@pytest.mark.gpu
+def test_command_writes_training_files(tmp_path):
+    """End to end on a B200: models dir + reference-style .cfg -> <output-dir>/<model>/tdata/<16 hex>.npz readable as training rows."""
+    import numpy as np
+    from katago_b200 import modelgen
+    models = tmp_path / "models"; models.mkdir()
+    modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
+    out = tmp_path / "out"
+    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", CFG, "-max-games-total", "3", "-games-per-gpu", "4",
+                 "-override-config", "bSizes=9,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=12,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
+    assert rc == 0
+    tdata = out / "tinynet" / "tdata"
+    files = sorted(os.listdir(tdata))
+    assert files and all(len(f) == 20 and f.endswith(".npz") for f in files)
+    rows = 0
+    for f in files:
+        with np.load(tdata / f) as z:
+            n = z["globalTargetsNC"].shape[0]
+            rows += n
+            assert n <= 50 and z["binaryInputNCHWPacked"].shape == (n, 22, 11) and z["policyTargetsNCMove"].shape == (n, 2, 82)
+            assert (z["globalTargetsNC"][:, 63] == 3.0).all() and (z["globalTargetsNC"][:, 25] == 1.0).all()
+    assert rows >= 3 * 2
