@@ -377,6 +377,7 @@ class FinishedGameData:
         self.nn_raw_stats_by_turn = []
         self.reanalysis_by_turn = []               # empty, or per turn (wasReanalyzed, usedOutcomeTargets, polSurprise, valSurprise, origVisits, netChangesSoFar)
         self.changed_neural_net_turns = []         # turn index at which each new net took over
+        self.side_positions = []                   # SidePosition objects
         self.final_full_area = self.final_ownership = self.final_white_scoring = None
 
     def self_komi(self, next_player):
@@ -386,6 +387,19 @@ class FinishedGameData:
         adj = _f32(self.draw_equivalent_wins_for_white - 0.5) if komi_is_int else _f32(0.0)
         w = _f32(_f32(self.komi) + adj)
         return w if next_player == P_WHITE else -w
+
+
+class SidePosition:
+    """A position off the main line that was searched on its own (dataio/trainingwrite.h:62-84): it gets rows with its own
+    policy / value / Q targets and none of the targets that need the game's continuation."""
+
+    def __init__(self, next_player, turn_idx, packed_input, global_input, policy_target, unreduced_num_visits, white_value_targets,
+                 white_q_value_targets, policy_surprise, policy_entropy, search_entropy, nn_raw_stats, target_weight=1.0, num_neural_net_changes_so_far=0):
+        self.next_player, self.turn_idx, self.packed_input, self.global_input = next_player, turn_idx, packed_input, global_input
+        self.policy_target, self.unreduced_num_visits = policy_target, unreduced_num_visits
+        self.white_value_targets, self.white_q_value_targets = white_value_targets, white_q_value_targets
+        self.policy_surprise, self.policy_entropy, self.search_entropy, self.nn_raw_stats = policy_surprise, policy_entropy, search_entropy, nn_raw_stats
+        self.target_weight, self.num_neural_net_changes_so_far = target_weight, num_neural_net_changes_so_far
 
 
 def final_value_targets(winner, final_white_minus_black_score, draw_equivalent_wins_for_white, komi, no_result=False):
@@ -452,8 +466,8 @@ class TrainingDataWriter:
             self.flush_if_nonempty()
 
     def write_game(self, data: FinishedGameData):
-        """writeGame, main-line rows (:1097-1256): a turn with target weight w gives floor(w) rows plus one more with probability
-        frac(w); policy target 1 is the next turn's policy target; reanalysed turns may drop the outcome-derived targets."""
+        """writeGame (:1097-1325): a turn with target weight w gives floor(w) rows plus one more with probability frac(w); policy
+        target 1 is the next turn's policy target; reanalysed turns may drop the outcome-derived targets; then the side positions."""
         n = len(data.target_weight_by_turn)
         if not (len(data.policy_targets_by_turn) == len(data.white_q_value_targets_by_turn) == len(data.nn_raw_stats_by_turn) == n
                 and len(data.white_value_targets_by_turn) == n + 1 and len(data.boards_by_turn) == n + 1
@@ -501,6 +515,28 @@ class TrainingDataWriter:
                         end_finished=data.end_finished, end_no_result=data.end_no_result,
                         always_pass_alive_under_suicide_rules=data.always_pass_alive_under_suicide_rules,
                         reanalysis=(bool(re[0]), re[2], re[3], re[4]))
+                    self._write_and_clear_if_full()
+                    self.row_count += 1
+                target_weight -= 1.0
+        # side rows (:1258-1323): their own targets only; the game's ending still decides the lead / finished flags
+        for sp in data.side_positions:
+            target_weight = float(_f32(sp.target_weight))
+            while target_weight > 0.0:
+                if target_weight >= 1.0 or self.rand.next_bool(target_weight):
+                    self.buffers.add_row(
+                        x_size=data.x_size, y_size=data.y_size, next_player=sp.next_player, packed_input=sp.packed_input, global_input=sp.global_input,
+                        turn_idx=sp.turn_idx, target_weight=_f32(data.training_weight), unreduced_num_visits=sp.unreduced_num_visits,
+                        policy_target0=sp.policy_target, policy_target1=None, policy_surprise=sp.policy_surprise, policy_entropy=sp.policy_entropy,
+                        search_entropy=sp.search_entropy, white_value_targets=[sp.white_value_targets], white_q_value_targets=sp.white_q_value_targets,
+                        white_value_targets_idx=0, value_target_weight=1.0, td_value_target_weight=1.0, lead_target_weight_factor=1.0,
+                        nn_raw_stats=sp.nn_raw_stats, final_full_area=None, final_ownership=None, final_white_scoring=None,
+                        pos_hist_for_future_boards=None, is_side_position=True,
+                        num_neural_nets_behind_latest=len(data.changed_neural_net_turns) - sp.num_neural_net_changes_so_far, game_hash=data.game_hash,
+                        num_changed_neural_nets=len(data.changed_neural_net_turns), hit_turn_limit=data.hit_turn_limit, num_extra_black=data.num_extra_black,
+                        mode=data.mode, rand=self.rand, self_komi=data.self_komi(sp.next_player), area_scoring_or_encore2=True,
+                        start_hist_moves=data.start_hist_moves, initial_turn_number=data.initial_turn_number,
+                        end_finished=data.end_finished, end_no_result=data.end_no_result,
+                        always_pass_alive_under_suicide_rules=data.always_pass_alive_under_suicide_rules)
                     self._write_and_clear_if_full()
                     self.row_count += 1
                 target_weight -= 1.0

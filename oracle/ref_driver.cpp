@@ -699,21 +699,26 @@ static int cmdWriteGame(int argc, char** argv) {
   Player pla = P_BLACK;
   BoardHistory hist(board, pla, rules, 0, false);
   data.startBoard = board; data.startHist = hist; data.startPla = pla;
-  vector<Board> boards; vector<Player> plas; vector<vector<Loc>> legalByTurn; vector<string> moveStrs, packedHex; vector<vector<float>> globalRows;
+  vector<Board> boards; vector<BoardHistory> hists; vector<Player> plas; vector<vector<Loc>> legalByTurn; vector<string> moveStrs, packedHex; vector<vector<float>> globalRows;
+  auto inputRows = [&](const Board& b, const BoardHistory& h, Player p, string& hex, vector<float>& rowGlobal) {
+    MiscNNInputParams ip; ip.drawEquivalentWinsForWhite = drawEq;
+    vector<float> rowBin((size_t)NNInputs::NUM_FEATURES_SPATIAL_V7 * D * D);
+    rowGlobal.assign(NNInputs::NUM_FEATURES_GLOBAL_V7, 0.0f);
+    NNInputs::fillRowV7(b, h, p, ip, D, D, false, rowBin.data(), rowGlobal.data());
+    hex.clear();
+    const int A = D * D, packed = (A + 7) / 8;
+    for(int c = 0; c < NNInputs::NUM_FEATURES_SPATIAL_V7; c++) for(int bb = 0; bb < packed; bb++) {
+      unsigned v = 0;
+      for(int k = 0; k < 8; k++) { const int idx = bb * 8 + k; if(idx < A && rowBin[(size_t)c * A + idx] != 0.0f) v |= 1u << (7 - k); }
+      hex += Global::strprintf("%02x", v);
+    }
+  };
   bool prevPass = false;
   for(int t = 0; t < nTurns; t++) {
-    boards.push_back(board); plas.push_back(pla);
+    boards.push_back(board); hists.push_back(hist); plas.push_back(pla);
     {   // the input rows addRow will compute for this turn (fillRowV7, NCHW, the game's drawEquivalentWinsForWhite), packed like packBits
-      MiscNNInputParams ip; ip.drawEquivalentWinsForWhite = drawEq;
-      vector<float> rowBin((size_t)NNInputs::NUM_FEATURES_SPATIAL_V7 * D * D), rowGlobal(NNInputs::NUM_FEATURES_GLOBAL_V7);
-      NNInputs::fillRowV7(board, hist, pla, ip, D, D, false, rowBin.data(), rowGlobal.data());
-      string hex;
-      const int A = D * D, packed = (A + 7) / 8;
-      for(int c = 0; c < NNInputs::NUM_FEATURES_SPATIAL_V7; c++) for(int b = 0; b < packed; b++) {
-        unsigned v = 0;
-        for(int k = 0; k < 8; k++) { const int idx = b * 8 + k; if(idx < A && rowBin[(size_t)c * A + idx] != 0.0f) v |= 1u << (7 - k); }
-        hex += Global::strprintf("%02x", v);
-      }
+      string hex; vector<float> rowGlobal;
+      inputRows(board, hist, pla, hex, rowGlobal);
       packedHex.push_back(hex); globalRows.push_back(rowGlobal);
     }
     vector<Loc> legal;
@@ -789,6 +794,38 @@ static int cmdWriteGame(int argc, char** argv) {
   }
   data.whiteValueTargetsByTurn.push_back(finalTargets);
 
+  // side positions (trainingwrite.cpp:1258-1323): an alternative move from a main-line position, searched on its own
+  struct SideDump { string hex; vector<float> global; };
+  vector<SideDump> sideDumps;
+  const int numSide = (int)(seedNum % 4);
+  for(int k = 0; k < numSide; k++) {
+    const int t = (int)(rng.next() % nTurns);
+    Board b = boards[t]; BoardHistory h = hists[t]; Player p = plas[t];
+    const vector<Loc>& legal = legalByTurn[t];
+    const Loc alt = legal[rng.next() % legal.size()];
+    h.makeBoardMoveAssumeLegal(b, alt, p, NULL);
+    p = getOpp(p);
+    if(h.isGameFinished) continue;
+    SidePosition* sp = new SidePosition(b, h, p, numChanges > 0 ? (int)(rng.next() % (numChanges + 1)) : 0);
+    static const float sw[4] = {1.0f, 0.4f, 2.0f, 1.5f};
+    sp->targetWeight = sw[rng.next() % 4]; sp->targetWeightUnrounded = sp->targetWeight;
+    sp->unreducedNumVisits = 50 + rng.next() % 900;
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) {
+      const Loc l = Location::getLoc(x, y, X);
+      if(!h.isLegal(b, l, p)) continue;
+      if(rng.next() % 3 == 0) sp->policyTarget.push_back(PolicyTargetMove(l, (int16_t)(1 + rng.next() % 300)));
+      if(rng.next() % 5 == 0) sp->whiteQValueTargets.targets.push_back(QValueTargetMove(l, unif() * 2.0f - 1.0f, (unif() - 0.5f) * 60.0f, (int64_t)(rng.next() % 300)));
+    }
+    sp->policySurprise = unif() * 2.0; sp->policyEntropy = unif() * 3.0; sp->searchEntropy = unif() * 3.0;
+    float a = unif(), bb = unif() * (1.0f - a);
+    sp->whiteValueTargets.win = a; sp->whiteValueTargets.loss = bb; sp->whiteValueTargets.noResult = 1.0f - a - bb;
+    sp->whiteValueTargets.score = (unif() - 0.5f) * 60.0f; sp->whiteValueTargets.hasLead = rng.next() % 2 == 0; sp->whiteValueTargets.lead = (unif() - 0.5f) * 40.0f;
+    sp->nnRawStats.whiteWinLoss = unif() * 2.0 - 1.0; sp->nnRawStats.whiteScoreMean = (unif() - 0.5) * 40.0; sp->nnRawStats.policyEntropy = unif() * 4.0;
+    SideDump sd; inputRows(b, h, p, sd.hex, sd.global);
+    sideDumps.push_back(sd);
+    data.sidePositions.push_back(sp);
+  }
+
   ostringstream sink;
   {
     TrainingDataWriter writer(&sink, 7, maxRows, firstFileProp, D, D, 1, "writegame" + seedStr);
@@ -838,6 +875,22 @@ static int cmdWriteGame(int argc, char** argv) {
         << ",\"nnRawStats\":[" << f17(data.nnRawStatsByTurn[t].whiteWinLoss) << "," << f17(data.nnRawStatsByTurn[t].whiteScoreMean) << "," << f17(data.nnRawStatsByTurn[t].policyEntropy) << "]";
     if(withReanalysis) { const ReanalysisData& re = data.reanalysisByTurn[t]; out << ",\"reanalysis\":[" << (re.wasReanalyzed ? 1 : 0) << "," << (re.usedOutcomeTargets ? 1 : 0) << "," << f9(re.selectionPolicySurprise) << "," << f9(re.selectionValueSurprise) << "," << re.originalNumVisits << "," << re.numNeuralNetChangesSoFar << "]"; }
     out << "}";
+  }
+  out << "\n],\n\"sidePositions\":[";
+  for(size_t k = 0; k < data.sidePositions.size(); k++) {
+    const SidePosition* sp = data.sidePositions[k];
+    out << (k ? ",\n" : "\n") << "{\"packedInput\":\"" << sideDumps[k].hex << "\",\"globalInput\":[";
+    for(size_t i = 0; i < sideDumps[k].global.size(); i++) out << (i ? "," : "") << f9(sideDumps[k].global[i]);
+    out << "],\"nextPlayer\":" << (int)sp->pla << ",\"turnIdx\":" << sp->hist.moveHistory.size() << ",\"targetWeight\":" << f9(sp->targetWeight)
+        << ",\"unreducedNumVisits\":" << sp->unreducedNumVisits << ",\"numNeuralNetChangesSoFar\":" << sp->numNeuralNetChangesSoFar << ",\"policyTarget\":[";
+    for(size_t i = 0; i < sp->policyTarget.size(); i++) out << (i ? "," : "") << "[" << locJson(sp->policyTarget[i].loc) << "," << sp->policyTarget[i].policyTarget << "]";
+    out << "],\"qTargets\":[";
+    const vector<QValueTargetMove>& q = sp->whiteQValueTargets.targets;
+    for(size_t i = 0; i < q.size(); i++) out << (i ? "," : "") << "[" << locJson(q[i].loc) << "," << f9(q[i].winLoss) << "," << f9(q[i].score) << "," << q[i].visits << "]";
+    const ValueTargets& v = sp->whiteValueTargets;
+    out << "],\"valueTargets\":[" << f9(v.win) << "," << f9(v.loss) << "," << f9(v.noResult) << "," << f9(v.score) << "," << (v.hasLead ? 1 : 0) << "," << f9(v.lead) << "]"
+        << ",\"policySurprise\":" << f17(sp->policySurprise) << ",\"policyEntropy\":" << f17(sp->policyEntropy) << ",\"searchEntropy\":" << f17(sp->searchEntropy)
+        << ",\"nnRawStats\":[" << f17(sp->nnRawStats.whiteWinLoss) << "," << f17(sp->nnRawStats.whiteScoreMean) << "," << f17(sp->nnRawStats.policyEntropy) << "]}";
   }
   out << "\n],\n\"dump\":\"";
   for(char c : sink.str()) { if(c == '\n') out << "\\n"; else if(c == '"' || c == '\\') out << '\\' << c; else out << c; }

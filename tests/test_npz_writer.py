@@ -200,7 +200,7 @@ def _parse_text_dump(text):
 
 
 def _game_from_fixture(d):
-    from katago_b200.npz_writer import FinishedGameData
+    from katago_b200.npz_writer import FinishedGameData, SidePosition
     L = d["dataLen"]
     packed = (L * L + 7) // 8
     g = FinishedGameData(d["X"], d["Y"], d["komi"])
@@ -223,6 +223,12 @@ def _game_from_fixture(d):
         g.nn_raw_stats_by_turn.append(t["nnRawStats"])
         if "reanalysis" in t:
             g.reanalysis_by_turn.append(tuple(t["reanalysis"]))
+    for sp in d.get("sidePositions", []):
+        g.side_positions.append(SidePosition(
+            sp["nextPlayer"], sp["turnIdx"], np.frombuffer(bytes.fromhex(sp["packedInput"]), np.uint8).reshape(22, packed),
+            np.asarray(sp["globalInput"], np.float32), sp["policyTarget"], sp["unreducedNumVisits"], sp["valueTargets"], sp["qTargets"],
+            sp["policySurprise"], sp["policyEntropy"], sp["searchEntropy"], sp["nnRawStats"], target_weight=sp["targetWeight"],
+            num_neural_net_changes_so_far=sp["numNeuralNetChangesSoFar"]))
     return g
 
 
