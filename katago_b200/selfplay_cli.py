@@ -12,6 +12,8 @@ searches, komi / rules / board-size randomisation, ...).  `-strict` turns the se
 
 The reference randomises rules and board size per game; one loop instance plays one rule set on one board size, so list-valued
 keys (`koRules`, `bSizes`, ...) must contain a value the loop supports and the first such value is used (reported).
+Under torchrun (one process per GPU) the ranks split `-max-games-total`, use LOCAL_RANK's GPU and their own seeds, and write into the
+same tdata directory (`shard_plan`); there is no collective on this path.
 There is no CPU fallback: without a B200 the command fails when it creates the evaluator."""
 import argparse
 import glob
@@ -132,6 +134,18 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     return kw, data, report
 
 
+def _game_hash(seed, slot, index):
+    """FinishedGameData::gameHash: 128 bits that identify the game (two draws of the game's Rand in the reference).  splitmix64 of
+    (seed, slot, index), so ranks and slots never repeat one."""
+    def mix(z):
+        z = (z + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return z ^ (z >> 31)
+    a = mix(mix(seed & (2 ** 64 - 1)) ^ (slot << 32) ^ index)
+    return a, mix(a)
+
+
 def newest_model(models_dir):
     """The reference polls the models dir for the newest net (command/selfplay.cpp:150-176); this takes the newest once."""
     files = [f for ext in ("*.bin.gz", "*.bin", "*.txt.gz", "*.txt") for f in glob.glob(os.path.join(models_dir, ext))]
@@ -139,6 +153,16 @@ def newest_model(models_dir):
     if not files:
         raise FileNotFoundError(f"no model file in {models_dir}")
     return max(files, key=os.path.getmtime)
+
+
+def shard_plan(rank, world_size, max_games_total, seed):
+    """One process per GPU (torchrun): games are independent, so ranks share nothing - each plays its own games on its own GPU with its
+    own seeds and writes its own files into the common tdata directory (names come from the writer's Rand, so they must not collide).
+    Returns (games this rank should finish, loop seed, writer seed string)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    games = 0 if max_games_total <= 0 else max_games_total // world_size + (1 if rank < max_games_total % world_size else 0)
+    return games, seed * 1000003 + rank, f"selfplay{seed}:rank{rank}of{world_size}"
 
 
 def main(argv=None):
@@ -171,14 +195,17 @@ def main(argv=None):
     os.makedirs(tdata, exist_ok=True)
     L = data["board_size"]
     games = min(a.games_per_gpu, data["num_game_threads"])
+    rank, world, gpu = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    my_games, loop_seed, writer_seed = shard_plan(rank, world, a.max_games_total, a.seed)
     lm = NeuralNet.loadModelFile(model_path)
-    ctx = NeuralNet.createComputeContext([0], L, L, True, lm)
-    h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, 0)
-    sp = SelfPlay(h, games, kw.pop("max_visits", 600), komi=data["komi"], seed=a.seed, debug_hold_at_max_visits=True, **kw)
-    writer = TrainingDataWriter(tdata, data["max_rows_per_train_file"], data["first_file_rand_min_prop"], L, f"selfplay{a.seed}")
-    rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5))
+    ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
+    sp = SelfPlay(h, games, kw.pop("max_visits", 600), komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, **kw)
+    writer = TrainingDataWriter(tdata, data["max_rows_per_train_file"], data["first_file_rand_min_prop"], L, writer_seed)
+    rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5),
+                       game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index))
     try:
-        while a.max_games_total <= 0 or rec.games_written < a.max_games_total:
+        while a.max_games_total <= 0 or rec.games_written < my_games:
             rec.step()
     except KeyboardInterrupt:
         pass

@@ -81,3 +81,19 @@ def test_command_writes_training_files(tmp_path):
             assert n <= 50 and z["binaryInputNCHWPacked"].shape == (n, 22, 11) and z["policyTargetsNCMove"].shape == (n, 2, 82)
             assert (z["globalTargetsNC"][:, 63] == 3.0).all() and (z["globalTargetsNC"][:, 25] == 1.0).all()
     assert rows >= 3 * 2
+
+
+def test_ranks_split_the_games_and_never_share_seeds_or_file_names():
+    """One process per GPU: the ranks' game counts add up, their loop seeds, writer Rand streams (= file names) and game hashes differ."""
+    from katago_b200.nn_backend import rand_uint32_stream
+    for world in (1, 2, 8):
+        plans = [C.shard_plan(r, world, 1001, 5) for r in range(world)]
+        assert sum(p[0] for p in plans) == 1001 and max(p[0] for p in plans) - min(p[0] for p in plans) <= 1
+        assert len({p[1] for p in plans}) == world and len({p[2] for p in plans}) == world
+        streams = {tuple(rand_uint32_stream(p[2], 4).tolist()) for p in plans}
+        assert len(streams) == world
+    assert C.shard_plan(0, 4, 0, 1)[0] == 0                      # 0 = run until interrupted
+    with pytest.raises(ValueError):
+        C.shard_plan(4, 4, 10, 1)
+    hashes = {C._game_hash(s, slot, i) for s in (1, 2) for slot in range(16) for i in range(16)}
+    assert len(hashes) == 2 * 16 * 16 and all(0 <= a < 2 ** 64 and 0 <= b < 2 ** 64 for a, b in hashes)
