@@ -64,6 +64,133 @@ def test_policy_target_matches_reference_extract_policy_target():
     assert saw_cap
 
 
+# ---- the recorder's host logic against a scripted stand-in for the device loop ------------------------------------------------------
+class ScriptedSlots:
+    """Stands in for nn_backend.SelfPlay in hold mode: every slot replays a move stream of the reference `Board` (boardstream
+    fixture: moves, position after each move, area) and reports made-up but reproducible search statistics."""
+
+    def __init__(self, stream, lengths, max_visits):
+        self.s, self.lengths, self.max_visits = stream, lengths, max_visits
+        self.x = self.y = int(stream["X"])
+        self.num_games = len(lengths)
+        self.t = [0] * self.num_games                 # moves played in the slot's current game
+        self.index = [0] * self.num_games
+        self.released = [False] * self.num_games
+        self.last = [None] * self.num_games
+        self.waves = 0
+
+    def _board(self, t):
+        return np.zeros((self.y, self.x), np.uint8) if t == 0 else self.s["colors"][t - 1]
+
+    def _rng(self, g):
+        return np.random.default_rng(1000 * self.index[g] + 37 * g + self.t[g])
+
+    def run(self, n):
+        self.waves += n
+        for g in range(self.num_games):
+            if not self.released[g]:
+                continue
+            self.released[g] = False
+            t = self.t[g]
+            x, y, pla = (int(v) for v in self.s["moves"][t])
+            over = t + 1 >= self.lengths[g]
+            area = self.s["area"][t]
+            self.last[g] = dict(pos=self.x * self.y if x < 0 else y * self.x + x, xy=(x, y), game_over=over, no_result=False, hit_move_limit=over,
+                                move_num=t, game_index=self.index[g], final_colors=self.s["colors"][t].copy(), final_area=area.copy(),
+                                final_white_minus_black_score=float((area == 2).sum()) - float((area == 1).sum()) + 6.5)
+            self.t[g] = 0 if over else t + 1
+            self.index[g] += 1 if over else 0
+
+    def root_visits(self):
+        return np.full(self.num_games, self.max_visits, np.int32)
+
+    def game(self, g):
+        t = self.t[g]
+        return self._board(t).copy(), dict(move_num=t, black_to_move=(t % 2 == 0), ko=-1, cap_b=0, cap_w=0, root_visits=self.max_visits + g)
+
+    def nn_row(self, g):
+        b = self._board(self.t[g]).reshape(-1)
+        own = 1 if self.t[g] % 2 == 0 else 2
+        sp = np.zeros((self.x * self.y, 22), np.float32)
+        sp[:, 0] = 1; sp[:, 1] = b == own; sp[:, 2] = b == 3 - own
+        return sp, np.full(19, 0.25 * self.t[g], np.float32)
+
+    def _children(self, g):
+        r = self._rng(g)
+        legal = np.append(self.s["legal_next"][self.t[g] - 1].reshape(-1) if self.t[g] else np.ones(self.x * self.y, np.uint8), 1).astype(bool)
+        visits = np.where(legal & (r.random(legal.size) < 0.4), r.integers(1, 30, legal.size), 0).astype(np.int32)
+        x, y, _ = self.s["moves"][self.t[g]]
+        visits[self.x * self.y if x < 0 else y * self.x + x] += 5      # the move that will be played has been searched
+        return r, legal, visits
+
+    def root_children(self, g):
+        r, legal, visits = self._children(g)
+        pol = np.where(legal, r.random(legal.size), 0).astype(np.float32)
+        pol = np.where(legal, pol / pol.sum(), -1).astype(np.float32)
+        return visits, pol, np.zeros(legal.size)
+
+    def root_value_stats(self, g):
+        r, legal, visits = self._children(g)
+        ch = np.zeros((legal.size, 5))
+        ch[:, 0] = np.where(visits > 0, r.uniform(-1, 1, legal.size), 0); ch[:, 2] = np.where(visits > 0, r.uniform(-20, 20, legal.size), 0)
+        return ch, np.array([0.2 - 0.01 * self.t[g], 0.0, 1.5 * g - 0.1 * self.t[g], 30.0, 0.0])
+
+    def play_selection_values(self, g):
+        _, _, visits = self._children(g)
+        return np.where(visits > 0, visits.astype(np.float64), -1.0)
+
+    def root_extra(self, g):
+        _, _, visits = self._children(g)
+        return dict(child_node_visits=visits + (visits > 0), root_nn_moments=np.array([0.1, 0.0, 2.0, 9.0, 0.0]))
+
+    def release(self, mask=None):
+        self.released = [True] * self.num_games
+
+    def last_move(self, g):
+        return self.last[g]
+
+
+def test_recorder_assembles_finished_games_from_scripted_slots():
+    """Host logic only (no GPU): three slots replaying reference move streams of different lengths.  Every finished game carries the
+    scripted moves, positions, per-turn targets and final area; rows reach the writer game by game; slots restart independently."""
+    stream = np.load(os.path.join(GOLDEN, "boardstream_9x9_multisuicide.npz"))
+    lengths = [12, 7, 20]
+    sp = ScriptedSlots(stream, lengths, 50)
+    flushed, games = [], []
+    writer = W.TrainingDataWriter(None, 100000, 1.0, 9, "scripted", on_flush=lambda b: flushed.append({k: v[:b.cur_rows].copy() for k, v in b.arrays.items()}))
+    rec = R.GameRecorder(sp, writer, 6.5, on_game=lambda g, data: games.append((g, data)))
+    for _ in range(21):
+        rec.step()
+    writer.flush_if_nonempty()
+    # 21 moves per slot: slot 0 finishes 1 game (12 moves), slot 1 three (7 each), slot 2 one (20)
+    assert [g for g, _ in games] == [1, 0, 1, 2, 1] and rec.games_written == 5 and rec.moves_recorded == 63
+    rows = flushed[0]
+    assert rows["globalTargetsNC"].shape[0] == 7 + 12 + 7 + 20 + 7 == writer.row_count
+    at = 0
+    for g, data in games:
+        n = lengths[g]
+        assert data.moves == [tuple(int(v) for v in stream["moves"][t][:2]) for t in range(n)]
+        assert data.hit_turn_limit and not data.end_finished and not data.end_no_result
+        assert (data.boards_by_turn[0] == 0).all() and all(np.array_equal(data.boards_by_turn[t + 1], stream["colors"][t].reshape(-1)) for t in range(n))
+        assert np.array_equal(data.final_ownership, stream["area"][n - 1].reshape(-1)) and data.final_full_area is data.final_ownership
+        score = float((stream["area"][n - 1] == 2).sum()) - float((stream["area"][n - 1] == 1).sum()) + 6.5
+        assert data.white_value_targets_by_turn[-1][:4] == (1.0 if score > 0 else 0.0, 0.0 if score > 0 else 1.0, 0.0, np.float32(score))
+        for t in range(n):
+            assert data.next_player_by_turn[t] == 1 + t % 2 and data.target_weight_by_turn[t] == 1.0
+            moves, visits = data.policy_targets_by_turn[t]
+            assert visits == 50 + g and tuple(data.moves[t]) in {(x, y) for x, y, _ in moves}
+            assert data.white_value_targets_by_turn[t][3] == np.float32(1.5 * g - 0.1 * t)
+            assert data.nn_raw_stats_by_turn[t][:2] == (0.1, 2.0)
+            assert all(v >= 2 for *_, v in data.white_q_value_targets_by_turn[t])     # node visits, not edge visits
+            # the row written for this turn: the slot's input row of that position, the turn index, the game's outcome
+            assert rows["globalInputNC"][at + t, 0] == np.float32(0.25 * t) and rows["globalTargetsNC"][at + t, 51] == t
+            assert rows["globalTargetsNC"][at + t, 52] == 1.0 and rows["globalTargetsNC"][at + t, 62] == 0.0       # hit the move limit, not finished
+            planes = np.unpackbits(rows["binaryInputNCHWPacked"][at + t], axis=1)[:, :81]
+            assert np.array_equal(planes[1], (data.boards_by_turn[t] == data.next_player_by_turn[t]).astype(np.uint8))
+        assert len({data.game_hash for _, data in games}) == len(games)
+        at += n
+
+
 # ------------------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("ko_rule,graph", [(0, True), (1, False)])
