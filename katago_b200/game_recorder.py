@@ -114,6 +114,9 @@ class GameRecorder:
                                                                   ((index + 1) * 0xC2B2AE3D27D4EB4F + slot) & (2 ** 64 - 1)))
         self.games_written = 0
         self.moves_recorded = 0
+        cfg = getattr(sp, "cfg", None)             # rules for the game record (write_sgf)
+        self.ko_rule_name = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[int(getattr(cfg, "ko_rule", 0))]
+        self.multi_stone_suicide_legal = bool(getattr(cfg, "multi_stone_suicide_legal", 1))
         sp.run(1)                                    # evaluates every root: the rows of this wave are the roots' input rows
         self.root_rows = [sp.nn_row(g) for g in range(sp.num_games)]
 
@@ -167,6 +170,8 @@ class GameRecorder:
         data.hit_turn_limit = bool(last["hit_move_limit"])
         data.end_no_result = bool(last["no_result"])
         data.moves = [t["move"] for t in gm.turns]
+        data.ko_rule = self.ko_rule_name
+        data.multi_stone_suicide_legal = self.multi_stone_suicide_legal
         data.boards_by_turn = gm.boards + [np.asarray(last["final_colors"], np.uint8).reshape(-1).copy()]
         for t in gm.turns:
             data.next_player_by_turn.append(t["next_player"])
@@ -185,6 +190,7 @@ class GameRecorder:
             area = np.asarray(last["final_area"], np.uint8).reshape(-1).copy()
             score = float(last["final_white_minus_black_score"])
             winner = P_WHITE if score > 0 else P_BLACK if score < 0 else 0
+            data.winner, data.final_white_minus_black_score = winner, score
             data.white_value_targets_by_turn.append(final_value_targets(winner, score, self.draw_eq, self.komi))
         data.final_full_area, data.final_ownership = area, area
         data.final_white_scoring = scoring_from_area(area)

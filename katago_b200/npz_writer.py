@@ -378,6 +378,11 @@ class FinishedGameData:
         self.reanalysis_by_turn = []               # empty, or per turn (wasReanalyzed, usedOutcomeTargets, polSurprise, valSurprise, origVisits, netChangesSoFar)
         self.changed_neural_net_turns = []         # turn index at which each new net took over
         self.side_positions = []                   # SidePosition objects
+        self.moves = []                            # (x, y) per turn, (-1, -1) = pass
+        self.ko_rule, self.multi_stone_suicide_legal = "SIMPLE", True
+        self.winner, self.final_white_minus_black_score = 0, 0.0      # winner: 0 draw, P_BLACK, P_WHITE (finished games with a result)
+        self.changed_neural_net_names = None       # names of the nets in changed_neural_net_turns (SGF comment only)
+        self.target_weight_by_turn_unrounded = None
         self.final_full_area = self.final_ownership = self.final_white_scoring = None
 
     def self_komi(self, next_player):
@@ -540,3 +545,60 @@ class TrainingDataWriter:
                     self._write_and_clear_if_full()
                     self.row_count += 1
                 target_weight -= 1.0
+
+
+_SGF_CHARS = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+_GTYPES = ("normal", "cleanuptraining", "fork", "handicap", "sgfpos", "hintpos", "hintfork", "asym")
+
+
+def write_sgf(data: FinishedGameData, b_name: str, w_name: str) -> str:
+    """The game record the reference's self-play writes next to its rows (WriteSgf::writeSgf with a FinishedGameData,
+    dataio/sgf.cpp:1997-2226, as called from program/selfplaymanager.cpp:377): root properties, the game comment
+    (startTurnIdx, initTurnNum, gameHash, gtype, net changes) and per move the value targets, visits and target weight.
+    For games that start from the empty board under the rule subset of the loop (no handicap, no encore)."""
+    g = lambda v: "%g" % float(_f32(v))           # ostream << float / Global::doubleToString
+    out = ["(;FF[4]GM[1]"]
+    out.append("SZ[%d]" % data.x_size if data.x_size == data.y_size else "SZ[%d:%d]" % (data.x_size, data.y_size))
+    out.append("PB[%s]PW[%s]HA[0]KM[%s]" % (b_name, w_name, g(data.komi)))
+    out.append("RU[ko%sscoreAREAtaxNONEsui%d]" % (data.ko_rule, 1 if data.multi_stone_suicide_legal else 0))
+    result = ""
+    if data.end_finished:
+        if data.end_no_result:
+            result = "Void"
+        elif data.winner == P_BLACK:
+            result = "B+" + g(-float(_f32(data.final_white_minus_black_score)))
+        elif data.winner == P_WHITE:
+            result = "W+" + g(data.final_white_minus_black_score)
+        else:
+            result = "0"
+        out.append("RE[%s]" % result)
+    mode = _GTYPES[data.mode] if 0 <= data.mode < len(_GTYPES) else "other"
+    comment = "startTurnIdx=%d,initTurnNum=%d,gameHash=%016X%016X,gtype=%s" % (
+        data.start_hist_moves, data.initial_turn_number, int(data.game_hash[1]), int(data.game_hash[0]), mode)
+    for j, turn in enumerate(data.changed_neural_net_turns):
+        name = data.changed_neural_net_names[j] if data.changed_neural_net_names else "net%d" % j
+        comment += ",newNeuralNetTurn%d=%s" % (turn, name)
+    out.append("C[%s]" % comment)
+    weights = data.target_weight_by_turn_unrounded if data.target_weight_by_turn_unrounded is not None else data.target_weight_by_turn
+    n = len(data.moves)
+    for i, (x, y) in enumerate(data.moves):
+        pla = data.next_player_by_turn[i]
+        out.append(";%s[%s]" % ("B" if pla == P_BLACK else "W", "" if x < 0 else _SGF_CHARS[x] + _SGF_CHARS[y]))
+        parts = []
+        if i < len(data.white_value_targets_by_turn):
+            t = data.white_value_targets_by_turn[i]
+            parts.append("%.2f %.2f %.2f %.1f" % tuple(float(_f32(v)) for v in t[:4]))
+        if i < len(data.policy_targets_by_turn):
+            re = data.reanalysis_by_turn[i] if i < len(data.reanalysis_by_turn) else None
+            if re is not None and re[0]:
+                parts.append("v=%d rv=%d" % (int(re[4]), int(data.policy_targets_by_turn[i][1])))
+            else:
+                parts.append("v=%d" % int(data.policy_targets_by_turn[i][1]))
+        if i < len(weights):
+            parts.append("weight=%.2f" % float(_f32(weights[i])))
+        if data.end_finished and i + 1 == n:
+            parts.append("result=" + result)
+        if parts:
+            out.append("C[%s]" % " ".join(parts))
+    out.append(")")
+    return "".join(out)

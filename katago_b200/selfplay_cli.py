@@ -4,7 +4,8 @@
     python -m katago_b200.selfplay_cli -models-dir DIR -output-dir DIR -config selfplay.cfg [-max-games-total N]
                                        [-override-config "key=value,key=value"] [-games-per-gpu N] [-strict]
 
-Same arguments and the same output layout as the reference (`<output-dir>/<model name>/tdata/<16 hex>.npz`, selfplay.cpp:177-221),
+Same arguments and the same output layout as the reference (`<output-dir>/<model name>/tdata/<16 hex>.npz` and `.../sgfs/<16 hex>.sgfs`,
+selfplay.cpp:177-225),
 and it reads the reference's own .cfg files: every search / rules / data key the device loop implements is mapped to its
 `kgb_selfplay_config` field (`selfplay_kwargs_from_cfg`), every other key is reported - either as irrelevant here (logging, thread
 and device placement of the reference's CPU threads) or as NOT BUILT (options that change the data distribution: forks, cheap
@@ -165,6 +166,25 @@ def shard_plan(rank, world_size, max_games_total, seed):
     return games, seed * 1000003 + rank, f"selfplay{seed}:rank{rank}of{world_size}"
 
 
+class SgfSink:
+    """<model dir>/sgfs/<16 hex>.sgfs: one game record per line, like the reference's self-play (command/selfplay.cpp:178, 225;
+    program/selfplaymanager.cpp:377)."""
+
+    def __init__(self, sgf_dir, name_seed, b_name, w_name):
+        from .npz_writer import RowRand
+        os.makedirs(sgf_dir, exist_ok=True)
+        r = RowRand(name_seed)
+        lo, hi = r.next_uint(), r.next_uint()
+        self.path = os.path.join(sgf_dir, "%016X.sgfs" % (lo | (hi << 32)))
+        self.b_name, self.w_name, self.count = b_name, w_name, 0
+
+    def add(self, slot, data):
+        from .npz_writer import write_sgf
+        with open(self.path, "a") as f:
+            f.write(write_sgf(data, self.b_name, self.w_name) + "\n")
+        self.count += 1
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="katago_b200.selfplay_cli", description="Self-play data generation on the B200 device loop", prefix_chars="-")
     ap.add_argument("-models-dir", required=True)
@@ -202,7 +222,8 @@ def main(argv=None):
     h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
     sp = SelfPlay(h, games, kw.pop("max_visits", 600), komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, **kw)
     writer = TrainingDataWriter(tdata, data["max_rows_per_train_file"], data["first_file_rand_min_prop"], L, writer_seed)
-    rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5),
+    sgfs = SgfSink(os.path.join(a.output_dir, model_name, "sgfs"), writer_seed + ":sgfs", model_name, model_name)
+    rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=sgfs.add,
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index))
     try:
         while a.max_games_total <= 0 or rec.games_written < my_games:

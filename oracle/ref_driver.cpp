@@ -26,6 +26,7 @@
 #include "dataio/numpywrite.h"
 #include "dataio/trainingwrite.h"
 #include "program/play.h"
+#include "dataio/sgf.h"
 #include "core/logger.h"
 
 #include <cstdint>
@@ -826,6 +827,10 @@ static int cmdWriteGame(int argc, char** argv) {
     data.sidePositions.push_back(sp);
   }
 
+  data.bName = "b200-black"; data.wName = "b200-white"; data.handicapForSgf = 0;
+  ostringstream sgf;   // what SelfplayManager writes next to the training rows (program/selfplaymanager.cpp:377)
+  WriteSgf::writeSgf(sgf, data.bName, data.wName, data.endHist, &data, false, true);
+
   ostringstream sink;
   {
     TrainingDataWriter writer(&sink, 7, maxRows, firstFileProp, D, D, 1, "writegame" + seedStr);
@@ -842,7 +847,11 @@ static int cmdWriteGame(int argc, char** argv) {
       << ",\"mode\":" << data.mode << ",\"trainingWeight\":" << f17(data.trainingWeight) << ",\"hitTurnLimit\":0,\"numExtraBlack\":0"
       << ",\"endFinished\":" << (data.endHist.isGameFinished ? 1 : 0) << ",\"endNoResult\":" << (data.endHist.isNoResult ? 1 : 0)
       << ",\"winner\":" << (int)data.endHist.winner << ",\"finalWhiteMinusBlackScore\":" << f9(data.endHist.finalWhiteMinusBlackScore) << ",\n";
-  out << "\"changedNeuralNetTurns\":[";
+  out << "\"sgf\":\"";
+  for(char ch : sgf.str()) { if(ch == '\n') out << "\\n"; else if(ch == '"' || ch == '\\') out << '\\' << ch; else out << ch; }
+  out << "\",\n\"changedNeuralNetNames\":[";
+  for(size_t i = 0; i < data.changedNeuralNets.size(); i++) out << (i ? "," : "") << "\"" << data.changedNeuralNets[i]->name << "\"";
+  out << "],\n\"changedNeuralNetTurns\":[";
   for(size_t i = 0; i < data.changedNeuralNets.size(); i++) out << (i ? "," : "") << data.changedNeuralNets[i]->turnIdx;
   out << "],\n\"moves\":[";
   for(size_t i = 0; i < moveStrs.size(); i++) out << (i ? "," : "") << "[" << moveStrs[i] << "]";

@@ -188,6 +188,8 @@ def test_recorder_assembles_finished_games_from_scripted_slots():
             planes = np.unpackbits(rows["binaryInputNCHWPacked"][at + t], axis=1)[:, :81]
             assert np.array_equal(planes[1], (data.boards_by_turn[t] == data.next_player_by_turn[t]).astype(np.uint8))
         assert len({data.game_hash for _, data in games}) == len(games)
+        sgf = W.write_sgf(data, "b", "w")          # the record of a game cut off by the move limit: no result tag, one node per move
+        assert sgf.startswith("(;FF[4]GM[1]SZ[9]PB[b]PW[w]HA[0]KM[6.5]RU[koSIMPLEscoreAREAtaxNONEsui1]C[startTurnIdx=0,") and sgf.count(";") == n + 1 and "RE[" not in sgf
         at += n
 
 

@@ -223,6 +223,9 @@ def _game_from_fixture(d):
         g.nn_raw_stats_by_turn.append(t["nnRawStats"])
         if "reanalysis" in t:
             g.reanalysis_by_turn.append(tuple(t["reanalysis"]))
+    g.moves = [tuple(m) for m in d["moves"]]
+    g.winner, g.final_white_minus_black_score = d["winner"], d["finalWhiteMinusBlackScore"]
+    g.changed_neural_net_names = d.get("changedNeuralNetNames")
     for sp in d.get("sidePositions", []):
         g.side_positions.append(SidePosition(
             sp["nextPlayer"], sp["turnIdx"], np.frombuffer(bytes.fromhex(sp["packedInput"]), np.uint8).reshape(22, packed),
@@ -285,3 +288,11 @@ def test_writer_file_names_and_split(tmp_path):
     assert all(len(f) == 20 and f.endswith(".npz") and f[:16] == f[:16].upper() for f in files)
     rows = [np.load(os.path.join(tmp_path, f))["globalTargetsNC"].shape[0] for f in files]
     assert sum(rows) == w.row_count and max(rows) <= 10 and len(files) == -(-w.row_count // 10)
+
+
+@pytest.mark.parametrize("path", WRITEGAME_FIXTURES, ids=[os.path.basename(p)[10:-8] for p in WRITEGAME_FIXTURES])
+def test_sgf_equals_the_reference_write_sgf(path):
+    """The game record written next to the rows: character for character the reference's WriteSgf::writeSgf output for the same game."""
+    from katago_b200.npz_writer import write_sgf
+    d = json.loads(gzip.open(path, "rb").read())
+    assert write_sgf(_game_from_fixture(d), "b200-black", "b200-white") == d["sgf"]

@@ -81,6 +81,8 @@ def test_command_writes_training_files(tmp_path):
             assert n <= 50 and z["binaryInputNCHWPacked"].shape == (n, 22, 11) and z["policyTargetsNCMove"].shape == (n, 2, 82)
             assert (z["globalTargetsNC"][:, 63] == 3.0).all() and (z["globalTargetsNC"][:, 25] == 1.0).all()
     assert rows >= 3 * 2
+    sgfs = os.listdir(out / "tinynet" / "sgfs")
+    assert len(sgfs) == 1 and sum(1 for _ in open(out / "tinynet" / "sgfs" / sgfs[0])) >= 3
 
 
 def test_ranks_split_the_games_and_never_share_seeds_or_file_names():
@@ -97,3 +99,14 @@ def test_ranks_split_the_games_and_never_share_seeds_or_file_names():
         C.shard_plan(4, 4, 10, 1)
     hashes = {C._game_hash(s, slot, i) for s in (1, 2) for slot in range(16) for i in range(16)}
     assert len(hashes) == 2 * 16 * 16 and all(0 <= a < 2 ** 64 and 0 <= b < 2 ** 64 for a, b in hashes)
+
+
+def test_sgf_sink_appends_one_record_per_game(tmp_path):
+    import gzip, json
+    from test_npz_writer import _game_from_fixture, WRITEGAME_FIXTURES
+    d = json.loads(gzip.open(WRITEGAME_FIXTURES[0], "rb").read())
+    sink = C.SgfSink(str(tmp_path / "sgfs"), "seed:sgfs", "b200-black", "b200-white")
+    sink.add(0, _game_from_fixture(d)); sink.add(3, _game_from_fixture(d))
+    name = os.path.basename(sink.path)
+    assert len(name) == 21 and name.endswith(".sgfs") and name[:16] == name[:16].upper()
+    assert open(sink.path).read() == (d["sgf"] + "\n") * 2 and sink.count == 2
