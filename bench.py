@@ -396,11 +396,13 @@ def main():
         conv_flop = 2.0 * 9 * mid * mid * 361 * n  # algorithmic: direct convolution over the 361 real board points
         achieved = conv_flop / (float(ms_conv[0]) * 1e-3) / 1e12
         whole = flop_per_eval * n * K / (ms_nn * 1e-3) / 1e12
-        try:     # every host core busy, like the reference's evaluator server threads; falls back to one process if workers cannot start
-            cpu_v, cpu_dt, cpu_workers, cpu_n = cpu_port_parallel(args.model, seconds=12.0)
-        except Exception:
-            cpu_v, cpu_dt = cpu_port_evals_per_sec(args.model, 4, 2)
-            cpu_workers, cpu_n = 1, 8
+        cpu_v, cpu_dt, cpu_workers, cpu_n = None, 0.0, 0, 0
+        if world == 1:      # the CPU baseline is a property of the box: measured at N=1 only
+            try:     # every host core busy, like the reference's evaluator server threads; falls back to one process if workers cannot start
+                cpu_v, cpu_dt, cpu_workers, cpu_n = cpu_port_parallel(args.model, seconds=12.0)
+            except Exception:
+                cpu_v, cpu_dt = cpu_port_evals_per_sec(args.model, 4, 2)
+                cpu_workers, cpu_n = 1, 8
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -449,7 +451,8 @@ def main():
                 "note": "latency-bound at 256 warps per launch (1.7 warps per SM); see DESIGN.md §6"})(
                     tree_depth * 362 * 20 + 362 * 20 + (22 * 361 + 19) * 4 * 2 + 128, 362 * 8 + tree_depth * 48 + 64),
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cpu_workers, "kind": "port",
-                             "sample": f"{cpu_n} evaluations of {args.model} 19x19 via the numpy restatement of the Eigen path ({cpu_dt:.1f} s, {cpu_workers} single-threaded processes side by side)"},
+                             "sample": (f"{cpu_n} evaluations of {args.model} 19x19 via the numpy restatement of the Eigen path ({cpu_dt:.1f} s, {cpu_workers} single-threaded processes side by side)"
+                                        if world == 1 else "measured at N=1 only")},
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
