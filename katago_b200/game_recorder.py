@@ -115,6 +115,13 @@ class GameRecorder:
         self.games_written = 0
         self.moves_recorded = 0
         cfg = getattr(sp, "cfg", None)             # rules for the game record (write_sgf)
+        # The root's input row is taken from the wave that evaluates the new root.  With the evaluation cache on and a single root
+        # evaluation, that root is normally a cache hit (it was a child of the previous tree) and no row is produced for it.
+        if cfg is not None and int(getattr(cfg, "nn_cache_size_power_of_two", 0)) > 0 and int(getattr(cfg, "root_num_symmetries_to_sample", 0)) <= 1:
+            raise ValueError("GameRecorder: with nn_cache_size_power_of_two > 0 the root must be evaluated by the net itself "
+                             "(root_num_symmetries_to_sample >= 2, as in the stock self-play configurations), or the cache switched off")
+        if cfg is not None and int(getattr(cfg, "ladder_nodes_per_wave", 0)) != 0:
+            raise ValueError("GameRecorder: ladder_nodes_per_wave must be 0 (a budgeted wave may deliver no row for the new root)")
         self.ko_rule_name = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[int(getattr(cfg, "ko_rule", 0))]
         self.multi_stone_suicide_legal = bool(getattr(cfg, "multi_stone_suicide_legal", 1))
         sp.run(1)                                    # evaluates every root: the rows of this wave are the roots' input rows
@@ -137,6 +144,12 @@ class GameRecorder:
             extra = sp.root_extra(g)
             surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
             nn = extra["root_nn_moments"]
+            # the captured row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
+            flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
+            sp_row = np.asarray(spatial, np.float32).reshape(self.X * self.Y, 22)
+            if not (np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own)):
+                raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
+                                   "(its input row belongs to another position)")
             gm = self.games[g]
             gm.boards.append(np.asarray(colors, np.uint8).reshape(-1).copy())
             gm.turns.append(dict(

@@ -150,6 +150,30 @@ class ScriptedSlots:
         return self.last[g]
 
 
+def test_recorder_refuses_configurations_that_give_no_root_row():
+    """Evaluation cache on + a single root evaluation: the new root is a cache hit and the loop produces no input row for it."""
+    stream = np.load(os.path.join(GOLDEN, "boardstream_9x9_multisuicide.npz"))
+
+    class Cfg:
+        nn_cache_size_power_of_two, root_num_symmetries_to_sample, ladder_nodes_per_wave, ko_rule, multi_stone_suicide_legal = 16, 1, 0, 0, 1
+    sp = ScriptedSlots(stream, [5], 10)
+    sp.cfg = Cfg()
+    with pytest.raises(ValueError, match="root must be evaluated"):
+        R.GameRecorder(sp, None, 6.5)
+    sp.cfg.root_num_symmetries_to_sample = 4
+    R.GameRecorder(sp, None, 6.5)
+    sp.cfg.ladder_nodes_per_wave = 256
+    with pytest.raises(ValueError, match="ladder_nodes_per_wave"):
+        R.GameRecorder(sp, None, 6.5)
+    # and at run time: a row that is not the root's is detected
+    sp = ScriptedSlots(stream, [5], 10)
+    rec = R.GameRecorder(sp, None, 6.5)
+    rec.step()
+    rec.root_rows[0] = (np.roll(rec.root_rows[0][0], 1, axis=0), rec.root_rows[0][1])
+    with pytest.raises(RuntimeError, match="did not evaluate the new root"):
+        rec.step()
+
+
 def test_recorder_assembles_finished_games_from_scripted_slots():
     """Host logic only (no GPU): three slots replaying reference move streams of different lengths.  Every finished game carries the
     scripted moves, positions, per-turn targets and final area; rows reach the writer game by game; slots restart independently."""

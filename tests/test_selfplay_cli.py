@@ -68,7 +68,7 @@ def test_command_writes_training_files(tmp_path):
     modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
     out = tmp_path / "out"
     rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", CFG, "-max-games-total", "3", "-games-per-gpu", "4",
-                 "-override-config", "bSizes=9,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=12,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
+                 "-override-config", "bSizes=9,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=0,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
     assert rc == 0
     tdata = out / "tinynet" / "tdata"
     files = sorted(os.listdir(tdata))
