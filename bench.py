@@ -151,96 +151,122 @@ import os, sys, time
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
 import kg_nn_oracle as orc
 from katago_b200 import modelgen
-name, batch, seconds = sys.argv[2], int(sys.argv[3]), float(sys.argv[4])
+name, batch = sys.argv[2], int(sys.argv[3])
 m = orc.parse_model(modelgen.model_bytes(name, seed=0), True)
-sp, gl = modelgen.synthetic_inputs(batch, 19, 19, seed=3 + int(sys.argv[5]))
+sp, gl = modelgen.synthetic_inputs(batch, 19, 19, seed=3 + int(sys.argv[4]))
 orc.get_output(m, sp[:1], gl[:1])
 print("READY", flush=True)
-sys.stdin.readline()
-t0 = time.time(); n = 0
-while time.time() - t0 < seconds:
-    orc.get_output(m, sp, gl); n += batch
-print("DONE %d %.6f" % (n, time.time() - t0), flush=True)
+for line in sys.stdin:
+    f = line.split()
+    if not f or f[0] != "go":
+        break
+    seconds = float(f[1])
+    t0 = time.time(); n = 0
+    while time.time() - t0 < seconds:
+        orc.get_output(m, sp, gl); n += batch
+    print("DONE %d %.6f" % (n, time.time() - t0), flush=True)
 """
 
 
-def cpu_port_parallel(model_name: str, seconds: float = 12.0, batch: int = 4, workers: int = 0):
+class CpuArm:
     """The CPU arm with every host core busy the way the reference keeps them busy: its CPU backend runs one single-threaded Eigen
     evaluation per NN server thread, many threads side by side (nneval.cpp server threads; numNNServerThreadsPerModel).  Here: one
-    process per core, one BLAS thread each, every process evaluating batches of the numpy restatement for `seconds`; throughput =
-    all evaluations / wall time from the common start to the last finisher.  Returns (evals per second, wall seconds, workers, evaluations)."""
-    import subprocess
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    if not workers:
-        # bound the memory: ~0.25 GB resident per worker (model + activations); use at most a quarter of what is available, at most 256 workers
-        avail_gb = 16.0
+    process per core, one BLAS thread each, all evaluating batches of the numpy restatement (oracle/kg_nn_oracle.py) for a bounded
+    time per step; throughput of a step = all evaluations / wall time from the common start to the last finisher."""
+
+    def __init__(self, model_name: str, batch: int = 4, workers: int = 0):
+        import subprocess
         try:
-            for ln in open("/proc/meminfo"):
-                if ln.startswith("MemAvailable:"):
-                    avail_gb = float(ln.split()[1]) / 1048576.0
-            lim = open("/sys/fs/cgroup/memory.max").read().strip()
-            if lim.isdigit():
-                avail_gb = min(avail_gb, int(lim) / 2 ** 30)
-        except OSError:
-            pass
-        workers = max(1, min(cores, 256, int(avail_gb * 0.25 / 0.3)))
-    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
-    procs = [subprocess.Popen([sys.executable, "-c", _CPU_WORKER, ROOT, model_name, str(batch), str(seconds), str(i)], env=env, stdin=subprocess.PIPE,
-                              stdout=subprocess.PIPE, text=True) for i in range(workers)]
-    try:
-        for pr in procs:
-            if pr.stdout.readline().strip() != "READY":
-                raise RuntimeError("cpu worker failed to start")
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        if not workers:
+            # bound the memory: ~0.25 GB resident per worker (model + activations); use at most a quarter of what is available, at most 256 workers
+            avail_gb = 16.0
+            try:
+                for ln in open("/proc/meminfo"):
+                    if ln.startswith("MemAvailable:"):
+                        avail_gb = float(ln.split()[1]) / 1048576.0
+                lim = open("/sys/fs/cgroup/memory.max").read().strip()
+                if lim.isdigit():
+                    avail_gb = min(avail_gb, int(lim) / 2 ** 30)
+            except OSError:
+                pass
+            workers = max(1, min(cores, 256, int(avail_gb * 0.25 / 0.3)))
+        self.workers, self.batch = workers, batch
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+        self.procs = [subprocess.Popen([sys.executable, "-c", _CPU_WORKER, ROOT, model_name, str(batch), str(i)], env=env, stdin=subprocess.PIPE,
+                                       stdout=subprocess.PIPE, text=True) for i in range(workers)]
+        try:
+            for pr in self.procs:
+                if pr.stdout.readline().strip() != "READY":
+                    raise RuntimeError("cpu worker failed to start")
+        except Exception:
+            self.close()
+            raise
+
+    def step(self, seconds: float):
+        """All workers evaluate for `seconds`.  Returns (evaluations, wall seconds)."""
         t0 = time.time()
-        for pr in procs:
-            pr.stdin.write("go\n"); pr.stdin.flush()
+        for pr in self.procs:
+            pr.stdin.write("go %.3f\n" % seconds); pr.stdin.flush()
         total = 0
-        for pr in procs:
+        for pr in self.procs:
             f = pr.stdout.readline().split()
             if len(f) != 3 or f[0] != "DONE":
                 raise RuntimeError("cpu worker failed")
             total += int(f[1])
-        wall = time.time() - t0
-    finally:
-        for pr in procs:
+        return total, time.time() - t0
+
+    def close(self):
+        for pr in self.procs:
             try:
                 pr.stdin.close()
             except Exception:
                 pass
+        for pr in self.procs:
             if pr.poll() is None:
                 try:
                     pr.wait(timeout=5)
                 except Exception:
                     pr.kill()
-    return total / wall, wall, workers, total
+
+
+def cpu_port_parallel(model_name: str, seconds: float = 12.0, batch: int = 4, workers: int = 0):
+    """One bounded sample of the CPU arm.  Returns (evals per second, wall seconds, workers, evaluations)."""
+    arm = CpuArm(model_name, batch, workers)
+    try:
+        total, wall = arm.step(seconds)
+    finally:
+        arm.close()
+    return total / wall, wall, arm.workers, total
 
 
 def run_reference(args, rank: int):
     """--impl reference: CPU arm.  The reference's Eigen build cannot be compiled here (Eigen3 is neither vendored nor
-    installed), so this times the oracle port of its NN path with every host core busy (cpu_port_parallel); rank 0 only.
+    installed), so this times the oracle port of its NN path with every host core busy (CpuArm); rank 0 only.
     A step = one bounded sample of the workload (a few seconds of evaluations on all cores)."""
     if rank != 0:
         return
     steps = max(1, args.steps)
-    per_step = max(2.0, min(10.0, 120.0 / (steps + min(args.warmup, 1))))
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_parallel(args.model, seconds=2.0)
-    t0 = time.time()
-    total, wall, workers = 0, 0.0, 0
-    for _ in range(steps):
-        v, w, workers, n = cpu_port_parallel(args.model, seconds=per_step)
-        total += n; wall += w
-        if time.time() - t0 > 200:
-            break
+    per_step = max(1.0, min(10.0, 100.0 / steps))
+    arm = CpuArm(args.model)
+    try:
+        for _ in range(max(0, args.warmup)):
+            arm.step(1.0)
+        total, wall = 0, 0.0
+        for _ in range(steps):
+            n, w = arm.step(per_step)
+            total += n; wall += w
+    finally:
+        arm.close()
+    workers = arm.workers
     value = total / wall
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"19x19 {args.model}, one NN evaluation per visit on the host CPU: {workers} single-threaded evaluator processes side by side, "
-                               f"batch 4 each, {per_step:.0f} s per step (bounded sample)",
+                               f"batch 4 each, {per_step:.1f} s per step (bounded sample)",
                    "stages": ["nn_eval"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                          "sample": f"{total} evaluations of {args.model} 19x19 via oracle/kg_nn_oracle.py (numpy, one BLAS thread per process, {workers} processes) in {wall:.1f} s"},
