@@ -7,11 +7,40 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from katago_b200 import selfplay_cli as C
 
-CFG = os.path.join(ROOT, "tests", "golden", "selfplay_like_b18.cfg")
+STOCK_B18_SETTINGS = {   # the settings of the reference's stock b18 self-play training configuration, as key -> value strings
+    "allowRectangleProb": "0.10", "bSizeRelProbs": "75,1,4,10", "bSizes": "19,7,9,13", "cheapSearchProb": "0.75", "cheapSearchTargetWeight": "0.0",
+    "cheapSearchVisits": "350", "chosenMovePrune": "1", "chosenMoveSubtract": "0", "chosenMoveTemperature": "0.15",
+    "chosenMoveTemperatureEarly": "0.75", "chosenMoveTemperatureHalflife": "19", "cpuctExploration": "1.05", "cpuctExplorationLog": "0.28",
+    "cudaDeviceToUseModel0Thread0": "0", "cudaUseFP16": "true", "dataBoardLen": "19", "drawEquivalentWinsForWhite": "0.5", "drawRandRadius": "0.5",
+    "dynamicScoreCenterScale": "0.50", "dynamicScoreCenterZeroWeight": "0.25", "dynamicScoreUtilityFactor": "0.30", "earlyForkGameProb": "0.04",
+    "estimateLeadProb": "0.50", "fancyKomiVarying": "true", "firstFileRandMinProp": "0.15", "forkGameProb": "0.01", "forkSidePositionProb": "0.020",
+    "fpuParentWeightByVisitedPolicy": "true", "fpuParentWeightByVisitedPolicyPow": "2.0", "fpuReductionMax": "0.2",
+    "handicapAsymmetricPlayoutProb": "0.5", "handicapProb": "0.10", "hasButtons": "false,false,true", "initGamesWithPolicy": "true",
+    "koRules": "SIMPLE,POSITIONAL,SITUATIONAL", "komiAuto": "True", "komiStdev": "1.0", "lcbStdevs": "5.0", "logSearchInfo": "false",
+    "logToStdout": "true", "maxMovesPerGame": "1600", "maxRowsPerTrainFile": "20000", "maxVisits": "2000", "minVisitPropForLCB": "0.15",
+    "multiStoneSuicideLegals": "false,true", "nnCacheSizePowerOfTwo": "24", "nnMaxBatchSize": "192", "nnRandomize": "true",
+    "noResultStdev": "0.166666666", "noResultUtilityForWhite": "0.0", "normalAsymmetricPlayoutProb": "0.01", "numGameThreads": "800",
+    "numSearchThreads": "1", "numVirtualLossesPerThread": "1", "policyInitAreaProp": "0.08", "policySurpriseDataWeight": "0.5",
+    "reduceVisits": "true", "reducedVisitsMin": "350", "rootDesiredPerChildVisitsCoeff": "2", "rootDirichletNoiseTotalConcentration": "10.83",
+    "rootDirichletNoiseWeight": "0.25", "rootEndingBonusPoints": "0.5", "rootFpuReductionMax": "0.0", "rootNoiseEnabled": "true",
+    "rootNumSymmetriesToSample": "4", "rootPolicyTemperature": "1.1", "rootPolicyTemperatureEarly": "1.5", "rootPruneUselessMoves": "true",
+    "scoringRules": "AREA,TERRITORY", "sekiForkHackProb": "0.01", "staticScoreUtilityFactor": "0.05", "subtreeValueBiasFactor": "0.30",
+    "subtreeValueBiasWeightExponent": "0.8", "switchNetsMidGame": "true", "taxRules": "NONE,NONE,SEKI,SEKI,ALL", "useGraphSearch": "true",
+    "useLcbForSelection": "true", "useNonBuggyLcb": "true", "valueSurpriseDataWeight": "0.1", "valueWeightExponent": "0.5",
+    "winLossUtilityFactor": "1.0",
+}
 
 
-def test_stock_training_config_maps_onto_the_loop():
-    cfg = C.parse_cfg(CFG)
+@pytest.fixture(scope="module")
+def stock_cfg(tmp_path_factory):
+    """A .cfg file in the reference's syntax holding those settings."""
+    path = tmp_path_factory.mktemp("cfg") / "selfplay.cfg"
+    path.write_text("# written by the test\n" + "".join(f"{k} = {v}\n" for k, v in STOCK_B18_SETTINGS.items()))
+    return str(path)
+
+
+def test_stock_training_config_maps_onto_the_loop(stock_cfg):
+    cfg = C.parse_cfg(stock_cfg)
     kw, data, report = C.selfplay_kwargs_from_cfg(cfg)
     # the search block of the stock configuration arrives under the loop's parameter names
     assert kw["max_visits"] == 2000 and kw["cpuct_exploration"] == 1.05 and kw["cpuct_exploration_log"] == 0.28
@@ -47,7 +76,7 @@ def test_neutral_values_and_unsupported_rules():
     assert C.parse_cfg("a = 1 # comment\n\n# only a comment\nb=x=y\n", is_text=True) == {"a": "1", "b": "x=y"}
 
 
-def test_command_fails_loudly_without_a_gpu(tmp_path):
+def test_command_fails_loudly_without_a_gpu(tmp_path, stock_cfg):
     """No CPU fallback: on a machine without a B200 the command stops at the evaluator with the library's error."""
     import torch
     if torch.cuda.is_available():
@@ -56,18 +85,18 @@ def test_command_fails_loudly_without_a_gpu(tmp_path):
     models = tmp_path / "models"; models.mkdir()
     modelgen.write_model(str(models / "tiny.bin"), "tiny_reg", seed=3)
     with pytest.raises(Exception, match="no CUDA device|CUDA"):
-        C.main(["-models-dir", str(models), "-output-dir", str(tmp_path / "out"), "-config", CFG, "-max-games-total", "1", "-override-config", "bSizes=9,dataBoardLen=9"])
+        C.main(["-models-dir", str(models), "-output-dir", str(tmp_path / "out"), "-config", stock_cfg, "-max-games-total", "1", "-override-config", "bSizes=9,dataBoardLen=9"])
 
 
 @pytest.mark.gpu
-def test_command_writes_training_files(tmp_path):
+def test_command_writes_training_files(tmp_path, stock_cfg):
     """End to end on a B200: models dir + reference-style .cfg -> <output-dir>/<model>/tdata/<16 hex>.npz readable as training rows."""
     import numpy as np
     from katago_b200 import modelgen
     models = tmp_path / "models"; models.mkdir()
     modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
     out = tmp_path / "out"
-    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", CFG, "-max-games-total", "3", "-games-per-gpu", "4",
+    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", stock_cfg, "-max-games-total", "3", "-games-per-gpu", "4",
                  "-override-config", "bSizes=9,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=0,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
     assert rc == 0
     tdata = out / "tinynet" / "tdata"
