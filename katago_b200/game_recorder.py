@@ -127,7 +127,47 @@ class GameRecorder:
         sp.run(1)                                    # evaluates every root: the rows of this wave are the roots' input rows
         self.root_rows = [sp.nn_row(g) for g in range(sp.num_games)]
 
+    def _record_root(self, g):
+        """Slot g is held: read its finished search and append this turn's targets (extractSearchTargetsThisTurn)."""
+        sp = self.sp
+        colors, info = sp.game(g)
+        spatial, glob = self.root_rows[g]
+        _, policy, _ = sp.root_children(g)
+        child_stats, root_stats = sp.root_value_stats(g)
+        psv = sp.play_selection_values(g)
+        extra = sp.root_extra(g)
+        surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
+        nn = extra["root_nn_moments"]
+        # the captured row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
+        flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
+        sp_row = np.asarray(spatial, np.float32).reshape(self.X * self.Y, 22)
+        if not (np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own)):
+            raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
+                               "(its input row belongs to another position)")
+        gm = self.games[g]
+        gm.boards.append(flat.copy())
+        gm.turns.append(dict(
+            next_player=own, move_num=info["move_num"],
+            packed=pack_bits(np.transpose(sp_row.reshape(1, self.X * self.Y, 22), (0, 2, 1)))[0],
+            global_input=np.asarray(glob, np.float32).copy(),
+            policy_target=(policy_target_moves(psv, self.X), int(info["root_visits"])),
+            value_targets=value_targets_from_root(root_stats),
+            q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
+            surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
+            # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy as searched
+            nn_raw_stats=(float(nn[0]), float(nn[2]), policy_entropy)))
+
+    def _after_move(self, g):
+        """Slot g was released and one wave has run: the device has played its move and evaluated the new root."""
+        sp = self.sp
+        self.root_rows[g] = sp.nn_row(g)
+        last = sp.last_move(g)
+        self.games[g].turns[-1]["move"] = last["xy"]
+        if last["game_over"]:
+            self._finish_game(g, last)
+
     def step(self, max_waves=1000000):
+        """One move of EVERY slot (lockstep): waves until all slots are held, record, release all, one wave."""
         sp, n = self.sp, self.sp.num_games
         waves = 0
         while int(sp.root_visits().min()) < sp.max_visits:
@@ -136,42 +176,31 @@ class GameRecorder:
             if waves > max_waves:
                 raise RuntimeError("GameRecorder: games did not reach max_visits")
         for g in range(n):
-            colors, info = sp.game(g)
-            spatial, glob = self.root_rows[g]
-            _, policy, _ = sp.root_children(g)
-            child_stats, root_stats = sp.root_value_stats(g)
-            psv = sp.play_selection_values(g)
-            extra = sp.root_extra(g)
-            surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
-            nn = extra["root_nn_moments"]
-            # the captured row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
-            flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
-            sp_row = np.asarray(spatial, np.float32).reshape(self.X * self.Y, 22)
-            if not (np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own)):
-                raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
-                                   "(its input row belongs to another position)")
-            gm = self.games[g]
-            gm.boards.append(np.asarray(colors, np.uint8).reshape(-1).copy())
-            gm.turns.append(dict(
-                next_player=P_BLACK if info["black_to_move"] else P_WHITE, move_num=info["move_num"],
-                packed=pack_bits(np.transpose(np.asarray(spatial, np.float32).reshape(1, self.X * self.Y, 22), (0, 2, 1)))[0],
-                global_input=np.asarray(glob, np.float32).copy(),
-                policy_target=(policy_target_moves(psv, self.X), int(info["root_visits"])),
-                value_targets=value_targets_from_root(root_stats),
-                q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
-                surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
-                # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy as searched
-                nn_raw_stats=(float(nn[0]), float(nn[2]), policy_entropy)))
+            self._record_root(g)
         sp.release()
         sp.run(1)
         self.moves_recorded += n
         for g in range(n):
-            self.root_rows[g] = sp.nn_row(g)
-            last = sp.last_move(g)
-            self.games[g].turns[-1]["move"] = last["xy"]
-            if last["game_over"]:
-                self._finish_game(g, last)
+            self._after_move(g)
         return waves + 1
+
+    def pump(self, waves=8):
+        """Without lockstep: `waves` waves for everybody, then only the slots that are held by now are recorded and released (the
+        others keep searching during the extra wave in which the released ones move).  Returns the number of moves recorded."""
+        sp = self.sp
+        sp.run(waves)
+        held = np.asarray(sp.root_visits()) >= sp.max_visits
+        if not held.any():
+            return 0
+        idx = [int(g) for g in np.flatnonzero(held)]
+        for g in idx:
+            self._record_root(g)
+        sp.release(held.astype(np.uint8))
+        sp.run(1)
+        self.moves_recorded += len(idx)
+        for g in idx:
+            self._after_move(g)
+        return len(idx)
 
     def _finish_game(self, g, last):
         gm = self.games[g]

@@ -195,6 +195,8 @@ def main(argv=None):
     ap.add_argument("-games-per-gpu", type=int, default=256, help="concurrent games (the evaluator batch); numGameThreads is capped by it")
     ap.add_argument("-strict", action="store_true", help="fail if the config asks for an option that is not built")
     ap.add_argument("-seed", type=int, default=0)
+    ap.add_argument("-per-game-release", action="store_true", help="record and release every game as soon as its own search is finished "
+                    "(GameRecorder.pump) instead of moving all games in lockstep")
     a = ap.parse_args(argv)
     cfg = parse_cfg(a.config)
     for kv in [s for s in a.override_config.split(",") if s.strip()]:
@@ -227,7 +229,10 @@ def main(argv=None):
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index))
     try:
         while a.max_games_total <= 0 or rec.games_written < my_games:
-            rec.step()
+            if a.per_game_release:
+                rec.pump(8)
+            else:
+                rec.step()
     except KeyboardInterrupt:
         pass
     writer.flush_if_nonempty()

@@ -144,7 +144,7 @@ class ScriptedSlots:
         return dict(child_node_visits=visits + (visits > 0), root_nn_moments=np.array([0.1, 0.0, 2.0, 9.0, 0.0]))
 
     def release(self, mask=None):
-        self.released = [True] * self.num_games
+        self.released = [True] * self.num_games if mask is None else [bool(m) for m in mask]
 
     def last_move(self, g):
         return self.last[g]
@@ -172,6 +172,49 @@ def test_recorder_refuses_configurations_that_give_no_root_row():
     rec.root_rows[0] = (np.roll(rec.root_rows[0][0], 1, axis=0), rec.root_rows[0][1])
     with pytest.raises(RuntimeError, match="did not evaluate the new root"):
         rec.step()
+
+
+class UnevenSlots(ScriptedSlots):
+    """Slots whose searches finish at different times: slot g needs 3 + 2 g waves per move."""
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.progress = [0] * self.num_games
+
+    def run(self, n):
+        was_released = list(self.released)
+        super().run(n)
+        for g in range(self.num_games):
+            self.progress[g] = 0 if was_released[g] else self.progress[g] + n
+
+    def root_visits(self):
+        return np.array([self.max_visits if self.progress[g] >= 3 + 2 * g else self.progress[g] for g in range(self.num_games)], np.int32)
+
+
+def test_pump_records_slots_as_they_finish():
+    """Without lockstep: a slot is recorded and released as soon as its own search is finished; slow slots do not hold fast ones
+    back, unreleased slots are left alone, and the games that come out are the same as under lockstep."""
+    stream = np.load(os.path.join(GOLDEN, "boardstream_9x9_multisuicide.npz"))
+    lengths = [6, 6, 6]
+    sp = UnevenSlots(stream, lengths, 50)
+    games = []
+    rec = R.GameRecorder(sp, None, 6.5, on_game=lambda g, data: games.append((g, data)))
+    recorded = 0
+    for _ in range(40):
+        recorded += rec.pump(1)
+    # slot g needs 3 + 2 g search waves per move: the fast slot has played twice as many moves as the slow one by now
+    moves = [sp.index[g] * 6 + sp.t[g] for g in range(3)]
+    assert recorded == rec.moves_recorded == sum(moves) and moves == [15, 10, 7]
+    assert [[g for g, _ in games].count(k) for k in range(3)] == [2, 1, 1]
+    lock = ScriptedSlots(stream, lengths, 50)
+    ref_games = []
+    rec2 = R.GameRecorder(lock, None, 6.5, on_game=lambda g, data: ref_games.append((g, data)))
+    for _ in range(6):
+        rec2.step()
+    first = {g: d for g, d in reversed(games)}
+    for g, d in ref_games:
+        assert first[g].moves == d.moves and first[g].policy_targets_by_turn == d.policy_targets_by_turn
+        assert all(np.array_equal(a, b) for a, b in zip(first[g].boards_by_turn, d.boards_by_turn))
 
 
 def test_recorder_assembles_finished_games_from_scripted_slots():
