@@ -158,3 +158,26 @@ def test_rand_reproduces_the_reference_self_test_vector():
                 0x4FE798FB, 0x26B4DD4B, 0x78B77C1B, 0x231C4DFB, 0x17FB87C6, 0x9CC23870, 0x1C2C2CF7, 0x62D51240, 0xF1D1A7FF, 0x44C45C0A, 0xF93ACFCE,
                 0x42B1D236, 0xC1069B75]
     assert rand_uint32_stream("abc", 24).tolist() == expected
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under katago_b200/ or integration/ may import, execute, link or open it (only tests/,
+    __graft_entry__.smoke() and bench.py's CPU legs do), and the product has no CPU fallback to route through."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for base in ("katago_b200", "integration"):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            if "_build" in dirpath:
+                continue
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for m in re.finditer(r"(import\s+kg_nn_oracle|from\s+oracle|kg_nn_oracle\.|[\"'/]oracle/[\w./]*\.(py|so|a)\b|kgref_driver|libkgref)", text):
+                    line = text[:m.start()].count("\n") + 1
+                    src_line = text.splitlines()[line - 1].strip()
+                    if src_line.startswith(("//", "#", "*")):       # mentions in comments (where a file is built from) are fine
+                        continue
+                    offenders.append((os.path.join(base, f), line, src_line[:120]))
+    assert not offenders, offenders
