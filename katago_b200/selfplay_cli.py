@@ -57,6 +57,21 @@ _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0
             "valueSurpriseDataWeight": 0.0, "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
             "handicapProb": 0.0, "komiStdev": 0.0, "komiBigStdevProb": 0.0, "komiBiggerStdevProb": 0.0, "allowRectangleProb": 0.0,
             "rootEndingBonusPoints": 0.0, "rootPruneUselessMoves": False, "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
+_REFERENCE_DEFAULTS = {
+    "cpuct_exploration": 1.0, "cpuct_exploration_log": 0.45, "cpuct_exploration_base": 500.0, "fpu_reduction_max": 0.2, "root_fpu_reduction_max": 0.1,
+    "win_loss_utility_factor": 1.0, "no_result_utility_for_white": 0.0, "static_score_utility_factor": 0.1, "dynamic_score_utility_factor": 0.3,
+    "dynamic_score_center_zero_weight": 0.2, "dynamic_score_center_scale": 0.75, "draw_equivalent_wins_for_white": 0.5, "value_weight_exponent": 0.25,
+    "fpu_parent_weight_by_visited_policy": True, "fpu_parent_weight_by_visited_policy_pow": 2.0, "fpu_parent_weight": 0.0, "fpu_loss_prop": 0.0,
+    "root_fpu_loss_prop": 0.0, "cpuct_utility_stdev_prior": 0.40, "cpuct_utility_stdev_prior_weight": 2.0, "cpuct_utility_stdev_scale": 0.0,
+    "root_desired_per_child_visits_coeff": 0.0, "subtree_value_bias_factor": 0.45, "subtree_value_bias_weight_exponent": 0.85, "use_graph_search": True,
+    "graph_search_rep_bound": 11, "root_noise_enabled": False, "root_dirichlet_noise_total_concentration": 10.83, "root_dirichlet_noise_weight": 0.25,
+    "root_policy_temperature": 1.0, "root_policy_temperature_early": 1.0, "chosen_move_temperature_halflife": 19.0, "use_lcb_for_selection": True,
+    "use_non_buggy_lcb": False, "lcb_stdevs": 5.0, "min_visit_prop_for_lcb": 0.15, "chosen_move_temperature": 0.10, "chosen_move_temperature_early": 0.50,
+    "chosen_move_temperature_only_below_prob": 1.0, "chosen_move_subtract": 0.0, "chosen_move_prune": 1.0, "nn_cache_size_power_of_two": 0,
+    "root_num_symmetries_to_sample": 1,
+}
+# options the reference switches ON by default and the loop does not have: reported even when the key is absent
+_DEFAULT_ON_NOT_BUILT = {"rootEndingBonusPoints": "0.5", "rootPruneUselessMoves": "true"}
 _KO_RULES = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2, "SPIGHT": 3}
 
 
@@ -99,6 +114,17 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
         if key in cfg:
             kw[name] = conv(cfg[key])
             used.add(key); report["mapped"].append(key)
+    # Keys that are absent get the defaults of the reference's own loader (Setup::loadParams, program/setup.cpp, as a self-play
+    # command sees them), not the loop's: tests/test_selfplay_cli.py compares both loaders on the same files.
+    by_policy = kw.get("fpu_parent_weight_by_visited_policy", True)
+    if by_policy:        # setup.cpp:501-513: the power is read only with the flag, the plain weight only without it
+        kw.pop("fpu_parent_weight", None)
+    else:
+        kw.pop("fpu_parent_weight_by_visited_policy_pow", None)
+    for name, ref_default in _REFERENCE_DEFAULTS.items():
+        kw.setdefault(name, ref_default)
+    if not by_policy:
+        kw["fpu_parent_weight_by_visited_policy_pow"] = 1.0
     kw["use_play_selection"] = True                       # Search::getChosenMoveLoc always goes through the play selection values
     # rules: one value per list
     ko = _first_supported(cfg, "koRules", set(_KO_RULES), report, "SIMPLE").upper()
@@ -130,6 +156,9 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
             if cur == neutral:
                 continue
         report["not_built"].append(f"{key} = {val}")
+    for key, val in _DEFAULT_ON_NOT_BUILT.items():
+        if key not in cfg:
+            report["not_built"].append(f"{key} = {val} (the reference's default)")
     if strict and report["not_built"]:
         raise ValueError("options that are not built: " + "; ".join(report["not_built"]))
     return kw, data, report

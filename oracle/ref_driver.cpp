@@ -27,6 +27,9 @@
 #include "dataio/trainingwrite.h"
 #include "program/play.h"
 #include "dataio/sgf.h"
+#include "program/setup.h"
+#include "core/config_parser.h"
+#include "integration/b200params.h"
 #include "core/logger.h"
 
 #include <cstdint>
@@ -907,6 +910,45 @@ static int cmdWriteGame(int argc, char** argv) {
   return 0;
 }
 
+// paramsmap CFG KORULE: the reference's own configuration loader (ConfigParser + Setup::loadSingleParams, program/setup.cpp) on a .cfg,
+// mapped onto the device loop's configuration by integration/b200params.h; prints the mapped fields and the options it reports as
+// not implemented.  tests/test_selfplay_cli.py compares this with katago_b200/selfplay_cli.py's own mapping of the same file.
+static int cmdParamsMap(int argc, char** argv) {
+  if(argc != 4) { cerr << "usage: paramsmap CFG KORULE" << endl; return 1; }
+  const string cfgPath = argv[2];
+  ConfigParser cfg(cfgPath);
+  SearchParams p = Setup::loadSingleParams(cfg, Setup::SETUP_FOR_OTHER);
+  Rules rules;
+  const int ko = atoi(argv[3]);
+  rules.koRule = ko == 1 ? Rules::KO_POSITIONAL : ko == 2 ? Rules::KO_SITUATIONAL : ko == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
+  rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE; rules.multiStoneSuicideLegal = false; rules.hasButton = false;
+  rules.whiteHandicapBonusRule = Rules::WHB_ZERO; rules.friendlyPassOk = false; rules.komi = 7.5f;
+  vector<string> unsupported;
+  const kgb_selfplay_config c = b200::configFromSearchParams(p, rules, 256, cfg.contains("maxMovesPerGame") ? cfg.getInt("maxMovesPerGame", 0, 100000) : 0, 1,
+                                                             cfg.contains("nnCacheSizePowerOfTwo") ? cfg.getInt("nnCacheSizePowerOfTwo", -1, 48) : 0, &unsupported);
+  auto d = [](double v) { return Global::strprintf("%.17g", v); };
+  cout << "{";
+#define FI(f) cout << "\"" #f "\":" << (long long)c.f << ","
+#define FD(f) cout << "\"" #f "\":" << d(c.f) << ","
+  FI(max_visits); FI(max_moves); FI(multi_stone_suicide_legal); FD(komi); FD(cpuct_exploration); FD(cpuct_exploration_log); FD(cpuct_exploration_base);
+  FD(fpu_reduction_max); FD(root_fpu_reduction_max); FD(win_loss_utility_factor); FD(no_result_utility_for_white);
+  FD(static_score_utility_factor); FD(dynamic_score_utility_factor); FD(dynamic_score_center_zero_weight); FD(dynamic_score_center_scale);
+  FD(draw_equivalent_wins_for_white); FD(value_weight_exponent); FI(fpu_parent_weight_by_visited_policy); FD(fpu_parent_weight_by_visited_policy_pow);
+  FD(fpu_parent_weight); FD(fpu_loss_prop); FD(root_fpu_loss_prop); FD(cpuct_utility_stdev_prior); FD(cpuct_utility_stdev_prior_weight);
+  FD(cpuct_utility_stdev_scale); FD(root_desired_per_child_visits_coeff); FD(subtree_value_bias_factor); FD(subtree_value_bias_weight_exponent);
+  FI(use_graph_search); FI(graph_search_rep_bound); FI(root_noise_enabled); FD(root_dirichlet_noise_total_concentration); FD(root_dirichlet_noise_weight);
+  FD(root_policy_temperature); FD(root_policy_temperature_early); FD(chosen_move_temperature_halflife); FI(use_play_selection); FI(use_lcb_for_selection);
+  FI(use_non_buggy_lcb); FD(lcb_stdevs); FD(min_visit_prop_for_lcb); FD(chosen_move_temperature); FD(chosen_move_temperature_early);
+  FD(chosen_move_temperature_only_below_prob); FD(chosen_move_subtract); FD(chosen_move_prune); FI(nn_cache_size_power_of_two);
+  FI(root_num_symmetries_to_sample); FI(ko_rule); FI(full_history_rules);
+#undef FI
+#undef FD
+  cout << "\"unsupported\":[";
+  for(size_t i = 0; i < unsupported.size(); i++) cout << (i ? "," : "") << "\"" << unsupported[i] << "\"";
+  cout << "]}" << endl;
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -990,6 +1032,7 @@ int main(int argc, char** argv) {
   if(cmd == "npyheader") return cmdNpyHeader(argc, argv);
   if(cmd == "addrow") return cmdAddRow(argc, argv);
   if(cmd == "writegame") return cmdWriteGame(argc, argv);
+  if(cmd == "paramsmap") return cmdParamsMap(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

@@ -65,8 +65,11 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
 
 
 def test_neutral_values_and_unsupported_rules():
-    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\ncheapSearchProb = 0\nreduceVisits = false\nkoRules = POSITIONAL\nbSizes = 9\nkomiMean = 7\n", is_text=True), strict=True)
+    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\ncheapSearchProb = 0\nreduceVisits = false\nkoRules = POSITIONAL\nbSizes = 9\nkomiMean = 7\nrootEndingBonusPoints = 0\nrootPruneUselessMoves = false\n", is_text=True), strict=True)
     assert kw["ko_rule"] == 1 and data["board_size"] == 9 and data["komi"] == 7.0 and report["not_built"] == [] and report["fixed"] == []
+    # the two root options the reference switches on by default are reported even when the file does not mention them
+    _, _, rep = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\n", is_text=True))
+    assert any("rootEndingBonusPoints" in s_ and "default" in s_ for s_ in rep["not_built"]) and any("rootPruneUselessMoves" in s_ for s_ in rep["not_built"])
     with pytest.raises(ValueError, match="none of these is built"):
         C.selfplay_kwargs_from_cfg(C.parse_cfg("scoringRules = TERRITORY\n", is_text=True))
     with pytest.raises(ValueError, match="dataBoardLen"):
@@ -139,3 +142,52 @@ def test_sgf_sink_appends_one_record_per_game(tmp_path):
     name = os.path.basename(sink.path)
     assert len(name) == 21 and name.endswith(".sgfs") and name[:16] == name[:16].upper()
     assert open(sink.path).read() == (d["sgf"] + "\n") * 2 and sink.count == 2
+
+
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "kgref_driver")
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/kgref_driver not built")
+@pytest.mark.parametrize("which", ["stock", "every_key_changed", "almost_empty", "plain_fpu_weight"])
+def test_config_mapping_agrees_with_the_reference_loader(tmp_path, which):
+    """The same .cfg through the reference's own ConfigParser + Setup::loadSingleParams and integration/b200params.h
+    (`kgref_driver paramsmap`) and through selfplay_cli.py: every mapped field of kgb_selfplay_config agrees, defaults of
+    absent keys included, and the C++ side reports the same search options as not implemented."""
+    import json, subprocess
+    from katago_b200.nn_backend import SelfPlay
+    if which == "stock":
+        settings = dict(STOCK_B18_SETTINGS)
+    elif which == "almost_empty":       # every default comes from the loader
+        settings = {"numSearchThreads": "1", "maxVisits": "500"}
+    elif which == "plain_fpu_weight":
+        settings = {"numSearchThreads": "1", "maxVisits": "500", "fpuParentWeightByVisitedPolicy": "false", "fpuParentWeight": "0.4", "fpuParentWeightByVisitedPolicyPow": "3.0"}
+    else:      # a value of its own for every key the loop implements
+        settings = {"maxVisits": "777", "maxMovesPerGame": "321", "cpuctExploration": "0.93", "cpuctExplorationLog": "0.41", "cpuctExplorationBase": "350",
+                    "fpuReductionMax": "0.13", "rootFpuReductionMax": "0.07", "fpuLossProp": "0.11", "rootFpuLossProp": "0.06", "fpuParentWeight": "0.3",
+                    "fpuParentWeightByVisitedPolicy": "false", "fpuParentWeightByVisitedPolicyPow": "1.5", "valueWeightExponent": "0.35",
+                    "cpuctUtilityStdevPrior": "0.33", "cpuctUtilityStdevPriorWeight": "1.7", "cpuctUtilityStdevScale": "0.85",
+                    "rootDesiredPerChildVisitsCoeff": "3", "subtreeValueBiasFactor": "0.45", "subtreeValueBiasWeightExponent": "0.85",
+                    "useGraphSearch": "false", "graphSearchRepBound": "9", "rootNoiseEnabled": "false", "rootDirichletNoiseTotalConcentration": "9.5",
+                    "rootDirichletNoiseWeight": "0.2", "rootPolicyTemperature": "1.2", "rootPolicyTemperatureEarly": "1.4", "chosenMoveTemperature": "0.2",
+                    "chosenMoveTemperatureEarly": "0.6", "chosenMoveTemperatureHalflife": "17", "chosenMoveTemperatureOnlyBelowProb": "0.9",
+                    "chosenMoveSubtract": "1", "chosenMovePrune": "2", "useLcbForSelection": "false", "lcbStdevs": "4", "minVisitPropForLCB": "0.1",
+                    "useNonBuggyLcb": "false", "winLossUtilityFactor": "0.9", "staticScoreUtilityFactor": "0.1", "dynamicScoreUtilityFactor": "0.2",
+                    "dynamicScoreCenterZeroWeight": "0.3", "dynamicScoreCenterScale": "0.75", "noResultUtilityForWhite": "-0.1",
+                    "drawEquivalentWinsForWhite": "0.6", "rootNumSymmetriesToSample": "2", "nnCacheSizePowerOfTwo": "18", "koRules": "POSITIONAL",
+                    "multiStoneSuicideLegals": "false", "wideRootNoise": "0.04", "antiMirror": "true", "numSearchThreads": "1"}
+    path = tmp_path / "c.cfg"
+    path.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
+    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg(str(path)))
+    ref = json.loads(subprocess.run([DRIVER, "paramsmap", str(path), str(kw["ko_rule"])], capture_output=True, text=True, check=True).stdout)
+    sig = inspect.signature(SelfPlay.__init__)
+    eff = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect._empty}
+    eff.update(kw)
+    eff["komi"] = data["komi"]
+    for k, v in ref.items():
+        if k in ("unsupported", "komi", "multi_stone_suicide_legal"):      # rules come from the game initialiser, not from the search parameters
+            continue
+        assert k in eff, k
+        assert abs(float(eff[k]) - float(v)) <= 1e-12, (k, eff[k], v)
+    nb = " ".join(report["not_built"])
+    for line in ref["unsupported"]:                   # search options the C++ side names must be named by the command too
+        assert line.split(" = ")[0] in nb, (line, nb)
