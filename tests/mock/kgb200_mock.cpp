@@ -1,0 +1,205 @@
+// tests/mock/kgb200_mock.cpp - TEST INFRASTRUCTURE: a CPU stand-in for the part of libkgb200's C ABI that the recording path uses
+// (include/kgb200.h: evaluator handle life cycle + kgb_selfplay_* in hold mode), so that integration/b200record.h and the reference's
+// own TrainingDataWriter can be exercised without a GPU (tests/test_game_recorder.py::test_cpp_recorder_against_python_recorder_on_scripted_slots).
+//
+// Each slot plays uniformly random legal moves on the reference's own Board / BoardHistory (this file is compiled against the
+// reference like oracle/ref_record_driver.cpp) and reports made-up, reproducible search statistics.  Everything it serves is also
+// appended to the JSON-lines file named by KGB_MOCK_LOG, from which the Python side replays exactly the same slots.
+#include "include/kgb200.h"
+
+#include "game/board.h"
+#include "game/boardhistory.h"
+#include "neuralnet/nninputs.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+namespace {
+struct Lcg {
+  uint64_t s;
+  explicit Lcg(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ULL + 777) {}
+  uint32_t next() { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(s >> 33); }
+  double unit() { return (next() & 0xFFFFFF) / 16777216.0; }
+};
+
+struct Slot {
+  Board board; BoardHistory hist; Player pla = P_BLACK;
+  int moveNum = 0, gameIndex = 0;
+  bool held = true;                 // searches finish instantly in the mock
+  // what the "search" of the current root found
+  std::vector<int32_t> edgeVisits, nodeVisits; std::vector<float> policy; std::vector<double> childStats, psv;
+  double rootStats[5], rootNN[5];
+  std::vector<float> rowSpatial, rowGlobal;
+  Loc nextMove = Board::PASS_LOC;
+  // last move
+  int32_t last[4] = {0, 0, 0, 0}; float lastScore = 0; std::vector<uint8_t> finalColors, finalArea;
+};
+}  // namespace
+
+struct kgb_model { int dummy; };
+struct kgb_context { int x, y; };
+struct kgb_handle { int x, y; };
+struct kgb_selfplay {
+  kgb_selfplay_config cfg; int X, Y; Rules rules; Lcg rng{1}; std::vector<Slot> slots; std::vector<uint8_t> released; std::ofstream log;
+};
+
+static std::string g_err;
+
+static void searchRoot(kgb_selfplay* sp, int g) {
+  Slot& s = sp->slots[g];
+  const int X = sp->X, Y = sp->Y, P = X * Y + 1;
+  Lcg& r = sp->rng;
+  s.edgeVisits.assign(P, 0); s.nodeVisits.assign(P, 0); s.policy.assign(P, -1.0f); s.childStats.assign((size_t)P * 5, 0.0); s.psv.assign(P, -1.0);
+  std::vector<int> legal;
+  for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) if(s.hist.isLegal(s.board, Location::getLoc(x, y, X), s.pla)) legal.push_back(y * X + x);
+  legal.push_back(P - 1);
+  double tot = 0;
+  for(int pos : legal) { s.policy[pos] = (float)(0.05 + r.unit()); tot += s.policy[pos]; }
+  for(int pos : legal) s.policy[pos] = (float)(s.policy[pos] / tot);
+  // the move the slot will play: uniform over the legal board points, a pass once in 25 moves, answered by a second pass one time in three
+  const bool lastWasPass = s.hist.moveHistory.size() > 0 && s.hist.moveHistory.back().loc == Board::PASS_LOC;
+  int chosen = (legal.size() == 1 || r.next() % 25 == 0 || (lastWasPass && r.next() % 3 == 0)) ? P - 1 : legal[r.next() % (legal.size() - 1)];
+  for(int pos : legal) {
+    if(pos != chosen && r.next() % 3 != 0) continue;
+    s.edgeVisits[pos] = 1 + (int)(r.next() % 40); s.nodeVisits[pos] = s.edgeVisits[pos] + (int)(r.next() % 3);
+    s.psv[pos] = (double)s.edgeVisits[pos] * (r.next() % 7 == 0 ? 0.0 : 1.0) + (pos == chosen ? 0.5 : 0.0);
+    s.childStats[(size_t)pos * 5 + 0] = r.unit() * 2 - 1; s.childStats[(size_t)pos * 5 + 1] = r.unit() * 0.05;
+    s.childStats[(size_t)pos * 5 + 2] = (r.unit() - 0.5) * 40; s.childStats[(size_t)pos * 5 + 3] = 500 * r.unit(); s.childStats[(size_t)pos * 5 + 4] = (r.unit() - 0.5) * 30;
+  }
+  s.nextMove = chosen == P - 1 ? Board::PASS_LOC : Location::getLoc(chosen % X, chosen / X, X);
+  s.rootStats[0] = r.unit() * 2 - 1; s.rootStats[1] = r.unit() * 0.04; s.rootStats[2] = (r.unit() - 0.5) * 30; s.rootStats[3] = 400 * r.unit(); s.rootStats[4] = (r.unit() - 0.5) * 20;
+  s.rootNN[0] = r.unit() * 2 - 1; s.rootNN[1] = 0.0; s.rootNN[2] = (r.unit() - 0.5) * 30; s.rootNN[3] = 300 * r.unit(); s.rootNN[4] = 0.0;
+  // the root's input row: the reference's own fillRowV7 (NHWC) - what the device loop's featurizer is pinned to
+  MiscNNInputParams ip; ip.drawEquivalentWinsForWhite = sp->cfg.draw_equivalent_wins_for_white;
+  s.rowSpatial.assign((size_t)X * Y * 22, 0.0f); s.rowGlobal.assign(19, 0.0f);
+  NNInputs::fillRowV7(s.board, s.hist, s.pla, ip, X, Y, true, s.rowSpatial.data(), s.rowGlobal.data());
+  s.held = true;
+  // log
+  std::ofstream& o = sp->log;
+  auto arr = [&](const char* name, auto& v, bool last = false) {
+    o << "\"" << name << "\":[";
+    for(size_t i = 0; i < v.size(); i++) { char b[64]; snprintf(b, sizeof b, "%.17g", (double)v[i]); o << (i ? "," : "") << b; }
+    o << "]" << (last ? "" : ",");
+  };
+  std::vector<int> colors;
+  for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) colors.push_back((int)s.board.colors[Location::getLoc(x, y, X)]);
+  std::vector<double> rs(s.rootStats, s.rootStats + 5), rn(s.rootNN, s.rootNN + 5);
+  o << "{\"ev\":\"root\",\"slot\":" << g << ",\"move_num\":" << s.moveNum << ",\"black_to_move\":" << (s.pla == P_BLACK ? 1 : 0) << ",";
+  arr("colors", colors); arr("edge_visits", s.edgeVisits); arr("node_visits", s.nodeVisits); arr("policy", s.policy); arr("child_stats", s.childStats);
+  arr("psv", s.psv); arr("root_stats", rs); arr("root_nn", rn); arr("row_spatial", s.rowSpatial); arr("row_global", s.rowGlobal, true);
+  o << "}\n";
+}
+
+static void startGame(kgb_selfplay* sp, int g) {
+  Slot& s = sp->slots[g];
+  s.board = Board(sp->X, sp->Y); s.pla = P_BLACK; s.hist = BoardHistory(s.board, s.pla, sp->rules, 0, false); s.moveNum = 0;
+}
+
+static void advance(kgb_selfplay* sp, int g) {
+  Slot& s = sp->slots[g];
+  const int X = sp->X, Y = sp->Y;
+  const Loc loc = s.nextMove;
+  s.hist.makeBoardMoveAssumeLegal(s.board, loc, s.pla, NULL);
+  s.pla = getOpp(s.pla);
+  const int maxMoves = sp->cfg.max_moves > 0 ? sp->cfg.max_moves : 2 * X * Y;
+  const bool finished = s.hist.isGameFinished, over = finished || s.moveNum + 1 >= maxMoves;
+  s.last[0] = loc == Board::PASS_LOC ? X * Y : Location::getY(loc, X) * X + Location::getX(loc, X);
+  s.last[1] = over ? (1 | ((finished && s.hist.isNoResult) ? 2 : 0) | (finished ? 0 : 4)) : 0;
+  s.last[2] = s.moveNum; s.last[3] = s.gameIndex;
+  if(over) {
+    Color area[Board::MAX_ARR_SIZE];
+    BoardHistory h2 = s.hist;
+    h2.endAndScoreGameNow(s.board, area);
+    s.lastScore = h2.finalWhiteMinusBlackScore;
+    s.finalColors.clear(); s.finalArea.clear();
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); s.finalColors.push_back(s.board.colors[l]); s.finalArea.push_back(area[l]); }
+  }
+  std::ofstream& o = sp->log;
+  o << "{\"ev\":\"move\",\"slot\":" << g << ",\"pos\":" << s.last[0] << ",\"flags\":" << s.last[1] << ",\"move_num\":" << s.last[2] << ",\"game_index\":" << s.last[3]
+    << ",\"score\":" << s.lastScore << ",\"final_colors\":[";
+  for(size_t i = 0; over && i < s.finalColors.size(); i++) o << (i ? "," : "") << (int)s.finalColors[i];
+  o << "],\"final_area\":[";
+  for(size_t i = 0; over && i < s.finalArea.size(); i++) o << (i ? "," : "") << (int)s.finalArea[i];
+  o << "]}\n";
+  if(over) { s.gameIndex++; startGame(sp, g); } else s.moveNum++;
+  searchRoot(sp, g);
+}
+
+#define GUARD(body) try { body; return 0; } catch(const std::exception& e) { g_err = e.what(); return 1; }
+
+extern "C" {
+int kgb_global_init(void) { return 0; }
+int kgb_global_cleanup(void) { return 0; }
+const char* kgb_last_error(void) { return g_err.c_str(); }
+int kgb_model_load_file(const char*, const char*, kgb_model** out) { *out = new kgb_model(); return 0; }
+void kgb_model_free(kgb_model* m) { delete m; }
+int kgb_context_create(const int*, int, int x, int y, int, const kgb_model*, kgb_context** out) { *out = new kgb_context{x, y}; return 0; }
+void kgb_context_free(kgb_context* c) { delete c; }
+int kgb_handle_create(kgb_context* c, const kgb_model*, int, int, int, int, kgb_handle** out) { *out = new kgb_handle{c->x, c->y}; return 0; }
+void kgb_handle_free(kgb_handle* h) { delete h; }
+int kgb_handle_sync(kgb_handle*) { return 0; }
+
+int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfplay** out) {
+  GUARD({
+    const char* path = getenv("KGB_MOCK_LOG");
+    if(!path) throw std::runtime_error("KGB_MOCK_LOG is not set");
+    kgb_selfplay* sp = new kgb_selfplay();
+    sp->cfg = *c; sp->X = h->x; sp->Y = h->y; sp->rng = Lcg(c->seed);
+    sp->rules.koRule = c->ko_rule == 1 ? Rules::KO_POSITIONAL : c->ko_rule == 2 ? Rules::KO_SITUATIONAL : c->ko_rule == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
+    sp->rules.scoringRule = Rules::SCORING_AREA; sp->rules.taxRule = Rules::TAX_NONE; sp->rules.multiStoneSuicideLegal = c->multi_stone_suicide_legal != 0;
+    sp->rules.hasButton = false; sp->rules.whiteHandicapBonusRule = Rules::WHB_ZERO; sp->rules.friendlyPassOk = false; sp->rules.komi = c->komi;
+    sp->log.open(path);
+    sp->slots.resize(c->num_games); sp->released.assign(c->num_games, 0);
+    for(int g = 0; g < c->num_games; g++) { startGame(sp, g); searchRoot(sp, g); }
+    *out = sp;
+  })
+}
+void kgb_selfplay_free(kgb_selfplay* sp) { delete sp; }
+int kgb_selfplay_run(kgb_selfplay* sp, int) {
+  GUARD({
+    for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) { sp->released[g] = 0; advance(sp, (int)g); }
+    sp->log.flush();
+  })
+}
+int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* mask) { for(size_t g = 0; g < sp->slots.size(); g++) sp->released[g] = mask ? mask[g] : 1; return 0; }
+int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) { for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->cfg.max_visits; return 0; }
+int kgb_selfplay_get_game(kgb_selfplay* sp, int g, uint8_t* colors, int32_t* info) {
+  Slot& s = sp->slots[g];
+  for(int y = 0; y < sp->Y; y++) for(int x = 0; x < sp->X; x++) colors[y * sp->X + x] = s.board.colors[Location::getLoc(x, y, sp->X)];
+  info[0] = s.moveNum; info[1] = s.pla == P_BLACK; info[2] = -1; info[3] = 0; info[4] = 0; info[5] = sp->cfg.max_visits + g;
+  return 0;
+}
+int kgb_selfplay_get_root_children(kgb_selfplay* sp, int g, int32_t* visits, float* policy, double* util) {
+  Slot& s = sp->slots[g];
+  for(size_t i = 0; i < s.edgeVisits.size(); i++) { visits[i] = s.edgeVisits[i]; policy[i] = s.policy[i]; util[i] = 0.0; }
+  return 0;
+}
+int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int g, double* child, double* root) {
+  Slot& s = sp->slots[g];
+  memcpy(child, s.childStats.data(), s.childStats.size() * sizeof(double)); memcpy(root, s.rootStats, sizeof(s.rootStats));
+  return 0;
+}
+int kgb_selfplay_get_play_selection_values(kgb_selfplay* sp, int g, double* v) { Slot& s = sp->slots[g]; memcpy(v, s.psv.data(), s.psv.size() * sizeof(double)); return 0; }
+int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int g, int32_t* nv, double* nn) {
+  Slot& s = sp->slots[g];
+  memcpy(nv, s.nodeVisits.data(), s.nodeVisits.size() * sizeof(int32_t)); memcpy(nn, s.rootNN, sizeof(s.rootNN));
+  return 0;
+}
+int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int g, float* spatial, float* global) {
+  Slot& s = sp->slots[g];
+  memcpy(spatial, s.rowSpatial.data(), s.rowSpatial.size() * sizeof(float)); memcpy(global, s.rowGlobal.data(), 19 * sizeof(float));
+  return 0;
+}
+int kgb_selfplay_get_last_move(kgb_selfplay* sp, int g, int32_t* info, float* score, uint8_t* colors, uint8_t* area) {
+  Slot& s = sp->slots[g];
+  memcpy(info, s.last, sizeof(s.last)); *score = s.lastScore;
+  for(size_t i = 0; i < s.finalColors.size(); i++) { colors[i] = s.finalColors[i]; area[i] = s.finalArea[i]; }
+  return 0;
+}
+int kgb_selfplay_get_stats(kgb_selfplay*, kgb_selfplay_stats* out) { memset(out, 0, sizeof(*out)); return 0; }
+int kgb_selfplay_play_moves(kgb_selfplay*, const int8_t*, int) { g_err = "mock: play_moves is not scripted"; return 1; }
+}

@@ -260,6 +260,128 @@ def test_recorder_assembles_finished_games_from_scripted_slots():
         at += n
 
 
+# ---- the C++ recorder + the reference's writer against the Python recorder + writer, both fed by the same CPU mock of the ABI ----------
+class ReplaySlots:
+    """nn_backend.SelfPlay as the mock library (tests/mock/kgb200_mock.cpp) behaved in a finished run: replays its JSON-lines log."""
+
+    def __init__(self, log_path, num_games, size, max_visits):
+        import json
+        self.x = self.y = size
+        self.num_games, self.max_visits = num_games, max_visits
+        self.queues = [[] for _ in range(num_games)]
+        for ln in open(log_path):
+            ev = json.loads(ln)
+            self.queues[ev["slot"]].append(ev)
+        self.root = [q.pop(0) for q in self.queues]
+        self.last = [None] * num_games
+        self.released = [False] * num_games
+
+    def run(self, n):
+        for g in range(self.num_games):
+            if self.released[g] and self.queues[g]:
+                self.released[g] = False
+                self.last[g] = self.queues[g].pop(0); assert self.last[g]["ev"] == "move"
+                self.root[g] = self.queues[g].pop(0); assert self.root[g]["ev"] == "root"
+
+    def release(self, mask=None):
+        self.released = [True] * self.num_games
+
+    def root_visits(self):
+        return np.full(self.num_games, self.max_visits, np.int32)
+
+    def game(self, g):
+        r = self.root[g]
+        return np.array(r["colors"], np.uint8).reshape(self.y, self.x), dict(move_num=r["move_num"], black_to_move=bool(r["black_to_move"]), ko=-1, cap_b=0,
+                                                                          cap_w=0, root_visits=self.max_visits + g)
+
+    def nn_row(self, g):
+        r = self.root[g]
+        return np.array(r["row_spatial"], np.float32).reshape(self.x * self.y, 22), np.array(r["row_global"], np.float32)
+
+    def root_children(self, g):
+        r = self.root[g]
+        return np.array(r["edge_visits"], np.int32), np.array(r["policy"], np.float32), np.zeros(len(r["policy"]))
+
+    def root_value_stats(self, g):
+        r = self.root[g]
+        return np.array(r["child_stats"]).reshape(-1, 5), np.array(r["root_stats"])
+
+    def play_selection_values(self, g):
+        return np.array(self.root[g]["psv"])
+
+    def root_extra(self, g):
+        return dict(child_node_visits=np.array(self.root[g]["node_visits"], np.int32), root_nn_moments=np.array(self.root[g]["root_nn"]))
+
+    def last_move(self, g):
+        m = self.last[g]
+        pos, fl = m["pos"], m["flags"]
+        n = self.x * self.y
+        return dict(pos=pos, xy=(-1, -1) if pos == n else (pos % self.x, pos // self.x), game_over=bool(fl & 1), no_result=bool(fl & 2), hit_move_limit=bool(fl & 4),
+                    move_num=m["move_num"], game_index=m["game_index"], final_white_minus_black_score=float(m["score"]),
+                    final_colors=np.array(m["final_colors"] or [0] * n, np.uint8), final_area=np.array(m["final_area"] or [0] * n, np.uint8))
+
+
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libkgref.a")
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/cpp") and os.path.exists(REF_LIB)), reason="needs the reference sources and oracle/_ref/libkgref.a")
+@pytest.mark.parametrize("size,ko_rule,komi,max_moves", [(9, 0, 6.5, 40), (5, 1, 7.0, 60)])
+def test_cpp_recorder_against_python_recorder_on_scripted_slots(tmp_path, size, ko_rule, komi, max_moves):
+    """No GPU: oracle/ref_record_driver.cpp (integration/b200record.h + the reference's own TrainingDataWriter) linked against a CPU mock
+    of the recording ABI that plays random legal games on the reference's Board.  The C++ recorder's own checks (legality, game end,
+    final score and area) run on every move; its rows - planes recomputed by the reference - must equal the rows the Python recorder
+    and writer produce from the mock's log: input planes bit for bit, integer targets exactly, floats to the text sink's 6 digits."""
+    import ctypes, subprocess
+    from katago_b200.nn_backend import SelfplayConfig
+    from test_npz_writer import _parse_text_dump
+    ref = "/root/reference/cpp"
+    exe = tmp_path / "record_mock"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-mfpmath=sse", "-DNDEBUG", "-DNO_GIT_REVISION", "-DNO_LIBZIP", "-w", "-I" + ref, "-I" + ref + "/external",
+                    "-isystem", ref + "/external/tclap-1.2.5/include", "-isystem", ref + "/external/filesystem-1.5.8/include", "-I" + ROOT, "-o", str(exe),
+                    os.path.join(ROOT, "oracle", "ref_record_driver.cpp"), os.path.join(ROOT, "tests", "mock", "kgb200_mock.cpp"),
+                    "-Wl,--start-group", REF_LIB, "-Wl,--end-group", "-lz", "-lpthread"], check=True, cwd=ROOT)
+    G, V, NUM = 3, 20, 5
+    c = SelfplayConfig()
+    c.num_games, c.max_visits, c.max_moves, c.multi_stone_suicide_legal, c.komi, c.seed = G, V, max_moves, 1, komi, 5 + size
+    c.debug_hold_at_max_visits, c.draw_equivalent_wins_for_white, c.ko_rule, c.full_history_rules = 1, 0.5, ko_rule, 1
+    (tmp_path / "cfg.bin").write_bytes(ctypes.string_at(ctypes.addressof(c), ctypes.sizeof(c)))
+    (tmp_path / "model.bin").write_bytes(b"unused")
+    log = tmp_path / "log.jsonl"
+    r = subprocess.run([str(exe), str(tmp_path / "model.bin"), str(size), str(tmp_path / "cfg.bin"), str(NUM), str(tmp_path / "rows.txt")],
+                       env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = _parse_text_dump((tmp_path / "rows.txt").read_text())
+    assert len(want) == 1
+
+    sp = ReplaySlots(str(log), G, size, V)
+    sp.cfg = c
+    got, games = [], []
+    writer = W.TrainingDataWriter(None, 4096, 1.0, size, "recorder-test", on_flush=lambda b: got.append({k: v[:b.cur_rows].copy() for k, v in b.arrays.items()}))
+
+    class FirstGames:
+        def write_game(self, data):
+            if len(games) < NUM:
+                writer.write_game(data)
+            games.append(data)
+    rec = R.GameRecorder(sp, FirstGames(), komi)
+    while len(games) < NUM:
+        rec.step()
+    writer.flush_if_nonempty()
+    fw, fg = want[0], got[0]
+    n = len(fw["globalTargetsNC"])
+    assert n == fg["globalTargetsNC"].shape[0] == sum(len(d.moves) for d in games[:NUM]) > 0
+    assert [bytes.fromhex(x) for x in fw["binaryInputNCHWPacked"]] == [fg["binaryInputNCHWPacked"][i].tobytes() for i in range(n)]
+    for name in ("policyTargetsNCMove", "scoreDistrN", "valueTargetsNCHW", "qValueTargetsNCMove"):
+        a = np.stack(fw[name]).astype(np.int64)
+        b = fg[name].reshape(n, -1).astype(np.int64)
+        assert np.array_equal(a, b), (name, np.argwhere(a != b)[:5])
+    for name in ("globalInputNC", "globalTargetsNC"):
+        a = np.stack(fw[name])
+        b = fg[name].reshape(n, -1).astype(np.float64)
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-30), (name, np.argwhere(~np.isclose(a, b, rtol=2e-5, atol=1e-30))[:5])
+    assert any(d.end_finished for d in games[:NUM]) or size == 9        # the small board also sees games that end by passes
+
+
 # ------------------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("ko_rule,graph", [(0, True), (1, False)])
