@@ -296,3 +296,33 @@ def test_sgf_equals_the_reference_write_sgf(path):
     from katago_b200.npz_writer import write_sgf
     d = json.loads(gzip.open(path, "rb").read())
     assert write_sgf(_game_from_fixture(d), "b200-black", "b200-white") == d["sgf"]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/python/shuffle.py"), reason="reference python not present")
+def test_files_go_through_the_reference_shuffler_into_its_training_reader(tmp_path):
+    """"must drop straight into python/shuffle.py -> train.py".  Full rows (every target filled by add_row) written as
+    .npz files, shuffled by the reference's own shuffle.py, read back by its training reader: no row is lost or altered."""
+    import torch
+    src = tmp_path / "selfplay"; out = tmp_path / "shuffled"; scratch = tmp_path / "scratch"
+    for d in (src, out, scratch):
+        d.mkdir()
+    total = []
+    for i, p in enumerate(p for p in ADDROW_FIXTURES if "_in_19" in p or "19x19" in p):
+        _, buf = _replay_addrow_fixture(p)
+        buf.write_to_zip_file(str(src / ("%016X.npz" % (i + 1))))
+        total.append({k: v[:buf.cur_rows].copy() for k, v in buf.arrays.items()})
+    n = sum(t["globalTargetsNC"].shape[0] for t in total)
+    r = subprocess.run([sys.executable, "/root/reference/python/shuffle.py", str(src), "-min-rows", "10", "-keep-target-rows", "all", "-out-dir", str(out),
+                        "-out-tmp-dir", str(scratch), "-num-processes", "1", "-approx-rows-per-out-file", "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    files = sorted(str(out / f) for f in os.listdir(out) if f.endswith(".npz"))
+    shuffled = {k: np.concatenate([np.load(f)[k] for f in files]) for k in W.schema(19)}
+    assert shuffled["globalTargetsNC"].shape[0] == n
+    key = lambda a: sorted(map(bytes, np.ascontiguousarray(a).reshape(a.shape[0], -1)))      # rows as a multiset
+    for k in W.schema(19):
+        assert key(shuffled[k]) == key(np.concatenate([t[k] for t in total])), k
+    sys.path.insert(0, "/root/reference/python")
+    from katago.train import data_processing_pytorch as dp, modelconfigs
+    batches = list(dp.read_npz_training_data(files, batch_size=16, world_size=1, rank=0, pos_len=19, device=torch.device("cpu"),
+                                             randomize_symmetries=False, include_meta=False, model_config=modelconfigs.config_of_name["b2c16"]))
+    assert len(batches) >= n // 16 - len(files) and all(tuple(b["globalTargetsNC"].shape) == (16, 80) for b in batches)
