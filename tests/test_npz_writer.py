@@ -326,3 +326,38 @@ def test_files_go_through_the_reference_shuffler_into_its_training_reader(tmp_pa
     batches = list(dp.read_npz_training_data(files, batch_size=16, world_size=1, rank=0, pos_len=19, device=torch.device("cpu"),
                                              randomize_symmetries=False, include_meta=False, model_config=modelconfigs.config_of_name["b2c16"]))
     assert len(batches) >= n // 16 - len(files) and all(tuple(b["globalTargetsNC"].shape) == (16, 80) for b in batches)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/python/train.py"), reason="reference python not present")
+def test_reference_trainer_trains_on_our_files(tmp_path):
+    """The whole consumer side of SURVEY §8f row 1 with the reference's own, unmodified tools: games written by TrainingDataWriter ->
+    python/shuffle.py -> python/train.py (one small epoch of its smallest net on the CPU) -> validation pass.  Every loss term the
+    trainer computes from our targets (policy, value, TD values, ownership, scoring, future position, score distribution, ...) is finite."""
+    d_in, d_out, d_tmp, d_data, d_tr = (tmp_path / n for n in ("in", "out", "tmp", "data", "tr"))
+    for d in (d_in, d_out, d_tmp, d_data / "train", d_data / "val"):
+        d.mkdir(parents=True)
+    w = W.TrainingDataWriter(str(d_in), 64, 1.0, 9, "trainpipe")
+    for p in WRITEGAME_FIXTURES:
+        d = json.loads(gzip.open(p, "rb").read())
+        if d["dataLen"] == 9:
+            for _ in range(3):
+                w.write_game(_game_from_fixture(d))
+    w.flush_if_nonempty()
+    r = subprocess.run([sys.executable, "/root/reference/python/shuffle.py", str(d_in), "-min-rows", "10", "-keep-target-rows", "all", "-out-dir", str(d_out),
+                        "-out-tmp-dir", str(d_tmp), "-num-processes", "1", "-approx-rows-per-out-file", "128"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    files = sorted(f for f in os.listdir(d_out) if f.endswith(".npz"))
+    assert len(files) >= 2
+    for f in files:
+        dst = d_data / ("val" if f == files[-1] else "train")
+        os.replace(d_out / f, dst / f)
+        os.replace(d_out / f.replace(".npz", ".json"), dst / f.replace(".npz", ".json"))
+    (d_data / "train.json").write_text(json.dumps({"range": [0, w.row_count]}))
+    r = subprocess.run([sys.executable, "train.py", "-traindir", str(d_tr), "-datadir", str(d_data), "-pos-len", "9", "-batch-size", "32", "-model-kind", "b2c16",
+                        "-samples-per-epoch", "128", "-max-epochs-this-instance", "1", "-no-compile", "-no-export", "-quit-if-no-data", "-max-val-samples", "64"],
+                       cwd="/root/reference/python", capture_output=True, text=True, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Finished training subepoch" in r.stdout + r.stderr                 # the optimiser stepped through the training batches
+    last = json.loads((d_tr / "metrics_val.json").read_text().strip().splitlines()[-1])
+    losses = {k: v for k, v in last.items() if k.endswith("loss")}
+    assert len(losses) >= 10 and all(np.isfinite(v) for v in losses.values()), losses
