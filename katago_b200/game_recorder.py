@@ -9,8 +9,10 @@ last).  CPU parity: tests/test_game_recorder.py against tests/golden/searchtarge
 `GameRecorder` drives a `SelfPlay` created with `debug_hold_at_max_visits=True`: a game whose search is finished idles until the
 recorder has read its root (a handful of small device reads per game and move, against a search of max_visits waves) and releases
 it; the device then chooses and plays the move exactly as it does without a recorder.  Finished games go to a `TrainingDataWriter`.
-Not recorded (the reference's options that the device loop does not have): side positions, cheap searches / reduced visits and
-their target weights (every turn has weight 1), lead estimation (hasLead only on the outcome entry), reanalysis, net changes.
+Target weights: every turn enters with weight 1 (no cheap searches / reduced visits on the device) and is then redistributed by policy and
+value surprise like runGame does (surprise_target_weights, parity against whole reference games in tests/golden/rungame.json.gz).
+Not recorded (the reference's options that the device loop does not have): side positions, lead estimation (hasLead only on the
+outcome entry), reanalysis, net changes.
 """
 import math
 
@@ -86,6 +88,78 @@ def policy_target_moves(play_selection_values, x_size):
     return [((-1, -1) if pos == n - 1 else (pos % x_size, pos // x_size)) + (int(vals[pos]),) for pos in range(n) if psv[pos] >= 0]
 
 
+def value_surprise_kl(win, loss, no_result, raw):
+    """valueSurpriseKL (program/play.cpp:1303-1314): KL divergence of a win / loss / noResult distribution from the raw net's (raw =
+    (win, loss, noResult)), floored at 0 and capped at 1."""
+    s = 0.0
+    for v, r in ((win, raw[0]), (loss, raw[1]), (no_result, raw[2])):
+        if v > 1e-100:
+            s += v * (math.log(v) - math.log(max(float(r), 1e-100)))
+    return min(max(s, 0.0), 1.0)
+
+
+def compute_value_surprise_by_turn(white_value_targets, raw_nn_values, board_area, use_search_value_surprise=False):
+    """computeValueSurpriseByTurn (play.cpp:1322-1352): how surprising each turn's value result was to the raw net - by default the
+    smoothed forward-looking game result (exponential average back from the outcome, nowFactor = 1 / (1 + area * 0.016)), or the
+    turn's own search values.  white_value_targets has one entry more than raw_nn_values (the outcome)."""
+    n = len(raw_nn_values)
+    if len(white_value_targets) != n + 1:
+        raise ValueError("white_value_targets must have one entry per turn plus the outcome")
+    f = lambda v: float(_f32(v))
+    if use_search_value_surprise:
+        return [value_surprise_kl(f(t[0]), f(t[1]), f(t[2]), raw_nn_values[i]) for i, t in enumerate(white_value_targets[:n])]
+    now = 1.0 / (1.0 + board_area * 0.016)
+    win, loss, nores = (f(v) for v in white_value_targets[-1][:3])
+    out = [0.0] * n
+    for i in range(n - 1, -1, -1):
+        t = white_value_targets[i]
+        win = win + now * (f(t[0]) - win)
+        loss = loss + now * (f(t[1]) - loss)
+        nores = nores + now * (f(t[2]) - nores)
+        out[i] = value_surprise_kl(win, loss, nores, raw_nn_values[i])
+    return out
+
+
+def surprise_target_weights(target_weights, policy_surprise, value_surprise, policy_surprise_data_weight, value_surprise_data_weight):
+    """The surprise weighting of Play::runGame (play.cpp:2084-2163) for games without cheap-search reanalysis: part of every turn's
+    weight is redistributed in proportion to its policy surprise (for reduced-weight turns: the surprise in excess of 1.5x the
+    average) and to its value surprise, keeping the game's total weight.  Returns float32 weights."""
+    w = [float(_f32(x)) for x in target_weights]
+    if not (policy_surprise_data_weight > 0 or value_surprise_data_weight > 0):
+        return [_f32(x) for x in w]
+    n = len(w)
+    sum_w = sum_p = sum_v = 0.0
+    for i in range(n):
+        if not (0.0 <= w[i] <= 1.0):
+            raise ValueError("surprise weighting expects target weights in [0, 1]")
+        sum_w += w[i]
+        sum_p += policy_surprise[i] * w[i]
+        sum_v += value_surprise[i] * w[i]
+    if sum_w < 1:
+        return [_f32(x) for x in w]
+    avg_p, avg_v = sum_p / sum_w, sum_v / sum_w
+    vsw = value_surprise_data_weight
+    if avg_v < 0.010:
+        vsw *= avg_v / 0.010
+    threshold = avg_p * 1.5
+    p_prop = [w[i] * policy_surprise[i] + (1 - w[i]) * max(0.0, policy_surprise[i] - threshold) for i in range(n)]
+    v_prop = [w[i] * value_surprise[i] for i in range(n)]
+    sp = sv = 0.0
+    for i in range(n):
+        sp += p_prop[i]
+        sv += v_prop[i]
+    sp, sv = max(sp, 1e-10), max(sv, 1e-10)
+    return [_f32((1.0 - policy_surprise_data_weight - vsw) * w[i] + policy_surprise_data_weight * p_prop[i] * sum_w / sp + vsw * v_prop[i] * sum_w / sv)
+            for i in range(n)]
+
+
+def resolve_target_weight(weight, rand):
+    """resolveWeight (play.cpp:2277-2283): a fractional weight becomes floor or floor + 1 with the matching probability."""
+    w = max(float(_f32(weight)), 0.0)
+    floored = math.floor(w)
+    return _f32(floored + 1 if rand.next_bool(float(_f32(_f32(w) - _f32(floored)))) else floored)
+
+
 class _GameInProgress:
     def __init__(self):
         self.turns = []       # per turn: what the finished root search gave
@@ -105,7 +179,12 @@ class GameRecorder:
          builds the FinishedGameData (game-end targets of program/play.cpp:1977-2027) and the slot has already started a new game.
     The game hash (FinishedGameData::gameHash, two 64-bit draws of the game's Rand in the reference) comes from `game_hash_fn`."""
 
-    def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None):
+    def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None,
+                 policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None):
+        """policy_surprise_data_weight / value_surprise_data_weight / use_search_value_surprise: PlaySettings of the same names - the
+        finished game's target weights are redistributed by surprise (surprise_target_weights).  weight_rand (a RowRand): fractional
+        weights are then resolved to integers like runGame does (resolve_target_weight); None leaves them fractional for the writer,
+        which draws the extra row itself."""
         self.sp, self.writer, self.X, self.Y, self.komi = sp, writer, sp.x, sp.y, float(komi)
         self.draw_eq = draw_equivalent_wins_for_white
         self.games = [_GameInProgress() for _ in range(sp.num_games)]
@@ -114,6 +193,8 @@ class GameRecorder:
                                                                   ((index + 1) * 0xC2B2AE3D27D4EB4F + slot) & (2 ** 64 - 1)))
         self.games_written = 0
         self.moves_recorded = 0
+        self.policy_surprise_data_weight, self.value_surprise_data_weight = float(policy_surprise_data_weight), float(value_surprise_data_weight)
+        self.use_search_value_surprise, self.weight_rand = bool(use_search_value_surprise), weight_rand
         cfg = getattr(sp, "cfg", None)             # rules for the game record (write_sgf)
         # The root's input row is taken from the wave that evaluates the new root.  With the evaluation cache on and a single root
         # evaluation, that root is normally a cache hit (it was a child of the previous tree) and no row is produced for it.
@@ -155,7 +236,8 @@ class GameRecorder:
             q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
             surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
             # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy as searched
-            nn_raw_stats=(float(nn[0]), float(nn[2]), policy_entropy)))
+            nn_raw_stats=(float(nn[0]), float(nn[2]), policy_entropy),
+            raw_nn_values=reported_search_values(nn)[:3]))       # Search::getRootRawNNValues: win, loss, noResult of the root's own evaluation
 
     def _after_move(self, g):
         """Slot g was released and one wave has run: the device has played its move and evaluated the new root."""
@@ -235,6 +317,17 @@ class GameRecorder:
             data.winner, data.final_white_minus_black_score = winner, score
             data.white_value_targets_by_turn.append(final_value_targets(winner, score, self.draw_eq, self.komi))
         data.final_full_area, data.final_ownership = area, area
+        if self.policy_surprise_data_weight > 0 or self.value_surprise_data_weight > 0:      # play.cpp:2034-2163
+            value_surprise = compute_value_surprise_by_turn(data.white_value_targets_by_turn, [t["raw_nn_values"] for t in gm.turns], X * Y,
+                                                            self.use_search_value_surprise)
+            data.value_surprise_by_turn = value_surprise
+            data.target_weight_by_turn = surprise_target_weights(data.target_weight_by_turn, data.policy_surprise_by_turn, value_surprise,
+                                                                 self.policy_surprise_data_weight, self.value_surprise_data_weight)
+            data.target_weight_by_turn_unrounded = list(data.target_weight_by_turn)
+        if self.weight_rand is not None:                                                      # play.cpp:2274-2289
+            if data.target_weight_by_turn_unrounded is None:
+                data.target_weight_by_turn_unrounded = list(data.target_weight_by_turn)
+            data.target_weight_by_turn = [resolve_target_weight(w, self.weight_rand) for w in data.target_weight_by_turn]
         data.final_white_scoring = scoring_from_area(area)
         if self.writer is not None:
             self.writer.write_game(data)

@@ -383,6 +383,7 @@ class FinishedGameData:
         self.winner, self.final_white_minus_black_score = 0, 0.0      # winner: 0 draw, P_BLACK, P_WHITE (finished games with a result)
         self.changed_neural_net_names = None       # names of the nets in changed_neural_net_turns (SGF comment only)
         self.target_weight_by_turn_unrounded = None
+        self.value_surprise_by_turn = None         # statistics only (FinishedGameData::valueSurpriseByTurn)
         self.final_full_area = self.final_ownership = self.final_white_scoring = None
 
     def self_komi(self, next_player):

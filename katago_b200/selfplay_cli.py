@@ -53,8 +53,8 @@ _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNN
                         "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir")
 # neutral values: the option is switched off, so not having it changes nothing
 _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0, "cheapSearchProb": 0.0,
-            "reduceVisits": False, "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0, "policySurpriseDataWeight": 0.0,
-            "valueSurpriseDataWeight": 0.0, "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
+            "reduceVisits": False, "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
+            "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
             "handicapProb": 0.0, "komiStdev": 0.0, "komiBigStdevProb": 0.0, "komiBiggerStdevProb": 0.0, "allowRectangleProb": 0.0,
             "rootEndingBonusPoints": 0.0, "rootPruneUselessMoves": False, "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
 _REFERENCE_DEFAULTS = {
@@ -142,6 +142,11 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
             "data_board_len": int(cfg.get("dataBoardLen", size)), "max_rows_per_train_file": int(cfg.get("maxRowsPerTrainFile", 20000)),
             "first_file_rand_min_prop": float(cfg.get("firstFileRandMinProp", 1.0)), "num_game_threads": int(cfg.get("numGameThreads", 256))}
     used.update(("dataBoardLen", "maxRowsPerTrainFile", "firstFileRandMinProp", "numGameThreads"))
+    # PlaySettings the recorder implements (program/playsettings.cpp): surprise weighting of the finished game's rows
+    data["policy_surprise_data_weight"] = float(cfg.get("policySurpriseDataWeight", 0.0))
+    data["value_surprise_data_weight"] = float(cfg.get("valueSurpriseDataWeight", 0.0))
+    data["use_search_value_surprise"] = _B(cfg.get("useSearchValueSurprise", "false"))
+    used.update(("policySurpriseDataWeight", "valueSurpriseDataWeight", "useSearchValueSurprise"))
     if data["data_board_len"] != size:
         raise ValueError(f"dataBoardLen = {data['data_board_len']} but the board is {size}x{size}: rows smaller than the data frame are not built")
     for key, val in cfg.items():
@@ -238,7 +243,7 @@ def main(argv=None):
         print("[config] NOT BUILT, ignored: " + "; ".join(report["not_built"]), file=sys.stderr)
 
     from .nn_backend import NeuralNet, SelfPlay          # loads libkgb200; fails loudly without a B200
-    from .npz_writer import TrainingDataWriter
+    from .npz_writer import RowRand, TrainingDataWriter
     from .game_recorder import GameRecorder
     model_path = newest_model(a.models_dir)
     model_name = os.path.basename(os.path.dirname(model_path)) if os.path.basename(model_path) == "model.bin.gz" else os.path.basename(model_path).split(".")[0]
@@ -255,7 +260,9 @@ def main(argv=None):
     writer = TrainingDataWriter(tdata, data["max_rows_per_train_file"], data["first_file_rand_min_prop"], L, writer_seed)
     sgfs = SgfSink(os.path.join(a.output_dir, model_name, "sgfs"), writer_seed + ":sgfs", model_name, model_name)
     rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=sgfs.add,
-                       game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index))
+                       game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
+                       policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
+                       use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"))
     try:
         while a.max_games_total <= 0 or rec.games_written < my_games:
             if a.per_game_release:

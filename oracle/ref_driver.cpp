@@ -949,6 +949,70 @@ static int cmdParamsMap(int argc, char** argv) {
   return 0;
 }
 
+// rungame MODELFILE SIZE MAXVISITS MAXMOVES SEED POLICYSURPRISEWEIGHT VALUESURPRISEWEIGHT USESEARCHVALUESURPRISE: one whole game of the
+// reference's own Play::runGame (program/play.cpp:1534-2354) with the fake net, full data recording, no cheap searches / forks / policy
+// init, so that every turn enters the surprise weighting with weight 1.  Dumps what the weighting and the value surprise are computed
+// from (per turn: value targets, raw net win / loss / noResult, policy surprise) and what runGame made of them (valueSurpriseByTurn,
+// targetWeightByTurnUnrounded, targetWeightByTurn).
+static int cmdRunGame(int argc, char** argv) {
+  if(argc != 10) { cerr << "usage: rungame MODELFILE SIZE MAXVISITS MAXMOVES SEED PSW VSW USESEARCHVALUESURPRISE" << endl; return 1; }
+  const string modelFile = argv[2];
+  const int L = atoi(argv[3]), maxVisits = atoi(argv[4]), maxMoves = atoi(argv[5]);
+  const string seed = argv[6];
+  Board::initHash();
+  ScoreValue::initTables();
+  Logger logger(nullptr, false, false, false);
+  ConfigParser cfg;
+  NNEvaluator* nnEval = new NNEvaluator("fake", modelFile, "", &logger, 4, L, L, true, true, 10, 8, false, "", enabled_t::False, 1,
+                                        vector<int>{0}, "seed", false, 0, true, cfg);
+  nnEval->spawnServerThreads();
+  SearchParams params;
+  params.maxVisits = maxVisits; params.numThreads = 1;
+  params.rootNoiseEnabled = true; params.chosenMoveTemperature = 0.5; params.chosenMoveTemperatureEarly = 0.9;
+  PlaySettings ps;
+  ps.policySurpriseDataWeight = atof(argv[7]); ps.valueSurpriseDataWeight = atof(argv[8]); ps.useSearchValueSurprise = atoi(argv[9]) != 0;
+  ps.forSelfPlay = true; ps.recordTimePerMove = false;
+  ps.noResolveTargetWeights = false;
+  Rules rules;
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE; rules.multiStoneSuicideLegal = true;
+  rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO; rules.friendlyPassOk = false; rules.komi = 6.5f;
+  Board board(L, L);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  ExtraBlackAndKomi ebk; ebk.extraBlack = 0; ebk.komiMean = 6.5f; ebk.komiStdev = 0.0f;
+  OtherGameProperties other; other.allowPolicyInit = false;
+  MatchPairer::BotSpec spec; spec.botIdx = 0; spec.botName = "fake"; spec.nnEval = nnEval; spec.baseParams = params;
+  MatchPairer::BotSpec specW = spec;
+  Rand gameRand("rungame" + seed);
+  vector<vector<double>> raw;
+  auto onEachMove = [&](const Board&, const BoardHistory&, Player, Loc, const vector<double>&, const vector<double>&, const vector<double>&, const Search* bot) {
+    const ReportedSearchValues v = bot->getRootRawNNValuesRequireSuccess();
+    raw.push_back(vector<double>{v.winValue, v.lossValue, v.noResultValue});
+  };
+  FinishedGameData* g = Play::runGame(board, pla, hist, ebk, spec, specW, "rungame" + seed, true, true, logger, false, false, maxMoves,
+                                      []() { return false; }, nullptr, ps, other, gameRand, nullptr, onEachMove);
+  auto d = [](double v) { return Global::strprintf("%.17g", v); };
+  const size_t n = g->targetWeightByTurn.size();
+  if(raw.size() != n) { cerr << "onEachMove count " << raw.size() << " != turns " << n << endl; return 1; }
+  cout << "{\"size\":" << L << ",\"turns\":" << n << ",\"policySurpriseDataWeight\":" << d(ps.policySurpriseDataWeight) << ",\"valueSurpriseDataWeight\":" << d(ps.valueSurpriseDataWeight)
+       << ",\"useSearchValueSurprise\":" << (ps.useSearchValueSurprise ? 1 : 0) << ",\"hitTurnLimit\":" << (g->hitTurnLimit ? 1 : 0);
+  auto arr = [&](const char* name, auto fn, size_t count) {
+    cout << ",\n\"" << name << "\":[";
+    for(size_t i = 0; i < count; i++) cout << (i ? "," : "") << fn(i);
+    cout << "]";
+  };
+  arr("valueTargets", [&](size_t i) { const ValueTargets& v = g->whiteValueTargetsByTurn[i]; return "[" + d(v.win) + "," + d(v.loss) + "," + d(v.noResult) + "," + d(v.score) + "]"; }, n + 1);
+  arr("rawNN", [&](size_t i) { return "[" + d(raw[i][0]) + "," + d(raw[i][1]) + "," + d(raw[i][2]) + "]"; }, n);
+  arr("policySurprise", [&](size_t i) { return d(g->policySurpriseByTurn[i]); }, n);
+  arr("valueSurprise", [&](size_t i) { return d(g->valueSurpriseByTurn[i]); }, n);
+  arr("targetWeightUnrounded", [&](size_t i) { return d(g->targetWeightByTurnUnrounded[i]); }, n);
+  arr("targetWeight", [&](size_t i) { return d(g->targetWeightByTurn[i]); }, n);
+  cout << "}" << endl;
+  delete g;
+  delete nnEval;
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -1033,6 +1097,7 @@ int main(int argc, char** argv) {
   if(cmd == "addrow") return cmdAddRow(argc, argv);
   if(cmd == "writegame") return cmdWriteGame(argc, argv);
   if(cmd == "paramsmap") return cmdParamsMap(argc, argv);
+  if(cmd == "rungame") return cmdRunGame(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

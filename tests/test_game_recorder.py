@@ -64,6 +64,31 @@ def test_policy_target_matches_reference_extract_policy_target():
     assert saw_cap
 
 
+def test_value_surprise_and_surprise_weights_match_reference_run_game():
+    """Six whole games of the reference's own Play::runGame (CPU, fake net; tests/golden/make_rungame_fixtures.py): from each turn's
+    value targets, raw net values and policy surprise our restatement reproduces runGame's value surprise (1e-12) and its
+    surprise-weighted target weights (float32, bit for bit) - both variants of the value surprise, several weight settings."""
+    import gzip, json
+    games = json.loads(gzip.open(os.path.join(GOLDEN, "rungame.json.gz"), "rb").read())
+    assert len(games) >= 6 and {g["useSearchValueSurprise"] for g in games} == {0, 1}
+    for g in games:
+        n = g["turns"]
+        vs = R.compute_value_surprise_by_turn(g["valueTargets"], g["rawNN"], g["size"] ** 2, bool(g["useSearchValueSurprise"]))
+        assert np.allclose(vs, g["valueSurprise"], rtol=1e-12, atol=1e-15), np.abs(np.array(vs) - np.array(g["valueSurprise"])).max()
+        w = R.surprise_target_weights([1.0] * n, g["policySurprise"], g["valueSurprise"], g["policySurpriseDataWeight"], g["valueSurpriseDataWeight"])
+        assert [float(x) for x in w] == [float(np.float32(x)) for x in g["targetWeightUnrounded"]]
+        assert abs(float(np.sum(w, dtype=np.float64)) - n) < 1e-3          # the game's total weight is kept
+        # what runGame then wrote: each weight resolved to one of its two neighbouring integers
+        assert all(r in (np.floor(u), np.floor(u) + 1) for r, u in zip(g["targetWeight"], g["targetWeightUnrounded"]))
+
+
+def test_resolve_target_weight_keeps_the_expectation():
+    rand = W.RowRand("resolve")
+    draws = [float(R.resolve_target_weight(1.3, rand)) for _ in range(4000)]
+    assert set(draws) == {1.0, 2.0} and abs(np.mean(draws) - 1.3) < 0.03
+    assert float(R.resolve_target_weight(-0.5, rand)) == 0.0 and float(R.resolve_target_weight(2.0, rand)) == 2.0
+
+
 # ---- the recorder's host logic against a scripted stand-in for the device loop ------------------------------------------------------
 class ScriptedSlots:
     """Stands in for nn_backend.SelfPlay in hold mode: every slot replays a move stream of the reference `Board` (boardstream
@@ -148,6 +173,29 @@ class ScriptedSlots:
 
     def last_move(self, g):
         return self.last[g]
+
+
+def test_recorder_applies_surprise_weights_to_finished_games():
+    """PlaySettings policySurpriseDataWeight / valueSurpriseDataWeight in the recorder: a finished game's weights are the restated runGame
+    weighting of its own policy surprises, value targets and raw net values; the game's total weight is kept; with a weight Rand the
+    weights the writer gets are integers and the fractional ones stay available for the game record."""
+    stream = np.load(os.path.join(GOLDEN, "boardstream_9x9_multisuicide.npz"))
+    sp = ScriptedSlots(stream, [15, 9], 30)
+    games = []
+    rec = R.GameRecorder(sp, None, 6.5, on_game=lambda g, d: games.append(d), policy_surprise_data_weight=0.5, value_surprise_data_weight=0.1,
+                         weight_rand=W.RowRand("weights"))
+    for _ in range(15):
+        rec.step()
+    assert len(games) == 2
+    for d in games:
+        n = len(d.moves)
+        vs = d.value_surprise_by_turn
+        assert len(vs) == n and all(0.0 <= v <= 1.0 for v in vs)
+        want = R.surprise_target_weights([1.0] * n, d.policy_surprise_by_turn, vs, 0.5, 0.1)
+        assert [float(x) for x in d.target_weight_by_turn_unrounded] == [float(x) for x in want]
+        assert abs(sum(float(x) for x in want) - n) < 1e-3 and len({float(x) for x in want}) > 1
+        assert all(float(r) in (np.floor(float(u)), np.floor(float(u)) + 1) for r, u in zip(d.target_weight_by_turn, want))
+        assert "weight=%.2f" % float(want[0]) in W.write_sgf(d, "b", "w")
 
 
 def test_recorder_refuses_configurations_that_give_no_root_row():

@@ -48,7 +48,8 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert kw["subtree_value_bias_factor"] == 0.30 and kw["root_num_symmetries_to_sample"] == 4 and kw["use_lcb_for_selection"] is True
     assert kw["root_policy_temperature_early"] == 1.5 and kw["chosen_move_temperature_halflife"] == 19.0 and kw["nn_cache_size_power_of_two"] == 24
     assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
-    assert data == {"board_size": 19, "komi": 7.5, "data_board_len": 19, "max_rows_per_train_file": 20000, "first_file_rand_min_prop": 0.15, "num_game_threads": 800}
+    assert data == {"board_size": 19, "komi": 7.5, "data_board_len": 19, "max_rows_per_train_file": 20000, "first_file_rand_min_prop": 0.15, "num_game_threads": 800,
+                    "policy_surprise_data_weight": 0.5, "value_surprise_data_weight": 0.1, "use_search_value_surprise": False}
     # every keyword exists on the loop
     from katago_b200.nn_backend import SelfPlay
     params = set(inspect.signature(SelfPlay.__init__).parameters)
@@ -67,6 +68,7 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
 def test_neutral_values_and_unsupported_rules():
     kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\ncheapSearchProb = 0\nreduceVisits = false\nkoRules = POSITIONAL\nbSizes = 9\nkomiMean = 7\nrootEndingBonusPoints = 0\nrootPruneUselessMoves = false\n", is_text=True), strict=True)
     assert kw["ko_rule"] == 1 and data["board_size"] == 9 and data["komi"] == 7.0 and report["not_built"] == [] and report["fixed"] == []
+    assert data["policy_surprise_data_weight"] == 0.0
     # the two root options the reference switches on by default are reported even when the file does not mention them
     _, _, rep = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\n", is_text=True))
     assert any("rootEndingBonusPoints" in s_ and "default" in s_ for s_ in rep["not_built"]) and any("rootPruneUselessMoves" in s_ for s_ in rep["not_built"])
