@@ -19,12 +19,12 @@ The reference computes 3x3 convolutions by Winograd F(4x4,3x3) in fp32 (eigenbac
 uses direct convolution (im2col + sgemm), which is the same function up to fp32 summation order, so agreement
 with the reference is ~1e-5 relative, not bitwise (Eigen itself is not under /root/reference - SURVEY.md §8c).
 
-Pinning (see tests/test_oracle_nn.py): tests/golden/torchref_*.npz hold outputs of the reference's PyTorch model
-(python/katago/train/model_pytorch.py) on nets exported by the reference's exporter (generator:
-tests/golden/make_torchref_fixtures.py), and the direct-convolution MAC counts equal those of the reference's own loader.
-The reference's embedded tiny-net known-answer test (cpp/tests/tinymodel.cpp) is run against the PRODUCT instead: the
-unmodified reference binary linked to libkgb200 passes `runtinynntests` on a B200
-(profiles/r01_reference_binary_on_b200_backend.log).
+Pinning (see tests/test_oracle_nn.py): (1) the reference's own known-answer test for this path, cpp/tests/tinymodel.cpp - its two
+embedded tiny nets, three positions, expected outputs and tolerances (tests/golden/tinymodel.json.gz + models/tiny*.bin.gz, read
+from the reference's test source by tests/golden/make_tinymodel_fixtures.py, input rows from the reference's fillRowV7); (2)
+tests/golden/torchref_*.npz: outputs of the reference's PyTorch model (python/katago/train/model_pytorch.py) on nets exported by
+the reference's exporter; (3) direct-convolution MAC counts equal to those of the reference's own loader.  The product passes
+the same known-answer test on a B200 through the unmodified reference binary (profiles/r01_reference_binary_on_b200_backend.log).
 """
 from __future__ import annotations
 

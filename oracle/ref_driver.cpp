@@ -1013,6 +1013,37 @@ static int cmdRunGame(int argc, char** argv) {
   return 0;
 }
 
+// tinyfeatures DIAGRAMFILE X Y: the inputs of the reference's tiny-net known-answer test (tests/tinymodel.cpp): Board::parseBoard on the
+// diagram, Tromp-Taylor-ish rules, black to move, no history; prints the fillRowV7 row on a 19x19 frame (NHWC) and which policy
+// positions are legal - what NNEvaluator::evaluate feeds the backend and masks the policy with.
+static int cmdTinyFeatures(int argc, char** argv) {
+  if(argc != 5) { cerr << "usage: tinyfeatures DIAGRAMFILE X Y" << endl; return 1; }
+  Board::initHash();
+  ScoreValue::initTables();
+  const int X = atoi(argv[3]), Y = atoi(argv[4]), L = 19;
+  std::ifstream in(argv[2]);
+  std::stringstream ss; ss << in.rdbuf();
+  Board board = Board::parseBoard(X, Y, ss.str());
+  const Player pla = P_BLACK;
+  const Rules rules = Rules::getTrompTaylorish();
+  const BoardHistory hist(board, pla, rules, 0, false);
+  MiscNNInputParams ip;
+  vector<float> sp((size_t)L * L * NNInputs::NUM_FEATURES_SPATIAL_V7), gl(NNInputs::NUM_FEATURES_GLOBAL_V7);
+  NNInputs::fillRowV7(board, hist, pla, ip, L, L, true, sp.data(), gl.data());
+  cout << "{\"spatial\":[";
+  for(size_t i = 0; i < sp.size(); i++) cout << (i ? "," : "") << sp[i];
+  cout << "],\"global\":[";
+  for(size_t i = 0; i < gl.size(); i++) cout << (i ? "," : "") << Global::strprintf("%.9g", gl[i]);
+  cout << "],\"legal\":[";
+  for(int pos = 0; pos < L * L; pos++) {
+    const int x = pos % L, y = pos / L;
+    const bool legal = x < X && y < Y && hist.isLegal(board, Location::getLoc(x, y, X), pla);
+    cout << (pos ? "," : "") << (legal ? 1 : 0);
+  }
+  cout << ",1],\"komi\":" << rules.komi << ",\"koRuleSimple\":" << (rules.koRule == Rules::KO_SIMPLE ? 1 : 0) << "}" << endl;
+  return 0;
+}
+
 static int cmdFeatStream(int argc, char** argv) {
   if(argc != 9 && argc != 10) { cerr << "usage: featstream X Y MULTISUICIDE KOMI MOVES EVERY OUT [KORULE 0 simple 1 positional 2 situational]" << endl; return 1; }
   int X = atoi(argv[2]), Y = atoi(argv[3]);
@@ -1098,6 +1129,7 @@ int main(int argc, char** argv) {
   if(cmd == "writegame") return cmdWriteGame(argc, argv);
   if(cmd == "paramsmap") return cmdParamsMap(argc, argv);
   if(cmd == "rungame") return cmdRunGame(argc, argv);
+  if(cmd == "tinyfeatures") return cmdTinyFeatures(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

@@ -89,3 +89,68 @@ def test_masked_rows_do_not_depend_on_offboard_garbage(tmp_models):
     on = sp[0, :, :, 0].reshape(-1) > 0
     assert np.abs(out["policy"][0, :361][on] - out2["policy"][0, :361][on]).max() < 1e-4 or True  # 3x3 halo sees garbage: documented
     assert np.isfinite(out2["value"]).all()
+
+
+def _post_process(raw, legal, version, black_to_move=True, ko_simple=False):
+    """NNEvaluator::evaluate's post-processing (neuralnet/nneval.cpp:960-1249) of one row of raw backend outputs into the NNOutput
+    fields the reference's tests look at, for model versions 4..13 (default multipliers 20 / 20 / 20 / 40 / 0.25 / 30)."""
+    import math
+    softplus = lambda x: x if x > 40 else math.log1p(math.exp(x))
+    logits = np.where(np.asarray(legal, bool), raw["policy"].astype(np.float64), -np.inf)
+    p = np.exp(logits - logits.max()); p /= p.sum()
+    policy = np.where(np.asarray(legal, bool), p, -1.0)
+    w, l, n = (float(v) for v in raw["value"])
+    if not ko_simple:
+        n -= 100000.0
+    m = max(w, l, n)
+    ew, el, en = math.exp(w - m), math.exp(l - m), (0.0 if not ko_simple else math.exp(n - m))
+    tot = ew + el + en
+    win, loss, nores = ew / tot, el / tot, en / tot
+    sv = [float(v) for v in raw["score_value"]]
+    mean = sv[0] * 20.0
+    stdev = softplus(sv[1]) * 20.0
+    mean_sq = (mean * mean + stdev * stdev) * (1.0 - nores)
+    mean *= (1.0 - nores)
+    lead = sv[2] * 20.0 * (1.0 - nores)
+    var_time = softplus(sv[3]) * 40.0
+    if version >= 10:
+        wl_err, sc_err = math.sqrt(softplus(sv[4]) * 0.25), math.sqrt(softplus(sv[5]) * 30.0)
+    else:
+        wl_err, sc_err = softplus(sv[4]), softplus(sv[5]) * 10.0
+    sign = -1.0 if black_to_move else 1.0
+    own = sign * np.tanh(raw["ownership"].astype(np.float64))
+    return dict(whiteWinProb=loss if black_to_move else win, whiteLossProb=win if black_to_move else loss, whiteNoResultProb=nores,
+                whiteScoreMean=sign * mean, whiteScoreMeanSq=mean_sq, whiteLead=sign * lead, varTimeLeft=var_time,
+                shorttermWinlossError=wl_err, shorttermScoreError=sc_err, policy=policy, ownership=own)
+
+
+def test_oracle_passes_the_reference_tiny_net_known_answer_test(golden_dir):
+    """The reference's own known-answer test for the NN path (cpp/tests/tinymodel.cpp): its two embedded nets (a v9 net and a v11 mish
+    net), its three positions (19x19 twice, 13x6 on a 19x19 frame) under the symmetries it fixes, the outputs it expects and the
+    tolerances it allows - all read from the reference's test source by tests/golden/make_tinymodel_fixtures.py, with the input rows
+    from the reference's fillRowV7.  The numpy oracle must pass it (the product passes it on a B200 through the reference binary)."""
+    import gzip, json
+    blocks = json.loads(gzip.open(os.path.join(golden_dir, "tinymodel.json.gz"), "rb").read())
+    assert [(b["model"], b["symmetry"], b["X"], b["Y"]) for b in blocks] == [("tinymodel", 6, 19, 19), ("tinymishmodel", 7, 19, 19), ("tinymishmodel", 1, 13, 6)]
+    for b in blocks:
+        m = orc.load_model(os.path.join(golden_dir, "models", b["model"] + ".bin.gz"))
+        sp = np.array(b["spatial"], np.float32).reshape(1, 19, 19, 22)
+        gl = np.array(b["global"], np.float32).reshape(1, 19)
+        out = orc.get_output(m, sp, gl, symmetries=[b["symmetry"]])
+        got = _post_process({k: v[0] for k, v in out.items()}, b["legal"], m.version, black_to_move=True, ko_simple=bool(b["koRuleSimple"]))
+        for name, (expected, tol) in b["scalars"].items():
+            assert abs(got[name] - expected) <= tol, (b["model"], b["symmetry"], name, got[name], expected, tol)
+        X, Y = b["X"], b["Y"]
+        idx = np.array([(i % X) + (i // X) * 19 for i in range(X * Y)])
+        k = 0.1 if b["model"] == "tinymodel" else 0.15                    # the tolerance expressions of the three blocks
+        cap = 120.0 if (X, Y) == (13, 6) else 60.0
+        own_tol = 300.0 if b["model"] == "tinymodel" else 600.0
+        assert b["tolerance_exprs"]["expectedPolicy"].replace("idx", "pos") == f"std::min({cap}, expectedPolicy[pos] * {k} + 2.0) + std::min(10.0, expectedPolicy[pos] * {k})"
+        assert float(b["tolerance_exprs"]["expectedOwnership"]) == own_tol
+        for e, p in zip(b["arrays"]["expectedPolicy"], got["policy"][idx]):
+            if e >= 0:
+                assert abs(p * 10000 - e) <= min(cap, e * k + 2.0) + min(10.0, e * k), (b["model"], e, p * 10000)
+            else:
+                assert p == -1.0                                           # the test marks illegal points with -1
+        for e, o in zip(b["arrays"]["expectedOwnership"], got["ownership"][idx]):
+            assert abs(o * 10000 - e) <= own_tol, (b["model"], e, o * 10000)
