@@ -184,3 +184,32 @@ def test_full_size_b18_batch256(cfg, tmp_path):
     for k in ref:
         assert np.abs(got32[k][idx] - ref[k]).max() <= FP32_TOL, (k, np.abs(got32[k][idx] - ref[k]).max())
         assert np.abs(got16[k][idx] - ref[k]).max() <= FP16_REL * max(1.0, np.abs(ref[k]).max()), k
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+def test_reference_tiny_net_known_answers_on_device(golden_dir, fp16):
+    """The reference's own known-answer test for the NN path (cpp/tests/tinymodel.cpp; fixture tests/golden/tinymodel.json.gz) through the
+    C ABI: its two embedded nets, three positions (one 13x6 on the 19x19 frame), the symmetries it fixes, the outputs it expects and
+    its own tolerances.  (The unmodified reference binary linked to this library passes the same test: profiles/.)"""
+    import gzip, json
+    from test_oracle_nn import _post_process
+    blocks = json.loads(gzip.open(os.path.join(golden_dir, "tinymodel.json.gz"), "rb").read())
+    for b in blocks:
+        path = os.path.join(golden_dir, "models", b["model"] + ".bin.gz")
+        version = orc.load_model(path).version
+        sp = np.array(b["spatial"], np.float32).reshape(1, 19, 19, 22)
+        gl = np.array(b["global"], np.float32).reshape(1, 19)
+        out = run_cuda(path, sp, gl, np.array([b["symmetry"]], np.int32), None, fp16)
+        got = _post_process({k: np.asarray(v)[0] for k, v in out.items()}, b["legal"], version, black_to_move=True, ko_simple=bool(b["koRuleSimple"]))
+        for name, (expected, tol) in b["scalars"].items():
+            assert abs(got[name] - expected) <= tol, (b["model"], b["symmetry"], name, got[name], expected, tol)
+        X, Y = b["X"], b["Y"]
+        idx = np.array([(i % X) + (i // X) * 19 for i in range(X * Y)])
+        k = 0.1 if b["model"] == "tinymodel" else 0.15
+        cap = 120.0 if (X, Y) == (13, 6) else 60.0
+        own_tol = 300.0 if b["model"] == "tinymodel" else 600.0
+        for e, p in zip(b["arrays"]["expectedPolicy"], got["policy"][idx]):
+            if e >= 0:
+                assert abs(p * 10000 - e) <= min(cap, e * k + 2.0) + min(10.0, e * k), (b["model"], e, p * 10000)
+        for e, o in zip(b["arrays"]["expectedOwnership"], got["ownership"][idx]):
+            assert abs(o * 10000 - e) <= own_tol, (b["model"], e, o * 10000)
