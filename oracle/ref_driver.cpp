@@ -953,9 +953,12 @@ static int cmdParamsMap(int argc, char** argv) {
 // reference's own Play::runGame (program/play.cpp:1534-2354) with the fake net, full data recording, no cheap searches / forks / policy
 // init, so that every turn enters the surprise weighting with weight 1.  Dumps what the weighting and the value surprise are computed
 // from (per turn: value targets, raw net win / loss / noResult, policy surprise) and what runGame made of them (valueSurpriseByTurn,
-// targetWeightByTurnUnrounded, targetWeightByTurn).
+// targetWeightByTurnUnrounded, targetWeightByTurn).  With SLOTLOG ROWSOUT: also what the device loop's getters would have exposed for
+// every finished root search of the game (one JSON line per event, the format of tests/mock/kgb200_mock.cpp) and the rows the
+// reference's own TrainingDataWriter makes of the game - the whole host chain of the recorder against a real reference game.
 static int cmdRunGame(int argc, char** argv) {
-  if(argc != 10) { cerr << "usage: rungame MODELFILE SIZE MAXVISITS MAXMOVES SEED PSW VSW USESEARCHVALUESURPRISE" << endl; return 1; }
+  if(argc != 10 && argc != 12) { cerr << "usage: rungame MODELFILE SIZE MAXVISITS MAXMOVES SEED PSW VSW USESEARCHVALUESURPRISE [SLOTLOG ROWSOUT]" << endl; return 1; }
+  const bool wantLog = argc == 12;
   const string modelFile = argv[2];
   const int L = atoi(argv[3]), maxVisits = atoi(argv[4]), maxMoves = atoi(argv[5]);
   const string seed = argv[6];
@@ -972,7 +975,7 @@ static int cmdRunGame(int argc, char** argv) {
   PlaySettings ps;
   ps.policySurpriseDataWeight = atof(argv[7]); ps.valueSurpriseDataWeight = atof(argv[8]); ps.useSearchValueSurprise = atoi(argv[9]) != 0;
   ps.forSelfPlay = true; ps.recordTimePerMove = false;
-  ps.noResolveTargetWeights = false;
+  ps.noResolveTargetWeights = wantLog;   // the chain test leaves the weights fractional: the writer's own Rand then decides the extra rows
   Rules rules;
   rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE; rules.multiStoneSuicideLegal = true;
   rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO; rules.friendlyPassOk = false; rules.komi = 6.5f;
@@ -985,9 +988,50 @@ static int cmdRunGame(int argc, char** argv) {
   MatchPairer::BotSpec specW = spec;
   Rand gameRand("rungame" + seed);
   vector<vector<double>> raw;
-  auto onEachMove = [&](const Board&, const BoardHistory&, Player, Loc, const vector<double>&, const vector<double>&, const vector<double>&, const Search* bot) {
+  vector<string> rootEvents; vector<int> movePos;
+  auto onEachMove = [&](const Board& b, const BoardHistory& h, Player p, Loc loc, const vector<double>&, const vector<double>&, const vector<double>&, const Search* bot) {
     const ReportedSearchValues v = bot->getRootRawNNValuesRequireSuccess();
     raw.push_back(vector<double>{v.winValue, v.lossValue, v.noResultValue});
+    if(!wantLog) return;
+    // what the device loop's getters expose for a finished root search (the event format of tests/mock/kgb200_mock.cpp)
+    const int P = L * L + 1;
+    auto g17 = [](double x) { return Global::strprintf("%.17g", x); };
+    vector<int> colors, edgeVisits(P, 0), nodeVisits(P, 0);
+    vector<double> childStats((size_t)P * 5, 0.0), psv(P, -1.0);
+    vector<float> policy(P, -1.0f);
+    for(int y = 0; y < L; y++) for(int x = 0; x < L; x++) colors.push_back((int)b.colors[Location::getLoc(x, y, L)]);
+    const SearchNode* root = bot->rootNode;
+    ConstSearchNodeChildrenReference children = root->getChildren();
+    auto posOf = [&](Loc l) { return l == Board::PASS_LOC ? L * L : Location::getY(l, L) * L + Location::getX(l, L); };
+    for(int i = 0; i < children.getCapacity(); i++) {
+      const SearchChildPointer& cp = children[i];
+      const SearchNode* child = cp.getIfAllocated();
+      if(child == NULL) break;
+      const int pos = posOf(cp.getMoveLoc());
+      edgeVisits[pos] = (int)cp.getEdgeVisits(); nodeVisits[pos] = (int)child->stats.visits.load();
+      childStats[(size_t)pos * 5 + 0] = child->stats.winLossValueAvg.load(); childStats[(size_t)pos * 5 + 1] = child->stats.noResultValueAvg.load();
+      childStats[(size_t)pos * 5 + 2] = child->stats.scoreMeanAvg.load(); childStats[(size_t)pos * 5 + 3] = child->stats.scoreMeanSqAvg.load();
+      childStats[(size_t)pos * 5 + 4] = child->stats.leadAvg.load();
+    }
+    const NNOutput* nn = root->getNNOutput();
+    for(int i = 0; i < P; i++) policy[i] = nn->getPolicyProbsMaybeNoised()[i];
+    { vector<Loc> locs; vector<double> vals; bot->getPlaySelectionValues(locs, vals, 0.0); for(size_t i = 0; i < locs.size(); i++) psv[posOf(locs[i])] = vals[i]; }
+    MiscNNInputParams ip; ip.drawEquivalentWinsForWhite = params.drawEquivalentWinsForWhite;
+    vector<float> rowSp((size_t)L * L * 22), rowGl(19);
+    NNInputs::fillRowV7(b, h, p, ip, L, L, true, rowSp.data(), rowGl.data());
+    std::ostringstream o;
+    auto arr = [&](const char* name, auto& vec, bool last = false) {
+      o << "\"" << name << "\":[";
+      for(size_t i = 0; i < vec.size(); i++) o << (i ? "," : "") << g17((double)vec[i]);
+      o << "]" << (last ? "" : ",");
+    };
+    vector<double> rs{root->stats.winLossValueAvg.load(), root->stats.noResultValueAvg.load(), root->stats.scoreMeanAvg.load(), root->stats.scoreMeanSqAvg.load(), root->stats.leadAvg.load()};
+    vector<double> rn{(double)nn->whiteWinProb - (double)nn->whiteLossProb, (double)nn->whiteNoResultProb, (double)nn->whiteScoreMean, (double)nn->whiteScoreMeanSq, (double)nn->whiteLead};
+    o << "{\"ev\":\"root\",\"slot\":0,\"move_num\":" << h.moveHistory.size() << ",\"black_to_move\":" << (p == P_BLACK ? 1 : 0) << ",\"root_visits\":" << bot->getRootVisits() << ",";
+    arr("colors", colors); arr("edge_visits", edgeVisits); arr("node_visits", nodeVisits); arr("policy", policy); arr("child_stats", childStats);
+    arr("psv", psv); arr("root_stats", rs); arr("root_nn", rn); arr("row_spatial", rowSp); arr("row_global", rowGl, true);
+    o << "}";
+    rootEvents.push_back(o.str()); movePos.push_back(posOf(loc));
   };
   FinishedGameData* g = Play::runGame(board, pla, hist, ebk, spec, specW, "rungame" + seed, true, true, logger, false, false, maxMoves,
                                       []() { return false; }, nullptr, ps, other, gameRand, nullptr, onEachMove);
@@ -1008,6 +1052,30 @@ static int cmdRunGame(int argc, char** argv) {
   arr("targetWeightUnrounded", [&](size_t i) { return d(g->targetWeightByTurnUnrounded[i]); }, n);
   arr("targetWeight", [&](size_t i) { return d(g->targetWeightByTurn[i]); }, n);
   cout << "}" << endl;
+  if(wantLog) {
+    ofstream lg(argv[10]);
+    for(size_t t = 0; t < n; t++) {
+      lg << rootEvents[t] << "\n";
+      const bool lastMove = t + 1 == n;
+      lg << "{\"ev\":\"move\",\"slot\":0,\"pos\":" << movePos[t] << ",\"flags\":"
+         << (lastMove ? (1 | ((g->endHist.isGameFinished && g->endHist.isNoResult) ? 2 : 0) | (g->hitTurnLimit ? 4 : 0)) : 0)
+         << ",\"move_num\":" << t << ",\"game_index\":0,\"game_hash\":[" << g->gameHash.hash0 << "," << g->gameHash.hash1 << "],\"score\":";
+      if(lastMove) {   // the outcome as runGame determined it (play.cpp:1989-2027): score, final position, ownership
+        BoardHistory h2 = g->endHist; Board b2 = g->endHist.getRecentBoard(0); Color area[Board::MAX_ARR_SIZE];
+        h2.endAndScoreGameNow(b2, area);
+        lg << Global::strprintf("%.9g", h2.finalWhiteMinusBlackScore) << ",\"final_colors\":[";
+        for(int y = 0; y < L; y++) for(int x = 0; x < L; x++) lg << ((y || x) ? "," : "") << (int)b2.colors[Location::getLoc(x, y, L)];
+        lg << "],\"final_area\":[";
+        for(int y = 0; y < L; y++) for(int x = 0; x < L; x++) lg << ((y || x) ? "," : "") << (int)g->finalOwnership[Location::getLoc(x, y, L)];
+        lg << "]}\n";
+      }
+      else lg << "0,\"final_colors\":[],\"final_area\":[]}\n";
+    }
+    ofstream rows(argv[11]);
+    TrainingDataWriter writer(&rows, 7, 100000, 1.0, L, L, 1, "chain-test");
+    writer.writeGame(*g);
+    writer.flushIfNonempty();
+  }
   delete g;
   delete nnEval;
   return 0;

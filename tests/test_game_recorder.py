@@ -329,7 +329,8 @@ class ReplaySlots:
             if self.released[g] and self.queues[g]:
                 self.released[g] = False
                 self.last[g] = self.queues[g].pop(0); assert self.last[g]["ev"] == "move"
-                self.root[g] = self.queues[g].pop(0); assert self.root[g]["ev"] == "root"
+                if self.queues[g]:               # (a log of a single game ends with its last move)
+                    self.root[g] = self.queues[g].pop(0); assert self.root[g]["ev"] == "root"
 
     def release(self, mask=None):
         self.released = [True] * self.num_games
@@ -340,7 +341,7 @@ class ReplaySlots:
     def game(self, g):
         r = self.root[g]
         return np.array(r["colors"], np.uint8).reshape(self.y, self.x), dict(move_num=r["move_num"], black_to_move=bool(r["black_to_move"]), ko=-1, cap_b=0,
-                                                                          cap_w=0, root_visits=self.max_visits + g)
+                                                                          cap_w=0, root_visits=r.get("root_visits", self.max_visits + g))
 
     def nn_row(self, g):
         r = self.root[g]
@@ -365,7 +366,7 @@ class ReplaySlots:
         pos, fl = m["pos"], m["flags"]
         n = self.x * self.y
         return dict(pos=pos, xy=(-1, -1) if pos == n else (pos % self.x, pos // self.x), game_over=bool(fl & 1), no_result=bool(fl & 2), hit_move_limit=bool(fl & 4),
-                    move_num=m["move_num"], game_index=m["game_index"], final_white_minus_black_score=float(m["score"]),
+                    move_num=m["move_num"], game_index=m["game_index"], game_hash=m.get("game_hash"), final_white_minus_black_score=float(m["score"]),
                     final_colors=np.array(m["final_colors"] or [0] * n, np.uint8), final_area=np.array(m["final_area"] or [0] * n, np.uint8))
 
 
@@ -428,6 +429,55 @@ def test_cpp_recorder_against_python_recorder_on_scripted_slots(tmp_path, size, 
         b = fg[name].reshape(n, -1).astype(np.float64)
         assert np.allclose(a, b, rtol=2e-5, atol=1e-30), (name, np.argwhere(~np.isclose(a, b, rtol=2e-5, atol=1e-30))[:5])
     assert any(d.end_finished for d in games[:NUM]) or size == 9        # the small board also sees games that end by passes
+
+
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "kgref_driver")
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/kgref_driver not built")
+@pytest.mark.parametrize("size,visits,max_moves,seed,psw,vsw", [(9, 40, 50, 3, 0.5, 0.1), (7, 60, 200, 12, 0.3, 0.2), (13, 25, 70, 5, 0.0, 0.0)])
+def test_recorder_chain_against_a_whole_reference_selfplay_game(tmp_path, size, visits, max_moves, seed, psw, vsw):
+    """The whole host chain against the reference's own self-play: `kgref_driver rungame` plays a game with Play::runGame (CPU, fake
+    net), logs what the device loop's getters would have exposed after every search, and lets the reference's TrainingDataWriter write
+    the FinishedGameData runGame produced.  The Python recorder, fed only with that log, must arrive at the same rows: per-turn
+    targets, game-end targets, surprise weights (left fractional on both sides, so the writers' identically seeded Rands decide the
+    extra rows) and every addRow column.  Two documented differences: the Q targets are listed in position order here and in child
+    creation order there, so their stochastic rounding may differ by one unit; and the three "raw net statistics" columns come from a
+    separate evaluation in the reference."""
+    import subprocess
+    from test_npz_writer import _parse_text_dump
+    log, rows = tmp_path / "slot.log", tmp_path / "rows.txt"
+    subprocess.run([DRIVER, "rungame", os.path.join(GOLDEN, "models", "torchref_b2c16.bin.gz"), str(size), str(visits), str(max_moves), str(seed),
+                    str(psw), str(vsw), "0", str(log), str(rows)], check=True, capture_output=True, timeout=300)
+    want = _parse_text_dump(rows.read_text())
+    assert len(want) == 1
+    sp = ReplaySlots(str(log), 1, size, visits)
+    got = []
+    writer = W.TrainingDataWriter(None, 100000, 1.0, size, "chain-test", on_flush=lambda b: got.append({k: v[:b.cur_rows].copy() for k, v in b.arrays.items()}))
+    rec = R.GameRecorder(sp, writer, 6.5, policy_surprise_data_weight=psw, value_surprise_data_weight=vsw,
+                         game_hash_fn=lambda slot, index: tuple(sp.last[slot]["game_hash"]))
+    while rec.games_written < 1:
+        rec.step()
+    writer.flush_if_nonempty()
+    fw, fg = want[0], got[0]
+    n = len(fw["globalTargetsNC"])
+    assert n == fg["globalTargetsNC"].shape[0] > 0
+    assert [bytes.fromhex(x) for x in fw["binaryInputNCHWPacked"]] == [fg["binaryInputNCHWPacked"][i].tobytes() for i in range(n)]
+    for name in ("policyTargetsNCMove", "scoreDistrN", "valueTargetsNCHW"):
+        a = np.stack(fw[name]).astype(np.int64)
+        b = fg[name].reshape(n, -1).astype(np.int64)
+        assert np.array_equal(a, b), (name, np.argwhere(a != b)[:5])
+    qa = np.stack(fw["qValueTargetsNCMove"]).astype(np.int64).reshape(n, 3, -1)
+    qb = fg["qValueTargetsNCMove"].astype(np.int64)
+    assert np.array_equal(qa[:, 2], qb[:, 2])                               # visits: exact
+    assert np.abs(qa[:, :2] - qb[:, :2]).max() <= 1                         # stochastically rounded win/loss and score: same value up to the rounding draw
+    assert (qa[:, :2] != qb[:, :2]).mean() < 0.5
+    for name in ("globalInputNC", "globalTargetsNC"):
+        a = np.stack(fw[name])
+        b = fg[name].reshape(n, -1).astype(np.float64)
+        if name == "globalTargetsNC":
+            a, b = np.delete(a, [57, 58, 59], axis=1), np.delete(b, [57, 58, 59], axis=1)
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-30), (name, np.argwhere(~np.isclose(a, b, rtol=2e-5, atol=1e-30))[:8])
 
 
 # ------------------------------------------------------------------------------------------------------------------------------------
