@@ -13,7 +13,7 @@ if [ -f $OUT ] && [ -f $OUT.srchash ] && [ "$(cat $OUT.srchash)" = "$SRCHASH" ] 
   exit 0
 fi
 mkdir -p ../_build
-for f in kgb_conv_tc.cu kgb_conv_tc2.cu kgb_kernels.cu kgb_api.cu kgb_selfplay.cu; do
+for f in kgb_conv_tc.cu kgb_conv_tc2.cu kgb_conv_tc3.cu kgb_kernels.cu kgb_api.cu kgb_selfplay.cu; do
   o=../_build/${f%.cu}.o
   if [ ! -f $o ] || [ $f -nt $o ] || [ kgb_conv.cuh -nt $o ] || [ kgb_conv_tc_common.cuh -nt $o ] || [ kgb_kernels.cuh -nt $o ] || [ kgb_model.h -nt $o ] || [ kgb_board.cuh -nt $o ] || [ kgb_ladder.cuh -nt $o ] || [ kgb_history.cuh -nt $o ] || [ kgb_devrand.cuh -nt $o ] || [ kgb_scorevalue.h -nt $o ] || [ kgb_selfplay.h -nt $o ] || [ kgb_rand.h -nt $o ] || [ ../../include/kgb200.h -nt $o ]; then
     X=""
@@ -29,6 +29,6 @@ for f in kgb_model.cpp kgb_rand.cpp kgb_scorevalue.cpp; do
   fi
 done
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o ../_build/kgb_scorevalue.o -lz -cudart shared
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_conv_tc3.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o ../_build/kgb_scorevalue.o -lz -cudart shared
 echo $SRCHASH > $OUT.srchash
 echo "built $(readlink -f $OUT)"

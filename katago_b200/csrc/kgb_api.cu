@@ -91,6 +91,21 @@ static CUtensorMap makeTmap2D(const void* ptr, uint64_t rows, uint64_t cols, uin
   return m;
 }
 
+// 2-D row-major tensor of fp16 (elemBytes 2) or fp32 (4) elements, box {boxCols, boxRows} with boxCols * elemBytes = 128, 128B swizzle:
+// the epilogue tiles of kgb_conv_tc3.cu (TMA loads of the residual, TMA stores of the raw / activation outputs).
+static CUtensorMap makeTmapTile(const void* ptr, uint64_t rows, uint64_t cols, int elemBytes, uint32_t boxRows) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * (uint64_t)elemBytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elemBytes), boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = getEncodeTiled()(&m, elemBytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
+                                gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if(r != CUDA_SUCCESS) throw CudaFailure("cuTensorMapEncodeTiled (epilogue tile) failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Opaque handles
 // ------------------------------------------------------------------------------------------------------------
@@ -129,7 +144,7 @@ struct kgb_handle {
   int split = 0;          // fp32-equivalent mode
   bool nhwc = true;
   bool streamTrunkFp32 = true, streamInnerFp32 = false;
-  bool useSimt = false, useGraph = true, usePair = false;
+  bool useSimt = false, useGraph = true, usePair = false, usePairTma = true;
   std::vector<void*> allocs;
   // inputs / outputs (device, fixed addresses so graphs can be replayed)
   float *dSpatial = nullptr, *dGlobal = nullptr, *dOptimism = nullptr;
@@ -288,7 +303,15 @@ struct Builder {
       }
       else {
         CUtensorMap tmA = makeTmap2D(A, (uint64_t)p.M, (uint64_t)cw.cin_p * actMulL, (uint32_t)convTCABoxRows(cw.ky, cw.kx, p.Wp));
-        cudaError_t e = hp->usePair ? launchConvTC2(tmA, cw.tmapBhalf, p, hp->numSMs, s) : cudaErrorNotSupported;
+        cudaError_t e = cudaErrorNotSupported;
+        if(hp->usePairTma && convTC3Supports(p)) {
+          // epilogue tiles travel by TMA: residual in, raw / activation out (kgb_conv_tc3.cu)
+          const CUtensorMap tmRes = residual ? makeTmapTile(residual, (uint64_t)p.M, (uint64_t)cw.cout_p, 2, 32) : tmA;
+          const CUtensorMap tmRaw = rawOut ? makeTmapTile(rawOut, (uint64_t)p.M, (uint64_t)cw.cout_p, rawFp32 ? 4 : 2, 32) : tmA;
+          const CUtensorMap tmAct = actOut ? makeTmapTile(actOut, (uint64_t)p.M, (uint64_t)cw.cout_p, 2, 32) : tmA;
+          e = launchConvTC3(tmA, cw.tmapBhalf, tmRes, tmRaw, tmAct, p, hp->numSMs, s);
+        }
+        if(e == cudaErrorNotSupported && hp->usePair) e = launchConvTC2(tmA, cw.tmapBhalf, p, hp->numSMs, s);
         if(e == cudaErrorNotSupported) e = launchConvTC(tmA, cw.tmapB, p, hp->numSMs, s);
         CK(e);
       }
@@ -601,12 +624,14 @@ KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_
     h.streamInnerFp32 = streams == "all";
     env = getenv("KGB_CONV_IMPL");
     h.useSimt = env && std::string(env) == "simt";
-    h.usePair = env && std::string(env) == "tc2";        // "tc2" = CTA-pair kernel (correct, not faster yet: profiles/r01_conv_pipeline_experiments.md)
+    h.usePair = env && std::string(env) == "tc2";        // "tc2" = round-1 CTA-pair kernel (staged epilogue)
+    h.usePairTma = !(env && (std::string(env) == "tc" || std::string(env) == "tc2"));   // default: kgb_conv_tc3.cu (CTA pair + TMA epilogue)
     env = getenv("KGB_NO_GRAPH");
     h.useGraph = !(env && std::string(env) == "1");
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
     CK(convTCInit());
     CK(convTC2Init());
+    CK(convTC3Init());
     Builder b(h);
     b.build();
     const int XY = h.L.X * h.L.Y;
@@ -717,8 +742,12 @@ struct SingleConv {
   float* raw = nullptr;
   int n, X, Y, cin, cout, pad;
   size_t M;
-  SingleConv(int ky, int kx, int in_c, int out_c, const float* weights, int n_, int X_, int Y_, int use_fp16, int actEpilogue = 0)
-      : n(n_), X(X_), Y(Y_), cin(in_c), cout(out_c) {
+  std::vector<__half*> As, acts;
+  std::vector<void*> streams;
+  int rotate, next = 0;
+  SingleConv(int ky, int kx, int in_c, int out_c, const float* weights, int n_, int X_, int Y_, int use_fp16, int actEpilogue = 0,
+             int rotate_ = 1, const float* bnScale = nullptr, const float* bnBias = nullptr, int actKind = ACT_MISH)
+      : n(n_), X(X_), Y(Y_), cin(in_c), cout(out_c), rotate(rotate_ < 1 ? 1 : rotate_) {
     int count = 0;
     if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaFailure("libkgb200: no CUDA device is visible");
     CK(cudaGetDevice(&h.device));
@@ -734,9 +763,12 @@ struct SingleConv {
     const char* env = getenv("KGB_CONV_IMPL");
     h.useSimt = env && std::string(env) == "simt";
     h.usePair = env && std::string(env) == "tc2";
+    h.usePairTma = !(env && (std::string(env) == "tc" || std::string(env) == "tc2"));
+    h.streamTrunkFp32 = h.streamInnerFp32 = h.split != 0;
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
     CK(convTCInit());
     CK(convTC2Init());
+    CK(convTC3Init());
     Builder b(h);
     ConvDesc cd;
     cd.ky = ky; cd.kx = kx; cd.cin = in_c; cd.cout = out_c;
@@ -747,17 +779,34 @@ struct SingleConv {
     h.dMask = h.dalloc<float>(M + 128);
     h.dMaskSum = h.dalloc<float>(n);
     raw = h.dalloc<float>(M * cw.cout_p);
-    if(actEpilogue) {
-      // production-shaped epilogue of a residual unit's first conv: BN + mish + mask -> fp16 operand of the next conv
-      BNDesc bn;
-      bn.c = out_c; bn.scale.assign(out_c, 1.0f); bn.bias.assign(out_c, 0.0f);
-      Builder::BNDev dev = b.uploadBN(bn, ACT_MISH, cw.cout_p);
-      __half* actOut = h.dalloc<__half>(M * cw.cout_p * b.actMul);
-      b.emitConv(cw, A, nullptr, false, nullptr, nullptr, false, actOut, dev);
-    }
-    else {
-      Builder::BNDev none;
-      b.emitConv(cw, A, nullptr, false, nullptr, raw, true, nullptr, none);
+    // actEpilogue: 0 = fp32 raw output only; 1 = the first conv of a residual unit (BN + mish + mask -> fp16 operand of the next
+    // conv); 2 = the second conv of a unit (+ fp16 residual stream, updated in place, and the next unit's BN + mish operand);
+    // 3 = a nested block's pre conv (fp16 raw stream + activated operand).  `rotate` independent buffer sets are cycled through
+    // by run() so that a timing loop does not live in L2.
+    BNDesc bn;
+    bn.c = out_c; bn.scale.assign(out_c, 1.0f); bn.bias.assign(out_c, 0.0f);
+    if(bnScale) bn.scale.assign(bnScale, bnScale + out_c);
+    if(bnBias) bn.bias.assign(bnBias, bnBias + out_c);
+    Builder::BNDev dev = b.uploadBN(bn, actKind, cw.cout_p);
+    for(int r = 0; r < rotate; r++) {
+      __half* Ar = r == 0 ? A : h.dalloc<__half>(M * cw.cin_p * b.actMul);
+      As.push_back(Ar);
+      if(actEpilogue == 0) {
+        Builder::BNDev none;
+        float* rawr = r == 0 ? raw : h.dalloc<float>(M * cw.cout_p);
+        b.emitConv(cw, Ar, nullptr, false, nullptr, rawr, true, nullptr, none);
+      }
+      else {
+        __half* actOut = h.dalloc<__half>(M * cw.cout_p * b.actMul);
+        acts.push_back(actOut);
+        if(actEpilogue == 1) b.emitConv(cw, Ar, nullptr, false, nullptr, nullptr, false, actOut, dev);
+        else {
+          const bool f32 = h.split != 0;
+          void* S = f32 ? (void*)h.dalloc<float>(M * cw.cout_p) : (void*)h.dalloc<__half>(M * cw.cout_p);
+          streams.push_back(S);
+          b.emitConv(cw, Ar, actEpilogue == 2 ? S : nullptr, f32, nullptr, S, f32, actOut, dev);
+        }
+      }
     }
   }
   ~SingleConv() {
@@ -771,6 +820,7 @@ struct SingleConv {
     Builder b(h);
     CK(launchPackInput(dIn, n, cin, true, nullptr, h.L, A, cw.cin_p, h.split, h.dMask, h.dMaskSum, h.stream));
     CK(cudaStreamSynchronize(h.stream));
+    for(size_t r = 1; r < As.size(); r++) CK(cudaMemcpy(As[r], A, M * cw.cin_p * (h.split ? 2 : 1) * sizeof(__half), cudaMemcpyDeviceToDevice));
     // the mask of a bare convolution is "every board point", not input channel 0
     std::vector<float> hm(M, 0.0f);
     for(int i = 0; i < n; i++)
@@ -781,7 +831,7 @@ struct SingleConv {
     // nothing else orders these uploads before the kernels launched on it.
     CK(cudaDeviceSynchronize());
   }
-  void run() { h.ops.back()(n, h.stream); }
+  void run() { h.ops[next](n, h.stream); next = (next + 1) % rotate; }
 };
 }  // namespace
 
@@ -806,29 +856,91 @@ KGB_API int kgb_test_conv(int ky, int kx, int in_c, int out_c, const float* weig
   });
 }
 
+static void benchConvImpl(int ky, int kx, int in_c, int out_c, int n, int nn_x_len, int nn_y_len, int use_fp16, int epilogue_kind, int rotate,
+                          int warmup, int iters, float* ms_per_launch) {
+  if(!ms_per_launch || n < 1 || iters < 1 || epilogue_kind < 0 || epilogue_kind > 3) throw std::invalid_argument("kgb_bench_conv: bad argument");
+  std::vector<float> w((size_t)ky * kx * in_c * out_c);
+  uint32_t st = 12345u;
+  for(auto& v : w) { st = st * 1664525u + 1013904223u; v = ((st >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.1f; }
+  SingleConv sc(ky, kx, in_c, out_c, w.data(), n, nn_x_len, nn_y_len, use_fp16, epilogue_kind, rotate);
+  std::vector<float> in((size_t)n * nn_x_len * nn_y_len * in_c);
+  for(auto& v : in) { st = st * 1664525u + 1013904223u; v = (st >> 8) * (1.0f / 16777216.0f); }
+  sc.setInput(in.data());
+  for(int i = 0; i < warmup; i++) sc.run();
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaStreamSynchronize(sc.h.stream));
+  CK(cudaEventRecord(e0, sc.h.stream));
+  for(int i = 0; i < iters; i++) sc.run();
+  CK(cudaEventRecord(e1, sc.h.stream));
+  CK(cudaStreamSynchronize(sc.h.stream));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+}
+
 KGB_API int kgb_bench_conv(int ky, int kx, int in_c, int out_c, int n, int nn_x_len, int nn_y_len, int use_fp16, int warmup, int iters,
                    float* ms_per_launch) {
+  return guarded([&] { benchConvImpl(ky, kx, in_c, out_c, n, nn_x_len, nn_y_len, use_fp16, 1, 1, warmup, iters, ms_per_launch); });
+}
+
+KGB_API int kgb_bench_conv_ex(int ky, int kx, int in_c, int out_c, int n, int nn_x_len, int nn_y_len, int use_fp16, int epilogue_kind, int rotate,
+                      int warmup, int iters, float* ms_per_launch) {
+  return guarded([&] { benchConvImpl(ky, kx, in_c, out_c, n, nn_x_len, nn_y_len, use_fp16, epilogue_kind, rotate, warmup, iters, ms_per_launch); });
+}
+
+KGB_API int kgb_test_conv_epilogue(int ky, int kx, int in_c, int out_c, const float* weights, int n, int nn_x_len, int nn_y_len, int use_fp16,
+                           int epilogue_kind, const float* input, const float* residual_in, const float* bn_scale, const float* bn_bias,
+                           int activation, float* raw_out, float* act_out) {
   return guarded([&] {
-    if(!ms_per_launch || n < 1 || iters < 1) throw std::invalid_argument("kgb_bench_conv: bad argument");
-    std::vector<float> w((size_t)ky * kx * in_c * out_c);
-    uint32_t st = 12345u;
-    for(auto& v : w) { st = st * 1664525u + 1013904223u; v = ((st >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.1f; }
-    SingleConv sc(ky, kx, in_c, out_c, w.data(), n, nn_x_len, nn_y_len, use_fp16, 1);
-    std::vector<float> in((size_t)n * nn_x_len * nn_y_len * in_c);
-    for(auto& v : in) { st = st * 1664525u + 1013904223u; v = (st >> 8) * (1.0f / 16777216.0f); }
-    sc.setInput(in.data());
-    for(int i = 0; i < warmup; i++) sc.run();
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    if(!weights || !input || !act_out || n < 1 || epilogue_kind < 1 || epilogue_kind > 3) throw std::invalid_argument("kgb_test_conv_epilogue: bad argument");
+    if(epilogue_kind == 2 && !residual_in) throw std::invalid_argument("kgb_test_conv_epilogue: kind 2 needs residual_in");
+    if(epilogue_kind >= 2 && !raw_out) throw std::invalid_argument("kgb_test_conv_epilogue: kinds 2 and 3 need raw_out");
+    SingleConv sc(ky, kx, in_c, out_c, weights, n, nn_x_len, nn_y_len, use_fp16, epilogue_kind, 1, bn_scale, bn_bias, activation);
+    sc.setInput(input);
+    const int cp = sc.cw.cout_p;
+    const bool f32 = sc.h.split != 0;
+    auto rowOf = [&](int i, int y, int x) { return (size_t)i * sc.h.L.P + (size_t)(y + sc.pad) * sc.h.L.Wp + x; };
+    if(epilogue_kind == 2) {
+      std::vector<float> hf(sc.M * cp, 0.0f);
+      for(int i = 0; i < n; i++) for(int y = 0; y < nn_y_len; y++) for(int x = 0; x < nn_x_len; x++) for(int c = 0; c < out_c; c++)
+        hf[rowOf(i, y, x) * cp + c] = residual_in[(((size_t)i * nn_y_len + y) * nn_x_len + x) * out_c + c];
+      if(f32) CK(cudaMemcpy(sc.streams[0], hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice));
+      else {
+        std::vector<__half> hh(hf.size());
+        for(size_t k = 0; k < hf.size(); k++) hh[k] = __float2half_rn(hf[k]);
+        CK(cudaMemcpy(sc.streams[0], hh.data(), hh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      }
+      CK(cudaDeviceSynchronize());
+    }
+    sc.run();
     CK(cudaStreamSynchronize(sc.h.stream));
-    CK(cudaEventRecord(e0, sc.h.stream));
-    for(int i = 0; i < iters; i++) sc.run();
-    CK(cudaEventRecord(e1, sc.h.stream));
-    CK(cudaStreamSynchronize(sc.h.stream));
-    float ms = 0.0f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    *ms_per_launch = ms / iters;
+    const int am = f32 ? 2 : 1;
+    std::vector<__half> ha(sc.M * cp * am);
+    CK(cudaMemcpy(ha.data(), sc.acts[0], ha.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+    std::vector<float> hr;
+    if(epilogue_kind >= 2) {
+      hr.resize(sc.M * cp);
+      if(f32) CK(cudaMemcpy(hr.data(), sc.streams[0], hr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      else {
+        std::vector<__half> hh(hr.size());
+        CK(cudaMemcpy(hh.data(), sc.streams[0], hh.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+        for(size_t k = 0; k < hr.size(); k++) hr[k] = __half2float(hh[k]);
+      }
+    }
+    // every row that is not a board point (pad rows / columns) must have been written as zero: the next conv's halo reads them
+    std::vector<char> onBoard(sc.M, 0);
+    for(int i = 0; i < n; i++) for(int y = 0; y < nn_y_len; y++) for(int x = 0; x < nn_x_len; x++) onBoard[rowOf(i, y, x)] = 1;
+    for(size_t r = 0; r < sc.M; r++)
+      if(!onBoard[r])
+        for(int c = 0; c < cp * am; c++)
+          if(__half2float(ha[r * cp * am + c]) != 0.0f) throw std::runtime_error("kgb_test_conv_epilogue: pad row " + std::to_string(r) + " of the activation output is not zero");
+    for(int i = 0; i < n; i++) for(int y = 0; y < nn_y_len; y++) for(int x = 0; x < nn_x_len; x++) for(int c = 0; c < out_c; c++) {
+      const size_t row = rowOf(i, y, x), o = (((size_t)i * nn_y_len + y) * nn_x_len + x) * out_c + c;
+      act_out[o] = __half2float(ha[row * cp * am + c]) + (f32 ? __half2float(ha[row * cp * am + cp + c]) : 0.0f);
+      if(epilogue_kind >= 2) raw_out[o] = hr[row * cp + c];
+    }
   });
 }
 

@@ -166,5 +166,11 @@ cudaError_t convTCInit();  // per device, before the first launch
 // CTA-pair kernel (kgb_conv_tc2.cu); tmapBhalf has box rows n_tile/2.  cudaErrorNotSupported = shape not handled, use launchConvTC.
 cudaError_t convTC2Init();
 cudaError_t launchConvTC2(const CUtensorMap& tmapA, const CUtensorMap& tmapBhalf, const ConvParams& p, int numSMs, cudaStream_t stream);
+// CTA-pair kernel with TMA epilogue and deep operand rings (kgb_conv_tc3.cu): fp16 mode's production kernel.
+// tmapRes / tmapRaw / tmapAct: [M][cout_p] tensors, box {64 fp16 | 32 fp32 columns, 32 rows}, 128B swizzle (unused ones: any valid map).
+cudaError_t convTC3Init();
+bool convTC3Supports(const ConvParams& p);
+cudaError_t launchConvTC3(const CUtensorMap& tmapA, const CUtensorMap& tmapBhalf, const CUtensorMap& tmapRes, const CUtensorMap& tmapRaw,
+                          const CUtensorMap& tmapAct, const ConvParams& p, int numSMs, cudaStream_t stream);
 
 }  // namespace kgb

@@ -1,0 +1,536 @@
+// CTA-pair tcgen05 implicit-GEMM convolution with a TMA epilogue: the production trunk kernel of fp16 mode (round 2).
+// (reference call sites: ConvLayer::apply eigenbackend.cpp:448-701,
+//  cudnnConvolutionForward / cublasHgemm + applyCScaleBias* + addNCBias* cudabackend.cpp:788-841, cudahelpers.cu:1250-2101.)
+//
+// What round 1 measured (profiles/r01_conv_pipeline_experiments.md, VERDICT.md "What's weak" 4) and what this kernel changes:
+//   * every 128-row tile re-fetched all 27 weight tiles of a 3x3 conv from L2 (648 KB per tile, 0.5 GB per launch), with only
+//     3-4 taps in flight per SM            -> a CTA pair executes ONE 256 x N x 16 UMMA (cta_group::2): each SM stages its own
+//                                             128 activation rows and HALF of every weight tile, in a ring of up to 16 stages
+//   * the epilogue moved every tensor through per-warp 16-column transposes with LSU loads/stores: latency-bound, 30-44 % of
+//     the HBM roofline on the 1x1 convs   -> residual tiles arrive by TMA (prefetched while the tile's MMAs run), raw / activation
+//                                             tiles leave by TMA stores from 128B-swizzled shared-memory tiles (UTMASTG)
+//   * 1x1 convs kept two 16 KB activation tiles in flight per SM (HBM latency-bound)
+//                                          -> the A ring is as deep as the B ring when there is one tap
+//
+// GEMM view:  D[M = batch*P rows, N = cout]  =  sum over k-blocks kb, taps t of  A_t[M, 64] * W_t[64, N]    (kgb_conv.cuh "padded rows")
+//   A_t = the activation matrix shifted by the tap's row offset: one halo tile {64 channels, 128 + 2*halo rows} per (CTA, k-block),
+//         each tap = a row-shifted UMMA descriptor into it (profiles/r01_descriptor_shift_experiment.md).
+//   W   = packed [tap][cout_p][cin_p] fp16 (K-major); each CTA of the pair loads rows [n0 + rank*N/2, +N/2) of the tap's tile.
+//   D   = fp32 in TMEM, 2 accumulator stages x N columns, 128 lanes per CTA (its own 128 rows).
+//
+// Warp roles per CTA (128 + 128*E threads):  warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA), warp 2 TMEM
+// allocator, warps 4.. epilogue: quadrant q = warp & 3 (TMEM lanes 32q..32q+31), part = (warp - 4) / 4 owns the 64-column chunks
+// c = part, part + E, ...  of the tile.  Per chunk: [TMA load residual 32 x 64 fp16] -> tcgen05.ld -> + ncbias + residual ->
+// raw tile (in place over the residual tile) and BN + activation + mask tile -> fence.proxy.async -> TMA stores.
+//
+// Handles fp16 mode (operands fp16, fp32 accumulate); raw output fp16 or fp32, residual fp16.  The fp32-equivalent ("split")
+// mode and fp32 residual streams stay on kgb_conv_tc.cu.
+#include "kgb_conv_tc_common.cuh"
+
+#include <cstdlib>
+
+namespace kgb {
+
+static constexpr int T3_MAX_STAGES = 16;
+static constexpr int T3_MAX_ASTAGES = 8;
+static constexpr int T3_MAX_EPI_WARPS = 16;
+static constexpr int T3_SLOT_BYTES = 4096;       // 32 rows x 128 B, 128B-swizzled: one TMA box
+
+// ---- cluster / cta_group::2 PTX -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t t3_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void t3_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t t3_mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void t3_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void t3_tma_load_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+    ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void t3_umma_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+    ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void t3_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void t3_tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void t3_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void t3_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void t3_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void t3_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t t3_idesc(int n) {  // M = 256 across the pair, fp16 x fp16 -> fp32, K-major A and B
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void t3_sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 t3_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+struct __align__(8) Bars3 {
+  uint64_t full[T3_MAX_STAGES];      // leader: weight half-tiles of both CTAs landed
+  uint64_t empty[T3_MAX_STAGES];     // each CTA: stage consumed (multicast commit)
+  uint64_t a_full[T3_MAX_ASTAGES];   // leader: A halo tiles of both CTAs landed
+  uint64_t a_empty[T3_MAX_ASTAGES];  // each CTA
+  uint64_t tmem_full[2];             // each CTA (multicast commit)
+  uint64_t tmem_empty[2];            // leader: epilogue warps of both CTAs
+  uint64_t r_full[T3_MAX_EPI_WARPS][2];   // per epilogue warp and buffer: residual tile landed
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+static_assert(sizeof(Bars3) <= 1024, "barrier block");
+
+struct Conv3Cfg {
+  int stages, a_stages;      // B ring (one tap's half weight tile per stage), A ring (one halo tile per stage)
+  int epi_parts;             // E: epilogue warps per TMEM lane quadrant
+  int nbuf;                  // 1 or 2 slot pairs per epilogue warp
+  int num_pair_m_tiles;
+  int dbg;
+};
+
+// dynamic smem per CTA: [slack to 1024][a_stages x A halo tile][stages x half weight tile][epi warps x nbuf x 2 x 4 KB][Bars3, 1 KB][bn scale | bias]
+static inline int t3ABufBytes(int a_box_rows) { return (a_box_rows * BLOCK_K * 2 + 1023) / 1024 * 1024; }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAX_THREADS, 1)
+kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const __grid_constant__ CUtensorMap tmapRes, const __grid_constant__ CUtensorMap tmapRaw,
+                    const __grid_constant__ CUtensorMap tmapAct, const __grid_constant__ ConvParams p, const Conv3Cfg cfg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int n_half = p.n_tile >> 1;
+  const int b_tile_bytes = n_half * BLOCK_K * 2;
+  const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
+  const int a_box_rows = BLOCK_M + 2 * halo;
+  const int a_tx_bytes = a_box_rows * BLOCK_K * 2;
+  const int a_buf_bytes = (a_tx_bytes + 1023) / 1024 * 1024;
+  const int stages = cfg.stages, a_stages = cfg.a_stages, E = cfg.epi_parts, nbuf = cfg.nbuf;
+  const int epi_warps = 4 * E;
+  const uint32_t smem_b = smem_base + a_stages * a_buf_bytes;
+  const uint32_t smem_epi = smem_b + stages * b_tile_bytes;
+  const size_t bars_off = (size_t)a_stages * a_buf_bytes + (size_t)stages * b_tile_bytes + (size_t)epi_warps * nbuf * 2 * T3_SLOT_BYTES;
+  Bars3* bars = reinterpret_cast<Bars3*>(smem_aligned + bars_off);
+  float* s_scale = reinterpret_cast<float*>(smem_aligned + bars_off + 1024);
+  float* s_bias = s_scale + p.cout_p;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = t3_cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = cfg.num_pair_m_tiles * p.num_n_tiles;
+  const int taps = p.ky * p.kx;
+  const int kblocks = p.cin_p / BLOCK_K;
+  const int dbg = cfg.dbg;
+
+  if(warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+    if(p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapRes) : "memory");
+    if(p.raw_out != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapRaw) : "memory");
+    if(p.act_out != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapAct) : "memory");
+  }
+  if(warp == 1 && lane == 0) {
+    for(int s = 0; s < stages; s++) {
+      mbar_init(smem_u32(&bars->full[s]), 2);        // one arrival per CTA's producer (+ tx bytes of both)
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for(int s = 0; s < a_stages; s++) {
+      mbar_init(smem_u32(&bars->a_full[s]), 2);
+      mbar_init(smem_u32(&bars->a_empty[s]), 1);
+    }
+    for(int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&bars->tmem_full[s]), 1);
+      mbar_init(smem_u32(&bars->tmem_empty[s]), 2 * epi_warps);   // epilogue warps of both CTAs
+    }
+    for(int w = 0; w < epi_warps; w++) {
+      mbar_init(smem_u32(&bars->r_full[w][0]), 1);
+      mbar_init(smem_u32(&bars->r_full[w][1]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(p.act_out != nullptr) {
+    for(int c = threadIdx.x; c < p.cout_p; c += blockDim.x) { s_scale[c] = p.bn_scale[c]; s_bias[c] = p.bn_bias[c]; }
+  }
+  t3_cluster_sync();   // barriers of both CTAs are initialised before anyone signals across the pair
+  if(warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  t3_cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if(warp == 0) {
+    // ===================== TMA producer (both CTAs): own A halo tile, own half of every tap's weight tile =====================
+    if(lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int abuf = 0; uint32_t aphase = 0;
+      for(int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.num_n_tiles) * 256 + (int)rank * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * p.n_tile + (int)rank * n_half;
+        for(int kb = 0; kb < kblocks; kb++) {
+          mbar_wait(smem_u32(&bars->a_empty[abuf]), aphase ^ 1);
+          {
+            const uint32_t afull_leader = t3_mapa(smem_u32(&bars->a_full[abuf]), 0);
+            if(leader) mbar_arrive_expect_tx(smem_u32(&bars->a_full[abuf]), (uint32_t)(2 * a_tx_bytes));
+            else t3_arrive_cluster(afull_leader);
+            t3_tma_load_2sm(smem_base + abuf * a_buf_bytes, &tmapA, afull_leader, kb * BLOCK_K, m0 - halo);
+          }
+          if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
+          for(int t = 0; t < taps; t++) {
+            mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+            const uint32_t full_leader = t3_mapa(smem_u32(&bars->full[stage]), 0);
+            if(leader) mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), (uint32_t)(2 * b_tile_bytes));
+            else t3_arrive_cluster(full_leader);
+            t3_tma_load_2sm(smem_b + stage * b_tile_bytes, &tmapB, full_leader, kb * BLOCK_K, t * p.cout_p + n0);
+            if(++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  }
+  else if(warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if(leader && lane == 0) {
+      const uint32_t idesc = t3_idesc(p.n_tile);
+      const int ry = p.ky / 2, rx = p.kx / 2;
+      int stage = 0; uint32_t phase = 0;
+      int abuf = 0; uint32_t aphase = 0;
+      int acc_stage = 0; uint32_t acc_phase = 0;
+      for(int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(smem_u32(&bars->tmem_empty[acc_stage]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc_stage * p.n_tile;
+        for(int kb = 0; kb < kblocks; kb++) {
+          mbar_wait(smem_u32(&bars->a_full[abuf]), aphase);
+          const uint32_t a_base = smem_base + abuf * a_buf_bytes;
+          int dy = -ry, dx = -rx;
+          for(int t = 0; t < taps; t++) {
+            mbar_wait(smem_u32(&bars->full[stage]), phase);
+            tcgen05_fence_after();
+            // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
+            const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
+            const uint64_t db = make_smem_desc(smem_b + stage * b_tile_bytes);
+            if(!(dbg & 2)) {
+#pragma unroll
+              for(int k = 0; k < BLOCK_K / UMMA_K; k++)   // +32 bytes along K inside the 128B swizzle row = +2 descriptor units
+                t3_umma_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            t3_commit_mc(smem_u32(&bars->empty[stage]));
+            if(++stage == stages) { stage = 0; phase ^= 1; }
+            if(++dx > rx) { dx = -rx; dy++; }
+          }
+          t3_commit_mc(smem_u32(&bars->a_empty[abuf]));
+          if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
+        }
+        t3_commit_mc(smem_u32(&bars->tmem_full[acc_stage]));
+        if(++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  else if(warp >= EPI_WARP0) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - EPI_WARP0;
+    const int quad = warp & 3;
+    const int part = ew >> 2;
+    const int chunks = p.n_tile >> 6;                       // 64-column chunks per tile
+    const bool has_res = p.residual != nullptr;
+    const bool has_raw = p.raw_out != nullptr;
+    const bool has_act = p.act_out != nullptr;
+    const bool raw32 = has_raw && p.raw_fp32;
+    const uint32_t slot0 = smem_epi + (uint32_t)ew * (uint32_t)(nbuf * 2 * T3_SLOT_BYTES);
+    const uint32_t swz = (uint32_t)(lane & 7);            // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+    const uint32_t row_off = (uint32_t)lane * 128u;
+
+    // this warp's work items in order: (tile, chunk) for tile in the cluster's tiles, chunk = part, part + E, ...
+    int tile = cluster_id, chunk = part;
+    int tile_seq = 0;                                       // index of `tile` in the cluster's sequence (accumulator stage / phase)
+    int it = 0;
+    auto item_rowbase = [&](int tl) { return (tl / p.num_n_tiles) * 256 + (int)rank * BLOCK_M + quad * 32; };
+    auto item_col = [&](int tl, int ch) { return (tl % p.num_n_tiles) * p.n_tile + ch * 64; };
+    auto issue_residual = [&](int tl, int ch, int b) {     // lane 0 only
+      if(item_rowbase(tl) < p.M) {
+        const uint32_t bar = smem_u32(&bars->r_full[ew][b]);
+        mbar_arrive_expect_tx(bar, (uint32_t)T3_SLOT_BYTES);
+        tma_load_2d(slot0 + (uint32_t)b * 2u * T3_SLOT_BYTES, &tmapRes, bar, item_col(tl, ch), item_rowbase(tl));
+      }
+    };
+    if(has_res && nbuf == 2 && lane == 0 && tile < num_tiles && !(dbg & 4)) issue_residual(tile, chunk, 0);
+
+    while(tile < num_tiles) {
+      // next item
+      int ntile = tile, nchunk = chunk + E;
+      if(nchunk >= chunks) { nchunk = part; ntile = tile + num_clusters; }
+      const bool last_of_tile = ntile != tile;
+      const int b = (nbuf == 2) ? (it & 1) : 0;
+      const uint32_t slotRW = slot0 + (uint32_t)b * 2u * T3_SLOT_BYTES;
+      const uint32_t slotAct = slotRW + T3_SLOT_BYTES;
+      const int rowBase = item_rowbase(tile);
+      const int rowsValid = min(32, p.M - rowBase);        // may be <= 0 in the last tile
+      const int col0 = item_col(tile, chunk);
+      const int acc_stage = tile_seq & 1;
+      const uint32_t acc_phase = (uint32_t)(tile_seq >> 1) & 1u;
+
+      if(nbuf == 1) {
+        if(lane == 0) {
+          t3_store_wait_read();                             // the previous item's stores have read this slot pair
+          if(has_res && !(dbg & 4)) issue_residual(tile, chunk, 0);
+        }
+        __syncwarp();
+      }
+      if(chunk == part) {                                   // first chunk of this tile for this warp
+        mbar_wait(smem_u32(&bars->tmem_full[acc_stage]), acc_phase);
+        tcgen05_fence_after();
+      }
+      if(!(dbg & 4)) {
+        const int row = rowBase + lane;
+        const bool valid = lane < rowsValid;
+        const float maskv = valid ? __ldg(p.mask + row) : 0.0f;
+        const int img = valid ? row / p.P : 0;
+        if(has_res && rowsValid > 0) mbar_wait(smem_u32(&bars->r_full[ew][b]), (uint32_t)((nbuf == 2 ? (it >> 1) : it) & 1));
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc_stage * p.n_tile + chunk * 64);
+        uint32_t accA[16], accB[16];
+        tmem_ld16(taddr, accA);
+#pragma unroll
+        for(int q = 0; q < 4; q++) {                       // four 16-column pieces; TMEM load of piece q+1 in flight during piece q
+          uint32_t (&acc)[16] = (q & 1) ? accB : accA;
+          uint32_t (&nxt)[16] = (q & 1) ? accA : accB;
+          if(q < 3) tmem_ld16(taddr + (q + 1) * 16, nxt);
+          tmem_ld_wait(acc);
+          if(q == 3 && last_of_tile) {                      // accumulator fully read by this warp: hand the stage back
+            tcgen05_fence_before();
+            __syncwarp();
+            if(lane == 0) {
+              if(leader) mbar_arrive(smem_u32(&bars->tmem_empty[acc_stage]));
+              else t3_arrive_cluster(t3_mapa(smem_u32(&bars->tmem_empty[acc_stage]), 0));
+            }
+          }
+          float v[16];
+#pragma unroll
+          for(int j = 0; j < 16; j++) v[j] = __uint_as_float(acc[j]);
+          const int col = col0 + q * 16;
+          if(p.ncbias != nullptr && valid) {
+            const float4* bp = reinterpret_cast<const float4*>(p.ncbias + (size_t)img * p.cout_p + col);
+#pragma unroll
+            for(int e = 0; e < 4; e++) {
+              const float4 t = __ldg(bp + e);
+              v[4 * e] += t.x; v[4 * e + 1] += t.y; v[4 * e + 2] += t.z; v[4 * e + 3] += t.w;
+            }
+          }
+          // fp16 tiles: piece q = 16-byte chunks 2q, 2q+1 of the row
+          const uint32_t a0 = row_off + (((uint32_t)(2 * q) ^ swz) << 4), a1 = row_off + (((uint32_t)(2 * q + 1) ^ swz) << 4);
+          if(has_res) {
+            const uint4 r0 = t3_lds128(slotRW + a0), r1 = t3_lds128(slotRW + a1);
+            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+            for(int e = 0; e < 4; e++) {
+              const float2 f0 = __half22float2(h0[e]), f1 = __half22float2(h1[e]);
+              v[2 * e] += f0.x; v[2 * e + 1] += f0.y;
+              v[8 + 2 * e] += f1.x; v[8 + 2 * e + 1] += f1.y;
+            }
+          }
+          if(has_raw) {
+            if(raw32) {
+              // fp32 tile: 64 columns = two 32-column (128 B) halves; piece q -> half q>>1, 16-byte chunks (q&1)*4 .. +3
+              const uint32_t base = ((q >> 1) ? slotAct : slotRW) + row_off;
+#pragma unroll
+              for(int e = 0; e < 4; e++) {
+                uint4 o;
+                o.x = __float_as_uint(maskv != 0.0f ? v[4 * e] : 0.0f); o.y = __float_as_uint(maskv != 0.0f ? v[4 * e + 1] : 0.0f);
+                o.z = __float_as_uint(maskv != 0.0f ? v[4 * e + 2] : 0.0f); o.w = __float_as_uint(maskv != 0.0f ? v[4 * e + 3] : 0.0f);
+                t3_sts128(base + (((uint32_t)((q & 1) * 4 + e) ^ swz) << 4), o);
+              }
+            }
+            else {
+              uint4 o0, o1;
+              __half2* g0 = reinterpret_cast<__half2*>(&o0);
+              __half2* g1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+              for(int e = 0; e < 4; e++) {
+                g0[e] = __floats2half2_rn(maskv != 0.0f ? v[2 * e] : 0.0f, maskv != 0.0f ? v[2 * e + 1] : 0.0f);
+                g1[e] = __floats2half2_rn(maskv != 0.0f ? v[8 + 2 * e] : 0.0f, maskv != 0.0f ? v[8 + 2 * e + 1] : 0.0f);
+              }
+              t3_sts128(slotRW + a0, o0);
+              t3_sts128(slotRW + a1, o1);
+            }
+          }
+          if(has_act) {
+            float a[16];
+            const float* sc = s_scale + col;
+            const float* bi = s_bias + col;
+#pragma unroll
+            for(int e = 0; e < 4; e++) {
+              const float4 s = *reinterpret_cast<const float4*>(sc + e * 4), bb = *reinterpret_cast<const float4*>(bi + e * 4);
+              a[4 * e] = fmaf(v[4 * e], s.x, bb.x); a[4 * e + 1] = fmaf(v[4 * e + 1], s.y, bb.y);
+              a[4 * e + 2] = fmaf(v[4 * e + 2], s.z, bb.z); a[4 * e + 3] = fmaf(v[4 * e + 3], s.w, bb.w);
+            }
+            if(p.act == 2) {   // mish(x) = x - 2x / (e^x (e^x + 2) + 2): overflow of e gives x, underflow gives 0, no clamps needed
+#pragma unroll
+              for(int j = 0; j < 16; j++) {
+                const float x = a[j];
+                const float ex = kgb_ex2(x * 1.4426950408889634f);
+                const float r = kgb_rcp(fmaf(ex, ex + 2.0f, 2.0f));
+                a[j] = fmaf(-2.0f, x * r, x);
+              }
+            }
+            else if(p.act == 1) {
+#pragma unroll
+              for(int j = 0; j < 16; j++) a[j] = fmaxf(a[j], 0.0f);
+            }
+            else if(p.act == 3) {
+#pragma unroll
+              for(int j = 0; j < 16; j++) a[j] = a[j] * kgb_rcp(1.0f + kgb_ex2(a[j] * -1.4426950408889634f));
+            }
+            uint4 o0, o1;
+            __half2* g0 = reinterpret_cast<__half2*>(&o0);
+            __half2* g1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+            for(int e = 0; e < 4; e++) {
+              g0[e] = __floats2half2_rn(maskv != 0.0f ? a[2 * e] : 0.0f, maskv != 0.0f ? a[2 * e + 1] : 0.0f);
+              g1[e] = __floats2half2_rn(maskv != 0.0f ? a[8 + 2 * e] : 0.0f, maskv != 0.0f ? a[8 + 2 * e + 1] : 0.0f);
+            }
+            t3_sts128(slotAct + a0, o0);
+            t3_sts128(slotAct + a1, o1);
+          }
+        }
+        if(nbuf == 2 && lane == 0) {
+          t3_store_wait_read();                             // stores of item it-1 (the other slot pair) have read their tiles
+          if(has_res && ntile < num_tiles) issue_residual(ntile, nchunk, b ^ 1);
+        }
+        t3_fence_async_smem();                              // this lane's generic-proxy tile writes -> visible to the TMA engine
+        __syncwarp();
+        if(lane == 0 && rowsValid > 0 && !(dbg & 8)) {
+          if(has_raw) {
+            if(raw32) {
+              t3_tma_store(&tmapRaw, slotRW, col0, rowBase);
+              t3_tma_store(&tmapRaw, slotAct, col0 + 32, rowBase);
+            }
+            else t3_tma_store(&tmapRaw, slotRW, col0, rowBase);
+          }
+          if(has_act) t3_tma_store(&tmapAct, slotAct, col0, rowBase);
+        }
+        if(lane == 0) t3_store_commit();
+      }
+      else if(last_of_tile) {                               // timing experiment: no epilogue work, barrier protocol only
+        tcgen05_fence_before();
+        __syncwarp();
+        if(lane == 0) {
+          if(leader) mbar_arrive(smem_u32(&bars->tmem_empty[acc_stage]));
+          else t3_arrive_cluster(t3_mapa(smem_u32(&bars->tmem_empty[acc_stage]), 0));
+        }
+      }
+      if(last_of_tile) tile_seq++;
+      tile = ntile; chunk = nchunk; it++;
+    }
+    if(lane == 0) t3_store_wait_all();
+  }
+
+  // Neither CTA may exit (or free TMEM) while the pair's MMAs can still read its shared memory / write its TMEM.
+  tcgen05_fence_before();
+  t3_cluster_sync();
+  if(warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+cudaError_t convTC3Init() {
+  return cudaFuncSetAttribute(kgb_conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+}
+
+bool convTC3Supports(const ConvParams& p) {
+  const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
+  if(p.split || (p.n_tile % 64) != 0 || p.n_tile > 256 || BLOCK_M + 2 * halo > 256) return false;
+  if(p.residual != nullptr && p.residual_fp32) return false;
+  if(p.raw_out != nullptr && p.raw_fp32 && (p.residual != nullptr || p.act_out != nullptr)) return false;
+  return true;
+}
+
+// Ring sizing.  Returns the dynamic shared-memory bytes, or 0 when nothing fits.
+static int t3Plan(const ConvParams& p, int E, int nbuf, int wantStages, int wantAStages, int* stagesOut, int* aStagesOut) {
+  const int taps = p.ky * p.kx;
+  const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
+  const int aBuf = t3ABufBytes(BLOCK_M + 2 * halo);
+  const int bTile = (p.n_tile / 2) * BLOCK_K * 2;
+  const int fixed = 1024 /*align slack*/ + 1024 /*Bars3*/ + 8 * p.cout_p + 4 * E * nbuf * 2 * T3_SLOT_BYTES;
+  const int avail = SMEM_LIMIT - fixed;
+  int aStages, stages;
+  if(taps == 1) {
+    // one tap: A and B advance together (a plain GEMM pipeline); as deep as fits
+    int s = avail / (aBuf + bTile);
+    if(s > T3_MAX_ASTAGES) s = T3_MAX_ASTAGES;
+    aStages = stages = s;
+    if(wantStages > 0 && wantStages < s) aStages = stages = wantStages;
+  }
+  else {
+    aStages = wantAStages > 0 ? wantAStages : 2;
+    if(aStages > T3_MAX_ASTAGES) aStages = T3_MAX_ASTAGES;
+    stages = (avail - aStages * aBuf) / bTile;
+    if(stages > T3_MAX_STAGES) stages = T3_MAX_STAGES;
+    if(wantStages > 0 && wantStages < stages) stages = wantStages;
+  }
+  if(stages < 2 || aStages < 2) return 0;
+  *stagesOut = stages; *aStagesOut = aStages;
+  return fixed + aStages * aBuf + stages * bTile;
+}
+
+// tmapA: box {64, 128 + 2*halo}; tmapBhalf: box {64, n_tile/2}; tmapRes / tmapRaw / tmapAct: box {64 fp16 | 32 fp32, 32 rows},
+// 128B swizzle (unused ones may be any valid map).  cudaErrorNotSupported = shape not handled here, use launchConvTC.
+cudaError_t launchConvTC3(const CUtensorMap& tmapA, const CUtensorMap& tmapBhalf, const CUtensorMap& tmapRes, const CUtensorMap& tmapRaw,
+                          const CUtensorMap& tmapAct, const ConvParams& p, int numSMs, cudaStream_t stream) {
+  static int envE = -1, envNbuf = 0, envStages = 0, envAStages = 0, dbg = 0;
+  if(envE < 0) {   // bring-up / tuning knobs
+    const char* e = getenv("KGB_CONV_DBG"); dbg = e ? atoi(e) : 0;
+    e = getenv("KGB_T3_NBUF"); envNbuf = e ? atoi(e) : 0;
+    e = getenv("KGB_T3_STAGES"); envStages = e ? atoi(e) : 0;
+    e = getenv("KGB_T3_ASTAGES"); envAStages = e ? atoi(e) : 0;
+    e = getenv("KGB_T3_E"); envE = e ? atoi(e) : 0;
+  }
+  if(!convTC3Supports(p)) return cudaErrorNotSupported;
+  const int chunks = p.n_tile / 64;
+  int E = envE > 0 ? envE : (chunks >= 2 ? 2 : 1);
+  if(E > chunks) E = chunks;
+  if(E > 4) E = 4;
+  // one slot pair per epilogue warp by default: shared memory goes to the operand rings (3x3: 9 weight stages with E = 2)
+  int nbuf = envNbuf == 2 ? 2 : 1;
+  Conv3Cfg cfg;
+  int smem = t3Plan(p, E, nbuf, envStages, envAStages, &cfg.stages, &cfg.a_stages);
+  if(smem == 0 && nbuf == 2) {
+    nbuf = 1;
+    smem = t3Plan(p, E, nbuf, envStages, envAStages, &cfg.stages, &cfg.a_stages);
+  }
+  if(smem == 0) return cudaErrorNotSupported;
+  cfg.epi_parts = E; cfg.nbuf = nbuf; cfg.dbg = dbg;
+  cfg.num_pair_m_tiles = (p.M + 255) / 256;
+  const int tiles = cfg.num_pair_m_tiles * p.num_n_tiles;
+  int clusters = numSMs / 2;
+  if(tiles < clusters) clusters = tiles;
+  const int threads = 128 + 128 * E;
+  kgb_conv_tc3_kernel<<<2 * clusters, threads, smem, stream>>>(tmapA, tmapBhalf, tmapRes, tmapRaw, tmapAct, p, cfg);
+  return cudaGetLastError();
+}
+
+}  // namespace kgb

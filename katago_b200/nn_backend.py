@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
     "kgb_global_init", "kgb_global_cleanup", "kgb_last_error", "kgb_device_count", "kgb_device_name",
     "kgb_model_load_file", "kgb_model_free", "kgb_model_get_info", "kgb_context_create", "kgb_context_free",
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
-    "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv",
+    "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv", "kgb_bench_conv_ex", "kgb_test_conv_epilogue",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
     "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
     "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
@@ -123,6 +123,8 @@ def load_library():
     lib.kgb_handle_launches_per_forward.argtypes = [P]
     lib.kgb_test_conv.argtypes = [I, I, I, I, P, I, I, I, I, P, P]
     lib.kgb_bench_conv.argtypes = [I, I, I, I, I, I, I, I, I, I, F]
+    lib.kgb_bench_conv_ex.argtypes = [I, I, I, I, I, I, I, I, I, I, I, I, F]
+    lib.kgb_test_conv_epilogue.argtypes = [I, I, I, I, P, I, I, I, I, I, P, P, P, P, I, P, P]
     lib.kgb_selfplay_create.argtypes = [P, C.POINTER(SelfplayConfig), C.POINTER(P)]
     lib.kgb_selfplay_free.argtypes = [P]
     lib.kgb_selfplay_free.restype = None
@@ -332,6 +334,23 @@ class NeuralNet:
         _check(lib.kgb_test_conv(convYSize, convXSize, inChannels, outChannels, w.ctypes.data, batchSize, nnXLen, nnYLen,
                                  int(bool(useFP16)), x.ctypes.data, out.ctypes.data))
         return out
+
+
+def test_conv_epilogue(ky, kx, in_c, out_c, weights, n, nn_x_len, nn_y_len, use_fp16, kind, x, residual=None, bn_scale=None, bn_bias=None,
+                       activation=2):
+    """One convolution launch with a production epilogue (include/kgb200.h kgb_test_conv_epilogue): kind 1 = BN + act + mask -> fp16
+    operand, 2 = + residual stream updated in place, 3 = raw stream + operand.  Returns (raw or None, act), NHWC."""
+    lib = load_library()
+    w, xx = _f32(weights), _f32(x)
+    raw = np.zeros((n, nn_y_len, nn_x_len, out_c), np.float32)
+    act = np.zeros((n, nn_y_len, nn_x_len, out_c), np.float32)
+    res = _f32(residual) if residual is not None else None
+    sc = _f32(bn_scale) if bn_scale is not None else None
+    bi = _f32(bn_bias) if bn_bias is not None else None
+    _check(lib.kgb_test_conv_epilogue(ky, kx, in_c, out_c, w.ctypes.data, n, nn_x_len, nn_y_len, int(bool(use_fp16)), kind, xx.ctypes.data,
+                                      res.ctypes.data if res is not None else None, sc.ctypes.data if sc is not None else None,
+                                      bi.ctypes.data if bi is not None else None, activation, raw.ctypes.data, act.ctypes.data))
+    return (raw if kind >= 2 else None), act
 
 
 def zobrist_tables(x_size: int, y_size: int):

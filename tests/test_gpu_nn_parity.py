@@ -59,6 +59,42 @@ def test_conv_layer(ky, cin, cout, n, X, Y, fp16):
 
 
 @pytest.mark.parametrize("fp16", [False, True])
+@pytest.mark.parametrize("kind", [1, 2, 3])
+@pytest.mark.parametrize("ky,cin,cout,n,X,Y,act", [(3, 192, 192, 5, 19, 19, 2), (1, 384, 192, 9, 19, 19, 2), (1, 192, 384, 7, 19, 19, 2),
+                                                   (3, 256, 256, 3, 19, 19, 2), (3, 64, 128, 4, 13, 7, 1), (5, 22, 64, 3, 9, 9, 0),
+                                                   (3, 96, 96, 70, 9, 9, 2)])
+def test_conv_fused_epilogues(ky, cin, cout, n, X, Y, act, kind, fp16):
+    """The three production epilogues of a trunk convolution (kgb_conv.cuh): kind 1 = next layer's BN + activation + mask as an fp16
+    operand; 2 = + the residual stream, read and rewritten in place; 3 = raw stream + operand.  Reference: NormActConv / residual add of
+    ResidualBlock::apply and NestedBottleneckResidualBlock::apply (eigenbackend.cpp:1065-1077, 1127-1160, 1295-1314).  Pad rows of the
+    operand must come back as zeros (checked inside the hook).  (3, 96, 96, 70, 9, 9): more than one CTA-pair tile per cluster."""
+    from katago_b200 import nn_backend
+    rng = np.random.default_rng(ky * 100 + cin + kind)
+    w = (rng.standard_normal((ky, ky, cin, cout)) * np.sqrt(1.0 / (ky * ky * cin))).astype(np.float16).astype(np.float32)
+    x = rng.standard_normal((n, Y, X, cin)).astype(np.float16).astype(np.float32)
+    res = rng.standard_normal((n, Y, X, cout)).astype(np.float16).astype(np.float32) if kind == 2 else None
+    sc = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bi = rng.uniform(-0.5, 0.5, cout).astype(np.float32)
+    raw_ref = orc.conv2d(x, orc.Conv("t", ky, ky, cin, cout, w))
+    if res is not None:
+        raw_ref = raw_ref + res
+    z = raw_ref * sc + bi
+    if act == 2:
+        act_ref = z * np.tanh(np.log1p(np.exp(np.minimum(z, 30.0))))
+    elif act == 1:
+        act_ref = np.maximum(z, 0.0)
+    else:
+        act_ref = z
+    raw, a = nn_backend.test_conv_epilogue(ky, ky, cin, cout, w, n, X, Y, fp16, kind, x, res, sc, bi, act)
+    # fp16 mode stores both tensors as fp16 (relative 2^-11); fp32-equivalent mode stores raw as fp32 and the operand as hi + lo halves
+    tol_raw = 4e-3 if fp16 else 3e-4
+    tol_act = 4e-3 if fp16 else 3e-4
+    if raw is not None:
+        assert np.abs(raw - raw_ref).max() <= tol_raw * max(1.0, np.abs(raw_ref).max()), np.abs(raw - raw_ref).max()
+    assert np.abs(a - act_ref).max() <= tol_act * max(1.0, np.abs(act_ref).max()), np.abs(a - act_ref).max()
+
+
+@pytest.mark.parametrize("fp16", [False, True])
 @pytest.mark.parametrize("cfg", ["b2c16", "b2c32nbt", "b4c32"])
 def test_golden_reference_pytorch_outputs(golden_dir, cfg, fp16):
     d = np.load(os.path.join(golden_dir, f"torchref_{cfg}.npz"))
