@@ -47,8 +47,16 @@ __device__ __forceinline__ uint32_t t3_mapa(uint32_t local_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Remote arrivals.  NOT mbarrier.arrive.release.cluster: ptxas turns a cluster-scope release into MEMBAR.ALL.GPU + CCTL.IVALL
+// (~1000+ cycles) in front of every arrival - measured as 0.7 us per pipeline stage on the round-1 pair kernel and the first
+// version of this one (profiles/r02_conv_tc3_bringup.md).  The producer's arrival orders nothing (the data is published by the
+// TMA's complete_tx on the same barrier), so it is relaxed; the epilogue's "accumulator drained" arrival follows a
+// tcgen05.fence::before_thread_sync and uses the default (release at CTA scope) form, like a local arrival.
+__device__ __forceinline__ void t3_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void t3_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void t3_tma_load_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
   asm volatile(
@@ -84,6 +92,16 @@ __device__ __forceinline__ uint4 t3_lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+
+// One lane of a converged warp.  Unlike `if(lane == 0)`, elect.sync tells ptxas that the guarded code runs on exactly one lane of a
+// warp whose control flow is uniform: descriptors, barrier addresses and coordinates then stay in uniform registers.  With the
+// lane test the issuer needed a waterfall loop (ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY) around every tcgen05.mma: ~75 cycles per MMA,
+// 660 per tap against 384 of tensor work (profiles/r02_conv_tc3_bringup.md).
+__device__ __forceinline__ bool t3_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 struct __align__(8) Bars3 {
@@ -132,7 +150,7 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   float* s_scale = reinterpret_cast<float*>(smem_aligned + bars_off + 1024);
   float* s_bias = s_scale + p.cout_p;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
   const uint32_t rank = t3_cluster_ctarank();
   const bool leader = rank == 0;
@@ -184,36 +202,39 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   if(warp == 0) {
     // ===================== TMA producer (both CTAs): own A halo tile, own half of every tap's weight tile =====================
-    if(lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int abuf = 0; uint32_t aphase = 0;
-      for(int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.num_n_tiles) * 256 + (int)rank * BLOCK_M;
-        const int n0 = (tile % p.num_n_tiles) * p.n_tile + (int)rank * n_half;
-        for(int kb = 0; kb < kblocks; kb++) {
-          mbar_wait(smem_u32(&bars->a_empty[abuf]), aphase ^ 1);
-          {
-            const uint32_t afull_leader = t3_mapa(smem_u32(&bars->a_full[abuf]), 0);
-            if(leader) mbar_arrive_expect_tx(smem_u32(&bars->a_full[abuf]), (uint32_t)(2 * a_tx_bytes));
-            else t3_arrive_cluster(afull_leader);
-            t3_tma_load_2sm(smem_base + abuf * a_buf_bytes, &tmapA, afull_leader, kb * BLOCK_K, m0 - halo);
-          }
-          if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
-          for(int t = 0; t < taps; t++) {
-            mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+    // The whole warp walks the loop and waits on the barriers; one elected lane arrives and issues the copies.
+    int stage = 0; uint32_t phase = 0;
+    int abuf = 0; uint32_t aphase = 0;
+    for(int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.num_n_tiles) * 256 + (int)rank * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * p.n_tile + (int)rank * n_half;
+      for(int kb = 0; kb < kblocks; kb++) {
+        mbar_wait(smem_u32(&bars->a_empty[abuf]), aphase ^ 1);
+        if(t3_elect_one()) {
+          const uint32_t afull_leader = t3_mapa(smem_u32(&bars->a_full[abuf]), 0);
+          if(leader) mbar_arrive_expect_tx(smem_u32(&bars->a_full[abuf]), (uint32_t)(2 * a_tx_bytes));
+          else t3_arrive_cluster_relaxed(afull_leader);
+          t3_tma_load_2sm(smem_base + abuf * a_buf_bytes, &tmapA, afull_leader, kb * BLOCK_K, m0 - halo);
+        }
+        __syncwarp();
+        if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
+        for(int t = 0; t < taps; t++) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+          if(t3_elect_one()) {
             const uint32_t full_leader = t3_mapa(smem_u32(&bars->full[stage]), 0);
             if(leader) mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), (uint32_t)(2 * b_tile_bytes));
-            else t3_arrive_cluster(full_leader);
+            else t3_arrive_cluster_relaxed(full_leader);
             t3_tma_load_2sm(smem_b + stage * b_tile_bytes, &tmapB, full_leader, kb * BLOCK_K, t * p.cout_p + n0);
-            if(++stage == stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if(++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   }
   else if(warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if(leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA only): whole warp in the loop, one elected lane issues =====================
+    if(leader) {
       const uint32_t idesc = t3_idesc(p.n_tile);
       const int ry = p.ky / 2, rx = p.kx / 2;
       int stage = 0; uint32_t phase = 0;
@@ -230,22 +251,27 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           for(int t = 0; t < taps; t++) {
             mbar_wait(smem_u32(&bars->full[stage]), phase);
             tcgen05_fence_after();
-            // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
-            const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
-            const uint64_t db = make_smem_desc(smem_b + stage * b_tile_bytes);
-            if(!(dbg & 2)) {
-#pragma unroll
-              for(int k = 0; k < BLOCK_K / UMMA_K; k++)   // +32 bytes along K inside the 128B swizzle row = +2 descriptor units
-                t3_umma_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || t > 0 || k > 0) ? 1u : 0u);
+            if(t3_elect_one()) {
+              // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
+              const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
+              const uint64_t db = make_smem_desc(smem_b + stage * b_tile_bytes);
+              if(!(dbg & 2)) {
+                // +32 bytes along K inside the 128B swizzle row = +2 descriptor units
+                t3_umma_2sm(tmem_d, da, db, idesc, (kb > 0 || t > 0) ? 1u : 0u);
+                t3_umma_2sm(tmem_d, da + 2, db + 2, idesc, 1u);
+                t3_umma_2sm(tmem_d, da + 4, db + 4, idesc, 1u);
+                t3_umma_2sm(tmem_d, da + 6, db + 6, idesc, 1u);
+              }
+              t3_commit_mc(smem_u32(&bars->empty[stage]));
+              if(t == taps - 1) t3_commit_mc(smem_u32(&bars->a_empty[abuf]));
+              if(t == taps - 1 && kb == kblocks - 1) t3_commit_mc(smem_u32(&bars->tmem_full[acc_stage]));
             }
-            t3_commit_mc(smem_u32(&bars->empty[stage]));
+            __syncwarp();
             if(++stage == stages) { stage = 0; phase ^= 1; }
             if(++dx > rx) { dx = -rx; dy++; }
           }
-          t3_commit_mc(smem_u32(&bars->a_empty[abuf]));
           if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
         }
-        t3_commit_mc(smem_u32(&bars->tmem_full[acc_stage]));
         if(++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
