@@ -103,6 +103,11 @@ struct Reader {
     return v;
   }
   void readFloats(size_t n, const std::string& name, std::vector<float>& buf) {
+    // A malformed or hostile file must not drive the allocation: a binary block cannot hold more floats than bytes remain / 4, a
+    // text block needs at least two bytes ("0 ") per float.  Checked BEFORE the resize (and before p + 4 * n could wrap).
+    const size_t remaining = p <= d.size() ? d.size() - p : 0;
+    if(n > remaining / (binary ? 4 : 2))
+      throw std::runtime_error(name + ": the file is too short for the " + std::to_string(n) + " floats its header announces");
     buf.resize(n);
     if(!binary) {
       for(size_t i = 0; i < n; i++) {
@@ -120,7 +125,7 @@ struct Reader {
     if(p + 5 > d.size() || d.compare(p, 5, "@BIN@") != 0)
       throw std::runtime_error(name + ": did not find expected header for binary float block");
     p += 5;
-    if(p + 4 * n > d.size()) throw std::runtime_error(name + ": did not find the expected number of floats in binary float block");
+    if(n > (d.size() - p) / 4) throw std::runtime_error(name + ": did not find the expected number of floats in binary float block");
     memcpy(buf.data(), d.data() + p, 4 * n);  // host is little-endian (x86-64 / aarch64)
     p += 4 * n;
     for(size_t i = 0; i < n; i++)
@@ -136,6 +141,8 @@ ConvDesc parseConv(Reader& r) {
   int dy = r.readInt("dilationY"), dx = r.readInt("dilationX");
   if(c.ky <= 0 || c.kx <= 0 || c.ky % 2 != 1 || c.kx % 2 != 1) throw std::runtime_error(c.name + ": convolution filter sizes must be positive and odd");
   if(c.cin <= 0 || c.cout <= 0) throw std::runtime_error(c.name + ": number of in and out channels must be positive");
+  // sane limits before the sizes are multiplied (the product below cannot wrap a size_t once these hold)
+  if(c.ky > 15 || c.kx > 15 || c.cin > 16384 || c.cout > 16384) throw std::runtime_error(c.name + ": convolution of unreasonable size (" + std::to_string(c.ky) + "x" + std::to_string(c.kx) + ", " + std::to_string(c.cin) + " -> " + std::to_string(c.cout) + " channels)");
   if(dy != 1 || dx != 1) throw std::runtime_error(c.name + ": dilated convolutions are not supported by the B200 backend");
   r.readFloats((size_t)c.ky * c.kx * c.cin * c.cout, c.name, c.w);
   return c;
@@ -178,6 +185,7 @@ MatMulDesc parseMatMul(Reader& r) {
   m.name = r.tok("matmul name");
   m.cin = r.readInt("matmul inChannels"); m.cout = r.readInt("matmul outChannels");
   if(m.cin <= 0 || m.cout <= 0) throw std::runtime_error(m.name + ": number of in and out channels must be positive");
+  if(m.cin > (1 << 20) || m.cout > (1 << 20)) throw std::runtime_error(m.name + ": matrix of unreasonable size");
   r.readFloats((size_t)m.cin * m.cout, m.name, m.w);
   return m;
 }

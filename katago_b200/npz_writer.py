@@ -284,6 +284,7 @@ class TrainingWriteBuffers:
             g[63] = 3.0
             if reanalysis[0]:
                 g[64], g[65], g[66], g[67] = 1.0, reanalysis[1], reanalysis[2], float(reanalysis[3])
+            g[68] = 1.0 if always_pass_alive_under_suicide_rules else 0.0      # trainingwrite.cpp:702
 
             sd = self.arrays["scoreDistrN"][r]
             own = self.arrays["valueTargetsNCHW"][r].reshape(VALUE_SPATIAL_CHANNELS, A)

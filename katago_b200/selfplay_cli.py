@@ -92,16 +92,27 @@ def parse_cfg(path_or_text, is_text=False):
     return out
 
 
-def _first_supported(cfg, key, supported, report, default):
+def _first_supported(cfg, key, supported, report, default, rel_probs_key=None):
+    """One value of a list-valued key.  The reference draws one per game (GameInitializer, program/play.cpp:83-650), uniformly or
+    with the weights of `rel_probs_key`; this loop plays ONE value in every game: the supported value the reference would draw most
+    often (largest relative probability; the first listed among equals), and says so under "fixed"."""
     if key not in cfg:
         return default
     vals = [v.strip() for v in cfg[key].split(",") if v.strip()]
-    ok = [v for v in vals if v.upper() in supported or v.lower() in supported]
+    probs = [1.0] * len(vals)
+    if rel_probs_key is not None and rel_probs_key in cfg:
+        probs = [float(v) for v in cfg[rel_probs_key].split(",") if v.strip()]
+        if len(probs) != len(vals):
+            raise ValueError(f"{rel_probs_key} has {len(probs)} entries, {key} has {len(vals)}")
+    ok = [(pr, -i, v) for i, (v, pr) in enumerate(zip(vals, probs)) if (v.upper() in supported or v.lower() in supported) and pr > 0]
     if not ok:
-        raise ValueError(f"{key} = {cfg[key]}: none of these is built (supported: {sorted(supported)})")
+        raise ValueError(f"{key} = {cfg[key]}: none of these is built (supported: {sorted(supported)}); pass an explicit single value")
+    best = max(ok)[2]
     if len(set(vals)) > 1:
-        report["fixed"].append(f"{key}: the reference draws one of [{cfg[key]}] per game; this loop plays '{ok[0]}' in every game")
-    return ok[0]
+        how = f" (weights {cfg[rel_probs_key]})" if rel_probs_key is not None and rel_probs_key in cfg else ""
+        report["fixed"].append(f"{key}: the reference draws one of [{cfg[key]}]{how} per game; this loop plays '{best}', the most likely "
+                               f"supported value, in every game - give a single value to choose another")
+    return best
 
 
 def selfplay_kwargs_from_cfg(cfg, strict=False):
@@ -134,10 +145,15 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     _first_supported(cfg, "taxRules", {"NONE"}, report, "NONE")
     _first_supported(cfg, "hasButtons", {"false"}, report, "false")
     kw["multi_stone_suicide_legal"] = _B(_first_supported(cfg, "multiStoneSuicideLegals", {"false", "true"}, report, "true"))
-    size = int(_first_supported(cfg, "bSizes", {str(s) for s in range(2, 20)}, report, "19"))
+    size = int(_first_supported(cfg, "bSizes", {str(s) for s in range(2, 20)}, report, "19", rel_probs_key="bSizeRelProbs"))
     used.update(("koRules", "scoringRules", "taxRules", "hasButtons", "multiStoneSuicideLegals", "bSizes", "bSizeRelProbs"))
-    komi = float(cfg["komiMean"]) if "komiMean" in cfg else 7.5      # komiAuto under area scoring
+    # komiAuto = true makes the reference find the komi that its own search calls even on the empty board
+    # (makeGameFairForEmptyBoard, program/play.cpp:640-644, playutils.cpp:591): that needs searches before the game and is NOT BUILT -
+    # the loop plays a fixed komi (komiMean, else 7.5) on every board size, which is off on small boards.  Listed so that -strict refuses it.
+    komi = float(cfg["komiMean"]) if "komiMean" in cfg else 7.5
     used.update(("komiMean", "komiAuto"))
+    if _B(cfg.get("komiAuto", "false")):
+        report["not_built"].append(f"komiAuto = true (komi fixed at {komi} instead of being adjusted to even by search)")
     data = {"board_size": size, "komi": komi,
             "data_board_len": int(cfg.get("dataBoardLen", size)), "max_rows_per_train_file": int(cfg.get("maxRowsPerTrainFile", 20000)),
             "first_file_rand_min_prop": float(cfg.get("firstFileRandMinProp", 1.0)), "num_game_threads": int(cfg.get("numGameThreads", 256))}

@@ -506,12 +506,14 @@ static int cmdNpyHeader(int argc, char** argv) {
   return 0;
 }
 
-// addrow X Y DATALEN NTURNS SEED NORESULT BONUS OUT.json: TrainingWriteBuffers::addRow (dataio/trainingwrite.cpp:448-852) on a synthetic
+// addrow X Y DATALEN NTURNS SEED NORESULT BONUS OUT.json [PASSALIVE]: TrainingWriteBuffers::addRow (dataio/trainingwrite.cpp:448-852) on a synthetic
 // finished game: NTURNS random legal moves, random value / Q / policy targets, Benson ownership of the final board, random scoring
 // plane; one row per turn with every optional argument toggled by the turn index.  Dumps each row's arguments and the seven
 // buffers the reference filled.  The row Rand is Rand("addrow"+SEED), shared by all rows like the writer's own.
 static int cmdAddRow(int argc, char** argv) {
-  if(argc != 10) { cerr << "usage: addrow X Y DATALEN NTURNS SEED NORESULT BONUS OUT.json" << endl; return 1; }
+  if(argc != 10 && argc != 11) { cerr << "usage: addrow X Y DATALEN NTURNS SEED NORESULT BONUS OUT.json [PASSALIVE]" << endl; return 1; }
+  // PASSALIVE = 1: multi-stone suicide illegal, history flagged alwaysComputePassAliveUnderSuicideRules (global target 68, trainingwrite.cpp:702)
+  const bool passAliveFlag = argc == 11 && atoi(argv[10]) != 0;
   const int X = atoi(argv[2]), Y = atoi(argv[3]), D = atoi(argv[4]), nTurns = atoi(argv[5]);
   const string seedStr = argv[6];
   const bool endNoResult = atoi(argv[7]) != 0;
@@ -520,14 +522,14 @@ static int cmdAddRow(int argc, char** argv) {
   ScoreValue::initTables();
   Rules rules;
   rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
-  rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.multiStoneSuicideLegal = !passAliveFlag; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
   rules.friendlyPassOk = false; rules.komi = 7.0f;
   Lcg rng(strtoull(seedStr.c_str(), NULL, 10));
   auto unif = [&]() { return (float)((rng.next() & 0xFFFFFF) / 16777216.0); };
 
   Board board(X, Y);
   Player pla = P_BLACK;
-  BoardHistory hist(board, pla, rules, 0, false);
+  BoardHistory hist(board, pla, rules, 0, passAliveFlag);
   const BoardHistory startHist = hist;
   vector<Board> boards; vector<BoardHistory> hists; vector<Player> plas;
   bool prevPass = false;

@@ -72,6 +72,13 @@ def test_loader_errors(tmp_path, tmp_models):
     trunc.write_bytes(open(tmp_models["tiny_reg"], "rb").read()[:5000])
     with pytest.raises(KGBError):
         NeuralNet.loadModelFile(str(trunc))
+    # a header that announces far more weights than the file holds must fail on the size check, not by allocating them
+    # (3 x 3 x 16000 x 16000 floats = 9 GB; 1 x 1 x 2^30 x 2^30 would wrap a size_t)
+    for conv, what in (("conv1 3 3 16000 16000 1 1 @BIN@", "too short"), ("conv1 1 1 1073741824 1073741824 1 1 @BIN@", "unreasonable size")):
+        huge = tmp_path / "huge.bin"
+        huge.write_bytes(("m 8 22 19 trunk 2 16 16 16 16 16 " + conv).encode() + b"\0" * 64)
+        with pytest.raises(KGBError, match=what):
+            NeuralNet.loadModelFile(str(huge))
     wrong = tmp_path / "model.weights"
     wrong.write_bytes(b"x")
     with pytest.raises(KGBError, match="should end with"):

@@ -142,8 +142,9 @@ def test_add_row_matches_reference_add_row(path):
 def test_add_row_fixtures_cover_the_branches():
     """The fixtures exercise what addRow branches on: missing policy / ownership / future boards / scoring, no-result ending,
     bonus points, reanalysed rows, capped scores and leads, both colours, boards smaller than the data frame."""
-    assert len(ADDROW_FIXTURES) >= 7
-    seen = dict(p0_null=0, p1_null=0, own_null=0, fut_null=0, sc_null=0, rean=0, white=0, black=0, nores=0, bonus=0, small=0, capped=0, distr_low=0, distr_high=0)
+    assert len(ADDROW_FIXTURES) >= 8
+    seen = dict(p0_null=0, p1_null=0, own_null=0, fut_null=0, sc_null=0, rean=0, white=0, black=0, nores=0, bonus=0, small=0, capped=0, distr_low=0, distr_high=0,
+                passalive=0, not_passalive=0)
     for path in ADDROW_FIXTURES:
         d = json.loads(gzip.open(path, "rb").read())
         seen["nores"] += d["endNoResult"]
@@ -156,6 +157,8 @@ def test_add_row_fixtures_cover_the_branches():
             seen["fut_null"] += not r["hasFutureBoards"]
             seen["sc_null"] += not r["hasScoring"]
             seen["rean"] += r["reanalysis"][0]
+            seen["passalive"] += r["alwaysComputePassAliveUnderSuicideRules"] == 1 and r["out_globalTargetsNC"][68] == 1.0
+            seen["not_passalive"] += r["alwaysComputePassAliveUnderSuicideRules"] == 0 and r["out_globalTargetsNC"][68] == 0.0
             seen["white"] += r["nextPlayer"] == 2
             seen["black"] += r["nextPlayer"] == 1
             seen["distr_low"] += r["out_scoreDistrN"][0] == 100

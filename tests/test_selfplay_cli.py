@@ -57,12 +57,28 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     # per-game randomisation the loop does not have is reported, as are the data-distribution options that are not built
     assert any(s.startswith("koRules") for s in report["fixed"]) and any(s.startswith("bSizes") for s in report["fixed"])
     nb = " ".join(report["not_built"])
-    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "rootEndingBonusPoints", "rootPruneUselessMoves", "handicapProb", "komiStdev"):
+    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "rootEndingBonusPoints", "rootPruneUselessMoves", "handicapProb", "komiStdev",
+                "komiAuto"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
     assert not any(k in nb for k in ("maxVisits", "cpuctExploration", "koRules", "dataBoardLen"))
     with pytest.raises(ValueError, match="not built"):
         C.selfplay_kwargs_from_cfg(cfg, strict=True)
+
+
+def test_list_valued_keys_take_the_most_likely_supported_value():
+    """bSizes with bSizeRelProbs as in the stock selfplay8mainb18.cfg: the board the reference draws most often, not the first listed."""
+    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 7,9,11,13,15,17,19\nbSizeRelProbs = 1,4,2,10,3,4,35\ndataBoardLen = 19\n", is_text=True))
+    assert data["board_size"] == 19 and any("most likely" in s_ for s_ in report["fixed"])
+    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9,13\nbSizeRelProbs = 1,1\n", is_text=True))
+    assert data["board_size"] == 9           # equal weights: the first listed
+    with pytest.raises(ValueError, match="entries"):
+        C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9,13\nbSizeRelProbs = 1\n", is_text=True))
+    # komiAuto asks for a search-adjusted komi that is not built: reported, and refused under -strict
+    _, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("komiAuto = true\n", is_text=True))
+    assert data["komi"] == 7.5 and any(s_.startswith("komiAuto") for s_ in report["not_built"])
+    _, _, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("komiAuto = false\nkomiMean = 6.5\n", is_text=True))
+    assert not any(s_.startswith("komiAuto") for s_ in report["not_built"])
 
 
 def test_neutral_values_and_unsupported_rules():
@@ -90,7 +106,7 @@ def test_command_fails_loudly_without_a_gpu(tmp_path, stock_cfg):
     models = tmp_path / "models"; models.mkdir()
     modelgen.write_model(str(models / "tiny.bin"), "tiny_reg", seed=3)
     with pytest.raises(Exception, match="no CUDA device|CUDA"):
-        C.main(["-models-dir", str(models), "-output-dir", str(tmp_path / "out"), "-config", stock_cfg, "-max-games-total", "1", "-override-config", "bSizes=9,dataBoardLen=9"])
+        C.main(["-models-dir", str(models), "-output-dir", str(tmp_path / "out"), "-config", stock_cfg, "-max-games-total", "1", "-override-config", "bSizes=9,bSizeRelProbs=1,dataBoardLen=9"])
 
 
 @pytest.mark.gpu
@@ -102,7 +118,7 @@ def test_command_writes_training_files(tmp_path, stock_cfg):
     modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
     out = tmp_path / "out"
     rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", stock_cfg, "-max-games-total", "3", "-games-per-gpu", "4",
-                 "-override-config", "bSizes=9,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=0,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
+                 "-override-config", "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=0,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
     assert rc == 0
     tdata = out / "tinynet" / "tdata"
     files = sorted(os.listdir(tdata))
