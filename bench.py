@@ -416,7 +416,8 @@ def main():
         mid = {"b18c384nbt": 192, "b28c512nbt": 256}.get(args.model, 192)
         ms_conv = (np.zeros(1, np.float32))
         import ctypes as C
-        rc = lib.kgb_bench_conv(3, 3, mid, mid, n, 19, 19, 0 if args.fp32 else 1, 5, 50, ms_conv.ctypes.data_as(C.POINTER(C.c_float)))
+        # epilogue kind 1 = the first conv of a residual unit (BN + mish + mask -> fp16); 4 rotating buffer sets (4 x 79 MB in + out > L2)
+        rc = lib.kgb_bench_conv_ex(3, 3, mid, mid, n, 19, 19, 0 if args.fp32 else 1, 1, 4, 5, 48, ms_conv.ctypes.data_as(C.POINTER(C.c_float)))
         if rc != 0:
             raise RuntimeError(lib.kgb_last_error().decode())
         conv_flop = 2.0 * 9 * mid * mid * 361 * n  # algorithmic: direct convolution over the 361 real board points
@@ -458,9 +459,9 @@ def main():
                        "weight_broadcast_ms": bcast_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
             "gpu_launches": sp.launches_per_step * K,
-            "roofline": {"bound": "tensor", "kernel": f"kgb_conv_tc_kernel 3x3 {mid}->{mid}, batch {n}", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": f"{'kgb_conv_tc_kernel (3-term split)' if args.fp32 else 'kgb_conv_tc3_kernel'} 3x3 {mid}->{mid}, batch {n}, 4 rotating buffer sets", "achieved": achieved,
                          "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"],
-                         "traffic": 43.1e6 if args.model == "b18c384nbt" and n == 256 else None,   # dram read 40.46 MB + write 2.62 MB per launch (profiles/r01_conv3x3_192_ncu_raw.csv)
+                         "traffic": 42.4e6 if args.model == "b18c384nbt" and n == 256 and not args.fp32 else None,   # dram read 40.45 MB + write 1.93 MB per launch (profiles/r02_conv_ncu_raw.md)
                          "peak_source": peaks["source"] + " (burst cuBLAS bf16, kernel timed alone)",
                          "ms_per_launch": float(ms_conv[0]),
                          "whole_forward_tflops": whole, "whole_forward_frac_of_sustained": whole / peaks["tflops_sustained"]},

@@ -132,6 +132,7 @@ struct ConvWeights {
   int ky = 0, kx = 0, cin_p = 0, cout_p = 0, n_tile = 0, num_n_tiles = 0;
   CUtensorMap tmapB;       // box {64, n_tile}
   CUtensorMap tmapBhalf;   // box {64, n_tile/2}: each CTA of a pair loads half of the weight tile
+  bool hasIdentity = false;  // cout_p extra K columns holding the identity: the residual can enter through the tensor pipe (ConvParams::res_via_mma)
 };
 
 struct kgb_handle {
@@ -145,6 +146,7 @@ struct kgb_handle {
   bool nhwc = true;
   bool streamTrunkFp32 = true, streamInnerFp32 = false;
   bool useSimt = false, useGraph = true, usePair = false, usePairTma = true;
+  int resViaMma = 1;       // 0: residuals are added in the epilogue; 1: 1x1 convs take them through the tensor pipe; 2: every conv does
   std::vector<void*> allocs;
   // inputs / outputs (device, fixed addresses so graphs can be replayed)
   float *dSpatial = nullptr, *dGlobal = nullptr, *dOptimism = nullptr;
@@ -224,7 +226,7 @@ struct Builder {
   }
 
   // Pack one or more convs (concatenated along cout) as fp16 [tap][cout_p][cin_p (* 2)]
-  ConvWeights packConv(const std::vector<const ConvDesc*>& convs) {
+  ConvWeights packConv(const std::vector<const ConvDesc*>& convs, bool withResidual = false) {
     const ConvDesc& c0 = *convs[0];
     ConvWeights cw;
     cw.ky = c0.ky; cw.kx = c0.kx;
@@ -240,8 +242,13 @@ struct Builder {
     cw.num_n_tiles = nt;
     cw.n_tile = cw.cout_p / nt;
     int taps = cw.ky * cw.kx;
-    int ldw = cw.cin_p * actMul;
+    // residual through the tensor pipe (kgb_conv.cuh res_via_mma): identity columns behind the real ones
+    cw.hasIdentity = withResidual && !h.split && !h.useSimt && h.usePairTma && (h.resViaMma == 2 || (h.resViaMma == 1 && taps == 1)) &&
+                     cw.n_tile % 64 == 0;
+    int ldw = cw.cin_p * actMul + (cw.hasIdentity ? cw.cout_p : 0);
     std::vector<__half> host((size_t)taps * cw.cout_p * ldw, __float2half(0.0f));
+    if(cw.hasIdentity)
+      for(int co = 0; co < cout; co++) host[(size_t)co * ldw + cw.cin_p + co] = __float2half(1.0f);
     int coBase = 0;
     for(auto c : convs) {
       for(int t = 0; t < taps; t++)
@@ -293,6 +300,7 @@ struct Builder {
       p.num_n_tiles = cw.num_n_tiles;
       p.split = hp->split;
       p.residual = residual; p.residual_fp32 = residualFp32 ? 1 : 0;
+      p.res_via_mma = 0;
       p.ncbias = ncbias;
       p.raw_out = rawOut; p.raw_fp32 = rawFp32 ? 1 : 0;
       p.act_out = actOut;
@@ -304,9 +312,16 @@ struct Builder {
       else {
         CUtensorMap tmA = makeTmap2D(A, (uint64_t)p.M, (uint64_t)cw.cin_p * actMulL, (uint32_t)convTCABoxRows(cw.ky, cw.kx, p.Wp));
         cudaError_t e = cudaErrorNotSupported;
+        if(hp->usePairTma && cw.hasIdentity && residual != nullptr && !residualFp32) {
+          ConvParams q = p;
+          q.residual = nullptr; q.res_via_mma = 1;
+          if(convTC3Supports(q)) p = q;
+        }
         if(hp->usePairTma && convTC3Supports(p)) {
-          // epilogue tiles travel by TMA: residual in, raw / activation out (kgb_conv_tc3.cu)
-          const CUtensorMap tmRes = residual ? makeTmapTile(residual, (uint64_t)p.M, (uint64_t)cw.cout_p, 2, 32) : tmA;
+          // epilogue tiles travel by TMA: residual in, raw / activation out (kgb_conv_tc3.cu); with res_via_mma the residual stream
+          // is a second A operand (box of 128 rows) instead
+          const CUtensorMap tmRes = p.res_via_mma ? makeTmap2D(residual, (uint64_t)p.M, (uint64_t)cw.cout_p, 128)
+                                                   : (residual ? makeTmapTile(residual, (uint64_t)p.M, (uint64_t)cw.cout_p, 2, 32) : tmA);
           const CUtensorMap tmRaw = rawOut ? makeTmapTile(rawOut, (uint64_t)p.M, (uint64_t)cw.cout_p, rawFp32 ? 4 : 2, 32) : tmA;
           const CUtensorMap tmAct = actOut ? makeTmapTile(actOut, (uint64_t)p.M, (uint64_t)cw.cout_p, 2, 32) : tmA;
           e = launchConvTC3(tmA, cw.tmapBhalf, tmRes, tmRaw, tmAct, p, hp->numSMs, s);
@@ -330,14 +345,14 @@ struct Builder {
       void* rawOut = (last && !keepFinalRaw) ? nullptr : lv.S;
       if(b.kind == BLOCK_ORDINARY) {
         ConvWeights w1 = packConv({&b.conv1});
-        ConvWeights w2 = packConv({&b.conv2});
+        ConvWeights w2 = packConv({&b.conv2}, true);
         BNDev mid = uploadBN(b.midBN, b.midAct, w1.cout_p);
         emitConv(w1, lv.A, nullptr, false, nullptr, nullptr, false, lv.T, mid);
         emitConv(w2, lv.T, lv.S, lv.fp32, nullptr, rawOut, lv.fp32, lv.A, nextBN);
       }
       else if(b.kind == BLOCK_GPOOL) {
         ConvWeights w1 = packConv({&b.conv1, &b.gpoolConv});
-        ConvWeights w2 = packConv({&b.conv2});
+        ConvWeights w2 = packConv({&b.conv2}, true);
         const int regC = b.conv1.cout, gC = b.gpoolConv.cout;
         BNDev none;
         emitConv(w1, lv.A, nullptr, false, nullptr, lv.G, true, nullptr, none);
@@ -359,7 +374,7 @@ struct Builder {
       }
       else {
         ConvWeights wpre = packConv({&b.conv1});
-        ConvWeights wpost = packConv({&b.conv2});
+        ConvWeights wpost = packConv({&b.conv2}, true);
         Level inner = makeLevel(b.conv1.cout, h.streamInnerFp32, b.blocks);
         BNDev innerPre = uploadBN(b.blocks[0].preBN, b.blocks[0].preAct, inner.cp);
         emitConv(wpre, lv.A, nullptr, false, nullptr, inner.S, inner.fp32, inner.A, innerPre);
@@ -626,6 +641,8 @@ KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_
     h.useSimt = env && std::string(env) == "simt";
     h.usePair = env && std::string(env) == "tc2";        // "tc2" = round-1 CTA-pair kernel (staged epilogue)
     h.usePairTma = !(env && (std::string(env) == "tc" || std::string(env) == "tc2"));   // default: kgb_conv_tc3.cu (CTA pair + TMA epilogue)
+    env = getenv("KGB_RES_MMA");
+    if(env) h.resViaMma = atoi(env);
     env = getenv("KGB_NO_GRAPH");
     h.useGraph = !(env && std::string(env) == "1");
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
@@ -764,6 +781,8 @@ struct SingleConv {
     h.useSimt = env && std::string(env) == "simt";
     h.usePair = env && std::string(env) == "tc2";
     h.usePairTma = !(env && (std::string(env) == "tc" || std::string(env) == "tc2"));
+    env = getenv("KGB_RES_MMA");
+    if(env) h.resViaMma = atoi(env);
     h.streamTrunkFp32 = h.streamInnerFp32 = h.split != 0;
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
     CK(convTCInit());
@@ -773,7 +792,7 @@ struct SingleConv {
     ConvDesc cd;
     cd.ky = ky; cd.kx = kx; cd.cin = in_c; cd.cout = out_c;
     cd.w.assign(weights, weights + (size_t)ky * kx * in_c * out_c);
-    cw = b.packConv({&cd});
+    cw = b.packConv({&cd}, actEpilogue == 2);
     M = (size_t)n * h.L.P;
     A = h.dalloc<__half>(M * cw.cin_p * b.actMul);
     h.dMask = h.dalloc<float>(M + 128);

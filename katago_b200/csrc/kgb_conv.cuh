@@ -42,6 +42,11 @@ struct ConvParams {
   const float* bn_bias;   // [cout_p]
   int act;                // kgb::Activation
   const float* mask;      // [M] 1.0 on-board, 0.0 pad/off-board
+  // kgb_conv_tc3.cu only: the residual enters through the tensor pipe instead of the epilogue.  The weights carry cout_p extra
+  // K columns holding the identity ([tap 0][co][cin_p + co] = 1), and after the cin_p / 64 real k-blocks the kernel runs n_tile / 64
+  // more whose A operand is the residual stream itself (fp16, exact in the fp32 accumulator): the residual rides the deep,
+  // prefetched A ring and the epilogue has no load left.  `residual` must then be null.
+  int res_via_mma;
 };
 
 // fp32 activation functions shared by every epilogue (reference: eigenbackend.cpp:780-809, cudahelpers.cu mish/silu).

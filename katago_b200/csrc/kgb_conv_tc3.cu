@@ -27,6 +27,7 @@
 // mode and fp32 residual streams stay on kgb_conv_tc.cu.
 #include "kgb_conv_tc_common.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace kgb {
@@ -123,7 +124,11 @@ struct Conv3Cfg {
   int nbuf;                  // 1 or 2 slot pairs per epilogue warp
   int num_pair_m_tiles;
   int dbg;
+  long long* trace;          // bring-up: clock64 stamps of CTA 0 (KGB_T3_TRACE=1), else null
 };
+// trace layout (CTA 0 only): [0..63] epilogue warp 0: 8 stamps per item for the first 8 items; [64..127] the same for the last
+// epilogue warp; [128..143] MMA issuer: tile start / tile committed for the first 8 tiles; [144..159] producer: first / last copy of a tile
+#define T3_STAMP(idx) do { if(cfg.trace != nullptr && blockIdx.x == 0 && lane == 0) cfg.trace[(idx)] = clock64(); } while(0)
 
 // dynamic smem per CTA: [slack to 1024][a_stages x A halo tile][stages x half weight tile][epi warps x nbuf x 2 x 4 KB][Bars3, 1 KB][bn scale | bias]
 static inline int t3ABufBytes(int a_box_rows) { return (a_box_rows * BLOCK_K * 2 + 1023) / 1024 * 1024; }
@@ -159,12 +164,13 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   const int num_tiles = cfg.num_pair_m_tiles * p.num_n_tiles;
   const int taps = p.ky * p.kx;
   const int kblocks = p.cin_p / BLOCK_K;
+  const int kblocks_all = kblocks + (p.res_via_mma ? p.n_tile / BLOCK_K : 0);   // + identity k-blocks fed by the residual stream
   const int dbg = cfg.dbg;
 
   if(warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
-    if(p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapRes) : "memory");
+    if(p.residual != nullptr || p.res_via_mma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapRes) : "memory");
     if(p.raw_out != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapRaw) : "memory");
     if(p.act_out != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapAct) : "memory");
   }
@@ -208,28 +214,37 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     for(int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = (tile / p.num_n_tiles) * 256 + (int)rank * BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * p.n_tile + (int)rank * n_half;
-      for(int kb = 0; kb < kblocks; kb++) {
+      const int tseq = (tile - cluster_id) / num_clusters;
+      const int ntile0 = (tile % p.num_n_tiles) * p.n_tile;
+      for(int kb = 0; kb < kblocks_all; kb++) {
+        const bool isres = kb >= kblocks;              // identity k-block: A = 128 rows of the residual stream, one tap, no halo
         mbar_wait(smem_u32(&bars->a_empty[abuf]), aphase ^ 1);
+        if(kb == 0 && tseq < 8) T3_STAMP(144 + 2 * tseq);
         if(t3_elect_one()) {
           const uint32_t afull_leader = t3_mapa(smem_u32(&bars->a_full[abuf]), 0);
-          if(leader) mbar_arrive_expect_tx(smem_u32(&bars->a_full[abuf]), (uint32_t)(2 * a_tx_bytes));
+          const uint32_t bytes = isres ? (uint32_t)(BLOCK_M * BLOCK_K * 2) : (uint32_t)a_tx_bytes;
+          if(leader) mbar_arrive_expect_tx(smem_u32(&bars->a_full[abuf]), 2 * bytes);
           else t3_arrive_cluster_relaxed(afull_leader);
-          t3_tma_load_2sm(smem_base + abuf * a_buf_bytes, &tmapA, afull_leader, kb * BLOCK_K, m0 - halo);
+          if(isres) t3_tma_load_2sm(smem_base + abuf * a_buf_bytes, &tmapRes, afull_leader, ntile0 + (kb - kblocks) * BLOCK_K, m0);
+          else t3_tma_load_2sm(smem_base + abuf * a_buf_bytes, &tmapA, afull_leader, kb * BLOCK_K, m0 - halo);
         }
         __syncwarp();
         if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
-        for(int t = 0; t < taps; t++) {
+        const int ntaps = isres ? 1 : taps;
+        for(int t = 0; t < ntaps; t++) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
           if(t3_elect_one()) {
             const uint32_t full_leader = t3_mapa(smem_u32(&bars->full[stage]), 0);
             if(leader) mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), (uint32_t)(2 * b_tile_bytes));
             else t3_arrive_cluster_relaxed(full_leader);
-            t3_tma_load_2sm(smem_b + stage * b_tile_bytes, &tmapB, full_leader, kb * BLOCK_K, t * p.cout_p + n0);
+            t3_tma_load_2sm(smem_b + stage * b_tile_bytes, &tmapB, full_leader,
+                            isres ? p.cin_p + ntile0 + (kb - kblocks) * BLOCK_K : kb * BLOCK_K, t * p.cout_p + n0);
           }
           __syncwarp();
           if(++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
+      if(tseq < 8) T3_STAMP(145 + 2 * tseq);
     }
   }
   else if(warp == 1) {
@@ -241,19 +256,23 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       int abuf = 0; uint32_t aphase = 0;
       int acc_stage = 0; uint32_t acc_phase = 0;
       for(int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int tseq = (tile - cluster_id) / num_clusters;
         mbar_wait(smem_u32(&bars->tmem_empty[acc_stage]), acc_phase ^ 1);
         tcgen05_fence_after();
+        if(tseq < 8) T3_STAMP(128 + 2 * tseq);
         const uint32_t tmem_d = tmem_base + acc_stage * p.n_tile;
-        for(int kb = 0; kb < kblocks; kb++) {
+        for(int kb = 0; kb < kblocks_all; kb++) {
+          const bool isres = kb >= kblocks;
+          const int ntaps = isres ? 1 : taps;
           mbar_wait(smem_u32(&bars->a_full[abuf]), aphase);
           const uint32_t a_base = smem_base + abuf * a_buf_bytes;
           int dy = -ry, dx = -rx;
-          for(int t = 0; t < taps; t++) {
+          for(int t = 0; t < ntaps; t++) {
             mbar_wait(smem_u32(&bars->full[stage]), phase);
             tcgen05_fence_after();
             if(t3_elect_one()) {
-              // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row)
-              const uint64_t da = make_smem_desc(a_base + (uint32_t)(halo + dy * p.Wp + dx) * 128u);
+              // tap (dy,dx) = the 128 rows starting `halo + dy*Wp + dx` rows into the halo tile (128 B per row); identity k-blocks: row 0
+              const uint64_t da = make_smem_desc(a_base + (isres ? 0u : (uint32_t)(halo + dy * p.Wp + dx) * 128u));
               const uint64_t db = make_smem_desc(smem_b + stage * b_tile_bytes);
               if(!(dbg & 2)) {
                 // +32 bytes along K inside the 128B swizzle row = +2 descriptor units
@@ -263,8 +282,8 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                 t3_umma_2sm(tmem_d, da + 6, db + 6, idesc, 1u);
               }
               t3_commit_mc(smem_u32(&bars->empty[stage]));
-              if(t == taps - 1) t3_commit_mc(smem_u32(&bars->a_empty[abuf]));
-              if(t == taps - 1 && kb == kblocks - 1) t3_commit_mc(smem_u32(&bars->tmem_full[acc_stage]));
+              if(t == ntaps - 1) t3_commit_mc(smem_u32(&bars->a_empty[abuf]));
+              if(t == ntaps - 1 && kb == kblocks_all - 1) t3_commit_mc(smem_u32(&bars->tmem_full[acc_stage]));
             }
             __syncwarp();
             if(++stage == stages) { stage = 0; phase ^= 1; }
@@ -272,6 +291,7 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           }
           if(++abuf == a_stages) { abuf = 0; aphase ^= 1; }
         }
+        if(tseq < 8) T3_STAMP(129 + 2 * tseq);
         if(++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -319,6 +339,11 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const int acc_stage = tile_seq & 1;
       const uint32_t acc_phase = (uint32_t)(tile_seq >> 1) & 1u;
 
+      // this item's row mask: requested here, long before the math needs it (a global load: ~1-2k cycles under load)
+      const float maskv = (lane < rowsValid && !(dbg & 4)) ? __ldg(p.mask + rowBase + lane) : 0.0f;
+      const int tbase = (ew == 0 ? 0 : 64) + it * 8;
+      const bool tr = (ew == 0 || ew == epi_warps - 1) && it < 8;
+      if(tr) T3_STAMP(tbase + 0);
       if(nbuf == 1) {
         if(lane == 0) {
           t3_store_wait_read();                             // the previous item's stores have read this slot pair
@@ -326,17 +351,19 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
         __syncwarp();
       }
+      if(tr) T3_STAMP(tbase + 1);
       if(chunk == part) {                                   // first chunk of this tile for this warp
         mbar_wait(smem_u32(&bars->tmem_full[acc_stage]), acc_phase);
         tcgen05_fence_after();
       }
+      if(tr) T3_STAMP(tbase + 2);
       if(!(dbg & 4)) {
         const int row = rowBase + lane;
         const bool valid = lane < rowsValid;
-        const float maskv = valid ? __ldg(p.mask + row) : 0.0f;
-        const int img = valid ? row / p.P : 0;
+        const int img = (valid && p.ncbias != nullptr) ? row / p.P : 0;
         if(has_res && rowsValid > 0) mbar_wait(smem_u32(&bars->r_full[ew][b]), (uint32_t)((nbuf == 2 ? (it >> 1) : it) & 1));
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc_stage * p.n_tile + chunk * 64);
+        if(tr) T3_STAMP(tbase + 3);
         uint32_t accA[16], accB[16];
         tmem_ld16(taddr, accA);
 #pragma unroll
@@ -442,12 +469,14 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             t3_sts128(slotAct + a1, o1);
           }
         }
+        if(tr) T3_STAMP(tbase + 4);
         if(nbuf == 2 && lane == 0) {
           t3_store_wait_read();                             // stores of item it-1 (the other slot pair) have read their tiles
           if(has_res && ntile < num_tiles) issue_residual(ntile, nchunk, b ^ 1);
         }
         t3_fence_async_smem();                              // this lane's generic-proxy tile writes -> visible to the TMA engine
         __syncwarp();
+        if(tr) T3_STAMP(tbase + 5);
         if(lane == 0 && rowsValid > 0 && !(dbg & 8)) {
           if(has_raw) {
             if(raw32) {
@@ -459,6 +488,7 @@ kgb_conv_tc3_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           if(has_act) t3_tma_store(&tmapAct, slotAct, col0, rowBase);
         }
         if(lane == 0) t3_store_commit();
+        if(tr) T3_STAMP(tbase + 6);
       }
       else if(last_of_tile) {                               // timing experiment: no epilogue work, barrier protocol only
         tcgen05_fence_before();
@@ -491,6 +521,7 @@ bool convTC3Supports(const ConvParams& p) {
   const int halo = (p.ky / 2) * p.Wp + (p.kx / 2);
   if(p.split || (p.n_tile % 64) != 0 || p.n_tile > 256 || BLOCK_M + 2 * halo > 256) return false;
   if(p.residual != nullptr && p.residual_fp32) return false;
+  if(p.res_via_mma && p.residual != nullptr) return false;
   if(p.raw_out != nullptr && p.raw_fp32 && (p.residual != nullptr || p.act_out != nullptr)) return false;
   return true;
 }
@@ -527,17 +558,23 @@ static int t3Plan(const ConvParams& p, int E, int nbuf, int wantStages, int want
 // 128B swizzle (unused ones may be any valid map).  cudaErrorNotSupported = shape not handled here, use launchConvTC.
 cudaError_t launchConvTC3(const CUtensorMap& tmapA, const CUtensorMap& tmapBhalf, const CUtensorMap& tmapRes, const CUtensorMap& tmapRaw,
                           const CUtensorMap& tmapAct, const ConvParams& p, int numSMs, cudaStream_t stream) {
-  static int envE = -1, envNbuf = 0, envStages = 0, envAStages = 0, dbg = 0;
+  static int envE = -1, envNbuf = 0, envStages = 0, envAStages = 0, dbg = 0, envTrace = 0, traceLeft = 0;
+  static long long* dTrace = nullptr;
   if(envE < 0) {   // bring-up / tuning knobs
     const char* e = getenv("KGB_CONV_DBG"); dbg = e ? atoi(e) : 0;
     e = getenv("KGB_T3_NBUF"); envNbuf = e ? atoi(e) : 0;
     e = getenv("KGB_T3_STAGES"); envStages = e ? atoi(e) : 0;
     e = getenv("KGB_T3_ASTAGES"); envAStages = e ? atoi(e) : 0;
     e = getenv("KGB_T3_E"); envE = e ? atoi(e) : 0;
+    e = getenv("KGB_T3_TRACE"); envTrace = e ? atoi(e) : 0;   // N: print the clock64 trace of CTA 0 for N launches (synchronises!)
+    traceLeft = envTrace;
+    if(envTrace > 0) { cudaMalloc(&dTrace, 160 * sizeof(long long)); }
   }
   if(!convTC3Supports(p)) return cudaErrorNotSupported;
   const int chunks = p.n_tile / 64;
-  int E = envE > 0 ? envE : (chunks >= 2 ? 2 : 1);
+  // epilogue warps per TMEM lane quadrant: one 64-column chunk per warp and tile when the tile has three (measured: 192-column
+  // tiles 3 > 2 > 1; 256-column tiles 2 > 3, 4 - profiles/r02_conv_tc3_bringup.md)
+  int E = envE > 0 ? envE : (chunks == 3 ? 3 : (chunks >= 2 ? 2 : 1));
   if(E > chunks) E = chunks;
   if(E > 4) E = 4;
   // one slot pair per epilogue warp by default: shared memory goes to the operand rings (3x3: 9 weight stages with E = 2)
@@ -550,12 +587,31 @@ cudaError_t launchConvTC3(const CUtensorMap& tmapA, const CUtensorMap& tmapBhalf
   }
   if(smem == 0) return cudaErrorNotSupported;
   cfg.epi_parts = E; cfg.nbuf = nbuf; cfg.dbg = dbg;
+  cfg.trace = traceLeft > 0 ? dTrace : nullptr;
+  if(cfg.trace) cudaMemsetAsync(dTrace, 0, 160 * sizeof(long long), stream);
   cfg.num_pair_m_tiles = (p.M + 255) / 256;
   const int tiles = cfg.num_pair_m_tiles * p.num_n_tiles;
   int clusters = numSMs / 2;
   if(tiles < clusters) clusters = tiles;
   const int threads = 128 + 128 * E;
   kgb_conv_tc3_kernel<<<2 * clusters, threads, smem, stream>>>(tmapA, tmapBhalf, tmapRes, tmapRaw, tmapAct, p, cfg);
+  if(cfg.trace) {
+    traceLeft--;
+    long long h[160];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dTrace, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = h[144];
+    fprintf(stderr, "T3 trace %dx%d %d->%d E=%d nbuf=%d stages=%d/%d (cycles since the producer's first copy)\n", p.ky, p.kx, p.cin_p, p.cout_p, E, nbuf, cfg.a_stages, cfg.stages);
+    for(int w = 0; w < 2; w++)
+      for(int i = 0; i < 8; i++) {
+        const long long* r = h + w * 64 + i * 8;
+        if(r[0] == 0) continue;
+        fprintf(stderr, "  epi warp %s item %d: start %6lld | store-read wait %5lld | tmem_full wait %6lld | res wait %5lld | math %5lld | fence %5lld | issue %4lld\n",
+                w ? "last" : "0", i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5]);
+      }
+    for(int i = 0; i < 8; i++)
+      if(h[128 + 2 * i]) fprintf(stderr, "  tile %d: producer %6lld..%6lld   mma start %6lld committed %6lld\n", i, h[144 + 2 * i] - t0, h[145 + 2 * i] - t0, h[128 + 2 * i] - t0, h[129 + 2 * i] - t0);
+  }
   return cudaGetLastError();
 }
 

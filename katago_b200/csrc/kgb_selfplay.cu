@@ -1062,7 +1062,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
 // With ladderNodesPerWave > 0 every warp stops after that many search moves: a game whose searches are unfinished delivers no
 // leaf this wave (leafValid = 0: the evaluator's row for it is ignored, nothing is backed up) and carries on in the next one,
 // so one deep ladder costs its own game a few waves instead of making all games wait.  Features are identical either way.
-__global__ void __launch_bounds__(SP_LADDER_WARPS * 32) spSelectKernel(const SPDev d) {
+__global__ void __launch_bounds__(SP_LADDER_WARPS * 32, 2) spSelectKernel(const SPDev d) {
   const int g = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
