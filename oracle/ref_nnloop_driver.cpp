@@ -99,11 +99,16 @@ int main(int argc, char** argv) {
   for(int i = 0; i < iters; i++) NeuralNet::getOutput(handle, inputBuffers, batch, bufs.data(), outs);
   auto t1 = chrono::steady_clock::now();
   const double ms = chrono::duration<double, milli>(t1 - t0).count() / iters;
+  // A backend may return its raw outputs scaled down: the reference's CUDA backend rewrites the net with
+  // ModelDesc::applyScale8ToReduceActivations (cudabackend.cpp:3168) and NNEvaluator multiplies every raw output by
+  // postProcessParams.outputScaleMultiplier (= 8 there, 1 for backends that leave the net alone; nneval.cpp:962-1131,1245).
+  // Checksum and dump are in the evaluator's units, i.e. after that multiplication.
+  const float outScale = desc.postProcessParams.outputScaleMultiplier;
   double chk = 0.0;
-  for(int b = 0; b < batch; b++) chk += outs[b]->policyProbs[b % (L * L)] + outs[b]->whiteWinProb;
+  for(int b = 0; b < batch; b++) chk += (double)outScale * (outs[b]->policyProbs[b % (L * L)] + outs[b]->whiteWinProb);
   cout << "{\"model\": \"" << desc.name << "\", \"batch\": " << batch << ", \"iters\": " << iters << ", \"fp16\": " << (fp16 ? 1 : 0)
        << ", \"nhwc\": " << (nhwc ? 1 : 0) << ", \"ms_per_getOutput\": " << ms << ", \"evals_per_s\": " << (batch / ms * 1e3)
-       << ", \"checksum\": " << chk << "}" << endl;
+       << ", \"output_scale_multiplier\": " << outScale << ", \"checksum\": " << chk << "}" << endl;
   if(dumpFile != "") {
     FILE* f = fopen(dumpFile.c_str(), "wb");
     const int rows = batch < 8 ? batch : 8;
@@ -114,12 +119,16 @@ int main(int argc, char** argv) {
       fwrite(&sym, 4, 1, f);
       fwrite(bufs[b]->rowSpatialBuf.data(), 4, (size_t)numSpatial * L * L, f);
       fwrite(bufs[b]->rowGlobalBuf.data(), 4, numGlobal, f);
-      fwrite(outs[b]->policyProbs, 4, L * L + 1, f);
+      vector<float> pol(outs[b]->policyProbs, outs[b]->policyProbs + L * L + 1);
+      for(float& x : pol) x *= outScale;
+      fwrite(pol.data(), 4, L * L + 1, f);
       float v[9] = {outs[b]->whiteWinProb, outs[b]->whiteLossProb, outs[b]->whiteNoResultProb, outs[b]->whiteScoreMean, outs[b]->whiteScoreMeanSq,
                     outs[b]->whiteLead, outs[b]->varTimeLeft, outs[b]->shorttermWinlossError, outs[b]->shorttermScoreError};
+      for(float& x : v) x *= outScale;
       fwrite(v, 4, 9, f);
       vector<float> own(L * L, 0.0f);
       if(outs[b]->whiteOwnerMap) std::copy(outs[b]->whiteOwnerMap, outs[b]->whiteOwnerMap + L * L, own.begin());
+      for(float& x : own) x *= outScale;
       fwrite(own.data(), 4, L * L, f);
     }
     fclose(f);
