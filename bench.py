@@ -131,145 +131,61 @@ def model_file(name: str, rank: int, world: int, device):
     return path, bcast_ms
 
 
-def cpu_port_evals_per_sec(model_name: str, batch: int, reps: int):
-    """The reference's CPU NN path (Eigen backend restated in numpy, oracle/kg_nn_oracle.py) on this box's host cores."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import kg_nn_oracle as orc
-    from katago_b200 import modelgen
-    m = orc.parse_model(modelgen.model_bytes(model_name, seed=0), True)
-    sp, gl = modelgen.synthetic_inputs(batch, 19, 19, seed=3)
-    orc.get_output(m, sp[:1], gl[:1])  # warm BLAS
-    t0 = time.time()
-    for _ in range(reps):
-        orc.get_output(m, sp, gl)
-    dt = time.time() - t0
-    return batch * reps / dt, dt
+CPU_SELFPLAY = os.path.join(ROOT, "oracle", "_ref", "kgref_cpu_selfplay")
 
 
-_CPU_WORKER = r"""
-import os, sys, time
-sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
-import kg_nn_oracle as orc
-from katago_b200 import modelgen
-name, batch = sys.argv[2], int(sys.argv[3])
-m = orc.parse_model(modelgen.model_bytes(name, seed=0), True)
-sp, gl = modelgen.synthetic_inputs(batch, 19, 19, seed=3 + int(sys.argv[4]))
-orc.get_output(m, sp[:1], gl[:1])
-print("READY", flush=True)
-for line in sys.stdin:
-    f = line.split()
-    if not f or f[0] != "go":
-        break
-    seconds = float(f[1])
-    t0 = time.time(); n = 0
-    while time.time() - t0 < seconds:
-        orc.get_output(m, sp, gl); n += batch
-    print("DONE %d %.6f" % (n, time.time() - t0), flush=True)
-"""
-
-
-class CpuArm:
-    """The CPU arm with every host core busy the way the reference keeps them busy: its CPU backend runs one single-threaded Eigen
-    evaluation per NN server thread, many threads side by side (nneval.cpp server threads; numNNServerThreadsPerModel).  Here: one
-    process per core, one BLAS thread each, all evaluating batches of the numpy restatement (oracle/kg_nn_oracle.py) for a bounded
-    time per step; throughput of a step = all evaluations / wall time from the common start to the last finisher."""
-
-    def __init__(self, model_name: str, batch: int = 4, workers: int = 0):
-        import subprocess
-        try:
-            cores = len(os.sched_getaffinity(0))
-        except AttributeError:
-            cores = os.cpu_count() or 1
-        if not workers:
-            # bound the memory: ~0.25 GB resident per worker (model + activations); use at most a quarter of what is available, at most 256 workers
-            avail_gb = 16.0
-            try:
-                for ln in open("/proc/meminfo"):
-                    if ln.startswith("MemAvailable:"):
-                        avail_gb = float(ln.split()[1]) / 1048576.0
-                lim = open("/sys/fs/cgroup/memory.max").read().strip()
-                if lim.isdigit():
-                    avail_gb = min(avail_gb, int(lim) / 2 ** 30)
-            except OSError:
-                pass
-            workers = max(1, min(cores, 256, int(avail_gb * 0.25 / 0.3)))
-        self.workers, self.batch = workers, batch
-        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
-        self.procs = [subprocess.Popen([sys.executable, "-c", _CPU_WORKER, ROOT, model_name, str(batch), str(i)], env=env, stdin=subprocess.PIPE,
-                                       stdout=subprocess.PIPE, text=True) for i in range(workers)]
-        try:
-            for pr in self.procs:
-                if pr.stdout.readline().strip() != "READY":
-                    raise RuntimeError("cpu worker failed to start")
-        except Exception:
-            self.close()
-            raise
-
-    def step(self, seconds: float):
-        """All workers evaluate for `seconds`.  Returns (evaluations, wall seconds)."""
-        t0 = time.time()
-        for pr in self.procs:
-            pr.stdin.write("go %.3f\n" % seconds); pr.stdin.flush()
-        total = 0
-        for pr in self.procs:
-            f = pr.stdout.readline().split()
-            if len(f) != 3 or f[0] != "DONE":
-                raise RuntimeError("cpu worker failed")
-            total += int(f[1])
-        return total, time.time() - t0
-
-    def close(self):
-        for pr in self.procs:
-            try:
-                pr.stdin.close()
-            except Exception:
-                pass
-        for pr in self.procs:
-            if pr.poll() is None:
-                try:
-                    pr.wait(timeout=5)
-                except Exception:
-                    pr.kill()
-
-
-def cpu_port_parallel(model_name: str, seconds: float = 12.0, batch: int = 4, workers: int = 0):
-    """One bounded sample of the CPU arm.  Returns (evals per second, wall seconds, workers, evaluations)."""
-    arm = CpuArm(model_name, batch, workers)
+def host_cores() -> int:
     try:
-        total, wall = arm.step(seconds)
-    finally:
-        arm.close()
-    return total / wall, wall, arm.workers, total
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_selfplay(model_name: str, seconds: float, warmup_seconds: float, visits: int = 600, cores: int = 0):
+    """The CPU arm: the reference's own self-play hot path on the host cores - the unmodified reference Search / Board / NNEvaluator
+    (linked from oracle/_ref/libkgref.a) around the restated CPU NN backend (oracle/cpubackend.cpp: the Eigen backend's algorithm in
+    C++ - Winograd F(4x4,3x3) + GEMM, AVX-512; Eigen3 itself is not in this image), oracle/ref_cpu_selfplay.cpp.  One NN server thread
+    per host core (single-threaded handles, batch <= 2, as the reference's CPU build runs), two game threads per core, 600-visit
+    searches on cleared trees, games starting from random legal play-outs like the GPU arm's.  Returns the driver's JSON."""
+    from katago_b200 import modelgen
+    if not os.path.exists(CPU_SELFPLAY):
+        raise RuntimeError("oracle/_ref/kgref_cpu_selfplay is not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference exists)")
+    cores = cores or host_cores()
+    path = os.path.join(tempfile.mkdtemp(prefix="kgb_cpuarm_"), f"{model_name}.bin")
+    modelgen.write_model(path, model_name, seed=0)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([CPU_SELFPLAY, path, f"{seconds:.1f}", str(2 * cores), str(cores), str(visits), "19", f"{warmup_seconds:.1f}", "150"],
+                         capture_output=True, text=True, env=env, timeout=seconds + warmup_seconds + 900)
+    if out.returncode != 0:
+        raise RuntimeError("kgref_cpu_selfplay failed: " + out.stderr[-500:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_baseline_object(r, model_name):
+    return {"value": r["visits_per_s"], "unit": UNIT, "cores": r["nn_server_threads"], "kind": "restated Eigen path (C++), full selfplay",
+            "sample": (f"{r['visits']} visits ({r['nn_rows']} evaluated rows) of {model_name} 19x19 self-play in {r['seconds']:.1f} s: reference Search + Board + NNEvaluator "
+                       f"with oracle/cpubackend.cpp, {r['nn_server_threads']} single-threaded NN server threads + {r['game_threads']} game threads, maxVisits {r['max_visits']}")}
 
 
 def run_reference(args, rank: int):
-    """--impl reference: CPU arm.  The reference's Eigen build cannot be compiled here (Eigen3 is neither vendored nor
-    installed), so this times the oracle port of its NN path with every host core busy (CpuArm); rank 0 only.
-    A step = one bounded sample of the workload (a few seconds of evaluations on all cores)."""
+    """--impl reference: the CPU arm (cpu_selfplay above), rank 0 only.  One process plays for warmup + steps x (seconds per step); a step
+    is a bounded sample of the workload."""
     if rank != 0:
         return
     steps = max(1, args.steps)
-    per_step = max(1.0, min(10.0, 100.0 / steps))
-    arm = CpuArm(args.model)
-    try:
-        for _ in range(max(0, args.warmup)):
-            arm.step(1.0)
-        total, wall = 0, 0.0
-        for _ in range(steps):
-            n, w = arm.step(per_step)
-            total += n; wall += w
-    finally:
-        arm.close()
-    workers = arm.workers
-    value = total / wall
+    per_step = max(1.0, min(6.0, 90.0 / steps))
+    r = cpu_selfplay(args.model, steps * per_step, max(2.0, args.warmup * 1.0), args.visits)
+    value = r["visits_per_s"]
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"19x19 {args.model}, one NN evaluation per visit on the host CPU: {workers} single-threaded evaluator processes side by side, "
-                               f"batch 4 each, {per_step:.1f} s per step (bounded sample)",
-                   "stages": ["nn_eval"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
-                         "sample": f"{total} evaluations of {args.model} 19x19 via oracle/kg_nn_oracle.py (numpy, one BLAS thread per process, {workers} processes) in {wall:.1f} s"},
+        "ms_per_step": r["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"19x19 {args.model} self-play on the host CPU, maxVisits {args.visits}: the reference's Search / Board / NNEvaluator with the restated "
+                               f"Eigen-path NN backend (Winograd F(4x4,3x3) + AVX-512 GEMM), {r['nn_server_threads']} NN server threads + {r['game_threads']} game threads, "
+                               f"{per_step:.1f} s per step (bounded sample)",
+                   "stages": ["board", "puct_select", "featurize", "nn_eval", "postprocess", "backup"],
+                   "search_params": "the search block of selfplay8mainb18.cfg incl. rootEndingBonusPoints and rootPruneUselessMoves (oracle/ref_cpu_selfplay.cpp)",
+                   "driver_output": r},
+        "cpu_baseline": cpu_baseline_object(r, args.model),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -423,13 +339,9 @@ def main():
         conv_flop = 2.0 * 9 * mid * mid * 361 * n  # algorithmic: direct convolution over the 361 real board points
         achieved = conv_flop / (float(ms_conv[0]) * 1e-3) / 1e12
         whole = flop_per_eval * n * K / (ms_nn * 1e-3) / 1e12
-        cpu_v, cpu_dt, cpu_workers, cpu_n = None, 0.0, 0, 0
+        cpu_obj = {"value": None, "unit": UNIT, "cores": 0, "kind": "restated Eigen path (C++), full selfplay", "sample": "measured at N=1 only"}
         if world == 1:      # the CPU baseline is a property of the box: measured at N=1 only
-            try:     # every host core busy, like the reference's evaluator server threads; falls back to one process if workers cannot start
-                cpu_v, cpu_dt, cpu_workers, cpu_n = cpu_port_parallel(args.model, seconds=12.0)
-            except Exception:
-                cpu_v, cpu_dt = cpu_port_evals_per_sec(args.model, 4, 2)
-                cpu_workers, cpu_n = 1, 8
+            cpu_obj = cpu_baseline_object(cpu_selfplay(args.model, 15.0, 5.0, args.visits), args.model)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -477,9 +389,7 @@ def main():
                 "bytes_per_playout": bytes_sel + bytes_bak, "traffic": None,
                 "note": "latency-bound at 256 warps per launch (1.7 warps per SM); see DESIGN.md §6"})(
                     tree_depth * 362 * 20 + 362 * 20 + (22 * 361 + 19) * 4 * 2 + 128, 362 * 8 + tree_depth * 48 + 64),
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cpu_workers, "kind": "port",
-                             "sample": (f"{cpu_n} evaluations of {args.model} 19x19 via the numpy restatement of the Eigen path ({cpu_dt:.1f} s, {cpu_workers} single-threaded processes side by side)"
-                                        if world == 1 else "measured at N=1 only")},
+            "cpu_baseline": cpu_obj,
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
