@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--model", default="b18c384nbt")
     ap.add_argument("--games", type=int, default=256, help="concurrent games (= NN batch) per GPU")
     ap.add_argument("--fp32", action="store_true", help="use the fp32-equivalent (3-term split) mode instead of fp16 operands")
+    ap.add_argument("--max-playouts-per-wave", type=int, default=0,
+                    help="playouts a game may finish inside one select launch without needing the evaluator (cache hits, graph-search catch-ups) before it "
+                         "skips the wave; bounds the slowest block of the launch, results are identical for every value")
     ap.add_argument("--ladder-nodes-per-wave", type=int, default=256,
                     help="ladder-reader moves per warp per wave before a game's unfinished searches are carried into the next wave "
                          "(0 = finish inside the wave); results are identical, only the schedule changes")
@@ -135,10 +138,25 @@ CPU_SELFPLAY = os.path.join(ROOT, "oracle", "_ref", "kgref_cpu_selfplay")
 
 
 def host_cores() -> int:
+    """CPUs this process may actually use: the affinity mask, cut down to the cgroup's CPU quota when there is one (a container can
+    see 128 CPUs in its mask and still be throttled to a few CPUs' worth of time - running 128 busy threads there measures the
+    throttle, not the cores)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.999)))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, (q + per - 1) // per))
+        except (OSError, ValueError):
+            pass
+    return n
 
 
 def cpu_selfplay(model_name: str, seconds: float, warmup_seconds: float, visits: int = 600, cores: int = 0):
@@ -285,7 +303,7 @@ def main():
                   nn_cache_size_power_of_two=args.nn_cache_pow2, root_num_symmetries_to_sample=4, ko_rule=0, full_history_rules=True,
                   use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
                   chosen_move_temperature=0.15, chosen_move_temperature_early=0.75, chosen_move_subtract=0.0, chosen_move_prune=1.0,
-                  seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave,
+                  seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave, max_playouts_per_wave=args.max_playouts_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
     # steady state before timing: games at different stages, trees hundreds of nodes deep, cache filled by the previous moves
@@ -361,6 +379,7 @@ def main():
                              f"e2e rotates {NBUF} distinct feature batches ({NBUF * n * 22 * 361 * 4 / 1e6:.0f} MB)",
                        "avg_leaf_depth": (after["sum_leaf_depth"] - before["sum_leaf_depth"]) / max(1, after["total_visits"] - before["total_visits"]),
                        "nn_only_ms_per_step": ms_nn / K,
+                       "max_playouts_per_wave": args.max_playouts_per_wave,
                        "ladder": {"nodes_per_warp_per_wave": args.ladder_nodes_per_wave,
                                   "searches": after["ladder_searches"] - before["ladder_searches"],
                                   "search_moves": after["ladder_nodes"] - before["ladder_nodes"],

@@ -148,7 +148,11 @@ typedef struct kgb_selfplay_config {
   int32_t ladder_nodes_per_wave;     /* > 0: each of a game's 8 ladder-reader warps plays at most this many search moves per wave;
                                         a game whose searches are unfinished skips the wave (no visit) and resumes in the next.
                                         0 = run every search to the end inside the wave.  Features are identical either way. */
-  int32_t reserved0;
+  int32_t max_playouts_per_wave;     /* a playout that ends without needing the evaluator (evaluation-cache hit, graph-search edge catch-up,
+                                        cycle) is backed up inside the select kernel and the game starts its next playout in the same wave,
+                                        up to this many (0 = 16).  The launch lasts as long as its slowest game, so a small bound (2-3) caps
+                                        the tail: a game that uses it up delivers no leaf this wave and carries on in the next.  The sequence
+                                        of playouts of a game, hence every result, is the same for every bound. */
   /* Score utility (Search::getScoreUtility, searchhelpers.cpp:272-279; selfplay8mainb18.cfg: 0.05, 0.30, 0.25, 0.50).
    * Both factors 0 = win/loss utility only. */
   double static_score_utility_factor;
@@ -295,6 +299,11 @@ KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, in
 /* Timing hook for bench.py's tree/board roofline entry: runs `iters` waves of ONLY the select(+board+featurize) and backup
  * kernels (evaluator outputs of the last wave are reused) and returns their CUDA-event averages per launch. */
 KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* ms_select, float* ms_backup);
+/* Profiling aid: SM-clock spans of every game's block in the LAST select launch, cycles[game][8] = whole block, root move + tree reset
+ * (only in waves where the game's visit budget was spent), warp 0 (descent + leaf features), ladder searches, then warp 0 split into
+ * descent, liberties + legality, area (Benson), feature-row writes.  The launch lasts as
+ * long as its slowest block; this shows which games those are and what they were doing.  clear != 0 zeroes the buffer afterwards. */
+KGB_API int kgb_selfplay_debug_cycles(kgb_selfplay* sp, int64_t* cycles, int clear);
 /* Kernel launches per playout wave (evaluator launches + 2). */
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp);
 

@@ -1238,6 +1238,15 @@ KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* m
   });
 }
 
+KGB_API int kgb_selfplay_debug_cycles(kgb_selfplay* sp, int64_t* cycles, int clear) {
+  return guarded([&] {
+    if(!sp || !cycles) throw std::invalid_argument("kgb_selfplay_debug_cycles: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadDebugCycles(sp->impl, (long long*)cycles, clear != 0);
+  });
+}
+
 KGB_API int kgb_selfplay_launches_per_step(const kgb_selfplay* sp) { return sp ? sp->h->launchesPerForward + 2 : 0; }
 
 KGB_API int kgb_zobrist_tables(int x_size, int y_size, uint64_t* board_hash, uint64_t* size_hash) {

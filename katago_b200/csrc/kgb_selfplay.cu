@@ -127,7 +127,9 @@ struct SPDev {
   int* ladPending;                  // [game] 1 = the leaf's ladder searches were cut off by ladderNodesPerWave; resume next wave
   int* leafValid;                   // [game] 1 = this wave produced a finished leaf (features complete) for the evaluator / backup
   int ladderNodesPerWave;           // per warp; 0 = unlimited
+  int maxPlayoutsPerWave;           // playouts a game may finish inside one select launch without needing the evaluator
   unsigned long long* stalledWaves; // game-waves that did not produce a leaf
+  long long* dbgCycles;             // [game][8] clock64 spans of the last select launch: whole block, root move + tree reset, warp 0 (descent + leaf features), ladder searches, descent, liberties + legality, area (Benson), feature-row writes
   uint32_t* ladderScratch;          // [game][SP_LADDER_WARPS][ladderScratchWordsPerWarp()]
   uint32_t* prevLad;                // [2][game][32]: laddered stones (plane 14) of those two boards = planes 15/16 at the root
   uint32_t* nodeLad;                // [game][maxNodes][32]: laddered stones of the node's own board, kept for its descendants
@@ -617,10 +619,10 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   int mv = d.moveNum[g] + 1;
   bool over = finished || mv >= d.maxMoves;
   if(lane == 0) {
-    d.lastMove[g * 4 + 0] = best;
-    d.lastMove[g * 4 + 1] = over ? (1 | (noResult ? 2 : 0) | (finished ? 0 : 4)) : 0;
-    d.lastMove[g * 4 + 2] = mv - 1;
-    d.lastMove[g * 4 + 3] = (int)d.gameCounter[g];
+    d.lastMove[g * 8 + 0] = best;
+    d.lastMove[g * 8 + 1] = over ? (1 | (noResult ? 2 : 0) | (finished ? 0 : 4)) : 0;
+    d.lastMove[g * 8 + 2] = mv - 1;
+    d.lastMove[g * 8 + 3] = (int)d.gameCounter[g];
   }
   if(over) {
     uint32_t areaB, areaW;
@@ -692,16 +694,18 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   HistState hst;
   hst.passes = 0; hst.finished = false; hst.noResult = false; hst.everOcc = 0; hst.banned = 0;
   bool bannedValid = false;     // hst.banned belongs to the current position
+  const long long tW0 = clock64();
   // Under graph search a playout can end without reaching a new leaf (edge catch-up, cycle): it is backed up at once and the
   // next playout starts, so that the wave still delivers a leaf for the evaluator.
-  for(int attempt = 0; attempt < SP_MAX_PLAYOUTS_PER_WAVE && !gotLeaf; attempt++) {
+  for(int attempt = 0; attempt < d.maxPlayoutsPerWave && !gotLeaf; attempt++) {
   if(d.nodeVisits[gb] >= d.maxVisits) {
     // hold mode (tests, game recording): keep the finished tree until the host has read it and released the game
     const bool released = d.releaseFlag[g] != 0;
     __syncwarp();
     if(d.holdAtMaxVisits && !released) break;
+    const long long tRA = clock64();
     rootAdvance(d, g, lane);
-    if(lane == 0) d.releaseFlag[g] = 0;
+    if(lane == 0) { d.releaseFlag[g] = 0; d.dbgCycles[g * 8 + 1] = clock64() - tRA; }
   }
   boardInit(bd, d.X, d.Y);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
@@ -949,6 +953,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     return;
   }
   terminal = d.nodeTerminal[gb + node] != 0;
+  const long long tLeaf = clock64();
 
   // ---- leaf: liberties, legality, features
   uint32_t lib1, lib2, lib3;
@@ -969,6 +974,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     float whiteScore = d.komi - (float)diff;
     if(lane == 0) d.leafTerminalScore[g] = whiteScore;
   }
+  const long long tLegal = clock64();
   // NN input row (NHWC [pos][22]) - zero fill, then the ones
   float* row = d.nnSpatial + (size_t)g * d.XY * 22;
   for(int i = lane; i < d.XY * 22; i += 32) row[i] = 0.0f;
@@ -978,7 +984,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   const uint32_t own = black ? bd.b : bd.w, opp = black ? bd.w : bd.b;
   // planes 18/19: pass-alive + territory area for area scoring without tax (nninputs.cpp:2375-2382, 2425-2436)
   uint32_t areaB, areaW;
+  const long long tZero = clock64();
   boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);
+  const long long tArea = clock64();
   const uint32_t areaOwn = black ? areaB : areaW, areaOpp = black ? areaW : areaB;
   // planes 14-17: ladders on the current board and on the boards 1 and 2 moves ago (nninputs.cpp:2547-2583).  15/16 come
   // from the ancestors' cached results; 14/17 are searched by the whole block after this function returns.
@@ -1053,6 +1061,8 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
     d.nnSymmetry[g] = sym;
     d.nnOptimism[g] = 0.0f;
+    d.dbgCycles[g * 8 + 4] = tLeaf - tW0; d.dbgCycles[g * 8 + 5] = tLegal - tLeaf; d.dbgCycles[g * 8 + 6] = tArea - tZero;
+    d.dbgCycles[g * 8 + 7] = (clock64() - tArea) + (tZero - tLegal);
   }
 }
 
@@ -1069,6 +1079,8 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32, 2) spSelectKernel(const 
   __shared__ uint32_t shB[32], shW[32], shCand[32];
   __shared__ int shKo, shDoLadders, shFresh, shUnfinished;
   __shared__ double shSum[64];
+  const long long tStart = clock64();
+  long long tWarp0 = tStart;
   if(warp == 0) {
     if(d.ladPending[g]) {
       shB[lane] = d.leafB[g * 32 + lane]; shW[lane] = d.leafW[g * 32 + lane]; shCand[lane] = d.leafCand[g * 32 + lane];
@@ -1079,9 +1091,13 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32, 2) spSelectKernel(const 
       if(lane == 0) shFresh = 1;
     }
     if(lane == 0) shUnfinished = 0;
+    tWarp0 = clock64();
   }
   __syncthreads();
-  if(!shDoLadders) return;
+  if(!shDoLadders) {
+    if(warp == 0 && lane == 0) { d.dbgCycles[g * 8 + 0] = clock64() - tStart; d.dbgCycles[g * 8 + 2] = tWarp0 - tStart; d.dbgCycles[g * 8 + 3] = 0; }
+    return;
+  }
   const LadderScratch sc0 = ladderScratchAt(d.ladderScratch + (size_t)g * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
   {
     WarpBoard bd;
@@ -1097,6 +1113,8 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32, 2) spSelectKernel(const 
   }
   __syncthreads();
   if(warp == 0) {
+    const long long tLad = clock64();
+    if(lane == 0) { d.dbgCycles[g * 8 + 0] = tLad - tStart; d.dbgCycles[g * 8 + 2] = tWarp0 - tStart; d.dbgCycles[g * 8 + 3] = tLad - tWarp0; }
     if(shUnfinished != 0) {
       if(lane == 0) { d.ladPending[g] = 1; d.leafValid[g] = 0; atomicAdd(d.stalledWaves, 1ULL); }
       return;
@@ -1928,6 +1946,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafB = sp->alloc<uint32_t>(G * 32); d.leafW = sp->alloc<uint32_t>(G * 32); d.leafCand = sp->alloc<uint32_t>(G * 32);
   d.leafKo = sp->alloc<int>(G); d.ladPending = sp->alloc<int>(G); d.leafValid = sp->alloc<int>(G);
   d.ladderNodesPerWave = c.ladder_nodes_per_wave > 0 ? c.ladder_nodes_per_wave : 0;
+  d.maxPlayoutsPerWave = c.max_playouts_per_wave > 0 ? c.max_playouts_per_wave : SP_MAX_PLAYOUTS_PER_WAVE;
   { std::vector<int> kos2(2 * G, -1); SPCK(cudaMemcpy(d.prevKo, kos2.data(), 2 * G * sizeof(int), cudaMemcpyHostToDevice)); }
   d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); 
   d.nodeWeightSum = sp->alloc<double>(G * N); d.nodeWeightSqSum = sp->alloc<double>(G * N); d.nodeUtilAvg = sp->alloc<double>(G * N);
@@ -2021,6 +2040,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafLegal = sp->alloc<uint32_t>(G * 32);
   unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
+  d.dbgCycles = sp->alloc<long long>(G * 8);
   d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8; d.instantPlayouts = stats + 9; d.cacheHits = stats + 10; d.cacheStores = stats + 11;
   d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
   d.nnPolicy = nn.policy; d.nnValue = nn.value; d.nnScore = nn.score;
@@ -2095,6 +2115,11 @@ void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s) {
   spRandomOpeningsKernel<<<(sp->d.numGames * 32 + 127) / 128, 128, 0, s>>>(sp->d, maxLen);
   SPCK(cudaGetLastError());
   SPCK(cudaStreamSynchronize(s));
+}
+
+void selfplayReadDebugCycles(SelfplayImpl* sp, long long* out /*[numGames][8]*/, bool clear) {
+  SPCK(cudaMemcpy(out, sp->d.dbgCycles, (size_t)sp->d.numGames * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if(clear) SPCK(cudaMemset(sp->d.dbgCycles, 0, (size_t)sp->d.numGames * 8 * sizeof(long long)));
 }
 
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out) {

@@ -43,7 +43,7 @@ class SelfplayConfig(C.Structure):
         ("cpuct_exploration", C.c_double), ("cpuct_exploration_log", C.c_double), ("cpuct_exploration_base", C.c_double),
         ("fpu_reduction_max", C.c_double), ("root_fpu_reduction_max", C.c_double), ("win_loss_utility_factor", C.c_double),
         ("no_result_utility_for_white", C.c_double), ("seed", C.c_uint64), ("debug_fake_nn", C.c_int32), ("disable_ladder_features", C.c_int32),
-        ("ladder_nodes_per_wave", C.c_int32), ("reserved0", C.c_int32),
+        ("ladder_nodes_per_wave", C.c_int32), ("max_playouts_per_wave", C.c_int32),
         ("static_score_utility_factor", C.c_double), ("dynamic_score_utility_factor", C.c_double),
         ("dynamic_score_center_zero_weight", C.c_double), ("dynamic_score_center_scale", C.c_double),
         ("draw_equivalent_wins_for_white", C.c_double),
@@ -80,7 +80,7 @@ ABI_SYMBOLS = [
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv", "kgb_bench_conv_ex", "kgb_test_conv_epilogue",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
     "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
-    "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
+    "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
 ]
 
 _lib = None
@@ -142,6 +142,7 @@ def load_library():
     lib.kgb_selfplay_get_last_move.argtypes = [P, I, P, P, P, P]
     lib.kgb_selfplay_set_search_rand.argtypes = [P, C.c_char_p]
     lib.kgb_selfplay_time_tree_kernels.argtypes = [P, I, F, F]
+    lib.kgb_selfplay_debug_cycles.argtypes = [P, P, I]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
     lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
@@ -438,7 +439,7 @@ class SelfPlay:
                  multi_stone_suicide_legal: bool = True, early_temperature_moves: int = 30, cpuct_exploration: float = 1.0,
                  cpuct_exploration_log: float = 0.45, cpuct_exploration_base: float = 500.0, fpu_reduction_max: float = 0.2,
                  root_fpu_reduction_max: float = 0.1, win_loss_utility_factor: float = 1.0, no_result_utility_for_white: float = 0.0,
-                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False, ladder_nodes_per_wave: int = 0,
+                 seed: int = 0, debug_fake_nn: bool = False, disable_ladder_features: bool = False, ladder_nodes_per_wave: int = 0, max_playouts_per_wave: int = 0,
                  static_score_utility_factor: float = 0.0, dynamic_score_utility_factor: float = 0.0,
                  dynamic_score_center_zero_weight: float = 0.0, dynamic_score_center_scale: float = 1.0,
                  draw_equivalent_wins_for_white: float = 0.5, value_weight_exponent: float = 0.0,
@@ -461,7 +462,7 @@ class SelfPlay:
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
                                   cpuct_exploration, cpuct_exploration_log, cpuct_exploration_base, fpu_reduction_max,
                                   root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features),
-                                  int(ladder_nodes_per_wave), 0, static_score_utility_factor, dynamic_score_utility_factor,
+                                  int(ladder_nodes_per_wave), int(max_playouts_per_wave), static_score_utility_factor, dynamic_score_utility_factor,
                                   dynamic_score_center_zero_weight, dynamic_score_center_scale, draw_equivalent_wins_for_white,
                                   value_weight_exponent, int(fpu_parent_weight_by_visited_policy), 0, fpu_parent_weight_by_visited_policy_pow,
                                   fpu_parent_weight, fpu_loss_prop, root_fpu_loss_prop, cpuct_utility_stdev_prior,
@@ -567,6 +568,13 @@ class SelfPlay:
         visits = np.zeros(n, np.int32); policy = np.zeros(n, np.float32); util = np.zeros(n, np.float64)
         _check(load_library().kgb_selfplay_get_root_children(self._p, g, visits.ctypes.data, policy.ctypes.data, util.ctypes.data))
         return visits, policy, util
+
+    def debug_cycles(self, clear: bool = True):
+        """int64 [games, 8]: SM-clock spans of every game's block in the last select launch (whole, root move + reset, warp 0, ladders,
+        descent, liberties + legality, area, feature-row writes)."""
+        out = np.zeros((self.num_games, 8), np.int64)
+        _check(load_library().kgb_selfplay_debug_cycles(self._p, out.ctypes.data, int(clear)))
+        return out
 
     def time_tree_kernels(self, iters: int = 20):
         """(ms_select, ms_backup): CUDA-event averages of the two tree kernels alone (evaluator skipped)."""
