@@ -210,6 +210,38 @@ def run_reference(args, rank: int):
     print(json.dumps(out), flush=True)
 
 
+class CountingSlots:
+    """The SelfPlay readers the recorder calls, counting the bytes each call brings back from (or sends to) the device."""
+
+    def __init__(self, sp):
+        self._sp, self.d2h, self.h2d = sp, 0, 0
+
+    def __getattr__(self, name):
+        attr = getattr(self._sp, name)
+        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row"):
+            def counted(*a, **k):
+                out = attr(*a, **k)
+                self.d2h += _nbytes(out)
+                return out
+            return counted
+        if name == "release":
+            def released(mask=None):
+                self.h2d += 0 if mask is None else int(np.asarray(mask).nbytes)
+                return attr(mask)
+            return released
+        return attr
+
+
+def _nbytes(x):
+    if isinstance(x, np.ndarray):
+        return int(x.nbytes)
+    if isinstance(x, dict):
+        return sum(_nbytes(v) for v in x.values())
+    if isinstance(x, (tuple, list)):
+        return sum(_nbytes(v) for v in x)
+    return 8 if isinstance(x, (int, float, bool)) else 0
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -293,7 +325,7 @@ def main():
 
     W, K = max(3, args.warmup), max(1, args.steps)
     # device-resident self-play loop: selfplay8mainb18.cfg search parameters that the loop implements
-    sp = SelfPlay(handle, n, args.visits, komi=7.5, multi_stone_suicide_legal=True, early_temperature_moves=30,
+    sp_kwargs = dict(komi=7.5, multi_stone_suicide_legal=True, early_temperature_moves=30,
                   cpuct_exploration=1.05, cpuct_exploration_log=0.28, cpuct_exploration_base=500.0, fpu_reduction_max=0.2,
                   root_fpu_reduction_max=0.0, value_weight_exponent=0.5, fpu_parent_weight_by_visited_policy=True,
                   fpu_parent_weight_by_visited_policy_pow=2.0, root_desired_per_child_visits_coeff=2.0,
@@ -306,6 +338,7 @@ def main():
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave, max_playouts_per_wave=args.max_playouts_per_wave,
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
+    sp = SelfPlay(handle, n, args.visits, **sp_kwargs)
     # steady state before timing: games at different stages, trees hundreds of nodes deep, cache filled by the previous moves
     sp.random_openings(args.opening_max)
     sp.run(W + args.settle_waves)
@@ -334,14 +367,103 @@ def main():
     tree_depth = (s1["sum_leaf_depth"] - s0["sum_leaf_depth"]) / max(1, s1["total_visits"] - s0["total_visits"])
     for i in range(W):
         step_host(i)
-    ms_e2e = timed(step_host, K)
+    ms_e2e_nn = timed(step_host, K)
     assert np.isfinite(hpol).all() and np.isfinite(hval).all()
+    launches_per_step = sp.launches_per_step
+    sp.free()
+
+    # ---- e2e: the repo's own data-producing path (what `python -m katago_b200.selfplay_cli -per-game-release` runs): the device loop in
+    # hold mode + katago_b200.game_recorder.GameRecorder (every game is read back and released as soon as ITS search is finished) +
+    # katago_b200.npz_writer.TrainingDataWriter writing .npz training files.  Host readbacks, target computation and file writing are
+    # inside the timed region; a step is still one playout wave.
+    from katago_b200.game_recorder import GameRecorder
+    from katago_b200.npz_writer import RowRand, TrainingDataWriter
+    sp_kwargs["debug_hold_at_max_visits"] = True
+    sp2 = SelfPlay(handle, n, args.visits, **sp_kwargs)
+    sp2.random_openings(args.opening_max)
+    slots = CountingSlots(sp2)
+    out_dir = tempfile.mkdtemp(prefix=f"kgb_bench_tdata_rank{rank}_")
+    writer = TrainingDataWriter(out_dir, 20000, 1.0, 19, f"bench:rank{rank}")
+    rec = GameRecorder(slots, writer, 7.5, draw_equivalent_wins_for_white=0.5, policy_surprise_data_weight=0.5, value_surprise_data_weight=0.1,
+                       weight_rand=RowRand(f"bench:rank{rank}:weights"))
+    PUMP = 8
+    settle = 0
+    while settle < W + args.settle_waves:        # games at all stages of their searches, recorder warm
+        rec.pump(PUMP)
+        settle += PUMP
+    handle.sync()
+    rb0, moves0, games0, rows0 = sp2.stats(), rec.moves_recorded, rec.games_written, writer.row_count
+    slots.d2h = slots.h2d = 0
+    if rank == 0:
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    pumps = max(1, (K + PUMP - 1) // PUMP)
+    for _ in range(pumps):
+        rec.pump(PUMP)
+    e1.record(stream)
+    handle.sync()
+    barrier()
+    clocks_e2e = sampler2.stop() if rank == 0 else None
+    ms_rec = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_rec, op=dist.ReduceOp.MAX)
+    ms_rec = float(ms_rec.item())
+    rb1 = sp2.stats()
+    rec_visits = torch.tensor([float(rb1["total_visits"] - rb0["total_visits"])], device=device)
+    if world > 1:
+        dist.all_reduce(rec_visits, op=dist.ReduceOp.SUM)
+    rec_visits = float(rec_visits.item())
+    rec_waves = pumps * PUMP + 0          # + the extra waves in which released games moved (counted from the stats below)
+    rec_moves, rec_games, rec_rows = rec.moves_recorded - moves0, rec.games_written - games0, writer.row_count - rows0
+    writer.flush_if_nonempty()
+    rec_files = len([f for f in os.listdir(out_dir) if f.endswith(".npz")])
+    sp2.free()
+
+    # ---- the precision-compliant mode (north_star: logits within 1e-3 of fp32): the same loop on an fp32-equivalent handle (3-term split
+    # fp16 on the tensor pipe, fp32 streams); N = 1 only, shorter settling (the wave time is dominated by the evaluator)
+    value_fp32 = None
+    if world == 1 and not args.fp32:
+        ctx32 = NeuralNet.createComputeContext([local_rank], 19, 19, False, model)
+        h32 = NeuralNet.createComputeHandle(ctx32, model, n, False, True, local_rank)
+        kw32 = dict(sp_kwargs); kw32["debug_hold_at_max_visits"] = False
+        sp32 = SelfPlay(h32, n, args.visits, **kw32)
+        sp32.random_openings(args.opening_max)
+        sp32.run(W + 60); h32.sync()
+        s32a = sp32.stats()
+        stream32 = torch.cuda.ExternalStream(h32.stream, device=device)
+        a32, b32 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a32.record(stream32); sp32.run(K); b32.record(stream32); h32.sync()
+        s32b = sp32.stats()
+        value_fp32 = {"value": (s32b["total_visits"] - s32a["total_visits"]) / (a32.elapsed_time(b32) * 1e-3), "unit": UNIT, "ms_per_step": a32.elapsed_time(b32) / K,
+                      "dtype": "f32-split3 (fp16 tensor pipe, fp32 accumulate and streams)", "tolerance": "logits within 1e-3 of the fp32 oracle (tests/test_gpu_nn_parity.py FP32_TOL)"}
+        sp32.free(); h32.free(); ctx32.free()
+
+    # ---- same-box GPU competitor: the reference's own CUDA/cuDNN backend against libkgb200 through the same caller
+    # (oracle/ref_nnloop_driver.cpp: NeuralNet::getOutput in a loop, host buffers, batch = games); N = 1, rank 0, if the binaries travelled
+    competitor = None
+    if world == 1 and rank == 0:
+        competitor = {}
+        for key, exe in (("reference_cuda_cudnn_backend", "kgref_nnloop_cuda"), ("libkgb200", "kgref_nnloop_b200")):
+            binp = os.path.join(ROOT, "oracle", "_ref", exe)
+            if not os.path.exists(binp):
+                competitor[key] = "binary not built"
+                continue
+            try:
+                r = subprocess.run([binp, path, str(n), "12", "0" if args.fp32 else "1", "1", "1"], capture_output=True, text=True, timeout=240)
+                competitor[key] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else "failed: " + (r.stderr or r.stdout)[-200:]
+            except Exception as e:       # the competitor is context, not the measurement
+                competitor[key] = "failed: " + str(e)[:200]
+        competitor["what"] = "ms per NeuralNet::getOutput at batch = games, host buffers in and out, identical caller code linked against either backend"
 
     total_games = n * world
     value = visits_done / (ms_dev * 1e-3)      # playouts actually completed by all ranks / max-over-ranks device time
-    e2e_value = total_games * K / (ms_e2e * 1e-3)
-    h2d = n * (22 * 361 + 19 + 2) * 4
-    d2h = n * (362 + 3 + 6 + 361) * 4
+    e2e_nn_value = total_games * K / (ms_e2e_nn * 1e-3)
+    h2d_nn = n * (22 * 361 + 19 + 2) * 4
+    d2h_nn = n * (362 + 3 + 6 + 361) * 4
+    e2e_value = rec_visits / (ms_rec * 1e-3)
 
     if rank == 0:
         peaks = load_peaks()
@@ -387,9 +509,17 @@ def main():
                                   "playouts_without_evaluation(graph search catch-up)": instant,
                                   "playouts_served_by_nn_cache": cache_hits, "nn_cache_entries": (1 << args.nn_cache_pow2) if args.nn_cache_pow2 > 0 else 0,
                                   "game_waves": n * K},
-                       "weight_broadcast_ms": bcast_ms},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
-            "gpu_launches": sp.launches_per_step * K,
+                       "weight_broadcast_ms": bcast_ms, "gpu_competitor": competitor},
+            "value_fp32_equivalent": value_fp32,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": slots.h2d / (pumps * PUMP), "d2h_bytes_per_step": slots.d2h / (pumps * PUMP),
+                    "ms_per_step": ms_rec / (pumps * PUMP),
+                    "what": "device loop in hold mode + GameRecorder.pump (per-game release every 8 waves: root readback, training targets) + TrainingDataWriter "
+                            ".npz files; host work inside the timed region; a step = one playout wave (the wave in which released games move is extra)",
+                    "moves_recorded": rec_moves, "games_finished": rec_games, "rows_written": rec_rows, "npz_files": rec_files, "frac_of_value": e2e_value / value,
+                    "clocks": clocks_e2e},
+            "e2e_nn_boundary": {"value": e2e_nn_value, "unit": UNIT, "h2d_bytes_per_step": h2d_nn, "d2h_bytes_per_step": d2h_nn, "ms_per_step": ms_e2e_nn / K,
+                                "what": "NeuralNet::getOutput -> kgb_forward with host buffers (boundary 1): one evaluated row = one visit of a host-side search"},
+            "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "tensor", "kernel": f"{'kgb_conv_tc_kernel (3-term split)' if args.fp32 else 'kgb_conv_tc3_kernel'} 3x3 {mid}->{mid}, batch {n}, 4 rotating buffer sets", "achieved": achieved,
                          "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"],
                          "traffic": 42.4e6 if args.model == "b18c384nbt" and n == 256 and not args.fp32 else None,   # dram read 40.45 MB + write 1.93 MB per launch (profiles/r02_conv_ncu_raw.md)

@@ -285,6 +285,10 @@ KGB_API int kgb_selfplay_get_last_move(kgb_selfplay* sp, int game, int32_t* info
 /* The NN input row (NHWC [X*Y][22] + 19 globals) the last wave wrote for game g - what NNInputs::fillRowV7 would produce
  * for that leaf (planes listed in DESIGN.md §8; used by the feature parity tests). */
 KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, float* global);
+/* The NN input row (NNInputs::fillRowV7, NHWC, no symmetry) of the game's CURRENT ROOT, kept on the device from the wave that evaluated
+ * the root until the next move: what TrainingWriteBuffers::addRow stores for the turn (dataio/trainingwrite.cpp:463-478).  Valid once the
+ * root has been evaluated by the net (always, when root_num_symmetries_to_sample >= 2 or the evaluation cache is off). */
+KGB_API int kgb_selfplay_get_root_row(kgb_selfplay* sp, int game, float* spatial, float* global);
 /* The moves from the root to the leaf the last wave selected for game g (x,y pairs, -1,-1 = pass; at most max_len pairs are
  * written, *len_out is the full length) and whether that wave delivered a finished leaf (see ladder_nodes_per_wave). */
 KGB_API int kgb_selfplay_get_leaf_path(kgb_selfplay* sp, int game, int32_t* moves_xy, int32_t max_len, int32_t* len_out, int32_t* valid_out);

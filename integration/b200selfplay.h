@@ -112,10 +112,15 @@ class GameSlots {
     check(kgb_selfplay_get_root_children(sp_, slot, visits.data(), policy.data(), util.data()));
     return policy;
   }
-  // the NN input row of the slot's last wave (NHWC [y*x][22] and 19 globals); right after a release + one wave it is the new root's
+  // the NN input row of the slot's last wave (NHWC [y*x][22] and 19 globals)
   void inputRow(int slot, std::vector<float>& spatial, std::vector<float>& global) const {
     spatial.resize((size_t)x_ * y_ * 22); global.resize(19);
     check(kgb_selfplay_get_nn_row(sp_, slot, spatial.data(), global.data()));
+  }
+  // the NN input row of the slot's current root, kept on the device since the wave that evaluated it
+  void rootInputRow(int slot, std::vector<float>& spatial, std::vector<float>& global) const {
+    spatial.resize((size_t)x_ * y_ * 22); global.resize(19);
+    check(kgb_selfplay_get_root_row(sp_, slot, spatial.data(), global.data()));
   }
   struct LastMove {
     Move move; bool gameOver = false, noResult = false, hitMoveLimit = false; int moveNumber = 0, gameIndex = 0;

@@ -1196,6 +1196,15 @@ KGB_API int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int game, float* spatial, 
   });
 }
 
+KGB_API int kgb_selfplay_get_root_row(kgb_selfplay* sp, int game, float* spatial, float* global) {
+  return guarded([&] {
+    if(!sp || !spatial || !global || game < 0 || game >= sp->n) throw std::invalid_argument("kgb_selfplay_get_root_row: bad argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadRootRow(sp->impl, game, spatial, global);
+  });
+}
+
 KGB_API int kgb_selfplay_get_leaf_path(kgb_selfplay* sp, int game, int32_t* moves_xy, int32_t max_len, int32_t* len_out, int32_t* valid_out) {
   return guarded([&] {
     if(!sp || !moves_xy || !len_out || !valid_out || max_len < 0) throw std::invalid_argument("kgb_selfplay_get_leaf_path: bad argument");

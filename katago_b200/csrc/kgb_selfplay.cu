@@ -129,6 +129,7 @@ struct SPDev {
   int ladderNodesPerWave;           // per warp; 0 = unlimited
   int maxPlayoutsPerWave;           // playouts a game may finish inside one select launch without needing the evaluator
   unsigned long long* stalledWaves; // game-waves that did not produce a leaf
+  float* rootRow;                   // [game][XY*22 + 19]: the NN input row (fillRowV7, no symmetry) of the game's current root, kept when the root is evaluated
   long long* dbgCycles;             // [game][8] clock64 spans of the last select launch: whole block, root move + tree reset, warp 0 (descent + leaf features), ladder searches, descent, liberties + legality, area (Benson), feature-row writes
   uint32_t* ladderScratch;          // [game][SP_LADDER_WARPS][ladderScratchWordsPerWarp()]
   uint32_t* prevLad;                // [2][game][32]: laddered stones (plane 14) of those two boards = planes 15/16 at the root
@@ -619,10 +620,10 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   int mv = d.moveNum[g] + 1;
   bool over = finished || mv >= d.maxMoves;
   if(lane == 0) {
-    d.lastMove[g * 8 + 0] = best;
-    d.lastMove[g * 8 + 1] = over ? (1 | (noResult ? 2 : 0) | (finished ? 0 : 4)) : 0;
-    d.lastMove[g * 8 + 2] = mv - 1;
-    d.lastMove[g * 8 + 3] = (int)d.gameCounter[g];
+    d.lastMove[g * 4 + 0] = best;
+    d.lastMove[g * 4 + 1] = over ? (1 | (noResult ? 2 : 0) | (finished ? 0 : 4)) : 0;
+    d.lastMove[g * 4 + 2] = mv - 1;
+    d.lastMove[g * 4 + 3] = (int)d.gameCounter[g];
   }
   if(over) {
     uint32_t areaB, areaW;
@@ -1475,6 +1476,16 @@ __global__ void spBackupKernel(const SPDev d) {
   const int node = d.leafNode[g];
   const bool terminal = d.leafTerminal[g] != 0;
   const bool leafBlack = d.leafBlackToMove[g] != 0;
+  if(node == 0 && d.nodeVisits[gb] == 0) {
+    // the leaf is the game's root: keep its input row for the recorder (TrainingWriteBuffers::addRow stores the root's fillRowV7 row,
+    // trainingwrite.cpp:463-478).  Every evaluation of an unvisited root carries the same un-symmetrised row; it stays valid until
+    // the next move replaces the root, whatever later waves write into the evaluator's input buffer.
+    const int n = d.XY * 22;
+    const float* src = d.nnSpatial + (size_t)g * n;
+    float* dst = d.rootRow + (size_t)g * (n + 19);
+    for(int i = lane; i < n; i += 32) dst[i] = src[i];
+    if(lane < 19) dst[n + lane] = d.nnGlobal[(size_t)g * 19 + lane];
+  }
   double u;
   if(d.leafTerminal[g] == 2) {
     // search.cpp:1204-1212: a game ended without result (long cycle under simple ko)
@@ -2041,6 +2052,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
   d.dbgCycles = sp->alloc<long long>(G * 8);
+  d.rootRow = sp->alloc<float>(G * ((size_t)X * Y * 22 + 19));
   d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8; d.instantPlayouts = stats + 9; d.cacheHits = stats + 10; d.cacheStores = stats + 11;
   d.nnSpatial = nn.spatial; d.nnGlobal = nn.global; d.nnOptimism = nn.optimism; d.nnSymmetry = nn.symmetry;
   d.nnPolicy = nn.policy; d.nnValue = nn.value; d.nnScore = nn.score;
@@ -2115,6 +2127,12 @@ void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s) {
   spRandomOpeningsKernel<<<(sp->d.numGames * 32 + 127) / 128, 128, 0, s>>>(sp->d, maxLen);
   SPCK(cudaGetLastError());
   SPCK(cudaStreamSynchronize(s));
+}
+
+void selfplayReadRootRow(SelfplayImpl* sp, int g, float* spatial, float* global) {
+  const size_t n = (size_t)sp->d.XY * 22;
+  SPCK(cudaMemcpy(spatial, sp->d.rootRow + (size_t)g * (n + 19), n * sizeof(float), cudaMemcpyDeviceToHost));
+  SPCK(cudaMemcpy(global, sp->d.rootRow + (size_t)g * (n + 19) + n, 19 * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 void selfplayReadDebugCycles(SelfplayImpl* sp, long long* out /*[numGames][8]*/, bool clear) {

@@ -26,6 +26,7 @@ void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cu
 void selfplaySetSearchRand(SelfplayImpl* sp, const char* seedString);
 void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);
+void selfplayReadRootRow(SelfplayImpl* sp, int g, float* spatial, float* global);
 void selfplayReadDebugCycles(SelfplayImpl* sp, long long* out, bool clear);
 void selfplayReadGame(SelfplayImpl* sp, int g, uint8_t* colors, int* info);
 void selfplayReadRootMoments(SelfplayImpl* sp, int g, double* childMoments, double* rootMoments);

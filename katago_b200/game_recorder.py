@@ -169,10 +169,10 @@ class _GameInProgress:
 class GameRecorder:
     """Records every game of a `SelfPlay` in hold mode and hands finished games to `writer.write_game`.
 
-    sp: katago_b200.nn_backend.SelfPlay created with debug_hold_at_max_visits=True (and ladder_nodes_per_wave=0, so that the wave
-    that evaluates a new root always carries its complete fillRowV7 row).  `step()` = one move of every game:
+    sp: katago_b200.nn_backend.SelfPlay created with debug_hold_at_max_visits=True.  `step()` = one move of every game:
       1. waves until every game is held at max_visits;
-      2. per game: root position, the root's input row (captured from the wave that evaluated the root), root / child statistics,
+      2. per game: root position, the root's input row (kept on the device since the wave that evaluated the root,
+         kgb_selfplay_get_root_row - any ladder budget, any number of waves ago), root / child statistics,
          play selection values, root policy -> this turn's targets (functions above);
       3. release; the next wave lets the device choose and play each move (its own Rand, temperature, LCB - unchanged) and
          evaluates the new roots; a move that ended a game leaves the final position, its area and score readable, the recorder
@@ -196,35 +196,32 @@ class GameRecorder:
         self.policy_surprise_data_weight, self.value_surprise_data_weight = float(policy_surprise_data_weight), float(value_surprise_data_weight)
         self.use_search_value_surprise, self.weight_rand = bool(use_search_value_surprise), weight_rand
         cfg = getattr(sp, "cfg", None)             # rules for the game record (write_sgf)
-        # The root's input row is taken from the wave that evaluates the new root.  With the evaluation cache on and a single root
+        # The root's input row is kept by the device when the net evaluates the root.  With the evaluation cache on and a single root
         # evaluation, that root is normally a cache hit (it was a child of the previous tree) and no row is produced for it.
         if cfg is not None and int(getattr(cfg, "nn_cache_size_power_of_two", 0)) > 0 and int(getattr(cfg, "root_num_symmetries_to_sample", 0)) <= 1:
             raise ValueError("GameRecorder: with nn_cache_size_power_of_two > 0 the root must be evaluated by the net itself "
                              "(root_num_symmetries_to_sample >= 2, as in the stock self-play configurations), or the cache switched off")
-        if cfg is not None and int(getattr(cfg, "ladder_nodes_per_wave", 0)) != 0:
-            raise ValueError("GameRecorder: ladder_nodes_per_wave must be 0 (a budgeted wave may deliver no row for the new root)")
         self.ko_rule_name = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[int(getattr(cfg, "ko_rule", 0))]
         self.multi_stone_suicide_legal = bool(getattr(cfg, "multi_stone_suicide_legal", 1))
-        sp.run(1)                                    # evaluates every root: the rows of this wave are the roots' input rows
-        self.root_rows = [sp.nn_row(g) for g in range(sp.num_games)]
+        sp.run(1)                                    # evaluates every root (its row stays on the device)
 
     def _record_root(self, g):
         """Slot g is held: read its finished search and append this turn's targets (extractSearchTargetsThisTurn)."""
         sp = self.sp
         colors, info = sp.game(g)
-        spatial, glob = self.root_rows[g]
+        spatial, glob = sp.root_row(g)
         _, policy, _ = sp.root_children(g)
         child_stats, root_stats = sp.root_value_stats(g)
         psv = sp.play_selection_values(g)
         extra = sp.root_extra(g)
         surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
         nn = extra["root_nn_moments"]
-        # the captured row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
+        # the kept row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
         flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
         sp_row = np.asarray(spatial, np.float32).reshape(self.X * self.Y, 22)
         if not (np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own)):
             raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
-                               "(its input row belongs to another position)")
+                               "(the kept input row belongs to another position)")
         gm = self.games[g]
         gm.boards.append(flat.copy())
         gm.turns.append(dict(
@@ -242,7 +239,6 @@ class GameRecorder:
     def _after_move(self, g):
         """Slot g was released and one wave has run: the device has played its move and evaluated the new root."""
         sp = self.sp
-        self.root_rows[g] = sp.nn_row(g)
         last = sp.last_move(g)
         self.games[g].turns[-1]["move"] = last["xy"]
         if last["game_over"]:

@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "kgb_handle_create", "kgb_handle_free", "kgb_handle_is_fp16", "kgb_forward", "kgb_forward_device", "kgb_handle_sync",
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv", "kgb_bench_conv_ex", "kgb_test_conv_epilogue",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
-    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
+    "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_selfplay_get_root_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
 ]
 
@@ -145,6 +145,7 @@ def load_library():
     lib.kgb_selfplay_debug_cycles.argtypes = [P, P, I]
     lib.kgb_zobrist_tables.argtypes = [I, I, P, P]
     lib.kgb_selfplay_get_nn_row.argtypes = [P, I, P, P]
+    lib.kgb_selfplay_get_root_row.argtypes = [P, I, P, P]
     lib.kgb_expected_white_score_value.argtypes = [I, P, P, P, P, P, P]
     lib.kgb_value_weight_cdf_table.argtypes = [P, I]
     lib.kgb_rand_uint32_stream.argtypes = [C.c_char_p, I, P]
@@ -500,6 +501,13 @@ class SelfPlay:
         """(spatial [X*Y, 22], global [19]) written by the last wave for game g."""
         sp = np.zeros((self.x * self.y, 22), np.float32); gl = np.zeros(19, np.float32)
         _check(load_library().kgb_selfplay_get_nn_row(self._p, g, sp.ctypes.data, gl.ctypes.data))
+        return sp, gl
+
+    def root_row(self, g: int):
+        """(spatial [X*Y, 22], global [19]): the fillRowV7 row of game g's current root, kept on the device since the wave that
+        evaluated it (kgb_selfplay_get_root_row)."""
+        sp = np.zeros((self.x * self.y, 22), np.float32); gl = np.zeros(19, np.float32)
+        _check(load_library().kgb_selfplay_get_root_row(self._p, g, sp.ctypes.data, gl.ctypes.data))
         return sp, gl
 
     def leaf_path(self, g: int, max_len: int = 512):

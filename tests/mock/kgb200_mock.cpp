@@ -189,6 +189,11 @@ int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int g, int32_t* nv, double* nn
   memcpy(nv, s.nodeVisits.data(), s.nodeVisits.size() * sizeof(int32_t)); memcpy(nn, s.rootNN, sizeof(s.rootNN));
   return 0;
 }
+int kgb_selfplay_get_root_row(kgb_selfplay* sp, int g, float* spatial, float* global) {
+  Slot& s = sp->slots[g];
+  memcpy(spatial, s.rowSpatial.data(), s.rowSpatial.size() * sizeof(float)); memcpy(global, s.rowGlobal.data(), 19 * sizeof(float));
+  return 0;
+}
 int kgb_selfplay_get_nn_row(kgb_selfplay* sp, int g, float* spatial, float* global) {
   Slot& s = sp->slots[g];
   memcpy(spatial, s.rowSpatial.data(), s.rowSpatial.size() * sizeof(float)); memcpy(global, s.rowGlobal.data(), 19 * sizeof(float));

@@ -133,7 +133,7 @@ class ScriptedSlots:
         t = self.t[g]
         return self._board(t).copy(), dict(move_num=t, black_to_move=(t % 2 == 0), ko=-1, cap_b=0, cap_w=0, root_visits=self.max_visits + g)
 
-    def nn_row(self, g):
+    def root_row(self, g):
         b = self._board(self.t[g]).reshape(-1)
         own = 1 if self.t[g] % 2 == 0 else 2
         sp = np.zeros((self.x * self.y, 22), np.float32)
@@ -210,14 +210,14 @@ def test_recorder_refuses_configurations_that_give_no_root_row():
         R.GameRecorder(sp, None, 6.5)
     sp.cfg.root_num_symmetries_to_sample = 4
     R.GameRecorder(sp, None, 6.5)
-    sp.cfg.ladder_nodes_per_wave = 256
-    with pytest.raises(ValueError, match="ladder_nodes_per_wave"):
-        R.GameRecorder(sp, None, 6.5)
+    sp.cfg.ladder_nodes_per_wave = 256          # a ladder budget is fine: the root's row is kept on the device, not read off the last wave
+    R.GameRecorder(sp, None, 6.5)
     # and at run time: a row that is not the root's is detected
     sp = ScriptedSlots(stream, [5], 10)
     rec = R.GameRecorder(sp, None, 6.5)
     rec.step()
-    rec.root_rows[0] = (np.roll(rec.root_rows[0][0], 1, axis=0), rec.root_rows[0][1])
+    good = sp.root_row
+    sp.root_row = lambda g: (np.roll(good(g)[0], 1, axis=0), good(g)[1])
     with pytest.raises(RuntimeError, match="did not evaluate the new root"):
         rec.step()
 
@@ -343,7 +343,7 @@ class ReplaySlots:
         return np.array(r["colors"], np.uint8).reshape(self.y, self.x), dict(move_num=r["move_num"], black_to_move=bool(r["black_to_move"]), ko=-1, cap_b=0,
                                                                           cap_w=0, root_visits=r.get("root_visits", self.max_visits + g))
 
-    def nn_row(self, g):
+    def root_row(self, g):
         r = self.root[g]
         return np.array(r["row_spatial"], np.float32).reshape(self.x * self.y, 22), np.array(r["row_global"], np.float32)
 
@@ -482,11 +482,13 @@ def test_recorder_chain_against_a_whole_reference_selfplay_game(tmp_path, size, 
 
 # ------------------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("ko_rule,graph", [(0, True), (1, False)])
-def test_recorder_turns_device_games_into_training_rows(tmp_path, tmp_models, ko_rule, graph):
+@pytest.mark.parametrize("ko_rule,graph,mode", [(0, True, "step"), (1, False, "step"), (0, True, "pump"), (1, True, "pump")])
+def test_recorder_turns_device_games_into_training_rows(tmp_path, tmp_models, ko_rule, graph, mode):
     """Games of the device loop (9x9, deterministic fake net, selfplay8mainb18-style search) recorded move by move in hold mode:
     the recorded moves replay to the recorded boards (device board replay), the final area / score / outcome targets agree with
-    each other, and the written .npz rows carry the positions, policy targets and outcome of the games they came from."""
+    each other, and the written .npz rows carry the positions, policy targets and outcome of the games they came from.
+    mode "pump" = per-game release (every game is recorded and released as soon as ITS search is finished, the others keep searching),
+    with a ladder budget per wave on: the root's input row comes from the device-kept copy, not from the last wave."""
     from katago_b200.nn_backend import NeuralNet, SelfPlay, board_replay
     lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
     L, G, V = 9, 6, 48
@@ -498,23 +500,36 @@ def test_recorder_turns_device_games_into_training_rows(tmp_path, tmp_models, ko
                   dynamic_score_center_zero_weight=0.25, dynamic_score_center_scale=0.5, use_play_selection=True, use_lcb_for_selection=True,
                   use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15, chosen_move_temperature=0.15,
                   chosen_move_temperature_early=0.75, root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83,
-                  root_dirichlet_noise_weight=0.25, ko_rule=ko_rule, full_history_rules=True)
+                  root_dirichlet_noise_weight=0.25, ko_rule=ko_rule, full_history_rules=True,
+                  ladder_nodes_per_wave=(6 if mode == "pump" else 0))
     games = []
     writer = W.TrainingDataWriter(str(tmp_path), 4096, 1.0, L, "recorder-test")    # one file: rows stay in write order
     rec = R.GameRecorder(sp, writer, komi, on_game=lambda g, data: games.append((g, data)))
     steps = 0
-    while len(games) < G and steps < 80:
-        rec.step()
-        steps += 1
-    st = sp.stats()
-    assert st["total_moves"] == steps * G            # hold / release: exactly one move per game and step
-    assert len(games) >= G, (len(games), steps)
+    if mode == "step":
+        while len(games) < G and steps < 80:
+            rec.step()
+            steps += 1
+        st = sp.stats()
+        assert st["total_moves"] == steps * G            # hold / release: exactly one move per game and step
+    else:
+        if ko_rule == 0:
+            sp.random_openings(12)                       # games at different stages: their searches finish in different waves
+            rec = R.GameRecorder(sp, writer, komi, on_game=lambda g, data: games.append((g, data)))
+        fresh = lambda: sum(1 for _, d in games if (d.boards_by_turn[0] == 0).all())
+        while (len(games) < G or fresh() < 2) and steps < 6000:
+            rec.pump(5)
+            steps += 1
+        assert sp.stats()["total_moves"] == rec.moves_recorded + (sp.stats()["total_moves"] - rec.moves_recorded)   # bookkeeping only
+    all_games = list(games)                              # in write order
+    if mode == "pump" and ko_rule == 0:
+        games = [(g, d) for g, d in games if (d.boards_by_turn[0] == 0).all()]     # games that began inside the recording (not from an opening)
+    assert len(games) >= (G if mode == "step" else 2), (len(games), steps)
     writer.flush_if_nonempty()
 
-    total_rows = 0
+    total_rows = sum(len(d.moves) for _, d in all_games)
     for g, data in games:
         n = len(data.moves)
-        total_rows += n
         assert n == len(data.target_weight_by_turn) and len(data.boards_by_turn) == n + 1 and len(data.white_value_targets_by_turn) == n + 1
         # the recorded moves reproduce the recorded boards, final position included
         mv = np.array([[(x, y, data.next_player_by_turn[t]) for t, (x, y) in enumerate(data.moves)]], np.int8)
@@ -548,6 +563,12 @@ def test_recorder_turns_device_games_into_training_rows(tmp_path, tmp_models, ko
     # rows come game by game, turn by turn: check positions, side to move and policy targets of the first recorded game
     g0, d0 = games[0]
     n0 = len(d0.moves)
+    first = 0
+    for _, d in all_games:                               # rows of the games written before it
+        if d is d0:
+            break
+        first += len(d.moves)
+    rows = {k: v[first:] for k, v in rows.items()}
     planes = np.unpackbits(rows["binaryInputNCHWPacked"][:n0], axis=2)[:, :, :L * L]
     for t in range(n0):
         own, opp = d0.next_player_by_turn[t], 3 - d0.next_player_by_turn[t]
