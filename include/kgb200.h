@@ -164,7 +164,8 @@ typedef struct kgb_selfplay_config {
    * PUCT + visit-weighted average of the first fixtures. */
   double value_weight_exponent;                   /* valueWeightExponent (0.5): t-CDF value weighting in the backup */
   int32_t fpu_parent_weight_by_visited_policy;    /* fpuParentWeightByVisitedPolicy */
-  int32_t reserved1;
+  int32_t debug_fixed_symmetry_plus_one;          /* TEST ONLY: k + 1 = evaluate every row under symmetry k (the reference's nnRandomize = false with
+                                                     nnForcedSymmetry / default symmetry k, nneval.cpp:698-707); 0 = a random symmetry per row */
   double fpu_parent_weight_by_visited_policy_pow; /* fpuParentWeightByVisitedPolicyPow */
   double fpu_parent_weight;                       /* fpuParentWeight */
   double fpu_loss_prop;                           /* fpuLossProp */

@@ -127,6 +127,7 @@ struct SPDev {
   int* ladPending;                  // [game] 1 = the leaf's ladder searches were cut off by ladderNodesPerWave; resume next wave
   int* leafValid;                   // [game] 1 = this wave produced a finished leaf (features complete) for the evaluator / backup
   int ladderNodesPerWave;           // per warp; 0 = unlimited
+  int fixedSymmetryPlusOne;         // TEST ONLY (kgb_selfplay_config.debug_fixed_symmetry_plus_one)
   int maxPlayoutsPerWave;           // playouts a game may finish inside one select launch without needing the evaluator
   unsigned long long* stalledWaves; // game-waves that did not produce a leaf
   float* rootRow;                   // [game][XY*22 + 19]: the NN input row (fillRowV7, no symmetry) of the game's current root, kept when the root is evaluated
@@ -1038,6 +1039,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     int sym = (int)(splitmix64(d.seed ^ ((uint64_t)g << 40) ^ (d.gameCounter[g] << 28) ^ ((uint64_t)d.moveNum[g] << 14) ^
                                (uint64_t)d.nodeVisits[gb]) & 7);   // nneval.cpp:698-707: random symmetry per row
     if(d.fakeNN) sym = 0;                                          // the reference's evaluator without nnRandomize
+    if(d.fixedSymmetryPlusOne > 0) sym = d.fixedSymmetryPlusOne - 1; // TEST ONLY: nnRandomize = false with a forced symmetry
     if(node == 0 && d.rootNumSymmetries > 1 && d.nodeVisits[gb] == 0) {
       // NNEvaluator::averageMultipleSymmetries: a partial Fisher-Yates shuffle of 0..7 drawn from the search thread's generator
       // With a dynamic score utility Search::beginSearch first takes ONE ordinary evaluation of the root to centre it on
@@ -1957,6 +1959,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafB = sp->alloc<uint32_t>(G * 32); d.leafW = sp->alloc<uint32_t>(G * 32); d.leafCand = sp->alloc<uint32_t>(G * 32);
   d.leafKo = sp->alloc<int>(G); d.ladPending = sp->alloc<int>(G); d.leafValid = sp->alloc<int>(G);
   d.ladderNodesPerWave = c.ladder_nodes_per_wave > 0 ? c.ladder_nodes_per_wave : 0;
+  d.fixedSymmetryPlusOne = (c.debug_fixed_symmetry_plus_one >= 1 && c.debug_fixed_symmetry_plus_one <= 8) ? c.debug_fixed_symmetry_plus_one : 0;
   d.maxPlayoutsPerWave = c.max_playouts_per_wave > 0 ? c.max_playouts_per_wave : SP_MAX_PLAYOUTS_PER_WAVE;
   { std::vector<int> kos2(2 * G, -1); SPCK(cudaMemcpy(d.prevKo, kos2.data(), 2 * G * sizeof(int), cudaMemcpyHostToDevice)); }
   d.nodeCount = sp->alloc<int>(G); d.nodeVisits = sp->alloc<int>(G * N); 

@@ -47,7 +47,7 @@ class SelfplayConfig(C.Structure):
         ("static_score_utility_factor", C.c_double), ("dynamic_score_utility_factor", C.c_double),
         ("dynamic_score_center_zero_weight", C.c_double), ("dynamic_score_center_scale", C.c_double),
         ("draw_equivalent_wins_for_white", C.c_double),
-        ("value_weight_exponent", C.c_double), ("fpu_parent_weight_by_visited_policy", C.c_int32), ("reserved1", C.c_int32),
+        ("value_weight_exponent", C.c_double), ("fpu_parent_weight_by_visited_policy", C.c_int32), ("debug_fixed_symmetry_plus_one", C.c_int32),
         ("fpu_parent_weight_by_visited_policy_pow", C.c_double), ("fpu_parent_weight", C.c_double), ("fpu_loss_prop", C.c_double),
         ("root_fpu_loss_prop", C.c_double), ("cpuct_utility_stdev_prior", C.c_double), ("cpuct_utility_stdev_prior_weight", C.c_double),
         ("cpuct_utility_stdev_scale", C.c_double), ("root_desired_per_child_visits_coeff", C.c_double),
@@ -457,7 +457,7 @@ class SelfPlay:
                  lcb_stdevs: float = 4.0, min_visit_prop_for_lcb: float = 0.05, chosen_move_temperature: float = 0.0,
                  chosen_move_temperature_early: float = 0.0, chosen_move_temperature_only_below_prob: float = 1.0,
                  chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0, nn_cache_size_power_of_two: int = 0, root_num_symmetries_to_sample: int = 1,
-                 ko_rule: int = 0, full_history_rules: bool = False):
+                 ko_rule: int = 0, full_history_rules: bool = False, debug_fixed_symmetry: int = -1):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -465,7 +465,7 @@ class SelfPlay:
                                   root_fpu_reduction_max, win_loss_utility_factor, no_result_utility_for_white, seed, int(debug_fake_nn), int(disable_ladder_features),
                                   int(ladder_nodes_per_wave), int(max_playouts_per_wave), static_score_utility_factor, dynamic_score_utility_factor,
                                   dynamic_score_center_zero_weight, dynamic_score_center_scale, draw_equivalent_wins_for_white,
-                                  value_weight_exponent, int(fpu_parent_weight_by_visited_policy), 0, fpu_parent_weight_by_visited_policy_pow,
+                                  value_weight_exponent, int(fpu_parent_weight_by_visited_policy), int(debug_fixed_symmetry) + 1, fpu_parent_weight_by_visited_policy_pow,
                                   fpu_parent_weight, fpu_loss_prop, root_fpu_loss_prop, cpuct_utility_stdev_prior,
                                   cpuct_utility_stdev_prior_weight, cpuct_utility_stdev_scale, root_desired_per_child_visits_coeff,
                                   subtree_value_bias_factor, subtree_value_bias_weight_exponent, int(use_graph_search),

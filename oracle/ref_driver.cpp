@@ -126,6 +126,7 @@ static inline uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
   return x ^ (x >> 31);
 }
+#ifndef KGREF_EXTERNAL_BACKEND   // kgref_driver_b200 (oracle/Makefile.drivers) links integration/b200backend.cpp instead: the same commands on a real net
 struct LoadedModel { ModelDesc modelDesc; };
 struct ComputeContext { int nnXLen, nnYLen; };
 struct ComputeHandle { int nnXLen, nnYLen; };
@@ -188,6 +189,8 @@ bool NeuralNet::testEvaluateConv(const ConvLayerDesc*, int, int, int, bool, bool
 bool NeuralNet::testEvaluateBatchNorm(const BatchNormLayerDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
 bool NeuralNet::testEvaluateResidualBlock(const ResidualBlockDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
 bool NeuralNet::testEvaluateGlobalPoolingResidualBlock(const GlobalPoolingResidualBlockDesc*, int, int, int, bool, bool, const std::vector<float>&, const std::vector<float>&, std::vector<float>&) { return false; }
+
+#endif
 
 static int cmdSearchFake(int argc, char** argv) {
   if(argc < 7) { cerr << "usage: searchfake MODELFILE X Y MAXVISITS MOVES [key=value ...]" << endl; return 1; }

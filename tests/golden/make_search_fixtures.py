@@ -37,14 +37,14 @@ LCB = {"useLcbForSelection": 1, "lcbStdevs": 5.0, "minVisitPropForLCB": 0.15, "u
 BIAS = {"subtreeValueBiasFactor": 0.30, "subtreeValueBiasWeightExponent": 0.8}
 
 
-def run(X, Y, visits, moves, score=None):
+def run(X, Y, visits, moves, score=None, driver=None, model=None):
     s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
     if score is None:
         score = {}
     elif not isinstance(score, dict):
         score = dict(zip(SCORE_KEYS, score))
     extra = [f"{k}={float(v)!r}" for k, v in score.items() if k != "fullHistoryRules"]
-    out = subprocess.run([DRIVER, "searchfake", MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([driver or DRIVER, "searchfake", model or MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     psv = np.full(X * Y + 1, -1.0, np.float64); threadseed = ""
     cstats = np.zeros((X * Y + 1, 5), np.float64); rstats = np.zeros(5, np.float64)
