@@ -180,7 +180,8 @@ def cpu_selfplay(model_name: str, seconds: float, warmup_seconds: float, visits:
 
 
 def cpu_baseline_object(r, model_name):
-    return {"value": r["visits_per_s"], "unit": UNIT, "cores": r["nn_server_threads"], "kind": "restated Eigen path (C++), full selfplay",
+    return {"value": r["visits_per_s"], "unit": UNIT, "cores": r["nn_server_threads"], "kind": "reference", "detail": "restated Eigen path (C++), full selfplay",
+            "nn_backend": "port: oracle/cpubackend.cpp behind the reference's nninterface.h (its Eigen backend needs Eigen3, absent here)",
             "sample": (f"{r['visits']} visits ({r['nn_rows']} evaluated rows) of {model_name} 19x19 self-play in {r['seconds']:.1f} s: reference Search + Board + NNEvaluator "
                        f"with oracle/cpubackend.cpp, {r['nn_server_threads']} single-threaded NN server threads + {r['game_threads']} game threads, maxVisits {r['max_visits']}")}
 
@@ -332,7 +333,7 @@ def main():
                   subtree_value_bias_factor=0.30, subtree_value_bias_weight_exponent=0.8, use_graph_search=True, graph_search_rep_bound=11,
                   root_noise_enabled=True, root_dirichlet_noise_total_concentration=10.83, root_dirichlet_noise_weight=0.25,
                   root_policy_temperature=1.1, root_policy_temperature_early=1.5, chosen_move_temperature_halflife=19.0,
-                  nn_cache_size_power_of_two=args.nn_cache_pow2, root_num_symmetries_to_sample=4, ko_rule=0, full_history_rules=True,
+                  nn_cache_size_power_of_two=args.nn_cache_pow2, root_num_symmetries_to_sample=4, root_ending_bonus_points=0.5, root_prune_useless_moves=True, ko_rule=0, full_history_rules=True,
                   use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
                   chosen_move_temperature=0.15, chosen_move_temperature_early=0.75, chosen_move_subtract=0.0, chosen_move_prune=1.0,
                   seed=1234 + rank, ladder_nodes_per_wave=args.ladder_nodes_per_wave, max_playouts_per_wave=args.max_playouts_per_wave,
@@ -479,7 +480,7 @@ def main():
         conv_flop = 2.0 * 9 * mid * mid * 361 * n  # algorithmic: direct convolution over the 361 real board points
         achieved = conv_flop / (float(ms_conv[0]) * 1e-3) / 1e12
         whole = flop_per_eval * n * K / (ms_nn * 1e-3) / 1e12
-        cpu_obj = {"value": None, "unit": UNIT, "cores": 0, "kind": "restated Eigen path (C++), full selfplay", "sample": "measured at N=1 only"}
+        cpu_obj = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "measured at N=1 only"}
         if world == 1:      # the CPU baseline is a property of the box: measured at N=1 only
             cpu_obj = cpu_baseline_object(cpu_selfplay(args.model, 15.0, 5.0, args.visits), args.model)
         out = {
@@ -491,8 +492,7 @@ def main():
                                   "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)",
                                   "backup = recomputeNodeStats per path node (value weighting, exponent 0.5)"],
                        "search_params": "selfplay8mainb18.cfg: cpuct 1.05/0.28/500, fpu 0.2 (root 0), fpuParentWeightByVisitedPolicy^2, valueWeightExponent 0.5, "
-                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8, useGraphSearch (repBound 11), root Dirichlet noise 10.83/0.25, root policy temperature 1.1 (early 1.5), move choice by play selection values with LCB 5.0/0.15 and chosenMoveTemperature 0.75->0.15; rootNumSymmetriesToSample 4; not yet: rootEndingBonusPoints, rootPruneUselessMoves, "
-                                        "",
+                                        "score utility 0.05/0.30/0.25/0.50, rootDesiredPerChildVisitsCoeff 2, subtreeValueBias 0.30/0.8, useGraphSearch (repBound 11), root Dirichlet noise 10.83/0.25, root policy temperature 1.1 (early 1.5), move choice by play selection values with LCB 5.0/0.15 and chosenMoveTemperature 0.75->0.15; rootNumSymmetriesToSample 4; rootEndingBonusPoints 0.5, rootPruneUselessMoves",
                        "rules": "area scoring, simple ko with BoardHistory's game-end rules (two passes, spight-like ending pass, third repetition = no result), multi-stone suicide legal, komi 7.5 (positional / situational / spight superko available via ko_rule; territory scoring and encore not built)",
                        "games_per_gpu": n, "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
                        "weights": "random init, real architecture (katago_b200/modelgen.py)",

@@ -113,6 +113,27 @@ KGB_API uint64_t kgb_handle_stream(kgb_handle* handle);
 /* Number of kernel launches one kgb_forward of batch n issues (for bench.py's gpu_launches accounting). */
 KGB_API int kgb_handle_launches_per_forward(const kgb_handle* handle);
 
+/* New weights into a live handle.  The reference polls its models directory and builds a fresh NNEvaluator for every new net
+ * (command/selfplay.cpp:142-231 loadLatestNeuralNetIntoManager, :336-352 the polling thread; dataio/loadmodel.cpp:58
+ * findLatestModel); games switch over between moves (switchNetsMidGame, program/play.cpp maybeGetNewNet).  Here the handle keeps
+ * its graphs and buffers and only the weight arena changes:
+ *   kgb_handle_stage_weights   packs `model` (same architecture as the handle's, else an error) for this handle's kernels and
+ *                              copies it to a shadow arena on a side stream - evaluation continues meanwhile
+ *   kgb_handle_commit_weights  orders "shadow -> live" on the handle's stream: every forward pass / self-play wave enqueued
+ *                              afterwards runs the new net, none sees a mixture
+ * Between GPUs of one node (one process per GPU) the packed arena travels by ncclBroadcast straight between device memories,
+ * so only one rank reads and packs the model file:
+ *   kgb_nccl_unique_id                   on one rank; the 128 bytes reach the others by any side channel (torch.distributed, MPI, a file)
+ *   kgb_handle_comm_init                 on every rank, once per handle
+ *   kgb_handle_broadcast_staged_weights  on every rank; the root must have staged; *ms_out = the collective's device time
+ * followed by kgb_handle_commit_weights on every rank.  NCCL is bound at run time (libnccl.so.2, or KGB_NCCL_LIB). */
+KGB_API int kgb_handle_weights_bytes(const kgb_handle* handle, uint64_t* bytes);
+KGB_API int kgb_handle_stage_weights(kgb_handle* handle, const kgb_model* model);
+KGB_API int kgb_handle_commit_weights(kgb_handle* handle);
+KGB_API int kgb_nccl_unique_id(void* id_out_128_bytes);
+KGB_API int kgb_handle_comm_init(kgb_handle* handle, const void* id_128_bytes, int rank, int num_ranks);
+KGB_API int kgb_handle_broadcast_staged_weights(kgb_handle* handle, int root, float* ms_out);
+
 /* FOR TESTING: NeuralNet::testEvaluateConv (nninterface.h:134-143).  weights in the model-file order
  * [ky][kx][in_c][out_c]; input/output [n][Y][X][C] (NHWC) fp32.  use_fp16 selects the operand mode as in
  * kgb_context_create.  Returns KGB_OK and fills output[n*Y*X*out_c]. */
@@ -190,7 +211,8 @@ typedef struct kgb_selfplay_config {
   int32_t use_play_selection;
   int32_t use_lcb_for_selection;                  /* useLcbForSelection */
   int32_t use_non_buggy_lcb;                      /* useNonBuggyLcb */
-  int32_t reserved3;
+  int32_t root_prune_useless_moves;               /* rootPruneUselessMoves: when the opponent's last four moves were passes, the root never plays
+                                                     inside either player's pass-alive area (Search::isAllowedRootMove, searchhelpers.cpp:310-342) */
   double lcb_stdevs;                              /* lcbStdevs (5.0) */
   double min_visit_prop_for_lcb;                  /* minVisitPropForLCB (0.15) */
   double chosen_move_temperature;                 /* chosenMoveTemperature (0.15) */
@@ -204,6 +226,11 @@ typedef struct kgb_selfplay_config {
   int32_t full_history_rules;                     /* 1 = BoardHistory's game-end rules also under simple ko: a pass in a situation the same
                                                      player already passed in ends the game, a third repetition since the last pass is "no
                                                      result".  Implied by ko_rule != 0.  0 = two consecutive passes only. */
+  double root_ending_bonus_points;                /* rootEndingBonusPoints (0.5 in the stock configs): at the root, moves into territory the net's
+                                                     ownership head is sure about (|ownership| >= 0.95) lose up to this many points of score
+                                                     utility unless they capture / touch the opponent / connect groups that are not pass-alive
+                                                     (Search::getEndingWhiteScoreBonus, searchhelpers.cpp:351-420; area scoring).  Needs the
+                                                     root to be evaluated by the net (root_num_symmetries_to_sample >= 2 or the cache off). */
 } kgb_selfplay_config;
 
 typedef struct kgb_selfplay_stats {
@@ -273,6 +300,9 @@ KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double
  * host reads the finished search (getters above and below), releases, and the next wave lets the device choose and play the move
  * as usual.  games_mask[num_games] (1 = release) or NULL = all.  A released game holds again at its next finished search. */
 KGB_API int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* games_mask);
+/* Empties the loop's evaluation cache, ordered on the handle's stream: call it with kgb_handle_commit_weights - cached outputs
+ * belong to the previous net (the reference gives every NNEvaluator its own NNCacheTable, nneval.cpp:129-130). */
+KGB_API int kgb_selfplay_clear_nn_cache(kgb_selfplay* sp);
 /* Root visits of every game (visits[num_games]): a game is held when its entry has reached max_visits. */
 KGB_API int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* visits);
 /* What extractQValueTargets / computeNNRawStats (play.cpp:859-914) read besides the NodeStats: visits of the root's child NODES by

@@ -88,6 +88,8 @@ inline kgb_selfplay_config configFromSearchParams(const SearchParams& p, const R
   c.lcb_stdevs = p.lcbStdevs;
   c.min_visit_prop_for_lcb = p.minVisitPropForLCB;
   c.use_non_buggy_lcb = p.useNonBuggyLcb ? 1 : 0;
+  c.root_ending_bonus_points = p.rootEndingBonusPoints;
+  c.root_prune_useless_moves = p.rootPruneUselessMoves ? 1 : 0;
 
   // options of the reference's search that the device loop does not have: reported when they are switched on
   no(p.policyOptimism != 0.0, "policyOptimism = " + num(p.policyOptimism));
@@ -96,8 +98,6 @@ inline kgb_selfplay_config configFromSearchParams(const SearchParams& p, const R
   no(p.useUncertainty, "useUncertainty = true");
   no(p.graphSearchCatchUpLeakProb != 0.0, "graphSearchCatchUpLeakProb = " + num(p.graphSearchCatchUpLeakProb));
   no(p.rootSymmetryPruning, "rootSymmetryPruning = true");
-  no(p.rootEndingBonusPoints != 0.0, "rootEndingBonusPoints = " + num(p.rootEndingBonusPoints));
-  no(p.rootPruneUselessMoves, "rootPruneUselessMoves = true");
   no(p.conservativePass, "conservativePass = true");
   no(p.fillDameBeforePass, "fillDameBeforePass = true");
   no(p.wideRootNoise != 0.0, "wideRootNoise = " + num(p.wideRootNoise));

@@ -19,16 +19,22 @@ for f in kgb_conv_tc.cu kgb_conv_tc2.cu kgb_conv_tc3.cu kgb_kernels.cu kgb_api.c
     X=""
     # the search arithmetic follows the reference's doubles operation by operation: no FMA contraction there
     if [ $f = kgb_selfplay.cu ]; then X="-fmad=false"; fi
+    rm -f $o
     $NVCC $FLAGS $X ${EXTRA_NVCC_FLAGS} -c $f -o $o &
   fi
 done
 for f in kgb_model.cpp kgb_rand.cpp kgb_scorevalue.cpp; do
   o=../_build/${f%.cpp}.o
   if [ ! -f $o ] || [ $f -nt $o ] || [ kgb_model.h -nt $o ] || [ kgb_rand.h -nt $o ] || [ kgb_scorevalue.h -nt $o ]; then
+    rm -f $o
     g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -c $f -o $o &
   fi
 done
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_conv_tc3.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o ../_build/kgb_scorevalue.o -lz -cudart shared
+# a failed compile leaves no object behind (removed above), so the link below fails too instead of reusing a stale one
+for o in kgb_conv_tc kgb_conv_tc2 kgb_conv_tc3 kgb_kernels kgb_api kgb_selfplay kgb_model kgb_rand kgb_scorevalue; do
+  [ -f ../_build/$o.o ] || { echo "build failed: $o" >&2; exit 1; }
+done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../_build/kgb_conv_tc.o ../_build/kgb_conv_tc2.o ../_build/kgb_conv_tc3.o ../_build/kgb_kernels.o ../_build/kgb_api.o ../_build/kgb_selfplay.o ../_build/kgb_model.o ../_build/kgb_rand.o ../_build/kgb_scorevalue.o -lz -ldl -cudart shared
 echo $SRCHASH > $OUT.srchash
 echo "built $(readlink -f $OUT)"

@@ -10,6 +10,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is looked up at run time (ncclApi below), libkgb200.so does not link against it
 
 #include <cstdio>
 #include <cstdlib>
@@ -161,18 +163,70 @@ struct kgb_handle {
   int launchesPerForward = 0;
   std::map<int, cudaGraphExec_t> graphs;
 
+  // Weights live in ONE arena: a net of the same architecture is swapped in between two waves by one device copy
+  // (kgb_handle_stage_weights / kgb_handle_commit_weights) and travels between the GPUs of a node as one ncclBroadcast
+  // (kgb_handle_broadcast_staged_weights).  The graph builder runs in three modes over the same code:
+  //   W_SIZE   on a scratch handle: only adds up the arena (nothing is allocated, no op is kept)
+  //   W_BUILD  the real build: device addresses from wLive, bytes packed into the pinned mirror wHost, one H2D copy at the end
+  //   W_REPACK on a scratch handle: packs ANOTHER model's weights into wHost at the same offsets, destined for wShadow
+  enum { W_BUILD = 0, W_SIZE = 1, W_REPACK = 2 };
+  int wMode = W_BUILD;
+  char *wLive = nullptr, *wShadow = nullptr, *wHost = nullptr;
+  size_t wBytes = 0, wCursor = 0, wIndex = 0;
+  std::vector<size_t> wSizes;     // the arena's spans in build order: a staged model must produce the same sequence
+  std::string wSignature;         // shapes, activations and head constants that ops capture by value (must match as well)
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t stagedEvent = nullptr, bcastStart = nullptr, bcastStop = nullptr;
+  bool staged = false;
+  bool wCheckSpans = true;        // false: free-form arena of a given size (the single-convolution test / bench objects)
+  void* ncclComm = nullptr;
+  int ncclRank = 0, ncclRanks = 0;
+
   template <class T>
   T* dalloc(size_t count) {
+    if(wMode != W_BUILD) return (T*)(uintptr_t)256;      // scratch pass: activations are never touched
     void* p = nullptr;
     CK(cudaMalloc(&p, count * sizeof(T)));
     CK(cudaMemset(p, 0, count * sizeof(T)));
     allocs.push_back(p);
     return (T*)p;
   }
+  // One span of the weight arena: returns its device address and (except in W_SIZE) where to pack its bytes on the host
+  void* walloc(size_t bytes, void** host) {
+    const size_t b = (bytes + 255) & ~(size_t)255;
+    const size_t o = wCursor;
+    wCursor += b;
+    if(wMode == W_SIZE) {
+      wSizes.push_back(b);
+      *host = nullptr;
+      return (void*)(uintptr_t)(256 + o);
+    }
+    if((wCheckSpans && (wIndex >= wSizes.size() || wSizes[wIndex] != b)) || o + b > wBytes)
+      throw std::invalid_argument("the model's weights do not have the layout this handle was built for (different architecture)");
+    wIndex++;
+    *host = wHost + o;
+    return (wMode == W_BUILD ? wLive : wShadow) + o;
+  }
+  void wAllocArena(size_t bytes) {
+    wBytes = bytes;
+    CK(cudaMalloc((void**)&wLive, std::max<size_t>(bytes, 256)));
+    CK(cudaMemset(wLive, 0, std::max<size_t>(bytes, 256)));
+    allocs.push_back(wLive);
+    CK(cudaMallocHost((void**)&wHost, std::max<size_t>(bytes, 256)));
+    memset(wHost, 0, std::max<size_t>(bytes, 256));
+  }
+  void wFlushLive() {       // the packed bytes reach the device in one copy
+    CK(cudaMemcpy(wLive, wHost, wCursor, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
+  }
   float* upload(const std::vector<float>& v, size_t padTo = 0) {
     size_t n = std::max(v.size(), padTo);
-    float* d = dalloc<float>(n);
-    if(!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    void* hp = nullptr;
+    float* d = (float*)walloc(n * sizeof(float), &hp);
+    if(hp) {
+      memset(hp, 0, n * sizeof(float));
+      if(!v.empty()) memcpy(hp, v.data(), v.size() * sizeof(float));
+    }
     return d;
   }
 };
@@ -246,7 +300,13 @@ struct Builder {
     cw.hasIdentity = withResidual && !h.split && !h.useSimt && h.usePairTma && (h.resViaMma == 2 || (h.resViaMma == 1 && taps == 1)) &&
                      cw.n_tile % 64 == 0;
     int ldw = cw.cin_p * actMul + (cw.hasIdentity ? cw.cout_p : 0);
-    std::vector<__half> host((size_t)taps * cw.cout_p * ldw, __float2half(0.0f));
+    h.wSignature += "conv" + std::to_string(cw.ky) + "x" + std::to_string(cw.kx) + ":" + std::to_string(c0.cin) + ">" + std::to_string(cout) +
+                    (cw.hasIdentity ? "+id;" : ";");
+    const size_t count = (size_t)taps * cw.cout_p * ldw;
+    void* hostDst = nullptr;
+    cw.w = (__half*)h.walloc(count * sizeof(__half), &hostDst);
+    if(h.wMode == kgb_handle::W_SIZE) return cw;
+    std::vector<__half> host(count, __float2half(0.0f));
     if(cw.hasIdentity)
       for(int co = 0; co < cout; co++) host[(size_t)co * ldw + cw.cin_p + co] = __float2half(1.0f);
     int coBase = 0;
@@ -262,8 +322,7 @@ struct Builder {
           }
       coBase += c->cout;
     }
-    cw.w = h.dalloc<__half>(host.size());
-    CK(cudaMemcpy(cw.w, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    memcpy(hostDst, host.data(), count * sizeof(__half));
     cw.tmapB = makeTmap2D(cw.w, (uint64_t)taps * cw.cout_p, (uint64_t)ldw, (uint32_t)cw.n_tile);
     cw.tmapBhalf = makeTmap2D(cw.w, (uint64_t)taps * cw.cout_p, (uint64_t)ldw, (uint32_t)(cw.n_tile / 2));
     return cw;
@@ -276,6 +335,7 @@ struct Builder {
   };
   BNDev uploadBN(const BNDesc& bn, int act, int cp) {
     BNDev d;
+    h.wSignature += "bn" + std::to_string(act) + "," + std::to_string(cp) + ";";
     d.scale = h.upload(bn.scale, cp);
     d.bias = h.upload(bn.bias, cp);
     d.act = act;
@@ -474,6 +534,14 @@ struct Builder {
                         hp->dValue, hp->dScore, s));
     });
     h.launchesPerForward += (version >= 15 ? 11 : 10);
+    // constants the ops above captured by value, and the post-processing constants callers read from the model: a staged model
+    // (kgb_handle_stage_weights) must agree on all of them
+    char buf[512];
+    snprintf(buf, sizeof(buf), "v%d in%d,%d trunk%d heads%d,%d,%d pol%d pass%d,%d v2:%d,%d sv%d own%d mult%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g", version,
+             m.numInputChannels, m.numInputGlobalChannels, m.trunkC, p1C, g1C, v1C, cp2, passMid, passAct, v2C, v2Act, numSV, m.ownershipConv.cout,
+             (double)m.tdScoreMultiplier, (double)m.scoreMeanMultiplier, (double)m.scoreStdevMultiplier, (double)m.leadMultiplier,
+             (double)m.varianceTimeMultiplier, (double)m.shorttermValueErrorMultiplier, (double)m.shorttermScoreErrorMultiplier);
+    h.wSignature += buf;
   }
 };
 
@@ -589,11 +657,58 @@ KGB_API int kgb_context_create(const int* gpu_idxs, int num_gpu_idxs, int nn_x_l
 
 KGB_API void kgb_context_free(kgb_context* ctx) { delete ctx; }
 
+// NCCL, bound at run time: a single-GPU process never needs it, and a process that has torch loaded shares torch's copy
+// (the same communicator library that torch.distributed uses over NVLink / NVSwitch).
+struct NcclApi {
+  ncclResult_t (*getUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*commInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*getErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+static NcclApi& ncclApi() {
+  static NcclApi api;
+  static bool tried = false;
+  if(tried) return api;
+  tried = true;
+  void* lib = nullptr;
+  const char* override_ = getenv("KGB_NCCL_LIB");
+  for(const char* name : {override_, "libnccl.so.2", "libnccl.so"}) {
+    if(name && (lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+  }
+  if(!lib) { api.why = std::string("libnccl.so.2 cannot be loaded (") + (dlerror() ? dlerror() : "not found") + "); set KGB_NCCL_LIB"; return api; }
+  api.getUniqueId = (decltype(api.getUniqueId))dlsym(lib, "ncclGetUniqueId");
+  api.commInitRank = (decltype(api.commInitRank))dlsym(lib, "ncclCommInitRank");
+  api.commDestroy = (decltype(api.commDestroy))dlsym(lib, "ncclCommDestroy");
+  api.broadcast = (decltype(api.broadcast))dlsym(lib, "ncclBroadcast");
+  api.getErrorString = (decltype(api.getErrorString))dlsym(lib, "ncclGetErrorString");
+  api.ok = api.getUniqueId && api.commInitRank && api.commDestroy && api.broadcast && api.getErrorString;
+  if(!api.ok) api.why = "the NCCL library lacks an expected symbol";
+  return api;
+}
+static void ncclCheck(ncclResult_t r, const char* what) {
+  if(r != ncclSuccess) throw CudaFailure(std::string(what) + ": " + ncclApi().getErrorString(r));
+}
+
+// The settings that decide how the graph builder lays the weights out
+static void copyBuildSettings(kgb_handle& dst, const kgb_handle& src) {
+  dst.device = src.device; dst.numSMs = src.numSMs; dst.model = src.model; dst.L = src.L; dst.maxBatch = src.maxBatch; dst.split = src.split;
+  dst.nhwc = src.nhwc; dst.streamTrunkFp32 = src.streamTrunkFp32; dst.streamInnerFp32 = src.streamInnerFp32; dst.useSimt = src.useSimt;
+  dst.useGraph = src.useGraph; dst.usePair = src.usePair; dst.usePairTma = src.usePairTma; dst.resViaMma = src.resViaMma;
+}
+
 static void destroyHandle(kgb_handle* h) {
   if(!h) return;
   cudaSetDevice(h->device);
   for(auto& g : h->graphs) cudaGraphExecDestroy(g.second);
   for(void* p : h->allocs) cudaFree(p);
+  if(h->wShadow) cudaFree(h->wShadow);
+  if(h->wHost) cudaFreeHost(h->wHost);
+  if(h->ncclComm && ncclApi().ok) ncclApi().commDestroy((ncclComm_t)h->ncclComm);
+  for(cudaEvent_t e : {h->stagedEvent, h->bcastStart, h->bcastStop}) if(e) cudaEventDestroy(e);
+  if(h->copyStream) cudaStreamDestroy(h->copyStream);
   for(void* p : {(void*)h->hSpatial, (void*)h->hGlobal, (void*)h->hOptimism, (void*)h->hPolicy, (void*)h->hValue, (void*)h->hScore,
                  (void*)h->hOwnership, (void*)h->hSymmetry})
     if(p) cudaFreeHost(p);
@@ -649,8 +764,25 @@ KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_
     CK(convTCInit());
     CK(convTC2Init());
     CK(convTC3Init());
+    CK(cudaStreamCreateWithFlags(&h.copyStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h.stagedEvent, cudaEventDisableTiming));
+    CK(cudaEventCreate(&h.bcastStart));
+    CK(cudaEventCreate(&h.bcastStop));
+    {
+      kgb_handle sizing;                       // pass 1: how large is the weight arena, and in which spans
+      copyBuildSettings(sizing, h);
+      sizing.wMode = kgb_handle::W_SIZE;
+      Builder(sizing).build();
+      h.wSizes = sizing.wSizes;
+      h.wSignature = sizing.wSignature;
+      h.wAllocArena(sizing.wCursor);
+    }
+    const std::string signature = h.wSignature;
+    h.wSignature.clear();
     Builder b(h);
     b.build();
+    if(h.wCursor != h.wBytes || h.wSignature != signature) throw std::logic_error("kgb_handle_create: the two builder passes disagree");
+    h.wFlushLive();
     const int XY = h.L.X * h.L.Y;
     const ModelDesc& m = *h.model;
     CK(cudaMallocHost((void**)&h.hSpatial, (size_t)h.maxBatch * m.numInputChannels * XY * sizeof(float)));
@@ -670,6 +802,105 @@ KGB_API int kgb_handle_create(kgb_context* ctx, const kgb_model* model, int max_
 }
 
 KGB_API void kgb_handle_free(kgb_handle* handle) { destroyHandle(handle); }
+
+// ---- new weights into a live handle (the reference: a new NNEvaluator per polled model file, command/selfplay.cpp:142-231,336-352) ----
+
+KGB_API int kgb_handle_weights_bytes(const kgb_handle* handle, uint64_t* bytes) {
+  return guarded([&] {
+    if(!handle || !bytes) throw std::invalid_argument("kgb_handle_weights_bytes: NULL argument");
+    *bytes = handle->wBytes;
+  });
+}
+
+static void ensureShadow(kgb_handle* h) {
+  if(h->wShadow) return;
+  CK(cudaMalloc((void**)&h->wShadow, std::max<size_t>(h->wBytes, 256)));
+  CK(cudaMemset(h->wShadow, 0, std::max<size_t>(h->wBytes, 256)));
+}
+
+KGB_API int kgb_handle_stage_weights(kgb_handle* handle, const kgb_model* model) {
+  return guarded([&] {
+    if(!handle || !model) throw std::invalid_argument("kgb_handle_stage_weights: NULL argument");
+    CK(cudaSetDevice(handle->device));
+    ensureShadow(handle);
+    CK(cudaStreamSynchronize(handle->copyStream));        // an earlier staging copy may still be reading the host mirror
+    kgb_handle pack;
+    copyBuildSettings(pack, *handle);
+    pack.model = model->desc.get();
+    if(pack.model->maxConvRadius() != handle->L.pad) throw std::invalid_argument("kgb_handle_stage_weights: the model's largest convolution differs");
+    pack.wMode = kgb_handle::W_REPACK;
+    pack.wHost = handle->wHost; pack.wShadow = handle->wShadow; pack.wBytes = handle->wBytes; pack.wSizes = handle->wSizes;
+    Builder(pack).build();
+    if(pack.wCursor != handle->wBytes || pack.wIndex != handle->wSizes.size() || pack.wSignature != handle->wSignature)
+      throw std::invalid_argument("kgb_handle_stage_weights: the model is not of the architecture this handle was built for");
+    CK(cudaMemcpyAsync(handle->wShadow, handle->wHost, handle->wBytes, cudaMemcpyHostToDevice, handle->copyStream));
+    CK(cudaEventRecord(handle->stagedEvent, handle->copyStream));
+    handle->staged = true;
+  });
+}
+
+KGB_API int kgb_handle_commit_weights(kgb_handle* handle) {
+  return guarded([&] {
+    if(!handle) throw std::invalid_argument("kgb_handle_commit_weights: NULL handle");
+    if(!handle->staged) throw std::invalid_argument("kgb_handle_commit_weights: nothing is staged (kgb_handle_stage_weights or kgb_handle_broadcast_staged_weights first)");
+    CK(cudaSetDevice(handle->device));
+    // ordered on the evaluation stream: every forward pass (and every self-play wave) enqueued after this call sees the new net whole
+    CK(cudaStreamWaitEvent(handle->stream, handle->stagedEvent, 0));
+    CK(cudaMemcpyAsync(handle->wLive, handle->wShadow, handle->wBytes, cudaMemcpyDeviceToDevice, handle->stream));
+    handle->staged = false;
+  });
+}
+
+KGB_API int kgb_nccl_unique_id(void* id_out_128_bytes) {
+  return guarded([&] {
+    if(!id_out_128_bytes) throw std::invalid_argument("kgb_nccl_unique_id: NULL argument");
+    NcclApi& api = ncclApi();
+    if(!api.ok) throw CudaFailure("kgb_nccl_unique_id: " + api.why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclCheck(api.getUniqueId(&id), "ncclGetUniqueId");
+    memcpy(id_out_128_bytes, &id, sizeof(id));
+  });
+}
+
+KGB_API int kgb_handle_comm_init(kgb_handle* handle, const void* id_128_bytes, int rank, int num_ranks) {
+  return guarded([&] {
+    if(!handle || !id_128_bytes) throw std::invalid_argument("kgb_handle_comm_init: NULL argument");
+    if(num_ranks < 1 || rank < 0 || rank >= num_ranks) throw std::invalid_argument("kgb_handle_comm_init: rank out of range");
+    if(handle->ncclComm) throw std::invalid_argument("kgb_handle_comm_init: the handle already has a communicator");
+    NcclApi& api = ncclApi();
+    if(!api.ok) throw CudaFailure("kgb_handle_comm_init: " + api.why);
+    CK(cudaSetDevice(handle->device));
+    ncclUniqueId id;
+    memcpy(&id, id_128_bytes, sizeof(id));
+    ncclComm_t comm = nullptr;
+    ncclCheck(api.commInitRank(&comm, num_ranks, id, rank), "ncclCommInitRank");
+    handle->ncclComm = comm; handle->ncclRank = rank; handle->ncclRanks = num_ranks;
+  });
+}
+
+KGB_API int kgb_handle_broadcast_staged_weights(kgb_handle* handle, int root, float* ms_out) {
+  return guarded([&] {
+    if(!handle) throw std::invalid_argument("kgb_handle_broadcast_staged_weights: NULL handle");
+    if(!handle->ncclComm) throw std::invalid_argument("kgb_handle_broadcast_staged_weights: kgb_handle_comm_init first");
+    if(root < 0 || root >= handle->ncclRanks) throw std::invalid_argument("kgb_handle_broadcast_staged_weights: root out of range");
+    if(handle->ncclRank == root && !handle->staged) throw std::invalid_argument("kgb_handle_broadcast_staged_weights: the root has nothing staged");
+    CK(cudaSetDevice(handle->device));
+    ensureShadow(handle);
+    // the packed arena (fp16 conv weights, fp32 scales / biases / head matrices), device to device, in place in the shadow arena;
+    // the copy stream orders it behind the root's own host-to-device staging copy
+    CK(cudaEventRecord(handle->bcastStart, handle->copyStream));
+    ncclCheck(ncclApi().broadcast(handle->wShadow, handle->wShadow, handle->wBytes, ncclChar, root, (ncclComm_t)handle->ncclComm, handle->copyStream),
+              "ncclBroadcast");
+    CK(cudaEventRecord(handle->bcastStop, handle->copyStream));
+    CK(cudaEventRecord(handle->stagedEvent, handle->copyStream));
+    CK(cudaStreamSynchronize(handle->copyStream));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, handle->bcastStart, handle->bcastStop));
+    if(ms_out) *ms_out = ms;
+    handle->staged = true;
+  });
+}
 
 KGB_API int kgb_handle_is_fp16(const kgb_handle* handle) { return handle && !handle->split ? 1 : 0; }
 KGB_API uint64_t kgb_handle_stream(kgb_handle* handle) { return handle ? (uint64_t)(uintptr_t)handle->stream : 0; }
@@ -788,6 +1019,8 @@ struct SingleConv {
     CK(convTCInit());
     CK(convTC2Init());
     CK(convTC3Init());
+    h.wCheckSpans = false;
+    h.wAllocArena((size_t)ky * kx * cpad(out_c) * ((size_t)cpad(in_c) * 2 + cpad(out_c)) * sizeof(__half) + 4 * (size_t)cpad(out_c) * sizeof(float) + 4096);
     Builder b(h);
     ConvDesc cd;
     cd.ky = ky; cd.kx = kx; cd.cin = in_c; cd.cout = out_c;
@@ -807,6 +1040,7 @@ struct SingleConv {
     if(bnScale) bn.scale.assign(bnScale, bnScale + out_c);
     if(bnBias) bn.bias.assign(bnBias, bnBias + out_c);
     Builder::BNDev dev = b.uploadBN(bn, actKind, cw.cout_p);
+    h.wFlushLive();
     for(int r = 0; r < rotate; r++) {
       __half* Ar = r == 0 ? A : h.dalloc<__half>(M * cw.cin_p * b.actMul);
       As.push_back(Ar);
@@ -830,6 +1064,7 @@ struct SingleConv {
   }
   ~SingleConv() {
     for(void* p : h.allocs) cudaFree(p);
+    if(h.wHost) cudaFreeHost(h.wHost);
     if(h.stream) cudaStreamDestroy(h.stream);
   }
   void setInput(const float* input /* NHWC */) {
@@ -974,7 +1209,7 @@ struct kgb_selfplay {
 
 static void selfplayStepLaunches(kgb_selfplay* sp, cudaStream_t s) {
   selfplayLaunchSelect(sp->impl, s);
-  if(sp->fakeNN) selfplayLaunchFakeNN(sp->impl, sp->h->dPolicy, sp->h->dValue, sp->h->dScore, s);
+  if(sp->fakeNN) selfplayLaunchFakeNN(sp->impl, sp->h->dPolicy, sp->h->dValue, sp->h->dScore, sp->h->dOwnership, s);
   else for(auto& op : sp->h->ops) op(sp->n, s);
   selfplayLaunchBackup(sp->impl, s);
 }
@@ -1059,7 +1294,7 @@ KGB_API int kgb_selfplay_create(kgb_handle* handle, const kgb_selfplay_config* c
     sp->h = handle;
     sp->n = config->num_games;
     sp->fakeNN = config->debug_fake_nn != 0;
-    SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue, handle->dScore,
+    SelfplayNNBuffers nn{handle->dSpatial, handle->dGlobal, handle->dOptimism, handle->dSymmetry, handle->dPolicy, handle->dValue, handle->dScore, handle->dOwnership,
                          (double)handle->model->scoreMeanMultiplier, (double)handle->model->scoreStdevMultiplier, (double)handle->model->leadMultiplier};
     sp->impl = selfplayCreate(*config, handle->L.X, handle->L.Y, nn, handle->stream);
     *out = sp.release();
@@ -1145,6 +1380,14 @@ KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double
     CK(cudaSetDevice(sp->h->device));
     CK(cudaStreamSynchronize(sp->h->stream));
     selfplayReadRootMoments(sp->impl, game, child_stats, root_stats);
+  });
+}
+
+KGB_API int kgb_selfplay_clear_nn_cache(kgb_selfplay* sp) {
+  return guarded([&] {
+    if(!sp) throw std::invalid_argument("kgb_selfplay_clear_nn_cache: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    selfplayClearNNCache(sp->impl, sp->h->stream);
   });
 }
 

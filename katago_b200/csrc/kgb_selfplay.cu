@@ -130,6 +130,13 @@ struct SPDev {
   int fixedSymmetryPlusOne;         // TEST ONLY (kgb_selfplay_config.debug_fixed_symmetry_plus_one)
   int maxPlayoutsPerWave;           // playouts a game may finish inside one select launch without needing the evaluator
   unsigned long long* stalledWaves; // game-waves that did not produce a leaf
+  // Search::getEndingWhiteScoreBonus / isAllowedRootMove (searchhelpers.cpp:310-420): per-root data, filled when the root's evaluation is final
+  double rootEndingBonusPoints; int rootPruneUselessMoves;
+  const float* nnOwnership;         // [game][XY] raw ownership logits of the last wave (original orientation, mover's perspective)
+  float* rootOwnAcc;                // [game][XY] sum over the root's evaluations of white's ownership (tanh, colour flipped): NNOutput averaging
+  double* rootEndBonus;             // [game][policySize] ending score bonus of every root move, white's perspective (0 = none)
+  uint32_t* rootAllowed;            // [game][32] root moves Search::isAllowedRootMove accepts (bit x of row y); the pass always is
+  int* passStreak;                  // [game][2] consecutive passes most recently made by black / white (the opponent's last four moves were passes <=> >= 4)
   float* rootRow;                   // [game][XY*22 + 19]: the NN input row (fillRowV7, no symmetry) of the game's current root, kept when the root is evaluated
   long long* dbgCycles;             // [game][8] clock64 spans of the last select launch: whole block, root move + tree reset, warp 0 (descent + leaf features), ladder searches, descent, liberties + legality, area (Benson), feature-row writes
   uint32_t* ladderScratch;          // [game][SP_LADDER_WARPS][ladderScratchWordsPerWarp()]
@@ -306,6 +313,7 @@ __device__ __forceinline__ void gameHistReset(const SPDev& d, int g, int lane) {
 }
 // One move of the GAME (root): board, Zobrist hash, pass count and - with the full rules - the game's lists, bans and end flags.
 __device__ void gameMakeMove(const SPDev& d, int g, WarpBoard& bd, int p, bool black, int lane, int& passes, bool& finished, bool& noResult) {
+  if(lane == 0) d.passStreak[g * 2 + (black ? 0 : 1)] = p < 0 ? d.passStreak[g * 2 + (black ? 0 : 1)] + 1 : 0;
   if(!d.histRules) {
     boardPlay(bd, p, black, d.zob);
     passes = p < 0 ? passes + 1 : 0;
@@ -376,6 +384,8 @@ __device__ __forceinline__ void rootHashesInit(const SPDev& d, int g, int lane) 
   if(lane == 0) { d.nodePosH0[gb] = h0; d.nodePosH1[gb] = h1; d.nodeGH0[gb] = s0; d.nodeGH1[gb] = s1; }
 }
 
+__device__ __forceinline__ double rootChildUtilityWithBonus(const SPDev& d, int g, size_t gb, int c, int mv, double utilityAvg);
+__device__ void computeRootExtras(const SPDev& d, int g, const WarpBoard& bd, bool rootBlack, bool haveOwnership, int numEvals, int lane);
 // Search::getPlaySelectionValues for the root (searchresults.cpp:66-330; no human policy, no pass suppression, no ending
 // bonus): values by child in creation order into psv[0..nc), their moves into moves[].  One thread.  Returns the child count.
 __device__ int rootPlaySelectionValues(const SPDev& d, int g, double* psv, double* lcbBuf, double* radiusBuf) {
@@ -430,7 +440,7 @@ __device__ int rootPlaySelectionValues(const SPDev& d, int g, double* psv, doubl
       const float P = d.policy[nb + mv];
       // getExploreSelectionValueOfChild outside the search: a child without visits or weight would take the FPU value; the
       // most explored child always has both
-      const double cu = d.nodeUtilAvg[gb + c];
+      const double cu = rootChildUtilityWithBonus(d, g, gb, c, mv, d.nodeUtilAvg[gb + c]);
       bestValue = P < 0 ? -1e50 : exploreScaling * (double)P / (1.0 + w) + (rootWhite ? cu : -cu);
     }
     for(int k = 0; k < nc; k++) {
@@ -440,7 +450,7 @@ __device__ int rootPlaySelectionValues(const SPDev& d, int g, double* psv, doubl
       double reduced = 0.0;
       if(!(cv <= 0 || w <= 0.0)) {
         const float P = d.policy[nb + mv];
-        const double cu = d.nodeUtilAvg[gb + c];
+        const double cu = rootChildUtilityWithBonus(d, g, gb, c, mv, d.nodeUtilAvg[gb + c]);
         double wanted = 0.0;                                               // getExploreSelectionValueInverse
         if(!(P < 0)) {
           const double valueComponent = rootWhite ? cu : -cu;
@@ -473,7 +483,7 @@ __device__ int rootPlaySelectionValues(const SPDev& d, int g, double* psv, doubl
         weightSum += priorWeight;
         weightSqSum += priorWeight * priorWeight;
         ess = weightSum * weightSum / weightSqSum;
-        const double utilityWithBonus = utilityAvg + 0.0;
+        const double utilityWithBonus = rootChildUtilityWithBonus(d, g, gb, c, mv, utilityAvg);
         const double selfUtility = rootWhite ? utilityWithBonus : -utilityWithBonus;
         const double utilityVariance = utilitySqAvg - utilityAvg * utilityAvg;
         const double radius = sqrt(utilityVariance / ess) * d.lcbStdevs;
@@ -643,7 +653,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     gameHistReset(d, g, lane);
     passes = 0; mv = 0;
     if(lane < 5) d.hist[g * 5 + lane] = -1;
-    if(lane == 0) d.rootBlackToMove[g] = 1;
+    if(lane == 0) { d.rootBlackToMove[g] = 1; d.passStreak[g * 2] = 0; d.passStreak[g * 2 + 1] = 0; }
   }
   else {
     int h = lane < 5 ? d.hist[g * 5 + lane] : -1;
@@ -803,7 +813,11 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(k >= nc) continue;
       double val = -1e50;                                           // POLICY_ILLEGAL_SELECTION_VALUE
       if(P[ch] >= 0.0f) {
-        const double cu = (CVis[ch] <= 0 || CW[ch] <= 0.0) ? fpuValue : CU[ch];
+        double cu = (CVis[ch] <= 0 || CW[ch] <= 0.0) ? fpuValue : CU[ch];
+        if(isRoot && d.rootEndingBonusPoints != 0.0 && !(CVis[ch] <= 0 || CW[ch] <= 0.0)) {
+          const int mvk = (int)d.childOrder[nb + k];
+          cu = rootChildUtilityWithBonus(d, g, gb, d.childNode[nb + mvk], mvk, cu);
+        }
         val = exploreScaling * (double)P[ch] / (1.0 + CW[ch]) + (black ? -cu : cu);
         if(isRoot && d.rootDesiredPerChildVisitsCoeff > 0.0 && P[ch] > 0.0f &&
            CW[ch] < sqrt((double)P[ch] * totalW * d.rootDesiredPerChildVisitsCoeff)) val = 1e20;
@@ -822,6 +836,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       const int i = ch * 32 + lane;
       if(i >= d.policySize) continue;
       const float p = d.policy[nb + i];
+      if(isRoot && d.rootPruneUselessMoves && i < d.XY && !((d.rootAllowed[g * 32 + i / d.X] >> (i % d.X)) & 1u)) continue;   // Search::isAllowedRootMove
       if(p >= 0.0f && d.childNode[nb + i] < 0 && p > bestNewP) { bestNewP = p; bestNewIdx = i; }
     }
 #pragma unroll
@@ -941,6 +956,8 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
     float vals[6];
     if(cacheLookup(d, g, node, k0, k1, vals, lane)) {
+      if(node == 0 && (d.rootEndingBonusPoints != 0.0 || d.rootPruneUselessMoves))
+        computeRootExtras(d, g, bd, black, false, 1, lane);     // a root served by the cache has no ownership map: allowed moves only
       maybeRootNoise(d, g, node, lane);
       const double u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], lane);
       finishPlayout(d, g, node, u, false, black, depth, shSum, lane);
@@ -1339,6 +1356,81 @@ __device__ double scoreUtilityOf(const SPDev& d, double scoreMean, double scoreM
     r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, center, d.dynamicScoreCenterScale, sqrtBoardArea) * d.dynamicScoreUtilityFactor;
   return r;
 }
+// Search::getScoreUtilityDiff (searchhelpers.cpp:281-293): what `delta` more points for white are worth at this child's score statistics
+__device__ double scoreUtilityDiff(const SPDev& d, double scoreMean, double scoreMeanSq, double delta, double center) {
+  const double sqrtBoardArea = sqrt((double)d.XY);
+  const double stdev = svScoreStdev(scoreMean, scoreMeanSq);
+  const double staticDiff = svExpectedWhiteScoreValue(d.svTable, scoreMean + delta, stdev, 0.0, 2.0, sqrtBoardArea) -
+                            svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, 0.0, 2.0, sqrtBoardArea);
+  const double dynamicDiff = svExpectedWhiteScoreValue(d.svTable, scoreMean + delta, stdev, center, d.dynamicScoreCenterScale, sqrtBoardArea) -
+                             svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, center, d.dynamicScoreCenterScale, sqrtBoardArea);
+  return staticDiff * d.staticScoreUtilityFactor + dynamicDiff * d.dynamicScoreUtilityFactor;
+}
+// utility of root child c with the ending score bonus of its move folded in (getExploreSelectionValueOfChild, searchexplorehelpers.cpp:135-139)
+__device__ __forceinline__ double rootChildUtilityWithBonus(const SPDev& d, int g, size_t gb, int c, int mv, double utilityAvg) {
+  const double bonus = d.rootEndBonus[(size_t)g * d.policySize + mv];
+  if(bonus == 0.0) return utilityAvg;
+  const double* cm = d.nodeMoments + (gb + c) * 5;
+  return utilityAvg + scoreUtilityDiff(d, cm[2], cm[3], bonus, d.recentScoreCenter[g]);
+}
+// Once the root's evaluation is final (one warp): which root moves are allowed (rootPruneUselessMoves) and the ending score bonus of every move.
+// bd = the root position, rootBlack = the player to move, haveOwnership = d.rootOwnAcc holds the summed ownership of `numEvals` evaluations.
+__device__ void computeRootExtras(const SPDev& d, int g, const WarpBoard& bd, bool rootBlack, bool haveOwnership, int numEvals, int lane) {
+  const uint32_t rm = bd.rowMask;
+  const uint32_t own = rootBlack ? bd.b : bd.w, opp = rootBlack ? bd.w : bd.b;
+  const uint32_t empty = ~(bd.b | bd.w) & rm;
+  uint32_t safeB = 0, safeW = 0;
+  if(d.rootPruneUselessMoves || d.rootEndingBonusPoints != 0.0)
+    boardCalculateArea(bd, false, false, false, d.multiSuicide != 0, safeB, safeW);   // rootSafeArea: pass-alive groups and strictly safe territory (search.cpp:1111-1122)
+  uint32_t allowed = 0xffffffffu;
+  if(d.rootPruneUselessMoves && d.passStreak[g * 2 + (rootBlack ? 1 : 0)] >= 4) allowed = ~(safeB | safeW);
+  d.rootAllowed[g * 32 + lane] = allowed;
+  double* bonus = d.rootEndBonus + (size_t)g * d.policySize;
+  for(int i = lane; i < d.policySize; i += 32) bonus[i] = 0.0;
+  __syncwarp();
+  if(d.rootEndingBonusPoints == 0.0 || !haveOwnership || bd.ko >= 0) return;   // area scoring, no button: nothing for the pass; nothing during a ko
+  uint32_t lib1, lib2, lib3;
+  boardLibertyClasses(bd, lib1, lib2, lib3);
+  const uint32_t captures = nbrs(opp & lib1, rm) & empty;          // Board::wouldBeCapture
+  const uint32_t touchesOpp = nbrs(opp, rm) & empty;               // Board::isAdjacentToPla(loc, opp)
+  const uint32_t safeOwn = rootBlack ? safeB : safeW;
+  // Board::isNonPassAliveSelfConnection: an empty point outside the player's own pass-alive area with a neighbouring own stone that
+  // is in nobody's pass-alive area, whose own neighbours belong to at least two different chains (the chain picked first does not matter)
+  uint32_t cand = empty & ~safeOwn & nbrs(own & ~(safeB | safeW), rm);
+  uint32_t selfConn = 0;
+  while(true) {
+    const int p = firstPoint(cand);
+    if(p < 0) break;
+    const uint32_t pt = pointMask(p);
+    cand &= ~pt;
+    const uint32_t nb = nbrs(pt, rm) & own;
+    const int q = firstPoint(nb);
+    if(q < 0) continue;
+    const uint32_t chain = flood(pointMask(q), own, rm);
+    if(__any_sync(KGB_FULL, (nb & ~chain) != 0)) selfConn |= pt;
+  }
+  const float floatLen = (float)numEvals;
+  const float* acc = d.rootOwnAcc + (size_t)g * d.XY;
+  const double extreme = 0.95, tail = 0.05;
+  if(lane < d.Y) {
+    for(int x = 0; x < d.X; x++) {
+      const uint32_t bit = 1u << x;
+      if(!(empty & bit)) continue;
+      const int pos = lane * d.X + x;
+      const float whiteOwn = numEvals > 1 ? acc[pos] / floatLen : acc[pos];
+      const double plaOwnership = rootBlack ? -(double)whiteOwn : (double)whiteOwn;
+      double extraRootPoints = 0.0;
+      if(plaOwnership <= -extreme) {
+        if(!(captures & bit)) extraRootPoints -= d.rootEndingBonusPoints * ((-extreme - plaOwnership) / tail);
+      }
+      else if(plaOwnership >= extreme) {
+        if(!(touchesOpp & bit) && !(selfConn & bit)) extraRootPoints -= d.rootEndingBonusPoints * ((plaOwnership - extreme) / tail);
+      }
+      bonus[pos] = rootBlack ? -extraRootPoints : extraRootPoints;
+    }
+  }
+  __syncwarp();
+}
 // Search::getUtilityFromNN (searchhelpers.cpp:304-307) from the NNOutput fields (floats, white's perspective); a fresh root
 // first centres the dynamic score utility on its expected score (Search::beginSearch, search.cpp:1125-1154).
 __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWin, float whiteLoss, float noResult, float whiteScoreMeanF,
@@ -1577,6 +1669,18 @@ __global__ void spBackupKernel(const SPDev d) {
     vals[0] = leafBlack ? lf : wf; vals[1] = leafBlack ? wf : lf; vals[2] = nf;
     vals[3] = leafBlack ? -(float)scoreMean : (float)scoreMean; vals[4] = (float)scoreMeanSq; vals[5] = leafBlack ? -(float)lead : (float)lead;
     __syncwarp();
+    const bool freshRoot = node == 0 && d.nodeVisits[gb] == 0;
+    const bool wantRootExtras = freshRoot && (d.rootEndingBonusPoints != 0.0 || d.rootPruneUselessMoves);
+    if(wantRootExtras && d.rootEndingBonusPoints != 0.0 && symCount >= 0) {
+      // NNOutput::whiteOwnerMap of this evaluation (nneval.cpp:1233-1250: tanh, flipped to white's perspective), summed like NNOutput(others)
+      const float* raw = d.nnOwnership + (size_t)g * d.XY;
+      float* oacc = d.rootOwnAcc + (size_t)g * d.XY;
+      for(int i = lane; i < d.XY; i += 32) {
+        const float o = leafBlack ? -tanhf(raw[i]) : tanhf(raw[i]);
+        oacc[i] = symCount > 0 ? oacc[i] + o : o;
+      }
+      __syncwarp();
+    }
     if(multiSymRoot) {
       if(symCount < 0) {
         // the centring evaluation: recentScoreCenter from its expected score (search.cpp:1148-1153), nothing else is kept
@@ -1603,6 +1707,12 @@ __global__ void spBackupKernel(const SPDev d) {
       __syncwarp();
     }
     else if(d.cacheSize > 0) cacheStore(d, g, node, d.leafKey[g * 2], d.leafKey[g * 2 + 1], vals, lane);   // before any root noise: the raw evaluation
+    if(wantRootExtras) {
+      WarpBoard rb;
+      boardInit(rb, d.X, d.Y);
+      rb.b = d.rootB[g * 32 + lane]; rb.w = d.rootW[g * 32 + lane]; rb.ko = d.rootKo[g];
+      computeRootExtras(d, g, rb, leafBlack, true, multiSymRoot ? d.rootNumSymmetries : 1, lane);
+    }
     maybeRootNoise(d, g, node, lane);
     u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], lane);
   }
@@ -1614,7 +1724,7 @@ __global__ void spBackupKernel(const SPDev d) {
 // TEST SUPPORT: deterministic fake net (identical to the one oracle/ref_driver.cpp gives the reference Search, so tree
 // parity can be checked against the reference without any real net) and root-position setup.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut, float* scoreOut) {
+__global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut, float* scoreOut, float* ownershipOut) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
@@ -1634,6 +1744,9 @@ __global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut,
     if(i == d.policySize - 1) logit -= 3.0f;
     policyOut[(size_t)g * d.policySize + i] = logit;
   }
+  if(ownershipOut != nullptr)   // raw ownership logits in [-4,4) per point, mover's perspective (oracle/ref_driver.cpp's fake net)
+    for(int i = lane; i < d.XY; i += 32)
+      ownershipOut[(size_t)g * d.XY + i] = (float)(uint32_t)(splitmix64(h + (uint64_t)(i + 1) * 0xD1B54A32D192ED03ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
   if(lane == 0) {
     valueOut[g * 3 + 0] = (float)(uint32_t)(splitmix64(h ^ 0x1111ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
     valueOut[g * 3 + 1] = (float)(uint32_t)(splitmix64(h ^ 0x2222ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
@@ -2054,6 +2167,11 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.leafLegal = sp->alloc<uint32_t>(G * 32);
   unsigned long long* stats = sp->alloc<unsigned long long>(16);
   d.totalVisits = stats; d.totalMoves = stats + 1; d.gamesFinished = stats + 2; d.blackWins = stats + 3; d.nodesAllocated = stats + 4;
+  d.rootEndingBonusPoints = c.root_ending_bonus_points; d.rootPruneUselessMoves = c.root_prune_useless_moves != 0 ? 1 : 0;
+  d.nnOwnership = nn.ownership;
+  d.rootOwnAcc = sp->alloc<float>(G * (size_t)X * Y); d.rootEndBonus = sp->alloc<double>(G * PS); d.rootAllowed = sp->alloc<uint32_t>(G * 32);
+  d.passStreak = sp->alloc<int>(G * 2);
+  SPCK(cudaMemset(d.rootAllowed, 0xff, G * 32 * sizeof(uint32_t)));
   d.dbgCycles = sp->alloc<long long>(G * 8);
   d.rootRow = sp->alloc<float>(G * ((size_t)X * Y * 22 + 19));
   d.sumDepth = stats + 5; d.ladderCounters = stats + 6; d.stalledWaves = stats + 8; d.instantPlayouts = stats + 9; d.cacheHits = stats + 10; d.cacheStores = stats + 11;
@@ -2086,6 +2204,15 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
 
 void selfplayDestroy(SelfplayImpl* sp) { delete sp; }
 
+// After a weight swap (kgb_handle_commit_weights) the cached outputs belong to the previous net: the reference gets the same effect by
+// giving every NNEvaluator its own NNCacheTable (nneval.cpp:129-130).  Ordered on the wave stream.
+void selfplayClearNNCache(SelfplayImpl* sp, cudaStream_t s) {
+  SPDev& d = sp->d;
+  if(d.cacheSize <= 0) return;
+  SPCK(cudaMemsetAsync(d.cacheKey0, 0, (size_t)d.cacheSize * sizeof(unsigned long long), s));
+  SPCK(cudaMemsetAsync(d.cacheKey1, 0, (size_t)d.cacheSize * sizeof(unsigned long long), s));
+}
+
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s) {
   spSelectKernel<<<sp->d.numGames, SP_LADDER_WARPS * 32, 0, s>>>(sp->d);
   SPCK(cudaGetLastError());
@@ -2096,9 +2223,9 @@ void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s) {
   SPCK(cudaGetLastError());
 }
 
-void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, cudaStream_t s) {
+void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, float* ownershipOut, cudaStream_t s) {
   int threads = 128, warpsPerBlock = threads / 32;
-  spFakeNNKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, policyOut, valueOut, scoreOut);
+  spFakeNNKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, policyOut, valueOut, scoreOut, ownershipOut);
   SPCK(cudaGetLastError());
 }
 

@@ -14,14 +14,16 @@ struct SelfplayImpl;
 struct SelfplayNNBuffers {  // device buffers of the evaluator handle the loop writes to / reads from
   float* spatial; float* global; float* optimism; int* symmetry;
   const float* policy; const float* value; const float* score;
+  const float* ownership;   // [game][XY] raw ownership logits of the last wave, original orientation, mover's perspective
   double scoreMeanMultiplier, scoreStdevMultiplier, leadMultiplier;   // ModelPostProcessParams (desc.h) of the loaded net
 };
 
 SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const SelfplayNNBuffers& nn, cudaStream_t stream);
 void selfplayDestroy(SelfplayImpl* sp);
+void selfplayClearNNCache(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
-void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, cudaStream_t s);
+void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, float* ownershipOut, cudaStream_t s);
 void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s);
 void selfplaySetSearchRand(SelfplayImpl* sp, const char* seedString);
 void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s);

@@ -57,12 +57,12 @@ class SelfplayConfig(C.Structure):
         ("root_dirichlet_noise_total_concentration", C.c_double), ("root_dirichlet_noise_weight", C.c_double),
         ("root_policy_temperature", C.c_double), ("root_policy_temperature_early", C.c_double),
         ("chosen_move_temperature_halflife", C.c_double),
-        ("use_play_selection", C.c_int32), ("use_lcb_for_selection", C.c_int32), ("use_non_buggy_lcb", C.c_int32), ("reserved3", C.c_int32),
+        ("use_play_selection", C.c_int32), ("use_lcb_for_selection", C.c_int32), ("use_non_buggy_lcb", C.c_int32), ("root_prune_useless_moves", C.c_int32),
         ("lcb_stdevs", C.c_double), ("min_visit_prop_for_lcb", C.c_double), ("chosen_move_temperature", C.c_double),
         ("chosen_move_temperature_early", C.c_double), ("chosen_move_temperature_only_below_prob", C.c_double),
         ("chosen_move_subtract", C.c_double), ("chosen_move_prune", C.c_double),
         ("nn_cache_size_power_of_two", C.c_int32), ("root_num_symmetries_to_sample", C.c_int32),
-        ("ko_rule", C.c_int32), ("full_history_rules", C.c_int32),
+        ("ko_rule", C.c_int32), ("full_history_rules", C.c_int32), ("root_ending_bonus_points", C.c_double),
     ]
 
 
@@ -457,7 +457,8 @@ class SelfPlay:
                  lcb_stdevs: float = 4.0, min_visit_prop_for_lcb: float = 0.05, chosen_move_temperature: float = 0.0,
                  chosen_move_temperature_early: float = 0.0, chosen_move_temperature_only_below_prob: float = 1.0,
                  chosen_move_subtract: float = 0.0, chosen_move_prune: float = 1.0, nn_cache_size_power_of_two: int = 0, root_num_symmetries_to_sample: int = 1,
-                 ko_rule: int = 0, full_history_rules: bool = False, debug_fixed_symmetry: int = -1):
+                 ko_rule: int = 0, full_history_rules: bool = False, debug_fixed_symmetry: int = -1,
+                 root_ending_bonus_points: float = 0.0, root_prune_useless_moves: bool = False):
         lib = load_library()
         self.handle = handle
         self.cfg = SelfplayConfig(num_games, max_visits, max_moves, int(multi_stone_suicide_legal), early_temperature_moves, komi,
@@ -472,10 +473,10 @@ class SelfPlay:
                                   int(graph_search_rep_bound), int(debug_hold_at_max_visits), int(root_noise_enabled),
                                   root_dirichlet_noise_total_concentration, root_dirichlet_noise_weight, root_policy_temperature,
                                   root_policy_temperature_early, chosen_move_temperature_halflife,
-                                  int(use_play_selection), int(use_lcb_for_selection), int(use_non_buggy_lcb), 0, lcb_stdevs, min_visit_prop_for_lcb,
+                                  int(use_play_selection), int(use_lcb_for_selection), int(use_non_buggy_lcb), int(root_prune_useless_moves), lcb_stdevs, min_visit_prop_for_lcb,
                                   chosen_move_temperature, chosen_move_temperature_early, chosen_move_temperature_only_below_prob,
                                   chosen_move_subtract, chosen_move_prune, int(nn_cache_size_power_of_two), int(root_num_symmetries_to_sample),
-                                  int(ko_rule), int(full_history_rules))
+                                  int(ko_rule), int(full_history_rules), float(root_ending_bonus_points))
         self._p = C.c_void_p()
         _check(lib.kgb_selfplay_create(handle._p, C.byref(self.cfg), C.byref(self._p)))
         self.x, self.y = handle.context.nnXLen, handle.context.nnYLen

@@ -47,6 +47,7 @@ _SEARCH_KEYS = {
     "noResultUtilityForWhite": ("no_result_utility_for_white", float), "drawEquivalentWinsForWhite": ("draw_equivalent_wins_for_white", float),
     "rootNumSymmetriesToSample": ("root_num_symmetries_to_sample", int), "nnCacheSizePowerOfTwo": ("nn_cache_size_power_of_two", int),
     "maxMovesPerGame": ("max_moves", int),
+    "rootEndingBonusPoints": ("root_ending_bonus_points", float), "rootPruneUselessMoves": ("root_prune_useless_moves", _B),
 }
 # keys that only place or log the reference's own CPU threads / evaluator servers: nothing to do here
 _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
@@ -56,7 +57,7 @@ _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0
             "reduceVisits": False, "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
             "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
             "handicapProb": 0.0, "komiStdev": 0.0, "komiBigStdevProb": 0.0, "komiBiggerStdevProb": 0.0, "allowRectangleProb": 0.0,
-            "rootEndingBonusPoints": 0.0, "rootPruneUselessMoves": False, "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
+            "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
 _REFERENCE_DEFAULTS = {
     "cpuct_exploration": 1.0, "cpuct_exploration_log": 0.45, "cpuct_exploration_base": 500.0, "fpu_reduction_max": 0.2, "root_fpu_reduction_max": 0.1,
     "win_loss_utility_factor": 1.0, "no_result_utility_for_white": 0.0, "static_score_utility_factor": 0.1, "dynamic_score_utility_factor": 0.3,
@@ -68,10 +69,10 @@ _REFERENCE_DEFAULTS = {
     "root_policy_temperature": 1.0, "root_policy_temperature_early": 1.0, "chosen_move_temperature_halflife": 19.0, "use_lcb_for_selection": True,
     "use_non_buggy_lcb": False, "lcb_stdevs": 5.0, "min_visit_prop_for_lcb": 0.15, "chosen_move_temperature": 0.10, "chosen_move_temperature_early": 0.50,
     "chosen_move_temperature_only_below_prob": 1.0, "chosen_move_subtract": 0.0, "chosen_move_prune": 1.0, "nn_cache_size_power_of_two": 0,
-    "root_num_symmetries_to_sample": 1,
+    "root_num_symmetries_to_sample": 1, "root_ending_bonus_points": 0.5, "root_prune_useless_moves": True,
 }
-# options the reference switches ON by default and the loop does not have: reported even when the key is absent
-_DEFAULT_ON_NOT_BUILT = {"rootEndingBonusPoints": "0.5", "rootPruneUselessMoves": "true"}
+# options the reference switches ON by default and the loop does not have: reported even when the key is absent (none at present)
+_DEFAULT_ON_NOT_BUILT = {}
 _KO_RULES = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2, "SPIGHT": 3}
 
 

@@ -182,7 +182,11 @@ void NeuralNet::getOutput(ComputeHandle* h, InputBuffers*, int n, NNResultBuf** 
     o->whiteScoreMeanSq = (float)(uint32_t)(splitmix64(hsh ^ 0x4444ULL) >> 48) * (1.0f / 16384.0f) - 2.0f;
     o->whiteLead = (float)(uint32_t)(splitmix64(hsh ^ 0x5555ULL) >> 48) * (1.0f / 32768.0f) - 1.0f;
     o->varTimeLeft = 0; o->shorttermWinlossError = 0; o->shorttermScoreError = 0;
-    if(o->whiteOwnerMap != NULL) std::fill(o->whiteOwnerMap, o->whiteOwnerMap + xy, 0.0f);
+    // raw ownership logits in [-4,4) per point (mover's perspective; NNEvaluator applies tanh and the colour flip, nneval.cpp:1233-1250):
+    // about half of the points end beyond |tanh| = 0.95, where Search::getEndingWhiteScoreBonus acts
+    if(o->whiteOwnerMap != NULL)
+      for(int i = 0; i < xy; i++)
+        o->whiteOwnerMap[i] = (float)(uint32_t)(splitmix64(hsh + (uint64_t)(i + 1) * 0xD1B54A32D192ED03ULL) >> 48) * (1.0f / 8192.0f) - 4.0f;
   }
 }
 bool NeuralNet::testEvaluateConv(const ConvLayerDesc*, int, int, int, bool, bool, const std::vector<float>&, std::vector<float>&) { return false; }
@@ -200,7 +204,10 @@ static int cmdSearchFake(int argc, char** argv) {
   ScoreValue::initTables();
   Logger logger(nullptr, false, false, false);
   ConfigParser cfg;
-  NNEvaluator* nnEval = new NNEvaluator("fake", modelFile, "", &logger, 4, X, Y, true, true, 10, 8, false, "", enabled_t::False, 1,
+  // KGREF_NN_CACHE_POW2 = -1 switches NNEvaluator's evaluation cache off (it is keyed by the situation, not the history: with a real net a
+  // transposition then returns the output computed for another move order - fine for play, but not what a cache-less search sees)
+  const int cachePow2 = getenv("KGREF_NN_CACHE_POW2") ? atoi(getenv("KGREF_NN_CACHE_POW2")) : 10;
+  NNEvaluator* nnEval = new NNEvaluator("fake", modelFile, "", &logger, 4, X, Y, true, true, cachePow2, 8, false, "", enabled_t::False, 1,
                                         vector<int>{0}, "seed", false, 0, true, cfg);
   nnEval->spawnServerThreads();
   // Reference SearchParams restricted to what the device loop implements: everything else at its default.
@@ -251,6 +258,8 @@ static int cmdSearchFake(int argc, char** argv) {
     else if(k == "graphSearchRepBound") params.graphSearchRepBound = (int)v;
     else if(k == "subtreeValueBiasFactor") params.subtreeValueBiasFactor = v;
     else if(k == "subtreeValueBiasWeightExponent") params.subtreeValueBiasWeightExponent = v;
+    else if(k == "rootEndingBonusPoints") params.rootEndingBonusPoints = v;
+    else if(k == "rootPruneUselessMoves") params.rootPruneUselessMoves = v != 0;
     else { cerr << "unknown override " << k << endl; return 1; }
   }
   Rules rules;  // defaults, then the rule subset of the loop
@@ -945,7 +954,7 @@ static int cmdParamsMap(int argc, char** argv) {
   FD(root_policy_temperature); FD(root_policy_temperature_early); FD(chosen_move_temperature_halflife); FI(use_play_selection); FI(use_lcb_for_selection);
   FI(use_non_buggy_lcb); FD(lcb_stdevs); FD(min_visit_prop_for_lcb); FD(chosen_move_temperature); FD(chosen_move_temperature_early);
   FD(chosen_move_temperature_only_below_prob); FD(chosen_move_subtract); FD(chosen_move_prune); FI(nn_cache_size_power_of_two);
-  FI(root_num_symmetries_to_sample); FI(ko_rule); FI(full_history_rules);
+  FI(root_num_symmetries_to_sample); FI(ko_rule); FI(full_history_rules); FD(root_ending_bonus_points); FI(root_prune_useless_moves);
 #undef FI
 #undef FD
   cout << "\"unsupported\":[";

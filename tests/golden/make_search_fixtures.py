@@ -37,14 +37,15 @@ LCB = {"useLcbForSelection": 1, "lcbStdevs": 5.0, "minVisitPropForLCB": 0.15, "u
 BIAS = {"subtreeValueBiasFactor": 0.30, "subtreeValueBiasWeightExponent": 0.8}
 
 
-def run(X, Y, visits, moves, score=None, driver=None, model=None):
+def run(X, Y, visits, moves, score=None, driver=None, model=None, env=None):
     s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
     if score is None:
         score = {}
     elif not isinstance(score, dict):
         score = dict(zip(SCORE_KEYS, score))
     extra = [f"{k}={float(v)!r}" for k, v in score.items() if k != "fullHistoryRules"]
-    out = subprocess.run([driver or DRIVER, "searchfake", model or MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([driver or DRIVER, "searchfake", model or MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True,
+                         env=(dict(os.environ, **env) if env else None)).stdout
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     psv = np.full(X * Y + 1, -1.0, np.float64); threadseed = ""
     cstats = np.zeros((X * Y + 1, 5), np.float64); rstats = np.zeros(5, np.float64)
@@ -69,6 +70,14 @@ def run(X, Y, visits, moves, score=None, driver=None, model=None):
         elif f[0] == "policy":
             pol = np.array([float(t) for t in f[1:]], np.float32)
     return root, v, u, pol, center, psv, threadseed, cstats, rstats
+
+
+# Black builds a two-eyed (pass-alive) group in the corner while White, after two stones, passes four times: Black to move, the
+# opponent's last four moves are passes -> Search::isAllowedRootMove refuses Black's own eyes (0,0), (2,0) and nothing else.
+PRUNE_7X7 = [(1, 0), (5, 5), (0, 1), (5, 4), (1, 1), None, (2, 1), None, (3, 0), None, (3, 1), None]
+# both sides own a two-eyed corner group; Black adds four stones in the centre while White passes four times
+PRUNE_9X9 = [(1, 0), (7, 8), (0, 1), (8, 7), (1, 1), (7, 7), (2, 1), (6, 7), (3, 0), (5, 8), (3, 1), (5, 7),
+             (4, 4), None, (4, 3), None, (3, 4), None, (3, 3), None]
 
 
 if __name__ == "__main__":
@@ -140,6 +149,18 @@ if __name__ == "__main__":
         (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"koRule": 2}),
         (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"useGraphSearch": 1}),
         (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {}),
+        # the two root options the stock self-play configs switch on (a21 / a22): rootEndingBonusPoints (the fake net's ownership head puts about
+        # half of the points beyond |0.95|) and rootPruneUselessMoves (positions with pass-alive groups reached while the opponent passed four times)
+        (9, 9, 600, prefix_from_stream("boardstream_9x9_multisuicide.npz", 31), dict(SELFPLAY8B18, useGraphSearch=1, rootEndingBonusPoints=0.5, **BIAS, **LCB)),
+        (19, 19, 600, prefix_from_stream("boardstream_19x19_multisuicide.npz", 131),
+         dict(SELFPLAY8B18, useGraphSearch=1, rootNumSymmetriesToSample=4, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.5, rootEndingBonusPoints=0.5,
+              rootPruneUselessMoves=1, **BIAS, **LCB)),
+        (5, 5, 800, prefix_from_stream("boardstream_5x5_multisuicide.npz", 20), {"rootEndingBonusPoints": 0.5, "fullHistoryRules": 1, "staticScoreUtilityFactor": 0.1}),
+        (13, 7, 500, prefix_from_stream("boardstream_13x7_nosuicide.npz", 20), dict(SELFPLAY8B18, rootEndingBonusPoints=1.0, rootNumSymmetriesToSample=2)),
+        (7, 7, 400, PRUNE_7X7, dict(SELFPLAY8B18, rootPruneUselessMoves=1)),
+        (7, 7, 400, PRUNE_7X7, dict(SELFPLAY8B18, useGraphSearch=1, rootPruneUselessMoves=1, rootEndingBonusPoints=0.5, rootNumSymmetriesToSample=4, **BIAS, **LCB)),
+        (9, 9, 500, PRUNE_9X9, dict(SELFPLAY8B18, useGraphSearch=1, rootPruneUselessMoves=1, rootEndingBonusPoints=0.5, **BIAS, **LCB)),
+        (9, 9, 500, PRUNE_9X9[:-2], dict(SELFPLAY8B18, rootPruneUselessMoves=1, rootEndingBonusPoints=0.5)),     # only three opponent passes: nothing pruned
     ]
     store = {"num_cases": len(cases)}
     for i, case in enumerate(cases):

@@ -57,7 +57,7 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     # per-game randomisation the loop does not have is reported, as are the data-distribution options that are not built
     assert any(s.startswith("koRules") for s in report["fixed"]) and any(s.startswith("bSizes") for s in report["fixed"])
     nb = " ".join(report["not_built"])
-    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "rootEndingBonusPoints", "rootPruneUselessMoves", "handicapProb", "komiStdev",
+    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "handicapProb", "komiStdev",
                 "komiAuto"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
@@ -85,9 +85,10 @@ def test_neutral_values_and_unsupported_rules():
     kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\ncheapSearchProb = 0\nreduceVisits = false\nkoRules = POSITIONAL\nbSizes = 9\nkomiMean = 7\nrootEndingBonusPoints = 0\nrootPruneUselessMoves = false\n", is_text=True), strict=True)
     assert kw["ko_rule"] == 1 and data["board_size"] == 9 and data["komi"] == 7.0 and report["not_built"] == [] and report["fixed"] == []
     assert data["policy_surprise_data_weight"] == 0.0
-    # the two root options the reference switches on by default are reported even when the file does not mention them
-    _, _, rep = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\n", is_text=True))
-    assert any("rootEndingBonusPoints" in s_ and "default" in s_ for s_ in rep["not_built"]) and any("rootPruneUselessMoves" in s_ for s_ in rep["not_built"])
+    assert kw["root_ending_bonus_points"] == 0.0 and kw["root_prune_useless_moves"] is False
+    # the two root options the reference switches on by default are on when the file does not mention them (Setup::loadParams)
+    kw2, _, rep = C.selfplay_kwargs_from_cfg(C.parse_cfg("maxVisits = 100\n", is_text=True), strict=True)
+    assert kw2["root_ending_bonus_points"] == 0.5 and kw2["root_prune_useless_moves"] is True and rep["not_built"] == []
     with pytest.raises(ValueError, match="none of these is built"):
         C.selfplay_kwargs_from_cfg(C.parse_cfg("scoringRules = TERRITORY\n", is_text=True))
     with pytest.raises(ValueError, match="dataBoardLen"):
