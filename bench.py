@@ -114,24 +114,43 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def model_file(name: str, rank: int, world: int, device):
-    """Rank 0 synthesises the weights (no network: random init, real architecture); other ranks receive the bytes over
-    NCCL - the only collective on this path (weight broadcast, reference analogue: selfplay.cpp:142-231 file polling)."""
+def model_file(name: str, rank: int):
+    """Every rank synthesises a net of the architecture (no network: random init): rank 0 THE net (seed 0), the others a different
+    one (seed 1, their "previous" net) which the weight broadcast below replaces."""
     from katago_b200 import modelgen
-    import torch
-    from katago_b200.dist_weights import broadcast_model_bytes
     path = os.path.join(tempfile.mkdtemp(prefix=f"kgb_rank{rank}_"), f"{name}.bin")
-    if world == 1:
-        return modelgen.write_model(path, name, seed=0), 0.0
-    data = modelgen.model_bytes(name, seed=0) if rank == 0 else None
-    torch.cuda.synchronize()
-    t0 = time.time()
-    data = broadcast_model_bytes(data, 0, device)
-    torch.cuda.synchronize()
-    bcast_ms = (time.time() - t0) * 1e3
-    with open(path, "wb") as f:
-        f.write(data)
-    return path, bcast_ms
+    return modelgen.write_model(path, name, seed=0 if rank == 0 else 1)
+
+
+def broadcast_weights(handle, model, rank: int, world: int, device):
+    """NCCL - the only collective on this path: rank 0 stages its net, the library's ncclBroadcast moves the packed weight arena
+    into every other rank's device memory, all commit (katago_b200/dist_weights.py; include/kgb200.h; reference analogue: every
+    process polls the models directory and loads the file itself, selfplay.cpp:142-231).  Device time per broadcast, max over
+    ranks; the first call includes NCCL's connection set-up.  Afterwards every rank must evaluate a fixed batch bit-identically."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from katago_b200 import NeuralNet, modelgen
+    from katago_b200.dist_weights import WeightBroadcaster
+    wb = WeightBroadcaster(handle, 0, device)
+    times = []
+    for _ in range(4):
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([wb.update(model if rank == 0 else None)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    sp, gl = modelgen.synthetic_inputs(2, 19, 19, seed=4242)
+    out = NeuralNet.getOutput(handle, sp.reshape(2, -1), gl)
+    sha = hashlib.sha256(np.ascontiguousarray(out["policy"]).tobytes() + np.ascontiguousarray(out["value"]).tobytes()).digest()
+    mine = torch.from_numpy(np.frombuffer(sha, np.uint8).copy()).to(device)
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)
+    if not all(bool((x == everyone[0]).all()) for x in everyone):
+        raise RuntimeError("bench.py: after the weight broadcast the ranks do not evaluate identically")
+    steady = sorted(times[1:])[len(times[1:]) // 2]
+    return {"ms": steady, "first_ms": times[0], "bytes": handle.weights_bytes, "GBps_per_receiver": handle.weights_bytes / (steady * 1e-3) / 1e9,
+            "how": "kgb_handle_stage_weights on rank 0 -> ncclBroadcast of the packed arena (device to device) -> kgb_handle_commit_weights on every rank; "
+                   "ranks > 0 started from a different net and evaluate bit-identically to rank 0 afterwards"}
 
 
 CPU_SELFPLAY = os.path.join(ROOT, "oracle", "_ref", "kgref_cpu_selfplay")
@@ -219,7 +238,7 @@ class CountingSlots:
 
     def __getattr__(self, name):
         attr = getattr(self._sp, name)
-        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row"):
+        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row", "komi_values"):
             def counted(*a, **k):
                 out = attr(*a, **k)
                 self.d2h += _nbytes(out)
@@ -264,12 +283,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    path, bcast_ms = model_file(args.model, rank, world, device)
+    path = model_file(args.model, rank)
     lib = load_library()
     model = NeuralNet.loadModelFile(path)
     ctx = NeuralNet.createComputeContext([local_rank], 19, 19, not args.fp32, model)
     n = args.games
     handle = NeuralNet.createComputeHandle(ctx, model, n, False, True, local_rank)
+    bcast = broadcast_weights(handle, model, rank, world, device) if world > 1 else None
+    bcast_ms = bcast["ms"] if bcast else 0.0
     macs = model.desc["conv_macs_per_position"]
     flop_per_eval = 2.0 * macs * 361
 
@@ -509,7 +530,7 @@ def main():
                                   "playouts_without_evaluation(graph search catch-up)": instant,
                                   "playouts_served_by_nn_cache": cache_hits, "nn_cache_entries": (1 << args.nn_cache_pow2) if args.nn_cache_pow2 > 0 else 0,
                                   "game_waves": n * K},
-                       "weight_broadcast_ms": bcast_ms, "gpu_competitor": competitor},
+                       "weight_broadcast_ms": bcast_ms, "weight_broadcast": bcast, "gpu_competitor": competitor},
             "value_fp32_equivalent": value_fp32,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": slots.h2d / (pumps * PUMP), "d2h_bytes_per_step": slots.d2h / (pumps * PUMP),
                     "ms_per_step": ms_rec / (pumps * PUMP),

@@ -130,6 +130,9 @@ KGB_API int kgb_handle_launches_per_forward(const kgb_handle* handle);
 KGB_API int kgb_handle_weights_bytes(const kgb_handle* handle, uint64_t* bytes);
 KGB_API int kgb_handle_stage_weights(kgb_handle* handle, const kgb_model* model);
 KGB_API int kgb_handle_commit_weights(kgb_handle* handle);
+/* Blocks the host until the staging copy (or a received broadcast) has landed in the shadow arena; not needed before a commit
+ * (ordered on the device), useful before a barrier that lines the ranks up for a timed broadcast. */
+KGB_API int kgb_handle_wait_staged(kgb_handle* handle);
 KGB_API int kgb_nccl_unique_id(void* id_out_128_bytes);
 KGB_API int kgb_handle_comm_init(kgb_handle* handle, const void* id_128_bytes, int rank, int num_ranks);
 KGB_API int kgb_handle_broadcast_staged_weights(kgb_handle* handle, int root, float* ms_out);
@@ -300,6 +303,17 @@ KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double
  * host reads the finished search (getters above and below), releases, and the next wave lets the device choose and play the move
  * as usual.  games_mask[num_games] (1 = release) or NULL = all.  A released game holds again at its next finished search. */
 KGB_API int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* games_mask);
+/* Komi per game.  The reference's GameInitializer draws a komi for every game (program/play.cpp:330-420: komiMean, komiStdev,
+ * komiBigStdevProb, komiAuto ...); here the host draws and the device applies: komi[num_games] (multiples of 0.5) becomes the komi of
+ * each slot's NEXT game, taken when the slot's game in progress ends; also_current_games != 0 replaces the komi of the games in
+ * progress too (for games that have not begun to search).  kgb_selfplay_get_komi: komi of the game in progress and of the slot's
+ * last finished game (either pointer may be NULL).  The evaluation cache keys on the mover's komi (NNInputs::getHash,
+ * neuralnet/nninputs.cpp:869-943 via BoardHistory::getSituationRulesAndKoHash), so games of different komi never share an entry. */
+KGB_API int kgb_selfplay_set_komi(kgb_selfplay* sp, const float* komi, int also_current_games);
+KGB_API int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* last_finished);
+/* FOR TESTING: the evaluation-cache key (the loop's NNInputs::getHash) of the leaf that slot `game` sent to the evaluator in the
+ * last wave; only meaningful with nn_cache_size_power_of_two > 0. */
+KGB_API int kgb_selfplay_get_leaf_cache_key(kgb_selfplay* sp, int game, uint64_t* key2);
 /* Empties the loop's evaluation cache, ordered on the handle's stream: call it with kgb_handle_commit_weights - cached outputs
  * belong to the previous net (the reference gives every NNEvaluator its own NNCacheTable, nneval.cpp:129-130). */
 KGB_API int kgb_selfplay_clear_nn_cache(kgb_selfplay* sp);

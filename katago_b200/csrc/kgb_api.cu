@@ -839,6 +839,14 @@ KGB_API int kgb_handle_stage_weights(kgb_handle* handle, const kgb_model* model)
   });
 }
 
+KGB_API int kgb_handle_wait_staged(kgb_handle* handle) {
+  return guarded([&] {
+    if(!handle) throw std::invalid_argument("kgb_handle_wait_staged: NULL handle");
+    CK(cudaSetDevice(handle->device));
+    CK(cudaStreamSynchronize(handle->copyStream));
+  });
+}
+
 KGB_API int kgb_handle_commit_weights(kgb_handle* handle) {
   return guarded([&] {
     if(!handle) throw std::invalid_argument("kgb_handle_commit_weights: NULL handle");
@@ -1380,6 +1388,35 @@ KGB_API int kgb_selfplay_get_root_value_stats(kgb_selfplay* sp, int game, double
     CK(cudaSetDevice(sp->h->device));
     CK(cudaStreamSynchronize(sp->h->stream));
     selfplayReadRootMoments(sp->impl, game, child_stats, root_stats);
+  });
+}
+
+KGB_API int kgb_selfplay_set_komi(kgb_selfplay* sp, const float* komi, int also_current_games) {
+  return guarded([&] {
+    if(!sp || !komi) throw std::invalid_argument("kgb_selfplay_set_komi: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplaySetKomi(sp->impl, komi, also_current_games != 0);
+  });
+}
+
+KGB_API int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* last_finished) {
+  return guarded([&] {
+    if(!sp) throw std::invalid_argument("kgb_selfplay_get_komi: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadKomi(sp->impl, current, last_finished);
+  });
+}
+
+KGB_API int kgb_selfplay_get_leaf_cache_key(kgb_selfplay* sp, int game, uint64_t* key2) {
+  return guarded([&] {
+    if(!sp || !key2) throw std::invalid_argument("kgb_selfplay_get_leaf_cache_key: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    unsigned long long k[2];
+    selfplayReadLeafKey(sp->impl, game, k);
+    key2[0] = k[0]; key2[1] = k[1];
   });
 }
 

@@ -174,6 +174,7 @@ struct SPDev {
   int *leafNode, *leafTerminal, *leafBlackToMove;
   uint32_t* leafLegal;              // [game][32] row masks of legal points for the player to move at the leaf
   // statistics
+  float *komiG, *nextKomi, *lastKomi;   // per game: komi of the game in progress, of the slot's next game, of its last finished game
   unsigned long long *totalVisits, *totalMoves, *gamesFinished, *blackWins, *nodesAllocated, *sumDepth;
   // evaluator buffers (owned by the kgb_handle)
   float *nnSpatial, *nnGlobal, *nnOptimism;
@@ -640,7 +641,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     uint32_t areaB, areaW;
     boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);    // = the area boardAreaScoreBlackMinusWhite counts
     int diff = warpCount(areaB) - warpCount(areaW);
-    float whiteScore = d.komi - (float)diff;
+    float whiteScore = d.komiG[g] - (float)diff;
     uint32_t* fb = d.finalBoard + (size_t)g * 128;
     fb[lane] = bd.b; fb[32 + lane] = bd.w; fb[64 + lane] = areaB; fb[96 + lane] = areaW;
     if(lane == 0) d.lastScore[g] = whiteScore;
@@ -648,6 +649,8 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
       atomicAdd(d.gamesFinished, 1ULL);
       if(whiteScore < 0 && !noResult) atomicAdd(d.blackWins, 1ULL);
       d.gameCounter[g] += 1;
+      d.lastKomi[g] = d.komiG[g];
+      d.komiG[g] = d.nextKomi[g];          // the slot's next game (kgb_selfplay_set_komi)
     }
     boardInit(bd, d.X, d.Y);
     gameHistReset(d, g, lane);
@@ -953,6 +956,14 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       stateHashX(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, histPassWouldEndPhase(bd, hst, HL, black, d.koRule),
                  (d.koRule != KGB_KO_SIMPLE && bannedValid) ? pointSetHash(hst.banned) : 0ULL, k0, k1);
     else stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
+    {
+      // NNInputs::getHash (nninputs.cpp:869-943) = situation + rules + the mover's komi (boardhistory.cpp:1268-1274) + evaluation
+      // options.  Komi varies from game to game inside one loop, so it is part of the key; ko / scoring / tax / suicide rules, board
+      // size, policy optimism and playoutDoublingAdvantage are the same for every game of a loop (and the table belongs to the loop).
+      const long long kd = (long long)((black ? -d.komiG[g] : d.komiG[g]) * 256.0f);
+      const unsigned long long kh = splitmix64((unsigned long long)kd + 0x6B6F6D69ULL);
+      k0 ^= kh; k1 ^= splitmix64(kh);
+    }
     if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
     float vals[6];
     if(cacheLookup(d, g, node, k0, k1, vals, lane)) {
@@ -990,7 +1001,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   }
   if(terminal) {
     int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
-    float whiteScore = d.komi - (float)diff;
+    float whiteScore = d.komiG[g] - (float)diff;
     if(lane == 0) d.leafTerminalScore[g] = whiteScore;
   }
   const long long tLegal = clock64();
@@ -1040,7 +1051,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(hs[k] == -2) gl[k] = 1.0f;
       else row[(size_t)posOf(hs[k], d.X) * 22 + 9 + k] = 1.0f;
     }
-    float selfKomi = black ? -d.komi : d.komi;
+    float selfKomi = black ? -d.komiG[g] : d.komiG[g];
     float bArea = (float)d.XY;
     selfKomi = fminf(fmaxf(selfKomi, -bArea - 20.0f), bArea + 20.0f);
     gl[5] = selfKomi / 20.0f;
@@ -2040,6 +2051,11 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
   d.maxMoves = c.max_moves > 0 ? c.max_moves : 2 * X * Y;
   d.multiSuicide = c.multi_stone_suicide_legal; d.earlyMoves = c.early_temperature_moves;
   d.komi = c.komi;
+  {
+    std::vector<float> k((size_t)c.num_games, (float)c.komi);
+    d.komiG = sp->alloc<float>(c.num_games); d.nextKomi = sp->alloc<float>(c.num_games); d.lastKomi = sp->alloc<float>(c.num_games);
+    for(float* dst : {d.komiG, d.nextKomi, d.lastKomi}) SPCK(cudaMemcpy(dst, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   d.cpuctExploration = c.cpuct_exploration; d.cpuctExplorationLog = c.cpuct_exploration_log; d.cpuctExplorationBase = c.cpuct_exploration_base;
   d.fpuReductionMax = c.fpu_reduction_max; d.rootFpuReductionMax = c.root_fpu_reduction_max;
   d.cpuctUtilityStdevPrior = c.cpuct_utility_stdev_prior; d.cpuctUtilityStdevPriorWeight = c.cpuct_utility_stdev_prior_weight;
@@ -2257,6 +2273,28 @@ void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s) {
   spRandomOpeningsKernel<<<(sp->d.numGames * 32 + 127) / 128, 128, 0, s>>>(sp->d, maxLen);
   SPCK(cudaGetLastError());
   SPCK(cudaStreamSynchronize(s));
+}
+
+// Komi per game (GameInitializer draws one per game: program/play.cpp:330-420 komiMean / komiStdev / ...).  `komi[numGames]` becomes
+// the komi of each slot's NEXT game; with alsoCurrent it also replaces the komi of the game in progress (meant for games that have
+// not started searching).  The host must have synchronised the wave stream.
+void selfplaySetKomi(SelfplayImpl* sp, const float* komi, bool alsoCurrent) {
+  const SPDev& d = sp->d;
+  for(int g = 0; g < d.numGames; g++)
+    if(!(komi[g] >= -150.0f && komi[g] <= 150.0f) || komi[g] * 2.0f != floorf(komi[g] * 2.0f))
+      throw std::invalid_argument("selfplay: komi must be a multiple of 0.5 in [-150, 150] (Rules::komiIsIntOrHalfInt)");
+  SPCK(cudaMemcpy(d.nextKomi, komi, (size_t)d.numGames * sizeof(float), cudaMemcpyHostToDevice));
+  if(alsoCurrent) SPCK(cudaMemcpy(d.komiG, komi, (size_t)d.numGames * sizeof(float), cudaMemcpyHostToDevice));
+}
+void selfplayReadLeafKey(SelfplayImpl* sp, int g, unsigned long long* key2) {
+  const SPDev& d = sp->d;
+  if(g < 0 || g >= d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  SPCK(cudaMemcpy(key2, d.leafKey + (size_t)g * 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+}
+void selfplayReadKomi(SelfplayImpl* sp, float* current, float* lastFinished) {
+  const SPDev& d = sp->d;
+  if(current) SPCK(cudaMemcpy(current, d.komiG, (size_t)d.numGames * sizeof(float), cudaMemcpyDeviceToHost));
+  if(lastFinished) SPCK(cudaMemcpy(lastFinished, d.lastKomi, (size_t)d.numGames * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 void selfplayReadRootRow(SelfplayImpl* sp, int g, float* spatial, float* global) {

@@ -21,6 +21,9 @@ struct SelfplayNNBuffers {  // device buffers of the evaluator handle the loop w
 SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const SelfplayNNBuffers& nn, cudaStream_t stream);
 void selfplayDestroy(SelfplayImpl* sp);
 void selfplayClearNNCache(SelfplayImpl* sp, cudaStream_t s);
+void selfplaySetKomi(SelfplayImpl* sp, const float* komi, bool alsoCurrent);
+void selfplayReadLeafKey(SelfplayImpl* sp, int g, unsigned long long* key2);
+void selfplayReadKomi(SelfplayImpl* sp, float* current, float* lastFinished);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, float* ownershipOut, cudaStream_t s);

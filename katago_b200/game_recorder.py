@@ -283,7 +283,9 @@ class GameRecorder:
     def _finish_game(self, g, last):
         gm = self.games[g]
         X, Y = self.X, self.Y
-        data = FinishedGameData(X, Y, self.komi)
+        # komi is per game (SelfPlay.set_komi; the reference's GameInitializer draws one per game): the slot's last finished game's
+        komi = float(self.sp.komi_values()[1][g]) if hasattr(self.sp, "komi_values") else self.komi
+        data = FinishedGameData(X, Y, komi)
         data.draw_equivalent_wins_for_white = self.draw_eq
         data.game_hash = self.game_hash_fn(g, last["game_index"])
         data.end_finished = not last["hit_move_limit"]
@@ -304,14 +306,14 @@ class GameRecorder:
             data.nn_raw_stats_by_turn.append(t["nn_raw_stats"])
         if data.end_no_result:
             area = np.zeros(X * Y, np.uint8)          # "nobody owns anything" (play.cpp:1977-1988)
-            data.white_value_targets_by_turn.append(final_value_targets(0, 0.0, self.draw_eq, self.komi, no_result=True))
+            data.white_value_targets_by_turn.append(final_value_targets(0, 0.0, self.draw_eq, komi, no_result=True))
         else:
             # area scoring without tax: ownership = full area = calculateArea with every flag on (boardhistory.cpp:591-610)
             area = np.asarray(last["final_area"], np.uint8).reshape(-1).copy()
             score = float(last["final_white_minus_black_score"])
             winner = P_WHITE if score > 0 else P_BLACK if score < 0 else 0
             data.winner, data.final_white_minus_black_score = winner, score
-            data.white_value_targets_by_turn.append(final_value_targets(winner, score, self.draw_eq, self.komi))
+            data.white_value_targets_by_turn.append(final_value_targets(winner, score, self.draw_eq, komi))
         data.final_full_area, data.final_ownership = area, area
         if self.policy_surprise_data_weight > 0 or self.value_surprise_data_weight > 0:      # play.cpp:2034-2163
             value_surprise = compute_value_surprise_by_turn(data.white_value_targets_by_turn, [t["raw_nn_values"] for t in gm.turns], X * Y,

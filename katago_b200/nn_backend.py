@@ -80,6 +80,8 @@ ABI_SYMBOLS = [
     "kgb_handle_stream", "kgb_handle_launches_per_forward", "kgb_test_conv", "kgb_bench_conv", "kgb_bench_conv_ex", "kgb_test_conv_epilogue",
     "kgb_selfplay_create", "kgb_selfplay_free", "kgb_selfplay_run", "kgb_selfplay_get_stats", "kgb_selfplay_get_game",
     "kgb_selfplay_get_root_children", "kgb_selfplay_launches_per_step", "kgb_selfplay_play_moves", "kgb_selfplay_time_tree_kernels", "kgb_zobrist_tables", "kgb_selfplay_get_nn_row", "kgb_selfplay_get_root_row", "kgb_test_board_replay", "kgb_selfplay_get_leaf_path", "kgb_expected_white_score_value", "kgb_value_weight_cdf_table", "kgb_rand_uint32_stream", "kgb_test_root_policy_noise", "kgb_test_history_replay", "kgb_test_repetition_bound", "kgb_selfplay_get_play_selection_values", "kgb_selfplay_random_openings", "kgb_selfplay_set_search_rand", "kgb_selfplay_get_root_value_stats", "kgb_test_choose_index_with_temperature",
+    "kgb_handle_weights_bytes", "kgb_handle_stage_weights", "kgb_handle_commit_weights", "kgb_handle_wait_staged", "kgb_nccl_unique_id", "kgb_handle_comm_init",
+    "kgb_handle_broadcast_staged_weights", "kgb_selfplay_clear_nn_cache", "kgb_selfplay_set_komi", "kgb_selfplay_get_komi", "kgb_selfplay_get_leaf_cache_key",
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
 ]
 
@@ -115,6 +117,17 @@ def load_library():
     lib.kgb_handle_free.argtypes = [P]
     lib.kgb_handle_free.restype = None
     lib.kgb_handle_is_fp16.argtypes = [P]
+    lib.kgb_handle_weights_bytes.argtypes = [P, C.POINTER(C.c_uint64)]
+    lib.kgb_handle_stage_weights.argtypes = [P, P]
+    lib.kgb_handle_commit_weights.argtypes = [P]
+    lib.kgb_handle_wait_staged.argtypes = [P]
+    lib.kgb_nccl_unique_id.argtypes = [P]
+    lib.kgb_handle_comm_init.argtypes = [P, P, I, I]
+    lib.kgb_handle_broadcast_staged_weights.argtypes = [P, I, C.POINTER(C.c_float)]
+    lib.kgb_selfplay_clear_nn_cache.argtypes = [P]
+    lib.kgb_selfplay_set_komi.argtypes = [P, P, I]
+    lib.kgb_selfplay_get_komi.argtypes = [P, P, P]
+    lib.kgb_selfplay_get_leaf_cache_key.argtypes = [P, I, P]
     lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_handle_sync.argtypes = [P]
@@ -231,6 +244,36 @@ class ComputeHandle:
     def sync(self):
         _check(load_library().kgb_handle_sync(self._p))
 
+    # ---- new weights into the live handle (kgb200.h: kgb_handle_stage_weights ...) ----
+    @property
+    def weights_bytes(self) -> int:
+        n = C.c_uint64()
+        _check(load_library().kgb_handle_weights_bytes(self._p, C.byref(n)))
+        return int(n.value)
+
+    def stage_weights(self, loadedModel: LoadedModel):
+        """Pack another net of the same architecture into the shadow arena (evaluation continues meanwhile)."""
+        _check(load_library().kgb_handle_stage_weights(self._p, loadedModel._p))
+
+    def wait_staged(self):
+        _check(load_library().kgb_handle_wait_staged(self._p))
+
+    def commit_weights(self):
+        """Every forward pass / wave enqueued after this call runs the staged (or received) net."""
+        _check(load_library().kgb_handle_commit_weights(self._p))
+
+    def comm_init(self, unique_id: bytes, rank: int, num_ranks: int):
+        if len(unique_id) != 128:
+            raise ValueError("comm_init: the NCCL unique id is 128 bytes")
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(load_library().kgb_handle_comm_init(self._p, C.cast(buf, C.c_void_p), rank, num_ranks))
+
+    def broadcast_staged_weights(self, root: int = 0) -> float:
+        """ncclBroadcast of the packed weight arena from `root`'s shadow arena into every rank's; returns the device time in ms."""
+        ms = C.c_float()
+        _check(load_library().kgb_handle_broadcast_staged_weights(self._p, root, C.byref(ms)))
+        return float(ms.value)
+
     def free(self):
         if self._p:
             load_library().kgb_handle_free(self._p)
@@ -241,6 +284,13 @@ class ComputeHandle:
             self.free()
         except Exception:
             pass
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (one rank calls it; the bytes reach the others by any side channel)."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().kgb_nccl_unique_id(C.cast(buf, C.c_void_p)))
+    return buf.raw
 
 
 def _f32(a):
@@ -545,6 +595,26 @@ class SelfPlay:
             if m.shape != (self.num_games,):
                 raise ValueError("release: mask must have one entry per game")
             _check(load_library().kgb_selfplay_release(self._p, m.ctypes.data))
+
+    def set_komi(self, komi, also_current_games: bool = False):
+        """komi[num_games] for each slot's next game (and, optionally, for the games in progress)."""
+        k = np.ascontiguousarray(np.broadcast_to(np.asarray(komi, np.float32), (self.num_games,)))
+        _check(load_library().kgb_selfplay_set_komi(self._p, k.ctypes.data, int(also_current_games)))
+
+    def komi_values(self):
+        """(komi of the games in progress, komi of each slot's last finished game)."""
+        cur = np.zeros(self.num_games, np.float32); last = np.zeros(self.num_games, np.float32)
+        _check(load_library().kgb_selfplay_get_komi(self._p, cur.ctypes.data, last.ctypes.data))
+        return cur, last
+
+    def leaf_cache_key(self, g: int):
+        k = np.zeros(2, np.uint64)
+        _check(load_library().kgb_selfplay_get_leaf_cache_key(self._p, g, k.ctypes.data))
+        return int(k[0]), int(k[1])
+
+    def clear_nn_cache(self):
+        """With ComputeHandle.commit_weights: the cached outputs belong to the previous net."""
+        _check(load_library().kgb_selfplay_clear_nn_cache(self._p))
 
     def root_visits(self):
         out = np.zeros(self.num_games, np.int32)

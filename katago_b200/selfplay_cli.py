@@ -236,6 +236,94 @@ class SgfSink:
         self.count += 1
 
 
+def model_name_of(model_path):
+    return os.path.basename(os.path.dirname(model_path)) if os.path.basename(model_path) == "model.bin.gz" else os.path.basename(model_path).split(".")[0]
+
+
+class ModelOutputs:
+    """<output-dir>/<model name>/{tdata,sgfs}: one writer per net, as the reference keeps one per NNEvaluator (selfplay.cpp:178-225).
+    switch_to() closes the files of the previous net and opens the new net's."""
+
+    def __init__(self, output_dir, data, board_len, writer_seed, writer_cls):
+        self.output_dir, self.data, self.L, self.writer_seed, self.writer_cls = output_dir, data, board_len, writer_seed, writer_cls
+        self.writer = self.sgfs = self.model_name = None
+        self.rows_total, self.dirs, self.generation = 0, [], 0
+
+    def switch_to(self, model_path):
+        self.close()
+        self.model_name = model_name_of(model_path)
+        tdata = os.path.join(self.output_dir, self.model_name, "tdata")
+        os.makedirs(tdata, exist_ok=True)
+        seed = self.writer_seed if self.generation == 0 else f"{self.writer_seed}:net{self.generation}"
+        self.writer = self.writer_cls(tdata, self.data["max_rows_per_train_file"], self.data["first_file_rand_min_prop"], self.L, seed)
+        self.sgfs = SgfSink(os.path.join(self.output_dir, self.model_name, "sgfs"), seed + ":sgfs", self.model_name, self.model_name)
+        self.dirs.append(tdata)
+        self.generation += 1
+
+    def add_game(self, slot, data):
+        self.writer.write_game(data)
+        self.sgfs.add(slot, data)
+
+    def close(self):
+        if self.writer is not None:
+            self.writer.flush_if_nonempty()
+            self.rows_total += self.writer.row_count
+            self.writer = None
+
+
+class BackgroundStage:
+    """Loads a model file and stages it into a live handle (ComputeHandle.stage_weights) on a side thread."""
+
+    def __init__(self, handle, path):
+        import threading
+        self.path, self.error = path, None
+
+        def work():
+            try:
+                from .nn_backend import NeuralNet
+                lm = NeuralNet.loadModelFile(path)
+                try:
+                    handle.stage_weights(lm)
+                finally:
+                    lm.free()
+            except Exception as e:      # reported by the loop
+                self.error = e
+        self._t = threading.Thread(target=work, daemon=True)
+        self._t.start()
+
+    def done(self):
+        return not self._t.is_alive()
+
+
+class ModelPoller:
+    """The models directory is looked at every `seconds` (the reference: 20, selfplay.cpp:336-352); poll() returns the path of a net
+    that is newer than the one in use, once."""
+
+    def __init__(self, models_dir, current, seconds):
+        import time
+        self.models_dir, self.current, self.seconds, self._clock = models_dir, current, seconds, time.monotonic
+        self.next = self._clock() + seconds
+        self.previous = current
+
+    def forget(self, path):
+        """`path` could not be used: report it again at a later poll."""
+        if self.current == path:
+            self.current = self.previous
+
+    def poll(self, force=False):
+        if not force and self._clock() < self.next:
+            return None
+        self.next = self._clock() + self.seconds
+        try:
+            newest = newest_model(self.models_dir)
+        except FileNotFoundError:
+            return None
+        if newest == self.current or os.path.getmtime(newest) <= os.path.getmtime(self.current):
+            return None
+        self.previous, self.current = self.current, newest
+        return newest
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="katago_b200.selfplay_cli", description="Self-play data generation on the B200 device loop", prefix_chars="-")
     ap.add_argument("-models-dir", required=True)
@@ -248,6 +336,9 @@ def main(argv=None):
     ap.add_argument("-seed", type=int, default=0)
     ap.add_argument("-per-game-release", action="store_true", help="record and release every game as soon as its own search is finished "
                     "(GameRecorder.pump) instead of moving all games in lockstep")
+    ap.add_argument("-model-poll-seconds", type=float, default=20.0, help="how often the models directory is checked for a newer net")
+    ap.add_argument("-nccl-weights", action="store_true", help="under torchrun: rank 0 alone polls and reads new nets, the packed weights reach the other GPUs by ncclBroadcast")
+    ap.add_argument("-model-poll-waves", type=int, default=64, help="with -nccl-weights: recorder iterations between two (collective) polls")
     a = ap.parse_args(argv)
     cfg = parse_cfg(a.config)
     for kv in [s for s in a.override_config.split(",") if s.strip()]:
@@ -259,13 +350,10 @@ def main(argv=None):
     if report["not_built"]:
         print("[config] NOT BUILT, ignored: " + "; ".join(report["not_built"]), file=sys.stderr)
 
-    from .nn_backend import NeuralNet, SelfPlay          # loads libkgb200; fails loudly without a B200
+    from .nn_backend import KGBError, NeuralNet, SelfPlay          # loads libkgb200; fails loudly without a B200
     from .npz_writer import RowRand, TrainingDataWriter
     from .game_recorder import GameRecorder
     model_path = newest_model(a.models_dir)
-    model_name = os.path.basename(os.path.dirname(model_path)) if os.path.basename(model_path) == "model.bin.gz" else os.path.basename(model_path).split(".")[0]
-    tdata = os.path.join(a.output_dir, model_name, "tdata")
-    os.makedirs(tdata, exist_ok=True)
     L = data["board_size"]
     games = min(a.games_per_gpu, data["num_game_threads"])
     rank, world, gpu = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -273,23 +361,108 @@ def main(argv=None):
     lm = NeuralNet.loadModelFile(model_path)
     ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
     h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
-    sp = SelfPlay(h, games, kw.pop("max_visits", 600), komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, **kw)
-    writer = TrainingDataWriter(tdata, data["max_rows_per_train_file"], data["first_file_rand_min_prop"], L, writer_seed)
-    sgfs = SgfSink(os.path.join(a.output_dir, model_name, "sgfs"), writer_seed + ":sgfs", model_name, model_name)
-    rec = GameRecorder(sp, writer, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=sgfs.add,
+    max_visits = kw.pop("max_visits", 600)
+    sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, **kw)
+    outputs = ModelOutputs(a.output_dir, data, L, writer_seed, TrainingDataWriter)
+    outputs.switch_to(model_path)
+    rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=outputs.add_game,
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                        use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"))
+    # New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory every 20 s; :142-231 load the newest one).
+    # Default: every rank polls and reads the file itself.  -nccl-weights: rank 0 polls, reads and packs; the packed weights reach
+    # the other GPUs by the library's ncclBroadcast (dist_weights.WeightBroadcaster) - the poll is then a collective, every
+    # `-model-poll-waves` recorder iterations.  Games move over between two waves (the reference's switchNetsMidGame = true) and a
+    # finished game's rows go to the directory of the net in use when it ended (selfplay.cpp:276-319).
+    poller = ModelPoller(a.models_dir, model_path, a.model_poll_seconds)
+    wb = None
+    if a.nccl_weights and world > 1:
+        import torch
+        import torch.distributed as dist
+        from .dist_weights import WeightBroadcaster
+        torch.cuda.set_device(gpu)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", gpu))
+        wb = WeightBroadcaster(h, 0, torch.device("cuda", gpu))
+    swaps, iters, done, stager, stager_error = 0, 0, False, None, None
     try:
-        while a.max_games_total <= 0 or rec.games_written < my_games:
-            if a.per_game_release:
-                rec.pump(8)
+        while True:
+            done = a.max_games_total > 0 and rec.games_written >= my_games
+            if wb is None and done:
+                break
+            if not done:
+                if a.per_game_release:
+                    rec.pump(8)
+                else:
+                    rec.step()
+            iters += 1
+            if wb is None:
+                # reading and packing a net takes the host ~0.1-0.2 s for a b18: done on a side thread (the library call releases the
+                # GIL), the waves keep coming; the swap itself is one device copy ordered between two waves
+                if stager is None:
+                    p_ = poller.poll()
+                    if p_ is not None:
+                        stager = BackgroundStage(h, p_)
+                    continue
+                if not stager.done():
+                    continue
+                new_path, stager_error, stager = stager.path, stager.error, None
+                if stager_error is None:
+                    h.commit_weights()
+                    sp.clear_nn_cache()
+                    swaps += 1
+                    outputs.switch_to(new_path)
+                    print(f"[model] now playing {outputs.model_name} (swap {swaps})", file=sys.stderr)
+                    continue
+            elif iters % a.model_poll_waves == 0 or done:
+                # collective: [all ranks done?] and rank 0's verdict on the models directory
+                import torch.distributed as dist
+                box = [poller.poll(force=True) if rank == 0 else None, done]
+                everyone = [None] * world
+                dist.all_gather_object(everyone, box)
+                if all(e[1] for e in everyone):
+                    break
+                new_path = everyone[0][0]
             else:
-                rec.step()
+                new_path = None
+            if new_path is None:
+                continue
+            try:
+                if wb is None:
+                    raise stager_error
+                else:
+                    new_lm = NeuralNet.loadModelFile(new_path) if rank == 0 else None
+                    wb.update(new_lm)
+                sp.clear_nn_cache()
+            except Exception as e:
+                if wb is not None:
+                    raise
+                if not (isinstance(e, KGBError) and any(w in str(e) for w in ("architecture", "layout", "largest convolution"))):
+                    # e.g. a file that is still being written: keep playing the current net, look again at the next poll
+                    print(f"[model] {new_path}: {e}; keeping {outputs.model_name}", file=sys.stderr)
+                    poller.forget(new_path)
+                    continue
+                # another architecture: the reference builds a new NNEvaluator for any net; here that means a new handle and loop, and
+                # the games in flight are dropped (their finished predecessors are already written)
+                print(f"[model] {new_path}: {e}; rebuilding the evaluator (games in progress are abandoned)", file=sys.stderr)
+                sp.free(); h.free(); ctx.free()
+                lm = NeuralNet.loadModelFile(new_path)
+                ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
+                h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
+                sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed + 7919 * (swaps + 1), debug_hold_at_max_visits=True, **kw)
+                written = rec.games_written
+                rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=outputs.add_game,
+                                   game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
+                                   policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
+                                   use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"))
+                rec.games_written = written
+            swaps += 1
+            outputs.switch_to(new_path)
+            print(f"[model] now playing {outputs.model_name} (swap {swaps})", file=sys.stderr)
     except KeyboardInterrupt:
         pass
-    writer.flush_if_nonempty()
-    print(f"{rec.games_written} games, {writer.row_count} rows -> {tdata}")
+    outputs.close()
+    print(f"{rec.games_written} games, {outputs.rows_total} rows -> {', '.join(outputs.dirs)}")
     sp.free(); h.free(); ctx.free()
     return 0
 

@@ -39,6 +39,43 @@ def test_weight_broadcast_and_game_sharding_world2(tmp_path):
     assert sorted(r[0]["games"] + r[1]["games"]) == list(range(10)) and not set(r[0]["games"]) & set(r[1]["games"])
 
 
+class _RecordingHandle:
+    """Stands in for nn_backend.ComputeHandle (no GPU here): records what WeightBroadcaster asks of it."""
+    def __init__(self):
+        self.calls = []
+    def comm_init(self, uid, rank, world): self.calls.append(("comm_init", uid, rank, world))
+    def stage_weights(self, m): self.calls.append(("stage", m))
+    def wait_staged(self): self.calls.append(("wait_staged",))
+    def broadcast_staged_weights(self, root): self.calls.append(("bcast", root)); return 1.5
+    def commit_weights(self): self.calls.append(("commit",))
+
+
+def _wb_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from katago_b200.dist_weights import WeightBroadcaster
+    h = _RecordingHandle()
+    wb = WeightBroadcaster(h, src=0, id_source=lambda: bytes(range(128)))
+    ms = wb.update("net-A" if rank == 0 else None)
+    with open(os.path.join(tmp, f"wb{rank}.json"), "w") as f:
+        json.dump({"calls": [[c[0]] + [x if not isinstance(x, bytes) else list(x) for x in c[1:]] for c in h.calls], "ms": ms}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_weight_broadcaster_world2_protocol(tmp_path):
+    """Every rank joins the communicator with the source's id; only the source stages; all broadcast, then commit."""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_wb_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [json.load(open(tmp_path / f"wb{i}.json")) for i in range(2)]
+    uid = list(range(128))
+    assert r[0]["calls"] == [["comm_init", uid, 0, 2], ["stage", "net-A"], ["wait_staged"], ["bcast", 0], ["commit"]]
+    assert r[1]["calls"] == [["comm_init", uid, 1, 2], ["bcast", 0], ["commit"]]
+    assert r[0]["ms"] == r[1]["ms"] == 1.5
+
+
 def test_bench_reference_arm_prints_contract_json():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny_nbt", "--steps", "2",
                         "--warmup", "1"], capture_output=True, text=True, timeout=300)

@@ -136,6 +136,57 @@ def test_command_writes_training_files(tmp_path, stock_cfg):
     assert len(sgfs) == 1 and sum(1 for _ in open(out / "tinynet" / "sgfs" / sgfs[0])) >= 3
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("new_cfg", ["tiny_reg", "tiny_nbt"])
+def test_command_moves_to_a_newer_net_while_games_run(tmp_path, stock_cfg, monkeypatch, new_cfg):
+    """Model polling (command/selfplay.cpp:336-352): a newer file in the models directory is picked up while games are running.  Same
+    architecture: the weights are swapped inside the live handle and the games go on (switchNetsMidGame); another architecture: the
+    evaluator is rebuilt.  Either way the rows of games that end afterwards land in the new net's directory."""
+    import time
+    import numpy as np
+    from katago_b200 import modelgen
+    models = tmp_path / "models"; models.mkdir()
+    modelgen.write_model(str(models / "net1.bin"), "tiny_reg", seed=3)
+    calls = {"n": 0}
+    orig = C.ModelPoller.poll
+
+    def poll(self, force=False):
+        calls["n"] += 1
+        if calls["n"] == 4:
+            path = modelgen.write_model(str(models / "net2.bin"), new_cfg, seed=4)
+            os.utime(path, (time.time() + 60, time.time() + 60))
+        return orig(self, force)
+    monkeypatch.setattr(C.ModelPoller, "poll", poll)
+    out = tmp_path / "out"
+    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", stock_cfg, "-max-games-total", "8", "-games-per-gpu", "4", "-per-game-release",
+                 "-model-poll-seconds", "0", "-override-config",
+                 "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=16,maxMovesPerGame=30,rootNumSymmetriesToSample=2,nnCacheSizePowerOfTwo=10,maxRowsPerTrainFile=1000,firstFileRandMinProp=1.0"])
+    assert rc == 0
+    rows = {}
+    for name in ("net1", "net2"):
+        tdata = out / name / "tdata"
+        rows[name] = sum(np.load(tdata / f)["globalTargetsNC"].shape[0] for f in os.listdir(tdata)) if tdata.exists() else 0
+    assert rows["net2"] > 0, rows                 # games finished under the new net
+    games = sum(sum(1 for _ in open(out / name / "sgfs" / f)) for name in ("net1", "net2") if (out / name / "sgfs").exists() for f in os.listdir(out / name / "sgfs"))
+    assert games >= 8
+
+
+def test_model_poller_reports_a_newer_file_once(tmp_path):
+    import time
+    a = tmp_path / "a.bin"; a.write_bytes(b"x")
+    p = C.ModelPoller(str(tmp_path), str(a), 0.0)
+    assert p.poll() is None
+    b = tmp_path / "b.bin.gz"; b.write_bytes(b"y")
+    os.utime(b, (time.time() + 5, time.time() + 5))
+    assert p.poll() == str(b) and p.poll() is None
+    older = tmp_path / "c.bin"; older.write_bytes(b"z")
+    os.utime(older, (time.time() - 100, time.time() - 100))
+    assert p.poll() is None
+    slow = C.ModelPoller(str(tmp_path), str(a), 3600.0)
+    assert slow.poll() is None and slow.poll(force=True) == str(b)
+    assert C.model_name_of("/x/y/kata1-b18c384nbt-s123/model.bin.gz") == "kata1-b18c384nbt-s123" and C.model_name_of("/x/net7.bin.gz") == "net7"
+
+
 def test_ranks_split_the_games_and_never_share_seeds_or_file_names():
     """One process per GPU: the ranks' game counts add up, their loop seeds, writer Rand streams (= file names) and game hashes differ."""
     from katago_b200.nn_backend import rand_uint32_stream
