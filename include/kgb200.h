@@ -311,6 +311,18 @@ KGB_API int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* games_mask);
  * neuralnet/nninputs.cpp:869-943 via BoardHistory::getSituationRulesAndKoHash), so games of different komi never share an entry. */
 KGB_API int kgb_selfplay_set_komi(kgb_selfplay* sp, const float* komi, int also_current_games);
 KGB_API int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* last_finished);
+/* Board size and ko / suicide rules per game.  The reference's GameInitializer draws them for every game (program/play.cpp:330-650:
+ * bSizes / bSizeRelProbs, koRules, multiStoneSuicideLegals; BASELINE config 4 "mixed 9/13/19 board sizes"); here the host draws and the
+ * device applies, like the komi.  setup[num_games][4] = board X, board Y (2..the context's nn_x_len / nn_y_len), ko rule (0-3 as in
+ * kgb_selfplay_config.ko_rule), multi-stone suicide legal (0/1).  A game's board occupies the top-left corner of the evaluator's frame:
+ * move positions stay y * nn_x_len + x (NNPos::locToPos, neuralnet/nninputs.cpp:27-33), input plane 0 marks the board and the conv
+ * trunk masks everything outside it (nneval.cpp:874-883 does the same with nnXLen > board size).  The values become each slot's NEXT
+ * game's; also_current_games != 0 applies them to the games in progress too, which must not have started (no move, no visit) -
+ * KGB_ERR_INVALID otherwise, nothing changed for those.  A ko rule different from the configuration's needs full_history_rules = 1.
+ * kgb_selfplay_get_game_setup: setup of the game in progress and of the slot's last finished game (either pointer may be NULL).
+ * The evaluation cache keys on board size and rules as NNInputs::getHash does, so such games never share an entry. */
+KGB_API int kgb_selfplay_set_game_setup(kgb_selfplay* sp, const int32_t* setup, int also_current_games);
+KGB_API int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int32_t* last_finished);
 /* FOR TESTING: the evaluation-cache key (the loop's NNInputs::getHash) of the leaf that slot `game` sent to the evaluator in the
  * last wave; only meaningful with nn_cache_size_power_of_two > 0. */
 KGB_API int kgb_selfplay_get_leaf_cache_key(kgb_selfplay* sp, int game, uint64_t* key2);
@@ -345,6 +357,8 @@ KGB_API int kgb_selfplay_set_search_rand(kgb_selfplay* sp, const char* seed_stri
 KGB_API int kgb_selfplay_random_openings(kgb_selfplay* sp, int max_moves);
 /* Play a fixed move list on EVERY game's root (x,y pairs, -1,-1 = pass; colours alternate) and clear the trees. */
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves);
+/* The same for one game only (games of different board sizes need different lists).  A move off the game's board is KGB_ERR_INVALID. */
+KGB_API int kgb_selfplay_play_moves_game(kgb_selfplay* sp, int game, const int8_t* moves_xy, int num_moves);
 /* Timing hook for bench.py's tree/board roofline entry: runs `iters` waves of ONLY the select(+board+featurize) and backup
  * kernels (evaluator outputs of the last wave are reused) and returns their CUDA-event averages per launch. */
 KGB_API int kgb_selfplay_time_tree_kernels(kgb_selfplay* sp, int iters, float* ms_select, float* ms_backup);

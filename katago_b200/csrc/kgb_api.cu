@@ -1400,6 +1400,24 @@ KGB_API int kgb_selfplay_set_komi(kgb_selfplay* sp, const float* komi, int also_
   });
 }
 
+KGB_API int kgb_selfplay_set_game_setup(kgb_selfplay* sp, const int32_t* setup, int also_current_games) {
+  return guarded([&] {
+    if(!sp || !setup) throw std::invalid_argument("kgb_selfplay_set_game_setup: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplaySetGameSetup(sp->impl, setup, also_current_games != 0, sp->h->stream);
+  });
+}
+
+KGB_API int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int32_t* last_finished) {
+  return guarded([&] {
+    if(!sp) throw std::invalid_argument("kgb_selfplay_get_game_setup: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadGameSetup(sp->impl, current, last_finished);
+  });
+}
+
 KGB_API int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* last_finished) {
   return guarded([&] {
     if(!sp) throw std::invalid_argument("kgb_selfplay_get_komi: NULL argument");
@@ -1499,6 +1517,15 @@ KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, in
     if(!sp || (!moves_xy && num_moves > 0) || num_moves < 0) throw std::invalid_argument("kgb_selfplay_play_moves: bad argument");
     CK(cudaSetDevice(sp->h->device));
     selfplayPlayMoves(sp->impl, moves_xy, num_moves, sp->h->stream);
+  });
+}
+
+KGB_API int kgb_selfplay_play_moves_game(kgb_selfplay* sp, int game, const int8_t* moves_xy, int num_moves) {
+  return guarded([&] {
+    if(!sp || game < 0 || (!moves_xy && num_moves > 0) || num_moves < 0) throw std::invalid_argument("kgb_selfplay_play_moves_game: bad argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayPlayMoves(sp->impl, moves_xy, num_moves, sp->h->stream, game);
   });
 }
 

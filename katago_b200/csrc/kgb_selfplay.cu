@@ -25,6 +25,7 @@
 // NOT written (stay 0, not reachable under the supported rule subset): superko bans in plane 6, encore planes 7/8/20/21.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -51,6 +52,11 @@ struct SPDev {
   // configuration
   int X, Y, XY, policySize, numGames, maxVisits, maxNodes, maxDepth, maxMoves, multiSuicide, earlyMoves;
   float komi;
+  // per-game board size and rules (GameInitializer::createGameSharedUnsynchronized, program/play.cpp:330-650 draws them per game): the
+  // evaluator's frame is X x Y (nnXLen x nnYLen), a game's board gX x gY <= the frame sits in its top-left corner, move positions are
+  // y * X + x in the frame (NNPos::locToPos, nninputs.cpp:27-33) and plane 0 marks the board.  setup arrays are [game][4] = X, Y, koRule, multiSuicide.
+  int *gX, *gY, *gKoRule, *gMultiSuicide;   // [game] of the game in progress
+  int *nextSetup, *lastSetup;               // [game][4]: of the slot's next game (kgb_selfplay_set_game_setup), of its last finished game
   double cpuctExploration, cpuctExplorationLog, cpuctExplorationBase, fpuReductionMax, rootFpuReductionMax;
   double cpuctUtilityStdevPrior, cpuctUtilityStdevPriorWeight, cpuctUtilityStdevScale;
   double fpuLossProp, rootFpuLossProp, fpuParentWeight, fpuParentWeightByVisitedPolicyPow, valueWeightExponent, rootDesiredPerChildVisitsCoeff;
@@ -310,7 +316,7 @@ __device__ __forceinline__ HistLists playoutLists(const SPDev& d, int g) {
 __device__ __forceinline__ void gameHistReset(const SPDev& d, int g, int lane) {
   if(!d.histRules) return;
   d.gEverOcc[g * 32 + lane] = 0; d.rootBanned[g * 32 + lane] = 0;
-  if(lane == 0) { d.gKo[(size_t)g * d.histCap] = koHashOf(d.koRule, 0ULL, true); d.gKoLen[g] = 1; d.gPassBLen[g] = 0; d.gPassWLen[g] = 0; }
+  if(lane == 0) { d.gKo[(size_t)g * d.histCap] = koHashOf(d.gKoRule[g], 0ULL, true); d.gKoLen[g] = 1; d.gPassBLen[g] = 0; d.gPassWLen[g] = 0; }
 }
 // One move of the GAME (root): board, Zobrist hash, pass count and - with the full rules - the game's lists, bans and end flags.
 __device__ void gameMakeMove(const SPDev& d, int g, WarpBoard& bd, int p, bool black, int lane, int& passes, bool& finished, bool& noResult) {
@@ -324,7 +330,7 @@ __device__ void gameMakeMove(const SPDev& d, int g, WarpBoard& bd, int p, bool b
   HistLists L = gameLists(d, g);
   HistState st;
   st.passes = passes; st.finished = false; st.noResult = false; st.everOcc = d.gEverOcc[g * 32 + lane]; st.banned = 0;
-  histMakeMove(bd, st, L, p, black, d.koRule, d.multiSuicide != 0, d.zob, true);
+  histMakeMove(bd, st, L, p, black, d.gKoRule[g], d.gMultiSuicide[g] != 0, d.zob, true);
   d.gEverOcc[g * 32 + lane] = st.everOcc; d.rootBanned[g * 32 + lane] = st.banned;
   __syncwarp();
   if(lane == 0) { d.gKoLen[g] = L.pKoLen; d.gPassBLen[g] = L.pPassBLen; d.gPassWLen[g] = L.pPassWLen; }
@@ -374,13 +380,13 @@ __device__ __forceinline__ void rootHashesInit(const SPDev& d, int g, int lane) 
   if(!d.histRules) stateHash(h0, h1, d.rootBlackToMove[g] != 0, d.rootKo[g], d.consecPasses[g], false, s0, s1);
   else {
     WarpBoard bd;
-    boardInit(bd, d.X, d.Y);
+    boardInit(bd, d.gX[g], d.gY[g]);
     bd.h0 = h0;
     HistLists L = playoutLists(d, g);
     HistState st;
     st.passes = d.consecPasses[g]; st.finished = false; st.noResult = false; st.everOcc = 0; st.banned = d.rootBanned[g * 32 + lane];
     const bool black = d.rootBlackToMove[g] != 0;
-    stateHashX(h0, h1, black, d.rootKo[g], st.passes, false, histPassWouldEndPhase(bd, st, L, black, d.koRule), pointSetHash(st.banned), s0, s1);
+    stateHashX(h0, h1, black, d.rootKo[g], st.passes, false, histPassWouldEndPhase(bd, st, L, black, d.gKoRule[g]), pointSetHash(st.banned), s0, s1);
   }
   if(lane == 0) { d.nodePosH0[gb] = h0; d.nodePosH1[gb] = h1; d.nodeGH0[gb] = s0; d.nodeGH1[gb] = s1; }
 }
@@ -557,7 +563,7 @@ __device__ int rootChooseMove(const SPDev& d, int g) {
   double* lcb = psv + d.policySize; double* radius = lcb + d.policySize;
   const int nc = rootPlaySelectionValues(d, g, psv, lcb, radius);
   if(nc <= 0) return -1;
-  const double halflives = ((double)d.moveNum[g] / d.chosenMoveTemperatureHalflife) * 19.0 / sqrt((double)d.XY);
+  const double halflives = ((double)d.moveNum[g] / d.chosenMoveTemperatureHalflife) * 19.0 / sqrt((double)(d.gX[g] * d.gY[g]));
   const double temperature = d.chosenMoveTemperature + (d.chosenMoveTemperatureEarly - d.chosenMoveTemperature) * pow(0.5, halflives);
   DevRand rand;
   rand.s = d.nonSearchRand[g];
@@ -618,7 +624,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   if(bestV <= 0) best = d.policySize - 1;  // nothing searched (cannot happen with maxVisits >= 2): pass
   // play it on the root board
   WarpBoard bd;
-  boardInit(bd, d.X, d.Y);
+  boardInit(bd, d.gX[g], d.gY[g]);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
   bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
   const bool black = d.rootBlackToMove[g] != 0;
@@ -639,7 +645,7 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   }
   if(over) {
     uint32_t areaB, areaW;
-    boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);    // = the area boardAreaScoreBlackMinusWhite counts
+    boardCalculateArea(bd, true, true, true, d.gMultiSuicide[g] != 0, areaB, areaW);    // = the area boardAreaScoreBlackMinusWhite counts
     int diff = warpCount(areaB) - warpCount(areaW);
     float whiteScore = d.komiG[g] - (float)diff;
     uint32_t* fb = d.finalBoard + (size_t)g * 128;
@@ -651,8 +657,12 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
       d.gameCounter[g] += 1;
       d.lastKomi[g] = d.komiG[g];
       d.komiG[g] = d.nextKomi[g];          // the slot's next game (kgb_selfplay_set_komi)
+      // ... and its board size and rules (kgb_selfplay_set_game_setup): what GameInitializer::createGame draws per game
+      d.lastSetup[g * 4 + 0] = d.gX[g]; d.lastSetup[g * 4 + 1] = d.gY[g]; d.lastSetup[g * 4 + 2] = d.gKoRule[g]; d.lastSetup[g * 4 + 3] = d.gMultiSuicide[g];
+      d.gX[g] = d.nextSetup[g * 4 + 0]; d.gY[g] = d.nextSetup[g * 4 + 1]; d.gKoRule[g] = d.nextSetup[g * 4 + 2]; d.gMultiSuicide[g] = d.nextSetup[g * 4 + 3];
     }
-    boardInit(bd, d.X, d.Y);
+    __syncwarp();
+    boardInit(bd, d.gX[g], d.gY[g]);
     gameHistReset(d, g, lane);
     passes = 0; mv = 0;
     if(lane < 5) d.hist[g * 5 + lane] = -1;
@@ -722,7 +732,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     rootAdvance(d, g, lane);
     if(lane == 0) { d.releaseFlag[g] = 0; d.dbgCycles[g * 8 + 1] = clock64() - tRA; }
   }
-  boardInit(bd, d.X, d.Y);
+  boardInit(bd, d.gX[g], d.gY[g]);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
   bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
   const bool rootBlack = d.rootBlackToMove[g] != 0;
@@ -766,9 +776,16 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
         const float p = in ? d.policy[nb + mv] : -1.0f;
         const double w = cw * ((double)ev / (double)(cv > 1 ? cv : 1));     // NodeStats::childWeight (searchnode.h:64-66)
         P[ch] = p; CW[ch] = w; CU[ch] = in ? d.nodeUtilAvg[gb + c] : 0.0; CVis[ch] = cv;
-        const bool counts = in && p >= 0.0f;
+      }
+    }
+    // the gathers above carry no barrier, so the dependent loads (childOrder -> childNode -> child statistics) of all chunks are in
+    // flight together; the ordered sums follow in the reference's order
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) {
+      if(ch * 32 < nc) {
+        const bool counts = ch * 32 + lane < nc && P[ch] >= 0.0f;
         const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
-        orderedAdd2(counts ? (double)p : 0.0, counts ? w : 0.0, n, massVisited, totalW, shSum, lane);
+        orderedAdd2(counts ? (double)P[ch] : 0.0, counts ? CW[ch] : 0.0, n, massVisited, totalW, shSum, lane);
       }
     }
     // ---- FPU and exploration scaling (searchexplorehelpers.cpp:22-29, 265-321)
@@ -864,15 +881,15 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     // a new child gets its subtree-value-bias entry from the position before the move (search.cpp:913-922): needs a previous
     // move in the history and a non-pass move
     unsigned long long biasKeyNew = 0;
-    if(d.subtreeValueBiasFactor != 0.0 && d.childNode[nb + move] < 0 && !isPass && h0 != -1) biasKeyNew = biasEntryKey(bd, d.X, d.Y, black, h0, p);
+    if(d.subtreeValueBiasFactor != 0.0 && d.childNode[nb + move] < 0 && !isPass && h0 != -1) biasKeyNew = biasEntryKey(bd, d.gX[g], d.gY[g], black, h0, p);
     int child = d.childNode[nb + move];
     const bool newEdge = child < 0;
     if(d.histRules) {
       // BoardHistory::makeBoardMoveAssumeLegal along the path: pass situations, ko-hash history, game end by repetition rules
-      histMakeMove(bd, hst, HL, p, black, d.koRule, d.multiSuicide != 0, d.zob, false);
+      histMakeMove(bd, hst, HL, p, black, d.gKoRule[g], d.gMultiSuicide[g] != 0, d.zob, false);
       bannedValid = false;
-      if(newEdge && d.koRule != KGB_KO_SIMPLE) {
-        hst.banned = histSuperKoBanned(bd, HL, hst.everOcc, !black, d.koRule, d.multiSuicide != 0, d.zob);
+      if(newEdge && d.gKoRule[g] != KGB_KO_SIMPLE) {
+        hst.banned = histSuperKoBanned(bd, HL, hst.everOcc, !black, d.gKoRule[g], d.gMultiSuicide[g] != 0, d.zob);
         bannedValid = true;
       }
       passes = hst.passes;
@@ -891,8 +908,8 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(d.useGraphSearch) {
         unsigned long long s0, s1;
         if(d.histRules)
-          stateHashX(bd.h0, bd.h1, black, bd.ko, passes, hst.finished, histPassWouldEndPhase(bd, hst, HL, black, d.koRule),
-                     d.koRule != KGB_KO_SIMPLE ? pointSetHash(hst.banned) : 0ULL, s0, s1);
+          stateHashX(bd.h0, bd.h1, black, bd.ko, passes, hst.finished, histPassWouldEndPhase(bd, hst, HL, black, d.gKoRule[g]),
+                     d.gKoRule[g] != KGB_KO_SIMPLE ? pointSetHash(hst.banned) : 0ULL, s0, s1);
         else stateHash(bd.h0, bd.h1, black, bd.ko, passes, passes >= 2, s0, s1);
         graphHashOfChild(d.nodeGH0[gb + node], d.nodeGH1[gb + node], s0, s1, simpleRepetitionBoundGt(bd, p, d.graphSearchRepBound), cg0, cg1);
         found = nodeTableFind(d, g, cg0, cg1, tableSlot);
@@ -953,15 +970,19 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     // NNEvaluator::evaluate's cache lookup (nneval.cpp:861-905): the key is the situation, not the history behind it
     unsigned long long k0, k1;
     if(d.histRules)
-      stateHashX(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, histPassWouldEndPhase(bd, hst, HL, black, d.koRule),
-                 (d.koRule != KGB_KO_SIMPLE && bannedValid) ? pointSetHash(hst.banned) : 0ULL, k0, k1);
+      stateHashX(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, histPassWouldEndPhase(bd, hst, HL, black, d.gKoRule[g]),
+                 (d.gKoRule[g] != KGB_KO_SIMPLE && bannedValid) ? pointSetHash(hst.banned) : 0ULL, k0, k1);
     else stateHash(d.nodePosH0[gb + node], d.nodePosH1[gb + node], black, bd.ko, passes >= 1 ? 1 : 0, false, k0, k1);
     {
       // NNInputs::getHash (nninputs.cpp:869-943) = situation + rules + the mover's komi (boardhistory.cpp:1268-1274) + evaluation
-      // options.  Komi varies from game to game inside one loop, so it is part of the key; ko / scoring / tax / suicide rules, board
-      // size, policy optimism and playoutDoublingAdvantage are the same for every game of a loop (and the table belongs to the loop).
+      // options.  Komi varies from game to game inside one loop, so it is part of the key; scoring / tax rules, policy optimism and
+      // playoutDoublingAdvantage are the same for every game of a loop (and the table belongs to the loop).
       const long long kd = (long long)((black ? -d.komiG[g] : d.komiG[g]) * 256.0f);
-      const unsigned long long kh = splitmix64((unsigned long long)kd + 0x6B6F6D69ULL);
+      // board size and the ko / suicide rules can differ from game to game too (kgb_selfplay_set_game_setup): the reference's hash starts
+      // from a board hash that contains the size (Board::ZOBRIST_SIZE_X/Y_HASH) and mixes in Rules (ZOBRIST_KO_RULE_HASH, MULTI_STONE_SUICIDE_HASH)
+      const unsigned long long setupBits = (unsigned long long)d.gX[g] | ((unsigned long long)d.gY[g] << 8) | ((unsigned long long)d.gKoRule[g] << 16) |
+                                           ((unsigned long long)(d.gMultiSuicide[g] != 0) << 24);
+      const unsigned long long kh = splitmix64((unsigned long long)kd + 0x6B6F6D69ULL) ^ splitmix64(setupBits * 0x9E3779B97F4A7C15ULL + 0x73657475ULL);
       k0 ^= kh; k1 ^= splitmix64(kh);
     }
     if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
@@ -989,18 +1010,18 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   uint32_t lib1, lib2, lib3;
   boardLibertyClasses(bd, lib1, lib2, lib3);
   uint32_t superKo = 0;
-  if(d.histRules && d.koRule != KGB_KO_SIMPLE) {
-    if(!bannedValid) { hst.banned = histSuperKoBanned(bd, HL, hst.everOcc, black, d.koRule, d.multiSuicide != 0, d.zob); bannedValid = true; }
+  if(d.histRules && d.gKoRule[g] != KGB_KO_SIMPLE) {
+    if(!bannedValid) { hst.banned = histSuperKoBanned(bd, HL, hst.everOcc, black, d.gKoRule[g], d.gMultiSuicide[g] != 0, d.zob); bannedValid = true; }
     superKo = hst.banned;
   }
-  const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, lib1) & ~superKo;    // BoardHistory::isLegal
+  const uint32_t legal = boardLegalMask(bd, black, d.gMultiSuicide[g] != 0, lib1) & ~superKo;    // BoardHistory::isLegal
   d.leafLegal[g * 32 + lane] = legal;
   if(lane == 0) {
     d.pathLen[g] = depth; d.leafNode[g] = node; d.leafTerminal[g] = (int)d.nodeTerminal[gb + node]; d.leafBlackToMove[g] = black ? 1 : 0;
     atomicAdd(d.sumDepth, (unsigned long long)depth);
   }
   if(terminal) {
-    int diff = boardAreaScoreBlackMinusWhite(bd, d.multiSuicide != 0);
+    int diff = boardAreaScoreBlackMinusWhite(bd, d.gMultiSuicide[g] != 0);
     float whiteScore = d.komiG[g] - (float)diff;
     if(lane == 0) d.leafTerminalScore[g] = whiteScore;
   }
@@ -1015,7 +1036,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   // planes 18/19: pass-alive + territory area for area scoring without tax (nninputs.cpp:2375-2382, 2425-2436)
   uint32_t areaB, areaW;
   const long long tZero = clock64();
-  boardCalculateArea(bd, true, true, true, d.multiSuicide != 0, areaB, areaW);
+  boardCalculateArea(bd, true, true, true, d.gMultiSuicide[g] != 0, areaB, areaW);
   const long long tArea = clock64();
   const uint32_t areaOwn = black ? areaB : areaW, areaOpp = black ? areaW : areaB;
   // planes 14-17: ladders on the current board and on the boards 1 and 2 moves ago (nninputs.cpp:2547-2583).  15/16 come
@@ -1027,8 +1048,8 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   shB[lane] = bd.b; shW[lane] = bd.w; shCand[lane] = lib1 | lib2;
   d.leafB[g * 32 + lane] = bd.b; d.leafW[g * 32 + lane] = bd.w; d.leafCand[g * 32 + lane] = lib1 | lib2;
   if(lane == 0) { shKo = bd.ko; d.leafKo[g] = bd.ko; shDoLadders = doLadders ? 1 : 0; d.leafNumHist[g] = numHist; d.leafValid[g] = 1; }
-  if(lane < d.Y) {
-    for(int x = 0; x < d.X; x++) {
+  if(lane < d.gY[g]) {
+    for(int x = 0; x < d.gX[g]; x++) {
       float* f = row + (size_t)(lane * d.X + x) * 22;
       const uint32_t bit = 1u << x;
       f[0] = 1.0f;
@@ -1041,7 +1062,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
   }
   __syncwarp();
-  const bool passEndsLeaf = d.histRules ? histPassWouldEndPhase(bd, hst, HL, black, d.koRule) : passes >= 1;
+  const bool passEndsLeaf = d.histRules ? histPassWouldEndPhase(bd, hst, HL, black, d.gKoRule[g]) : passes >= 1;
   if(lane == 0) {
     if(bd.ko >= 0) row[(size_t)posOf(bd.ko, d.X) * 22 + 6] = 1.0f;
     // history planes 9..13: the move k plies ago must have been made by the right colour, which alternation guarantees
@@ -1052,15 +1073,15 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       else row[(size_t)posOf(hs[k], d.X) * 22 + 9 + k] = 1.0f;
     }
     float selfKomi = black ? -d.komiG[g] : d.komiG[g];
-    float bArea = (float)d.XY;
+    float bArea = (float)(d.gX[g] * d.gY[g]);
     selfKomi = fminf(fmaxf(selfKomi, -bArea - 20.0f), bArea + 20.0f);
     gl[5] = selfKomi / 20.0f;
-    if(d.multiSuicide) gl[8] = 1.0f;
+    if(d.gMultiSuicide[g]) gl[8] = 1.0f;
     gl[14] = passEndsLeaf ? 1.0f : 0.0f;         // BoardHistory::passWouldEndPhase
-    if(d.koRule == KGB_KO_POSITIONAL || d.koRule == KGB_KO_SPIGHT) { gl[6] = 1.0f; gl[7] = 0.5f; }   // ko rule (nninputs.cpp:2612-2621)
-    else if(d.koRule == KGB_KO_SITUATIONAL) { gl[6] = 1.0f; gl[7] = -0.5f; }
+    if(d.gKoRule[g] == KGB_KO_POSITIONAL || d.gKoRule[g] == KGB_KO_SPIGHT) { gl[6] = 1.0f; gl[7] = 0.5f; }   // ko rule (nninputs.cpp:2612-2621)
+    else if(d.gKoRule[g] == KGB_KO_SITUATIONAL) { gl[6] = 1.0f; gl[7] = -0.5f; }
     // komi parity wave (nninputs.cpp:2696-2729)
-    bool drawableKomisAreEven = (d.XY % 2) == 0;
+    bool drawableKomisAreEven = ((d.gX[g] * d.gY[g]) % 2) == 0;
     float komiFloor = drawableKomisAreEven ? floorf(selfKomi / 2.0f) * 2.0f : floorf((selfKomi - 1.0f) / 2.0f) * 2.0f + 1.0f;
     float delta = fminf(fmaxf(selfKomi - komiFloor, 0.0f), 2.0f);
     gl[18] = delta < 0.5f ? delta : (delta < 1.5f ? 1.0f - delta : delta - 2.0f);
@@ -1132,14 +1153,14 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32, 2) spSelectKernel(const 
   const LadderScratch sc0 = ladderScratchAt(d.ladderScratch + (size_t)g * SP_LADDER_WARPS * ladderScratchWordsPerWarp());
   {
     WarpBoard bd;
-    boardInit(bd, d.X, d.Y);
+    boardInit(bd, d.gX[g], d.gY[g]);
     bd.b = shB[lane]; bd.w = shW[lane]; bd.ko = shKo;
     LadderScratch sc = ladderScratchAt(d.ladderScratch + ((size_t)g * SP_LADDER_WARPS + warp) * ladderScratchWordsPerWarp());
     sc.counters = d.ladderCounters;
     int budget = d.ladderNodesPerWave > 0 ? d.ladderNodesPerWave : 0x7fffffff;
     const bool fresh = shFresh != 0;
     bool done = true;
-    if(fresh || sc.st[LST_NEXT_ITEM] != 0x7fffffff) done = boardLaddersResumable(bd, shCand[lane], sc, d.X, d.Y, warp, SP_LADDER_WARPS, budget, fresh);
+    if(fresh || sc.st[LST_NEXT_ITEM] != 0x7fffffff) done = boardLaddersResumable(bd, shCand[lane], sc, d.gX[g], d.gY[g], warp, SP_LADDER_WARPS, budget, fresh);
     if(!done && lane == 0) atomicAdd(&shUnfinished, 1);
   }
   __syncthreads();
@@ -1161,8 +1182,8 @@ __global__ void __launch_bounds__(SP_LADDER_WARPS * 32, 2) spSelectKernel(const 
     if(lane == 0) { d.ladPending[g] = 0; d.leafValid[g] = 1; }
     float* row = d.nnSpatial + (size_t)g * d.XY * 22;
     const int numHist = d.leafNumHist[g];
-    if(lane < d.Y) {
-      for(int x = 0; x < d.X; x++) {
+    if(lane < d.gY[g]) {
+      for(int x = 0; x < d.gX[g]; x++) {
         float* f = row + (size_t)(lane * d.X + x) * 22;
         const uint32_t bit = 1u << x;
         if(lad0 & bit) {
@@ -1249,15 +1270,17 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
   const size_t gb = (size_t)g * d.maxNodes, gn = gb + node, nb = gn * d.policySize;
   const int nc = d.nodeNumChildren[gn];
   double WA[12], CU[12], CUSQ[12], CWS[12], CWSQ[12];   // weightAdjusted, child utilityAvg / utilitySqAvg / weightSum / weightSqSum
+  int CI[12];                                             // the child's node index
   double origTotal = 0.0, simpleValueSum = 0.0;
 #pragma unroll
   for(int ch = 0; ch < 12; ch++) {
-    WA[ch] = 0.0; CU[ch] = 0.0; CUSQ[ch] = 0.0; CWS[ch] = 1.0; CWSQ[ch] = 0.0;
+    WA[ch] = 0.0; CU[ch] = 0.0; CUSQ[ch] = 0.0; CWS[ch] = 1.0; CWSQ[ch] = 0.0; CI[ch] = 0;
     if(ch * 32 < nc) {
       const int k = ch * 32 + lane;
       const bool in = k < nc;
       const int mv = in ? (int)d.childOrder[nb + k] : 0;
       const int c = in ? d.childNode[nb + mv] : 0;
+      CI[ch] = c;
       const int ev = in ? d.childVisits[nb + mv] : 0;
       const int cv = in ? d.nodeVisits[gb + c] : 0;
       const double cw = in ? d.nodeWeightSum[gb + c] : 0.0;
@@ -1266,9 +1289,16 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
         WA[ch] = cw * ((double)ev / (double)(cv > 1 ? cv : 1));
         CU[ch] = d.nodeUtilAvg[gb + c]; CUSQ[ch] = d.nodeUtilSqAvg[gb + c]; CWS[ch] = cw; CWSQ[ch] = d.nodeWeightSqSum[gb + c];
       }
+    }
+  }
+  // (gathers first, without a barrier between the chunks: their dependent loads overlap; then the sums in the reference's order.
+  // A child that is not `good` has WA = 0 and CU = 0, so its terms are exactly 0 as before.)
+#pragma unroll
+  for(int ch = 0; ch < 12; ch++) {
+    if(ch * 32 < nc) {
       const double selfU = nodePlaWhite ? CU[ch] : -CU[ch];
       const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
-      orderedAdd2(WA[ch], good ? selfU * WA[ch] : 0.0, n, origTotal, simpleValueSum, sh, lane);
+      orderedAdd2(WA[ch], WA[ch] != 0.0 ? selfU * WA[ch] : 0.0, n, origTotal, simpleValueSum, sh, lane);
     }
   }
   // downweightBadChildrenAndNormalizeWeight (:402-491) with nothing to subtract or prune
@@ -1304,20 +1334,27 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
       orderedAdd2(scaling * scaling * CWSQ[ch], 0.0, n, weightSqSum, unused, sh, lane);
     }
   }
-  // the other moments: sum of weightAdjusted * child average (searchupdatehelpers.cpp:246-251), same order
+  // the other moments: sum of weightAdjusted * child average (searchupdatehelpers.cpp:246-251), same order.  Per pair of moments the
+  // children's values are gathered first (loads of all chunks in flight together), then added in order.
   double mom[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-  for(int ch = 0; ch < 12; ch++) {
-    if(ch * 32 < nc) {
-      const int k = ch * 32 + lane;
-      const bool in = k < nc;
-      const int c = in ? d.childNode[nb + (int)d.childOrder[nb + k]] : 0;
-      const double* cm = d.nodeMoments + (gb + c) * 5;
-      const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
-      const bool use = in && WA[ch] > 0.0;
-      orderedAdd2(use ? WA[ch] * cm[0] : 0.0, use ? WA[ch] * cm[1] : 0.0, n, mom[0], mom[1], sh, lane);
-      orderedAdd2(use ? WA[ch] * cm[2] : 0.0, use ? WA[ch] * cm[3] : 0.0, n, mom[2], mom[3], sh, lane);
-      orderedAdd2(use ? WA[ch] * cm[4] : 0.0, 0.0, n, mom[4], mom[5], sh, lane);
+  for(int pair = 0; pair < 3; pair++) {
+    double MA[12], MB[12];
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) {
+      MA[ch] = 0.0; MB[ch] = 0.0;
+      if(ch * 32 < nc) {
+        const bool use = ch * 32 + lane < nc && WA[ch] > 0.0;
+        const double* cm = d.nodeMoments + (gb + (use ? CI[ch] : 0)) * 5;
+        if(use) { MA[ch] = WA[ch] * cm[2 * pair]; if(pair < 2) MB[ch] = WA[ch] * cm[2 * pair + 1]; }
+      }
+    }
+#pragma unroll
+    for(int ch = 0; ch < 12; ch++) {
+      if(ch * 32 < nc) {
+        const int n = nc - ch * 32 < 32 ? nc - ch * 32 : 32;
+        orderedAdd2(MA[ch], MB[ch], n, mom[2 * pair], mom[2 * pair + 1], sh, lane);
+      }
     }
   }
   double weightSum = origTotal;
@@ -1358,8 +1395,8 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
 }
 
 // Search::getScoreUtility (searchhelpers.cpp:272-279)
-__device__ double scoreUtilityOf(const SPDev& d, double scoreMean, double scoreMeanSq, double center) {
-  const double sqrtBoardArea = sqrt((double)d.XY);
+__device__ double scoreUtilityOf(const SPDev& d, int g, double scoreMean, double scoreMeanSq, double center) {
+  const double sqrtBoardArea = sqrt((double)(d.gX[g] * d.gY[g]));
   const double stdev = svScoreStdev(scoreMean, scoreMeanSq);
   double r = 0.0;
   if(d.staticScoreUtilityFactor != 0.0) r += svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, 0.0, 2.0, sqrtBoardArea) * d.staticScoreUtilityFactor;
@@ -1368,8 +1405,8 @@ __device__ double scoreUtilityOf(const SPDev& d, double scoreMean, double scoreM
   return r;
 }
 // Search::getScoreUtilityDiff (searchhelpers.cpp:281-293): what `delta` more points for white are worth at this child's score statistics
-__device__ double scoreUtilityDiff(const SPDev& d, double scoreMean, double scoreMeanSq, double delta, double center) {
-  const double sqrtBoardArea = sqrt((double)d.XY);
+__device__ double scoreUtilityDiff(const SPDev& d, int g, double scoreMean, double scoreMeanSq, double delta, double center) {
+  const double sqrtBoardArea = sqrt((double)(d.gX[g] * d.gY[g]));
   const double stdev = svScoreStdev(scoreMean, scoreMeanSq);
   const double staticDiff = svExpectedWhiteScoreValue(d.svTable, scoreMean + delta, stdev, 0.0, 2.0, sqrtBoardArea) -
                             svExpectedWhiteScoreValue(d.svTable, scoreMean, stdev, 0.0, 2.0, sqrtBoardArea);
@@ -1382,7 +1419,7 @@ __device__ __forceinline__ double rootChildUtilityWithBonus(const SPDev& d, int 
   const double bonus = d.rootEndBonus[(size_t)g * d.policySize + mv];
   if(bonus == 0.0) return utilityAvg;
   const double* cm = d.nodeMoments + (gb + c) * 5;
-  return utilityAvg + scoreUtilityDiff(d, cm[2], cm[3], bonus, d.recentScoreCenter[g]);
+  return utilityAvg + scoreUtilityDiff(d, g, cm[2], cm[3], bonus, d.recentScoreCenter[g]);
 }
 // Once the root's evaluation is final (one warp): which root moves are allowed (rootPruneUselessMoves) and the ending score bonus of every move.
 // bd = the root position, rootBlack = the player to move, haveOwnership = d.rootOwnAcc holds the summed ownership of `numEvals` evaluations.
@@ -1392,7 +1429,7 @@ __device__ void computeRootExtras(const SPDev& d, int g, const WarpBoard& bd, bo
   const uint32_t empty = ~(bd.b | bd.w) & rm;
   uint32_t safeB = 0, safeW = 0;
   if(d.rootPruneUselessMoves || d.rootEndingBonusPoints != 0.0)
-    boardCalculateArea(bd, false, false, false, d.multiSuicide != 0, safeB, safeW);   // rootSafeArea: pass-alive groups and strictly safe territory (search.cpp:1111-1122)
+    boardCalculateArea(bd, false, false, false, d.gMultiSuicide[g] != 0, safeB, safeW);   // rootSafeArea: pass-alive groups and strictly safe territory (search.cpp:1111-1122)
   uint32_t allowed = 0xffffffffu;
   if(d.rootPruneUselessMoves && d.passStreak[g * 2 + (rootBlack ? 1 : 0)] >= 4) allowed = ~(safeB | safeW);
   d.rootAllowed[g * 32 + lane] = allowed;
@@ -1423,8 +1460,8 @@ __device__ void computeRootExtras(const SPDev& d, int g, const WarpBoard& bd, bo
   const float floatLen = (float)numEvals;
   const float* acc = d.rootOwnAcc + (size_t)g * d.XY;
   const double extreme = 0.95, tail = 0.05;
-  if(lane < d.Y) {
-    for(int x = 0; x < d.X; x++) {
+  if(lane < d.gY[g]) {
+    for(int x = 0; x < d.gX[g]; x++) {
       const uint32_t bit = 1u << x;
       if(!(empty & bit)) continue;
       const int pos = lane * d.X + x;
@@ -1457,14 +1494,14 @@ __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWi
     const double whiteScoreMean = (double)whiteScoreMeanF, whiteScoreMeanSq = (double)whiteScoreMeanSqF;
     if(node == 0 && d.nodeVisits[gb] == 0 && d.rootNumSymmetries <= 1) {
       double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
-      const double cap = sqrt((double)d.XY) * d.dynamicScoreCenterScale;
+      const double cap = sqrt((double)(d.gX[g] * d.gY[g])) * d.dynamicScoreCenterScale;
       if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
       if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
       __syncwarp();
       if(lane == 0) d.recentScoreCenter[g] = c;
       __syncwarp();
     }
-    u += scoreUtilityOf(d, whiteScoreMean, whiteScoreMeanSq, d.recentScoreCenter[g]);
+    u += scoreUtilityOf(d, g, whiteScoreMean, whiteScoreMeanSq, d.recentScoreCenter[g]);
   }
   return u;
 }
@@ -1474,7 +1511,7 @@ __device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane) {
   if(node == 0 && d.nodeVisits[gb] == 0 && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
     __syncwarp();
     if(lane == 0)
-      rootPolicyTemperatureAndNoise(d.policy + gb * d.policySize, d.policySize, d.X, d.Y, d.moveNum[g], d.rootNoiseEnabled != 0,
+      rootPolicyTemperatureAndNoise(d.policy + gb * d.policySize, d.policySize, d.gX[g], d.gY[g], d.moveNum[g], d.rootNoiseEnabled != 0,
                                     d.rootDirichletNoiseTotalConcentration, d.rootDirichletNoiseWeight, d.rootPolicyTemperature,
                                     d.rootPolicyTemperatureEarly, d.chosenMoveTemperatureHalflife, d.searchRand + g, d.noiseScratch + (size_t)g * d.policySize);
     __syncwarp();
@@ -1594,7 +1631,7 @@ __global__ void spBackupKernel(const SPDev d) {
   double u;
   if(d.leafTerminal[g] == 2) {
     // search.cpp:1204-1212: a game ended without result (long cycle under simple ko)
-    u = 1.0 * d.noResultUtilityForWhite + scoreUtilityOf(d, 0.0, 0.0, d.recentScoreCenter[g]);
+    u = 1.0 * d.noResultUtilityForWhite + scoreUtilityOf(d, g, 0.0, 0.0, d.recentScoreCenter[g]);
     if(lane == 0) { d.leafMoments[g * 5 + 0] = 0.0; d.leafMoments[g * 5 + 1] = 1.0; d.leafMoments[g * 5 + 2] = 0.0; d.leafMoments[g * 5 + 3] = 0.0; d.leafMoments[g * 5 + 4] = 0.0; }
     __syncwarp();
   }
@@ -1611,7 +1648,7 @@ __global__ void spBackupKernel(const SPDev d) {
       const double lo = (score - 0.5) * (score - 0.5), hi = (score + 0.5) * (score + 0.5);
       scoreMeanSq = lo + (hi - lo) * d.drawEquivalentWinsForWhite;
     }
-    u = winLoss * d.winLossUtilityFactor + scoreUtilityOf(d, scoreMean, scoreMeanSq, d.recentScoreCenter[g]);
+    u = winLoss * d.winLossUtilityFactor + scoreUtilityOf(d, g, scoreMean, scoreMeanSq, d.recentScoreCenter[g]);
     if(lane == 0) {   // search.cpp:1213-1222: winLoss, no "no result", score, its square, lead = score
       d.leafMoments[g * 5 + 0] = winLoss; d.leafMoments[g * 5 + 1] = 0.0; d.leafMoments[g * 5 + 2] = scoreMean;
       d.leafMoments[g * 5 + 3] = scoreMeanSq; d.leafMoments[g * 5 + 4] = scoreMean;
@@ -1661,9 +1698,9 @@ __global__ void spBackupKernel(const SPDev d) {
     const float* val = d.nnValue + (size_t)g * 3;
     double wl = val[0], ll = val[1], nl = val[2];
     double m = fmax(fmax(wl, ll), nl);
-    if(d.koRule != KGB_KO_SIMPLE) { nl -= 100000.0; m = fmax(fmax(wl, ll), nl); }   // nneval.cpp:1136-1147: no "no result" under superko
+    if(d.gKoRule[g] != KGB_KO_SIMPLE) { nl -= 100000.0; m = fmax(fmax(wl, ll), nl); }   // nneval.cpp:1136-1147: no "no result" under superko
     double w = exp(wl - m), l = exp(ll - m), n = exp(nl - m);
-    if(d.koRule != KGB_KO_SIMPLE) n = 0.0;
+    if(d.gKoRule[g] != KGB_KO_SIMPLE) n = 0.0;
     double s = w + l + n;
     w /= s; l /= s; n /= s;
     const float wf = (float)w, lf = (float)l, nf = (float)n;
@@ -1697,7 +1734,7 @@ __global__ void spBackupKernel(const SPDev d) {
         // the centring evaluation: recentScoreCenter from its expected score (search.cpp:1148-1153), nothing else is kept
         const double whiteScoreMean = (double)vals[3];
         double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
-        const double cap = sqrt((double)d.XY) * d.dynamicScoreCenterScale;
+        const double cap = sqrt((double)(d.gX[g] * d.gY[g])) * d.dynamicScoreCenterScale;
         if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
         if(c < whiteScoreMean - cap) c = whiteScoreMean - cap;
         if(lane == 0) { d.recentScoreCenter[g] = c; d.rootSymCount[g] = 1; atomicAdd(d.stalledWaves, 1ULL); }   // a wave without a playout
@@ -1720,7 +1757,7 @@ __global__ void spBackupKernel(const SPDev d) {
     else if(d.cacheSize > 0) cacheStore(d, g, node, d.leafKey[g * 2], d.leafKey[g * 2 + 1], vals, lane);   // before any root noise: the raw evaluation
     if(wantRootExtras) {
       WarpBoard rb;
-      boardInit(rb, d.X, d.Y);
+      boardInit(rb, d.gX[g], d.gY[g]);
       rb.b = d.rootB[g * 32 + lane]; rb.w = d.rootW[g * 32 + lane]; rb.ko = d.rootKo[g];
       computeRootExtras(d, g, rb, leafBlack, true, multiSymRoot ? d.rootNumSymmetries : 1, lane);
     }
@@ -1770,12 +1807,12 @@ __global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut,
 }
 
 // Apply a move list (x, y, or -1,-1 = pass; colours alternate from the current player) to every game's root.
-__global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMoves) {
+__global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMoves, int onlyGame) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if(g >= d.numGames) return;
+  if(g >= d.numGames || (onlyGame >= 0 && g != onlyGame)) return;
   WarpBoard bd;
-  boardInit(bd, d.X, d.Y);
+  boardInit(bd, d.gX[g], d.gY[g]);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
   bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
   bool black = d.rootBlackToMove[g] != 0;
@@ -1804,9 +1841,9 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     WarpBoard pb = bd;
     uint32_t l1, l2, wB, wW;
     pb.b = p1B; pb.w = p1W; pb.ko = p1Ko;
-    boardLadders(pb, sc, d.X, d.Y, l1, wB, wW);
+    boardLadders(pb, sc, d.gX[g], d.gY[g], l1, wB, wW);
     pb.b = p2B; pb.w = p2W; pb.ko = p2Ko;
-    boardLadders(pb, sc, d.X, d.Y, l2, wB, wW);
+    boardLadders(pb, sc, d.gX[g], d.gY[g], l2, wB, wW);
     d.prevLad[g * 32 + lane] = l1; d.prevLad[G32 + g * 32 + lane] = l2;
   }
   const size_t gb = (size_t)g * d.maxNodes;
@@ -1834,7 +1871,7 @@ __global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
   WarpBoard bd;
-  boardInit(bd, d.X, d.Y);
+  boardInit(bd, d.gX[g], d.gY[g]);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
   bd.ko = d.rootKo[g]; bd.capB = d.rootCapB[g]; bd.capW = d.rootCapW[g];
   bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];
@@ -1853,7 +1890,7 @@ __global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
   for(unsigned m = 0; m < len; m++) {
     uint32_t l1, l2, l3;
     boardLibertyClasses(bd, l1, l2, l3);
-    const uint32_t legal = boardLegalMask(bd, black, d.multiSuicide != 0, l1) & ~(d.histRules ? d.rootBanned[g * 32 + lane] : 0u);
+    const uint32_t legal = boardLegalMask(bd, black, d.gMultiSuicide[g] != 0, l1) & ~(d.histRules ? d.rootBanned[g * 32 + lane] : 0u);
     const int n = warpCount(legal);
     if(n == 0) break;
     unsigned r = 0;
@@ -1886,9 +1923,9 @@ __global__ void spRandomOpeningsKernel(const SPDev d, int maxLen) {
     WarpBoard pb = bd;
     uint32_t la, lb, wB, wW;
     pb.b = p1B; pb.w = p1W; pb.ko = p1Ko;
-    boardLadders(pb, sc, d.X, d.Y, la, wB, wW);
+    boardLadders(pb, sc, d.gX[g], d.gY[g], la, wB, wW);
     pb.b = p2B; pb.w = p2W; pb.ko = p2Ko;
-    boardLadders(pb, sc, d.X, d.Y, lb, wB, wW);
+    boardLadders(pb, sc, d.gX[g], d.gY[g], lb, wB, wW);
     d.prevLad[g * 32 + lane] = la; d.prevLad[G32 + g * 32 + lane] = lb;
   }
   const size_t gb = (size_t)g * d.maxNodes;
@@ -2055,6 +2092,22 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     std::vector<float> k((size_t)c.num_games, (float)c.komi);
     d.komiG = sp->alloc<float>(c.num_games); d.nextKomi = sp->alloc<float>(c.num_games); d.lastKomi = sp->alloc<float>(c.num_games);
     for(float* dst : {d.komiG, d.nextKomi, d.lastKomi}) SPCK(cudaMemcpy(dst, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  {   // every game starts with the frame as its board and the configuration's rules (kgb_selfplay_set_game_setup changes that per game)
+    if(c.ko_rule < 0 || c.ko_rule > 3) throw std::invalid_argument("selfplay: ko_rule must be 0 (simple), 1 (positional), 2 (situational) or 3 (spight)");
+    const int G = c.num_games;
+    d.gX = sp->alloc<int>(G); d.gY = sp->alloc<int>(G); d.gKoRule = sp->alloc<int>(G); d.gMultiSuicide = sp->alloc<int>(G);
+    d.nextSetup = sp->alloc<int>((size_t)G * 4); d.lastSetup = sp->alloc<int>((size_t)G * 4);
+    const int vals[4] = {X, Y, c.ko_rule, c.multi_stone_suicide_legal ? 1 : 0};
+    int* const dst[4] = {d.gX, d.gY, d.gKoRule, d.gMultiSuicide};
+    std::vector<int> one((size_t)G), four((size_t)G * 4);
+    for(int k = 0; k < 4; k++) {
+      std::fill(one.begin(), one.end(), vals[k]);
+      SPCK(cudaMemcpy(dst[k], one.data(), one.size() * sizeof(int), cudaMemcpyHostToDevice));
+      for(int g = 0; g < G; g++) four[(size_t)g * 4 + k] = vals[k];
+    }
+    SPCK(cudaMemcpy(d.nextSetup, four.data(), four.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SPCK(cudaMemcpy(d.lastSetup, four.data(), four.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   d.cpuctExploration = c.cpuct_exploration; d.cpuctExplorationLog = c.cpuct_exploration_log; d.cpuctExplorationBase = c.cpuct_exploration_base;
   d.fpuReductionMax = c.fpu_reduction_max; d.rootFpuReductionMax = c.root_fpu_reduction_max;
@@ -2245,12 +2298,24 @@ void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, f
   SPCK(cudaGetLastError());
 }
 
-void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s) {
+void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s, int onlyGame) {
+  if(onlyGame >= sp->d.numGames) throw std::invalid_argument("selfplay: game index out of range");
+  {   // every move must lie on the board of every game it is played on (a game's board can be smaller than the evaluator's frame)
+    std::vector<int> gx((size_t)sp->d.numGames), gy((size_t)sp->d.numGames);
+    SPCK(cudaMemcpy(gx.data(), sp->d.gX, gx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    SPCK(cudaMemcpy(gy.data(), sp->d.gY, gy.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for(int g = 0; g < sp->d.numGames; g++) {
+      if(onlyGame >= 0 && g != onlyGame) continue;
+      for(int m = 0; m < numMoves; m++)
+        if(movesXY[2 * m] >= 0 && (movesXY[2 * m] >= gx[g] || movesXY[2 * m + 1] < 0 || movesXY[2 * m + 1] >= gy[g]))
+          throw std::invalid_argument("selfplay: move " + std::to_string(m) + " is off the board of game " + std::to_string(g));
+    }
+  }
   int8_t* dm = nullptr;
   SPCK(cudaMalloc(&dm, (size_t)numMoves * 2));
   SPCK(cudaMemcpyAsync(dm, movesXY, (size_t)numMoves * 2, cudaMemcpyHostToDevice, s));
   int threads = 128, warpsPerBlock = threads / 32;
-  spPlayMovesKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, dm, numMoves);
+  spPlayMovesKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, dm, numMoves, onlyGame);
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(dm);
   SPCK(e);
@@ -2295,6 +2360,58 @@ void selfplayReadKomi(SelfplayImpl* sp, float* current, float* lastFinished) {
   const SPDev& d = sp->d;
   if(current) SPCK(cudaMemcpy(current, d.komiG, (size_t)d.numGames * sizeof(float), cudaMemcpyDeviceToHost));
   if(lastFinished) SPCK(cudaMemcpy(lastFinished, d.lastKomi, (size_t)d.numGames * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+// Board size and ko / suicide rules per game (GameInitializer::createGameSharedUnsynchronized, program/play.cpp:330-650: bSizes /
+// bSizeRelProbs, koRules, multiStoneSuicideLegals drawn per game).  setup[numGames][4] = X, Y, ko rule, multi-stone suicide: taken by each slot's
+// NEXT game; with alsoCurrent also by the game in progress, which must not have started (no move played, root not searched) - its history
+// restarts under the new rules.  Ko rules other than the loop's own need full_history_rules (BoardHistory's lists are per game already).
+__global__ void spApplySetupKernel(const SPDev d, int* refused) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if(g >= d.numGames) return;
+  const size_t gb = (size_t)g * d.maxNodes;
+  if(d.moveNum[g] != 0 || d.nodeVisits[gb] != 0 || d.rootSymCount[g] != 0 || d.ladPending[g] != 0) { if(lane == 0) atomicAdd(refused, 1); return; }
+  __syncwarp();
+  if(lane == 0) { d.gX[g] = d.nextSetup[g * 4 + 0]; d.gY[g] = d.nextSetup[g * 4 + 1]; d.gKoRule[g] = d.nextSetup[g * 4 + 2]; d.gMultiSuicide[g] = d.nextSetup[g * 4 + 3]; }
+  __syncwarp();
+  gameHistReset(d, g, lane);
+  __syncwarp();
+  rootHashesInit(d, g, lane);
+}
+void selfplaySetGameSetup(SelfplayImpl* sp, const int* setup, bool alsoCurrent, cudaStream_t s) {
+  const SPDev& d = sp->d;
+  for(int g = 0; g < d.numGames; g++) {
+    const int* q = setup + (size_t)g * 4;
+    if(q[0] < 2 || q[0] > d.X || q[1] < 2 || q[1] > d.Y) throw std::invalid_argument("selfplay: a game's board must be at least 2x2 and fit the evaluator's frame");
+    if(q[2] < 0 || q[2] > 3) throw std::invalid_argument("selfplay: ko_rule must be 0 (simple), 1 (positional), 2 (situational) or 3 (spight)");
+    if(q[2] != d.koRule && !d.histRules) throw std::invalid_argument("selfplay: per-game ko rules need full_history_rules = 1 (or a superko rule) in the loop's configuration");
+    if(q[3] != 0 && q[3] != 1) throw std::invalid_argument("selfplay: multi_stone_suicide_legal must be 0 or 1");
+  }
+  SPCK(cudaMemcpy(d.nextSetup, setup, (size_t)d.numGames * 4 * sizeof(int), cudaMemcpyHostToDevice));
+  if(!alsoCurrent) return;
+  int* refused = nullptr;
+  SPCK(cudaMalloc(&refused, sizeof(int)));
+  SPCK(cudaMemsetAsync(refused, 0, sizeof(int), s));
+  spApplySetupKernel<<<(d.numGames * 32 + 127) / 128, 128, 0, s>>>(d, refused);
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, refused, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if(e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(refused);
+  SPCK(e);
+  if(h != 0) throw std::invalid_argument("selfplay: " + std::to_string(h) + " game(s) in progress have already started; their setup was left unchanged");
+}
+void selfplayReadGameSetup(SelfplayImpl* sp, int* current, int* lastFinished) {
+  const SPDev& d = sp->d;
+  if(current) {
+    std::vector<int> a((size_t)d.numGames);
+    int* const src[4] = {d.gX, d.gY, d.gKoRule, d.gMultiSuicide};
+    for(int k = 0; k < 4; k++) {
+      SPCK(cudaMemcpy(a.data(), src[k], a.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      for(int g = 0; g < d.numGames; g++) current[(size_t)g * 4 + k] = a[g];
+    }
+  }
+  if(lastFinished) SPCK(cudaMemcpy(lastFinished, d.lastSetup, (size_t)d.numGames * 4 * sizeof(int), cudaMemcpyDeviceToHost));
 }
 
 void selfplayReadRootRow(SelfplayImpl* sp, int g, float* spatial, float* global) {

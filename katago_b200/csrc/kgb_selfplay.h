@@ -24,10 +24,12 @@ void selfplayClearNNCache(SelfplayImpl* sp, cudaStream_t s);
 void selfplaySetKomi(SelfplayImpl* sp, const float* komi, bool alsoCurrent);
 void selfplayReadLeafKey(SelfplayImpl* sp, int g, unsigned long long* key2);
 void selfplayReadKomi(SelfplayImpl* sp, float* current, float* lastFinished);
+void selfplaySetGameSetup(SelfplayImpl* sp, const int* setup, bool alsoCurrent, cudaStream_t s);
+void selfplayReadGameSetup(SelfplayImpl* sp, int* current, int* lastFinished);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, float* ownershipOut, cudaStream_t s);
-void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s);
+void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cudaStream_t s, int onlyGame = -1);
 void selfplaySetSearchRand(SelfplayImpl* sp, const char* seedString);
 void selfplayRandomOpenings(SelfplayImpl* sp, int maxLen, cudaStream_t s);
 void selfplayReadStats(SelfplayImpl* sp, kgb_selfplay_stats* out);

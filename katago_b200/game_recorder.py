@@ -164,6 +164,7 @@ class _GameInProgress:
     def __init__(self):
         self.turns = []       # per turn: what the finished root search gave
         self.boards = []      # position before each move
+        self.setup = None     # (board X, board Y, ko rule, multi-stone suicide legal) of this game, read when its first turn is recorded
 
 
 class GameRecorder:
@@ -201,8 +202,7 @@ class GameRecorder:
         if cfg is not None and int(getattr(cfg, "nn_cache_size_power_of_two", 0)) > 0 and int(getattr(cfg, "root_num_symmetries_to_sample", 0)) <= 1:
             raise ValueError("GameRecorder: with nn_cache_size_power_of_two > 0 the root must be evaluated by the net itself "
                              "(root_num_symmetries_to_sample >= 2, as in the stock self-play configurations), or the cache switched off")
-        self.ko_rule_name = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[int(getattr(cfg, "ko_rule", 0))]
-        self.multi_stone_suicide_legal = bool(getattr(cfg, "multi_stone_suicide_legal", 1))
+        self.default_setup = (self.X, self.Y, int(getattr(cfg, "ko_rule", 0)), int(bool(getattr(cfg, "multi_stone_suicide_legal", 1))))
         sp.run(1)                                    # evaluates every root (its row stays on the device)
 
     def _record_root(self, g):
@@ -223,7 +223,12 @@ class GameRecorder:
             raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
                                "(the kept input row belongs to another position)")
         gm = self.games[g]
-        gm.boards.append(flat.copy())
+        if gm.setup is None:
+            # board size and rules are per game (SelfPlay.set_game_setup; GameInitializer draws them per game): X, Y below stay the
+            # evaluator's frame = the data frame (dataBoardLen) the rows are written in, the game's own board is its top-left corner
+            gm.setup = tuple(int(v) for v in sp.game_setups()[0][g]) if hasattr(sp, "game_setups") else self.default_setup
+        bx, by = gm.setup[0], gm.setup[1]
+        gm.boards.append(np.ascontiguousarray(flat.reshape(self.Y, self.X)[:by, :bx]).reshape(-1).copy())
         gm.turns.append(dict(
             next_player=own, move_num=info["move_num"],
             packed=pack_bits(np.transpose(sp_row.reshape(1, self.X * self.Y, 22), (0, 2, 1)))[0],
@@ -282,7 +287,8 @@ class GameRecorder:
 
     def _finish_game(self, g, last):
         gm = self.games[g]
-        X, Y = self.X, self.Y
+        X, Y, ko_rule, multi_suicide = gm.setup if gm.setup is not None else self.default_setup     # this game's own board and rules
+        crop = lambda a: np.ascontiguousarray(np.asarray(a, np.uint8).reshape(self.Y, self.X)[:Y, :X]).reshape(-1).copy()
         # komi is per game (SelfPlay.set_komi; the reference's GameInitializer draws one per game): the slot's last finished game's
         komi = float(self.sp.komi_values()[1][g]) if hasattr(self.sp, "komi_values") else self.komi
         data = FinishedGameData(X, Y, komi)
@@ -292,9 +298,9 @@ class GameRecorder:
         data.hit_turn_limit = bool(last["hit_move_limit"])
         data.end_no_result = bool(last["no_result"])
         data.moves = [t["move"] for t in gm.turns]
-        data.ko_rule = self.ko_rule_name
-        data.multi_stone_suicide_legal = self.multi_stone_suicide_legal
-        data.boards_by_turn = gm.boards + [np.asarray(last["final_colors"], np.uint8).reshape(-1).copy()]
+        data.ko_rule = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[ko_rule]
+        data.multi_stone_suicide_legal = bool(multi_suicide)
+        data.boards_by_turn = gm.boards + [crop(last["final_colors"])]
         for t in gm.turns:
             data.next_player_by_turn.append(t["next_player"])
             data.packed_input_by_turn.append(t["packed"]); data.global_input_by_turn.append(t["global_input"])
@@ -309,7 +315,7 @@ class GameRecorder:
             data.white_value_targets_by_turn.append(final_value_targets(0, 0.0, self.draw_eq, komi, no_result=True))
         else:
             # area scoring without tax: ownership = full area = calculateArea with every flag on (boardhistory.cpp:591-610)
-            area = np.asarray(last["final_area"], np.uint8).reshape(-1).copy()
+            area = crop(last["final_area"])
             score = float(last["final_white_minus_black_score"])
             winner = P_WHITE if score > 0 else P_BLACK if score < 0 else 0
             data.winner, data.final_white_minus_black_score = winner, score

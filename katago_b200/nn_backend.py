@@ -83,6 +83,7 @@ ABI_SYMBOLS = [
     "kgb_handle_weights_bytes", "kgb_handle_stage_weights", "kgb_handle_commit_weights", "kgb_handle_wait_staged", "kgb_nccl_unique_id", "kgb_handle_comm_init",
     "kgb_handle_broadcast_staged_weights", "kgb_selfplay_clear_nn_cache", "kgb_selfplay_set_komi", "kgb_selfplay_get_komi", "kgb_selfplay_get_leaf_cache_key",
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
+    "kgb_selfplay_set_game_setup", "kgb_selfplay_get_game_setup", "kgb_selfplay_play_moves_game",
 ]
 
 _lib = None
@@ -127,6 +128,9 @@ def load_library():
     lib.kgb_selfplay_clear_nn_cache.argtypes = [P]
     lib.kgb_selfplay_set_komi.argtypes = [P, P, I]
     lib.kgb_selfplay_get_komi.argtypes = [P, P, P]
+    lib.kgb_selfplay_set_game_setup.argtypes = [P, P, I]
+    lib.kgb_selfplay_get_game_setup.argtypes = [P, P, P]
+    lib.kgb_selfplay_play_moves_game.argtypes = [P, I, P, I]
     lib.kgb_selfplay_get_leaf_cache_key.argtypes = [P, I, P]
     lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
@@ -548,6 +552,11 @@ class SelfPlay:
         arr = np.array([(-1, -1) if m is None else (m[0], m[1]) for m in moves_xy], dtype=np.int8).reshape(-1, 2)
         _check(load_library().kgb_selfplay_play_moves(self._p, arr.ctypes.data if len(arr) else None, len(arr)))
 
+    def play_moves_game(self, g: int, moves_xy):
+        """The same for game g only (games of different board sizes need different lists)."""
+        arr = np.array([(-1, -1) if m is None else (m[0], m[1]) for m in moves_xy], dtype=np.int8).reshape(-1, 2)
+        _check(load_library().kgb_selfplay_play_moves_game(self._p, g, arr.ctypes.data if len(arr) else None, len(arr)))
+
     def nn_row(self, g: int):
         """(spatial [X*Y, 22], global [19]) written by the last wave for game g."""
         sp = np.zeros((self.x * self.y, 22), np.float32); gl = np.zeros(19, np.float32)
@@ -600,6 +609,18 @@ class SelfPlay:
         """komi[num_games] for each slot's next game (and, optionally, for the games in progress)."""
         k = np.ascontiguousarray(np.broadcast_to(np.asarray(komi, np.float32), (self.num_games,)))
         _check(load_library().kgb_selfplay_set_komi(self._p, k.ctypes.data, int(also_current_games)))
+
+    def set_game_setup(self, setup, also_current_games: bool = False):
+        """setup[num_games][4] = board X, board Y, ko rule (0-3), multi-stone suicide legal, for each slot's next game (and, optionally,
+        the games in progress that have not started): what GameInitializer draws per game (program/play.cpp:330-650)."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(setup, np.int32), (self.num_games, 4)))
+        _check(load_library().kgb_selfplay_set_game_setup(self._p, a.ctypes.data, int(also_current_games)))
+
+    def game_setups(self):
+        """(setup [num_games, 4] of the games in progress, of each slot's last finished game)."""
+        cur = np.zeros((self.num_games, 4), np.int32); last = np.zeros((self.num_games, 4), np.int32)
+        _check(load_library().kgb_selfplay_get_game_setup(self._p, cur.ctypes.data, last.ctypes.data))
+        return cur, last
 
     def komi_values(self):
         """(komi of the games in progress, komi of each slot's last finished game)."""

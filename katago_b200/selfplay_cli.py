@@ -9,10 +9,11 @@ selfplay.cpp:177-225),
 and it reads the reference's own .cfg files: every search / rules / data key the device loop implements is mapped to its
 `kgb_selfplay_config` field (`selfplay_kwargs_from_cfg`), every other key is reported - either as irrelevant here (logging, thread
 and device placement of the reference's CPU threads) or as NOT BUILT (options that change the data distribution: forks, cheap
-searches, komi / rules / board-size randomisation, ...).  `-strict` turns the second group into an error.
+searches, handicap games, ...).  `-strict` turns the second group into an error.
 
-The reference randomises rules and board size per game; one loop instance plays one rule set on one board size, so list-valued
-keys (`koRules`, `bSizes`, ...) must contain a value the loop supports and the first such value is used (reported).
+The reference randomises rules, board size and komi per game (GameInitializer); the device loop takes them per game slot
+(kgb_selfplay_set_game_setup / set_komi), so list-valued
+keys (`koRules`, `bSizes`, ...) are drawn per game like the reference does (game_initializer.py); values the loop lacks are left out (reported).
 Under torchrun (one process per GPU) the ranks split `-max-games-total`, use LOCAL_RANK's GPU and their own seeds, and write into the
 same tdata directory (`shard_plan`); there is no collective on this path.
 There is no CPU fallback: without a B200 the command fails when it creates the evaluator."""
@@ -56,7 +57,7 @@ _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNN
 _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0, "cheapSearchProb": 0.0,
             "reduceVisits": False, "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
             "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
-            "handicapProb": 0.0, "komiStdev": 0.0, "komiBigStdevProb": 0.0, "komiBiggerStdevProb": 0.0, "allowRectangleProb": 0.0,
+            "handicapProb": 0.0,
             "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
 _REFERENCE_DEFAULTS = {
     "cpuct_exploration": 1.0, "cpuct_exploration_log": 0.45, "cpuct_exploration_base": 500.0, "fpu_reduction_max": 0.2, "root_fpu_reduction_max": 0.1,
@@ -93,27 +94,20 @@ def parse_cfg(path_or_text, is_text=False):
     return out
 
 
-def _first_supported(cfg, key, supported, report, default, rel_probs_key=None):
-    """One value of a list-valued key.  The reference draws one per game (GameInitializer, program/play.cpp:83-650), uniformly or
-    with the weights of `rel_probs_key`; this loop plays ONE value in every game: the supported value the reference would draw most
-    often (largest relative probability; the first listed among equals), and says so under "fixed"."""
+def _supported_values(cfg, key, supported, report, default):
+    """The values of a list-valued key that the loop can play, in the order listed.  The reference draws one per game (GameInitializer,
+    program/play.cpp:83-650) and so does this command (katago_b200/game_initializer.py); values the loop does not have are left out of
+    the draw and named under "fixed"."""
     if key not in cfg:
-        return default
+        return [default]
     vals = [v.strip() for v in cfg[key].split(",") if v.strip()]
-    probs = [1.0] * len(vals)
-    if rel_probs_key is not None and rel_probs_key in cfg:
-        probs = [float(v) for v in cfg[rel_probs_key].split(",") if v.strip()]
-        if len(probs) != len(vals):
-            raise ValueError(f"{rel_probs_key} has {len(probs)} entries, {key} has {len(vals)}")
-    ok = [(pr, -i, v) for i, (v, pr) in enumerate(zip(vals, probs)) if (v.upper() in supported or v.lower() in supported) and pr > 0]
+    ok = [v for v in vals if v.upper() in supported or v.lower() in supported]
     if not ok:
         raise ValueError(f"{key} = {cfg[key]}: none of these is built (supported: {sorted(supported)}); pass an explicit single value")
-    best = max(ok)[2]
-    if len(set(vals)) > 1:
-        how = f" (weights {cfg[rel_probs_key]})" if rel_probs_key is not None and rel_probs_key in cfg else ""
-        report["fixed"].append(f"{key}: the reference draws one of [{cfg[key]}]{how} per game; this loop plays '{best}', the most likely "
-                               f"supported value, in every game - give a single value to choose another")
-    return best
+    dropped = [v for v in vals if v not in ok]
+    if dropped:
+        report["fixed"].append(f"{key}: the reference draws one of [{cfg[key]}] per game; {', '.join(dropped)} not built, this loop draws from [{', '.join(ok)}]")
+    return ok
 
 
 def selfplay_kwargs_from_cfg(cfg, strict=False):
@@ -138,34 +132,50 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     if not by_policy:
         kw["fpu_parent_weight_by_visited_policy_pow"] = 1.0
     kw["use_play_selection"] = True                       # Search::getChosenMoveLoc always goes through the play selection values
-    # rules: one value per list
-    ko = _first_supported(cfg, "koRules", set(_KO_RULES), report, "SIMPLE").upper()
-    kw["ko_rule"] = _KO_RULES[ko]
+    # rules, board size and komi: drawn per game like the reference's GameInitializer does (game_initializer.py); the loop's own
+    # configuration carries the first listed ko / suicide rule as its default
+    kos = [_KO_RULES[v.upper()] for v in _supported_values(cfg, "koRules", set(_KO_RULES), report, "SIMPLE")]
+    kw["ko_rule"] = kos[0]
     kw["full_history_rules"] = True
-    _first_supported(cfg, "scoringRules", {"AREA"}, report, "AREA")
-    _first_supported(cfg, "taxRules", {"NONE"}, report, "NONE")
-    _first_supported(cfg, "hasButtons", {"false"}, report, "false")
-    kw["multi_stone_suicide_legal"] = _B(_first_supported(cfg, "multiStoneSuicideLegals", {"false", "true"}, report, "true"))
-    size = int(_first_supported(cfg, "bSizes", {str(s) for s in range(2, 20)}, report, "19", rel_probs_key="bSizeRelProbs"))
-    used.update(("koRules", "scoringRules", "taxRules", "hasButtons", "multiStoneSuicideLegals", "bSizes", "bSizeRelProbs"))
+    _supported_values(cfg, "scoringRules", {"AREA"}, report, "AREA")
+    _supported_values(cfg, "taxRules", {"NONE"}, report, "NONE")
+    _supported_values(cfg, "hasButtons", {"false"}, report, "false")
+    suicides = [_B(v) for v in _supported_values(cfg, "multiStoneSuicideLegals", {"false", "true"}, report, "true")]
+    kw["multi_stone_suicide_legal"] = suicides[0]
+    edges = [int(v) for v in _supported_values(cfg, "bSizes", {str(s) for s in range(2, 20)}, report, "19")]
+    all_edges = [v.strip() for v in cfg.get("bSizes", "19").split(",") if v.strip()]
+    rel = [float(v) for v in cfg["bSizeRelProbs"].split(",") if v.strip()] if "bSizeRelProbs" in cfg else [1.0] * len(all_edges)
+    if len(rel) != len(all_edges):
+        raise ValueError(f"bSizeRelProbs has {len(rel)} entries, bSizes has {len(all_edges)}")
+    rel = [pr for v, pr in zip(all_edges, rel) if v in {str(e) for e in edges}]
+    from .game_initializer import board_size_distribution
+    sizes, size_probs = board_size_distribution(edges, rel, float(cfg.get("allowRectangleProb", 0.0)))
+    size = max(edges)                                     # the evaluator's frame holds the largest board
+    used.update(("koRules", "scoringRules", "taxRules", "hasButtons", "multiStoneSuicideLegals", "bSizes", "bSizeRelProbs", "allowRectangleProb"))
     # komiAuto = true makes the reference find the komi that its own search calls even on the empty board
     # (makeGameFairForEmptyBoard, program/play.cpp:640-644, playutils.cpp:591): that needs searches before the game and is NOT BUILT -
-    # the loop plays a fixed komi (komiMean, else 7.5) on every board size, which is off on small boards.  Listed so that -strict refuses it.
+    # the games start from komiMean (else 7.5) with the configured noise on every board size, which is off on small boards.  Listed so
+    # that -strict refuses it.
     komi = float(cfg["komiMean"]) if "komiMean" in cfg else 7.5
-    used.update(("komiMean", "komiAuto"))
+    used.update(("komiMean", "komiAuto", "komiStdev", "komiBigStdevProb", "komiBigStdev", "komiBiggerStdevProb", "komiBiggerStdev", "komiAllowIntegerProb"))
     if _B(cfg.get("komiAuto", "false")):
-        report["not_built"].append(f"komiAuto = true (komi fixed at {komi} instead of being adjusted to even by search)")
+        report["not_built"].append(f"komiAuto = true (komi drawn around {komi} instead of being adjusted to even by search)")
     data = {"board_size": size, "komi": komi,
             "data_board_len": int(cfg.get("dataBoardLen", size)), "max_rows_per_train_file": int(cfg.get("maxRowsPerTrainFile", 20000)),
             "first_file_rand_min_prop": float(cfg.get("firstFileRandMinProp", 1.0)), "num_game_threads": int(cfg.get("numGameThreads", 256))}
+    data["game_init"] = dict(sizes=sizes, size_probs=size_probs, ko_rules=kos, multi_stone_suicide_legals=suicides, komi_mean=komi,
+                             komi_stdev=float(cfg.get("komiStdev", 0.0)), komi_big_stdev_prob=float(cfg.get("komiBigStdevProb", 0.0)),
+                             komi_big_stdev=float(cfg.get("komiBigStdev", 10.0)), komi_bigger_stdev_prob=float(cfg.get("komiBiggerStdevProb", 0.0)),
+                             komi_bigger_stdev=float(cfg.get("komiBiggerStdev", 0.0)), komi_allow_integer_prob=float(cfg.get("komiAllowIntegerProb", 1.0)))
     used.update(("dataBoardLen", "maxRowsPerTrainFile", "firstFileRandMinProp", "numGameThreads"))
     # PlaySettings the recorder implements (program/playsettings.cpp): surprise weighting of the finished game's rows
     data["policy_surprise_data_weight"] = float(cfg.get("policySurpriseDataWeight", 0.0))
     data["value_surprise_data_weight"] = float(cfg.get("valueSurpriseDataWeight", 0.0))
     data["use_search_value_surprise"] = _B(cfg.get("useSearchValueSurprise", "false"))
     used.update(("policySurpriseDataWeight", "valueSurpriseDataWeight", "useSearchValueSurprise"))
-    if data["data_board_len"] != size:
-        raise ValueError(f"dataBoardLen = {data['data_board_len']} but the board is {size}x{size}: rows smaller than the data frame are not built")
+    if data["data_board_len"] < size:
+        raise ValueError(f"dataBoardLen = {data['data_board_len']} but bSizes goes up to {size}: the data frame must hold the largest board")
+    data["board_size"] = size = data["data_board_len"]    # rows are written in the data frame, so the evaluator's frame is that (nnXLen = dataBoardLen)
     for key, val in cfg.items():
         if key in used:
             continue
@@ -184,6 +194,29 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     if strict and report["not_built"]:
         raise ValueError("options that are not built: " + "; ".join(report["not_built"]))
     return kw, data, report
+
+
+class SlotSetups:
+    """Host side of the per-game setup: draws from a GameInitializer and hands them to the loop (SelfPlay.set_game_setup / set_komi)."""
+
+    def __init__(self, init, num_games):
+        self.init, self.n = init, num_games
+        self.setups, self.komis = init.draw_many(num_games)
+
+    def start(self, sp):
+        """A fresh loop: the drawn values become the games in progress (none has started), new ones are drawn for the games after them."""
+        sp.set_game_setup(self.setups, also_current_games=True)
+        sp.set_komi(self.komis, also_current_games=True)
+        self.setups, self.komis = self.init.draw_many(self.n)
+        sp.set_game_setup(self.setups)
+        sp.set_komi(self.komis)
+
+    def redraw(self, sp, slot):
+        x, y, ko, suicide, komi = self.init.draw()
+        self.setups[slot] = (x, y, ko, suicide)
+        self.komis[slot] = komi
+        sp.set_game_setup(self.setups)
+        sp.set_komi(self.komis)
 
 
 def _game_hash(seed, slot, index):
@@ -365,7 +398,17 @@ def main(argv=None):
     sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, **kw)
     outputs = ModelOutputs(a.output_dir, data, L, writer_seed, TrainingDataWriter)
     outputs.switch_to(model_path)
-    rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=outputs.add_game,
+    # board size, ko / suicide rule and komi of every game: drawn on the host like the reference's GameInitializer, applied by the device
+    # when the slot's next game starts.  `slots` always holds what has been handed to the device for each slot's NEXT game.
+    from .game_initializer import GameInitializer
+    init = GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"])
+    slots = SlotSetups(init, games)
+    slots.start(sp)
+
+    def on_game(slot, finished):
+        outputs.add_game(slot, finished)
+        slots.redraw(sp, slot)           # the slot's new game has taken the values drawn before; draw the ones for the game after it
+    rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                        use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"))
@@ -450,8 +493,9 @@ def main(argv=None):
                 ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
                 h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
                 sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed + 7919 * (swaps + 1), debug_hold_at_max_visits=True, **kw)
+                slots.start(sp)
                 written = rec.games_written
-                rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=outputs.add_game,
+                rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                                    game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
                                    policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                                    use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"))

@@ -207,7 +207,12 @@ static int cmdSearchFake(int argc, char** argv) {
   // KGREF_NN_CACHE_POW2 = -1 switches NNEvaluator's evaluation cache off (it is keyed by the situation, not the history: with a real net a
   // transposition then returns the output computed for another move order - fine for play, but not what a cache-less search sees)
   const int cachePow2 = getenv("KGREF_NN_CACHE_POW2") ? atoi(getenv("KGREF_NN_CACHE_POW2")) : 10;
-  NNEvaluator* nnEval = new NNEvaluator("fake", modelFile, "", &logger, 4, X, Y, true, true, cachePow2, 8, false, "", enabled_t::False, 1,
+  // KGREF_NN_LEN = L: the evaluator's frame is L x L while the board is X x Y (nnXLen > board size: padded rows + mask, nneval.cpp:874-883;
+  // BASELINE config 4 "mixed board sizes"); move positions and the policy are then indexed in the frame (NNPos::locToPos)
+  const int nnLenEnv = getenv("KGREF_NN_LEN") ? atoi(getenv("KGREF_NN_LEN")) : 0;
+  const int NX = nnLenEnv > 0 ? nnLenEnv : X, NY = nnLenEnv > 0 ? nnLenEnv : Y;
+  if(NX < X || NY < Y) { cerr << "KGREF_NN_LEN smaller than the board" << endl; return 1; }
+  NNEvaluator* nnEval = new NNEvaluator("fake", modelFile, "", &logger, 4, NX, NY, NX == X && NY == Y, true, cachePow2, 8, false, "", enabled_t::False, 1,
                                         vector<int>{0}, "seed", false, 0, true, cfg);
   nnEval->spawnServerThreads();
   // Reference SearchParams restricted to what the device loop implements: everything else at its default.
@@ -319,7 +324,7 @@ static int cmdSearchFake(int argc, char** argv) {
   }
   const NNOutput* nn = root->getNNOutput();
   cout << "policy";
-  for(int i = 0; i <= X * Y; i++) cout << " " << Global::strprintf("%.9g", nn->getPolicyProbsMaybeNoised()[i]);
+  for(int i = 0; i <= NX * NY; i++) cout << " " << Global::strprintf("%.9g", nn->getPolicyProbsMaybeNoised()[i]);
   cout << endl;
   {   // what Play::runGame records for this turn (program/play.cpp:848-948): value / Q / policy targets, surprise and entropies
     ReportedSearchValues rv;
@@ -1170,10 +1175,14 @@ static int cmdFeatStream(int argc, char** argv) {
   std::istringstream in(movesArg);
   string tok;
   int n = 0, written = 0;
-  vector<float> rowBin(NNInputs::NUM_FEATURES_SPATIAL_V7 * X * Y), rowGlobal(NNInputs::NUM_FEATURES_GLOBAL_V7);
+  // KGREF_NN_LEN = L: rows for an L x L evaluator frame with the X x Y board in its corner (see searchfake)
+  const int nnLenEnv = getenv("KGREF_NN_LEN") ? atoi(getenv("KGREF_NN_LEN")) : 0;
+  const int NX = nnLenEnv > 0 ? nnLenEnv : X, NY = nnLenEnv > 0 ? nnLenEnv : Y;
+  if(NX < X || NY < Y) { cerr << "KGREF_NN_LEN smaller than the board" << endl; return 1; }
+  vector<float> rowBin(NNInputs::NUM_FEATURES_SPATIAL_V7 * NX * NY), rowGlobal(NNInputs::NUM_FEATURES_GLOBAL_V7);
   auto dump = [&]() {
     MiscNNInputParams params;
-    NNInputs::fillRowV7(board, hist, pla, params, X, Y, true, rowBin.data(), rowGlobal.data());
+    NNInputs::fillRowV7(board, hist, pla, params, NX, NY, true, rowBin.data(), rowGlobal.data());
     put<int32_t>(out, n);
     out.write((const char*)rowBin.data(), rowBin.size() * sizeof(float));
     out.write((const char*)rowGlobal.data(), rowGlobal.size() * sizeof(float));

@@ -37,15 +37,20 @@ LCB = {"useLcbForSelection": 1, "lcbStdevs": 5.0, "minVisitPropForLCB": 0.15, "u
 BIAS = {"subtreeValueBiasFactor": 0.30, "subtreeValueBiasWeightExponent": 0.8}
 
 
-def run(X, Y, visits, moves, score=None, driver=None, model=None, env=None):
+def run(X, Y, visits, moves, score=None, driver=None, model=None, env=None, frame=None):
     s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
     if score is None:
         score = {}
     elif not isinstance(score, dict):
         score = dict(zip(SCORE_KEYS, score))
     extra = [f"{k}={float(v)!r}" for k, v in score.items() if k != "fullHistoryRules"]
+    if frame is not None:      # the evaluator's frame is frame x frame, the board X x Y in its corner: positions are y * frame + x
+        env = dict(env or {}, KGREF_NN_LEN=str(frame))
     out = subprocess.run([driver or DRIVER, "searchfake", model or MODEL, str(X), str(Y), str(visits), s] + extra, capture_output=True, text=True, check=True,
                          env=(dict(os.environ, **env) if env else None)).stdout
+    bx = X
+    if frame is not None:
+        X = Y = frame
     v = np.zeros(X * Y + 1, np.int32); u = np.zeros(X * Y + 1, np.float64); pol = None; root = None; center = 0.0
     psv = np.full(X * Y + 1, -1.0, np.float64); threadseed = ""
     cstats = np.zeros((X * Y + 1, 5), np.float64); rstats = np.zeros(5, np.float64)

@@ -1,6 +1,7 @@
 """CPU tests of the `selfplay` command's configuration layer: the reference's .cfg syntax and key names."""
 import inspect, os, sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -48,16 +49,25 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert kw["subtree_value_bias_factor"] == 0.30 and kw["root_num_symmetries_to_sample"] == 4 and kw["use_lcb_for_selection"] is True
     assert kw["root_policy_temperature_early"] == 1.5 and kw["chosen_move_temperature_halflife"] == 19.0 and kw["nn_cache_size_power_of_two"] == 24
     assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
+    gi = data.pop("game_init")
     assert data == {"board_size": 19, "komi": 7.5, "data_board_len": 19, "max_rows_per_train_file": 20000, "first_file_rand_min_prop": 0.15, "num_game_threads": 800,
                     "policy_surprise_data_weight": 0.5, "value_surprise_data_weight": 0.1, "use_search_value_surprise": False}
+    # rules, board size and komi are drawn per game from the file's lists like GameInitializer does (bSizes 19,7,9,13 with weights
+    # 75,1,4,10 and allowRectangleProb 0.10: every ordered pair of edges, play.cpp:152-172; komiStdev 1.0)
+    assert gi["ko_rules"] == [0, 1, 2] and gi["multi_stone_suicide_legals"] == [False, True] and gi["komi_stdev"] == 1.0
+    assert len(gi["sizes"]) == 16 and abs(sum(gi["size_probs"]) - 1.0) < 1e-12
+    p = dict(zip(gi["sizes"], gi["size_probs"]))
+    assert abs(p[(19, 19)] - (0.9 * 75 / 90 + 0.1 * 75 * 75 / 8100)) < 1e-12 and abs(p[(9, 13)] - 0.1 * 4 * 10 / 8100) < 1e-12
     # every keyword exists on the loop
     from katago_b200.nn_backend import SelfPlay
     params = set(inspect.signature(SelfPlay.__init__).parameters)
     assert set(kw) <= params, set(kw) - params
     # per-game randomisation the loop does not have is reported, as are the data-distribution options that are not built
-    assert any(s.startswith("koRules") for s in report["fixed"]) and any(s.startswith("bSizes") for s in report["fixed"])
+    assert any(s.startswith("scoringRules") and "TERRITORY" in s for s in report["fixed"])      # left out of the draw, and said so
+    assert not any(s.startswith(("koRules", "bSizes")) for s in report["fixed"])
     nb = " ".join(report["not_built"])
-    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "handicapProb", "komiStdev",
+    assert "komiStdev" not in nb
+    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "handicapProb",
                 "komiAuto"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
@@ -66,12 +76,28 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
         C.selfplay_kwargs_from_cfg(cfg, strict=True)
 
 
-def test_list_valued_keys_take_the_most_likely_supported_value():
-    """bSizes with bSizeRelProbs as in the stock selfplay8mainb18.cfg: the board the reference draws most often, not the first listed."""
-    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 7,9,11,13,15,17,19\nbSizeRelProbs = 1,4,2,10,3,4,35\ndataBoardLen = 19\n", is_text=True))
-    assert data["board_size"] == 19 and any("most likely" in s_ for s_ in report["fixed"])
+def test_list_valued_keys_are_drawn_per_game_like_the_reference():
+    """bSizes with bSizeRelProbs as in the stock selfplay8mainb18.cfg: the evaluator's frame is the data frame, the per-game draw follows
+    the weights; komi noise scales with the board (PlayUtils::chooseExtraBlackAndKomi) and stays a half-integer inside the clip range."""
+    from katago_b200.game_initializer import GameInitializer, round_and_clip_komi
+    kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 7,9,11,13,15,17,19\nbSizeRelProbs = 1,4,2,10,3,4,35\ndataBoardLen = 19\nkomiMean = 7\nkomiStdev = 1.0\n"
+                                                              "komiBigStdevProb = 0.06\nkomiBigStdev = 12.0\nkoRules = SIMPLE,POSITIONAL\nmultiStoneSuicideLegals = false,true\n", is_text=True))
+    assert data["board_size"] == 19 and report["fixed"] == []
+    init = GameInitializer(seed=5, **data["game_init"])
+    setups, komis = init.draw_many(20000)
+    assert setups.shape == (20000, 4) and (setups[:, 0] == setups[:, 1]).all()            # allowRectangleProb absent: squares only
+    freq = {e: float((setups[:, 0] == e).mean()) for e in (7, 9, 11, 13, 15, 17, 19)}
+    for e, w in zip((7, 9, 11, 13, 15, 17, 19), (1, 4, 2, 10, 3, 4, 35)):
+        assert abs(freq[e] - w / 59) < 0.012, (e, freq[e])
+    assert set(setups[:, 2]) == {0, 1} and set(setups[:, 3]) == {0, 1} and abs(float(setups[:, 2].mean()) - 0.5) < 0.02
+    assert (komis * 2 == np.round(komis * 2)).all() and (np.abs(komis) <= 20 + setups[:, 0] * setups[:, 1]).all()
+    small, big = komis[setups[:, 0] == 9], komis[setups[:, 0] == 19]
+    assert abs(float(big.mean()) - 7.0) < 0.1 and float(small.std()) < float(big.std())           # noise scaled by sqrt(area) / 19
+    assert 0.9 < float(np.std(big[np.abs(big - 7.0) < 3.5])) < 1.25                               # the common komiStdev = 1.0 part
+    assert round_and_clip_komi(7.25, 19, 19) == 7.5 and round_and_clip_komi(-7.25, 19, 19) == -7.5 and round_and_clip_komi(500, 9, 9) == 101.0
+    # the frame follows the largest board when dataBoardLen is absent
     kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9,13\nbSizeRelProbs = 1,1\n", is_text=True))
-    assert data["board_size"] == 9           # equal weights: the first listed
+    assert data["board_size"] == 13 and data["data_board_len"] == 13 and [s_ for s_ in data["game_init"]["sizes"]] == [(9, 9), (13, 13)]
     with pytest.raises(ValueError, match="entries"):
         C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9,13\nbSizeRelProbs = 1\n", is_text=True))
     # komiAuto asks for a search-adjusted komi that is not built: reported, and refused under -strict
@@ -92,7 +118,9 @@ def test_neutral_values_and_unsupported_rules():
     with pytest.raises(ValueError, match="none of these is built"):
         C.selfplay_kwargs_from_cfg(C.parse_cfg("scoringRules = TERRITORY\n", is_text=True))
     with pytest.raises(ValueError, match="dataBoardLen"):
-        C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9\ndataBoardLen = 19\n", is_text=True))
+        C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9,19\ndataBoardLen = 13\n", is_text=True))
+    _, d9, _ = C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9\ndataBoardLen = 19\n", is_text=True))      # small boards inside a 19x19 data frame
+    assert d9["board_size"] == 19 and d9["game_init"]["sizes"] == [(9, 9)]
     with pytest.raises(ValueError, match="expected 'key = value'"):
         C.parse_cfg("maxVisits 100\n", is_text=True)
     assert C.parse_cfg("a = 1 # comment\n\n# only a comment\nb=x=y\n", is_text=True) == {"a": "1", "b": "x=y"}
@@ -134,6 +162,48 @@ def test_command_writes_training_files(tmp_path, stock_cfg):
     assert rows >= 3 * 2
     sgfs = os.listdir(out / "tinynet" / "sgfs")
     assert len(sgfs) == 1 and sum(1 for _ in open(out / "tinynet" / "sgfs" / sgfs[0])) >= 3
+
+
+@pytest.mark.gpu
+def test_command_plays_mixed_board_sizes_rules_and_komi(tmp_path):
+    """BASELINE config 4 through the command: bSizes 5,7,9 (+ rectangles) inside a 9x9 data frame, two ko rules, both suicide rules and komi
+    noise drawn per game; the training rows carry each game's own board (plane 0), rules (globals 6-8) and komi (global 5), the game
+    records their own sizes."""
+    import re
+    from katago_b200 import modelgen
+    models = tmp_path / "models"; models.mkdir()
+    modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
+    settings = dict(STOCK_B18_SETTINGS, bSizes="5,7,9", bSizeRelProbs="2,1,1", allowRectangleProb="0.3", dataBoardLen="9", koRules="SIMPLE,POSITIONAL",
+                    multiStoneSuicideLegals="false,true", komiMean="6", komiStdev="2.0", maxVisits="16", maxMovesPerGame="50", rootNumSymmetriesToSample="2",
+                    nnCacheSizePowerOfTwo="10", maxRowsPerTrainFile="100000", firstFileRandMinProp="1.0")
+    settings.pop("komiAuto")
+    cfg = tmp_path / "mixed.cfg"
+    cfg.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
+    out = tmp_path / "out"
+    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", str(cfg), "-max-games-total", "24", "-games-per-gpu", "8", "-per-game-release"])
+    assert rc == 0
+    tdata = out / "tinynet" / "tdata"
+    areas, komis, ko_flags, suicide_flags = set(), set(), set(), set()
+    for f in os.listdir(tdata):
+        with np.load(tdata / f) as z:
+            planes = np.unpackbits(z["binaryInputNCHWPacked"], axis=2)[:, :, :81].reshape(-1, 22, 9, 9)
+            g = z["globalInputNC"]
+            for on, row in zip(planes[:, 0], g):
+                ys, xs = np.nonzero(on)
+                by, bx = ys.max() + 1, xs.max() + 1
+                assert on[:by, :bx].all() and on.sum() == by * bx and bx in (5, 7, 9) and by in (5, 7, 9)      # a full rectangle in the corner
+                areas.add((int(bx), int(by)))
+                komis.add(round(abs(float(row[5])) * 20.0, 1)); ko_flags.add(float(row[6])); suicide_flags.add(float(row[8]))
+            assert ((planes[:, 1] + planes[:, 2]) <= planes[:, 0]).all()           # stones only on the game's own board
+    assert len(areas) >= 3 and any(a[0] != a[1] for a in areas), areas
+    assert len(komis) >= 3 and ko_flags == {0.0, 1.0} and suicide_flags == {0.0, 1.0}, (komis, ko_flags, suicide_flags)
+    sgf_dir = out / "tinynet" / "sgfs"
+    sizes = set()
+    for f in os.listdir(sgf_dir):
+        for line in open(sgf_dir / f):
+            m = re.search(r"SZ\[(\d+)(?::(\d+))?\]", line)
+            sizes.add((int(m.group(1)), int(m.group(2) or m.group(1))))
+    assert sizes == areas or sizes >= {a for a in areas}, (sizes, areas)
 
 
 @pytest.mark.gpu
