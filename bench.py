@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--settle-waves", type=int, default=700, help="untimed waves after the openings, so that every game has finished a move "
                     "and the evaluation cache holds what a running server's cache would hold")
     ap.add_argument("--nn-cache-pow2", type=int, default=20, help="evaluation cache entries per GPU = 2^N (nnCacheSizePowerOfTwo; 0 = off)")
+    ap.add_argument("--mixed-sizes", action="store_true", help="BASELINE.json configs[3]: every game draws its board from 9x9 / 13x13 / 19x19 (equal "
+                    "probabilities, like bSizes = 9,13,19) inside the 19x19 evaluator frame; a finished game's slot draws again")
     ap.add_argument("--visits", type=int, default=600, help="maxVisits per move (BASELINE.json configs[1]: 600)")
     return ap.parse_args()
 
@@ -238,7 +240,7 @@ class CountingSlots:
 
     def __getattr__(self, name):
         attr = getattr(self._sp, name)
-        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row", "komi_values"):
+        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row", "komi_values", "game_setups"):
             def counted(*a, **k):
                 out = attr(*a, **k)
                 self.d2h += _nbytes(out)
@@ -361,6 +363,20 @@ def main():
                   static_score_utility_factor=0.05, dynamic_score_utility_factor=0.30, dynamic_score_center_zero_weight=0.25,
                   dynamic_score_center_scale=0.50, draw_equivalent_wins_for_white=0.5)
     sp = SelfPlay(handle, n, args.visits, **sp_kwargs)
+    mixed_rng = np.random.default_rng(99 + rank)
+
+    def mixed_setups(loop):
+        """--mixed-sizes: what GameInitializer draws with bSizes = 9,13,19 and equal bSizeRelProbs; the slots' next games get a second draw."""
+        if not args.mixed_sizes:
+            return None
+        def draw():
+            e = mixed_rng.choice([9, 13, 19], size=n)
+            return np.stack([e, e, np.zeros(n, np.int64), np.ones(n, np.int64)], 1).astype(np.int32)
+        first = draw()
+        loop.set_game_setup(first, also_current_games=True)
+        loop.set_game_setup(draw())
+        return {int(e): int((first[:, 0] == e).sum()) for e in (9, 13, 19)}
+    mixed_counts = mixed_setups(sp)
     # steady state before timing: games at different stages, trees hundreds of nodes deep, cache filled by the previous moves
     sp.random_openings(args.opening_max)
     sp.run(W + args.settle_waves)
@@ -402,6 +418,7 @@ def main():
     from katago_b200.npz_writer import RowRand, TrainingDataWriter
     sp_kwargs["debug_hold_at_max_visits"] = True
     sp2 = SelfPlay(handle, n, args.visits, **sp_kwargs)
+    mixed_setups(sp2)
     sp2.random_openings(args.opening_max)
     slots = CountingSlots(sp2)
     out_dir = tempfile.mkdtemp(prefix=f"kgb_bench_tdata_rank{rank}_")
@@ -508,7 +525,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32-split3(fp16 tensor pipe)" if args.fp32 else "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"19x19 {args.model}, {n} concurrent games per GPU, maxVisits {args.visits}, one playout (visit) per game per step, device-resident loop",
+            "config": {"workload": (f"mixed 9x9 / 13x13 / 19x19 boards ({mixed_counts} games at the start) in a 19x19 evaluator frame, per-board masking, "
+                                    if args.mixed_sizes else "19x19 ") +
+                                   f"{args.model}, {n} concurrent games per GPU, maxVisits {args.visits}, one playout (visit) per game per step, device-resident loop",
                        "stages": ["root_move+tree_reset", "puct_select", "board_playmove(bitboard)", "featurize(all 22 V7 planes incl. ladders 14-17 and pass-alive area 18-19, 19 globals)",
                                   "nn_eval", "policy/value/score postprocess", "utility (win/loss + static/dynamic score utility)",
                                   "backup = recomputeNodeStats per path node (value weighting, exponent 0.5)"],

@@ -357,7 +357,10 @@ KGB_API int kgb_selfplay_set_search_rand(kgb_selfplay* sp, const char* seed_stri
 KGB_API int kgb_selfplay_random_openings(kgb_selfplay* sp, int max_moves);
 /* Play a fixed move list on EVERY game's root (x,y pairs, -1,-1 = pass; colours alternate) and clear the trees. */
 KGB_API int kgb_selfplay_play_moves(kgb_selfplay* sp, const int8_t* moves_xy, int num_moves);
-/* The same for one game only (games of different board sizes need different lists).  A move off the game's board is KGB_ERR_INVALID. */
+/* The same for one game only (games of different board sizes need different lists; match play mirrors the opponent's moves into the
+ * other net's loop).  A move off the game's board is KGB_ERR_INVALID.  Unlike kgb_selfplay_play_moves, a move that ends the game - by
+ * the rules or by max_moves - is treated like the loop's own: result readable with kgb_selfplay_get_last_move, the slot's next game
+ * starts (next setup and komi), later moves of the list go to that game. */
 KGB_API int kgb_selfplay_play_moves_game(kgb_selfplay* sp, int game, const int8_t* moves_xy, int num_moves);
 /* Timing hook for bench.py's tree/board roofline entry: runs `iters` waves of ONLY the select(+board+featurize) and backup
  * kernels (evaluator outputs of the last wave are reused) and returns their CUDA-event averages per launch. */

@@ -392,6 +392,7 @@ __device__ __forceinline__ void rootHashesInit(const SPDev& d, int g, int lane) 
 }
 
 __device__ __forceinline__ double rootChildUtilityWithBonus(const SPDev& d, int g, size_t gb, int c, int mv, double utilityAvg);
+__device__ double scoreUtilityDiff(const SPDev& d, int g, double scoreMean, double scoreMeanSq, double delta, double center);
 __device__ void computeRootExtras(const SPDev& d, int g, const WarpBoard& bd, bool rootBlack, bool haveOwnership, int numEvals, int lane);
 // Search::getPlaySelectionValues for the root (searchresults.cpp:66-330; no human policy, no pass suppression, no ending
 // bonus): values by child in creation order into psv[0..nc), their moves into moves[].  One thread.  Returns the child count.
@@ -572,6 +573,34 @@ __device__ int rootChooseMove(const SPDev& d, int g) {
   return (int)d.childOrder[(size_t)g * d.maxNodes * d.policySize + k];
 }
 
+// The game of slot g is over on board bd: score it (area scoring: komi - (black area - white area)), keep the final position and its
+// area readable, count it, and start the slot's next game - empty board of the next game's size, its rules and komi (what the host
+// handed over with kgb_selfplay_set_game_setup / set_komi), fresh history.  bd is the new game's empty board afterwards.
+__device__ void gameOverStartNext(const SPDev& d, int g, WarpBoard& bd, bool noResult, int lane) {
+  uint32_t areaB, areaW;
+  boardCalculateArea(bd, true, true, true, d.gMultiSuicide[g] != 0, areaB, areaW);    // = the area boardAreaScoreBlackMinusWhite counts
+  int diff = warpCount(areaB) - warpCount(areaW);
+  float whiteScore = d.komiG[g] - (float)diff;
+  uint32_t* fb = d.finalBoard + (size_t)g * 128;
+  fb[lane] = bd.b; fb[32 + lane] = bd.w; fb[64 + lane] = areaB; fb[96 + lane] = areaW;
+  if(lane == 0) d.lastScore[g] = whiteScore;
+  if(lane == 0) {
+    atomicAdd(d.gamesFinished, 1ULL);
+    if(whiteScore < 0 && !noResult) atomicAdd(d.blackWins, 1ULL);
+    d.gameCounter[g] += 1;
+    d.lastKomi[g] = d.komiG[g];
+    d.komiG[g] = d.nextKomi[g];          // the slot's next game (kgb_selfplay_set_komi)
+    // ... and its board size and rules (kgb_selfplay_set_game_setup): what GameInitializer::createGame draws per game
+    d.lastSetup[g * 4 + 0] = d.gX[g]; d.lastSetup[g * 4 + 1] = d.gY[g]; d.lastSetup[g * 4 + 2] = d.gKoRule[g]; d.lastSetup[g * 4 + 3] = d.gMultiSuicide[g];
+    d.gX[g] = d.nextSetup[g * 4 + 0]; d.gY[g] = d.nextSetup[g * 4 + 1]; d.gKoRule[g] = d.nextSetup[g * 4 + 2]; d.gMultiSuicide[g] = d.nextSetup[g * 4 + 3];
+  }
+  __syncwarp();
+  boardInit(bd, d.gX[g], d.gY[g]);
+  gameHistReset(d, g, lane);
+  if(lane < 5) d.hist[g * 5 + lane] = -1;
+  if(lane == 0) { d.rootBlackToMove[g] = 1; d.passStreak[g * 2] = 0; d.passStreak[g * 2 + 1] = 0; }
+}
+
 // Choose and play the root move once the visit budget is spent; restart the game when it is over.
 __device__ void rootAdvance(const SPDev& d, int g, int lane) {
   const size_t gb = (size_t)g * d.maxNodes;
@@ -644,29 +673,8 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     d.lastMove[g * 4 + 3] = (int)d.gameCounter[g];
   }
   if(over) {
-    uint32_t areaB, areaW;
-    boardCalculateArea(bd, true, true, true, d.gMultiSuicide[g] != 0, areaB, areaW);    // = the area boardAreaScoreBlackMinusWhite counts
-    int diff = warpCount(areaB) - warpCount(areaW);
-    float whiteScore = d.komiG[g] - (float)diff;
-    uint32_t* fb = d.finalBoard + (size_t)g * 128;
-    fb[lane] = bd.b; fb[32 + lane] = bd.w; fb[64 + lane] = areaB; fb[96 + lane] = areaW;
-    if(lane == 0) d.lastScore[g] = whiteScore;
-    if(lane == 0) {
-      atomicAdd(d.gamesFinished, 1ULL);
-      if(whiteScore < 0 && !noResult) atomicAdd(d.blackWins, 1ULL);
-      d.gameCounter[g] += 1;
-      d.lastKomi[g] = d.komiG[g];
-      d.komiG[g] = d.nextKomi[g];          // the slot's next game (kgb_selfplay_set_komi)
-      // ... and its board size and rules (kgb_selfplay_set_game_setup): what GameInitializer::createGame draws per game
-      d.lastSetup[g * 4 + 0] = d.gX[g]; d.lastSetup[g * 4 + 1] = d.gY[g]; d.lastSetup[g * 4 + 2] = d.gKoRule[g]; d.lastSetup[g * 4 + 3] = d.gMultiSuicide[g];
-      d.gX[g] = d.nextSetup[g * 4 + 0]; d.gY[g] = d.nextSetup[g * 4 + 1]; d.gKoRule[g] = d.nextSetup[g * 4 + 2]; d.gMultiSuicide[g] = d.nextSetup[g * 4 + 3];
-    }
-    __syncwarp();
-    boardInit(bd, d.gX[g], d.gY[g]);
-    gameHistReset(d, g, lane);
+    gameOverStartNext(d, g, bd, noResult, lane);
     passes = 0; mv = 0;
-    if(lane < 5) d.hist[g * 5 + lane] = -1;
-    if(lane == 0) { d.rootBlackToMove[g] = 1; d.passStreak[g * 2] = 0; d.passStreak[g * 2 + 1] = 0; }
   }
   else {
     int h = lane < 5 ? d.hist[g * 5 + lane] : -1;
@@ -720,6 +728,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   hst.passes = 0; hst.finished = false; hst.noResult = false; hst.everOcc = 0; hst.banned = 0;
   bool bannedValid = false;     // hst.banned belongs to the current position
   const long long tW0 = clock64();
+#ifdef KGB_PROFILE_DESCENT
+  long long pfGather = 0, pfSelect = 0, pfMove = 0, pfEdge = 0, pfSteps = 0, pfT = clock64(), pfBackup = 0, pfAttempts = 0, pfAdvance = 0;
+#endif
   // Under graph search a playout can end without reaching a new leaf (edge catch-up, cycle): it is backed up at once and the
   // next playout starts, so that the wave still delivers a leaf for the evaluator.
   for(int attempt = 0; attempt < d.maxPlayoutsPerWave && !gotLeaf; attempt++) {
@@ -731,6 +742,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     const long long tRA = clock64();
     rootAdvance(d, g, lane);
     if(lane == 0) { d.releaseFlag[g] = 0; d.dbgCycles[g * 8 + 1] = clock64() - tRA; }
+#ifdef KGB_PROFILE_DESCENT
+    { const long long t_ = clock64(); pfAdvance += t_ - pfT; pfT = t_; }
+#endif
   }
   boardInit(bd, d.gX[g], d.gY[g]);
   bd.b = d.rootB[g * 32 + lane]; bd.w = d.rootW[g * 32 + lane];
@@ -753,22 +767,30 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     bd.h0 = d.rootPosH[g * 2]; bd.h1 = d.rootPosH[g * 2 + 1];   // the hash follows the whole path: ko hashes are taken from it
   }
   bool instant = false;   // this playout ended on an existing edge: back it up here, no leaf
+#ifdef KGB_PROFILE_DESCENT   // build variant for tests/gpu_checks/descent_profile.py: where a descent step spends its cycles
+  pfAttempts++;
+#define PF(acc) do { const long long t_ = clock64(); acc += t_ - pfT; pfT = t_; } while(0)
+#else
+#define PF(acc) do {} while(0)
+#endif
   while(true) {
+    PF(pfEdge);
     const int visits = d.nodeVisits[gb + node];
     terminal = d.nodeTerminal[gb + node] != 0;
     if(visits == 0 || terminal || depth >= d.maxDepth - 1) break;
     const size_t nb = (gb + node) * d.policySize;
     const int nc = d.nodeNumChildren[gb + node];
     // ---- pass 1 over the children in creation order (searchexplorehelpers.cpp:338-364): visited policy mass, total child weight
-    float P[12]; double CW[12], CU[12]; int CVis[12];
+    float P[12]; double CW[12], CU[12]; int CVis[12]; int MV[12];
     double massVisited = 0.0, totalW = 0.0;
 #pragma unroll
     for(int ch = 0; ch < 12; ch++) {
-      P[ch] = -1.0f; CW[ch] = 0.0; CU[ch] = 0.0; CVis[ch] = 0;
+      P[ch] = -1.0f; CW[ch] = 0.0; CU[ch] = 0.0; CVis[ch] = 0; MV[ch] = 0;
       if(ch * 32 < nc) {
         const int k = ch * 32 + lane;
         const bool in = k < nc;
         const int mv = in ? (int)d.childOrder[nb + k] : 0;
+        MV[ch] = mv;
         const int c = in ? d.childNode[nb + mv] : 0;
         const int ev = in ? d.childVisits[nb + mv] : 0;
         const int cv = in ? d.nodeVisits[gb + c] : 0;
@@ -788,6 +810,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
         orderedAdd2(counts ? (double)P[ch] : 0.0, counts ? CW[ch] : 0.0, n, massVisited, totalW, shSum, lane);
       }
     }
+    PF(pfGather);
     // ---- FPU and exploration scaling (searchexplorehelpers.cpp:22-29, 265-321)
     const double parentUtility = d.nodeUtilAvg[gb + node];
     const bool isRoot = node == 0;
@@ -835,8 +858,13 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(P[ch] >= 0.0f) {
         double cu = (CVis[ch] <= 0 || CW[ch] <= 0.0) ? fpuValue : CU[ch];
         if(isRoot && d.rootEndingBonusPoints != 0.0 && !(CVis[ch] <= 0 || CW[ch] <= 0.0)) {
-          const int mvk = (int)d.childOrder[nb + k];
-          cu = rootChildUtilityWithBonus(d, g, gb, d.childNode[nb + mvk], mvk, cu);
+          // rootChildUtilityWithBonus with the move kept from the gather: the bonus table (one line per game) is read directly, the
+          // child's score moments only for the few moves that carry a bonus
+          const double bonus = d.rootEndBonus[(size_t)g * d.policySize + MV[ch]];
+          if(bonus != 0.0) {
+            const double* cm = d.nodeMoments + (gb + d.childNode[nb + MV[ch]]) * 5;
+            cu = cu + scoreUtilityDiff(d, g, cm[2], cm[3], bonus, d.recentScoreCenter[g]);
+          }
         }
         val = exploreScaling * (double)P[ch] / (1.0 + CW[ch]) + (black ? -cu : cu);
         if(isRoot && d.rootDesiredPerChildVisitsCoeff > 0.0 && P[ch] > 0.0f &&
@@ -851,13 +879,31 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
     // ... and the unexpanded move with the largest prior (first in position order among equals, :548-590)
     float bestNewP = -1.0f; int bestNewIdx = -1;
+    {
+      // all loads first (two coalesced arrays, no branch between them), then the comparisons
+      float PP[12]; int CN[12];
 #pragma unroll
-    for(int ch = 0; ch < 12; ch++) {
-      const int i = ch * 32 + lane;
-      if(i >= d.policySize) continue;
-      const float p = d.policy[nb + i];
-      if(isRoot && d.rootPruneUselessMoves && i < d.XY && !((d.rootAllowed[g * 32 + i / d.X] >> (i % d.X)) & 1u)) continue;   // Search::isAllowedRootMove
-      if(p >= 0.0f && d.childNode[nb + i] < 0 && p > bestNewP) { bestNewP = p; bestNewIdx = i; }
+      for(int ch = 0; ch < 12; ch++) {
+        const int i = ch * 32 + lane;
+        const bool in = i < d.policySize;
+        PP[ch] = in ? d.policy[nb + i] : -1.0f;
+        CN[ch] = in ? d.childNode[nb + i] : 0;
+      }
+      if(isRoot && d.rootPruneUselessMoves) {     // Search::isAllowedRootMove: this lane's row of the allowed points, handed round by shuffle
+        const uint32_t allowedMine = d.rootAllowed[g * 32 + lane];
+#pragma unroll
+        for(int ch = 0; ch < 12; ch++) {
+          const int i = ch * 32 + lane;
+          const int ic = i < d.XY ? i : 0;
+          const uint32_t rowBits = __shfl_sync(KGB_FULL, allowedMine, ic / d.X);
+          if(i < d.XY && !((rowBits >> (ic % d.X)) & 1u)) PP[ch] = -1.0f;
+        }
+      }
+#pragma unroll
+      for(int ch = 0; ch < 12; ch++) {
+        const int i = ch * 32 + lane;
+        if(PP[ch] >= 0.0f && CN[ch] < 0 && PP[ch] > bestNewP) { bestNewP = PP[ch]; bestNewIdx = i; }
+      }
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) {
@@ -870,6 +916,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       if(bestK < 0 || newVal > bestVal) move = bestNewIdx;
     }
     if(move < 0) break;  // no legal move at all (cannot happen: pass is always legal)
+    PF(pfSelect);
+#ifdef KGB_PROFILE_DESCENT
+    pfSteps++;
+#endif
     if(lane == 0) { d.pathNode[(size_t)g * d.maxDepth + depth] = node; d.pathMove[(size_t)g * d.maxDepth + depth] = move; }
     __syncwarp();
     // ---- graph search: an edge with fewer visits than its (shared) child catches up without descending (search.cpp:1468-1504)
@@ -901,6 +951,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
     h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = isPass ? -2 : p;
     black = !black;
+    PF(pfMove);
     if(newEdge) {
       // Search::allocateOrFindNode (search.cpp:875-936): under graph search the child may already exist (transposition)
       unsigned long long cg0 = 0, cg1 = 0;
@@ -964,6 +1015,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       __syncwarp();
     }
     if(lane == 0) { atomicAdd(d.totalVisits, 1ULL); atomicAdd(d.instantPlayouts, 1ULL); }
+    PF(pfBackup);
     continue;
   }
   if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0 && !(node == 0 && d.rootNumSymmetries > 1)) {
@@ -994,9 +1046,11 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
       const double u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], lane);
       finishPlayout(d, g, node, u, false, black, depth, shSum, lane);
       if(lane == 0) atomicAdd(d.cacheHits, 1ULL);
+      PF(pfBackup);
       continue;
     }
   }
+  PF(pfEdge);
   gotLeaf = true;
   }   // attempts
   if(!gotLeaf) {   // every playout of this wave ended on an existing edge: nothing for the evaluator
@@ -1115,6 +1169,10 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     d.nnOptimism[g] = 0.0f;
     d.dbgCycles[g * 8 + 4] = tLeaf - tW0; d.dbgCycles[g * 8 + 5] = tLegal - tLeaf; d.dbgCycles[g * 8 + 6] = tArea - tZero;
     d.dbgCycles[g * 8 + 7] = (clock64() - tArea) + (tZero - tLegal);
+#ifdef KGB_PROFILE_DESCENT   // slots 1 and 5-7 re-used: steps of the wave's last descent, gather + ordered sums, selection, move + history, new-edge work
+    d.dbgCycles[g * 8 + 1] = (pfEdge << 16) | (pfAttempts << 10) | pfSteps; d.dbgCycles[g * 8 + 5] = pfGather; d.dbgCycles[g * 8 + 6] = pfSelect; d.dbgCycles[g * 8 + 7] = pfMove;
+    d.dbgCycles[g * 8 + 4] = (pfBackup << 32) | (pfAdvance & 0xffffffffLL);      // replaces the descent total (= sum of the parts)
+#endif
   }
 }
 
@@ -1807,7 +1865,7 @@ __global__ void spFakeNNKernel(const SPDev d, float* policyOut, float* valueOut,
 }
 
 // Apply a move list (x, y, or -1,-1 = pass; colours alternate from the current player) to every game's root.
-__global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMoves, int onlyGame) {
+__global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMoves, int onlyGame, int endGames) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames || (onlyGame >= 0 && g != onlyGame)) return;
@@ -1833,6 +1891,21 @@ __global__ void spPlayMovesKernel(const SPDev d, const int8_t* moves, int numMov
     h[0] = isPass ? -2 : p;
     black = !black;
     mv++;
+    if(endGames && (fin || mv >= d.maxMoves)) {
+      // a move of the list ended the game (match play mirrors the opponent's moves into this loop, kgb_selfplay_play_moves_game): the same
+      // game-over handling as when the loop's own move ends it - result kept readable, next game started; further moves go to that game
+      if(lane == 0) {
+        d.lastMove[g * 4 + 0] = isPass ? d.policySize - 1 : posOf(p, d.X);
+        d.lastMove[g * 4 + 1] = 1 | (nores ? 2 : 0) | (fin ? 0 : 4);
+        d.lastMove[g * 4 + 2] = mv - 1;
+        d.lastMove[g * 4 + 3] = (int)d.gameCounter[g];
+      }
+      __syncwarp();
+      gameOverStartNext(d, g, bd, nores, lane);
+      passes = 0; mv = 0; black = true;
+      for(int k = 0; k < 5; k++) h[k] = -1;
+      p1B = 0; p1W = 0; p2B = 0; p2W = 0; p1Ko = -1; p2Ko = -1;
+    }
   }
   d.rootB[g * 32 + lane] = bd.b; d.rootW[g * 32 + lane] = bd.w;
   d.prevB[g * 32 + lane] = p1B; d.prevW[g * 32 + lane] = p1W; d.prevB[G32 + g * 32 + lane] = p2B; d.prevW[G32 + g * 32 + lane] = p2W;
@@ -2315,7 +2388,7 @@ void selfplayPlayMoves(SelfplayImpl* sp, const int8_t* movesXY, int numMoves, cu
   SPCK(cudaMalloc(&dm, (size_t)numMoves * 2));
   SPCK(cudaMemcpyAsync(dm, movesXY, (size_t)numMoves * 2, cudaMemcpyHostToDevice, s));
   int threads = 128, warpsPerBlock = threads / 32;
-  spPlayMovesKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, dm, numMoves, onlyGame);
+  spPlayMovesKernel<<<(sp->d.numGames + warpsPerBlock - 1) / warpsPerBlock, threads, 0, s>>>(sp->d, dm, numMoves, onlyGame, onlyGame >= 0 ? 1 : 0);
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(dm);
   SPCK(e);
