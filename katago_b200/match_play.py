@@ -1,0 +1,145 @@
+"""Games between two nets on the device loops - the engine under `gatekeeper` and `match` (reference:
+command/gatekeeper.cpp, command/match.cpp, program/play.cpp:2712-2714 "two nets per game", MatchPairer program/play.cpp:653-790).
+
+Every bot has its own device loop (`SelfPlay` in hold mode on its own handle: own net, own search parameters, own stream) with the same
+number of game slots; slot g of every loop holds THE SAME game.  Both loops search every position of it (on the GPU their waves overlap:
+one loop's select / backup kernels run while the other's evaluator has the tensor pipes); the move comes from the loop of the bot whose
+turn it is - released when its search is finished, the device chooses and plays the move with that bot's temperature rules - and is
+mirrored into the other loop with `play_moves_game`, which clears that loop's tree of the position and, when the move ended the game,
+starts the slot's next game there too (`kgb_selfplay_play_moves_game`).  A slot's bots swap colours from game to game (the reference's
+MatchPairer alternates sides per pairing).  Board size, rules and komi of every game come from a `GameInitializer`, identical for both
+loops.  Nothing here touches the evaluator or the search: it is host bookkeeping between waves."""
+import numpy as np
+
+from .npz_writer import FinishedGameData, P_BLACK, P_WHITE
+
+
+class MatchPlay:
+    def __init__(self, loops, names, num_games_total, game_initializer=None, on_game=None, draw_equivalent_wins_for_white=0.5,
+                 no_result_utility_for_white=0.0, game_hash_fn=None):
+        if len(loops) != 2 or len(names) != 2:
+            raise ValueError("MatchPlay: exactly two bots")
+        a, b = loops
+        if a.num_games != b.num_games or (a.x, a.y) != (b.x, b.y):
+            raise ValueError("MatchPlay: both loops need the same number of game slots and the same evaluator frame")
+        self.loops, self.names, self.n, self.total = loops, list(names), a.num_games, int(num_games_total)
+        self.on_game = on_game
+        self.draw_eq, self.no_result_utility = float(draw_equivalent_wins_for_white), float(no_result_utility_for_white)
+        self.game_hash_fn = game_hash_fn or (lambda slot, index: (((slot + 1) * 0x9E3779B97F4A7C15 + index) & (2 ** 64 - 1), (index * 0xC2B2AE3D27D4EB4F + slot) & (2 ** 64 - 1)))
+        self.black_bot = np.array([g % 2 for g in range(self.n)], np.int32)      # which bot plays black in the slot's current game
+        self.to_move = self.black_bot.copy()
+        self.moves = [[] for _ in range(self.n)]
+        self.games_started = self.n
+        self.live = np.ones(self.n, bool)                                          # slots whose current game counts towards the total
+        if self.total > 0 and self.total < self.n:
+            self.live[self.total:] = False
+            self.games_started = self.total
+        self.games_tallied, self.win_points = 0, [0.0, 0.0]
+        self.results = []                   # (black bot, white bot, "B+.." / "W+.." / "0" / "Void", moves)
+        self.terminated = False
+        self.init = game_initializer
+        if game_initializer is not None:
+            self.setups, self.komis = game_initializer.draw_many(self.n)
+            for sp in loops:
+                sp.set_game_setup(self.setups, also_current_games=True); sp.set_komi(self.komis, also_current_games=True)
+            self.setups, self.komis = game_initializer.draw_many(self.n)
+            for sp in loops:
+                sp.set_game_setup(self.setups); sp.set_komi(self.komis)
+        for sp in loops:
+            sp.run(1)
+
+    # ---- what the reference's data-write loop tallies (gatekeeper.cpp:127-196)
+    def _tally(self, black_bot, result_kind, winner):
+        if result_kind == "noresult":
+            white_points = self.draw_eq
+        elif winner == P_BLACK:
+            white_points = 0.0
+        elif winner == P_WHITE:
+            white_points = 1.0
+        else:
+            white_points = 0.5 * self.no_result_utility + 0.5
+        self.win_points[black_bot] += 1.0 - white_points
+        self.win_points[1 - black_bot] += white_points
+        self.games_tallied += 1
+
+    def _finish(self, g, last, mover):
+        sp = self.loops[mover]
+        X, Y, ko_rule, multi = (int(v) for v in sp.game_setups()[1][g])          # the finished game's own board and rules
+        komi = float(sp.komi_values()[1][g])
+        bb = int(self.black_bot[g])
+        data = FinishedGameData(X, Y, komi)
+        data.game_hash = self.game_hash_fn(g, int(last["game_index"]))
+        data.mode = 0
+        data.end_finished = not last["hit_move_limit"]
+        data.hit_turn_limit = bool(last["hit_move_limit"])
+        data.end_no_result = bool(last["no_result"])
+        data.moves = list(self.moves[g])
+        data.next_player_by_turn = [P_BLACK if i % 2 == 0 else P_WHITE for i in range(len(data.moves))]
+        data.ko_rule = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[ko_rule]
+        data.multi_stone_suicide_legal = bool(multi)
+        if data.end_no_result:
+            kind, winner, text = "noresult", 0, "Void"
+        else:
+            # a game stopped by the move limit is scored as it stands (gatekeeper.cpp:143-146 endAndScoreGameNow): the device has done that
+            score = float(last["final_white_minus_black_score"])
+            winner = P_WHITE if score > 0 else P_BLACK if score < 0 else 0
+            data.winner, data.final_white_minus_black_score = winner, score
+            kind, text = "scored", ("W+%g" % score if winner == P_WHITE else "B+%g" % -score if winner == P_BLACK else "0")
+            data.end_finished = True
+        if self.live[g]:
+            self._tally(bb, kind, winner)
+            self.results.append((bb, 1 - bb, text, len(data.moves)))
+            if self.on_game is not None:
+                self.on_game(g, data, self.names[bb], self.names[1 - bb], text)
+        # the slot's next game: colours swapped, fresh setup for the game after it
+        self.moves[g] = []
+        self.black_bot[g] = 1 - bb
+        self.to_move[g] = self.black_bot[g]
+        if self.total > 0 and self.games_started >= self.total:
+            self.live[g] = False
+        else:
+            self.live[g] = True
+            self.games_started += 1
+        if self.init is not None:
+            x, y, ko, suicide, k = self.init.draw()
+            self.setups[g] = (x, y, ko, suicide); self.komis[g] = k
+            for lp in self.loops:
+                lp.set_game_setup(self.setups); lp.set_komi(self.komis)
+
+    def pump(self, waves=8):
+        """`waves` waves for both loops, then every slot whose bot-to-move has finished its search moves once.  Returns moves made."""
+        for sp in self.loops:
+            sp.run(waves)
+        made = 0
+        for b, sp in enumerate(self.loops):
+            held = np.asarray(sp.root_visits()) >= sp.max_visits
+            mine = held & (self.to_move == b)
+            if not mine.any():
+                continue
+            sp.release(mine.astype(np.uint8))
+            sp.run(1)
+            other = self.loops[1 - b]
+            for g in (int(v) for v in np.flatnonzero(mine)):
+                last = sp.last_move(g)
+                x, y = last["xy"]
+                other.play_moves_game(g, [None if x < 0 else (int(x), int(y))])
+                self.moves[g].append((int(x), int(y)))
+                made += 1
+                if last["game_over"]:
+                    self._finish(g, last, b)
+                else:
+                    self.to_move[g] = 1 - b
+        return made
+
+    def done(self):
+        return self.terminated or (self.total > 0 and self.games_tallied >= self.total)
+
+    def run(self, waves=8, max_pumps=10 ** 9, stop=None):
+        """Play until `num_games_total` games are tallied (or stop(self) says so - the gatekeeper's early termination)."""
+        pumps = 0
+        while not self.done() and pumps < max_pumps:
+            self.pump(waves)
+            pumps += 1
+            if stop is not None and stop(self):
+                self.terminated = True
+        return self.win_points
