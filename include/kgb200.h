@@ -323,6 +323,18 @@ KGB_API int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* last_
  * The evaluation cache keys on board size and rules as NNInputs::getHash does, so such games never share an entry. */
 KGB_API int kgb_selfplay_set_game_setup(kgb_selfplay* sp, const int32_t* setup, int also_current_games);
 KGB_API int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int32_t* last_finished);
+/* Search limits per move.  Play::runGame gives every move its own limits (getSearchLimitsThisMove / runBotWithLimits, program/play.cpp:
+ * 1093-1300): a "cheap search" (cheapSearchProb, cheapSearchVisits) or a visit count reduced in decided positions (reduceVisits), and for
+ * cheap searches that are not recorded the root-only parameters off (no Dirichlet noise, root policy temperature 1, the tree's FPU
+ * parameters at the root, no per-child visit floor, a single root symmetry).  Here the host draws (katago_b200/game_recorder.py) and the
+ * device applies: visits[num_games][2] in [2, max_visits] and plain_root[num_games][2] (NULL = all 0) are taken by the root that follows
+ * the slot's NEXT move - entry 0 if the game goes on, entry 1 if that move ends the game (first root of the slot's next game);
+ * also_current_roots != 0 applies entry 0 to the current roots too, which must not have been searched yet (KGB_ERR_INVALID otherwise).
+ * A game is held / moves when its root's visits reach ITS budget: kgb_selfplay_get_search_limits returns the current roots' budgets and
+ * flags (either pointer may be NULL).  Deviation: the reference keeps the previous tree for unrecorded cheap searches, this loop always
+ * starts a move on a cleared tree. */
+KGB_API int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits, const uint8_t* plain_root, int also_current_roots);
+KGB_API int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, uint8_t* plain_root);
 /* FOR TESTING: the evaluation-cache key (the loop's NNInputs::getHash) of the leaf that slot `game` sent to the evaluator in the
  * last wave; only meaningful with nn_cache_size_power_of_two > 0. */
 KGB_API int kgb_selfplay_get_leaf_cache_key(kgb_selfplay* sp, int game, uint64_t* key2);

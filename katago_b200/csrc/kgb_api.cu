@@ -1409,6 +1409,24 @@ KGB_API int kgb_selfplay_set_game_setup(kgb_selfplay* sp, const int32_t* setup, 
   });
 }
 
+KGB_API int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits, const uint8_t* plain_root, int also_current_roots) {
+  return guarded([&] {
+    if(!sp || !visits) throw std::invalid_argument("kgb_selfplay_set_next_search_limits: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplaySetNextSearchLimits(sp->impl, visits, plain_root, also_current_roots != 0, sp->h->stream);
+  });
+}
+
+KGB_API int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, uint8_t* plain_root) {
+  return guarded([&] {
+    if(!sp) throw std::invalid_argument("kgb_selfplay_get_search_limits: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadSearchLimits(sp->impl, visits, plain_root);
+  });
+}
+
 KGB_API int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int32_t* last_finished) {
   return guarded([&] {
     if(!sp) throw std::invalid_argument("kgb_selfplay_get_game_setup: NULL argument");

@@ -55,6 +55,12 @@ struct SPDev {
   // per-game board size and rules (GameInitializer::createGameSharedUnsynchronized, program/play.cpp:330-650 draws them per game): the
   // evaluator's frame is X x Y (nnXLen x nnYLen), a game's board gX x gY <= the frame sits in its top-left corner, move positions are
   // y * X + x in the frame (NNPos::locToPos, nninputs.cpp:27-33) and plane 0 marks the board.  setup arrays are [game][4] = X, Y, koRule, multiSuicide.
+  // search limits per move (getSearchLimitsThisMove / runBotWithLimits, program/play.cpp:1093-1300: cheap searches, reduced visits): the
+  // visit budget of the current root and whether its root-only parameters are switched off (removeRootNoise: no Dirichlet noise, root
+  // policy temperature 1, the root takes the tree's FPU parameters, no per-child visit floor, one root symmetry); next* = what the
+  // following root gets, [game][2]: 0 = the game goes on, 1 = this move ends it and the slot's next game starts
+  int *visitBudget, *nextBudget;
+  uint8_t *plainRoot, *nextPlain;
   int *gX, *gY, *gKoRule, *gMultiSuicide;   // [game] of the game in progress
   int *nextSetup, *lastSetup;               // [game][4]: of the slot's next game (kgb_selfplay_set_game_setup), of its last finished game
   double cpuctExploration, cpuctExplorationLog, cpuctExplorationBase, fpuReductionMax, rootFpuReductionMax;
@@ -187,6 +193,8 @@ struct SPDev {
   int* nnSymmetry;
   const float *nnPolicy, *nnValue;
 };
+
+__device__ __forceinline__ int rootSyms(const SPDev& d, int g) { return d.plainRoot[g] ? 1 : d.rootNumSymmetries; }   // rootNumSymmetriesToSample of game g's current root
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
@@ -698,6 +706,9 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     d.nodeCount[g] = 1;
     nodeStatsReset(d, gb, false);
     d.rootSymCount[g] = 0;
+    // the new root's search limits (kgb_selfplay_set_next_search_limits)
+    d.visitBudget[g] = d.nextBudget[g * 2 + (over ? 1 : 0)];
+    d.plainRoot[g] = d.nextPlain[g * 2 + (over ? 1 : 0)];
   }
   nodeInit(d, rootBase, lane);
   biasTableClear(d, g, lane);   // all nodes freed: every entry is unused and dropped (search.cpp:860-861)
@@ -734,7 +745,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
   // Under graph search a playout can end without reaching a new leaf (edge catch-up, cycle): it is backed up at once and the
   // next playout starts, so that the wave still delivers a leaf for the evaluator.
   for(int attempt = 0; attempt < d.maxPlayoutsPerWave && !gotLeaf; attempt++) {
-  if(d.nodeVisits[gb] >= d.maxVisits) {
+  if(d.nodeVisits[gb] >= d.visitBudget[g]) {
     // hold mode (tests, game recording): keep the finished tree until the host has read it and released the game
     const bool released = d.releaseFlag[g] != 0;
     __syncwarp();
@@ -839,8 +850,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     else if(d.fpuParentWeight > 0.0) parentUtilityForFPU = d.fpuParentWeight * d.nodeNNUtil[gb + node] + (1.0 - d.fpuParentWeight) * parentUtility;
     double fpuValue;
     {
-      const double reduction = (isRoot ? d.rootFpuReductionMax : d.fpuReductionMax) * sqrt(massVisited);
-      const double lossProp = isRoot ? d.rootFpuLossProp : d.fpuLossProp;
+      const bool rootParams = isRoot && !d.plainRoot[g];      // a "plain" root searches like any other node (runBotWithLimits removeRootNoise)
+      const double reduction = (rootParams ? d.rootFpuReductionMax : d.fpuReductionMax) * sqrt(massVisited);
+      const double lossProp = rootParams ? d.rootFpuLossProp : d.fpuLossProp;
       const double utilityRadius = d.winLossUtilityFactor + d.staticScoreUtilityFactor + d.dynamicScoreUtilityFactor;
       fpuValue = black ? parentUtilityForFPU + reduction : parentUtilityForFPU - reduction;   // utilities are white's
       const double lossValue = black ? utilityRadius : -utilityRadius;
@@ -867,7 +879,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
           }
         }
         val = exploreScaling * (double)P[ch] / (1.0 + CW[ch]) + (black ? -cu : cu);
-        if(isRoot && d.rootDesiredPerChildVisitsCoeff > 0.0 && P[ch] > 0.0f &&
+        if(isRoot && !d.plainRoot[g] && d.rootDesiredPerChildVisitsCoeff > 0.0 && P[ch] > 0.0f &&
            CW[ch] < sqrt((double)P[ch] * totalW * d.rootDesiredPerChildVisitsCoeff)) val = 1e20;
       }
       if(val > bestVal) { bestVal = val; bestK = k; }
@@ -1018,7 +1030,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     PF(pfBackup);
     continue;
   }
-  if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0 && !(node == 0 && d.rootNumSymmetries > 1)) {
+  if(d.cacheSize > 0 && d.nodeTerminal[gb + node] == 0 && d.nodeVisits[gb + node] == 0 && !(node == 0 && rootSyms(d, g) > 1)) {
     // NNEvaluator::evaluate's cache lookup (nneval.cpp:861-905): the key is the situation, not the history behind it
     unsigned long long k0, k1;
     if(d.histRules)
@@ -1039,7 +1051,9 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     }
     if(lane == 0) { d.leafKey[g * 2] = k0; d.leafKey[g * 2 + 1] = k1; }
     float vals[6];
-    if(cacheLookup(d, g, node, k0, k1, vals, lane)) {
+    // a plain root (cheap search) is evaluated by the net even when the cache knows it: its input row is kept for the recorder; the key is
+    // still set, so that the backup stores the fresh evaluation under it
+    if(!(node == 0 && d.plainRoot[g]) && cacheLookup(d, g, node, k0, k1, vals, lane)) {
       if(node == 0 && (d.rootEndingBonusPoints != 0.0 || d.rootPruneUselessMoves))
         computeRootExtras(d, g, bd, black, false, 1, lane);     // a root served by the cache has no ownership map: allowed moves only
       maybeRootNoise(d, g, node, lane);
@@ -1143,7 +1157,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
                                (uint64_t)d.nodeVisits[gb]) & 7);   // nneval.cpp:698-707: random symmetry per row
     if(d.fakeNN) sym = 0;                                          // the reference's evaluator without nnRandomize
     if(d.fixedSymmetryPlusOne > 0) sym = d.fixedSymmetryPlusOne - 1; // TEST ONLY: nnRandomize = false with a forced symmetry
-    if(node == 0 && d.rootNumSymmetries > 1 && d.nodeVisits[gb] == 0) {
+    if(node == 0 && rootSyms(d, g) > 1 && d.nodeVisits[gb] == 0) {
       // NNEvaluator::averageMultipleSymmetries: a partial Fisher-Yates shuffle of 0..7 drawn from the search thread's generator
       // With a dynamic score utility Search::beginSearch first takes ONE ordinary evaluation of the root to centre it on
       // (computeRootNNEvaluation, search.cpp:1140-1147): evaluation 0 of the root is that one, the symmetric ones follow.
@@ -1550,7 +1564,7 @@ __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWi
   double u = ((double)whiteWin - (double)whiteLoss) * d.winLossUtilityFactor + (double)noResult * d.noResultUtilityForWhite;
   if(d.staticScoreUtilityFactor != 0.0 || d.dynamicScoreUtilityFactor != 0.0) {
     const double whiteScoreMean = (double)whiteScoreMeanF, whiteScoreMeanSq = (double)whiteScoreMeanSqF;
-    if(node == 0 && d.nodeVisits[gb] == 0 && d.rootNumSymmetries <= 1) {
+    if(node == 0 && d.nodeVisits[gb] == 0 && rootSyms(d, g) <= 1) {
       double c = whiteScoreMean * (1.0 - d.dynamicScoreCenterZeroWeight);
       const double cap = sqrt((double)(d.gX[g] * d.gY[g])) * d.dynamicScoreCenterScale;
       if(c > whiteScoreMean + cap) c = whiteScoreMean + cap;
@@ -1566,7 +1580,7 @@ __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWi
 // Root policy temperature + Dirichlet noise on the root's first evaluation (searchnnhelpers.cpp:61-173).
 __device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane) {
   const size_t gb = (size_t)g * d.maxNodes;
-  if(node == 0 && d.nodeVisits[gb] == 0 && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
+  if(node == 0 && d.nodeVisits[gb] == 0 && !d.plainRoot[g] && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
     __syncwarp();
     if(lane == 0)
       rootPolicyTemperatureAndNoise(d.policy + gb * d.policySize, d.policySize, d.gX[g], d.gY[g], d.moveNum[g], d.rootNoiseEnabled != 0,
@@ -1740,7 +1754,7 @@ __global__ void spBackupKernel(const SPDev d) {
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(KGB_FULL, sum, o);
     const size_t nb = (gb + node) * d.policySize;
-    const bool multiSymRoot = node == 0 && d.rootNumSymmetries > 1 && d.nodeVisits[gb] == 0;
+    const bool multiSymRoot = node == 0 && rootSyms(d, g) > 1 && d.nodeVisits[gb] == 0;
     const int symLead = d.dynamicScoreUtilityFactor != 0.0 ? 1 : 0;           // evaluation 0 only centres the dynamic score utility
     const int symCount = multiSymRoot ? d.rootSymCount[g] - symLead : 0;
 #pragma unroll
@@ -2181,6 +2195,12 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     }
     SPCK(cudaMemcpy(d.nextSetup, four.data(), four.size() * sizeof(int), cudaMemcpyHostToDevice));
     SPCK(cudaMemcpy(d.lastSetup, four.data(), four.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // every root gets the full budget and its root parameters unless the host says otherwise (kgb_selfplay_set_next_search_limits)
+    d.visitBudget = sp->alloc<int>(G); d.nextBudget = sp->alloc<int>((size_t)G * 2);
+    d.plainRoot = sp->alloc<uint8_t>(G); d.nextPlain = sp->alloc<uint8_t>((size_t)G * 2);
+    std::vector<int> full((size_t)G * 2, c.max_visits);
+    SPCK(cudaMemcpy(d.visitBudget, full.data(), (size_t)G * sizeof(int), cudaMemcpyHostToDevice));
+    SPCK(cudaMemcpy(d.nextBudget, full.data(), (size_t)G * 2 * sizeof(int), cudaMemcpyHostToDevice));
   }
   d.cpuctExploration = c.cpuct_exploration; d.cpuctExplorationLog = c.cpuct_exploration_log; d.cpuctExplorationBase = c.cpuct_exploration_base;
   d.fpuReductionMax = c.fpu_reduction_max; d.rootFpuReductionMax = c.root_fpu_reduction_max;
@@ -2474,6 +2494,41 @@ void selfplaySetGameSetup(SelfplayImpl* sp, const int* setup, bool alsoCurrent, 
   SPCK(e);
   if(h != 0) throw std::invalid_argument("selfplay: " + std::to_string(h) + " game(s) in progress have already started; their setup was left unchanged");
 }
+// Search limits of the roots to come (getSearchLimitsThisMove, program/play.cpp:1093-1223: cheap searches, reduced visits).  visits[numGames][2],
+// plain[numGames][2] (may be NULL = all 0): index 0 applies to the root after the slot's next move when the game goes on, index 1 when that
+// move ends the game (first root of the slot's next game).  alsoCurrent: index 0 also replaces the limits of the current roots, which
+// must not have been searched yet.
+__global__ void spApplyLimitsKernel(const SPDev d, int* refused) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= d.numGames) return;
+  if(d.nodeVisits[(size_t)g * d.maxNodes] != 0 || d.rootSymCount[g] != 0) { atomicAdd(refused, 1); return; }
+  d.visitBudget[g] = d.nextBudget[g * 2]; d.plainRoot[g] = d.nextPlain[g * 2];
+}
+void selfplaySetNextSearchLimits(SelfplayImpl* sp, const int* visits, const uint8_t* plain, bool alsoCurrent, cudaStream_t s) {
+  const SPDev& d = sp->d;
+  for(int i = 0; i < d.numGames * 2; i++)
+    if(visits[i] < 2 || visits[i] > d.maxVisits) throw std::invalid_argument("selfplay: a visit budget must lie between 2 and max_visits");
+  SPCK(cudaMemcpy(d.nextBudget, visits, (size_t)d.numGames * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  if(plain) SPCK(cudaMemcpy(d.nextPlain, plain, (size_t)d.numGames * 2, cudaMemcpyHostToDevice));
+  else SPCK(cudaMemset(d.nextPlain, 0, (size_t)d.numGames * 2));
+  if(!alsoCurrent) return;
+  int* refused = nullptr;
+  SPCK(cudaMalloc(&refused, sizeof(int)));
+  SPCK(cudaMemsetAsync(refused, 0, sizeof(int), s));
+  spApplyLimitsKernel<<<(d.numGames + 127) / 128, 128, 0, s>>>(d, refused);
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, refused, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if(e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(refused);
+  SPCK(e);
+  if(h != 0) throw std::invalid_argument("selfplay: " + std::to_string(h) + " root(s) have already been searched; their limits were left unchanged");
+}
+void selfplayReadSearchLimits(SelfplayImpl* sp, int* visits, uint8_t* plain) {
+  const SPDev& d = sp->d;
+  if(visits) SPCK(cudaMemcpy(visits, d.visitBudget, (size_t)d.numGames * sizeof(int), cudaMemcpyDeviceToHost));
+  if(plain) SPCK(cudaMemcpy(plain, d.plainRoot, (size_t)d.numGames, cudaMemcpyDeviceToHost));
+}
+
 void selfplayReadGameSetup(SelfplayImpl* sp, int* current, int* lastFinished) {
   const SPDev& d = sp->d;
   if(current) {

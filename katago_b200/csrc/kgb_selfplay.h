@@ -26,6 +26,8 @@ void selfplayReadLeafKey(SelfplayImpl* sp, int g, unsigned long long* key2);
 void selfplayReadKomi(SelfplayImpl* sp, float* current, float* lastFinished);
 void selfplaySetGameSetup(SelfplayImpl* sp, const int* setup, bool alsoCurrent, cudaStream_t s);
 void selfplayReadGameSetup(SelfplayImpl* sp, int* current, int* lastFinished);
+void selfplaySetNextSearchLimits(SelfplayImpl* sp, const int* visits, const uint8_t* plain, bool alsoCurrent, cudaStream_t s);
+void selfplayReadSearchLimits(SelfplayImpl* sp, int* visits, uint8_t* plain);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchBackup(SelfplayImpl* sp, cudaStream_t s);
 void selfplayLaunchFakeNN(SelfplayImpl* sp, float* policyOut, float* valueOut, float* scoreOut, float* ownershipOut, cudaStream_t s);

@@ -160,11 +160,46 @@ def resolve_target_weight(weight, rand):
     return _f32(floored + 1 if rand.next_bool(float(_f32(_f32(w) - _f32(floored)))) else floored)
 
 
+def search_limits_this_move(max_visits, settings, rand, historical_win_loss):
+    """getSearchLimitsThisMove (program/play.cpp:1093-1223) without hint moves and asymmetric playouts: (visits, remove root noise, target
+    weight, is cheap search) of the next search.  settings: PlaySettings fields by their cfg names in snake case (cheap_search_prob,
+    cheap_search_visits, cheap_search_target_weight, reduce_visits, reduce_visits_threshold, reduce_visits_threshold_lookback,
+    reduced_visits_min, reduced_visits_weight); rand: random.Random (the reference draws from the game's Rand);
+    historical_win_loss: the root's winLossValue (white's perspective) after every search of the game so far."""
+    visits, plain, weight, cheap = int(max_visits), False, _f32(1.0), False
+    p = float(settings.get("cheap_search_prob", 0.0))
+    if p > 0.0 and rand.random() < p:
+        cv = int(settings["cheap_search_visits"])
+        if cv <= 0 or cv > max_visits:
+            raise ValueError("cheapSearchVisits must lie in 1..maxVisits")
+        cheap, visits = True, min(visits, cv)
+        weight = _f32(float(weight) * float(_f32(settings.get("cheap_search_target_weight", 0.0))))
+        if float(settings.get("cheap_search_target_weight", 0.0)) <= 0.0:
+            plain = True          # not recorded: no noise / temperature at the root (the reference also keeps the tree; this loop clears it)
+    elif settings.get("reduce_visits", False):
+        vmin = int(settings["reduced_visits_min"])
+        if vmin <= 0 or vmin > max_visits:
+            raise ValueError("reducedVisitsMin must lie in 1..maxVisits")
+        look, thr = int(settings.get("reduce_visits_threshold_lookback", 1)), float(settings.get("reduce_visits_threshold", 100.0))
+        if len(historical_win_loss) >= look:
+            recent = [historical_win_loss[len(historical_win_loss) - 1 - j] for j in range(look)]
+            lo, hi = (min(recent), max(recent)) if recent else (1e20, -1e20)
+            most_extreme = min(max(lo, -hi), 1.0)
+            through = most_extreme - thr
+            if through > 0:
+                prop = (through / (1.0 - thr)) ** 2
+                visits = int(math.floor(visits + prop * (vmin - visits) + 0.5))
+                weight = _f32(float(weight) + prop * (float(_f32(settings.get("reduced_visits_weight", 1.0))) - float(weight)))
+                visits = max(visits, vmin)
+    return max(2, visits), plain, weight, cheap
+
+
 class _GameInProgress:
     def __init__(self):
         self.turns = []       # per turn: what the finished root search gave
         self.boards = []      # position before each move
         self.setup = None     # (board X, board Y, ko rule, multi-stone suicide legal) of this game, read when its first turn is recorded
+        self.win_loss = []    # the root's winLossValue after each search (historicalMctsWinLossValues of Play::runGame)
 
 
 class GameRecorder:
@@ -181,7 +216,8 @@ class GameRecorder:
     The game hash (FinishedGameData::gameHash, two 64-bit draws of the game's Rand in the reference) comes from `game_hash_fn`."""
 
     def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None,
-                 policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None):
+                 policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None,
+                 play_settings=None, limits_rand=None):
         """policy_surprise_data_weight / value_surprise_data_weight / use_search_value_surprise: PlaySettings of the same names - the
         finished game's target weights are redistributed by surprise (surprise_target_weights).  weight_rand (a RowRand): fractional
         weights are then resolved to integers like runGame does (resolve_target_weight); None leaves them fractional for the writer,
@@ -203,7 +239,27 @@ class GameRecorder:
             raise ValueError("GameRecorder: with nn_cache_size_power_of_two > 0 the root must be evaluated by the net itself "
                              "(root_num_symmetries_to_sample >= 2, as in the stock self-play configurations), or the cache switched off")
         self.default_setup = (self.X, self.Y, int(getattr(cfg, "ko_rule", 0)), int(bool(getattr(cfg, "multi_stone_suicide_legal", 1))))
+        # search limits per move (cheap searches, reduced visits): the host draws what getSearchLimitsThisMove would, the device applies it
+        # to the root after each slot's next move (SelfPlay.set_next_search_limits); cur_limits[g] = (target weight, is cheap) of slot g's root
+        ps = play_settings or {}
+        self.play_settings = ps if (float(ps.get("cheap_search_prob", 0.0)) > 0.0 or ps.get("reduce_visits", False)) else None
+        n = sp.num_games
+        self.cur_limits = [(_f32(1.0), False)] * n
+        if self.play_settings is not None:
+            import random
+            self.limits_rand = limits_rand or random.Random(0x4C696D69)
+            first = [search_limits_this_move(sp.max_visits, self.play_settings, self.limits_rand, []) for _ in range(n)]
+            self.next_visits = np.array([[f[0], f[0]] for f in first], np.int32)
+            self.next_plain = np.array([[f[1], f[1]] for f in first], np.uint8)
+            sp.set_next_search_limits(self.next_visits, self.next_plain, also_current_roots=True)
+            self.cur_limits = [(f[2], f[3]) for f in first]
+            self.pending = [(f, f) for f in first]
         sp.run(1)                                    # evaluates every root (its row stays on the device)
+
+    def _held(self):
+        """Slots whose search is finished: root visits have reached the root's own budget."""
+        budget = self.sp.search_limits()[0] if self.play_settings is not None else self.sp.max_visits
+        return np.asarray(self.sp.root_visits()) >= budget
 
     def _record_root(self, g):
         """Slot g is held: read its finished search and append this turn's targets (extractSearchTargetsThisTurn)."""
@@ -219,6 +275,7 @@ class GameRecorder:
         # the kept row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
         flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
         sp_row = np.asarray(spatial, np.float32).reshape(self.X * self.Y, 22)
+        target_weight, is_cheap = self.cur_limits[g]
         if not (np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own)):
             raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
                                "(the kept input row belongs to another position)")
@@ -229,12 +286,19 @@ class GameRecorder:
             gm.setup = tuple(int(v) for v in sp.game_setups()[0][g]) if hasattr(sp, "game_setups") else self.default_setup
         bx, by = gm.setup[0], gm.setup[1]
         gm.boards.append(np.ascontiguousarray(flat.reshape(self.Y, self.X)[:by, :bx]).reshape(-1).copy())
+        values = value_targets_from_root(root_stats)
+        gm.win_loss.append(float(values[0]) - float(values[1]))
+        if self.play_settings is not None:       # limits of the search that follows this slot's move: the game goes on / a new game starts
+            nxt = (search_limits_this_move(sp.max_visits, self.play_settings, self.limits_rand, gm.win_loss),
+                   search_limits_this_move(sp.max_visits, self.play_settings, self.limits_rand, []))
+            self.pending[g] = nxt
+            self.next_visits[g] = (nxt[0][0], nxt[1][0]); self.next_plain[g] = (nxt[0][1], nxt[1][1])
         gm.turns.append(dict(
-            next_player=own, move_num=info["move_num"],
+            next_player=own, move_num=info["move_num"], target_weight=target_weight, is_cheap_search=is_cheap,
             packed=pack_bits(np.transpose(sp_row.reshape(1, self.X * self.Y, 22), (0, 2, 1)))[0],
             global_input=np.asarray(glob, np.float32).copy(),
             policy_target=(policy_target_moves(psv, self.X), int(info["root_visits"])),
-            value_targets=value_targets_from_root(root_stats),
+            value_targets=values,
             q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
             surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
             # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy as searched
@@ -246,6 +310,9 @@ class GameRecorder:
         sp = self.sp
         last = sp.last_move(g)
         self.games[g].turns[-1]["move"] = last["xy"]
+        if self.play_settings is not None:
+            cont, fresh = self.pending[g]
+            self.cur_limits[g] = (fresh[2], fresh[3]) if last["game_over"] else (cont[2], cont[3])
         if last["game_over"]:
             self._finish_game(g, last)
 
@@ -253,13 +320,15 @@ class GameRecorder:
         """One move of EVERY slot (lockstep): waves until all slots are held, record, release all, one wave."""
         sp, n = self.sp, self.sp.num_games
         waves = 0
-        while int(sp.root_visits().min()) < sp.max_visits:
+        while not self._held().all():
             sp.run(8)
             waves += 8
             if waves > max_waves:
                 raise RuntimeError("GameRecorder: games did not reach max_visits")
         for g in range(n):
             self._record_root(g)
+        if self.play_settings is not None:
+            sp.set_next_search_limits(self.next_visits, self.next_plain)
         sp.release()
         sp.run(1)
         self.moves_recorded += n
@@ -272,12 +341,14 @@ class GameRecorder:
         others keep searching during the extra wave in which the released ones move).  Returns the number of moves recorded."""
         sp = self.sp
         sp.run(waves)
-        held = np.asarray(sp.root_visits()) >= sp.max_visits
+        held = self._held()
         if not held.any():
             return 0
         idx = [int(g) for g in np.flatnonzero(held)]
         for g in idx:
             self._record_root(g)
+        if self.play_settings is not None:
+            sp.set_next_search_limits(self.next_visits, self.next_plain)
         sp.release(held.astype(np.uint8))
         sp.run(1)
         self.moves_recorded += len(idx)
@@ -304,7 +375,7 @@ class GameRecorder:
         for t in gm.turns:
             data.next_player_by_turn.append(t["next_player"])
             data.packed_input_by_turn.append(t["packed"]); data.global_input_by_turn.append(t["global_input"])
-            data.target_weight_by_turn.append(1.0)
+            data.target_weight_by_turn.append(float(t.get("target_weight", 1.0)))
             data.policy_targets_by_turn.append(t["policy_target"])
             data.policy_surprise_by_turn.append(t["surprise"]); data.policy_entropy_by_turn.append(t["policy_entropy"]); data.search_entropy_by_turn.append(t["search_entropy"])
             data.white_value_targets_by_turn.append(t["value_targets"])

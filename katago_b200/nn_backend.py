@@ -84,6 +84,7 @@ ABI_SYMBOLS = [
     "kgb_handle_broadcast_staged_weights", "kgb_selfplay_clear_nn_cache", "kgb_selfplay_set_komi", "kgb_selfplay_get_komi", "kgb_selfplay_get_leaf_cache_key",
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
     "kgb_selfplay_set_game_setup", "kgb_selfplay_get_game_setup", "kgb_selfplay_play_moves_game",
+    "kgb_selfplay_set_next_search_limits", "kgb_selfplay_get_search_limits",
 ]
 
 _lib = None
@@ -131,6 +132,8 @@ def load_library():
     lib.kgb_selfplay_set_game_setup.argtypes = [P, P, I]
     lib.kgb_selfplay_get_game_setup.argtypes = [P, P, P]
     lib.kgb_selfplay_play_moves_game.argtypes = [P, I, P, I]
+    lib.kgb_selfplay_set_next_search_limits.argtypes = [P, P, P, I]
+    lib.kgb_selfplay_get_search_limits.argtypes = [P, P, P]
     lib.kgb_selfplay_get_leaf_cache_key.argtypes = [P, I, P]
     lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
@@ -615,6 +618,19 @@ class SelfPlay:
         the games in progress that have not started): what GameInitializer draws per game (program/play.cpp:330-650)."""
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(setup, np.int32), (self.num_games, 4)))
         _check(load_library().kgb_selfplay_set_game_setup(self._p, a.ctypes.data, int(also_current_games)))
+
+    def set_next_search_limits(self, visits, plain_root=None, also_current_roots: bool = False):
+        """visits[num_games][2], plain_root[num_games][2]: limits of the root after each slot's next move ([:, 0] the game goes on,
+        [:, 1] the move ends it) - cheap searches / reduced visits of Play::runGame (kgb_selfplay_set_next_search_limits)."""
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(visits, np.int32), (self.num_games, 2)))
+        p = None if plain_root is None else np.ascontiguousarray(np.broadcast_to(np.asarray(plain_root, np.uint8), (self.num_games, 2)))
+        _check(load_library().kgb_selfplay_set_next_search_limits(self._p, v.ctypes.data, None if p is None else p.ctypes.data, int(also_current_roots)))
+
+    def search_limits(self):
+        """(visit budget [num_games], plain-root flag [num_games]) of the current roots: a game holds / moves at ITS budget."""
+        v = np.zeros(self.num_games, np.int32); p = np.zeros(self.num_games, np.uint8)
+        _check(load_library().kgb_selfplay_get_search_limits(self._p, v.ctypes.data, p.ctypes.data))
+        return v, p
 
     def game_setups(self):
         """(setup [num_games, 4] of the games in progress, of each slot's last finished game)."""

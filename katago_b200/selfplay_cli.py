@@ -54,8 +54,8 @@ _SEARCH_KEYS = {
 _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
                         "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir")
 # neutral values: the option is switched off, so not having it changes nothing
-_NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0, "cheapSearchProb": 0.0,
-            "reduceVisits": False, "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
+_NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
+            "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
             "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
             "handicapProb": 0.0,
             "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
@@ -173,6 +173,16 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     data["value_surprise_data_weight"] = float(cfg.get("valueSurpriseDataWeight", 0.0))
     data["use_search_value_surprise"] = _B(cfg.get("useSearchValueSurprise", "false"))
     used.update(("policySurpriseDataWeight", "valueSurpriseDataWeight", "useSearchValueSurprise"))
+    # search limits per move (getSearchLimitsThisMove, program/play.cpp:1093-1223): cheap searches and reduced visits, drawn by the recorder
+    data["play_settings"] = dict(
+        cheap_search_prob=float(cfg.get("cheapSearchProb", 0.0)), cheap_search_visits=int(cfg.get("cheapSearchVisits", 0)),
+        cheap_search_target_weight=float(cfg.get("cheapSearchTargetWeight", 0.0)), reduce_visits=_B(cfg.get("reduceVisits", "false")),
+        reduce_visits_threshold=float(cfg.get("reduceVisitsThreshold", 100.0)), reduce_visits_threshold_lookback=int(cfg.get("reduceVisitsThresholdLookback", 1)),
+        reduced_visits_min=int(cfg.get("reducedVisitsMin", 0)), reduced_visits_weight=float(cfg.get("reducedVisitsWeight", 1.0)))
+    used.update(("cheapSearchProb", "cheapSearchVisits", "cheapSearchTargetWeight", "reduceVisits", "reduceVisitsThreshold", "reduceVisitsThresholdLookback",
+                 "reducedVisitsMin", "reducedVisitsWeight"))
+    if data["play_settings"]["cheap_search_prob"] > 0 and data["play_settings"]["cheap_search_target_weight"] <= 0:
+        report["fixed"].append("cheapSearchProb: the reference keeps the previous move's tree for cheap searches it does not record; this loop starts every move on a cleared tree")
     if data["data_board_len"] < size:
         raise ValueError(f"dataBoardLen = {data['data_board_len']} but bSizes goes up to {size}: the data frame must hold the largest board")
     data["board_size"] = size = data["data_board_len"]    # rows are written in the data frame, so the evaluator's frame is that (nnXLen = dataBoardLen)
@@ -411,7 +421,8 @@ def main(argv=None):
     rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
-                       use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"))
+                       use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"),
+                       play_settings=data["play_settings"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
     # New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory every 20 s; :142-231 load the newest one).
     # Default: every rank polls and reads the file itself.  -nccl-weights: rank 0 polls, reads and packs; the packed weights reach
     # the other GPUs by the library's ncclBroadcast (dist_weights.WeightBroadcaster) - the poll is then a collective, every
@@ -498,7 +509,8 @@ def main(argv=None):
                 rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                                    game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
                                    policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
-                                   use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"))
+                                   use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"),
+                                   play_settings=data["play_settings"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
                 rec.games_written = written
             swaps += 1
             outputs.switch_to(new_path)

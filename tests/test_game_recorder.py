@@ -656,3 +656,69 @@ def test_recorded_games_through_the_reference_writer(tmp_path, tmp_models, ko_ru
         b = fg[name].reshape(n, -1).astype(np.float64)
         assert np.allclose(a, b, rtol=2e-5, atol=1e-30), (name, np.argwhere(~np.isclose(a, b, rtol=2e-5, atol=1e-30))[:5])
     sp.free(); h.free(); ctx.free()
+
+
+def test_search_limits_this_move_restates_the_reference_rules():
+    """getSearchLimitsThisMove (program/play.cpp:1093-1223): cheap searches with their probability, visit count and target weight (root noise
+    off when they are not recorded), otherwise visits reduced quadratically once the recent root values are decided beyond the threshold."""
+    import random
+    from katago_b200.game_recorder import search_limits_this_move as L
+    ps = dict(cheap_search_prob=0.75, cheap_search_visits=100, cheap_search_target_weight=0.0, reduce_visits=True, reduce_visits_threshold=0.9,
+              reduce_visits_threshold_lookback=3, reduced_visits_min=50, reduced_visits_weight=0.1)
+    r = random.Random(1)
+    draws = [L(600, ps, r, []) for _ in range(4000)]
+    cheap = [d for d in draws if d[3]]
+    assert abs(len(cheap) / 4000 - 0.75) < 0.03 and all(d == (100, True, 0.0, True) for d in cheap)
+    assert all(d == (600, False, 1.0, False) for d in draws if not d[3])           # no history: nothing to reduce
+    full = dict(ps, cheap_search_prob=0.0)
+    assert L(600, full, r, [0.95, 0.2, 0.97]) == (600, False, 1.0, False)           # one undecided value among the last three
+    assert L(600, full, r, [0.1, 0.95, 0.96, 0.97])[0] == round(600 + ((0.95 - 0.9) / 0.1) ** 2 * (50 - 600))      # min over the lookback, white ahead
+    v, plain, w, ch = L(600, full, r, [-0.99, -0.98, -1.0])                         # black ahead: max of the values, sign flipped
+    assert (v, plain, ch) == (round(600 + 0.8 ** 2 * (50 - 600)), False, False) and abs(float(w) - (1.0 + 0.64 * (0.1 - 1.0))) < 1e-6
+    assert L(600, full, r, [1.0, 1.0, 1.0])[0] == 50 and abs(float(L(600, full, r, [1.0, 1.0, 1.0])[2]) - 0.1) < 1e-6
+    recorded = dict(ps, cheap_search_prob=1.0, cheap_search_target_weight=0.25)
+    assert L(600, recorded, r, []) == (100, False, 0.25, True)                      # recorded cheap searches keep their root noise
+    with pytest.raises(ValueError):
+        L(80, dict(ps, cheap_search_prob=1.0), random.Random(2), [])        # cheapSearchVisits above maxVisits
+
+
+@pytest.mark.gpu
+def test_device_applies_per_move_search_limits(golden_dir, tmp_models):
+    """kgb_selfplay_set_next_search_limits: a root with a reduced budget is held at that budget, and a "plain" root searches exactly like a
+    loop whose root parameters are the tree's (runBotWithLimits removeRootNoise: no noise, temperature 1, tree FPU, no visit floor, one
+    symmetry) - identical visit counts; the limits handed over for the following root take effect after the move."""
+    from katago_b200 import NeuralNet, SelfPlay
+    d = np.load(os.path.join(golden_dir, "searchfake.npz"))
+    moves = [None if m[0] < 0 else (int(m[0]), int(m[1])) for m in d["c1_moves"]]
+    lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
+    ctx = NeuralNet.createComputeContext([0], 9, 9, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, 4, False, True, 0)
+    common = dict(komi=7.5, seed=1, debug_fake_nn=True, debug_hold_at_max_visits=True, use_graph_search=True, value_weight_exponent=0.5,
+                  fpu_reduction_max=0.2, fpu_loss_prop=0.1, static_score_utility_factor=0.05, dynamic_score_utility_factor=0.3,
+                  dynamic_score_center_zero_weight=0.25, dynamic_score_center_scale=0.5, use_play_selection=True)
+    a = SelfPlay(h, 3, 64, root_noise_enabled=True, root_policy_temperature=1.1, root_policy_temperature_early=1.5, root_fpu_reduction_max=0.0,
+                 root_fpu_loss_prop=0.3, root_desired_per_child_visits_coeff=2.0, root_num_symmetries_to_sample=4, **common)
+    b = SelfPlay(h, 3, 40, root_noise_enabled=False, root_fpu_reduction_max=0.2, root_fpu_loss_prop=0.1, **common)
+    with pytest.raises(Exception, match="between 2 and max_visits"):
+        a.set_next_search_limits(np.full((3, 2), 65, np.int32))
+    for sp in (a, b):
+        sp.play_moves(moves)
+    a.set_next_search_limits(np.array([[40, 40], [40, 40], [64, 64]], np.int32), np.array([[1, 1], [1, 1], [0, 0]], np.uint8), also_current_roots=True)
+    assert np.array_equal(a.search_limits()[0], [40, 40, 64]) and np.array_equal(a.search_limits()[1], [1, 1, 0])
+    for sp in (a, b):
+        for _ in range(60):
+            sp.run(8)
+    va, vb = a.root_visits(), b.root_visits()
+    assert list(va) == [40, 40, 64] and list(vb) == [40, 40, 40]
+    for g in (0, 1):
+        ca, pa, ua = a.root_children(g); cb, pb, ub = b.root_children(g)
+        assert np.array_equal(ca, cb) and np.array_equal(pa, pb) and np.abs(ua - ub)[ca > 0].max() < 1e-12
+    assert not np.array_equal(a.root_children(2)[1], b.root_children(2)[1])            # the ordinary root of game 2 carries noise and temperature
+    with pytest.raises(Exception, match="already been searched"):
+        a.set_next_search_limits(np.full((3, 2), 30, np.int32), also_current_roots=True)
+    a.set_next_search_limits(np.array([[24, 50], [16, 50], [64, 50]], np.int32), np.array([[0, 0], [1, 0], [0, 0]], np.uint8))
+    a.release()
+    for _ in range(40):
+        a.run(8)
+    assert list(a.root_visits()) == [24, 16, 64] and np.array_equal(a.search_limits()[1], [0, 1, 0])
+    a.free(); b.free(); h.free(); ctx.free()

@@ -50,6 +50,9 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert kw["root_policy_temperature_early"] == 1.5 and kw["chosen_move_temperature_halflife"] == 19.0 and kw["nn_cache_size_power_of_two"] == 24
     assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
     gi = data.pop("game_init")
+    ps = data.pop("play_settings")
+    assert ps["cheap_search_prob"] == 0.75 and ps["cheap_search_visits"] == 350 and ps["cheap_search_target_weight"] == 0.0 and ps["reduce_visits"] is True
+    assert ps["reduced_visits_min"] == 350
     assert data == {"board_size": 19, "komi": 7.5, "data_board_len": 19, "max_rows_per_train_file": 20000, "first_file_rand_min_prop": 0.15, "num_game_threads": 800,
                     "policy_surprise_data_weight": 0.5, "value_surprise_data_weight": 0.1, "use_search_value_surprise": False}
     # rules, board size and komi are drawn per game from the file's lists like GameInitializer does (bSizes 19,7,9,13 with weights
@@ -67,7 +70,8 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert not any(s.startswith(("koRules", "bSizes")) for s in report["fixed"])
     nb = " ".join(report["not_built"])
     assert "komiStdev" not in nb
-    for key in ("cheapSearchProb", "reduceVisits", "forkGameProb", "estimateLeadProb", "handicapProb",
+    assert "cheapSearchProb" not in nb and "reduceVisits" not in nb        # built: drawn by the recorder, applied by the device
+    for key in ("forkGameProb", "estimateLeadProb", "handicapProb",
                 "komiAuto"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
@@ -147,7 +151,7 @@ def test_command_writes_training_files(tmp_path, stock_cfg):
     modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
     out = tmp_path / "out"
     rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", stock_cfg, "-max-games-total", "3", "-games-per-gpu", "4",
-                 "-override-config", "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=0,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0"])
+                 "-override-config", "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=24,maxMovesPerGame=40,rootNumSymmetriesToSample=1,nnCacheSizePowerOfTwo=0,maxRowsPerTrainFile=50,firstFileRandMinProp=1.0,cheapSearchProb=0,reduceVisits=false"])
     assert rc == 0
     tdata = out / "tinynet" / "tdata"
     files = sorted(os.listdir(tdata))
@@ -175,7 +179,7 @@ def test_command_plays_mixed_board_sizes_rules_and_komi(tmp_path):
     modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
     settings = dict(STOCK_B18_SETTINGS, bSizes="5,7,9", bSizeRelProbs="2,1,1", allowRectangleProb="0.3", dataBoardLen="9", koRules="SIMPLE,POSITIONAL",
                     multiStoneSuicideLegals="false,true", komiMean="6", komiStdev="2.0", maxVisits="16", maxMovesPerGame="50", rootNumSymmetriesToSample="2",
-                    nnCacheSizePowerOfTwo="10", maxRowsPerTrainFile="100000", firstFileRandMinProp="1.0")
+                    nnCacheSizePowerOfTwo="10", maxRowsPerTrainFile="100000", firstFileRandMinProp="1.0", cheapSearchProb="0", reduceVisits="false")
     settings.pop("komiAuto")
     cfg = tmp_path / "mixed.cfg"
     cfg.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
@@ -207,6 +211,36 @@ def test_command_plays_mixed_board_sizes_rules_and_komi(tmp_path):
 
 
 @pytest.mark.gpu
+def test_command_plays_cheap_and_reduced_searches(tmp_path, stock_cfg):
+    """cheapSearchProb / cheapSearchVisits / cheapSearchTargetWeight and reduceVisits through the command: every move's search stops at ITS
+    budget (the visit count in the game record), unrecorded cheap searches enter the training files only through the surprise weighting."""
+    import re
+    from katago_b200 import modelgen
+    models = tmp_path / "models"; models.mkdir()
+    modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
+    out = tmp_path / "out"
+    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", stock_cfg, "-max-games-total", "6", "-games-per-gpu", "6", "-per-game-release",
+                 "-override-config", "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=32,maxMovesPerGame=40,rootNumSymmetriesToSample=2,nnCacheSizePowerOfTwo=10,"
+                 "maxRowsPerTrainFile=100000,firstFileRandMinProp=1.0,cheapSearchProb=0.5,cheapSearchVisits=8,cheapSearchTargetWeight=0.0,reduceVisits=true,"
+                 "reduceVisitsThreshold=0.3,reduceVisitsThresholdLookback=2,reducedVisitsMin=12,reducedVisitsWeight=0.5,allowRectangleProb=0"])
+    assert rc == 0
+    visits, weights = [], []
+    for f in os.listdir(out / "tinynet" / "sgfs"):
+        for line in open(out / "tinynet" / "sgfs" / f):
+            visits += [int(v) for v in re.findall(r" v=(\d+)", line)]
+            weights += [float(w) for w in re.findall(r"weight=([0-9.]+)", line)]
+    assert len(visits) >= 6 * 10 and set(visits) <= set(range(8, 33)), sorted(set(visits))
+    cheap = sum(v == 8 for v in visits)
+    assert 0.3 < cheap / len(visits) < 0.7 and 32 in visits, (cheap, len(visits))
+    assert set(visits) <= {8} | set(range(12, 33))       # a full search, a cheap one, or one reduced towards reducedVisitsMin (formula: CPU test)
+    rows = 0
+    for f in os.listdir(out / "tinynet" / "tdata"):
+        with np.load(out / "tinynet" / "tdata" / f) as z:
+            rows += z["globalTargetsNC"].shape[0]
+    assert 0 < rows < len(visits)                  # unrecorded cheap searches are (mostly) not rows
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("new_cfg", ["tiny_reg", "tiny_nbt"])
 def test_command_moves_to_a_newer_net_while_games_run(tmp_path, stock_cfg, monkeypatch, new_cfg):
     """Model polling (command/selfplay.cpp:336-352): a newer file in the models directory is picked up while games are running.  Same
@@ -230,7 +264,7 @@ def test_command_moves_to_a_newer_net_while_games_run(tmp_path, stock_cfg, monke
     out = tmp_path / "out"
     rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", stock_cfg, "-max-games-total", "8", "-games-per-gpu", "4", "-per-game-release",
                  "-model-poll-seconds", "0", "-override-config",
-                 "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=16,maxMovesPerGame=30,rootNumSymmetriesToSample=2,nnCacheSizePowerOfTwo=10,maxRowsPerTrainFile=1000,firstFileRandMinProp=1.0"])
+                 "bSizes=9,bSizeRelProbs=1,dataBoardLen=9,maxVisits=16,maxMovesPerGame=30,rootNumSymmetriesToSample=2,nnCacheSizePowerOfTwo=10,maxRowsPerTrainFile=1000,firstFileRandMinProp=1.0,cheapSearchProb=0,reduceVisits=false"])
     assert rc == 0
     rows = {}
     for name in ("net1", "net2"):
