@@ -575,7 +575,8 @@ def main():
                 "achieved": (bytes_sel + bytes_bak) * n / ((ms_select + ms_backup) * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (bytes_sel + bytes_bak) * n / ((ms_select + ms_backup) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "ms_select": ms_select, "ms_backup": ms_backup, "avg_depth": tree_depth,
-                "bytes_per_playout": bytes_sel + bytes_bak, "traffic": None,
+                "bytes_per_playout": bytes_sel + bytes_bak,
+                "traffic": 13.2e6 if args.model == "b18c384nbt" and n == 256 and not args.mixed_sizes else None,   # DRAM bytes per wave, both kernels: ncu dram__bytes_read + write (profiles/r02_tree_kernels_ncu_summary.md)
                 "note": "latency-bound at 256 warps per launch (1.7 warps per SM); see DESIGN.md §6"})(
                     tree_depth * 362 * 20 + 362 * 20 + (22 * 361 + 19) * 4 * 2 + 128, 362 * 8 + tree_depth * 48 + 64),
             "cpu_baseline": cpu_obj,
