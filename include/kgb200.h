@@ -335,6 +335,17 @@ KGB_API int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int3
  * starts a move on a cleared tree. */
 KGB_API int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits, const uint8_t* plain_root, int also_current_roots);
 KGB_API int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, uint8_t* plain_root);
+/* Policy-initialised openings (PlaySettings::initGamesWithPolicy, policyInitAreaProp, policyInitAreaTemperature; PlayUtils::initializeGameUsingPolicy,
+ * program/playutils.cpp:232-266, called from Play::runGame, play.cpp:1675-1700): the first num_moves[g] moves of slot g's NEXT game are drawn
+ * from the net's own policy ^ (1 / temperature) of each position - one plain evaluation per move, no search, no noise; a slot in its opening is
+ * never held for recording (the moves belong to the game's start history, not to its training turns).  The host draws the count (floor of an
+ * exponential with mean board area * policyInitAreaProp).  also_current_games != 0: the games in progress take them too; they must not have
+ * started (KGB_ERR_INVALID otherwise).  kgb_selfplay_get_policy_init: moves_left[num_games] (> 0 = still in its opening), count[num_games] and
+ * moves[num_games][max_moves] = the opening of the game in progress (move positions, pass = nn_x_len * nn_y_len; max_moves <= 512); any
+ * pointer may be NULL.  Not restated: the separately noised komi during the opening and the komi compensation after it
+ * (compensateAfterPolicyInitProb needs searches before the game). */
+KGB_API int kgb_selfplay_set_policy_init(kgb_selfplay* sp, const int32_t* num_moves, double temperature, int also_current_games);
+KGB_API int kgb_selfplay_get_policy_init(kgb_selfplay* sp, int32_t* moves_left, int32_t* count, int16_t* moves, int max_moves);
 /* FOR TESTING: the evaluation-cache key (the loop's NNInputs::getHash) of the leaf that slot `game` sent to the evaluator in the
  * last wave; only meaningful with nn_cache_size_power_of_two > 0. */
 KGB_API int kgb_selfplay_get_leaf_cache_key(kgb_selfplay* sp, int game, uint64_t* key2);

@@ -1427,6 +1427,24 @@ KGB_API int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, ui
   });
 }
 
+KGB_API int kgb_selfplay_set_policy_init(kgb_selfplay* sp, const int32_t* num_moves, double temperature, int also_current_games) {
+  return guarded([&] {
+    if(!sp || !num_moves) throw std::invalid_argument("kgb_selfplay_set_policy_init: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplaySetPolicyInit(sp->impl, num_moves, temperature, also_current_games != 0, sp->h->stream);
+  });
+}
+
+KGB_API int kgb_selfplay_get_policy_init(kgb_selfplay* sp, int32_t* moves_left, int32_t* count, int16_t* moves, int max_moves) {
+  return guarded([&] {
+    if(!sp) throw std::invalid_argument("kgb_selfplay_get_policy_init: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadPolicyInit(sp->impl, moves_left, count, moves, max_moves);
+  });
+}
+
 KGB_API int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int32_t* last_finished) {
   return guarded([&] {
     if(!sp) throw std::invalid_argument("kgb_selfplay_get_game_setup: NULL argument");

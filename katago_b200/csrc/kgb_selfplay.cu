@@ -46,6 +46,7 @@
 namespace kgb {
 
 static constexpr int SP_MAX_PLAYOUTS_PER_WAVE = 16;   // playouts a game may finish inside one wave without needing the evaluator
+static constexpr int SP_MAX_INIT_MOVES = 512;   // policy-initialised opening moves kept per game (longer openings are cut there)
 static constexpr int SP_LADDER_WARPS = 8;   // warps per game in the select kernel (ladder searches are dealt out to all of them)
 
 struct SPDev {
@@ -61,6 +62,12 @@ struct SPDev {
   // following root gets, [game][2]: 0 = the game goes on, 1 = this move ends it and the slot's next game starts
   int *visitBudget, *nextBudget;
   uint8_t *plainRoot, *nextPlain;
+  // policy-initialised openings (PlayUtils::initializeGameUsingPolicy, program/playutils.cpp:232-266): the first initMovesLeft moves of a game
+  // are drawn from the net's raw policy ^ (1 / temperature) of the position (one evaluation per move, no search, never held for recording);
+  // they are kept in initMoves for the game record.  nextInitMoves = the count for the slot's next game (the host draws it)
+  int *initMovesLeft, *nextInitMoves, *initMoveCount;
+  int16_t* initMoves;               // [game][SP_MAX_INIT_MOVES] move positions of the current game's opening
+  double* policyInitTemperature;    // [1] in device memory (the wave's kernel arguments are frozen in its CUDA graph)
   int *gX, *gY, *gKoRule, *gMultiSuicide;   // [game] of the game in progress
   int *nextSetup, *lastSetup;               // [game][4]: of the slot's next game (kgb_selfplay_set_game_setup), of its last finished game
   double cpuctExploration, cpuctExplorationLog, cpuctExplorationBase, fpuReductionMax, rootFpuReductionMax;
@@ -601,6 +608,7 @@ __device__ void gameOverStartNext(const SPDev& d, int g, WarpBoard& bd, bool noR
     // ... and its board size and rules (kgb_selfplay_set_game_setup): what GameInitializer::createGame draws per game
     d.lastSetup[g * 4 + 0] = d.gX[g]; d.lastSetup[g * 4 + 1] = d.gY[g]; d.lastSetup[g * 4 + 2] = d.gKoRule[g]; d.lastSetup[g * 4 + 3] = d.gMultiSuicide[g];
     d.gX[g] = d.nextSetup[g * 4 + 0]; d.gY[g] = d.nextSetup[g * 4 + 1]; d.gKoRule[g] = d.nextSetup[g * 4 + 2]; d.gMultiSuicide[g] = d.nextSetup[g * 4 + 3];
+    d.initMovesLeft[g] = d.nextInitMoves[g]; d.initMoveCount[g] = 0;       // the next game's policy-initialised opening
   }
   __syncwarp();
   boardInit(bd, d.gX[g], d.gY[g]);
@@ -652,11 +660,37 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     }
     best = chosen;
   }
-  if(d.usePlaySelection) {
+  if(d.usePlaySelection && d.initMovesLeft[g] <= 0) {
     int chosen = -1;
     if(lane == 0) chosen = rootChooseMove(d, g);
     chosen = __shfl_sync(KGB_FULL, chosen, 0);
     if(chosen >= 0) { best = chosen; bestV = 1; }
+  }
+  const bool initMove = d.initMovesLeft[g] > 0;
+  if(initMove) {
+    // PlayUtils::getGameInitializationMove (playutils.cpp:177-226): a legal move drawn in proportion to policy ^ (1 / temperature) of the
+    // root's own evaluation (with probability 0.0002 uniformly), from the game's non-search generator
+    int chosen = d.policySize - 1;
+    if(lane == 0) {
+      const float* pol = d.policy + rootBase;
+      DevRand rand;
+      rand.s = d.nonSearchRand[g];
+      const double invT = 1.0 / d.policyInitTemperature[0];
+      double sum = 0.0; int cnt = 0;
+      for(int i = 0; i < d.policySize; i++) if(pol[i] > 0.0f) { sum += invT == 1.0 ? (double)pol[i] : pow((double)pol[i], invT); cnt++; }
+      if(cnt > 0) {
+        const bool uniform = rand.nextDouble() < 0.0002;
+        double r = rand.nextDouble() * (uniform ? (double)cnt : sum), run = 0.0;
+        for(int i = 0; i < d.policySize; i++) {
+          if(!(pol[i] > 0.0f)) continue;
+          run += uniform ? 1.0 : (invT == 1.0 ? (double)pol[i] : pow((double)pol[i], invT));
+          chosen = i;
+          if(run > r) break;
+        }
+      }
+      d.nonSearchRand[g] = rand.s;
+    }
+    best = __shfl_sync(KGB_FULL, chosen, 0); bestV = 1;
   }
   if(bestV <= 0) best = d.policySize - 1;  // nothing searched (cannot happen with maxVisits >= 2): pass
   // play it on the root board
@@ -709,6 +743,13 @@ __device__ void rootAdvance(const SPDev& d, int g, int lane) {
     // the new root's search limits (kgb_selfplay_set_next_search_limits)
     d.visitBudget[g] = d.nextBudget[g * 2 + (over ? 1 : 0)];
     d.plainRoot[g] = d.nextPlain[g * 2 + (over ? 1 : 0)];
+    if(initMove && !over) {
+      const int k = d.initMoveCount[g];
+      if(k < SP_MAX_INIT_MOVES) d.initMoves[(size_t)g * SP_MAX_INIT_MOVES + k] = (int16_t)best;
+      d.initMoveCount[g] = k + 1;
+      d.initMovesLeft[g] -= 1;
+    }
+    if(d.initMovesLeft[g] > 0) { d.visitBudget[g] = 1; d.plainRoot[g] = 1; }   // an opening root: one plain evaluation, then the policy draw
   }
   nodeInit(d, rootBase, lane);
   biasTableClear(d, g, lane);   // all nodes freed: every entry is unused and dropped (search.cpp:860-861)
@@ -749,7 +790,7 @@ __device__ void spSelectWarp0(const SPDev& d, int g, int lane, uint32_t* shB, ui
     // hold mode (tests, game recording): keep the finished tree until the host has read it and released the game
     const bool released = d.releaseFlag[g] != 0;
     __syncwarp();
-    if(d.holdAtMaxVisits && !released) break;
+    if(d.holdAtMaxVisits && !released && d.initMovesLeft[g] <= 0) break;      // opening moves drawn from the policy are not recorded turns
     const long long tRA = clock64();
     rootAdvance(d, g, lane);
     if(lane == 0) { d.releaseFlag[g] = 0; d.dbgCycles[g * 8 + 1] = clock64() - tRA; }
@@ -2198,6 +2239,10 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     // every root gets the full budget and its root parameters unless the host says otherwise (kgb_selfplay_set_next_search_limits)
     d.visitBudget = sp->alloc<int>(G); d.nextBudget = sp->alloc<int>((size_t)G * 2);
     d.plainRoot = sp->alloc<uint8_t>(G); d.nextPlain = sp->alloc<uint8_t>((size_t)G * 2);
+    d.initMovesLeft = sp->alloc<int>(G); d.nextInitMoves = sp->alloc<int>(G); d.initMoveCount = sp->alloc<int>(G);
+    d.initMoves = sp->alloc<int16_t>((size_t)G * SP_MAX_INIT_MOVES);
+    d.policyInitTemperature = sp->alloc<double>(1);
+    { const double one = 1.0; SPCK(cudaMemcpy(d.policyInitTemperature, &one, sizeof(double), cudaMemcpyHostToDevice)); }
     std::vector<int> full((size_t)G * 2, c.max_visits);
     SPCK(cudaMemcpy(d.visitBudget, full.data(), (size_t)G * sizeof(int), cudaMemcpyHostToDevice));
     SPCK(cudaMemcpy(d.nextBudget, full.data(), (size_t)G * 2 * sizeof(int), cudaMemcpyHostToDevice));
@@ -2523,6 +2568,48 @@ void selfplaySetNextSearchLimits(SelfplayImpl* sp, const int* visits, const uint
   SPCK(e);
   if(h != 0) throw std::invalid_argument("selfplay: " + std::to_string(h) + " root(s) have already been searched; their limits were left unchanged");
 }
+// Policy-initialised openings (PlaySettings::initGamesWithPolicy / policyInitAreaProp / policyInitAreaTemperature; playutils.cpp:232-266): moves[numGames] =
+// how many opening moves each slot's NEXT game draws from the raw policy before its first searched move (the host draws the count: floor of an
+// exponential with mean area * policyInitAreaProp).  alsoCurrent: the games in progress take them too; they must not have started.
+__global__ void spApplyPolicyInitKernel(const SPDev d, int* refused) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= d.numGames) return;
+  if(d.moveNum[g] != 0 || d.nodeVisits[(size_t)g * d.maxNodes] != 0 || d.rootSymCount[g] != 0) { atomicAdd(refused, 1); return; }
+  d.initMovesLeft[g] = d.nextInitMoves[g]; d.initMoveCount[g] = 0;
+  if(d.initMovesLeft[g] > 0) { d.visitBudget[g] = 1; d.plainRoot[g] = 1; }
+}
+void selfplaySetPolicyInit(SelfplayImpl* sp, const int* moves, double temperature, bool alsoCurrent, cudaStream_t s) {
+  const SPDev& d = sp->d;
+  if(!(temperature > 0.0 && temperature < 10.0)) throw std::invalid_argument("selfplay: policy init temperature must lie in (0, 10)");
+  for(int g = 0; g < d.numGames; g++)
+    if(moves[g] < 0) throw std::invalid_argument("selfplay: negative number of opening moves");
+  SPCK(cudaMemcpy(d.policyInitTemperature, &temperature, sizeof(double), cudaMemcpyHostToDevice));
+  SPCK(cudaMemcpy(d.nextInitMoves, moves, (size_t)d.numGames * sizeof(int), cudaMemcpyHostToDevice));
+  if(!alsoCurrent) return;
+  int* refused = nullptr;
+  SPCK(cudaMalloc(&refused, sizeof(int)));
+  SPCK(cudaMemsetAsync(refused, 0, sizeof(int), s));
+  spApplyPolicyInitKernel<<<(d.numGames + 127) / 128, 128, 0, s>>>(d, refused);
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, refused, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if(e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(refused);
+  SPCK(e);
+  if(h != 0) throw std::invalid_argument("selfplay: " + std::to_string(h) + " game(s) in progress have already started; their openings were left unchanged");
+}
+// movesLeft[numGames]: opening moves still to be drawn (> 0 = the slot is not a recorded turn yet); count / moves[numGames][maxMoves]: the opening played so far
+// in the current game (move positions, pass = policy size - 1).  Any pointer may be NULL.
+void selfplayReadPolicyInit(SelfplayImpl* sp, int* movesLeft, int* count, int16_t* moves, int maxMoves) {
+  const SPDev& d = sp->d;
+  if(movesLeft) SPCK(cudaMemcpy(movesLeft, d.initMovesLeft, (size_t)d.numGames * sizeof(int), cudaMemcpyDeviceToHost));
+  if(count) SPCK(cudaMemcpy(count, d.initMoveCount, (size_t)d.numGames * sizeof(int), cudaMemcpyDeviceToHost));
+  if(moves) {
+    if(maxMoves < 1 || maxMoves > SP_MAX_INIT_MOVES) throw std::invalid_argument("selfplay: max_moves must lie in 1..512");
+    SPCK(cudaMemcpy2D(moves, (size_t)maxMoves * sizeof(int16_t), d.initMoves, (size_t)SP_MAX_INIT_MOVES * sizeof(int16_t), (size_t)maxMoves * sizeof(int16_t),
+                      (size_t)d.numGames, cudaMemcpyDeviceToHost));
+  }
+}
+
 void selfplayReadSearchLimits(SelfplayImpl* sp, int* visits, uint8_t* plain) {
   const SPDev& d = sp->d;
   if(visits) SPCK(cudaMemcpy(visits, d.visitBudget, (size_t)d.numGames * sizeof(int), cudaMemcpyDeviceToHost));

@@ -200,6 +200,7 @@ class _GameInProgress:
         self.boards = []      # position before each move
         self.setup = None     # (board X, board Y, ko rule, multi-stone suicide legal) of this game, read when its first turn is recorded
         self.win_loss = []    # the root's winLossValue after each search (historicalMctsWinLossValues of Play::runGame)
+        self.start_moves = [] # moves before the first recorded turn (policy-initialised opening)
 
 
 class GameRecorder:
@@ -217,7 +218,7 @@ class GameRecorder:
 
     def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None,
                  policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None,
-                 play_settings=None, limits_rand=None):
+                 play_settings=None, limits_rand=None, policy_init=False):
         """policy_surprise_data_weight / value_surprise_data_weight / use_search_value_surprise: PlaySettings of the same names - the
         finished game's target weights are redistributed by surprise (surprise_target_weights).  weight_rand (a RowRand): fractional
         weights are then resolved to integers like runGame does (resolve_target_weight); None leaves them fractional for the writer,
@@ -241,6 +242,7 @@ class GameRecorder:
         self.default_setup = (self.X, self.Y, int(getattr(cfg, "ko_rule", 0)), int(bool(getattr(cfg, "multi_stone_suicide_legal", 1))))
         # search limits per move (cheap searches, reduced visits): the host draws what getSearchLimitsThisMove would, the device applies it
         # to the root after each slot's next move (SelfPlay.set_next_search_limits); cur_limits[g] = (target weight, is cheap) of slot g's root
+        self.policy_init_active = bool(policy_init) and hasattr(sp, "policy_init")
         ps = play_settings or {}
         self.play_settings = ps if (float(ps.get("cheap_search_prob", 0.0)) > 0.0 or ps.get("reduce_visits", False)) else None
         n = sp.num_games
@@ -259,7 +261,10 @@ class GameRecorder:
     def _held(self):
         """Slots whose search is finished: root visits have reached the root's own budget."""
         budget = self.sp.search_limits()[0] if self.play_settings is not None else self.sp.max_visits
-        return np.asarray(self.sp.root_visits()) >= budget
+        held = np.asarray(self.sp.root_visits()) >= budget
+        if self.policy_init_active:          # a slot in its policy-drawn opening moves on by itself: those are not recorded turns
+            held &= np.asarray(self.sp.policy_init()[0]) <= 0
+        return held
 
     def _record_root(self, g):
         """Slot g is held: read its finished search and append this turn's targets (extractSearchTargetsThisTurn)."""
@@ -284,6 +289,10 @@ class GameRecorder:
             # board size and rules are per game (SelfPlay.set_game_setup; GameInitializer draws them per game): X, Y below stay the
             # evaluator's frame = the data frame (dataBoardLen) the rows are written in, the game's own board is its top-left corner
             gm.setup = tuple(int(v) for v in sp.game_setups()[0][g]) if hasattr(sp, "game_setups") else self.default_setup
+            if self.policy_init_active:      # the opening the device drew from the policy: the game's start history (startHist)
+                gm.start_moves = sp.policy_init(max_moves=512)[2][g]
+                if len(gm.start_moves) != info["move_num"]:
+                    raise RuntimeError(f"GameRecorder: slot {g}: {info['move_num']} moves played before the first searched move, {len(gm.start_moves)} opening moves kept")
         bx, by = gm.setup[0], gm.setup[1]
         gm.boards.append(np.ascontiguousarray(flat.reshape(self.Y, self.X)[:by, :bx]).reshape(-1).copy())
         values = value_targets_from_root(root_stats)
@@ -369,6 +378,8 @@ class GameRecorder:
         data.hit_turn_limit = bool(last["hit_move_limit"])
         data.end_no_result = bool(last["no_result"])
         data.moves = [t["move"] for t in gm.turns]
+        data.start_moves = list(gm.start_moves)                 # startHist: played before the training period (policy-initialised opening)
+        data.start_hist_moves = len(data.start_moves)
         data.ko_rule = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[ko_rule]
         data.multi_stone_suicide_legal = bool(multi_suicide)
         data.boards_by_turn = gm.boards + [crop(last["final_colors"])]

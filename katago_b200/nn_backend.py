@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
     "kgb_handle_broadcast_staged_weights", "kgb_selfplay_clear_nn_cache", "kgb_selfplay_set_komi", "kgb_selfplay_get_komi", "kgb_selfplay_get_leaf_cache_key",
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
     "kgb_selfplay_set_game_setup", "kgb_selfplay_get_game_setup", "kgb_selfplay_play_moves_game",
-    "kgb_selfplay_set_next_search_limits", "kgb_selfplay_get_search_limits",
+    "kgb_selfplay_set_next_search_limits", "kgb_selfplay_get_search_limits", "kgb_selfplay_set_policy_init", "kgb_selfplay_get_policy_init",
 ]
 
 _lib = None
@@ -134,6 +134,8 @@ def load_library():
     lib.kgb_selfplay_play_moves_game.argtypes = [P, I, P, I]
     lib.kgb_selfplay_set_next_search_limits.argtypes = [P, P, P, I]
     lib.kgb_selfplay_get_search_limits.argtypes = [P, P, P]
+    lib.kgb_selfplay_set_policy_init.argtypes = [P, P, C.c_double, I]
+    lib.kgb_selfplay_get_policy_init.argtypes = [P, P, P, P, I]
     lib.kgb_selfplay_get_leaf_cache_key.argtypes = [P, I, P]
     lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
@@ -631,6 +633,24 @@ class SelfPlay:
         v = np.zeros(self.num_games, np.int32); p = np.zeros(self.num_games, np.uint8)
         _check(load_library().kgb_selfplay_get_search_limits(self._p, v.ctypes.data, p.ctypes.data))
         return v, p
+
+    def set_policy_init(self, num_moves, temperature: float = 1.0, also_current_games: bool = False):
+        """num_moves[num_games]: opening moves the slot's next game draws from the net's raw policy before its first search
+        (PlayUtils::initializeGameUsingPolicy; kgb_selfplay_set_policy_init)."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(num_moves, np.int32), (self.num_games,)))
+        _check(load_library().kgb_selfplay_set_policy_init(self._p, a.ctypes.data, float(temperature), int(also_current_games)))
+
+    def policy_init(self, max_moves: int = 0):
+        """(moves_left [num_games], count [num_games], moves) - moves: per game the list of (x, y) / (-1, -1) opening moves played so far (only
+        when max_moves > 0)."""
+        left = np.zeros(self.num_games, np.int32); cnt = np.zeros(self.num_games, np.int32)
+        mv = np.zeros((self.num_games, max_moves), np.int16) if max_moves > 0 else None
+        _check(load_library().kgb_selfplay_get_policy_init(self._p, left.ctypes.data, cnt.ctypes.data, None if mv is None else mv.ctypes.data, max_moves))
+        moves = None
+        if mv is not None:
+            n = self.x * self.y
+            moves = [[(-1, -1) if int(p) == n else (int(p) % self.x, int(p) // self.x) for p in mv[g, :min(int(cnt[g]), max_moves)]] for g in range(self.num_games)]
+        return left, cnt, moves
 
     def game_setups(self):
         """(setup [num_games, 4] of the games in progress, of each slot's last finished game)."""

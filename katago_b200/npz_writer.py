@@ -380,6 +380,7 @@ class FinishedGameData:
         self.changed_neural_net_turns = []         # turn index at which each new net took over
         self.side_positions = []                   # SidePosition objects
         self.moves = []                            # (x, y) per turn, (-1, -1) = pass
+        self.start_moves = []                      # (x, y) of the moves before the training period (startHist.moveHistory), black first
         self.ko_rule, self.multi_stone_suicide_legal = "SIMPLE", True
         self.winner, self.final_white_minus_black_score = 0, 0.0      # winner: 0 draw, P_BLACK, P_WHITE (finished games with a result)
         self.changed_neural_net_names = None       # names of the nets in changed_neural_net_turns (SGF comment only)
@@ -583,6 +584,8 @@ def write_sgf(data: FinishedGameData, b_name: str, w_name: str) -> str:
     out.append("C[%s]" % comment)
     weights = data.target_weight_by_turn_unrounded if data.target_weight_by_turn_unrounded is not None else data.target_weight_by_turn
     n = len(data.moves)
+    for j, (x, y) in enumerate(getattr(data, "start_moves", [])):       # endHist.moveHistory starts with startHist's moves: no comments on those
+        out.append(";%s[%s]" % ("B" if (j % 2 == 0) == (data.start_pla == P_BLACK) else "W", "" if x < 0 else _SGF_CHARS[x] + _SGF_CHARS[y]))
     for i, (x, y) in enumerate(data.moves):
         pla = data.next_player_by_turn[i]
         out.append(";%s[%s]" % ("B" if pla == P_BLACK else "W", "" if x < 0 else _SGF_CHARS[x] + _SGF_CHARS[y]))

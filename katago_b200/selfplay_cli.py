@@ -56,7 +56,7 @@ _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNN
 # neutral values: the option is switched off, so not having it changes nothing
 _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
             "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
-            "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False, "initGamesWithPolicy": False,
+            "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False,
             "handicapProb": 0.0,
             "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
 _REFERENCE_DEFAULTS = {
@@ -181,6 +181,12 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
         reduced_visits_min=int(cfg.get("reducedVisitsMin", 0)), reduced_visits_weight=float(cfg.get("reducedVisitsWeight", 1.0)))
     used.update(("cheapSearchProb", "cheapSearchVisits", "cheapSearchTargetWeight", "reduceVisits", "reduceVisitsThreshold", "reduceVisitsThresholdLookback",
                  "reducedVisitsMin", "reducedVisitsWeight"))
+    # policy-initialised openings (initializeGameUsingPolicy): the device draws the moves, the host the count per game
+    data["policy_init"] = dict(enabled=_B(cfg.get("initGamesWithPolicy", "false")), area_prop=float(cfg.get("policyInitAreaProp", 0.04)),
+                               temperature=float(cfg.get("policyInitAreaTemperature", 1.0)))
+    used.update(("initGamesWithPolicy", "policyInitAreaProp", "policyInitAreaTemperature"))
+    if data["policy_init"]["enabled"] and float(cfg.get("compensateAfterPolicyInitProb", 0.0)) > 0:
+        pass          # reported below through _NEUTRAL (komi compensation after the opening needs searches before the game: not built)
     if data["play_settings"]["cheap_search_prob"] > 0 and data["play_settings"]["cheap_search_target_weight"] <= 0:
         report["fixed"].append("cheapSearchProb: the reference keeps the previous move's tree for cheap searches it does not record; this loop starts every move on a cleared tree")
     if data["data_board_len"] < size:
@@ -209,17 +215,33 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
 class SlotSetups:
     """Host side of the per-game setup: draws from a GameInitializer and hands them to the loop (SelfPlay.set_game_setup / set_komi)."""
 
-    def __init__(self, init, num_games):
+    def __init__(self, init, num_games, policy_init=None):
         self.init, self.n = init, num_games
+        self.policy_init = policy_init if policy_init and policy_init.get("enabled") and policy_init.get("area_prop", 0) > 0 else None
         self.setups, self.komis = init.draw_many(num_games)
+        self.openings = self._openings(self.setups)
+
+    def _opening_len(self, x, y):
+        """numInitialMovesToPlay (playutils.cpp:243-250, gamma shape 1): floor of an exponential with mean area * policyInitAreaProp."""
+        import math
+        return int(math.floor(self.init.rand.expovariate(1.0) * x * y * self.policy_init["area_prop"])) if self.policy_init else 0
+
+    def _openings(self, setups):
+        import numpy as np
+        return np.array([self._opening_len(int(q[0]), int(q[1])) for q in setups], np.int32)
 
     def start(self, sp):
         """A fresh loop: the drawn values become the games in progress (none has started), new ones are drawn for the games after them."""
         sp.set_game_setup(self.setups, also_current_games=True)
         sp.set_komi(self.komis, also_current_games=True)
+        if self.policy_init:
+            sp.set_policy_init(self.openings, self.policy_init["temperature"], also_current_games=True)
         self.setups, self.komis = self.init.draw_many(self.n)
+        self.openings = self._openings(self.setups)
         sp.set_game_setup(self.setups)
         sp.set_komi(self.komis)
+        if self.policy_init:
+            sp.set_policy_init(self.openings, self.policy_init["temperature"])
 
     def redraw(self, sp, slot):
         x, y, ko, suicide, komi = self.init.draw()
@@ -227,6 +249,9 @@ class SlotSetups:
         self.komis[slot] = komi
         sp.set_game_setup(self.setups)
         sp.set_komi(self.komis)
+        if self.policy_init:
+            self.openings[slot] = self._opening_len(x, y)
+            sp.set_policy_init(self.openings, self.policy_init["temperature"])
 
 
 def _game_hash(seed, slot, index):
@@ -412,7 +437,7 @@ def main(argv=None):
     # when the slot's next game starts.  `slots` always holds what has been handed to the device for each slot's NEXT game.
     from .game_initializer import GameInitializer
     init = GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"])
-    slots = SlotSetups(init, games)
+    slots = SlotSetups(init, games, data["policy_init"])
     slots.start(sp)
 
     def on_game(slot, finished):
@@ -422,7 +447,7 @@ def main(argv=None):
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                        use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"),
-                       play_settings=data["play_settings"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
+                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
     # New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory every 20 s; :142-231 load the newest one).
     # Default: every rank polls and reads the file itself.  -nccl-weights: rank 0 polls, reads and packs; the packed weights reach
     # the other GPUs by the library's ncclBroadcast (dist_weights.WeightBroadcaster) - the poll is then a collective, every
@@ -510,7 +535,7 @@ def main(argv=None):
                                    game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
                                    policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                                    use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"),
-                                   play_settings=data["play_settings"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
+                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
                 rec.games_written = written
             swaps += 1
             outputs.switch_to(new_path)

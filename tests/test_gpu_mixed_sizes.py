@@ -169,3 +169,61 @@ def test_games_of_different_sizes_never_share_an_evaluation_cache_entry(tmp_mode
     keys = [tuple(int(k) for k in sp.leaf_cache_key(g)) for g in range(4)]
     assert keys[0] == keys[3] and len({keys[0], keys[1], keys[2]}) == 3, keys
     sp.free(); h.free(); ctx.free()
+
+
+def test_policy_initialised_openings(tmp_models, golden_dir):
+    """PlayUtils::initializeGameUsingPolicy on the device: the first moves of a game are drawn from the net's raw policy, one evaluation per
+    move, without holding the slot; the recorder's first turn comes after them.  The kept opening replays to the slot's root position, and at a
+    low temperature the draw concentrates on the policy's best move."""
+    from katago_b200 import nn_backend
+    lm = NeuralNet.loadModelFile(tmp_models["tiny_reg"])
+    ctx = NeuralNet.createComputeContext([0], 9, 9, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, 64, False, True, 0)
+    want = np.array([0, 3, 10, 5, 0, 7, 1, 12], np.int32)
+    sp = SelfPlay(h, 8, 16, komi=7.5, seed=11, debug_hold_at_max_visits=True, nn_cache_size_power_of_two=10, root_num_symmetries_to_sample=2, root_noise_enabled=True,
+                  use_play_selection=True, full_history_rules=True)
+    sizes = np.array([[9, 9, 0, 1]] * 6 + [[7, 7, 0, 1], [9, 5, 0, 1]], np.int32)
+    sp.set_game_setup(sizes, also_current_games=True)
+    sp.set_policy_init(want, 1.0, also_current_games=True)
+    sp.set_policy_init(np.full(8, 2, np.int32), 1.0)                      # the slots' next games
+    for _ in range(100):
+        sp.run(8)
+        if (sp.root_visits() >= 16).all():
+            break
+    left, cnt, moves = sp.policy_init(max_moves=64)
+    assert (left == 0).all() and np.array_equal(cnt, want), (left, cnt)
+    for g in range(8):
+        colors, info = sp.game(g)
+        assert info["move_num"] == want[g] and info["root_visits"] == 16
+        X, Y = int(sizes[g, 0]), int(sizes[g, 1])
+        assert all(m == (-1, -1) or (0 <= m[0] < X and 0 <= m[1] < Y) for m in moves[g])
+        if want[g] > 0:
+            rep = nn_backend.board_replay(X, Y, np.array([[[m[0], m[1], 1 + (i % 2)] for i, m in enumerate(moves[g])]], np.int8), True)
+            assert np.array_equal(rep["colors"][0, -1], colors[:Y, :X]), g          # the opening leads to the root the search is held at
+    with pytest.raises(Exception, match="already started"):
+        sp.set_policy_init(want, 1.0, also_current_games=True)
+    sp.free()
+    h.free(); ctx.free()
+    # the draw follows policy ^ (1 / T): a trained net (peaked policy), 128 games draw one move each from the same empty-board evaluation
+    lm = NeuralNet.loadModelFile(os.path.join(golden_dir, "models", "g170-b6c96-s175395328-d26788732.bin.gz"))
+    ctx = NeuralNet.createComputeContext([0], 9, 9, True, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, 128, False, True, 0)
+    ref = SelfPlay(h, 1, 4, komi=7.5, seed=1, debug_hold_at_max_visits=True, debug_fixed_symmetry=0)
+    ref.run(2)
+    pol = ref.root_children(0)[1]
+    ref.free()
+    T = 0.5
+    sp = SelfPlay(h, 128, 4, komi=7.5, seed=5, debug_hold_at_max_visits=True, debug_fixed_symmetry=0)
+    sp.set_policy_init(np.ones(128, np.int32), T, also_current_games=True)
+    for _ in range(8):
+        sp.run(4)
+    _, cnt, moves = sp.policy_init(max_moves=4)
+    assert (cnt == 1).all()
+    drawn = np.array([m[0][1] * 9 + m[0][0] if m[0][0] >= 0 else 81 for m in moves])
+    weights = np.where(pol > 0, pol.astype(np.float64), 0.0) ** (1.0 / T)
+    weights /= weights.sum()
+    top = np.argsort(-weights)[:4]
+    expect, got = float(weights[top].sum()), float(np.isin(drawn, top).mean())
+    assert expect > 0.3 and abs(got - expect) < 4 * np.sqrt(expect * (1 - expect) / 128) + 0.02, (got, expect)
+    assert (weights[drawn] > 0).all()
+    sp.free(); h.free(); ctx.free()

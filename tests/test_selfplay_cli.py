@@ -51,6 +51,7 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
     gi = data.pop("game_init")
     ps = data.pop("play_settings")
+    assert data.pop("policy_init") == {"enabled": True, "area_prop": 0.08, "temperature": 1.0}
     assert ps["cheap_search_prob"] == 0.75 and ps["cheap_search_visits"] == 350 and ps["cheap_search_target_weight"] == 0.0 and ps["reduce_visits"] is True
     assert ps["reduced_visits_min"] == 350
     assert data == {"board_size": 19, "komi": 7.5, "data_board_len": 19, "max_rows_per_train_file": 20000, "first_file_rand_min_prop": 0.15, "num_game_threads": 800,
@@ -71,6 +72,7 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     nb = " ".join(report["not_built"])
     assert "komiStdev" not in nb
     assert "cheapSearchProb" not in nb and "reduceVisits" not in nb        # built: drawn by the recorder, applied by the device
+    assert "initGamesWithPolicy" not in nb and "policyInitAreaProp" not in nb
     for key in ("forkGameProb", "estimateLeadProb", "handicapProb",
                 "komiAuto"):
         assert key in nb, key
@@ -230,6 +232,16 @@ def test_command_plays_cheap_and_reduced_searches(tmp_path, stock_cfg):
             visits += [int(v) for v in re.findall(r" v=(\d+)", line)]
             weights += [float(w) for w in re.findall(r"weight=([0-9.]+)", line)]
     assert len(visits) >= 6 * 10 and set(visits) <= set(range(8, 33)), sorted(set(visits))
+    # initGamesWithPolicy = true in the stock file: the games begin with policy-drawn moves that carry no search comment, and the record says how many
+    openings = []
+    for f in os.listdir(out / "tinynet" / "sgfs"):
+        for line in open(out / "tinynet" / "sgfs" / f):
+            start = int(re.search(r"startTurnIdx=(\d+)", line).group(1))
+            body = line[line.index("C[startTurnIdx"):]
+            nodes = body.split(";")[1:]
+            assert all("C[" not in nd for nd in nodes[:start]) and (len(nodes) == start or "C[" in nodes[start])
+            openings.append(start)
+    assert max(openings) > 0, openings
     cheap = sum(v == 8 for v in visits)
     assert 0.3 < cheap / len(visits) < 0.7 and 32 in visits, (cheap, len(visits))
     assert set(visits) <= {8} | set(range(12, 33))       # a full search, a cheap one, or one reduced towards reducedVisitsMin (formula: CPU test)
