@@ -404,6 +404,9 @@ def main(argv=None):
     ap.add_argument("-seed", type=int, default=0)
     ap.add_argument("-per-game-release", action="store_true", help="record and release every game as soon as its own search is finished "
                     "(GameRecorder.pump) instead of moving all games in lockstep")
+    ap.add_argument("-max-playouts-per-wave", type=int, default=4, help="playouts a game may finish inside one wave without needing the evaluator (cache hits, "
+                    "graph-search catch-ups); the wave lasts as long as its slowest game, so a small bound pays with trained nets "
+                    "(profiles/r02_trained_net_playouts_per_wave_sweep.log); results do not depend on it")
     ap.add_argument("-model-poll-seconds", type=float, default=20.0, help="how often the models directory is checked for a newer net")
     ap.add_argument("-nccl-weights", action="store_true", help="under torchrun: rank 0 alone polls and reads new nets, the packed weights reach the other GPUs by ncclBroadcast")
     ap.add_argument("-model-poll-waves", type=int, default=64, help="with -nccl-weights: recorder iterations between two (collective) polls")
@@ -430,7 +433,7 @@ def main(argv=None):
     ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
     h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
     max_visits = kw.pop("max_visits", 600)
-    sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, **kw)
+    sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, max_playouts_per_wave=a.max_playouts_per_wave, **kw)
     outputs = ModelOutputs(a.output_dir, data, L, writer_seed, TrainingDataWriter)
     outputs.switch_to(model_path)
     # board size, ko / suicide rule and komi of every game: drawn on the host like the reference's GameInitializer, applied by the device
@@ -528,7 +531,7 @@ def main(argv=None):
                 lm = NeuralNet.loadModelFile(new_path)
                 ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
                 h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
-                sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed + 7919 * (swaps + 1), debug_hold_at_max_visits=True, **kw)
+                sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed + 7919 * (swaps + 1), debug_hold_at_max_visits=True, max_playouts_per_wave=a.max_playouts_per_wave, **kw)
                 slots.start(sp)
                 written = rec.games_written
                 rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,

@@ -10,6 +10,7 @@ sys.path.insert(0, ROOT)
 from katago_b200 import NeuralNet, SelfPlay
 games = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 waves = int(sys.argv[2]) if len(sys.argv) > 2 else 1200
+mppw = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # max_playouts_per_wave (0 = 16)
 model = os.path.join(ROOT, "tests", "golden", "models", "g170-b6c96-s175395328-d26788732.bin.gz")
 lm = NeuralNet.loadModelFile(model)
 ctx = NeuralNet.createComputeContext([0], 19, 19, True, lm)
@@ -21,7 +22,7 @@ sp = SelfPlay(h, games, 600, komi=7.5, seed=1234, cpuct_exploration=1.05, cpuct_
               use_play_selection=True, use_lcb_for_selection=True, use_non_buggy_lcb=True, lcb_stdevs=5.0, min_visit_prop_for_lcb=0.15,
               chosen_move_temperature=0.15, chosen_move_temperature_early=0.75, static_score_utility_factor=0.05, dynamic_score_utility_factor=0.3,
               dynamic_score_center_zero_weight=0.25, dynamic_score_center_scale=0.5, ladder_nodes_per_wave=256, root_num_symmetries_to_sample=4,
-              full_history_rules=True, root_ending_bonus_points=0.5, root_prune_useless_moves=True)
+              full_history_rules=True, root_ending_bonus_points=0.5, root_prune_useless_moves=True, max_playouts_per_wave=mppw)
 sp.random_openings(150)
 sp.run(700); h.sync()
 import torch
@@ -44,4 +45,4 @@ print(json.dumps({"check": "trained_net_loop", "net": "g170-b6c96 (trained)", "b
                   "instant_playout_fraction": (s1["instant_playouts"] - s0["instant_playouts"]) / max(1, dv),
                   "stalled_game_waves_fraction": (s1["stalled_waves"] - s0["stalled_waves"]) / (waves * games),
                   "moves_played": s1["total_moves"] - s0["total_moves"], "games_finished": s1["games_finished"] - s0["games_finished"],
-                  "root_children_mean": float(np.mean(kids)), "ms_select": sel, "ms_backup": bak}))
+                  "max_playouts_per_wave": mppw, "root_children_mean": float(np.mean(kids)), "ms_select": sel, "ms_backup": bak}))
