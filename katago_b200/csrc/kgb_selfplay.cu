@@ -1379,7 +1379,16 @@ __global__ void rootNoiseTestKernel(float* pol, int policySize, int X, int Y, in
 // Search::recomputeNodeStats (searchupdatehelpers.cpp:167-360) for the parameter subset of the loop (no noise pruning, no root
 // noise subtraction, no subtree value bias, no uncertainty weights: the node's own evaluation has weight 1), one warp per node.
 // Children are visited in creation order and every sum is accumulated in that order (orderedAdd2), like the reference's loops.
+#ifdef KGB_PROFILE_DESCENT   // profiling build: cycles of the recompute's phases, accumulated per game (spBackupKernel zeroes the slots first)
+#define RPF(slot) do { const long long t_ = clock64(); if(lane == 0) d.dbgCycles[g * 8 + (slot)] += t_ - rpT; rpT = t_; } while(0)
+#else
+#define RPF(slot) do {} while(0)
+#endif
 __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePlaWhite, double* sh, int lane) {
+#ifdef KGB_PROFILE_DESCENT
+  long long rpT = clock64();
+  if(lane == 0) d.dbgCycles[g * 8 + 1] += 1;
+#endif
   const size_t gb = (size_t)g * d.maxNodes, gn = gb + node, nb = gn * d.policySize;
   const int nc = d.nodeNumChildren[gn];
   double WA[12], CU[12], CUSQ[12], CWS[12], CWSQ[12];   // weightAdjusted, child utilityAvg / utilitySqAvg / weightSum / weightSqSum
@@ -1404,6 +1413,7 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
       }
     }
   }
+  RPF(4);
   // (gathers first, without a barrier between the chunks: their dependent loads overlap; then the sums in the reference's order.
   // A child that is not `good` has WA = 0 and CU = 0, so its terms are exactly 0 as before.)
 #pragma unroll
@@ -1437,6 +1447,7 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
 #pragma unroll
     for(int ch = 0; ch < 12; ch++) WA[ch] *= factor;
   }
+  RPF(5);
   double utilitySum = 0.0, utilitySqSum = 0.0, weightSqSum = 0.0, unused = 0.0;
 #pragma unroll
   for(int ch = 0; ch < 12; ch++) {
@@ -1470,6 +1481,7 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
       }
     }
   }
+  RPF(6);
   double weightSum = origTotal;
   // the node's own evaluation, weight 1
   double utility = d.nodeNNUtil[gn];
@@ -1505,6 +1517,7 @@ __device__ void recomputeNodeStats(const SPDev& d, int g, int node, bool nodePla
     d.nodeVisits[gn] = d.nodeVisits[gn] + 1;
   }
   __syncwarp();
+  RPF(7);
 }
 
 // Search::getScoreUtility (searchhelpers.cpp:272-279)
@@ -1727,6 +1740,11 @@ __global__ void spBackupKernel(const SPDev d) {
   const int lane = threadIdx.x & 31;
   if(g >= d.numGames) return;
   if(!d.leafValid[g]) return;   // no leaf this wave (ladder searches still running, or every playout ended inside the select kernel)
+#ifdef KGB_PROFILE_DESCENT
+  const long long tBk0 = clock64();
+  if(lane == 0) { d.dbgCycles[g * 8 + 1] = 0; d.dbgCycles[g * 8 + 4] = 0; d.dbgCycles[g * 8 + 5] = 0; d.dbgCycles[g * 8 + 6] = 0; d.dbgCycles[g * 8 + 7] = 0; }
+  __syncwarp();
+#endif
   const size_t gb = (size_t)g * d.maxNodes;
   const int node = d.leafNode[g];
   const bool terminal = d.leafTerminal[g] != 0;
@@ -1878,7 +1896,13 @@ __global__ void spBackupKernel(const SPDev d) {
     u = utilityFromEval(d, g, node, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], lane);
   }
   __syncwarp();
+#ifdef KGB_PROFILE_DESCENT
+  const long long tBk1 = clock64();
+#endif
   finishPlayout(d, g, node, u, terminal, leafBlack, d.pathLen[g], shSum, lane);
+#ifdef KGB_PROFILE_DESCENT
+  if(lane == 0) { d.dbgCycles[g * 8 + 0] = clock64() - tBk0; d.dbgCycles[g * 8 + 2] = tBk1 - tBk0; d.dbgCycles[g * 8 + 3] = d.pathLen[g]; }   // whole warp, before the path update, path length
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
