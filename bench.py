@@ -240,7 +240,7 @@ class CountingSlots:
 
     def __getattr__(self, name):
         attr = getattr(self._sp, name)
-        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row", "komi_values", "game_setups"):
+        if name in ("game", "root_value_stats", "root_visits", "root_extra", "last_move", "play_selection_values", "root_children", "root_row", "komi_values", "game_setups", "root_raw_policy_entropy"):
             def counted(*a, **k):
                 out = attr(*a, **k)
                 self.d2h += _nbytes(out)

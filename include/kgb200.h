@@ -357,6 +357,10 @@ KGB_API int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* visits);
 /* What extractQValueTargets / computeNNRawStats (play.cpp:859-914) read besides the NodeStats: visits of the root's child NODES by
  * move position (0 = no child), and the root's own evaluation root_nn_stats[5] = winLoss, noResult, scoreMean, scoreMeanSq, lead (white). */
 KGB_API int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int game, int32_t* child_node_visits, double* root_nn_stats);
+/* entropy[num_games]: the entropy of every current root's policy as the net gave it (averaged over the root's symmetric evaluations), BEFORE the
+ * root policy temperature and the Dirichlet noise - NNRawStats::policyEntropy of computeNNRawStats (program/play.cpp:890-914; training global 59).
+ * The reference takes it from a fresh single-symmetry evaluation of the root; here it is the root's own evaluation. */
+KGB_API int kgb_selfplay_get_root_raw_policy_entropy(kgb_selfplay* sp, double* entropy);
 /* The last root move of slot `game`: info[4] = move position (X*Y = pass), flags (1 = it ended the game | 2 = without result | 4 = by
  * the move limit), the move number it was played at, the slot's game index.  If it ended the game: final_score = white minus black
  * with komi, final_colors[Y*X] and final_area[Y*X] (0 none, 1 black, 2 white; Board::calculateArea with every flag on, which under

@@ -65,6 +65,7 @@ struct SPDev {
   // policy-initialised openings (PlayUtils::initializeGameUsingPolicy, program/playutils.cpp:232-266): the first initMovesLeft moves of a game
   // are drawn from the net's raw policy ^ (1 / temperature) of the position (one evaluation per move, no search, never held for recording);
   // they are kept in initMoves for the game record.  nextInitMoves = the count for the slot's next game (the host draws it)
+  double* rootRawEntropy;           // [game] entropy of the current root's policy as evaluated, before temperature and noise (NNRawStats::policyEntropy, play.cpp:890-914)
   int *initMovesLeft, *nextInitMoves, *initMoveCount;
   int16_t* initMoves;               // [game][SP_MAX_INIT_MOVES] move positions of the current game's opening
   double* policyInitTemperature;    // [1] in device memory (the wave's kernel arguments are frozen in its CUDA graph)
@@ -1634,6 +1635,14 @@ __device__ double utilityFromEval(const SPDev& d, int g, int node, float whiteWi
 // Root policy temperature + Dirichlet noise on the root's first evaluation (searchnnhelpers.cpp:61-173).
 __device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane) {
   const size_t gb = (size_t)g * d.maxNodes;
+  if(node == 0 && d.nodeVisits[gb] == 0) {
+    // what computeNNRawStats records of the net's own opinion (play.cpp:890-914): the policy entropy BEFORE temperature and noise
+    const float* pol = d.policy + gb * d.policySize;
+    double e = 0.0;
+    for(int i = lane; i < d.policySize; i += 32) { const double p = (double)pol[i]; if(p > 1e-30) e -= p * log(p); }
+    e = warpSumD(e);
+    if(lane == 0) d.rootRawEntropy[g] = e;
+  }
   if(node == 0 && d.nodeVisits[gb] == 0 && !d.plainRoot[g] && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
     __syncwarp();
     if(lane == 0)
@@ -2263,6 +2272,7 @@ SelfplayImpl* selfplayCreate(const kgb_selfplay_config& c, int X, int Y, const S
     // every root gets the full budget and its root parameters unless the host says otherwise (kgb_selfplay_set_next_search_limits)
     d.visitBudget = sp->alloc<int>(G); d.nextBudget = sp->alloc<int>((size_t)G * 2);
     d.plainRoot = sp->alloc<uint8_t>(G); d.nextPlain = sp->alloc<uint8_t>((size_t)G * 2);
+    d.rootRawEntropy = sp->alloc<double>(G);
     d.initMovesLeft = sp->alloc<int>(G); d.nextInitMoves = sp->alloc<int>(G); d.initMoveCount = sp->alloc<int>(G);
     d.initMoves = sp->alloc<int16_t>((size_t)G * SP_MAX_INIT_MOVES);
     d.policyInitTemperature = sp->alloc<double>(1);
@@ -2634,6 +2644,9 @@ void selfplayReadPolicyInit(SelfplayImpl* sp, int* movesLeft, int* count, int16_
   }
 }
 
+void selfplayReadRootRawEntropy(SelfplayImpl* sp, double* out) {
+  SPCK(cudaMemcpy(out, sp->d.rootRawEntropy, (size_t)sp->d.numGames * sizeof(double), cudaMemcpyDeviceToHost));
+}
 void selfplayReadSearchLimits(SelfplayImpl* sp, int* visits, uint8_t* plain) {
   const SPDev& d = sp->d;
   if(visits) SPCK(cudaMemcpy(visits, d.visitBudget, (size_t)d.numGames * sizeof(int), cudaMemcpyDeviceToHost));

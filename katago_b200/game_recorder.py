@@ -310,8 +310,8 @@ class GameRecorder:
             value_targets=values,
             q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
             surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
-            # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy as searched
-            nn_raw_stats=(float(nn[0]), float(nn[2]), policy_entropy),
+            # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy before temperature and noise
+            nn_raw_stats=(float(nn[0]), float(nn[2]), float(sp.root_raw_policy_entropy()[g]) if hasattr(sp, "root_raw_policy_entropy") else policy_entropy),
             raw_nn_values=reported_search_values(nn)[:3]))       # Search::getRootRawNNValues: win, loss, noResult of the root's own evaluation
 
     def _after_move(self, g):

@@ -85,6 +85,7 @@ ABI_SYMBOLS = [
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
     "kgb_selfplay_set_game_setup", "kgb_selfplay_get_game_setup", "kgb_selfplay_play_moves_game",
     "kgb_selfplay_set_next_search_limits", "kgb_selfplay_get_search_limits", "kgb_selfplay_set_policy_init", "kgb_selfplay_get_policy_init",
+    "kgb_selfplay_get_root_raw_policy_entropy",
 ]
 
 _lib = None
@@ -136,6 +137,7 @@ def load_library():
     lib.kgb_selfplay_get_search_limits.argtypes = [P, P, P]
     lib.kgb_selfplay_set_policy_init.argtypes = [P, P, C.c_double, I]
     lib.kgb_selfplay_get_policy_init.argtypes = [P, P, P, P, I]
+    lib.kgb_selfplay_get_root_raw_policy_entropy.argtypes = [P, P]
     lib.kgb_selfplay_get_leaf_cache_key.argtypes = [P, I, P]
     lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
@@ -651,6 +653,12 @@ class SelfPlay:
             n = self.x * self.y
             moves = [[(-1, -1) if int(p) == n else (int(p) % self.x, int(p) // self.x) for p in mv[g, :min(int(cnt[g]), max_moves)]] for g in range(self.num_games)]
         return left, cnt, moves
+
+    def root_raw_policy_entropy(self):
+        """Entropy of every root's policy before temperature and noise (NNRawStats::policyEntropy)."""
+        e = np.zeros(self.num_games, np.float64)
+        _check(load_library().kgb_selfplay_get_root_raw_policy_entropy(self._p, e.ctypes.data))
+        return e
 
     def game_setups(self):
         """(setup [num_games, 4] of the games in progress, of each slot's last finished game)."""
