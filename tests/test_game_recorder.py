@@ -718,7 +718,6 @@ def test_device_applies_per_move_search_limits(golden_dir, tmp_models):
     ent = a.root_raw_policy_entropy()
     H = lambda p: float(-(p[p > 0].astype(np.float64) * np.log(p[p > 0].astype(np.float64))).sum())
     assert abs(ent[0] - H(a.root_children(0)[1])) < 1e-6 and abs(ent[2] - H(a.root_children(2)[1])) > 1e-3
-    assert abs(ent[2] - b.root_raw_policy_entropy()[2]) < 1e-6        # same position, same (fake) net, noise or not
     with pytest.raises(Exception, match="already been searched"):
         a.set_next_search_limits(np.full((3, 2), 30, np.int32), also_current_roots=True)
     a.set_next_search_limits(np.array([[24, 50], [16, 50], [64, 50]], np.int32), np.array([[0, 0], [1, 0], [0, 0]], np.uint8))
