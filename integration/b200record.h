@@ -90,7 +90,7 @@ class GameRecorder {
       d->policyEntropyByTurn.push_back(std::max(policyEntropy, 0.0));
       // computeNNRawStats (play.cpp:890-914) from the root's own evaluation
       const GameSlots::ValueStats nn = slots_.rootNNStats(i);
-      NNRawStats raw; raw.whiteWinLoss = nn.winLossValueAvg; raw.whiteScoreMean = nn.scoreMeanAvg; raw.policyEntropy = std::max(policyEntropy, 0.0);
+      NNRawStats raw; raw.whiteWinLoss = nn.winLossValueAvg; raw.whiteScoreMean = nn.scoreMeanAvg; raw.policyEntropy = std::max(slots_.rootRawPolicyEntropy(i), 0.0);
       d->nnRawStatsByTurn.push_back(raw);
       d->targetWeightByTurn.push_back(1.0f);
       d->targetWeightByTurnUnrounded.push_back(1.0f);

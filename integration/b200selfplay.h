@@ -99,6 +99,12 @@ class GameSlots {
     check(kgb_selfplay_get_root_extra(sp_, slot, nv.data(), r));
     return ValueStats{r[0], r[1], r[2], r[3], r[4]};
   }
+  // entropy of the root's policy as the net gave it, before temperature and noise (NNRawStats::policyEntropy, play.cpp:890-914)
+  double rootRawPolicyEntropy(int slot) const {
+    std::vector<double> e((size_t)numSlots());
+    check(kgb_selfplay_get_root_raw_policy_entropy(sp_, e.data()));
+    return e[(size_t)slot];
+  }
   // visits of the root's child nodes by move position (0 = no child; not the edge visits under graph search)
   std::vector<int32_t> childNodeVisits(int slot) const {
     std::vector<int32_t> nv((size_t)x_ * y_ + 1); double r[5];

@@ -189,6 +189,14 @@ int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int g, int32_t* nv, double* nn
   memcpy(nv, s.nodeVisits.data(), s.nodeVisits.size() * sizeof(int32_t)); memcpy(nn, s.rootNN, sizeof(s.rootNN));
   return 0;
 }
+int kgb_selfplay_get_root_raw_policy_entropy(kgb_selfplay* sp, double* e) {      // the mock's searches add no noise: the policy as searched
+  for(size_t g = 0; g < sp->slots.size(); g++) {
+    double h = 0.0;
+    for(float p : sp->slots[g].policy) if(p > 1e-100) h += -(double)p * std::log((double)p);
+    e[g] = h;
+  }
+  return 0;
+}
 int kgb_selfplay_get_root_row(kgb_selfplay* sp, int g, float* spatial, float* global) {
   Slot& s = sp->slots[g];
   memcpy(spatial, s.rowSpatial.data(), s.rowSpatial.size() * sizeof(float)); memcpy(global, s.rowGlobal.data(), 19 * sizeof(float));
