@@ -72,8 +72,8 @@ class GameInitializer:
             d = self.rand.gauss(0.0, 1.0)
         return d
 
-    def draw_komi(self, x_size, y_size):
-        """chooseExtraBlackAndKomi (no handicap) + setKomiWithNoise."""
+    def draw_komi(self, x_size, y_size, mean=None):
+        """chooseExtraBlackAndKomi (no handicap) + setKomiWithNoise.  mean: instead of komiMean (komiAuto: the fair komi of the empty board)."""
         r = self.rand
         stdev = self.komi_stdev if self.komi_stdev > 0 else 0.0
         if self.komi_big_stdev > 0 and r.random() < self.komi_big_stdev_prob:
@@ -82,7 +82,7 @@ class GameInitializer:
             stdev = self.komi_bigger_stdev
         stdev *= math.sqrt(x_size * y_size) / 19.0        # no massive komis on small boards
         allow_integer = r.random() < self.komi_allow_integer_prob
-        komi = self.komi_mean
+        komi = self.komi_mean if mean is None else float(mean)
         if stdev > 0:
             komi += stdev * self._gaussian_truncated(3.0)
         lower, upper = math.floor(komi * 2.0) / 2.0, math.ceil(komi * 2.0) / 2.0       # roundKomiWithLinearProb

@@ -218,7 +218,7 @@ class GameRecorder:
 
     def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None,
                  policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None,
-                 play_settings=None, limits_rand=None, policy_init=False):
+                 play_settings=None, limits_rand=None, policy_init=False, lead_estimator=None, estimate_lead_prob=0.0, lead_rand=None):
         """policy_surprise_data_weight / value_surprise_data_weight / use_search_value_surprise: PlaySettings of the same names - the
         finished game's target weights are redistributed by surprise (surprise_target_weights).  weight_rand (a RowRand): fractional
         weights are then resolved to integers like runGame does (resolve_target_weight); None leaves them fractional for the writer,
@@ -243,6 +243,13 @@ class GameRecorder:
         # search limits per move (cheap searches, reduced visits): the host draws what getSearchLimitsThisMove would, the device applies it
         # to the root after each slot's next move (SelfPlay.set_next_search_limits); cur_limits[g] = (target weight, is cheap) of slot g's root
         self.policy_init_active = bool(policy_init) and hasattr(sp, "policy_init")
+        # lead targets (play.cpp:2290-2324): after a game, turns drawn with estimateLeadProb get the komi-bisection searches of computeLead as
+        # jobs on a side loop (katago_b200/komi_search.py KomiSearcher); the game is written when they are back
+        self.lead, self.lead_prob = lead_estimator, float(estimate_lead_prob)
+        if self.lead is not None:
+            import random
+            self.lead_rand = lead_rand or random.Random(0x4C656164)
+        self.games_waiting_for_lead = 0
         ps = play_settings or {}
         self.play_settings = ps if (float(ps.get("cheap_search_prob", 0.0)) > 0.0 or ps.get("reduce_visits", False)) else None
         n = sp.num_games
@@ -415,9 +422,32 @@ class GameRecorder:
                 data.target_weight_by_turn_unrounded = list(data.target_weight_by_turn)
             data.target_weight_by_turn = [resolve_target_weight(w, self.weight_rand) for w in data.target_weight_by_turn]
         data.final_white_scoring = scoring_from_area(area)
+        self.games[g] = _GameInProgress()
+        if self.lead is not None and self.lead_prob > 0 and not data.end_no_result:
+            from .komi_search import compute_lead
+            turns = [t for t in range(len(gm.turns)) if float(data.target_weight_by_turn[t]) > 0 and float(data.white_value_targets_by_turn[t][2]) < 0.3 and
+                     self.lead_rand.random() < self.lead_prob]
+            if turns:
+                waiting = {"data": data, "slot": g, "left": len(turns)}
+                self.games_waiting_for_lead += 1
+                for t in turns:
+                    self.lead.submit(compute_lead(komi, X, Y), (X, Y, ko_rule, multi_suicide), list(data.start_moves) + list(data.moves[:t]),
+                                     lambda lead, t=t, w=waiting: self._lead_done(w, t, lead))
+                return
+        self._emit(g, data)
+
+    def _lead_done(self, waiting, t, lead):
+        data = waiting["data"]
+        v = data.white_value_targets_by_turn[t]
+        data.white_value_targets_by_turn[t] = (v[0], v[1], v[2], v[3], 1, _f32(lead))           # hasLead, lead (ValueTargets, trainingwrite.h)
+        waiting["left"] -= 1
+        if waiting["left"] == 0:
+            self.games_waiting_for_lead -= 1
+            self._emit(waiting["slot"], data)
+
+    def _emit(self, g, data):
         if self.writer is not None:
             self.writer.write_game(data)
         self.games_written += 1
         if self.on_game is not None:
             self.on_game(g, data)
-        self.games[g] = _GameInProgress()

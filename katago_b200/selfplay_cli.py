@@ -56,7 +56,7 @@ _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNN
 # neutral values: the option is switched off, so not having it changes nothing
 _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
             "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
-            "estimateLeadProb": 0.0, "switchNetsMidGame": False, "fancyKomiVarying": False,
+            "switchNetsMidGame": False, "fancyKomiVarying": False,
             "handicapProb": 0.0,
             "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
 _REFERENCE_DEFAULTS = {
@@ -158,11 +158,15 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     # that -strict refuses it.
     komi = float(cfg["komiMean"]) if "komiMean" in cfg else 7.5
     used.update(("komiMean", "komiAuto", "komiStdev", "komiBigStdevProb", "komiBigStdev", "komiBiggerStdevProb", "komiBiggerStdev", "komiAllowIntegerProb"))
-    if _B(cfg.get("komiAuto", "false")):
-        report["not_built"].append(f"komiAuto = true (komi drawn around {komi} instead of being adjusted to even by search)")
+    # komiAuto (fair komi of the empty board found by search, play.cpp:1563-1575) and lead targets (play.cpp:2290-2324): komi-bisection searches
+    # on a side loop (komi_search.py)
+    komi_search = dict(komi_auto=_B(cfg.get("komiAuto", "false")), compensate_komi_visits=int(cfg.get("compensateKomiVisits", 20)),
+                       estimate_lead_prob=float(cfg.get("estimateLeadProb", 0.0)), estimate_lead_visits=int(cfg.get("estimateLeadVisits", 6)))
+    used.update(("compensateKomiVisits", "estimateLeadProb", "estimateLeadVisits"))
     data = {"board_size": size, "komi": komi,
             "data_board_len": int(cfg.get("dataBoardLen", size)), "max_rows_per_train_file": int(cfg.get("maxRowsPerTrainFile", 20000)),
             "first_file_rand_min_prop": float(cfg.get("firstFileRandMinProp", 1.0)), "num_game_threads": int(cfg.get("numGameThreads", 256))}
+    data["komi_search"] = komi_search
     data["game_init"] = dict(sizes=sizes, size_probs=size_probs, ko_rules=kos, multi_stone_suicide_legals=suicides, komi_mean=komi,
                              komi_stdev=float(cfg.get("komiStdev", 0.0)), komi_big_stdev_prob=float(cfg.get("komiBigStdevProb", 0.0)),
                              komi_big_stdev=float(cfg.get("komiBigStdev", 10.0)), komi_bigger_stdev_prob=float(cfg.get("komiBiggerStdevProb", 0.0)),
@@ -215,8 +219,10 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
 class SlotSetups:
     """Host side of the per-game setup: draws from a GameInitializer and hands them to the loop (SelfPlay.set_game_setup / set_komi)."""
 
-    def __init__(self, init, num_games, policy_init=None):
+    def __init__(self, init, num_games, policy_init=None, fair_komi=None):
         self.init, self.n = init, num_games
+        self.fair_komi = fair_komi            # KomiSearcher for komiAuto, or None
+        self.serial = [0] * num_games
         self.policy_init = policy_init if policy_init and policy_init.get("enabled") and policy_init.get("area_prop", 0) > 0 else None
         self.setups, self.komis = init.draw_many(num_games)
         self.openings = self._openings(self.setups)
@@ -242,11 +248,32 @@ class SlotSetups:
         sp.set_komi(self.komis)
         if self.policy_init:
             sp.set_policy_init(self.openings, self.policy_init["temperature"])
+        if self.fair_komi is not None:
+            for slot in range(self.n):
+                self._ask_fair_komi(sp, slot)
+
+    def _ask_fair_komi(self, sp, slot):
+        """komiAuto: the komi at which the net calls the empty board of the slot's NEXT game even (makeGameFairForEmptyBoard, play.cpp:1563-1575)
+        becomes the mean the komi noise is drawn around.  Searched on the side loop while the slot's current game is played; the answer
+        replaces the komi handed over so far (drawn around komiMean) unless that game has started meanwhile."""
+        from .komi_search import adjust_komi_to_even
+        x, y, ko, suicide = (int(v) for v in self.setups[slot])
+        self.serial[slot] += 1
+        serial = self.serial[slot]
+
+        def done(fair):
+            if self.serial[slot] != serial:
+                return
+            self.komis[slot] = self.init.draw_komi(x, y, mean=fair)
+            sp.set_komi(self.komis)
+        self.fair_komi.submit(adjust_komi_to_even(self.init.komi_mean, x, y, self.init.rand), (x, y, ko, suicide), [], done)
 
     def redraw(self, sp, slot):
         x, y, ko, suicide, komi = self.init.draw()
         self.setups[slot] = (x, y, ko, suicide)
         self.komis[slot] = komi
+        if self.fair_komi is not None:
+            self._ask_fair_komi(sp, slot)
         sp.set_game_setup(self.setups)
         sp.set_komi(self.komis)
         if self.policy_init:
@@ -342,7 +369,7 @@ class ModelOutputs:
 class BackgroundStage:
     """Loads a model file and stages it into a live handle (ComputeHandle.stage_weights) on a side thread."""
 
-    def __init__(self, handle, path):
+    def __init__(self, handle, path, more_handles=()):
         import threading
         self.path, self.error = path, None
 
@@ -352,6 +379,8 @@ class BackgroundStage:
                 lm = NeuralNet.loadModelFile(path)
                 try:
                     handle.stage_weights(lm)
+                    for hx in more_handles:          # the side loops of the komi searches play the same net
+                        hx.stage_weights(lm)
                 finally:
                     lm.free()
             except Exception as e:      # reported by the loop
@@ -440,7 +469,32 @@ def main(argv=None):
     # when the slot's next game starts.  `slots` always holds what has been handed to the device for each slot's NEXT game.
     from .game_initializer import GameInitializer
     init = GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"])
-    slots = SlotSetups(init, games, data["policy_init"])
+    # komi-bisection searches (komiAuto, estimateLeadProb) run on side loops of their own (komi_search.KomiSearcher), one per visit count
+    from .komi_search import KomiSearcher
+    ks = data["komi_search"]
+    if a.nccl_weights and world > 1 and (ks["komi_auto"] or ks["estimate_lead_prob"] > 0):
+        raise ValueError("komiAuto / estimateLeadProb with -nccl-weights: the side loops' handles are not part of the weight broadcast yet")
+    aux = {"handles": [], "loops": [], "fair": None, "lead": None}
+
+    def make_aux(context, model, seed_offset):
+        """(fair-komi searcher, lead searcher) on fresh handles of `model`; the previous ones are dropped."""
+        for lp in aux["loops"]:
+            lp.free()
+        for hx in aux["handles"]:
+            hx.free()
+        aux.update(handles=[], loops=[], fair=None, lead=None)
+        side_kw = KomiSearcher.noiseless_kwargs(kw)
+        side_kw["max_moves"] = int(kw.get("max_moves", 0) or 2 * L * L) + 8
+        for name, want, visits in (("fair", ks["komi_auto"], ks["compensate_komi_visits"]), ("lead", ks["estimate_lead_prob"] > 0, ks["estimate_lead_visits"])):
+            if not want:
+                continue
+            n_side = max(4, min(32, games // 4))
+            hx = NeuralNet.createComputeHandle(context, model, n_side, False, True, gpu)
+            lp = SelfPlay(hx, n_side, max(2, visits), komi=data["komi"], seed=loop_seed + 104729 + seed_offset, debug_hold_at_max_visits=True, **side_kw)
+            aux["handles"].append(hx); aux["loops"].append(lp)
+            aux[name] = KomiSearcher(lp)
+    make_aux(ctx, lm, 0)
+    slots = SlotSetups(init, games, data["policy_init"], fair_komi=aux["fair"])
     slots.start(sp)
 
     def on_game(slot, finished):
@@ -450,7 +504,7 @@ def main(argv=None):
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                        use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"),
-                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
+                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
     # New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory every 20 s; :142-231 load the newest one).
     # Default: every rank polls and reads the file itself.  -nccl-weights: rank 0 polls, reads and packs; the packed weights reach
     # the other GPUs by the library's ncclBroadcast (dist_weights.WeightBroadcaster) - the poll is then a collective, every
@@ -477,6 +531,9 @@ def main(argv=None):
                     rec.pump(8)
                 else:
                     rec.step()
+            for searcher in (aux["fair"], aux["lead"]):       # the side loops advance with the main loop
+                if searcher is not None:
+                    searcher.step(8)
             iters += 1
             if wb is None:
                 # reading and packing a net takes the host ~0.1-0.2 s for a b18: done on a side thread (the library call releases the
@@ -484,7 +541,7 @@ def main(argv=None):
                 if stager is None:
                     p_ = poller.poll()
                     if p_ is not None:
-                        stager = BackgroundStage(h, p_)
+                        stager = BackgroundStage(h, p_, aux["handles"])
                     continue
                 if not stager.done():
                     continue
@@ -492,6 +549,8 @@ def main(argv=None):
                 if stager_error is None:
                     h.commit_weights()
                     sp.clear_nn_cache()
+                    for hx, lp in zip(aux["handles"], aux["loops"]):
+                        hx.commit_weights(); lp.clear_nn_cache()
                     swaps += 1
                     outputs.switch_to(new_path)
                     print(f"[model] now playing {outputs.model_name} (swap {swaps})", file=sys.stderr)
@@ -527,26 +586,39 @@ def main(argv=None):
                 # another architecture: the reference builds a new NNEvaluator for any net; here that means a new handle and loop, and
                 # the games in flight are dropped (their finished predecessors are already written)
                 print(f"[model] {new_path}: {e}; rebuilding the evaluator (games in progress are abandoned)", file=sys.stderr)
+                for lp in aux["loops"]:
+                    lp.free()
+                for hx in aux["handles"]:
+                    hx.free()
+                aux.update(handles=[], loops=[], fair=None, lead=None)
                 sp.free(); h.free(); ctx.free()
                 lm = NeuralNet.loadModelFile(new_path)
                 ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
                 h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
                 sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed + 7919 * (swaps + 1), debug_hold_at_max_visits=True, max_playouts_per_wave=a.max_playouts_per_wave, **kw)
+                make_aux(ctx, lm, swaps + 1)               # (lead jobs of games that ended under the old evaluator are dropped with it)
+                slots.fair_komi = aux["fair"]
                 slots.start(sp)
                 written = rec.games_written
                 rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                                    game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
                                    policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                                    use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"),
-                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
+                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
                 rec.games_written = written
             swaps += 1
             outputs.switch_to(new_path)
             print(f"[model] now playing {outputs.model_name} (swap {swaps})", file=sys.stderr)
     except KeyboardInterrupt:
         pass
+    if aux["lead"] is not None and rec.games_waiting_for_lead > 0:      # finished games whose lead searches are still running
+        aux["lead"].drain()
     outputs.close()
     print(f"{rec.games_written} games, {outputs.rows_total} rows -> {', '.join(outputs.dirs)}")
+    for lp in aux["loops"]:
+        lp.free()
+    for hx in aux["handles"]:
+        hx.free()
     sp.free(); h.free(); ctx.free()
     return 0
 

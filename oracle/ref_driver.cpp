@@ -26,6 +26,7 @@
 #include "dataio/numpywrite.h"
 #include "dataio/trainingwrite.h"
 #include "program/play.h"
+#include "program/playutils.h"
 #include "dataio/sgf.h"
 #include "program/setup.h"
 #include "core/config_parser.h"
@@ -1204,6 +1205,61 @@ static int cmdFeatStream(int argc, char** argv) {
   return 0;
 }
 
+// computelead MODELFILE X Y VISITS KOMI MOVES: PlayUtils::computeLead (program/playutils.cpp:612-660) of the position after MOVES at KOMI, one bot,
+// the driver's default search parameters (as in searchfake), no evaluation cache, symmetry 0 - the komi-bisection searches that
+// katago_b200/komi_search.py restates as jobs on a side loop.  Prints "lead <value>" and, for the same position,
+// "evenkomi <value>" = KOMI - lead.  With kgref_driver_b200 the evaluator is libkgb200 (GPU box).
+static int cmdComputeLead(int argc, char** argv) {
+  if(argc != 8) { cerr << "usage: computelead MODELFILE X Y VISITS KOMI MOVES" << endl; return 1; }
+  const string modelFile = argv[2];
+  const int X = atoi(argv[3]), Y = atoi(argv[4]), visits = atoi(argv[5]);
+  const float komi = (float)atof(argv[6]);
+  Board::initHash();
+  ScoreValue::initTables();
+  Logger logger(nullptr, false, false, false);
+  ConfigParser cfg;
+  NNEvaluator* nnEval = new NNEvaluator("lead", modelFile, "", &logger, 4, X, Y, true, true, -1, 8, false, "", enabled_t::False, 1,
+                                        vector<int>{0}, "seed", false, 0, true, cfg);
+  nnEval->spawnServerThreads();
+  SearchParams params;
+  params.maxVisits = 1000;
+  params.numThreads = 1;
+  params.cpuctExploration = 1.0; params.cpuctExplorationLog = 0.45; params.cpuctExplorationBase = 500;
+  params.fpuReductionMax = 0.2; params.rootFpuReductionMax = 0.1;
+  params.staticScoreUtilityFactor = 0.0; params.dynamicScoreUtilityFactor = 0.0;
+  params.valueWeightExponent = 0.0;
+  params.rootNoiseEnabled = true;            // computeLead switches the root noise off itself (getNoiselessParams)
+  params.rootEndingBonusPoints = 0.0; params.rootPruneUselessMoves = false; params.subtreeValueBiasFactor = 0.0; params.useGraphSearch = false;
+  params.useLcbForSelection = false; params.cpuctUtilityStdevScale = 0.0; params.useUncertainty = false; params.useNoisePruning = false;
+  Rules rules;
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.friendlyPassOk = false; rules.komi = komi;
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  {
+    std::istringstream in(argv[7]);
+    string tok;
+    while(in >> tok) {
+      Loc loc;
+      if(tok == "pass") loc = Board::PASS_LOC;
+      else { int x, y; if(sscanf(tok.c_str(), "%d,%d", &x, &y) != 2) { cerr << "bad move " << tok << endl; return 1; } loc = Location::getLoc(x, y, X); }
+      if(!hist.isLegal(board, loc, pla)) { cerr << "illegal move " << tok << endl; return 1; }
+      hist.makeBoardMoveAssumeLegal(board, loc, pla, NULL);
+      pla = getOpp(pla);
+    }
+  }
+  Search* bot = new Search(params, nnEval, &logger, "computelead");
+  OtherGameProperties props;
+  const float lead = PlayUtils::computeLead(bot, bot, board, hist, pla, visits, props);
+  cout << "lead " << Global::strprintf("%.9g", lead) << endl;
+  cout << "evenkomi " << Global::strprintf("%.9g", komi - lead) << endl;
+  delete bot;
+  delete nnEval;
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if(argc < 2) { cerr << "usage: kgref_driver <boardstream|...> ..." << endl; return 1; }
   string cmd = argv[1];
@@ -1222,6 +1278,7 @@ int main(int argc, char** argv) {
   if(cmd == "rungame") return cmdRunGame(argc, argv);
   if(cmd == "tinyfeatures") return cmdTinyFeatures(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
+  if(cmd == "computelead") return cmdComputeLead(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;
 }

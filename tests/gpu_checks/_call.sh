@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
-L=gpurun_out/r02_c26.log
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -12 > $L
-echo "== smoke" >> $L
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 >> $L
-cat $L | cut -c1-4000
+L=gpurun_out/r02_c27.log
+timeout 600 python -m pytest tests/test_komi_search.py -q -x -m gpu -s 2>&1 | tail -25 > $L
+timeout 600 python -m pytest tests/test_selfplay_cli.py -q -x -m gpu -k "fair_komi" 2>&1 | tail -30 >> $L
+cat $L | cut -c1-6000

@@ -1,0 +1,123 @@
+"""Komi-bisection searches (katago_b200/komi_search.py): PlayUtils::getNaiveEvenKomiHelper / adjustKomiToEven / computeLead as generators, and the
+side loop that runs them on the device."""
+import math
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from katago_b200.komi_search import KomiSearcher, adjust_komi_to_even, compute_lead, naive_even_komi
+
+
+def _run(gen, oracle):
+    asked = [gen.send(None)]
+    while True:
+        try:
+            asked.append(gen.send(oracle(asked[-1])))
+        except StopIteration as st:
+            return st.value, asked[:-1] if False else asked
+
+
+def test_generators_find_the_even_komi_of_a_synthetic_position():
+    """A position in which white's lead at komi k is k - 3.2 and the win/loss value a smooth function of it: the helpers converge on 3.2 with the
+    reference's sequence of queries (first the lead-sized shift, then the window around it), never asking a komi twice."""
+    oracle = lambda k, even=3.2: (k - even, math.tanh((k - even) / 4.0))
+    (even, _), asked = _run(naive_even_komi(7.5, 19, 19), oracle)
+    assert abs(even - 3.2) < 0.01 and asked[0] == 7.5 and asked[1] == 3.0 and len(asked) == len(set(asked)) <= 6, asked
+    assert all(a * 2 == round(a * 2) for a in asked)
+    fair, _ = _run(adjust_komi_to_even(7.5, 19, 19, random.Random(1)), oracle)
+    assert fair in (3.0, 3.5)
+    lead, _ = _run(compute_lead(7.5, 19, 19), oracle)
+    assert abs(lead - 4.3) < 0.01
+    lead, _ = _run(compute_lead(-40.0, 9, 9), oracle)
+    assert abs(lead + 43.2) < 0.01
+    # a hopeless position: the window grows to its limit (32 points) and the answer stays inside the komi clip range of the board
+    lead, asked = _run(compute_lead(7.5, 9, 9), lambda k: (k + 300.0, 1.0))
+    assert all(abs(a) <= 20 + 81 for a in asked) and lead > 30
+
+
+class _Loop:
+    """The part of SelfPlay the KomiSearcher drives, with a scripted evaluator: lead(komi) = komi - even(position)."""
+
+    def __init__(self, n):
+        self.num_games, self.x, self.y, self.max_visits = n, 9, 9, 6
+        self.moves = [[] for _ in range(n)]; self.komi = np.full(n, 7.5, np.float32); self.next_komi = self.komi.copy()
+        self.visits = np.zeros(n, np.int32); self.loads = 0
+
+    def set_game_setup(self, setups, also_current_games=False):
+        pass
+
+    def set_komi(self, komis, also_current_games=False):
+        self.next_komi = np.array(komis, np.float32)
+
+    def play_moves_game(self, g, moves):
+        for m in moves:
+            self.moves[g].append(m)
+            if len(self.moves[g]) >= 2 and self.moves[g][-1] is None and self.moves[g][-2] is None:      # two passes: next game, next komi
+                self.moves[g] = []; self.komi[g] = self.next_komi[g]
+        self.visits[g] = 0; self.loads += 1
+
+    def game(self, g):
+        return None, dict(move_num=len(self.moves[g]))
+
+    def run(self, waves):
+        self.visits = np.minimum(self.visits + waves, self.max_visits)
+
+    def root_visits(self):
+        return self.visits.copy()
+
+    def root_value_stats(self, g):
+        even = 2.0 + len(self.moves[g])          # the "position" is its number of moves
+        lead = float(self.komi[g]) - even
+        return None, np.array([math.tanh(lead / 3.0), 0.0, lead, lead * lead, lead])
+
+
+def test_komi_searcher_schedules_jobs_over_its_slots():
+    loop = _Loop(3)
+    ks = KomiSearcher(loop)
+    got = {}
+    for i in range(7):                          # more jobs than slots
+        ks.submit(compute_lead(7.5, 9, 9), (9, 9, 0, 1), [(k % 9, k // 9) for k in range(i)], lambda v, i=i: got.__setitem__(i, v))
+    assert ks.pending() == 7 and len(ks.running) == 3
+    ks.drain()
+    assert ks.pending() == 0 and sorted(got) == list(range(7))
+    for i, v in got.items():
+        assert abs(v - (7.5 - (2.0 + i))) < 0.05, (i, v)
+
+
+REAL_NET_DRIVER = os.path.join(ROOT, "oracle", "_ref", "kgref_driver_b200")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REAL_NET_DRIVER), reason="oracle/_ref/kgref_driver_b200 not built (needs the reference sources at build time)")
+@pytest.mark.parametrize("stream,size,prefix_len,komi,visits", [("boardstream_9x9_multisuicide.npz", 9, 12, 7.5, 6), ("boardstream_9x9_multisuicide.npz", 9, 31, 0.5, 10),
+                                                               ("boardstream_19x19_multisuicide.npz", 19, 40, 7.5, 6)])
+def test_lead_of_a_position_equals_the_reference_computeLead(golden_dir, stream, size, prefix_len, komi, visits):
+    """PlayUtils::computeLead of the UNMODIFIED reference (its Search + NNEvaluator on libkgb200, fp32-equivalent, trained g170-b6c96 net,
+    symmetry 0, no cache) against the same computation as jobs on the device's side loop: the same komis are searched with the same few
+    visits, so the interpolated lead agrees to the evaluator's rounding."""
+    sys.path.insert(0, golden_dir)
+    import make_search_fixtures as F
+    from katago_b200 import NeuralNet, SelfPlay
+    model = os.path.join(golden_dir, "models", "g170-b6c96-s175395328-d26788732.bin.gz")
+    moves = F.prefix_from_stream(stream, prefix_len)
+    s = " ".join("pass" if m is None else f"{m[0]},{m[1]}" for m in moves)
+    out = subprocess.run([REAL_NET_DRIVER, "computelead", model, str(size), str(size), str(visits), repr(komi), s], capture_output=True, text=True, check=True).stdout
+    ref = float([ln.split()[1] for ln in out.splitlines() if ln.startswith("lead ")][0])
+    lm = NeuralNet.loadModelFile(model)
+    ctx = NeuralNet.createComputeContext([0], size, size, False, lm)
+    h = NeuralNet.createComputeHandle(ctx, lm, 4, False, True, 0)
+    kw = KomiSearcher.noiseless_kwargs(dict(cpuct_exploration=1.0, cpuct_exploration_log=0.45, cpuct_exploration_base=500.0, fpu_reduction_max=0.2, root_fpu_reduction_max=0.1))
+    sp = SelfPlay(h, 4, visits, komi=7.5, multi_stone_suicide_legal=True, seed=1, debug_hold_at_max_visits=True, debug_fixed_symmetry=0, full_history_rules=True, **kw)
+    ks = KomiSearcher(sp)
+    got = []
+    ks.submit(compute_lead(komi, size, size), (size, size, 0, 1), moves, got.append)
+    ks.drain()
+    print(f"{size}x{size} after {len(moves)} moves at komi {komi}, {visits} visits per search, {ks.searches} searches: lead {got[0]:.4f} (reference {ref:.4f})")
+    assert abs(got[0] - ref) < 0.02, (got, ref)
+    sp.free(); h.free(); ctx.free()

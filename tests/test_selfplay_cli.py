@@ -253,6 +253,38 @@ def test_command_plays_cheap_and_reduced_searches(tmp_path, stock_cfg):
 
 
 @pytest.mark.gpu
+def test_command_searches_fair_komi_and_lead_targets(tmp_path, stock_cfg, golden_dir):
+    """komiAuto and estimateLeadProb through the command, with the trained g170 net on small boards: the komi of a game is drawn around the
+    komi the net calls even for ITS empty board (found by the bisection searches of the side loop) instead of komiMean, and about half of the
+    recorded rows carry a lead target (global target 21 with weight 29) from computeLead."""
+    import shutil
+    models = tmp_path / "models"; models.mkdir()
+    shutil.copy(os.path.join(golden_dir, "models", "g170-b6c96-s175395328-d26788732.bin.gz"), models / "g170.bin.gz")
+    settings = dict(STOCK_B18_SETTINGS, bSizes="7,9", bSizeRelProbs="1,1", allowRectangleProb="0", dataBoardLen="9", koRules="SIMPLE", multiStoneSuicideLegals="true",
+                    komiAuto="true", komiStdev="0.0", maxVisits="20", maxMovesPerGame="30", rootNumSymmetriesToSample="2", nnCacheSizePowerOfTwo="10",
+                    maxRowsPerTrainFile="100000", firstFileRandMinProp="1.0", cheapSearchProb="0", reduceVisits="false", initGamesWithPolicy="false",
+                    estimateLeadProb="0.5", estimateLeadVisits="4", compensateKomiVisits="6", policySurpriseDataWeight="0", valueSurpriseDataWeight="0")
+    cfg = tmp_path / "komi.cfg"
+    cfg.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
+    out = tmp_path / "out"
+    rc = C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", str(cfg), "-max-games-total", "16", "-games-per-gpu", "8", "-per-game-release"])
+    assert rc == 0
+    komi_by_size, lead_rows, rows = {}, 0, 0
+    for f in os.listdir(out / "g170" / "tdata"):
+        with np.load(out / "g170" / "tdata" / f) as z:
+            planes = np.unpackbits(z["binaryInputNCHWPacked"], axis=2)[:, :, :81].reshape(-1, 22, 9, 9)
+            gin, gt = z["globalInputNC"], z["globalTargetsNC"]
+            for on, gi, g in zip(planes[:, 0], gin, gt):
+                rows += 1
+                lead_rows += int(g[29] > 0)
+                komi_by_size.setdefault(int(on.sum()), set()).add(round(abs(float(gi[5])) * 20.0, 1))
+    assert rows >= 16 * 10 and 0.25 < lead_rows / rows < 0.75, (lead_rows, rows)
+    # the fair komi of the empty 7x7 board is not the fair komi of the empty 9x9 board (and neither is komiMean's 7.5 by construction)
+    assert set(komi_by_size) == {49, 81} and komi_by_size[49] != komi_by_size[81], komi_by_size
+    assert all(len(v) <= 3 for v in komi_by_size.values()), komi_by_size       # no komi noise configured: the linear rounding of one fair value (+ the first games)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("new_cfg", ["tiny_reg", "tiny_nbt"])
 def test_command_moves_to_a_newer_net_while_games_run(tmp_path, stock_cfg, monkeypatch, new_cfg):
     """Model polling (command/selfplay.cpp:336-352): a newer file in the models directory is picked up while games are running.  Same
