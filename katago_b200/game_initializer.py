@@ -14,7 +14,8 @@ Restates, for the options the device loop has, `GameInitializer::initShared` / `
 The draws go to the device loop through `SelfPlay.set_game_setup` / `set_komi` (include/kgb200.h), one per slot, and take effect when
 the slot's next game starts.  The reference seeds its GameInitializer from the clock (command/selfplay.cpp:94), so there is no stream to
 reproduce: this class uses Python's Mersenne Twister, the distributions are the reference's.
-Not built (the caller reports them): handicap stones (`handicapProb`), `komiAuto` / makeGameFair, start positions, scoring / tax /
+`komiAuto` replaces komiMean by the fair komi of the game's empty board (katago_b200/komi_search.py; `draw_komi(mean=...)`).
+Not built (the caller reports them): handicap stones (`handicapProb`), makeGameFair for forks / handicap, start positions, scoring / tax /
 button rules other than area scoring without tax and button."""
 import math
 import random

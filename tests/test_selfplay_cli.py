@@ -50,6 +50,7 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert kw["root_policy_temperature_early"] == 1.5 and kw["chosen_move_temperature_halflife"] == 19.0 and kw["nn_cache_size_power_of_two"] == 24
     assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
     gi = data.pop("game_init")
+    ks = data.pop("komi_search")
     ps = data.pop("play_settings")
     assert data.pop("policy_init") == {"enabled": True, "area_prop": 0.08, "temperature": 1.0}
     assert ps["cheap_search_prob"] == 0.75 and ps["cheap_search_visits"] == 350 and ps["cheap_search_target_weight"] == 0.0 and ps["reduce_visits"] is True
@@ -73,8 +74,9 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert "komiStdev" not in nb
     assert "cheapSearchProb" not in nb and "reduceVisits" not in nb        # built: drawn by the recorder, applied by the device
     assert "initGamesWithPolicy" not in nb and "policyInitAreaProp" not in nb
-    for key in ("forkGameProb", "estimateLeadProb", "handicapProb",
-                "komiAuto"):
+    assert "komiAuto" not in nb and "estimateLeadProb" not in nb             # built: komi-bisection searches on a side loop (komi_search.py)
+    assert ks == {"komi_auto": True, "compensate_komi_visits": 20, "estimate_lead_prob": 0.5, "estimate_lead_visits": 6}
+    for key in ("forkGameProb", "handicapProb"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
     assert not any(k in nb for k in ("maxVisits", "cpuctExploration", "koRules", "dataBoardLen"))
@@ -106,11 +108,11 @@ def test_list_valued_keys_are_drawn_per_game_like_the_reference():
     assert data["board_size"] == 13 and data["data_board_len"] == 13 and [s_ for s_ in data["game_init"]["sizes"]] == [(9, 9), (13, 13)]
     with pytest.raises(ValueError, match="entries"):
         C.selfplay_kwargs_from_cfg(C.parse_cfg("bSizes = 9,13\nbSizeRelProbs = 1\n", is_text=True))
-    # komiAuto asks for a search-adjusted komi that is not built: reported, and refused under -strict
-    _, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("komiAuto = true\n", is_text=True))
-    assert data["komi"] == 7.5 and any(s_.startswith("komiAuto") for s_ in report["not_built"])
-    _, _, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("komiAuto = false\nkomiMean = 6.5\n", is_text=True))
-    assert not any(s_.startswith("komiAuto") for s_ in report["not_built"])
+    # komiAuto: the komi noise is drawn around the fair komi of the empty board, found by search on the side loop; komiMean is where that search starts
+    _, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("komiAuto = true\n", is_text=True), strict=True)
+    assert data["komi"] == 7.5 and data["komi_search"]["komi_auto"] is True and report["not_built"] == []
+    _, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg("komiAuto = false\nkomiMean = 6.5\n", is_text=True))
+    assert data["komi_search"]["komi_auto"] is False and data["komi"] == 6.5
 
 
 def test_neutral_values_and_unsupported_rules():
