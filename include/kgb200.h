@@ -357,6 +357,11 @@ KGB_API int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* visits);
 /* What extractQValueTargets / computeNNRawStats (play.cpp:859-914) read besides the NodeStats: visits of the root's child NODES by
  * move position (0 = no child), and the root's own evaluation root_nn_stats[5] = winLoss, noResult, scoreMean, scoreMeanSq, lead (white). */
 KGB_API int kgb_selfplay_get_root_extra(kgb_selfplay* sp, int game, int32_t* child_node_visits, double* root_nn_stats);
+/* symmetries[num_games]: the symmetry (0-7) under which each game's row of the LAST wave was evaluated.  The wave is the loop's batcher (row a9:
+ * one row per game, NNEvaluator::serve's batching replaced by the fixed wave); like the reference with nnRandomize = true every row draws its
+ * own symmetry (nneval.cpp:698-707) - here from splitmix64 of (seed, game, game index, move, root visits) - except for a root's sampled
+ * symmetries (root_num_symmetries_to_sample) and debug_fixed_symmetry. */
+KGB_API int kgb_selfplay_get_nn_symmetries(kgb_selfplay* sp, int32_t* symmetries);
 /* entropy[num_games]: the entropy of every current root's policy as the net gave it (averaged over the root's symmetric evaluations), BEFORE the
  * root policy temperature and the Dirichlet noise - NNRawStats::policyEntropy of computeNNRawStats (program/play.cpp:890-914; training global 59).
  * The reference takes it from a fresh single-symmetry evaluation of the root; here it is the root's own evaluation. */

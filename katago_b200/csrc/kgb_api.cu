@@ -1445,6 +1445,15 @@ KGB_API int kgb_selfplay_get_policy_init(kgb_selfplay* sp, int32_t* moves_left, 
   });
 }
 
+KGB_API int kgb_selfplay_get_nn_symmetries(kgb_selfplay* sp, int32_t* symmetries) {
+  return guarded([&] {
+    if(!sp || !symmetries) throw std::invalid_argument("kgb_selfplay_get_nn_symmetries: NULL argument");
+    CK(cudaSetDevice(sp->h->device));
+    CK(cudaStreamSynchronize(sp->h->stream));
+    selfplayReadSymmetries(sp->impl, symmetries);
+  });
+}
+
 KGB_API int kgb_selfplay_get_root_raw_policy_entropy(kgb_selfplay* sp, double* entropy) {
   return guarded([&] {
     if(!sp || !entropy) throw std::invalid_argument("kgb_selfplay_get_root_raw_policy_entropy: NULL argument");

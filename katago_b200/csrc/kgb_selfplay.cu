@@ -2644,6 +2644,9 @@ void selfplayReadPolicyInit(SelfplayImpl* sp, int* movesLeft, int* count, int16_
   }
 }
 
+void selfplayReadSymmetries(SelfplayImpl* sp, int* out) {
+  SPCK(cudaMemcpy(out, sp->d.nnSymmetry, (size_t)sp->d.numGames * sizeof(int), cudaMemcpyDeviceToHost));
+}
 void selfplayReadRootRawEntropy(SelfplayImpl* sp, double* out) {
   SPCK(cudaMemcpy(out, sp->d.rootRawEntropy, (size_t)sp->d.numGames * sizeof(double), cudaMemcpyDeviceToHost));
 }

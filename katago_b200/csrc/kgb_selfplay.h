@@ -29,6 +29,7 @@ void selfplayReadGameSetup(SelfplayImpl* sp, int* current, int* lastFinished);
 void selfplaySetNextSearchLimits(SelfplayImpl* sp, const int* visits, const uint8_t* plain, bool alsoCurrent, cudaStream_t s);
 void selfplayReadSearchLimits(SelfplayImpl* sp, int* visits, uint8_t* plain);
 void selfplayReadRootRawEntropy(SelfplayImpl* sp, double* out);
+void selfplayReadSymmetries(SelfplayImpl* sp, int* out);
 void selfplaySetPolicyInit(SelfplayImpl* sp, const int* moves, double temperature, bool alsoCurrent, cudaStream_t s);
 void selfplayReadPolicyInit(SelfplayImpl* sp, int* movesLeft, int* count, int16_t* moves, int maxMoves);
 void selfplayLaunchSelect(SelfplayImpl* sp, cudaStream_t s);

@@ -85,7 +85,7 @@ ABI_SYMBOLS = [
     "kgb_selfplay_debug_cycles", "kgb_selfplay_release", "kgb_selfplay_get_root_visits", "kgb_selfplay_get_root_extra", "kgb_selfplay_get_last_move",
     "kgb_selfplay_set_game_setup", "kgb_selfplay_get_game_setup", "kgb_selfplay_play_moves_game",
     "kgb_selfplay_set_next_search_limits", "kgb_selfplay_get_search_limits", "kgb_selfplay_set_policy_init", "kgb_selfplay_get_policy_init",
-    "kgb_selfplay_get_root_raw_policy_entropy",
+    "kgb_selfplay_get_root_raw_policy_entropy", "kgb_selfplay_get_nn_symmetries",
 ]
 
 _lib = None
@@ -138,6 +138,7 @@ def load_library():
     lib.kgb_selfplay_set_policy_init.argtypes = [P, P, C.c_double, I]
     lib.kgb_selfplay_get_policy_init.argtypes = [P, P, P, P, I]
     lib.kgb_selfplay_get_root_raw_policy_entropy.argtypes = [P, P]
+    lib.kgb_selfplay_get_nn_symmetries.argtypes = [P, P]
     lib.kgb_selfplay_get_leaf_cache_key.argtypes = [P, I, P]
     lib.kgb_forward.argtypes = [P, I, P, P, P, P, P, P, P, P]
     lib.kgb_forward_device.argtypes = [P, I, P, P, P, P, P, P, P, P]
@@ -653,6 +654,12 @@ class SelfPlay:
             n = self.x * self.y
             moves = [[(-1, -1) if int(p) == n else (int(p) % self.x, int(p) // self.x) for p in mv[g, :min(int(cnt[g]), max_moves)]] for g in range(self.num_games)]
         return left, cnt, moves
+
+    def nn_symmetries(self):
+        """Symmetry (0-7) of every game's row in the last wave (kgb_selfplay_get_nn_symmetries)."""
+        a = np.zeros(self.num_games, np.int32)
+        _check(load_library().kgb_selfplay_get_nn_symmetries(self._p, a.ctypes.data))
+        return a
 
     def root_raw_policy_entropy(self):
         """Entropy of every root's policy before temperature and noise (NNRawStats::policyEntropy)."""

@@ -56,7 +56,7 @@ _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNN
 # neutral values: the option is switched off, so not having it changes nothing
 _NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
             "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
-            "switchNetsMidGame": False, "fancyKomiVarying": False,
+            "switchNetsMidGame": True, "fancyKomiVarying": False,
             "handicapProb": 0.0,
             "drawRandRadius": 0.0, "noResultStdev": 0.0, "compensateAfterPolicyInitProb": 0.0}
 _REFERENCE_DEFAULTS = {
@@ -445,6 +445,11 @@ def main(argv=None):
         k, v = kv.split("=", 1)
         cfg[k.strip()] = v.strip()
     kw, data, report = selfplay_kwargs_from_cfg(cfg, strict=a.strict)
+    import time
+    log = lambda msg: print(msg, file=sys.stderr, flush=True)          # the reference's own log lines (command/selfplay.cpp, program/selfplaymanager.cpp)
+    log("Self Play Engine starting...")
+    t_start = time.time()
+    log_games_every = int(cfg.get("logGamesEvery", 50))
     for line in report["fixed"]:
         print("[config] " + line, file=sys.stderr)
     if report["not_built"]:
@@ -465,6 +470,9 @@ def main(argv=None):
     sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed, debug_hold_at_max_visits=True, max_playouts_per_wave=a.max_playouts_per_wave, **kw)
     outputs = ModelOutputs(a.output_dir, data, L, writer_seed, TrainingDataWriter)
     outputs.switch_to(model_path)
+    log(f"Found new neural net {outputs.model_name}")
+    log(f"Loaded latest neural net {outputs.model_name} from: {model_path}")
+    log("Loaded all config stuff, starting self play")
     # board size, ko / suicide rule and komi of every game: drawn on the host like the reference's GameInitializer, applied by the device
     # when the slot's next game starts.  `slots` always holds what has been handed to the device for each slot's NEXT game.
     from .game_initializer import GameInitializer
@@ -497,8 +505,28 @@ def main(argv=None):
     slots = SlotSetups(init, games, data["policy_init"], fair_komi=aux["fair"])
     slots.start(sp)
 
+    counts = {"started": games, "finished": 0, "moves": 0}
+
+    def log_stats():
+        """SelfplayManager::countOneGameStarted's periodic block (selfplaymanager.cpp:290-303), from the device counters."""
+        st = sp.stats()
+        log(f"Games finished: {counts['finished']}")
+        log(f"Moves played: {st['total_moves']}")
+        log(f"Data rows: {outputs.rows_total + (outputs.writer.row_count if outputs.writer is not None else 0)}")
+        rows_nn = st["total_visits"] - st["nn_cache_hits"] - st["instant_playouts"]
+        log(f"NN rows: {rows_nn}")
+        log(f"NN batches: {max(1, rows_nn // max(1, games))}")
+        log(f"NN avg batch size: {float(games)}")
+        log(f"NN cache hits: {st['nn_cache_hits']}")
+
     def on_game(slot, finished):
         outputs.add_game(slot, finished)
+        counts["finished"] += 1
+        counts["started"] += 1          # the slot's next game started on the device when this one ended
+        if counts["started"] % log_games_every == 0:
+            log(f"Started {counts['started']} games with {outputs.model_name}")
+        if counts["started"] % max(1000, log_games_every * 100) == 0:
+            log_stats()
         slots.redraw(sp, slot)           # the slot's new game has taken the values drawn before; draw the ones for the game after it
     rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
@@ -553,7 +581,7 @@ def main(argv=None):
                         hx.commit_weights(); lp.clear_nn_cache()
                     swaps += 1
                     outputs.switch_to(new_path)
-                    print(f"[model] now playing {outputs.model_name} (swap {swaps})", file=sys.stderr)
+                    log(f"Model loading loop thread loaded new neural net {outputs.model_name}"); log(f"Game loop changing midgame to new neural net: {outputs.model_name} (swap {swaps})")
                     continue
             elif iters % a.model_poll_waves == 0 or done:
                 # collective: [all ranks done?] and rank 0's verdict on the models directory
@@ -608,12 +636,16 @@ def main(argv=None):
                 rec.games_written = written
             swaps += 1
             outputs.switch_to(new_path)
-            print(f"[model] now playing {outputs.model_name} (swap {swaps})", file=sys.stderr)
+            log(f"Model loading loop thread loaded new neural net {outputs.model_name}"); log(f"Game loop changing midgame to new neural net: {outputs.model_name} (swap {swaps})")
     except KeyboardInterrupt:
         pass
     if aux["lead"] is not None and rec.games_waiting_for_lead > 0:      # finished games whose lead searches are still running
         aux["lead"].drain()
     outputs.close()
+    log_stats()
+    log(f"Total games: {counts['started']}")
+    log(f"Total selfplay runtime (seconds): {time.time() - t_start}")
+    log("All cleaned up, quitting")
     print(f"{rec.games_written} games, {outputs.rows_total} rows -> {', '.join(outputs.dirs)}")
     for lp in aux["loops"]:
         lp.free()

@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
-L=gpurun_out/r02_c27.log
-timeout 600 python -m pytest tests/test_komi_search.py -q -x -m gpu -s 2>&1 | tail -25 > $L
-timeout 600 python -m pytest tests/test_selfplay_cli.py -q -x -m gpu -k "fair_komi" 2>&1 | tail -30 >> $L
-cat $L | cut -c1-6000
+L=gpurun_out/r02_c28.log
+timeout 900 python tests/gpu_checks/soak_cli.py 48 64 > gpurun_out/r02_soak_cli_stdout.log 2> gpurun_out/r02_soak_cli_stderr.log
+tail -2 gpurun_out/r02_soak_cli_stdout.log > $L
+tail -5 gpurun_out/r02_soak_cli_stderr.log | cut -c1-600 >> $L
+cat $L | cut -c1-4000
