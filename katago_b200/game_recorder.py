@@ -200,7 +200,9 @@ class _GameInProgress:
         self.boards = []      # position before each move
         self.setup = None     # (board X, board Y, ko rule, multi-stone suicide legal) of this game, read when its first turn is recorded
         self.win_loss = []    # the root's winLossValue after each search (historicalMctsWinLossValues of Play::runGame)
-        self.start_moves = [] # moves before the first recorded turn (policy-initialised opening)
+        self.start_moves = [] # moves before the first recorded turn (fork prefix + policy-initialised opening)
+        self.preset_moves = []   # moves the host played into the slot before the game's first search (a forked game's position)
+        self.mode = 0            # FinishedGameData::mode: 0 normal, 2 fork
 
 
 class GameRecorder:
@@ -218,7 +220,7 @@ class GameRecorder:
 
     def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None,
                  policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None,
-                 play_settings=None, limits_rand=None, policy_init=False, lead_estimator=None, estimate_lead_prob=0.0, lead_rand=None):
+                 play_settings=None, limits_rand=None, policy_init=False, lead_estimator=None, estimate_lead_prob=0.0, lead_rand=None, on_game_start=None):
         """policy_surprise_data_weight / value_surprise_data_weight / use_search_value_surprise: PlaySettings of the same names - the
         finished game's target weights are redistributed by surprise (surprise_target_weights).  weight_rand (a RowRand): fractional
         weights are then resolved to integers like runGame does (resolve_target_weight); None leaves them fractional for the writer,
@@ -250,6 +252,7 @@ class GameRecorder:
             import random
             self.lead_rand = lead_rand or random.Random(0x4C656164)
         self.games_waiting_for_lead = 0
+        self.on_game_start = on_game_start         # called with the slot when its next game has begun on the device (before any of its turns is recorded)
         ps = play_settings or {}
         self.play_settings = ps if (float(ps.get("cheap_search_prob", 0.0)) > 0.0 or ps.get("reduce_visits", False)) else None
         n = sp.num_games
@@ -296,8 +299,10 @@ class GameRecorder:
             # board size and rules are per game (SelfPlay.set_game_setup; GameInitializer draws them per game): X, Y below stay the
             # evaluator's frame = the data frame (dataBoardLen) the rows are written in, the game's own board is its top-left corner
             gm.setup = tuple(int(v) for v in sp.game_setups()[0][g]) if hasattr(sp, "game_setups") else self.default_setup
+            gm.start_moves = list(gm.preset_moves)
             if self.policy_init_active:      # the opening the device drew from the policy: the game's start history (startHist)
-                gm.start_moves = sp.policy_init(max_moves=512)[2][g]
+                gm.start_moves = gm.start_moves + sp.policy_init(max_moves=512)[2][g]
+            if self.policy_init_active or gm.preset_moves:
                 if len(gm.start_moves) != info["move_num"]:
                     raise RuntimeError(f"GameRecorder: slot {g}: {info['move_num']} moves played before the first searched move, {len(gm.start_moves)} opening moves kept")
         bx, by = gm.setup[0], gm.setup[1]
@@ -422,7 +427,10 @@ class GameRecorder:
                 data.target_weight_by_turn_unrounded = list(data.target_weight_by_turn)
             data.target_weight_by_turn = [resolve_target_weight(w, self.weight_rand) for w in data.target_weight_by_turn]
         data.final_white_scoring = scoring_from_area(area)
+        data.mode = gm.mode
         self.games[g] = _GameInProgress()
+        if self.on_game_start is not None:
+            self.on_game_start(g)
         if self.lead is not None and self.lead_prob > 0 and not data.end_no_result:
             from .komi_search import compute_lead
             turns = [t for t in range(len(gm.turns)) if float(data.target_weight_by_turn[t]) > 0 and float(data.white_value_targets_by_turn[t][2]) < 0.3 and
@@ -435,6 +443,11 @@ class GameRecorder:
                                      lambda lead, t=t, w=waiting: self._lead_done(w, t, lead))
                 return
         self._emit(g, data)
+
+    def start_from(self, g, moves, mode=2):
+        """The slot's game that has just begun starts from `moves` (already played into the device slot by the caller): a forked game."""
+        self.games[g].preset_moves = [tuple(m) for m in moves]
+        self.games[g].mode = mode
 
     def _lead_done(self, waiting, t, lead):
         data = waiting["data"]

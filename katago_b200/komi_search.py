@@ -138,14 +138,17 @@ class KomiSearcher:
         return out
 
     def submit(self, gen, setup, moves, on_done):
-        self.queue.append([gen, tuple(int(v) for v in setup), [None if (m is None or m[0] < 0) else (int(m[0]), int(m[1])) for m in moves], on_done])
+        self.queue.append([gen, tuple(int(v) for v in setup), list(moves), on_done, None, None])
         self._dispatch()
 
     def pending(self):
         return len(self.queue) + len(self.running)
 
-    def _load(self, slot, job, komi):
-        """Slot <- the job's position at `komi`: end the slot's game (its next game takes the setup and komi set here), replay the moves."""
+    def _load(self, slot, job, query):
+        """Slot <- the job's position at the komi it asks for - or, for a query {"moves": ..., "komi": ...}, that position (fork_play.py): end
+        the slot's game (its next game takes the setup and komi set here), replay the moves."""
+        komi, moves = (query["komi"], query["moves"]) if isinstance(query, dict) else (query, job[2])
+        job[4:] = [query, moves]
         self.setups[slot] = job[1]
         self.komis[slot] = komi
         self.sp.set_game_setup(self.setups)
@@ -156,7 +159,7 @@ class KomiSearcher:
                 break
         else:
             raise RuntimeError("KomiSearcher: could not end the slot's previous game")
-        self.sp.play_moves_game(slot, job[2])
+        self.sp.play_moves_game(slot, [None if (m is None or m[0] < 0) else (int(m[0]), int(m[1])) for m in moves])
         self.searches += 1
 
     def _advance(self, slot, job, answer):
@@ -183,8 +186,16 @@ class KomiSearcher:
         self.sp.run(waves)
         done = np.asarray(self.sp.root_visits()) >= self.sp.max_visits
         for slot in [s for s in list(self.running) if done[s]]:
+            job = self.running[slot]
             _, root = self.sp.root_value_stats(slot)          # winLoss, noResult, scoreMean, scoreMeanSq, lead - white's perspective
-            self._advance(slot, self.running[slot], (float(root[4]), float(root[0])))
+            if not isinstance(job[4], dict):
+                answer = (float(root[4]), float(root[0]))
+            elif self.sp.game(slot)[1]["move_num"] != len(job[5]):
+                answer = None                                 # the replay ended the game on the way: no such position
+            else:                                             # a position query: also the net's own score of the root and the legal moves
+                answer = dict(lead=float(root[4]), win_loss=float(root[0]), nn_score_mean=float(self.sp.root_extra(slot)["root_nn_moments"][2]),
+                              legal=np.asarray(self.sp.root_children(slot)[1]) >= 0)
+            self._advance(slot, job, answer)
         self._dispatch()
         return self.pending()
 

@@ -54,7 +54,7 @@ _SEARCH_KEYS = {
 _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
                         "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir")
 # neutral values: the option is switched off, so not having it changes nothing
-_NEUTRAL = {"earlyForkGameProb": 0.0, "forkGameProb": 0.0, "sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
+_NEUTRAL = {"sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
             "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
             "switchNetsMidGame": True, "fancyKomiVarying": False,
             "handicapProb": 0.0,
@@ -167,6 +167,13 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
             "data_board_len": int(cfg.get("dataBoardLen", size)), "max_rows_per_train_file": int(cfg.get("maxRowsPerTrainFile", 20000)),
             "first_file_rand_min_prop": float(cfg.get("firstFileRandMinProp", 1.0)), "num_game_threads": int(cfg.get("numGameThreads", 256))}
     data["komi_search"] = komi_search
+    # forked games (Play::maybeForkGame, play.cpp:2413-2508; fork_play.py)
+    data["forks"] = dict(early_fork_game_prob=float(cfg.get("earlyForkGameProb", 0.0)), early_fork_game_expected_move_prop=float(cfg.get("earlyForkGameExpectedMoveProp", 0.0)),
+                         fork_game_prob=float(cfg.get("forkGameProb", 0.0)), fork_game_min_choices=int(cfg.get("forkGameMinChoices", 1)),
+                         early_fork_game_max_choices=int(cfg.get("earlyForkGameMaxChoices", 1)), fork_game_max_choices=int(cfg.get("forkGameMaxChoices", 1)),
+                         fork_compensate_komi_prob=float(cfg.get("forkCompensateKomiProb", cfg.get("handicapCompensateKomiProb", 0.0))))
+    used.update(("earlyForkGameProb", "earlyForkGameExpectedMoveProp", "forkGameProb", "forkGameMinChoices", "earlyForkGameMaxChoices", "forkGameMaxChoices",
+                 "forkCompensateKomiProb", "handicapCompensateKomiProb"))
     data["game_init"] = dict(sizes=sizes, size_probs=size_probs, ko_rules=kos, multi_stone_suicide_legals=suicides, komi_mean=komi,
                              komi_stdev=float(cfg.get("komiStdev", 0.0)), komi_big_stdev_prob=float(cfg.get("komiBigStdevProb", 0.0)),
                              komi_big_stdev=float(cfg.get("komiBigStdev", 10.0)), komi_bigger_stdev_prob=float(cfg.get("komiBiggerStdevProb", 0.0)),
@@ -219,9 +226,11 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
 class SlotSetups:
     """Host side of the per-game setup: draws from a GameInitializer and hands them to the loop (SelfPlay.set_game_setup / set_komi)."""
 
-    def __init__(self, init, num_games, policy_init=None, fair_komi=None):
+    def __init__(self, init, num_games, policy_init=None, fair_komi=None, forks=None, searcher=None):
         self.init, self.n = init, num_games
         self.fair_komi = fair_komi            # KomiSearcher for komiAuto, or None
+        self.forks, self.searcher = forks, searcher      # fork_play.ForkManager and the side loop its komi compensation runs on
+        self.fork_next = [None] * num_games   # the forked position the slot's NEXT game starts from (its setup and komi are the ones handed over)
         self.serial = [0] * num_games
         self.policy_init = policy_init if policy_init and policy_init.get("enabled") and policy_init.get("area_prop", 0) > 0 else None
         self.setups, self.komis = init.draw_many(num_games)
@@ -268,7 +277,40 @@ class SlotSetups:
             sp.set_komi(self.komis)
         self.fair_komi.submit(adjust_komi_to_even(self.init.komi_mean, x, y, self.init.rand), (x, y, ko, suicide), [], done)
 
+    def game_started(self, sp, rec, slot):
+        """The slot's next game has begun on the device (empty board, the setup handed over): if it is a forked game, play the fork's moves into the
+        slot and tell the recorder; then draw for the game after it."""
+        fork, self.fork_next[slot] = self.fork_next[slot], None
+        if fork is not None:
+            sp.play_moves_game(slot, [None if m[0] < 0 else m for m in fork["moves"]])
+            rec.start_from(slot, fork["moves"], mode=2)
+        self.redraw(sp, slot)
+
     def redraw(self, sp, slot):
+        fork = self.forks.pop() if self.forks is not None else None
+        if fork is not None:
+            # GameInitializer's initialPosition branch (play.cpp:497-526): the forked game's board, rules and komi, komi noise redrawn around it,
+            # with probability forkCompensateKomiProb first adjusted to even at the forked position; no policy-initialised opening
+            x, y, ko, suicide = fork["setup"]
+            self.serial[slot] += 1
+            self.setups[slot] = (x, y, ko, suicide)
+            self.komis[slot] = self.init.draw_komi(x, y, mean=fork["komi"])
+            self.fork_next[slot] = fork
+            if self.searcher is not None and self.init.rand.random() < float(self.forks.s.get("fork_compensate_komi_prob", 0.0)):
+                from .komi_search import adjust_komi_to_even
+                serial = self.serial[slot]
+
+                def done(fair, slot=slot, x=x, y=y):
+                    if self.serial[slot] == serial and self.fork_next[slot] is fork:
+                        self.komis[slot] = self.init.draw_komi(x, y, mean=fair)
+                        sp.set_komi(self.komis)
+                self.searcher.submit(adjust_komi_to_even(fork["komi"], x, y, self.init.rand), fork["setup"], fork["moves"], done)
+            sp.set_game_setup(self.setups)
+            sp.set_komi(self.komis)
+            if self.policy_init:
+                self.openings[slot] = 0
+                sp.set_policy_init(self.openings, self.policy_init["temperature"])
+            return
         x, y, ko, suicide, komi = self.init.draw()
         self.setups[slot] = (x, y, ko, suicide)
         self.komis[slot] = komi
@@ -493,7 +535,8 @@ def main(argv=None):
         aux.update(handles=[], loops=[], fair=None, lead=None)
         side_kw = KomiSearcher.noiseless_kwargs(kw)
         side_kw["max_moves"] = int(kw.get("max_moves", 0) or 2 * L * L) + 8
-        for name, want, visits in (("fair", ks["komi_auto"], ks["compensate_komi_visits"]), ("lead", ks["estimate_lead_prob"] > 0, ks["estimate_lead_visits"])):
+        fork_needs_loop = forks.enabled and not (ks["komi_auto"] or ks["estimate_lead_prob"] > 0)      # the fork's evaluations need some side loop
+        for name, want, visits in (("fair", ks["komi_auto"] or fork_needs_loop, ks["compensate_komi_visits"]), ("lead", ks["estimate_lead_prob"] > 0, ks["estimate_lead_visits"])):
             if not want:
                 continue
             n_side = max(4, min(32, games // 4))
@@ -501,8 +544,11 @@ def main(argv=None):
             lp = SelfPlay(hx, n_side, max(2, visits), komi=data["komi"], seed=loop_seed + 104729 + seed_offset, debug_hold_at_max_visits=True, **side_kw)
             aux["handles"].append(hx); aux["loops"].append(lp)
             aux[name] = KomiSearcher(lp)
+    from .fork_play import ForkManager
+    forks = ForkManager(data["forks"], __import__("random").Random(loop_seed ^ 0x466F726B))
     make_aux(ctx, lm, 0)
-    slots = SlotSetups(init, games, data["policy_init"], fair_komi=aux["fair"])
+    fork_searcher = lambda: aux["lead"] or aux["fair"]       # where fork evaluations and their komi compensation run
+    slots = SlotSetups(init, games, data["policy_init"], fair_komi=aux["fair"] if ks["komi_auto"] else None, forks=forks if forks.enabled else None, searcher=fork_searcher())
     slots.start(sp)
 
     counts = {"started": games, "finished": 0, "moves": 0}
@@ -522,17 +568,26 @@ def main(argv=None):
     def on_game(slot, finished):
         outputs.add_game(slot, finished)
         counts["finished"] += 1
-        counts["started"] += 1          # the slot's next game started on the device when this one ended
+        if forks.enabled and fork_searcher() is not None and not finished.end_no_result:        # Play::maybeForkGame on the finished game
+            all_moves = list(finished.start_moves) + list(finished.moves)
+            ko = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2, "SPIGHT": 3}[finished.ko_rule]
+            setup = (finished.x_size, finished.y_size, ko, int(finished.multi_stone_suicide_legal))
+            job = forks.job(all_moves, setup, finished.komi, L)
+            if job is not None:
+                fork_searcher().submit(job, setup, [], lambda moves, setup=setup, komi=finished.komi: forks.add(moves, setup, komi) if moves else None)
+
+    def on_game_start(slot):
+        counts["started"] += 1          # the slot's next game started on the device when the previous one ended
         if counts["started"] % log_games_every == 0:
             log(f"Started {counts['started']} games with {outputs.model_name}")
         if counts["started"] % max(1000, log_games_every * 100) == 0:
             log_stats()
-        slots.redraw(sp, slot)           # the slot's new game has taken the values drawn before; draw the ones for the game after it
+        slots.game_started(sp, rec, slot)      # a forked game gets its position; then the draw for the game after it
     rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                        use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"),
-                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
+                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], on_game_start=on_game_start, limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
     # New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory every 20 s; :142-231 load the newest one).
     # Default: every rank polls and reads the file itself.  -nccl-weights: rank 0 polls, reads and packs; the packed weights reach
     # the other GPUs by the library's ncclBroadcast (dist_weights.WeightBroadcaster) - the poll is then a collective, every
@@ -625,14 +680,15 @@ def main(argv=None):
                 h = NeuralNet.createComputeHandle(ctx, lm, games, False, True, gpu)
                 sp = SelfPlay(h, games, max_visits, komi=data["komi"], seed=loop_seed + 7919 * (swaps + 1), debug_hold_at_max_visits=True, max_playouts_per_wave=a.max_playouts_per_wave, **kw)
                 make_aux(ctx, lm, swaps + 1)               # (lead jobs of games that ended under the old evaluator are dropped with it)
-                slots.fair_komi = aux["fair"]
+                slots.fair_komi = aux["fair"] if ks["komi_auto"] else None
+                slots.searcher = fork_searcher()
                 slots.start(sp)
                 written = rec.games_written
                 rec = GameRecorder(sp, None, data["komi"], draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), on_game=on_game,
                                    game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
                                    policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                                    use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"),
-                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
+                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], on_game_start=on_game_start, limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
                 rec.games_written = written
             swaps += 1
             outputs.switch_to(new_path)

@@ -121,3 +121,38 @@ def test_lead_of_a_position_equals_the_reference_computeLead(golden_dir, stream,
     print(f"{size}x{size} after {len(moves)} moves at komi {komi}, {visits} visits per search, {ks.searches} searches: lead {got[0]:.4f} (reference {ref:.4f})")
     assert abs(got[0] - ref) < 0.02, (got, ref)
     sp.free(); h.free(); ctx.free()
+
+
+def test_fork_manager_picks_the_move_the_net_scores_best():
+    """Play::maybeForkGame: early forks near the start, late forks anywhere; among the drawn legal moves the one with the best whiteScoreMean for
+    the player to move; the pool hands positions out at random and empties."""
+    from katago_b200.fork_play import ForkManager
+    settings = dict(early_fork_game_prob=1.0, early_fork_game_expected_move_prop=0.05, fork_game_prob=0.0, fork_game_min_choices=3, early_fork_game_max_choices=5,
+                    fork_game_max_choices=5, fork_compensate_komi_prob=0.0)
+    fm = ForkManager(settings, random.Random(3))
+    game = [(k % 9, k // 9) for k in range(40)]
+    legal = np.ones(82, bool); legal[:10] = False
+    scores = lambda moves: 0.1 * (moves[-1][0] + 9 * moves[-1][1]) if moves and moves[-1][0] >= 0 else 100.0       # white likes high positions and the pass most
+    for trial in range(20):
+        gen = fm.job(game, (9, 9, 0, 1), 7.5, 9)
+        q = gen.send(None)
+        idx = len(q["moves"])
+        assert q["moves"] == game[:idx] and q["komi"] == 7.5 and idx <= 39
+        asked, answer = [], dict(legal=legal, nn_score_mean=0.0, lead=0.0, win_loss=0.0)
+        try:
+            while True:
+                q = gen.send(answer)
+                asked.append(q["moves"][-1])
+                assert q["moves"][:-1] == game[:idx] and (q["moves"][-1] == (-1, -1) or q["moves"][-1][1] * 9 + q["moves"][-1][0] >= 10)
+                answer = dict(legal=legal, nn_score_mean=scores(q["moves"]), lead=0.0, win_loss=0.0)
+        except StopIteration as st:
+            fork = st.value
+        assert 3 <= len(asked) <= 5 and fork[:-1] == game[:idx]
+        best = (min if idx % 2 == 0 else max)(asked, key=lambda m: scores([m]))          # black (even index) wants white's score low
+        assert scores([fork[-1]]) == scores([best])
+        fm.add(fork, (9, 9, 0, 1), 7.5)
+    assert fm.forks_made == 20 and len(fm.pool) == 20
+    seen = [fm.pop() for _ in range(20)]
+    assert fm.pop() is None and len({tuple(f["moves"]) for f in seen}) >= 10 and all(f["setup"] == (9, 9, 0, 1) for f in seen)
+    off = ForkManager(dict(settings, early_fork_game_prob=0.0), random.Random(1))
+    assert not off.enabled and off.job(game, (9, 9, 0, 1), 7.5, 9) is None

@@ -51,6 +51,8 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert kw["max_moves"] == 1600 and kw["ko_rule"] == 0 and kw["full_history_rules"] is True and kw["multi_stone_suicide_legal"] is False
     gi = data.pop("game_init")
     ks = data.pop("komi_search")
+    fk = data.pop("forks")
+    assert fk["early_fork_game_prob"] == 0.04 and fk["fork_game_prob"] == 0.01 and fk["fork_game_min_choices"] == 1
     ps = data.pop("play_settings")
     assert data.pop("policy_init") == {"enabled": True, "area_prop": 0.08, "temperature": 1.0}
     assert ps["cheap_search_prob"] == 0.75 and ps["cheap_search_visits"] == 350 and ps["cheap_search_target_weight"] == 0.0 and ps["reduce_visits"] is True
@@ -76,7 +78,8 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert "initGamesWithPolicy" not in nb and "policyInitAreaProp" not in nb
     assert "komiAuto" not in nb and "estimateLeadProb" not in nb             # built: komi-bisection searches on a side loop (komi_search.py)
     assert ks == {"komi_auto": True, "compensate_komi_visits": 20, "estimate_lead_prob": 0.5, "estimate_lead_visits": 6}
-    for key in ("forkGameProb", "handicapProb"):
+    assert "forkGameProb" not in nb and "earlyForkGameProb" not in nb           # built: fork_play.py
+    for key in ("forkSidePositionProb", "handicapProb"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
     assert not any(k in nb for k in ("maxVisits", "cpuctExploration", "koRules", "dataBoardLen"))
@@ -284,6 +287,47 @@ def test_command_searches_fair_komi_and_lead_targets(tmp_path, stock_cfg, golden
     # the fair komi of the empty 7x7 board is not the fair komi of the empty 9x9 board (and neither is komiMean's 7.5 by construction)
     assert set(komi_by_size) == {49, 81} and komi_by_size[49] != komi_by_size[81], komi_by_size
     assert all(len(v) <= 3 for v in komi_by_size.values()), komi_by_size       # no komi noise configured: the linear rounding of one fair value (+ the first games)
+
+
+@pytest.mark.gpu
+def test_command_forks_finished_games(tmp_path, stock_cfg):
+    """earlyForkGameProb / forkGameProb through the command: finished games are forked (a position of theirs, replayed, plus one of a few random
+    legal moves - the one the net scores best), forked games are marked gtype=fork, start from that position (startTurnIdx = its length) on the
+    forked game's board, and their training rows carry the start-history length."""
+    import re
+    from katago_b200 import modelgen
+    models = tmp_path / "models"; models.mkdir()
+    modelgen.write_model(str(models / "tinynet.bin"), "tiny_reg", seed=3)
+    settings = dict(STOCK_B18_SETTINGS, bSizes="7,9", bSizeRelProbs="1,1", allowRectangleProb="0", dataBoardLen="9", maxVisits="12", maxMovesPerGame="40",
+                    rootNumSymmetriesToSample="2", nnCacheSizePowerOfTwo="10", maxRowsPerTrainFile="100000", firstFileRandMinProp="1.0", cheapSearchProb="0",
+                    reduceVisits="false", initGamesWithPolicy="false", estimateLeadProb="0", komiAuto="false", komiMean="7", earlyForkGameProb="0.5",
+                    earlyForkGameExpectedMoveProp="0.1", forkGameProb="0.9", forkGameMinChoices="2", earlyForkGameMaxChoices="4", forkGameMaxChoices="4",
+                    forkCompensateKomiProb="0.5", policySurpriseDataWeight="0", valueSurpriseDataWeight="0")
+    cfg = tmp_path / "forks.cfg"
+    cfg.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
+    out = tmp_path / "out"
+    assert C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", str(cfg), "-max-games-total", "40", "-games-per-gpu", "8", "-per-game-release"]) == 0
+    games = []
+    for f in os.listdir(out / "tinynet" / "sgfs"):
+        for line in open(out / "tinynet" / "sgfs" / f):
+            size = int(re.search(r"SZ\[(\d+)", line).group(1))
+            start = int(re.search(r"startTurnIdx=(\d+)", line).group(1))
+            gtype = re.search(r"gtype=(\w+)", line).group(1)
+            moves = re.findall(r";([BW])\[([a-z]*)\]", line)
+            games.append((size, start, gtype, moves))
+    forked = [g for g in games if g[2] == "fork"]
+    normal = [g for g in games if g[2] == "normal"]
+    assert len(forked) >= 5 and len(normal) >= 8, (len(forked), len(normal))
+    for size, start, _, moves in forked:
+        assert start >= 1 and len(moves) > start
+        # all but the last start move are the opening of some other game on the same board (the forked one); the last is the fork's own move
+        assert any(g[0] == size and g[3][:start - 1] == moves[:start - 1] and g[3] is not moves for g in games), (size, start, moves[:start])
+    assert all(g[1] == 0 for g in normal)
+    rows_start = []
+    for f in os.listdir(out / "tinynet" / "tdata"):
+        with np.load(out / "tinynet" / "tdata" / f) as z:
+            rows_start += list(z["globalTargetsNC"][:, 53])
+    assert max(rows_start) >= 1 and min(rows_start) == 0
 
 
 @pytest.mark.gpu
