@@ -38,6 +38,34 @@ class GameSlots {
     for(const Move& m : moves) { xy.push_back((int8_t)m.x); xy.push_back((int8_t)m.y); }
     check(kgb_selfplay_play_moves(sp_, xy.data(), (int)moves.size()));
   }
+  // the same for one slot (games of different board sizes; the opponent's move in match play): a move that ends the game restarts the slot
+  void playMoves(int slot, const std::vector<Move>& moves) {
+    std::vector<int8_t> xy;
+    for(const Move& m : moves) { xy.push_back((int8_t)m.x); xy.push_back((int8_t)m.y); }
+    check(kgb_selfplay_play_moves_game(sp_, slot, xy.data(), (int)moves.size()));
+  }
+  // GameInitializer::createGame's draws for the slots' next games (play.cpp:330-650): board X, board Y, ko rule, multi-stone suicide per slot; komi per slot
+  struct GameSetup { int32_t x, y, koRule, multiStoneSuicideLegal; };
+  void setGameSetups(const std::vector<GameSetup>& setups, bool alsoCurrentGames = false) {
+    if((int)setups.size() != n_) throw std::invalid_argument("setGameSetups: one entry per slot");
+    check(kgb_selfplay_set_game_setup(sp_, &setups[0].x, alsoCurrentGames ? 1 : 0));
+  }
+  std::vector<GameSetup> currentGameSetups() const { std::vector<GameSetup> v((size_t)n_); check(kgb_selfplay_get_game_setup(sp_, &v[0].x, nullptr)); return v; }
+  void setKomis(const std::vector<float>& komis, bool alsoCurrentGames = false) {
+    if((int)komis.size() != n_) throw std::invalid_argument("setKomis: one entry per slot");
+    check(kgb_selfplay_set_komi(sp_, komis.data(), alsoCurrentGames ? 1 : 0));
+  }
+  // getSearchLimitsThisMove (play.cpp:1093-1223): visit budget and "plain root" of the root after each slot's next move, [slot][0] the game goes on, [slot][1] it ends
+  void setNextSearchLimits(const std::vector<int32_t>& visits2, const std::vector<uint8_t>& plain2, bool alsoCurrentRoots = false) {
+    if((int)visits2.size() != 2 * n_ || (!plain2.empty() && (int)plain2.size() != 2 * n_)) throw std::invalid_argument("setNextSearchLimits: two entries per slot");
+    check(kgb_selfplay_set_next_search_limits(sp_, visits2.data(), plain2.empty() ? nullptr : plain2.data(), alsoCurrentRoots ? 1 : 0));
+  }
+  std::vector<int32_t> visitBudgets() const { std::vector<int32_t> v((size_t)n_); check(kgb_selfplay_get_search_limits(sp_, v.data(), nullptr)); return v; }
+  // PlayUtils::initializeGameUsingPolicy (playutils.cpp:232-266): opening moves each slot's next game draws from the raw policy
+  void setPolicyInit(const std::vector<int32_t>& numMoves, double temperature, bool alsoCurrentGames = false) {
+    if((int)numMoves.size() != n_) throw std::invalid_argument("setPolicyInit: one entry per slot");
+    check(kgb_selfplay_set_policy_init(sp_, numMoves.data(), temperature, alsoCurrentGames ? 1 : 0));
+  }
   // the playout loop: `waves` playout waves for every slot (asynchronous), then wait
   void runWaves(int waves) { check(kgb_selfplay_run(sp_, waves)); check(kgb_handle_sync(handle_)); }
 
