@@ -12,7 +12,7 @@ device loops, one per net), stopping early once the verdict cannot change (:181-
 the points, ties going to the candidate (:581), and its file or directory is moved to the accepted or the rejected directory (:225-238);
 for an accepted net the self-play directories are created first (:613-619).  One game record per line goes to
 `<sgf-output-dir>/<candidate>/<16 hex>.sgfs`.  The search block, rules, board sizes and komi come from the reference's .cfg keys through
-the same mapping as the selfplay command.  Not built here: resignation (`allowResignation`), which the report lists."""
+the same mapping as the selfplay command; resignation (`allowResignation`, `resignThreshold`, `resignConsecTurns`) is the match engine's."""
 import argparse
 import glob
 import os
@@ -101,7 +101,9 @@ def play_gating_match(cfg, baseline_file, candidate_file, names, sgf_dir, games_
             log(f"Game {mp.games_tallied - 1}: " + ("noresult" if result == "Void" else "draw " + result if result == "0" else
                                                       f"winner {'black ' + b_name if result.startswith('B') else 'white ' + w_name} {result}"))
         mp = MatchPlay(loops, names, total, GameInitializer(seed=seed ^ 0x4761746B, **data["game_init"]), on_game=on_game,
-                       draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), no_result_utility_for_white=kw.get("no_result_utility_for_white", 0.0))
+                       draw_equivalent_wins_for_white=kw.get("draw_equivalent_wins_for_white", 0.5), no_result_utility_for_white=kw.get("no_result_utility_for_white", 0.0),
+                       allow_resignation=C._B(cfg.get("allowResignation", "false")), resign_threshold=float(cfg.get("resignThreshold", -0.90)),
+                       resign_consec_turns=int(cfg.get("resignConsecTurns", 5)))
 
         def stop(m):
             v = early_verdict(m.win_points[1], m.games_tallied, total, required_prop)

@@ -7,7 +7,7 @@ Reads the reference's match configuration: `numBots = 2`, `botName0/1`, `nnModel
 `numGamesTotal`, the shared search / rules / board-size / komi keys of the selfplay mapping, and per-bot search keys with the bot's index
 appended (`maxVisits0`, `cpuctExploration1`, ... - Setup::loadParams with SETUP_FOR_MATCH).  The bots alternate colours; results are
 logged in the reference's words and written one record per line to `<sgf-output-dir>/<16 hex>.sgfs`.  Not built: more than two bots,
-`secondaryBots` / `extraPairs` pairing tables, resignation, per-bot time controls."""
+`secondaryBots` / `extraPairs` pairing tables, per-bot time controls."""
 import argparse
 import os
 import sys
@@ -103,7 +103,8 @@ def main(argv=None):
             draws[0] += 1
         log(f"Game {mp.games_tallied - 1}: {b_name} (black) vs {w_name} (white): {result} in {len(game.moves)} moves")
     mp = MatchPlay(loops, names, total, GameInitializer(seed=a.seed ^ 0x4D617463, **data0["game_init"]), on_game=on_game,
-                   draw_equivalent_wins_for_white=0.5, no_result_utility_for_white=0.0)
+                   draw_equivalent_wins_for_white=0.5, no_result_utility_for_white=0.0, allow_resignation=C._B(cfg.get("allowResignation", "false")),
+                   resign_threshold=float(cfg.get("resignThreshold", -0.90)), resign_consec_turns=int(cfg.get("resignConsecTurns", 5)))
     try:
         mp.run()
     except KeyboardInterrupt:

@@ -16,7 +16,7 @@ from .npz_writer import FinishedGameData, P_BLACK, P_WHITE
 
 class MatchPlay:
     def __init__(self, loops, names, num_games_total, game_initializer=None, on_game=None, draw_equivalent_wins_for_white=0.5,
-                 no_result_utility_for_white=0.0, game_hash_fn=None):
+                 no_result_utility_for_white=0.0, game_hash_fn=None, allow_resignation=False, resign_threshold=-0.90, resign_consec_turns=5):
         if len(loops) != 2 or len(names) != 2:
             raise ValueError("MatchPlay: exactly two bots")
         a, b = loops
@@ -29,6 +29,11 @@ class MatchPlay:
         self.black_bot = np.array([g % 2 for g in range(self.n)], np.int32)      # which bot plays black in the slot's current game
         self.to_move = self.black_bot.copy()
         self.moves = [[] for _ in range(self.n)]
+        # resignation (PlaySettings allowResignation / resignThreshold / resignConsecTurns, play.cpp:1903-1929): the mover's root win/loss values
+        self.allow_resignation, self.resign_threshold, self.resign_consec = bool(allow_resignation), float(resign_threshold), int(resign_consec_turns)
+        if self.allow_resignation and not self.resign_threshold <= 0:
+            raise ValueError("resignThreshold must not be positive")
+        self.win_loss = [[] for _ in range(self.n)]
         self.games_started = self.n
         self.live = np.ones(self.n, bool)                                          # slots whose current game counts towards the total
         if self.total > 0 and self.total < self.n:
@@ -62,7 +67,32 @@ class MatchPlay:
         self.win_points[1 - black_bot] += white_points
         self.games_tallied += 1
 
-    def _finish(self, g, last, mover):
+    def _restart(self, g):
+        """End slot g's game in both loops without a result on the board (resignation): passes until the slot's next game has begun."""
+        for sp in self.loops:
+            for _ in range(4):
+                sp.play_moves_game(g, [None])
+                if sp.game(g)[1]["move_num"] == 0:
+                    break
+            else:
+                raise RuntimeError("MatchPlay: could not end the resigned game")
+
+    def _should_resign(self, g, mover_is_black):
+        """play.cpp:1903-1929 after the mover's move: the last resignConsecTurns root values all say the mover is lost, and the game is past its
+        first 1 + area / 5 turns."""
+        hist = self.win_loss[g]
+        if not self.allow_resignation or len(hist) < self.resign_consec:
+            return False
+        x, y = (int(v) for v in self.loops[0].game_setups()[0][g][:2])
+        if len(self.moves[g]) - 1 < 1 + x * y // 5:
+            return False
+        for wl in hist[-self.resign_consec:]:
+            loser_is_black = None if self.resign_threshold <= wl <= -self.resign_threshold else (wl > -self.resign_threshold)
+            if loser_is_black is None or loser_is_black != mover_is_black:
+                return False
+        return True
+
+    def _finish(self, g, last, mover, resigned_black=None):
         sp = self.loops[mover]
         X, Y, ko_rule, multi = (int(v) for v in sp.game_setups()[1][g])          # the finished game's own board and rules
         komi = float(sp.komi_values()[1][g])
@@ -77,7 +107,11 @@ class MatchPlay:
         data.next_player_by_turn = [P_BLACK if i % 2 == 0 else P_WHITE for i in range(len(data.moves))]
         data.ko_rule = ("SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT")[ko_rule]
         data.multi_stone_suicide_legal = bool(multi)
-        if data.end_no_result:
+        if resigned_black is not None:                     # BoardHistory::setWinnerByResignation
+            winner = P_WHITE if resigned_black else P_BLACK
+            data.winner, data.resigned, data.end_finished, data.end_no_result = winner, True, True, False
+            kind, text = "scored", ("W+R" if resigned_black else "B+R")
+        elif data.end_no_result:
             kind, winner, text = "noresult", 0, "Void"
         else:
             # a game stopped by the move limit is scored as it stands (gatekeeper.cpp:143-146 endAndScoreGameNow): the device has done that
@@ -93,6 +127,7 @@ class MatchPlay:
                 self.on_game(g, data, self.names[bb], self.names[1 - bb], text)
         # the slot's next game: colours swapped, fresh setup for the game after it
         self.moves[g] = []
+        self.win_loss[g] = []
         self.black_bot[g] = 1 - bb
         self.to_move[g] = self.black_bot[g]
         if self.total > 0 and self.games_started >= self.total:
@@ -116,6 +151,9 @@ class MatchPlay:
             mine = held & (self.to_move == b)
             if not mine.any():
                 continue
+            if self.allow_resignation:          # historicalMctsWinLossValues: the root value of the search the move comes from
+                for g in (int(v) for v in np.flatnonzero(mine)):
+                    self.win_loss[g].append(float(sp.root_value_stats(g)[1][0]))
             sp.release(mine.astype(np.uint8))
             sp.run(1)
             other = self.loops[1 - b]
@@ -127,6 +165,10 @@ class MatchPlay:
                 made += 1
                 if last["game_over"]:
                     self._finish(g, last, b)
+                elif self._should_resign(g, mover_is_black=(self.black_bot[g] == b)):
+                    black = bool(self.black_bot[g] == b)
+                    self._restart(g)
+                    self._finish(g, dict(last, game_over=True, no_result=False, hit_move_limit=False, final_white_minus_black_score=0.0), b, resigned_black=black)
                 else:
                     self.to_move[g] = 1 - b
         return made

@@ -568,6 +568,8 @@ def write_sgf(data: FinishedGameData, b_name: str, w_name: str) -> str:
     if data.end_finished:
         if data.end_no_result:
             result = "Void"
+        elif getattr(data, "resigned", False):               # BoardHistory::isResignation (WriteSgf::printGameResult)
+            result = "B+R" if data.winner == P_BLACK else "W+R"
         elif data.winner == P_BLACK:
             result = "B+" + g(-float(_f32(data.final_white_minus_black_score)))
         elif data.winner == P_WHITE:

@@ -204,7 +204,7 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
         raise ValueError(f"dataBoardLen = {data['data_board_len']} but bSizes goes up to {size}: the data frame must hold the largest board")
     data["board_size"] = size = data["data_board_len"]    # rows are written in the data frame, so the evaluator's frame is that (nnXLen = dataBoardLen)
     for key, val in cfg.items():
-        if key in used or key in ("numGamesPerGating", "numGamesTotal", "numBots"):       # read by the gatekeeper / match commands themselves
+        if key in used or key in ("numGamesPerGating", "numGamesTotal", "numBots", "allowResignation", "resignThreshold", "resignConsecTurns"):   # read by the gatekeeper / match commands themselves
             continue
         if key.startswith(_IRRELEVANT_PREFIXES):
             report["irrelevant"].append(key)

@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
-L=gpurun_out/r02_c30.log
-timeout 900 python bench.py --steps 50 2>&1 | tail -1 > gpurun_out/bench_r02_final_n1.json
-cut -c1-400 gpurun_out/bench_r02_final_n1.json > $L
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-600 >> $L
-cat $L
+L=gpurun_out/r02_c31.log
+timeout 600 python -m pytest tests/test_match_and_gatekeeper.py -q -x -m gpu -s 2>&1 | grep -v "^Game \|^\[config\]\|^Loaded\|^Moving\|^Found" | tail -25 > $L
+cat $L | cut -c1-4000

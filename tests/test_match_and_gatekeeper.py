@@ -97,6 +97,47 @@ def test_match_play_mirrors_moves_alternates_colours_and_tallies():
     assert abs(pts["base"] - mp.win_points[0]) < 1e-12 and abs(pts["cand"] - mp.win_points[1]) < 1e-12
 
 
+class ResigningLoop(ScriptedLoop):
+    """ScriptedLoop whose searches always say white is lost (root win/loss -0.95) and which understands the passes that end a resigned game."""
+
+    def root_value_stats(self, g):
+        return None, np.array([-0.95, 0.0, -20.0, 400.0, -20.0])
+
+    def game(self, g):
+        return None, dict(move_num=self.t[g])
+
+    def play_moves_game(self, g, moves):
+        if moves == [None]:
+            self.passes = getattr(self, "passes", {})
+            self.passes[g] = self.passes.get(g, 0) + 1
+            self.t[g] += 1
+            if self.passes[g] == 2:                # two passes: the slot's next game begins
+                self.passes[g] = 0; self.t[g] = 0; self.k[g] += 1
+            return
+        super().play_moves_game(g, moves)
+
+
+def test_match_play_resignation():
+    """allowResignation (play.cpp:1903-1929): after its move, a player whose last resignConsecTurns root values were all beyond the threshold
+    resigns - not before turn 1 + area / 5 - the game counts for the opponent ("B+R"), both loops start the slot's next game."""
+    n = 2
+    lengths = [[30] * 6, [30] * 6]
+    scores = [[5.5] * 6, [5.5] * 6]                # never reached: white resigns long before move 30
+    a, b = ResigningLoop(n, lengths, scores), ResigningLoop(n, lengths, scores)
+    seen = []
+    mp = MatchPlay([a, b], ["base", "cand"], 4, on_game=lambda slot, game, bn, wn, res: seen.append((slot, bn, wn, res, len(game.moves), getattr(game, "resigned", False))),
+                   allow_resignation=True, resign_threshold=-0.9, resign_consec_turns=3)
+    mp.run(waves=1, max_pumps=400)
+    assert mp.games_tallied == 4 and all(res == "B+R" and resigned for _, _, _, res, _, resigned in seen)
+    # 5x5 board: no resignation before turn index 1 + 25 // 5 = 6; white moves on odd indices, so its first chance is its move with index 7 (8 moves made)
+    assert all(nm == 8 for _, _, _, _, nm, _ in seen), [s[4] for s in seen]
+    pts = {"base": 0.0, "cand": 0.0}
+    for slot, bn, wn, res, nm, _ in seen:
+        pts[bn] += 1.0
+    assert pts["base"] == mp.win_points[0] and pts["cand"] == mp.win_points[1]
+    assert a.k == b.k and a.t == b.t
+
+
 def test_gatekeeper_protocol_with_a_scripted_match(tmp_path):
     """The directory protocol of command/gatekeeper.cpp: candidate = newest test net, baseline = newest accepted net, auto-rejection of
     older candidates, acceptance with ties going to the candidate, files or model directories moved, self-play directories prepared."""
@@ -258,3 +299,29 @@ def test_match_command_plays_two_named_bots(tmp_path, tmp_models):
     assert 2 <= sum("PB[reg]" in r for r in records) <= 4          # a slot's bots swap colours from game to game
     log = open(tmp_path / "match.log").read()
     assert "Match finished" in log and "maxVisits 24" in log and "maxVisits 16" in log
+
+
+@pytest.mark.gpu
+def test_match_with_resignation_between_a_deep_and_a_shallow_search(tmp_path, golden_dir):
+    """Two bots on the same trained net, 48 visits against 4, allowResignation: games may end by resignation - then the loser is the player
+    who made the last move (a player resigns after its own move), the record says "+R", and both loops carry on with the slot's next game."""
+    import re
+    from katago_b200 import match_cli
+    model = os.path.join(golden_dir, "models", "g170-b6c96-s175395328-d26788732.bin.gz")
+    cfg = tmp_path / "match.cfg"
+    cfg.write_text(GATE_CFG.format(games=10, visits=48).replace("numGamesPerGating", "numGamesTotal").replace("bSizes = 7,9", "bSizes = 9").replace("bSizeRelProbs = 1,2", "bSizeRelProbs = 1") +
+                   f"numBots = 2\nbotName0 = deep\nbotName1 = shallow\nnnModelFile = {model}\nmaxVisits1 = 4\nallowResignation = true\nresignThreshold = -0.80\nresignConsecTurns = 3\n")
+    out = tmp_path / "sgfs"
+    assert match_cli.main(["-config", str(cfg), "-sgf-output-dir", str(out), "-log-file", str(tmp_path / "match.log"), "-games-per-gpu", "6"]) == 0
+    records = [l for f in os.listdir(out) for l in open(out / f)]
+    assert len(records) == 10
+    resigned = 0
+    for r in records:
+        res = re.search(r"RE\[([^\]]*)\]", r).group(1)
+        moves = re.findall(r";([BW])\[", r)
+        if res.endswith("+R"):
+            resigned += 1
+            assert moves and moves[-1] != res[0] and len(moves) >= 1 + 81 // 5        # the last mover lost; not before turn 1 + area / 5
+    log = open(tmp_path / "match.log").read()
+    print(f"{resigned} of 10 games ended by resignation")
+    assert "Match finished" in log
