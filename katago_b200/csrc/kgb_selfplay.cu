@@ -1356,6 +1356,76 @@ __device__ void rootPolicyTemperatureAndNoise(float* pol, int policySize, int X,
     if(pol[i] >= 0) pol[i] = (float)(r[i] * weight + pol[i] * (1.0 - weight));
 }
 
+// The same computation by a whole warp: every per-element expression (log / exp / pow, the divisions) is evaluated by the lanes in parallel, every
+// sum is still added in position order (all lanes run the short loop over the staged values), and the gamma draws - one sequential stream of the
+// reference's generator - are made by lane 0 without their final pow, which the lanes then apply in parallel.  Bit-identical to the function
+// above (tests/test_gpu_board_selfplay.py::test_root_dirichlet_noise_matches_reference runs this one).  r: [policySize], r2: [2 * policySize] doubles.
+__device__ void rootPolicyTemperatureAndNoiseWarp(float* pol, int policySize, int X, int Y, int turnNumber, bool noise, double concentration,
+                                                  double weight, double temperature, double temperatureEarly, double halflife, DevRandState* randState,
+                                                  double* r, double* r2, int lane) {
+  if(temperature != 1.0 || temperatureEarly != 1.0) {
+    const double rawHalflives = (double)turnNumber / halflife;
+    const double halflives = rawHalflives * 19.0 / sqrt((double)(X * Y));
+    const double temp = temperature + (temperatureEarly - temperature) * pow(0.5, halflives);
+    double maxValue = 0.0;
+    for(int i = lane; i < policySize; i += 32) { const double prob = pol[i]; if(prob > maxValue) maxValue = prob; }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) maxValue = fmax(maxValue, __shfl_xor_sync(KGB_FULL, maxValue, o));
+    const double logMaxValue = log(maxValue), invTemp = 1.0 / temp;
+    for(int i = lane; i < policySize; i += 32)
+      if(pol[i] > 0) pol[i] = (float)exp((log((double)pol[i]) - logMaxValue) * invTemp);
+    __syncwarp();
+    double sum = 0.0;
+    for(int i = 0; i < policySize; i++) { const float p = pol[i]; if(p > 0) sum += p; }      // (a value that underflowed to 0 adds nothing either way)
+    __syncwarp();
+    for(int i = lane; i < policySize; i += 32)
+      if(pol[i] >= 0) pol[i] = (float)(pol[i] / sum);
+    __syncwarp();
+  }
+  if(!noise) return;
+  int legalCount = 0;
+  for(int i = lane; i < policySize; i += 32) if(pol[i] >= 0) legalCount++;
+  legalCount = __reduce_add_sync(KGB_FULL, legalCount);
+  for(int i = lane; i < policySize; i += 32)
+    if(pol[i] >= 0) r[i] = log(fmin(0.01, (double)pol[i]) + 1e-20);
+  __syncwarp();
+  double logPolicySum = 0.0;
+  for(int i = 0; i < policySize; i++) if(pol[i] >= 0) logPolicySum += r[i];
+  const double logPolicyMean = logPolicySum / legalCount;
+  __syncwarp();
+  for(int i = lane; i < policySize; i += 32)
+    if(pol[i] >= 0) r[i] = fmax(0.0, r[i] - logPolicyMean);
+  __syncwarp();
+  double alphaPropSum = 0.0;
+  for(int i = 0; i < policySize; i++) if(pol[i] >= 0) alphaPropSum += r[i];
+  const double uniformProb = 1.0 / legalCount;
+  __syncwarp();
+  for(int i = lane; i < policySize; i += 32)
+    if(pol[i] >= 0) r[i] = alphaPropSum <= 0.0 ? uniformProb : 0.5 * (r[i] / alphaPropSum + uniformProb);
+  __syncwarp();
+  if(lane == 0) {
+    DevRand rand;
+    rand.s = *randState;
+    for(int i = 0; i < policySize; i++) {
+      if(pol[i] >= 0) { double u, inva; r[i] = rand.nextGammaCore(r[i] * concentration, u, inva); r2[i] = u; r2[policySize + i] = inva; }
+      else { r[i] = 0.0; r2[i] = -1.0; }
+    }
+    *randState = rand.s;
+  }
+  __syncwarp();
+  for(int i = lane; i < policySize; i += 32)
+    if(r2[i] >= 0.0) r[i] = r[i] * pow(r2[i], r2[policySize + i]);
+  __syncwarp();
+  double rSum = 0.0;
+  for(int i = 0; i < policySize; i++) if(pol[i] >= 0) rSum += r[i];
+  __syncwarp();
+  for(int i = lane; i < policySize; i += 32) {
+    const double ri = r[i] / rSum;
+    if(pol[i] >= 0) pol[i] = (float)(ri * weight + pol[i] * (1.0 - weight));
+  }
+  __syncwarp();
+}
+
 __global__ void playSelectionKernel(const SPDev d, int g, double* out /*[policySize] by move position*/) {
   if(threadIdx.x != 0 || blockIdx.x != 0) return;
   double* psv = d.selScratch + (size_t)g * 3 * d.policySize;
@@ -1373,8 +1443,9 @@ __global__ void chooseIndexTestKernel(DevRandState* st, const double* probs, int
 
 __global__ void rootNoiseTestKernel(float* pol, int policySize, int X, int Y, int turnNumber, int noise, double concentration, double weight,
                                     double temperature, double temperatureEarly, double halflife, DevRandState* randState, double* scratch) {
-  if(threadIdx.x == 0 && blockIdx.x == 0)
-    rootPolicyTemperatureAndNoise(pol, policySize, X, Y, turnNumber, noise != 0, concentration, weight, temperature, temperatureEarly, halflife, randState, scratch);
+  if(blockIdx.x == 0 && threadIdx.x < 32)
+    rootPolicyTemperatureAndNoiseWarp(pol, policySize, X, Y, turnNumber, noise != 0, concentration, weight, temperature, temperatureEarly, halflife, randState, scratch,
+                                      scratch + policySize, threadIdx.x);
 }
 
 // Search::recomputeNodeStats (searchupdatehelpers.cpp:167-360) for the parameter subset of the loop (no noise pruning, no root
@@ -1645,10 +1716,11 @@ __device__ void maybeRootNoise(const SPDev& d, int g, int node, int lane) {
   }
   if(node == 0 && d.nodeVisits[gb] == 0 && !d.plainRoot[g] && (d.rootNoiseEnabled || d.rootPolicyTemperature != 1.0 || d.rootPolicyTemperatureEarly != 1.0)) {
     __syncwarp();
-    if(lane == 0)
-      rootPolicyTemperatureAndNoise(d.policy + gb * d.policySize, d.policySize, d.gX[g], d.gY[g], d.moveNum[g], d.rootNoiseEnabled != 0,
-                                    d.rootDirichletNoiseTotalConcentration, d.rootDirichletNoiseWeight, d.rootPolicyTemperature,
-                                    d.rootPolicyTemperatureEarly, d.chosenMoveTemperatureHalflife, d.searchRand + g, d.noiseScratch + (size_t)g * d.policySize);
+    // the whole warp (the play-selection scratch is free while a root is being evaluated)
+    rootPolicyTemperatureAndNoiseWarp(d.policy + gb * d.policySize, d.policySize, d.gX[g], d.gY[g], d.moveNum[g], d.rootNoiseEnabled != 0,
+                                      d.rootDirichletNoiseTotalConcentration, d.rootDirichletNoiseWeight, d.rootPolicyTemperature,
+                                      d.rootPolicyTemperatureEarly, d.chosenMoveTemperatureHalflife, d.searchRand + g, d.noiseScratch + (size_t)g * d.policySize,
+                                      d.selScratch + (size_t)g * 3 * d.policySize, lane);
     __syncwarp();
   }
 }
@@ -2858,7 +2930,7 @@ void rootNoiseTest(const char* seedString, int X, int Y, int policySize, int tur
   for(int i = 0; i < 16; i++) st.a[i] = a[i];
   st.aIdx = idx; st.pcg = pcg;
   float* dp; DevRandState* ds; double* dr;
-  SPCK(cudaMalloc(&dp, policySize * sizeof(float))); SPCK(cudaMalloc(&ds, sizeof(st))); SPCK(cudaMalloc(&dr, policySize * sizeof(double)));
+  SPCK(cudaMalloc(&dp, policySize * sizeof(float))); SPCK(cudaMalloc(&ds, sizeof(st))); SPCK(cudaMalloc(&dr, 3 * policySize * sizeof(double)));
   SPCK(cudaMemcpy(dp, policyIn, policySize * sizeof(float), cudaMemcpyHostToDevice));
   SPCK(cudaMemcpy(ds, &st, sizeof(st), cudaMemcpyHostToDevice));
   rootNoiseTestKernel<<<1, 32>>>(dp, policySize, X, Y, turnNumber, noise, concentration, weight, temperature, temperatureEarly, halflife, ds, dr);
