@@ -18,7 +18,7 @@ import math
 
 import numpy as np
 
-from .npz_writer import FinishedGameData, P_BLACK, P_WHITE, final_value_targets, pack_bits, policy_target_from_play_selection, scoring_from_area
+from .npz_writer import FinishedGameData, P_BLACK, P_WHITE, SidePosition, final_value_targets, pack_bits, policy_target_from_play_selection, scoring_from_area
 
 _f32 = np.float32
 
@@ -194,6 +194,47 @@ def search_limits_this_move(max_visits, settings, rand, historical_win_loss):
     return max(2, visits), plain, weight, cheap
 
 
+def extract_root_targets(sp, g, X, Y):
+    """What extractSearchTargetsThisTurn / the side-position block of Play::runGame (play.cpp:931-948, 2178-2203) read of a finished search, from
+    slot g of loop `sp` held at its budget: position, input row, policy / value / Q targets, surprise and entropies, NNRawStats."""
+    colors, info = sp.game(g)
+    spatial, glob = sp.root_row(g)
+    _, policy, _ = sp.root_children(g)
+    child_stats, root_stats = sp.root_value_stats(g)
+    psv = sp.play_selection_values(g)
+    extra = sp.root_extra(g)
+    surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
+    nn = extra["root_nn_moments"]
+    flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
+    sp_row = np.asarray(spatial, np.float32).reshape(X * Y, 22)
+    # the kept row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
+    row_ok = bool(np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own))
+    return dict(info=info, flat=flat, own=own, policy=np.asarray(policy, np.float32), row_ok=row_ok,
+                packed=pack_bits(np.transpose(sp_row.reshape(1, X * Y, 22), (0, 2, 1)))[0], global_input=np.asarray(glob, np.float32).copy(),
+                policy_target=(policy_target_moves(psv, X), int(info["root_visits"])), value_targets=value_targets_from_root(root_stats),
+                q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], X),
+                surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
+                # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy before temperature and noise
+                nn_raw_stats=(float(nn[0]), float(nn[2]), float(sp.root_raw_policy_entropy()[g]) if hasattr(sp, "root_raw_policy_entropy") else policy_entropy),
+                raw_nn_values=reported_search_values(nn)[:3])       # Search::getRootRawNNValues: win, loss, noResult of the root's own evaluation
+
+
+def choose_random_forking_move(policy, x_frame, rand, ban_pos):
+    """PlayUtils::chooseRandomForkingMove (playutils.cpp): 70 % a temperature-1 policy move, 25 % a temperature-2 policy move, 5 % a uniformly random
+    legal move; never `ban_pos` (the move the game actually played); the pass is allowed.  policy: by move position, -1 = illegal (here the root
+    policy as searched - the reference reads the un-noised one).  Returns a move position or None."""
+    r = rand.random()
+    legal = [i for i in range(len(policy)) if policy[i] >= 0 and i != ban_pos]
+    if r >= 0.95:
+        return legal[rand.randrange(len(legal))] if legal else None
+    t = 1.0 if r < 0.70 else 2.0
+    cand = [i for i in legal if policy[i] > 0]
+    if not cand:
+        return None
+    w = [float(policy[i]) ** (1.0 / t) for i in cand]
+    return rand.choices(cand, weights=w)[0]
+
+
 class _GameInProgress:
     def __init__(self):
         self.turns = []       # per turn: what the finished root search gave
@@ -203,6 +244,8 @@ class _GameInProgress:
         self.start_moves = [] # moves before the first recorded turn (fork prefix + policy-initialised opening)
         self.preset_moves = []   # moves the host played into the slot before the game's first search (a forked game's position)
         self.mode = 0            # FinishedGameData::mode: 0 normal, 2 fork
+        self.side = {"list": [], "pending": 0, "waiting": None}     # side positions of this game: searched ones, jobs in flight, the finished game waiting for them
+        self.last_policy = None  # the root policy of the turn being played (for the side position's forking move)
 
 
 class GameRecorder:
@@ -220,7 +263,8 @@ class GameRecorder:
 
     def __init__(self, sp, writer, komi, draw_equivalent_wins_for_white=0.5, on_game=None, game_hash_fn=None,
                  policy_surprise_data_weight=0.0, value_surprise_data_weight=0.0, use_search_value_surprise=False, weight_rand=None,
-                 play_settings=None, limits_rand=None, policy_init=False, lead_estimator=None, estimate_lead_prob=0.0, lead_rand=None, on_game_start=None):
+                 play_settings=None, limits_rand=None, policy_init=False, lead_estimator=None, estimate_lead_prob=0.0, lead_rand=None, on_game_start=None,
+                 side_searcher=None, side_position_prob=0.0):
         """policy_surprise_data_weight / value_surprise_data_weight / use_search_value_surprise: PlaySettings of the same names - the
         finished game's target weights are redistributed by surprise (surprise_target_weights).  weight_rand (a RowRand): fractional
         weights are then resolved to integers like runGame does (resolve_target_weight); None leaves them fractional for the writer,
@@ -252,6 +296,13 @@ class GameRecorder:
             import random
             self.lead_rand = lead_rand or random.Random(0x4C656164)
         self.games_waiting_for_lead = 0
+        # side positions (PlaySettings::sidePositionProb = cfg forkSidePositionProb, play.cpp:1846-1860, 2166-2203): with that probability per turn a
+        # forking move is made off the main line and the position searched on a side loop with the game's own search parameters; its row is
+        # written with the game.  Not restated: the 25 % chance of continuing a side position by the search's reply.
+        self.side_searcher, self.side_prob = side_searcher, float(side_position_prob)
+        if self.side_searcher is not None:
+            import random
+            self.side_rand = random.Random(0x53696465)
         self.on_game_start = on_game_start         # called with the slot when its next game has begun on the device (before any of its turns is recorded)
         ps = play_settings or {}
         self.play_settings = ps if (float(ps.get("cheap_search_prob", 0.0)) > 0.0 or ps.get("reduce_visits", False)) else None
@@ -279,19 +330,10 @@ class GameRecorder:
     def _record_root(self, g):
         """Slot g is held: read its finished search and append this turn's targets (extractSearchTargetsThisTurn)."""
         sp = self.sp
-        colors, info = sp.game(g)
-        spatial, glob = sp.root_row(g)
-        _, policy, _ = sp.root_children(g)
-        child_stats, root_stats = sp.root_value_stats(g)
-        psv = sp.play_selection_values(g)
-        extra = sp.root_extra(g)
-        surprise, search_entropy, policy_entropy = policy_surprise_and_entropy(psv, policy)
-        nn = extra["root_nn_moments"]
-        # the kept row must be this root's: its own / opponent stone planes are the root position (a row of any other leaf differs)
-        flat, own = np.asarray(colors, np.uint8).reshape(-1), (P_BLACK if info["black_to_move"] else P_WHITE)
-        sp_row = np.asarray(spatial, np.float32).reshape(self.X * self.Y, 22)
+        ex = extract_root_targets(sp, g, self.X, self.Y)
+        info, flat, own = ex["info"], ex["flat"], ex["own"]
         target_weight, is_cheap = self.cur_limits[g]
-        if not (np.array_equal(sp_row[:, 1] != 0, flat == own) and np.array_equal(sp_row[:, 2] != 0, flat == 3 - own)):
+        if not ex["row_ok"]:
             raise RuntimeError(f"GameRecorder: slot {g}, move {info['move_num']}: the wave after the previous move did not evaluate the new root "
                                "(the kept input row belongs to another position)")
         gm = self.games[g]
@@ -307,30 +349,26 @@ class GameRecorder:
                     raise RuntimeError(f"GameRecorder: slot {g}: {info['move_num']} moves played before the first searched move, {len(gm.start_moves)} opening moves kept")
         bx, by = gm.setup[0], gm.setup[1]
         gm.boards.append(np.ascontiguousarray(flat.reshape(self.Y, self.X)[:by, :bx]).reshape(-1).copy())
-        values = value_targets_from_root(root_stats)
+        values = ex["value_targets"]
         gm.win_loss.append(float(values[0]) - float(values[1]))
+        gm.last_policy = ex["policy"]
         if self.play_settings is not None:       # limits of the search that follows this slot's move: the game goes on / a new game starts
             nxt = (search_limits_this_move(sp.max_visits, self.play_settings, self.limits_rand, gm.win_loss),
                    search_limits_this_move(sp.max_visits, self.play_settings, self.limits_rand, []))
             self.pending[g] = nxt
             self.next_visits[g] = (nxt[0][0], nxt[1][0]); self.next_plain[g] = (nxt[0][1], nxt[1][1])
-        gm.turns.append(dict(
-            next_player=own, move_num=info["move_num"], target_weight=target_weight, is_cheap_search=is_cheap,
-            packed=pack_bits(np.transpose(sp_row.reshape(1, self.X * self.Y, 22), (0, 2, 1)))[0],
-            global_input=np.asarray(glob, np.float32).copy(),
-            policy_target=(policy_target_moves(psv, self.X), int(info["root_visits"])),
-            value_targets=values,
-            q_targets=q_targets_from_children(child_stats, extra["child_node_visits"], self.X),
-            surprise=surprise, search_entropy=search_entropy, policy_entropy=policy_entropy,
-            # NNRawStats (play.cpp:890-914) from the root's own evaluation; the entropy is that of the root policy before temperature and noise
-            nn_raw_stats=(float(nn[0]), float(nn[2]), float(sp.root_raw_policy_entropy()[g]) if hasattr(sp, "root_raw_policy_entropy") else policy_entropy),
-            raw_nn_values=reported_search_values(nn)[:3]))       # Search::getRootRawNNValues: win, loss, noResult of the root's own evaluation
+        turn = {k: ex[k] for k in ("packed", "global_input", "policy_target", "value_targets", "q_targets", "surprise", "search_entropy", "policy_entropy",
+                                   "nn_raw_stats", "raw_nn_values")}
+        turn.update(next_player=own, move_num=info["move_num"], target_weight=target_weight, is_cheap_search=is_cheap)
+        gm.turns.append(turn)
 
     def _after_move(self, g):
         """Slot g was released and one wave has run: the device has played its move and evaluated the new root."""
         sp = self.sp
         last = sp.last_move(g)
         self.games[g].turns[-1]["move"] = last["xy"]
+        if self.side_searcher is not None and not last["game_over"] and self.side_rand.random() < self.side_prob:
+            self._submit_side_position(g, last)
         if self.play_settings is not None:
             cont, fresh = self.pending[g]
             self.cur_limits[g] = (fresh[2], fresh[3]) if last["game_over"] else (cont[2], cont[3])
@@ -428,6 +466,7 @@ class GameRecorder:
             data.target_weight_by_turn = [resolve_target_weight(w, self.weight_rand) for w in data.target_weight_by_turn]
         data.final_white_scoring = scoring_from_area(area)
         data.mode = gm.mode
+        data.side_positions = gm.side["list"]            # (jobs still in flight append to this list)
         self.games[g] = _GameInProgress()
         if self.on_game_start is not None:
             self.on_game_start(g)
@@ -436,13 +475,54 @@ class GameRecorder:
             turns = [t for t in range(len(gm.turns)) if float(data.target_weight_by_turn[t]) > 0 and float(data.white_value_targets_by_turn[t][2]) < 0.3 and
                      self.lead_rand.random() < self.lead_prob]
             if turns:
-                waiting = {"data": data, "slot": g, "left": len(turns)}
+                waiting = {"data": data, "slot": g, "left": len(turns) + gm.side["pending"]}
+                gm.side["waiting"] = waiting
                 self.games_waiting_for_lead += 1
                 for t in turns:
                     self.lead.submit(compute_lead(komi, X, Y), (X, Y, ko_rule, multi_suicide), list(data.start_moves) + list(data.moves[:t]),
                                      lambda lead, t=t, w=waiting: self._lead_done(w, t, lead))
                 return
+        if gm.side["pending"] > 0:                      # side positions of this game are still being searched
+            gm.side["waiting"] = {"data": data, "slot": g, "left": gm.side["pending"]}
+            self.games_waiting_for_lead += 1
+            return
         self._emit(g, data)
+
+    def _submit_side_position(self, g, last):
+        """play.cpp:1846-1860: a forking move from the position just left (not the move played), the resulting position searched off line."""
+        gm = self.games[g]
+        turn = gm.turns[-1]
+        pos = choose_random_forking_move(gm.last_policy, self.X, self.side_rand, last["pos"])
+        if pos is None or gm.setup is None:
+            return
+        n = self.X * self.Y
+        mv = (-1, -1) if pos == n else (pos % self.X, pos // self.X)
+        moves = list(gm.start_moves) + [t["move"] for t in gm.turns[:-1]] + [mv]
+        komi = float(self.sp.komi_values()[0][g]) if hasattr(self.sp, "komi_values") else self.komi
+        side, turn_idx, X, Y = gm.side, int(turn["move_num"]) + 1, self.X, self.Y
+        side["pending"] += 1
+
+        def job():
+            ans = yield {"moves": moves, "komi": komi}
+            if ans is None:                       # the forking move ended the game: no side position
+                return None
+            ex = extract_root_targets(ans["loop"], ans["slot"], X, Y)
+            if not ex["row_ok"]:
+                return None
+            return SidePosition(ex["own"], turn_idx, ex["packed"], ex["global_input"], ex["policy_target"][0], ex["policy_target"][1], ex["value_targets"],
+                                ex["q_targets"], ex["surprise"], ex["policy_entropy"], ex["search_entropy"], ex["nn_raw_stats"])
+
+        def done(obj):
+            if obj is not None:
+                side["list"].append(obj)
+            side["pending"] -= 1
+            w = side["waiting"]
+            if w is not None:
+                w["left"] -= 1
+                if w["left"] == 0:
+                    self.games_waiting_for_lead -= 1
+                    self._emit(w["slot"], w["data"])
+        self.side_searcher.submit(job(), gm.setup, [], done)
 
     def start_from(self, g, moves, mode=2):
         """The slot's game that has just begun starts from `moves` (already played into the device slot by the caller): a forked game."""

@@ -194,7 +194,7 @@ class KomiSearcher:
                 answer = None                                 # the replay ended the game on the way: no such position
             else:                                             # a position query: also the net's own score of the root and the legal moves
                 answer = dict(lead=float(root[4]), win_loss=float(root[0]), nn_score_mean=float(self.sp.root_extra(slot)["root_nn_moments"][2]),
-                              legal=np.asarray(self.sp.root_children(slot)[1]) >= 0)
+                              legal=np.asarray(self.sp.root_children(slot)[1]) >= 0, loop=self.sp, slot=slot)      # (the slot stays held while the job reads it)
             self._advance(slot, job, answer)
         self._dispatch()
         return self.pending()

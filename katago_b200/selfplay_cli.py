@@ -54,7 +54,7 @@ _SEARCH_KEYS = {
 _IRRELEVANT_PREFIXES = ("log", "cuda", "trt", "opencl", "eigen", "metal", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
                         "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir")
 # neutral values: the option is switched off, so not having it changes nothing
-_NEUTRAL = {"sekiForkHackProb": 0.0, "forkSidePositionProb": 0.0,
+_NEUTRAL = {"sekiForkHackProb": 0.0,
             "handicapAsymmetricPlayoutProb": 0.0, "normalAsymmetricPlayoutProb": 0.0,
             "switchNetsMidGame": True, "fancyKomiVarying": False,
             "handicapProb": 0.0,
@@ -172,6 +172,8 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
                          fork_game_prob=float(cfg.get("forkGameProb", 0.0)), fork_game_min_choices=int(cfg.get("forkGameMinChoices", 1)),
                          early_fork_game_max_choices=int(cfg.get("earlyForkGameMaxChoices", 1)), fork_game_max_choices=int(cfg.get("forkGameMaxChoices", 1)),
                          fork_compensate_komi_prob=float(cfg.get("forkCompensateKomiProb", cfg.get("handicapCompensateKomiProb", 0.0))))
+    data["side_position_prob"] = float(cfg.get("forkSidePositionProb", 0.0))      # PlaySettings::sidePositionProb (playsettings.cpp: cfg key forkSidePositionProb)
+    used.add("forkSidePositionProb")
     used.update(("earlyForkGameProb", "earlyForkGameExpectedMoveProp", "forkGameProb", "forkGameMinChoices", "earlyForkGameMaxChoices", "forkGameMaxChoices",
                  "forkCompensateKomiProb", "handicapCompensateKomiProb"))
     data["game_init"] = dict(sizes=sizes, size_probs=size_probs, ko_rules=kos, multi_stone_suicide_legals=suicides, komi_mean=komi,
@@ -524,7 +526,7 @@ def main(argv=None):
     ks = data["komi_search"]
     if a.nccl_weights and world > 1 and (ks["komi_auto"] or ks["estimate_lead_prob"] > 0):
         raise ValueError("komiAuto / estimateLeadProb with -nccl-weights: the side loops' handles are not part of the weight broadcast yet")
-    aux = {"handles": [], "loops": [], "fair": None, "lead": None}
+    aux = {"handles": [], "loops": [], "fair": None, "lead": None, "side": None}
 
     def make_aux(context, model, seed_offset):
         """(fair-komi searcher, lead searcher) on fresh handles of `model`; the previous ones are dropped."""
@@ -532,7 +534,7 @@ def main(argv=None):
             lp.free()
         for hx in aux["handles"]:
             hx.free()
-        aux.update(handles=[], loops=[], fair=None, lead=None)
+        aux.update(handles=[], loops=[], fair=None, lead=None, side=None)
         side_kw = KomiSearcher.noiseless_kwargs(kw)
         side_kw["max_moves"] = int(kw.get("max_moves", 0) or 2 * L * L) + 8
         fork_needs_loop = forks.enabled and not (ks["komi_auto"] or ks["estimate_lead_prob"] > 0)      # the fork's evaluations need some side loop
@@ -544,6 +546,13 @@ def main(argv=None):
             lp = SelfPlay(hx, n_side, max(2, visits), komi=data["komi"], seed=loop_seed + 104729 + seed_offset, debug_hold_at_max_visits=True, **side_kw)
             aux["handles"].append(hx); aux["loops"].append(lp)
             aux[name] = KomiSearcher(lp)
+        if data["side_position_prob"] > 0:      # side positions are searched like the game's own turns: the loop's parameters, noise and all, full visits
+            n_side = max(4, min(32, games // 4))
+            hx = NeuralNet.createComputeHandle(context, model, n_side, False, True, gpu)
+            full_kw = dict(kw); full_kw["max_moves"] = side_kw["max_moves"]
+            lp = SelfPlay(hx, n_side, max_visits, komi=data["komi"], seed=loop_seed + 1299709 + seed_offset, debug_hold_at_max_visits=True, **full_kw)
+            aux["handles"].append(hx); aux["loops"].append(lp)
+            aux["side"] = KomiSearcher(lp)
     from .fork_play import ForkManager
     forks = ForkManager(data["forks"], __import__("random").Random(loop_seed ^ 0x466F726B))
     make_aux(ctx, lm, 0)
@@ -587,7 +596,7 @@ def main(argv=None):
                        game_hash_fn=lambda slot, index: _game_hash(loop_seed, slot, index),
                        policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                        use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + ":weights"),
-                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], on_game_start=on_game_start, limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
+                       play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], on_game_start=on_game_start, side_searcher=aux["side"], side_position_prob=data["side_position_prob"], limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
     # New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory every 20 s; :142-231 load the newest one).
     # Default: every rank polls and reads the file itself.  -nccl-weights: rank 0 polls, reads and packs; the packed weights reach
     # the other GPUs by the library's ncclBroadcast (dist_weights.WeightBroadcaster) - the poll is then a collective, every
@@ -614,7 +623,7 @@ def main(argv=None):
                     rec.pump(8)
                 else:
                     rec.step()
-            for searcher in (aux["fair"], aux["lead"]):       # the side loops advance with the main loop
+            for searcher in (aux["fair"], aux["lead"], aux["side"]):       # the side loops advance with the main loop
                 if searcher is not None:
                     searcher.step(8)
             iters += 1
@@ -673,7 +682,7 @@ def main(argv=None):
                     lp.free()
                 for hx in aux["handles"]:
                     hx.free()
-                aux.update(handles=[], loops=[], fair=None, lead=None)
+                aux.update(handles=[], loops=[], fair=None, lead=None, side=None)
                 sp.free(); h.free(); ctx.free()
                 lm = NeuralNet.loadModelFile(new_path)
                 ctx = NeuralNet.createComputeContext([gpu], L, L, True, lm)
@@ -688,15 +697,16 @@ def main(argv=None):
                                    game_hash_fn=lambda slot, index, s_=swaps + 1: _game_hash(loop_seed + 7919 * s_, slot, index),
                                    policy_surprise_data_weight=data["policy_surprise_data_weight"], value_surprise_data_weight=data["value_surprise_data_weight"],
                                    use_search_value_surprise=data["use_search_value_surprise"], weight_rand=RowRand(writer_seed + f":weights{swaps + 1}"),
-                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], on_game_start=on_game_start, limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
+                                   play_settings=data["play_settings"], policy_init=data["policy_init"]["enabled"], lead_estimator=aux["lead"], estimate_lead_prob=ks["estimate_lead_prob"], on_game_start=on_game_start, side_searcher=aux["side"], side_position_prob=data["side_position_prob"], limits_rand=__import__("random").Random(loop_seed ^ (0x4C696D69 + swaps + 1)))
                 rec.games_written = written
             swaps += 1
             outputs.switch_to(new_path)
             log(f"Model loading loop thread loaded new neural net {outputs.model_name}"); log(f"Game loop changing midgame to new neural net: {outputs.model_name} (swap {swaps})")
     except KeyboardInterrupt:
         pass
-    if aux["lead"] is not None and rec.games_waiting_for_lead > 0:      # finished games whose lead searches are still running
-        aux["lead"].drain()
+    for searcher in (aux["lead"], aux["side"]):      # finished games whose lead searches / side positions are still running
+        if searcher is not None and rec.games_waiting_for_lead > 0:
+            searcher.drain()
     outputs.close()
     log_stats()
     log(f"Total games: {counts['started']}")

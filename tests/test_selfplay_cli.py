@@ -52,6 +52,7 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     gi = data.pop("game_init")
     ks = data.pop("komi_search")
     fk = data.pop("forks")
+    assert data.pop("side_position_prob") == 0.02
     assert fk["early_fork_game_prob"] == 0.04 and fk["fork_game_prob"] == 0.01 and fk["fork_game_min_choices"] == 1
     ps = data.pop("play_settings")
     assert data.pop("policy_init") == {"enabled": True, "area_prop": 0.08, "temperature": 1.0}
@@ -79,7 +80,8 @@ def test_stock_training_config_maps_onto_the_loop(stock_cfg):
     assert "komiAuto" not in nb and "estimateLeadProb" not in nb             # built: komi-bisection searches on a side loop (komi_search.py)
     assert ks == {"komi_auto": True, "compensate_komi_visits": 20, "estimate_lead_prob": 0.5, "estimate_lead_visits": 6}
     assert "forkGameProb" not in nb and "earlyForkGameProb" not in nb           # built: fork_play.py
-    for key in ("forkSidePositionProb", "handicapProb"):
+    assert "forkSidePositionProb" not in nb                                       # built: side positions searched on a side loop
+    for key in ("sekiForkHackProb", "handicapProb"):
         assert key in nb, key
     assert "cudaUseFP16" in report["irrelevant"] and "logSearchInfo" in report["irrelevant"] and "numSearchThreads" in report["irrelevant"]
     assert not any(k in nb for k in ("maxVisits", "cpuctExploration", "koRules", "dataBoardLen"))
@@ -328,6 +330,34 @@ def test_command_forks_finished_games(tmp_path, stock_cfg):
         with np.load(out / "tinynet" / "tdata" / f) as z:
             rows_start += list(z["globalTargetsNC"][:, 53])
     assert max(rows_start) >= 1 and min(rows_start) == 0
+
+
+@pytest.mark.gpu
+def test_command_records_side_positions(tmp_path, golden_dir):
+    """forkSidePositionProb through the command (trained g170 net, 9x9): about that share of the turns gets a forking move off the main line whose
+    position is searched on the side loop with the game's own search parameters; its row is written with the game - own policy / value targets,
+    no outcome-dependent ones (global target 62 = 0 where the game's own rows have 1, ownership planes empty) - at the turn index after the fork."""
+    import shutil
+    models = tmp_path / "models"; models.mkdir()
+    shutil.copy(os.path.join(golden_dir, "models", "g170-b6c96-s175395328-d26788732.bin.gz"), models / "g170.bin.gz")
+    settings = dict(STOCK_B18_SETTINGS, bSizes="9", bSizeRelProbs="1", allowRectangleProb="0", dataBoardLen="9", koRules="SIMPLE", multiStoneSuicideLegals="true",
+                    komiAuto="false", komiMean="7", komiStdev="0.0", maxVisits="16", maxMovesPerGame="300", rootNumSymmetriesToSample="2", nnCacheSizePowerOfTwo="10",
+                    maxRowsPerTrainFile="100000", firstFileRandMinProp="1.0", cheapSearchProb="0", reduceVisits="false", initGamesWithPolicy="false",
+                    estimateLeadProb="0", earlyForkGameProb="0", forkGameProb="0", forkSidePositionProb="0.25", policySurpriseDataWeight="0", valueSurpriseDataWeight="0")
+    cfg = tmp_path / "side.cfg"
+    cfg.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
+    out = tmp_path / "out"
+    assert C.main(["-models-dir", str(models), "-output-dir", str(out), "-config", str(cfg), "-max-games-total", "8", "-games-per-gpu", "8", "-per-game-release"]) == 0
+    main_rows = side_rows = 0
+    for f in os.listdir(out / "g170" / "tdata"):
+        with np.load(out / "g170" / "tdata" / f) as z:
+            g, own = z["globalTargetsNC"], z["valueTargetsNCHW"]
+            side = (g[:, 62] == 0) & (g[:, 52] == 0)                    # not "game finished", and not because of the move limit
+            main_rows += int((~side).sum()); side_rows += int(side.sum())
+            assert (g[side, 60] == 16).all() and (g[side, 25] > 0).all()  # searched with the full budget, written with the game's weight
+            assert not own[side][:, 0].any() and own[~side][:, 0].any()  # a side position has no final ownership
+            assert (g[side, 51] >= 1).all()
+    assert main_rows >= 8 * 20 and 0.1 * main_rows < side_rows < 0.4 * main_rows, (main_rows, side_rows)
 
 
 @pytest.mark.gpu
