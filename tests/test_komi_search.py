@@ -156,3 +156,19 @@ def test_fork_manager_picks_the_move_the_net_scores_best():
     assert fm.pop() is None and len({tuple(f["moves"]) for f in seen}) >= 10 and all(f["setup"] == (9, 9, 0, 1) for f in seen)
     off = ForkManager(dict(settings, early_fork_game_prob=0.0), random.Random(1))
     assert not off.enabled and off.job(game, (9, 9, 0, 1), 7.5, 9) is None
+
+
+def test_forking_move_distribution_and_side_position_bookkeeping():
+    """chooseRandomForkingMove: never the banned move, mostly policy-proportional; and the recorder's bookkeeping of side positions that are still being
+    searched when their game ends (the game is written once they are back, with them attached)."""
+    from katago_b200.game_recorder import choose_random_forking_move
+    pol = np.full(26, -1.0, np.float32)
+    pol[[3, 7, 11, 25]] = [0.6, 0.3, 0.1, 0.0]                      # three moves with mass, a legal pass with none
+    r = random.Random(5)
+    draws = [choose_random_forking_move(pol, 5, r, ban_pos=7) for _ in range(4000)]
+    assert 7 not in draws and set(draws) <= {3, 11, 25}
+    f3 = draws.count(3) / 4000
+    # 70 %: 0.6 / 0.7 = 0.857; 25 %: sqrt weights 0.775 / (0.775 + 0.316) = 0.710; 5 %: uniform over {3, 11, 25} = 1/3
+    assert abs(f3 - (0.70 * 0.857 + 0.25 * 0.710 + 0.05 / 3)) < 0.03, f3
+    assert 0 < draws.count(25) / 4000 < 0.04                         # the mass-less pass only through the uniform 5 %
+    assert choose_random_forking_move(np.full(5, -1.0, np.float32), 2, r, ban_pos=0) is None
