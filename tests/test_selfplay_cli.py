@@ -485,3 +485,63 @@ def test_config_mapping_agrees_with_the_reference_loader(tmp_path, which):
     nb = " ".join(report["not_built"])
     for line in ref["unsupported"]:                   # search options the C++ side names must be named by the command too
         assert line.split(" = ")[0] in nb, (line, nb)
+
+
+def test_slot_setups_hand_over_draws_forks_and_fair_komi():
+    """The host side of the per-game setup (SlotSetups): every slot's NEXT game has its board, rules, komi and opening length on the device before it
+    starts; a pooled fork replaces the draw (the forked game's setup, no opening, its moves played in when the game starts); komiAuto asks the side
+    loop for the fair komi of the next game's empty board and redraws the komi around the answer - unless the game has started meanwhile."""
+    from katago_b200.fork_play import ForkManager
+    from katago_b200.game_initializer import GameInitializer
+    import random
+
+    class Loop:
+        num_games = 4
+        def __init__(self):
+            self.calls = []
+        def set_game_setup(self, s, also_current_games=False):
+            self.calls.append(("setup", np.array(s).copy(), also_current_games))
+        def set_komi(self, k, also_current_games=False):
+            self.calls.append(("komi", np.array(k).copy(), also_current_games))
+        def set_policy_init(self, n, t, also_current_games=False):
+            self.calls.append(("init", np.array(n).copy(), t, also_current_games))
+        def play_moves_game(self, g, moves):
+            self.calls.append(("moves", g, list(moves)))
+
+    class Searcher:
+        def __init__(self):
+            self.jobs = []
+        def submit(self, gen, setup, moves, on_done):
+            self.jobs.append((gen, setup, moves, on_done))
+
+    class Rec:
+        def __init__(self):
+            self.started = []
+        def start_from(self, g, moves, mode=2):
+            self.started.append((g, list(moves), mode))
+
+    init = GameInitializer([(9, 9), (13, 13)], [1, 1], ko_rules=(0, 1), multi_stone_suicide_legals=(True,), komi_mean=7.0, komi_stdev=0.0, seed=2)
+    forks = ForkManager(dict(early_fork_game_prob=1.0, fork_compensate_komi_prob=0.0), random.Random(1))
+    searcher, loop, rec = Searcher(), Loop(), Rec()
+    slots = C.SlotSetups(init, 4, dict(enabled=True, area_prop=0.05, temperature=1.2), fair_komi=searcher, forks=forks, searcher=searcher)
+    slots.start(loop)
+    kinds = [c[0] for c in loop.calls]
+    assert kinds[:3] == ["setup", "komi", "init"] and loop.calls[0][2] and loop.calls[1][2] and loop.calls[2][3]        # the games in progress ...
+    assert kinds[3:6] == ["setup", "komi", "init"] and not loop.calls[3][2] and loop.calls[5][2] == 1.2                # ... and the ones after them
+    assert len(searcher.jobs) == 4 and all(j[2] == [] for j in searcher.jobs)                                          # komiAuto: one empty-board job per slot
+    # the fair-komi answer for slot 2 replaces its next game's komi (7.0 from komiMean) by a draw around it
+    before = float(slots.komis[2])
+    searcher.jobs[2][3](3.5)
+    assert before == 7.0 and float(slots.komis[2]) == 3.5 and loop.calls[-1][0] == "komi"
+    # slot 1's game ends: the new game is an ordinary one; the draw for the game after it pops the fork that is in the pool by then
+    forks.add([(2, 2), (3, 3), (4, 4)], (13, 13, 1, 1), 5.5)
+    n_jobs = len(searcher.jobs)
+    slots.game_started(loop, rec, 1)
+    assert rec.started == [] and tuple(slots.setups[1]) == (13, 13, 1, 1) and slots.openings[1] == 0 and float(slots.komis[1]) == 5.5
+    assert slots.fork_next[1] is not None and len(searcher.jobs) == n_jobs                                             # no komiAuto job for a forked game
+    # an answer that arrives for a slot whose draw has been replaced since is ignored
+    searcher.jobs[1][3](1.0)
+    assert float(slots.komis[1]) == 5.5
+    # ... and when THAT game starts, the fork's moves are played into the slot and the recorder is told
+    slots.game_started(loop, rec, 1)
+    assert ("moves", 1, [(2, 2), (3, 3), (4, 4)]) in loop.calls and rec.started == [(1, [(2, 2), (3, 3), (4, 4)], 2)] and slots.fork_next[1] is None
