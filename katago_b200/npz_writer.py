@@ -587,7 +587,7 @@ def write_sgf(data: FinishedGameData, b_name: str, w_name: str) -> str:
     weights = data.target_weight_by_turn_unrounded if data.target_weight_by_turn_unrounded is not None else data.target_weight_by_turn
     n = len(data.moves)
     for j, (x, y) in enumerate(getattr(data, "start_moves", [])):       # endHist.moveHistory starts with startHist's moves: no comments on those
-        out.append(";%s[%s]" % ("B" if (j % 2 == 0) == (data.start_pla == P_BLACK) else "W", "" if x < 0 else _SGF_CHARS[x] + _SGF_CHARS[y]))
+        out.append(";%s[%s]" % ("B" if j % 2 == 0 else "W", "" if x < 0 else _SGF_CHARS[x] + _SGF_CHARS[y]))       # (no handicap: black moves first)
     for i, (x, y) in enumerate(data.moves):
         pla = data.next_player_by_turn[i]
         out.append(";%s[%s]" % ("B" if pla == P_BLACK else "W", "" if x < 0 else _SGF_CHARS[x] + _SGF_CHARS[y]))

@@ -722,6 +722,18 @@ static int cmdWriteGame(int argc, char** argv) {
   Board board(X, Y);
   Player pla = P_BLACK;
   BoardHistory hist(board, pla, rules, 0, false);
+  // KGREF_START_MOVES = S: the game's first S moves (random legal ones) happen before the training period - they are its startHist, like a
+  // policy-initialised opening or a forked game's position (startTurnIdx = S in the record, start-history length S in the rows)
+  vector<string> startMoveStrs;
+  for(int i = 0, S = getenv("KGREF_START_MOVES") ? atoi(getenv("KGREF_START_MOVES")) : 0; i < S; i++) {
+    vector<Loc> legal;
+    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); if(hist.isLegal(board, l, pla)) legal.push_back(l); }
+    if(legal.empty()) break;
+    const Loc mv = legal[rng.next() % legal.size()];
+    startMoveStrs.push_back(Global::intToString(Location::getX(mv, X)) + "," + Global::intToString(Location::getY(mv, X)));
+    hist.makeBoardMoveAssumeLegal(board, mv, pla, NULL);
+    pla = getOpp(pla);
+  }
   data.startBoard = board; data.startHist = hist; data.startPla = pla;
   vector<Board> boards; vector<BoardHistory> hists; vector<Player> plas; vector<vector<Loc>> legalByTurn; vector<string> moveStrs, packedHex; vector<vector<float>> globalRows;
   auto inputRows = [&](const Board& b, const BoardHistory& h, Player p, string& hex, vector<float>& rowGlobal) {
@@ -876,6 +888,8 @@ static int cmdWriteGame(int argc, char** argv) {
   for(size_t i = 0; i < data.changedNeuralNets.size(); i++) out << (i ? "," : "") << "\"" << data.changedNeuralNets[i]->name << "\"";
   out << "],\n\"changedNeuralNetTurns\":[";
   for(size_t i = 0; i < data.changedNeuralNets.size(); i++) out << (i ? "," : "") << data.changedNeuralNets[i]->turnIdx;
+  out << "],\n\"startMoves\":[";
+  for(size_t i = 0; i < startMoveStrs.size(); i++) out << (i ? "," : "") << "[" << startMoveStrs[i] << "]";
   out << "],\n\"moves\":[";
   for(size_t i = 0; i < moveStrs.size(); i++) out << (i ? "," : "") << "[" << moveStrs[i] << "]";
   out << "],\n\"valueTargets\":[";

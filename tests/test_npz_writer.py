@@ -227,6 +227,8 @@ def _game_from_fixture(d):
         if "reanalysis" in t:
             g.reanalysis_by_turn.append(tuple(t["reanalysis"]))
     g.moves = [tuple(m) for m in d["moves"]]
+    g.start_moves = [tuple(m) for m in d.get("startMoves", [])]      # startHist: moves before the training period (KGREF_START_MOVES)
+    g.start_hist_moves = len(g.start_moves)
     g.winner, g.final_white_minus_black_score = d["winner"], d["finalWhiteMinusBlackScore"]
     g.changed_neural_net_names = d.get("changedNeuralNetNames")
     for sp in d.get("sidePositions", []):
