@@ -13,7 +13,8 @@ Restates, for the options the device loop has, `GameInitializer::initShared` / `
 
 The draws go to the device loop through `SelfPlay.set_game_setup` / `set_komi` (include/kgb200.h), one per slot, and take effect when
 the slot's next game starts.  The reference seeds its GameInitializer from the clock (command/selfplay.cpp:94), so there is no stream to
-reproduce: this class uses Python's Mersenne Twister, the distributions are the reference's.
+reproduce: this class uses Python's Mersenne Twister, the distributions are the reference's (tests/golden/gameinit_hist.json: 200 000 games
+of the reference's createGame, test_game_initializer_reproduces_the_reference_distributions).
 `komiAuto` replaces komiMean by the fair komi of the game's empty board (katago_b200/komi_search.py; `draw_komi(mean=...)`).
 Not built (the caller reports them): handicap stones (`handicapProb`), makeGameFair for forks / handicap, start positions, scoring / tax /
 button rules other than area scoring without tax and button."""
@@ -52,7 +53,7 @@ def round_and_clip_komi(unrounded, x_size, y_size):
 
 class GameInitializer:
     def __init__(self, sizes, size_probs, ko_rules=(0,), multi_stone_suicide_legals=(True,), komi_mean=7.5, komi_stdev=0.0,
-                 komi_big_stdev_prob=0.0, komi_big_stdev=10.0, komi_bigger_stdev_prob=0.0, komi_bigger_stdev=0.0, komi_allow_integer_prob=1.0, seed=0):
+                 komi_big_stdev_prob=0.0, komi_big_stdev=10.0, komi_bigger_stdev_prob=0.0, komi_bigger_stdev=30.0, komi_allow_integer_prob=1.0, seed=0):
         if not sizes or len(sizes) != len(size_probs):
             raise ValueError("GameInitializer: one probability per board size")
         self.sizes, self.size_probs = [tuple(s) for s in sizes], [float(p) for p in size_probs]

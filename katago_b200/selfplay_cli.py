@@ -179,7 +179,7 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     data["game_init"] = dict(sizes=sizes, size_probs=size_probs, ko_rules=kos, multi_stone_suicide_legals=suicides, komi_mean=komi,
                              komi_stdev=float(cfg.get("komiStdev", 0.0)), komi_big_stdev_prob=float(cfg.get("komiBigStdevProb", 0.0)),
                              komi_big_stdev=float(cfg.get("komiBigStdev", 10.0)), komi_bigger_stdev_prob=float(cfg.get("komiBiggerStdevProb", 0.0)),
-                             komi_bigger_stdev=float(cfg.get("komiBiggerStdev", 0.0)), komi_allow_integer_prob=float(cfg.get("komiAllowIntegerProb", 1.0)))
+                             komi_bigger_stdev=float(cfg.get("komiBiggerStdev", 30.0)), komi_allow_integer_prob=float(cfg.get("komiAllowIntegerProb", 1.0)))
     used.update(("dataBoardLen", "maxRowsPerTrainFile", "firstFileRandMinProp", "numGameThreads"))
     # PlaySettings the recorder implements (program/playsettings.cpp): surprise weighting of the finished game's rows
     data["policy_surprise_data_weight"] = float(cfg.get("policySurpriseDataWeight", 0.0))

@@ -1274,6 +1274,27 @@ static int cmdComputeLead(int argc, char** argv) {
   return 0;
 }
 
+// gameinit CFGFILE N SEED: N games of the reference's GameInitializer::createGame (program/play.cpp:330-650) on the given .cfg: per game
+// "X Y koRule multiStoneSuicide komi" - the per-game draws katago_b200/game_initializer.py restates (board size with rectangle probability,
+// rules, komi noise scaled by the board, linear rounding, integer komi allowed with probability komiAllowIntegerProb).
+static int cmdGameInit(int argc, char** argv) {
+  if(argc != 5) { cerr << "usage: gameinit CFGFILE N SEED" << endl; return 1; }
+  Board::initHash();
+  ScoreValue::initTables();
+  Logger logger(nullptr, false, false, false);
+  ConfigParser cfg(argv[2]);
+  GameInitializer gi(cfg, logger, argv[4]);
+  PlaySettings ps;
+  const int n = atoi(argv[3]);
+  for(int i = 0; i < n; i++) {
+    Board board; Player pla; BoardHistory hist; ExtraBlackAndKomi ebk; OtherGameProperties props;
+    gi.createGame(board, pla, hist, ebk, NULL, ps, props, NULL, false);
+    cout << board.x_size << " " << board.y_size << " " << hist.rules.koRule << " " << (hist.rules.multiStoneSuicideLegal ? 1 : 0) << " "
+         << Global::strprintf("%.1f", hist.rules.komi) << "\n";
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if(argc < 2) { cerr << "usage: kgref_driver <boardstream|...> ..." << endl; return 1; }
   string cmd = argv[1];
@@ -1293,6 +1314,7 @@ int main(int argc, char** argv) {
   if(cmd == "tinyfeatures") return cmdTinyFeatures(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   if(cmd == "computelead") return cmdComputeLead(argc, argv);
+  if(cmd == "gameinit") return cmdGameInit(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;
 }

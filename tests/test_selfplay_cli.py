@@ -545,3 +545,36 @@ def test_slot_setups_hand_over_draws_forks_and_fair_komi():
     # ... and when THAT game starts, the fork's moves are played into the slot and the recorder is told
     slots.game_started(loop, rec, 1)
     assert ("moves", 1, [(2, 2), (3, 3), (4, 4)]) in loop.calls and rec.started == [(1, [(2, 2), (3, 3), (4, 4)], 2)] and slots.fork_next[1] is None
+
+
+def test_game_initializer_reproduces_the_reference_distributions(golden_dir):
+    """200 000 games of the reference's GameInitializer::createGame (tests/golden/make_gameinit_fixture.py) against 200 000 draws of
+    katago_b200/game_initializer.py from the same configuration: board sizes incl. rectangles, ko and suicide rules, and the komi histograms on
+    9x9 and 19x19 (noise scaled by the board, big-stdev mixture, linear rounding, integers allowed half of the time) agree to sampling error."""
+    import json
+    from katago_b200.game_initializer import GameInitializer
+    ref = json.load(open(os.path.join(golden_dir, "gameinit_hist.json")))
+    cfg = C.parse_cfg("".join(f"{k} = {v}\n" for k, v in ref["cfg"].items()), is_text=True)
+    _, data, report = C.selfplay_kwargs_from_cfg(cfg)
+    assert report["fixed"] == []
+    n = ref["n"]
+    setups, komis = GameInitializer(seed=17, **data["game_init"]).draw_many(n)
+
+    def tv(a, b):           # total variation distance of two histograms over the union of their keys
+        keys = set(a) | set(b)
+        return 0.5 * sum(abs(a.get(k, 0) / sum(a.values()) - b.get(k, 0) / sum(b.values())) for k in keys)
+    mine_sizes = {}
+    for x, y in setups[:, :2]:
+        mine_sizes[f"{x}x{y}"] = mine_sizes.get(f"{x}x{y}", 0) + 1
+    assert set(mine_sizes) == set(ref["sizes"]) and tv(mine_sizes, ref["sizes"]) < 0.005, (mine_sizes, ref["sizes"])
+    assert tv({str(k): int((setups[:, 2] == k).sum()) for k in (0, 1, 2)}, ref["ko_rules"]) < 0.005
+    assert tv({str(k): int((setups[:, 3] == k).sum()) for k in (0, 1)}, ref["multi_stone_suicide"]) < 0.005
+    for size, edge in (("9x9", 9), ("19x19", 19)):
+        sel = komis[(setups[:, 0] == edge) & (setups[:, 1] == edge)]
+        mine = {}
+        for k in sel:
+            mine["%.1f" % k] = mine.get("%.1f" % k, 0) + 1
+        d = tv(mine, ref["komi_by_size"][size])
+        assert d < 0.012, (size, d)
+        ints = sum(v for k, v in mine.items() if float(k) == int(float(k))) / len(sel)
+        assert 0.2 < ints < 0.3, ints          # integers allowed half of the time: about a quarter of the komis
