@@ -1010,6 +1010,20 @@ static int cmdRunGame(int argc, char** argv) {
   ps.policySurpriseDataWeight = atof(argv[7]); ps.valueSurpriseDataWeight = atof(argv[8]); ps.useSearchValueSurprise = atoi(argv[9]) != 0;
   ps.forSelfPlay = true; ps.recordTimePerMove = false;
   ps.noResolveTargetWeights = wantLog;   // the chain test leaves the weights fractional: the writer's own Rand then decides the extra rows
+  // search limits per move (getSearchLimitsThisMove, play.cpp:1093-1223): KGREF_REDUCE = "threshold,lookback,minVisits,weight", KGREF_CHEAP = "prob,visits,weight"
+  if(getenv("KGREF_REDUCE")) {
+    double thr, w; int look, mn;
+    if(sscanf(getenv("KGREF_REDUCE"), "%lf,%d,%d,%lf", &thr, &look, &mn, &w) != 4) { cerr << "bad KGREF_REDUCE" << endl; return 1; }
+    ps.reduceVisits = true; ps.reduceVisitsThreshold = thr; ps.reduceVisitsThresholdLookback = look; ps.reducedVisitsMin = mn; ps.reducedVisitsWeight = (float)w;
+    ps.noResolveTargetWeights = true;
+  }
+  if(getenv("KGREF_CHEAP")) {
+    double pr, w; int v;
+    if(sscanf(getenv("KGREF_CHEAP"), "%lf,%d,%lf", &pr, &v, &w) != 3) { cerr << "bad KGREF_CHEAP" << endl; return 1; }
+    ps.cheapSearchProb = pr; ps.cheapSearchVisits = v; ps.cheapSearchTargetWeight = (float)w;
+    ps.noResolveTargetWeights = true;
+  }
+  vector<double> rootWinLoss; vector<int64_t> rootVisitsByTurn;
   Rules rules;
   rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE; rules.multiStoneSuicideLegal = true;
   rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO; rules.friendlyPassOk = false; rules.komi = 6.5f;
@@ -1026,6 +1040,8 @@ static int cmdRunGame(int argc, char** argv) {
   auto onEachMove = [&](const Board& b, const BoardHistory& h, Player p, Loc loc, const vector<double>&, const vector<double>&, const vector<double>&, const Search* bot) {
     const ReportedSearchValues v = bot->getRootRawNNValuesRequireSuccess();
     raw.push_back(vector<double>{v.winValue, v.lossValue, v.noResultValue});
+    rootWinLoss.push_back(bot->getRootValuesRequireSuccess().winLossValue);      // what runGame appends to historicalMctsWinLossValues
+    rootVisitsByTurn.push_back(bot->getRootVisits());
     if(!wantLog) return;
     // what the device loop's getters expose for a finished root search (the event format of tests/mock/kgb200_mock.cpp)
     const int P = L * L + 1;
@@ -1085,6 +1101,8 @@ static int cmdRunGame(int argc, char** argv) {
   arr("valueSurprise", [&](size_t i) { return d(g->valueSurpriseByTurn[i]); }, n);
   arr("targetWeightUnrounded", [&](size_t i) { return d(g->targetWeightByTurnUnrounded[i]); }, n);
   arr("targetWeight", [&](size_t i) { return d(g->targetWeightByTurn[i]); }, n);
+  arr("rootWinLoss", [&](size_t i) { return d(rootWinLoss[i]); }, n);
+  arr("rootVisits", [&](size_t i) { return Global::int64ToString(rootVisitsByTurn[i]); }, n);
   cout << "}" << endl;
   if(wantLog) {
     ofstream lg(argv[10]);

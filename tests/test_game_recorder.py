@@ -726,3 +726,34 @@ def test_device_applies_per_move_search_limits(golden_dir, tmp_models):
         a.run(8)
     assert list(a.root_visits()) == [24, 16, 64] and np.array_equal(a.search_limits()[1], [0, 1, 0])
     a.free(); b.free(); h.free(); ctx.free()
+
+
+def test_search_limits_equal_the_reference_games(tmp_path):
+    """Whole games of the reference's Play::runGame with reduceVisits and recorded cheap searches on (tests/golden/make_searchlimits_fixture.py): the
+    budget (root visits) and target weight of every turn equal what search_limits_this_move derives from the root win/loss values of the turns
+    before it - exactly for reduced searches; a cheap turn has the cheap budget and weight, and cheap turns occur with cheapSearchProb."""
+    import gzip, json, random
+    from katago_b200.game_recorder import search_limits_this_move as L
+    games = json.loads(gzip.open(os.path.join(GOLDEN, "searchlimits.json.gz")).read())
+    checked = reduced = cheap_turns = cheap_games_turns = 0
+    for g in games:
+        ps = {}
+        if g["reduce"]:
+            thr, look, mn, w = g["reduce"].split(",")
+            ps.update(reduce_visits=True, reduce_visits_threshold=float(thr), reduce_visits_threshold_lookback=int(look), reduced_visits_min=int(mn), reduced_visits_weight=float(w))
+        cheap = None
+        if g["cheap"]:
+            pr, v, w = g["cheap"].split(",")
+            cheap = (int(v), float(w))
+        for t, (visits, weight) in enumerate(zip(g["rootVisits"], g["targetWeight"])):
+            want_v, _, want_w, _ = L(g["maxVisits"], ps, random.Random(0), g["rootWinLoss"][:t])       # the non-cheap branch (no cheap_search_prob in ps)
+            if cheap is not None and visits == cheap[0] and abs(weight - cheap[1]) < 1e-6:
+                cheap_turns += 1
+            else:
+                assert visits == want_v and abs(weight - float(want_w)) < 1e-6, (g["size"], t, visits, want_v, weight, want_w)
+                reduced += int(visits < g["maxVisits"])
+            checked += 1
+        if cheap is not None:
+            cheap_games_turns += len(g["rootVisits"])
+    assert checked > 250 and reduced > 20, (checked, reduced)
+    assert 0.35 < cheap_turns / cheap_games_turns < 0.65, (cheap_turns, cheap_games_turns)      # games with cheapSearchProb 0.4 and 0.6
