@@ -14,6 +14,19 @@ import numpy as np
 from .npz_writer import FinishedGameData, P_BLACK, P_WHITE
 
 
+def should_resign(win_loss_values, turn_index, board_area, mover_is_black, resign_threshold, resign_consec_turns):
+    """The resignation check of Play::runGame after move `turn_index` (0-based) by the mover (play.cpp:1903-1929): not before turn 1 + area / 5; the
+    last resignConsecTurns root win/loss values (white's perspective, one per search so far) must each say that THIS player is lost - below
+    the (non-positive) threshold for white, above its negative for black."""
+    if len(win_loss_values) < resign_consec_turns or turn_index < 1 + board_area // 5:
+        return False
+    for wl in win_loss_values[len(win_loss_values) - resign_consec_turns:]:
+        loser_is_black = False if wl < resign_threshold else True if wl > -resign_threshold else None
+        if loser_is_black is None or loser_is_black != mover_is_black:
+            return False
+    return True
+
+
 class MatchPlay:
     def __init__(self, loops, names, num_games_total, game_initializer=None, on_game=None, draw_equivalent_wins_for_white=0.5,
                  no_result_utility_for_white=0.0, game_hash_fn=None, allow_resignation=False, resign_threshold=-0.90, resign_consec_turns=5):
@@ -78,19 +91,10 @@ class MatchPlay:
                 raise RuntimeError("MatchPlay: could not end the resigned game")
 
     def _should_resign(self, g, mover_is_black):
-        """play.cpp:1903-1929 after the mover's move: the last resignConsecTurns root values all say the mover is lost, and the game is past its
-        first 1 + area / 5 turns."""
-        hist = self.win_loss[g]
-        if not self.allow_resignation or len(hist) < self.resign_consec:
+        if not self.allow_resignation:
             return False
         x, y = (int(v) for v in self.loops[0].game_setups()[0][g][:2])
-        if len(self.moves[g]) - 1 < 1 + x * y // 5:
-            return False
-        for wl in hist[-self.resign_consec:]:
-            loser_is_black = None if self.resign_threshold <= wl <= -self.resign_threshold else (wl > -self.resign_threshold)
-            if loser_is_black is None or loser_is_black != mover_is_black:
-                return False
-        return True
+        return should_resign(self.win_loss[g], len(self.moves[g]) - 1, x * y, mover_is_black, self.resign_threshold, self.resign_consec)
 
     def _finish(self, g, last, mover, resigned_black=None):
         sp = self.loops[mover]

@@ -1023,6 +1023,12 @@ static int cmdRunGame(int argc, char** argv) {
     ps.cheapSearchProb = pr; ps.cheapSearchVisits = v; ps.cheapSearchTargetWeight = (float)w;
     ps.noResolveTargetWeights = true;
   }
+  if(getenv("KGREF_RESIGN")) {   // allowResignation (play.cpp:1903-1929): "threshold,consecTurns"
+    double thr; int consec;
+    if(sscanf(getenv("KGREF_RESIGN"), "%lf,%d", &thr, &consec) != 2) { cerr << "bad KGREF_RESIGN" << endl; return 1; }
+    ps.allowResignation = true; ps.resignThreshold = thr; ps.resignConsecTurns = consec;
+    ps.forSelfPlay = false;      // runGame refuses to record full training data together with resignation
+  }
   vector<double> rootWinLoss; vector<int64_t> rootVisitsByTurn;
   Rules rules;
   rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE; rules.multiStoneSuicideLegal = true;
@@ -1086,6 +1092,14 @@ static int cmdRunGame(int argc, char** argv) {
   FinishedGameData* g = Play::runGame(board, pla, hist, ebk, spec, specW, "rungame" + seed, true, true, logger, false, false, maxMoves,
                                       []() { return false; }, nullptr, ps, other, gameRand, nullptr, onEachMove);
   auto d = [](double v) { return Global::strprintf("%.17g", v); };
+  if(ps.allowResignation) {    // no training data in this mode: the root values and how the game ended
+    cout << "{\"size\":" << L << ",\"turns\":" << rootWinLoss.size() << ",\"hitTurnLimit\":" << (g->hitTurnLimit ? 1 : 0) << ",\"rootWinLoss\":[";
+    for(size_t i = 0; i < rootWinLoss.size(); i++) cout << (i ? "," : "") << d(rootWinLoss[i]);
+    cout << "],\"resigned\":" << (g->endHist.isResignation ? 1 : 0) << ",\"winner\":" << (int)g->endHist.winner << ",\"gameFinished\":" << (g->endHist.isGameFinished ? 1 : 0)
+         << ",\"moves\":" << g->endHist.moveHistory.size() << "}" << endl;
+    delete g; delete nnEval;
+    return 0;
+  }
   const size_t n = g->targetWeightByTurn.size();
   if(raw.size() != n) { cerr << "onEachMove count " << raw.size() << " != turns " << n << endl; return 1; }
   cout << "{\"size\":" << L << ",\"turns\":" << n << ",\"policySurpriseDataWeight\":" << d(ps.policySurpriseDataWeight) << ",\"valueSurpriseDataWeight\":" << d(ps.valueSurpriseDataWeight)
@@ -1103,6 +1117,7 @@ static int cmdRunGame(int argc, char** argv) {
   arr("targetWeight", [&](size_t i) { return d(g->targetWeightByTurn[i]); }, n);
   arr("rootWinLoss", [&](size_t i) { return d(rootWinLoss[i]); }, n);
   arr("rootVisits", [&](size_t i) { return Global::int64ToString(rootVisitsByTurn[i]); }, n);
+  cout << ",\n\"resigned\":" << (g->endHist.isResignation ? 1 : 0) << ",\"winner\":" << (int)g->endHist.winner << ",\"gameFinished\":" << (g->endHist.isGameFinished ? 1 : 0);
   cout << "}" << endl;
   if(wantLog) {
     ofstream lg(argv[10]);

@@ -325,3 +325,23 @@ def test_match_with_resignation_between_a_deep_and_a_shallow_search(tmp_path, go
     log = open(tmp_path / "match.log").read()
     print(f"{resigned} of 10 games ended by resignation")
     assert "Match finished" in log
+
+
+def test_resignation_rule_equals_the_reference_games(golden_dir):
+    """Seven games of the reference's Play::runGame with allowResignation (tests/golden/make_resign_fixture.py: thresholds -0.02 .. -0.6, 1-4 consecutive
+    turns, 5x5 .. 13x13): replaying the root win/loss values through `should_resign`, the rule fires exactly at the move after which the
+    reference's game was resigned - by the player who made that move, won by the other - and never in the game that ended otherwise."""
+    import gzip, json
+    from katago_b200.match_play import should_resign
+    games = json.loads(gzip.open(os.path.join(golden_dir, "resign.json.gz")).read())
+    assert sum(g["resigned"] for g in games) >= 5 and any(not g["resigned"] for g in games)
+    for g in games:
+        thr, consec = g["resign"].split(",")
+        thr, consec, area = float(thr), int(consec), g["size"] ** 2
+        fired = [i for i in range(g["turns"]) if should_resign(g["rootWinLoss"][:i + 1], i, area, i % 2 == 0, thr, consec)]
+        if g["resigned"]:
+            last = g["turns"] - 1
+            assert fired and fired[0] == last, (g["size"], g["resign"], fired, last)
+            assert g["winner"] == (2 if last % 2 == 0 else 1)          # the mover of the last move (black on even indices) lost: P_WHITE = 2, P_BLACK = 1
+        else:
+            assert fired == [], (g["size"], g["resign"], fired)
