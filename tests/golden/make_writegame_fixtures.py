@@ -11,7 +11,7 @@ CASES = [("9x9",           9,  9,  9,     30,   7,   16,     0.5,          0),
          ("13x13",         13, 13, 13,    36,   34,  20,     0.8,          0),
          # the game's first 7 / 12 moves are its start history (a policy-initialised opening, a forked game): KGREF_START_MOVES
          ("9x9_start7",    9,  9,  9,     28,   41,  1000,   1.0,          0),
-         ("7x7_in_9_start12", 7, 7, 9,    24,   43,  18,     0.4,          0)]
+         ("7x7_in_9_start12", 7, 7, 9,    16,   43,  18,     0.4,          0)]
 START_MOVES = {"9x9_start7": 7, "7x7_in_9_start12": 12}
 for name, X, Y, D, turns, seed, max_rows, prop, nores in CASES:
     with tempfile.TemporaryDirectory() as td:
