@@ -1,0 +1,302 @@
+// Standalone C++ host of the device-resident self-play loop: model file + .cfg in, games (SGF) and a throughput line out.
+//
+// What `katago selfplay` is around its game threads (command/selfplay.cpp:34-330, program/play.cpp:1757-2027), reduced to the part a
+// host has left when search, rules, features and the net all run on the GPU: read the configuration by the reference's key names
+// (SearchParams: program/setup.cpp:381-700; the selfplay keys of configs/training/selfplay*.cfg), create evaluator and game slots
+// through the C ABI (include/kgb200.h), run playout waves, collect every move a slot has played and write finished games.
+// Plain C++17 over integration/b200selfplay.h - no CUDA headers, no reference headers, no Python.
+//
+//   g++ -std=c++17 -O2 -I. integration/b200_selfplay_main.cpp -o b200_selfplay -Lkatago_b200 -lkgb200 -Wl,-rpath,$PWD/katago_b200
+//   ./b200_selfplay -model net.bin.gz -config selfplay.cfg -output-dir games [-max-games-total N] [-override-config k=v,k=v]
+//
+// The full-featured host (npz training rows, per-game board sizes and komi, cheap searches, lead targets, forks, model polling, several
+// GPUs) is katago_b200/selfplay_cli.py; the reference-side recorder that fills the reference's own FinishedGameData is
+// integration/b200record.h.  This program shows boundary 2 used from C++ alone.  Without a CUDA device it stops with the library's
+// error (there is no CPU path).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+
+#include "b200selfplay.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string& what) { std::fprintf(stderr, "b200_selfplay: %s\n", what.c_str()); std::exit(1); }
+
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+  return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+
+// key = value lines, '#' comments (core/config_parser.cpp: the subset without @include and quoting)
+struct Cfg {
+  std::map<std::string, std::string> kv;
+  mutable std::map<std::string, bool> used;
+  void line(const std::string& raw, const std::string& where) {
+    std::string s = trim(raw.substr(0, raw.find('#')));
+    if(s.empty()) return;
+    size_t eq = s.find('=');
+    if(eq == std::string::npos) die(where + ": expected key = value, got '" + s + "'");
+    kv[trim(s.substr(0, eq))] = trim(s.substr(eq + 1));
+  }
+  void load(const std::string& path) {
+    std::ifstream in(path);
+    if(!in) die("cannot read config file " + path);
+    std::string l; int n = 0;
+    while(std::getline(in, l)) line(l, path + ":" + std::to_string(++n));
+  }
+  void overrides(const std::string& list) {
+    std::stringstream ss(list); std::string item;
+    while(std::getline(ss, item, ',')) line(item, "-override-config");
+  }
+  bool has(const std::string& k) const { return kv.count(k) > 0; }
+  double num(const std::string& k, double dflt) const {
+    used[k] = true;
+    auto it = kv.find(k);
+    if(it == kv.end()) return dflt;
+    char* end = nullptr;
+    double v = std::strtod(it->second.c_str(), &end);
+    if(end == it->second.c_str() || *end) die("config key " + k + ": not a number: '" + it->second + "'");
+    return v;
+  }
+  bool flag(const std::string& k, bool dflt) const {
+    used[k] = true;
+    auto it = kv.find(k);
+    if(it == kv.end()) return dflt;
+    if(it->second == "true") return true;
+    if(it->second == "false") return false;
+    die("config key " + k + ": expected true or false, got '" + it->second + "'");
+  }
+  std::string str(const std::string& k, const std::string& dflt) const { used[k] = true; auto it = kv.find(k); return it == kv.end() ? dflt : it->second; }
+  // a key of the reference this host does not read: fine while it keeps its neutral value, an error otherwise
+  void neutral(const std::string& k, const std::string& value) const {
+    used[k] = true;
+    auto it = kv.find(k);
+    if(it != kv.end() && it->second != value) die("config key " + k + " = " + it->second + " is not supported by this host (only " + value + "); use katago_b200/selfplay_cli.py");
+  }
+};
+
+// SearchParams and Rules by their cfg names -> kgb_selfplay_config (defaults of absent keys: the reference loader's for a self-play command, program/setup.cpp:445-760, like katago_b200/selfplay_cli.py)
+kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
+  kgb_selfplay_config k = {};
+  k.num_games = numGames;
+  k.max_visits = (int32_t)c.num("maxVisits", 0);
+  if(k.max_visits <= 0) die("maxVisits must be set: the loop needs a visit budget per move");
+  k.max_moves = (int32_t)c.num("maxMovesPerGame", 0);        // 0 = 2 * X * Y
+  k.seed = (uint64_t)c.num("searchRandSeed", 1.0);
+  k.nn_cache_size_power_of_two = (int32_t)c.num("nnCacheSizePowerOfTwo", 0);
+  k.komi = (float)c.num("komiMean", 7.5);
+  const std::string ko = c.str("koRules", "SIMPLE");
+  k.ko_rule = ko == "SIMPLE" ? 0 : ko == "POSITIONAL" ? 1 : ko == "SITUATIONAL" ? 2 : ko == "SPIGHT" ? 3 : -1;
+  if(k.ko_rule < 0) die("koRules: this host takes ONE of SIMPLE, POSITIONAL, SITUATIONAL, SPIGHT (per-game draws: selfplay_cli.py)");
+  k.multi_stone_suicide_legal = c.flag("multiStoneSuicideLegals", true) ? 1 : 0;
+  k.full_history_rules = 1;
+  c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
+  c.neutral("handicapProb", "0.0"); c.neutral("komiStdev", "0.0"); c.neutral("komiAuto", "false");
+  c.neutral("cheapSearchProb", "0.0"); c.neutral("reduceVisits", "false"); c.neutral("estimateLeadProb", "0.0");
+  c.neutral("initGamesWithPolicy", "false"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
+  c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0"); c.neutral("policySurpriseDataWeight", "0.0");
+
+  k.win_loss_utility_factor = c.num("winLossUtilityFactor", 1.0);
+  k.static_score_utility_factor = c.num("staticScoreUtilityFactor", 0.1);
+  k.dynamic_score_utility_factor = c.num("dynamicScoreUtilityFactor", 0.3);
+  k.dynamic_score_center_zero_weight = c.num("dynamicScoreCenterZeroWeight", 0.2);
+  k.dynamic_score_center_scale = c.num("dynamicScoreCenterScale", 0.75);
+  k.no_result_utility_for_white = c.num("noResultUtilityForWhite", 0.0);
+  k.draw_equivalent_wins_for_white = c.num("drawEquivalentWinsForWhite", 0.5);
+  k.cpuct_exploration = c.num("cpuctExploration", 1.0);
+  k.cpuct_exploration_log = c.num("cpuctExplorationLog", 0.45);
+  k.cpuct_exploration_base = c.num("cpuctExplorationBase", 500.0);
+  k.cpuct_utility_stdev_prior = c.num("cpuctUtilityStdevPrior", 0.4);
+  k.cpuct_utility_stdev_prior_weight = c.num("cpuctUtilityStdevPriorWeight", 2.0);
+  k.cpuct_utility_stdev_scale = c.num("cpuctUtilityStdevScale", 0.0);
+  k.fpu_reduction_max = c.num("fpuReductionMax", 0.2);
+  k.fpu_loss_prop = c.num("fpuLossProp", 0.0);
+  k.fpu_parent_weight_by_visited_policy = c.flag("fpuParentWeightByVisitedPolicy", true) ? 1 : 0;
+  // setup.cpp:501-513: the power is read only with the flag, the plain weight only without it
+  k.fpu_parent_weight_by_visited_policy_pow = k.fpu_parent_weight_by_visited_policy ? c.num("fpuParentWeightByVisitedPolicyPow", 2.0) : 1.0;
+  k.fpu_parent_weight = k.fpu_parent_weight_by_visited_policy ? 0.0 : c.num("fpuParentWeight", 0.0);
+  k.root_fpu_reduction_max = c.num("rootFpuReductionMax", c.flag("rootNoiseEnabled", false) ? 0.0 : 0.1);   // setup.cpp:578-583
+  k.root_fpu_loss_prop = c.num("rootFpuLossProp", k.fpu_loss_prop);
+  k.root_desired_per_child_visits_coeff = c.num("rootDesiredPerChildVisitsCoeff", 0.0);
+  k.value_weight_exponent = c.num("valueWeightExponent", 0.25);
+  k.subtree_value_bias_factor = c.num("subtreeValueBiasFactor", 0.45);
+  k.subtree_value_bias_weight_exponent = c.num("subtreeValueBiasWeightExponent", 0.85);
+  k.use_graph_search = c.flag("useGraphSearch", true) ? 1 : 0;
+  k.graph_search_rep_bound = (int32_t)c.num("graphSearchRepBound", 11);
+  k.root_noise_enabled = c.flag("rootNoiseEnabled", false) ? 1 : 0;
+  k.root_dirichlet_noise_total_concentration = c.num("rootDirichletNoiseTotalConcentration", 10.83);
+  k.root_dirichlet_noise_weight = c.num("rootDirichletNoiseWeight", 0.25);
+  k.root_policy_temperature = c.num("rootPolicyTemperature", 1.0);
+  k.root_policy_temperature_early = c.num("rootPolicyTemperatureEarly", k.root_policy_temperature);
+  k.root_num_symmetries_to_sample = (int32_t)c.num("rootNumSymmetriesToSample", 1);
+  k.use_play_selection = 1;
+  k.chosen_move_temperature = c.num("chosenMoveTemperature", 0.1);
+  k.chosen_move_temperature_early = c.num("chosenMoveTemperatureEarly", 0.5);
+  k.chosen_move_temperature_halflife = c.num("chosenMoveTemperatureHalflife", 19.0);
+  k.chosen_move_temperature_only_below_prob = c.num("chosenMoveTemperatureOnlyBelowProb", 1.0);
+  k.chosen_move_subtract = c.num("chosenMoveSubtract", 0.0);
+  k.chosen_move_prune = c.num("chosenMovePrune", 1.0);
+  k.use_lcb_for_selection = c.flag("useLcbForSelection", true) ? 1 : 0;
+  k.lcb_stdevs = c.num("lcbStdevs", 5.0);
+  k.min_visit_prop_for_lcb = c.num("minVisitPropForLCB", 0.15);
+  k.use_non_buggy_lcb = c.flag("useNonBuggyLcb", false) ? 1 : 0;
+  k.root_ending_bonus_points = c.num("rootEndingBonusPoints", 0.5);
+  k.root_prune_useless_moves = c.flag("rootPruneUselessMoves", true) ? 1 : 0;
+  k.max_playouts_per_wave = (int32_t)c.num("b200MaxPlayoutsPerWave", 4);
+  k.debug_hold_at_max_visits = 1;       // a slot whose search is finished waits for this host to read its move
+  return k;
+}
+
+// -print-config: the mapped fields as JSON (tests/test_abi_and_loader.py compares them with the reference's own loader through
+// integration/b200params.h, `kgref_driver paramsmap`)
+void printConfig(const kgb_selfplay_config& c) {
+  std::printf("{");
+#define FI(f) std::printf("\"" #f "\":%lld,", (long long)c.f)
+#define FD(f) std::printf("\"" #f "\":%.17g,", (double)c.f)
+  FI(num_games); FI(max_visits); FI(max_moves); FI(multi_stone_suicide_legal); FD(komi); FD(cpuct_exploration); FD(cpuct_exploration_log); FD(cpuct_exploration_base);
+  FD(fpu_reduction_max); FD(root_fpu_reduction_max); FD(win_loss_utility_factor); FD(no_result_utility_for_white);
+  FD(static_score_utility_factor); FD(dynamic_score_utility_factor); FD(dynamic_score_center_zero_weight); FD(dynamic_score_center_scale);
+  FD(draw_equivalent_wins_for_white); FD(value_weight_exponent); FI(fpu_parent_weight_by_visited_policy); FD(fpu_parent_weight_by_visited_policy_pow);
+  FD(fpu_parent_weight); FD(fpu_loss_prop); FD(root_fpu_loss_prop); FD(cpuct_utility_stdev_prior); FD(cpuct_utility_stdev_prior_weight);
+  FD(cpuct_utility_stdev_scale); FD(root_desired_per_child_visits_coeff); FD(subtree_value_bias_factor); FD(subtree_value_bias_weight_exponent);
+  FI(use_graph_search); FI(graph_search_rep_bound); FI(root_noise_enabled); FD(root_dirichlet_noise_total_concentration); FD(root_dirichlet_noise_weight);
+  FD(root_policy_temperature); FD(root_policy_temperature_early); FD(chosen_move_temperature_halflife); FI(use_play_selection); FI(use_lcb_for_selection);
+  FI(use_non_buggy_lcb); FD(lcb_stdevs); FD(min_visit_prop_for_lcb); FD(chosen_move_temperature); FD(chosen_move_temperature_early);
+  FD(chosen_move_temperature_only_below_prob); FD(chosen_move_subtract); FD(chosen_move_prune); FI(nn_cache_size_power_of_two);
+  FI(root_num_symmetries_to_sample); FI(ko_rule); FI(full_history_rules); FD(root_ending_bonus_points); FI(root_prune_useless_moves);
+  FI(max_playouts_per_wave);
+#undef FI
+#undef FD
+  std::printf("\"debug_hold_at_max_visits\":%d}\n", (int)c.debug_hold_at_max_visits);
+}
+
+const char* SGF_COLUMNS = "abcdefghijklmnopqrstuvwxyz";
+
+struct Game { std::vector<b200::Move> moves; };
+
+void writeSgf(const std::string& path, int x, int y, float komi, const Game& g, const std::string& result, const std::string& net) {
+  std::ofstream out(path);
+  if(!out) die("cannot write " + path);
+  out << "(;FF[4]GM[1]SZ[" << x; if(x != y) out << ":" << y;
+  out << "]PB[" << net << "]PW[" << net << "]HA[0]KM[" << komi << "]RU[koSIMPLEscoreAREAtaxNONEsui1]RE[" << result << "]";
+  for(size_t i = 0; i < g.moves.size(); i++) {
+    const b200::Move& m = g.moves[i];
+    out << ";" << (i % 2 == 0 ? "B" : "W") << "[";
+    if(!m.isPass()) out << SGF_COLUMNS[m.x] << SGF_COLUMNS[m.y];
+    out << "]";
+  }
+  out << ")\n";
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::string modelPath, cfgPath, outDir, overrides;
+  long maxGamesTotal = 0;
+  bool printOnly = false;
+  for(int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() { if(i + 1 >= argc) die("missing value after " + a); return std::string(argv[++i]); };
+    if(a == "-model") modelPath = next();
+    else if(a == "-config") cfgPath = next();
+    else if(a == "-output-dir") outDir = next();
+    else if(a == "-override-config") overrides = next();
+    else if(a == "-print-config") printOnly = true;
+    else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
+    else if(a == "-help" || a == "--help") {
+      std::printf("usage: %s -model FILE -config FILE -output-dir DIR [-max-games-total N] [-override-config k=v,...] [-print-config]\n", argv[0]);
+      return 0;
+    } else die("unknown argument " + a);
+  }
+  if(cfgPath.empty() || (!printOnly && (modelPath.empty() || outDir.empty()))) die("-model, -config and -output-dir are required (-help)");
+  Cfg cfg;
+  cfg.load(cfgPath);
+  cfg.overrides(overrides);
+
+  auto check = [](int rc, const char* what) { if(rc != 0) die(std::string(what) + ": " + kgb_last_error()); };
+  const int numGames = (int)cfg.num("numGameThreads", 256);          // concurrent games = the evaluator's batch
+  const std::string sizes = cfg.str("bSizes", "19");
+  if(sizes.find(',') != std::string::npos) die("bSizes: this host plays one board size (per-game draws: selfplay_cli.py)");
+  const int edge = std::atoi(sizes.c_str());
+  if(edge < 2 || edge > 19) die("bSizes: 2..19");
+  const int nnLen = (int)cfg.num("dataBoardLen", edge);
+  if(nnLen != edge) die("dataBoardLen must equal the board size for this host");
+  if(maxGamesTotal <= 0) maxGamesTotal = (long)cfg.num("numGamesTotal", 0);
+  const int wavesPerPoll = (int)cfg.num("b200WavesPerPoll", 16);
+  const kgb_selfplay_config sc = configFromCfg(cfg, numGames);
+  // keys that only place or log the reference's own CPU threads and evaluator servers: nothing to do here
+  static const char* irrelevant[] = {"log", "cuda", "trt", "opencl", "eigen", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
+                                     "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir"};
+  for(const auto& e : cfg.kv)
+    for(const char* prefix : irrelevant)
+      if(e.first.compare(0, std::strlen(prefix), prefix) == 0) cfg.used[e.first] = true;
+  for(const auto& e : cfg.kv)
+    if(!cfg.used.count(e.first)) std::fprintf(stderr, "b200_selfplay: note: config key %s is not read by this host\n", e.first.c_str());
+
+  if(printOnly) { printConfig(sc); return 0; }
+
+  check(kgb_global_init(), "kgb_global_init");
+  kgb_model* model = nullptr;
+  check(kgb_model_load_file(modelPath.c_str(), nullptr, &model), "loading the model");
+  kgb_model_info info;
+  check(kgb_model_get_info(model, &info), "kgb_model_get_info");
+  kgb_context* ctx = nullptr;
+  const int gpu = 0;
+  check(kgb_context_create(&gpu, 1, edge, edge, cfg.flag("useFP16", true) ? 1 : 0, model, &ctx), "creating the evaluator context");
+  kgb_handle* handle = nullptr;
+  check(kgb_handle_create(ctx, model, numGames, 1, /*inputs_nhwc=*/1, gpu, &handle), "creating the evaluator handle");
+
+  int rc = 0;
+  try {
+    b200::GameSlots slots(handle, sc, edge, edge);
+    std::vector<Game> games((size_t)numGames);
+    std::vector<uint8_t> mask((size_t)numGames);
+    long written = 0; uint64_t movesSeen = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while(maxGamesTotal <= 0 || written < maxGamesTotal) {
+      slots.runWaves(wavesPerPoll);
+      const std::vector<int32_t> visits = slots.visitBudgets();
+      const std::vector<int32_t> rootVisits = slots.rootVisitsAll();
+      bool any = false;
+      for(int g = 0; g < numGames; g++) { mask[(size_t)g] = rootVisits[(size_t)g] >= visits[(size_t)g]; any = any || mask[(size_t)g]; }
+      if(!any) continue;
+      slots.release(mask);
+      slots.runWaves(1);                                  // the wave in which the released slots choose and play their moves
+      for(int g = 0; g < numGames; g++) {
+        if(!mask[(size_t)g]) continue;
+        const b200::GameSlots::LastMove lm = slots.lastMove(g);
+        games[(size_t)g].moves.push_back(lm.move);
+        movesSeen++;
+        if(!lm.gameOver) continue;
+        std::ostringstream res;
+        if(lm.noResult) res << "Void";
+        else if(lm.finalWhiteMinusBlackScore > 0) res << "W+" << lm.finalWhiteMinusBlackScore;
+        else if(lm.finalWhiteMinusBlackScore < 0) res << "B+" << -lm.finalWhiteMinusBlackScore;
+        else res << "0";
+        if(maxGamesTotal <= 0 || written < maxGamesTotal) {
+          writeSgf(outDir + "/game" + std::to_string(written) + ".sgf", edge, edge, sc.komi, games[(size_t)g], res.str(), info.name);
+          written++;
+        }
+        games[(size_t)g].moves.clear();
+      }
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const kgb_selfplay_stats st = slots.stats();
+    std::printf("{\"games_written\": %ld, \"moves\": %llu, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",
+                written, (unsigned long long)movesSeen, (unsigned long long)st.total_visits, secs, st.total_visits / secs, (unsigned long long)st.nn_cache_hits);
+  } catch(const std::exception& e) {
+    std::fprintf(stderr, "b200_selfplay: %s\n", e.what());
+    rc = 1;
+  }
+  kgb_handle_free(handle);
+  kgb_context_free(ctx);
+  kgb_model_free(model);
+  kgb_global_cleanup();
+  return rc;
+}

@@ -127,6 +127,14 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
         kw.pop("fpu_parent_weight", None)
     else:
         kw.pop("fpu_parent_weight_by_visited_policy_pow", None)
+    # three defaults follow other keys (setup.cpp:575-583): the early root temperature the plain one, the root's fpu loss proportion the tree's,
+    # and the root fpu reduction is 0 once root noise is on
+    if "root_policy_temperature" in kw:
+        kw.setdefault("root_policy_temperature_early", kw["root_policy_temperature"])
+    if "fpu_loss_prop" in kw:
+        kw.setdefault("root_fpu_loss_prop", kw["fpu_loss_prop"])
+    if kw.get("root_noise_enabled", False):
+        kw.setdefault("root_fpu_reduction_max", 0.0)
     for name, ref_default in _REFERENCE_DEFAULTS.items():
         kw.setdefault(name, ref_default)
     if not by_policy:
@@ -152,10 +160,6 @@ def selfplay_kwargs_from_cfg(cfg, strict=False):
     sizes, size_probs = board_size_distribution(edges, rel, float(cfg.get("allowRectangleProb", 0.0)))
     size = max(edges)                                     # the evaluator's frame holds the largest board
     used.update(("koRules", "scoringRules", "taxRules", "hasButtons", "multiStoneSuicideLegals", "bSizes", "bSizeRelProbs", "allowRectangleProb"))
-    # komiAuto = true makes the reference find the komi that its own search calls even on the empty board
-    # (makeGameFairForEmptyBoard, program/play.cpp:640-644, playutils.cpp:591): that needs searches before the game and is NOT BUILT -
-    # the games start from komiMean (else 7.5) with the configured noise on every board size, which is off on small boards.  Listed so
-    # that -strict refuses it.
     komi = float(cfg["komiMean"]) if "komiMean" in cfg else 7.5
     used.update(("komiMean", "komiAuto", "komiStdev", "komiBigStdevProb", "komiBigStdev", "komiBiggerStdevProb", "komiBiggerStdev", "komiAllowIntegerProb"))
     # komiAuto (fair komi of the empty board found by search, play.cpp:1563-1575) and lead targets (play.cpp:2290-2324): komi-bisection searches

@@ -441,18 +441,14 @@ def test_sgf_sink_appends_one_record_per_game(tmp_path):
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "kgref_driver")
 
 
-@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/kgref_driver not built")
-@pytest.mark.parametrize("which", ["stock", "every_key_changed", "almost_empty", "plain_fpu_weight"])
-def test_config_mapping_agrees_with_the_reference_loader(tmp_path, which):
-    """The same .cfg through the reference's own ConfigParser + Setup::loadSingleParams and integration/b200params.h
-    (`kgref_driver paramsmap`) and through selfplay_cli.py: every mapped field of kgb_selfplay_config agrees, defaults of
-    absent keys included, and the C++ side reports the same search options as not implemented."""
-    import json, subprocess
-    from katago_b200.nn_backend import SelfPlay
+def _loader_case(which):
+    """The .cfg variants both configuration loaders are compared on."""
     if which == "stock":
         settings = dict(STOCK_B18_SETTINGS)
     elif which == "almost_empty":       # every default comes from the loader
         settings = {"numSearchThreads": "1", "maxVisits": "500"}
+    elif which == "dependent_defaults":  # defaults that follow other keys: rootPolicyTemperatureEarly, rootFpuLossProp, rootFpuReductionMax (setup.cpp:575-583)
+        settings = {"numSearchThreads": "1", "maxVisits": "500", "rootNoiseEnabled": "true", "rootPolicyTemperature": "1.3", "fpuLossProp": "0.15"}
     elif which == "plain_fpu_weight":
         settings = {"numSearchThreads": "1", "maxVisits": "500", "fpuParentWeightByVisitedPolicy": "false", "fpuParentWeight": "0.4", "fpuParentWeightByVisitedPolicyPow": "3.0"}
     else:      # a value of its own for every key the loop implements
@@ -469,6 +465,18 @@ def test_config_mapping_agrees_with_the_reference_loader(tmp_path, which):
                     "dynamicScoreCenterZeroWeight": "0.3", "dynamicScoreCenterScale": "0.75", "noResultUtilityForWhite": "-0.1",
                     "drawEquivalentWinsForWhite": "0.6", "rootNumSymmetriesToSample": "2", "nnCacheSizePowerOfTwo": "18", "koRules": "POSITIONAL",
                     "multiStoneSuicideLegals": "false", "wideRootNoise": "0.04", "antiMirror": "true", "numSearchThreads": "1"}
+    return settings
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/kgref_driver not built")
+@pytest.mark.parametrize("which", ["stock", "every_key_changed", "almost_empty", "plain_fpu_weight", "dependent_defaults"])
+def test_config_mapping_agrees_with_the_reference_loader(tmp_path, which):
+    """The same .cfg through the reference's own ConfigParser + Setup::loadSingleParams and integration/b200params.h
+    (`kgref_driver paramsmap`) and through selfplay_cli.py: every mapped field of kgb_selfplay_config agrees, defaults of
+    absent keys included, and the C++ side reports the same search options as not implemented."""
+    import json, subprocess
+    from katago_b200.nn_backend import SelfPlay
+    settings = _loader_case(which)
     path = tmp_path / "c.cfg"
     path.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
     kw, data, report = C.selfplay_kwargs_from_cfg(C.parse_cfg(str(path)))
@@ -485,6 +493,53 @@ def test_config_mapping_agrees_with_the_reference_loader(tmp_path, which):
     nb = " ".join(report["not_built"])
     for line in ref["unsupported"]:                   # search options the C++ side names must be named by the command too
         assert line.split(" = ")[0] in nb, (line, nb)
+
+
+@pytest.fixture(scope="module")
+def cpp_host(tmp_path_factory):
+    """integration/b200_selfplay_main.cpp (the C++-only host of boundary 2) built against the library."""
+    import subprocess
+    exe = tmp_path_factory.mktemp("cpphost") / "b200_selfplay"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", ROOT, os.path.join(ROOT, "integration", "b200_selfplay_main.cpp"), "-o", str(exe),
+                    "-L", os.path.join(ROOT, "katago_b200"), "-lkgb200", "-Wl,-rpath," + os.path.join(ROOT, "katago_b200")], check=True)
+    return str(exe)
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/kgref_driver not built")
+@pytest.mark.parametrize("which", ["stock", "every_key_changed", "almost_empty", "plain_fpu_weight", "dependent_defaults"])
+def test_cpp_host_config_mapping_agrees_with_the_reference_loader(tmp_path, cpp_host, which):
+    """The C++ host reads a .cfg by the reference's key names itself (no reference headers): its kgb_selfplay_config agrees field by field
+    with the reference's own loader mapped by integration/b200params.h, defaults of absent keys included."""
+    import json, subprocess
+    settings = {k: v.split(",")[0] for k, v in _loader_case(which).items() if k in C._SEARCH_KEYS or k in ("koRules", "multiStoneSuicideLegals", "numSearchThreads")}
+    path = tmp_path / "c.cfg"
+    path.write_text("".join(f"{k} = {v}\n" for k, v in settings.items()))
+    mine = json.loads(subprocess.run([cpp_host, "-config", str(path), "-print-config"], capture_output=True, text=True, check=True).stdout)
+    ref = json.loads(subprocess.run([DRIVER, "paramsmap", str(path), str(mine["ko_rule"])], capture_output=True, text=True, check=True).stdout)
+    for k, v in ref.items():
+        if k in ("unsupported", "komi", "multi_stone_suicide_legal"):      # rules are the game's, not the search parameters'
+            continue
+        assert abs(float(mine[k]) - float(v)) <= 1e-12, (k, mine[k], v)
+    assert mine["debug_hold_at_max_visits"] == 1 and mine["num_games"] == 256
+
+
+def test_cpp_host_refuses_what_it_does_not_play_and_needs_a_gpu(tmp_path, cpp_host, tmp_models):
+    """Options this small host does not have are an error, not a silent difference; and without a CUDA device it stops with the library's
+    error - there is no CPU path behind the C ABI."""
+    import subprocess
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\ncheapSearchProb = 0.25\n")
+    r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "cheapSearchProb" in r.stderr and "selfplay_cli.py" in r.stderr
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\n")
+    r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "bSizes" in r.stderr
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the loud failure without one is checked on CPU boxes")
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\n")
+    r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path), "-max-games-total", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "b200_selfplay:" in r.stderr and not list(tmp_path.glob("*.sgf")), r.stderr
 
 
 def test_slot_setups_hand_over_draws_forks_and_fair_komi():
