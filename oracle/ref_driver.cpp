@@ -1307,6 +1307,63 @@ static int cmdComputeLead(int argc, char** argv) {
   return 0;
 }
 
+// komitable MODELFILE X Y VISITS KOMI_LO KOMI_HI MOVES: for every half-integer komi in [KOMI_LO, KOMI_HI], PlayUtils::getWhiteScoreValues
+// (program/playutils.cpp:389-417: the noiseless VISITS-visit search that evalKomi runs) of the position after MOVES - one line
+// "komi lead winLoss" each.  The bot is the one computelead uses, so the table is the function the komi bisection of computeLead sees
+// (its searches do not depend on each other: no noise, symmetry 0, a cleared tree for every komi).  tests/golden/make_komitable_fixture.py.
+static int cmdKomiTable(int argc, char** argv) {
+  if(argc != 9) { cerr << "usage: komitable MODELFILE X Y VISITS KOMI_LO KOMI_HI MOVES" << endl; return 1; }
+  const string modelFile = argv[2];
+  const int X = atoi(argv[3]), Y = atoi(argv[4]), visits = atoi(argv[5]);
+  const double lo = atof(argv[6]), hi = atof(argv[7]);
+  Board::initHash();
+  ScoreValue::initTables();
+  Logger logger(nullptr, false, false, false);
+  ConfigParser cfg;
+  NNEvaluator* nnEval = new NNEvaluator("lead", modelFile, "", &logger, 4, X, Y, true, true, -1, 8, false, "", enabled_t::False, 1,
+                                        vector<int>{0}, "seed", false, 0, true, cfg);
+  nnEval->spawnServerThreads();
+  SearchParams params;                       // the same bot as cmdComputeLead
+  params.maxVisits = 1000;
+  params.numThreads = 1;
+  params.cpuctExploration = 1.0; params.cpuctExplorationLog = 0.45; params.cpuctExplorationBase = 500;
+  params.fpuReductionMax = 0.2; params.rootFpuReductionMax = 0.1;
+  params.staticScoreUtilityFactor = 0.0; params.dynamicScoreUtilityFactor = 0.0;
+  params.valueWeightExponent = 0.0;
+  params.rootNoiseEnabled = true;
+  params.rootEndingBonusPoints = 0.0; params.rootPruneUselessMoves = false; params.subtreeValueBiasFactor = 0.0; params.useGraphSearch = false;
+  params.useLcbForSelection = false; params.cpuctUtilityStdevScale = 0.0; params.useUncertainty = false; params.useNoisePruning = false;
+  Rules rules;
+  rules.koRule = Rules::KO_SIMPLE; rules.scoringRule = Rules::SCORING_AREA; rules.taxRule = Rules::TAX_NONE;
+  rules.multiStoneSuicideLegal = true; rules.hasButton = false; rules.whiteHandicapBonusRule = Rules::WHB_ZERO;
+  rules.friendlyPassOk = false; rules.komi = 7.5f;
+  Board board(X, Y);
+  Player pla = P_BLACK;
+  BoardHistory hist(board, pla, rules, 0, false);
+  {
+    std::istringstream in(argv[8]);
+    string tok;
+    while(in >> tok) {
+      Loc loc;
+      if(tok == "pass") loc = Board::PASS_LOC;
+      else { int x, y; if(sscanf(tok.c_str(), "%d,%d", &x, &y) != 2) { cerr << "bad move " << tok << endl; return 1; } loc = Location::getLoc(x, y, X); }
+      if(!hist.isLegal(board, loc, pla)) { cerr << "illegal move " << tok << endl; return 1; }
+      hist.makeBoardMoveAssumeLegal(board, loc, pla, NULL);
+      pla = getOpp(pla);
+    }
+  }
+  Search* bot = new Search(params, nnEval, &logger, "computelead");
+  OtherGameProperties props;
+  for(double k = lo; k <= hi + 1e-9; k += 0.5) {
+    hist.setKomi((float)k);
+    const ReportedSearchValues v = PlayUtils::getWhiteScoreValues(bot, board, hist, pla, visits, props);
+    cout << Global::strprintf("%.1f %.17g %.17g", k, v.lead, v.winLossValue) << "\n";
+  }
+  delete bot;
+  delete nnEval;
+  return 0;
+}
+
 // gameinit CFGFILE N SEED: N games of the reference's GameInitializer::createGame (program/play.cpp:330-650) on the given .cfg: per game
 // "X Y koRule multiStoneSuicide komi" - the per-game draws katago_b200/game_initializer.py restates (board size with rectangle probability,
 // rules, komi noise scaled by the board, linear rounding, integer komi allowed with probability komiAllowIntegerProb).
@@ -1347,6 +1404,7 @@ int main(int argc, char** argv) {
   if(cmd == "tinyfeatures") return cmdTinyFeatures(argc, argv);
   if(cmd == "featstream") return cmdFeatStream(argc, argv);
   if(cmd == "computelead") return cmdComputeLead(argc, argv);
+  if(cmd == "komitable") return cmdKomiTable(argc, argv);
   if(cmd == "gameinit") return cmdGameInit(argc, argv);
   cerr << "unknown command " << cmd << endl;
   return 1;

@@ -93,6 +93,35 @@ def test_komi_searcher_schedules_jobs_over_its_slots():
 REAL_NET_DRIVER = os.path.join(ROOT, "oracle", "_ref", "kgref_driver_b200")
 
 
+def _komitable_cases():
+    import gzip, json
+    return json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", "komitable.json.gz"), "rb").read())["cases"]
+
+
+@pytest.mark.parametrize("case", _komitable_cases(), ids=lambda c: c["name"])
+def test_compute_lead_lands_on_the_reference_value_given_the_reference_searches(case):
+    """PlayUtils::computeLead of the unmodified reference (trained g170-b6c96 net on host cores) against `compute_lead` driven by the function the
+    reference's komi bisection saw: tests/golden/komitable.json.gz holds, per position, (lead, winLoss) of PlayUtils::getWhiteScoreValues for every
+    komi the board allows and the reference's own result.  The generator must reach that result to the last bit (float32, as the reference
+    returns it) - i.e. bracket, bisect and interpolate exactly like getNaiveEvenKomiHelper / computeLead - asking only for rounded, clipped komis
+    and never twice for the same one (scoreWLCache)."""
+    table = case["table"]
+    assert len(case["leads"]) >= 25
+    for start, ref_lead in case["leads"].items():      # the case's own komi and ~25 more starting komis over the whole range the board allows
+        start, asked = float(start), []
+
+        def oracle(k):
+            assert k == float(np.float32(k)) and 2 * k == int(2 * k) and abs(k) <= 20 + case["x"] * case["y"], k
+            asked.append(k)
+            return tuple(table["%.1f" % k])
+        lead, _ = _run(compute_lead(start, case["x"], case["y"]), oracle)
+        assert len(set(asked)) == len(asked), asked
+        assert np.float32(lead) == np.float32(ref_lead), (start, lead, ref_lead, asked)
+        # the even komi that adjustKomiToEven rounds is the one this lead was taken from (coarse area-scoring granularity aside)
+        (naive, _), asked_naive = _run(naive_even_komi(start, case["x"], case["y"]), lambda k: tuple(table["%.1f" % k]))
+        assert asked_naive == asked[:len(asked_naive)] and abs((start - naive) - lead) <= 1.0
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(REAL_NET_DRIVER), reason="oracle/_ref/kgref_driver_b200 not built (needs the reference sources at build time)")
 @pytest.mark.parametrize("stream,size,prefix_len,komi,visits", [("boardstream_9x9_multisuicide.npz", 9, 12, 7.5, 6), ("boardstream_9x9_multisuicide.npz", 9, 31, 0.5, 10),
