@@ -265,6 +265,87 @@ def test_pump_records_slots_as_they_finish():
         assert all(np.array_equal(a, b) for a, b in zip(first[g].boards_by_turn, d.boards_by_turn))
 
 
+class _JobSink:
+    """Stands in for komi_search.KomiSearcher: keeps what the recorder submits; the test answers the jobs when and in the order it likes."""
+
+    def __init__(self):
+        self.jobs = []
+
+    def submit(self, gen, setup, moves, on_done):
+        self.jobs.append(dict(gen=gen, setup=tuple(setup), moves=list(moves), on_done=on_done))
+
+
+def test_recorder_holds_a_finished_game_until_its_lead_and_side_jobs_are_back():
+    """Host logic only (no GPU).  With estimateLeadProb the drawn turns of a finished game get a computeLead job for the position BEFORE that turn's
+    move (play.cpp:2290-2324) and the game is written when the last answer is in - the slot plays on meanwhile and a later game may overtake it;
+    the answers land in the turns' value targets as (hasLead, lead).  With side positions (play.cpp:1846-1860) a job carries the game so far plus a
+    forking move that is not the move played; a finished game also waits for those, and the searched positions become the game's side positions."""
+    import random
+    stream = np.load(os.path.join(GOLDEN, "boardstream_9x9_multisuicide.npz"))
+    sp = ScriptedSlots(stream, [5], 50)
+    lead_jobs, side_jobs, games = _JobSink(), _JobSink(), []
+    rec = R.GameRecorder(sp, None, 6.5, on_game=lambda g, data: games.append(data), lead_estimator=lead_jobs, estimate_lead_prob=0.6, lead_rand=random.Random(1),
+                         side_searcher=side_jobs, side_position_prob=0.7)
+    moves = [tuple(int(v) for v in stream["moves"][t][:2]) for t in range(5)]
+    for _ in range(5):
+        rec.step()
+    # the first game (A) is over: nothing is written while its jobs are out
+    assert games == [] and rec.games_written == 0 and rec.games_waiting_for_lead == 1
+    lead_a, side_a = list(lead_jobs.jobs), list(side_jobs.jobs)
+    assert 1 <= len(lead_a) <= 5 and all(j["setup"] == (9, 9, 0, 1) for j in lead_a)
+    turns = [len(j["moves"]) for j in lead_a]
+    assert turns == sorted(set(turns)) and all(j["moves"] == moves[:t] for j, t in zip(lead_a, turns))      # the position before turn t's move
+    assert 1 <= len(side_a) <= 4                      # (never after the move that ended the game)
+    for j in side_a:                                   # the game up to some turn, then ONE other move than the one played there
+        q = j["gen"].send(None)
+        n = len(q["moves"]) - 1
+        assert q["komi"] == 6.5 and q["moves"][:n] == moves[:n] and tuple(q["moves"][n]) != moves[n] and j["setup"] == (9, 9, 0, 1)
+    # all but one lead answer of A, in reverse order: still waiting
+    for k, j in enumerate(reversed(lead_a[1:])):
+        j["on_done"](10.0 + k)
+    assert games == [] and rec.games_waiting_for_lead == 1
+    # the slot plays on: its second game (B) ends, and waits as well
+    for _ in range(5):
+        rec.step()
+    lead_b, side_b = lead_jobs.jobs[len(lead_a):], side_jobs.jobs[len(side_a):]
+    assert rec.games_waiting_for_lead == (2 if (lead_b or side_b) else 1)
+
+    def answer_side(j, started):
+        side_loop = ScriptedSlots(stream, [30], 50)            # a side loop whose slot holds some searched position: read like a game turn
+        side_loop.t[0] = 3
+        if not started:
+            j["gen"].send(None)
+        try:
+            j["gen"].send(dict(lead=0.0, win_loss=0.0, nn_score_mean=0.0, legal=None, loop=side_loop, slot=0))
+        except StopIteration as st:
+            j["on_done"](st.value)
+    # B's jobs come back first: B overtakes A
+    for j in side_b:
+        answer_side(j, False)
+    for j in lead_b:
+        j["on_done"](1.5)
+    assert len(games) == 1 and games[0].game_hash != rec.game_hash_fn(0, 0) and rec.games_waiting_for_lead == 1
+    b = games[0]
+    assert len(b.side_positions) == len(side_b) and [len(v) > 4 and v[4] == 1 for v in b.white_value_targets_by_turn[:5]].count(True) == len(lead_b)
+    # A: its side positions, then the last lead answer
+    for j in side_a:
+        answer_side(j, True)
+    assert len(games) == 1
+    lead_a[0]["on_done"](-3.25)
+    assert len(games) == 2 and rec.games_waiting_for_lead == 0 and rec.games_written == 2
+    a = games[1]
+    assert a.game_hash == rec.game_hash_fn(0, 0) and a.moves == moves
+    for t in range(5):
+        v = a.white_value_targets_by_turn[t]
+        if t in turns:
+            want = -3.25 if t == turns[0] else 10.0 + list(reversed(turns[1:])).index(t)
+            assert v[4] == 1 and v[5] == np.float32(want), (t, v)
+        else:
+            assert len(v) < 5 or v[4] == 0
+    assert len(a.side_positions) == len(side_a) and all(isinstance(x, W.SidePosition) for x in a.side_positions)
+    assert all(x.turn_idx >= 1 and x.unreduced_num_visits == 50 and x.next_player == 2 for x in a.side_positions)
+
+
 def test_recorder_assembles_finished_games_from_scripted_slots():
     """Host logic only (no GPU): three slots replaying reference move streams of different lengths.  Every finished game carries the
     scripted moves, positions, per-turn targets and final area; rows reach the writer game by game; slots restart independently."""
