@@ -346,6 +346,72 @@ def test_recorder_holds_a_finished_game_until_its_lead_and_side_jobs_are_back():
     assert all(x.turn_idx >= 1 and x.unreduced_num_visits == 50 and x.next_player == 2 for x in a.side_positions)
 
 
+class LimitedSlots(ScriptedSlots):
+    """ScriptedSlots with the device's per-root search limits (kgb_selfplay_set_next_search_limits): a root's budget and plain flag are the ones handed
+    over for "after this slot's next move" - entry 0 when the game goes on, entry 1 when a new game starts."""
+
+    def __init__(self, stream, lengths, max_visits):
+        super().__init__(stream, lengths, max_visits)
+        n = self.num_games
+        self.budget, self.plain = np.full(n, max_visits, np.int32), np.zeros(n, np.uint8)
+        self.next_budget, self.next_plain = np.full((n, 2), max_visits, np.int32), np.zeros((n, 2), np.uint8)
+        self.roots = [[] for _ in range(n)]           # (game index, move number, budget, plain) of every root the slot has searched
+
+    def set_next_search_limits(self, visits2, plain2=None, also_current_roots=False):
+        self.next_budget = np.array(visits2, np.int32).reshape(self.num_games, 2)
+        self.next_plain = np.zeros((self.num_games, 2), np.uint8) if plain2 is None else np.array(plain2, np.uint8).reshape(self.num_games, 2)
+        if also_current_roots:
+            self.budget, self.plain = self.next_budget[:, 0].copy(), self.next_plain[:, 0].copy()
+
+    def search_limits(self):
+        return self.budget.copy(), self.plain.copy()
+
+    def root_visits(self):
+        return self.budget.copy()
+
+    def run(self, n):
+        moving = [g for g in range(self.num_games) if self.released[g]]
+        for g in moving:
+            self.roots[g].append((self.index[g], self.t[g], int(self.budget[g]), int(self.plain[g])))
+        super().run(n)
+        for g in moving:
+            k = 1 if self.last[g]["game_over"] else 0
+            self.budget[g], self.plain[g] = self.next_budget[g, k], self.next_plain[g, k]
+
+
+def test_recorder_hands_search_limits_over_one_root_ahead():
+    """Host logic only (no GPU).  Cheap searches (play.cpp:1093-1223): the limits of a root are drawn while the slot's PREVIOUS move is recorded and
+    handed to the device for "the root after the next move" - once for the game going on, once for a new game.  Every recorded turn's target weight
+    and cheap flag must describe the search the device really ran for that root: a cheap turn has cheapSearchVisits visits and the cheap weight,
+    any other the full budget and weight 1; an unrecorded cheap search (weight 0) runs with a plain root."""
+    import random
+    stream = np.load(os.path.join(GOLDEN, "boardstream_9x9_multisuicide.npz"))
+    for cheap_weight in (0.25, 0.0):
+        sp = LimitedSlots(stream, [7, 4, 11], 50)
+        games = []
+        ps = dict(cheap_search_prob=0.4, cheap_search_visits=12, cheap_search_target_weight=cheap_weight)
+        rec = R.GameRecorder(sp, None, 6.5, on_game=lambda g, data: games.append((g, data)), play_settings=ps, limits_rand=random.Random(11))
+        for _ in range(40):
+            rec.pump(1)
+        assert len(games) >= 12
+        seen = {g: 0 for g in range(3)}
+        cheap_turns = total = 0
+        for g, data in games:
+            n = len(data.moves)
+            roots = sp.roots[g][seen[g]:seen[g] + n]
+            seen[g] += n
+            assert [r[1] for r in roots] == list(range(n)) and len({r[0] for r in roots}) == 1          # this game's roots, in order
+            for t, (_, _, budget, plain) in enumerate(roots):
+                w = data.target_weight_by_turn[t]
+                total += 1
+                if budget == 12:
+                    cheap_turns += 1
+                    assert w == np.float32(cheap_weight) and plain == (1 if cheap_weight == 0.0 else 0), (g, t, w, plain)
+                else:
+                    assert budget == 50 and w == 1.0 and plain == 0, (g, t, budget, w, plain)
+        assert 0.25 < cheap_turns / total < 0.55, (cheap_turns, total)
+
+
 def test_recorder_assembles_finished_games_from_scripted_slots():
     """Host logic only (no GPU): three slots replaying reference move streams of different lengths.  Every finished game carries the
     scripted moves, positions, per-turn targets and final area; rows reach the writer game by game; slots restart independently."""
