@@ -1,0 +1,279 @@
+// Game recorder of the C++ host: device game slots in hold mode -> FinishedGame (integration/b200_npz.h), without any reference header.
+//
+// The stand-alone twin of katago_b200/game_recorder.py (GameRecorder.pump / _record_root / _after_move / _finish_game) for games that are
+// recorded in full: what Play::runGame does around its Search (program/play.cpp:1757-2163) once search, rules and features live on the device -
+//   extractSearchTargetsThisTurn (:931-948): value targets (ReportedSearchValues of the root's NodeStats), Q targets (child nodes), policy
+//     target (Play::extractPolicyTarget :810-846 on the play selection values), policy surprise and entropies
+//     (Search::getPolicySurpriseAndEntropy, search/searchresults.cpp:631-695), NNRawStats (:890-914);
+//   the game-end block (:1964-2027): outcome value targets, ownership / area / scoring planes from the device's final area;
+//   surprise weighting (:2034-2163: computeValueSurpriseByTurn, policy- and value-surprise redistribution of the turn weights) and
+//     resolveWeight (:2274-2289).
+// (integration/b200record.h is the reference-side variant of this file: it fills the reference's own FinishedGameData.)
+// Parity: tests/test_cpp_host.py runs the C++ host against a CPU mock of the ABI and compares its .npz rows and .sgfs records with the Python
+// recorder's on the same games, bit for bit.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <memory>
+
+#include "b200_npz.h"
+#include "b200selfplay.h"
+
+namespace b200 {
+
+// ReportedSearchValues (search/reportedsearchvalues.cpp:10-51) from NodeStats moments, white's perspective
+struct Reported { double win, loss, noResult, winLoss, score; };
+inline Reported reportedSearchValues(const double* m) {
+  Reported r;
+  r.winLoss = std::min(std::max(m[0], -1.0), 1.0);
+  r.noResult = std::min(std::max(m[1], 0.0), 1.0 - std::fabs(r.winLoss));
+  r.win = std::min(std::max(0.5 * (r.winLoss + (1.0 - r.noResult)), 0.0), 1.0);
+  r.loss = std::min(std::max(0.5 * (-r.winLoss + (1.0 - r.noResult)), 0.0), 1.0);
+  r.score = m[2];
+  return r;
+}
+
+// Play::extractPolicyTarget (play.cpp:810-846): scaleMaxToAtLeast = 10, cap at 30000, C round(), int16 - for every child, in position order
+inline std::vector<PolicyTargetMove> policyTargetMoves(const std::vector<double>& psv, int xLen) {
+  const size_t n = psv.size();
+  std::vector<double> v(n);
+  double mx = 0.0;
+  for(size_t i = 0; i < n; i++) { v[i] = psv[i] > 0 ? psv[i] : 0.0; mx = std::max(mx, v[i]); }
+  if(mx > 0 && mx < 10.0) { const double f = 10.0 / std::max(mx, 1e-300); mx = 0.0; for(double& x : v) { x *= f; mx = std::max(mx, x); } }
+  if(mx > 30000.0) { const double f = 30000.0 / std::max(mx, 1e-300); for(double& x : v) x *= f; }
+  std::vector<PolicyTargetMove> out;
+  for(size_t pos = 0; pos < n; pos++)
+    if(psv[pos] >= 0) out.push_back(PolicyTargetMove{pos == n - 1 ? -1 : (int)(pos % xLen), pos == n - 1 ? -1 : (int)(pos / xLen), (int16_t)std::floor(v[pos] + 0.5)});
+  return out;
+}
+
+// Search::getPolicySurpriseAndEntropy: KL(target || policy), entropy of the target, entropy of the policy
+inline void policySurpriseAndEntropy(const std::vector<double>& psv, const std::vector<float>& policy, double& surprise, double& searchEntropy, double& policyEntropy) {
+  double total = 0.0;
+  for(size_t i = 0; i < psv.size(); i++) if(psv[i] >= 0) total += psv[i];
+  surprise = searchEntropy = policyEntropy = 0.0;
+  for(size_t i = 0; i < psv.size(); i++) {
+    if(psv[i] < 0) continue;
+    const double p = std::max((double)policy[i], 1e-100), target = psv[i] / total;
+    if(target > 1e-100) { const double lt = std::log(target); surprise += target * (lt - std::log(p)); searchEntropy += -target * lt; }
+  }
+  for(float pf : policy) { const double p = pf; if(p > 1e-100) policyEntropy += -p * std::log(p); }
+  surprise = std::max(surprise, 0.0); searchEntropy = std::max(searchEntropy, 0.0); policyEntropy = std::max(policyEntropy, 0.0);
+}
+
+// valueSurpriseKL (play.cpp:1303-1314)
+inline double valueSurpriseKL(double win, double loss, double noResult, const std::array<double, 3>& raw) {
+  double s = 0.0;
+  const double v[3] = {win, loss, noResult};
+  for(int i = 0; i < 3; i++) if(v[i] > 1e-100) s += v[i] * (std::log(v[i]) - std::log(std::max(raw[i], 1e-100)));
+  return std::min(std::max(s, 0.0), 1.0);
+}
+
+// computeValueSurpriseByTurn (play.cpp:1322-1352)
+inline std::vector<double> computeValueSurpriseByTurn(const std::vector<ValueTargets>& vt, const std::vector<std::array<double, 3>>& rawNN, int boardArea, bool useSearchValueSurprise) {
+  const size_t n = rawNN.size();
+  std::vector<double> out(n, 0.0);
+  if(useSearchValueSurprise) { for(size_t i = 0; i < n; i++) out[i] = valueSurpriseKL(vt[i].win, vt[i].loss, vt[i].noResult, rawNN[i]); return out; }
+  const double now = 1.0 / (1.0 + boardArea * 0.016);
+  double win = vt.back().win, loss = vt.back().loss, nores = vt.back().noResult;
+  for(size_t k = n; k-- > 0;) {
+    win += now * ((double)vt[k].win - win); loss += now * ((double)vt[k].loss - loss); nores += now * ((double)vt[k].noResult - nores);
+    out[k] = valueSurpriseKL(win, loss, nores, rawNN[k]);
+  }
+  return out;
+}
+
+// The surprise weighting of Play::runGame (play.cpp:2084-2163) for games without cheap-search reanalysis
+inline std::vector<float> surpriseTargetWeights(const std::vector<float>& targetWeights, const std::vector<double>& policySurprise, const std::vector<double>& valueSurprise,
+                                                double policySurpriseDataWeight, double valueSurpriseDataWeight) {
+  const size_t n = targetWeights.size();
+  std::vector<double> w(targetWeights.begin(), targetWeights.end());
+  if(!(policySurpriseDataWeight > 0 || valueSurpriseDataWeight > 0)) return targetWeights;
+  double sumW = 0, sumP = 0, sumV = 0;
+  for(size_t i = 0; i < n; i++) {
+    if(!(w[i] >= 0.0 && w[i] <= 1.0)) throw std::runtime_error("surprise weighting expects target weights in [0, 1]");
+    sumW += w[i]; sumP += policySurprise[i] * w[i]; sumV += valueSurprise[i] * w[i];
+  }
+  if(sumW < 1) return targetWeights;
+  const double avgP = sumP / sumW, avgV = sumV / sumW;
+  double vsw = valueSurpriseDataWeight;
+  if(avgV < 0.010) vsw *= avgV / 0.010;
+  const double threshold = avgP * 1.5;
+  std::vector<double> pProp(n), vProp(n);
+  double sp = 0, sv = 0;
+  for(size_t i = 0; i < n; i++) {
+    pProp[i] = w[i] * policySurprise[i] + (1 - w[i]) * std::max(0.0, policySurprise[i] - threshold);
+    vProp[i] = w[i] * valueSurprise[i];
+  }
+  for(size_t i = 0; i < n; i++) { sp += pProp[i]; sv += vProp[i]; }
+  sp = std::max(sp, 1e-10); sv = std::max(sv, 1e-10);
+  std::vector<float> out(n);
+  for(size_t i = 0; i < n; i++)
+    out[i] = (float)((1.0 - policySurpriseDataWeight - vsw) * w[i] + policySurpriseDataWeight * pProp[i] * sumW / sp + vsw * vProp[i] * sumW / sv);
+  return out;
+}
+
+// resolveWeight (play.cpp:2277-2283)
+inline float resolveTargetWeight(float weight, RowRand& rand) {
+  const double w = std::max((double)weight, 0.0), floored = std::floor(w);
+  return (float)(rand.nextBool((double)((float)w - (float)floored)) ? floored + 1 : floored);
+}
+
+// FinishedGameData::gameHash: splitmix64 of (seed, slot, game index), as katago_b200/selfplay_cli.py _game_hash
+inline void gameHashOf(uint64_t seed, int slot, int index, uint64_t out[2]) {
+  auto mix = [](uint64_t z) { z += 0x9E3779B97F4A7C15ULL; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31); };
+  out[0] = mix(mix(seed) ^ ((uint64_t)slot << 32) ^ (uint64_t)index);
+  out[1] = mix(out[0]);
+}
+
+class HostRecorder {
+ public:
+  struct Settings {
+    float komi = 7.5f; double drawEquivalentWinsForWhite = 0.5; int koRule = 0; bool multiStoneSuicideLegal = true; int maxVisits = 0;
+    double policySurpriseDataWeight = 0.0, valueSurpriseDataWeight = 0.0; bool useSearchValueSurprise = false;
+    uint64_t hashSeed = 0; std::string weightRandSeed;      // weightRandSeed empty: fractional weights go to the writer unresolved
+  };
+  using OnGame = std::function<void(int slot, const FinishedGame&)>;
+
+  HostRecorder(GameSlots& slots, const Settings& s, OnGame onGame) : slots_(slots), s_(s), onGame_(std::move(onGame)), games_((size_t)slots.numSlots()) {
+    if(!s.weightRandSeed.empty()) weightRand_.reset(new RowRand(s.weightRandSeed));
+    slots_.runWaves(1);            // evaluates every root (its input row stays on the device)
+  }
+  int64_t movesRecorded() const { return movesRecorded_; }
+  int64_t gamesFinished() const { return gamesFinished_; }
+
+  // `waves` playout waves for every slot; then the slots whose search is finished are read, released, and move in one more wave
+  // (the others keep searching in it).  Returns the number of moves recorded.
+  int pump(int waves) {
+    const int n = slots_.numSlots();
+    slots_.runWaves(waves);
+    const std::vector<int32_t> visits = slots_.rootVisitsAll();
+    std::vector<uint8_t> held((size_t)n, 0);
+    std::vector<int> idx;
+    for(int g = 0; g < n; g++) if(visits[(size_t)g] >= s_.maxVisits) { held[(size_t)g] = 1; idx.push_back(g); }
+    if(idx.empty()) return 0;
+    const std::vector<double> rawEntropy = slots_.rootRawPolicyEntropies();
+    for(int g : idx) recordRoot(g, rawEntropy[(size_t)g]);
+    slots_.release(held);
+    slots_.runWaves(1);
+    movesRecorded_ += (int64_t)idx.size();
+    for(int g : idx) afterMove(g);
+    return (int)idx.size();
+  }
+
+ private:
+  struct Turn {
+    int nextPlayer, moveNum; std::pair<int, int> move{-1, -1};
+    std::vector<uint8_t> packed; std::array<float, NUM_GLOBAL> global;
+    std::vector<PolicyTargetMove> policyTarget; int64_t unreducedNumVisits;
+    ValueTargets valueTargets; std::vector<QValueTarget> qTargets;
+    double surprise, searchEntropy, policyEntropy; std::array<double, 3> nnRawStats, rawNNValues;
+  };
+  struct InProgress { std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; };
+
+  void recordRoot(int g, double rawPolicyEntropy) {
+    const int X = slots_.xLen(), Y = slots_.yLen(), A = X * Y;
+    const GameSlots::RootPosition pos = slots_.rootPosition(g);
+    std::vector<float> spatial, global;
+    slots_.rootInputRow(g, spatial, global);
+    const std::vector<float> policy = slots_.rootPolicy(g);
+    std::vector<double> childMoments; double rootMoments[5], nn[5];
+    slots_.rootValueStatsByPos(g, childMoments, rootMoments);
+    const std::vector<double> psv = slots_.playSelectionValuesByPos(g);
+    std::vector<int32_t> nodeVisits;
+    slots_.rootExtraByPos(g, nodeVisits, nn);
+    Turn t;
+    t.nextPlayer = pos.blackToMove ? P_BLACK : P_WHITE;
+    t.moveNum = pos.moveNumber;
+    // the kept row must be this root's: its own / opponent stone planes are the root position
+    for(int p = 0; p < A; p++)
+      if((spatial[(size_t)p * NUM_BIN + 1] != 0) != (pos.colors[(size_t)p] == t.nextPlayer) || (spatial[(size_t)p * NUM_BIN + 2] != 0) != (pos.colors[(size_t)p] == 3 - t.nextPlayer))
+        throw std::runtime_error("HostRecorder: slot " + std::to_string(g) + ", move " + std::to_string(pos.moveNumber) + ": the kept input row belongs to another position");
+    const int packedLen = (A + 7) / 8;
+    t.packed.assign((size_t)NUM_BIN * packedLen, 0);          // packBits: 8 points per byte, first point in the high bit
+    for(int p = 0; p < A; p++)
+      for(int c = 0; c < NUM_BIN; c++)
+        if(spatial[(size_t)p * NUM_BIN + c] != 0) t.packed[(size_t)c * packedLen + p / 8] |= (uint8_t)(0x80 >> (p % 8));
+    for(int i = 0; i < NUM_GLOBAL; i++) t.global[(size_t)i] = global[(size_t)i];
+    t.policyTarget = policyTargetMoves(psv, X);
+    t.unreducedNumVisits = pos.rootVisits;
+    const Reported rv = reportedSearchValues(rootMoments);
+    t.valueTargets.win = (float)rv.win; t.valueTargets.loss = (float)rv.loss; t.valueTargets.noResult = (float)rv.noResult; t.valueTargets.score = (float)rv.score;
+    for(size_t p = 0; p < nodeVisits.size(); p++) {             // extractQValueTargets (play.cpp:859-888)
+      if(nodeVisits[p] <= 0) continue;
+      const Reported c = reportedSearchValues(&childMoments[p * 5]);
+      const bool pass = p == nodeVisits.size() - 1;
+      t.qTargets.push_back(QValueTarget{pass ? -1 : (int)(p % X), pass ? -1 : (int)(p / X), (float)c.winLoss, (float)c.score, nodeVisits[p]});
+    }
+    policySurpriseAndEntropy(psv, policy, t.surprise, t.searchEntropy, t.policyEntropy);
+    t.nnRawStats = {nn[0], nn[2], rawPolicyEntropy};
+    const Reported rn = reportedSearchValues(nn);
+    t.rawNNValues = {rn.win, rn.loss, rn.noResult};
+    InProgress& gm = games_[(size_t)g];
+    gm.boards.push_back(pos.colors);
+    gm.turns.push_back(std::move(t));
+  }
+
+  void afterMove(int g) {
+    const GameSlots::LastMove last = slots_.lastMove(g);
+    games_[(size_t)g].turns.back().move = {last.move.x, last.move.y};
+    if(last.gameOver) finishGame(g, last);
+  }
+
+  void finishGame(int g, const GameSlots::LastMove& last) {
+    InProgress gm = std::move(games_[(size_t)g]);
+    games_[(size_t)g] = InProgress();
+    const int X = slots_.xLen(), Y = slots_.yLen();
+    FinishedGame d;
+    d.xSize = X; d.ySize = Y; d.komi = s_.komi;
+    d.drawEquivalentWinsForWhite = s_.drawEquivalentWinsForWhite;
+    gameHashOf(s_.hashSeed, g, last.gameIndex, d.gameHash);
+    d.endFinished = !last.hitMoveLimit; d.hitTurnLimit = last.hitMoveLimit; d.endNoResult = last.noResult;
+    static const char* KO[] = {"SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT"};
+    d.koRule = KO[s_.koRule & 3]; d.multiStoneSuicideLegal = s_.multiStoneSuicideLegal;
+    d.boardsByTurn = std::move(gm.boards);
+    d.boardsByTurn.push_back(last.finalColors);
+    std::vector<std::array<double, 3>> rawNN;
+    for(Turn& t : gm.turns) {
+      d.moves.push_back(t.move); d.nextPlayerByTurn.push_back(t.nextPlayer);
+      d.packedInputByTurn.push_back(std::move(t.packed)); d.globalInputByTurn.push_back(t.global);
+      d.targetWeightByTurn.push_back(1.0f);
+      d.policyTargetsByTurn.push_back(std::move(t.policyTarget)); d.unreducedNumVisitsByTurn.push_back(t.unreducedNumVisits);
+      d.policySurpriseByTurn.push_back(t.surprise); d.policyEntropyByTurn.push_back(t.policyEntropy); d.searchEntropyByTurn.push_back(t.searchEntropy);
+      d.whiteValueTargetsByTurn.push_back(t.valueTargets); d.whiteQValueTargetsByTurn.push_back(std::move(t.qTargets));
+      d.nnRawStatsByTurn.push_back(t.nnRawStats); rawNN.push_back(t.rawNNValues);
+    }
+    std::vector<uint8_t> area((size_t)X * Y, 0);           // a game without a result: nobody owns anything (play.cpp:1977-1988)
+    if(d.endNoResult) d.whiteValueTargetsByTurn.push_back(finalValueTargets(0, 0.0f, s_.drawEquivalentWinsForWhite, d.komi, true));
+    else {
+      // area scoring without tax: ownership = full area = calculateArea with every flag on (boardhistory.cpp:591-610)
+      area = last.finalArea;
+      const float score = last.finalWhiteMinusBlackScore;
+      d.winner = score > 0 ? P_WHITE : score < 0 ? P_BLACK : 0;
+      d.finalWhiteMinusBlackScore = score;
+      d.whiteValueTargetsByTurn.push_back(finalValueTargets(d.winner, score, s_.drawEquivalentWinsForWhite, d.komi, false));
+    }
+    d.finalFullArea = area; d.finalOwnership = area;
+    if(s_.policySurpriseDataWeight > 0 || s_.valueSurpriseDataWeight > 0) {        // play.cpp:2034-2163
+      const std::vector<double> valueSurprise = computeValueSurpriseByTurn(d.whiteValueTargetsByTurn, rawNN, X * Y, s_.useSearchValueSurprise);
+      d.targetWeightByTurn = surpriseTargetWeights(d.targetWeightByTurn, d.policySurpriseByTurn, valueSurprise, s_.policySurpriseDataWeight, s_.valueSurpriseDataWeight);
+      d.targetWeightByTurnUnrounded = d.targetWeightByTurn;
+    }
+    if(weightRand_) {                                                               // play.cpp:2274-2289
+      if(d.targetWeightByTurnUnrounded.empty()) d.targetWeightByTurnUnrounded = d.targetWeightByTurn;
+      for(float& w : d.targetWeightByTurn) w = resolveTargetWeight(w, *weightRand_);
+    }
+    d.finalWhiteScoring.resize(area.size());                // NNInputs::fillScoring without group tax: white area +1, black area -1
+    for(size_t i = 0; i < area.size(); i++) d.finalWhiteScoring[i] = area[i] == P_WHITE ? 1.0f : area[i] == P_BLACK ? -1.0f : 0.0f;
+    gamesFinished_++;
+    if(onGame_) onGame_(g, d);
+  }
+
+  GameSlots& slots_; Settings s_; OnGame onGame_;
+  std::vector<InProgress> games_;
+  std::unique_ptr<RowRand> weightRand_;
+  int64_t movesRecorded_ = 0, gamesFinished_ = 0;
+};
+
+}  // namespace b200

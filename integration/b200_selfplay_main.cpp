@@ -1,18 +1,21 @@
-// Standalone C++ host of the device-resident self-play loop: model file + .cfg in, games (SGF) and a throughput line out.
+// Standalone C++ host of the device-resident self-play loop: model file + .cfg in, training rows (.npz), game records (.sgfs) and a
+// throughput line out.
 //
-// What `katago selfplay` is around its game threads (command/selfplay.cpp:34-330, program/play.cpp:1757-2027), reduced to the part a
+// What `katago selfplay` is around its game threads (command/selfplay.cpp:34-330, program/play.cpp:1757-2163), reduced to the part a
 // host has left when search, rules, features and the net all run on the GPU: read the configuration by the reference's key names
-// (SearchParams: program/setup.cpp:381-700; the selfplay keys of configs/training/selfplay*.cfg), create evaluator and game slots
-// through the C ABI (include/kgb200.h), run playout waves, collect every move a slot has played and write finished games.
-// Plain C++17 over integration/b200selfplay.h - no CUDA headers, no reference headers, no Python.
+// (SearchParams: program/setup.cpp:381-760; the selfplay keys of configs/training/selfplay*.cfg), create evaluator and game slots
+// through the C ABI (include/kgb200.h), run playout waves, read every finished root search into per-turn training targets
+// (integration/b200_recorder.h), and write finished games as rows of <output-dir>/tdata/<16 hex>.npz and lines of
+// <output-dir>/sgfs/<16 hex>.sgfs (integration/b200_npz.h) - files python/train.py's loader and shuffle.py read.
+// Plain C++17 - no CUDA headers, no reference headers, no Python.
 //
-//   g++ -std=c++17 -O2 -I. integration/b200_selfplay_main.cpp -o b200_selfplay -Lkatago_b200 -lkgb200 -Wl,-rpath,$PWD/katago_b200
-//   ./b200_selfplay -model net.bin.gz -config selfplay.cfg -output-dir games [-max-games-total N] [-override-config k=v,k=v]
+//   g++ -std=c++17 -O2 -I. integration/b200_selfplay_main.cpp -o b200_selfplay -Lkatago_b200 -lkgb200 -lz -Wl,-rpath,$PWD/katago_b200
+//   ./b200_selfplay -model net.bin.gz -config selfplay.cfg -output-dir out [-max-games-total N] [-seed S] [-override-config k=v,k=v]
 //
-// The full-featured host (npz training rows, per-game board sizes and komi, cheap searches, lead targets, forks, model polling, several
-// GPUs) is katago_b200/selfplay_cli.py; the reference-side recorder that fills the reference's own FinishedGameData is
-// integration/b200record.h.  This program shows boundary 2 used from C++ alone.  Without a CUDA device it stops with the library's
-// error (there is no CPU path).
+// Games are recorded in full (every turn one row before the surprise weighting of policySurpriseDataWeight / valueSurpriseDataWeight).
+// The wider host (per-game board sizes, rules and komi, cheap / reduced searches, policy-initialised openings, lead targets, forks, side
+// positions, model polling and weight hot-swap, several GPUs) is katago_b200/selfplay_cli.py: options of that kind are refused here, not
+// ignored.  Without a CUDA device the program stops with the library's error (there is no CPU path).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -21,8 +24,9 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <sys/stat.h>
 
-#include "b200selfplay.h"
+#include "b200_recorder.h"
 
 namespace {
 
@@ -100,7 +104,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   c.neutral("handicapProb", "0.0"); c.neutral("komiStdev", "0.0"); c.neutral("komiAuto", "false");
   c.neutral("cheapSearchProb", "0.0"); c.neutral("reduceVisits", "false"); c.neutral("estimateLeadProb", "0.0");
   c.neutral("initGamesWithPolicy", "false"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
-  c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0"); c.neutral("policySurpriseDataWeight", "0.0");
+  c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
 
   k.win_loss_utility_factor = c.num("winLossUtilityFactor", 1.0);
   k.static_score_utility_factor = c.num("staticScoreUtilityFactor", 0.1);
@@ -176,29 +180,11 @@ void printConfig(const kgb_selfplay_config& c) {
   std::printf("\"debug_hold_at_max_visits\":%d}\n", (int)c.debug_hold_at_max_visits);
 }
 
-const char* SGF_COLUMNS = "abcdefghijklmnopqrstuvwxyz";
-
-struct Game { std::vector<b200::Move> moves; };
-
-void writeSgf(const std::string& path, int x, int y, float komi, const Game& g, const std::string& result, const std::string& net) {
-  std::ofstream out(path);
-  if(!out) die("cannot write " + path);
-  out << "(;FF[4]GM[1]SZ[" << x; if(x != y) out << ":" << y;
-  out << "]PB[" << net << "]PW[" << net << "]HA[0]KM[" << komi << "]RU[koSIMPLEscoreAREAtaxNONEsui1]RE[" << result << "]";
-  for(size_t i = 0; i < g.moves.size(); i++) {
-    const b200::Move& m = g.moves[i];
-    out << ";" << (i % 2 == 0 ? "B" : "W") << "[";
-    if(!m.isPass()) out << SGF_COLUMNS[m.x] << SGF_COLUMNS[m.y];
-    out << "]";
-  }
-  out << ")\n";
-}
-
 }  // namespace
 
 int main(int argc, char** argv) {
   std::string modelPath, cfgPath, outDir, overrides;
-  long maxGamesTotal = 0;
+  long maxGamesTotal = 0, seed = 1;
   bool printOnly = false;
   for(int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -208,9 +194,10 @@ int main(int argc, char** argv) {
     else if(a == "-output-dir") outDir = next();
     else if(a == "-override-config") overrides = next();
     else if(a == "-print-config") printOnly = true;
+    else if(a == "-seed") seed = std::atol(next().c_str());
     else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
     else if(a == "-help" || a == "--help") {
-      std::printf("usage: %s -model FILE -config FILE -output-dir DIR [-max-games-total N] [-override-config k=v,...] [-print-config]\n", argv[0]);
+      std::printf("usage: %s -model FILE -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-override-config k=v,...] [-print-config]\n", argv[0]);
       return 0;
     } else die("unknown argument " + a);
   }
@@ -230,6 +217,9 @@ int main(int argc, char** argv) {
   if(maxGamesTotal <= 0) maxGamesTotal = (long)cfg.num("numGamesTotal", 0);
   const int wavesPerPoll = (int)cfg.num("b200WavesPerPoll", 16);
   const kgb_selfplay_config sc = configFromCfg(cfg, numGames);
+  const double policySurpriseDataWeight = cfg.num("policySurpriseDataWeight", 0.0), valueSurpriseDataWeight = cfg.num("valueSurpriseDataWeight", 0.0);
+  const bool useSearchValueSurprise = cfg.flag("useSearchValueSurprise", false);
+  cfg.num("maxRowsPerTrainFile", 20000); cfg.num("firstFileRandMinProp", 1.0);
   // keys that only place or log the reference's own CPU threads and evaluator servers: nothing to do here
   static const char* irrelevant[] = {"log", "cuda", "trt", "opencl", "eigen", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
                                      "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir"};
@@ -254,42 +244,42 @@ int main(int argc, char** argv) {
 
   int rc = 0;
   try {
+    // <output-dir>/tdata and <output-dir>/sgfs like the reference's per-net directories (command/selfplay.cpp:178-225)
+    const std::string tdataDir = outDir + "/tdata", sgfDir = outDir + "/sgfs";
+    for(const std::string& dir : {outDir, tdataDir, sgfDir})
+      if(mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create " + dir);
+    const std::string writerSeed = "selfplay" + std::to_string(seed) + ":rank0of1";       // as katago_b200/selfplay_cli.py shard_plan
+    b200::TrainingDataWriter writer(tdataDir, (int)cfg.num("maxRowsPerTrainFile", 20000), cfg.num("firstFileRandMinProp", 1.0), edge, writerSeed);
+    b200::RowRand nameRand(writerSeed + ":sgfs");
+    const uint64_t lo = nameRand.nextUInt(), hi = nameRand.nextUInt();
+    char sgfName[32];
+    std::snprintf(sgfName, sizeof(sgfName), "%016llX.sgfs", (unsigned long long)(lo | (hi << 32)));
+    std::ofstream sgfs(sgfDir + "/" + sgfName, std::ios::app);
+    if(!sgfs) die("cannot write " + sgfDir + "/" + sgfName);
+
     b200::GameSlots slots(handle, sc, edge, edge);
-    std::vector<Game> games((size_t)numGames);
-    std::vector<uint8_t> mask((size_t)numGames);
-    long written = 0; uint64_t movesSeen = 0;
+    b200::HostRecorder::Settings rs;
+    rs.komi = sc.komi; rs.drawEquivalentWinsForWhite = sc.draw_equivalent_wins_for_white; rs.koRule = sc.ko_rule;
+    rs.multiStoneSuicideLegal = sc.multi_stone_suicide_legal != 0; rs.maxVisits = sc.max_visits;
+    rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
+    rs.hashSeed = (uint64_t)seed * 1000003ULL; rs.weightRandSeed = writerSeed + ":weights";
+    long written = 0;
+    const std::string netName = info.name;
+    b200::HostRecorder recorder(slots, rs, [&](int, const b200::FinishedGame& game) {
+      if(maxGamesTotal > 0 && written >= maxGamesTotal) return;        // games that end after the last counted one are dropped, like the Python host
+      writer.writeGame(game);
+      sgfs << b200::writeSgf(game, netName, netName) << "\n";
+      written++;
+    });
     const auto t0 = std::chrono::steady_clock::now();
-    while(maxGamesTotal <= 0 || written < maxGamesTotal) {
-      slots.runWaves(wavesPerPoll);
-      const std::vector<int32_t> visits = slots.visitBudgets();
-      const std::vector<int32_t> rootVisits = slots.rootVisitsAll();
-      bool any = false;
-      for(int g = 0; g < numGames; g++) { mask[(size_t)g] = rootVisits[(size_t)g] >= visits[(size_t)g]; any = any || mask[(size_t)g]; }
-      if(!any) continue;
-      slots.release(mask);
-      slots.runWaves(1);                                  // the wave in which the released slots choose and play their moves
-      for(int g = 0; g < numGames; g++) {
-        if(!mask[(size_t)g]) continue;
-        const b200::GameSlots::LastMove lm = slots.lastMove(g);
-        games[(size_t)g].moves.push_back(lm.move);
-        movesSeen++;
-        if(!lm.gameOver) continue;
-        std::ostringstream res;
-        if(lm.noResult) res << "Void";
-        else if(lm.finalWhiteMinusBlackScore > 0) res << "W+" << lm.finalWhiteMinusBlackScore;
-        else if(lm.finalWhiteMinusBlackScore < 0) res << "B+" << -lm.finalWhiteMinusBlackScore;
-        else res << "0";
-        if(maxGamesTotal <= 0 || written < maxGamesTotal) {
-          writeSgf(outDir + "/game" + std::to_string(written) + ".sgf", edge, edge, sc.komi, games[(size_t)g], res.str(), info.name);
-          written++;
-        }
-        games[(size_t)g].moves.clear();
-      }
-    }
+    while(maxGamesTotal <= 0 || written < maxGamesTotal) recorder.pump(wavesPerPoll);
+    writer.flushIfNonempty();
+    sgfs.close();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const kgb_selfplay_stats st = slots.stats();
-    std::printf("{\"games_written\": %ld, \"moves\": %llu, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",
-                written, (unsigned long long)movesSeen, (unsigned long long)st.total_visits, secs, st.total_visits / secs, (unsigned long long)st.nn_cache_hits);
+    std::printf("{\"games_written\": %ld, \"rows\": %lld, \"files\": %zu, \"moves\": %lld, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",
+                written, (long long)writer.rowCount(), writer.filesWritten().size(), (long long)recorder.movesRecorded(), (unsigned long long)st.total_visits, secs,
+                st.total_visits / secs, (unsigned long long)st.nn_cache_hits);
   } catch(const std::exception& e) {
     std::fprintf(stderr, "b200_selfplay: %s\n", e.what());
     rc = 1;

@@ -172,6 +172,31 @@ class GameSlots {
   int xLen() const { return x_; }
   int yLen() const { return y_; }
 
+  // ---- the same readers as plain arrays by move position (0 .. X*Y, pass last), for a recorder without the reference's types
+  //      (integration/b200_recorder.h) ----
+  struct RootPosition { std::vector<uint8_t> colors; int moveNumber = 0; bool blackToMove = true; int64_t rootVisits = 0; };
+  RootPosition rootPosition(int slot) const {
+    RootPosition r; r.colors.resize((size_t)x_ * y_);
+    int32_t info[6];
+    check(kgb_selfplay_get_game(sp_, slot, r.colors.data(), info));
+    r.moveNumber = info[0]; r.blackToMove = info[1] != 0; r.rootVisits = info[5];
+    return r;
+  }
+  std::vector<double> playSelectionValuesByPos(int slot) const {      // -1 = no child
+    std::vector<double> v((size_t)x_ * y_ + 1);
+    check(kgb_selfplay_get_play_selection_values(sp_, slot, v.data()));
+    return v;
+  }
+  void rootValueStatsByPos(int slot, std::vector<double>& childMoments /* [X*Y+1][5] */, double rootMoments[5]) const {
+    childMoments.resize(((size_t)x_ * y_ + 1) * 5);
+    check(kgb_selfplay_get_root_value_stats(sp_, slot, childMoments.data(), rootMoments));
+  }
+  void rootExtraByPos(int slot, std::vector<int32_t>& childNodeVisitsOut, double rootNNMoments[5]) const {
+    childNodeVisitsOut.resize((size_t)x_ * y_ + 1);
+    check(kgb_selfplay_get_root_extra(sp_, slot, childNodeVisitsOut.data(), rootNNMoments));
+  }
+  std::vector<double> rootRawPolicyEntropies() const { std::vector<double> e((size_t)n_); check(kgb_selfplay_get_root_raw_policy_entropy(sp_, e.data())); return e; }
+
  private:
   struct Info { int32_t v[6]; int32_t operator[](int i) const { return v[i]; } };
   Info gameInfo(int slot) const {

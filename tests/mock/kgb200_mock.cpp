@@ -10,6 +10,7 @@
 #include "game/board.h"
 #include "game/boardhistory.h"
 #include "neuralnet/nninputs.h"
+#include "core/rand.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -132,11 +133,14 @@ static void advance(kgb_selfplay* sp, int g) {
 #define GUARD(body) try { body; return 0; } catch(const std::exception& e) { g_err = e.what(); return 1; }
 
 extern "C" {
-int kgb_global_init(void) { return 0; }
+int kgb_global_init(void) { static bool done = false; if(!done) { Board::initHash(); done = true; } return 0; }     // (returns at once when the caller has done it)
 int kgb_global_cleanup(void) { return 0; }
 const char* kgb_last_error(void) { return g_err.c_str(); }
 int kgb_model_load_file(const char*, const char*, kgb_model** out) { *out = new kgb_model(); return 0; }
 void kgb_model_free(kgb_model* m) { delete m; }
+int kgb_model_get_info(const kgb_model*, kgb_model_info* out) { memset(out, 0, sizeof(*out)); strcpy(out->name, "mocknet"); return 0; }
+// the reference's own Rand: the stream the library's host generator reproduces (tests/test_abi_and_loader.py)
+int kgb_rand_uint32_stream(const char* seed, int n, uint32_t* out) { Rand r(seed); for(int i = 0; i < n; i++) out[i] = r.nextUInt(); return 0; }
 int kgb_context_create(const int*, int, int x, int y, int, const kgb_model*, kgb_context** out) { *out = new kgb_context{x, y}; return 0; }
 void kgb_context_free(kgb_context* c) { delete c; }
 int kgb_handle_create(kgb_context* c, const kgb_model*, int, int, int, int, kgb_handle** out) { *out = new kgb_handle{c->x, c->y}; return 0; }

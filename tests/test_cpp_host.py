@@ -1,0 +1,94 @@
+"""The C++-only host (integration/b200_selfplay_main.cpp + b200_recorder.h + b200_npz.h) end to end on the CPU: linked against the mock of the
+recording ABI (tests/mock/kgb200_mock.cpp: random legal games on the reference's Board, made-up search statistics, the reference's fillRowV7 rows
+and Rand), it must write the same files as the Python host's recorder and writer do from the mock's log - whole .npz files array by array,
+bit for bit, under the same names, and the same .sgfs records.  The Python writer is pinned to the reference's own addRow / writeGame / writeSgf
+(tests/test_npz_writer.py), the Python recorder to whole reference games (tests/test_game_recorder.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = "/root/reference/cpp"
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libkgref.a")
+
+pytestmark = pytest.mark.skipif(not (os.path.isdir(REF) and os.path.exists(REF_LIB)), reason="needs the reference sources and oracle/_ref/libkgref.a (the mock plays on the reference's Board)")
+
+
+@pytest.fixture(scope="module")
+def host_on_mock(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("cpphost_mock") / "b200_selfplay_mock"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-mfpmath=sse", "-DNDEBUG", "-DNO_GIT_REVISION", "-DNO_LIBZIP", "-w", "-I" + REF, "-I" + REF + "/external",
+                    "-isystem", REF + "/external/tclap-1.2.5/include", "-isystem", REF + "/external/filesystem-1.5.8/include", "-I" + ROOT, "-o", str(exe),
+                    os.path.join(ROOT, "integration", "b200_selfplay_main.cpp"), os.path.join(ROOT, "tests", "mock", "kgb200_mock.cpp"),
+                    "-Wl,--start-group", REF_LIB, "-Wl,--end-group", "-lz", "-lpthread"], check=True, cwd=ROOT)
+    return str(exe)
+
+
+@pytest.mark.parametrize("size,ko,komi,max_moves,psw,vsw,search_surprise,games,seed", [
+    (9, "SIMPLE", 6.5, 40, 0.5, 0.1, False, 7, 3),          # stock-like surprise weighting, games stopped by the move limit, several files
+    (5, "POSITIONAL", 7.0, 60, 0.0, 0.0, False, 9, 11),     # integer komi (draws), games ended by passes, every weight 1
+    (7, "SITUATIONAL", -2.5, 30, 0.3, 0.2, True, 5, 5),     # search-value surprise
+])
+def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed):
+    from test_game_recorder import ReplaySlots
+    from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
+    G, V, ROWS_PER_FILE = 3, 20, 60
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nbSizes = {size}\nkoRules = {ko}\nkomiMean = {komi}\nmaxMovesPerGame = {max_moves}\n"
+                   f"policySurpriseDataWeight = {psw}\nvalueSurpriseDataWeight = {vsw}\nuseSearchValueSurprise = {'true' if search_surprise else 'false'}\n"
+                   f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n")
+    (tmp_path / "model.bin").write_bytes(b"unused")
+    out, log = tmp_path / "cpp", tmp_path / "log.jsonl"
+    r = subprocess.run([host_on_mock, "-model", str(tmp_path / "model.bin"), "-config", str(cfg), "-output-dir", str(out), "-max-games-total", str(games), "-seed", str(seed)],
+                       env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+    # the Python host's recorder and writer on the same slots (the mock's log replayed), seeded like selfplay_cli.py seeds them
+    _, loop_seed, writer_seed = C.shard_plan(0, 1, games, seed)
+    sp = ReplaySlots(str(log), G, size, V)
+    py = tmp_path / "py"
+    os.makedirs(py / "tdata")
+    writer = W.TrainingDataWriter(str(py / "tdata"), ROWS_PER_FILE, 0.3, size, writer_seed)
+    sink = C.SgfSink(str(py / "sgfs"), writer_seed + ":sgfs", "mocknet", "mocknet")
+    done = []
+
+    def on_game(slot, data):
+        if len(done) < games:
+            data.ko_rule = ko
+            writer.write_game(data)
+            sink.add(slot, data)
+            done.append(data)
+
+    class Cfg:
+        ko_rule, multi_stone_suicide_legal = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2}[ko], 1
+    sp.cfg = Cfg()
+    rec = R.GameRecorder(sp, None, komi, on_game=on_game, game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
+                         policy_surprise_data_weight=psw, value_surprise_data_weight=vsw, use_search_value_surprise=search_surprise,
+                         weight_rand=W.RowRand(writer_seed + ":weights"))
+    while len(done) < games:
+        rec.pump(4)
+    writer.flush_if_nonempty()
+
+    cpp_files, py_files = sorted(os.listdir(out / "tdata")), sorted(os.listdir(py / "tdata"))
+    assert cpp_files == py_files and len(cpp_files) >= 2 and all(len(f) == 20 and f.endswith(".npz") for f in cpp_files)
+    rows = 0
+    for f in cpp_files:
+        a, b = np.load(out / "tdata" / f), np.load(py / "tdata" / f)
+        assert sorted(a.files) == sorted(b.files) == sorted(W.schema(size))
+        for k in a.files:
+            assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, (f, k)
+            assert a[k].tobytes() == b[k].tobytes(), (f, k, np.argwhere(a[k] != b[k])[:5])
+        rows += a["globalTargetsNC"].shape[0]
+    assert rows == writer.row_count > 0
+    if psw == 0 and vsw == 0:
+        assert rows == sum(len(d.moves) for d in done)
+    cpp_sgfs = os.listdir(out / "sgfs")
+    assert cpp_sgfs == [os.path.basename(sink.path)]
+    assert open(out / "sgfs" / cpp_sgfs[0]).read() == open(sink.path).read() and sink.count == games
+    summary = __import__("json").loads(r.stdout.strip().splitlines()[-1])
+    assert summary["games_written"] == games and summary["rows"] == rows and summary["files"] == len(cpp_files)

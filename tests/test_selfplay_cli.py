@@ -501,7 +501,7 @@ def cpp_host(tmp_path_factory):
     import subprocess
     exe = tmp_path_factory.mktemp("cpphost") / "b200_selfplay"
     subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", ROOT, os.path.join(ROOT, "integration", "b200_selfplay_main.cpp"), "-o", str(exe),
-                    "-L", os.path.join(ROOT, "katago_b200"), "-lkgb200", "-Wl,-rpath," + os.path.join(ROOT, "katago_b200")], check=True)
+                    "-L", os.path.join(ROOT, "katago_b200"), "-lkgb200", "-lz", "-Wl,-rpath," + os.path.join(ROOT, "katago_b200")], check=True)
     return str(exe)
 
 
