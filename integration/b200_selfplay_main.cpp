@@ -10,7 +10,7 @@
 // Plain C++17 - no CUDA headers, no reference headers, no Python.
 //
 //   g++ -std=c++17 -O2 -I. integration/b200_selfplay_main.cpp -o b200_selfplay -Lkatago_b200 -lkgb200 -lz -Wl,-rpath,$PWD/katago_b200
-//   ./b200_selfplay -model net.bin.gz -config selfplay.cfg -output-dir out [-max-games-total N] [-seed S] [-override-config k=v,k=v]
+//   ./b200_selfplay (-model net.bin.gz | -models-dir DIR) -config selfplay.cfg -output-dir out [-max-games-total N] [-seed S] [-override-config k=v,k=v]
 //
 // Games are recorded in full (every turn one row before the surprise weighting of policySurpriseDataWeight / valueSurpriseDataWeight).
 // The wider host (per-game board sizes, rules and komi, cheap / reduced searches, policy-initialised openings, lead targets, forks, side
@@ -24,6 +24,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <dirent.h>
 #include <sys/stat.h>
 
 #include "b200_recorder.h"
@@ -180,16 +181,51 @@ void printConfig(const kgb_selfplay_config& c) {
   std::printf("\"debug_hold_at_max_visits\":%d}\n", (int)c.debug_hold_at_max_visits);
 }
 
+// The newest net of a models directory (command/selfplay.cpp:150-176 LoadModel::findLatestModel; as katago_b200/selfplay_cli.py newest_model):
+// <dir>/*.bin.gz | *.bin | *.txt.gz | *.txt and <dir>/<name>/model.bin.gz, by modification time.
+bool endsWith(const std::string& s, const std::string& suffix) { return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0; }
+std::string newestModel(const std::string& dir) {
+  std::string best; double bestTime = -1;
+  auto consider = [&](const std::string& path) {
+    struct stat st;
+    if(stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return;
+    const double t = (double)st.st_mtim.tv_sec + 1e-9 * (double)st.st_mtim.tv_nsec;
+    if(t > bestTime) { bestTime = t; best = path; }
+  };
+  DIR* d = opendir(dir.c_str());
+  if(!d) die("cannot read the models directory " + dir);
+  while(dirent* e = readdir(d)) {
+    const std::string name = e->d_name;
+    if(name == "." || name == "..") continue;
+    if(endsWith(name, ".bin.gz") || endsWith(name, ".bin") || endsWith(name, ".txt.gz") || endsWith(name, ".txt")) consider(dir + "/" + name);
+    consider(dir + "/" + name + "/model.bin.gz");
+  }
+  closedir(d);
+  if(best.empty()) die("no model file in " + dir);
+  return best;
+}
+// the net's name in the output tree: <name>/model.bin.gz -> name, else the file name up to its first dot
+std::string modelNameOf(const std::string& path) {
+  const size_t slash = path.find_last_of('/');
+  const std::string base = slash == std::string::npos ? path : path.substr(slash + 1);
+  if(base == "model.bin.gz" && slash != std::string::npos && slash > 0) {
+    const size_t prev = path.find_last_of('/', slash - 1);
+    return path.substr(prev == std::string::npos ? 0 : prev + 1, slash - (prev == std::string::npos ? 0 : prev + 1));
+  }
+  return base.substr(0, base.find('.'));
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
-  std::string modelPath, cfgPath, outDir, overrides;
+  std::string modelPath, modelsDir, cfgPath, outDir, overrides;
   long maxGamesTotal = 0, seed = 1;
   bool printOnly = false;
   for(int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() { if(i + 1 >= argc) die("missing value after " + a); return std::string(argv[++i]); };
     if(a == "-model") modelPath = next();
+    else if(a == "-models-dir") modelsDir = next();
     else if(a == "-config") cfgPath = next();
     else if(a == "-output-dir") outDir = next();
     else if(a == "-override-config") overrides = next();
@@ -197,11 +233,14 @@ int main(int argc, char** argv) {
     else if(a == "-seed") seed = std::atol(next().c_str());
     else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
     else if(a == "-help" || a == "--help") {
-      std::printf("usage: %s -model FILE -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-override-config k=v,...] [-print-config]\n", argv[0]);
+      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-override-config k=v,...] [-print-config]\n", argv[0]);
       return 0;
     } else die("unknown argument " + a);
   }
-  if(cfgPath.empty() || (!printOnly && (modelPath.empty() || outDir.empty()))) die("-model, -config and -output-dir are required (-help)");
+  if(cfgPath.empty() || (!printOnly && ((modelPath.empty() == modelsDir.empty()) || outDir.empty())))
+    die("-config, -output-dir and one of -model / -models-dir are required (-help)");
+  // `katago selfplay -models-dir DIR`: the newest net of the directory, its files under <output-dir>/<net name>/ (command/selfplay.cpp:178-225)
+  if(!printOnly && !modelsDir.empty()) { modelPath = newestModel(modelsDir); outDir = outDir + "/" + modelNameOf(modelPath); }
   Cfg cfg;
   cfg.load(cfgPath);
   cfg.overrides(overrides);
@@ -246,7 +285,7 @@ int main(int argc, char** argv) {
   try {
     // <output-dir>/tdata and <output-dir>/sgfs like the reference's per-net directories (command/selfplay.cpp:178-225)
     const std::string tdataDir = outDir + "/tdata", sgfDir = outDir + "/sgfs";
-    for(const std::string& dir : {outDir, tdataDir, sgfDir})
+    for(const std::string& dir : {modelsDir.empty() ? outDir : outDir.substr(0, outDir.find_last_of('/')), outDir, tdataDir, sgfDir})
       if(mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create " + dir);
     const std::string writerSeed = "selfplay" + std::to_string(seed) + ":rank0of1";       // as katago_b200/selfplay_cli.py shard_plan
     b200::TrainingDataWriter writer(tdataDir, (int)cfg.num("maxRowsPerTrainFile", 20000), cfg.num("firstFileRandMinProp", 1.0), edge, writerSeed);
@@ -264,7 +303,7 @@ int main(int argc, char** argv) {
     rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
     rs.hashSeed = (uint64_t)seed * 1000003ULL; rs.weightRandSeed = writerSeed + ":weights";
     long written = 0;
-    const std::string netName = info.name;
+    const std::string netName = modelsDir.empty() ? std::string(info.name) : modelNameOf(modelPath);
     b200::HostRecorder recorder(slots, rs, [&](int, const b200::FinishedGame& game) {
       if(maxGamesTotal > 0 && written >= maxGamesTotal) return;        // games that end after the last counted one are dropped, like the Python host
       writer.writeGame(game);

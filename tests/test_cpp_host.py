@@ -42,11 +42,20 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nbSizes = {size}\nkoRules = {ko}\nkomiMean = {komi}\nmaxMovesPerGame = {max_moves}\n"
                    f"policySurpriseDataWeight = {psw}\nvalueSurpriseDataWeight = {vsw}\nuseSearchValueSurprise = {'true' if search_surprise else 'false'}\n"
                    f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n")
-    (tmp_path / "model.bin").write_bytes(b"unused")
     out, log = tmp_path / "cpp", tmp_path / "log.jsonl"
-    r = subprocess.run([host_on_mock, "-model", str(tmp_path / "model.bin"), "-config", str(cfg), "-output-dir", str(out), "-max-games-total", str(games), "-seed", str(seed)],
+    if size == 5:      # `katago selfplay -models-dir`: the newest net of the directory, its files under <output-dir>/<net name>/
+        os.makedirs(tmp_path / "nets" / "b6c96-s100-d200")
+        (tmp_path / "nets" / "older.bin.gz").write_bytes(b"unused")
+        os.utime(tmp_path / "nets" / "older.bin.gz", (1, 1))
+        (tmp_path / "nets" / "b6c96-s100-d200" / "model.bin.gz").write_bytes(b"unused")
+        model_args, net_name, out_dir = ["-models-dir", str(tmp_path / "nets")], "b6c96-s100-d200", out / "b6c96-s100-d200"
+    else:
+        (tmp_path / "model.bin").write_bytes(b"unused")
+        model_args, net_name, out_dir = ["-model", str(tmp_path / "model.bin")], "mocknet", out
+    r = subprocess.run([host_on_mock] + model_args + ["-config", str(cfg), "-output-dir", str(out), "-max-games-total", str(games), "-seed", str(seed)],
                        env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+    out = out_dir
 
     # the Python host's recorder and writer on the same slots (the mock's log replayed), seeded like selfplay_cli.py seeds them
     _, loop_seed, writer_seed = C.shard_plan(0, 1, games, seed)
@@ -54,7 +63,7 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     py = tmp_path / "py"
     os.makedirs(py / "tdata")
     writer = W.TrainingDataWriter(str(py / "tdata"), ROWS_PER_FILE, 0.3, size, writer_seed)
-    sink = C.SgfSink(str(py / "sgfs"), writer_seed + ":sgfs", "mocknet", "mocknet")
+    sink = C.SgfSink(str(py / "sgfs"), writer_seed + ":sgfs", net_name, net_name)
     done = []
 
     def on_game(slot, data):
