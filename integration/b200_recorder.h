@@ -1,13 +1,13 @@
 // Game recorder of the C++ host: device game slots in hold mode -> FinishedGame (integration/b200_npz.h), without any reference header.
 //
-// The stand-alone twin of katago_b200/game_recorder.py (GameRecorder.pump / _record_root / _after_move / _finish_game) for games that are
-// recorded in full: what Play::runGame does around its Search (program/play.cpp:1757-2163) once search, rules and features live on the device -
+// The stand-alone twin of katago_b200/game_recorder.py (GameRecorder.pump / _record_root / _after_move / _finish_game, search_limits_this_move): what Play::runGame does around its Search (program/play.cpp:1757-2163) once search, rules and features live on the device -
 //   extractSearchTargetsThisTurn (:931-948): value targets (ReportedSearchValues of the root's NodeStats), Q targets (child nodes), policy
 //     target (Play::extractPolicyTarget :810-846 on the play selection values), policy surprise and entropies
 //     (Search::getPolicySurpriseAndEntropy, search/searchresults.cpp:631-695), NNRawStats (:890-914);
 //   the game-end block (:1964-2027): outcome value targets, ownership / area / scoring planes from the device's final area;
 //   surprise weighting (:2034-2163: computeValueSurpriseByTurn, policy- and value-surprise redistribution of the turn weights) and
-//     resolveWeight (:2274-2289).
+//     resolveWeight (:2274-2289);
+//   getSearchLimitsThisMove (:1093-1223): cheap searches and reduced visits, drawn one root ahead and applied by the device.
 // (integration/b200record.h is the reference-side variant of this file: it fills the reference's own FinishedGameData.)
 // Parity: tests/test_cpp_host.py runs the C++ host against a CPU mock of the ABI and compares its .npz rows and .sgfs records with the Python
 // recorder's on the same games, bit for bit.
@@ -127,17 +127,108 @@ inline void gameHashOf(uint64_t seed, int slot, int index, uint64_t out[2]) {
   out[1] = mix(out[0]);
 }
 
+// Python's random.Random(seed).random() for a non-negative integer seed (MT19937 seeded by init_by_array over the seed's 32-bit words, 53-bit
+// doubles from two outputs): the stream katago_b200/game_recorder.py draws the per-move search limits from, so that both hosts make the same draws.
+class PyRandom {
+ public:
+  explicit PyRandom(uint64_t seed) {
+    uint32_t key[2] = {(uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32)};
+    const int keyLength = key[1] != 0 ? 2 : 1;
+    mt_[0] = 19650218u;
+    for(int i = 1; i < N; i++) mt_[i] = 1812433253u * (mt_[i - 1] ^ (mt_[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for(int k = N > keyLength ? N : keyLength; k > 0; k--) {
+      mt_[i] = (mt_[i] ^ ((mt_[i - 1] ^ (mt_[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+      if(++i >= N) { mt_[0] = mt_[N - 1]; i = 1; }
+      if(++j >= keyLength) j = 0;
+    }
+    for(int k = N - 1; k > 0; k--) {
+      mt_[i] = (mt_[i] ^ ((mt_[i - 1] ^ (mt_[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+      if(++i >= N) { mt_[0] = mt_[N - 1]; i = 1; }
+    }
+    mt_[0] = 0x80000000u;
+    idx_ = N;
+  }
+  double random() { const uint32_t a = next() >> 5, b = next() >> 6; return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0); }
+ private:
+  static constexpr int N = 624, M = 397;
+  uint32_t next() {
+    if(idx_ >= N) {
+      for(int k = 0; k < N; k++) {
+        const uint32_t y = (mt_[k] & 0x80000000u) | (mt_[(k + 1) % N] & 0x7FFFFFFFu);
+        mt_[k] = mt_[(k + M) % N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+      }
+      idx_ = 0;
+    }
+    uint32_t y = mt_[idx_++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9D2C5680u; y ^= (y << 15) & 0xEFC60000u; y ^= y >> 18;
+    return y;
+  }
+  uint32_t mt_[N]; int idx_;
+};
+
+// getSearchLimitsThisMove (program/play.cpp:1093-1223) without hint moves and asymmetric playouts: the next search's visits, whether its root
+// is plain (no noise / temperature: an unrecorded cheap search), the turn's target weight, whether it is a cheap search
+struct PlaySettings {
+  double cheapSearchProb = 0.0; int cheapSearchVisits = 0; double cheapSearchTargetWeight = 0.0;
+  bool reduceVisits = false; double reduceVisitsThreshold = 100.0; int reduceVisitsThresholdLookback = 1; int reducedVisitsMin = 0; double reducedVisitsWeight = 1.0;
+  bool active() const { return cheapSearchProb > 0.0 || reduceVisits; }
+};
+struct SearchLimits { int visits; bool plainRoot; float targetWeight; bool cheap; };
+inline SearchLimits searchLimitsThisMove(int maxVisits, const PlaySettings& ps, PyRandom& rand, const std::vector<double>& historicalWinLoss) {
+  SearchLimits r{maxVisits, false, 1.0f, false};
+  if(ps.cheapSearchProb > 0.0 && rand.random() < ps.cheapSearchProb) {
+    if(ps.cheapSearchVisits <= 0 || ps.cheapSearchVisits > maxVisits) throw std::runtime_error("cheapSearchVisits must lie in 1..maxVisits");
+    r.cheap = true; r.visits = std::min(r.visits, ps.cheapSearchVisits);
+    r.targetWeight = (float)((double)r.targetWeight * (double)(float)ps.cheapSearchTargetWeight);
+    if(ps.cheapSearchTargetWeight <= 0.0) r.plainRoot = true;
+  }
+  else if(ps.reduceVisits) {
+    if(ps.reducedVisitsMin <= 0 || ps.reducedVisitsMin > maxVisits) throw std::runtime_error("reducedVisitsMin must lie in 1..maxVisits");
+    const size_t look = (size_t)ps.reduceVisitsThresholdLookback, h = historicalWinLoss.size();
+    if(h >= look) {
+      double lo = 1e20, hi = -1e20;
+      for(size_t j = 0; j < look; j++) { lo = std::min(lo, historicalWinLoss[h - 1 - j]); hi = std::max(hi, historicalWinLoss[h - 1 - j]); }
+      const double mostExtreme = std::min(std::max(lo, -hi), 1.0), through = mostExtreme - ps.reduceVisitsThreshold;
+      if(through > 0) {
+        static double (*volatile libmPow)(double, double) = std::pow;       // the same libm call as Python's `** 2`, not folded into a product
+        const double prop = libmPow(through / (1.0 - ps.reduceVisitsThreshold), 2.0);
+        r.visits = (int)std::floor(r.visits + prop * (ps.reducedVisitsMin - r.visits) + 0.5);
+        r.targetWeight = (float)((double)r.targetWeight + prop * ((double)(float)ps.reducedVisitsWeight - (double)r.targetWeight));
+        r.visits = std::max(r.visits, ps.reducedVisitsMin);
+      }
+    }
+  }
+  r.visits = std::max(2, r.visits);
+  return r;
+}
+
 class HostRecorder {
  public:
   struct Settings {
     float komi = 7.5f; double drawEquivalentWinsForWhite = 0.5; int koRule = 0; bool multiStoneSuicideLegal = true; int maxVisits = 0;
     double policySurpriseDataWeight = 0.0, valueSurpriseDataWeight = 0.0; bool useSearchValueSurprise = false;
     uint64_t hashSeed = 0; std::string weightRandSeed;      // weightRandSeed empty: fractional weights go to the writer unresolved
+    PlaySettings play; uint64_t limitsRandSeed = 0x4C696D69;   // cheap searches / reduced visits, drawn per move
   };
   using OnGame = std::function<void(int slot, const FinishedGame&)>;
 
   HostRecorder(GameSlots& slots, const Settings& s, OnGame onGame) : slots_(slots), s_(s), onGame_(std::move(onGame)), games_((size_t)slots.numSlots()) {
     if(!s.weightRandSeed.empty()) weightRand_.reset(new RowRand(s.weightRandSeed));
+    const size_t n = (size_t)slots.numSlots();
+    curLimits_.assign(n, SearchLimits{s.maxVisits, false, 1.0f, false});
+    if(s_.play.active()) {
+      // the limits of a root are drawn one move ahead and handed to the device for "the root after this slot's next move" - once for the game
+      // going on, once for a new game (kgb_selfplay_set_next_search_limits); the very first roots get theirs here
+      limitsRand_.reset(new PyRandom(s.limitsRandSeed));
+      nextVisits_.resize(2 * n); nextPlain_.resize(2 * n); pending_.resize(n);
+      for(size_t g = 0; g < n; g++) {
+        const SearchLimits f = searchLimitsThisMove(s.maxVisits, s_.play, *limitsRand_, {});
+        nextVisits_[2 * g] = nextVisits_[2 * g + 1] = f.visits; nextPlain_[2 * g] = nextPlain_[2 * g + 1] = f.plainRoot ? 1 : 0;
+        curLimits_[g] = f; pending_[g] = {f, f};
+      }
+      slots_.setNextSearchLimits(nextVisits_, nextPlain_, true);
+    }
     slots_.runWaves(1);            // evaluates every root (its input row stays on the device)
   }
   int64_t movesRecorded() const { return movesRecorded_; }
@@ -149,12 +240,14 @@ class HostRecorder {
     const int n = slots_.numSlots();
     slots_.runWaves(waves);
     const std::vector<int32_t> visits = slots_.rootVisitsAll();
+    const std::vector<int32_t> budgets = s_.play.active() ? slots_.visitBudgets() : std::vector<int32_t>((size_t)n, s_.maxVisits);
     std::vector<uint8_t> held((size_t)n, 0);
     std::vector<int> idx;
-    for(int g = 0; g < n; g++) if(visits[(size_t)g] >= s_.maxVisits) { held[(size_t)g] = 1; idx.push_back(g); }
+    for(int g = 0; g < n; g++) if(visits[(size_t)g] >= budgets[(size_t)g]) { held[(size_t)g] = 1; idx.push_back(g); }
     if(idx.empty()) return 0;
     const std::vector<double> rawEntropy = slots_.rootRawPolicyEntropies();
     for(int g : idx) recordRoot(g, rawEntropy[(size_t)g]);
+    if(s_.play.active()) slots_.setNextSearchLimits(nextVisits_, nextPlain_);
     slots_.release(held);
     slots_.runWaves(1);
     movesRecorded_ += (int64_t)idx.size();
@@ -169,8 +262,9 @@ class HostRecorder {
     std::vector<PolicyTargetMove> policyTarget; int64_t unreducedNumVisits;
     ValueTargets valueTargets; std::vector<QValueTarget> qTargets;
     double surprise, searchEntropy, policyEntropy; std::array<double, 3> nnRawStats, rawNNValues;
+    float targetWeight = 1.0f;
   };
-  struct InProgress { std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; };
+  struct InProgress { std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; std::vector<double> winLoss; };   // winLoss: historicalMctsWinLossValues
 
   void recordRoot(int g, double rawPolicyEntropy) {
     const int X = slots_.xLen(), Y = slots_.yLen(), A = X * Y;
@@ -210,14 +304,24 @@ class HostRecorder {
     t.nnRawStats = {nn[0], nn[2], rawPolicyEntropy};
     const Reported rn = reportedSearchValues(nn);
     t.rawNNValues = {rn.win, rn.loss, rn.noResult};
+    t.targetWeight = curLimits_[(size_t)g].targetWeight;
     InProgress& gm = games_[(size_t)g];
     gm.boards.push_back(pos.colors);
+    gm.winLoss.push_back((double)t.valueTargets.win - (double)t.valueTargets.loss);
+    if(s_.play.active()) {         // limits of the search that follows this slot's move: the game goes on / a new game starts
+      const SearchLimits cont = searchLimitsThisMove(s_.maxVisits, s_.play, *limitsRand_, gm.winLoss);
+      const SearchLimits fresh = searchLimitsThisMove(s_.maxVisits, s_.play, *limitsRand_, {});
+      pending_[(size_t)g] = {cont, fresh};
+      nextVisits_[2 * (size_t)g] = cont.visits; nextVisits_[2 * (size_t)g + 1] = fresh.visits;
+      nextPlain_[2 * (size_t)g] = cont.plainRoot ? 1 : 0; nextPlain_[2 * (size_t)g + 1] = fresh.plainRoot ? 1 : 0;
+    }
     gm.turns.push_back(std::move(t));
   }
 
   void afterMove(int g) {
     const GameSlots::LastMove last = slots_.lastMove(g);
     games_[(size_t)g].turns.back().move = {last.move.x, last.move.y};
+    if(s_.play.active()) curLimits_[(size_t)g] = last.gameOver ? pending_[(size_t)g].second : pending_[(size_t)g].first;
     if(last.gameOver) finishGame(g, last);
   }
 
@@ -238,7 +342,7 @@ class HostRecorder {
     for(Turn& t : gm.turns) {
       d.moves.push_back(t.move); d.nextPlayerByTurn.push_back(t.nextPlayer);
       d.packedInputByTurn.push_back(std::move(t.packed)); d.globalInputByTurn.push_back(t.global);
-      d.targetWeightByTurn.push_back(1.0f);
+      d.targetWeightByTurn.push_back(t.targetWeight);
       d.policyTargetsByTurn.push_back(std::move(t.policyTarget)); d.unreducedNumVisitsByTurn.push_back(t.unreducedNumVisits);
       d.policySurpriseByTurn.push_back(t.surprise); d.policyEntropyByTurn.push_back(t.policyEntropy); d.searchEntropyByTurn.push_back(t.searchEntropy);
       d.whiteValueTargetsByTurn.push_back(t.valueTargets); d.whiteQValueTargetsByTurn.push_back(std::move(t.qTargets));
@@ -273,6 +377,9 @@ class HostRecorder {
   GameSlots& slots_; Settings s_; OnGame onGame_;
   std::vector<InProgress> games_;
   std::unique_ptr<RowRand> weightRand_;
+  std::unique_ptr<PyRandom> limitsRand_;
+  std::vector<SearchLimits> curLimits_; std::vector<std::pair<SearchLimits, SearchLimits>> pending_;
+  std::vector<int32_t> nextVisits_; std::vector<uint8_t> nextPlain_;
   int64_t movesRecorded_ = 0, gamesFinished_ = 0;
 };
 

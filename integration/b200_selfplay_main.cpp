@@ -12,8 +12,8 @@
 //   g++ -std=c++17 -O2 -I. integration/b200_selfplay_main.cpp -o b200_selfplay -Lkatago_b200 -lkgb200 -lz -Wl,-rpath,$PWD/katago_b200
 //   ./b200_selfplay (-model net.bin.gz | -models-dir DIR) -config selfplay.cfg -output-dir out [-max-games-total N] [-seed S] [-override-config k=v,k=v]
 //
-// Games are recorded in full (every turn one row before the surprise weighting of policySurpriseDataWeight / valueSurpriseDataWeight).
-// The wider host (per-game board sizes, rules and komi, cheap / reduced searches, policy-initialised openings, lead targets, forks, side
+// Every turn is recorded; its weight comes from the per-move search limits (cheapSearchProb / reduceVisits ...) and the surprise weighting
+// (policySurpriseDataWeight / valueSurpriseDataWeight).  The wider host (per-game board sizes, rules and komi, policy-initialised openings, lead targets, forks, side
 // positions, model polling and weight hot-swap, several GPUs) is katago_b200/selfplay_cli.py: options of that kind are refused here, not
 // ignored.  Without a CUDA device the program stops with the library's error (there is no CPU path).
 #include <chrono>
@@ -103,7 +103,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.full_history_rules = 1;
   c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
   c.neutral("handicapProb", "0.0"); c.neutral("komiStdev", "0.0"); c.neutral("komiAuto", "false");
-  c.neutral("cheapSearchProb", "0.0"); c.neutral("reduceVisits", "false"); c.neutral("estimateLeadProb", "0.0");
+  c.neutral("estimateLeadProb", "0.0");
   c.neutral("initGamesWithPolicy", "false"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
   c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
 
@@ -259,6 +259,12 @@ int main(int argc, char** argv) {
   const double policySurpriseDataWeight = cfg.num("policySurpriseDataWeight", 0.0), valueSurpriseDataWeight = cfg.num("valueSurpriseDataWeight", 0.0);
   const bool useSearchValueSurprise = cfg.flag("useSearchValueSurprise", false);
   cfg.num("maxRowsPerTrainFile", 20000); cfg.num("firstFileRandMinProp", 1.0);
+  // search limits per move (getSearchLimitsThisMove, program/play.cpp:1093-1223): cheap searches and reduced visits
+  b200::PlaySettings play;
+  play.cheapSearchProb = cfg.num("cheapSearchProb", 0.0); play.cheapSearchVisits = (int)cfg.num("cheapSearchVisits", 0);
+  play.cheapSearchTargetWeight = cfg.num("cheapSearchTargetWeight", 0.0); play.reduceVisits = cfg.flag("reduceVisits", false);
+  play.reduceVisitsThreshold = cfg.num("reduceVisitsThreshold", 100.0); play.reduceVisitsThresholdLookback = (int)cfg.num("reduceVisitsThresholdLookback", 1);
+  play.reducedVisitsMin = (int)cfg.num("reducedVisitsMin", 0); play.reducedVisitsWeight = cfg.num("reducedVisitsWeight", 1.0);
   // keys that only place or log the reference's own CPU threads and evaluator servers: nothing to do here
   static const char* irrelevant[] = {"log", "cuda", "trt", "opencl", "eigen", "numNNServerThreads", "nnMaxBatchSize", "nnMutexPool", "numSearchThreads",
                                      "maxDataQueueSize", "nnRandomize", "numVirtualLossesPerThread", "gpuToUse", "homeDataDir"};
@@ -302,6 +308,7 @@ int main(int argc, char** argv) {
     rs.multiStoneSuicideLegal = sc.multi_stone_suicide_legal != 0; rs.maxVisits = sc.max_visits;
     rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
     rs.hashSeed = (uint64_t)seed * 1000003ULL; rs.weightRandSeed = writerSeed + ":weights";
+    rs.play = play; rs.limitsRandSeed = ((uint64_t)seed * 1000003ULL) ^ 0x4C696D69ULL;        // as selfplay_cli.py: Random(loop_seed ^ 0x4C696D69)
     long written = 0;
     const std::string netName = modelsDir.empty() ? std::string(info.name) : modelNameOf(modelPath);
     b200::HostRecorder recorder(slots, rs, [&](int, const b200::FinishedGame& game) {

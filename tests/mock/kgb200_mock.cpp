@@ -46,6 +46,8 @@ struct kgb_context { int x, y; };
 struct kgb_handle { int x, y; };
 struct kgb_selfplay {
   kgb_selfplay_config cfg; int X, Y; Rules rules; Lcg rng{1}; std::vector<Slot> slots; std::vector<uint8_t> released; std::ofstream log;
+  // per-root search limits (kgb_selfplay_set_next_search_limits): the current roots' and, per slot, those of the root after its next move [goes on, new game]
+  std::vector<int32_t> budget, nextBudget; std::vector<uint8_t> plain, nextPlain;
 };
 
 static std::string g_err;
@@ -158,6 +160,8 @@ int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfpla
     sp->rules.hasButton = false; sp->rules.whiteHandicapBonusRule = Rules::WHB_ZERO; sp->rules.friendlyPassOk = false; sp->rules.komi = c->komi;
     sp->log.open(path);
     sp->slots.resize(c->num_games); sp->released.assign(c->num_games, 0);
+    sp->budget.assign(c->num_games, c->max_visits); sp->nextBudget.assign(2 * (size_t)c->num_games, c->max_visits);
+    sp->plain.assign(c->num_games, 0); sp->nextPlain.assign(2 * (size_t)c->num_games, 0);
     for(int g = 0; g < c->num_games; g++) { startGame(sp, g); searchRoot(sp, g); }
     *out = sp;
   })
@@ -165,16 +169,33 @@ int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfpla
 void kgb_selfplay_free(kgb_selfplay* sp) { delete sp; }
 int kgb_selfplay_run(kgb_selfplay* sp, int) {
   GUARD({
-    for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) { sp->released[g] = 0; advance(sp, (int)g); }
+    for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) {
+      sp->released[g] = 0; advance(sp, (int)g);
+      const size_t k = 2 * g + ((sp->slots[g].last[1] & 1) ? 1 : 0);       // the new root takes the limits handed over for it
+      sp->budget[g] = sp->nextBudget[k]; sp->plain[g] = sp->nextPlain[k];
+    }
     sp->log.flush();
   })
 }
 int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* mask) { for(size_t g = 0; g < sp->slots.size(); g++) sp->released[g] = mask ? mask[g] : 1; return 0; }
-int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) { for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->cfg.max_visits; return 0; }
+int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) { for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->budget[g]; return 0; }   // searches finish instantly
+int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits, const uint8_t* plainRoot, int alsoCurrentRoots) {
+  const size_t n = sp->slots.size();
+  for(size_t i = 0; i < 2 * n; i++) {
+    if(visits[i] < 2 || visits[i] > sp->cfg.max_visits) { g_err = "mock: search limit out of range"; return 1; }
+    sp->nextBudget[i] = visits[i]; sp->nextPlain[i] = plainRoot ? plainRoot[i] : 0;
+  }
+  if(alsoCurrentRoots) for(size_t g = 0; g < n; g++) { sp->budget[g] = sp->nextBudget[2 * g]; sp->plain[g] = sp->nextPlain[2 * g]; }
+  return 0;
+}
+int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, uint8_t* plainRoot) {
+  for(size_t g = 0; g < sp->slots.size(); g++) { if(visits) visits[g] = sp->budget[g]; if(plainRoot) plainRoot[g] = sp->plain[g]; }
+  return 0;
+}
 int kgb_selfplay_get_game(kgb_selfplay* sp, int g, uint8_t* colors, int32_t* info) {
   Slot& s = sp->slots[g];
   for(int y = 0; y < sp->Y; y++) for(int x = 0; x < sp->X; x++) colors[y * sp->X + x] = s.board.colors[Location::getLoc(x, y, sp->X)];
-  info[0] = s.moveNum; info[1] = s.pla == P_BLACK; info[2] = -1; info[3] = 0; info[4] = 0; info[5] = sp->cfg.max_visits + g;
+  info[0] = s.moveNum; info[1] = s.pla == P_BLACK; info[2] = -1; info[3] = 0; info[4] = 0; info[5] = sp->budget[g] + g;
   return 0;
 }
 int kgb_selfplay_get_root_children(kgb_selfplay* sp, int g, int32_t* visits, float* policy, double* util) {

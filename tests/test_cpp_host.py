@@ -29,19 +29,62 @@ def host_on_mock(tmp_path_factory):
     return str(exe)
 
 
-@pytest.mark.parametrize("size,ko,komi,max_moves,psw,vsw,search_surprise,games,seed", [
-    (9, "SIMPLE", 6.5, 40, 0.5, 0.1, False, 7, 3),          # stock-like surprise weighting, games stopped by the move limit, several files
-    (5, "POSITIONAL", 7.0, 60, 0.0, 0.0, False, 9, 11),     # integer komi (draws), games ended by passes, every weight 1
-    (7, "SITUATIONAL", -2.5, 30, 0.3, 0.2, True, 5, 5),     # search-value surprise
-])
-def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed):
+def _replay_slots_with_limits(log, G, size, V):
+    """ReplaySlots plus the device's per-root search limits as the mock keeps them: a root's budget and plain flag are the ones handed over for "after
+    this slot's next move" (entry 0 the game goes on, entry 1 a new game starts); searches finish instantly, root visits = budget (+ slot in the info)."""
     from test_game_recorder import ReplaySlots
+
+    class Slots(ReplaySlots):
+        def __init__(self):
+            super().__init__(log, G, size, V)
+            self.budget, self.plain = np.full(G, V, np.int32), np.zeros(G, np.uint8)
+            self.next_budget, self.next_plain = np.full((G, 2), V, np.int32), np.zeros((G, 2), np.uint8)
+
+        def set_next_search_limits(self, visits2, plain2=None, also_current_roots=False):
+            self.next_budget = np.array(visits2, np.int32).reshape(G, 2)
+            self.next_plain = np.zeros((G, 2), np.uint8) if plain2 is None else np.array(plain2, np.uint8).reshape(G, 2)
+            if also_current_roots:
+                self.budget, self.plain = self.next_budget[:, 0].copy(), self.next_plain[:, 0].copy()
+
+        def search_limits(self):
+            return self.budget.copy(), self.plain.copy()
+
+        def root_visits(self):
+            return self.budget.copy()
+
+        def game(self, g):
+            colors, info = super().game(g)
+            info["root_visits"] = int(self.budget[g]) + g
+            return colors, info
+
+        def run(self, n):
+            moving = [g for g in range(G) if self.released[g] and self.queues[g]]
+            super().run(n)
+            for g in moving:
+                k = 1 if self.last[g]["flags"] & 1 else 0
+                self.budget[g], self.plain[g] = self.next_budget[g, k], self.next_plain[g, k]
+    return Slots()
+
+
+LIMITS = {"none": "", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
+          "cheap_unrecorded_and_reduced": "cheapSearchProb = 0.25\ncheapSearchVisits = 5\ncheapSearchTargetWeight = 0.0\nreduceVisits = true\nreduceVisitsThreshold = 0.3\n"
+                                          "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n"}
+
+
+@pytest.mark.parametrize("size,ko,komi,max_moves,psw,vsw,search_surprise,games,seed,limits", [
+    (9, "SIMPLE", 6.5, 40, 0.5, 0.1, False, 7, 3, "none"),          # stock-like surprise weighting, games stopped by the move limit, several files
+    (5, "POSITIONAL", 7.0, 60, 0.0, 0.0, False, 9, 11, "none"),     # integer komi (draws), games ended by passes, every weight 1
+    (7, "SITUATIONAL", -2.5, 30, 0.3, 0.2, True, 5, 5, "none"),     # search-value surprise
+    (9, "SIMPLE", 7.5, 40, 0.5, 0.1, False, 7, 21, "cheap"),        # recorded cheap searches (weight 0.25) under the surprise weighting
+    (7, "POSITIONAL", 6.5, 50, 0.5, 0.1, False, 8, 8, "cheap_unrecorded_and_reduced"),   # unrecorded cheap searches (plain roots) and reduced visits
+])
+def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
     G, V, ROWS_PER_FILE = 3, 20, 60
     cfg = tmp_path / "c.cfg"
     cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nbSizes = {size}\nkoRules = {ko}\nkomiMean = {komi}\nmaxMovesPerGame = {max_moves}\n"
                    f"policySurpriseDataWeight = {psw}\nvalueSurpriseDataWeight = {vsw}\nuseSearchValueSurprise = {'true' if search_surprise else 'false'}\n"
-                   f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n")
+                   f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n" + LIMITS[limits])
     out, log = tmp_path / "cpp", tmp_path / "log.jsonl"
     if size == 5:      # `katago selfplay -models-dir`: the newest net of the directory, its files under <output-dir>/<net name>/
         os.makedirs(tmp_path / "nets" / "b6c96-s100-d200")
@@ -59,7 +102,9 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
 
     # the Python host's recorder and writer on the same slots (the mock's log replayed), seeded like selfplay_cli.py seeds them
     _, loop_seed, writer_seed = C.shard_plan(0, 1, games, seed)
-    sp = ReplaySlots(str(log), G, size, V)
+    sp = _replay_slots_with_limits(str(log), G, size, V)
+    sp.max_visits = V
+    kw, data, _ = C.selfplay_kwargs_from_cfg(C.parse_cfg(str(cfg)))
     py = tmp_path / "py"
     os.makedirs(py / "tdata")
     writer = W.TrainingDataWriter(str(py / "tdata"), ROWS_PER_FILE, 0.3, size, writer_seed)
@@ -78,7 +123,8 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     sp.cfg = Cfg()
     rec = R.GameRecorder(sp, None, komi, on_game=on_game, game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
                          policy_surprise_data_weight=psw, value_surprise_data_weight=vsw, use_search_value_surprise=search_surprise,
-                         weight_rand=W.RowRand(writer_seed + ":weights"))
+                         weight_rand=W.RowRand(writer_seed + ":weights"), play_settings=data["play_settings"],
+                         limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
     while len(done) < games:
         rec.pump(4)
     writer.flush_if_nonempty()
@@ -96,6 +142,10 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     assert rows == writer.row_count > 0
     if psw == 0 and vsw == 0:
         assert rows == sum(len(d.moves) for d in done)
+    weights = [float(w) for d in done for w in (d.target_weight_by_turn_unrounded or d.target_weight_by_turn)]
+    if limits == "cheap_unrecorded_and_reduced":       # turns that are not recorded at all, and visit counts between the minimum and the full budget
+        visits = [v - g for d in done for (_, v), g in zip(d.policy_targets_by_turn, [0] * len(d.moves))]
+        assert any(w == 0.0 for w in weights) and any(6 + 0 <= v <= V + 2 and v not in (V, V + 1, V + 2) for v in visits)
     cpp_sgfs = os.listdir(out / "sgfs")
     assert cpp_sgfs == [os.path.basename(sink.path)]
     assert open(out / "sgfs" / cpp_sgfs[0]).read() == open(sink.path).read() and sink.count == games

@@ -528,9 +528,9 @@ def test_cpp_host_refuses_what_it_does_not_play_and_needs_a_gpu(tmp_path, cpp_ho
     error - there is no CPU path behind the C ABI."""
     import subprocess
     cfg = tmp_path / "c.cfg"
-    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\ncheapSearchProb = 0.25\n")
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nestimateLeadProb = 0.05\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode != 0 and "cheapSearchProb" in r.stderr and "selfplay_cli.py" in r.stderr
+    assert r.returncode != 0 and "estimateLeadProb" in r.stderr and "selfplay_cli.py" in r.stderr
     cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0 and "bSizes" in r.stderr
