@@ -150,7 +150,36 @@ class PyRandom {
     idx_ = N;
   }
   double random() { const uint32_t a = next() >> 5, b = next() >> 6; return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0); }
+  // randrange(n): _randbelow_with_getrandbits - k = bit length of n, k-bit draws until one is below n
+  uint32_t randrange(uint32_t n) {
+    int k = 0;
+    for(uint32_t v = n; v; v >>= 1) k++;
+    uint32_t r = next() >> (32 - k);
+    while(r >= n) r = next() >> (32 - k);
+    return r;
+  }
+  // gauss(mu, sigma): a pair of normal deviates per two uniform draws, the second one kept for the next call
+  double gauss(double mu, double sigma) {
+    double z;
+    if(haveGaussNext_) { z = gaussNext_; haveGaussNext_ = false; }
+    else {
+      const double x2pi = random() * (2.0 * 3.141592653589793), g2rad = std::sqrt(-2.0 * std::log(1.0 - random()));
+      z = std::cos(x2pi) * g2rad;
+      gaussNext_ = std::sin(x2pi) * g2rad; haveGaussNext_ = true;
+    }
+    return mu + z * sigma;
+  }
+  // choices(population, weights)[0]: bisect_right of random() * total in the running sums, capped at the last index
+  size_t choiceIndex(const std::vector<double>& weights) {
+    std::vector<double> cum; double acc = 0.0;
+    for(size_t i = 0; i < weights.size(); i++) { acc = i == 0 ? weights[0] : acc + weights[i]; cum.push_back(acc); }
+    const double x = random() * (cum.back() + 0.0);
+    size_t lo = 0, hi = weights.size() - 1;
+    while(lo < hi) { const size_t mid = (lo + hi) / 2; if(x < cum[mid]) hi = mid; else lo = mid + 1; }
+    return lo;
+  }
  private:
+  double gaussNext_ = 0.0; bool haveGaussNext_ = false;
   static constexpr int N = 624, M = 397;
   uint32_t next() {
     if(idx_ >= N) {
@@ -210,8 +239,11 @@ class HostRecorder {
     double policySurpriseDataWeight = 0.0, valueSurpriseDataWeight = 0.0; bool useSearchValueSurprise = false;
     uint64_t hashSeed = 0; std::string weightRandSeed;      // weightRandSeed empty: fractional weights go to the writer unresolved
     PlaySettings play; uint64_t limitsRandSeed = 0x4C696D69;   // cheap searches / reduced visits, drawn per move
+    bool perGameSetups = false;    // board size, rules and komi are per game (kgb_selfplay_set_game_setup / set_komi): read them from the device
   };
   using OnGame = std::function<void(int slot, const FinishedGame&)>;
+  // called with the slot when its next game has begun on the device (before any of its turns is recorded): the host's draw for the game after it
+  std::function<void(int slot)> onGameStart;
 
   HostRecorder(GameSlots& slots, const Settings& s, OnGame onGame) : slots_(slots), s_(s), onGame_(std::move(onGame)), games_((size_t)slots.numSlots()) {
     if(!s.weightRandSeed.empty()) weightRand_.reset(new RowRand(s.weightRandSeed));
@@ -264,7 +296,17 @@ class HostRecorder {
     double surprise, searchEntropy, policyEntropy; std::array<double, 3> nnRawStats, rawNNValues;
     float targetWeight = 1.0f;
   };
-  struct InProgress { std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; std::vector<double> winLoss; };   // winLoss: historicalMctsWinLossValues
+  struct InProgress {
+    std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; std::vector<double> winLoss;      // winLoss: historicalMctsWinLossValues
+    bool haveSetup = false; GameSlots::GameSetup setup{0, 0, 0, 1};     // this game's own board and rules, read when its first turn is recorded
+  };
+  // a board or area of the evaluator's frame cut down to the game's own board (its top-left corner)
+  std::vector<uint8_t> crop(const std::vector<uint8_t>& frame, int bx, int by) const {
+    const int X = slots_.xLen();
+    std::vector<uint8_t> out((size_t)bx * by);
+    for(int y = 0; y < by; y++) for(int x = 0; x < bx; x++) out[(size_t)y * bx + x] = frame[(size_t)y * X + x];
+    return out;
+  }
 
   void recordRoot(int g, double rawPolicyEntropy) {
     const int X = slots_.xLen(), Y = slots_.yLen(), A = X * Y;
@@ -306,7 +348,12 @@ class HostRecorder {
     t.rawNNValues = {rn.win, rn.loss, rn.noResult};
     t.targetWeight = curLimits_[(size_t)g].targetWeight;
     InProgress& gm = games_[(size_t)g];
-    gm.boards.push_back(pos.colors);
+    if(!gm.haveSetup) {
+      gm.setup = GameSlots::GameSetup{X, Y, s_.koRule, s_.multiStoneSuicideLegal ? 1 : 0};
+      if(s_.perGameSetups) { std::vector<GameSlots::GameSetup> cur; slots_.gameSetups(&cur, nullptr); gm.setup = cur[(size_t)g]; }
+      gm.haveSetup = true;
+    }
+    gm.boards.push_back(crop(pos.colors, gm.setup.x, gm.setup.y));
     gm.winLoss.push_back((double)t.valueTargets.win - (double)t.valueTargets.loss);
     if(s_.play.active()) {         // limits of the search that follows this slot's move: the game goes on / a new game starts
       const SearchLimits cont = searchLimitsThisMove(s_.maxVisits, s_.play, *limitsRand_, gm.winLoss);
@@ -328,16 +375,17 @@ class HostRecorder {
   void finishGame(int g, const GameSlots::LastMove& last) {
     InProgress gm = std::move(games_[(size_t)g]);
     games_[(size_t)g] = InProgress();
-    const int X = slots_.xLen(), Y = slots_.yLen();
+    const int X = gm.setup.x, Y = gm.setup.y;            // this game's own board; rows are written inside the evaluator's frame
     FinishedGame d;
     d.xSize = X; d.ySize = Y; d.komi = s_.komi;
+    if(s_.perGameSetups) { std::vector<float> last_; slots_.komis(nullptr, &last_); d.komi = last_[(size_t)g]; }      // the slot's last finished game's
     d.drawEquivalentWinsForWhite = s_.drawEquivalentWinsForWhite;
     gameHashOf(s_.hashSeed, g, last.gameIndex, d.gameHash);
     d.endFinished = !last.hitMoveLimit; d.hitTurnLimit = last.hitMoveLimit; d.endNoResult = last.noResult;
     static const char* KO[] = {"SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT"};
-    d.koRule = KO[s_.koRule & 3]; d.multiStoneSuicideLegal = s_.multiStoneSuicideLegal;
+    d.koRule = KO[gm.setup.koRule & 3]; d.multiStoneSuicideLegal = gm.setup.multiStoneSuicideLegal != 0;
     d.boardsByTurn = std::move(gm.boards);
-    d.boardsByTurn.push_back(last.finalColors);
+    d.boardsByTurn.push_back(crop(last.finalColors, X, Y));
     std::vector<std::array<double, 3>> rawNN;
     for(Turn& t : gm.turns) {
       d.moves.push_back(t.move); d.nextPlayerByTurn.push_back(t.nextPlayer);
@@ -352,7 +400,7 @@ class HostRecorder {
     if(d.endNoResult) d.whiteValueTargetsByTurn.push_back(finalValueTargets(0, 0.0f, s_.drawEquivalentWinsForWhite, d.komi, true));
     else {
       // area scoring without tax: ownership = full area = calculateArea with every flag on (boardhistory.cpp:591-610)
-      area = last.finalArea;
+      area = crop(last.finalArea, X, Y);
       const float score = last.finalWhiteMinusBlackScore;
       d.winner = score > 0 ? P_WHITE : score < 0 ? P_BLACK : 0;
       d.finalWhiteMinusBlackScore = score;
@@ -371,6 +419,7 @@ class HostRecorder {
     d.finalWhiteScoring.resize(area.size());                // NNInputs::fillScoring without group tax: white area +1, black area -1
     for(size_t i = 0; i < area.size(); i++) d.finalWhiteScoring[i] = area[i] == P_WHITE ? 1.0f : area[i] == P_BLACK ? -1.0f : 0.0f;
     gamesFinished_++;
+    if(onGameStart) onGameStart(g);
     if(onGame_) onGame_(g, d);
   }
 

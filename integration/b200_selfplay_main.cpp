@@ -13,7 +13,8 @@
 //   ./b200_selfplay (-model net.bin.gz | -models-dir DIR) -config selfplay.cfg -output-dir out [-max-games-total N] [-seed S] [-override-config k=v,k=v]
 //
 // Every turn is recorded; its weight comes from the per-move search limits (cheapSearchProb / reduceVisits ...) and the surprise weighting
-// (policySurpriseDataWeight / valueSurpriseDataWeight).  The wider host (per-game board sizes, rules and komi, policy-initialised openings, lead targets, forks, side
+// (policySurpriseDataWeight / valueSurpriseDataWeight); board size, ko / suicide rule and komi are drawn per game like the reference's
+// GameInitializer (integration/b200_gameinit.h).  The wider host (komiAuto, policy-initialised openings, lead targets, forks, side
 // positions, model polling and weight hot-swap, several GPUs) is katago_b200/selfplay_cli.py: options of that kind are refused here, not
 // ignored.  Without a CUDA device the program stops with the library's error (there is no CPU path).
 #include <chrono>
@@ -27,7 +28,7 @@
 #include <dirent.h>
 #include <sys/stat.h>
 
-#include "b200_recorder.h"
+#include "b200_gameinit.h"
 
 namespace {
 
@@ -77,6 +78,12 @@ struct Cfg {
     if(it->second == "false") return false;
     die("config key " + k + ": expected true or false, got '" + it->second + "'");
   }
+  std::vector<std::string> list(const std::string& k, const std::string& dflt) const {      // comma-separated values
+    std::vector<std::string> out; std::stringstream ss(str(k, dflt)); std::string item;
+    while(std::getline(ss, item, ',')) { item = trim(item); if(!item.empty()) out.push_back(item); }
+    if(out.empty()) die("config key " + k + ": no value");
+    return out;
+  }
   std::string str(const std::string& k, const std::string& dflt) const { used[k] = true; auto it = kv.find(k); return it == kv.end() ? dflt : it->second; }
   // a key of the reference this host does not read: fine while it keeps its neutral value, an error otherwise
   void neutral(const std::string& k, const std::string& value) const {
@@ -85,6 +92,17 @@ struct Cfg {
     if(it != kv.end() && it->second != value) die("config key " + k + " = " + it->second + " is not supported by this host (only " + value + "); use katago_b200/selfplay_cli.py");
   }
 };
+
+int koRuleOf(const std::string& ko) {
+  const int r = ko == "SIMPLE" ? 0 : ko == "POSITIONAL" ? 1 : ko == "SITUATIONAL" ? 2 : ko == "SPIGHT" ? 3 : -1;
+  if(r < 0) die("koRules: SIMPLE, POSITIONAL, SITUATIONAL or SPIGHT, got '" + ko + "'");
+  return r;
+}
+bool boolOf(const std::string& key, const std::string& v) {
+  if(v == "true") return true;
+  if(v == "false") return false;
+  die("config key " + key + ": expected true or false, got '" + v + "'");
+}
 
 // SearchParams and Rules by their cfg names -> kgb_selfplay_config (defaults of absent keys: the reference loader's for a self-play command, program/setup.cpp:445-760, like katago_b200/selfplay_cli.py)
 kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
@@ -96,13 +114,12 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.seed = (uint64_t)c.num("searchRandSeed", 1.0);
   k.nn_cache_size_power_of_two = (int32_t)c.num("nnCacheSizePowerOfTwo", 0);
   k.komi = (float)c.num("komiMean", 7.5);
-  const std::string ko = c.str("koRules", "SIMPLE");
-  k.ko_rule = ko == "SIMPLE" ? 0 : ko == "POSITIONAL" ? 1 : ko == "SITUATIONAL" ? 2 : ko == "SPIGHT" ? 3 : -1;
-  if(k.ko_rule < 0) die("koRules: this host takes ONE of SIMPLE, POSITIONAL, SITUATIONAL, SPIGHT (per-game draws: selfplay_cli.py)");
-  k.multi_stone_suicide_legal = c.flag("multiStoneSuicideLegals", true) ? 1 : 0;
+  // rules, board size and komi are drawn per game (b200_gameinit.h); the loop's own configuration carries the first listed values
+  k.ko_rule = koRuleOf(c.list("koRules", "SIMPLE")[0]);
+  k.multi_stone_suicide_legal = boolOf("multiStoneSuicideLegals", c.list("multiStoneSuicideLegals", "true")[0]) ? 1 : 0;
   k.full_history_rules = 1;
   c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
-  c.neutral("handicapProb", "0.0"); c.neutral("komiStdev", "0.0"); c.neutral("komiAuto", "false");
+  c.neutral("handicapProb", "0.0"); c.neutral("komiAuto", "false");
   c.neutral("estimateLeadProb", "0.0");
   c.neutral("initGamesWithPolicy", "false"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
   c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
@@ -247,12 +264,23 @@ int main(int argc, char** argv) {
 
   auto check = [](int rc, const char* what) { if(rc != 0) die(std::string(what) + ": " + kgb_last_error()); };
   const int numGames = (int)cfg.num("numGameThreads", 256);          // concurrent games = the evaluator's batch
-  const std::string sizes = cfg.str("bSizes", "19");
-  if(sizes.find(',') != std::string::npos) die("bSizes: this host plays one board size (per-game draws: selfplay_cli.py)");
-  const int edge = std::atoi(sizes.c_str());
-  if(edge < 2 || edge > 19) die("bSizes: 2..19");
-  const int nnLen = (int)cfg.num("dataBoardLen", edge);
-  if(nnLen != edge) die("dataBoardLen must equal the board size for this host");
+  // board size, ko / suicide rule and komi of every game: drawn on the host like the reference's GameInitializer (b200_gameinit.h), applied by the
+  // device when the slot's next game starts; the evaluator's frame (= the data frame, dataBoardLen) holds the largest board
+  b200::GameInitializer::Config gi;
+  for(const std::string& v : cfg.list("bSizes", "19")) { gi.edges.push_back(std::atoi(v.c_str())); if(gi.edges.back() < 2 || gi.edges.back() > 19) die("bSizes: 2..19"); }
+  if(cfg.has("bSizeRelProbs")) for(const std::string& v : cfg.list("bSizeRelProbs", "")) gi.relProbs.push_back(std::atof(v.c_str()));
+  else gi.relProbs.assign(gi.edges.size(), 1.0);
+  if(gi.relProbs.size() != gi.edges.size()) die("bSizeRelProbs has " + std::to_string(gi.relProbs.size()) + " entries, bSizes has " + std::to_string(gi.edges.size()));
+  gi.allowRectangleProb = cfg.num("allowRectangleProb", 0.0);
+  gi.koRules.clear(); for(const std::string& v : cfg.list("koRules", "SIMPLE")) gi.koRules.push_back(koRuleOf(v));
+  gi.multiStoneSuicideLegals.clear(); for(const std::string& v : cfg.list("multiStoneSuicideLegals", "true")) gi.multiStoneSuicideLegals.push_back(boolOf("multiStoneSuicideLegals", v) ? 1 : 0);
+  gi.komiMean = cfg.num("komiMean", 7.5); gi.komiStdev = cfg.num("komiStdev", 0.0); gi.komiBigStdevProb = cfg.num("komiBigStdevProb", 0.0);
+  gi.komiBigStdev = cfg.num("komiBigStdev", 10.0); gi.komiBiggerStdevProb = cfg.num("komiBiggerStdevProb", 0.0); gi.komiBiggerStdev = cfg.num("komiBiggerStdev", 30.0);
+  gi.komiAllowIntegerProb = cfg.num("komiAllowIntegerProb", 1.0);
+  int maxEdge = 0; for(int e : gi.edges) maxEdge = std::max(maxEdge, e);
+  const int edge = (int)cfg.num("dataBoardLen", maxEdge);
+  if(edge < maxEdge) die("dataBoardLen = " + std::to_string(edge) + " but bSizes goes up to " + std::to_string(maxEdge) + ": the data frame must hold the largest board");
+  if(edge > 19) die("dataBoardLen: at most 19");
   if(maxGamesTotal <= 0) maxGamesTotal = (long)cfg.num("numGamesTotal", 0);
   const int wavesPerPoll = (int)cfg.num("b200WavesPerPoll", 16);
   const kgb_selfplay_config sc = configFromCfg(cfg, numGames);
@@ -303,7 +331,17 @@ int main(int argc, char** argv) {
     if(!sgfs) die("cannot write " + sgfDir + "/" + sgfName);
 
     b200::GameSlots slots(handle, sc, edge, edge);
+    // the draws become the games in progress (none has started), new ones are drawn for the games after them; a slot's draw for the game
+    // after next is made when its next game begins (katago_b200/selfplay_cli.py SlotSetups)
+    b200::GameInitializer init(gi, ((uint64_t)seed * 1000003ULL) ^ 0x47616D65ULL);
+    std::vector<b200::GameSlots::GameSetup> setups((size_t)numGames); std::vector<float> komis((size_t)numGames);
+    auto drawInto = [&](int g) { const b200::GameInitializer::Game d = init.draw(); setups[(size_t)g] = {d.x, d.y, d.koRule, d.multiStoneSuicideLegal}; komis[(size_t)g] = d.komi; };
+    for(int g = 0; g < numGames; g++) drawInto(g);
+    slots.setGameSetups(setups, true); slots.setKomis(komis, true);
+    for(int g = 0; g < numGames; g++) drawInto(g);
+    slots.setGameSetups(setups); slots.setKomis(komis);
     b200::HostRecorder::Settings rs;
+    rs.perGameSetups = true;
     rs.komi = sc.komi; rs.drawEquivalentWinsForWhite = sc.draw_equivalent_wins_for_white; rs.koRule = sc.ko_rule;
     rs.multiStoneSuicideLegal = sc.multi_stone_suicide_legal != 0; rs.maxVisits = sc.max_visits;
     rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
@@ -317,6 +355,7 @@ int main(int argc, char** argv) {
       sgfs << b200::writeSgf(game, netName, netName) << "\n";
       written++;
     });
+    recorder.onGameStart = [&](int g) { drawInto(g); slots.setGameSetups(setups); slots.setKomis(komis); };
     const auto t0 = std::chrono::steady_clock::now();
     while(maxGamesTotal <= 0 || written < maxGamesTotal) recorder.pump(wavesPerPoll);
     writer.flushIfNonempty();

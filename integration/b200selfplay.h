@@ -195,6 +195,17 @@ class GameSlots {
     childNodeVisitsOut.resize((size_t)x_ * y_ + 1);
     check(kgb_selfplay_get_root_extra(sp_, slot, childNodeVisitsOut.data(), rootNNMoments));
   }
+  // board, rules and komi of the games in progress and of each slot's last finished game
+  void gameSetups(std::vector<GameSetup>* current, std::vector<GameSetup>* lastFinished) const {
+    if(current) current->resize((size_t)n_);
+    if(lastFinished) lastFinished->resize((size_t)n_);
+    check(kgb_selfplay_get_game_setup(sp_, current ? &(*current)[0].x : nullptr, lastFinished ? &(*lastFinished)[0].x : nullptr));
+  }
+  void komis(std::vector<float>* current, std::vector<float>* lastFinished) const {
+    if(current) current->resize((size_t)n_);
+    if(lastFinished) lastFinished->resize((size_t)n_);
+    check(kgb_selfplay_get_komi(sp_, current ? current->data() : nullptr, lastFinished ? lastFinished->data() : nullptr));
+  }
   std::vector<double> rootRawPolicyEntropies() const { std::vector<double> e((size_t)n_); check(kgb_selfplay_get_root_raw_policy_entropy(sp_, e.data())); return e; }
 
  private:

@@ -30,6 +30,7 @@ struct Lcg {
 struct Slot {
   Board board; BoardHistory hist; Player pla = P_BLACK;
   int moveNum = 0, gameIndex = 0;
+  int32_t setup[4] = {0, 0, 0, 1}; float komi = 7.5f;      // this game's board X, Y, ko rule, multi-stone suicide; komi
   bool held = true;                 // searches finish instantly in the mock
   // what the "search" of the current root found
   std::vector<int32_t> edgeVisits, nodeVisits; std::vector<float> policy; std::vector<double> childStats, psv;
@@ -48,17 +49,21 @@ struct kgb_selfplay {
   kgb_selfplay_config cfg; int X, Y; Rules rules; Lcg rng{1}; std::vector<Slot> slots; std::vector<uint8_t> released; std::ofstream log;
   // per-root search limits (kgb_selfplay_set_next_search_limits): the current roots' and, per slot, those of the root after its next move [goes on, new game]
   std::vector<int32_t> budget, nextBudget; std::vector<uint8_t> plain, nextPlain;
+  // per-game board, rules and komi (kgb_selfplay_set_game_setup / set_komi): of each slot's next game and of its last finished one
+  std::vector<int32_t> nextSetup, lastSetup; std::vector<float> nextKomi, lastKomi;
+  bool started = false;             // the first games begin with the first run / read, after the host has handed over their setups
 };
 
 static std::string g_err;
 
 static void searchRoot(kgb_selfplay* sp, int g) {
   Slot& s = sp->slots[g];
-  const int X = sp->X, Y = sp->Y, P = X * Y + 1;
+  const int X = sp->X, Y = sp->Y, P = X * Y + 1;          // the evaluator's frame; the game's board is its top-left corner
+  const int BX = s.setup[0], BY = s.setup[1];
   Lcg& r = sp->rng;
   s.edgeVisits.assign(P, 0); s.nodeVisits.assign(P, 0); s.policy.assign(P, -1.0f); s.childStats.assign((size_t)P * 5, 0.0); s.psv.assign(P, -1.0);
   std::vector<int> legal;
-  for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) if(s.hist.isLegal(s.board, Location::getLoc(x, y, X), s.pla)) legal.push_back(y * X + x);
+  for(int y = 0; y < BY; y++) for(int x = 0; x < BX; x++) if(s.hist.isLegal(s.board, Location::getLoc(x, y, BX), s.pla)) legal.push_back(y * X + x);
   legal.push_back(P - 1);
   double tot = 0;
   for(int pos : legal) { s.policy[pos] = (float)(0.05 + r.unit()); tot += s.policy[pos]; }
@@ -73,7 +78,7 @@ static void searchRoot(kgb_selfplay* sp, int g) {
     s.childStats[(size_t)pos * 5 + 0] = r.unit() * 2 - 1; s.childStats[(size_t)pos * 5 + 1] = r.unit() * 0.05;
     s.childStats[(size_t)pos * 5 + 2] = (r.unit() - 0.5) * 40; s.childStats[(size_t)pos * 5 + 3] = 500 * r.unit(); s.childStats[(size_t)pos * 5 + 4] = (r.unit() - 0.5) * 30;
   }
-  s.nextMove = chosen == P - 1 ? Board::PASS_LOC : Location::getLoc(chosen % X, chosen / X, X);
+  s.nextMove = chosen == P - 1 ? Board::PASS_LOC : Location::getLoc(chosen % X, chosen / X, BX);
   s.rootStats[0] = r.unit() * 2 - 1; s.rootStats[1] = r.unit() * 0.04; s.rootStats[2] = (r.unit() - 0.5) * 30; s.rootStats[3] = 400 * r.unit(); s.rootStats[4] = (r.unit() - 0.5) * 20;
   s.rootNN[0] = r.unit() * 2 - 1; s.rootNN[1] = 0.0; s.rootNN[2] = (r.unit() - 0.5) * 30; s.rootNN[3] = 300 * r.unit(); s.rootNN[4] = 0.0;
   // the root's input row: the reference's own fillRowV7 (NHWC) - what the device loop's featurizer is pinned to
@@ -88,8 +93,8 @@ static void searchRoot(kgb_selfplay* sp, int g) {
     for(size_t i = 0; i < v.size(); i++) { char b[64]; snprintf(b, sizeof b, "%.17g", (double)v[i]); o << (i ? "," : "") << b; }
     o << "]" << (last ? "" : ",");
   };
-  std::vector<int> colors;
-  for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) colors.push_back((int)s.board.colors[Location::getLoc(x, y, X)]);
+  std::vector<int> colors((size_t)X * Y, 0);
+  for(int y = 0; y < BY; y++) for(int x = 0; x < BX; x++) colors[(size_t)y * X + x] = (int)s.board.colors[Location::getLoc(x, y, BX)];
   std::vector<double> rs(s.rootStats, s.rootStats + 5), rn(s.rootNN, s.rootNN + 5);
   o << "{\"ev\":\"root\",\"slot\":" << g << ",\"move_num\":" << s.moveNum << ",\"black_to_move\":" << (s.pla == P_BLACK ? 1 : 0) << ",";
   arr("colors", colors); arr("edge_visits", s.edgeVisits); arr("node_visits", s.nodeVisits); arr("policy", s.policy); arr("child_stats", s.childStats);
@@ -99,18 +104,21 @@ static void searchRoot(kgb_selfplay* sp, int g) {
 
 static void startGame(kgb_selfplay* sp, int g) {
   Slot& s = sp->slots[g];
-  s.board = Board(sp->X, sp->Y); s.pla = P_BLACK; s.hist = BoardHistory(s.board, s.pla, sp->rules, 0, false); s.moveNum = 0;
+  Rules rules = sp->rules;
+  rules.koRule = s.setup[2] == 1 ? Rules::KO_POSITIONAL : s.setup[2] == 2 ? Rules::KO_SITUATIONAL : s.setup[2] == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
+  rules.multiStoneSuicideLegal = s.setup[3] != 0; rules.komi = s.komi;
+  s.board = Board(s.setup[0], s.setup[1]); s.pla = P_BLACK; s.hist = BoardHistory(s.board, s.pla, rules, 0, false); s.moveNum = 0;
 }
 
 static void advance(kgb_selfplay* sp, int g) {
   Slot& s = sp->slots[g];
-  const int X = sp->X, Y = sp->Y;
+  const int X = sp->X, Y = sp->Y, BX = s.setup[0], BY = s.setup[1];
   const Loc loc = s.nextMove;
   s.hist.makeBoardMoveAssumeLegal(s.board, loc, s.pla, NULL);
   s.pla = getOpp(s.pla);
-  const int maxMoves = sp->cfg.max_moves > 0 ? sp->cfg.max_moves : 2 * X * Y;
+  const int maxMoves = sp->cfg.max_moves > 0 ? sp->cfg.max_moves : 2 * BX * BY;
   const bool finished = s.hist.isGameFinished, over = finished || s.moveNum + 1 >= maxMoves;
-  s.last[0] = loc == Board::PASS_LOC ? X * Y : Location::getY(loc, X) * X + Location::getX(loc, X);
+  s.last[0] = loc == Board::PASS_LOC ? X * Y : Location::getY(loc, BX) * X + Location::getX(loc, BX);
   s.last[1] = over ? (1 | ((finished && s.hist.isNoResult) ? 2 : 0) | (finished ? 0 : 4)) : 0;
   s.last[2] = s.moveNum; s.last[3] = s.gameIndex;
   if(over) {
@@ -118,8 +126,8 @@ static void advance(kgb_selfplay* sp, int g) {
     BoardHistory h2 = s.hist;
     h2.endAndScoreGameNow(s.board, area);
     s.lastScore = h2.finalWhiteMinusBlackScore;
-    s.finalColors.clear(); s.finalArea.clear();
-    for(int y = 0; y < Y; y++) for(int x = 0; x < X; x++) { Loc l = Location::getLoc(x, y, X); s.finalColors.push_back(s.board.colors[l]); s.finalArea.push_back(area[l]); }
+    s.finalColors.assign((size_t)X * Y, 0); s.finalArea.assign((size_t)X * Y, 0);
+    for(int y = 0; y < BY; y++) for(int x = 0; x < BX; x++) { Loc l = Location::getLoc(x, y, BX); s.finalColors[(size_t)y * X + x] = s.board.colors[l]; s.finalArea[(size_t)y * X + x] = area[l]; }
   }
   std::ofstream& o = sp->log;
   o << "{\"ev\":\"move\",\"slot\":" << g << ",\"pos\":" << s.last[0] << ",\"flags\":" << s.last[1] << ",\"move_num\":" << s.last[2] << ",\"game_index\":" << s.last[3]
@@ -128,8 +136,19 @@ static void advance(kgb_selfplay* sp, int g) {
   o << "],\"final_area\":[";
   for(size_t i = 0; over && i < s.finalArea.size(); i++) o << (i ? "," : "") << (int)s.finalArea[i];
   o << "]}\n";
-  if(over) { s.gameIndex++; startGame(sp, g); } else s.moveNum++;
+  if(over) {                        // the slot's next game takes the setup and komi handed over for it
+    for(int k = 0; k < 4; k++) { sp->lastSetup[4 * (size_t)g + k] = s.setup[k]; s.setup[k] = sp->nextSetup[4 * (size_t)g + k]; }
+    sp->lastKomi[g] = s.komi; s.komi = sp->nextKomi[g];
+    s.gameIndex++; startGame(sp, g);
+  }
+  else s.moveNum++;
   searchRoot(sp, g);
+}
+
+static void ensureStarted(kgb_selfplay* sp) {
+  if(sp->started) return;
+  sp->started = true;
+  for(size_t g = 0; g < sp->slots.size(); g++) { startGame(sp, (int)g); searchRoot(sp, (int)g); }
 }
 
 #define GUARD(body) try { body; return 0; } catch(const std::exception& e) { g_err = e.what(); return 1; }
@@ -162,13 +181,19 @@ int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfpla
     sp->slots.resize(c->num_games); sp->released.assign(c->num_games, 0);
     sp->budget.assign(c->num_games, c->max_visits); sp->nextBudget.assign(2 * (size_t)c->num_games, c->max_visits);
     sp->plain.assign(c->num_games, 0); sp->nextPlain.assign(2 * (size_t)c->num_games, 0);
-    for(int g = 0; g < c->num_games; g++) { startGame(sp, g); searchRoot(sp, g); }
+    for(int g = 0; g < c->num_games; g++) {
+      Slot& s = sp->slots[g];
+      s.setup[0] = sp->X; s.setup[1] = sp->Y; s.setup[2] = c->ko_rule; s.setup[3] = c->multi_stone_suicide_legal != 0; s.komi = c->komi;
+      for(int k = 0; k < 4; k++) { sp->nextSetup.push_back(s.setup[k]); sp->lastSetup.push_back(s.setup[k]); }
+      sp->nextKomi.push_back(c->komi); sp->lastKomi.push_back(c->komi);
+    }
     *out = sp;
   })
 }
 void kgb_selfplay_free(kgb_selfplay* sp) { delete sp; }
 int kgb_selfplay_run(kgb_selfplay* sp, int) {
   GUARD({
+    ensureStarted(sp);
     for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) {
       sp->released[g] = 0; advance(sp, (int)g);
       const size_t k = 2 * g + ((sp->slots[g].last[1] & 1) ? 1 : 0);       // the new root takes the limits handed over for it
@@ -178,7 +203,7 @@ int kgb_selfplay_run(kgb_selfplay* sp, int) {
   })
 }
 int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* mask) { for(size_t g = 0; g < sp->slots.size(); g++) sp->released[g] = mask ? mask[g] : 1; return 0; }
-int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) { for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->budget[g]; return 0; }   // searches finish instantly
+int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) { ensureStarted(sp); for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->budget[g]; return 0; }   // searches finish instantly
 int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits, const uint8_t* plainRoot, int alsoCurrentRoots) {
   const size_t n = sp->slots.size();
   for(size_t i = 0; i < 2 * n; i++) {
@@ -188,13 +213,40 @@ int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits,
   if(alsoCurrentRoots) for(size_t g = 0; g < n; g++) { sp->budget[g] = sp->nextBudget[2 * g]; sp->plain[g] = sp->nextPlain[2 * g]; }
   return 0;
 }
+int kgb_selfplay_set_game_setup(kgb_selfplay* sp, const int32_t* setups, int alsoCurrentGames) {
+  if(alsoCurrentGames && sp->started) { g_err = "mock: the games in progress have begun"; return 1; }
+  for(size_t g = 0; g < sp->slots.size(); g++) {
+    const int32_t* q = setups + 4 * g;
+    if(q[0] < 2 || q[0] > sp->X || q[1] < 2 || q[1] > sp->Y || q[2] < 0 || q[2] > 3) { g_err = "mock: game setup out of range"; return 1; }
+    for(int k = 0; k < 4; k++) { sp->nextSetup[4 * g + k] = q[k]; if(alsoCurrentGames) sp->slots[g].setup[k] = q[k]; }
+  }
+  return 0;
+}
+int kgb_selfplay_get_game_setup(kgb_selfplay* sp, int32_t* current, int32_t* lastFinished) {
+  for(size_t g = 0; g < sp->slots.size(); g++) for(int k = 0; k < 4; k++) {
+    if(current) current[4 * g + k] = sp->slots[g].setup[k];
+    if(lastFinished) lastFinished[4 * g + k] = sp->lastSetup[4 * g + k];
+  }
+  return 0;
+}
+int kgb_selfplay_set_komi(kgb_selfplay* sp, const float* komi, int alsoCurrentGames) {
+  if(alsoCurrentGames && sp->started) { g_err = "mock: the games in progress have begun"; return 1; }
+  for(size_t g = 0; g < sp->slots.size(); g++) { sp->nextKomi[g] = komi[g]; if(alsoCurrentGames) sp->slots[g].komi = komi[g]; }
+  return 0;
+}
+int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* lastFinished) {
+  for(size_t g = 0; g < sp->slots.size(); g++) { if(current) current[g] = sp->slots[g].komi; if(lastFinished) lastFinished[g] = sp->lastKomi[g]; }
+  return 0;
+}
 int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, uint8_t* plainRoot) {
   for(size_t g = 0; g < sp->slots.size(); g++) { if(visits) visits[g] = sp->budget[g]; if(plainRoot) plainRoot[g] = sp->plain[g]; }
   return 0;
 }
 int kgb_selfplay_get_game(kgb_selfplay* sp, int g, uint8_t* colors, int32_t* info) {
+  ensureStarted(sp);
   Slot& s = sp->slots[g];
-  for(int y = 0; y < sp->Y; y++) for(int x = 0; x < sp->X; x++) colors[y * sp->X + x] = s.board.colors[Location::getLoc(x, y, sp->X)];
+  memset(colors, 0, (size_t)sp->X * sp->Y);
+  for(int y = 0; y < s.setup[1]; y++) for(int x = 0; x < s.setup[0]; x++) colors[y * sp->X + x] = s.board.colors[Location::getLoc(x, y, s.setup[0])];
   info[0] = s.moveNum; info[1] = s.pla == P_BLACK; info[2] = -1; info[3] = 0; info[4] = 0; info[5] = sp->budget[g] + g;
   return 0;
 }

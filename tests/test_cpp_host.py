@@ -39,6 +39,10 @@ def _replay_slots_with_limits(log, G, size, V):
             super().__init__(log, G, size, V)
             self.budget, self.plain = np.full(G, V, np.int32), np.zeros(G, np.uint8)
             self.next_budget, self.next_plain = np.full((G, 2), V, np.int32), np.zeros((G, 2), np.uint8)
+            self.cur_setup = np.tile(np.array([size, size, 0, 1], np.int32), (G, 1))
+            self.next_setup, self.last_setup = self.cur_setup.copy(), self.cur_setup.copy()
+            self.cur_komi = np.full(G, 7.5, np.float32)
+            self.next_komi, self.last_komi = self.cur_komi.copy(), self.cur_komi.copy()
 
         def set_next_search_limits(self, visits2, plain2=None, also_current_roots=False):
             self.next_budget = np.array(visits2, np.int32).reshape(G, 2)
@@ -48,6 +52,23 @@ def _replay_slots_with_limits(log, G, size, V):
 
         def search_limits(self):
             return self.budget.copy(), self.plain.copy()
+
+        # per-game board, rules and komi: of the games in progress, of each slot's next game and of its last finished one
+        def set_game_setup(self, setups, also_current_games=False):
+            self.next_setup = np.array(setups, np.int32).reshape(G, 4).copy()
+            if also_current_games:
+                self.cur_setup = self.next_setup.copy()
+
+        def set_komi(self, komis, also_current_games=False):
+            self.next_komi = np.array(komis, np.float32).copy()
+            if also_current_games:
+                self.cur_komi = self.next_komi.copy()
+
+        def game_setups(self):
+            return self.cur_setup.copy(), self.last_setup.copy()
+
+        def komi_values(self):
+            return self.cur_komi.copy(), self.last_komi.copy()
 
         def root_visits(self):
             return self.budget.copy()
@@ -63,6 +84,9 @@ def _replay_slots_with_limits(log, G, size, V):
             for g in moving:
                 k = 1 if self.last[g]["flags"] & 1 else 0
                 self.budget[g], self.plain[g] = self.next_budget[g, k], self.next_plain[g, k]
+                if k:
+                    self.last_setup[g], self.cur_setup[g] = self.cur_setup[g].copy(), self.next_setup[g].copy()
+                    self.last_komi[g], self.cur_komi[g] = self.cur_komi[g], self.next_komi[g]
     return Slots()
 
 
@@ -71,18 +95,24 @@ LIMITS = {"none": "", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\nch
                                           "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n"}
 
 
+MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRules = SIMPLE,POSITIONAL,SITUATIONAL\nmultiStoneSuicideLegals = false,true\n"
+         "komiStdev = 1.0\nkomiBigStdevProb = 0.2\nkomiBigStdev = 8.0\nkomiBiggerStdevProb = 0.05\nkomiAllowIntegerProb = 0.5\n")
+
+
 @pytest.mark.parametrize("size,ko,komi,max_moves,psw,vsw,search_surprise,games,seed,limits", [
     (9, "SIMPLE", 6.5, 40, 0.5, 0.1, False, 7, 3, "none"),          # stock-like surprise weighting, games stopped by the move limit, several files
     (5, "POSITIONAL", 7.0, 60, 0.0, 0.0, False, 9, 11, "none"),     # integer komi (draws), games ended by passes, every weight 1
     (7, "SITUATIONAL", -2.5, 30, 0.3, 0.2, True, 5, 5, "none"),     # search-value surprise
     (9, "SIMPLE", 7.5, 40, 0.5, 0.1, False, 7, 21, "cheap"),        # recorded cheap searches (weight 0.25) under the surprise weighting
     (7, "POSITIONAL", 6.5, 50, 0.5, 0.1, False, 8, 8, "cheap_unrecorded_and_reduced"),   # unrecorded cheap searches (plain roots) and reduced visits
+    (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 12, 4, "cheap"),         # board size (rectangles), ko / suicide rule and komi noise drawn per game, inside a 9x9 data frame
 ])
 def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
     G, V, ROWS_PER_FILE = 3, 20, 60
     cfg = tmp_path / "c.cfg"
-    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nbSizes = {size}\nkoRules = {ko}\nkomiMean = {komi}\nmaxMovesPerGame = {max_moves}\n"
+    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nkomiMean = {komi}\n" + (f"maxMovesPerGame = {max_moves}\n" if max_moves else "") +
+                   (MIXED + f"dataBoardLen = {size}\n" if ko == "MIXED" else f"bSizes = {size}\nkoRules = {ko}\n") +
                    f"policySurpriseDataWeight = {psw}\nvalueSurpriseDataWeight = {vsw}\nuseSearchValueSurprise = {'true' if search_surprise else 'false'}\n"
                    f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n" + LIMITS[limits])
     out, log = tmp_path / "cpp", tmp_path / "log.jsonl"
@@ -113,15 +143,14 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
 
     def on_game(slot, data):
         if len(done) < games:
-            data.ko_rule = ko
             writer.write_game(data)
             sink.add(slot, data)
             done.append(data)
 
-    class Cfg:
-        ko_rule, multi_stone_suicide_legal = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2}[ko], 1
-    sp.cfg = Cfg()
-    rec = R.GameRecorder(sp, None, komi, on_game=on_game, game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
+    from katago_b200.game_initializer import GameInitializer
+    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G)      # the command's own per-game draws
+    setups.start(sp)
+    rec = R.GameRecorder(sp, None, komi, on_game=on_game, on_game_start=lambda slot: setups.game_started(sp, rec, slot), game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
                          policy_surprise_data_weight=psw, value_surprise_data_weight=vsw, use_search_value_surprise=search_surprise,
                          weight_rand=W.RowRand(writer_seed + ":weights"), play_settings=data["play_settings"],
                          limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
@@ -143,6 +172,9 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     if psw == 0 and vsw == 0:
         assert rows == sum(len(d.moves) for d in done)
     weights = [float(w) for d in done for w in (d.target_weight_by_turn_unrounded or d.target_weight_by_turn)]
+    if ko == "MIXED":
+        assert len({(d.x_size, d.y_size) for d in done}) >= 4 and any(d.x_size != d.y_size for d in done) and len({d.ko_rule for d in done}) >= 2
+        assert len({d.komi for d in done}) >= 5 and {d.multi_stone_suicide_legal for d in done} == {False, True}
     if limits == "cheap_unrecorded_and_reduced":       # turns that are not recorded at all, and visit counts between the minimum and the full budget
         visits = [v - g for d in done for (_, v), g in zip(d.policy_targets_by_turn, [0] * len(d.moves))]
         assert any(w == 0.0 for w in weights) and any(6 + 0 <= v <= V + 2 and v not in (V, V + 1, V + 2) for v in visits)

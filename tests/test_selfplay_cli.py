@@ -531,9 +531,12 @@ def test_cpp_host_refuses_what_it_does_not_play_and_needs_a_gpu(tmp_path, cpp_ho
     cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nestimateLeadProb = 0.05\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0 and "estimateLeadProb" in r.stderr and "selfplay_cli.py" in r.stderr
-    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\n")
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\ndataBoardLen = 9\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode != 0 and "bSizes" in r.stderr
+    assert r.returncode != 0 and "dataBoardLen" in r.stderr          # the data frame must hold the largest board
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nkomiAuto = true\n")
+    r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "komiAuto" in r.stderr
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present: the loud failure without one is checked on CPU boxes")
