@@ -67,6 +67,9 @@ class GameInitializer {
     if(!allowInteger && komi == (double)(long)komi) komi += rand_.random() < 0.5 ? -0.5 : 0.5;
     return (float)komi;
   }
+  // numInitialMovesToPlay of PlayUtils::initializeGameUsingPolicy (playutils.cpp:243-250, gamma shape 1): floor of an exponential with mean
+  // board area * policyInitAreaProp - drawn from the same stream, after the game's own draws
+  int openingLength(int xSize, int ySize, double areaProp) { return (int)std::floor(rand_.expovariate(1.0) * xSize * ySize * areaProp); }
   Game draw() {
     const std::pair<int, int> size = sizes_[rand_.choiceIndex(sizeProbs_)];
     const int ko = c_.koRules[rand_.randrange((uint32_t)c_.koRules.size())];

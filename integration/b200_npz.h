@@ -74,6 +74,7 @@ struct FinishedGame {
   std::vector<std::vector<QValueTarget>> whiteQValueTargetsByTurn;
   std::vector<std::array<double, 3>> nnRawStatsByTurn;    // whiteWinLoss, whiteScoreMean, policyEntropy of the root's own evaluation
   std::vector<std::pair<int, int>> moves;                 // (x, y), (-1, -1) = pass
+  std::vector<std::pair<int, int>> startMoves;            // the moves before the training period (startHist.moveHistory: policy-initialised opening), black first
   std::string koRule = "SIMPLE"; bool multiStoneSuicideLegal = true;
   int winner = 0; float finalWhiteMinusBlackScore = 0;
   std::vector<uint8_t> finalFullArea, finalOwnership;     // row-major [ySize * xSize]: 0 none, 1 black, 2 white
@@ -431,6 +432,11 @@ inline std::string writeSgf(const FinishedGame& d, const std::string& bName, con
          (d.mode >= 0 && d.mode < 8 ? GTYPES[d.mode] : "other") + "]";
   const std::vector<float>& weights = d.targetWeightByTurnUnrounded.empty() ? d.targetWeightByTurn : d.targetWeightByTurnUnrounded;
   const size_t n = d.moves.size();
+  for(size_t j = 0; j < d.startMoves.size(); j++) {       // endHist.moveHistory starts with startHist's moves: no comments on those
+    out += std::string(";") + (j % 2 == 0 ? "B" : "W") + "[";
+    if(d.startMoves[j].first >= 0) { out += SGF_CHARS[d.startMoves[j].first]; out += SGF_CHARS[d.startMoves[j].second]; }
+    out += "]";
+  }
   for(size_t i = 0; i < n; i++) {
     const int x = d.moves[i].first, y = d.moves[i].second;
     out += std::string(";") + (d.nextPlayerByTurn[i] == P_BLACK ? "B" : "W") + "[";

@@ -150,6 +150,7 @@ class PyRandom {
     idx_ = N;
   }
   double random() { const uint32_t a = next() >> 5, b = next() >> 6; return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0); }
+  double expovariate(double lambd) { return -std::log(1.0 - random()) / lambd; }
   // randrange(n): _randbelow_with_getrandbits - k = bit length of n, k-bit draws until one is below n
   uint32_t randrange(uint32_t n) {
     int k = 0;
@@ -239,6 +240,7 @@ class HostRecorder {
     double policySurpriseDataWeight = 0.0, valueSurpriseDataWeight = 0.0; bool useSearchValueSurprise = false;
     uint64_t hashSeed = 0; std::string weightRandSeed;      // weightRandSeed empty: fractional weights go to the writer unresolved
     PlaySettings play; uint64_t limitsRandSeed = 0x4C696D69;   // cheap searches / reduced visits, drawn per move
+    bool policyInit = false;       // policy-initialised openings (kgb_selfplay_set_policy_init): a slot in its opening is not held; the opening is the game's start history
     bool perGameSetups = false;    // board size, rules and komi are per game (kgb_selfplay_set_game_setup / set_komi): read them from the device
   };
   using OnGame = std::function<void(int slot, const FinishedGame&)>;
@@ -275,7 +277,8 @@ class HostRecorder {
     const std::vector<int32_t> budgets = s_.play.active() ? slots_.visitBudgets() : std::vector<int32_t>((size_t)n, s_.maxVisits);
     std::vector<uint8_t> held((size_t)n, 0);
     std::vector<int> idx;
-    for(int g = 0; g < n; g++) if(visits[(size_t)g] >= budgets[(size_t)g]) { held[(size_t)g] = 1; idx.push_back(g); }
+    const std::vector<int32_t> openingLeft = s_.policyInit ? slots_.policyInitState() : std::vector<int32_t>((size_t)n, 0);
+    for(int g = 0; g < n; g++) if(visits[(size_t)g] >= budgets[(size_t)g] && openingLeft[(size_t)g] <= 0) { held[(size_t)g] = 1; idx.push_back(g); }
     if(idx.empty()) return 0;
     const std::vector<double> rawEntropy = slots_.rootRawPolicyEntropies();
     for(int g : idx) recordRoot(g, rawEntropy[(size_t)g]);
@@ -299,6 +302,7 @@ class HostRecorder {
   struct InProgress {
     std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; std::vector<double> winLoss;      // winLoss: historicalMctsWinLossValues
     bool haveSetup = false; GameSlots::GameSetup setup{0, 0, 0, 1};     // this game's own board and rules, read when its first turn is recorded
+    std::vector<std::pair<int, int>> startMoves;                         // the opening the device drew from the policy (startHist)
   };
   // a board or area of the evaluator's frame cut down to the game's own board (its top-left corner)
   std::vector<uint8_t> crop(const std::vector<uint8_t>& frame, int bx, int by) const {
@@ -352,6 +356,14 @@ class HostRecorder {
       gm.setup = GameSlots::GameSetup{X, Y, s_.koRule, s_.multiStoneSuicideLegal ? 1 : 0};
       if(s_.perGameSetups) { std::vector<GameSlots::GameSetup> cur; slots_.gameSetups(&cur, nullptr); gm.setup = cur[(size_t)g]; }
       gm.haveSetup = true;
+      if(s_.policyInit) {
+        std::vector<std::vector<Move>> openings;
+        slots_.policyInitState(&openings);
+        for(const Move& m : openings[(size_t)g]) gm.startMoves.push_back({m.x, m.y});
+        if((int)gm.startMoves.size() != pos.moveNumber)
+          throw std::runtime_error("HostRecorder: slot " + std::to_string(g) + ": " + std::to_string(pos.moveNumber) + " moves played before the first searched move, " +
+                                   std::to_string(gm.startMoves.size()) + " opening moves kept");
+      }
     }
     gm.boards.push_back(crop(pos.colors, gm.setup.x, gm.setup.y));
     gm.winLoss.push_back((double)t.valueTargets.win - (double)t.valueTargets.loss);
@@ -384,6 +396,7 @@ class HostRecorder {
     d.endFinished = !last.hitMoveLimit; d.hitTurnLimit = last.hitMoveLimit; d.endNoResult = last.noResult;
     static const char* KO[] = {"SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT"};
     d.koRule = KO[gm.setup.koRule & 3]; d.multiStoneSuicideLegal = gm.setup.multiStoneSuicideLegal != 0;
+    d.startMoves = gm.startMoves; d.startHistMoves = (int)gm.startMoves.size();
     d.boardsByTurn = std::move(gm.boards);
     d.boardsByTurn.push_back(crop(last.finalColors, X, Y));
     std::vector<std::array<double, 3>> rawNN;

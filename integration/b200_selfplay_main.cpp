@@ -14,7 +14,7 @@
 //
 // Every turn is recorded; its weight comes from the per-move search limits (cheapSearchProb / reduceVisits ...) and the surprise weighting
 // (policySurpriseDataWeight / valueSurpriseDataWeight); board size, ko / suicide rule and komi are drawn per game like the reference's
-// GameInitializer (integration/b200_gameinit.h).  The wider host (komiAuto, policy-initialised openings, lead targets, forks, side
+// GameInitializer (integration/b200_gameinit.h).  Openings can be drawn from the policy (initGamesWithPolicy).  The wider host (komiAuto, lead targets, forks, side
 // positions, model polling and weight hot-swap, several GPUs) is katago_b200/selfplay_cli.py: options of that kind are refused here, not
 // ignored.  Without a CUDA device the program stops with the library's error (there is no CPU path).
 #include <chrono>
@@ -121,7 +121,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
   c.neutral("handicapProb", "0.0"); c.neutral("komiAuto", "false");
   c.neutral("estimateLeadProb", "0.0");
-  c.neutral("initGamesWithPolicy", "false"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
+  c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
   c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
 
   k.win_loss_utility_factor = c.num("winLossUtilityFactor", 1.0);
@@ -277,6 +277,9 @@ int main(int argc, char** argv) {
   gi.komiMean = cfg.num("komiMean", 7.5); gi.komiStdev = cfg.num("komiStdev", 0.0); gi.komiBigStdevProb = cfg.num("komiBigStdevProb", 0.0);
   gi.komiBigStdev = cfg.num("komiBigStdev", 10.0); gi.komiBiggerStdevProb = cfg.num("komiBiggerStdevProb", 0.0); gi.komiBiggerStdev = cfg.num("komiBiggerStdev", 30.0);
   gi.komiAllowIntegerProb = cfg.num("komiAllowIntegerProb", 1.0);
+  // policy-initialised openings (initializeGameUsingPolicy): the device draws the moves, the host the count per game
+  const bool policyInit = cfg.flag("initGamesWithPolicy", false) && cfg.num("policyInitAreaProp", 0.04) > 0;
+  const double policyInitAreaProp = cfg.num("policyInitAreaProp", 0.04), policyInitTemperature = cfg.num("policyInitAreaTemperature", 1.0);
   int maxEdge = 0; for(int e : gi.edges) maxEdge = std::max(maxEdge, e);
   const int edge = (int)cfg.num("dataBoardLen", maxEdge);
   if(edge < maxEdge) die("dataBoardLen = " + std::to_string(edge) + " but bSizes goes up to " + std::to_string(maxEdge) + ": the data frame must hold the largest board");
@@ -336,12 +339,18 @@ int main(int argc, char** argv) {
     b200::GameInitializer init(gi, ((uint64_t)seed * 1000003ULL) ^ 0x47616D65ULL);
     std::vector<b200::GameSlots::GameSetup> setups((size_t)numGames); std::vector<float> komis((size_t)numGames);
     auto drawInto = [&](int g) { const b200::GameInitializer::Game d = init.draw(); setups[(size_t)g] = {d.x, d.y, d.koRule, d.multiStoneSuicideLegal}; komis[(size_t)g] = d.komi; };
+    std::vector<int32_t> openings((size_t)numGames, 0);
+    auto drawOpenings = [&]() { if(policyInit) for(int g = 0; g < numGames; g++) openings[(size_t)g] = init.openingLength(setups[(size_t)g].x, setups[(size_t)g].y, policyInitAreaProp); };
     for(int g = 0; g < numGames; g++) drawInto(g);
+    drawOpenings();
     slots.setGameSetups(setups, true); slots.setKomis(komis, true);
+    if(policyInit) slots.setPolicyInit(openings, policyInitTemperature, true);
     for(int g = 0; g < numGames; g++) drawInto(g);
+    drawOpenings();
     slots.setGameSetups(setups); slots.setKomis(komis);
+    if(policyInit) slots.setPolicyInit(openings, policyInitTemperature);
     b200::HostRecorder::Settings rs;
-    rs.perGameSetups = true;
+    rs.perGameSetups = true; rs.policyInit = policyInit;
     rs.komi = sc.komi; rs.drawEquivalentWinsForWhite = sc.draw_equivalent_wins_for_white; rs.koRule = sc.ko_rule;
     rs.multiStoneSuicideLegal = sc.multi_stone_suicide_legal != 0; rs.maxVisits = sc.max_visits;
     rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
@@ -355,7 +364,10 @@ int main(int argc, char** argv) {
       sgfs << b200::writeSgf(game, netName, netName) << "\n";
       written++;
     });
-    recorder.onGameStart = [&](int g) { drawInto(g); slots.setGameSetups(setups); slots.setKomis(komis); };
+    recorder.onGameStart = [&](int g) {
+      drawInto(g); slots.setGameSetups(setups); slots.setKomis(komis);
+      if(policyInit) { openings[(size_t)g] = init.openingLength(setups[(size_t)g].x, setups[(size_t)g].y, policyInitAreaProp); slots.setPolicyInit(openings, policyInitTemperature); }
+    };
     const auto t0 = std::chrono::steady_clock::now();
     while(maxGamesTotal <= 0 || written < maxGamesTotal) recorder.pump(wavesPerPoll);
     writer.flushIfNonempty();

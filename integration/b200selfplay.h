@@ -7,6 +7,7 @@
 // (search/search.h: getRootVisits, getPlaySelectionValues; search/searchresults.cpp) so that the game-recording code above them can
 // stay as it is.  Plain C++17, no CUDA headers: everything goes through the C ABI of include/kgb200.h.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -65,6 +66,23 @@ class GameSlots {
   void setPolicyInit(const std::vector<int32_t>& numMoves, double temperature, bool alsoCurrentGames = false) {
     if((int)numMoves.size() != n_) throw std::invalid_argument("setPolicyInit: one entry per slot");
     check(kgb_selfplay_set_policy_init(sp_, numMoves.data(), temperature, alsoCurrentGames ? 1 : 0));
+  }
+  // moves left in each slot's opening (> 0: the slot moves on by itself and is not held) and, if asked for, the opening played so far
+  std::vector<int32_t> policyInitState(std::vector<std::vector<Move>>* openings = nullptr) const {
+    const int maxMoves = 512;
+    std::vector<int32_t> left((size_t)n_), count((size_t)n_);
+    std::vector<int16_t> mv(openings ? (size_t)n_ * maxMoves : 0);
+    check(kgb_selfplay_get_policy_init(sp_, left.data(), count.data(), openings ? mv.data() : nullptr, openings ? maxMoves : 0));
+    if(openings) {
+      openings->assign((size_t)n_, {});
+      for(int g = 0; g < n_; g++)
+        for(int i = 0; i < std::min(count[(size_t)g], maxMoves); i++) {
+          const int p = mv[(size_t)g * maxMoves + i];
+          Move m; if(p < x_ * y_) { m.x = p % x_; m.y = p / x_; }
+          (*openings)[(size_t)g].push_back(m);
+        }
+    }
+    return left;
   }
   // the playout loop: `waves` playout waves for every slot (asynchronous), then wait
   void runWaves(int waves) { check(kgb_selfplay_run(sp_, waves)); check(kgb_handle_sync(handle_)); }

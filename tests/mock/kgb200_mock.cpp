@@ -31,6 +31,7 @@ struct Slot {
   Board board; BoardHistory hist; Player pla = P_BLACK;
   int moveNum = 0, gameIndex = 0;
   int32_t setup[4] = {0, 0, 0, 1}; float komi = 7.5f;      // this game's board X, Y, ko rule, multi-stone suicide; komi
+  int initPending = 0; std::vector<int16_t> initMoves;      // policy-initialised opening: moves to play when the game starts / the ones played (frame positions)
   bool held = true;                 // searches finish instantly in the mock
   // what the "search" of the current root found
   std::vector<int32_t> edgeVisits, nodeVisits; std::vector<float> policy; std::vector<double> childStats, psv;
@@ -51,6 +52,7 @@ struct kgb_selfplay {
   std::vector<int32_t> budget, nextBudget; std::vector<uint8_t> plain, nextPlain;
   // per-game board, rules and komi (kgb_selfplay_set_game_setup / set_komi): of each slot's next game and of its last finished one
   std::vector<int32_t> nextSetup, lastSetup; std::vector<float> nextKomi, lastKomi;
+  std::vector<int32_t> nextInit;    // opening length of each slot's next game (kgb_selfplay_set_policy_init)
   bool started = false;             // the first games begin with the first run / read, after the host has handed over their setups
 };
 
@@ -98,7 +100,7 @@ static void searchRoot(kgb_selfplay* sp, int g) {
   std::vector<double> rs(s.rootStats, s.rootStats + 5), rn(s.rootNN, s.rootNN + 5);
   o << "{\"ev\":\"root\",\"slot\":" << g << ",\"move_num\":" << s.moveNum << ",\"black_to_move\":" << (s.pla == P_BLACK ? 1 : 0) << ",";
   arr("colors", colors); arr("edge_visits", s.edgeVisits); arr("node_visits", s.nodeVisits); arr("policy", s.policy); arr("child_stats", s.childStats);
-  arr("psv", s.psv); arr("root_stats", rs); arr("root_nn", rn); arr("row_spatial", s.rowSpatial); arr("row_global", s.rowGlobal, true);
+  arr("psv", s.psv); arr("root_stats", rs); arr("root_nn", rn); arr("init_moves", s.initMoves); arr("row_spatial", s.rowSpatial); arr("row_global", s.rowGlobal, true);
   o << "}\n";
 }
 
@@ -108,6 +110,19 @@ static void startGame(kgb_selfplay* sp, int g) {
   rules.koRule = s.setup[2] == 1 ? Rules::KO_POSITIONAL : s.setup[2] == 2 ? Rules::KO_SITUATIONAL : s.setup[2] == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
   rules.multiStoneSuicideLegal = s.setup[3] != 0; rules.komi = s.komi;
   s.board = Board(s.setup[0], s.setup[1]); s.pla = P_BLACK; s.hist = BoardHistory(s.board, s.pla, rules, 0, false); s.moveNum = 0;
+  // the opening the device would draw from the policy: here uniformly random legal board moves, played at once and never held for recording
+  s.initMoves.clear();
+  for(int i = 0; i < s.initPending; i++) {
+    std::vector<Loc> legal;
+    for(int y = 0; y < s.setup[1]; y++) for(int x = 0; x < s.setup[0]; x++) { Loc l = Location::getLoc(x, y, s.setup[0]); if(s.hist.isLegal(s.board, l, s.pla)) legal.push_back(l); }
+    if(legal.empty()) break;
+    const Loc l = legal[sp->rng.next() % legal.size()];
+    s.hist.makeBoardMoveAssumeLegal(s.board, l, s.pla, NULL);
+    s.pla = getOpp(s.pla);
+    s.initMoves.push_back((int16_t)(Location::getY(l, s.setup[0]) * sp->X + Location::getX(l, s.setup[0])));
+    s.moveNum++;
+  }
+  s.initPending = 0;
 }
 
 static void advance(kgb_selfplay* sp, int g) {
@@ -139,6 +154,7 @@ static void advance(kgb_selfplay* sp, int g) {
   if(over) {                        // the slot's next game takes the setup and komi handed over for it
     for(int k = 0; k < 4; k++) { sp->lastSetup[4 * (size_t)g + k] = s.setup[k]; s.setup[k] = sp->nextSetup[4 * (size_t)g + k]; }
     sp->lastKomi[g] = s.komi; s.komi = sp->nextKomi[g];
+    s.initPending = sp->nextInit[g];
     s.gameIndex++; startGame(sp, g);
   }
   else s.moveNum++;
@@ -185,7 +201,7 @@ int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfpla
       Slot& s = sp->slots[g];
       s.setup[0] = sp->X; s.setup[1] = sp->Y; s.setup[2] = c->ko_rule; s.setup[3] = c->multi_stone_suicide_legal != 0; s.komi = c->komi;
       for(int k = 0; k < 4; k++) { sp->nextSetup.push_back(s.setup[k]); sp->lastSetup.push_back(s.setup[k]); }
-      sp->nextKomi.push_back(c->komi); sp->lastKomi.push_back(c->komi);
+      sp->nextKomi.push_back(c->komi); sp->lastKomi.push_back(c->komi); sp->nextInit.push_back(0);
     }
     *out = sp;
   })
@@ -236,6 +252,21 @@ int kgb_selfplay_set_komi(kgb_selfplay* sp, const float* komi, int alsoCurrentGa
 }
 int kgb_selfplay_get_komi(kgb_selfplay* sp, float* current, float* lastFinished) {
   for(size_t g = 0; g < sp->slots.size(); g++) { if(current) current[g] = sp->slots[g].komi; if(lastFinished) lastFinished[g] = sp->lastKomi[g]; }
+  return 0;
+}
+int kgb_selfplay_set_policy_init(kgb_selfplay* sp, const int32_t* numMoves, double, int alsoCurrentGames) {
+  if(alsoCurrentGames && sp->started) { g_err = "mock: the games in progress have begun"; return 1; }
+  for(size_t g = 0; g < sp->slots.size(); g++) { sp->nextInit[g] = numMoves[g]; if(alsoCurrentGames) sp->slots[g].initPending = numMoves[g]; }
+  return 0;
+}
+int kgb_selfplay_get_policy_init(kgb_selfplay* sp, int32_t* movesLeft, int32_t* count, int16_t* moves, int maxMoves) {
+  ensureStarted(sp);
+  for(size_t g = 0; g < sp->slots.size(); g++) {
+    const std::vector<int16_t>& m = sp->slots[g].initMoves;
+    if(movesLeft) movesLeft[g] = 0;                  // the mock plays a whole opening at once
+    if(count) count[g] = (int32_t)m.size();
+    if(moves) for(int i = 0; i < maxMoves; i++) moves[g * (size_t)maxMoves + i] = i < (int)m.size() ? m[i] : 0;
+  }
   return 0;
 }
 int kgb_selfplay_get_search_limits(kgb_selfplay* sp, int32_t* visits, uint8_t* plainRoot) {

@@ -67,6 +67,15 @@ def _replay_slots_with_limits(log, G, size, V):
         def game_setups(self):
             return self.cur_setup.copy(), self.last_setup.copy()
 
+        # policy-initialised openings: the mock plays a whole opening when the game starts and lists it with every root of the game
+        def set_policy_init(self, num_moves, temperature=1.0, also_current_games=False):
+            pass
+
+        def policy_init(self, max_moves=0):
+            n = self.x * self.y
+            moves = [[(-1, -1) if p == n else (p % self.x, p // self.x) for p in self.root[g]["init_moves"]] for g in range(G)]
+            return np.zeros(G, np.int32), np.array([len(m) for m in moves], np.int32), (moves if max_moves > 0 else None)
+
         def komi_values(self):
             return self.cur_komi.copy(), self.last_komi.copy()
 
@@ -90,7 +99,7 @@ def _replay_slots_with_limits(log, G, size, V):
     return Slots()
 
 
-LIMITS = {"none": "", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
+LIMITS = {"none": "", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
           "cheap_unrecorded_and_reduced": "cheapSearchProb = 0.25\ncheapSearchVisits = 5\ncheapSearchTargetWeight = 0.0\nreduceVisits = true\nreduceVisitsThreshold = 0.3\n"
                                           "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n"}
 
@@ -106,6 +115,7 @@ MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRul
     (9, "SIMPLE", 7.5, 40, 0.5, 0.1, False, 7, 21, "cheap"),        # recorded cheap searches (weight 0.25) under the surprise weighting
     (7, "POSITIONAL", 6.5, 50, 0.5, 0.1, False, 8, 8, "cheap_unrecorded_and_reduced"),   # unrecorded cheap searches (plain roots) and reduced visits
     (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 12, 4, "cheap"),         # board size (rectangles), ko / suicide rule and komi noise drawn per game, inside a 9x9 data frame
+    (9, "MIXED", 7.0, 0, 0.5, 0.1, False, 12, 9, "openings"),      # the same with policy-initialised openings: a start history before the recorded turns
 ])
 def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
@@ -148,12 +158,12 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
             done.append(data)
 
     from katago_b200.game_initializer import GameInitializer
-    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G)      # the command's own per-game draws
+    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G, policy_init=data["policy_init"])      # the command's own per-game draws
     setups.start(sp)
     rec = R.GameRecorder(sp, None, komi, on_game=on_game, on_game_start=lambda slot: setups.game_started(sp, rec, slot), game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
                          policy_surprise_data_weight=psw, value_surprise_data_weight=vsw, use_search_value_surprise=search_surprise,
                          weight_rand=W.RowRand(writer_seed + ":weights"), play_settings=data["play_settings"],
-                         limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69))
+                         limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69), policy_init=data["policy_init"]["enabled"])
     while len(done) < games:
         rec.pump(4)
     writer.flush_if_nonempty()
@@ -175,6 +185,9 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     if ko == "MIXED":
         assert len({(d.x_size, d.y_size) for d in done}) >= 4 and any(d.x_size != d.y_size for d in done) and len({d.ko_rule for d in done}) >= 2
         assert len({d.komi for d in done}) >= 5 and {d.multi_stone_suicide_legal for d in done} == {False, True}
+    if limits == "openings":
+        assert sum(1 for d in done if d.start_hist_moves > 0) >= 4 and max(d.start_hist_moves for d in done) >= 3
+        assert all(len(d.start_moves) == d.start_hist_moves for d in done)
     if limits == "cheap_unrecorded_and_reduced":       # turns that are not recorded at all, and visit counts between the minimum and the full budget
         visits = [v - g for d in done for (_, v), g in zip(d.policy_targets_by_turn, [0] * len(d.moves))]
         assert any(w == 0.0 for w in weights) and any(6 + 0 <= v <= V + 2 and v not in (V, V + 1, V + 2) for v in visits)
