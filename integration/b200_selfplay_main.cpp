@@ -232,11 +232,49 @@ std::string modelNameOf(const std::string& path) {
   return base.substr(0, base.find('.'));
 }
 
+// <output-dir>[/<net name>]/{tdata,sgfs}: one writer per net, as the reference keeps one per NNEvaluator (command/selfplay.cpp:178-225;
+// katago_b200/selfplay_cli.py ModelOutputs).  switchTo() closes the files of the previous net and opens the new net's.
+struct Outputs {
+  std::string baseDir, writerSeed; bool perNet; int maxRowsPerFile; double firstFileMinRandProp; int dataLen;
+  std::unique_ptr<b200::TrainingDataWriter> writer; std::ofstream sgfs; std::string netName;
+  int generation = 0; long long rowsTotal = 0; size_t filesTotal = 0;
+
+  void close() {
+    if(!writer) return;
+    writer->flushIfNonempty();
+    rowsTotal += writer->rowCount(); filesTotal += writer->filesWritten().size();
+    writer.reset();
+    sgfs.close();
+  }
+  void switchTo(const std::string& modelPath, const std::string& nameInFile) {
+    close();
+    netName = perNet ? modelNameOf(modelPath) : nameInFile;
+    const std::string dir = perNet ? baseDir + "/" + netName : baseDir;
+    for(const std::string& d : {baseDir, dir, dir + "/tdata", dir + "/sgfs"})
+      if(mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create " + d);
+    const std::string seed = generation == 0 ? writerSeed : writerSeed + ":net" + std::to_string(generation);
+    writer.reset(new b200::TrainingDataWriter(dir + "/tdata", maxRowsPerFile, firstFileMinRandProp, dataLen, seed));
+    b200::RowRand nameRand(seed + ":sgfs");
+    const uint64_t lo = nameRand.nextUInt(), hi = nameRand.nextUInt();
+    char sgfName[32];
+    std::snprintf(sgfName, sizeof(sgfName), "%016llX.sgfs", (unsigned long long)(lo | (hi << 32)));
+    sgfs.open(dir + "/sgfs/" + sgfName, std::ios::app);
+    if(!sgfs) die("cannot write " + dir + "/sgfs/" + sgfName);
+    generation++;
+  }
+  void addGame(const b200::FinishedGame& game) {
+    writer->writeGame(game);
+    sgfs << b200::writeSgf(game, netName, netName) << "\n";
+  }
+};
+
 }  // namespace
 
 int main(int argc, char** argv) {
   std::string modelPath, modelsDir, cfgPath, outDir, overrides;
   long maxGamesTotal = 0, seed = 1;
+  double modelPollSeconds = 20.0;
+  int rank = 0, worldSize = 1, gpuIdx = -1;
   bool printOnly = false;
   for(int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -248,16 +286,26 @@ int main(int argc, char** argv) {
     else if(a == "-override-config") overrides = next();
     else if(a == "-print-config") printOnly = true;
     else if(a == "-seed") seed = std::atol(next().c_str());
+    else if(a == "-model-poll-seconds") modelPollSeconds = std::atof(next().c_str());
+    else if(a == "-rank") rank = std::atoi(next().c_str());
+    else if(a == "-world-size") worldSize = std::atoi(next().c_str());
+    else if(a == "-gpu") gpuIdx = std::atoi(next().c_str());
     else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
     else if(a == "-help" || a == "--help") {
-      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-override-config k=v,...] [-print-config]\n", argv[0]);
+      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-model-poll-seconds T] [-rank R -world-size N] [-gpu I] [-override-config k=v,...] [-print-config]\n", argv[0]);
       return 0;
     } else die("unknown argument " + a);
   }
   if(cfgPath.empty() || (!printOnly && ((modelPath.empty() == modelsDir.empty()) || outDir.empty())))
     die("-config, -output-dir and one of -model / -models-dir are required (-help)");
   // `katago selfplay -models-dir DIR`: the newest net of the directory, its files under <output-dir>/<net name>/ (command/selfplay.cpp:178-225)
-  if(!printOnly && !modelsDir.empty()) { modelPath = newestModel(modelsDir); outDir = outDir + "/" + modelNameOf(modelPath); }
+  if(!printOnly && !modelsDir.empty()) modelPath = newestModel(modelsDir);
+  // One process per GPU: games are independent, so ranks share nothing - each plays its share of the games on its own GPU with its own seeds
+  // and writes its own files into the common directories (names come from the writers' Rand streams); katago_b200/selfplay_cli.py shard_plan
+  if(worldSize < 1 || rank < 0 || rank >= worldSize) die("-rank must lie in 0 .. -world-size - 1");
+  if(maxGamesTotal > 0) maxGamesTotal = maxGamesTotal / worldSize + (rank < maxGamesTotal % worldSize ? 1 : 0);
+  if(gpuIdx < 0) gpuIdx = rank;
+  const uint64_t loopSeed = (uint64_t)seed * 1000003ULL + (uint64_t)rank;
   Cfg cfg;
   cfg.load(cfgPath);
   cfg.overrides(overrides);
@@ -284,9 +332,10 @@ int main(int argc, char** argv) {
   const int edge = (int)cfg.num("dataBoardLen", maxEdge);
   if(edge < maxEdge) die("dataBoardLen = " + std::to_string(edge) + " but bSizes goes up to " + std::to_string(maxEdge) + ": the data frame must hold the largest board");
   if(edge > 19) die("dataBoardLen: at most 19");
-  if(maxGamesTotal <= 0) maxGamesTotal = (long)cfg.num("numGamesTotal", 0);
+  if(maxGamesTotal <= 0 && worldSize == 1) maxGamesTotal = (long)cfg.num("numGamesTotal", 0);
   const int wavesPerPoll = (int)cfg.num("b200WavesPerPoll", 16);
-  const kgb_selfplay_config sc = configFromCfg(cfg, numGames);
+  kgb_selfplay_config sc = configFromCfg(cfg, numGames);
+  if(!cfg.has("searchRandSeed")) sc.seed = loopSeed;            // every rank its own games
   const double policySurpriseDataWeight = cfg.num("policySurpriseDataWeight", 0.0), valueSurpriseDataWeight = cfg.num("valueSurpriseDataWeight", 0.0);
   const bool useSearchValueSurprise = cfg.flag("useSearchValueSurprise", false);
   cfg.num("maxRowsPerTrainFile", 20000); cfg.num("firstFileRandMinProp", 1.0);
@@ -313,30 +362,23 @@ int main(int argc, char** argv) {
   kgb_model_info info;
   check(kgb_model_get_info(model, &info), "kgb_model_get_info");
   kgb_context* ctx = nullptr;
-  const int gpu = 0;
+  const int gpu = gpuIdx;
   check(kgb_context_create(&gpu, 1, edge, edge, cfg.flag("useFP16", true) ? 1 : 0, model, &ctx), "creating the evaluator context");
   kgb_handle* handle = nullptr;
   check(kgb_handle_create(ctx, model, numGames, 1, /*inputs_nhwc=*/1, gpu, &handle), "creating the evaluator handle");
 
   int rc = 0;
   try {
-    // <output-dir>/tdata and <output-dir>/sgfs like the reference's per-net directories (command/selfplay.cpp:178-225)
-    const std::string tdataDir = outDir + "/tdata", sgfDir = outDir + "/sgfs";
-    for(const std::string& dir : {modelsDir.empty() ? outDir : outDir.substr(0, outDir.find_last_of('/')), outDir, tdataDir, sgfDir})
-      if(mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create " + dir);
-    const std::string writerSeed = "selfplay" + std::to_string(seed) + ":rank0of1";       // as katago_b200/selfplay_cli.py shard_plan
-    b200::TrainingDataWriter writer(tdataDir, (int)cfg.num("maxRowsPerTrainFile", 20000), cfg.num("firstFileRandMinProp", 1.0), edge, writerSeed);
-    b200::RowRand nameRand(writerSeed + ":sgfs");
-    const uint64_t lo = nameRand.nextUInt(), hi = nameRand.nextUInt();
-    char sgfName[32];
-    std::snprintf(sgfName, sizeof(sgfName), "%016llX.sgfs", (unsigned long long)(lo | (hi << 32)));
-    std::ofstream sgfs(sgfDir + "/" + sgfName, std::ios::app);
-    if(!sgfs) die("cannot write " + sgfDir + "/" + sgfName);
+    const std::string writerSeed = "selfplay" + std::to_string(seed) + ":rank" + std::to_string(rank) + "of" + std::to_string(worldSize);
+    Outputs outputs;
+    outputs.baseDir = outDir; outputs.writerSeed = writerSeed; outputs.perNet = !modelsDir.empty();
+    outputs.maxRowsPerFile = (int)cfg.num("maxRowsPerTrainFile", 20000); outputs.firstFileMinRandProp = cfg.num("firstFileRandMinProp", 1.0); outputs.dataLen = edge;
+    outputs.switchTo(modelPath, info.name);
 
     b200::GameSlots slots(handle, sc, edge, edge);
     // the draws become the games in progress (none has started), new ones are drawn for the games after them; a slot's draw for the game
     // after next is made when its next game begins (katago_b200/selfplay_cli.py SlotSetups)
-    b200::GameInitializer init(gi, ((uint64_t)seed * 1000003ULL) ^ 0x47616D65ULL);
+    b200::GameInitializer init(gi, loopSeed ^ 0x47616D65ULL);
     std::vector<b200::GameSlots::GameSetup> setups((size_t)numGames); std::vector<float> komis((size_t)numGames);
     auto drawInto = [&](int g) { const b200::GameInitializer::Game d = init.draw(); setups[(size_t)g] = {d.x, d.y, d.koRule, d.multiStoneSuicideLegal}; komis[(size_t)g] = d.komi; };
     std::vector<int32_t> openings((size_t)numGames, 0);
@@ -354,14 +396,12 @@ int main(int argc, char** argv) {
     rs.komi = sc.komi; rs.drawEquivalentWinsForWhite = sc.draw_equivalent_wins_for_white; rs.koRule = sc.ko_rule;
     rs.multiStoneSuicideLegal = sc.multi_stone_suicide_legal != 0; rs.maxVisits = sc.max_visits;
     rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
-    rs.hashSeed = (uint64_t)seed * 1000003ULL; rs.weightRandSeed = writerSeed + ":weights";
-    rs.play = play; rs.limitsRandSeed = ((uint64_t)seed * 1000003ULL) ^ 0x4C696D69ULL;        // as selfplay_cli.py: Random(loop_seed ^ 0x4C696D69)
+    rs.hashSeed = loopSeed; rs.weightRandSeed = writerSeed + ":weights";
+    rs.play = play; rs.limitsRandSeed = loopSeed ^ 0x4C696D69ULL;        // as selfplay_cli.py: Random(loop_seed ^ 0x4C696D69)
     long written = 0;
-    const std::string netName = modelsDir.empty() ? std::string(info.name) : modelNameOf(modelPath);
     b200::HostRecorder recorder(slots, rs, [&](int, const b200::FinishedGame& game) {
       if(maxGamesTotal > 0 && written >= maxGamesTotal) return;        // games that end after the last counted one are dropped, like the Python host
-      writer.writeGame(game);
-      sgfs << b200::writeSgf(game, netName, netName) << "\n";
+      outputs.addGame(game);          // a finished game's rows go to the directory of the net in use when it ended (selfplay.cpp:276-319)
       written++;
     });
     recorder.onGameStart = [&](int g) {
@@ -369,13 +409,46 @@ int main(int argc, char** argv) {
       if(policyInit) { openings[(size_t)g] = init.openingLength(setups[(size_t)g].x, setups[(size_t)g].y, policyInitAreaProp); slots.setPolicyInit(openings, policyInitTemperature); }
     };
     const auto t0 = std::chrono::steady_clock::now();
-    while(maxGamesTotal <= 0 || written < maxGamesTotal) recorder.pump(wavesPerPoll);
-    writer.flushIfNonempty();
-    sgfs.close();
+    // New nets (command/selfplay.cpp:336-352 modelLoadLoop: re-poll the models directory; :142-231 load the newest one): between two pumps
+    // the newest file of -models-dir is compared with the net in use; a new one of the same architecture is packed into the handle's shadow
+    // weight arena and committed between two waves (kgb_handle_stage_weights / commit_weights), the evaluation cache of the old net is
+    // dropped, games move over mid-game (the reference's switchNetsMidGame) and the output directory follows the net.
+    auto lastPoll = std::chrono::steady_clock::now();
+    long pumps = 0; int swaps = 0;
+    std::string ignoredModel;
+    while(maxGamesTotal <= 0 || written < maxGamesTotal) {
+      recorder.pump(wavesPerPoll);
+      pumps++;
+      if(modelsDir.empty() || (maxGamesTotal > 0 && written >= maxGamesTotal)) continue;
+      const auto now = std::chrono::steady_clock::now();
+      if(std::chrono::duration<double>(now - lastPoll).count() < modelPollSeconds) continue;
+      lastPoll = now;
+      const std::string newest = newestModel(modelsDir);
+      if(newest == modelPath || newest == ignoredModel) continue;
+      kgb_model* next = nullptr;
+      if(kgb_model_load_file(newest.c_str(), nullptr, &next) != 0) {        // e.g. a file that is still being written: look again at the next poll
+        std::fprintf(stderr, "b200_selfplay: %s: %s; keeping %s\n", newest.c_str(), kgb_last_error(), outputs.netName.c_str());
+        continue;
+      }
+      if(kgb_handle_stage_weights(handle, next) != 0) {                     // another architecture needs a new evaluator: selfplay_cli.py rebuilds one, this host keeps its net
+        std::fprintf(stderr, "b200_selfplay: %s: %s; keeping %s\n", newest.c_str(), kgb_last_error(), outputs.netName.c_str());
+        kgb_model_free(next); ignoredModel = newest;
+        continue;
+      }
+      check(kgb_handle_commit_weights(handle), "committing the new weights");
+      slots.clearNNCache();
+      kgb_model_info nextInfo;
+      check(kgb_model_get_info(next, &nextInfo), "kgb_model_get_info");
+      kgb_model_free(model); model = next; modelPath = newest;
+      swaps++;
+      outputs.switchTo(modelPath, nextInfo.name);
+      std::fprintf(stderr, "b200_selfplay: Game loop changing midgame to new neural net: %s (swap %d, after pump %ld)\n", outputs.netName.c_str(), swaps, pumps);
+    }
+    outputs.close();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const kgb_selfplay_stats st = slots.stats();
-    std::printf("{\"games_written\": %ld, \"rows\": %lld, \"files\": %zu, \"moves\": %lld, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",
-                written, (long long)writer.rowCount(), writer.filesWritten().size(), (long long)recorder.movesRecorded(), (unsigned long long)st.total_visits, secs,
+    std::printf("{\"games_written\": %ld, \"rows\": %lld, \"files\": %zu, \"moves\": %lld, \"net_swaps\": %d, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",
+                written, outputs.rowsTotal, outputs.filesTotal, (long long)recorder.movesRecorded(), swaps, (unsigned long long)st.total_visits, secs,
                 st.total_visits / secs, (unsigned long long)st.nn_cache_hits);
   } catch(const std::exception& e) {
     std::fprintf(stderr, "b200_selfplay: %s\n", e.what());

@@ -126,6 +126,8 @@ class GameSlots {
     }
     return out;
   }
+  // with kgb_handle_commit_weights: the cached evaluations belong to the previous net
+  void clearNNCache() { check(kgb_selfplay_clear_nn_cache(sp_)); }
   kgb_selfplay_stats stats() const { kgb_selfplay_stats s; check(kgb_selfplay_get_stats(sp_, &s)); return s; }
 
   // ---- game recording (kgb_selfplay_config.debug_hold_at_max_visits = 1): a slot whose search is finished idles until release() ----

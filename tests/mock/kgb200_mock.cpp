@@ -183,6 +183,9 @@ void kgb_context_free(kgb_context* c) { delete c; }
 int kgb_handle_create(kgb_context* c, const kgb_model*, int, int, int, int, kgb_handle** out) { *out = new kgb_handle{c->x, c->y}; return 0; }
 void kgb_handle_free(kgb_handle* h) { delete h; }
 int kgb_handle_sync(kgb_handle*) { return 0; }
+int kgb_handle_stage_weights(kgb_handle*, const kgb_model*) { return 0; }       // weight hot-swap: nothing to swap in the mock
+int kgb_handle_commit_weights(kgb_handle*) { return 0; }
+int kgb_selfplay_clear_nn_cache(kgb_selfplay*) { return 0; }
 
 int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfplay** out) {
   GUARD({
@@ -210,6 +213,12 @@ void kgb_selfplay_free(kgb_selfplay* sp) { delete sp; }
 int kgb_selfplay_run(kgb_selfplay* sp, int) {
   GUARD({
     ensureStarted(sp);
+    // KGB_MOCK_NEW_MODEL = "<runs>:<path>": a new net appears in the models directory while the host is running (the trainer's export)
+    if(const char* nm = getenv("KGB_MOCK_NEW_MODEL")) {
+      static int runs = 0;
+      const std::string spec = nm; const size_t colon = spec.find(':');
+      if(++runs == atoi(spec.substr(0, colon).c_str())) { std::ofstream f(spec.substr(colon + 1)); f << "unused"; }
+    }
     for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) {
       sp->released[g] = 0; advance(sp, (int)g);
       const size_t k = 2 * g + ((sp->slots[g].last[1] & 1) ? 1 : 0);       // the new root takes the limits handed over for it
