@@ -122,6 +122,39 @@ def test_compute_lead_lands_on_the_reference_value_given_the_reference_searches(
         assert asked_naive == asked[:len(asked_naive)] and abs((start - naive) - lead) <= 1.0
 
 
+@pytest.fixture(scope="module")
+def cpp_komi_driver(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("komi") / "komi_table_driver"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", ROOT, os.path.join(ROOT, "tests", "cpp", "komi_table_driver.cpp"), "-o", str(exe),
+                    "-L", os.path.join(ROOT, "katago_b200"), "-lkgb200", "-lz", "-Wl,-rpath," + os.path.join(ROOT, "katago_b200")], check=True)
+    return str(exe)
+
+
+def test_cpp_compute_lead_lands_on_the_reference_value_too(cpp_komi_driver):
+    """integration/b200_komi.h - the C++ host's twin of the generators, written as a plain function that is re-run from the top whenever an evaluation
+    is missing - against the same 472 reference results: the reference's lead bit for bit, and exactly the komis, in exactly the order, that the
+    Python generator asks for."""
+    total = 0
+    for case in _komitable_cases():
+        table = case["table"]
+        text = f"{case['x']} {case['y']} {len(table)}\n" + "".join(f"{k} {v[0]!r} {v[1]!r}\n" for k, v in table.items()) + "".join(f"{k}\n" for k in case["leads"])
+        out = subprocess.run([cpp_komi_driver], input=text, capture_output=True, text=True, check=True).stdout.splitlines()
+        assert len(out) == len(case["leads"])
+        for line, (start, ref_lead) in zip(out, case["leads"].items()):
+            parts = line.split()
+            assert parts[0] == "lead" and parts[2] == "asked", line
+            asked_py = []
+
+            def oracle(k):
+                asked_py.append(k)
+                return tuple(table["%.1f" % k])
+            _run(compute_lead(float(start), case["x"], case["y"]), oracle)
+            assert np.float32(float(parts[1])) == np.float32(ref_lead), (case["name"], start, line)
+            assert [float(v) for v in parts[3:]] == asked_py, (case["name"], start)
+            total += 1
+    assert total >= 470
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(REAL_NET_DRIVER), reason="oracle/_ref/kgref_driver_b200 not built (needs the reference sources at build time)")
 @pytest.mark.parametrize("stream,size,prefix_len,komi,visits", [("boardstream_9x9_multisuicide.npz", 9, 12, 7.5, 6), ("boardstream_9x9_multisuicide.npz", 9, 31, 0.5, 10),
