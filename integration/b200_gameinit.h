@@ -49,13 +49,16 @@ class GameInitializer {
   int maxEdge() const { int m = 0; for(int e : c_.edges) m = std::max(m, e); return m; }
 
   // chooseExtraBlackAndKomi (no handicap) + setKomiWithNoise
-  float drawKomi(int xSize, int ySize) {
+  double komiMean() const { return c_.komiMean; }
+  double uniform() { return rand_.random(); }        // one draw of the initializer's own stream (adjustKomiToEven's rounding draws from it)
+  // mean: instead of komiMean (komiAuto: the fair komi of the empty board; NaN = komiMean)
+  float drawKomi(int xSize, int ySize, double mean = std::nan("")) {
     double stdev = c_.komiStdev > 0 ? c_.komiStdev : 0.0;
     if(c_.komiBigStdev > 0 && rand_.random() < c_.komiBigStdevProb) stdev = c_.komiBigStdev;
     if(c_.komiBiggerStdev > 0 && c_.komiBiggerStdevProb > 0 && rand_.random() < c_.komiBiggerStdevProb) stdev = c_.komiBiggerStdev;
     stdev *= std::sqrt((double)(xSize * ySize)) / 19.0;       // no massive komis on small boards
     const bool allowInteger = rand_.random() < c_.komiAllowIntegerProb;
-    double komi = c_.komiMean;
+    double komi = std::isnan(mean) ? c_.komiMean : mean;
     if(stdev > 0) {
       double d = rand_.gauss(0.0, 1.0);
       while(d < -3.0 || d > 3.0) d = rand_.gauss(0.0, 1.0);   // nextGaussianTruncated(3.0)

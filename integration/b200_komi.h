@@ -13,6 +13,7 @@
 #include <cmath>
 #include <functional>
 #include <map>
+#include <memory>
 #include <utility>
 
 #include "b200_gameinit.h"
@@ -108,5 +109,92 @@ inline float computeLead(double oldKomi, const KomiOracle& ev) {
   }
   return (float)(oldKomi - result);
 }
+
+// Runs komi-search jobs on a side device loop: its own handle, a few slots in hold mode, the game's search parameters with the root noise off and
+// numVisits visits (getNoiselessParams, playutils.cpp:372-387).  A job is an algorithm over a KomiOracle (above) plus the position it is about; a
+// slot is loaded with the position at the komi the job asks for by ending whatever game it holds (passes: kgb_selfplay_play_moves_game restarts
+// the slot with the setup and komi handed over for its next game) and replaying the position's moves from the empty board.  The twin of
+// katago_b200/komi_search.py KomiSearcher, scheduling included (which job gets which slot when), so that both hosts finish jobs in the same order.
+class KomiSearcher {
+ public:
+  using Algorithm = std::function<void(const KomiOracle&)>;     // throws NeedKomi until it can finish; then delivers its result itself
+
+  KomiSearcher(GameSlots& side, int maxVisits) : sp_(side), maxVisits_(maxVisits), n_(side.numSlots()) {
+    for(int g = 0; g < n_; g++) free_.push_back(g);
+    setups_.assign((size_t)n_, GameSlots::GameSetup{side.xLen(), side.yLen(), 0, 1});
+    komis_.assign((size_t)n_, 7.5f);
+  }
+  void submit(const GameSlots::GameSetup& setup, const std::vector<Move>& moves, Algorithm algorithm) {
+    queue_.push_back(std::unique_ptr<Job>(new Job{setup, moves, KomiOracle(setup.x, setup.y), std::move(algorithm), 0.0f}));
+    dispatch();
+  }
+  int pending() const { return (int)(queue_.size() + running_.size()); }
+  long searches() const { return searches_; }
+
+  // `waves` waves of the side loop; searches that have finished hand their (lead, winLoss) to their jobs.  Returns the jobs in flight.
+  int step(int waves) {
+    if(running_.empty() && queue_.empty()) return 0;
+    sp_.runWaves(waves);
+    const std::vector<int32_t> visits = sp_.rootVisitsAll();
+    std::vector<int> done;
+    for(const auto& r : running_) if(visits[(size_t)r.first] >= maxVisits_) done.push_back(r.first);
+    for(int slot : done) {
+      std::vector<double> childMoments; double root[5];
+      sp_.rootValueStatsByPos(slot, childMoments, root);      // winLoss, noResult, scoreMean, scoreMeanSq, lead - white's perspective
+      Job* job = nullptr;
+      for(auto& r : running_) if(r.first == slot) job = r.second.get();
+      job->oracle.add(job->asked, root[4], root[0]);
+      advance(slot);
+    }
+    dispatch();
+    return pending();
+  }
+  void drain(int maxSteps = 100000) {
+    for(int i = 0; i < maxSteps; i++) if(step(8) == 0) return;
+    throw std::runtime_error("KomiSearcher: jobs did not finish");
+  }
+
+ private:
+  struct Job { GameSlots::GameSetup setup; std::vector<Move> moves; KomiOracle oracle; Algorithm algorithm; float asked; };
+
+  // run the job's algorithm on what is known: it finishes (slot freed) or names the next komi (slot loaded with it)
+  void advance(int slot) {
+    size_t at = 0;
+    while(running_[at].first != slot) at++;
+    Job& job = *running_[at].second;
+    try { job.algorithm(job.oracle); }
+    catch(const NeedKomi& need) { load(slot, job, need.komi); return; }
+    running_.erase(running_.begin() + (long)at);
+    free_.push_back(slot);
+  }
+  void load(int slot, Job& job, float komi) {
+    job.asked = komi;
+    setups_[(size_t)slot] = job.setup; komis_[(size_t)slot] = komi;
+    sp_.setGameSetups(setups_); sp_.setKomis(komis_);
+    bool empty = false;
+    for(int i = 0; i < 4 && !empty; i++) {         // two passes end a game (three under spight ko; one if the position's last move was a pass)
+      sp_.playMoves(slot, {Move()});
+      empty = sp_.moveNumber(slot) == 0;
+    }
+    if(!empty) throw std::runtime_error("KomiSearcher: could not end the slot's previous game");
+    sp_.playMoves(slot, job.moves);
+    searches_++;
+  }
+  void dispatch() {
+    while(!queue_.empty() && !free_.empty()) {
+      const int slot = free_.back(); free_.pop_back();
+      running_.emplace_back(slot, std::move(queue_.front()));
+      queue_.erase(queue_.begin());
+      advance(slot);
+    }
+  }
+
+  GameSlots& sp_; int maxVisits_, n_;
+  std::vector<int> free_;
+  std::vector<std::pair<int, std::unique_ptr<Job>>> running_;      // in the order the slots were taken (the Python dict's iteration order)
+  std::vector<std::unique_ptr<Job>> queue_;
+  std::vector<GameSlots::GameSetup> setups_; std::vector<float> komis_;
+  long searches_ = 0;
+};
 
 }  // namespace b200

@@ -246,6 +246,13 @@ class HostRecorder {
   using OnGame = std::function<void(int slot, const FinishedGame&)>;
   // called with the slot when its next game has begun on the device (before any of its turns is recorded): the host's draw for the game after it
   std::function<void(int slot)> onGameStart;
+  // Lead targets (play.cpp:2290-2324): after a game, turns drawn with estimateLeadProb get PlayUtils::computeLead of the position before their move
+  // as a job on a side loop (integration/b200_komi.h KomiSearcher); the game is handed on when the last answer is back, the slot plays on meanwhile.
+  // submitLead(komi, setup, moves, done): `done(lead)` is called once with the job's result.
+  using LeadDone = std::function<void(float lead)>;
+  std::function<void(float komi, const GameSlots::GameSetup& setup, const std::vector<Move>& moves, LeadDone done)> submitLead;
+  double estimateLeadProb = 0.0;
+  int gamesWaitingForLead() const { return gamesWaiting_; }
 
   HostRecorder(GameSlots& slots, const Settings& s, OnGame onGame) : slots_(slots), s_(s), onGame_(std::move(onGame)), games_((size_t)slots.numSlots()) {
     if(!s.weightRandSeed.empty()) weightRand_.reset(new RowRand(s.weightRandSeed));
@@ -433,6 +440,26 @@ class HostRecorder {
     for(size_t i = 0; i < area.size(); i++) d.finalWhiteScoring[i] = area[i] == P_WHITE ? 1.0f : area[i] == P_BLACK ? -1.0f : 0.0f;
     gamesFinished_++;
     if(onGameStart) onGameStart(g);
+    if(submitLead && estimateLeadProb > 0 && !d.endNoResult) {
+      std::vector<size_t> turns;
+      for(size_t t = 0; t < d.targetWeightByTurn.size(); t++)         // (the draw is made only for turns that qualify)
+        if(d.targetWeightByTurn[t] > 0 && (double)d.whiteValueTargetsByTurn[t].noResult < 0.3 && leadRand_.random() < estimateLeadProb) turns.push_back(t);
+      if(!turns.empty()) {
+        struct Waiting { FinishedGame game; int slot; size_t left; };
+        std::shared_ptr<Waiting> w(new Waiting{std::move(d), g, turns.size()});
+        gamesWaiting_++;
+        for(size_t t : turns) {
+          std::vector<Move> moves;
+          for(const auto& m : w->game.startMoves) { Move mv; mv.x = m.first; mv.y = m.second; moves.push_back(mv); }
+          for(size_t i = 0; i < t; i++) { Move mv; mv.x = w->game.moves[i].first; mv.y = w->game.moves[i].second; moves.push_back(mv); }
+          submitLead(w->game.komi, gm.setup, moves, [this, w, t](float lead) {
+            w->game.whiteValueTargetsByTurn[t].hasLead = true; w->game.whiteValueTargetsByTurn[t].lead = lead;      // ValueTargets::hasLead, lead
+            if(--w->left == 0) { gamesWaiting_--; if(onGame_) onGame_(w->slot, w->game); }
+          });
+        }
+        return;
+      }
+    }
     if(onGame_) onGame_(g, d);
   }
 
@@ -440,6 +467,7 @@ class HostRecorder {
   std::vector<InProgress> games_;
   std::unique_ptr<RowRand> weightRand_;
   std::unique_ptr<PyRandom> limitsRand_;
+  PyRandom leadRand_{0x4C656164}; int gamesWaiting_ = 0;
   std::vector<SearchLimits> curLimits_; std::vector<std::pair<SearchLimits, SearchLimits>> pending_;
   std::vector<int32_t> nextVisits_; std::vector<uint8_t> nextPlain_;
   int64_t movesRecorded_ = 0, gamesFinished_ = 0;

@@ -14,7 +14,8 @@
 //
 // Every turn is recorded; its weight comes from the per-move search limits (cheapSearchProb / reduceVisits ...) and the surprise weighting
 // (policySurpriseDataWeight / valueSurpriseDataWeight); board size, ko / suicide rule and komi are drawn per game like the reference's
-// GameInitializer (integration/b200_gameinit.h).  Openings can be drawn from the policy (initGamesWithPolicy).  The wider host (komiAuto, lead targets, forks, side
+// GameInitializer (integration/b200_gameinit.h).  Openings can be drawn from the policy (initGamesWithPolicy).  komiAuto and estimateLeadProb run their komi-bisection
+// searches on side loops (integration/b200_komi.h).  The wider host ( lead targets, forks, side
 // positions, model polling and weight hot-swap, several GPUs) is katago_b200/selfplay_cli.py: options of that kind are refused here, not
 // ignored.  Without a CUDA device the program stops with the library's error (there is no CPU path).
 #include <chrono>
@@ -28,7 +29,7 @@
 #include <dirent.h>
 #include <sys/stat.h>
 
-#include "b200_gameinit.h"
+#include "b200_komi.h"
 
 namespace {
 
@@ -119,8 +120,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.multi_stone_suicide_legal = boolOf("multiStoneSuicideLegals", c.list("multiStoneSuicideLegals", "true")[0]) ? 1 : 0;
   k.full_history_rules = 1;
   c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
-  c.neutral("handicapProb", "0.0"); c.neutral("komiAuto", "false");
-  c.neutral("estimateLeadProb", "0.0");
+  c.neutral("handicapProb", "0.0");
   c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
   c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
 
@@ -325,6 +325,11 @@ int main(int argc, char** argv) {
   gi.komiMean = cfg.num("komiMean", 7.5); gi.komiStdev = cfg.num("komiStdev", 0.0); gi.komiBigStdevProb = cfg.num("komiBigStdevProb", 0.0);
   gi.komiBigStdev = cfg.num("komiBigStdev", 10.0); gi.komiBiggerStdevProb = cfg.num("komiBiggerStdevProb", 0.0); gi.komiBiggerStdev = cfg.num("komiBiggerStdev", 30.0);
   gi.komiAllowIntegerProb = cfg.num("komiAllowIntegerProb", 1.0);
+  // komi-bisection searches on side loops (b200_komi.h): komiAuto = the fair komi of the next game's empty board becomes the mean of its komi draw
+  // (makeGameFairForEmptyBoard, play.cpp:1563-1575); estimateLeadProb = lead targets of recorded turns (play.cpp:2290-2324)
+  const bool komiAuto = cfg.flag("komiAuto", false);
+  const int compensateKomiVisits = (int)cfg.num("compensateKomiVisits", 20), estimateLeadVisits = (int)cfg.num("estimateLeadVisits", 6);
+  const double estimateLeadProb = cfg.num("estimateLeadProb", 0.0);
   // policy-initialised openings (initializeGameUsingPolicy): the device draws the moves, the host the count per game
   const bool policyInit = cfg.flag("initGamesWithPolicy", false) && cfg.num("policyInitAreaProp", 0.04) > 0;
   const double policyInitAreaProp = cfg.num("policyInitAreaProp", 0.04), policyInitTemperature = cfg.num("policyInitAreaTemperature", 1.0);
@@ -376,6 +381,22 @@ int main(int argc, char** argv) {
     outputs.switchTo(modelPath, info.name);
 
     b200::GameSlots slots(handle, sc, edge, edge);
+    // side loops for the komi searches: own handles of the same net, a few slots, the loop's parameters without root noise (getNoiselessParams,
+    // playutils.cpp:372-387), numVisits visits; as katago_b200/selfplay_cli.py make_aux
+    struct SideLoop { kgb_handle* handle = nullptr; std::unique_ptr<b200::GameSlots> slots; std::unique_ptr<b200::KomiSearcher> searcher; };
+    SideLoop fairLoop, leadLoop;
+    auto makeSide = [&](SideLoop& side, int visits) {
+      kgb_selfplay_config c = sc;
+      c.root_noise_enabled = 0; c.root_policy_temperature = 1.0; c.root_policy_temperature_early = 1.0; c.root_fpu_reduction_max = sc.fpu_reduction_max;
+      c.root_fpu_loss_prop = sc.fpu_loss_prop; c.root_desired_per_child_visits_coeff = 0.0; c.root_num_symmetries_to_sample = 1;
+      c.max_moves = (sc.max_moves > 0 ? sc.max_moves : 2 * edge * edge) + 8;
+      c.num_games = std::max(4, std::min(32, numGames / 4)); c.max_visits = std::max(2, visits); c.seed = loopSeed + 104729; c.max_playouts_per_wave = 0;
+      check(kgb_handle_create(ctx, model, c.num_games, 0, /*inputs_nhwc=*/1, gpu, &side.handle), "creating a side evaluator handle");
+      side.slots.reset(new b200::GameSlots(side.handle, c, edge, edge));
+      side.searcher.reset(new b200::KomiSearcher(*side.slots, c.max_visits));
+    };
+    if(komiAuto) makeSide(fairLoop, compensateKomiVisits);
+    if(estimateLeadProb > 0) makeSide(leadLoop, estimateLeadVisits);
     // the draws become the games in progress (none has started), new ones are drawn for the games after them; a slot's draw for the game
     // after next is made when its next game begins (katago_b200/selfplay_cli.py SlotSetups)
     b200::GameInitializer init(gi, loopSeed ^ 0x47616D65ULL);
@@ -391,6 +412,21 @@ int main(int argc, char** argv) {
     drawOpenings();
     slots.setGameSetups(setups); slots.setKomis(komis);
     if(policyInit) slots.setPolicyInit(openings, policyInitTemperature);
+    // komiAuto: the komi at which the net calls the empty board of the slot's NEXT game even becomes the mean the komi noise is drawn around.
+    // Searched on the side loop while the slot's current game is played; the answer replaces the komi handed over so far unless that game has
+    // started meanwhile (the slot's serial has moved on).
+    std::vector<long> serial((size_t)numGames, 0);
+    auto askFairKomi = [&](int g) {
+      const b200::GameSlots::GameSetup setup = setups[(size_t)g];
+      const long mine = ++serial[(size_t)g];
+      fairLoop.searcher->submit(setup, {}, [&, g, setup, mine](const b200::KomiOracle& ev) {
+        const float fair = b200::adjustKomiToEven(init.komiMean(), setup.x, setup.y, ev, [&]() { return init.uniform(); });
+        if(serial[(size_t)g] != mine) return;
+        komis[(size_t)g] = init.drawKomi(setup.x, setup.y, (double)fair);
+        slots.setKomis(komis);
+      });
+    };
+    if(komiAuto) for(int g = 0; g < numGames; g++) askFairKomi(g);
     b200::HostRecorder::Settings rs;
     rs.perGameSetups = true; rs.policyInit = policyInit;
     rs.komi = sc.komi; rs.drawEquivalentWinsForWhite = sc.draw_equivalent_wins_for_white; rs.koRule = sc.ko_rule;
@@ -404,8 +440,16 @@ int main(int argc, char** argv) {
       outputs.addGame(game);          // a finished game's rows go to the directory of the net in use when it ended (selfplay.cpp:276-319)
       written++;
     });
+    if(estimateLeadProb > 0) {
+      recorder.estimateLeadProb = estimateLeadProb;
+      recorder.submitLead = [&](float komi, const b200::GameSlots::GameSetup& setup, const std::vector<b200::Move>& moves, b200::HostRecorder::LeadDone done) {
+        leadLoop.searcher->submit(setup, moves, [komi, done](const b200::KomiOracle& ev) { done(b200::computeLead((double)komi, ev)); });
+      };
+    }
     recorder.onGameStart = [&](int g) {
-      drawInto(g); slots.setGameSetups(setups); slots.setKomis(komis);
+      drawInto(g);
+      if(komiAuto) askFairKomi(g);
+      slots.setGameSetups(setups); slots.setKomis(komis);
       if(policyInit) { openings[(size_t)g] = init.openingLength(setups[(size_t)g].x, setups[(size_t)g].y, policyInitAreaProp); slots.setPolicyInit(openings, policyInitTemperature); }
     };
     const auto t0 = std::chrono::steady_clock::now();
@@ -419,6 +463,8 @@ int main(int argc, char** argv) {
     while(maxGamesTotal <= 0 || written < maxGamesTotal) {
       recorder.pump(wavesPerPoll);
       pumps++;
+      if(fairLoop.searcher) fairLoop.searcher->step(8);        // the side loops advance with the main loop
+      if(leadLoop.searcher) leadLoop.searcher->step(8);
       if(modelsDir.empty() || (maxGamesTotal > 0 && written >= maxGamesTotal)) continue;
       const auto now = std::chrono::steady_clock::now();
       if(std::chrono::duration<double>(now - lastPoll).count() < modelPollSeconds) continue;
@@ -437,6 +483,12 @@ int main(int argc, char** argv) {
       }
       check(kgb_handle_commit_weights(handle), "committing the new weights");
       slots.clearNNCache();
+      for(SideLoop* side : {&fairLoop, &leadLoop})
+        if(side->handle) {
+          check(kgb_handle_stage_weights(side->handle, next), "staging the new weights on a side loop");
+          check(kgb_handle_commit_weights(side->handle), "committing the new weights on a side loop");
+          side->slots->clearNNCache();
+        }
       kgb_model_info nextInfo;
       check(kgb_model_get_info(next, &nextInfo), "kgb_model_get_info");
       kgb_model_free(model); model = next; modelPath = newest;
@@ -445,6 +497,7 @@ int main(int argc, char** argv) {
       std::fprintf(stderr, "b200_selfplay: Game loop changing midgame to new neural net: %s (swap %d, after pump %ld)\n", outputs.netName.c_str(), swaps, pumps);
     }
     outputs.close();
+    for(SideLoop* side : {&fairLoop, &leadLoop}) { side->searcher.reset(); side->slots.reset(); if(side->handle) kgb_handle_free(side->handle); side->handle = nullptr; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const kgb_selfplay_stats st = slots.stats();
     std::printf("{\"games_written\": %ld, \"rows\": %lld, \"files\": %zu, \"moves\": %lld, \"net_swaps\": %d, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",

@@ -92,7 +92,10 @@ static void searchRoot(kgb_selfplay* sp, int g) {
   std::ofstream& o = sp->log;
   auto arr = [&](const char* name, auto& v, bool last = false) {
     o << "\"" << name << "\":[";
-    for(size_t i = 0; i < v.size(); i++) { char b[64]; snprintf(b, sizeof b, "%.17g", (double)v[i]); o << (i ? "," : "") << b; }
+    for(size_t i = 0; i < v.size(); i++) {
+      char b[64]; snprintf(b, sizeof b, "%.17g", (double)v[i]);
+      o << (i ? "," : "") << (strcmp(b, "-0") == 0 ? "-0.0" : b);       // (JSON readers take "-0" for the integer 0 and drop the sign)
+    }
     o << "]" << (last ? "" : ",");
   };
   std::vector<int> colors((size_t)X * Y, 0);
@@ -125,10 +128,10 @@ static void startGame(kgb_selfplay* sp, int g) {
   s.initPending = 0;
 }
 
-static void advance(kgb_selfplay* sp, int g) {
+static void advance(kgb_selfplay* sp, int g, bool searched = true, Loc given = Board::NULL_LOC) {
   Slot& s = sp->slots[g];
   const int X = sp->X, Y = sp->Y, BX = s.setup[0], BY = s.setup[1];
-  const Loc loc = s.nextMove;
+  const Loc loc = searched ? s.nextMove : given;       // (searched = false: a move the host plays into the slot, kgb_selfplay_play_moves_game)
   s.hist.makeBoardMoveAssumeLegal(s.board, loc, s.pla, NULL);
   s.pla = getOpp(s.pla);
   const int maxMoves = sp->cfg.max_moves > 0 ? sp->cfg.max_moves : 2 * BX * BY;
@@ -145,12 +148,14 @@ static void advance(kgb_selfplay* sp, int g) {
     for(int y = 0; y < BY; y++) for(int x = 0; x < BX; x++) { Loc l = Location::getLoc(x, y, BX); s.finalColors[(size_t)y * X + x] = s.board.colors[l]; s.finalArea[(size_t)y * X + x] = area[l]; }
   }
   std::ofstream& o = sp->log;
-  o << "{\"ev\":\"move\",\"slot\":" << g << ",\"pos\":" << s.last[0] << ",\"flags\":" << s.last[1] << ",\"move_num\":" << s.last[2] << ",\"game_index\":" << s.last[3]
-    << ",\"score\":" << s.lastScore << ",\"final_colors\":[";
-  for(size_t i = 0; over && i < s.finalColors.size(); i++) o << (i ? "," : "") << (int)s.finalColors[i];
-  o << "],\"final_area\":[";
-  for(size_t i = 0; over && i < s.finalArea.size(); i++) o << (i ? "," : "") << (int)s.finalArea[i];
-  o << "]}\n";
+  if(searched) {
+    o << "{\"ev\":\"move\",\"slot\":" << g << ",\"pos\":" << s.last[0] << ",\"flags\":" << s.last[1] << ",\"move_num\":" << s.last[2] << ",\"game_index\":" << s.last[3]
+      << ",\"score\":" << s.lastScore << ",\"final_colors\":[";
+    for(size_t i = 0; over && i < s.finalColors.size(); i++) o << (i ? "," : "") << (int)s.finalColors[i];
+    o << "],\"final_area\":[";
+    for(size_t i = 0; over && i < s.finalArea.size(); i++) o << (i ? "," : "") << (int)s.finalArea[i];
+    o << "]}\n";
+  }
   if(over) {                        // the slot's next game takes the setup and komi handed over for it
     for(int k = 0; k < 4; k++) { sp->lastSetup[4 * (size_t)g + k] = s.setup[k]; s.setup[k] = sp->nextSetup[4 * (size_t)g + k]; }
     sp->lastKomi[g] = s.komi; s.komi = sp->nextKomi[g];
@@ -158,7 +163,7 @@ static void advance(kgb_selfplay* sp, int g) {
     s.gameIndex++; startGame(sp, g);
   }
   else s.moveNum++;
-  searchRoot(sp, g);
+  if(searched) searchRoot(sp, g);
 }
 
 static void ensureStarted(kgb_selfplay* sp) {
@@ -189,8 +194,11 @@ int kgb_selfplay_clear_nn_cache(kgb_selfplay*) { return 0; }
 
 int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfplay** out) {
   GUARD({
-    const char* path = getenv("KGB_MOCK_LOG");
-    if(!path) throw std::runtime_error("KGB_MOCK_LOG is not set");
+    const char* base = getenv("KGB_MOCK_LOG");
+    if(!base) throw std::runtime_error("KGB_MOCK_LOG is not set");
+    static int instances = 0;                         // a second / third loop of the process (side loops) logs to <path>.2 / <path>.3
+    instances++;
+    const std::string path = instances == 1 ? std::string(base) : std::string(base) + "." + std::to_string(instances);
     kgb_selfplay* sp = new kgb_selfplay();
     sp->cfg = *c; sp->X = h->x; sp->Y = h->y; sp->rng = Lcg(c->seed);
     sp->rules.koRule = c->ko_rule == 1 ? Rules::KO_POSITIONAL : c->ko_rule == 2 ? Rules::KO_SITUATIONAL : c->ko_rule == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
@@ -332,4 +340,26 @@ int kgb_selfplay_get_last_move(kgb_selfplay* sp, int g, int32_t* info, float* sc
 }
 int kgb_selfplay_get_stats(kgb_selfplay*, kgb_selfplay_stats* out) { memset(out, 0, sizeof(*out)); return 0; }
 int kgb_selfplay_play_moves(kgb_selfplay*, const int8_t*, int) { g_err = "mock: play_moves is not scripted"; return 1; }
+// the host plays moves into one slot (a side loop's position; the opponent's move in match play): a move that ends the game restarts the slot with
+// the setup and komi handed over for its next game, like the loop's own moves; the resulting root is searched (instantly) and logged
+int kgb_selfplay_play_moves_game(kgb_selfplay* sp, int g, const int8_t* xy, int n) {
+  try {
+    ensureStarted(sp);
+    Slot& s = sp->slots[g];
+    sp->log << "{\"ev\":\"playmoves\",\"slot\":" << g << ",\"moves\":[";
+    for(int i = 0; i < n; i++) {
+      const int x = xy[2 * i];
+      const int y = xy[2 * i + 1];
+      const Loc loc = x < 0 ? Board::PASS_LOC : Location::getLoc(x, y, s.setup[0]);
+      if(x >= s.setup[0] || y >= s.setup[1] || !s.hist.isLegal(s.board, loc, s.pla)) throw std::runtime_error("mock: illegal move in play_moves_game");
+      sp->log << (i ? "," : "") << "[" << x << "," << y << "]";
+      advance(sp, g, false, loc);
+    }
+    sp->log << "]}\n";
+    searchRoot(sp, g);
+    sp->log.flush();
+    return 0;
+  }
+  catch(const std::exception& e) { g_err = e.what(); return 1; }
+}
 }

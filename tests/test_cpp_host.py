@@ -67,6 +67,13 @@ def _replay_slots_with_limits(log, G, size, V):
         def game_setups(self):
             return self.cur_setup.copy(), self.last_setup.copy()
 
+        # a side loop's position: the host ends the slot's game with passes and replays the position's moves (komi_search.KomiSearcher._load)
+        def play_moves_game(self, slot, moves):
+            ev = self.queues[slot].pop(0)
+            assert ev["ev"] == "playmoves" and [tuple(m) for m in ev["moves"]] == [(-1, -1) if m is None else (int(m[0]), int(m[1])) for m in moves], (ev, moves)
+            self.root[slot] = self.queues[slot].pop(0)
+            assert self.root[slot]["ev"] == "root"
+
         # policy-initialised openings: the mock plays a whole opening when the game starts and lists it with every root of the game
         def set_policy_init(self, num_moves, temperature=1.0, also_current_games=False):
             pass
@@ -99,7 +106,7 @@ def _replay_slots_with_limits(log, G, size, V):
     return Slots()
 
 
-LIMITS = {"none": "", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
+LIMITS = {"none": "", "komi_searches": "komiAuto = true\ncompensateKomiVisits = 10\nestimateLeadProb = 0.3\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\n", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
           "cheap_unrecorded_and_reduced": "cheapSearchProb = 0.25\ncheapSearchVisits = 5\ncheapSearchTargetWeight = 0.0\nreduceVisits = true\nreduceVisitsThreshold = 0.3\n"
                                           "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n"}
 
@@ -116,6 +123,7 @@ MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRul
     (7, "POSITIONAL", 6.5, 50, 0.5, 0.1, False, 8, 8, "cheap_unrecorded_and_reduced"),   # unrecorded cheap searches (plain roots) and reduced visits
     (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 12, 4, "cheap"),         # board size (rectangles), ko / suicide rule and komi noise drawn per game, inside a 9x9 data frame
     (9, "MIXED", 7.0, 0, 0.5, 0.1, False, 12, 9, "openings"),      # the same with policy-initialised openings: a start history before the recorded turns
+    (9, "MIXED", 6.0, 0, 0.5, 0.1, False, 10, 13, "komi_searches"),  # komiAuto and lead targets: komi bisections as jobs on two side loops, games written when their jobs are back
 ])
 def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
@@ -158,14 +166,28 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
             done.append(data)
 
     from katago_b200.game_initializer import GameInitializer
-    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G, policy_init=data["policy_init"])      # the command's own per-game draws
+    fair = lead = None
+    if limits == "komi_searches":       # the side loops of the command (make_aux): the mock's second and third loop, replayed from their own logs
+        from katago_b200.komi_search import KomiSearcher
+        ks = data["komi_search"]
+        side = []
+        for i, visits in ((2, ks["compensate_komi_visits"]), (3, ks["estimate_lead_visits"])):
+            lp = _replay_slots_with_limits(f"{log}.{i}", 4, size, max(2, visits))
+            lp.max_visits = max(2, visits)
+            side.append(KomiSearcher(lp))
+        fair, lead = side
+    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G, policy_init=data["policy_init"], fair_komi=fair)      # the command's own per-game draws
     setups.start(sp)
-    rec = R.GameRecorder(sp, None, komi, on_game=on_game, on_game_start=lambda slot: setups.game_started(sp, rec, slot), game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
+    rec = R.GameRecorder(sp, None, komi, on_game=on_game, on_game_start=lambda slot: setups.game_started(sp, rec, slot), lead_estimator=lead,
+                         estimate_lead_prob=data["komi_search"]["estimate_lead_prob"], game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
                          policy_surprise_data_weight=psw, value_surprise_data_weight=vsw, use_search_value_surprise=search_surprise,
                          weight_rand=W.RowRand(writer_seed + ":weights"), play_settings=data["play_settings"],
                          limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69), policy_init=data["policy_init"]["enabled"])
     while len(done) < games:
         rec.pump(4)
+        for searcher in (fair, lead):
+            if searcher is not None:
+                searcher.step(8)
     writer.flush_if_nonempty()
 
     cpp_files, py_files = sorted(os.listdir(out / "tdata")), sorted(os.listdir(py / "tdata"))
@@ -185,6 +207,10 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     if ko == "MIXED":
         assert len({(d.x_size, d.y_size) for d in done}) >= 4 and any(d.x_size != d.y_size for d in done) and len({d.ko_rule for d in done}) >= 2
         assert len({d.komi for d in done}) >= 3 and {d.multi_stone_suicide_legal for d in done} == {False, True}
+    if limits == "komi_searches":
+        with_lead = [sum(1 for v in d.white_value_targets_by_turn[:-1] if len(v) > 4 and v[4]) for d in done]
+        assert sum(with_lead) >= 20 and fair.searches > 30 and lead.searches > 100 and rec.games_waiting_for_lead >= 0
+        assert len({d.komi for d in done}) >= 5            # komis drawn around the searched fair komi of each board
     if limits == "openings":
         assert sum(1 for d in done if d.start_hist_moves > 0) >= 4 and max(d.start_hist_moves for d in done) >= 3
         assert all(len(d.start_moves) == d.start_hist_moves for d in done)
