@@ -110,6 +110,28 @@ inline float computeLead(double oldKomi, const KomiOracle& ev) {
   return (float)(oldKomi - result);
 }
 
+// Position queries of a job (forked games, fork_play.py): "search the position after these moves at this komi" -> lead, winLoss, the net's own score of
+// the root and the legal moves, or invalid when replaying the moves ended the game on the way.  Like KomiOracle the oracle answers from what is
+// known and throws for the first query that is missing; since the algorithm is re-run from the top every time, its queries - and the random
+// draws it makes on the way (draw()) - are remembered in the order they were made, so that a re-run sees the same draws and arrives at the same place.
+struct PositionAnswer { bool valid = false; double lead = 0, winLoss = 0, nnScoreMean = 0; std::vector<uint8_t> legal; };
+struct NeedPosition { std::vector<Move> moves; float komi; };
+class PositionOracle {
+ public:
+  const PositionAnswer& operator()(const std::vector<Move>& moves, float komi) {
+    if(queryCursor_ < answers_.size()) return answers_[queryCursor_++];
+    throw NeedPosition{moves, komi};
+  }
+  uint32_t draw(const std::function<uint32_t()>& fresh) {
+    if(drawCursor_ == draws_.size()) draws_.push_back(fresh());
+    return draws_[drawCursor_++];
+  }
+  void restart() { queryCursor_ = drawCursor_ = 0; }
+  void add(PositionAnswer a) { answers_.push_back(std::move(a)); }
+ private:
+  std::vector<PositionAnswer> answers_; std::vector<uint32_t> draws_; size_t queryCursor_ = 0, drawCursor_ = 0;
+};
+
 // Runs komi-search jobs on a side device loop: its own handle, a few slots in hold mode, the game's search parameters with the root noise off and
 // numVisits visits (getNoiselessParams, playutils.cpp:372-387).  A job is an algorithm over a KomiOracle (above) plus the position it is about; a
 // slot is loaded with the position at the komi the job asks for by ending whatever game it holds (passes: kgb_selfplay_play_moves_game restarts
@@ -118,6 +140,7 @@ inline float computeLead(double oldKomi, const KomiOracle& ev) {
 class KomiSearcher {
  public:
   using Algorithm = std::function<void(const KomiOracle&)>;     // throws NeedKomi until it can finish; then delivers its result itself
+  using PositionAlgorithm = std::function<void(PositionOracle&)>;   // the same over position queries (throws NeedPosition)
 
   KomiSearcher(GameSlots& side, int maxVisits) : sp_(side), maxVisits_(maxVisits), n_(side.numSlots()) {
     for(int g = 0; g < n_; g++) free_.push_back(g);
@@ -125,7 +148,11 @@ class KomiSearcher {
     komis_.assign((size_t)n_, 7.5f);
   }
   void submit(const GameSlots::GameSetup& setup, const std::vector<Move>& moves, Algorithm algorithm) {
-    queue_.push_back(std::unique_ptr<Job>(new Job{setup, moves, KomiOracle(setup.x, setup.y), std::move(algorithm), 0.0f}));
+    queue_.push_back(std::unique_ptr<Job>(new Job{setup, moves, KomiOracle(setup.x, setup.y), std::move(algorithm), 0.0f, false, PositionOracle(), nullptr, {}}));
+    dispatch();
+  }
+  void submitPositions(const GameSlots::GameSetup& setup, PositionAlgorithm algorithm) {
+    queue_.push_back(std::unique_ptr<Job>(new Job{setup, {}, KomiOracle(setup.x, setup.y), nullptr, 0.0f, true, PositionOracle(), std::move(algorithm), {}}));
     dispatch();
   }
   int pending() const { return (int)(queue_.size() + running_.size()); }
@@ -143,7 +170,18 @@ class KomiSearcher {
       sp_.rootValueStatsByPos(slot, childMoments, root);      // winLoss, noResult, scoreMean, scoreMeanSq, lead - white's perspective
       Job* job = nullptr;
       for(auto& r : running_) if(r.first == slot) job = r.second.get();
-      job->oracle.add(job->asked, root[4], root[0]);
+      if(!job->positions) job->oracle.add(job->asked, root[4], root[0]);
+      else {                                   // a position query: also the net's own score of the root and the legal moves
+        PositionAnswer a;
+        a.valid = sp_.moveNumber(slot) == (int)job->askedMoves.size();       // else the replay ended the game on the way: no such position
+        if(a.valid) {
+          std::vector<int32_t> nodeVisits; double nn[5];
+          sp_.rootExtraByPos(slot, nodeVisits, nn);
+          a.lead = root[4]; a.winLoss = root[0]; a.nnScoreMean = nn[2];
+          for(float p : sp_.rootPolicy(slot)) a.legal.push_back(p >= 0 ? 1 : 0);
+        }
+        job->posOracle.add(std::move(a));
+      }
       advance(slot);
     }
     dispatch();
@@ -155,19 +193,26 @@ class KomiSearcher {
   }
 
  private:
-  struct Job { GameSlots::GameSetup setup; std::vector<Move> moves; KomiOracle oracle; Algorithm algorithm; float asked; };
+  struct Job {
+    GameSlots::GameSetup setup; std::vector<Move> moves; KomiOracle oracle; Algorithm algorithm; float asked;
+    bool positions; PositionOracle posOracle; PositionAlgorithm posAlgorithm; std::vector<Move> askedMoves;
+  };
 
   // run the job's algorithm on what is known: it finishes (slot freed) or names the next komi (slot loaded with it)
   void advance(int slot) {
     size_t at = 0;
     while(running_[at].first != slot) at++;
     Job& job = *running_[at].second;
-    try { job.algorithm(job.oracle); }
-    catch(const NeedKomi& need) { load(slot, job, need.komi); return; }
+    try {
+      if(job.positions) { job.posOracle.restart(); job.posAlgorithm(job.posOracle); }
+      else job.algorithm(job.oracle);
+    }
+    catch(const NeedKomi& need) { load(slot, job, need.komi, job.moves); return; }
+    catch(const NeedPosition& need) { job.askedMoves = need.moves; load(slot, job, need.komi, need.moves); return; }
     running_.erase(running_.begin() + (long)at);
     free_.push_back(slot);
   }
-  void load(int slot, Job& job, float komi) {
+  void load(int slot, Job& job, float komi, const std::vector<Move>& moves) {
     job.asked = komi;
     setups_[(size_t)slot] = job.setup; komis_[(size_t)slot] = komi;
     sp_.setGameSetups(setups_); sp_.setKomis(komis_);
@@ -177,7 +222,7 @@ class KomiSearcher {
       empty = sp_.moveNumber(slot) == 0;
     }
     if(!empty) throw std::runtime_error("KomiSearcher: could not end the slot's previous game");
-    sp_.playMoves(slot, job.moves);
+    sp_.playMoves(slot, moves);
     searches_++;
   }
   void dispatch() {

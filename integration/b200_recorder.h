@@ -253,6 +253,13 @@ class HostRecorder {
   std::function<void(float komi, const GameSlots::GameSetup& setup, const std::vector<Move>& moves, LeadDone done)> submitLead;
   double estimateLeadProb = 0.0;
   int gamesWaitingForLead() const { return gamesWaiting_; }
+  // the slot's game that has just begun starts from `moves` (already played into the device slot by the caller): a forked game (mode 2)
+  void startFrom(int slot, const std::vector<Move>& moves, int mode = 2) {
+    InProgress& gm = games_[(size_t)slot];
+    gm.presetMoves.clear();
+    for(const Move& m : moves) gm.presetMoves.push_back({m.x, m.y});
+    gm.mode = mode;
+  }
 
   HostRecorder(GameSlots& slots, const Settings& s, OnGame onGame) : slots_(slots), s_(s), onGame_(std::move(onGame)), games_((size_t)slots.numSlots()) {
     if(!s.weightRandSeed.empty()) weightRand_.reset(new RowRand(s.weightRandSeed));
@@ -309,7 +316,8 @@ class HostRecorder {
   struct InProgress {
     std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; std::vector<double> winLoss;      // winLoss: historicalMctsWinLossValues
     bool haveSetup = false; GameSlots::GameSetup setup{0, 0, 0, 1};     // this game's own board and rules, read when its first turn is recorded
-    std::vector<std::pair<int, int>> startMoves;                         // the opening the device drew from the policy (startHist)
+    std::vector<std::pair<int, int>> startMoves;                         // moves before the first recorded turn (fork prefix + policy-initialised opening): startHist
+    std::vector<std::pair<int, int>> presetMoves; int mode = 0;         // moves the host played into the slot before the game's first search (a forked game); FinishedGameData::mode
   };
   // a board or area of the evaluator's frame cut down to the game's own board (its top-left corner)
   std::vector<uint8_t> crop(const std::vector<uint8_t>& frame, int bx, int by) const {
@@ -363,10 +371,13 @@ class HostRecorder {
       gm.setup = GameSlots::GameSetup{X, Y, s_.koRule, s_.multiStoneSuicideLegal ? 1 : 0};
       if(s_.perGameSetups) { std::vector<GameSlots::GameSetup> cur; slots_.gameSetups(&cur, nullptr); gm.setup = cur[(size_t)g]; }
       gm.haveSetup = true;
+      gm.startMoves = gm.presetMoves;
       if(s_.policyInit) {
         std::vector<std::vector<Move>> openings;
         slots_.policyInitState(&openings);
         for(const Move& m : openings[(size_t)g]) gm.startMoves.push_back({m.x, m.y});
+      }
+      if(s_.policyInit || !gm.presetMoves.empty()) {
         if((int)gm.startMoves.size() != pos.moveNumber)
           throw std::runtime_error("HostRecorder: slot " + std::to_string(g) + ": " + std::to_string(pos.moveNumber) + " moves played before the first searched move, " +
                                    std::to_string(gm.startMoves.size()) + " opening moves kept");
@@ -403,7 +414,7 @@ class HostRecorder {
     d.endFinished = !last.hitMoveLimit; d.hitTurnLimit = last.hitMoveLimit; d.endNoResult = last.noResult;
     static const char* KO[] = {"SIMPLE", "POSITIONAL", "SITUATIONAL", "SPIGHT"};
     d.koRule = KO[gm.setup.koRule & 3]; d.multiStoneSuicideLegal = gm.setup.multiStoneSuicideLegal != 0;
-    d.startMoves = gm.startMoves; d.startHistMoves = (int)gm.startMoves.size();
+    d.startMoves = gm.startMoves; d.startHistMoves = (int)gm.startMoves.size(); d.mode = gm.mode;
     d.boardsByTurn = std::move(gm.boards);
     d.boardsByTurn.push_back(crop(last.finalColors, X, Y));
     std::vector<std::array<double, 3>> rawNN;

@@ -29,7 +29,7 @@
 #include <dirent.h>
 #include <sys/stat.h>
 
-#include "b200_komi.h"
+#include "b200_forks.h"
 
 namespace {
 
@@ -121,8 +121,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.full_history_rules = 1;
   c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
   c.neutral("handicapProb", "0.0");
-  c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("earlyForkGameProb", "0.0");
-  c.neutral("forkGameProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
+  c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
 
   k.win_loss_utility_factor = c.num("winLossUtilityFactor", 1.0);
   k.static_score_utility_factor = c.num("staticScoreUtilityFactor", 0.1);
@@ -330,6 +329,12 @@ int main(int argc, char** argv) {
   const bool komiAuto = cfg.flag("komiAuto", false);
   const int compensateKomiVisits = (int)cfg.num("compensateKomiVisits", 20), estimateLeadVisits = (int)cfg.num("estimateLeadVisits", 6);
   const double estimateLeadProb = cfg.num("estimateLeadProb", 0.0);
+  // forked games (Play::maybeForkGame, play.cpp:2413-2508; b200_forks.h)
+  b200::ForkManager::Settings forkSettings;
+  forkSettings.earlyForkGameProb = cfg.num("earlyForkGameProb", 0.0); forkSettings.earlyForkGameExpectedMoveProp = cfg.num("earlyForkGameExpectedMoveProp", 0.0);
+  forkSettings.forkGameProb = cfg.num("forkGameProb", 0.0); forkSettings.forkGameMinChoices = (int)cfg.num("forkGameMinChoices", 1);
+  forkSettings.earlyForkGameMaxChoices = (int)cfg.num("earlyForkGameMaxChoices", 1); forkSettings.forkGameMaxChoices = (int)cfg.num("forkGameMaxChoices", 1);
+  forkSettings.forkCompensateKomiProb = cfg.num("forkCompensateKomiProb", cfg.num("handicapCompensateKomiProb", 0.0));
   // policy-initialised openings (initializeGameUsingPolicy): the device draws the moves, the host the count per game
   const bool policyInit = cfg.flag("initGamesWithPolicy", false) && cfg.num("policyInitAreaProp", 0.04) > 0;
   const double policyInitAreaProp = cfg.num("policyInitAreaProp", 0.04), policyInitTemperature = cfg.num("policyInitAreaTemperature", 1.0);
@@ -395,8 +400,11 @@ int main(int argc, char** argv) {
       side.slots.reset(new b200::GameSlots(side.handle, c, edge, edge));
       side.searcher.reset(new b200::KomiSearcher(*side.slots, c.max_visits));
     };
-    if(komiAuto) makeSide(fairLoop, compensateKomiVisits);
+    b200::ForkManager forks(forkSettings, loopSeed ^ 0x466F726BULL);
+    const bool forkNeedsLoop = forks.enabled() && !(komiAuto || estimateLeadProb > 0);        // the fork's evaluations need some side loop
+    if(komiAuto || forkNeedsLoop) makeSide(fairLoop, compensateKomiVisits);
     if(estimateLeadProb > 0) makeSide(leadLoop, estimateLeadVisits);
+    b200::KomiSearcher* forkSearcher = leadLoop.searcher ? leadLoop.searcher.get() : fairLoop.searcher.get();      // where fork evaluations and their komi compensation run
     // the draws become the games in progress (none has started), new ones are drawn for the games after them; a slot's draw for the game
     // after next is made when its next game begins (katago_b200/selfplay_cli.py SlotSetups)
     b200::GameInitializer init(gi, loopSeed ^ 0x47616D65ULL);
@@ -439,6 +447,17 @@ int main(int argc, char** argv) {
       if(maxGamesTotal > 0 && written >= maxGamesTotal) return;        // games that end after the last counted one are dropped, like the Python host
       outputs.addGame(game);          // a finished game's rows go to the directory of the net in use when it ended (selfplay.cpp:276-319)
       written++;
+      if(forks.enabled() && forkSearcher && !game.endNoResult) {        // Play::maybeForkGame on the finished game
+        std::vector<b200::Move> all;
+        for(const auto& m : game.startMoves) { b200::Move mv; mv.x = m.first; mv.y = m.second; all.push_back(mv); }
+        for(const auto& m : game.moves) { b200::Move mv; mv.x = m.first; mv.y = m.second; all.push_back(mv); }
+        const int ko = game.koRule == "POSITIONAL" ? 1 : game.koRule == "SITUATIONAL" ? 2 : game.koRule == "SPIGHT" ? 3 : 0;
+        const b200::GameSlots::GameSetup setup{game.xSize, game.ySize, ko, game.multiStoneSuicideLegal ? 1 : 0};
+        const float gameKomi = game.komi;
+        b200::KomiSearcher::PositionAlgorithm job;
+        if(forks.job(all, setup, gameKomi, edge, edge, job, [&forks, setup, gameKomi](const std::vector<b200::Move>& moves) { if(!moves.empty()) forks.add(moves, setup, gameKomi); }))
+          forkSearcher->submitPositions(setup, job);
+      }
     });
     if(estimateLeadProb > 0) {
       recorder.estimateLeadProb = estimateLeadProb;
@@ -446,7 +465,35 @@ int main(int argc, char** argv) {
         leadLoop.searcher->submit(setup, moves, [komi, done](const b200::KomiOracle& ev) { done(b200::computeLead((double)komi, ev)); });
       };
     }
+    // A slot's next game has begun on the device (empty board, the setup handed over): if it is a forked game, its position is played into the
+    // slot and the recorder told; then the draw for the game after it - a pooled fork replaces the draw (the forked game's board, rules and komi,
+    // komi noise redrawn around it, with probability forkCompensateKomiProb first adjusted to even at that position; no opening)
+    struct PendingFork { bool have = false; long id = 0; b200::ForkManager::Fork fork; };
+    std::vector<PendingFork> forkNext((size_t)numGames);
+    long forkIds = 0;
     recorder.onGameStart = [&](int g) {
+      PendingFork started = forkNext[(size_t)g];
+      forkNext[(size_t)g] = PendingFork();
+      if(started.have) { slots.playMoves(g, started.fork.moves); recorder.startFrom(g, started.fork.moves, 2); }
+      b200::ForkManager::Fork fork;
+      if(forks.enabled() && forks.pop(fork)) {
+        const long mine = ++serial[(size_t)g], id = ++forkIds;
+        setups[(size_t)g] = fork.setup;
+        komis[(size_t)g] = init.drawKomi(fork.setup.x, fork.setup.y, (double)fork.komi);
+        forkNext[(size_t)g].have = true; forkNext[(size_t)g].id = id; forkNext[(size_t)g].fork = fork;
+        if(forkSearcher && init.uniform() < forkSettings.forkCompensateKomiProb) {
+          const b200::GameSlots::GameSetup setup = fork.setup; const float forkKomi = fork.komi;
+          forkSearcher->submit(setup, fork.moves, [&, g, setup, forkKomi, mine, id](const b200::KomiOracle& ev) {
+            const float fair = b200::adjustKomiToEven((double)forkKomi, setup.x, setup.y, ev, [&]() { return init.uniform(); });
+            if(serial[(size_t)g] != mine || !forkNext[(size_t)g].have || forkNext[(size_t)g].id != id) return;
+            komis[(size_t)g] = init.drawKomi(setup.x, setup.y, (double)fair);
+            slots.setKomis(komis);
+          });
+        }
+        slots.setGameSetups(setups); slots.setKomis(komis);
+        if(policyInit) { openings[(size_t)g] = 0; slots.setPolicyInit(openings, policyInitTemperature); }
+        return;
+      }
       drawInto(g);
       if(komiAuto) askFairKomi(g);
       slots.setGameSetups(setups); slots.setKomis(komis);

@@ -106,7 +106,9 @@ def _replay_slots_with_limits(log, G, size, V):
     return Slots()
 
 
-LIMITS = {"none": "", "komi_searches": "komiAuto = true\ncompensateKomiVisits = 10\nestimateLeadProb = 0.3\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\n", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
+FORKS = ("earlyForkGameProb = 0.4\nearlyForkGameExpectedMoveProp = 0.15\nforkGameProb = 0.5\nforkGameMinChoices = 2\nearlyForkGameMaxChoices = 4\nforkGameMaxChoices = 3\n"
+         "forkCompensateKomiProb = 0.5\n")
+LIMITS = {"none": "", "forks": FORKS + "estimateLeadProb = 0.15\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\ninitGamesWithPolicy = true\npolicyInitAreaProp = 0.05\n", "forks_only": FORKS, "komi_searches": "komiAuto = true\ncompensateKomiVisits = 10\nestimateLeadProb = 0.3\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\n", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
           "cheap_unrecorded_and_reduced": "cheapSearchProb = 0.25\ncheapSearchVisits = 5\ncheapSearchTargetWeight = 0.0\nreduceVisits = true\nreduceVisitsThreshold = 0.3\n"
                                           "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n"}
 
@@ -124,6 +126,8 @@ MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRul
     (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 12, 4, "cheap"),         # board size (rectangles), ko / suicide rule and komi noise drawn per game, inside a 9x9 data frame
     (9, "MIXED", 7.0, 0, 0.5, 0.1, False, 12, 9, "openings"),      # the same with policy-initialised openings: a start history before the recorded turns
     (9, "MIXED", 6.0, 0, 0.5, 0.1, False, 10, 13, "komi_searches"),  # komiAuto and lead targets: komi bisections as jobs on two side loops, games written when their jobs are back
+    (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 24, 17, "forks"),          # forked games: positions of finished games, a forking move chosen by the net's score, komi compensation, the fork pool
+    (7, "SIMPLE", 7.5, 30, 0.0, 0.0, False, 15, 2, "forks_only"),    # forks without any other side-loop feature: the fork evaluations get a side loop of their own
 ])
 def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
@@ -159,24 +163,37 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     sink = C.SgfSink(str(py / "sgfs"), writer_seed + ":sgfs", net_name, net_name)
     done = []
 
-    def on_game(slot, data):
+    def on_game(slot, finished):
         if len(done) < games:
-            writer.write_game(data)
-            sink.add(slot, data)
-            done.append(data)
+            writer.write_game(finished)
+            sink.add(slot, finished)
+            done.append(finished)
+            if forks.enabled and fork_searcher is not None and not finished.end_no_result:        # Play::maybeForkGame on the finished game (as the command's on_game)
+                all_moves = list(finished.start_moves) + list(finished.moves)
+                ko_idx = {"SIMPLE": 0, "POSITIONAL": 1, "SITUATIONAL": 2, "SPIGHT": 3}[finished.ko_rule]
+                setup = (finished.x_size, finished.y_size, ko_idx, int(finished.multi_stone_suicide_legal))
+                job = forks.job(all_moves, setup, finished.komi, size)
+                if job is not None:
+                    fork_searcher.submit(job, setup, [], lambda moves, setup=setup, komi=finished.komi: forks.add(moves, setup, komi) if moves else None)
 
     from katago_b200.game_initializer import GameInitializer
-    fair = lead = None
-    if limits == "komi_searches":       # the side loops of the command (make_aux): the mock's second and third loop, replayed from their own logs
-        from katago_b200.komi_search import KomiSearcher
-        ks = data["komi_search"]
-        side = []
-        for i, visits in ((2, ks["compensate_komi_visits"]), (3, ks["estimate_lead_visits"])):
-            lp = _replay_slots_with_limits(f"{log}.{i}", 4, size, max(2, visits))
+    # the side loops of the command (selfplay_cli.py make_aux): the mock's second and third loop, replayed from their own logs
+    from katago_b200.komi_search import KomiSearcher
+    from katago_b200.fork_play import ForkManager
+    ks = data["komi_search"]
+    forks = ForkManager(data["forks"], __import__("random").Random(loop_seed ^ 0x466F726B))
+    fork_needs_loop = forks.enabled and not (ks["komi_auto"] or ks["estimate_lead_prob"] > 0)
+    aux, instance = {"fair": None, "lead": None}, 1
+    for name, want, visits in (("fair", ks["komi_auto"] or fork_needs_loop, ks["compensate_komi_visits"]), ("lead", ks["estimate_lead_prob"] > 0, ks["estimate_lead_visits"])):
+        if want:
+            instance += 1
+            lp = _replay_slots_with_limits(f"{log}.{instance}", 4, size, max(2, visits))
             lp.max_visits = max(2, visits)
-            side.append(KomiSearcher(lp))
-        fair, lead = side
-    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G, policy_init=data["policy_init"], fair_komi=fair)      # the command's own per-game draws
+            aux[name] = KomiSearcher(lp)
+    fair, lead = aux["fair"], aux["lead"]
+    fork_searcher = lead or fair
+    setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G, policy_init=data["policy_init"], fair_komi=fair if ks["komi_auto"] else None,
+                          forks=forks if forks.enabled else None, searcher=fork_searcher)      # the command's own per-game draws
     setups.start(sp)
     rec = R.GameRecorder(sp, None, komi, on_game=on_game, on_game_start=lambda slot: setups.game_started(sp, rec, slot), lead_estimator=lead,
                          estimate_lead_prob=data["komi_search"]["estimate_lead_prob"], game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
@@ -205,8 +222,14 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
         assert rows == sum(len(d.moves) for d in done)
     weights = [float(w) for d in done for w in (d.target_weight_by_turn_unrounded or d.target_weight_by_turn)]
     if ko == "MIXED":
-        assert len({(d.x_size, d.y_size) for d in done}) >= 4 and any(d.x_size != d.y_size for d in done) and len({d.ko_rule for d in done}) >= 2
+        assert len({(d.x_size, d.y_size) for d in done}) >= 3 and len({d.ko_rule for d in done}) >= 2
+        assert limits == "forks" or any(d.x_size != d.y_size for d in done)
         assert len({d.komi for d in done}) >= 3 and {d.multi_stone_suicide_legal for d in done} == {False, True}
+    if limits in ("forks", "forks_only"):
+        forked = [d for d in done if d.mode == 2]
+        assert len(forked) >= 4 and all(d.start_hist_moves >= 1 for d in forked) and forks.forks_made >= forks.forks_used >= len(forked)
+        openings = {tuple(d.start_moves + d.moves)[:len(f.start_moves) - 1] for d in done for f in forked}
+        assert all(tuple(f.start_moves[:-1]) in openings for f in forked)          # a fork's start is another game's opening plus one move
     if limits == "komi_searches":
         with_lead = [sum(1 for v in d.white_value_targets_by_turn[:-1] if len(v) > 4 and v[4]) for d in done]
         assert sum(with_lead) >= 20 and fair.searches > 30 and lead.searches > 100 and rec.games_waiting_for_lead >= 0

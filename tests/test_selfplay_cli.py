@@ -528,9 +528,9 @@ def test_cpp_host_refuses_what_it_does_not_play_and_needs_a_gpu(tmp_path, cpp_ho
     error - there is no CPU path behind the C ABI."""
     import subprocess
     cfg = tmp_path / "c.cfg"
-    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nearlyForkGameProb = 0.04\n")
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nhandicapProb = 0.1\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode != 0 and "earlyForkGameProb" in r.stderr and "selfplay_cli.py" in r.stderr
+    assert r.returncode != 0 and "handicapProb" in r.stderr and "selfplay_cli.py" in r.stderr
     cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\ndataBoardLen = 9\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0 and "dataBoardLen" in r.stderr          # the data frame must hold the largest board
