@@ -114,7 +114,7 @@ inline float computeLead(double oldKomi, const KomiOracle& ev) {
 // the root and the legal moves, or invalid when replaying the moves ended the game on the way.  Like KomiOracle the oracle answers from what is
 // known and throws for the first query that is missing; since the algorithm is re-run from the top every time, its queries - and the random
 // draws it makes on the way (draw()) - are remembered in the order they were made, so that a re-run sees the same draws and arrives at the same place.
-struct PositionAnswer { bool valid = false; double lead = 0, winLoss = 0, nnScoreMean = 0; std::vector<uint8_t> legal; };
+struct PositionAnswer { bool valid = false; double lead = 0, winLoss = 0, nnScoreMean = 0; std::vector<uint8_t> legal; std::shared_ptr<void> payload; };
 struct NeedPosition { std::vector<Move> moves; float komi; };
 class PositionOracle {
  public:
@@ -155,6 +155,9 @@ class KomiSearcher {
     queue_.push_back(std::unique_ptr<Job>(new Job{setup, {}, KomiOracle(setup.x, setup.y), nullptr, 0.0f, true, PositionOracle(), std::move(algorithm), {}}));
     dispatch();
   }
+  // called for every valid position answer while the slot still holds the searched position: what else the job wants read from it (a side
+  // position's training targets) goes into the answer's payload
+  std::function<std::shared_ptr<void>(const GameSlots& loop, int slot)> readPosition;
   int pending() const { return (int)(queue_.size() + running_.size()); }
   long searches() const { return searches_; }
 
@@ -179,6 +182,7 @@ class KomiSearcher {
           sp_.rootExtraByPos(slot, nodeVisits, nn);
           a.lead = root[4]; a.winLoss = root[0]; a.nnScoreMean = nn[2];
           for(float p : sp_.rootPolicy(slot)) a.legal.push_back(p >= 0 ? 1 : 0);
+          if(readPosition) a.payload = readPosition(sp_, slot);
         }
         job->posOracle.add(std::move(a));
       }

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -55,6 +56,17 @@ struct ValueTargets { float win = 0, loss = 0, noResult = 0, score = 0; bool has
 struct PolicyTargetMove { int x, y; int16_t value; };                       // x < 0: pass
 struct QValueTarget { int x, y; float winLoss, score; int visits; };       // white's perspective; visits of the child NODE
 
+// A position off the main line that was searched on its own (dataio/trainingwrite.h:62-84): it gets a row with its own policy / value / Q
+// targets and none of the targets that need the game's continuation.
+struct SidePosition {
+  int nextPlayer = P_BLACK, turnIdx = 0;
+  std::vector<uint8_t> packedInput; std::array<float, NUM_GLOBAL> globalInput{};
+  std::vector<PolicyTargetMove> policyTarget; int64_t unreducedNumVisits = 0;
+  ValueTargets whiteValueTargets; std::vector<QValueTarget> whiteQValueTargets;
+  double policySurprise = 0, policyEntropy = 0, searchEntropy = 0; std::array<double, 3> nnRawStats{};
+  float targetWeight = 1.0f;
+};
+
 // What Play::runGame hands to the writer (dataio/trainingwrite.h:84-170), for games of this host.
 struct FinishedGame {
   int xSize = 19, ySize = 19; float komi = 7.5f;
@@ -79,6 +91,7 @@ struct FinishedGame {
   int winner = 0; float finalWhiteMinusBlackScore = 0;
   std::vector<uint8_t> finalFullArea, finalOwnership;     // row-major [ySize * xSize]: 0 none, 1 black, 2 white
   std::vector<float> finalWhiteScoring;
+  std::vector<std::shared_ptr<SidePosition>> sidePositions;
 
   // BoardHistory::currentSelfKomi (game/boardhistory.cpp:570-589) without bonus points
   float selfKomi(int nextPlayer) const {
@@ -194,19 +207,24 @@ class TrainingWriteBuffers {
 
   // One main-line row of `game` for turn `idx` (addRow with valueTargetWeight = tdValueTargetWeight = leadTargetWeightFactor = 1, no
   // reanalysis, no side position, no net changes, no bonus points).  policyTarget1: the next turn's policy target or nullptr.
-  void addRow(const FinishedGame& game, int idx, const std::vector<PolicyTargetMove>* policyTarget1, RowRand& rand) {
+  // side != nullptr: the row of a side position of `game` instead (writeGame's second loop, trainingwrite.cpp:1258-1323): its own targets only -
+  // the value targets are its own search's (one entry), no outcome, ownership, future boards or scoring; the game's ending still decides the
+  // lead / finished flags.  idx is ignored then.
+  void addRow(const FinishedGame& game, int idx, const std::vector<PolicyTargetMove>* policyTarget1, RowRand& rand, const SidePosition* side = nullptr) {
     if(curRows >= maxRows) throw std::runtime_error("TrainingWriteBuffers full");
-    const int r = curRows, P = A + 1, xSize = game.xSize, ySize = game.ySize, nextPlayer = game.nextPlayerByTurn[idx];
+    if(side) idx = 0;
+    const int r = curRows, P = A + 1, xSize = game.xSize, ySize = game.ySize, nextPlayer = side ? side->nextPlayer : game.nextPlayerByTurn[idx];
     const bool white = nextPlayer == P_WHITE;
     const int opp = white ? P_BLACK : P_WHITE;
-    if((int)game.packedInputByTurn[idx].size() != NUM_BIN * packedLen) throw std::runtime_error("addRow: packed input of the wrong size");
-    std::memcpy(&binaryInput[(size_t)r * NUM_BIN * packedLen], game.packedInputByTurn[idx].data(), (size_t)NUM_BIN * packedLen);
-    std::memcpy(&globalInput[(size_t)r * NUM_GLOBAL], game.globalInputByTurn[idx].data(), sizeof(float) * NUM_GLOBAL);
+    const std::vector<uint8_t>& packed = side ? side->packedInput : game.packedInputByTurn[idx];
+    if((int)packed.size() != NUM_BIN * packedLen) throw std::runtime_error("addRow: packed input of the wrong size");
+    std::memcpy(&binaryInput[(size_t)r * NUM_BIN * packedLen], packed.data(), (size_t)NUM_BIN * packedLen);
+    std::memcpy(&globalInput[(size_t)r * NUM_GLOBAL], side ? side->globalInput.data() : game.globalInputByTurn[idx].data(), sizeof(float) * NUM_GLOBAL);
     float* g = &globalTargets[(size_t)r * GLOBAL_TARGET_CHANNELS];
     std::fill(g, g + GLOBAL_TARGET_CHANNELS, 0.0f);
     g[25] = game.trainingWeight;
     int16_t* pol = &policyTargets[(size_t)r * POLICY_TARGET_CHANNELS * P];
-    const std::vector<PolicyTargetMove>* targets[2] = {&game.policyTargetsByTurn[idx], policyTarget1};
+    const std::vector<PolicyTargetMove>* targets[2] = {side ? &side->policyTarget : &game.policyTargetsByTurn[idx], side ? nullptr : policyTarget1};
     const int weightCol[2] = {26, 28};
     for(int ch = 0; ch < 2; ch++) {
       if(targets[ch] == nullptr) { std::fill(pol + ch * P, pol + (ch + 1) * P, (int16_t)1); g[weightCol[ch]] = 0.0f; }      // uniformPolicyTarget, weight 0
@@ -217,7 +235,8 @@ class TrainingWriteBuffers {
       }
     }
     const int boardArea = xSize * ySize;
-    const std::vector<ValueTargets>& vt = game.whiteValueTargetsByTurn;
+    const std::vector<ValueTargets> sideTargets = side ? std::vector<ValueTargets>{side->whiteValueTargets} : std::vector<ValueTargets>();
+    const std::vector<ValueTargets>& vt = side ? sideTargets : game.whiteValueTargetsByTurn;
     const double nowFactors[5] = {0.0, 1.0 / (1.0 + boardArea * 0.176), 1.0 / (1.0 + boardArea * 0.056), 1.0 / (1.0 + boardArea * 0.016), 1.0};
     for(int k = 0; k < 5; k++) valueTDTargets(vt, idx, white, nowFactors[k], g + 4 * k);
     const float vtw = 1.0f, tdw = 1.0f;
@@ -235,7 +254,8 @@ class TrainingWriteBuffers {
     }
     g[22] = (float)s;
     g[24] = 1.0f - tdw;
-    g[30] = (float)game.policySurpriseByTurn[idx]; g[31] = (float)game.policyEntropyByTurn[idx]; g[32] = (float)game.searchEntropyByTurn[idx];
+    g[30] = (float)(side ? side->policySurprise : game.policySurpriseByTurn[idx]); g[31] = (float)(side ? side->policyEntropy : game.policyEntropyByTurn[idx]);
+    g[32] = (float)(side ? side->searchEntropy : game.searchEntropyByTurn[idx]);
     g[35] = 1.0f - vtw;
     bool use = true;
     for(int k = 0; k < 5; k++) {                 // each earlier history step is kept with probability 0.98 (:628-637)
@@ -247,17 +267,17 @@ class TrainingWriteBuffers {
     g[44] = (float)(h1 & 0x3FFFFF); g[45] = (float)((h1 >> 22) & 0x3FFFFF); g[46] = (float)((h1 >> 44) & 0xFFFFF);
     g[47] = game.selfKomi(nextPlayer);
     g[48] = 1.0f;                                // area scoring
-    g[51] = (float)(idx + game.startHistMoves);
+    g[51] = (float)(side ? side->turnIdx : idx + game.startHistMoves);
     g[52] = game.hitTurnLimit ? 1.0f : 0.0f;
     g[53] = (float)game.startHistMoves;
     g[55] = (float)game.mode;
     g[56] = (float)game.initialTurnNumber;
-    const std::array<double, 3>& raw = game.nnRawStatsByTurn[idx];
+    const std::array<double, 3>& raw = side ? side->nnRawStats : game.nnRawStatsByTurn[idx];
     g[57] = (float)(white ? raw[0] : -raw[0]);
     g[58] = (float)(white ? raw[1] : -raw[1]);
     g[59] = (float)raw[2];
-    g[60] = (float)game.unreducedNumVisitsByTurn[idx];
-    g[62] = (game.endFinished && !game.hitTurnLimit) ? 1.0f : 0.0f;
+    g[60] = (float)(side ? side->unreducedNumVisits : game.unreducedNumVisitsByTurn[idx]);
+    g[62] = (!side && game.endFinished && !game.hitTurnLimit) ? 1.0f : 0.0f;
     g[63] = 3.0f;
 
     int8_t* sd = &scoreDistr[(size_t)r * sdLen];
@@ -266,7 +286,7 @@ class TrainingWriteBuffers {
     std::fill(own, own + (size_t)VALUE_SPATIAL_CHANNELS * A, (int8_t)0);
     const int sdMid = A + SCORE_DISTR_RADIUS;
     auto frame = [&](int j) { return (j / xSize) * L + (j % xSize); };      // NNPos::xyToPos of the board's j-th point
-    if(game.finalOwnership.empty() || noResultEnd) { sd[sdMid - 1] = 50; sd[sdMid] = 50; }
+    if(side || game.finalOwnership.empty() || noResultEnd) { sd[sdMid - 1] = 50; sd[sdMid] = 50; }
     else {
       g[27] = vtw;
       const float score = white ? vt.back().score : -vt.back().score;
@@ -287,7 +307,7 @@ class TrainingWriteBuffers {
         sd[upper] = (int8_t)up;
       }
     }
-    {                                            // posHistForFutureBoards: the game's own positions 8 and 32 turns ahead
+    if(!side) {                                  // posHistForFutureBoards: the game's own positions 8 and 32 turns ahead
       if(game.boardsByTurn.size() != vt.size()) throw std::runtime_error("addRow: one board per value target expected");
       g[33] = 1.0f;
       const int end = (int)game.boardsByTurn.size() - 1;
@@ -297,7 +317,7 @@ class TrainingWriteBuffers {
         for(int j = 0; j < boardArea; j++) own[(size_t)(2 + c) * A + frame(j)] = b[j] == nextPlayer ? 1 : b[j] == opp ? -1 : 0;
       }
     }
-    if(!game.finalWhiteScoring.empty() && !noResultEnd) {
+    if(!side && !game.finalWhiteScoring.empty() && !noResultEnd) {
       g[34] = vtw;
       for(int j = 0; j < boardArea; j++) {       // y, x order: the order the reference draws its random numbers in
         const float v = white ? game.finalWhiteScoring[j] : -game.finalWhiteScoring[j];
@@ -306,7 +326,7 @@ class TrainingWriteBuffers {
     }
     int16_t* q = &qValueTargets[(size_t)r * QVALUE_CHANNELS * P];
     std::fill(q, q + (size_t)QVALUE_CHANNELS * P, (int16_t)0);
-    for(const QValueTarget& t : game.whiteQValueTargetsByTurn[idx]) {        // fillQValueTarget (:385-409)
+    for(const QValueTarget& t : (side ? side->whiteQValueTargets : game.whiteQValueTargetsByTurn[idx])) {        // fillQValueTarget (:385-409)
       const int pos = posOf(t.x, t.y);
       const float wl = white ? t.winLoss : -t.winLoss;
       float sc = white ? t.score : -t.score;
@@ -394,6 +414,17 @@ class TrainingDataWriter {
       while(targetWeight > 0.0) {
         if(targetWeight >= 1.0 || rand_.nextBool(targetWeight)) {
           buffers_.addRow(game, (int)t, policy1, rand_);
+          if(buffers_.curRows >= buffers_.maxRows || (isFirstFile_ && buffers_.curRows >= firstFileMaxRows_)) flushIfNonempty();
+          rowCount_++;
+        }
+        targetWeight -= 1.0;
+      }
+    }
+    for(const std::shared_ptr<SidePosition>& sp : game.sidePositions) {      // side rows (:1258-1323)
+      double targetWeight = (double)sp->targetWeight;
+      while(targetWeight > 0.0) {
+        if(targetWeight >= 1.0 || rand_.nextBool(targetWeight)) {
+          buffers_.addRow(game, 0, nullptr, rand_, sp.get());
           if(buffers_.curRows >= buffers_.maxRows || (isFirstFile_ && buffers_.curRows >= firstFileMaxRows_)) flushIfNonempty();
           rowCount_++;
         }

@@ -243,6 +243,14 @@ class HostRecorder {
     bool policyInit = false;       // policy-initialised openings (kgb_selfplay_set_policy_init): a slot in its opening is not held; the opening is the game's start history
     bool perGameSetups = false;    // board size, rules and komi are per game (kgb_selfplay_set_game_setup / set_komi): read them from the device
   };
+  struct Turn {      // what a finished root search gave
+    int nextPlayer, moveNum; std::pair<int, int> move{-1, -1};
+    std::vector<uint8_t> packed; std::array<float, NUM_GLOBAL> global;
+    std::vector<PolicyTargetMove> policyTarget; int64_t unreducedNumVisits;
+    ValueTargets valueTargets; std::vector<QValueTarget> qTargets;
+    double surprise, searchEntropy, policyEntropy; std::array<double, 3> nnRawStats, rawNNValues;
+    float targetWeight = 1.0f;
+  };
   using OnGame = std::function<void(int slot, const FinishedGame&)>;
   // called with the slot when its next game has begun on the device (before any of its turns is recorded): the host's draw for the game after it
   std::function<void(int slot)> onGameStart;
@@ -253,6 +261,22 @@ class HostRecorder {
   std::function<void(float komi, const GameSlots::GameSetup& setup, const std::vector<Move>& moves, LeadDone done)> submitLead;
   double estimateLeadProb = 0.0;
   int gamesWaitingForLead() const { return gamesWaiting_; }
+  // Side positions (PlaySettings::sidePositionProb = cfg forkSidePositionProb, play.cpp:1846-1860, 2166-2203): with that probability per turn a forking
+  // move is made off the main line (chooseRandomForkingMove: 70 % a temperature-1 policy move, 25 % temperature-2, 5 % any legal move, never the move
+  // played) and the position searched on a side loop with the game's own search parameters; its row is written with the game.
+  // submitSide(setup, moves, komi, done): `done(position or null)` is called once; sidePositionFrom(loop, slot) reads a searched side-loop slot.
+  using SideDone = std::function<void(std::shared_ptr<SidePosition>)>;
+  std::function<void(const GameSlots::GameSetup& setup, const std::vector<Move>& moves, float komi, SideDone done)> submitSide;
+  double sidePositionProb = 0.0;
+  static std::shared_ptr<SidePosition> sidePositionFrom(const GameSlots& loop, int slot) {
+    Turn t; GameSlots::RootPosition pos; std::vector<float> policy;
+    if(!extractTurn(loop, slot, loop.rootRawPolicyEntropies()[(size_t)slot], t, pos, policy)) return nullptr;
+    std::shared_ptr<SidePosition> sp(new SidePosition());
+    sp->nextPlayer = t.nextPlayer; sp->packedInput = std::move(t.packed); sp->globalInput = t.global; sp->policyTarget = std::move(t.policyTarget);
+    sp->unreducedNumVisits = t.unreducedNumVisits; sp->whiteValueTargets = t.valueTargets; sp->whiteQValueTargets = std::move(t.qTargets);
+    sp->policySurprise = t.surprise; sp->policyEntropy = t.policyEntropy; sp->searchEntropy = t.searchEntropy; sp->nnRawStats = t.nnRawStats;
+    return sp;
+  }
   // the slot's game that has just begun starts from `moves` (already played into the device slot by the caller): a forked game (mode 2)
   void startFrom(int slot, const std::vector<Move>& moves, int mode = 2) {
     InProgress& gm = games_[(size_t)slot];
@@ -305,18 +329,22 @@ class HostRecorder {
   }
 
  private:
-  struct Turn {
-    int nextPlayer, moveNum; std::pair<int, int> move{-1, -1};
-    std::vector<uint8_t> packed; std::array<float, NUM_GLOBAL> global;
-    std::vector<PolicyTargetMove> policyTarget; int64_t unreducedNumVisits;
-    ValueTargets valueTargets; std::vector<QValueTarget> qTargets;
-    double surprise, searchEntropy, policyEntropy; std::array<double, 3> nnRawStats, rawNNValues;
-    float targetWeight = 1.0f;
-  };
+  // a finished game that waits for its lead and side-position jobs; the side positions of a game: searched ones, jobs in flight, the waiting game
+  struct SideState;
+  struct Waiting { FinishedGame game; int slot; size_t left; std::weak_ptr<SideState> side; };      // (weak: the side state owns its waiting game, not the other way round)
+  struct SideState { std::vector<std::shared_ptr<SidePosition>> list; int pending = 0; std::shared_ptr<Waiting> waiting; };
+  void jobBack(std::shared_ptr<Waiting> w) {
+    if(--w->left != 0) return;
+    gamesWaiting_--;
+    if(std::shared_ptr<SideState> side = w->side.lock()) { w->game.sidePositions = side->list; side->waiting.reset(); }
+    if(onGame_) onGame_(w->slot, w->game);
+  }
   struct InProgress {
     std::vector<Turn> turns; std::vector<std::vector<uint8_t>> boards; std::vector<double> winLoss;      // winLoss: historicalMctsWinLossValues
     bool haveSetup = false; GameSlots::GameSetup setup{0, 0, 0, 1};     // this game's own board and rules, read when its first turn is recorded
     std::vector<std::pair<int, int>> startMoves;                         // moves before the first recorded turn (fork prefix + policy-initialised opening): startHist
+    std::vector<float> lastPolicy;                                       // the root policy of the turn being played (for the side position's forking move)
+    std::shared_ptr<SideState> side{new SideState()};                    // side positions of this game
     std::vector<std::pair<int, int>> presetMoves; int mode = 0;         // moves the host played into the slot before the game's first search (a forked game); FinishedGameData::mode
   };
   // a board or area of the evaluator's frame cut down to the game's own board (its top-left corner)
@@ -327,24 +355,25 @@ class HostRecorder {
     return out;
   }
 
-  void recordRoot(int g, double rawPolicyEntropy) {
-    const int X = slots_.xLen(), Y = slots_.yLen(), A = X * Y;
-    const GameSlots::RootPosition pos = slots_.rootPosition(g);
+  // What extractSearchTargetsThisTurn / the side-position block of Play::runGame (play.cpp:931-948, 2178-2203) read of a finished search, from slot g
+  // of loop `sp` held at its budget.  Returns false when the kept input row belongs to another position.
+  static bool extractTurn(const GameSlots& sp, int g, double rawPolicyEntropy, Turn& t, GameSlots::RootPosition& pos, std::vector<float>& policy) {
+    const int X = sp.xLen(), Y = sp.yLen(), A = X * Y;
+    pos = sp.rootPosition(g);
     std::vector<float> spatial, global;
-    slots_.rootInputRow(g, spatial, global);
-    const std::vector<float> policy = slots_.rootPolicy(g);
+    sp.rootInputRow(g, spatial, global);
+    policy = sp.rootPolicy(g);
     std::vector<double> childMoments; double rootMoments[5], nn[5];
-    slots_.rootValueStatsByPos(g, childMoments, rootMoments);
-    const std::vector<double> psv = slots_.playSelectionValuesByPos(g);
+    sp.rootValueStatsByPos(g, childMoments, rootMoments);
+    const std::vector<double> psv = sp.playSelectionValuesByPos(g);
     std::vector<int32_t> nodeVisits;
-    slots_.rootExtraByPos(g, nodeVisits, nn);
-    Turn t;
+    sp.rootExtraByPos(g, nodeVisits, nn);
     t.nextPlayer = pos.blackToMove ? P_BLACK : P_WHITE;
     t.moveNum = pos.moveNumber;
     // the kept row must be this root's: its own / opponent stone planes are the root position
     for(int p = 0; p < A; p++)
       if((spatial[(size_t)p * NUM_BIN + 1] != 0) != (pos.colors[(size_t)p] == t.nextPlayer) || (spatial[(size_t)p * NUM_BIN + 2] != 0) != (pos.colors[(size_t)p] == 3 - t.nextPlayer))
-        throw std::runtime_error("HostRecorder: slot " + std::to_string(g) + ", move " + std::to_string(pos.moveNumber) + ": the kept input row belongs to another position");
+        return false;
     const int packedLen = (A + 7) / 8;
     t.packed.assign((size_t)NUM_BIN * packedLen, 0);          // packBits: 8 points per byte, first point in the high bit
     for(int p = 0; p < A; p++)
@@ -365,8 +394,17 @@ class HostRecorder {
     t.nnRawStats = {nn[0], nn[2], rawPolicyEntropy};
     const Reported rn = reportedSearchValues(nn);
     t.rawNNValues = {rn.win, rn.loss, rn.noResult};
+    return true;
+  }
+
+  void recordRoot(int g, double rawPolicyEntropy) {
+    const int X = slots_.xLen(), Y = slots_.yLen();
+    Turn t; GameSlots::RootPosition pos; std::vector<float> policy;
+    if(!extractTurn(slots_, g, rawPolicyEntropy, t, pos, policy))
+      throw std::runtime_error("HostRecorder: slot " + std::to_string(g) + ", move " + std::to_string(pos.moveNumber) + ": the kept input row belongs to another position");
     t.targetWeight = curLimits_[(size_t)g].targetWeight;
     InProgress& gm = games_[(size_t)g];
+    gm.lastPolicy = policy;
     if(!gm.haveSetup) {
       gm.setup = GameSlots::GameSetup{X, Y, s_.koRule, s_.multiStoneSuicideLegal ? 1 : 0};
       if(s_.perGameSetups) { std::vector<GameSlots::GameSetup> cur; slots_.gameSetups(&cur, nullptr); gm.setup = cur[(size_t)g]; }
@@ -398,8 +436,45 @@ class HostRecorder {
   void afterMove(int g) {
     const GameSlots::LastMove last = slots_.lastMove(g);
     games_[(size_t)g].turns.back().move = {last.move.x, last.move.y};
+    if(submitSide && !last.gameOver && sideRand_.random() < sidePositionProb) submitSidePosition(g, last);
     if(s_.play.active()) curLimits_[(size_t)g] = last.gameOver ? pending_[(size_t)g].second : pending_[(size_t)g].first;
     if(last.gameOver) finishGame(g, last);
+  }
+
+  // PlayUtils::chooseRandomForkingMove (play.cpp:796-808): a move position or -1.  policy by move position, -1 = illegal (here the root policy as
+  // searched - the reference reads the un-noised one)
+  int chooseRandomForkingMove(const std::vector<float>& policy, int banPos) {
+    const double r = sideRand_.random();
+    std::vector<int> legal;
+    for(size_t i = 0; i < policy.size(); i++) if(policy[i] >= 0 && (int)i != banPos) legal.push_back((int)i);
+    if(r >= 0.95) return legal.empty() ? -1 : legal[sideRand_.randrange((uint32_t)legal.size())];
+    const double t = r < 0.70 ? 1.0 : 2.0;
+    std::vector<int> cand; std::vector<double> w;
+    static double (*volatile libmPow)(double, double) = std::pow;       // the same libm call as Python's `**`
+    for(int i : legal) if(policy[(size_t)i] > 0) { cand.push_back(i); w.push_back(libmPow((double)policy[(size_t)i], 1.0 / t)); }
+    if(cand.empty()) return -1;
+    return cand[sideRand_.choiceIndex(w)];
+  }
+  void submitSidePosition(int g, const GameSlots::LastMove& last) {
+    InProgress& gm = games_[(size_t)g];
+    const int X = slots_.xLen(), A = X * slots_.yLen();
+    const int pos = chooseRandomForkingMove(gm.lastPolicy, last.move.isPass() ? A : last.move.y * X + last.move.x);
+    if(pos < 0 || !gm.haveSetup) return;
+    std::vector<Move> moves;
+    for(const auto& m : gm.startMoves) { Move mv; mv.x = m.first; mv.y = m.second; moves.push_back(mv); }
+    for(size_t i = 0; i + 1 < gm.turns.size(); i++) { Move mv; mv.x = gm.turns[i].move.first; mv.y = gm.turns[i].move.second; moves.push_back(mv); }
+    Move fork; if(pos != A) { fork.x = pos % X; fork.y = pos / X; }
+    moves.push_back(fork);
+    float komi = s_.komi;
+    if(s_.perGameSetups) { std::vector<float> cur; slots_.komis(&cur, nullptr); komi = cur[(size_t)g]; }
+    const int turnIdx = gm.turns.back().moveNum + 1;
+    std::shared_ptr<SideState> side = gm.side;
+    side->pending++;
+    submitSide(gm.setup, moves, komi, [this, side, turnIdx](std::shared_ptr<SidePosition> sp) {
+      if(sp) { sp->turnIdx = turnIdx; side->list.push_back(sp); }      // (null: the forking move ended the game, or the row was not the root's)
+      side->pending--;
+      if(side->waiting) jobBack(side->waiting);
+    });
   }
 
   void finishGame(int g, const GameSlots::LastMove& last) {
@@ -451,13 +526,15 @@ class HostRecorder {
     for(size_t i = 0; i < area.size(); i++) d.finalWhiteScoring[i] = area[i] == P_WHITE ? 1.0f : area[i] == P_BLACK ? -1.0f : 0.0f;
     gamesFinished_++;
     if(onGameStart) onGameStart(g);
+    std::shared_ptr<SideState> side = gm.side;
+    d.sidePositions = side->list;
     if(submitLead && estimateLeadProb > 0 && !d.endNoResult) {
       std::vector<size_t> turns;
       for(size_t t = 0; t < d.targetWeightByTurn.size(); t++)         // (the draw is made only for turns that qualify)
         if(d.targetWeightByTurn[t] > 0 && (double)d.whiteValueTargetsByTurn[t].noResult < 0.3 && leadRand_.random() < estimateLeadProb) turns.push_back(t);
       if(!turns.empty()) {
-        struct Waiting { FinishedGame game; int slot; size_t left; };
-        std::shared_ptr<Waiting> w(new Waiting{std::move(d), g, turns.size()});
+        std::shared_ptr<Waiting> w(new Waiting{std::move(d), g, turns.size() + (size_t)side->pending, side});
+        side->waiting = w;
         gamesWaiting_++;
         for(size_t t : turns) {
           std::vector<Move> moves;
@@ -465,11 +542,16 @@ class HostRecorder {
           for(size_t i = 0; i < t; i++) { Move mv; mv.x = w->game.moves[i].first; mv.y = w->game.moves[i].second; moves.push_back(mv); }
           submitLead(w->game.komi, gm.setup, moves, [this, w, t](float lead) {
             w->game.whiteValueTargetsByTurn[t].hasLead = true; w->game.whiteValueTargetsByTurn[t].lead = lead;      // ValueTargets::hasLead, lead
-            if(--w->left == 0) { gamesWaiting_--; if(onGame_) onGame_(w->slot, w->game); }
+            jobBack(w);
           });
         }
         return;
       }
+    }
+    if(side->pending > 0) {                  // side positions of this game are still being searched
+      side->waiting.reset(new Waiting{std::move(d), g, (size_t)side->pending, side});
+      gamesWaiting_++;
+      return;
     }
     if(onGame_) onGame_(g, d);
   }
@@ -478,7 +560,7 @@ class HostRecorder {
   std::vector<InProgress> games_;
   std::unique_ptr<RowRand> weightRand_;
   std::unique_ptr<PyRandom> limitsRand_;
-  PyRandom leadRand_{0x4C656164}; int gamesWaiting_ = 0;
+  PyRandom leadRand_{0x4C656164}, sideRand_{0x53696465}; int gamesWaiting_ = 0;
   std::vector<SearchLimits> curLimits_; std::vector<std::pair<SearchLimits, SearchLimits>> pending_;
   std::vector<int32_t> nextVisits_; std::vector<uint8_t> nextPlain_;
   int64_t movesRecorded_ = 0, gamesFinished_ = 0;

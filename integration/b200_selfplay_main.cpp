@@ -121,7 +121,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.full_history_rules = 1;
   c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
   c.neutral("handicapProb", "0.0");
-  c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("forkSidePositionProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
+  c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
 
   k.win_loss_utility_factor = c.num("winLossUtilityFactor", 1.0);
   k.static_score_utility_factor = c.num("staticScoreUtilityFactor", 0.1);
@@ -329,6 +329,7 @@ int main(int argc, char** argv) {
   const bool komiAuto = cfg.flag("komiAuto", false);
   const int compensateKomiVisits = (int)cfg.num("compensateKomiVisits", 20), estimateLeadVisits = (int)cfg.num("estimateLeadVisits", 6);
   const double estimateLeadProb = cfg.num("estimateLeadProb", 0.0);
+  const double sidePositionProb = cfg.num("forkSidePositionProb", 0.0);      // PlaySettings::sidePositionProb (playsettings.cpp: cfg key forkSidePositionProb)
   // forked games (Play::maybeForkGame, play.cpp:2413-2508; b200_forks.h)
   b200::ForkManager::Settings forkSettings;
   forkSettings.earlyForkGameProb = cfg.num("earlyForkGameProb", 0.0); forkSettings.earlyForkGameExpectedMoveProp = cfg.num("earlyForkGameExpectedMoveProp", 0.0);
@@ -389,13 +390,16 @@ int main(int argc, char** argv) {
     // side loops for the komi searches: own handles of the same net, a few slots, the loop's parameters without root noise (getNoiselessParams,
     // playutils.cpp:372-387), numVisits visits; as katago_b200/selfplay_cli.py make_aux
     struct SideLoop { kgb_handle* handle = nullptr; std::unique_ptr<b200::GameSlots> slots; std::unique_ptr<b200::KomiSearcher> searcher; };
-    SideLoop fairLoop, leadLoop;
-    auto makeSide = [&](SideLoop& side, int visits) {
+    SideLoop fairLoop, leadLoop, sideLoop;
+    auto makeSide = [&](SideLoop& side, int visits, bool noiseless = true) {
       kgb_selfplay_config c = sc;
-      c.root_noise_enabled = 0; c.root_policy_temperature = 1.0; c.root_policy_temperature_early = 1.0; c.root_fpu_reduction_max = sc.fpu_reduction_max;
-      c.root_fpu_loss_prop = sc.fpu_loss_prop; c.root_desired_per_child_visits_coeff = 0.0; c.root_num_symmetries_to_sample = 1;
+      if(noiseless) {
+        c.root_noise_enabled = 0; c.root_policy_temperature = 1.0; c.root_policy_temperature_early = 1.0; c.root_fpu_reduction_max = sc.fpu_reduction_max;
+        c.root_fpu_loss_prop = sc.fpu_loss_prop; c.root_desired_per_child_visits_coeff = 0.0; c.root_num_symmetries_to_sample = 1;
+      }
       c.max_moves = (sc.max_moves > 0 ? sc.max_moves : 2 * edge * edge) + 8;
-      c.num_games = std::max(4, std::min(32, numGames / 4)); c.max_visits = std::max(2, visits); c.seed = loopSeed + 104729; c.max_playouts_per_wave = 0;
+      c.num_games = std::max(4, std::min(32, numGames / 4)); c.max_visits = noiseless ? std::max(2, visits) : visits;
+      c.seed = loopSeed + (noiseless ? 104729 : 1299709); c.max_playouts_per_wave = 0;
       check(kgb_handle_create(ctx, model, c.num_games, 0, /*inputs_nhwc=*/1, gpu, &side.handle), "creating a side evaluator handle");
       side.slots.reset(new b200::GameSlots(side.handle, c, edge, edge));
       side.searcher.reset(new b200::KomiSearcher(*side.slots, c.max_visits));
@@ -404,6 +408,11 @@ int main(int argc, char** argv) {
     const bool forkNeedsLoop = forks.enabled() && !(komiAuto || estimateLeadProb > 0);        // the fork's evaluations need some side loop
     if(komiAuto || forkNeedsLoop) makeSide(fairLoop, compensateKomiVisits);
     if(estimateLeadProb > 0) makeSide(leadLoop, estimateLeadVisits);
+    // side positions are searched like the game's own turns: the loop's parameters, noise and all, full visits
+    if(sidePositionProb > 0) {
+      makeSide(sideLoop, sc.max_visits, false);
+      sideLoop.searcher->readPosition = [](const b200::GameSlots& loop, int slot) { return std::static_pointer_cast<void>(b200::HostRecorder::sidePositionFrom(loop, slot)); };
+    }
     b200::KomiSearcher* forkSearcher = leadLoop.searcher ? leadLoop.searcher.get() : fairLoop.searcher.get();      // where fork evaluations and their komi compensation run
     // the draws become the games in progress (none has started), new ones are drawn for the games after them; a slot's draw for the game
     // after next is made when its next game begins (katago_b200/selfplay_cli.py SlotSetups)
@@ -455,7 +464,8 @@ int main(int argc, char** argv) {
         const b200::GameSlots::GameSetup setup{game.xSize, game.ySize, ko, game.multiStoneSuicideLegal ? 1 : 0};
         const float gameKomi = game.komi;
         b200::KomiSearcher::PositionAlgorithm job;
-        if(forks.job(all, setup, gameKomi, edge, edge, job, [&forks, setup, gameKomi](const std::vector<b200::Move>& moves) { if(!moves.empty()) forks.add(moves, setup, gameKomi); }))
+        const size_t cap = (size_t)(sc.max_moves > 0 ? sc.max_moves : 2 * game.xSize * game.ySize);      // (a fork at the game length cap would be over before its first search)
+        if(forks.job(all, setup, gameKomi, edge, edge, job, [&forks, setup, gameKomi, cap](const std::vector<b200::Move>& moves) { if(!moves.empty() && moves.size() < cap) forks.add(moves, setup, gameKomi); }))
           forkSearcher->submitPositions(setup, job);
       }
     });
@@ -471,6 +481,15 @@ int main(int argc, char** argv) {
     struct PendingFork { bool have = false; long id = 0; b200::ForkManager::Fork fork; };
     std::vector<PendingFork> forkNext((size_t)numGames);
     long forkIds = 0;
+    if(sidePositionProb > 0) {
+      recorder.sidePositionProb = sidePositionProb;
+      recorder.submitSide = [&](const b200::GameSlots::GameSetup& setup, const std::vector<b200::Move>& moves, float komi, b200::HostRecorder::SideDone done) {
+        sideLoop.searcher->submitPositions(setup, [moves, komi, done](b200::PositionOracle& ev) {
+          const b200::PositionAnswer& a = ev(moves, komi);
+          done(a.valid ? std::static_pointer_cast<b200::SidePosition>(a.payload) : nullptr);       // (invalid: the forking move ended the game)
+        });
+      };
+    }
     recorder.onGameStart = [&](int g) {
       PendingFork started = forkNext[(size_t)g];
       forkNext[(size_t)g] = PendingFork();
@@ -512,6 +531,7 @@ int main(int argc, char** argv) {
       pumps++;
       if(fairLoop.searcher) fairLoop.searcher->step(8);        // the side loops advance with the main loop
       if(leadLoop.searcher) leadLoop.searcher->step(8);
+      if(sideLoop.searcher) sideLoop.searcher->step(8);
       if(modelsDir.empty() || (maxGamesTotal > 0 && written >= maxGamesTotal)) continue;
       const auto now = std::chrono::steady_clock::now();
       if(std::chrono::duration<double>(now - lastPoll).count() < modelPollSeconds) continue;
@@ -530,7 +550,7 @@ int main(int argc, char** argv) {
       }
       check(kgb_handle_commit_weights(handle), "committing the new weights");
       slots.clearNNCache();
-      for(SideLoop* side : {&fairLoop, &leadLoop})
+      for(SideLoop* side : {&fairLoop, &leadLoop, &sideLoop})
         if(side->handle) {
           check(kgb_handle_stage_weights(side->handle, next), "staging the new weights on a side loop");
           check(kgb_handle_commit_weights(side->handle), "committing the new weights on a side loop");
@@ -544,7 +564,7 @@ int main(int argc, char** argv) {
       std::fprintf(stderr, "b200_selfplay: Game loop changing midgame to new neural net: %s (swap %d, after pump %ld)\n", outputs.netName.c_str(), swaps, pumps);
     }
     outputs.close();
-    for(SideLoop* side : {&fairLoop, &leadLoop}) { side->searcher.reset(); side->slots.reset(); if(side->handle) kgb_handle_free(side->handle); side->handle = nullptr; }
+    for(SideLoop* side : {&fairLoop, &leadLoop, &sideLoop}) { side->searcher.reset(); side->slots.reset(); if(side->handle) kgb_handle_free(side->handle); side->handle = nullptr; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const kgb_selfplay_stats st = slots.stats();
     std::printf("{\"games_written\": %ld, \"rows\": %lld, \"files\": %zu, \"moves\": %lld, \"net_swaps\": %d, \"visits\": %llu, \"seconds\": %.3f, \"visits_per_second\": %.1f, \"nn_cache_hits\": %llu}\n",

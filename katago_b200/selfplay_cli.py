@@ -587,7 +587,9 @@ def main(argv=None):
             setup = (finished.x_size, finished.y_size, ko, int(finished.multi_stone_suicide_legal))
             job = forks.job(all_moves, setup, finished.komi, L)
             if job is not None:
-                fork_searcher().submit(job, setup, [], lambda moves, setup=setup, komi=finished.komi: forks.add(moves, setup, komi) if moves else None)
+                # (a fork at the game length cap would be over before its first search: play_moves_game restarts the slot)
+                cap = int(kw.get("max_moves", 0) or 2 * finished.x_size * finished.y_size)
+                fork_searcher().submit(job, setup, [], lambda moves, setup=setup, komi=finished.komi, cap=cap: forks.add(moves, setup, komi) if moves and len(moves) < cap else None)
 
     def on_game_start(slot):
         counts["started"] += 1          # the slot's next game started on the device when the previous one ended

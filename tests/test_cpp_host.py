@@ -108,7 +108,11 @@ def _replay_slots_with_limits(log, G, size, V):
 
 FORKS = ("earlyForkGameProb = 0.4\nearlyForkGameExpectedMoveProp = 0.15\nforkGameProb = 0.5\nforkGameMinChoices = 2\nearlyForkGameMaxChoices = 4\nforkGameMaxChoices = 3\n"
          "forkCompensateKomiProb = 0.5\n")
-LIMITS = {"none": "", "forks": FORKS + "estimateLeadProb = 0.15\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\ninitGamesWithPolicy = true\npolicyInitAreaProp = 0.05\n", "forks_only": FORKS, "komi_searches": "komiAuto = true\ncompensateKomiVisits = 10\nestimateLeadProb = 0.3\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\n", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
+SIDE = "forkSidePositionProb = 0.25\n"
+LIMITS = {"none": "", "side_positions": SIDE + "estimateLeadProb = 0.1\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\n",
+          "everything": SIDE + FORKS + "komiAuto = true\ncompensateKomiVisits = 10\nestimateLeadProb = 0.15\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\ninitGamesWithPolicy = true\n"
+                        "policyInitAreaProp = 0.05\ncheapSearchProb = 0.25\ncheapSearchVisits = 5\ncheapSearchTargetWeight = 0.0\nreduceVisits = true\nreduceVisitsThreshold = 0.3\n"
+                        "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n", "forks": FORKS + "estimateLeadProb = 0.15\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\ninitGamesWithPolicy = true\npolicyInitAreaProp = 0.05\n", "forks_only": FORKS, "komi_searches": "komiAuto = true\ncompensateKomiVisits = 10\nestimateLeadProb = 0.3\nestimateLeadVisits = 6\nmaxMovesPerGame = 30\n", "openings": "initGamesWithPolicy = true\npolicyInitAreaProp = 0.08\npolicyInitAreaTemperature = 0.7\ncheapSearchProb = 0.2\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n", "cheap": "cheapSearchProb = 0.3\ncheapSearchVisits = 8\ncheapSearchTargetWeight = 0.25\n",
           "cheap_unrecorded_and_reduced": "cheapSearchProb = 0.25\ncheapSearchVisits = 5\ncheapSearchTargetWeight = 0.0\nreduceVisits = true\nreduceVisitsThreshold = 0.3\n"
                                           "reduceVisitsThresholdLookback = 2\nreducedVisitsMin = 6\nreducedVisitsWeight = 0.2\n"}
 
@@ -128,6 +132,8 @@ MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRul
     (9, "MIXED", 6.0, 0, 0.5, 0.1, False, 10, 13, "komi_searches"),  # komiAuto and lead targets: komi bisections as jobs on two side loops, games written when their jobs are back
     (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 24, 17, "forks"),          # forked games: positions of finished games, a forking move chosen by the net's score, komi compensation, the fork pool
     (7, "SIMPLE", 7.5, 30, 0.0, 0.0, False, 15, 2, "forks_only"),    # forks without any other side-loop feature: the fork evaluations get a side loop of their own
+    (9, "MIXED", 7.0, 0, 0.5, 0.1, False, 14, 19, "side_positions"), # side positions: forking moves off the main line searched on a third side loop, their rows written with the game
+    (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 20, 23, "everything"),     # every option this host has, together
 ])
 def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
@@ -174,7 +180,8 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
                 setup = (finished.x_size, finished.y_size, ko_idx, int(finished.multi_stone_suicide_legal))
                 job = forks.job(all_moves, setup, finished.komi, size)
                 if job is not None:
-                    fork_searcher.submit(job, setup, [], lambda moves, setup=setup, komi=finished.komi: forks.add(moves, setup, komi) if moves else None)
+                    cap = int(kw.get("max_moves", 0) or 2 * finished.x_size * finished.y_size)
+                    fork_searcher.submit(job, setup, [], lambda moves, setup=setup, komi=finished.komi, cap=cap: forks.add(moves, setup, komi) if moves and len(moves) < cap else None)
 
     from katago_b200.game_initializer import GameInitializer
     # the side loops of the command (selfplay_cli.py make_aux): the mock's second and third loop, replayed from their own logs
@@ -190,19 +197,25 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
             lp = _replay_slots_with_limits(f"{log}.{instance}", 4, size, max(2, visits))
             lp.max_visits = max(2, visits)
             aux[name] = KomiSearcher(lp)
+    side = None
+    if data["side_position_prob"] > 0:       # side positions are searched on a loop with the game's own parameters and full visits
+        instance += 1
+        lp = _replay_slots_with_limits(f"{log}.{instance}", 4, size, V)
+        lp.max_visits = V
+        side = KomiSearcher(lp)
     fair, lead = aux["fair"], aux["lead"]
     fork_searcher = lead or fair
     setups = C.SlotSetups(GameInitializer(seed=loop_seed ^ 0x47616D65, **data["game_init"]), G, policy_init=data["policy_init"], fair_komi=fair if ks["komi_auto"] else None,
                           forks=forks if forks.enabled else None, searcher=fork_searcher)      # the command's own per-game draws
     setups.start(sp)
     rec = R.GameRecorder(sp, None, komi, on_game=on_game, on_game_start=lambda slot: setups.game_started(sp, rec, slot), lead_estimator=lead,
-                         estimate_lead_prob=data["komi_search"]["estimate_lead_prob"], game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
+                         estimate_lead_prob=data["komi_search"]["estimate_lead_prob"], side_searcher=side, side_position_prob=data["side_position_prob"], game_hash_fn=lambda slot, index: C._game_hash(loop_seed, slot, index),
                          policy_surprise_data_weight=psw, value_surprise_data_weight=vsw, use_search_value_surprise=search_surprise,
                          weight_rand=W.RowRand(writer_seed + ":weights"), play_settings=data["play_settings"],
                          limits_rand=__import__("random").Random(loop_seed ^ 0x4C696D69), policy_init=data["policy_init"]["enabled"])
     while len(done) < games:
         rec.pump(4)
-        for searcher in (fair, lead):
+        for searcher in (fair, lead, side):
             if searcher is not None:
                 searcher.step(8)
     writer.flush_if_nonempty()
@@ -223,8 +236,11 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     weights = [float(w) for d in done for w in (d.target_weight_by_turn_unrounded or d.target_weight_by_turn)]
     if ko == "MIXED":
         assert len({(d.x_size, d.y_size) for d in done}) >= 3 and len({d.ko_rule for d in done}) >= 2
-        assert limits == "forks" or any(d.x_size != d.y_size for d in done)
+        assert limits in ("forks", "everything") or any(d.x_size != d.y_size for d in done)
         assert len({d.komi for d in done}) >= 3 and {d.multi_stone_suicide_legal for d in done} == {False, True}
+    if limits in ("side_positions", "everything"):
+        n_side = sum(len(d.side_positions) for d in done)
+        assert n_side >= 10 and rows >= sum(1 for d in done for w in d.target_weight_by_turn if float(w) >= 1) + n_side - 5
     if limits in ("forks", "forks_only"):
         forked = [d for d in done if d.mode == 2]
         assert len(forked) >= 4 and all(d.start_hist_moves >= 1 for d in forked) and forks.forks_made >= forks.forks_used >= len(forked)

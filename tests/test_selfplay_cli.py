@@ -534,9 +534,9 @@ def test_cpp_host_refuses_what_it_does_not_play_and_needs_a_gpu(tmp_path, cpp_ho
     cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\ndataBoardLen = 9\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0 and "dataBoardLen" in r.stderr          # the data frame must hold the largest board
-    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nforkSidePositionProb = 0.02\n")
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nsekiForkHackProb = 0.04\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode != 0 and "forkSidePositionProb" in r.stderr
+    assert r.returncode != 0 and "sekiForkHackProb" in r.stderr
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present: the loud failure without one is checked on CPU boxes")
