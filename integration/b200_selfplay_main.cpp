@@ -12,12 +12,13 @@
 //   g++ -std=c++17 -O2 -I. integration/b200_selfplay_main.cpp -o b200_selfplay -Lkatago_b200 -lkgb200 -lz -Wl,-rpath,$PWD/katago_b200
 //   ./b200_selfplay (-model net.bin.gz | -models-dir DIR) -config selfplay.cfg -output-dir out [-max-games-total N] [-seed S] [-override-config k=v,k=v]
 //
-// Every turn is recorded; its weight comes from the per-move search limits (cheapSearchProb / reduceVisits ...) and the surprise weighting
-// (policySurpriseDataWeight / valueSurpriseDataWeight); board size, ko / suicide rule and komi are drawn per game like the reference's
-// GameInitializer (integration/b200_gameinit.h).  Openings can be drawn from the policy (initGamesWithPolicy).  komiAuto and estimateLeadProb run their komi-bisection
-// searches on side loops (integration/b200_komi.h).  The wider host ( lead targets, forks, side
-// positions, model polling and weight hot-swap, several GPUs) is katago_b200/selfplay_cli.py: options of that kind are refused here, not
-// ignored.  Without a CUDA device the program stops with the library's error (there is no CPU path).
+// What it plays is what katago_b200/selfplay_cli.py plays, draw for draw (tests/test_cpp_host.py: the same files, bit for bit, on a CPU mock of the
+// ABI): per-game board size / rules / komi like the reference's GameInitializer (b200_gameinit.h), komiAuto, policy-initialised openings,
+// per-move search limits (cheap searches, reduced visits), per-turn targets, surprise weighting, lead targets, forked games, side positions
+// (b200_recorder.h, b200_komi.h, b200_forks.h: the komi bisections, fork evaluations and side positions are jobs on side loops), model polling
+// with weight hot-swap, one process per GPU (-rank / -world-size).  Options neither host has (handicap, seki forks, territory scoring ...) are
+// listed as NOT BUILT and left out; -strict refuses them.  Without a CUDA device the program stops with the library's error (there is no CPU path).
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,8 @@
 namespace {
 
 [[noreturn]] void die(const std::string& what) { std::fprintf(stderr, "b200_selfplay: %s\n", what.c_str()); std::exit(1); }
+
+std::string lower(std::string s) { for(char& c : s) c = (char)std::tolower((unsigned char)c); return s; }      // (the reference's stock files write True / False)
 
 std::string trim(const std::string& s) {
   size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
@@ -75,8 +78,8 @@ struct Cfg {
     used[k] = true;
     auto it = kv.find(k);
     if(it == kv.end()) return dflt;
-    if(it->second == "true") return true;
-    if(it->second == "false") return false;
+    if(lower(it->second) == "true") return true;
+    if(lower(it->second) == "false") return false;
     die("config key " + k + ": expected true or false, got '" + it->second + "'");
   }
   std::vector<std::string> list(const std::string& k, const std::string& dflt) const {      // comma-separated values
@@ -86,11 +89,28 @@ struct Cfg {
     return out;
   }
   std::string str(const std::string& k, const std::string& dflt) const { used[k] = true; auto it = kv.find(k); return it == kv.end() ? dflt : it->second; }
-  // a key of the reference this host does not read: fine while it keeps its neutral value, an error otherwise
+  // Options of the reference that neither host of the device loop has (katago_b200/selfplay_cli.py reports the same ones): fine while they keep their
+  // neutral value, else listed as NOT BUILT - the loop then runs WITHOUT them, or, with -strict, not at all.
+  mutable std::vector<std::string> notBuilt;
   void neutral(const std::string& k, const std::string& value) const {
     used[k] = true;
     auto it = kv.find(k);
-    if(it != kv.end() && it->second != value) die("config key " + k + " = " + it->second + " is not supported by this host (only " + value + "); use katago_b200/selfplay_cli.py");
+    if(it == kv.end()) return;
+    if(value == "true" || value == "false") { if(lower(it->second) == value) return; }
+    else { char* end = nullptr; const double v = std::strtod(it->second.c_str(), &end); if(end != it->second.c_str() && !*end && v == std::atof(value.c_str())) return; }
+    notBuilt.push_back(k + " = " + it->second);
+  }
+  // a list-valued key of which the loop has only some values: the others are left out of the per-game draw and named
+  std::vector<std::string> supportedOf(const std::string& k, const std::string& dflt, const std::vector<std::string>& supported) const {
+    std::vector<std::string> ok, dropped;
+    for(const std::string& v : list(k, dflt)) {
+      bool have = false;
+      for(const std::string& sup : supported) have = have || sup == v || sup == lower(v);
+      (have ? ok : dropped).push_back(v);
+    }
+    if(ok.empty()) die("config key " + k + " = " + str(k, dflt) + ": none of these is built");
+    if(!dropped.empty()) { std::string d; for(const std::string& v : dropped) d += (d.empty() ? "" : ", ") + v; notBuilt.push_back(k + ": the reference draws one of [" + str(k, dflt) + "] per game; " + d + " not built"); }
+    return ok;
   }
 };
 
@@ -100,8 +120,8 @@ int koRuleOf(const std::string& ko) {
   return r;
 }
 bool boolOf(const std::string& key, const std::string& v) {
-  if(v == "true") return true;
-  if(v == "false") return false;
+  if(lower(v) == "true") return true;
+  if(lower(v) == "false") return false;
   die("config key " + key + ": expected true or false, got '" + v + "'");
 }
 
@@ -119,9 +139,10 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.ko_rule = koRuleOf(c.list("koRules", "SIMPLE")[0]);
   k.multi_stone_suicide_legal = boolOf("multiStoneSuicideLegals", c.list("multiStoneSuicideLegals", "true")[0]) ? 1 : 0;
   k.full_history_rules = 1;
-  c.neutral("scoringRules", "AREA"); c.neutral("taxRules", "NONE"); c.neutral("hasButtons", "false");
-  c.neutral("handicapProb", "0.0");
-  c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
+  c.supportedOf("scoringRules", "AREA", {"AREA"}); c.supportedOf("taxRules", "NONE", {"NONE"}); c.supportedOf("hasButtons", "false", {"false"});
+  c.neutral("handicapProb", "0.0"); c.neutral("compensateAfterPolicyInitProb", "0.0"); c.neutral("sekiForkHackProb", "0.0");
+  c.neutral("handicapAsymmetricPlayoutProb", "0.0"); c.neutral("normalAsymmetricPlayoutProb", "0.0"); c.neutral("switchNetsMidGame", "true");
+  c.neutral("fancyKomiVarying", "false"); c.neutral("drawRandRadius", "0.0"); c.neutral("noResultStdev", "0.0");
 
   k.win_loss_utility_factor = c.num("winLossUtilityFactor", 1.0);
   k.static_score_utility_factor = c.num("staticScoreUtilityFactor", 0.1);
@@ -274,7 +295,7 @@ int main(int argc, char** argv) {
   long maxGamesTotal = 0, seed = 1;
   double modelPollSeconds = 20.0;
   int rank = 0, worldSize = 1, gpuIdx = -1;
-  bool printOnly = false;
+  bool printOnly = false, strict = false;
   for(int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() { if(i + 1 >= argc) die("missing value after " + a); return std::string(argv[++i]); };
@@ -284,6 +305,7 @@ int main(int argc, char** argv) {
     else if(a == "-output-dir") outDir = next();
     else if(a == "-override-config") overrides = next();
     else if(a == "-print-config") printOnly = true;
+    else if(a == "-strict") strict = true;
     else if(a == "-seed") seed = std::atol(next().c_str());
     else if(a == "-model-poll-seconds") modelPollSeconds = std::atof(next().c_str());
     else if(a == "-rank") rank = std::atoi(next().c_str());
@@ -291,7 +313,7 @@ int main(int argc, char** argv) {
     else if(a == "-gpu") gpuIdx = std::atoi(next().c_str());
     else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
     else if(a == "-help" || a == "--help") {
-      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-model-poll-seconds T] [-rank R -world-size N] [-gpu I] [-override-config k=v,...] [-print-config]\n", argv[0]);
+      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-model-poll-seconds T] [-rank R -world-size N] [-gpu I] [-override-config k=v,...] [-strict] [-print-config]\n", argv[0]);
       return 0;
     } else die("unknown argument " + a);
   }
@@ -363,7 +385,9 @@ int main(int argc, char** argv) {
     for(const char* prefix : irrelevant)
       if(e.first.compare(0, std::strlen(prefix), prefix) == 0) cfg.used[e.first] = true;
   for(const auto& e : cfg.kv)
-    if(!cfg.used.count(e.first)) std::fprintf(stderr, "b200_selfplay: note: config key %s is not read by this host\n", e.first.c_str());
+    if(!cfg.used.count(e.first)) cfg.notBuilt.push_back(e.first + " = " + e.second);
+  for(const std::string& what : cfg.notBuilt) std::fprintf(stderr, "b200_selfplay: NOT BUILT (the loop runs WITHOUT it): %s\n", what.c_str());
+  if(strict && !cfg.notBuilt.empty()) die("-strict: options that are not built (listed above)");
 
   if(printOnly) { printConfig(sc); return 0; }
 

@@ -134,15 +134,23 @@ MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRul
     (7, "SIMPLE", 7.5, 30, 0.0, 0.0, False, 15, 2, "forks_only"),    # forks without any other side-loop feature: the fork evaluations get a side loop of their own
     (9, "MIXED", 7.0, 0, 0.5, 0.1, False, 14, 19, "side_positions"), # side positions: forking moves off the main line searched on a third side loop, their rows written with the game
     (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 20, 23, "everything"),     # every option this host has, together
+    (19, "STOCK", 7.5, 40, 0.5, 0.1, False, 12, 29, "none"),         # the reference's stock b18 training configuration (what neither host has is left out and named)
 ])
 def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
     G, V, ROWS_PER_FILE = 3, 20, 60
     cfg = tmp_path / "c.cfg"
-    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nkomiMean = {komi}\n" + (f"maxMovesPerGame = {max_moves}\n" if max_moves else "") +
-                   (MIXED + f"dataBoardLen = {size}\n" if ko == "MIXED" else f"bSizes = {size}\nkoRules = {ko}\n") +
-                   f"policySurpriseDataWeight = {psw}\nvalueSurpriseDataWeight = {vsw}\nuseSearchValueSurprise = {'true' if search_surprise else 'false'}\n"
-                   f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n" + LIMITS[limits])
+    if ko == "STOCK":
+        from test_selfplay_cli import STOCK_B18_SETTINGS
+        V = int(STOCK_B18_SETTINGS["maxVisits"])
+        stock = dict(STOCK_B18_SETTINGS, numGameThreads=G, maxMovesPerGame=max_moves, maxRowsPerTrainFile=ROWS_PER_FILE, firstFileRandMinProp=0.3, b200WavesPerPoll=4)
+        psw, vsw = float(stock["policySurpriseDataWeight"]), float(stock["valueSurpriseDataWeight"])
+        cfg.write_text("".join(f"{k} = {v}\n" for k, v in stock.items()))
+    else:
+        cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nkomiMean = {komi}\n" + (f"maxMovesPerGame = {max_moves}\n" if max_moves else "") +
+                       (MIXED + f"dataBoardLen = {size}\n" if ko == "MIXED" else f"bSizes = {size}\nkoRules = {ko}\n") +
+                       f"policySurpriseDataWeight = {psw}\nvalueSurpriseDataWeight = {vsw}\nuseSearchValueSurprise = {'true' if search_surprise else 'false'}\n"
+                       f"maxRowsPerTrainFile = {ROWS_PER_FILE}\nfirstFileRandMinProp = 0.3\nb200WavesPerPoll = 4\n" + LIMITS[limits])
     out, log = tmp_path / "cpp", tmp_path / "log.jsonl"
     if size == 5:      # `katago selfplay -models-dir`: the newest net of the directory, its files under <output-dir>/<net name>/
         os.makedirs(tmp_path / "nets" / "b6c96-s100-d200")
@@ -234,6 +242,9 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
     if psw == 0 and vsw == 0:
         assert rows == sum(len(d.moves) for d in done)
     weights = [float(w) for d in done for w in (d.target_weight_by_turn_unrounded or d.target_weight_by_turn)]
+    if ko == "STOCK":
+        assert "NOT BUILT (the loop runs WITHOUT it): handicapProb" in r.stderr and "TERRITORY not built" in r.stderr
+        assert any(d.start_hist_moves > 0 for d in done) and len({d.komi for d in done}) >= 3 and any(len(d.side_positions) for d in done)
     if ko == "MIXED":
         assert len({(d.x_size, d.y_size) for d in done}) >= 3 and len({d.ko_rule for d in done}) >= 2
         assert limits in ("forks", "everything") or any(d.x_size != d.y_size for d in done)

@@ -528,15 +528,16 @@ def test_cpp_host_refuses_what_it_does_not_play_and_needs_a_gpu(tmp_path, cpp_ho
     error - there is no CPU path behind the C ABI."""
     import subprocess
     cfg = tmp_path / "c.cfg"
-    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nhandicapProb = 0.1\n")
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nhandicapProb = 0.1\nscoringRules = AREA,TERRITORY\n")
+    r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path), "-strict"], capture_output=True, text=True)
+    assert r.returncode != 0 and "NOT BUILT (the loop runs WITHOUT it): handicapProb = 0.1" in r.stderr and "TERRITORY not built" in r.stderr and "-strict" in r.stderr
+    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nscoringRules = TERRITORY\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode != 0 and "handicapProb" in r.stderr and "selfplay_cli.py" in r.stderr
+    assert r.returncode != 0 and "none of these is built" in r.stderr
     cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9,13\ndataBoardLen = 9\n")
     r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0 and "dataBoardLen" in r.stderr          # the data frame must hold the largest board
-    cfg.write_text("maxVisits = 50\nnumGameThreads = 4\nbSizes = 9\nsekiForkHackProb = 0.04\n")
-    r = subprocess.run([cpp_host, "-config", str(cfg), "-model", tmp_models["tiny_reg"], "-output-dir", str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode != 0 and "sekiForkHackProb" in r.stderr
+
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present: the loud failure without one is checked on CPU boxes")
