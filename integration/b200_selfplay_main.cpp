@@ -178,6 +178,7 @@ kgb_selfplay_config configFromCfg(const Cfg& c, int numGames) {
   k.root_policy_temperature_early = c.num("rootPolicyTemperatureEarly", k.root_policy_temperature);
   k.root_num_symmetries_to_sample = (int32_t)c.num("rootNumSymmetriesToSample", 1);
   k.use_play_selection = 1;
+  k.early_temperature_moves = 30;            // (only read without use_play_selection; the value the Python host passes)
   k.chosen_move_temperature = c.num("chosenMoveTemperature", 0.1);
   k.chosen_move_temperature_early = c.num("chosenMoveTemperatureEarly", 0.5);
   k.chosen_move_temperature_halflife = c.num("chosenMoveTemperatureHalflife", 19.0);
@@ -400,7 +401,7 @@ int main(int argc, char** argv) {
   const int gpu = gpuIdx;
   check(kgb_context_create(&gpu, 1, edge, edge, cfg.flag("useFP16", true) ? 1 : 0, model, &ctx), "creating the evaluator context");
   kgb_handle* handle = nullptr;
-  check(kgb_handle_create(ctx, model, numGames, 1, /*inputs_nhwc=*/1, gpu, &handle), "creating the evaluator handle");
+  check(kgb_handle_create(ctx, model, numGames, /*require_exact_nn_len=*/0, /*inputs_nhwc=*/1, gpu, &handle), "creating the evaluator handle");   // (games may be smaller than the frame)
 
   int rc = 0;
   try {
