@@ -410,6 +410,11 @@ int main(int argc, char** argv) {
     outputs.baseDir = outDir; outputs.writerSeed = writerSeed; outputs.perNet = !modelsDir.empty();
     outputs.maxRowsPerFile = (int)cfg.num("maxRowsPerTrainFile", 20000); outputs.firstFileMinRandProp = cfg.num("firstFileRandMinProp", 1.0); outputs.dataLen = edge;
     outputs.switchTo(modelPath, info.name);
+    // the reference's own log lines (command/selfplay.cpp, program/selfplaymanager.cpp:290-303), on stderr
+    auto logLine = [](const std::string& msg) { std::fprintf(stderr, "%s\n", msg.c_str()); };
+    const long logGamesEvery = std::max(1L, (long)cfg.num("logGamesEvery", 50));
+    logLine("Found new neural net " + outputs.netName);
+    logLine("Loaded latest neural net " + outputs.netName + " from: " + modelPath);
 
     b200::GameSlots slots(handle, sc, edge, edge);
     // side loops for the komi searches: own handles of the same net, a few slots, the loop's parameters without root noise (getNoiselessParams,
@@ -476,11 +481,11 @@ int main(int argc, char** argv) {
     rs.policySurpriseDataWeight = policySurpriseDataWeight; rs.valueSurpriseDataWeight = valueSurpriseDataWeight; rs.useSearchValueSurprise = useSearchValueSurprise;
     rs.hashSeed = loopSeed; rs.weightRandSeed = writerSeed + ":weights";
     rs.play = play; rs.limitsRandSeed = loopSeed ^ 0x4C696D69ULL;        // as selfplay_cli.py: Random(loop_seed ^ 0x4C696D69)
-    long written = 0;
+    long written = 0, gamesStarted = numGames, gamesFinished = 0;
     b200::HostRecorder recorder(slots, rs, [&](int, const b200::FinishedGame& game) {
       if(maxGamesTotal > 0 && written >= maxGamesTotal) return;        // games that end after the last counted one are dropped, like the Python host
       outputs.addGame(game);          // a finished game's rows go to the directory of the net in use when it ended (selfplay.cpp:276-319)
-      written++;
+      written++; gamesFinished++;
       if(forks.enabled() && forkSearcher && !game.endNoResult) {        // Play::maybeForkGame on the finished game
         std::vector<b200::Move> all;
         for(const auto& m : game.startMoves) { b200::Move mv; mv.x = m.first; mv.y = m.second; all.push_back(mv); }
@@ -515,7 +520,21 @@ int main(int argc, char** argv) {
         });
       };
     }
+    auto logStats = [&]() {
+      const kgb_selfplay_stats st = slots.stats();
+      const unsigned long long nnRows = st.total_visits - st.nn_cache_hits - st.instant_playouts;
+      logLine("Games finished: " + std::to_string(gamesFinished));
+      logLine("Moves played: " + std::to_string(st.total_moves));
+      logLine("Data rows: " + std::to_string(outputs.rowsTotal + (outputs.writer ? outputs.writer->rowCount() : 0)));
+      logLine("NN rows: " + std::to_string(nnRows));
+      logLine("NN batches: " + std::to_string(std::max(1ULL, nnRows / (unsigned long long)std::max(1, numGames))));
+      logLine("NN avg batch size: " + std::to_string((double)numGames));
+      logLine("NN cache hits: " + std::to_string(st.nn_cache_hits));
+    };
     recorder.onGameStart = [&](int g) {
+      gamesStarted++;          // the slot's next game started on the device when the previous one ended
+      if(gamesStarted % logGamesEvery == 0) logLine("Started " + std::to_string(gamesStarted) + " games with " + outputs.netName);
+      if(gamesStarted % std::max(1000L, logGamesEvery * 100) == 0) logStats();
       PendingFork started = forkNext[(size_t)g];
       forkNext[(size_t)g] = PendingFork();
       if(started.have) { slots.playMoves(g, started.fork.moves); recorder.startFrom(g, started.fork.moves, 2); }
@@ -586,9 +605,14 @@ int main(int argc, char** argv) {
       kgb_model_free(model); model = next; modelPath = newest;
       swaps++;
       outputs.switchTo(modelPath, nextInfo.name);
-      std::fprintf(stderr, "b200_selfplay: Game loop changing midgame to new neural net: %s (swap %d, after pump %ld)\n", outputs.netName.c_str(), swaps, pumps);
+      logLine("Model loading loop thread loaded new neural net " + outputs.netName);
+      std::fprintf(stderr, "Game loop changing midgame to new neural net: %s (swap %d, after pump %ld)\n", outputs.netName.c_str(), swaps, pumps);
     }
     outputs.close();
+    logStats();
+    logLine("Total games: " + std::to_string(gamesStarted));
+    logLine("Total selfplay runtime (seconds): " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+    logLine("All cleaned up, quitting");
     for(SideLoop* side : {&fairLoop, &leadLoop, &sideLoop}) { side->searcher.reset(); side->slots.reset(); if(side->handle) kgb_handle_free(side->handle); side->handle = nullptr; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const kgb_selfplay_stats st = slots.stats();
