@@ -368,6 +368,8 @@ int main(int argc, char** argv) {
   if(edge > 19) die("dataBoardLen: at most 19");
   if(maxGamesTotal <= 0 && worldSize == 1) maxGamesTotal = (long)cfg.num("numGamesTotal", 0);
   const int wavesPerPoll = (int)cfg.num("b200WavesPerPoll", 16);
+  const bool useFP16 = cfg.flag("b200UseFP16", true);          // false = the fp32-equivalent evaluator (3-term split-fp16 on the tensor pipe)
+  cfg.num("numGamesTotal", 0); cfg.num("logGamesEvery", 50);
   kgb_selfplay_config sc = configFromCfg(cfg, numGames);
   if(!cfg.has("searchRandSeed")) sc.seed = loopSeed;            // every rank its own games
   const double policySurpriseDataWeight = cfg.num("policySurpriseDataWeight", 0.0), valueSurpriseDataWeight = cfg.num("valueSurpriseDataWeight", 0.0);
@@ -399,7 +401,7 @@ int main(int argc, char** argv) {
   check(kgb_model_get_info(model, &info), "kgb_model_get_info");
   kgb_context* ctx = nullptr;
   const int gpu = gpuIdx;
-  check(kgb_context_create(&gpu, 1, edge, edge, cfg.flag("useFP16", true) ? 1 : 0, model, &ctx), "creating the evaluator context");
+  check(kgb_context_create(&gpu, 1, edge, edge, useFP16 ? 1 : 0, model, &ctx), "creating the evaluator context");
   kgb_handle* handle = nullptr;
   check(kgb_handle_create(ctx, model, numGames, /*require_exact_nn_len=*/0, /*inputs_nhwc=*/1, gpu, &handle), "creating the evaluator handle");   // (games may be smaller than the frame)
 
