@@ -29,6 +29,7 @@
 #include <sstream>
 #include <dirent.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "b200_forks.h"
 
@@ -253,6 +254,29 @@ std::string modelNameOf(const std::string& path) {
   return base.substr(0, base.find('.'));
 }
 
+// Rendezvous of the ranks of one node through small files in <output-dir>/.b200_rendezvous (they share the output directory anyway): written
+// under a temporary name and renamed, so a reader sees a whole file or none.
+bool readWhole(const std::string& path, std::string& out) {
+  std::ifstream f(path, std::ios::binary);
+  if(!f) return false;
+  std::stringstream ss; ss << f.rdbuf(); out = ss.str();
+  return true;
+}
+void writeAtomically(const std::string& path, const std::string& bytes) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  { std::ofstream f(tmp, std::ios::binary); if(!f) die("cannot write " + tmp); f << bytes; }
+  if(std::rename(tmp.c_str(), path.c_str()) != 0) die("cannot rename " + tmp);
+}
+std::string waitForFile(const std::string& path, double timeoutSeconds) {
+  const auto t0 = std::chrono::steady_clock::now();
+  std::string bytes;
+  while(!readWhole(path, bytes)) {
+    if(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeoutSeconds) die("timed out waiting for " + path + " (are all ranks running with the same -output-dir, -seed and -nccl-token?)");
+    usleep(20000);
+  }
+  return bytes;
+}
+
 // <output-dir>[/<net name>]/{tdata,sgfs}: one writer per net, as the reference keeps one per NNEvaluator (command/selfplay.cpp:178-225;
 // katago_b200/selfplay_cli.py ModelOutputs).  switchTo() closes the files of the previous net and opens the new net's.
 struct Outputs {
@@ -296,6 +320,7 @@ int main(int argc, char** argv) {
   long maxGamesTotal = 0, seed = 1;
   double modelPollSeconds = 20.0;
   int rank = 0, worldSize = 1, gpuIdx = -1;
+  bool ncclWeights = false; std::string ncclToken;
   bool printOnly = false, strict = false;
   for(int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -312,9 +337,11 @@ int main(int argc, char** argv) {
     else if(a == "-rank") rank = std::atoi(next().c_str());
     else if(a == "-world-size") worldSize = std::atoi(next().c_str());
     else if(a == "-gpu") gpuIdx = std::atoi(next().c_str());
+    else if(a == "-nccl-weights") ncclWeights = true;
+    else if(a == "-nccl-token") ncclToken = next();
     else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
     else if(a == "-help" || a == "--help") {
-      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-model-poll-seconds T] [-rank R -world-size N] [-gpu I] [-override-config k=v,...] [-strict] [-print-config]\n", argv[0]);
+      std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-model-poll-seconds T] [-rank R -world-size N] [-gpu I] [-nccl-weights [-nccl-token T]] [-override-config k=v,...] [-strict] [-print-config]\n", argv[0]);
       return 0;
     } else die("unknown argument " + a);
   }
@@ -417,6 +444,23 @@ int main(int argc, char** argv) {
     const long logGamesEvery = std::max(1L, (long)cfg.num("logGamesEvery", 50));
     logLine("Found new neural net " + outputs.netName);
     logLine("Loaded latest neural net " + outputs.netName + " from: " + modelPath);
+
+    // -nccl-weights (one process per GPU of one node): rank 0 alone polls, reads and packs a new net; the packed weight arena travels from its
+    // device memory into the other ranks' by the library's own ncclBroadcast (kgb_handle_broadcast_staged_weights), every rank commits between
+    // two waves.  The 128-byte NCCL id and the swap announcements go through files in the shared output directory.
+    const std::string rendezvous = outDir + "/.b200_rendezvous", token = "seed" + std::to_string(seed) + (ncclToken.empty() ? "" : "." + ncclToken);
+    const bool collective = ncclWeights && worldSize > 1;
+    if(collective) {
+      if(modelsDir.empty()) die("-nccl-weights needs -models-dir");
+      if(komiAuto || estimateLeadProb > 0 || sidePositionProb > 0 || forkSettings.earlyForkGameProb > 0 || forkSettings.forkGameProb > 0)
+        die("-nccl-weights: the side loops' handles are not part of the weight broadcast (komiAuto, estimateLeadProb, forks, side positions)");
+      if(mkdir(rendezvous.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create " + rendezvous);
+      std::string id(128, '\0');
+      if(rank == 0) { check(kgb_nccl_unique_id(&id[0]), "kgb_nccl_unique_id"); writeAtomically(rendezvous + "/nccl_id." + token, id); }
+      else id = waitForFile(rendezvous + "/nccl_id." + token, 300.0);
+      if(id.size() != 128) die("bad NCCL id file");
+      check(kgb_handle_comm_init(handle, id.data(), rank, worldSize), "kgb_handle_comm_init");
+    }
 
     b200::GameSlots slots(handle, sc, edge, edge);
     // side loops for the komi searches: own handles of the same net, a few slots, the loop's parameters without root noise (getNoiselessParams,
@@ -572,12 +616,58 @@ int main(int argc, char** argv) {
     auto lastPoll = std::chrono::steady_clock::now();
     long pumps = 0; int swaps = 0;
     std::string ignoredModel;
-    while(maxGamesTotal <= 0 || written < maxGamesTotal) {
-      recorder.pump(wavesPerPoll);
-      pumps++;
-      if(fairLoop.searcher) fairLoop.searcher->step(8);        // the side loops advance with the main loop
-      if(leadLoop.searcher) leadLoop.searcher->step(8);
-      if(sideLoop.searcher) sideLoop.searcher->step(8);
+    bool announcedDone = false;
+    auto allRanksDone = [&]() { for(int r = 0; r < worldSize; r++) { std::string x; if(!readWhole(rendezvous + "/done." + token + "." + std::to_string(r), x)) return false; } return true; };
+    for(;;) {
+      const bool done = maxGamesTotal > 0 && written >= maxGamesTotal;
+      if(done && !collective) break;
+      if(!done) {
+        recorder.pump(wavesPerPoll);
+        pumps++;
+        if(fairLoop.searcher) fairLoop.searcher->step(8);        // the side loops advance with the main loop
+        if(leadLoop.searcher) leadLoop.searcher->step(8);
+        if(sideLoop.searcher) sideLoop.searcher->step(8);
+      }
+      if(collective) {
+        // a rank that has finished its games stays in the collective until every rank has: a swap announced meanwhile needs all of them
+        if(done && !announcedDone) { writeAtomically(rendezvous + "/done." + token + "." + std::to_string(rank), "done"); announcedDone = true; }
+        const std::string swapFile = rendezvous + "/swap." + token + "." + std::to_string(swaps + 1);
+        std::string announced;
+        if(rank == 0 && !done) {
+          const auto now = std::chrono::steady_clock::now();
+          if(std::chrono::duration<double>(now - lastPoll).count() >= modelPollSeconds) {
+            lastPoll = now;
+            const std::string newest = newestModel(modelsDir);
+            kgb_model* next = nullptr;
+            if(newest != modelPath && newest != ignoredModel) {
+              if(kgb_model_load_file(newest.c_str(), nullptr, &next) != 0 || kgb_handle_stage_weights(handle, next) != 0) {
+                std::fprintf(stderr, "b200_selfplay: %s: %s; keeping %s\n", newest.c_str(), kgb_last_error(), outputs.netName.c_str());
+                if(next) { kgb_model_free(next); ignoredModel = newest; }
+              }
+              else {
+                check(kgb_handle_wait_staged(handle), "kgb_handle_wait_staged");
+                kgb_model_free(model); model = next;
+                writeAtomically(swapFile, newest);         // the other ranks enter the broadcast when they see this
+                announced = newest;
+              }
+            }
+          }
+        }
+        else if(rank != 0) readWhole(swapFile, announced);
+        if(!announced.empty()) {
+          float ms = 0.0f;
+          check(kgb_handle_broadcast_staged_weights(handle, 0, &ms), "kgb_handle_broadcast_staged_weights");
+          check(kgb_handle_commit_weights(handle), "committing the new weights");
+          slots.clearNNCache();
+          modelPath = announced;
+          swaps++;
+          outputs.switchTo(modelPath, modelNameOf(modelPath));
+          logLine("Model loading loop thread loaded new neural net " + outputs.netName);
+          std::fprintf(stderr, "Game loop changing midgame to new neural net: %s (swap %d, after pump %ld, ncclBroadcast %.3f ms)\n", outputs.netName.c_str(), swaps, pumps, ms);
+        }
+        else if(done) { if(allRanksDone()) break; usleep(20000); }       // (an announcement is always answered before leaving)
+        continue;
+      }
       if(modelsDir.empty() || (maxGamesTotal > 0 && written >= maxGamesTotal)) continue;
       const auto now = std::chrono::steady_clock::now();
       if(std::chrono::duration<double>(now - lastPoll).count() < modelPollSeconds) continue;

@@ -191,6 +191,15 @@ int kgb_handle_sync(kgb_handle*) { return 0; }
 int kgb_handle_stage_weights(kgb_handle*, const kgb_model*) { return 0; }       // weight hot-swap: nothing to swap in the mock
 int kgb_handle_commit_weights(kgb_handle*) { return 0; }
 int kgb_selfplay_clear_nn_cache(kgb_selfplay*) { return 0; }
+int kgb_handle_wait_staged(kgb_handle*) { return 0; }
+// the weight broadcast between ranks: no device memory here, the calls only have to line up
+int kgb_nccl_unique_id(void* id) { for(int i = 0; i < 128; i++) ((unsigned char*)id)[i] = (unsigned char)(i * 7 + 1); return 0; }
+int kgb_handle_comm_init(kgb_handle*, const void* id, int rank, int numRanks) {
+  for(int i = 0; i < 128; i++) if(((const unsigned char*)id)[i] != (unsigned char)(i * 7 + 1)) { g_err = "mock: not the id rank 0 made"; return 1; }
+  if(rank < 0 || rank >= numRanks) { g_err = "mock: bad rank"; return 1; }
+  return 0;
+}
+int kgb_handle_broadcast_staged_weights(kgb_handle*, int, float* ms) { if(ms) *ms = 0.0f; return 0; }
 
 int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfplay** out) {
   GUARD({

@@ -345,3 +345,44 @@ def test_cpp_host_follows_a_new_net_in_the_models_directory(tmp_path, host_on_mo
     assert set(done) == {"netA-s100", "netB-s200"} and sorted(os.listdir(out)) == ["netA-s100", "netB-s200"]
     rows = sum(_same_tree(str(out / name), str(tmp_path / "py" / name), size) for name in ("netA-s100", "netB-s200"))
     assert rows == summary["rows"] == outputs.rows_total
+
+
+def test_cpp_host_ranks_swap_nets_together_under_nccl_weights(tmp_path, host_on_mock):
+    """-nccl-weights, two ranks of one node (one process per GPU): rank 0 alone polls the models directory, packs the new net and announces the swap; both
+    ranks join the library's broadcast of the packed weights and commit, each keeps playing its share of the games with its own seeds and file names, and a
+    rank that finishes early stays until every rank has.  (On the mock the collective calls only have to line up; the broadcast itself is the library's,
+    measured on GPUs through the Python host: profiles/r02_*weight_broadcast*.)"""
+    import json, re
+    G, V, size = 3, 20, 7
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nbSizes = {size}\nkomiMean = 6.5\nmaxMovesPerGame = 20\nmaxRowsPerTrainFile = 40\nb200WavesPerPoll = 4\n")
+    nets = tmp_path / "nets"
+    os.makedirs(nets / "netA-s100"); os.makedirs(nets / "netB-s200")
+    (nets / "netA-s100" / "model.bin.gz").write_bytes(b"unused")
+    os.utime(nets / "netA-s100" / "model.bin.gz", (1000, 1000))
+    out = tmp_path / "out"
+    os.makedirs(out)
+    procs = []
+    for rank in (0, 1):
+        env = dict(os.environ, KGB_MOCK_LOG=str(tmp_path / f"log{rank}.jsonl"))
+        if rank == 0:
+            env["KGB_MOCK_NEW_MODEL"] = f"60:{nets / 'netB-s200' / 'model.bin.gz'}"
+        procs.append(subprocess.Popen([host_on_mock, "-models-dir", str(nets), "-config", str(cfg), "-output-dir", str(out), "-max-games-total", "25", "-seed", "4",
+                                       "-model-poll-seconds", "0", "-rank", str(rank), "-world-size", "2", "-gpu", "0", "-nccl-weights"],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert [p.returncode for p in procs] == [0, 0], [o[1][-1500:] for o in outs]
+    summaries = [json.loads(o[0].strip().splitlines()[-1]) for o in outs]
+    assert [s["games_written"] for s in summaries] == [13, 12] and [s["net_swaps"] for s in summaries] == [1, 1]
+    for o in outs:
+        assert re.search(r"changing midgame to new neural net: netB-s200 \(swap 1, after pump \d+, ncclBroadcast", o[1]), o[1][-800:]
+    files = {name: sorted(os.listdir(out / name / "tdata")) for name in ("netA-s100", "netB-s200")}
+    assert len(files["netA-s100"]) >= 2 and len(files["netB-s200"]) >= 2 and len(set(files["netA-s100"]) | set(files["netB-s200"])) == sum(len(v) for v in files.values())
+    rows = sum(np.load(out / name / "tdata" / f)["globalTargetsNC"].shape[0] for name, fs in files.items() for f in fs)
+    assert rows == sum(s["rows"] for s in summaries)
+    assert len(os.listdir(out / "netA-s100" / "sgfs")) == 2 and len(os.listdir(out / "netB-s200" / "sgfs")) == 2        # one record file per rank and net
+    hashes = set()
+    for name in files:
+        for f in os.listdir(out / name / "sgfs"):
+            hashes.update(re.findall(r"gameHash=([0-9A-F]{32})", open(out / name / "sgfs" / f).read()))
+    assert len(hashes) == 25          # every rank its own games
