@@ -2,6 +2,7 @@
 // kgb_selfplay_config and the per-game draws, the newest net of a models directory.  Plain C++17.
 #pragma once
 #include <cctype>
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -258,6 +259,45 @@ inline b200::GameInitializer::Config gameInitConfigFromCfg(const Cfg& cfg, int* 
   if(edge > 19) die("dataBoardLen: at most 19");
   *dataLen = edge;
   return gi;
+}
+
+// The search keys a bot of a match can have of its own (`maxVisits0` overrides the shared `maxVisits` for bot 0: Setup::loadParams with
+// SETUP_FOR_MATCH, program/setup.cpp) - the keys configFromCfg reads
+inline const std::vector<std::string>& searchKeys() {
+  static const std::vector<std::string> keys = {
+    "maxVisits", "cpuctExploration", "cpuctExplorationLog", "cpuctExplorationBase", "fpuReductionMax", "rootFpuReductionMax", "fpuLossProp", "rootFpuLossProp",
+    "fpuParentWeight", "fpuParentWeightByVisitedPolicy", "fpuParentWeightByVisitedPolicyPow", "valueWeightExponent", "cpuctUtilityStdevPrior",
+    "cpuctUtilityStdevPriorWeight", "cpuctUtilityStdevScale", "rootDesiredPerChildVisitsCoeff", "subtreeValueBiasFactor", "subtreeValueBiasWeightExponent",
+    "useGraphSearch", "graphSearchRepBound", "rootNoiseEnabled", "rootDirichletNoiseTotalConcentration", "rootDirichletNoiseWeight", "rootPolicyTemperature",
+    "rootPolicyTemperatureEarly", "chosenMoveTemperature", "chosenMoveTemperatureEarly", "chosenMoveTemperatureHalflife", "chosenMoveTemperatureOnlyBelowProb",
+    "chosenMoveSubtract", "chosenMovePrune", "useLcbForSelection", "lcbStdevs", "minVisitPropForLCB", "useNonBuggyLcb", "winLossUtilityFactor",
+    "staticScoreUtilityFactor", "dynamicScoreUtilityFactor", "dynamicScoreCenterZeroWeight", "dynamicScoreCenterScale", "noResultUtilityForWhite",
+    "drawEquivalentWinsForWhite", "rootNumSymmetriesToSample", "nnCacheSizePowerOfTwo", "maxMovesPerGame", "rootEndingBonusPoints", "rootPruneUselessMoves"};
+  return keys;
+}
+// The configuration bot `idx` of a match sees: a search key with the bot's index appended overrides the shared one; keys of other bots, bot
+// names and model files are left out (katago_b200/match_cli.py bot_cfg)
+inline Cfg botCfg(const Cfg& cfg, int idx) {
+  Cfg out;
+  auto perBot = [](const std::string& base) {
+    if(base == "botName" || base == "nnModelFile") return true;
+    for(const std::string& k : searchKeys()) if(k == base) return true;
+    return false;
+  };
+  for(const auto& e : cfg.kv) {
+    const std::string& k = e.first;
+    size_t digits = k.size();
+    while(digits > 0 && std::isdigit((unsigned char)k[digits - 1])) digits--;
+    if(k == "botName" || k == "nnModelFile" || (digits < k.size() && digits > 0 && perBot(k.substr(0, digits)))) continue;
+    out.kv[k] = e.second;
+  }
+  for(const std::string& k : searchKeys()) { auto it = cfg.kv.find(k + std::to_string(idx)); if(it != cfg.kv.end()) out.kv[k] = it->second; }
+  return out;
+}
+
+inline void makeDirsFor(const std::string& path) {       // mkdir -p
+  for(size_t i = 1; i <= path.size(); i++)
+    if(i == path.size() || path[i] == '/') { const std::string p = path.substr(0, i); if(mkdir(p.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create " + p); }
 }
 
 // keys that only place or log the reference's own CPU threads and evaluator servers: nothing to do here

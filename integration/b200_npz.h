@@ -88,7 +88,7 @@ struct FinishedGame {
   std::vector<std::pair<int, int>> moves;                 // (x, y), (-1, -1) = pass
   std::vector<std::pair<int, int>> startMoves;            // the moves before the training period (startHist.moveHistory: policy-initialised opening), black first
   std::string koRule = "SIMPLE"; bool multiStoneSuicideLegal = true;
-  int winner = 0; float finalWhiteMinusBlackScore = 0;
+  int winner = 0; float finalWhiteMinusBlackScore = 0; bool resigned = false;      // resigned: BoardHistory::isResignation (match play)
   std::vector<uint8_t> finalFullArea, finalOwnership;     // row-major [ySize * xSize]: 0 none, 1 black, 2 white
   std::vector<float> finalWhiteScoring;
   std::vector<std::shared_ptr<SidePosition>> sidePositions;
@@ -452,6 +452,7 @@ inline std::string writeSgf(const FinishedGame& d, const std::string& bName, con
   std::string result;
   if(d.endFinished) {
     if(d.endNoResult) result = "Void";
+    else if(d.resigned) result = d.winner == P_BLACK ? "B+R" : "W+R";          // WriteSgf::printGameResult
     else if(d.winner == P_BLACK) result = "B+" + g(-d.finalWhiteMinusBlackScore);
     else if(d.winner == P_WHITE) result = "W+" + g(d.finalWhiteMinusBlackScore);
     else result = "0";

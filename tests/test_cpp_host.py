@@ -53,6 +53,9 @@ def _replay_slots_with_limits(log, G, size, V):
         def search_limits(self):
             return self.budget.copy(), self.plain.copy()
 
+        def release(self, mask=None):
+            self.released = [True] * G if mask is None else [bool(m) for m in mask]
+
         # per-game board, rules and komi: of the games in progress, of each slot's next game and of its last finished one
         def set_game_setup(self, setups, also_current_games=False):
             self.next_setup = np.array(setups, np.int32).reshape(G, 4).copy()
@@ -71,8 +74,12 @@ def _replay_slots_with_limits(log, G, size, V):
         def play_moves_game(self, slot, moves):
             ev = self.queues[slot].pop(0)
             assert ev["ev"] == "playmoves" and [tuple(m) for m in ev["moves"]] == [(-1, -1) if m is None else (int(m[0]), int(m[1])) for m in moves], (ev, moves)
+            before = self.root[slot]["move_num"]
             self.root[slot] = self.queues[slot].pop(0)
             assert self.root[slot]["ev"] == "root"
+            if moves and self.root[slot]["move_num"] < before + len(moves):        # a move ended the game: the slot took the setup and komi handed over
+                self.last_setup[slot], self.cur_setup[slot] = self.cur_setup[slot].copy(), self.next_setup[slot].copy()
+                self.last_komi[slot], self.cur_komi[slot] = self.cur_komi[slot], self.next_komi[slot]
 
         # policy-initialised openings: the mock plays a whole opening when the game starts and lists it with every root of the game
         def set_policy_init(self, num_moves, temperature=1.0, also_current_games=False):
@@ -386,3 +393,114 @@ def test_cpp_host_ranks_swap_nets_together_under_nccl_weights(tmp_path, host_on_
         for f in os.listdir(out / name / "sgfs"):
             hashes.update(re.findall(r"gameHash=([0-9A-F]{32})", open(out / name / "sgfs" / f).read()))
     assert len(hashes) == 25          # every rank its own games
+
+
+@pytest.fixture(scope="module")
+def gatekeeper_on_mock(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("cppgate_mock") / "b200_gatekeeper_mock"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-mfpmath=sse", "-DNDEBUG", "-DNO_GIT_REVISION", "-DNO_LIBZIP", "-w", "-I" + REF, "-I" + REF + "/external",
+                    "-isystem", REF + "/external/tclap-1.2.5/include", "-isystem", REF + "/external/filesystem-1.5.8/include", "-I" + ROOT, "-o", str(exe),
+                    os.path.join(ROOT, "integration", "b200_gatekeeper_main.cpp"), os.path.join(ROOT, "tests", "mock", "kgb200_mock.cpp"),
+                    "-Wl,--start-group", REF_LIB, "-Wl,--end-group", "-lz", "-lpthread"], check=True, cwd=ROOT)
+    return str(exe)
+
+
+@pytest.mark.parametrize("resign,required,seed", [(False, 0.5, 3), (True, 0.5, 8), (False, 0.9, 5)])
+def test_cpp_gatekeeper_plays_the_match_the_python_gatekeeper_plays(tmp_path, gatekeeper_on_mock, resign, required, seed):
+    """`katago gatekeeper` as a C++-only host (integration/b200_gatekeeper_main.cpp + b200_match.h) on the mock's two loops against the Python match
+    engine (katago_b200/match_play.py) on their logs: the same games move for move and colour for colour (the record file character for character), the
+    same points, the same early stop, and the directory protocol's verdict - the candidate moved to the accepted or the rejected directory, the
+    self-play directories of an accepted net created."""
+    import re
+    from katago_b200 import gatekeeper_cli as GK, selfplay_cli as C
+    from katago_b200.game_initializer import GameInitializer
+    from katago_b200.match_play import MatchPlay
+    from katago_b200.npz_writer import write_sgf
+    G, V, size, total = 4, 20, 9, 14
+    cfg = tmp_path / "g.cfg"
+    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nnumGamesPerGating = {total}\nbSizes = 7,9\nbSizeRelProbs = 1,1\nkoRules = SIMPLE,POSITIONAL\nkomiMean = 7.0\nkomiStdev = 1.0\n"
+                   "maxMovesPerGame = 40\nb200WavesPerPoll = 4\n" + ("allowResignation = true\nresignThreshold = -0.2\nresignConsecTurns = 2\n" if resign else ""))
+    dirs = {k: tmp_path / k for k in ("test", "accepted", "rejected", "sgfs", "selfplay")}
+    os.makedirs(dirs["test"] / "cand-s300"); os.makedirs(dirs["accepted"] / "base-s200")
+    (dirs["accepted"] / "base-s200" / "model.bin.gz").write_bytes(b"unused")
+    os.utime(dirs["accepted"] / "base-s200", (1000, 1000))
+    (dirs["test"] / "cand-s300" / "model.bin.gz").write_bytes(b"unused")
+    log = tmp_path / "log.jsonl"
+    r = subprocess.run([gatekeeper_on_mock, "-config", str(cfg), "-test-models-dir", str(dirs["test"]), "-sgf-output-dir", str(dirs["sgfs"]), "-accepted-models-dir", str(dirs["accepted"]),
+                        "-rejected-models-dir", str(dirs["rejected"]), "-selfplay-dir", str(dirs["selfplay"]), "-required-candidate-win-prop", str(required), "-games-per-gpu", "8",
+                        "-quit-if-no-nets-to-test", "-seed", str(seed)], env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+    # the Python match engine on the two loops' logs
+    kw, data, _ = C.selfplay_kwargs_from_cfg(C.parse_cfg(str(cfg)))
+    loops = []
+    for i in (1, 2):
+        lp = _replay_slots_with_limits(str(log) if i == 1 else f"{log}.{i}", G, size, V)
+        lp.max_visits = V
+        loops.append(lp)
+    records = []
+    mp = MatchPlay(loops, ("base-s200", "cand-s300"), total, GameInitializer(seed=seed ^ 0x4761746B, **data["game_init"]),
+                   on_game=lambda slot, game, b, w, result: records.append(write_sgf(game, b, w)), allow_resignation=resign, resign_threshold=-0.2, resign_consec_turns=2)
+    mp.run(waves=4, stop=lambda m: GK.early_verdict(m.win_points[1], m.games_tallied, total, required) != 0)
+    m = re.search(r"Candidate (won|lost) match, score ([0-9.]+) to ([0-9.]+) in (\d+) games", r.stderr)
+    assert m, r.stderr[-1500:]
+    assert (float(m.group(2)), float(m.group(3)), int(m.group(4))) == (round(mp.win_points[1], 3), round(mp.win_points[0], 3), mp.games_tallied)
+    accepted = GK.candidate_is_accepted(mp.win_points[1], mp.games_tallied, required)
+    assert (m.group(1) == "won") == accepted
+    sgf_files = os.listdir(dirs["sgfs"] / "cand-s300")
+    assert len(sgf_files) == 1 and open(dirs["sgfs"] / "cand-s300" / sgf_files[0]).read() == "".join(s + "\n" for s in records) and len(records) == mp.games_tallied
+    assert os.path.isdir(dirs["accepted" if accepted else "rejected"] / "cand-s300") and not os.listdir(dirs["test"])
+    assert os.path.isdir(dirs["selfplay"] / "cand-s300" / "tdata") == accepted
+    if resign:
+        assert any("+R]" in s for s in records)
+    if required == 0.9:
+        assert mp.games_tallied < total and "terminating remaning games" in r.stderr          # stopped as soon as the verdict could not change
+
+
+def test_cpp_match_plays_two_named_bots_like_the_python_match(tmp_path):
+    """`katago match` for two named bots as a C++-only host (integration/b200_match_main.cpp): per-bot search keys (maxVisits0 / maxVisits1), alternating
+    colours, per-game setups - against the Python match engine on the mock loops' logs: the record file character for character, the same wins and points."""
+    import re
+    exe = tmp_path / "b200_match_mock"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-mfpmath=sse", "-DNDEBUG", "-DNO_GIT_REVISION", "-DNO_LIBZIP", "-w", "-I" + REF, "-I" + REF + "/external",
+                    "-isystem", REF + "/external/tclap-1.2.5/include", "-isystem", REF + "/external/filesystem-1.5.8/include", "-I" + ROOT, "-o", str(exe),
+                    os.path.join(ROOT, "integration", "b200_match_main.cpp"), os.path.join(ROOT, "tests", "mock", "kgb200_mock.cpp"),
+                    "-Wl,--start-group", REF_LIB, "-Wl,--end-group", "-lz", "-lpthread"], check=True, cwd=ROOT)
+    from katago_b200 import match_cli as MC, selfplay_cli as C
+    from katago_b200.game_initializer import GameInitializer
+    from katago_b200.match_play import MatchPlay
+    from katago_b200.npz_writer import write_sgf
+    G, size, total, seed = 4, 9, 11, 6
+    (tmp_path / "a.bin").write_bytes(b"unused"); (tmp_path / "b.bin").write_bytes(b"unused")
+    cfg = tmp_path / "m.cfg"
+    cfg.write_text(f"numBots = 2\nbotName0 = deep\nbotName1 = shallow\nnnModelFile0 = {tmp_path / 'a.bin'}\nnnModelFile1 = {tmp_path / 'b.bin'}\nmaxVisits0 = 24\nmaxVisits1 = 8\n"
+                   f"cpuctExploration1 = 1.3\nnumGameThreads = {G}\nnumGamesTotal = {total}\nbSizes = 7,9\nbSizeRelProbs = 1,2\nkomiMean = 6.5\nkomiStdev = 0.5\nmaxMovesPerGame = 36\n"
+                   "b200WavesPerPoll = 4\nallowResignation = true\nresignThreshold = -0.3\nresignConsecTurns = 3\n")
+    log = tmp_path / "log.jsonl"
+    r = subprocess.run([str(exe), "-config", str(cfg), "-sgf-output-dir", str(tmp_path / "sgfs"), "-log-file", str(tmp_path / "match.log"), "-seed", str(seed)],
+                       env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "for bot deep (maxVisits 24)" in r.stderr and "for bot shallow (maxVisits 8)" in r.stderr
+
+    full = C.parse_cfg(str(cfg))
+    assert MC.bot_cfg(full, 1)["cpuctExploration"] == "1.3" and "cpuctExploration" not in MC.bot_cfg(full, 0)
+    _, data0, _ = C.selfplay_kwargs_from_cfg({k: v for k, v in MC.bot_cfg(full, 0).items() if k not in ("numBots", "numGamesTotal")})
+    loops = []
+    for i, visits in ((1, 24), (2, 8)):
+        lp = _replay_slots_with_limits(str(log) if i == 1 else f"{log}.{i}", G, size, visits)
+        lp.max_visits = visits
+        loops.append(lp)
+    records, wins = [], {"deep": 0, "shallow": 0, "none": 0}
+
+    def on_game(slot, game, b, w, result):
+        records.append(write_sgf(game, b, w))
+        wins[b if result.startswith("B") else w if result.startswith("W") else "none"] += 1
+    mp = MatchPlay(loops, ["deep", "shallow"], total, GameInitializer(seed=seed ^ 0x4D617463, **data0["game_init"]), on_game=on_game, draw_equivalent_wins_for_white=0.5,
+                   no_result_utility_for_white=0.0, allow_resignation=True, resign_threshold=-0.3, resign_consec_turns=3)
+    mp.run(waves=4)
+    files = os.listdir(tmp_path / "sgfs")
+    assert len(files) == 1 and open(tmp_path / "sgfs" / files[0]).read() == "".join(s + "\n" for s in records) and len(records) == total == mp.games_tallied
+    m = re.search(r"Match finished: deep (\d+) wins, shallow (\d+) wins, (\d+) draws or void; points ([0-9.]+) - ([0-9.]+) in (\d+) games", r.stderr)
+    assert m and (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (wins["deep"], wins["shallow"], wins["none"]), r.stderr[-600:]
+    assert (float(m.group(4)), float(m.group(5)), int(m.group(6))) == (round(mp.win_points[0], 1), round(mp.win_points[1], 1), total)
+    assert open(tmp_path / "match.log").read().count("\n") >= total + 3
