@@ -1,0 +1,106 @@
+"""First runs of the C++-only hosts (katago_b200/b200_selfplay, b200_gatekeeper: integration/*_main.cpp) on a real GPU.
+
+They were written after this round's GPU minutes were spent, so until now they are validated on the CPU only - against the Python hosts on a mock of
+the C ABI (tests/test_cpp_host.py).  These tests run last (file name) and are marked xfail(strict=False): a pass shows up as XPASS in the GPU suite's
+summary, a failure as xfailed - it cannot turn the suite red or stop it (-x) - and the processes run under a timeout of their own."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SELFPLAY = os.path.join(ROOT, "katago_b200", "b200_selfplay")
+GATEKEEPER = os.path.join(ROOT, "katago_b200", "b200_gatekeeper")
+
+CFG = """maxVisits = 24
+numGameThreads = 16
+bSizes = 7,9
+bSizeRelProbs = 1,2
+koRules = SIMPLE,POSITIONAL
+multiStoneSuicideLegals = false,true
+komiMean = 7.0
+komiStdev = 1.0
+maxMovesPerGame = 60
+dataBoardLen = 9
+nnCacheSizePowerOfTwo = 16
+rootNoiseEnabled = true
+rootNumSymmetriesToSample = 2
+policySurpriseDataWeight = 0.5
+valueSurpriseDataWeight = 0.1
+cheapSearchProb = 0.25
+cheapSearchVisits = 8
+cheapSearchTargetWeight = 0.0
+initGamesWithPolicy = true
+policyInitAreaProp = 0.04
+estimateLeadProb = 0.1
+estimateLeadVisits = 6
+earlyForkGameProb = 0.2
+earlyForkGameExpectedMoveProp = 0.1
+forkGameProb = 0.1
+forkGameMinChoices = 2
+earlyForkGameMaxChoices = 3
+forkGameMaxChoices = 3
+forkSidePositionProb = 0.05
+maxRowsPerTrainFile = 400
+b200WavesPerPoll = 8
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU run of the C++-only selfplay host (CPU-validated so far)")
+@pytest.mark.skipif(not os.path.exists(SELFPLAY), reason="katago_b200/b200_selfplay not built (__graft_entry__.build())")
+def test_cpp_selfplay_host_on_the_device(tmp_path, tmp_models):
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text(CFG)
+    out = tmp_path / "out"
+    r = subprocess.run([SELFPLAY, "-model", tmp_models["tiny_reg"], "-config", str(cfg), "-output-dir", str(out), "-max-games-total", "24", "-seed", "3"],
+                       capture_output=True, text=True, timeout=150)
+    print(r.stderr[-3000:])
+    assert r.returncode == 0, r.stderr[-2000:]
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    print("C++ selfplay host on the device:", summary)
+    assert summary["games_written"] == 24 and summary["rows"] > 100 and summary["visits"] > 1000
+    files = sorted(os.listdir(out / "tdata"))
+    assert files and all(f.endswith(".npz") and len(f) == 20 for f in files)
+    rows = 0
+    for f in files:
+        z = np.load(out / "tdata" / f)
+        n = z["globalTargetsNC"].shape[0]
+        rows += n
+        assert z["binaryInputNCHWPacked"].shape == (n, 22, 11) and z["policyTargetsNCMove"].shape == (n, 2, 82) and z["valueTargetsNCHW"].shape == (n, 5, 9, 9)
+        planes = np.unpackbits(z["binaryInputNCHWPacked"], axis=2)[:, :, :81]
+        assert (planes[:, 0].sum(axis=1) >= 49).all()                       # the board mask: 7x7 .. 9x9 points
+        assert not (planes[:, 1] & planes[:, 2]).any()                      # own and opponent stones never overlap
+        assert (z["policyTargetsNCMove"][:, 0].sum(axis=1) > 0).all() and np.isfinite(z["globalTargetsNC"]).all()
+        assert set(np.unique(z["globalTargetsNC"][:, 63])) == {3.0}         # data format version
+    assert rows == summary["rows"]
+    sgfs = os.listdir(out / "sgfs")
+    assert len(sgfs) == 1 and open(out / "sgfs" / sgfs[0]).read().count("\n") == 24
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU run of the C++-only gatekeeper host (CPU-validated so far)")
+@pytest.mark.skipif(not os.path.exists(GATEKEEPER), reason="katago_b200/b200_gatekeeper not built (__graft_entry__.build())")
+def test_cpp_gatekeeper_host_on_the_device(tmp_path, tmp_models):
+    import shutil
+    cfg = tmp_path / "g.cfg"
+    cfg.write_text("maxVisits = 16\nnumGameThreads = 8\nnumGamesPerGating = 10\nbSizes = 9\nkomiMean = 7.0\nmaxMovesPerGame = 60\nchosenMoveTemperatureEarly = 0.5\n")
+    for d in ("test/cand-s2", "accepted/base-s1"):
+        os.makedirs(tmp_path / d)
+    shutil.copy(tmp_models["tiny_reg"], tmp_path / "accepted" / "base-s1" / "model.bin")
+    os.utime(tmp_path / "accepted" / "base-s1", (1000, 1000))
+    shutil.copy(tmp_models["tiny_nbt"], tmp_path / "test" / "cand-s2" / "model.bin")
+    r = subprocess.run([GATEKEEPER, "-config", str(cfg), "-test-models-dir", str(tmp_path / "test"), "-sgf-output-dir", str(tmp_path / "sgfs"),
+                        "-accepted-models-dir", str(tmp_path / "accepted"), "-rejected-models-dir", str(tmp_path / "rejected"), "-quit-if-no-nets-to-test", "-games-per-gpu", "8"],
+                       capture_output=True, text=True, timeout=150)
+    print(r.stderr[-3000:])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert ("Candidate won match" in r.stderr) != ("Candidate lost match" in r.stderr)
+    won = "Candidate won match" in r.stderr
+    assert os.path.isdir(tmp_path / ("accepted" if won else "rejected") / "cand-s2") and not os.listdir(tmp_path / "test")
+    records = os.listdir(tmp_path / "sgfs" / "cand-s2")
+    assert len(records) == 1 and open(tmp_path / "sgfs" / "cand-s2" / records[0]).read().count("(;FF[4]") >= 5
