@@ -14,6 +14,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -31,6 +32,7 @@ struct Slot {
   Board board; BoardHistory hist; Player pla = P_BLACK;
   int moveNum = 0, gameIndex = 0;
   int32_t setup[4] = {0, 0, 0, 1}; float komi = 7.5f;      // this game's board X, Y, ko rule, multi-stone suicide; komi
+  int wavesLeft = 0;                // KGB_MOCK_UNEVEN: waves the search of the current root still needs before its visits reach the budget
   int initPending = 0; std::vector<int16_t> initMoves;      // policy-initialised opening: moves to play when the game starts / the ones played (frame positions)
   bool held = true;                 // searches finish instantly in the mock
   // what the "search" of the current root found
@@ -47,7 +49,7 @@ struct kgb_model { int dummy; };
 struct kgb_context { int x, y; };
 struct kgb_handle { int x, y; };
 struct kgb_selfplay {
-  kgb_selfplay_config cfg; int X, Y; Rules rules; Lcg rng{1}; std::vector<Slot> slots; std::vector<uint8_t> released; std::ofstream log;
+  kgb_selfplay_config cfg; int X, Y; Rules rules; Lcg rng{1}, waveRng{12345}; std::vector<Slot> slots; std::vector<uint8_t> released; std::ofstream log;
   // per-root search limits (kgb_selfplay_set_next_search_limits): the current roots' and, per slot, those of the root after its next move [goes on, new game]
   std::vector<int32_t> budget, nextBudget; std::vector<uint8_t> plain, nextPlain;
   // per-game board, rules and komi (kgb_selfplay_set_game_setup / set_komi): of each slot's next game and of its last finished one
@@ -88,6 +90,9 @@ static void searchRoot(kgb_selfplay* sp, int g) {
   s.rowSpatial.assign((size_t)X * Y * 22, 0.0f); s.rowGlobal.assign(19, 0.0f);
   NNInputs::fillRowV7(s.board, s.hist, s.pla, ip, X, Y, true, s.rowSpatial.data(), s.rowGlobal.data());
   s.held = true;
+  // KGB_MOCK_UNEVEN = K: searches take 1..K waves (else they finish at once), so that hosts see slots finish at different times like on the device
+  static const int uneven = getenv("KGB_MOCK_UNEVEN") ? atoi(getenv("KGB_MOCK_UNEVEN")) : 0;
+  s.wavesLeft = uneven > 0 ? 1 + (int)(sp->waveRng.next() % (uint32_t)uneven) : 0;
   // log
   std::ofstream& o = sp->log;
   auto arr = [&](const char* name, auto& v, bool last = false) {
@@ -101,7 +106,7 @@ static void searchRoot(kgb_selfplay* sp, int g) {
   std::vector<int> colors((size_t)X * Y, 0);
   for(int y = 0; y < BY; y++) for(int x = 0; x < BX; x++) colors[(size_t)y * X + x] = (int)s.board.colors[Location::getLoc(x, y, BX)];
   std::vector<double> rs(s.rootStats, s.rootStats + 5), rn(s.rootNN, s.rootNN + 5);
-  o << "{\"ev\":\"root\",\"slot\":" << g << ",\"move_num\":" << s.moveNum << ",\"black_to_move\":" << (s.pla == P_BLACK ? 1 : 0) << ",";
+  o << "{\"ev\":\"root\",\"slot\":" << g << ",\"waves_needed\":" << s.wavesLeft << ",\"move_num\":" << s.moveNum << ",\"black_to_move\":" << (s.pla == P_BLACK ? 1 : 0) << ",";
   arr("colors", colors); arr("edge_visits", s.edgeVisits); arr("node_visits", s.nodeVisits); arr("policy", s.policy); arr("child_stats", s.childStats);
   arr("psv", s.psv); arr("root_stats", rs); arr("root_nn", rn); arr("init_moves", s.initMoves); arr("row_spatial", s.rowSpatial); arr("row_global", s.rowGlobal, true);
   o << "}\n";
@@ -227,7 +232,7 @@ int kgb_selfplay_create(kgb_handle* h, const kgb_selfplay_config* c, kgb_selfpla
   })
 }
 void kgb_selfplay_free(kgb_selfplay* sp) { delete sp; }
-int kgb_selfplay_run(kgb_selfplay* sp, int) {
+int kgb_selfplay_run(kgb_selfplay* sp, int waves) {
   GUARD({
     ensureStarted(sp);
     // KGB_MOCK_NEW_MODEL = "<runs>:<path>": a new net appears in the models directory while the host is running (the trainer's export)
@@ -236,7 +241,9 @@ int kgb_selfplay_run(kgb_selfplay* sp, int) {
       const std::string spec = nm; const size_t colon = spec.find(':');
       if(++runs == atoi(spec.substr(0, colon).c_str())) { std::ofstream f(spec.substr(colon + 1)); f << "unused"; }
     }
+    for(size_t g = 0; g < sp->slots.size(); g++) if(!sp->released[g]) sp->slots[g].wavesLeft = std::max(0, sp->slots[g].wavesLeft - waves);      // searches go on
     for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) {
+      if(sp->slots[g].wavesLeft > 0) throw std::runtime_error("mock: a slot was released before its search had finished");
       sp->released[g] = 0; advance(sp, (int)g);
       const size_t k = 2 * g + ((sp->slots[g].last[1] & 1) ? 1 : 0);       // the new root takes the limits handed over for it
       sp->budget[g] = sp->nextBudget[k]; sp->plain[g] = sp->nextPlain[k];
@@ -245,7 +252,11 @@ int kgb_selfplay_run(kgb_selfplay* sp, int) {
   })
 }
 int kgb_selfplay_release(kgb_selfplay* sp, const uint8_t* mask) { for(size_t g = 0; g < sp->slots.size(); g++) sp->released[g] = mask ? mask[g] : 1; return 0; }
-int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) { ensureStarted(sp); for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->budget[g]; return 0; }   // searches finish instantly
+int kgb_selfplay_get_root_visits(kgb_selfplay* sp, int32_t* v) {      // the budget once the search has finished (at once without KGB_MOCK_UNEVEN), one less before
+  ensureStarted(sp);
+  for(size_t g = 0; g < sp->slots.size(); g++) v[g] = sp->budget[g] - (sp->slots[g].wavesLeft > 0 ? 1 : 0);
+  return 0;
+}
 int kgb_selfplay_set_next_search_limits(kgb_selfplay* sp, const int32_t* visits, const uint8_t* plainRoot, int alsoCurrentRoots) {
   const size_t n = sp->slots.size();
   for(size_t i = 0; i < 2 * n; i++) {

@@ -39,6 +39,7 @@ def _replay_slots_with_limits(log, G, size, V):
             super().__init__(log, G, size, V)
             self.budget, self.plain = np.full(G, V, np.int32), np.zeros(G, np.uint8)
             self.next_budget, self.next_plain = np.full((G, 2), V, np.int32), np.zeros((G, 2), np.uint8)
+            self.waves_run = [0] * G
             self.cur_setup = np.tile(np.array([size, size, 0, 1], np.int32), (G, 1))
             self.next_setup, self.last_setup = self.cur_setup.copy(), self.cur_setup.copy()
             self.cur_komi = np.full(G, 7.5, np.float32)
@@ -76,6 +77,7 @@ def _replay_slots_with_limits(log, G, size, V):
             assert ev["ev"] == "playmoves" and [tuple(m) for m in ev["moves"]] == [(-1, -1) if m is None else (int(m[0]), int(m[1])) for m in moves], (ev, moves)
             before = self.root[slot]["move_num"]
             self.root[slot] = self.queues[slot].pop(0)
+            self.waves_run[slot] = 0
             assert self.root[slot]["ev"] == "root"
             if moves and self.root[slot]["move_num"] < before + len(moves):        # a move ended the game: the slot took the setup and komi handed over
                 self.last_setup[slot], self.cur_setup[slot] = self.cur_setup[slot].copy(), self.next_setup[slot].copy()
@@ -93,8 +95,11 @@ def _replay_slots_with_limits(log, G, size, V):
         def komi_values(self):
             return self.cur_komi.copy(), self.last_komi.copy()
 
-        def root_visits(self):
-            return self.budget.copy()
+        def root_visits(self):          # the budget once the root's search has had the waves it needs (KGB_MOCK_UNEVEN), one less before
+            return self.budget - np.array([1 if self.waves_left(g) > 0 else 0 for g in range(G)], np.int32)
+
+        def waves_left(self, g):
+            return max(0, self.root[g].get("waves_needed", 0) - self.waves_run[g])
 
         def game(self, g):
             colors, info = super().game(g)
@@ -103,7 +108,13 @@ def _replay_slots_with_limits(log, G, size, V):
 
         def run(self, n):
             moving = [g for g in range(G) if self.released[g] and self.queues[g]]
+            for g in range(G):
+                if not self.released[g]:
+                    self.waves_run[g] += n
+            assert all(self.waves_left(g) == 0 for g in moving), "a slot was released before its search had finished"
             super().run(n)
+            for g in moving:
+                self.waves_run[g] = 0
             for g in moving:
                 k = 1 if self.last[g]["flags"] & 1 else 0
                 self.budget[g], self.plain[g] = self.next_budget[g, k], self.next_plain[g, k]
@@ -143,7 +154,8 @@ MIXED = ("bSizes = 5,7,9\nbSizeRelProbs = 1,2,1\nallowRectangleProb = 0.3\nkoRul
     (9, "MIXED", 6.5, 0, 0.5, 0.1, False, 20, 23, "everything"),     # every option this host has, together
     (19, "STOCK", 7.5, 40, 0.5, 0.1, False, 12, 29, "none"),         # the reference's stock b18 training configuration (what neither host has is left out and named)
 ])
-def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits):
+@pytest.mark.parametrize("uneven", [0, 9], ids=["instant_searches", "uneven_searches"])       # searches that finish at once / after 1..9 waves, each slot on its own (KGB_MOCK_UNEVEN)
+def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock, size, ko, komi, max_moves, psw, vsw, search_surprise, games, seed, limits, uneven):
     from katago_b200 import game_recorder as R, npz_writer as W, selfplay_cli as C
     G, V, ROWS_PER_FILE = 3, 20, 60
     cfg = tmp_path / "c.cfg"
@@ -169,7 +181,7 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
         (tmp_path / "model.bin").write_bytes(b"unused")
         model_args, net_name, out_dir = ["-model", str(tmp_path / "model.bin")], "mocknet", out
     r = subprocess.run([host_on_mock] + model_args + ["-config", str(cfg), "-output-dir", str(out), "-max-games-total", str(games), "-seed", str(seed)],
-                       env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+                       env=dict(os.environ, KGB_MOCK_LOG=str(log), **({"KGB_MOCK_UNEVEN": str(uneven)} if uneven else {})), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     out = out_dir
 
@@ -405,8 +417,9 @@ def gatekeeper_on_mock(tmp_path_factory):
     return str(exe)
 
 
+@pytest.mark.parametrize("uneven", [0, 9], ids=["instant_searches", "uneven_searches"])
 @pytest.mark.parametrize("resign,required,seed", [(False, 0.5, 3), (True, 0.5, 8), (False, 0.9, 5)])
-def test_cpp_gatekeeper_plays_the_match_the_python_gatekeeper_plays(tmp_path, gatekeeper_on_mock, resign, required, seed):
+def test_cpp_gatekeeper_plays_the_match_the_python_gatekeeper_plays(tmp_path, gatekeeper_on_mock, resign, required, seed, uneven):
     """`katago gatekeeper` as a C++-only host (integration/b200_gatekeeper_main.cpp + b200_match.h) on the mock's two loops against the Python match
     engine (katago_b200/match_play.py) on their logs: the same games move for move and colour for colour (the record file character for character), the
     same points, the same early stop, and the directory protocol's verdict - the candidate moved to the accepted or the rejected directory, the
@@ -428,7 +441,8 @@ def test_cpp_gatekeeper_plays_the_match_the_python_gatekeeper_plays(tmp_path, ga
     log = tmp_path / "log.jsonl"
     r = subprocess.run([gatekeeper_on_mock, "-config", str(cfg), "-test-models-dir", str(dirs["test"]), "-sgf-output-dir", str(dirs["sgfs"]), "-accepted-models-dir", str(dirs["accepted"]),
                         "-rejected-models-dir", str(dirs["rejected"]), "-selfplay-dir", str(dirs["selfplay"]), "-required-candidate-win-prop", str(required), "-games-per-gpu", "8",
-                        "-quit-if-no-nets-to-test", "-seed", str(seed)], env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+                        "-quit-if-no-nets-to-test", "-seed", str(seed)], env=dict(os.environ, KGB_MOCK_LOG=str(log), **({"KGB_MOCK_UNEVEN": str(uneven)} if uneven else {})),
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
 
     # the Python match engine on the two loops' logs
