@@ -310,7 +310,8 @@ def _same_tree(a_dir, b_dir, size):
     return rows
 
 
-def test_cpp_host_follows_a_new_net_in_the_models_directory(tmp_path, host_on_mock):
+@pytest.mark.parametrize("uneven", [0, 9], ids=["instant_searches", "uneven_searches"])
+def test_cpp_host_follows_a_new_net_in_the_models_directory(tmp_path, host_on_mock, uneven):
     """`katago selfplay`'s model loop (command/selfplay.cpp:142-231, 336-352): a newer net appears in -models-dir while the host plays; between two
     pumps it stages and commits the new weights into the live handle, drops the evaluation cache, and the finished games' files move to
     <output-dir>/<new net>/ with a writer of their own - the same files, under both nets, as the Python host's ModelOutputs writes when it switches at
@@ -329,7 +330,8 @@ def test_cpp_host_follows_a_new_net_in_the_models_directory(tmp_path, host_on_mo
     out, log = tmp_path / "cpp", tmp_path / "log.jsonl"
     r = subprocess.run([host_on_mock, "-models-dir", str(nets), "-config", str(cfg), "-output-dir", str(out), "-max-games-total", str(games), "-seed", str(seed),
                         "-model-poll-seconds", "0"],
-                       env=dict(os.environ, KGB_MOCK_LOG=str(log), KGB_MOCK_NEW_MODEL=f"70:{nets / 'netB-s200' / 'model.bin.gz'}"), capture_output=True, text=True, timeout=300)
+                       env=dict(os.environ, KGB_MOCK_LOG=str(log), KGB_MOCK_NEW_MODEL=f"{70 * (3 if uneven else 1)}:{nets / 'netB-s200' / 'model.bin.gz'}",
+                                **({"KGB_MOCK_UNEVEN": str(uneven)} if uneven else {})), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     m = re.search(r"changing midgame to new neural net: netB-s200 \(swap 1, after pump (\d+)\)", r.stderr)
     assert m, r.stderr
@@ -471,7 +473,8 @@ def test_cpp_gatekeeper_plays_the_match_the_python_gatekeeper_plays(tmp_path, ga
         assert mp.games_tallied < total and "terminating remaning games" in r.stderr          # stopped as soon as the verdict could not change
 
 
-def test_cpp_match_plays_two_named_bots_like_the_python_match(tmp_path):
+@pytest.mark.parametrize("uneven", [0, 9], ids=["instant_searches", "uneven_searches"])
+def test_cpp_match_plays_two_named_bots_like_the_python_match(tmp_path, uneven):
     """`katago match` for two named bots as a C++-only host (integration/b200_match_main.cpp): per-bot search keys (maxVisits0 / maxVisits1), alternating
     colours, per-game setups - against the Python match engine on the mock loops' logs: the record file character for character, the same wins and points."""
     import re
@@ -492,7 +495,7 @@ def test_cpp_match_plays_two_named_bots_like_the_python_match(tmp_path):
                    "b200WavesPerPoll = 4\nallowResignation = true\nresignThreshold = -0.3\nresignConsecTurns = 3\n")
     log = tmp_path / "log.jsonl"
     r = subprocess.run([str(exe), "-config", str(cfg), "-sgf-output-dir", str(tmp_path / "sgfs"), "-log-file", str(tmp_path / "match.log"), "-seed", str(seed)],
-                       env=dict(os.environ, KGB_MOCK_LOG=str(log)), capture_output=True, text=True, timeout=300)
+                       env=dict(os.environ, KGB_MOCK_LOG=str(log), **({"KGB_MOCK_UNEVEN": str(uneven)} if uneven else {})), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "for bot deep (maxVisits 24)" in r.stderr and "for bot shallow (maxVisits 8)" in r.stderr
 
