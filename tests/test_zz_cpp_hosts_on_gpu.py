@@ -16,6 +16,18 @@ sys.path.insert(0, ROOT)
 SELFPLAY = os.path.join(ROOT, "katago_b200", "b200_selfplay")
 GATEKEEPER = os.path.join(ROOT, "katago_b200", "b200_gatekeeper")
 
+def _env():
+    """The loader must find libcudart for a stand-alone binary (a Python process gets it from torch's own wheels): the CUDA runtime directories of
+    this image in front of whatever LD_LIBRARY_PATH holds."""
+    dirs = ["/usr/local/cuda/lib64"]
+    try:
+        import nvidia.cuda_runtime
+        dirs.insert(0, os.path.join(os.path.dirname(nvidia.cuda_runtime.__file__), "lib"))
+    except Exception:
+        pass
+    return dict(os.environ, LD_LIBRARY_PATH=":".join(dirs + [os.environ.get("LD_LIBRARY_PATH", "")]))
+
+
 CFG = """maxVisits = 24
 numGameThreads = 16
 bSizes = 7,9
@@ -58,7 +70,7 @@ def test_cpp_selfplay_host_on_the_device(tmp_path, tmp_models):
     cfg.write_text(CFG)
     out = tmp_path / "out"
     r = subprocess.run([SELFPLAY, "-model", tmp_models["tiny_reg"], "-config", str(cfg), "-output-dir", str(out), "-max-games-total", "24", "-seed", "3"],
-                       capture_output=True, text=True, timeout=150)
+                       capture_output=True, text=True, timeout=150, env=_env())
     print(r.stderr[-3000:])
     assert r.returncode == 0, r.stderr[-2000:]
     summary = json.loads(r.stdout.strip().splitlines()[-1])
@@ -96,7 +108,7 @@ def test_cpp_gatekeeper_host_on_the_device(tmp_path, tmp_models):
     shutil.copy(tmp_models["tiny_nbt"], tmp_path / "test" / "cand-s2" / "model.bin")
     r = subprocess.run([GATEKEEPER, "-config", str(cfg), "-test-models-dir", str(tmp_path / "test"), "-sgf-output-dir", str(tmp_path / "sgfs"),
                         "-accepted-models-dir", str(tmp_path / "accepted"), "-rejected-models-dir", str(tmp_path / "rejected"), "-quit-if-no-nets-to-test", "-games-per-gpu", "8"],
-                       capture_output=True, text=True, timeout=150)
+                       capture_output=True, text=True, timeout=150, env=_env())
     print(r.stderr[-3000:])
     assert r.returncode == 0, r.stderr[-2000:]
     assert ("Candidate won match" in r.stderr) != ("Candidate lost match" in r.stderr)
