@@ -303,6 +303,7 @@ class HostRecorder {
     }
     slots_.runWaves(1);            // evaluates every root (its input row stays on the device)
   }
+  ~HostRecorder() { for(const std::weak_ptr<Waiting>& weak : waitingGames_) if(std::shared_ptr<Waiting> w = weak.lock()) w->side->waiting.reset(); }      // games still waiting at the end
   int64_t movesRecorded() const { return movesRecorded_; }
   int64_t gamesFinished() const { return gamesFinished_; }
 
@@ -331,12 +332,20 @@ class HostRecorder {
  private:
   // a finished game that waits for its lead and side-position jobs; the side positions of a game: searched ones, jobs in flight, the waiting game
   struct SideState;
-  struct Waiting { FinishedGame game; int slot; size_t left; std::weak_ptr<SideState> side; };      // (weak: the side state owns its waiting game, not the other way round)
+  // (the two point at each other while the game waits: the side state must outlive its last job for the waiting game to see every side
+  //  position, the waiting game must outlive the side state's jobs; the link is cut when the game is handed on, or by the destructor)
+  struct Waiting { FinishedGame game; int slot; size_t left; std::shared_ptr<SideState> side; };
   struct SideState { std::vector<std::shared_ptr<SidePosition>> list; int pending = 0; std::shared_ptr<Waiting> waiting; };
+  std::vector<std::weak_ptr<Waiting>> waitingGames_;
+  void rememberWaiting(const std::shared_ptr<Waiting>& w) {
+    if(waitingGames_.size() >= 1024) waitingGames_.erase(std::remove_if(waitingGames_.begin(), waitingGames_.end(), [](const std::weak_ptr<Waiting>& x) { return x.expired(); }), waitingGames_.end());
+    waitingGames_.push_back(w);
+  }
   void jobBack(std::shared_ptr<Waiting> w) {
     if(--w->left != 0) return;
     gamesWaiting_--;
-    if(std::shared_ptr<SideState> side = w->side.lock()) { w->game.sidePositions = side->list; side->waiting.reset(); }
+    w->game.sidePositions = w->side->list;
+    w->side->waiting.reset();
     if(onGame_) onGame_(w->slot, w->game);
   }
   struct InProgress {
@@ -535,6 +544,7 @@ class HostRecorder {
       if(!turns.empty()) {
         std::shared_ptr<Waiting> w(new Waiting{std::move(d), g, turns.size() + (size_t)side->pending, side});
         side->waiting = w;
+        rememberWaiting(w);
         gamesWaiting_++;
         for(size_t t : turns) {
           std::vector<Move> moves;
@@ -550,6 +560,7 @@ class HostRecorder {
     }
     if(side->pending > 0) {                  // side positions of this game are still being searched
       side->waiting.reset(new Waiting{std::move(d), g, (size_t)side->pending, side});
+      rememberWaiting(side->waiting);
       gamesWaiting_++;
       return;
     }

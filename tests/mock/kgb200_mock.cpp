@@ -32,6 +32,7 @@ struct Slot {
   Board board; BoardHistory hist; Player pla = P_BLACK;
   int moveNum = 0, gameIndex = 0;
   int32_t setup[4] = {0, 0, 0, 1}; float komi = 7.5f;      // this game's board X, Y, ko rule, multi-stone suicide; komi
+  int openingLeft = 0;              // KGB_MOCK_UNEVEN: opening moves still to be played, one per wave; the slot has no root meanwhile
   int wavesLeft = 0;                // KGB_MOCK_UNEVEN: waves the search of the current root still needs before its visits reach the budget
   int initPending = 0; std::vector<int16_t> initMoves;      // policy-initialised opening: moves to play when the game starts / the ones played (frame positions)
   bool held = true;                 // searches finish instantly in the mock
@@ -60,8 +61,11 @@ struct kgb_selfplay {
 
 static std::string g_err;
 
+static int unevenWaves() { static const int k = getenv("KGB_MOCK_UNEVEN") ? atoi(getenv("KGB_MOCK_UNEVEN")) : 0; return k; }
+
 static void searchRoot(kgb_selfplay* sp, int g) {
   Slot& s = sp->slots[g];
+  if(s.openingLeft > 0) return;       // still in its opening: the root comes when the last opening move has been played
   const int X = sp->X, Y = sp->Y, P = X * Y + 1;          // the evaluator's frame; the game's board is its top-left corner
   const int BX = s.setup[0], BY = s.setup[1];
   Lcg& r = sp->rng;
@@ -91,7 +95,7 @@ static void searchRoot(kgb_selfplay* sp, int g) {
   NNInputs::fillRowV7(s.board, s.hist, s.pla, ip, X, Y, true, s.rowSpatial.data(), s.rowGlobal.data());
   s.held = true;
   // KGB_MOCK_UNEVEN = K: searches take 1..K waves (else they finish at once), so that hosts see slots finish at different times like on the device
-  static const int uneven = getenv("KGB_MOCK_UNEVEN") ? atoi(getenv("KGB_MOCK_UNEVEN")) : 0;
+  const int uneven = unevenWaves();
   s.wavesLeft = uneven > 0 ? 1 + (int)(sp->waveRng.next() % (uint32_t)uneven) : 0;
   // log
   std::ofstream& o = sp->log;
@@ -112,15 +116,10 @@ static void searchRoot(kgb_selfplay* sp, int g) {
   o << "}\n";
 }
 
-static void startGame(kgb_selfplay* sp, int g) {
+// the opening the device would draw from the policy: here uniformly random legal board moves, never held for recording
+static void playOpeningMoves(kgb_selfplay* sp, int g, int count) {
   Slot& s = sp->slots[g];
-  Rules rules = sp->rules;
-  rules.koRule = s.setup[2] == 1 ? Rules::KO_POSITIONAL : s.setup[2] == 2 ? Rules::KO_SITUATIONAL : s.setup[2] == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
-  rules.multiStoneSuicideLegal = s.setup[3] != 0; rules.komi = s.komi;
-  s.board = Board(s.setup[0], s.setup[1]); s.pla = P_BLACK; s.hist = BoardHistory(s.board, s.pla, rules, 0, false); s.moveNum = 0;
-  // the opening the device would draw from the policy: here uniformly random legal board moves, played at once and never held for recording
-  s.initMoves.clear();
-  for(int i = 0; i < s.initPending; i++) {
+  for(int i = 0; i < count; i++) {
     std::vector<Loc> legal;
     for(int y = 0; y < s.setup[1]; y++) for(int x = 0; x < s.setup[0]; x++) { Loc l = Location::getLoc(x, y, s.setup[0]); if(s.hist.isLegal(s.board, l, s.pla)) legal.push_back(l); }
     if(legal.empty()) break;
@@ -130,6 +129,18 @@ static void startGame(kgb_selfplay* sp, int g) {
     s.initMoves.push_back((int16_t)(Location::getY(l, s.setup[0]) * sp->X + Location::getX(l, s.setup[0])));
     s.moveNum++;
   }
+}
+
+static void startGame(kgb_selfplay* sp, int g) {
+  Slot& s = sp->slots[g];
+  Rules rules = sp->rules;
+  rules.koRule = s.setup[2] == 1 ? Rules::KO_POSITIONAL : s.setup[2] == 2 ? Rules::KO_SITUATIONAL : s.setup[2] == 3 ? Rules::KO_SPIGHT : Rules::KO_SIMPLE;
+  rules.multiStoneSuicideLegal = s.setup[3] != 0; rules.komi = s.komi;
+  s.board = Board(s.setup[0], s.setup[1]); s.pla = P_BLACK; s.hist = BoardHistory(s.board, s.pla, rules, 0, false); s.moveNum = 0;
+  // the opening: played at once - or, with KGB_MOCK_UNEVEN, one move per wave like the device (the slot has no root meanwhile)
+  s.initMoves.clear();
+  if(unevenWaves() > 0) s.openingLeft = s.initPending;
+  else playOpeningMoves(sp, g, s.initPending);
   s.initPending = 0;
 }
 
@@ -241,9 +252,18 @@ int kgb_selfplay_run(kgb_selfplay* sp, int waves) {
       const std::string spec = nm; const size_t colon = spec.find(':');
       if(++runs == atoi(spec.substr(0, colon).c_str())) { std::ofstream f(spec.substr(colon + 1)); f << "unused"; }
     }
-    for(size_t g = 0; g < sp->slots.size(); g++) if(!sp->released[g]) sp->slots[g].wavesLeft = std::max(0, sp->slots[g].wavesLeft - waves);      // searches go on
+    for(size_t g = 0; g < sp->slots.size(); g++) if(!sp->released[g]) {
+      Slot& s = sp->slots[g];
+      if(s.openingLeft > 0) {               // one opening move per wave; then the game's first root
+        const int k = std::min(waves, s.openingLeft);
+        playOpeningMoves(sp, (int)g, k);
+        s.openingLeft -= k;
+        if(s.openingLeft == 0) searchRoot(sp, (int)g);
+      }
+      else s.wavesLeft = std::max(0, s.wavesLeft - waves);      // searches go on
+    }
     for(size_t g = 0; g < sp->slots.size(); g++) if(sp->released[g]) {
-      if(sp->slots[g].wavesLeft > 0) throw std::runtime_error("mock: a slot was released before its search had finished");
+      if(sp->slots[g].wavesLeft > 0 || sp->slots[g].openingLeft > 0) throw std::runtime_error("mock: a slot was released before its search had finished");
       sp->released[g] = 0; advance(sp, (int)g);
       const size_t k = 2 * g + ((sp->slots[g].last[1] & 1) ? 1 : 0);       // the new root takes the limits handed over for it
       sp->budget[g] = sp->nextBudget[k]; sp->plain[g] = sp->nextPlain[k];
@@ -300,7 +320,7 @@ int kgb_selfplay_get_policy_init(kgb_selfplay* sp, int32_t* movesLeft, int32_t* 
   ensureStarted(sp);
   for(size_t g = 0; g < sp->slots.size(); g++) {
     const std::vector<int16_t>& m = sp->slots[g].initMoves;
-    if(movesLeft) movesLeft[g] = 0;                  // the mock plays a whole opening at once
+    if(movesLeft) movesLeft[g] = sp->slots[g].openingLeft;      // (0 unless KGB_MOCK_UNEVEN: then one opening move per wave)
     if(count) count[g] = (int32_t)m.size();
     if(moves) for(int i = 0; i < maxMoves; i++) moves[g * (size_t)maxMoves + i] = i < (int)m.size() ? m[i] : 0;
   }
@@ -366,6 +386,7 @@ int kgb_selfplay_play_moves_game(kgb_selfplay* sp, int g, const int8_t* xy, int 
   try {
     ensureStarted(sp);
     Slot& s = sp->slots[g];
+    if(s.openingLeft > 0) throw std::runtime_error("mock: play_moves_game on a slot that is in its opening");
     sp->log << "{\"ev\":\"playmoves\",\"slot\":" << g << ",\"moves\":[";
     for(int i = 0; i < n; i++) {
       const int x = xy[2 * i];

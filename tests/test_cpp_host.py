@@ -29,7 +29,7 @@ def host_on_mock(tmp_path_factory):
     return str(exe)
 
 
-def _replay_slots_with_limits(log, G, size, V):
+def _replay_slots_with_limits(log, G, size, V, uneven=0):
     """ReplaySlots plus the device's per-root search limits as the mock keeps them: a root's budget and plain flag are the ones handed over for "after
     this slot's next move" (entry 0 the game goes on, entry 1 a new game starts); searches finish instantly, root visits = budget (+ slot in the info)."""
     from test_game_recorder import ReplaySlots
@@ -40,6 +40,8 @@ def _replay_slots_with_limits(log, G, size, V):
             self.budget, self.plain = np.full(G, V, np.int32), np.zeros(G, np.uint8)
             self.next_budget, self.next_plain = np.full((G, 2), V, np.int32), np.zeros((G, 2), np.uint8)
             self.waves_run = [0] * G
+            # KGB_MOCK_UNEVEN: a game's opening takes one wave per move; the slot has no root meanwhile (and reports its budget as visits, like stale device state)
+            self.opening_left = [len(self.root[g].get("init_moves", [])) if uneven else 0 for g in range(G)]
             self.cur_setup = np.tile(np.array([size, size, 0, 1], np.int32), (G, 1))
             self.next_setup, self.last_setup = self.cur_setup.copy(), self.cur_setup.copy()
             self.cur_komi = np.full(G, 7.5, np.float32)
@@ -90,7 +92,7 @@ def _replay_slots_with_limits(log, G, size, V):
         def policy_init(self, max_moves=0):
             n = self.x * self.y
             moves = [[(-1, -1) if p == n else (p % self.x, p // self.x) for p in self.root[g]["init_moves"]] for g in range(G)]
-            return np.zeros(G, np.int32), np.array([len(m) for m in moves], np.int32), (moves if max_moves > 0 else None)
+            return np.array(self.opening_left, np.int32), np.array([len(m) for m in moves], np.int32), (moves if max_moves > 0 else None)
 
         def komi_values(self):
             return self.cur_komi.copy(), self.last_komi.copy()
@@ -99,7 +101,7 @@ def _replay_slots_with_limits(log, G, size, V):
             return self.budget - np.array([1 if self.waves_left(g) > 0 else 0 for g in range(G)], np.int32)
 
         def waves_left(self, g):
-            return max(0, self.root[g].get("waves_needed", 0) - self.waves_run[g])
+            return 0 if self.opening_left[g] > 0 else max(0, self.root[g].get("waves_needed", 0) - self.waves_run[g])
 
         def game(self, g):
             colors, info = super().game(g)
@@ -109,12 +111,19 @@ def _replay_slots_with_limits(log, G, size, V):
         def run(self, n):
             moving = [g for g in range(G) if self.released[g] and self.queues[g]]
             for g in range(G):
-                if not self.released[g]:
+                if self.released[g]:
+                    continue
+                if self.opening_left[g] > 0:
+                    self.opening_left[g] -= min(n, self.opening_left[g])
+                    self.waves_run[g] = 0
+                else:
                     self.waves_run[g] += n
-            assert all(self.waves_left(g) == 0 for g in moving), "a slot was released before its search had finished"
+            assert all(self.waves_left(g) == 0 and self.opening_left[g] == 0 for g in moving), "a slot was released before its search had finished"
             super().run(n)
             for g in moving:
                 self.waves_run[g] = 0
+                if uneven and self.last[g]["flags"] & 1:
+                    self.opening_left[g] = len(self.root[g].get("init_moves", []))
             for g in moving:
                 k = 1 if self.last[g]["flags"] & 1 else 0
                 self.budget[g], self.plain[g] = self.next_budget[g, k], self.next_plain[g, k]
@@ -187,7 +196,7 @@ def test_cpp_host_writes_the_files_the_python_host_writes(tmp_path, host_on_mock
 
     # the Python host's recorder and writer on the same slots (the mock's log replayed), seeded like selfplay_cli.py seeds them
     _, loop_seed, writer_seed = C.shard_plan(0, 1, games, seed)
-    sp = _replay_slots_with_limits(str(log), G, size, V)
+    sp = _replay_slots_with_limits(str(log), G, size, V, uneven)
     sp.max_visits = V
     kw, data, _ = C.selfplay_kwargs_from_cfg(C.parse_cfg(str(cfg)))
     py = tmp_path / "py"
