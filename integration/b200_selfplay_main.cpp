@@ -106,6 +106,7 @@ int main(int argc, char** argv) {
   double modelPollSeconds = 20.0;
   int rank = 0, worldSize = 1, gpuIdx = -1;
   bool ncclWeights = false; std::string ncclToken;
+  long restartGeneration = 0;            // internal: how often this run has re-started itself for a net of another architecture
   bool printOnly = false, strict = false;
   for(int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -124,6 +125,7 @@ int main(int argc, char** argv) {
     else if(a == "-gpu") gpuIdx = std::atoi(next().c_str());
     else if(a == "-nccl-weights") ncclWeights = true;
     else if(a == "-nccl-token") ncclToken = next();
+    else if(a == "-restart-generation") restartGeneration = std::atol(next().c_str());
     else if(a == "-max-games-total") maxGamesTotal = std::atol(next().c_str());
     else if(a == "-help" || a == "--help") {
       std::printf("usage: %s (-model FILE | -models-dir DIR) -config FILE -output-dir DIR [-max-games-total N] [-seed S] [-model-poll-seconds T] [-rank R -world-size N] [-gpu I] [-nccl-weights [-nccl-token T]] [-override-config k=v,...] [-strict] [-print-config]\n", argv[0]);
@@ -137,9 +139,9 @@ int main(int argc, char** argv) {
   // One process per GPU: games are independent, so ranks share nothing - each plays its share of the games on its own GPU with its own seeds
   // and writes its own files into the common directories (names come from the writers' Rand streams); katago_b200/selfplay_cli.py shard_plan
   if(worldSize < 1 || rank < 0 || rank >= worldSize) die("-rank must lie in 0 .. -world-size - 1");
-  if(maxGamesTotal > 0) maxGamesTotal = maxGamesTotal / worldSize + (rank < maxGamesTotal % worldSize ? 1 : 0);
+  if(maxGamesTotal > 0 && restartGeneration == 0) maxGamesTotal = maxGamesTotal / worldSize + (rank < maxGamesTotal % worldSize ? 1 : 0);      // (a re-started run is handed its own remainder)
   if(gpuIdx < 0) gpuIdx = rank;
-  const uint64_t loopSeed = (uint64_t)seed * 1000003ULL + (uint64_t)rank;
+  const uint64_t loopSeed = (uint64_t)seed * 1000003ULL + (uint64_t)rank + 7919ULL * (uint64_t)restartGeneration;       // (selfplay_cli.py: loop_seed + 7919 * swaps for a rebuilt evaluator)
   Cfg cfg;
   cfg.load(cfgPath);
   cfg.overrides(overrides);
@@ -205,6 +207,7 @@ int main(int argc, char** argv) {
     Outputs outputs;
     outputs.baseDir = outDir; outputs.writerSeed = writerSeed; outputs.perNet = !modelsDir.empty();
     outputs.maxRowsPerFile = (int)cfg.num("maxRowsPerTrainFile", 20000); outputs.firstFileMinRandProp = cfg.num("firstFileRandMinProp", 1.0); outputs.dataLen = edge;
+    outputs.generation = (int)restartGeneration;
     outputs.switchTo(modelPath, info.name);
     // the reference's own log lines (command/selfplay.cpp, program/selfplaymanager.cpp:290-303), on stderr
     auto logLine = [](const std::string& msg) { std::fprintf(stderr, "%s\n", msg.c_str()); };
@@ -446,10 +449,33 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "b200_selfplay: %s: %s; keeping %s\n", newest.c_str(), kgb_last_error(), outputs.netName.c_str());
         continue;
       }
-      if(kgb_handle_stage_weights(handle, next) != 0) {                     // another architecture needs a new evaluator: selfplay_cli.py rebuilds one, this host keeps its net
-        std::fprintf(stderr, "b200_selfplay: %s: %s; keeping %s\n", newest.c_str(), kgb_last_error(), outputs.netName.c_str());
-        kgb_model_free(next); ignoredModel = newest;
-        continue;
+      if(kgb_handle_stage_weights(handle, next) != 0) {
+        const std::string why = kgb_last_error();
+        kgb_model_free(next);
+        if(why.find("architecture") == std::string::npos && why.find("layout") == std::string::npos && why.find("largest convolution") == std::string::npos) {
+          std::fprintf(stderr, "b200_selfplay: %s: %s; keeping %s\n", newest.c_str(), why.c_str(), outputs.netName.c_str());
+          ignoredModel = newest;
+          continue;
+        }
+        // Another architecture: the reference builds a new NNEvaluator for any net; here that means a new evaluator, handles and loops, and the games
+        // in flight are dropped (their finished predecessors are already written) - done by starting this program afresh on the new net, with the
+        // games still to play, the next output generation and loop seeds of its own (as selfplay_cli.py rebuilds its evaluator in place).
+        std::fprintf(stderr, "b200_selfplay: %s: %s; rebuilding the evaluator (games in progress are abandoned)\n", newest.c_str(), why.c_str());
+        outputs.close();
+        std::vector<std::string> args;
+        for(int i = 0; i < argc; i++) {
+          const std::string a = argv[i];
+          if(a == "-max-games-total" || a == "-restart-generation") { i++; continue; }
+          args.push_back(a);
+        }
+        if(maxGamesTotal > 0) { args.push_back("-max-games-total"); args.push_back(std::to_string(maxGamesTotal - written)); }
+        args.push_back("-restart-generation"); args.push_back(std::to_string(std::max((long)outputs.generation, restartGeneration + 1)));
+        std::vector<char*> raw;
+        for(std::string& a : args) raw.push_back(&a[0]);
+        raw.push_back(nullptr);
+        std::fflush(nullptr);
+        execv(argv[0], raw.data());
+        die(std::string("cannot re-start ") + argv[0]);
       }
       check(kgb_handle_commit_weights(handle), "committing the new weights");
       slots.clearNNCache();

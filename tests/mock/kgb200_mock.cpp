@@ -46,9 +46,9 @@ struct Slot {
 };
 }  // namespace
 
-struct kgb_model { int dummy; };
+struct kgb_model { std::string path; };
 struct kgb_context { int x, y; };
-struct kgb_handle { int x, y; };
+struct kgb_handle { int x, y; bool otherArch; };
 struct kgb_selfplay {
   kgb_selfplay_config cfg; int X, Y; Rules rules; Lcg rng{1}, waveRng{12345}; std::vector<Slot> slots; std::vector<uint8_t> released; std::ofstream log;
   // per-root search limits (kgb_selfplay_set_next_search_limits): the current roots' and, per slot, those of the root after its next move [goes on, new game]
@@ -194,17 +194,21 @@ extern "C" {
 int kgb_global_init(void) { static bool done = false; if(!done) { Board::initHash(); done = true; } return 0; }     // (returns at once when the caller has done it)
 int kgb_global_cleanup(void) { return 0; }
 const char* kgb_last_error(void) { return g_err.c_str(); }
-int kgb_model_load_file(const char*, const char*, kgb_model** out) { *out = new kgb_model(); return 0; }
+int kgb_model_load_file(const char* path, const char*, kgb_model** out) { *out = new kgb_model{path}; return 0; }
 void kgb_model_free(kgb_model* m) { delete m; }
 int kgb_model_get_info(const kgb_model*, kgb_model_info* out) { memset(out, 0, sizeof(*out)); strcpy(out->name, "mocknet"); return 0; }
 // the reference's own Rand: the stream the library's host generator reproduces (tests/test_abi_and_loader.py)
 int kgb_rand_uint32_stream(const char* seed, int n, uint32_t* out) { Rand r(seed); for(int i = 0; i < n; i++) out[i] = r.nextUInt(); return 0; }
 int kgb_context_create(const int*, int, int x, int y, int, const kgb_model*, kgb_context** out) { *out = new kgb_context{x, y}; return 0; }
 void kgb_context_free(kgb_context* c) { delete c; }
-int kgb_handle_create(kgb_context* c, const kgb_model*, int, int, int, int, kgb_handle** out) { *out = new kgb_handle{c->x, c->y}; return 0; }
+int kgb_handle_create(kgb_context* c, const kgb_model* m, int, int, int, int, kgb_handle** out) { *out = new kgb_handle{c->x, c->y, m->path.find("otherarch") != std::string::npos}; return 0; }
 void kgb_handle_free(kgb_handle* h) { delete h; }
 int kgb_handle_sync(kgb_handle*) { return 0; }
-int kgb_handle_stage_weights(kgb_handle*, const kgb_model*) { return 0; }       // weight hot-swap: nothing to swap in the mock
+// weight hot-swap: nothing to swap in the mock; a net whose path contains "otherarch" is of another architecture than a handle built for one without
+int kgb_handle_stage_weights(kgb_handle* h, const kgb_model* m) {
+  if((m->path.find("otherarch") != std::string::npos) != h->otherArch) { g_err = "kgb_handle_stage_weights: the model is not of the architecture this handle was built for"; return 1; }
+  return 0;
+}
 int kgb_handle_commit_weights(kgb_handle*) { return 0; }
 int kgb_selfplay_clear_nn_cache(kgb_selfplay*) { return 0; }
 int kgb_handle_wait_staged(kgb_handle*) { return 0; }

@@ -530,3 +530,31 @@ def test_cpp_match_plays_two_named_bots_like_the_python_match(tmp_path, uneven):
     assert m and (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (wins["deep"], wins["shallow"], wins["none"]), r.stderr[-600:]
     assert (float(m.group(4)), float(m.group(5)), int(m.group(6))) == (round(mp.win_points[0], 1), round(mp.win_points[1], 1), total)
     assert open(tmp_path / "match.log").read().count("\n") >= total + 3
+
+
+def test_cpp_host_rebuilds_its_evaluator_for_a_net_of_another_architecture(tmp_path, host_on_mock):
+    """A new net that the live handle cannot take (another architecture: kgb_handle_stage_weights refuses it) makes the host start afresh on it - a
+    new evaluator, the games in flight dropped, the games still to play, the next output generation and loop seeds of its own - like
+    selfplay_cli.py rebuilds its evaluator in place (the reference builds a new NNEvaluator for every net)."""
+    import json, re
+    G, V, size, games = 3, 20, 7, 14
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text(f"maxVisits = {V}\nnumGameThreads = {G}\nbSizes = {size}\nkomiMean = 6.5\nmaxMovesPerGame = 16\nmaxRowsPerTrainFile = 50\nb200WavesPerPoll = 4\n")
+    nets = tmp_path / "nets"
+    os.makedirs(nets / "netA-s100"); os.makedirs(nets / "netB-otherarch-s200")
+    (nets / "netA-s100" / "model.bin.gz").write_bytes(b"unused")
+    os.utime(nets / "netA-s100" / "model.bin.gz", (1000, 1000))
+    out = tmp_path / "out"
+    r = subprocess.run([host_on_mock, "-models-dir", str(nets), "-config", str(cfg), "-output-dir", str(out), "-max-games-total", str(games), "-seed", "5", "-model-poll-seconds", "0"],
+                       env=dict(os.environ, KGB_MOCK_LOG=str(tmp_path / "log.jsonl"), KGB_MOCK_NEW_MODEL=f"50:{nets / 'netB-otherarch-s200' / 'model.bin.gz'}"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "rebuilding the evaluator (games in progress are abandoned)" in r.stderr and "Loaded latest neural net netB-otherarch-s200" in r.stderr
+    summary = json.loads(r.stdout.strip().splitlines()[-1])          # the re-started run's own count
+    records = {name: open(out / name / "sgfs" / os.listdir(out / name / "sgfs")[0]).read() for name in ("netA-s100", "netB-otherarch-s200")}
+    played = {name: text.count("\n") for name, text in records.items()}
+    assert played["netA-s100"] >= 3 and played["netB-otherarch-s200"] == summary["games_written"] and sum(played.values()) == games
+    hashes = [h for text in records.values() for h in re.findall(r"gameHash=([0-9A-F]{32})", text)]
+    assert len(set(hashes)) == games                                   # the re-started run has loop seeds of its own
+    files = [f for name in records for f in os.listdir(out / name / "tdata")]
+    assert len(set(files)) == len(files) >= 2
