@@ -116,3 +116,34 @@ def test_cpp_gatekeeper_host_on_the_device(tmp_path, tmp_models):
     assert os.path.isdir(tmp_path / ("accepted" if won else "rejected") / "cand-s2") and not os.listdir(tmp_path / "test")
     records = os.listdir(tmp_path / "sgfs" / "cand-s2")
     assert len(records) == 1 and open(tmp_path / "sgfs" / "cand-s2" / records[0]).read().count("(;FF[4]") >= 5
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU run of the C++-only selfplay host next to the Python host (CPU-validated so far)")
+@pytest.mark.skipif(not os.path.exists(SELFPLAY), reason="katago_b200/b200_selfplay not built (__graft_entry__.build())")
+def test_cpp_and_python_selfplay_hosts_write_the_same_rows_on_the_device(tmp_path, tmp_models):
+    """Both hosts make the same ABI calls in the same order (that is what tests/test_cpp_host.py shows on the mock), the device loop is deterministic,
+    so the same seed gives the same games: the C++ host's rows and records are the Python host's, bit for bit (the Python command does not cap the
+    games of its last pump, so it may write a few more at the end: compared is the common prefix, which must be everything the C++ host wrote).
+    The evaluation cache is off here: which of two colliding entries survives a wave is the one thing a slot's timing could change."""
+    import shutil
+    os.makedirs(tmp_path / "nets")
+    shutil.copy(tmp_models["tiny_reg"], tmp_path / "nets" / "tiny-s1.bin")
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text(CFG.replace("nnCacheSizePowerOfTwo = 16", "nnCacheSizePowerOfTwo = 0").replace("maxRowsPerTrainFile = 400", "maxRowsPerTrainFile = 100000"))
+    runs = {}
+    for name, cmd in (("cpp", [SELFPLAY]), ("py", [sys.executable, "-m", "katago_b200.selfplay_cli", "-per-game-release"])):
+        r = subprocess.run(cmd + ["-models-dir", str(tmp_path / "nets"), "-config", str(cfg), "-output-dir", str(tmp_path / name), "-max-games-total", "20", "-seed", "7"],
+                           capture_output=True, text=True, timeout=200, env=_env(), cwd=ROOT)
+        print(name, r.stderr[-1500:])
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        d = tmp_path / name / "tiny-s1"
+        files = sorted(os.listdir(d / "tdata"), key=lambda f: os.path.getmtime(d / "tdata" / f))
+        z = [np.load(d / "tdata" / f) for f in files]
+        runs[name] = ({k: np.concatenate([x[k] for x in z]) for k in z[0].files}, open(d / "sgfs" / os.listdir(d / "sgfs")[0]).read().splitlines())
+    (cpp_rows, cpp_sgf), (py_rows, py_sgf) = runs["cpp"], runs["py"]
+    n = cpp_rows["globalTargetsNC"].shape[0]
+    print(f"C++ host: {len(cpp_sgf)} games, {n} rows; Python host: {len(py_sgf)} games, {py_rows['globalTargetsNC'].shape[0]} rows")
+    assert len(cpp_sgf) == 20 and py_sgf[:20] == cpp_sgf
+    for k in cpp_rows:
+        assert py_rows[k].shape[0] >= n and cpp_rows[k].tobytes() == py_rows[k][:n].tobytes(), k
