@@ -70,7 +70,7 @@ def test_cpp_selfplay_host_on_the_device(tmp_path, tmp_models):
     cfg.write_text(CFG)
     out = tmp_path / "out"
     r = subprocess.run([SELFPLAY, "-model", tmp_models["tiny_reg"], "-config", str(cfg), "-output-dir", str(out), "-max-games-total", "24", "-seed", "3"],
-                       capture_output=True, text=True, timeout=150, env=_env())
+                       capture_output=True, text=True, timeout=75, env=_env())
     print(r.stderr[-3000:])
     assert r.returncode == 0, r.stderr[-2000:]
     summary = json.loads(r.stdout.strip().splitlines()[-1])
@@ -108,7 +108,7 @@ def test_cpp_gatekeeper_host_on_the_device(tmp_path, tmp_models):
     shutil.copy(tmp_models["tiny_nbt"], tmp_path / "test" / "cand-s2" / "model.bin")
     r = subprocess.run([GATEKEEPER, "-config", str(cfg), "-test-models-dir", str(tmp_path / "test"), "-sgf-output-dir", str(tmp_path / "sgfs"),
                         "-accepted-models-dir", str(tmp_path / "accepted"), "-rejected-models-dir", str(tmp_path / "rejected"), "-quit-if-no-nets-to-test", "-games-per-gpu", "8"],
-                       capture_output=True, text=True, timeout=150, env=_env())
+                       capture_output=True, text=True, timeout=75, env=_env())
     print(r.stderr[-3000:])
     assert r.returncode == 0, r.stderr[-2000:]
     assert ("Candidate won match" in r.stderr) != ("Candidate lost match" in r.stderr)
@@ -134,7 +134,7 @@ def test_cpp_and_python_selfplay_hosts_write_the_same_rows_on_the_device(tmp_pat
     runs = {}
     for name, cmd in (("cpp", [SELFPLAY]), ("py", [sys.executable, "-m", "katago_b200.selfplay_cli", "-per-game-release"])):
         r = subprocess.run(cmd + ["-models-dir", str(tmp_path / "nets"), "-config", str(cfg), "-output-dir", str(tmp_path / name), "-max-games-total", "20", "-seed", "7"],
-                           capture_output=True, text=True, timeout=200, env=_env(), cwd=ROOT)
+                           capture_output=True, text=True, timeout=75 if name == "cpp" else 150, env=_env(), cwd=ROOT)
         print(name, r.stderr[-1500:])
         assert r.returncode == 0, (name, r.stderr[-2000:])
         d = tmp_path / name / "tiny-s1"
